@@ -1,0 +1,37 @@
+# Builds libvelox_b200.so (CUDA kernels for sm_100a + C++ operator layer + C ABI) in-tree,
+# and the CPU oracle used by the tests (oracle/liboracle.so).
+NVCC ?= nvcc
+CXX ?= g++
+ARCH = -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS = -std=c++20 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -Iinclude -Ivelox_b200
+CXXFLAGS = -std=c++20 -O2 -fPIC -Wall -Iinclude -Ivelox_b200 -I/usr/local/cuda/include
+BUILD = build
+LIB = velox_b200/lib/libvelox_b200.so
+
+CU_SRCS = $(wildcard velox_b200/csrc/*.cu)
+CPP_SRCS = $(wildcard velox_b200/csrc/host/*.cpp)
+OBJS = $(patsubst velox_b200/csrc/%.cu,$(BUILD)/%.o,$(CU_SRCS)) \
+       $(patsubst velox_b200/csrc/host/%.cpp,$(BUILD)/host_%.o,$(CPP_SRCS))
+
+all: $(LIB) oracle
+
+$(BUILD)/%.o: velox_b200/csrc/%.cu $(wildcard velox_b200/csrc/*.cuh) $(wildcard include/*.h)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(BUILD)/host_%.o: velox_b200/csrc/host/%.cpp $(wildcard velox_b200/csrc/host/*.h) $(wildcard velox_b200/abi/*.h) $(wildcard include/*.h)
+	@mkdir -p $(BUILD)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	@mkdir -p velox_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -l:libnccl.so.2
+
+oracle:
+	$(MAKE) -s -C oracle
+
+clean:
+	rm -rf $(BUILD) $(LIB)
+	$(MAKE) -s -C oracle clean
+
+.PHONY: all oracle clean

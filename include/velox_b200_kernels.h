@@ -1,0 +1,271 @@
+/*
+ * velox_b200 — kernel-level C ABI (device pointers in, device pointers out).
+ *
+ * These are the entry points the C++ operator layer (velox_b200/csrc/host) calls; Velox itself
+ * never sees them (SURVEY.md §8b "What a C-ABI replacement must export"). Every function
+ * takes raw device pointers, row counts and a cudaStream_t (as void*), returns 0 or a VB2_ERR_*
+ * code, and never synchronises the stream unless stated. vb2_last_error() gives the message.
+ *
+ * Each entry cites the reference code whose work it takes over (paths into
+ * /root/reference/velox).
+ */
+#ifndef VELOX_B200_KERNELS_H_
+#define VELOX_B200_KERNELS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  VB2_OK = 0,
+  VB2_ERR_CUDA = 1,        /* CUDA runtime / NCCL failure -> VeloxRuntimeError */
+  VB2_ERR_INVALID = 2,     /* bad argument -> VeloxRuntimeError */
+  VB2_ERR_UNSUPPORTED = 3, /* shape not covered by this build -> VeloxRuntimeError (never a CPU fallback) */
+  VB2_ERR_USER = 4         /* data error: integer overflow, division by zero, bad cast -> VeloxUserError */
+};
+
+/* TypeKind numbering of velox/type/Type.h. DATE is INTEGER days (velox/type/Type.h:1305). */
+enum { VB2_BOOLEAN = 0, VB2_INTEGER = 3, VB2_BIGINT = 4, VB2_DOUBLE = 6, VB2_VARCHAR = 7 };
+/* VectorEncoding::Simple subset of velox/vector/VectorEncoding.h. */
+enum { VB2_FLAT = 0, VB2_DICTIONARY = 1, VB2_CONSTANT = 2 };
+
+/*
+ * One column of a batch (mirror of FlatVector / DictionaryVector / ConstantVector buffers,
+ * velox/vector/FlatVector.h:604-607, DictionaryVector.h:275-278):
+ *   FLAT        values = T[size]; BOOLEAN is bit-packed (u64 words, LSB first); VARCHAR is
+ *               int32 offsets[size+1] into aux (chars). nulls = validity bitmap, 1 = not null
+ *               (velox/common/base/Nulls.h:26-27), or NULL when the column has no nulls.
+ *   DICTIONARY  indices = int32[size]; nulls = validity of the wrapper; values/aux/dict_nulls
+ *               describe the dict_size base values.
+ *   CONSTANT    values holds one element; nulls (if set) bit 0 gives validity.
+ * At this level every pointer is a device pointer.
+ */
+typedef struct vb2_column {
+  int32_t type;
+  int32_t encoding;
+  int64_t size;
+  const void* values;
+  const uint64_t* nulls;
+  const int32_t* indices;
+  int64_t dict_size;
+  const uint64_t* dict_nulls;
+  const void* aux;
+} vb2_column;
+
+const char* vb2_last_error(void);
+int vb2k_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Key hashing and partitioning.
+ * Replaces VectorHasher::hash (velox/exec/VectorHasher.cpp:567-594, hashValues :87-126) and
+ * HashPartitionFunction::partition (velox/exec/HashPartitionFunction.cpp:75-118): bit-exact
+ * folly::hasher<T> per key column, bits::hashMix across columns, kNullHash for nulls, then
+ * hash % num_partitions.
+ * ------------------------------------------------------------------------------------------ */
+int vb2k_hash_columns(const vb2_column* cols, int32_t ncols, int64_t rows, uint64_t* hashes, void* stream);
+int vb2k_partition_ids(const uint64_t* hashes, int64_t rows, int32_t num_partitions, uint32_t* ids, void* stream);
+/* counts[p] = rows with id p; offsets computed on device; row_order = rows grouped by partition
+ * (stable within a partition). All outputs device memory: counts int64[P], row_order int32[rows]. */
+int vb2k_partition_scatter_order(const uint32_t* ids, int64_t rows, int32_t num_partitions, int64_t* counts,
+                                 int32_t* row_order, void* stream);
+/* out[i] = in[order[i]] for fixed-width columns (elem_bytes 4 or 8). */
+int vb2k_gather(const void* in, const int32_t* order, int64_t n, int32_t elem_bytes, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Expression VM: evaluates a compiled ExprSet (filter + projections) in one kernel.
+ * Replaces ExprSet::eval / Expr::eval / evalFlatNoNulls / evalAll / applyFunction
+ * (velox/expression/Expr.cpp:2339,848,801,1513,1787), ConjunctExpr / SwitchExpr special forms
+ * (expression/ConjunctExpr.cpp:93, SwitchExpr.cpp:71), the scalar kernels of
+ * functions/prestosql/{Arithmetic,Comparisons}.h, CastExpr, LIKE (functions/lib/Re2Functions.cpp:710)
+ * and processFilterResults (velox/exec/OperatorUtils.cpp:231-321).
+ * ------------------------------------------------------------------------------------------ */
+enum vb2_opcode {
+  VB2_OP_LOAD = 1,    /* dst <- column a (decodes flat/dictionary/constant, nulls) */
+  VB2_OP_CONST = 2,   /* dst <- constant a */
+  VB2_OP_ADD = 3, VB2_OP_SUB = 4, VB2_OP_MUL = 5, VB2_OP_DIV = 6, VB2_OP_MOD = 7, VB2_OP_NEG = 8,
+  VB2_OP_LT = 9, VB2_OP_LTE = 10, VB2_OP_GT = 11, VB2_OP_GTE = 12, VB2_OP_EQ = 13, VB2_OP_NEQ = 14,
+  VB2_OP_BETWEEN = 15, /* a between b and c */
+  VB2_OP_AND = 16, VB2_OP_OR = 17, VB2_OP_NOT = 18, VB2_OP_IS_NULL = 19,
+  VB2_OP_SELECT = 20,  /* dst <- (a is true and not null) ? b : c  — CASE/IF */
+  VB2_OP_CAST = 21,    /* dst <- cast(a); type = target, b = source type */
+  VB2_OP_LIKE = 22,    /* dst <- column a LIKE constant b (VARCHAR column, pattern constant) */
+  VB2_OP_STRCMP = 23,  /* dst <- column a <cmp c> constant b, c = vb2 compare code (0 lt .. 5 neq) */
+  VB2_OP_NULL = 24     /* dst <- NULL of `type` */
+};
+
+typedef struct vb2_instr {
+  int32_t op;
+  int32_t type; /* operand type for arithmetic/compare, result type otherwise */
+  int32_t dst;
+  int32_t a, b, c;
+} vb2_instr;
+
+typedef struct vb2_const {
+  int32_t type;
+  int32_t is_null;
+  int64_t i; /* BOOLEAN / INTEGER / BIGINT payload */
+  double d;  /* DOUBLE payload */
+  const char* str; /* VARCHAR payload (device pointer) */
+  int32_t len;
+  int32_t pad;
+} vb2_const;
+
+typedef struct vb2_program {
+  const vb2_instr* instrs; /* host pointer; copied to the kernel as an argument block */
+  int32_t n_instrs;        /* <= 256 */
+  int32_t n_filter_instrs; /* instrs [0, n_filter_instrs) compute the filter register */
+  int32_t filter_reg;      /* -1 when there is no filter */
+  int32_t n_regs;          /* <= 32 */
+  const vb2_const* consts; /* host pointer */
+  int32_t n_consts;        /* <= 32 */
+  int32_t pad;
+} vb2_program;
+
+typedef struct vb2_output {
+  int32_t reg;
+  int32_t type;
+  void* values;    /* T[n_out]; BOOLEAN written one byte per row */
+  uint64_t* nulls; /* validity bitmap of n_out bits, always written */
+} vb2_output;
+
+/* Pass 1: evaluates the filter over `rows` input rows. Writes the selection bitmap (1 = row kept:
+ * predicate true and not null) and per-block popcounts for the compaction that follows. */
+int vb2k_eval_filter(const vb2_program* prog, const vb2_column* cols, int32_t ncols, int64_t rows,
+                     uint64_t* sel_bits, int32_t* error_flag, void* stream);
+/* Expands a selection bitmap into ascending row numbers (`selectedIndices` of
+ * exec/OperatorUtils.cpp:291). count_out is a device int64. */
+int vb2k_bits_to_indices(const uint64_t* sel_bits, int64_t rows, int32_t* indices, int64_t* count_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+size_t vb2k_bits_to_indices_workspace(int64_t rows);
+/* Pass 2: evaluates the projections for rows sel[0..n) (sel == NULL: rows 0..n) and writes them
+ * densely. error_flag receives the first VB2 user-error code hit by a live row. */
+int vb2k_eval_project(const vb2_program* prog, const vb2_column* cols, int32_t ncols, const int32_t* sel,
+                      int64_t n, const vb2_output* outs, int32_t nouts, int32_t* error_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused scan -> filter -> project -> aggregate pipelines (ahead-of-time specialised).
+ * One pass over null-free flat input columns: the expression DAG is a C++ expression template,
+ * the registry key is the canonical text the same template prints, so code and key cannot drift.
+ * Replaces, for one batch, FilterProject::getOutput (velox/exec/FilterProject.cpp:200-259) +
+ * GroupingSet::addInputForActiveRows in array mode (velox/exec/GroupingSet.cpp:288,
+ * HashTable::arrayGroupProbe exec/HashTable.cpp:560) + SUM/AVG/COUNT addRawInput
+ * (functions/lib/aggregates/SimpleNumericAggregate.h:94-150).
+ * ------------------------------------------------------------------------------------------ */
+#define VB2_FUSED_MAX_COLS 8
+#define VB2_FUSED_MAX_PARAMS 12
+#define VB2_FUSED_MAX_KEYS 2
+
+typedef struct vb2_fused_args {
+  const void* cols[VB2_FUSED_MAX_COLS]; /* expression inputs, renumbered in first-use order */
+  double pf[VB2_FUSED_MAX_PARAMS];      /* DOUBLE constants in first-use order */
+  int64_t pl[VB2_FUSED_MAX_PARAMS];     /* BIGINT constants */
+  int32_t pi[VB2_FUSED_MAX_PARAMS];     /* INTEGER/DATE constants */
+  int64_t rows;
+  int32_t nkeys;                        /* 0 = global aggregation */
+  int32_t ngroups;                      /* size of the group-id space (product of key ranges) */
+  const void* key[VB2_FUSED_MAX_KEYS];  /* int32 (dictionary indices / INTEGER) or int64 key values */
+  int32_t key_is64[VB2_FUSED_MAX_KEYS];
+  int32_t key_mult[VB2_FUSED_MAX_KEYS]; /* gid = sum_k id_k * key_mult[k] */
+  int64_t key_min[VB2_FUSED_MAX_KEYS];  /* id_k = lut ? lut[v - min] : v - min */
+  const int32_t* key_lut[VB2_FUSED_MAX_KEYS];
+  /* Optional join probe fused between filter and projection (Q14 shape): probe column
+   * cols[probe_col] (int64) is looked up in a dense array table; a miss drops the row, a hit
+   * yields the build-side payload code that a projection can test through a flag table. */
+  const int32_t* join_head;             /* int32[join_range]: build row + 1, 0 = no match (array-mode table) */
+  const int32_t* join_codes;            /* int32[build rows]: dictionary code of the payload column, or NULL (code = row) */
+  const uint8_t* join_flag;             /* uint8[codes]: build-side predicate evaluated per dictionary entry */
+  int64_t join_min, join_range;
+} vb2_fused_args;
+
+int vb2k_fused_find(const char* signature);  /* kernel id >= 0, or -1 when no specialisation matches */
+int vb2k_fused_count(void);
+const char* vb2k_fused_signature(int32_t id);
+int32_t vb2k_fused_nproj(int32_t id);
+size_t vb2k_fused_workspace_bytes(int32_t id, int32_t ngroups);
+/* Adds this batch into the persistent accumulators: sums is double[ngroups][nproj] (one running
+ * sum per projection and group, accumulated in a fixed, run-to-run deterministic order),
+ * counts is int64[ngroups] (rows that passed the filter per group). */
+int vb2k_fused_scan_agg(int32_t id, const vb2_fused_args* args, double* sums, int64_t* counts, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic aggregation over materialised columns.
+ * Array mode (small group-id space): replaces HashTable::arrayGroupProbe + Aggregate::addRawInput /
+ * addIntermediateResults scatter loops. Hash mode: open-addressing table over 64-bit normalized
+ * keys (exec/HashTable.cpp:470-523 groupProbe / groupNormalizedKeyProbe, insertEntry :337).
+ * ------------------------------------------------------------------------------------------ */
+enum vb2_agg_kind { VB2_AGG_SUM_F64 = 1, VB2_AGG_SUM_I64 = 2, VB2_AGG_COUNT = 3, VB2_AGG_MIN_F64 = 4,
+                    VB2_AGG_MAX_F64 = 5, VB2_AGG_MIN_I64 = 6, VB2_AGG_MAX_I64 = 7, VB2_AGG_COUNT_MERGE = 8 };
+
+typedef struct vb2_agg_update {
+  int32_t kind;
+  int32_t input_type;       /* VB2_DOUBLE / VB2_BIGINT / VB2_INTEGER (converted as the reference does) */
+  const void* input;        /* dense input values (NULL for COUNT(*)) */
+  const uint64_t* nulls;    /* validity bitmap of the input or NULL */
+  const uint64_t* mask;     /* optional aggregate mask bitmap (exec/AggregationMasks.cpp), 1 = use row */
+  void* acc;                /* double[capacity] or int64[capacity] */
+  int64_t* nonnull;         /* int64[capacity]: non-null inputs seen (drives NULL results and AVG counts), may be NULL */
+} vb2_agg_update;
+
+/* group_ids: int32[n], one slot per row (negative = skip row). */
+int vb2k_agg_update(const int32_t* group_ids, int64_t n, const vb2_agg_update* aggs, int32_t naggs,
+                    int32_t* error_flag, void* stream);
+
+/* Normalized-key group table (open addressing, linear probing, 64-bit keys, load factor <= 0.5):
+ * keys uint64[capacity] initialised to VB2_EMPTY_KEY. Finds or inserts each row's key and
+ * writes its slot to group_ids. capacity must be a power of two. */
+#define VB2_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+int vb2k_group_probe(const uint64_t* row_keys, const uint64_t* row_valid, int64_t n, uint64_t* table_keys,
+                     int64_t capacity, int32_t* group_ids, int64_t* num_groups, int32_t* error_flag, void* stream);
+/* Packs up to 4 key columns into one 64-bit normalized key per row:
+ * key = sum_k (v_k - min_k + 1) * mult_k, 0 reserved for NULL per column (VectorHasher value ids,
+ * velox/exec/VectorHasher.h:523-585). Columns may be flat/dictionary/constant. */
+int vb2k_normalize_keys(const vb2_column* cols, int32_t ncols, const int64_t* mins, const uint64_t* mults,
+                        int64_t rows, const int32_t* sel, int64_t n, uint64_t* keys_out, void* stream);
+/* min/max of an integer column over non-null rows: out = {min, max, nonnull_count} (device int64[3]). */
+int vb2k_column_minmax(const vb2_column* col, int64_t rows, int64_t* out3, void* stream);
+/* Compacts occupied slots: slot_list int32[<=capacity] ascending, count device int64. */
+int vb2k_table_occupied(const uint64_t* table_keys, int64_t capacity, int32_t* slot_list, int64_t* count,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hash join. Build: replaces HashBuild::addInput row store + HashTable::prepareJoinTable /
+ * insertForJoin (velox/exec/HashBuild.cpp:442-598, exec/HashTable.cpp:1989,1518): key -> first
+ * build row, duplicates chained through next[]. Probe: replaces HashTable::joinProbe +
+ * listJoinResults (exec/HashTable.cpp:610-725,2133-2350): emits (probe row, build row) pairs in
+ * probe-row order. Null keys never match (exec/HashBuild.cpp:475-479).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct vb2_join_table {
+  int32_t mode;        /* 0 = array (dense key range), 1 = hash */
+  int32_t pad;
+  int64_t key_min;     /* array mode: slot = key - key_min */
+  int64_t capacity;    /* slots (array: range; hash: power of two) */
+  uint64_t* keys;      /* hash mode: uint64[capacity], VB2_EMPTY_KEY = free */
+  int32_t* head;       /* int32[capacity]: first build row + 1, 0 = empty */
+  int32_t* next;       /* int32[build_rows]: next build row + 1 with the same key, 0 = end */
+  int64_t build_rows;
+} vb2_join_table;
+
+int vb2k_join_build(const vb2_join_table* t, const uint64_t* build_keys, const uint64_t* valid, int64_t n,
+                    int32_t* error_flag, void* stream);
+/* Counts matches per probe row (hit_counts int32[n]), then after an exclusive scan the caller
+ * asks for the pairs. total_out: device int64. */
+int vb2k_join_probe_count(const vb2_join_table* t, const uint64_t* probe_keys, const uint64_t* valid, int64_t n,
+                          int32_t* hit_counts, void* stream);
+int vb2k_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, int64_t* total_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+size_t vb2k_scan_workspace(int64_t n);
+int vb2k_join_probe_emit(const vb2_join_table* t, const uint64_t* probe_keys, const uint64_t* valid, int64_t n,
+                         const int64_t* offsets, int32_t* probe_rows, int32_t* build_rows, void* stream);
+
+/* Misc */
+int vb2k_fill_u64(uint64_t* p, int64_t n, uint64_t v, void* stream);
+int vb2k_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELOX_B200_KERNELS_H_ */

@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """The oracle is test infrastructure; build it on demand. The product library must already
+    be built (make / __graft_entry__.build()) — tests fail loudly if it is missing."""
+    from oracle import pyoracle
+    pyoracle.lib()
+    yield

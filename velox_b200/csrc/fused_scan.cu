@@ -1,0 +1,200 @@
+// Registry, launch logic and the ahead-of-time specialised pipelines of the fused scan path.
+#include "fused_scan.cuh"
+
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace vb2 {
+namespace fx {
+
+__global__ void fused_finalize_kernel(const double* __restrict__ partials, int nblocks, int kvals, int np, int maxg,
+                                      int ngroups, double* __restrict__ sums, int64_t* __restrict__ counts) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= kvals) return;
+  const int g = t / (np + 1), p = t % (np + 1);
+  if (g >= ngroups || g >= maxg) return;
+  if (p == np) {
+    int64_t c = 0;
+    for (int b = 0; b < nblocks; ++b) c += __double_as_longlong(partials[static_cast<int64_t>(b) * kvals + t]);
+    counts[g] += c;
+  } else {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s = __dadd_rn(s, partials[static_cast<int64_t>(b) * kvals + t]);
+    sums[g * np + p] = __dadd_rn(sums[g * np + p], s);
+  }
+}
+
+static std::vector<Entry>& registry() {
+  static std::vector<Entry> r;
+  return r;
+}
+
+int register_pipeline(const Entry& e) {
+  registry().push_back(e);
+  return static_cast<int>(registry().size()) - 1;
+}
+
+constexpr int kMaxBlocksPerSM = 8;
+constexpr int kFusedMaxGroups = 8;
+
+template <class P, int kMaxG, int kUnroll, bool kPair, class KeyT>
+static int launch_variant(const KernelArgs& a, double* sums, int64_t* counts, void* ws, size_t ws_bytes, cudaStream_t st) {
+  auto kernel = fused_scan_agg_kernel<P, kMaxG, kUnroll, kPair, KeyT>;
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    int n = 0;
+    VB2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, 0));
+    blocks_per_sm = n < 1 ? 1 : (n > kMaxBlocksPerSM ? kMaxBlocksPerSM : n);
+  }
+  const int64_t units = kPair ? (a.rows >> 1) : a.rows;
+  int64_t want = (units + kThreads - 1) / kThreads;
+  int64_t grid = static_cast<int64_t>(device_sm_count()) * blocks_per_sm;
+  if (want < grid) grid = want < 1 ? 1 : want;
+  constexpr int kVals = kMaxG * (P::kNP + 1);
+  if (ws_bytes < static_cast<size_t>(grid) * kVals * sizeof(double)) return fail_msg(VB2_ERR_INVALID, "fused workspace too small");
+  kernel<<<static_cast<unsigned>(grid), kThreads, 0, st>>>(a, reinterpret_cast<double*>(ws));
+  VB2_CUDA_OK(cudaGetLastError());
+  fused_finalize_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const double*>(ws), static_cast<int>(grid), kVals, P::kNP, kMaxG,
+                                           a.ngroups, sums, counts);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <class P>
+static int launch(const KernelArgs& a, double* sums, int64_t* counts, void* ws, size_t ws_bytes, cudaStream_t st) {
+  bool pair = true;
+  for (int c = 0; c < kMaxCols; ++c)
+    if (((P::fmask | P::imask | P::lmask) >> c) & 1u) pair = pair && aligned16(a.cols[c]);
+  for (int k = 0; k < a.nkeys; ++k) pair = pair && aligned16(a.key[k]);
+  const int g = a.nkeys == 0 ? 1 : a.ngroups;
+  if (g > kFusedMaxGroups) return fail_msg(VB2_ERR_UNSUPPORTED, "fused register aggregation holds at most 8 groups");
+  bool key64 = false;
+  for (int k = 0; k < a.nkeys; ++k) key64 = key64 || a.key_is64[k];
+#define VB2_GO(G, U, K)                                                                              \
+  return pair ? launch_variant<P, G, U, true, K>(a, sums, counts, ws, ws_bytes, st)                 \
+              : launch_variant<P, G, U, false, K>(a, sums, counts, ws, ws_bytes, st)
+  if (g <= 1) { VB2_GO(1, 4, int32_t); }
+  if (g <= 4) {
+    if (key64) { VB2_GO(4, 2, int64_t); }
+    VB2_GO(4, 2, int32_t);
+  }
+  if (key64) { VB2_GO(8, 1, int64_t); }
+  VB2_GO(8, 1, int32_t);
+#undef VB2_GO
+}
+
+template <class P>
+static int add_pipeline() {
+  return register_pipeline(Entry{P::sig(), P::kNP, P::kJoin, &launch<P>});
+}
+
+// ---------------------------------------------------------------------------------------------
+// Specialised pipelines. Column / constant numbering = first use in a depth-first walk of the
+// filter, then the join key, then the aggregate-input expressions (see host/fused_match.cpp).
+// ---------------------------------------------------------------------------------------------
+// TPC-H Q6 (exec/tests/utils/TpchQueryBuilder.cpp:756-788):
+//   l_shipdate between d0 and d1 and l_discount between 0.05 and 0.07 and l_quantity < 24.0
+//   sum(l_extendedprice * l_discount)
+using Q6 = Pipeline<And<Between<ColI<0>, PI<0>, PI<1>>, Between<ColF<1>, PF<0>, PF<1>>, Lt<ColF<2>, PF<2>>>,
+                    TypeList<Multiply<ColF<3>, ColF<1>>>>;
+
+// TPC-H Q1 (TpchQueryBuilder.cpp:203-256): l_shipdate < d; aggregate inputs l_quantity,
+// l_extendedprice, ep*(1-disc), ep*(1-disc)*(1+tax), l_discount.
+using Q1 = Pipeline<Lt<ColI<0>, PI<0>>,
+                    TypeList<ColF<1>, ColF<2>, Multiply<ColF<2>, Minus<PF<0>, ColF<3>>>,
+                             Multiply<Multiply<ColF<2>, Minus<PF<1>, ColF<3>>>, Plus<PF<2>, ColF<4>>>, ColF<3>>>;
+
+// TPC-H Q14 probe side (TpchQueryBuilder.cpp:1639-1702): l_shipdate between d0 and d1, probe
+// l_partkey, sum(ep*(1-disc)), sum(case when p_type like 'PROMO%' then ep*(1-disc) else 0.0 end).
+using Q14 = Pipeline<Between<ColI<0>, PI<0>, PI<1>>,
+                     TypeList<Multiply<ColF<2>, Minus<PF<0>, ColF<3>>>,
+                              Switch<JoinFlag, Multiply<ColF<2>, Minus<PF<1>, ColF<3>>>, PF<2>>>,
+                     1>;
+
+// Generic small shapes: sum of one column / product under a single range or comparison filter.
+using SumUnderLt = Pipeline<Lt<ColF<0>, PF<0>>, TypeList<Multiply<ColF<1>, Minus<PF<1>, ColF<2>>>>>;
+using SumNoFilter = Pipeline<True, TypeList<ColF<0>>>;
+
+static std::once_flag g_once;
+static void ensure_registered() {
+  std::call_once(g_once, [] {
+    add_pipeline<Q6>();
+    add_pipeline<Q1>();
+    add_pipeline<Q14>();
+    add_pipeline<SumUnderLt>();
+    add_pipeline<SumNoFilter>();
+  });
+}
+
+}  // namespace fx
+}  // namespace vb2
+
+using namespace vb2;
+using namespace vb2::fx;
+
+extern "C" {
+
+int vb2k_fused_find(const char* signature) {
+  ensure_registered();
+  auto& r = registry();
+  for (size_t i = 0; i < r.size(); ++i)
+    if (r[i].signature == signature) return static_cast<int>(i);
+  return -1;
+}
+int vb2k_fused_count(void) {
+  ensure_registered();
+  return static_cast<int>(registry().size());
+}
+const char* vb2k_fused_signature(int32_t id) {
+  ensure_registered();
+  if (id < 0 || id >= static_cast<int>(registry().size())) return nullptr;
+  return registry()[id].signature.c_str();
+}
+int32_t vb2k_fused_nproj(int32_t id) {
+  ensure_registered();
+  if (id < 0 || id >= static_cast<int>(registry().size())) return -1;
+  return registry()[id].nproj;
+}
+size_t vb2k_fused_workspace_bytes(int32_t id, int32_t ngroups) {
+  ensure_registered();
+  if (id < 0 || id >= static_cast<int>(registry().size())) return 0;
+  const int g = ngroups <= 1 ? 1 : (ngroups <= 4 ? 4 : 8);
+  return static_cast<size_t>(device_sm_count()) * kMaxBlocksPerSM * g * (registry()[id].nproj + 1) * sizeof(double);
+}
+
+int vb2k_fused_scan_agg(int32_t id, const vb2_fused_args* args, double* sums, int64_t* counts, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  ensure_registered();
+  if (id < 0 || id >= static_cast<int>(registry().size())) return fail_msg(VB2_ERR_INVALID, "bad fused kernel id");
+  if (!args || args->rows < 0 || args->nkeys < 0 || args->nkeys > VB2_FUSED_MAX_KEYS) return fail_msg(VB2_ERR_INVALID, "bad fused args");
+  if (args->rows == 0) return VB2_OK;
+  const Entry& e = registry()[id];
+  KernelArgs a;
+  std::memset(&a, 0, sizeof(a));
+  for (int c = 0; c < kMaxCols; ++c) a.cols[c] = args->cols[c];
+  std::memcpy(a.consts.pf, args->pf, sizeof(a.consts.pf));
+  std::memcpy(a.consts.pl, args->pl, sizeof(a.consts.pl));
+  std::memcpy(a.consts.pi, args->pi, sizeof(a.consts.pi));
+  a.rows = args->rows;
+  a.nkeys = args->nkeys;
+  a.ngroups = args->nkeys == 0 ? 1 : args->ngroups;
+  for (int k = 0; k < VB2_FUSED_MAX_KEYS; ++k) {
+    a.key[k] = args->key[k];
+    a.key_is64[k] = args->key_is64[k];
+    a.key_mult[k] = args->key_mult[k];
+    a.key_min[k] = args->key_min[k];
+    a.key_lut[k] = args->key_lut[k];
+  }
+  a.join_head = args->join_head;
+  a.join_codes = args->join_codes;
+  a.join_flag = args->join_flag;
+  a.join_min = args->join_min;
+  a.join_range = args->join_range;
+  if (e.join && (!a.join_head || !a.join_flag)) return fail_msg(VB2_ERR_INVALID, "fused join pipeline needs join_head and join_flag");
+  return e.launch(a, sums, counts, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

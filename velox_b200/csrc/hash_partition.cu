@@ -1,0 +1,212 @@
+// Key hashing (VectorHasher::hash), partition ids (HashPartitionFunction), partition scatter order
+// and gather. HBM-bound integer work: one coalesced pass per kernel, no tensor cores.
+#include "common.cuh"
+
+namespace vb2 {
+
+constexpr int kMaxKeyCols = 8;
+struct ColSet {
+  vb2_column c[kMaxKeyCols];
+  int n;
+};
+
+// Decodes row -> (base index, is_null) for flat / dictionary / constant columns.
+__device__ __forceinline__ bool decode_row(const vb2_column& c, int64_t row, int64_t& base) {
+  if (c.encoding == VB2_FLAT) {
+    base = row;
+    return c.nulls && !bit_at(c.nulls, row);
+  }
+  if (c.encoding == VB2_DICTIONARY) {
+    if (c.nulls && !bit_at(c.nulls, row)) { base = 0; return true; }
+    base = c.indices[row];
+    return c.dict_nulls && !bit_at(c.dict_nulls, base);
+  }
+  base = 0;
+  return c.nulls && !bit_at(c.nulls, 0);
+}
+
+__device__ __forceinline__ uint64_t hash_value(const vb2_column& c, int64_t base) {
+  switch (c.type) {
+    case VB2_BIGINT: return twang_mix64(static_cast<uint64_t>(reinterpret_cast<const int64_t*>(c.values)[base]));
+    case VB2_INTEGER: return jenkins_rev_mix32(static_cast<uint32_t>(reinterpret_cast<const int32_t*>(c.values)[base]));
+    case VB2_DOUBLE: return hash_f64(reinterpret_cast<const double*>(c.values)[base]);
+    case VB2_BOOLEAN: return bit_at(reinterpret_cast<const uint64_t*>(c.values), base) ? 1 : 0;
+    default: {
+      const int32_t* off = reinterpret_cast<const int32_t*>(c.values);
+      const int32_t b = off[base], e = off[base + 1];
+      return hash_bytes(1, reinterpret_cast<const uint8_t*>(c.aux) + b, e - b);
+    }
+  }
+}
+
+__global__ void hash_columns_kernel(const __grid_constant__ ColSet cs, int64_t rows, uint64_t* __restrict__ out) {
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < rows;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    uint64_t h = 0;
+    for (int k = 0; k < cs.n; ++k) {
+      int64_t base;
+      const bool is_null = decode_row(cs.c[k], r, base);
+      const uint64_t hk = is_null ? kNullHash : hash_value(cs.c[k], base);
+      h = k == 0 ? hk : hash_mix(h, hk);
+    }
+    out[r] = h;
+  }
+}
+
+__global__ void partition_ids_kernel(const uint64_t* __restrict__ hashes, int64_t rows, uint32_t parts, uint32_t* __restrict__ ids) {
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < rows;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    ids[r] = static_cast<uint32_t>(hashes[r] % parts);
+}
+
+// --- stable partition order: per-block histograms -> exclusive offsets -> scatter -------------
+constexpr int kPartThreads = 256;
+constexpr int kPartRowsPerBlock = 4096;
+constexpr int kMaxParts = 64;
+
+__global__ void part_hist_kernel(const uint32_t* __restrict__ ids, int64_t rows, int parts, int32_t* __restrict__ block_hist) {
+  __shared__ int32_t h[kMaxParts];
+  for (int p = threadIdx.x; p < parts; p += blockDim.x) h[p] = 0;
+  __syncthreads();
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kPartRowsPerBlock;
+  for (int i = threadIdx.x; i < kPartRowsPerBlock; i += blockDim.x) {
+    const int64_t r = r0 + i;
+    if (r < rows) atomicAdd(&h[ids[r]], 1);
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < parts; p += blockDim.x) block_hist[static_cast<int64_t>(blockIdx.x) * parts + p] = h[p];
+}
+
+// One block: for each partition, exclusive scan of block counts (partition-major order).
+__global__ void part_offsets_kernel(int32_t* __restrict__ block_hist, int64_t nblocks, int parts, int64_t* __restrict__ counts,
+                                    int64_t* __restrict__ block_base) {
+  // thread p handles partition p sequentially over blocks (nblocks is rows/4096: small)
+  __shared__ int64_t totals[kMaxParts];
+  const int p = threadIdx.x;
+  if (p < parts) {
+    int64_t run = 0;
+    for (int64_t b = 0; b < nblocks; ++b) {
+      const int32_t c = block_hist[b * parts + p];
+      block_base[b * parts + p] = run;
+      run += c;
+    }
+    totals[p] = run;
+    counts[p] = run;
+  }
+  __syncthreads();
+  if (p < parts) {
+    int64_t start = 0;
+    for (int q = 0; q < p; ++q) start += totals[q];
+    for (int64_t b = 0; b < nblocks; ++b) block_base[b * parts + p] += start;
+  }
+}
+
+__global__ void part_scatter_kernel(const uint32_t* __restrict__ ids, int64_t rows, int parts, const int64_t* __restrict__ block_base,
+                                    int32_t* __restrict__ order) {
+  // Stable within a partition: each warp ranks its rows with ballots, warps proceed in order.
+  __shared__ int64_t base[kMaxParts];
+  __shared__ int32_t warp_counts[kPartThreads / kWarp][kMaxParts];
+  for (int p = threadIdx.x; p < parts; p += blockDim.x) base[p] = block_base[static_cast<int64_t>(blockIdx.x) * parts + p];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kPartRowsPerBlock;
+  for (int i0 = 0; i0 < kPartRowsPerBlock; i0 += kPartThreads) {
+    const int64_t r = r0 + i0 + threadIdx.x;
+    const bool live = r < rows;
+    const uint32_t id = live ? ids[r] : 0xffffffffu;
+    // rank among lanes of the warp with the same partition
+    const unsigned peers = __match_any_sync(0xffffffffu, id);
+    const int rank = __popc(peers & ((1u << lane) - 1));
+    const int cnt = __popc(peers);
+    for (int p = lane; p < parts; p += kWarp) warp_counts[warp][p] = 0;
+    __syncwarp();
+    if (live && rank == 0) warp_counts[warp][id] = cnt;
+    __syncthreads();
+    if (live) {
+      int64_t pos = base[id];
+      for (int w = 0; w < warp; ++w) pos += warp_counts[w][id];
+      order[pos + rank] = static_cast<int32_t>(r);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < parts; p += blockDim.x) {
+      int32_t s = 0;
+      for (int w = 0; w < kPartThreads / kWarp; ++w) s += warp_counts[w][p];
+      base[p] += s;
+    }
+    __syncthreads();
+  }
+}
+
+template <class T>
+__global__ void gather_kernel(const T* __restrict__ in, const int32_t* __restrict__ order, int64_t n, T* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = in[order[i]];
+}
+
+static unsigned grid_for(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
+  return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace vb2
+
+using namespace vb2;
+
+extern "C" {
+
+int vb2k_hash_columns(const vb2_column* cols, int32_t ncols, int64_t rows, uint64_t* hashes, void* stream) {
+  if (ncols < 1 || ncols > kMaxKeyCols) return fail_msg(VB2_ERR_INVALID, "hash_columns: 1..8 key columns");
+  if (rows <= 0) return VB2_OK;
+  ColSet cs;
+  cs.n = ncols;
+  for (int i = 0; i < ncols; ++i) cs.c[i] = cols[i];
+  hash_columns_kernel<<<grid_for(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cs, rows, hashes);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_partition_ids(const uint64_t* hashes, int64_t rows, int32_t num_partitions, uint32_t* ids, void* stream) {
+  if (num_partitions < 1) return fail_msg(VB2_ERR_INVALID, "partition_ids: num_partitions < 1");
+  if (rows <= 0) return VB2_OK;
+  partition_ids_kernel<<<grid_for(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(hashes, rows, static_cast<uint32_t>(num_partitions), ids);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_partition_scatter_order(const uint32_t* ids, int64_t rows, int32_t num_partitions, int64_t* counts,
+                                 int32_t* row_order, void* stream) {
+  if (num_partitions < 1 || num_partitions > kMaxParts) return fail_msg(VB2_ERR_INVALID, "partition_scatter_order: 1..64 partitions");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows <= 0) {
+    VB2_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int64_t) * num_partitions, st));
+    return VB2_OK;
+  }
+  const int64_t nblocks = (rows + kPartRowsPerBlock - 1) / kPartRowsPerBlock;
+  int32_t* hist = nullptr;
+  int64_t* base = nullptr;
+  VB2_CUDA_OK(cudaMallocAsync(&hist, sizeof(int32_t) * nblocks * num_partitions, st));
+  VB2_CUDA_OK(cudaMallocAsync(&base, sizeof(int64_t) * nblocks * num_partitions, st));
+  part_hist_kernel<<<static_cast<unsigned>(nblocks), kPartThreads, 0, st>>>(ids, rows, num_partitions, hist);
+  part_offsets_kernel<<<1, kMaxParts, 0, st>>>(hist, nblocks, num_partitions, counts, base);
+  part_scatter_kernel<<<static_cast<unsigned>(nblocks), kPartThreads, 0, st>>>(ids, rows, num_partitions, base, row_order);
+  VB2_CUDA_OK(cudaGetLastError());
+  VB2_CUDA_OK(cudaFreeAsync(hist, st));
+  VB2_CUDA_OK(cudaFreeAsync(base, st));
+  return VB2_OK;
+}
+
+int vb2k_gather(const void* in, const int32_t* order, int64_t n, int32_t elem_bytes, void* out, void* stream) {
+  if (n <= 0) return VB2_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (elem_bytes == 8)
+    gather_kernel<uint64_t><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(in), order, n, reinterpret_cast<uint64_t*>(out));
+  else if (elem_bytes == 4)
+    gather_kernel<uint32_t><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(in), order, n, reinterpret_cast<uint32_t*>(out));
+  else
+    return fail_msg(VB2_ERR_INVALID, "gather: elem_bytes must be 4 or 8");
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+}  // extern "C"

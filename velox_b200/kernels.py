@@ -1,0 +1,171 @@
+"""ctypes binding of the kernel-level C ABI (include/velox_b200_kernels.h) over torch device
+memory. torch is plumbing here (allocation, streams); every computation is one of our kernels."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from ._lib import check, lib
+from .vector import (BIGINT, BOOLEAN, CColumn, CONSTANT, DICTIONARY, DOUBLE, FLAT, INTEGER, VARCHAR, Column)
+
+MAX_COLS, MAX_PARAMS, MAX_KEYS = 8, 12, 2
+
+
+class FusedArgs(C.Structure):
+    _fields_ = [
+        ("cols", C.c_void_p * MAX_COLS),
+        ("pf", C.c_double * MAX_PARAMS),
+        ("pl", C.c_int64 * MAX_PARAMS),
+        ("pi", C.c_int32 * MAX_PARAMS),
+        ("rows", C.c_int64),
+        ("nkeys", C.c_int32),
+        ("ngroups", C.c_int32),
+        ("key", C.c_void_p * MAX_KEYS),
+        ("key_is64", C.c_int32 * MAX_KEYS),
+        ("key_mult", C.c_int32 * MAX_KEYS),
+        ("key_min", C.c_int64 * MAX_KEYS),
+        ("key_lut", C.c_void_p * MAX_KEYS),
+        ("join_head", C.c_void_p),
+        ("join_codes", C.c_void_p),
+        ("join_flag", C.c_void_p),
+        ("join_min", C.c_int64),
+        ("join_range", C.c_int64),
+    ]
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class DeviceColumn:
+    """A column resident in HBM (torch tensors own the buffers)."""
+
+    def __init__(self, type_: int, encoding: int, size: int, values=None, nulls=None, indices=None,
+                 dict_size: int = 0, dict_nulls=None, aux=None):
+        self.type, self.encoding, self.size = type_, encoding, size
+        self.values, self.nulls, self.indices = values, nulls, indices
+        self.dict_size, self.dict_nulls, self.aux = dict_size, dict_nulls, aux
+
+    @staticmethod
+    def from_host(col: Column, device="cuda") -> "DeviceColumn":
+        c = col.to_c()  # packs nulls; keeps numpy buffers alive in col._keep
+
+        def up(a):
+            return None if a is None else torch.from_numpy(a).to(device)
+
+        import numpy as np
+        from .vector import pack_bits
+        return DeviceColumn(
+            col.type, col.encoding, col.size,
+            values=up(col.values), nulls=up(pack_bits(~col.nulls).view(np.int64)) if col.nulls is not None else None,
+            indices=up(col.indices), dict_size=col.dict_size,
+            dict_nulls=up(pack_bits(~col.dict_nulls).view(np.int64)) if col.dict_nulls is not None else None,
+            aux=up(col.chars))
+
+    def to_c(self) -> CColumn:
+        c = CColumn()
+        c.type, c.encoding, c.size = self.type, self.encoding, self.size
+        c.values, c.nulls, c.indices = _ptr(self.values), _ptr(self.nulls), _ptr(self.indices)
+        c.dict_size, c.dict_nulls, c.aux = self.dict_size, _ptr(self.dict_nulls), _ptr(self.aux)
+        return c
+
+
+def flat_device(type_: int, t: torch.Tensor) -> DeviceColumn:
+    return DeviceColumn(type_, FLAT, t.numel(), values=t)
+
+
+def hash_columns(cols: Sequence[DeviceColumn]) -> torch.Tensor:
+    n = cols[0].size
+    out = torch.empty(n, dtype=torch.int64, device="cuda")
+    arr = (CColumn * len(cols))(*[c.to_c() for c in cols])
+    check(lib().vb2k_hash_columns(arr, len(cols), C.c_int64(n), C.c_void_p(out.data_ptr()), _stream()))
+    return out  # uint64 bit pattern in int64
+
+
+def partition_ids(hashes: torch.Tensor, num_partitions: int) -> torch.Tensor:
+    out = torch.empty(hashes.numel(), dtype=torch.int32, device="cuda")
+    check(lib().vb2k_partition_ids(C.c_void_p(hashes.data_ptr()), C.c_int64(hashes.numel()), num_partitions,
+                                   C.c_void_p(out.data_ptr()), _stream()))
+    return out
+
+
+def partition_scatter_order(ids: torch.Tensor, num_partitions: int):
+    counts = torch.zeros(num_partitions, dtype=torch.int64, device="cuda")
+    order = torch.empty(ids.numel(), dtype=torch.int32, device="cuda")
+    check(lib().vb2k_partition_scatter_order(C.c_void_p(ids.data_ptr()), C.c_int64(ids.numel()), num_partitions,
+                                             C.c_void_p(counts.data_ptr()), C.c_void_p(order.data_ptr()), _stream()))
+    return counts, order
+
+
+def gather(src: torch.Tensor, order: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(order.numel(), dtype=src.dtype, device="cuda")
+    check(lib().vb2k_gather(C.c_void_p(src.data_ptr()), C.c_void_p(order.data_ptr()), C.c_int64(order.numel()),
+                            src.element_size(), C.c_void_p(out.data_ptr()), _stream()))
+    return out
+
+
+def fused_find(signature: str) -> int:
+    return lib().vb2k_fused_find(signature.encode())
+
+
+def fused_signatures():
+    L = lib()
+    L.vb2k_fused_signature.restype = C.c_char_p
+    return [L.vb2k_fused_signature(i).decode() for i in range(L.vb2k_fused_count())]
+
+
+class FusedScanAgg:
+    """Persistent accumulators + workspace for one fused pipeline instance."""
+
+    def __init__(self, signature: str, ngroups: int = 1):
+        L = lib()
+        self.id = L.vb2k_fused_find(signature.encode())
+        if self.id < 0:
+            raise KeyError(f"no fused pipeline for {signature}")
+        self.nproj = L.vb2k_fused_nproj(self.id)
+        self.ngroups = max(1, ngroups)
+        L.vb2k_fused_workspace_bytes.restype = C.c_size_t
+        self.ws_bytes = L.vb2k_fused_workspace_bytes(self.id, self.ngroups)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device="cuda")
+        self.sums = torch.zeros(self.ngroups * self.nproj, dtype=torch.float64, device="cuda")
+        self.counts = torch.zeros(self.ngroups, dtype=torch.int64, device="cuda")
+
+    def reset(self):
+        self.sums.zero_()
+        self.counts.zero_()
+
+    def add_batch(self, cols: Sequence[torch.Tensor], rows: int, pf=(), pl=(), pi=(), keys=(), key_min=(),
+                  key_mult=(), key_lut=(), join=None):
+        a = FusedArgs()
+        for i, t in enumerate(cols):
+            a.cols[i] = t.data_ptr()
+        for i, v in enumerate(pf):
+            a.pf[i] = v
+        for i, v in enumerate(pl):
+            a.pl[i] = v
+        for i, v in enumerate(pi):
+            a.pi[i] = v
+        a.rows = rows
+        a.nkeys = len(keys)
+        a.ngroups = self.ngroups
+        for k, t in enumerate(keys):
+            a.key[k] = t.data_ptr()
+            a.key_is64[k] = 1 if t.dtype == torch.int64 else 0
+            a.key_min[k] = key_min[k] if key_min else 0
+            a.key_mult[k] = key_mult[k]
+            a.key_lut[k] = key_lut[k].data_ptr() if key_lut and key_lut[k] is not None else None
+        if join is not None:
+            a.join_head = join["head"].data_ptr()
+            a.join_codes = join["codes"].data_ptr() if join.get("codes") is not None else None
+            a.join_flag = join["flag"].data_ptr()
+            a.join_min = join["min"]
+            a.join_range = join["head"].numel()
+        check(lib().vb2k_fused_scan_agg(self.id, C.byref(a), C.c_void_p(self.sums.data_ptr()),
+                                        C.c_void_p(self.counts.data_ptr()), C.c_void_p(self.ws.data_ptr()),
+                                        C.c_size_t(self.ws_bytes), _stream()))
