@@ -171,15 +171,19 @@ typedef struct vb2_fused_args {
   int32_t key_mult[VB2_FUSED_MAX_KEYS]; /* gid = sum_k id_k * key_mult[k] */
   int64_t key_min[VB2_FUSED_MAX_KEYS];  /* id_k = lut ? lut[v - min] : v - min */
   const int32_t* key_lut[VB2_FUSED_MAX_KEYS];
-  /* Optional join probe fused between filter and projection (Q14 shape): probe column
-   * cols[probe_col] (int64) is looked up in a dense array table; a miss drops the row, a hit
-   * yields the build-side payload code that a projection can test through a flag table. */
-  const int32_t* join_head;             /* int32[join_range]: build row + 1, 0 = no match (array-mode table) */
-  const int32_t* join_codes;            /* int32[build rows]: dictionary code of the payload column, or NULL (code = row) */
-  const uint8_t* join_flag;             /* uint8[codes]: build-side predicate evaluated per dictionary entry */
+  /* Optional inner-join probe fused between filter and projection (Q14 shape): the probe key
+   * column named by the pipeline signature (";J:l<col>") is looked up in a dense array table of
+   * one byte per key slot (slot = key - join_min): 0 = no build row (row dropped), 1 = match,
+   * 2 = match and the build-side predicate (e.g. p_type LIKE 'PROMO%') holds. Build keys must be
+   * unique; vb2k_join_slot_flags prepares the table from an array-mode vb2_join_table. */
+  const uint8_t* join_slot_flags;
   int64_t join_min, join_range;
 } vb2_fused_args;
 
+/* head: int32[range] build row + 1 (0 = empty); codes: int32[build rows] dictionary code of the
+ * payload column or NULL (code = row); flag: uint8[codes] predicate per code or NULL (all false). */
+int vb2k_join_slot_flags(const int32_t* head, const int32_t* codes, const uint8_t* flag, int64_t range, uint8_t* out,
+                         void* stream);
 int vb2k_fused_find(const char* signature);  /* kernel id >= 0, or -1 when no specialisation matches */
 int vb2k_fused_count(void);
 const char* vb2k_fused_signature(int32_t id);
@@ -210,8 +214,10 @@ typedef struct vb2_agg_update {
   int64_t* nonnull;         /* int64[capacity]: non-null inputs seen (drives NULL results and AVG counts), may be NULL */
 } vb2_agg_update;
 
-/* group_ids: int32[n], one slot per row (negative = skip row). */
-int vb2k_agg_update(const int32_t* group_ids, int64_t n, const vb2_agg_update* aggs, int32_t naggs,
+/* group_ids: int32[n], one slot per row (negative = skip row). capacity = size of the group-id
+ * space; spaces of <= 8 groups take a register-accumulator kernel (one launch per aggregate),
+ * larger ones one atomic per row and aggregate. SUM(BIGINT) overflow sets *error_flag. */
+int vb2k_agg_update(const int32_t* group_ids, int64_t n, int64_t capacity, const vb2_agg_update* aggs, int32_t naggs,
                     int32_t* error_flag, void* stream);
 
 /* Normalized-key group table (open addressing, linear probing, 64-bit keys, load factor <= 0.5):
@@ -230,6 +236,11 @@ int vb2k_column_minmax(const vb2_column* col, int64_t rows, int64_t* out3, void*
 /* Compacts occupied slots: slot_list int32[<=capacity] ascending, count device int64. */
 int vb2k_table_occupied(const uint64_t* table_keys, int64_t capacity, int32_t* slot_list, int64_t* count,
                         void* workspace, size_t workspace_bytes, void* stream);
+size_t vb2k_table_occupied_workspace(int64_t capacity);
+/* Inverse of vb2k_normalize_keys for one key column over the listed slots: value = id - 1 + min
+ * with id = (key / mult) % range; id 0 -> NULL. values: T[n] (BOOLEAN one byte per row). */
+int vb2k_denormalize_keys(const uint64_t* table_keys, const int32_t* slots, int64_t n, int64_t min, uint64_t mult,
+                          uint64_t range, int32_t type, void* values, uint64_t* valid, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Hash join. Build: replaces HashBuild::addInput row store + HashTable::prepareJoinTable /

@@ -13,7 +13,13 @@ from velox_b200.plan import PlanBuilder
 from velox_b200.vector import (BIGINT, DOUBLE, INTEGER, VARCHAR, dictionary_vector, flat_vector, row_vector)
 
 pytestmark = pytest.mark.gpu
-REL_TOL = 1e-12
+
+
+def rel_tol(n):
+    """Stated FP tolerance for SUM/AVG(double): the reference adds sequentially in input order,
+    which carries up to (n-1)*2^-53 relative error on same-sign data; the kernel's fixed tree
+    order carries ~log2(n)*2^-53. Results agree within max(1e-12, n*2^-53) relative."""
+    return max(1e-12, n * 2.0 ** -53)
 
 
 def _host_lineitem(n, nparts=2000, seed=7):
@@ -65,7 +71,11 @@ def test_q6_matches_oracle(n):
     if cnt == 0:
         assert want is None and got == 0.0
     else:
-        assert abs(got - want) <= REL_TOL * abs(want)
+        assert abs(got - want) <= rel_tol(n) * abs(want)
+        # and within 1e-13 of the correctly rounded sum of the same per-row products
+        import math
+        exact = math.fsum((h["l_extendedprice"][m] * h["l_discount"][m]).tolist())
+        assert abs(got - exact) <= 1e-13 * abs(exact)
 
 
 def test_q6_unaligned_and_multibatch():
@@ -83,7 +93,7 @@ def test_q6_unaligned_and_multibatch():
          & (h["l_discount"] <= 0.07) & (h["l_quantity"] < 24.0))
     want = float(np.sum(h["l_extendedprice"][m] * h["l_discount"][m]))
     assert f.counts.item() == int(m.sum())
-    assert abs(f.sums.item() - want) <= REL_TOL * abs(want)
+    assert abs(f.sums.item() - want) <= rel_tol(n) * abs(want)
 
 
 def test_q6_nan_ordering():
@@ -136,18 +146,17 @@ def test_q1_matches_oracle(n):
         g = got[key]
         assert g[7] == w[7]  # count: bit exact
         for a, b in zip(g[:7], w[:7]):
-            assert abs(a - b) <= REL_TOL * abs(b), (key, a, b)
+            assert abs(a - b) <= rel_tol(n) * abs(b), (key, a, b)
 
 
 def test_q14_matches_oracle():
-    from velox_b200.kernels import FusedScanAgg
+    from velox_b200.kernels import FusedScanAgg, join_slot_flags
     n, nparts = 300_000, 5000
     h = _host_lineitem(n, nparts=nparts, seed=3)
     part = {k: v.numpy() for k, v in tpch.gen_part(nparts, seed=5).items()}
     li = _lineitem_rowvector(h, ["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"])
     pt = row_vector(["p_partkey", "p_type"], [flat_vector(BIGINT, part["p_partkey"]),
                                              dictionary_vector(VARCHAR, part["p_type"], tpch.PTYPE_DICT)])
-    PlanBuilder.reset_ids()
     build = PlanBuilder().values(pt.names, pt.types, source=1)
     plan = (PlanBuilder().values(li.names, li.types, source=0)
             .filter("l_shipdate between '1995-09-01'::DATE and '1995-09-30'::DATE")
@@ -166,7 +175,7 @@ def test_q14_matches_oracle():
     f = FusedScanAgg(tpch.Q14_SIG)
     f.add_batch([_dev(h, "l_shipdate"), _dev(h, "l_partkey"), _dev(h, "l_extendedprice"), _dev(h, "l_discount")], n,
                 pf=[1.0, 1.0, 0.0], pi=[tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI],
-                join={"head": head, "codes": torch.from_numpy(part["p_type"]).cuda(), "flag": flag, "min": 1})
+                join={"slot_flags": join_slot_flags(head, torch.from_numpy(part["p_type"]).cuda(), flag), "min": 1})
     total, promo = f.sums.cpu().tolist()
     got = 100.00 * promo / total
     assert abs(got - want) <= 1e-12 * abs(want)

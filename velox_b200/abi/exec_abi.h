@@ -1,0 +1,619 @@
+// Contract shim — the plan / expression / operator boundary of the reference, restated without
+// its dependencies. The B200 operators are written against exactly these names; with real Velox
+// headers (VELOX_B200_WITH_REAL_VELOX) the same operator sources bind to the real classes.
+//
+//   core::PlanNode family ....... velox/core/PlanNode.h:175 (FilterNode :671, ProjectNode :876,
+//                                 AggregationNode :1120, HashJoinNode :3437, ValuesNode)
+//   core::ITypedExpr family ..... velox/core/Expressions.h (FieldAccess / Constant / Call / Cast)
+//   core::QueryConfig ........... velox/core/QueryConfig.h (string map with typed accessors)
+//   exec::ExprSet ............... velox/expression/Expr.h:837
+//   exec::VectorFunction + registry  velox/expression/VectorFunction.h:38,241,293
+//   exec::Operator .............. velox/exec/Operator.h:120-702 (virtuals :232-342)
+//   exec::Driver / DriverFactory / DriverAdapter  velox/exec/Driver.h:364,789-847;
+//                                 loop order of Driver::runInternal velox/exec/Driver.cpp:538-850
+//   exec::LocalPlanner .......... velox/exec/LocalPlanner.cpp:374-810 (adapters run :762-766)
+//   exec::HashJoinBridge ........ velox/exec/HashJoinBridge.h:42-130
+//   exec::Task .................. velox/exec/Task.h (single-threaded serial execution mode)
+#pragma once
+#ifndef VELOX_B200_WITH_REAL_VELOX
+
+#include <functional>
+#include <map>
+#include <mutex>
+#include <set>
+#include <unordered_map>
+#include <variant>
+
+#include "vector_abi.h"
+
+namespace facebook::velox {
+
+// A constant value (velox/type/Variant.h, the subset of kinds on the hot path).
+struct Variant {
+  TypeKind kind = TypeKind::UNKNOWN;
+  bool isNull = true;
+  std::variant<bool, int32_t, int64_t, double, std::string> value;
+  static Variant null(TypeKind k) { Variant v; v.kind = k; return v; }
+  template <class T> static Variant of(TypeKind k, T x) { Variant v; v.kind = k; v.isNull = false; v.value = std::move(x); return v; }
+};
+
+namespace core {
+
+// ---- expressions ------------------------------------------------------------------------------
+class ITypedExpr {
+ public:
+  ITypedExpr(TypePtr type, std::vector<std::shared_ptr<const ITypedExpr>> inputs) : type_(std::move(type)), inputs_(std::move(inputs)) {}
+  virtual ~ITypedExpr() = default;
+  const TypePtr& type() const { return type_; }
+  const std::vector<std::shared_ptr<const ITypedExpr>>& inputs() const { return inputs_; }
+  virtual std::string toString() const = 0;
+
+ private:
+  TypePtr type_;
+  std::vector<std::shared_ptr<const ITypedExpr>> inputs_;
+};
+using TypedExprPtr = std::shared_ptr<const ITypedExpr>;
+
+class FieldAccessTypedExpr : public ITypedExpr {
+ public:
+  FieldAccessTypedExpr(TypePtr type, std::string name, int32_t index = -1) : ITypedExpr(std::move(type), {}), name_(std::move(name)), index_(index) {}
+  const std::string& name() const { return name_; }
+  int32_t index() const { return index_; }  // column of the input row (the shim resolves names eagerly)
+  std::string toString() const override { return name_; }
+
+ private:
+  std::string name_;
+  int32_t index_;
+};
+class ConstantTypedExpr : public ITypedExpr {
+ public:
+  ConstantTypedExpr(TypePtr type, Variant value) : ITypedExpr(std::move(type), {}), value_(std::move(value)) {}
+  const Variant& value() const { return value_; }
+  std::string toString() const override { return "const"; }
+
+ private:
+  Variant value_;
+};
+class CallTypedExpr : public ITypedExpr {
+ public:
+  CallTypedExpr(TypePtr type, std::vector<TypedExprPtr> inputs, std::string name) : ITypedExpr(std::move(type), std::move(inputs)), name_(std::move(name)) {}
+  const std::string& name() const { return name_; }
+  std::string toString() const override {
+    std::string s = name_ + "(";
+    for (size_t i = 0; i < inputs().size(); ++i) s += (i ? "," : "") + inputs()[i]->toString();
+    return s + ")";
+  }
+
+ private:
+  std::string name_;
+};
+class CastTypedExpr : public ITypedExpr {
+ public:
+  CastTypedExpr(TypePtr type, TypedExprPtr input, bool nullOnFailure = false) : ITypedExpr(std::move(type), {std::move(input)}), nullOnFailure_(nullOnFailure) {}
+  bool nullOnFailure() const { return nullOnFailure_; }
+  std::string toString() const override { return "cast(" + inputs()[0]->toString() + " as " + type()->toString() + ")"; }
+
+ private:
+  bool nullOnFailure_;
+};
+
+// ---- plan nodes -------------------------------------------------------------------------------
+using PlanNodeId = std::string;
+class PlanNode {
+ public:
+  explicit PlanNode(PlanNodeId id) : id_(std::move(id)) {}
+  virtual ~PlanNode() = default;
+  const PlanNodeId& id() const { return id_; }
+  virtual const RowTypePtr& outputType() const = 0;
+  virtual const std::vector<std::shared_ptr<const PlanNode>>& sources() const = 0;
+  virtual std::string_view name() const = 0;
+
+ private:
+  PlanNodeId id_;
+};
+using PlanNodePtr = std::shared_ptr<const PlanNode>;
+
+class ValuesNode : public PlanNode {
+ public:
+  ValuesNode(PlanNodeId id, RowTypePtr type, int32_t sourceId) : PlanNode(std::move(id)), type_(std::move(type)), sourceId_(sourceId) {}
+  const RowTypePtr& outputType() const override { return type_; }
+  const std::vector<PlanNodePtr>& sources() const override { static const std::vector<PlanNodePtr> kEmpty; return kEmpty; }
+  std::string_view name() const override { return "Values"; }
+  int32_t sourceId() const { return sourceId_; }  // batches are supplied at run time (Task::addInput)
+
+ private:
+  RowTypePtr type_;
+  int32_t sourceId_;
+};
+class FilterNode : public PlanNode {
+ public:
+  FilterNode(PlanNodeId id, TypedExprPtr filter, PlanNodePtr source) : PlanNode(std::move(id)), sources_{std::move(source)}, filter_(std::move(filter)) {}
+  const RowTypePtr& outputType() const override { return sources_[0]->outputType(); }
+  const std::vector<PlanNodePtr>& sources() const override { return sources_; }
+  const TypedExprPtr& filter() const { return filter_; }
+  std::string_view name() const override { return "Filter"; }
+
+ private:
+  std::vector<PlanNodePtr> sources_;
+  TypedExprPtr filter_;
+};
+class ProjectNode : public PlanNode {
+ public:
+  ProjectNode(PlanNodeId id, std::vector<std::string> names, std::vector<TypedExprPtr> projections, PlanNodePtr source)
+      : PlanNode(std::move(id)), sources_{std::move(source)}, names_(std::move(names)), projections_(std::move(projections)) {
+    std::vector<TypePtr> types;
+    for (auto& p : projections_) types.push_back(p->type());
+    type_ = ROW(names_, types);
+  }
+  const RowTypePtr& outputType() const override { return type_; }
+  const std::vector<PlanNodePtr>& sources() const override { return sources_; }
+  const std::vector<std::string>& names() const { return names_; }
+  const std::vector<TypedExprPtr>& projections() const { return projections_; }
+  std::string_view name() const override { return "Project"; }
+
+ private:
+  std::vector<PlanNodePtr> sources_;
+  std::vector<std::string> names_;
+  std::vector<TypedExprPtr> projections_;
+  RowTypePtr type_;
+};
+class AggregationNode : public PlanNode {
+ public:
+  enum class Step { kPartial, kFinal, kIntermediate, kSingle };
+  struct Aggregate {
+    std::string function;               // sum avg count min max
+    std::vector<int32_t> inputs;        // input columns: raw argument, or intermediate column(s) for kFinal / kIntermediate
+    int32_t mask = -1;                  // optional BOOLEAN mask column
+    TypePtr rawInputType;               // type of the raw argument (decides sum's accumulator)
+  };
+  AggregationNode(PlanNodeId id, Step step, std::vector<int32_t> groupingKeys, std::vector<Aggregate> aggregates,
+                  RowTypePtr outputType, PlanNodePtr source)
+      : PlanNode(std::move(id)), step_(step), keys_(std::move(groupingKeys)), aggregates_(std::move(aggregates)),
+        type_(std::move(outputType)), sources_{std::move(source)} {}
+  Step step() const { return step_; }
+  const std::vector<int32_t>& groupingKeys() const { return keys_; }
+  const std::vector<Aggregate>& aggregates() const { return aggregates_; }
+  const RowTypePtr& outputType() const override { return type_; }
+  const std::vector<PlanNodePtr>& sources() const override { return sources_; }
+  std::string_view name() const override { return "Aggregation"; }
+  bool isRawInput() const { return step_ == Step::kPartial || step_ == Step::kSingle; }
+  bool isFinalOutput() const { return step_ == Step::kFinal || step_ == Step::kSingle; }
+
+ private:
+  Step step_;
+  std::vector<int32_t> keys_;
+  std::vector<Aggregate> aggregates_;
+  RowTypePtr type_;
+  std::vector<PlanNodePtr> sources_;
+};
+enum class JoinType { kInner, kLeft, kLeftSemiFilter, kAnti };
+class HashJoinNode : public PlanNode {
+ public:
+  struct Output { bool fromProbe; int32_t column; };
+  HashJoinNode(PlanNodeId id, JoinType type, std::vector<int32_t> leftKeys, std::vector<int32_t> rightKeys, TypedExprPtr filter,
+               PlanNodePtr left, PlanNodePtr right, std::vector<Output> outputs, RowTypePtr outputType)
+      : PlanNode(std::move(id)), joinType_(type), leftKeys_(std::move(leftKeys)), rightKeys_(std::move(rightKeys)),
+        filter_(std::move(filter)), sources_{std::move(left), std::move(right)}, outputs_(std::move(outputs)), type_(std::move(outputType)) {}
+  JoinType joinType() const { return joinType_; }
+  const std::vector<int32_t>& leftKeys() const { return leftKeys_; }   // probe side
+  const std::vector<int32_t>& rightKeys() const { return rightKeys_; }  // build side
+  const TypedExprPtr& filter() const { return filter_; }
+  const std::vector<Output>& outputs() const { return outputs_; }
+  const RowTypePtr& outputType() const override { return type_; }
+  const std::vector<PlanNodePtr>& sources() const override { return sources_; }
+  std::string_view name() const override { return "HashJoin"; }
+
+ private:
+  JoinType joinType_;
+  std::vector<int32_t> leftKeys_, rightKeys_;
+  TypedExprPtr filter_;
+  std::vector<PlanNodePtr> sources_;
+  std::vector<Output> outputs_;
+  RowTypePtr type_;
+};
+
+class QueryConfig {
+ public:
+  explicit QueryConfig(std::unordered_map<std::string, std::string> values = {}) : values_(std::move(values)) {}
+  template <class T>
+  T get(const std::string& key, T defaultValue) const {
+    auto it = values_.find(key);
+    if (it == values_.end()) return defaultValue;
+    if constexpr (std::is_same_v<T, bool>) return it->second == "true" || it->second == "1";
+    else if constexpr (std::is_integral_v<T>) return static_cast<T>(std::stoll(it->second));
+    else return it->second;
+  }
+  // velox/core/QueryConfig.h:479-494
+  int32_t preferredOutputBatchRows() const { return get<int32_t>("preferred_output_batch_rows", 1024); }
+  // B200 keys, following the CudfConfig pattern (velox/experimental/cudf/CudfConfig.h:29-127)
+  bool b200Enabled() const { return get<bool>("b200.enabled", true); }
+  bool b200FusedPipelines() const { return get<bool>("b200.fused_pipelines", true); }
+  int32_t b200DeviceId() const { return get<int32_t>("b200.device_id", -1); }
+
+ private:
+  std::unordered_map<std::string, std::string> values_;
+};
+
+}  // namespace core
+
+namespace exec {
+
+// ---- expression set -----------------------------------------------------------------------------
+// Compiled expressions of an operator. The shim keeps the typed trees; the CPU interpreter of the
+// reference is not part of this repo — B200 operators compile `exprs()` to a device program.
+class ExprSet {
+ public:
+  explicit ExprSet(std::vector<core::TypedExprPtr> exprs) : exprs_(std::move(exprs)) {}
+  const std::vector<core::TypedExprPtr>& exprs() const { return exprs_; }
+  size_t size() const { return exprs_.size(); }
+
+ private:
+  std::vector<core::TypedExprPtr> exprs_;
+};
+
+class EvalCtx;
+
+// ---- VectorFunction registry --------------------------------------------------------------------
+struct FunctionSignature {
+  std::string returnType;             // "boolean" "double" "bigint" "integer" "T"
+  std::vector<std::string> argTypes;  // same vocabulary; "T" = any one type, all Ts equal
+};
+using FunctionSignaturePtr = std::shared_ptr<FunctionSignature>;
+struct VectorFunctionMetadata {
+  bool defaultNullBehavior = true;  // NULL in -> NULL out, function not called on those rows
+  bool deterministic = true;
+};
+class VectorFunction {
+ public:
+  virtual ~VectorFunction() = default;
+  // velox/expression/VectorFunction.h:81-86. `rows` selects the rows to compute; `result` may be
+  // pre-allocated. Device implementations receive device-resident argument vectors.
+  virtual void apply(const SelectivityVector& rows, std::vector<VectorPtr>& args, const TypePtr& outputType, EvalCtx& context,
+                     VectorPtr& result) const = 0;
+};
+struct VectorFunctionEntry {
+  std::vector<FunctionSignaturePtr> signatures;
+  std::shared_ptr<VectorFunction> function;
+  VectorFunctionMetadata metadata;
+};
+using VectorFunctionMap = std::unordered_map<std::string, VectorFunctionEntry>;
+inline VectorFunctionMap& vectorFunctionFactories() {
+  static VectorFunctionMap m;
+  return m;
+}
+inline std::mutex& vectorFunctionMutex() {
+  static std::mutex m;
+  return m;
+}
+inline bool registerVectorFunction(const std::string& name, std::vector<FunctionSignaturePtr> signatures,
+                                   std::unique_ptr<VectorFunction> func, VectorFunctionMetadata metadata = {}, bool overwrite = true) {
+  std::lock_guard<std::mutex> l(vectorFunctionMutex());
+  auto& m = vectorFunctionFactories();
+  if (!overwrite && m.count(name)) return false;
+  m[name] = VectorFunctionEntry{std::move(signatures), std::shared_ptr<VectorFunction>(std::move(func)), metadata};
+  return true;
+}
+inline std::shared_ptr<VectorFunction> getVectorFunction(const std::string& name) {
+  std::lock_guard<std::mutex> l(vectorFunctionMutex());
+  auto& m = vectorFunctionFactories();
+  auto it = m.find(name);
+  return it == m.end() ? nullptr : it->second.function;
+}
+
+// ---- operators --------------------------------------------------------------------------------
+enum class BlockingReason { kNotBlocked, kWaitForProducer, kWaitForJoinBuild, kWaitForConsumer };
+// The shim runs drivers serially, so a future is a flag the unblocking side sets.
+struct ContinueFuture {
+  std::shared_ptr<bool> ready;
+  bool valid() const { return ready != nullptr; }
+  bool isReady() const { return ready && *ready; }
+};
+
+class Task;
+struct DriverCtx {
+  int32_t driverId = 0;
+  int32_t pipelineId = 0;
+  Task* task = nullptr;
+  const core::QueryConfig* config = nullptr;
+  memory::MemoryPool* pool = nullptr;
+  const core::QueryConfig& queryConfig() const { return *config; }
+};
+
+struct RuntimeCounter { int64_t value = 0; };
+struct OperatorStats {  // velox/exec/OperatorStats.h:93
+  int32_t operatorId = 0;
+  std::string operatorType;
+  int64_t inputPositions = 0, inputVectors = 0, outputPositions = 0, outputVectors = 0;
+  std::map<std::string, int64_t> runtimeStats;
+};
+
+class Operator {
+ public:
+  Operator(DriverCtx* driverCtx, RowTypePtr outputType, int32_t operatorId, std::string planNodeId, std::string operatorType)
+      : driverCtx_(driverCtx), outputType_(std::move(outputType)), planNodeId_(std::move(planNodeId)) {
+    stats_.operatorId = operatorId;
+    stats_.operatorType = std::move(operatorType);
+  }
+  virtual ~Operator() = default;
+  virtual void initialize() { initialized_ = true; }
+  virtual bool needsInput() const = 0;
+  virtual void addInput(RowVectorPtr input) = 0;
+  virtual void noMoreInput() { noMoreInput_ = true; }
+  virtual RowVectorPtr getOutput() = 0;
+  virtual BlockingReason isBlocked(ContinueFuture* future) = 0;
+  virtual bool isFinished() = 0;
+  virtual void close() { input_ = nullptr; }
+  virtual bool canReclaim() const { return false; }  // no spill on device
+  virtual bool isSourceOperator() const { return false; }
+
+  const RowTypePtr& outputType() const { return outputType_; }
+  const std::string& planNodeId() const { return planNodeId_; }
+  int32_t operatorId() const { return stats_.operatorId; }
+  void setOperatorIdFromAdapter(int32_t id) { stats_.operatorId = id; }
+  const std::string& operatorType() const { return stats_.operatorType; }
+  OperatorStats& stats() { return stats_; }
+  void addRuntimeStat(const std::string& name, const RuntimeCounter& c) { stats_.runtimeStats[name] += c.value; }
+  memory::MemoryPool* pool() const { return driverCtx_->pool; }
+  DriverCtx* driverCtx() const { return driverCtx_; }
+
+ protected:
+  DriverCtx* driverCtx_;
+  RowTypePtr outputType_;
+  std::string planNodeId_;
+  OperatorStats stats_;
+  RowVectorPtr input_;
+  bool noMoreInput_ = false;
+  bool initialized_ = false;
+};
+
+class SourceOperator : public Operator {
+ public:
+  using Operator::Operator;
+  bool needsInput() const override { return false; }
+  void addInput(RowVectorPtr) override { VELOX_CHECK(false, "SourceOperator does not take input"); }
+  bool isSourceOperator() const override { return true; }
+};
+
+// ---- join bridge --------------------------------------------------------------------------------
+// One-shot hand-off of the finished build side from the build pipeline to the probe pipeline
+// (velox/exec/HashJoinBridge.h:57 setHashTable, :116 tableOrFuture). The payload is opaque here;
+// the B200 operators store their device table holder in it (the reference does the same for its
+// Wave backend: setHashTable(shared_ptr<wave::HashTableHolder>) :63-65).
+class JoinBridge {
+ public:
+  virtual ~JoinBridge() = default;
+};
+class HashJoinBridge : public JoinBridge {
+ public:
+  void setHashTable(std::shared_ptr<void> table) {
+    table_ = std::move(table);
+    for (auto& f : waiters_) *f = true;
+    waiters_.clear();
+  }
+  std::shared_ptr<void> tableOrFuture(ContinueFuture* future) {
+    if (table_) return table_;
+    future->ready = std::make_shared<bool>(false);
+    waiters_.push_back(future->ready);
+    return nullptr;
+  }
+
+ private:
+  std::shared_ptr<void> table_;
+  std::vector<std::shared_ptr<bool>> waiters_;
+};
+
+// ---- CPU operators of the reference, as the LocalPlanner instantiates them ----------------------
+// The reference's CPU implementations are not part of this repo (no CPU fallback): these classes
+// carry the plan information and the accelerator hooks the adapter reads, and refuse to run.
+class CpuOperatorStub : public Operator {
+ public:
+  using Operator::Operator;
+  bool needsInput() const override { unavailable(); }
+  void addInput(RowVectorPtr) override { unavailable(); }
+  RowVectorPtr getOutput() override { unavailable(); }
+  BlockingReason isBlocked(ContinueFuture*) override { return BlockingReason::kNotBlocked; }
+  bool isFinished() override { unavailable(); }
+
+ private:
+  [[noreturn]] void unavailable() const {
+    throw VeloxRuntimeError("CPU operator '" + stats_.operatorType +
+                            "' is not available in this build: register the B200 adapter (registerB200())");
+  }
+};
+
+class FilterProject : public CpuOperatorStub {
+ public:
+  FilterProject(int32_t operatorId, DriverCtx* ctx, std::shared_ptr<const core::FilterNode> filter,
+                std::shared_ptr<const core::ProjectNode> project)
+      : CpuOperatorStub(ctx, project ? project->outputType() : filter->outputType(), operatorId,
+                        project ? project->id() : filter->id(), "FilterProject"),
+        filter_(std::move(filter)), project_(std::move(project)) {
+    std::vector<core::TypedExprPtr> all;
+    if (filter_) all.push_back(filter_->filter());
+    if (project_) for (auto& p : project_->projections()) all.push_back(p);
+    exprs_ = std::make_unique<ExprSet>(std::move(all));
+  }
+  // velox/exec/FilterProject.h:70-78
+  struct Export { const ExprSet* exprs; bool hasFilter; };
+  Export exprsAndProjection() const { return Export{exprs_.get(), filter_ != nullptr}; }
+  const std::shared_ptr<const core::FilterNode>& filterNode() const { return filter_; }
+  const std::shared_ptr<const core::ProjectNode>& projectNode() const { return project_; }
+  RowTypePtr inputType() const { return (filter_ ? filter_->sources()[0] : project_->sources()[0])->outputType(); }
+
+ private:
+  std::shared_ptr<const core::FilterNode> filter_;
+  std::shared_ptr<const core::ProjectNode> project_;
+  std::unique_ptr<ExprSet> exprs_;
+};
+class HashAggregation : public CpuOperatorStub {
+ public:
+  HashAggregation(int32_t operatorId, DriverCtx* ctx, std::shared_ptr<const core::AggregationNode> node)
+      : CpuOperatorStub(ctx, node->outputType(), operatorId, node->id(), "Aggregation"), node_(std::move(node)) {}
+  const std::shared_ptr<const core::AggregationNode>& node() const { return node_; }
+
+ private:
+  std::shared_ptr<const core::AggregationNode> node_;
+};
+class HashBuild : public CpuOperatorStub {
+ public:
+  HashBuild(int32_t operatorId, DriverCtx* ctx, std::shared_ptr<const core::HashJoinNode> node, std::shared_ptr<HashJoinBridge> bridge)
+      : CpuOperatorStub(ctx, nullptr, operatorId, node->id(), "HashBuild"), node_(std::move(node)), bridge_(std::move(bridge)) {}
+  const std::shared_ptr<const core::HashJoinNode>& node() const { return node_; }
+  const std::shared_ptr<HashJoinBridge>& joinBridge() const { return bridge_; }  // velox/exec/HashBuild.h:101-107
+
+ private:
+  std::shared_ptr<const core::HashJoinNode> node_;
+  std::shared_ptr<HashJoinBridge> bridge_;
+};
+class HashProbe : public CpuOperatorStub {
+ public:
+  HashProbe(int32_t operatorId, DriverCtx* ctx, std::shared_ptr<const core::HashJoinNode> node, std::shared_ptr<HashJoinBridge> bridge)
+      : CpuOperatorStub(ctx, node->outputType(), operatorId, node->id(), "HashProbe"), node_(std::move(node)), bridge_(std::move(bridge)) {}
+  const std::shared_ptr<const core::HashJoinNode>& node() const { return node_; }
+  const std::shared_ptr<HashJoinBridge>& joinBridge() const { return bridge_; }
+
+ private:
+  std::shared_ptr<const core::HashJoinNode> node_;
+  std::shared_ptr<HashJoinBridge> bridge_;
+};
+
+// Source fed with batches at run time (velox/exec/Values.h:21 holds its vectors in the plan node;
+// here the Task owns the queue so multi-GB inputs are not copied into the plan).
+class Values : public SourceOperator {
+ public:
+  Values(int32_t operatorId, DriverCtx* ctx, std::shared_ptr<const core::ValuesNode> node, std::shared_ptr<std::vector<RowVectorPtr>> batches)
+      : SourceOperator(ctx, node->outputType(), operatorId, node->id(), "Values"), batches_(std::move(batches)) {}
+  RowVectorPtr getOutput() override {
+    if (next_ >= batches_->size()) return nullptr;
+    return (*batches_)[next_++];
+  }
+  BlockingReason isBlocked(ContinueFuture*) override { return BlockingReason::kNotBlocked; }
+  bool isFinished() override { return next_ >= batches_->size(); }
+
+ private:
+  std::shared_ptr<std::vector<RowVectorPtr>> batches_;
+  size_t next_ = 0;
+};
+
+// Sink collecting the task's results (velox/exec/CallbackSink.h).
+class CallbackSink : public Operator {
+ public:
+  CallbackSink(int32_t operatorId, DriverCtx* ctx, std::function<void(RowVectorPtr)> consumer)
+      : Operator(ctx, nullptr, operatorId, "sink", "CallbackSink"), consumer_(std::move(consumer)) {}
+  bool needsInput() const override { return !noMoreInput_; }
+  void addInput(RowVectorPtr input) override { consumer_(std::move(input)); }
+  RowVectorPtr getOutput() override { return nullptr; }
+  BlockingReason isBlocked(ContinueFuture*) override { return BlockingReason::kNotBlocked; }
+  bool isFinished() override { return noMoreInput_; }
+
+ private:
+  std::function<void(RowVectorPtr)> consumer_;
+};
+
+// ---- driver -------------------------------------------------------------------------------------
+class Driver;
+struct DriverFactory;
+struct DriverAdapter {  // velox/exec/Driver.h:789-793
+  std::string label;
+  std::function<void(const DriverFactory&)> inspect;
+  std::function<bool(const DriverFactory&, Driver&)> adapt;
+};
+
+struct DriverFactory {  // velox/exec/Driver.h:795-847
+  std::vector<core::PlanNodePtr> planNodes;
+  std::function<std::unique_ptr<Operator>(int32_t operatorId, DriverCtx* ctx)> consumerSupplier;
+  bool inputDriver = false, outputDriver = false;
+  int32_t pipelineId = 0;
+  // Replaces operators [begin, end) of `driver` (velox/exec/LocalPlanner.cpp:772-810).
+  std::vector<std::unique_ptr<Operator>> replaceOperators(Driver& driver, int32_t begin, int32_t end,
+                                                          std::vector<std::unique_ptr<Operator>> replaceWith) const;
+  static std::vector<DriverAdapter>& adapters() {
+    static std::vector<DriverAdapter> a;
+    return a;
+  }
+  static void registerAdapter(DriverAdapter adapter) { adapters().push_back(std::move(adapter)); }
+};
+
+class Driver {
+ public:
+  explicit Driver(std::unique_ptr<DriverCtx> ctx) : ctx_(std::move(ctx)) {}
+  DriverCtx* driverCtx() const { return ctx_.get(); }
+  std::vector<std::unique_ptr<Operator>>& operators() { return operators_; }
+  const std::vector<std::unique_ptr<Operator>>& operators() const { return operators_; }
+  void init(std::vector<std::unique_ptr<Operator>> ops) { operators_ = std::move(ops); }
+  void initializeOperators() {
+    if (initialized_) return;
+    initialized_ = true;
+    for (auto& op : operators_) op->initialize();
+  }
+  // One pass of the loop of Driver::runInternal (velox/exec/Driver.cpp:598-835): walks from the
+  // sink toward the source, moving at most one batch per operator pair. Returns kNotBlocked with
+  // *finished set when the pipeline has drained, or the reason it cannot progress.
+  BlockingReason runOnce(bool* finished, bool* progressed);
+  void close() {
+    for (auto& op : operators_) op->close();
+  }
+
+ private:
+  std::unique_ptr<DriverCtx> ctx_;
+  std::vector<std::unique_ptr<Operator>> operators_;
+  std::set<Operator*> signalled_;  // consumers already told noMoreInput
+  bool initialized_ = false;
+};
+
+inline std::vector<std::unique_ptr<Operator>> DriverFactory::replaceOperators(Driver& driver, int32_t begin, int32_t end,
+                                                                              std::vector<std::unique_ptr<Operator>> replaceWith) const {
+  auto& ops = driver.operators();
+  VELOX_CHECK(begin >= 0 && end <= static_cast<int32_t>(ops.size()) && begin <= end, "replaceOperators: bad range");
+  std::vector<std::unique_ptr<Operator>> replaced;
+  for (int32_t i = begin; i < end; ++i) replaced.push_back(std::move(ops[i]));
+  ops.erase(ops.begin() + begin, ops.begin() + end);
+  ops.insert(ops.begin() + begin, std::make_move_iterator(replaceWith.begin()), std::make_move_iterator(replaceWith.end()));
+  for (size_t i = 0; i < ops.size(); ++i) ops[i]->setOperatorIdFromAdapter(static_cast<int32_t>(i));
+  return replaced;
+}
+
+inline BlockingReason Driver::runOnce(bool* finished, bool* progressed) {
+  initializeOperators();
+  *finished = false;
+  *progressed = false;
+  const int32_t n = static_cast<int32_t>(operators_.size());
+  ContinueFuture future;
+  for (int32_t i = n - 1; i >= 0; --i) {
+    Operator* op = operators_[i].get();
+    BlockingReason r = op->isBlocked(&future);
+    if (r != BlockingReason::kNotBlocked) return r;
+    if (i == n - 1) {
+      if (op->isFinished()) {
+        *finished = true;
+        return BlockingReason::kNotBlocked;
+      }
+      continue;
+    }
+    Operator* next = operators_[i + 1].get();
+    if (!next->needsInput()) continue;
+    RowVectorPtr out = op->getOutput();
+    if (out) {
+      VELOX_CHECK(out->size() > 0, "operators must not emit empty vectors");
+      op->stats().outputPositions += out->size();
+      op->stats().outputVectors += 1;
+      next->stats().inputPositions += out->size();
+      next->stats().inputVectors += 1;
+      next->addInput(std::move(out));
+      *progressed = true;
+      return BlockingReason::kNotBlocked;  // restart from the sink, as runInternal does
+    }
+    if (op->isFinished() && !signalled_.count(next)) {
+      next->noMoreInput();
+      signalled_.insert(next);
+      *progressed = true;
+      return BlockingReason::kNotBlocked;
+    }
+  }
+  return BlockingReason::kNotBlocked;
+}
+
+}  // namespace exec
+}  // namespace facebook::velox
+
+#endif  // VELOX_B200_WITH_REAL_VELOX

@@ -8,20 +8,37 @@
 namespace vb2 {
 namespace fx {
 
+// One warp per accumulator: lanes stride over the per-block partials, then a fixed butterfly.
 __global__ void fused_finalize_kernel(const double* __restrict__ partials, int nblocks, int kvals, int np, int maxg,
                                       int ngroups, double* __restrict__ sums, int64_t* __restrict__ counts) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= kvals) return;
+  const int t = blockIdx.x;
+  const int lane = threadIdx.x;
   const int g = t / (np + 1), p = t % (np + 1);
-  if (g >= ngroups || g >= maxg) return;
+  if (t >= kvals || g >= ngroups || g >= maxg) return;
   if (p == np) {
     int64_t c = 0;
-    for (int b = 0; b < nblocks; ++b) c += __double_as_longlong(partials[static_cast<int64_t>(b) * kvals + t]);
-    counts[g] += c;
+    for (int b = lane; b < nblocks; b += 32) c += __double_as_longlong(partials[static_cast<int64_t>(b) * kvals + t]);
+    c = warp_sum(c);
+    if (lane == 0) counts[g] += c;
   } else {
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s = __dadd_rn(s, partials[static_cast<int64_t>(b) * kvals + t]);
-    sums[g * np + p] = __dadd_rn(sums[g * np + p], s);
+    for (int b = lane; b < nblocks; b += 32) s = __dadd_rn(s, partials[static_cast<int64_t>(b) * kvals + t]);
+    s = warp_sum(s);
+    if (lane == 0) sums[g * np + p] = __dadd_rn(sums[g * np + p], s);
+  }
+}
+
+// join_slot_flags[slot] = 0 (no build row) | 1 (match) | 2 (match and build-side predicate true)
+__global__ void join_slot_flags_kernel(const int32_t* __restrict__ head, const int32_t* __restrict__ codes,
+                                       const uint8_t* __restrict__ flag, int64_t range, uint8_t* __restrict__ out) {
+  for (int64_t s = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; s < range; s += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t h = head[s];
+    uint8_t v = 0;
+    if (h != 0) {
+      const int32_t code = codes ? codes[h - 1] : (h - 1);
+      v = (flag && flag[code]) ? 2 : 1;
+    }
+    out[s] = v;
   }
 }
 
@@ -38,51 +55,83 @@ int register_pipeline(const Entry& e) {
 constexpr int kMaxBlocksPerSM = 8;
 constexpr int kFusedMaxGroups = 8;
 
-template <class P, int kMaxG, int kUnroll, bool kPair, class KeyT>
-static int launch_variant(const KernelArgs& a, double* sums, int64_t* counts, void* ws, size_t ws_bytes, cudaStream_t st) {
-  auto kernel = fused_scan_agg_kernel<P, kMaxG, kUnroll, kPair, KeyT>;
+static int run_finalize(const KernelArgs& a, void* ws, int64_t grid, int kvals, int np, int maxg, double* sums, int64_t* counts,
+                        cudaStream_t st) {
+  fused_finalize_kernel<<<kvals, 32, 0, st>>>(reinterpret_cast<const double*>(ws), static_cast<int>(grid), kvals, np, maxg, a.ngroups, sums, counts);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+// Direct-load variant: unaligned slices and inputs smaller than one tile.
+template <class P, int kMaxG, class KeyT>
+static int launch_direct(const KernelArgs& a, double* sums, int64_t* counts, void* ws, size_t ws_bytes, cudaStream_t st) {
+  auto kernel = fused_scan_agg_kernel<P, kMaxG, 2, false, KeyT>;
   static int blocks_per_sm = 0;
   if (blocks_per_sm == 0) {
     int n = 0;
     VB2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, 0));
     blocks_per_sm = n < 1 ? 1 : (n > kMaxBlocksPerSM ? kMaxBlocksPerSM : n);
   }
-  const int64_t units = kPair ? (a.rows >> 1) : a.rows;
-  int64_t want = (units + kThreads - 1) / kThreads;
+  int64_t want = (a.rows + kThreads - 1) / kThreads;
   int64_t grid = static_cast<int64_t>(device_sm_count()) * blocks_per_sm;
   if (want < grid) grid = want < 1 ? 1 : want;
   constexpr int kVals = kMaxG * (P::kNP + 1);
   if (ws_bytes < static_cast<size_t>(grid) * kVals * sizeof(double)) return fail_msg(VB2_ERR_INVALID, "fused workspace too small");
   kernel<<<static_cast<unsigned>(grid), kThreads, 0, st>>>(a, reinterpret_cast<double*>(ws));
   VB2_CUDA_OK(cudaGetLastError());
-  fused_finalize_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const double*>(ws), static_cast<int>(grid), kVals, P::kNP, kMaxG,
-                                           a.ngroups, sums, counts);
+  return run_finalize(a, ws, grid, kVals, P::kNP, kMaxG, sums, counts, st);
+}
+
+// TMA-staged variant (main path): persistent grid, stages sized to ~96 KB of shared memory per block.
+template <class P, int kMaxG, class KeyT>
+static int launch_tma(const KernelArgs& a, double* sums, int64_t* counts, void* ws, size_t ws_bytes, cudaStream_t st) {
+  auto kernel = fused_scan_agg_tma_kernel<P, kMaxG, KeyT>;
+  const int stage_bytes = TileLayout<P, sizeof(KeyT)>::stage_bytes(kMaxG > 1 ? a.nkeys : 0);
+  constexpr int kSmemBudget = 100 * 1024;
+  int stages = kSmemBudget / stage_bytes;
+  stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes;
+  static size_t configured = 0;
+  if (configured < smem) {
+    VB2_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  int blocks_per_sm = 0;
+  VB2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kTmaThreads, smem));
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  if (blocks_per_sm > kMaxBlocksPerSM) blocks_per_sm = kMaxBlocksPerSM;
+  const int64_t ntiles = a.rows / kTileRows;
+  int64_t grid = static_cast<int64_t>(device_sm_count()) * blocks_per_sm;
+  if (ntiles < grid) grid = ntiles < 1 ? 1 : ntiles;
+  constexpr int kVals = kMaxG * (P::kNP + 1);
+  if (ws_bytes < static_cast<size_t>(grid) * kVals * sizeof(double)) return fail_msg(VB2_ERR_INVALID, "fused workspace too small");
+  kernel<<<static_cast<unsigned>(grid), kTmaThreads, smem, st>>>(a, stages, reinterpret_cast<double*>(ws));
   VB2_CUDA_OK(cudaGetLastError());
-  return VB2_OK;
+  return run_finalize(a, ws, grid, kVals, P::kNP, kMaxG, sums, counts, st);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <class P>
 static int launch(const KernelArgs& a, double* sums, int64_t* counts, void* ws, size_t ws_bytes, cudaStream_t st) {
-  bool pair = true;
+  bool bulk = a.rows >= kTileRows;  // cp.async.bulk needs 16-byte aligned sources
   for (int c = 0; c < kMaxCols; ++c)
-    if (((P::fmask | P::imask | P::lmask) >> c) & 1u) pair = pair && aligned16(a.cols[c]);
-  for (int k = 0; k < a.nkeys; ++k) pair = pair && aligned16(a.key[k]);
+    if (((P::fmask | P::imask | P::lmask) >> c) & 1u) bulk = bulk && aligned16(a.cols[c]);
+  for (int k = 0; k < a.nkeys; ++k) bulk = bulk && aligned16(a.key[k]);
   const int g = a.nkeys == 0 ? 1 : a.ngroups;
   if (g > kFusedMaxGroups) return fail_msg(VB2_ERR_UNSUPPORTED, "fused register aggregation holds at most 8 groups");
-  bool key64 = false;
-  for (int k = 0; k < a.nkeys; ++k) key64 = key64 || a.key_is64[k];
-#define VB2_GO(G, U, K)                                                                              \
-  return pair ? launch_variant<P, G, U, true, K>(a, sums, counts, ws, ws_bytes, st)                 \
-              : launch_variant<P, G, U, false, K>(a, sums, counts, ws, ws_bytes, st)
-  if (g <= 1) { VB2_GO(1, 4, int32_t); }
+  bool key64 = false, key32 = false;
+  for (int k = 0; k < a.nkeys; ++k) (a.key_is64[k] ? key64 : key32) = true;
+  if (key64 && key32) return fail_msg(VB2_ERR_UNSUPPORTED, "fused aggregation: group keys must have one width");
+#define VB2_GO(G, K)                                                                                  \
+  return bulk ? launch_tma<P, G, K>(a, sums, counts, ws, ws_bytes, st) : launch_direct<P, G, K>(a, sums, counts, ws, ws_bytes, st)
+  if (g <= 1) { VB2_GO(1, int32_t); }
   if (g <= 4) {
-    if (key64) { VB2_GO(4, 2, int64_t); }
-    VB2_GO(4, 2, int32_t);
+    if (key64) { VB2_GO(4, int64_t); }
+    VB2_GO(4, int32_t);
   }
-  if (key64) { VB2_GO(8, 1, int64_t); }
-  VB2_GO(8, 1, int32_t);
+  if (key64) { VB2_GO(8, int64_t); }
+  VB2_GO(8, int32_t);
 #undef VB2_GO
 }
 
@@ -165,6 +214,14 @@ size_t vb2k_fused_workspace_bytes(int32_t id, int32_t ngroups) {
   return static_cast<size_t>(device_sm_count()) * kMaxBlocksPerSM * g * (registry()[id].nproj + 1) * sizeof(double);
 }
 
+int vb2k_join_slot_flags(const int32_t* head, const int32_t* codes, const uint8_t* flag, int64_t range, uint8_t* out, void* stream) {
+  if (range <= 0) return VB2_OK;
+  int64_t b = (range + 255) / 256, cap = static_cast<int64_t>(device_sm_count()) * 8;
+  join_slot_flags_kernel<<<static_cast<unsigned>(b > cap ? cap : b), 256, 0, static_cast<cudaStream_t>(stream)>>>(head, codes, flag, range, out);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
 int vb2k_fused_scan_agg(int32_t id, const vb2_fused_args* args, double* sums, int64_t* counts, void* workspace,
                         size_t workspace_bytes, void* stream) {
   ensure_registered();
@@ -188,12 +245,10 @@ int vb2k_fused_scan_agg(int32_t id, const vb2_fused_args* args, double* sums, in
     a.key_min[k] = args->key_min[k];
     a.key_lut[k] = args->key_lut[k];
   }
-  a.join_head = args->join_head;
-  a.join_codes = args->join_codes;
-  a.join_flag = args->join_flag;
+  a.join_slot_flags = args->join_slot_flags;
   a.join_min = args->join_min;
   a.join_range = args->join_range;
-  if (e.join && (!a.join_head || !a.join_flag)) return fail_msg(VB2_ERR_INVALID, "fused join pipeline needs join_head and join_flag");
+  if (e.join && (!a.join_slot_flags || a.join_range <= 0)) return fail_msg(VB2_ERR_INVALID, "fused join pipeline needs join_slot_flags");
   return e.launch(a, sums, counts, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

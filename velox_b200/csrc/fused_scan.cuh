@@ -239,9 +239,9 @@ struct KernelArgs {
   int32_t key_mult[VB2_FUSED_MAX_KEYS];
   int64_t key_min[VB2_FUSED_MAX_KEYS];
   const int32_t* key_lut[VB2_FUSED_MAX_KEYS];
-  const int32_t* join_head;
-  const int32_t* join_codes;
-  const uint8_t* join_flag;
+  // Array-mode join table prepared for the fused probe: one byte per key slot,
+  // 0 = no build row, 1 = match with build-side predicate false, 2 = match with predicate true.
+  const uint8_t* join_slot_flags;
   int64_t join_min, join_range;
 };
 
@@ -331,51 +331,84 @@ struct Accum {
       for (int p = 0; p < P::kNP; ++p) sum[g][p] = 0.0;
     }
   }
-  // Predicated adds keep every accumulator in a register (no dynamic indexing).
+  // Branch-free: every accumulator stays in a register (no dynamic indexing, no divergence);
+  // rows of other groups (and rows dropped by the filter, gid = -1) leave it untouched.
   __device__ __forceinline__ void add(int gid, const double (&v)[P::kNP]) {
 #pragma unroll
     for (int g = 0; g < kMaxG; ++g) {
-      if (gid == g) {
-        cnt[g] += 1;
+      const int hit = gid == g;
+      cnt[g] += hit;
+      // one predicated DADD per accumulator (ptxas shares the setp across the group's adds)
 #pragma unroll
-        for (int p = 0; p < P::kNP; ++p) sum[g][p] = __dadd_rn(sum[g][p], v[p]);
-      }
+      for (int p = 0; p < P::kNP; ++p)
+        asm("{ .reg .pred q; setp.ne.s32 q, %1, 0; @q add.rn.f64 %0, %0, %2; }" : "+d"(sum[g][p]) : "r"(hit), "d"(v[p]));
     }
   }
 };
+
+// Evaluates filter (+ join probe), group id and projections of one row slot.
+template <class P, int kMaxG, class KeyT>
+__device__ __forceinline__ void eval_slot(const KernelArgs& a, PairRegs& r, const KeyT (&kv)[VB2_FUSED_MAX_KEYS][2], int s,
+                                          int& gid, double (&v)[P::kNP]) {
+  bool keep = P::F::eval(r, a.consts, s);
+  if constexpr (P::kJoin) {
+    // Array-mode probe, branch-free: rows that failed the filter (or fall outside the key range)
+    // read slot 0, which every lane shares, so the load costs no extra sectors.
+    const int64_t slot = r.l[P::kJoinCol][s] - a.join_min;
+    const bool in_range = keep && slot >= 0 && slot < a.join_range;
+    const uint8_t hit = __ldg(a.join_slot_flags + (in_range ? slot : 0));
+    keep = in_range && hit != 0;
+    r.join_flag[s] = hit == 2;
+  }
+  P::template project<0>(r, a.consts, s, v);
+  const int g = (kMaxG == 1) ? 0 : group_of<KeyT>(a, kv, s);
+  gid = keep ? g : -1;
+}
 
 template <class P, int kMaxG, bool kPair, class KeyT>
 __device__ __forceinline__ void process(const KernelArgs& a, const PairRegs& r0, const KeyT (&kv)[VB2_FUSED_MAX_KEYS][2],
                                         Accum<P, kMaxG>& acc) {
   PairRegs r = r0;
+  int gid[2];
+  double v[2][P::kNP];
 #pragma unroll
-  for (int s = 0; s < (kPair ? 2 : 1); ++s) {
-    bool keep = P::F::eval(r, a.consts, s);
-    if constexpr (P::kJoin) {
-      r.join_flag[s] = false;
-      if (keep) {
-        // Array-mode probe: slot = key - min; head holds build row + 1 (0 = no match).
-        const int64_t key = r.l[P::kJoinCol][s];
-        const int64_t slot = key - a.join_min;
-        int32_t hit = 0;
-        if (slot >= 0 && slot < a.join_range) hit = __ldg(a.join_head + slot);
-        keep = hit != 0;
-        if (keep) {
-          const int32_t code = a.join_codes ? __ldg(a.join_codes + (hit - 1)) : (hit - 1);
-          r.join_flag[s] = __ldg(a.join_flag + code) != 0;
-        }
-      }
+  for (int s = 0; s < (kPair ? 2 : 1); ++s) eval_slot<P, kMaxG, KeyT>(a, r, kv, s, gid[s], v[s]);
+#pragma unroll
+  for (int s = 0; s < (kPair ? 2 : 1); ++s) acc.add(gid[s], v[s]);
+}
+
+// Block reduction: shuffles within warps, then across warps in fixed order; one partial per block.
+constexpr int kMaxWarps = 9;
+template <class P, int kMaxG>
+__device__ __forceinline__ void block_reduce_store(const Accum<P, kMaxG>& acc, double* __restrict__ partials) {
+  constexpr int kVals = kMaxG * (P::kNP + 1);
+  __shared__ double red[kMaxWarps][kVals];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int g = 0; g < kMaxG; ++g) {
+#pragma unroll
+    for (int p = 0; p < P::kNP; ++p) {
+      double v = warp_sum(acc.sum[g][p]);
+      if (lane == 0) red[warp][g * (P::kNP + 1) + p] = v;
     }
-    int gid = -1;
-    double v[P::kNP];
-    if (keep) {
-      gid = (kMaxG == 1) ? 0 : group_of(a, kv, s);
-      P::template project<0>(r, a.consts, s, v);
+    int64_t c = warp_sum(static_cast<int64_t>(acc.cnt[g]));
+    if (lane == 0) red[warp][g * (P::kNP + 1) + P::kNP] = __longlong_as_double(c);
+  }
+  __syncthreads();
+  if (threadIdx.x < kVals) {
+    const bool is_cnt = (threadIdx.x % (P::kNP + 1)) == P::kNP;
+    double out;
+    if (is_cnt) {
+      int64_t c = 0;
+      for (int w = 0; w < nwarps; ++w) c += __double_as_longlong(red[w][threadIdx.x]);
+      out = __longlong_as_double(c);
     } else {
-#pragma unroll
-      for (int p = 0; p < P::kNP; ++p) v[p] = 0.0;
+      double s = 0.0;
+      for (int w = 0; w < nwarps; ++w) s = __dadd_rn(s, red[w][threadIdx.x]);
+      out = s;
     }
-    acc.add(gid, v);
+    partials[static_cast<int64_t>(blockIdx.x) * kVals + threadIdx.x] = out;
   }
 }
 
@@ -412,35 +445,169 @@ __global__ void __launch_bounds__(kThreads, kMaxG <= 4 ? 2 : 1) fused_scan_agg_k
     if (kMaxG > 1) load_keys<false, KeyT>(a, a.rows - 1, kv);
     process<P, kMaxG, false, KeyT>(a, r, kv, acc);
   }
-  // block reduction: shuffle within warps, then across warps in fixed order
-  constexpr int kVals = kMaxG * (P::kNP + 1);
-  __shared__ double smem[kThreads / kWarp][kVals];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int g = 0; g < kMaxG; ++g) {
-#pragma unroll
-    for (int p = 0; p < P::kNP; ++p) {
-      double v = warp_sum(acc.sum[g][p]);
-      if (lane == 0) smem[warp][g * (P::kNP + 1) + p] = v;
+  block_reduce_store<P, kMaxG>(acc, partials);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged variant (main path). One producer warp streams kTileRows-row slices of every
+// referenced column into a ring of shared-memory stages with 1-D bulk async copies
+// (cp.async.bulk ... mbarrier::complete_tx), eight consumer warps evaluate the pipeline out of
+// shared memory. The bytes in flight per SM are stages x tile bytes (~90-180 KB) regardless of
+// how ptxas schedules the consumers' code, which is what an HBM-bound scan needs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileRows = 1024;
+constexpr int kConsumerThreads = 256;
+constexpr int kTmaThreads = kConsumerThreads + 32;
+constexpr int kMaxStages = 4;
+constexpr int kRowsPerThread = kTileRows / kConsumerThreads;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+// 1-D bulk async copy global -> shared; completion is signalled on `bar` as transaction bytes.
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Byte offsets of the referenced columns inside one stage: f64 columns, i64 columns, 8-byte keys,
+// i32 columns, 4-byte keys. Everything but the key count is a compile-time constant.
+template <class P, int kKeyBytes>
+struct TileLayout {
+  __host__ __device__ static constexpr int popc(uint32_t m) { int n = 0; for (; m; m &= m - 1) ++n; return n; }
+  __host__ __device__ static constexpr uint32_t low(int c) { return (1u << c) - 1u; }
+  static constexpr int kBase8 = 8 * kTileRows * (popc(P::fmask) + popc(P::lmask));
+  __host__ __device__ static constexpr int f_off(int c) { return 8 * kTileRows * popc(P::fmask & low(c)); }
+  __host__ __device__ static constexpr int l_off(int c) { return 8 * kTileRows * (popc(P::fmask) + popc(P::lmask & low(c))); }
+  __host__ __device__ static constexpr int i_base(int nkeys) { return kBase8 + (kKeyBytes == 8 ? nkeys * 8 * kTileRows : 0); }
+  __host__ __device__ static constexpr int i_off(int c, int nkeys) { return i_base(nkeys) + 4 * kTileRows * popc(P::imask & low(c)); }
+  __host__ __device__ static constexpr int key_off(int k, int nkeys) {
+    return kKeyBytes == 8 ? kBase8 + 8 * kTileRows * k : i_base(nkeys) + 4 * kTileRows * (popc(P::imask) + k);
+  }
+  __host__ __device__ static constexpr int stage_bytes(int nkeys) {
+    const int end = i_base(nkeys) + 4 * kTileRows * popc(P::imask) + (kKeyBytes == 4 ? nkeys * 4 * kTileRows : 0);
+    return (end + 127) / 128 * 128;
+  }
+};
+
+template <class P, int kMaxG, class KeyT>
+__global__ void __launch_bounds__(kTmaThreads, kMaxG <= 4 ? 2 : 1)
+fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, double* __restrict__ partials) {
+  extern __shared__ __align__(128) uint8_t tile_smem[];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  using Lay = TileLayout<P, sizeof(KeyT)>;
+  const int nk = kMaxG > 1 ? a.nkeys : 0;
+  const int stage_bytes = Lay::stage_bytes(nk);
+  const int64_t ntiles = a.rows / kTileRows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);                        // producer's expect_tx arrival
+      mbar_init(&empty_bar[s], kConsumerThreads / kWarp);  // one arrival per consumer warp
     }
-    int64_t c = warp_sum(static_cast<int64_t>(acc.cnt[g]));
-    if (lane == 0) smem[warp][g * (P::kNP + 1) + P::kNP] = __longlong_as_double(c);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x < kVals) {
-    const bool is_cnt = (threadIdx.x % (P::kNP + 1)) == P::kNP;
-    double out;
-    if (is_cnt) {
-      int64_t c = 0;
-      for (int w = 0; w < kThreads / kWarp; ++w) c += __double_as_longlong(smem[w][threadIdx.x]);
-      out = __longlong_as_double(c);
-    } else {
-      double s = 0.0;
-      for (int w = 0; w < kThreads / kWarp; ++w) s = __dadd_rn(s, smem[w][threadIdx.x]);
-      out = s;
+  Accum<P, kMaxG> acc;
+  acc.init();
+  if (warp == kConsumerThreads / kWarp) {
+    // ---- producer warp: one elected lane issues the copies ----
+    if (lane == 0) {
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % stages;
+        const uint32_t round = static_cast<uint32_t>(it / stages);
+        if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+        uint8_t* base = tile_smem + static_cast<size_t>(s) * stage_bytes;
+        const int64_t row0 = t * kTileRows;
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) {
+          if (P::fmask & (1u << c)) bytes += kTileRows * 8;
+          if (P::lmask & (1u << c)) bytes += kTileRows * 8;
+          if (P::imask & (1u << c)) bytes += kTileRows * 4;
+        }
+        if (kMaxG > 1) bytes += a.nkeys * kTileRows * sizeof(KeyT);
+        mbar_expect_tx(&full_bar[s], bytes);
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) {
+          if (P::fmask & (1u << c)) bulk_load(base + Lay::f_off(c), reinterpret_cast<const double*>(a.cols[c]) + row0, kTileRows * 8, &full_bar[s]);
+          if (P::lmask & (1u << c)) bulk_load(base + Lay::l_off(c), reinterpret_cast<const int64_t*>(a.cols[c]) + row0, kTileRows * 8, &full_bar[s]);
+          if (P::imask & (1u << c)) bulk_load(base + Lay::i_off(c, nk), reinterpret_cast<const int32_t*>(a.cols[c]) + row0, kTileRows * 4, &full_bar[s]);
+        }
+        if (kMaxG > 1) {
+          for (int k = 0; k < a.nkeys; ++k)
+            bulk_load(base + Lay::key_off(k, nk), reinterpret_cast<const KeyT*>(a.key[k]) + row0, kTileRows * sizeof(KeyT), &full_bar[s]);
+        }
+      }
     }
-    partials[static_cast<int64_t>(blockIdx.x) * kVals + threadIdx.x] = out;
+  } else {
+    // ---- consumer warps ----
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it % stages;
+      const uint32_t round = static_cast<uint32_t>(it / stages);
+      mbar_wait(&full_bar[s], round & 1);
+      const uint8_t* base = tile_smem + static_cast<size_t>(s) * stage_bytes;
+      PairRegs r[kRowsPerThread];
+      KeyT kv[kRowsPerThread][VB2_FUSED_MAX_KEYS][2];
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        const int row = j * kConsumerThreads + threadIdx.x;
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) {
+          if (P::fmask & (1u << c)) r[j].f[c][0] = reinterpret_cast<const double*>(base + Lay::f_off(c))[row];
+          if (P::lmask & (1u << c)) r[j].l[c][0] = reinterpret_cast<const int64_t*>(base + Lay::l_off(c))[row];
+          if (P::imask & (1u << c)) r[j].i[c][0] = reinterpret_cast<const int32_t*>(base + Lay::i_off(c, nk))[row];
+        }
+        if (kMaxG > 1) {
+#pragma unroll
+          for (int k = 0; k < VB2_FUSED_MAX_KEYS; ++k)
+            if (k < a.nkeys) kv[j][k][0] = reinterpret_cast<const KeyT*>(base + Lay::key_off(k, nk))[row];
+        }
+      }
+      // all reads of this stage are done: hand it back to the producer before computing
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      int gid[kRowsPerThread];
+      double v[kRowsPerThread][P::kNP];
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) eval_slot<P, kMaxG, KeyT>(a, r[j], kv[j], 0, gid[j], v[j]);
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) acc.add(gid[j], v[j]);
+    }
+    // tail rows (rows % kTileRows) by direct loads, spread over the blocks' consumer threads
+    const int64_t tail0 = ntiles * kTileRows;
+    for (int64_t row = tail0 + static_cast<int64_t>(blockIdx.x) * kConsumerThreads + threadIdx.x; row < a.rows;
+         row += static_cast<int64_t>(gridDim.x) * kConsumerThreads) {
+      PairRegs r;
+      KeyT kv[VB2_FUSED_MAX_KEYS][2];
+      load_rows<P, false>(a, row, r);
+      if (kMaxG > 1) load_keys<false, KeyT>(a, row, kv);
+      process<P, kMaxG, false, KeyT>(a, r, kv, acc);
+    }
   }
+  block_reduce_store<P, kMaxG>(acc, partials);
 }
 
 // Folds per-block partials in block order into the persistent accumulators.

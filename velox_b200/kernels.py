@@ -27,9 +27,7 @@ class FusedArgs(C.Structure):
         ("key_mult", C.c_int32 * MAX_KEYS),
         ("key_min", C.c_int64 * MAX_KEYS),
         ("key_lut", C.c_void_p * MAX_KEYS),
-        ("join_head", C.c_void_p),
-        ("join_codes", C.c_void_p),
-        ("join_flag", C.c_void_p),
+        ("join_slot_flags", C.c_void_p),
         ("join_min", C.c_int64),
         ("join_range", C.c_int64),
     ]
@@ -110,6 +108,13 @@ def gather(src: torch.Tensor, order: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def join_slot_flags(head: torch.Tensor, codes: Optional[torch.Tensor], flag: Optional[torch.Tensor]) -> torch.Tensor:
+    out = torch.empty(head.numel(), dtype=torch.uint8, device="cuda")
+    check(lib().vb2k_join_slot_flags(C.c_void_p(head.data_ptr()), C.c_void_p(_ptr(codes)), C.c_void_p(_ptr(flag)),
+                                     C.c_int64(head.numel()), C.c_void_p(out.data_ptr()), _stream()))
+    return out
+
+
 def fused_find(signature: str) -> int:
     return lib().vb2k_fused_find(signature.encode())
 
@@ -161,11 +166,9 @@ class FusedScanAgg:
             a.key_mult[k] = key_mult[k]
             a.key_lut[k] = key_lut[k].data_ptr() if key_lut and key_lut[k] is not None else None
         if join is not None:
-            a.join_head = join["head"].data_ptr()
-            a.join_codes = join["codes"].data_ptr() if join.get("codes") is not None else None
-            a.join_flag = join["flag"].data_ptr()
+            a.join_slot_flags = join["slot_flags"].data_ptr()
             a.join_min = join["min"]
-            a.join_range = join["head"].numel()
+            a.join_range = join["slot_flags"].numel()
         check(lib().vb2k_fused_scan_agg(self.id, C.byref(a), C.c_void_p(self.sums.data_ptr()),
                                         C.c_void_p(self.counts.data_ptr()), C.c_void_p(self.ws.data_ptr()),
                                         C.c_size_t(self.ws_bytes), _stream()))

@@ -340,23 +340,14 @@ class _Node:
 
 
 class PlanBuilder:
-    """Mirrors velox/exec/tests/utils/PlanBuilder.h. Sources are numbered in creation order;
-    `values()` declares a source fed at run time through Task.add_input / the `sources` list."""
-
-    _next_source = [0]
+    """Mirrors velox/exec/tests/utils/PlanBuilder.h. `values()` declares a source (default id 0;
+    join build sides name theirs explicitly) fed at run time through the `sources` list."""
 
     def __init__(self):
         self.node: Optional[_Node] = None
         self.sources: List[int] = []
 
-    @classmethod
-    def reset_ids(cls):
-        cls._next_source[0] = 0
-
-    def values(self, names, types, source: Optional[int] = None) -> "PlanBuilder":
-        if source is None:
-            source = PlanBuilder._next_source[0]
-            PlanBuilder._next_source[0] += 1
+    def values(self, names, types, source: int = 0) -> "PlanBuilder":
         self.sources.append(source)
         ts = " ".join(TYPE_NAMES[t] for t in types)
         self.node = _Node(f"(values {source} ({ts}))", list(names), list(types))
