@@ -1,0 +1,75 @@
+/*
+ * velox_b200 — operator-level C ABI: the drop-in boundary a host application binds.
+ *
+ * A task is a Velox plan fragment (values -> filter -> project -> aggregation / hash join ...)
+ * executed by an unmodified Driver loop (velox/exec/Driver.cpp:538-850) whose FilterProject,
+ * HashAggregation, HashBuild and HashProbe operators have been replaced through
+ * DriverFactory::registerAdapter (velox/exec/Driver.h:789-847) by the B200 operators of this
+ * library. Inputs are column batches in the layout of velox_b200_kernels.h (`vb2_column`), in
+ * host memory (copied to the device by the inserted B200FromHost operator, as
+ * velox/experimental/cudf/exec/CudfConversion.h:32 does) or already resident in HBM.
+ *
+ * Error behaviour mirrors the reference (SURVEY.md §8b "Errors"): data errors (integer overflow,
+ * division by zero, failed cast — VeloxUserError) return VB2_ERR_USER, everything else
+ * (VeloxRuntimeError: bad plan, CUDA failure, unsupported shape) a VB2_ERR_* code; the message
+ * is written to `err`. There is no CPU fallback: an unsupported shape is an error.
+ */
+#ifndef VELOX_B200_H_
+#define VELOX_B200_H_
+
+#include "velox_b200_kernels.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vb2_task vb2_task;
+
+enum { VB2_HOST = 0, VB2_DEVICE = 1 };
+
+/* plan_text: grammar in DESIGN.md / velox_b200/plan.py. config: "key=value;key=value" query
+ * config (core::QueryConfig, velox/core/QueryConfig.h): b200.enabled, b200.fused_pipelines,
+ * b200.device_id. Returns NULL on error. */
+vb2_task* vb2_task_create(const char* plan_text, const char* config, char* err, int32_t errlen);
+/* Queues one batch for ValuesNode `source_id` (exec::Values, velox/exec/Values.h:21). The column
+ * memory is borrowed: it must stay valid until vb2_task_run returns. */
+int32_t vb2_task_add_input(vb2_task* task, int32_t source_id, const vb2_column* cols, int32_t ncols, int64_t rows,
+                           int32_t location, char* err, int32_t errlen);
+/* Runs the task to completion (Task::start + drivers; serial execution mode). */
+int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen);
+
+/* Result batches concatenated; copy-out into caller buffers. */
+int64_t vb2_result_rows(vb2_task* task);
+int32_t vb2_result_cols(vb2_task* task);
+int32_t vb2_result_type(vb2_task* task, int32_t col);
+/* Fixed width: values (BOOLEAN one byte per row) and one null flag byte per row (1 = NULL). */
+void vb2_result_copy(vb2_task* task, int32_t col, void* values, uint8_t* nulls);
+int64_t vb2_result_str_bytes(vb2_task* task, int32_t col);
+void vb2_result_copy_str(vb2_task* task, int32_t col, int32_t* offsets, char* chars, uint8_t* nulls);
+/* Operator runtime stats as "pipeline.operator.type.name=value\n" lines (OperatorStats,
+ * velox/exec/OperatorStats.h:93). Valid until the task is freed. */
+const char* vb2_task_stats(vb2_task* task);
+void vb2_task_free(vb2_task* task);
+
+/* Hash-partitioned exchange across the GPUs of one node: partition ids follow
+ * HashPartitionFunction (hash % world), payload moves with one grouped ncclSend/ncclRecv
+ * all-to-all over NVLink. The communicator is created from an ncclUniqueId the caller broadcasts
+ * (e.g. with torch.distributed). */
+typedef struct vb2_comm vb2_comm;
+int32_t vb2_comm_unique_id(uint8_t out[128]);
+vb2_comm* vb2_comm_create(const uint8_t unique_id[128], int32_t world, int32_t rank, char* err, int32_t errlen);
+void vb2_comm_free(vb2_comm* comm);
+/* send: world contiguous segments of `elem_bytes`-wide elements described by send_counts (host
+ * int64[world]); recv_counts (host int64[world]) is filled first through a count exchange when
+ * recv == NULL, otherwise the payload is exchanged. Device pointers; stream-ordered. */
+int32_t vb2_comm_exchange_counts(vb2_comm* comm, const int64_t* send_counts, int64_t* recv_counts, void* stream);
+int32_t vb2_comm_all_to_all(vb2_comm* comm, const void* send, const int64_t* send_counts, void* recv, const int64_t* recv_counts,
+                            int32_t elem_bytes, void* stream);
+/* Sum-reduces n doubles / int64s in place across ranks (merge of per-GPU partial aggregates). */
+int32_t vb2_comm_all_reduce_f64(vb2_comm* comm, double* data, int64_t n, void* stream);
+int32_t vb2_comm_all_reduce_i64(vb2_comm* comm, int64_t* data, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELOX_B200_H_ */

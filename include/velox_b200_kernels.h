@@ -214,7 +214,8 @@ typedef struct vb2_agg_update {
   int64_t* nonnull;         /* int64[capacity]: non-null inputs seen (drives NULL results and AVG counts), may be NULL */
 } vb2_agg_update;
 
-/* group_ids: int32[n], one slot per row (negative = skip row). capacity = size of the group-id
+/* group_ids: int32[n], one slot per row (negative = skip row); NULL = every row in group 0
+ * (global aggregation). capacity = size of the group-id
  * space; spaces of <= 8 groups take a register-accumulator kernel (one launch per aggregate),
  * larger ones one atomic per row and aggregate. SUM(BIGINT) overflow sets *error_flag. */
 int vb2k_agg_update(const int32_t* group_ids, int64_t n, int64_t capacity, const vb2_agg_update* aggs, int32_t naggs,
@@ -224,23 +225,37 @@ int vb2k_agg_update(const int32_t* group_ids, int64_t n, int64_t capacity, const
  * keys uint64[capacity] initialised to VB2_EMPTY_KEY. Finds or inserts each row's key and
  * writes its slot to group_ids. capacity must be a power of two. */
 #define VB2_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+/* table_keys == NULL: array mode, the normalized key itself is the slot (capacity = key space). */
 int vb2k_group_probe(const uint64_t* row_keys, const uint64_t* row_valid, int64_t n, uint64_t* table_keys,
                      int64_t capacity, int32_t* group_ids, int64_t* num_groups, int32_t* error_flag, void* stream);
 /* Packs up to 4 key columns into one 64-bit normalized key per row:
- * key = sum_k (v_k - min_k + 1) * mult_k, 0 reserved for NULL per column (VectorHasher value ids,
- * velox/exec/VectorHasher.h:523-585). Columns may be flat/dictionary/constant. */
-int vb2k_normalize_keys(const vb2_column* cols, int32_t ncols, const int64_t* mins, const uint64_t* mults,
-                        int64_t rows, const int32_t* sel, int64_t n, uint64_t* keys_out, void* stream);
+ * key = sum_k id_k * mult_k with id_k = v_k - min_k + 1 and id 0 reserved for NULL (VectorHasher
+ * value ids, velox/exec/VectorHasher.h:523-585). Columns may be flat/dictionary/constant of
+ * BOOLEAN/INTEGER/BIGINT type. valid_out (optional bitmap): cleared for rows with a NULL key when
+ * nulls_invalid (joins never match NULL keys, exec/HashBuild.cpp:475-479) and for ids outside
+ * [1, ranges[k]) when ranges != NULL (probe keys the build side cannot contain). */
+int vb2k_normalize_keys(const vb2_column* cols, int32_t ncols, const int64_t* mins, const uint64_t* mults, const uint64_t* ranges,
+                        int32_t nulls_invalid, const int32_t* sel, int64_t n, uint64_t* keys_out, uint64_t* valid_out, void* stream);
 /* min/max of an integer column over non-null rows: out = {min, max, nonnull_count} (device int64[3]). */
 int vb2k_column_minmax(const vb2_column* col, int64_t rows, int64_t* out3, void* stream);
 /* Compacts occupied slots: slot_list int32[<=capacity] ascending, count device int64. */
 int vb2k_table_occupied(const uint64_t* table_keys, int64_t capacity, int32_t* slot_list, int64_t* count,
                         void* workspace, size_t workspace_bytes, void* stream);
 size_t vb2k_table_occupied_workspace(int64_t capacity);
+/* Re-encodes the keys of the listed slots for a new layout after value ranges grew (the rehash
+ * step of HashTable::checkSize / decideHashMode, velox/exec/HashTable.cpp:772,1751). table_keys
+ * NULL = array mode (key = slot). */
+int vb2k_rekey(const uint64_t* table_keys, const int32_t* slots, int64_t n, int32_t ncols, const int64_t* old_mins,
+               const uint64_t* old_mults, const uint64_t* old_ranges, const int32_t* old_null_reserved, const int64_t* new_mins,
+               const uint64_t* new_mults, uint64_t* keys_out, void* stream);
+/* out = a & b over n bits (aggregate masks combined with validity) */
+int vb2k_and_bits(const uint64_t* a, const uint64_t* b, int64_t n, uint64_t* out, void* stream);
 /* Inverse of vb2k_normalize_keys for one key column over the listed slots: value = id - 1 + min
- * with id = (key / mult) % range; id 0 -> NULL. values: T[n] (BOOLEAN one byte per row). */
+ * with id = (key / mult) % range; id 0 is NULL when null_reserved (a layout for a column that
+ * never held NULLs uses min + 1 and keeps id 0 for the smallest value). table_keys NULL = array
+ * mode (key = slot). values: T[n] (BOOLEAN one byte per row). */
 int vb2k_denormalize_keys(const uint64_t* table_keys, const int32_t* slots, int64_t n, int64_t min, uint64_t mult,
-                          uint64_t range, int32_t type, void* values, uint64_t* valid, void* stream);
+                          uint64_t range, int32_t null_reserved, int32_t type, void* values, uint64_t* valid, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Hash join. Build: replaces HashBuild::addInput row store + HashTable::prepareJoinTable /
@@ -272,9 +287,28 @@ size_t vb2k_scan_workspace(int64_t n);
 int vb2k_join_probe_emit(const vb2_join_table* t, const uint64_t* probe_keys, const uint64_t* valid, int64_t n,
                          const int64_t* offsets, int32_t* probe_rows, int32_t* build_rows, void* stream);
 
-/* Misc */
+/* Misc building blocks of the operator layer */
 int vb2k_fill_u64(uint64_t* p, int64_t n, uint64_t v, void* stream);
 int vb2k_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream);
+int vb2k_iota_i32(int32_t* p, int64_t n, void* stream);
+/* out[i] = (int32) in[i] */
+int vb2k_narrow_i64(const int64_t* in, int64_t n, int32_t* out, void* stream);
+/* out[i] = in[i] (widen) / out[i] = in[i] == 0 (widen_not): matched flags of outer/semi/anti joins */
+int vb2k_widen_i32(const int32_t* in, int64_t n, int64_t* out, void* stream);
+int vb2k_widen_not_i32(const int32_t* in, int64_t n, int64_t* out, void* stream);
+/* valid bit k = idx[k] >= 0, clamped[k] = max(idx[k], 0): build side of unmatched left-join rows */
+int vb2k_index_validity(const int32_t* idx, int64_t n, uint64_t* valid, int32_t* clamped, void* stream);
+/* out bit k = in bit sel[k] (validity bitmaps under a selection) */
+int vb2k_gather_bits(const uint64_t* in, const int32_t* sel, int64_t n, uint64_t* out, void* stream);
+/* one byte per row (0/1) -> bit-packed BOOLEAN values (FlatVector<bool> layout) */
+int vb2k_pack_bools(const uint8_t* in, int64_t n, uint64_t* out, void* stream);
+/* out[dst[i]] = in[src ? src[i] : i] for 4- or 8-byte elements (accumulator moves on rehash) */
+int vb2k_scatter(const void* in, const int32_t* src, const int32_t* dst, int64_t n, int32_t elem_bytes, void* out, void* stream);
+/* Aggregate result extraction (Aggregate::extractValues, velox/exec/Aggregate.h:281-302):
+ * validity bit k = counts[slots ? slots[k] : k] > 0; avg = sum / count. */
+int vb2k_counts_to_valid(const int64_t* counts, const int32_t* slots, int64_t n, uint64_t* out, void* stream);
+int vb2k_avg_finalize(const double* sums, const int64_t* counts, const int32_t* slots, int64_t n, double* out, void* stream);
+int vb2k_positive_bits(const int64_t* counts, int64_t n, uint64_t* out, void* stream);
 
 #ifdef __cplusplus
 }

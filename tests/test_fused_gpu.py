@@ -225,3 +225,26 @@ def test_hash_and_partition_match_oracle():
         assert np.array_equal(counts, np.bincount(want, minlength=p))
         # stable grouping by partition
         assert np.array_equal(order, np.argsort(want, kind="stable").astype(np.int32))
+
+
+@pytest.mark.parametrize("card", [(2, 2), (3, 2), (5, 1), (8, 5), (50, 1)])
+@pytest.mark.parametrize("n", [1000, 300_001])
+def test_fused_groupby_variants(card, n):
+    """Register accumulators (<= 4 groups) and shared-memory accumulators (more groups), 32- and
+    64-bit keys, against numpy: counts bit exact, sums within the stated tolerance."""
+    from velox_b200.kernels import FusedScanAgg
+    rng = np.random.default_rng(card[0] * 100 + card[1] + n)
+    k0 = rng.integers(10, 10 + card[0], n).astype(np.int32)
+    k1 = rng.integers(-3, -3 + card[1], n).astype(np.int32)
+    x = np.round(rng.uniform(-1000, 1000, n), 2)
+    G = card[0] * card[1]
+    for dtype in (np.int32, np.int64):
+        f = FusedScanAgg("F:true;P:f0", ngroups=G)
+        f.add_batch([torch.from_numpy(x).cuda()], n, keys=[torch.from_numpy(k0.astype(dtype)).cuda(), torch.from_numpy(k1.astype(dtype)).cuda()],
+                    key_min=[10, -3], key_mult=[card[1], 1])
+        gid = (k0 - 10) * card[1] + (k1 + 3)
+        want_cnt = np.bincount(gid, minlength=G)
+        want_sum = np.bincount(gid, weights=x, minlength=G)
+        assert np.array_equal(f.counts.cpu().numpy(), want_cnt)
+        got = f.sums.cpu().numpy()
+        assert np.all(np.abs(got - want_sum) <= 1e-9 + rel_tol(n) * np.abs(want_sum))

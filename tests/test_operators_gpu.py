@@ -1,0 +1,326 @@
+"""Operator-level parity: plans run through the C ABI (Task -> Driver -> B200 operators installed
+by the DriverAdapter) against the CPU oracle. Modelled on the reference's
+velox/exec/tests/FilterProjectTest.cpp, AggregationTest.cpp, HashJoinTest.cpp and the scalar
+known-answer tests in velox/functions/prestosql/tests/{Arithmetic,Comparisons}Test.cpp."""
+import numpy as np
+import pytest
+
+from velox_b200 import tpch
+from velox_b200.plan import PlanBuilder
+from velox_b200.vector import (BIGINT, BOOLEAN, DOUBLE, INTEGER, VARCHAR, constant_vector, dictionary_vector, flat_vector,
+                               row_vector)
+
+from util import FUSED, GENERIC, check_plan, check_user_error, stat
+
+pytestmark = pytest.mark.gpu
+
+NAN, INF = float("nan"), float("inf")
+
+
+def table(n=1000, seed=0, nulls=True):
+    rng = np.random.default_rng(seed)
+    def maybe(vals, p=0.1):
+        if not nulls:
+            return list(vals)
+        return [None if rng.random() < p else v for v in vals]
+    return row_vector(
+        ["c0", "c1", "c2", "c3", "c4", "c5"],
+        [flat_vector(BIGINT, maybe(rng.integers(-50, 50, n).tolist())),
+         flat_vector(INTEGER, maybe(rng.integers(0, 10, n).tolist())),
+         flat_vector(DOUBLE, maybe(np.round(rng.normal(0, 100, n), 3).tolist())),
+         flat_vector(DOUBLE, maybe(rng.integers(0, 20, n).astype(float).tolist())),
+         flat_vector(BOOLEAN, maybe((rng.random(n) < 0.5).tolist())),
+         dictionary_vector(VARCHAR, rng.integers(0, 5, n), ["apple", "banana", "cherry", "date", None if nulls else "egg"])])
+
+
+# ---- FilterProject / expression engine --------------------------------------------------------
+@pytest.mark.parametrize("nulls", [False, True])
+def test_filter(nulls):
+    rv = table(nulls=nulls)
+    for f in ["c0 < 10", "c2 >= 0.0 and c3 < 10.0", "c0 % 2 = 0 or c1 > 7", "c4", "not c4", "c2 is null", "c2 is not null",
+              "c0 between -10 and 10", "c5 = 'banana'", "c5 like 'b%'", "c5 like '%e%' and c1 <> 3", "c3 not between 5.0 and 9.0"]:
+        check_plan(PlanBuilder().values(rv.names, rv.types).filter(f).planNode(), [rv])
+
+
+@pytest.mark.parametrize("nulls", [False, True])
+def test_project(nulls):
+    rv = table(nulls=nulls)
+    check_plan(PlanBuilder().values(rv.names, rv.types).project(
+        ["c0", "c0 + 1", "c2 * (1.0 - c3)", "c2 / c3", "c1 - 4", "cast(c1 as bigint) * c0", "cast(c0 as double) + c2",
+         "case when c0 > 0 then c2 else 0.0 end", "case when c4 then c0 when c1 > 5 then c0 * 2 end", "c2 < c3", "c5",
+         "c0 is null or c1 is null", "-c2", "c4 and c0 > 0", "c4 or c0 > 0", "if(c1 = 3, c1, c1 + 100)"]).planNode(), [rv])
+
+
+def test_filter_project_all_filtered_and_all_pass():
+    rv = table(nulls=False)
+    check_plan(PlanBuilder().values(rv.names, rv.types).filter("c0 > 1000").project(["c0", "c2 * 2.0"]).planNode(), [rv])
+    check_plan(PlanBuilder().values(rv.names, rv.types).filter("c0 > -1000").project(["c0", "c2 * 2.0", "c5"]).planNode(), [rv])
+
+
+def test_filter_project_encodings_and_batches():
+    """Dictionary / constant inputs, dictionary over the filter's own wrap (two filters), several batches."""
+    n = 5000
+    rng = np.random.default_rng(3)
+    rv = row_vector(["a", "b", "c", "d"], [
+        dictionary_vector(DOUBLE, rng.integers(0, 7, n), [1.5, -2.0, None, 4.25, NAN, 0.0, 1e10], index_nulls=rng.random(n) < 0.05),
+        constant_vector(BIGINT, 7, n),
+        dictionary_vector(BIGINT, rng.integers(0, 3, n), [10, 20, 30]),
+        constant_vector(DOUBLE, None, n)])
+    plan = (PlanBuilder().values(rv.names, rv.types).filter("c > 10").project(["a", "b", "c", "d", "a * 2.0 as e"])
+            .filter("b = 7 and (e > 0.0 or e is null)").project(["a", "c", "e", "d is null as f", "cast(c as double) + e"]).planNode())
+    check_plan(plan, [rv])
+    check_plan(plan, [rv], batch_rows=1024)
+
+
+def test_nan_comparisons():
+    """NaN is the largest value and equal to itself (ComparisonsTest.cpp:650-720)."""
+    vals = [1.0, NAN, -INF, INF, 0.0, -0.0, NAN, None]
+    rv = row_vector(["a", "b"], [flat_vector(DOUBLE, vals), flat_vector(DOUBLE, vals[::-1])])
+    check_plan(PlanBuilder().values(rv.names, rv.types).project(
+        ["a < b", "a <= b", "a > b", "a >= b", "a = b", "a <> b", "a between 0.0 and b", "a < 1.0", "a >= 1.0"]).planNode(), [rv])
+
+
+def test_three_valued_logic():
+    t, f, n = True, False, None
+    a = [t, t, t, f, f, f, n, n, n]
+    b = [t, f, n, t, f, n, t, f, n]
+    rv = row_vector(["a", "b"], [flat_vector(BOOLEAN, a), flat_vector(BOOLEAN, b)])
+    check_plan(PlanBuilder().values(rv.names, rv.types).project(["a and b", "a or b", "not a", "a and b and a", "a or b or a"]).planNode(), [rv])
+    check_plan(PlanBuilder().values(rv.names, rv.types).filter("a or b").planNode(), [rv])
+
+
+def test_checked_arithmetic_errors():
+    big = 2**62
+    rv = row_vector(["a", "b"], [flat_vector(BIGINT, [1, big, -big, 5]), flat_vector(BIGINT, [2, big, -big - 5, 0])])
+    ok = PlanBuilder().values(rv.names, rv.types).project(["a + 1", "a - b"]).planNode()
+    check_plan(ok, [row_vector(["a", "b"], [flat_vector(BIGINT, [1, 2]), flat_vector(BIGINT, [3, 4])])])
+    for expr in ["a + b", "a * b", "a / b", "a % b", "a - b - b"]:
+        check_user_error(PlanBuilder().values(rv.names, rv.types).project([expr]).planNode(), [rv])
+    # errors on rows that end up not selected are suppressed inside AND / CASE (ConjunctExpr.cpp:98-99)
+    check_plan(PlanBuilder().values(rv.names, rv.types).filter("b <> 0 and a / b > 0").planNode(), [rv])
+    check_plan(PlanBuilder().values(rv.names, rv.types).project(["case when b <> 0 then a / b else 0 end"]).planNode(),
+               [row_vector(["a", "b"], [flat_vector(BIGINT, [6, 5]), flat_vector(BIGINT, [3, 0])])])
+    i32 = row_vector(["a"], [flat_vector(INTEGER, [2**31 - 1, 1])])
+    check_user_error(PlanBuilder().values(i32.names, i32.types).project(["a + a"]).planNode(), [i32])
+    dbl = row_vector(["a"], [flat_vector(DOUBLE, [1.5, NAN])])
+    check_user_error(PlanBuilder().values(dbl.names, dbl.types).project(["cast(a as bigint)"]).planNode(), [dbl])
+
+
+def test_plumbing_config_exprset():
+    """BASELINE.json configs[0]: l_extendedprice*(1-l_discount) WHERE l_quantity<24 on 1M-row
+    DOUBLE/BIGINT flat vectors."""
+    n = 1_000_000
+    t = tpch.gen_lineitem(n, 1000, seed=21, device="cpu")
+    rv = row_vector(["l_partkey", "l_quantity", "l_extendedprice", "l_discount"],
+                    [flat_vector(BIGINT, t["l_partkey"].numpy()), flat_vector(DOUBLE, t["l_quantity"].numpy()),
+                     flat_vector(DOUBLE, t["l_extendedprice"].numpy()), flat_vector(DOUBLE, t["l_discount"].numpy())])
+    plan = (PlanBuilder().values(rv.names, rv.types).filter("l_quantity < 24.0")
+            .project(["l_partkey", "l_extendedprice * (1.0 - l_discount)"]).planNode())
+    check_plan(plan, [rv], oracle_batch_rows=100_000)
+
+
+# ---- HashAggregation ------------------------------------------------------------------------------
+AGGS = ["sum(c0)", "sum(c1)", "sum(c2)", "avg(c2)", "avg(c0)", "count(0)", "count(c2)", "min(c0)", "max(c2)", "min(c1)", "max(c0)"]
+
+
+@pytest.mark.parametrize("keys", [[], ["c1"], ["c5"], ["c1", "c5"], ["c4", "c1", "c5"], ["c0"]])
+@pytest.mark.parametrize("nulls", [False, True])
+def test_aggregation_single(keys, nulls):
+    rv = table(n=3000, seed=5, nulls=nulls)
+    plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(keys, AGGS).planNode()
+    check_plan(plan, [rv], rel_tol=1e-11)
+    check_plan(plan, [rv], batch_rows=700, rel_tol=1e-11)
+
+
+@pytest.mark.parametrize("keys", [[], ["c1", "c5"]])
+def test_aggregation_partial_final(keys):
+    rv = table(n=3000, seed=6)
+    plan = PlanBuilder().values(rv.names, rv.types).partialAggregation(keys, AGGS).localPartition([]).finalAggregation().planNode()
+    check_plan(plan, [rv], rel_tol=1e-11)
+    plan = (PlanBuilder().values(rv.names, rv.types).partialAggregation(keys, AGGS).intermediateAggregation()
+            .finalAggregation().planNode())
+    check_plan(plan, [rv], batch_rows=900, rel_tol=1e-11)
+    # partial output itself (intermediate types)
+    check_plan(PlanBuilder().values(rv.names, rv.types).partialAggregation(keys, AGGS).planNode(), [rv], rel_tol=1e-11)
+
+
+def test_aggregation_empty_and_all_null():
+    rv = table(n=50, seed=1)
+    # empty input after a filter: global aggregation still emits one row (sum NULL, count 0)
+    plan = PlanBuilder().values(rv.names, rv.types).filter("c0 > 1000").singleAggregation([], ["sum(c2)", "count(0)", "avg(c0)", "min(c1)"]).planNode()
+    check_plan(plan, [rv])
+    plan = PlanBuilder().values(rv.names, rv.types).filter("c0 > 1000").singleAggregation(["c1"], ["sum(c2)", "count(0)"]).planNode()
+    check_plan(plan, [rv])
+    allnull = row_vector(["k", "v"], [flat_vector(INTEGER, [1, 1, 2]), flat_vector(DOUBLE, [None, None, None])])
+    check_plan(PlanBuilder().values(allnull.names, allnull.types).singleAggregation(["k"], ["sum(v)", "avg(v)", "count(v)", "max(v)"]).planNode(), [allnull])
+
+
+def test_aggregation_masks():
+    rv = table(n=2000, seed=9)
+    plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(["c1"], ["sum(c2)", "count(0)", "avg(c0)"], masks=["c4", "c4", None]).planNode()
+    check_plan(plan, [rv], rel_tol=1e-11)
+
+
+def test_aggregation_sum_overflow():
+    rv = row_vector(["k", "v"], [flat_vector(INTEGER, [1, 1, 2]), flat_vector(BIGINT, [2**62, 2**62, 5])])
+    check_user_error(PlanBuilder().values(rv.names, rv.types).singleAggregation(["k"], ["sum(v)"]).planNode(), [rv])
+    check_user_error(PlanBuilder().values(rv.names, rv.types).singleAggregation([], ["sum(v)"]).planNode(), [rv])
+
+
+def test_aggregation_high_cardinality_hash_mode():
+    """BASELINE.json configs[4] in miniature: BIGINT keys whose range exceeds array mode."""
+    n = 400_000
+    rng = np.random.default_rng(11)
+    keys = rng.integers(0, 2**40, 60_000)[rng.integers(0, 60_000, n)]
+    rv = row_vector(["k", "v"], [flat_vector(BIGINT, keys), flat_vector(BIGINT, (np.arange(n) % 1000))])
+    plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(["k"], ["sum(v)", "count(0)", "min(v)"]).planNode()
+    (st,) = check_plan(plan, [rv], oracle_batch_rows=100_000)
+    assert stat(st, "b200.aggMode") == 2  # hash mode
+    check_plan(plan, [rv], batch_rows=50_000, oracle_batch_rows=100_000)  # growth / rehash across batches
+    two = row_vector(["a", "b", "v"], [flat_vector(BIGINT, keys), flat_vector(INTEGER, (keys % 7).astype(np.int32)), flat_vector(DOUBLE, np.ones(n))])
+    check_plan(PlanBuilder().values(two.names, two.types).singleAggregation(["a", "b"], ["sum(v)", "count(0)"]).planNode(), [two], oracle_batch_rows=100_000)
+
+
+def _lineitem(n, seed, nparts=2000):
+    t = tpch.gen_lineitem(n, nparts, seed=seed, device="cpu")
+    h = {k: v.numpy() for k, v in t.items()}
+    def col(name):
+        if name == "l_returnflag":
+            return dictionary_vector(VARCHAR, h[name], tpch.RETURNFLAG_DICT)
+        if name == "l_linestatus":
+            return dictionary_vector(VARCHAR, h[name], tpch.LINESTATUS_DICT)
+        if name == "l_shipdate":
+            return flat_vector(INTEGER, h[name])
+        if name == "l_partkey":
+            return flat_vector(BIGINT, h[name])
+        return flat_vector(DOUBLE, h[name])
+    return h, col
+
+
+def q1_plan(rv):
+    return (PlanBuilder().values(rv.names, rv.types)
+            .filter("l_shipdate < '1998-09-03'::DATE")
+            .project(["l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice",
+                      "l_extendedprice * (1.0 - l_discount) AS l_sum_disc_price",
+                      "l_extendedprice * (1.0 - l_discount) * (1.0 + l_tax) AS l_sum_charge", "l_discount"])
+            .partialAggregation(["l_returnflag", "l_linestatus"],
+                                ["sum(l_quantity)", "sum(l_extendedprice)", "sum(l_sum_disc_price)", "sum(l_sum_charge)",
+                                 "avg(l_quantity)", "avg(l_extendedprice)", "avg(l_discount)", "count(0)"])
+            .localPartition([]).finalAggregation().planNode())
+
+
+def q6_plan(rv):
+    return (PlanBuilder().values(rv.names, rv.types)
+            .filter("l_shipdate between '1994-01-01'::DATE and '1994-12-31'::DATE and "
+                    "l_discount between 0.05 and 0.07 and l_quantity < 24.0")
+            .project(["l_extendedprice * l_discount"])
+            .partialAggregation([], ["sum(p0)"]).localPartition([]).finalAggregation().planNode())
+
+
+def q14_plan(li, pt):
+    build = PlanBuilder().values(pt.names, pt.types, source=1)
+    return (PlanBuilder().values(li.names, li.types, source=0)
+            .filter("l_shipdate between '1995-09-01'::DATE and '1995-09-30'::DATE")
+            .project(["l_extendedprice * (1.0 - l_discount) as part_revenue", "l_shipdate", "l_partkey"])
+            .hashJoin(["l_partkey"], ["p_partkey"], build, "", ["part_revenue", "p_type"])
+            .project(["(CASE WHEN (p_type LIKE 'PROMO%') THEN part_revenue ELSE 0.0 END) as filter_revenue", "part_revenue"])
+            .partialAggregation([], ["sum(part_revenue) as total_revenue", "sum(filter_revenue) as total_promo_revenue"])
+            .localPartition([]).finalAggregation()
+            .project(["100.00 * total_promo_revenue/total_revenue as promo_revenue"]).planNode())
+
+
+@pytest.mark.parametrize("n", [1000, 250_000])
+def test_tpch_q1_q6_fused_and_generic(n):
+    """TPC-H Q1 / Q6 (TpchQueryBuilder.cpp:203-256,756-788): the fused kernel and the generic
+    operator chain both match the oracle; the fused path must really have been taken."""
+    h, col = _lineitem(n, seed=31)
+    names = ["l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_shipdate"]
+    rv = row_vector(names, [col(c) for c in names])
+    tol = max(1e-12, n * 2.0 ** -53)
+    st_f, st_g = check_plan(q1_plan(rv), [rv], configs=(FUSED, GENERIC), rel_tol=tol, oracle_batch_rows=100_000)
+    assert stat(st_f, "b200.fusedBatches") == 1 and stat(st_f, "b200.genericBatches") == 0
+    assert stat(st_g, "b200.fusedBatches") == 0
+    check_plan(q1_plan(rv), [rv], configs=(FUSED, GENERIC), batch_rows=60_000, rel_tol=tol, oracle_batch_rows=100_000)
+    names6 = ["l_shipdate", "l_extendedprice", "l_quantity", "l_discount"]
+    rv6 = row_vector(names6, [col(c) for c in names6])
+    st_f, st_g = check_plan(q6_plan(rv6), [rv6], configs=(FUSED, GENERIC), rel_tol=tol, oracle_batch_rows=100_000)
+    assert stat(st_f, "b200.fusedBatches") == 1
+
+
+def test_tpch_q1_nulls_fall_back_to_generic_kernels():
+    """A batch with NULLs cannot take the fused kernel; the same operator then runs the generic
+    kernels for it and the result still matches."""
+    h, col = _lineitem(5000, seed=2)
+    names = ["l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_shipdate"]
+    cols = [col(c) for c in names]
+    qn = np.zeros(5000, dtype=bool)
+    qn[::17] = True
+    cols[2] = flat_vector(DOUBLE, h["l_quantity"], qn)
+    rv = row_vector(names, cols)
+    (st,) = check_plan(q1_plan(rv), [rv], rel_tol=1e-12)
+    assert stat(st, "b200.fusedBatches") == 0 and stat(st, "b200.genericBatches") == 1
+
+
+# ---- HashBuild / HashProbe ----------------------------------------------------------------------
+def _join_tables(seed=0, nulls=True, dup=True):
+    rng = np.random.default_rng(seed)
+    n, m = 2000, 300
+    pk = rng.integers(0, 400, n).tolist()
+    bk = (rng.integers(0, 350, m) if dup else rng.permutation(400)[:m]).tolist()
+    if nulls:
+        pk = [None if rng.random() < 0.05 else v for v in pk]
+        bk = [None if rng.random() < 0.05 else v for v in bk]
+    probe = row_vector(["pk", "pv", "ps"], [flat_vector(BIGINT, pk), flat_vector(DOUBLE, rng.normal(size=n).round(3).tolist()),
+                                             dictionary_vector(VARCHAR, rng.integers(0, 3, n), ["x", "y", "z"])])
+    build = row_vector(["bk", "bv", "bs"], [flat_vector(BIGINT, bk), flat_vector(INTEGER, rng.integers(0, 100, m).tolist()),
+                                             dictionary_vector(VARCHAR, rng.integers(0, 4, m), ["red", "green", "blue", None])])
+    return probe, build
+
+
+@pytest.mark.parametrize("join_type", ["inner", "left", "semi", "anti"])
+@pytest.mark.parametrize("dup", [False, True])
+def test_hash_join_types(join_type, dup):
+    probe, build = _join_tables(seed=4, dup=dup)
+    b = PlanBuilder().values(build.names, build.types, source=1)
+    outs = ["pk", "pv", "ps"] if join_type in ("semi", "anti") else ["pk", "pv", "ps", "bv", "bs"]
+    plan = PlanBuilder().values(probe.names, probe.types, source=0).hashJoin(["pk"], ["bk"], b, "", outs, joinType=join_type).planNode()
+    check_plan(plan, [probe, build])
+    check_plan(plan, [probe, build], batch_rows=512)
+
+
+def test_hash_join_filter_multikey_and_empty_build():
+    probe, build = _join_tables(seed=8)
+    b = PlanBuilder().values(build.names, build.types, source=1)
+    plan = PlanBuilder().values(probe.names, probe.types, source=0).hashJoin(["pk"], ["bk"], b, "pv > 0.0 and bv < 50", ["pk", "pv", "bv"]).planNode()
+    check_plan(plan, [probe, build])
+    # two keys (BIGINT + INTEGER)
+    rng = np.random.default_rng(1)
+    p2 = row_vector(["a", "b", "v"], [flat_vector(BIGINT, rng.integers(0, 20, 1000)), flat_vector(INTEGER, rng.integers(0, 5, 1000).astype(np.int32)),
+                                      flat_vector(DOUBLE, rng.normal(size=1000))])
+    b2 = row_vector(["x", "y", "w"], [flat_vector(BIGINT, rng.integers(0, 25, 80)), flat_vector(INTEGER, rng.integers(0, 6, 80).astype(np.int32)),
+                                      flat_vector(BIGINT, rng.integers(0, 1000, 80))])
+    bb = PlanBuilder().values(b2.names, b2.types, source=1)
+    check_plan(PlanBuilder().values(p2.names, p2.types, source=0).hashJoin(["a", "b"], ["x", "y"], bb, "", ["a", "b", "v", "w"]).planNode(), [p2, b2])
+    # sparse keys -> hash-mode table
+    b3 = row_vector(["x", "w"], [flat_vector(BIGINT, rng.integers(0, 2**50, 500)), flat_vector(BIGINT, np.arange(500))])
+    p3 = row_vector(["a"], [flat_vector(BIGINT, np.concatenate([b3.columns[0].values[:200], rng.integers(0, 2**50, 800)]))])
+    bb3 = PlanBuilder().values(b3.names, b3.types, source=1)
+    (st,) = check_plan(PlanBuilder().values(p3.names, p3.types, source=0).hashJoin(["a"], ["x"], bb3, "", ["a", "w"]).planNode(), [p3, b3])
+    assert stat(st, "b200.joinTableMode") == 1
+    # empty build side
+    empty = row_vector(["bk", "bv", "bs"], [flat_vector(BIGINT, []), flat_vector(INTEGER, []), flat_vector(VARCHAR, [])])
+    for jt, outs in (("inner", ["pk", "bv"]), ("left", ["pk", "bv"]), ("anti", ["pk"])):
+        check_plan(PlanBuilder().values(probe.names, probe.types, source=0)
+                   .hashJoin(["pk"], ["bk"], PlanBuilder().values(empty.names, empty.types, source=1), "", outs, joinType=jt).planNode(), [probe, empty])
+
+
+@pytest.mark.parametrize("n", [50_000])
+def test_tpch_q14_fused_and_generic(n):
+    nparts = 3000
+    h, col = _lineitem(n, seed=13, nparts=nparts)
+    li = row_vector(["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"], [col(c) for c in ["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"]])
+    part = {k: v.numpy() for k, v in tpch.gen_part(nparts, seed=5).items()}
+    pt = row_vector(["p_partkey", "p_type"], [flat_vector(BIGINT, part["p_partkey"]), dictionary_vector(VARCHAR, part["p_type"], tpch.PTYPE_DICT)])
+    st_f, st_g = check_plan(q14_plan(li, pt), [li, pt], configs=(FUSED, GENERIC), rel_tol=1e-12)
+    assert stat(st_f, "b200.fusedBatches") == 1 and stat(st_g, "b200.fusedBatches") == 0
+    check_plan(q14_plan(li, pt), [li, pt], configs=(FUSED, GENERIC), batch_rows=20_000, rel_tol=1e-12)

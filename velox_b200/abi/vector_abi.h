@@ -176,7 +176,10 @@ class Buffer {
     if (!data_) throw VeloxRuntimeError("allocation failed");
     if (pool_) pool_->reserve(static_cast<int64_t>(capacity_));
   }
+  // Non-owning view over caller memory (BufferView in velox/buffer/Buffer.h): zero-copy import.
+  Buffer(const void* borrowed, size_t bytes) : data_(const_cast<uint8_t*>(static_cast<const uint8_t*>(borrowed))), size_(bytes), capacity_(bytes), pool_(nullptr), owned_(false) {}
   ~Buffer() {
+    if (!owned_) return;
     std::free(data_);
     if (pool_) pool_->release(static_cast<int64_t>(capacity_));
   }
@@ -190,6 +193,7 @@ class Buffer {
   uint8_t* data_;
   size_t size_, capacity_;
   memory::MemoryPool* pool_;
+  bool owned_ = true;
 };
 using BufferPtr = std::shared_ptr<Buffer>;
 

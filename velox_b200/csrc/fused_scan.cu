@@ -53,7 +53,8 @@ int register_pipeline(const Entry& e) {
 }
 
 constexpr int kMaxBlocksPerSM = 8;
-constexpr int kFusedMaxGroups = 8;
+constexpr int kFusedMaxGroups = 64;       // upper bound; the real limit is shared-memory capacity
+constexpr size_t kSmemLimit = 220 * 1024;  // of the 227 KB a block may use
 
 static int run_finalize(const KernelArgs& a, void* ws, int64_t grid, int kvals, int np, int maxg, double* sums, int64_t* counts,
                         cudaStream_t st) {
@@ -86,11 +87,14 @@ static int launch_direct(const KernelArgs& a, double* sums, int64_t* counts, voi
 template <class P, int kMaxG, class KeyT>
 static int launch_tma(const KernelArgs& a, double* sums, int64_t* counts, void* ws, size_t ws_bytes, cudaStream_t st) {
   auto kernel = fused_scan_agg_tma_kernel<P, kMaxG, KeyT>;
-  const int stage_bytes = TileLayout<P, sizeof(KeyT)>::stage_bytes(kMaxG > 1 ? a.nkeys : 0);
-  constexpr int kSmemBudget = 100 * 1024;
-  int stages = kSmemBudget / stage_bytes;
-  stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes;
+  constexpr bool kSmemAcc = kMaxG == 0;
+  const int stage_bytes = TileLayout<P, sizeof(KeyT)>::stage_bytes((kSmemAcc || kMaxG > 1) ? a.nkeys : 0);
+  const size_t acc_bytes = kSmemAcc ? SmemAccum<P>::bytes(a.ngroups, kConsumerThreads) : 0;
+  const int budget = kSmemAcc ? static_cast<int>(kSmemLimit - acc_bytes) : 100 * 1024;
+  int stages = budget / stage_bytes;
+  if (stages < 2) return fail_msg(VB2_ERR_UNSUPPORTED, "fused aggregation: too many groups for shared-memory accumulators");
+  stages = stages > kMaxStages ? kMaxStages : stages;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + acc_bytes;
   static size_t configured = 0;
   if (configured < smem) {
     VB2_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -103,11 +107,12 @@ static int launch_tma(const KernelArgs& a, double* sums, int64_t* counts, void* 
   const int64_t ntiles = a.rows / kTileRows;
   int64_t grid = static_cast<int64_t>(device_sm_count()) * blocks_per_sm;
   if (ntiles < grid) grid = ntiles < 1 ? 1 : ntiles;
-  constexpr int kVals = kMaxG * (P::kNP + 1);
-  if (ws_bytes < static_cast<size_t>(grid) * kVals * sizeof(double)) return fail_msg(VB2_ERR_INVALID, "fused workspace too small");
+  const int maxg = kSmemAcc ? a.ngroups : kMaxG;
+  const int kvals = maxg * (P::kNP + 1);
+  if (ws_bytes < static_cast<size_t>(grid) * kvals * sizeof(double)) return fail_msg(VB2_ERR_INVALID, "fused workspace too small");
   kernel<<<static_cast<unsigned>(grid), kTmaThreads, smem, st>>>(a, stages, reinterpret_cast<double*>(ws));
   VB2_CUDA_OK(cudaGetLastError());
-  return run_finalize(a, ws, grid, kVals, P::kNP, kMaxG, sums, counts, st);
+  return run_finalize(a, ws, grid, kvals, P::kNP, maxg, sums, counts, st);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -119,20 +124,22 @@ static int launch(const KernelArgs& a, double* sums, int64_t* counts, void* ws, 
     if (((P::fmask | P::imask | P::lmask) >> c) & 1u) bulk = bulk && aligned16(a.cols[c]);
   for (int k = 0; k < a.nkeys; ++k) bulk = bulk && aligned16(a.key[k]);
   const int g = a.nkeys == 0 ? 1 : a.ngroups;
-  if (g > kFusedMaxGroups) return fail_msg(VB2_ERR_UNSUPPORTED, "fused register aggregation holds at most 8 groups");
+  if (g > kFusedMaxGroups) return fail_msg(VB2_ERR_UNSUPPORTED, "fused aggregation: group-id space too large");
   bool key64 = false, key32 = false;
   for (int k = 0; k < a.nkeys; ++k) (a.key_is64[k] ? key64 : key32) = true;
   if (key64 && key32) return fail_msg(VB2_ERR_UNSUPPORTED, "fused aggregation: group keys must have one width");
-#define VB2_GO(G, K)                                                                                  \
-  return bulk ? launch_tma<P, G, K>(a, sums, counts, ws, ws_bytes, st) : launch_direct<P, G, K>(a, sums, counts, ws, ws_bytes, st)
-  if (g <= 1) { VB2_GO(1, int32_t); }
+  if (g <= 1) return bulk ? launch_tma<P, 1, int32_t>(a, sums, counts, ws, ws_bytes, st) : launch_direct<P, 1, int32_t>(a, sums, counts, ws, ws_bytes, st);
   if (g <= 4) {
-    if (key64) { VB2_GO(4, int64_t); }
-    VB2_GO(4, int32_t);
+    if (key64) return bulk ? launch_tma<P, 4, int64_t>(a, sums, counts, ws, ws_bytes, st) : launch_direct<P, 4, int64_t>(a, sums, counts, ws, ws_bytes, st);
+    return bulk ? launch_tma<P, 4, int32_t>(a, sums, counts, ws, ws_bytes, st) : launch_direct<P, 4, int32_t>(a, sums, counts, ws, ws_bytes, st);
   }
-  if (key64) { VB2_GO(8, int64_t); }
-  VB2_GO(8, int32_t);
-#undef VB2_GO
+  if (bulk) {  // shared-memory accumulators, cost independent of the group count
+    if (key64) return launch_tma<P, 0, int64_t>(a, sums, counts, ws, ws_bytes, st);
+    return launch_tma<P, 0, int32_t>(a, sums, counts, ws, ws_bytes, st);
+  }
+  if (g > 8) return fail_msg(VB2_ERR_UNSUPPORTED, "fused aggregation: unaligned input with more than 8 groups");
+  if (key64) return launch_direct<P, 8, int64_t>(a, sums, counts, ws, ws_bytes, st);
+  return launch_direct<P, 8, int32_t>(a, sums, counts, ws, ws_bytes, st);
 }
 
 template <class P>
@@ -210,7 +217,7 @@ int32_t vb2k_fused_nproj(int32_t id) {
 size_t vb2k_fused_workspace_bytes(int32_t id, int32_t ngroups) {
   ensure_registered();
   if (id < 0 || id >= static_cast<int>(registry().size())) return 0;
-  const int g = ngroups <= 1 ? 1 : (ngroups <= 4 ? 4 : 8);
+  const int g = ngroups <= 1 ? 1 : (ngroups <= 4 ? 4 : (ngroups < 8 ? 8 : ngroups));
   return static_cast<size_t>(device_sm_count()) * kMaxBlocksPerSM * g * (registry()[id].nproj + 1) * sizeof(double);
 }
 

@@ -412,6 +412,53 @@ __device__ __forceinline__ void block_reduce_store(const Accum<P, kMaxG>& acc, d
   }
 }
 
+// Shared-memory accumulators for 5..kSmemMaxGroups groups: every consumer thread owns a private
+// slot per (group, projection) at [(g * NP + p) * kConsumerThreads + tid] — dynamic group index,
+// no atomics, no bank conflicts (a lane's bank pair depends on tid only). Cost per row is
+// independent of the number of groups. Rows dropped by the filter go to a spare group.
+template <class P>
+struct SmemAccum {
+  double* sums;   // [(G + 1) * NP][threads]
+  int32_t* cnts;  // [(G + 1)][threads]
+  int ngroups;    // G (spare group = index G)
+  int threads;
+  __device__ __forceinline__ void init(uint8_t* base, int g, int nthreads, int tid) {
+    ngroups = g;
+    threads = nthreads;
+    sums = reinterpret_cast<double*>(base);
+    cnts = reinterpret_cast<int32_t*>(base + static_cast<size_t>(g + 1) * P::kNP * nthreads * 8);
+    for (int i = tid; i < (g + 1) * P::kNP * nthreads; i += nthreads) sums[i] = 0.0;
+    for (int i = tid; i < (g + 1) * nthreads; i += nthreads) cnts[i] = 0;
+  }
+  static __host__ __device__ size_t bytes(int g, int nthreads) { return static_cast<size_t>(g + 1) * nthreads * (P::kNP * 8 + 4); }
+  __device__ __forceinline__ void add(int gid, const double (&v)[P::kNP], int tid) {
+    const int g = gid < 0 ? ngroups : gid;
+    double* s = sums + static_cast<size_t>(g) * P::kNP * threads + tid;
+#pragma unroll
+    for (int p = 0; p < P::kNP; ++p) s[p * threads] = __dadd_rn(s[p * threads], v[p]);
+    cnts[g * threads + tid] += 1;
+  }
+  // one partial per block: kvals = G * (NP + 1), fixed reduction order over the threads
+  __device__ __forceinline__ void reduce_store(double* __restrict__ partials, int kvals) {
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int t = warp; t < kvals; t += nwarps) {
+      const int g = t / (P::kNP + 1), p = t % (P::kNP + 1);
+      double out;
+      if (p == P::kNP) {
+        int64_t c = 0;
+        for (int i = lane; i < threads; i += 32) c += cnts[g * threads + i];
+        out = __longlong_as_double(warp_sum(c));
+      } else {
+        double x = 0.0;
+        for (int i = lane; i < threads; i += 32) x = __dadd_rn(x, sums[(static_cast<size_t>(g) * P::kNP + p) * threads + i]);
+        out = warp_sum(x);
+      }
+      if (lane == 0) partials[static_cast<int64_t>(blockIdx.x) * kvals + t] = out;
+    }
+  }
+};
+
 template <class P, int kMaxG, int kUnroll, bool kPair, class KeyT>
 __global__ void __launch_bounds__(kThreads, kMaxG <= 4 ? 2 : 1) fused_scan_agg_kernel(const __grid_constant__ KernelArgs a, double* __restrict__ partials) {
   Accum<P, kMaxG> acc;
@@ -510,13 +557,17 @@ struct TileLayout {
   }
 };
 
+// kMaxG > 0: register accumulators for up to kMaxG groups; kMaxG == 0: shared-memory accumulators.
 template <class P, int kMaxG, class KeyT>
-__global__ void __launch_bounds__(kTmaThreads, kMaxG <= 4 ? 2 : 1)
+__global__ void __launch_bounds__(kTmaThreads, kMaxG == 0 ? 1 : 2)
 fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, double* __restrict__ partials) {
   extern __shared__ __align__(128) uint8_t tile_smem[];
+  constexpr bool kSmemAcc = kMaxG == 0;
+  constexpr int kRegG = kSmemAcc ? 1 : kMaxG;
+  constexpr bool kHasKeys = kSmemAcc || kMaxG > 1;
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
   using Lay = TileLayout<P, sizeof(KeyT)>;
-  const int nk = kMaxG > 1 ? a.nkeys : 0;
+  const int nk = kHasKeys ? a.nkeys : 0;
   const int stage_bytes = Lay::stage_bytes(nk);
   const int64_t ntiles = a.rows / kTileRows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -527,9 +578,15 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  Accum<P, kMaxG> acc;
+  Accum<P, kRegG> acc;
   acc.init();
+  SmemAccum<P> sacc;
+  if constexpr (kSmemAcc) {
+    // accumulators live behind the tile stages; the producer warp helps zeroing them
+    sacc.init(tile_smem + static_cast<size_t>(stages) * stage_bytes, a.ngroups, kConsumerThreads, threadIdx.x);
+    sacc.threads = kConsumerThreads;
+  }
+  __syncthreads();
   if (warp == kConsumerThreads / kWarp) {
     // ---- producer warp: one elected lane issues the copies ----
     if (lane == 0) {
@@ -547,7 +604,7 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
           if (P::lmask & (1u << c)) bytes += kTileRows * 8;
           if (P::imask & (1u << c)) bytes += kTileRows * 4;
         }
-        if (kMaxG > 1) bytes += a.nkeys * kTileRows * sizeof(KeyT);
+        if (kHasKeys) bytes += a.nkeys * kTileRows * sizeof(KeyT);
         mbar_expect_tx(&full_bar[s], bytes);
 #pragma unroll
         for (int c = 0; c < kMaxCols; ++c) {
@@ -555,7 +612,7 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
           if (P::lmask & (1u << c)) bulk_load(base + Lay::l_off(c), reinterpret_cast<const int64_t*>(a.cols[c]) + row0, kTileRows * 8, &full_bar[s]);
           if (P::imask & (1u << c)) bulk_load(base + Lay::i_off(c, nk), reinterpret_cast<const int32_t*>(a.cols[c]) + row0, kTileRows * 4, &full_bar[s]);
         }
-        if (kMaxG > 1) {
+        if (kHasKeys) {
           for (int k = 0; k < a.nkeys; ++k)
             bulk_load(base + Lay::key_off(k, nk), reinterpret_cast<const KeyT*>(a.key[k]) + row0, kTileRows * sizeof(KeyT), &full_bar[s]);
         }
@@ -580,7 +637,7 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
           if (P::lmask & (1u << c)) r[j].l[c][0] = reinterpret_cast<const int64_t*>(base + Lay::l_off(c))[row];
           if (P::imask & (1u << c)) r[j].i[c][0] = reinterpret_cast<const int32_t*>(base + Lay::i_off(c, nk))[row];
         }
-        if (kMaxG > 1) {
+        if (kHasKeys) {
 #pragma unroll
           for (int k = 0; k < VB2_FUSED_MAX_KEYS; ++k)
             if (k < a.nkeys) kv[j][k][0] = reinterpret_cast<const KeyT*>(base + Lay::key_off(k, nk))[row];
@@ -592,9 +649,12 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
       int gid[kRowsPerThread];
       double v[kRowsPerThread][P::kNP];
 #pragma unroll
-      for (int j = 0; j < kRowsPerThread; ++j) eval_slot<P, kMaxG, KeyT>(a, r[j], kv[j], 0, gid[j], v[j]);
+      for (int j = 0; j < kRowsPerThread; ++j) eval_slot<P, kHasKeys ? 2 : 1, KeyT>(a, r[j], kv[j], 0, gid[j], v[j]);
 #pragma unroll
-      for (int j = 0; j < kRowsPerThread; ++j) acc.add(gid[j], v[j]);
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        if constexpr (kSmemAcc) sacc.add(gid[j], v[j], threadIdx.x);
+        else acc.add(gid[j], v[j]);
+      }
     }
     // tail rows (rows % kTileRows) by direct loads, spread over the blocks' consumer threads
     const int64_t tail0 = ntiles * kTileRows;
@@ -603,11 +663,16 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
       PairRegs r;
       KeyT kv[VB2_FUSED_MAX_KEYS][2];
       load_rows<P, false>(a, row, r);
-      if (kMaxG > 1) load_keys<false, KeyT>(a, row, kv);
-      process<P, kMaxG, false, KeyT>(a, r, kv, acc);
+      if (kHasKeys) load_keys<false, KeyT>(a, row, kv);
+      int gid;
+      double v[P::kNP];
+      eval_slot<P, kHasKeys ? 2 : 1, KeyT>(a, r, kv, 0, gid, v);
+      if constexpr (kSmemAcc) sacc.add(gid, v, threadIdx.x);
+      else acc.add(gid, v);
     }
   }
-  block_reduce_store<P, kMaxG>(acc, partials);
+  if constexpr (kSmemAcc) sacc.reduce_store(partials, a.ngroups * (P::kNP + 1));
+  else block_reduce_store<P, kRegG>(acc, partials);
 }
 
 // Folds per-block partials in block order into the persistent accumulators.

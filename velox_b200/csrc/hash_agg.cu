@@ -19,7 +19,10 @@ struct NormArgs {
   vb2_column c[kMaxNormCols];
   int64_t mins[kMaxNormCols];
   uint64_t mults[kMaxNormCols];
+  uint64_t ranges[kMaxNormCols];
   int n;
+  int nulls_invalid;  // a NULL key column clears the row's valid bit (joins) instead of using id 0 (group by)
+  int check_ranges;   // ids outside [1, range) clear the valid bit (probe side of a join)
 };
 
 __device__ __forceinline__ bool decode_row2(const vb2_column& c, int64_t row, int64_t& base) {
@@ -48,24 +51,42 @@ __device__ __forceinline__ int64_t key_value(const vb2_column& c, int64_t base) 
 }
 
 __global__ void normalize_keys_kernel(const __grid_constant__ NormArgs a, const int32_t* __restrict__ sel, int64_t n,
-                                      uint64_t* __restrict__ out) {
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t row = sel ? sel[i] : i;
-    uint64_t key = 0;
-    for (int k = 0; k < a.n; ++k) {
-      int64_t base;
-      const bool is_null = decode_row2(a.c[k], row, base);
-      const uint64_t id = is_null ? 0 : static_cast<uint64_t>(key_value(a.c[k], base) - a.mins[k]) + 1;
-      key += id * a.mults[k];
+                                      uint64_t* __restrict__ out, uint32_t* __restrict__ valid_out) {
+  const int64_t nwords = (n + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t w = warp_global; w < nwords; w += nwarps) {
+    const int64_t i = (w << 5) + lane;
+    bool valid = i < n;
+    if (i < n) {
+      const int64_t row = sel ? sel[i] : i;
+      uint64_t key = 0;
+      for (int k = 0; k < a.n; ++k) {
+        int64_t base;
+        const bool is_null = decode_row2(a.c[k], row, base);
+        uint64_t id = 0;
+        if (is_null) {
+          valid = valid && !a.nulls_invalid;
+        } else {
+          id = static_cast<uint64_t>(key_value(a.c[k], base) - a.mins[k]) + 1;
+          if (a.check_ranges && (id == 0 || id >= a.ranges[k])) { valid = false; id = 0; }
+        }
+        key += id * a.mults[k];
+      }
+      out[i] = key;
     }
-    out[i] = key;
+    if (valid_out) {
+      const unsigned word = __ballot_sync(0xffffffffu, valid);
+      if (lane == 0) valid_out[w] = word;
+    }
   }
 }
 
 // Keys of occupied slots back to per-column values: id_k = (key / mult_k) % range_k.
 __global__ void denormalize_keys_kernel(const uint64_t* __restrict__ table_keys, const int32_t* __restrict__ slots, int64_t n,
-                                        int64_t min, uint64_t mult, uint64_t range, int32_t type, void* __restrict__ values,
-                                        uint32_t* __restrict__ valid_words) {
+                                        int64_t min, uint64_t mult, uint64_t range, int32_t null_reserved, int32_t type,
+                                        void* __restrict__ values, uint32_t* __restrict__ valid_words) {
   const int64_t nwords = (n + 31) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -74,10 +95,10 @@ __global__ void denormalize_keys_kernel(const uint64_t* __restrict__ table_keys,
     const int64_t i = (w << 5) + lane;
     bool valid = false;
     if (i < n) {
-      const uint64_t key = table_keys[slots[i]];
+      const uint64_t key = table_keys ? table_keys[slots[i]] : static_cast<uint64_t>(slots[i]);
       const uint64_t id = (key / mult) % range;
-      valid = id != 0;
-      const int64_t v = valid ? static_cast<int64_t>(id - 1) + min : 0;
+      valid = !(null_reserved && id == 0);
+      const int64_t v = valid ? static_cast<int64_t>(id) - 1 + min : 0;
       if (type == VB2_INTEGER) reinterpret_cast<int32_t*>(values)[i] = static_cast<int32_t>(v);
       else if (type == VB2_BOOLEAN) reinterpret_cast<uint8_t*>(values)[i] = static_cast<uint8_t>(v);
       else reinterpret_cast<int64_t*>(values)[i] = v;
@@ -124,6 +145,11 @@ __global__ void group_probe_kernel(const uint64_t* __restrict__ row_keys, const 
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     if (row_valid && !bit_at(row_valid, i)) { group_ids[i] = -1; continue; }
     const uint64_t key = row_keys[i];
+    if (table == nullptr) {  // array mode: the normalized key is the slot
+      group_ids[i] = key <= mask ? static_cast<int32_t>(key) : -1;
+      if (key > mask) atomicCAS(error_flag, 0, 100);
+      continue;
+    }
     uint64_t slot = twang_mix64(key) & mask;
     int32_t found = -1;
     for (uint64_t probes = 0; probes <= mask; ++probes) {
@@ -182,7 +208,7 @@ __device__ __forceinline__ void atomic_min_f64(double* addr, double v, bool is_m
 __global__ void agg_update_atomic_kernel(const int32_t* __restrict__ group_ids, int64_t n, const __grid_constant__ AggArgs args,
                                          int32_t* __restrict__ error_flag) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int32_t g = group_ids[i];
+    const int32_t g = group_ids ? group_ids[i] : 0;
     if (g < 0) continue;
     for (int k = 0; k < args.n; ++k) {
       const vb2_agg_update& u = args.a[k];
@@ -221,7 +247,7 @@ __global__ void agg_update_tiny_kernel(const int32_t* __restrict__ group_ids, in
   for (int g = 0; g < kTinyG; ++g) { fs[g] = 0.0; is[g] = 0; cnt[g] = 0; }
   bool ovf = false;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    int32_t g = group_ids[i];
+    int32_t g = group_ids ? group_ids[i] : 0;
     if (u.mask && !bit_at(u.mask, i)) g = -1;
     if (u.nulls && !bit_at(u.nulls, i)) g = -1;
     if (g < 0) continue;
@@ -281,6 +307,29 @@ __global__ void agg_update_tiny_kernel(const int32_t* __restrict__ group_ids, in
   }
 }
 
+// Re-encodes the keys of occupied slots for a new layout (value ranges grew): decodes the
+// per-column ids with the old (mult, range), re-bases them on the new mins and packs again.
+struct RekeyArgs {
+  int n;
+  int64_t old_min[kMaxNormCols], new_min[kMaxNormCols];
+  uint64_t old_mult[kMaxNormCols], old_range[kMaxNormCols], new_mult[kMaxNormCols];
+  int old_null_reserved[kMaxNormCols];
+};
+__global__ void rekey_kernel(const uint64_t* __restrict__ table_keys, const int32_t* __restrict__ slots, int64_t n,
+                             const __grid_constant__ RekeyArgs a, uint64_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t key = table_keys ? table_keys[slots[i]] : static_cast<uint64_t>(slots[i]);
+    uint64_t nk = 0;
+    for (int k = 0; k < a.n; ++k) {
+      const uint64_t id = (key / a.old_mult[k]) % a.old_range[k];
+      const bool is_null = a.old_null_reserved[k] && id == 0;
+      const uint64_t nid = is_null ? 0 : static_cast<uint64_t>(static_cast<int64_t>(id) - 1 + a.old_min[k] - a.new_min[k] + 1);
+      nk += nid * a.new_mult[k];
+    }
+    out[i] = nk;
+  }
+}
+
 // ---- occupied slots ---------------------------------------------------------------------------
 __global__ void occupied_bits_kernel(const uint64_t* __restrict__ table, int64_t capacity, uint32_t* __restrict__ bits) {
   const int64_t nwords = (capacity + 31) >> 5;
@@ -307,29 +356,33 @@ using namespace vb2;
 
 extern "C" {
 
-int vb2k_normalize_keys(const vb2_column* cols, int32_t ncols, const int64_t* mins, const uint64_t* mults,
-                        int64_t rows, const int32_t* sel, int64_t n, uint64_t* keys_out, void* stream) {
-  (void)rows;
+int vb2k_normalize_keys(const vb2_column* cols, int32_t ncols, const int64_t* mins, const uint64_t* mults, const uint64_t* ranges,
+                        int32_t nulls_invalid, const int32_t* sel, int64_t n, uint64_t* keys_out, uint64_t* valid_out, void* stream) {
   if (ncols < 1 || ncols > kMaxNormCols) return fail_msg(VB2_ERR_UNSUPPORTED, "normalize_keys: 1..4 key columns");
   if (n <= 0) return VB2_OK;
   NormArgs a;
   a.n = ncols;
+  a.nulls_invalid = nulls_invalid;
+  a.check_ranges = ranges != nullptr;
   for (int i = 0; i < ncols; ++i) {
     if (cols[i].type == VB2_DOUBLE || cols[i].type == VB2_VARCHAR) return fail_msg(VB2_ERR_INVALID, "normalize_keys: integer-typed key columns expected");
     a.c[i] = cols[i];
     a.mins[i] = mins[i];
     a.mults[i] = mults[i];
+    a.ranges[i] = ranges ? ranges[i] : 0;
   }
-  normalize_keys_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, sel, n, keys_out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (valid_out) VB2_CUDA_OK(cudaMemsetAsync(valid_out + ((n + 63) >> 6) - 1, 0, 8, st));
+  normalize_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, sel, n, keys_out, reinterpret_cast<uint32_t*>(valid_out));
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 
 int vb2k_denormalize_keys(const uint64_t* table_keys, const int32_t* slots, int64_t n, int64_t min, uint64_t mult,
-                          uint64_t range, int32_t type, void* values, uint64_t* valid, void* stream) {
+                          uint64_t range, int32_t null_reserved, int32_t type, void* values, uint64_t* valid, void* stream) {
   if (n <= 0) return VB2_OK;
   denormalize_keys_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      table_keys, slots, n, min, mult, range, type, values, reinterpret_cast<uint32_t*>(valid));
+      table_keys, slots, n, min, mult, range, null_reserved, type, values, reinterpret_cast<uint32_t*>(valid));
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -344,7 +397,7 @@ int vb2k_column_minmax(const vb2_column* col, int64_t rows, int64_t* out3, void*
 
 int vb2k_group_probe(const uint64_t* row_keys, const uint64_t* row_valid, int64_t n, uint64_t* table_keys,
                      int64_t capacity, int32_t* group_ids, int64_t* num_groups, int32_t* error_flag, void* stream) {
-  if (capacity <= 0 || (capacity & (capacity - 1))) return fail_msg(VB2_ERR_INVALID, "group_probe: capacity must be a power of two");
+  if (capacity <= 0 || (table_keys && (capacity & (capacity - 1)))) return fail_msg(VB2_ERR_INVALID, "group_probe: capacity must be a power of two");
   if (capacity > (1ll << 31)) return fail_msg(VB2_ERR_UNSUPPORTED, "group_probe: capacity above 2^31 slots");
   if (n <= 0) return VB2_OK;
   group_probe_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -391,6 +444,23 @@ int vb2k_table_occupied(const uint64_t* table_keys, int64_t capacity, int32_t* s
   VB2_CUDA_OK(cudaGetLastError());
   return vb2k_bits_to_indices(bits, capacity, slot_list, count, reinterpret_cast<char*>(workspace) + bitmap_bytes,
                               workspace_bytes - bitmap_bytes, stream);
+}
+
+int vb2k_rekey(const uint64_t* table_keys, const int32_t* slots, int64_t n, int32_t ncols, const int64_t* old_mins,
+               const uint64_t* old_mults, const uint64_t* old_ranges, const int32_t* old_null_reserved, const int64_t* new_mins,
+               const uint64_t* new_mults, uint64_t* keys_out, void* stream) {
+  if (ncols < 1 || ncols > kMaxNormCols) return fail_msg(VB2_ERR_UNSUPPORTED, "rekey: 1..4 key columns");
+  if (n <= 0) return VB2_OK;
+  RekeyArgs a;
+  a.n = ncols;
+  for (int i = 0; i < ncols; ++i) {
+    a.old_min[i] = old_mins[i]; a.new_min[i] = new_mins[i];
+    a.old_mult[i] = old_mults[i]; a.old_range[i] = old_ranges[i]; a.new_mult[i] = new_mults[i];
+    a.old_null_reserved[i] = old_null_reserved ? old_null_reserved[i] : 1;
+  }
+  rekey_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table_keys, slots, n, a, keys_out);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
 }
 
 size_t vb2k_table_occupied_workspace(int64_t capacity) {

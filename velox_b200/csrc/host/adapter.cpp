@@ -1,0 +1,85 @@
+// registerB200(): installs the DriverAdapter that replaces the CPU operators of a pipeline with
+// the B200 ones and inserts the host<->device conversion operators at the seams.
+// Reference pattern: velox/experimental/cudf/exec/ToCudf.cpp:71-338 (per-operator adapters,
+// automatic FromVelox / ToVelox insertion), Wave's fused runs velox/experimental/wave/exec/ToWave.cpp:221.
+#include "operators.h"
+
+namespace velox_b200 {
+
+namespace {
+
+bool adaptDriver(const exec::DriverFactory& factory, exec::Driver& driver) {
+  const core::QueryConfig& config = driver.driverCtx()->queryConfig();
+  if (!config.b200Enabled()) return false;
+  auto& ops = driver.operators();
+  exec::DriverCtx* ctx = driver.driverCtx();
+  std::vector<std::unique_ptr<exec::Operator>> out;
+  bool replacedAny = false;
+  const bool fuse = config.b200FusedPipelines();
+  for (size_t i = 0; i < ops.size(); ++i) {
+    exec::Operator* op = ops[i].get();
+    const int32_t id = static_cast<int32_t>(out.size());
+    if (auto values = dynamic_cast<exec::Values*>(op)) {
+      RowTypePtr type = values->outputType();
+      out.push_back(std::move(ops[i]));
+      out.push_back(std::make_unique<B200FromHost>(id + 1, ctx, type));
+      replacedAny = true;
+    } else if (auto fp = dynamic_cast<exec::FilterProject*>(op)) {
+      out.push_back(std::make_unique<B200FilterProject>(id, ctx, *fp));
+      replacedAny = true;
+    } else if (auto agg = dynamic_cast<exec::HashAggregation*>(op)) {
+      // Fuse the run of B200FilterProject / B200HashProbe operators feeding the aggregation into
+      // it: the aggregation then sees the source batches and can run the whole chain as one
+      // kernel; functionally the absorbed operators still run batch by batch when it cannot.
+      std::vector<std::unique_ptr<exec::Operator>> absorbed;
+      if (fuse && agg->node()->isRawInput()) {
+        size_t first = out.size();
+        while (first > 0 && (dynamic_cast<B200FilterProject*>(out[first - 1].get()) || dynamic_cast<B200HashProbe*>(out[first - 1].get()))) --first;
+        // only the shapes the fused path understands; anything else stays unfused
+        const size_t run = out.size() - first;
+        const bool shapeOk = run == 1 ? dynamic_cast<B200FilterProject*>(out[first].get()) != nullptr
+                                      : (run == 3 && dynamic_cast<B200FilterProject*>(out[first].get()) &&
+                                         dynamic_cast<B200HashProbe*>(out[first + 1].get()) && dynamic_cast<B200FilterProject*>(out[first + 2].get()));
+        if (shapeOk) {
+          for (size_t j = first; j < out.size(); ++j) absorbed.push_back(std::move(out[j]));
+          out.resize(first);
+        }
+      }
+      out.push_back(std::make_unique<B200HashAggregation>(static_cast<int32_t>(out.size()), ctx, agg->node(), std::move(absorbed)));
+      replacedAny = true;
+    } else if (auto build = dynamic_cast<exec::HashBuild*>(op)) {
+      out.push_back(std::make_unique<B200HashBuild>(id, ctx, *build));
+      replacedAny = true;
+    } else if (auto probe = dynamic_cast<exec::HashProbe*>(op)) {
+      out.push_back(std::make_unique<B200HashProbe>(id, ctx, *probe));
+      replacedAny = true;
+    } else if (dynamic_cast<exec::CallbackSink*>(op)) {
+      RowTypePtr type = out.empty() ? nullptr : out.back()->outputType();
+      out.push_back(std::make_unique<B200ToHost>(id, ctx, type));
+      out.push_back(std::move(ops[i]));
+    } else {
+      out.push_back(std::move(ops[i]));
+    }
+  }
+  if (!replacedAny) return false;
+  // every original operator was moved or superseded: swap the whole list
+  std::vector<std::unique_ptr<exec::Operator>> replaced = factory.replaceOperators(driver, 0, static_cast<int32_t>(ops.size()), std::move(out));
+  (void)replaced;
+  return true;
+}
+
+}  // namespace
+
+void registerB200() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  registerB200Functions();
+  exec::DriverAdapter adapter;
+  adapter.label = "b200";
+  adapter.inspect = nullptr;
+  adapter.adapt = adaptDriver;
+  exec::DriverFactory::registerAdapter(std::move(adapter));
+}
+
+}  // namespace velox_b200

@@ -1,0 +1,900 @@
+// B200HashAggregation: GROUP BY on the device (array mode / normalized-key hash mode), with the
+// fused scan->filter->[probe]->project->aggregate fast path for null-free flat batches.
+#include <algorithm>
+
+#include "join.h"
+#include "operators.h"
+
+namespace velox_b200 {
+
+namespace {
+
+using Step = core::AggregationNode::Step;
+
+constexpr uint64_t kArrayModeMax = 1ull << 22;  // slots; accumulators are SoA arrays of this length
+constexpr int kFusedMaxGroups = 48;
+
+uint64_t nextPow2(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+enum class Mode { kGlobal, kArray, kHash };
+
+struct KeyState {
+  TypeKind kind;
+  bool isVarchar = false;
+  // VARCHAR keys arrive dictionary-encoded; every distinct value gets a global id (1-based)
+  std::unordered_map<std::string, int32_t> valueIds;
+  std::vector<std::string> valuesById;
+  // cache: alphabet -> device LUT (dictionary entry -> global id, 0 = NULL entry)
+  const HostAlphabet* cachedAlphabet = nullptr;
+  DeviceBufferPtr lut;
+  DeviceBufferPtr fusedLut;   // dictionary entry -> id under the current layout (fused kernel)
+  bool hasRange = false;
+  int64_t lo = 0, hi = 0;
+  bool nullable = false;      // a NULL key was (or may have been) seen: the layout reserves id 0
+};
+
+struct AccState {
+  std::string fn;
+  int32_t kind = 0;          // vb2_agg_kind of the main accumulator
+  bool isDouble = false;     // accumulator holds doubles
+  TypePtr inputType;
+  DeviceBufferPtr acc, nonnull;
+};
+
+}  // namespace
+
+struct B200HashAggregation::Impl {
+  B200HashAggregation* self;
+  std::shared_ptr<const core::AggregationNode> node;
+  std::vector<std::unique_ptr<exec::Operator>> absorbed;
+  std::shared_ptr<DeviceContext> dev;
+  bool raw, fin;
+  Mode mode = Mode::kGlobal;
+  std::vector<KeyState> keys;
+  KeyLayout layout;             // mins are adjusted: id = v - mins[k] + 1 (mins[k] = lo + 1 - nullReserved[k])
+  std::vector<int64_t> covLo, covHi;  // value interval each key's layout covers
+  std::vector<int32_t> nullReserved;  // 1 = id 0 means NULL for that key
+  int64_t capacity = 1;
+  DeviceBufferPtr tableKeys;   // hash mode
+  DeviceBufferPtr groupRows;   // int64[capacity]: input rows per slot (slot occupied <=> > 0)
+  DeviceBufferPtr numGroupsDev;
+  int64_t numGroupsUpper = 0;  // upper bound of distinct groups seen (hash mode sizing)
+  std::vector<AccState> accs;
+  DeviceBufferPtr errorFlag;
+  bool sawInput = false;
+  bool outputDone = false;
+
+  // ---- fused fast path --------------------------------------------------------------------------
+  bool fusedPlanned = false;      // plan shape allows it
+  int fusedId = -1;
+  FusedBinding binding;
+  std::vector<int> aggToProj;     // aggregate -> fused projection (-1 for count(*))
+  std::vector<int> fusedKeySourceCols;  // source-batch column of each group key
+  int fusedJoinKeySourceCol = -1;
+  core::TypedExprPtr joinFlagExpr;     // over build columns (field index = build column)
+  B200HashProbe* fusedProbe = nullptr;
+  DeviceBufferPtr joinSlotFlags;
+  DeviceBufferPtr fusedSums, fusedCounts, fusedWs;
+  size_t fusedWsBytes = 0;
+  int fusedGroups = 0;
+  int64_t fusedBatches = 0, genericBatches = 0;
+
+  cudaStream_t st() const { return dev->stream; }
+
+  // =================================================================================================
+  void init() {
+    raw = node->isRawInput();
+    fin = node->isFinalOutput();
+    const auto& inType = node->sources()[0]->outputType();
+    for (int32_t k : node->groupingKeys()) {
+      KeyState ks;
+      ks.kind = inType->childAt(k)->kind();
+      ks.isVarchar = ks.kind == TypeKind::VARCHAR;
+      if (ks.kind == TypeKind::DOUBLE) VELOX_UNSUPPORTED("GROUP BY on DOUBLE keys");
+      keys.push_back(std::move(ks));
+    }
+    VELOX_CHECK(keys.size() <= 4, "at most 4 grouping keys");
+    mode = keys.empty() ? Mode::kGlobal : Mode::kArray;
+    for (auto& a : node->aggregates()) {
+      AccState s;
+      s.fn = a.function;
+      s.inputType = a.rawInputType;
+      const bool dbl = a.rawInputType && a.rawInputType->kind() == TypeKind::DOUBLE;
+      if (a.function == "sum") { s.isDouble = dbl; s.kind = dbl ? VB2_AGG_SUM_F64 : VB2_AGG_SUM_I64; }
+      else if (a.function == "avg") { s.isDouble = true; s.kind = VB2_AGG_SUM_F64; }
+      else if (a.function == "count") { s.isDouble = false; s.kind = raw ? VB2_AGG_COUNT : VB2_AGG_COUNT_MERGE; }
+      else if (a.function == "min") { s.isDouble = dbl; s.kind = dbl ? VB2_AGG_MIN_F64 : VB2_AGG_MIN_I64; }
+      else if (a.function == "max") { s.isDouble = dbl; s.kind = dbl ? VB2_AGG_MAX_F64 : VB2_AGG_MAX_I64; }
+      else VELOX_UNSUPPORTED("aggregate function " + a.function);
+      if (a.rawInputType && a.rawInputType->kind() == TypeKind::VARCHAR) VELOX_UNSUPPORTED("aggregates over VARCHAR");
+      accs.push_back(std::move(s));
+    }
+    errorFlag = allocDeviceZeroed(8, st());
+    numGroupsDev = allocDeviceZeroed(8, st());
+    layout.mins.assign(keys.size(), 1);
+    layout.ranges.assign(keys.size(), 0);
+    layout.mults.assign(keys.size(), 1);
+    layout.product = 1;
+    covLo.assign(keys.size(), 0);
+    covHi.assign(keys.size(), -1);
+    nullReserved.assign(keys.size(), 0);
+    capacity = 1;
+    allocateStorage(capacity, mode);
+    planFused();
+  }
+
+  uint64_t identityBits(const AccState& s) const {
+    switch (s.kind) {
+      case VB2_AGG_MIN_F64: return 0x7ff8000000000000ull;                      // NaN: the largest value
+      case VB2_AGG_MAX_F64: return 0xfff0000000000000ull;                      // -inf
+      case VB2_AGG_MIN_I64: return static_cast<uint64_t>(INT64_MAX);
+      case VB2_AGG_MAX_I64: return static_cast<uint64_t>(INT64_MIN);
+      default: return 0;
+    }
+  }
+
+  struct Storage {
+    DeviceBufferPtr tableKeys, groupRows;
+    std::vector<DeviceBufferPtr> acc, nonnull;
+  };
+  Storage makeStorage(int64_t cap, Mode m) {
+    Storage s;
+    s.groupRows = allocDeviceZeroed(static_cast<size_t>(cap) * 8, st());
+    if (m == Mode::kHash) {
+      s.tableKeys = allocDevice(static_cast<size_t>(cap) * 8, st());
+      kernelCheck(vb2k_fill_u64(s.tableKeys->as<uint64_t>(), cap, VB2_EMPTY_KEY, st()));
+    }
+    for (auto& a : accs) {
+      auto acc = allocDevice(static_cast<size_t>(cap) * 8, st());
+      kernelCheck(vb2k_fill_u64(acc->as<uint64_t>(), cap, identityBits(a), st()));
+      s.acc.push_back(acc);
+      s.nonnull.push_back(allocDeviceZeroed(static_cast<size_t>(cap) * 8, st()));
+    }
+    return s;
+  }
+  void adopt(Storage&& s) {
+    tableKeys = s.tableKeys;
+    groupRows = s.groupRows;
+    for (size_t i = 0; i < accs.size(); ++i) { accs[i].acc = s.acc[i]; accs[i].nonnull = s.nonnull[i]; }
+  }
+  void allocateStorage(int64_t cap, Mode m) { adopt(makeStorage(cap, m)); }
+
+  // Occupied slots of the current table (synchronises for the count).
+  DeviceBufferPtr occupiedSlots(int64_t& count) {
+    auto slots = allocDevice(static_cast<size_t>(capacity) * 4, st());
+    auto cnt = allocDevice(8, st());
+    if (mode == Mode::kHash) {
+      const size_t wsb = vb2k_table_occupied_workspace(capacity);
+      auto ws = allocDevice(wsb, st());
+      kernelCheck(vb2k_table_occupied(tableKeys->as<uint64_t>(), capacity, slots->as<int32_t>(), cnt->as<int64_t>(), ws->data(), wsb, st()));
+    } else {
+      auto bitsBuf = allocDevice(bits::nbytes(capacity), st());
+      kernelCheck(vb2k_positive_bits(groupRows->as<int64_t>(), capacity, bitsBuf->as<uint64_t>(), st()));
+      const size_t wsb = vb2k_bits_to_indices_workspace(capacity);
+      auto ws = allocDevice(wsb, st());
+      kernelCheck(vb2k_bits_to_indices(bitsBuf->as<uint64_t>(), capacity, slots->as<int32_t>(), cnt->as<int64_t>(), ws->data(), wsb, st()));
+    }
+    VB2_CU(cudaMemcpyAsync(&count, cnt->data(), 8, cudaMemcpyDeviceToHost, st()));
+    VB2_CU(cudaStreamSynchronize(st()));
+    return slots;
+  }
+
+  // Moves every group to a new layout / mode / capacity (ranges grew or the table filled up).
+  void relayout(const KeyLayout& nl, const std::vector<int32_t>& newNullReserved, Mode nm, int64_t ncap) {
+    flushFused();  // fused partial sums are laid out by the old group ids
+    int64_t m = 0;
+    DeviceBufferPtr slots = sawInput ? occupiedSlots(m) : nullptr;
+    Storage ns = makeStorage(ncap, nm);
+    if (m > 0) {
+      auto newKeys = allocDevice(static_cast<size_t>(m) * 8, st());
+      kernelCheck(vb2k_rekey(mode == Mode::kHash ? tableKeys->as<uint64_t>() : nullptr, slots->as<int32_t>(), m, static_cast<int32_t>(keys.size()),
+                             layout.mins.data(), layout.mults.data(), layout.ranges.data(), nullReserved.data(), nl.mins.data(),
+                             nl.mults.data(), newKeys->as<uint64_t>(), st()));
+      auto newSlots = allocDevice(static_cast<size_t>(m) * 4, st());
+      VB2_CU(cudaMemsetAsync(numGroupsDev->data(), 0, 8, st()));  // the new table counts its groups afresh
+      kernelCheck(vb2k_group_probe(newKeys->as<uint64_t>(), nullptr, m, nm == Mode::kHash ? ns.tableKeys->as<uint64_t>() : nullptr, ncap,
+                                   newSlots->as<int32_t>(), numGroupsDev->as<int64_t>(), errorFlag->as<int32_t>(), st()));
+      auto move = [&](const DeviceBufferPtr& from, const DeviceBufferPtr& to) {
+        kernelCheck(vb2k_scatter(from->data(), slots->as<int32_t>(), newSlots->as<int32_t>(), m, 8, to->data(), st()));
+      };
+      move(groupRows, ns.groupRows);
+      for (size_t i = 0; i < accs.size(); ++i) { move(accs[i].acc, ns.acc[i]); move(accs[i].nonnull, ns.nonnull[i]); }
+      checkDeviceError(errorFlag, st(), "aggregation rehash");
+    }
+    layout = nl;
+    nullReserved = newNullReserved;
+    for (auto& ks : keys) ks.fusedLut = nullptr;
+    mode = nm;
+    capacity = ncap;
+    adopt(std::move(ns));
+    self->addRuntimeStat("b200.aggRelayouts", exec::RuntimeCounter{1});
+  }
+
+  // ---- key handling -----------------------------------------------------------------------------
+  // Returns the column the normalize kernel should read for key k of this batch and updates the
+  // key's observed range. VARCHAR dictionary keys become INTEGER dictionary columns over a LUT of
+  // global value ids.
+  vb2_column keyColumn(size_t k, const DeviceColumn& col, int64_t rows, std::vector<DeviceBufferPtr>& keep) {
+    KeyState& ks = keys[k];
+    vb2_column d = col.desc;
+    if (col.mayHaveNulls()) ks.nullable = true;
+    if (ks.isVarchar) {
+      if (d.encoding == VB2_FLAT) VELOX_UNSUPPORTED("GROUP BY on flat VARCHAR keys (dictionary-encoded VARCHAR keys are supported)");
+      VELOX_CHECK(col.alphabet != nullptr, "VARCHAR key without a host alphabet (dictionary above 65536 entries)");
+      if (ks.cachedAlphabet != col.alphabet.get()) {
+        std::vector<int32_t> lut(col.alphabet->values.size());
+        for (size_t i = 0; i < lut.size(); ++i) {
+          if (col.alphabet->nulls[i]) { lut[i] = 0; ks.nullable = true; continue; }
+          auto it = ks.valueIds.find(col.alphabet->values[i]);
+          if (it == ks.valueIds.end()) {
+            ks.valuesById.push_back(col.alphabet->values[i]);
+            it = ks.valueIds.emplace(col.alphabet->values[i], static_cast<int32_t>(ks.valuesById.size())).first;
+          }
+          lut[i] = it->second;
+        }
+        ks.lut = allocDevice(lut.size() * 4 + 4, st());
+        VB2_CU(cudaMemcpyAsync(ks.lut->data(), lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, st()));
+        VB2_CU(cudaStreamSynchronize(st()));
+        ks.cachedAlphabet = col.alphabet.get();
+        ks.fusedLut = nullptr;
+      }
+      keep.push_back(ks.lut);
+      d.type = VB2_INTEGER;
+      d.values = ks.lut->data();
+      d.aux = nullptr;
+      if (d.encoding == VB2_CONSTANT) d.dict_size = 1;
+      ks.hasRange = true;
+      ks.lo = 1;
+      ks.hi = std::max<int64_t>(1, static_cast<int64_t>(ks.valuesById.size()));
+      return d;
+    }
+    int64_t lo, hi, nn;
+    columnMinMax(col, rows, st(), lo, hi, nn);
+    if (nn > 0) {
+      if (!ks.hasRange) { ks.lo = lo; ks.hi = hi; ks.hasRange = true; }
+      else { ks.lo = std::min(ks.lo, lo); ks.hi = std::max(ks.hi, hi); }
+    }
+    return d;
+  }
+
+  // Makes sure the layout covers the observed key ranges and the table can take `incoming` more
+  // groups; relayouts otherwise.
+  void ensureLayout(int64_t incoming) {
+    if (keys.empty()) return;
+    bool covers = true;
+    for (size_t k = 0; k < keys.size(); ++k) {
+      const KeyState& ks = keys[k];
+      if (ks.nullable && !nullReserved[k]) covers = false;
+      if (ks.hasRange && (covHi[k] < covLo[k] || ks.lo < covLo[k] || ks.hi > covHi[k])) covers = false;
+    }
+    KeyLayout nl = layout;
+    std::vector<int64_t> nLo = covLo, nHi = covHi;
+    std::vector<int32_t> nRes = nullReserved;
+    if (!covers) {
+      // exact ranges first; if that already needs hash mode, widen integer ranges (free there)
+      auto build = [&](bool widen, unsigned __int128& product) {
+        product = 1;
+        bool overflow = false;
+        for (size_t k = 0; k < keys.size(); ++k) {
+          const KeyState& ks = keys[k];
+          __int128 lo = ks.hasRange ? ks.lo : 0, hi = ks.hasRange ? ks.hi : 0;
+          if (covHi[k] >= covLo[k]) { lo = std::min<__int128>(lo, covLo[k]); hi = std::max<__int128>(hi, covHi[k]); }
+          if (widen && !ks.isVarchar) {
+            const __int128 span = hi - lo + 1;
+            lo = std::max<__int128>(lo - span, INT64_MIN / 2);
+            hi = std::min<__int128>(hi + span, INT64_MAX / 2);
+          }
+          nRes[k] = (ks.nullable || nullReserved[k]) ? 1 : 0;
+          const unsigned __int128 range = static_cast<unsigned __int128>(hi - lo) + 1 + nRes[k];
+          if (range > (static_cast<unsigned __int128>(1) << 62)) overflow = true;
+          nLo[k] = static_cast<int64_t>(lo);
+          nHi[k] = static_cast<int64_t>(hi);
+          nl.mins[k] = static_cast<int64_t>(lo) + 1 - nRes[k];
+          nl.ranges[k] = static_cast<uint64_t>(range);
+          product *= range;
+          if (product > (static_cast<unsigned __int128>(1) << 62)) overflow = true;
+        }
+        return !overflow;
+      };
+      unsigned __int128 product;
+      bool ok = build(false, product);
+      if (ok && product > kArrayModeMax) {
+        unsigned __int128 wide;
+        if (build(true, wide)) product = wide;
+        else ok = build(false, product);
+      }
+      if (!ok) VELOX_UNSUPPORTED("grouping key ranges do not fit one 64-bit normalized key");
+      nl.product = static_cast<uint64_t>(product);
+      nl.mults.assign(keys.size(), 1);
+      for (int i = static_cast<int>(keys.size()) - 2; i >= 0; --i) nl.mults[i] = nl.mults[i + 1] * nl.ranges[i + 1];
+    }
+    Mode nm = nl.product <= kArrayModeMax ? Mode::kArray : Mode::kHash;
+    int64_t ncap = capacity;
+    if (nm == Mode::kArray) {
+      ncap = static_cast<int64_t>(nl.product);
+    } else {
+      const uint64_t bound = std::min<uint64_t>(nl.product, static_cast<uint64_t>(numGroupsUpper + incoming));
+      const uint64_t want = nextPow2(bound * 2 + 16);
+      if (mode != Mode::kHash || static_cast<uint64_t>(capacity) < want) ncap = static_cast<int64_t>(want);
+      VELOX_CHECK(ncap <= (1ll << 31), "hash aggregation above 2^31 slots");
+    }
+    if (!covers || nm != mode || ncap != capacity) {
+      relayout(nl, nRes, nm, ncap);
+      covLo = nLo;
+      covHi = nHi;
+    }
+  }
+
+  // ---- generic path -------------------------------------------------------------------------------
+  void addGeneric(const B200VectorPtr& in) {
+    const int64_t n = in->size();
+    ++genericBatches;
+    std::vector<DeviceBufferPtr> keep;
+    DeviceBufferPtr groupIds;
+    if (!keys.empty()) {
+      std::vector<vb2_column> keyCols;
+      for (size_t k = 0; k < keys.size(); ++k) keyCols.push_back(keyColumn(k, *in->column(node->groupingKeys()[k]), n, keep));
+      ensureLayout(n);
+      auto nk = allocDevice(static_cast<size_t>(n) * 8, st());
+      kernelCheck(vb2k_normalize_keys(keyCols.data(), static_cast<int32_t>(keyCols.size()), layout.mins.data(), layout.mults.data(), nullptr, 0,
+                                      nullptr, n, nk->as<uint64_t>(), nullptr, st()));
+      groupIds = allocDevice(static_cast<size_t>(n) * 4, st());
+      kernelCheck(vb2k_group_probe(nk->as<uint64_t>(), nullptr, n, mode == Mode::kHash ? tableKeys->as<uint64_t>() : nullptr, capacity,
+                                   groupIds->as<int32_t>(), numGroupsDev->as<int64_t>(), errorFlag->as<int32_t>(), st()));
+      numGroupsUpper += n;
+      if (mode == Mode::kHash) {
+        // tighten the bound with the real group count (one 8-byte read per batch)
+        int64_t g = 0;
+        VB2_CU(cudaMemcpyAsync(&g, numGroupsDev->data(), 8, cudaMemcpyDeviceToHost, st()));
+        VB2_CU(cudaStreamSynchronize(st()));
+        numGroupsUpper = g;
+      }
+    }
+    std::vector<vb2_agg_update> ups;
+    {
+      vb2_agg_update u{};
+      u.kind = VB2_AGG_COUNT;
+      u.acc = groupRows->data();
+      ups.push_back(u);
+    }
+    auto flatInput = [&](int32_t colIdx, const void*& values, const uint64_t*& nulls, int32_t& type) {
+      const DeviceColumnPtr& c = in->column(colIdx);
+      type = c->desc.type;
+      if (c->desc.encoding == VB2_FLAT && type != VB2_BOOLEAN) {
+        values = c->desc.values;
+        nulls = c->desc.nulls;
+        return;
+      }
+      FlatColumn f = flattenColumn(c, nullptr, n, st());
+      keep.push_back(f.values);
+      if (f.nulls) keep.push_back(f.nulls);
+      values = f.values->data();
+      nulls = f.nulls ? f.nulls->as<uint64_t>() : nullptr;
+    };
+    const auto& aggs = node->aggregates();
+    for (size_t i = 0; i < aggs.size(); ++i) {
+      const auto& a = aggs[i];
+      AccState& s = accs[i];
+      const uint64_t* mask = nullptr;
+      if (a.mask >= 0) {
+        const DeviceColumnPtr& mc = in->column(a.mask);
+        VELOX_CHECK(mc->desc.type == VB2_BOOLEAN && mc->desc.encoding == VB2_FLAT, "aggregate masks must be flat BOOLEAN columns");
+        if (mc->desc.nulls) {
+          auto mb = allocDevice(bits::nbytes(n), st());
+          kernelCheck(vb2k_and_bits(reinterpret_cast<const uint64_t*>(mc->desc.values), mc->desc.nulls, n, mb->as<uint64_t>(), st()));
+          keep.push_back(mb);
+          mask = mb->as<uint64_t>();
+        } else {
+          mask = reinterpret_cast<const uint64_t*>(mc->desc.values);
+        }
+      }
+      vb2_agg_update u{};
+      u.mask = mask;
+      u.acc = s.acc->data();
+      u.nonnull = s.nonnull->as<int64_t>();
+      if (a.function == "count") {
+        u.kind = raw ? VB2_AGG_COUNT : VB2_AGG_COUNT_MERGE;
+        u.nonnull = nullptr;
+        if (!a.inputs.empty()) flatInput(a.inputs[0], u.input, u.nulls, u.input_type);
+        ups.push_back(u);
+        continue;
+      }
+      flatInput(a.inputs[0], u.input, u.nulls, u.input_type);
+      u.kind = s.kind;
+      if (a.function == "avg" && !raw) {
+        // intermediate (sum, count): add the sums, merge the counts into the non-null counter
+        u.nonnull = nullptr;
+        ups.push_back(u);
+        vb2_agg_update c{};
+        c.kind = VB2_AGG_COUNT_MERGE;
+        c.mask = mask;
+        flatInput(a.inputs[1], c.input, c.nulls, c.input_type);
+        c.acc = s.nonnull->data();
+        ups.push_back(c);
+        continue;
+      }
+      ups.push_back(u);
+    }
+    for (size_t i = 0; i < ups.size(); i += 16) {
+      const int32_t cnt = static_cast<int32_t>(std::min<size_t>(16, ups.size() - i));
+      kernelCheck(vb2k_agg_update(groupIds ? groupIds->as<int32_t>() : nullptr, n, capacity, ups.data() + i, cnt, errorFlag->as<int32_t>(), st()));
+    }
+    // buffers in `keep` are freed stream-ordered after the kernels above
+  }
+
+  // ---- fused path -----------------------------------------------------------------------------------
+  // Decides at plan time whether the absorbed chain can be expressed as one fused pipeline.
+  void planFused() {
+    if (!raw || !self->driverCtx()->queryConfig().b200FusedPipelines()) return;
+    if (keys.size() > VB2_FUSED_MAX_KEYS) return;
+    // shape of the absorbed chain
+    B200FilterProject *fp1 = nullptr, *fp2 = nullptr;
+    B200HashProbe* probe = nullptr;
+    if (absorbed.size() == 1) fp1 = dynamic_cast<B200FilterProject*>(absorbed[0].get());
+    else if (absorbed.size() == 3) {
+      fp1 = dynamic_cast<B200FilterProject*>(absorbed[0].get());
+      probe = dynamic_cast<B200HashProbe*>(absorbed[1].get());
+      fp2 = dynamic_cast<B200FilterProject*>(absorbed[2].get());
+      if (!probe || !fp2 || fp2->hasFilter()) return;
+      if (probe->node()->joinType() != core::JoinType::kInner || probe->node()->filter() || probe->node()->leftKeys().size() != 1) return;
+    }
+    if (!fp1) return;
+    const RowTypePtr& srcType = fp1->inputType();
+    // expressions of the stage feeding the aggregation, in terms of source columns; build-side
+    // columns are marked with index = -(buildColumn + 1)
+    std::vector<core::TypedExprPtr> stage;
+    core::TypedExprPtr filter;
+    {
+      const auto& e = fp1->exprs();
+      size_t first = 0;
+      if (fp1->hasFilter()) { filter = e[0]; first = 1; }
+      for (size_t i = first; i < e.size(); ++i) stage.push_back(e[i]);
+    }
+    int joinKeySource = -1;
+    if (probe) {
+      auto keyExpr = stage.at(probe->node()->leftKeys()[0]);
+      auto kf = dynamic_cast<const core::FieldAccessTypedExpr*>(keyExpr.get());
+      if (!kf) return;
+      joinKeySource = kf->index();
+      std::vector<core::TypedExprPtr> joined;
+      const auto& bt = probe->node()->sources()[1]->outputType();
+      for (auto& o : probe->node()->outputs()) {
+        if (o.fromProbe) joined.push_back(stage.at(o.column));
+        else joined.push_back(std::make_shared<core::FieldAccessTypedExpr>(bt->childAt(o.column), "__build", -(o.column + 1)));
+      }
+      std::vector<core::TypedExprPtr> after;
+      for (auto& e : fp2->exprs()) after.push_back(substituteFields(e, joined));
+      stage = after;
+    }
+    // aggregate inputs -> deduplicated projections
+    std::vector<core::TypedExprPtr> projs;
+    std::vector<std::string> projKeys;
+    aggToProj.clear();
+    for (auto& a : node->aggregates()) {
+      if (a.mask >= 0) return;
+      if (a.function == "count") {
+        if (!a.inputs.empty()) return;  // count(x) needs x's nulls; count(*) only
+        aggToProj.push_back(-1);
+        continue;
+      }
+      if (a.function != "sum" && a.function != "avg") return;
+      auto e = stage.at(a.inputs[0]);
+      if (e->type()->kind() != TypeKind::DOUBLE) return;
+      const std::string key = e->toString() + "#" + std::to_string(reinterpret_cast<uintptr_t>(e.get()));
+      int found = -1;
+      for (size_t i = 0; i < projs.size(); ++i)
+        if (projs[i].get() == e.get()) found = static_cast<int>(i);
+      if (found < 0) { projs.push_back(e); found = static_cast<int>(projs.size()) - 1; }
+      aggToProj.push_back(found);
+    }
+    if (projs.empty()) return;
+    // group keys must be plain source columns
+    fusedKeySourceCols.clear();
+    for (int32_t k : node->groupingKeys()) {
+      auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(stage.at(k).get());
+      if (!f || f->index() < 0) return;
+      fusedKeySourceCols.push_back(f->index());
+    }
+    // the build-side predicate: the one BOOLEAN sub-expression that touches build columns
+    const core::ITypedExpr* flag = nullptr;
+    if (probe) {
+      std::function<bool(const core::TypedExprPtr&)> touchesBuild = [&](const core::TypedExprPtr& e) {
+        if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) return f->index() < 0;
+        for (auto& in : e->inputs()) if (touchesBuild(in)) return true;
+        return false;
+      };
+      std::function<bool(const core::TypedExprPtr&)> onlyBuild = [&](const core::TypedExprPtr& e) {
+        if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) return f->index() < 0;
+        if (dynamic_cast<const core::ConstantTypedExpr*>(e.get())) return true;
+        for (auto& in : e->inputs()) if (!onlyBuild(in)) return false;
+        return true;
+      };
+      bool bad = false;
+      std::function<void(const core::TypedExprPtr&)> find = [&](const core::TypedExprPtr& e) {
+        if (!touchesBuild(e)) return;
+        if (onlyBuild(e) && e->type()->kind() == TypeKind::BOOLEAN) {
+          if (flag && flag != e.get() && flag->toString() != e->toString()) bad = true;
+          if (!flag) { flag = e.get(); joinFlagExpr = e; }
+          return;
+        }
+        if (dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) { bad = true; return; }
+        for (auto& in : e->inputs()) find(in);
+      };
+      for (auto& p : projs) find(p);
+      if (bad) return;
+    }
+    binding = fusedSignature(filter, projs, srcType, joinKeySource, flag);
+    if (!binding.ok) return;
+    fusedId = vb2k_fused_find(binding.signature.c_str());
+    self->addRuntimeStat("b200.fusedSignatureMatched", exec::RuntimeCounter{fusedId >= 0 ? 1 : 0});
+    if (fusedId < 0) return;
+    fusedProbe = probe;
+    fusedJoinKeySourceCol = joinKeySource;
+    fusedPlanned = true;
+  }
+
+  // Build-side preparation of the fused probe: dense key -> flag table. Returns false when the
+  // build side does not qualify (duplicate keys, hash mode ...).
+  bool prepareFusedJoin() {
+    if (!fusedProbe) return true;
+    if (joinSlotFlags) return true;
+    auto jt = fusedProbe->table();
+    if (!jt || jt->table.mode != 0 || jt->hasDuplicateKeys || !jt->rows) return false;
+    DeviceBufferPtr flagBuf;
+    const int32_t* codes = nullptr;
+    if (joinFlagExpr) {
+      // the predicate's single build column
+      int buildCol = -1;
+      std::function<void(const core::TypedExprPtr&)> scan = [&](const core::TypedExprPtr& e) {
+        if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) {
+          const int c = -f->index() - 1;
+          if (buildCol >= 0 && buildCol != c) buildCol = -2;
+          else if (buildCol != -2) buildCol = c;
+        }
+        for (auto& in : e->inputs()) scan(in);
+      };
+      scan(joinFlagExpr);
+      if (buildCol < 0) return false;
+      const DeviceColumnPtr& bc = jt->rows->column(buildCol);
+      // evaluate the predicate once per dictionary entry (or per build row when flat)
+      vb2_column view = bc->desc;
+      int64_t entries = bc->desc.size;
+      if (bc->desc.encoding == VB2_DICTIONARY) {
+        if (bc->desc.nulls) return false;
+        view.encoding = VB2_FLAT;
+        view.size = bc->desc.dict_size;
+        view.nulls = bc->desc.dict_nulls;
+        view.indices = nullptr;
+        entries = bc->desc.dict_size;
+        codes = bc->desc.indices;
+      } else if (bc->desc.encoding != VB2_FLAT) {
+        return false;
+      }
+      std::vector<core::TypedExprPtr> one{std::make_shared<core::FieldAccessTypedExpr>(bc->type, "b", 0)};
+      auto pred = substituteBuild(joinFlagExpr, one[0]);
+      CompiledProgram prog = compileExprs({pred}, false, ROW({"b"}, {bc->type}));
+      prog.uploadConstants(st());
+      const vb2_program pv = prog.view();
+      flagBuf = allocDevice(static_cast<size_t>(entries) + 8, st());
+      auto nulls = allocDevice(bits::nbytes(entries), st());
+      vb2_output o{prog.outputs[0].reg, VB2_BOOLEAN, flagBuf->data(), nulls->as<uint64_t>()};
+      kernelCheck(vb2k_eval_project(&pv, &view, 1, nullptr, entries, &o, 1, errorFlag->as<int32_t>(), st()));
+      // NULL predicate results were written as 0 = false, matching CASE semantics
+    }
+    joinSlotFlags = allocDevice(static_cast<size_t>(jt->table.capacity) + 8, st());
+    kernelCheck(vb2k_join_slot_flags(jt->table.head, codes, flagBuf ? flagBuf->as<uint8_t>() : nullptr, jt->table.capacity,
+                                     joinSlotFlags->as<uint8_t>(), st()));
+    return true;
+  }
+  static core::TypedExprPtr substituteBuild(const core::TypedExprPtr& e, const core::TypedExprPtr& field) {
+    if (dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) return field;
+    if (dynamic_cast<const core::ConstantTypedExpr*>(e.get())) return e;
+    std::vector<core::TypedExprPtr> in;
+    for (auto& i : e->inputs()) in.push_back(substituteBuild(i, field));
+    if (auto c = dynamic_cast<const core::CallTypedExpr*>(e.get())) return std::make_shared<core::CallTypedExpr>(e->type(), std::move(in), c->name());
+    if (auto c = dynamic_cast<const core::CastTypedExpr*>(e.get())) return std::make_shared<core::CastTypedExpr>(e->type(), in[0], c->nullOnFailure());
+    VELOX_UNSUPPORTED("unknown expression node");
+  }
+
+  // Tries the fused kernel for this source batch. Returns false when the batch does not qualify.
+  bool tryFused(const B200VectorPtr& src) {
+    if (!fusedPlanned || fusedId < 0) return false;
+    const int64_t n = src->size();
+    vb2_fused_args a{};
+    for (size_t i = 0; i < binding.columns.size(); ++i) {
+      const vb2_column& d = src->column(binding.columns[i])->desc;
+      if (d.encoding != VB2_FLAT || d.nulls) return false;
+      a.cols[i] = d.values;
+    }
+    for (size_t i = 0; i < binding.pf.size(); ++i) a.pf[i] = binding.pf[i];
+    for (size_t i = 0; i < binding.pl.size(); ++i) a.pl[i] = binding.pl[i];
+    for (size_t i = 0; i < binding.pi.size(); ++i) a.pi[i] = binding.pi[i];
+    a.rows = n;
+    std::vector<DeviceBufferPtr> keep;
+    // group keys: dictionary VARCHAR (indices + LUT of global ids) or flat INTEGER/BIGINT
+    a.nkeys = static_cast<int32_t>(keys.size());
+    for (size_t k = 0; k < keys.size(); ++k) {
+      const DeviceColumn& col = *src->column(fusedKeySourceCols[k]);
+      const vb2_column& d = col.desc;
+      if (d.nulls || d.dict_nulls) return false;
+      if (keys[k].isVarchar) {
+        if (d.encoding != VB2_DICTIONARY || !col.alphabet) return false;
+        for (bool isNull : col.alphabet->nulls) if (isNull) return false;
+        (void)keyColumn(k, col, n, keep);  // assigns global ids, refreshes the LUT and the range
+        a.key[k] = d.indices;
+        a.key_is64[k] = 0;
+      } else {
+        if (d.encoding != VB2_FLAT || (d.type != VB2_INTEGER && d.type != VB2_BIGINT)) return false;
+        (void)keyColumn(k, col, n, keep);
+        a.key[k] = d.values;
+        a.key_is64[k] = d.type == VB2_BIGINT;
+      }
+    }
+    if (!keys.empty()) {
+      ensureLayout(n);
+      if (mode != Mode::kArray || layout.product > static_cast<uint64_t>(kFusedMaxGroups)) return false;
+      for (size_t k = 0; k < keys.size(); ++k) {
+        // kernel: id = lut ? lut[v - key_min] : v - key_min ; layout: id = v - mins[k] + 1
+        a.key_mult[k] = static_cast<int32_t>(layout.mults[k]);
+        if (!keys[k].isVarchar) { a.key_min[k] = layout.mins[k] - 1; continue; }
+        // VARCHAR: per-dictionary LUT of layout ids (global id - mins + 1), rebuilt when either changes
+        KeyState& ks = keys[k];
+        const DeviceColumn& col = *src->column(fusedKeySourceCols[k]);
+        if (!ks.fusedLut) {
+          std::vector<int32_t> lut(col.alphabet->values.size());
+          for (size_t i = 0; i < lut.size(); ++i) lut[i] = static_cast<int32_t>(ks.valueIds.at(col.alphabet->values[i]) - layout.mins[k] + 1);
+          ks.fusedLut = allocDevice(lut.size() * 4 + 4, st());
+          VB2_CU(cudaMemcpyAsync(ks.fusedLut->data(), lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, st()));
+          VB2_CU(cudaStreamSynchronize(st()));
+        }
+        a.key_min[k] = 0;
+        a.key_lut[k] = ks.fusedLut->as<int32_t>();
+      }
+    }
+    const int groups = keys.empty() ? 1 : static_cast<int>(layout.product);
+    if (!prepareFusedJoin()) return false;
+    if (fusedProbe) {
+      auto jt = fusedProbe->table();
+      a.join_slot_flags = joinSlotFlags->as<uint8_t>();
+      // slot = normalized key = v - min + 1  =>  v - (min - 1)
+      a.join_min = jt->layout.mins[0] - 1;
+      a.join_range = jt->table.capacity;
+    }
+    a.ngroups = groups;
+    const int np = vb2k_fused_nproj(fusedId);
+    if (!fusedSums || fusedGroups != groups) {
+      flushFused();
+      fusedGroups = groups;
+      fusedSums = allocDeviceZeroed(static_cast<size_t>(groups) * np * 8, st());
+      fusedCounts = allocDeviceZeroed(static_cast<size_t>(groups) * 8, st());
+      fusedWsBytes = vb2k_fused_workspace_bytes(fusedId, groups);
+      fusedWs = allocDevice(fusedWsBytes, st());
+    }
+    const int rc = vb2k_fused_scan_agg(fusedId, &a, fusedSums->as<double>(), fusedCounts->as<int64_t>(), fusedWs->data(), fusedWsBytes, st());
+    if (rc == VB2_ERR_UNSUPPORTED) return false;
+    kernelCheck(rc);
+    ++fusedBatches;
+    return true;
+  }
+
+  // Folds the fused partial sums into the generic accumulators (small: <= kFusedMaxGroups groups).
+  void flushFused() {
+    if (!fusedSums) return;
+    const int np = vb2k_fused_nproj(fusedId);
+    std::vector<double> sums(static_cast<size_t>(fusedGroups) * np);
+    std::vector<int64_t> counts(fusedGroups);
+    VB2_CU(cudaMemcpyAsync(sums.data(), fusedSums->data(), sums.size() * 8, cudaMemcpyDeviceToHost, st()));
+    VB2_CU(cudaMemcpyAsync(counts.data(), fusedCounts->data(), counts.size() * 8, cudaMemcpyDeviceToHost, st()));
+    VB2_CU(cudaStreamSynchronize(st()));
+    fusedSums = nullptr;
+    fusedCounts = nullptr;
+    VELOX_CHECK(static_cast<int64_t>(fusedGroups) <= capacity, "fused group space larger than the table");
+    // read-modify-write of the few affected accumulator entries
+    auto rmw = [&](const DeviceBufferPtr& buf, auto fn) {
+      using T = std::remove_reference_t<decltype(fn(0, static_cast<uint64_t>(0)))>;
+      (void)sizeof(T);
+      std::vector<uint64_t> h(fusedGroups);
+      VB2_CU(cudaMemcpyAsync(h.data(), buf->data(), h.size() * 8, cudaMemcpyDeviceToHost, st()));
+      VB2_CU(cudaStreamSynchronize(st()));
+      for (int g = 0; g < fusedGroups; ++g) h[g] = fn(g, h[g]);
+      VB2_CU(cudaMemcpyAsync(buf->data(), h.data(), h.size() * 8, cudaMemcpyHostToDevice, st()));
+      VB2_CU(cudaStreamSynchronize(st()));
+    };
+    auto addI64 = [&](const DeviceBufferPtr& buf) {
+      rmw(buf, [&](int g, uint64_t cur) { return static_cast<uint64_t>(static_cast<int64_t>(cur) + counts[g]); });
+    };
+    addI64(groupRows);
+    for (size_t i = 0; i < accs.size(); ++i) {
+      const int p = aggToProj[i];
+      if (p < 0) { addI64(accs[i].acc); continue; }
+      rmw(accs[i].acc, [&](int g, uint64_t cur) {
+        double d;
+        std::memcpy(&d, &cur, 8);
+        d += sums[static_cast<size_t>(g) * np + p];
+        uint64_t out;
+        std::memcpy(&out, &d, 8);
+        return out;
+      });
+      addI64(accs[i].nonnull);
+    }
+  }
+
+  // ---- input ------------------------------------------------------------------------------------
+  void addInput(const B200VectorPtr& src) {
+    sawInput = true;
+    if (tryFused(src)) return;
+    B200VectorPtr cur = src;
+    for (auto& op : absorbed) {
+      if (auto fp = dynamic_cast<B200FilterProject*>(op.get())) cur = fp->apply(cur);
+      else if (auto pr = dynamic_cast<B200HashProbe*>(op.get())) cur = pr->apply(cur);
+      if (!cur) return;  // every row filtered out
+    }
+    addGeneric(cur);
+  }
+
+  // ---- output -----------------------------------------------------------------------------------
+  DeviceColumnPtr flatOutput(const TypePtr& type, DeviceBufferPtr values, DeviceBufferPtr valid, int64_t n) {
+    auto col = std::make_shared<DeviceColumn>();
+    col->type = type;
+    col->desc.type = veloxTypeToVb2(type);
+    col->desc.encoding = VB2_FLAT;
+    col->desc.size = n;
+    col->desc.values = values->data();
+    col->owners.push_back(values);
+    if (valid) {
+      col->desc.nulls = valid->as<uint64_t>();
+      col->owners.push_back(valid);
+    }
+    return col;
+  }
+
+  B200VectorPtr output() {
+    flushFused();
+    checkDeviceError(errorFlag, st(), "sum");  // SUM(BIGINT) overflow (functions/prestosql/aggregates/SumAggregate.cpp:24)
+    int64_t m = 0;
+    DeviceBufferPtr slots;
+    if (mode == Mode::kGlobal) {
+      m = 1;  // a global aggregation always emits one row (exec/GroupingSet.cpp:499-770)
+      slots = allocDeviceZeroed(8, st());
+    } else {
+      slots = occupiedSlots(m);
+      if (m == 0) return nullptr;
+    }
+    const auto& outType = node->outputType();
+    const auto& inType = node->sources()[0]->outputType();
+    std::vector<DeviceColumnPtr> cols;
+    uint32_t oc = 0;
+    // keys
+    for (size_t k = 0; k < keys.size(); ++k, ++oc) {
+      const TypePtr& t = inType->childAt(node->groupingKeys()[k]);
+      auto valid = allocDevice(bits::nbytes(m), st());
+      if (keys[k].isVarchar) {
+        // dictionary over the global alphabet: index = id - 1
+        auto idx = allocDevice(static_cast<size_t>(m) * 4, st());
+        kernelCheck(vb2k_denormalize_keys(mode == Mode::kHash ? tableKeys->as<uint64_t>() : nullptr, slots->as<int32_t>(), m, layout.mins[k] - 1,
+                                          layout.mults[k], layout.ranges[k], nullReserved[k], VB2_INTEGER, idx->data(), valid->as<uint64_t>(), st()));
+        auto alpha = std::make_shared<HostAlphabet>();
+        alpha->values = keys[k].valuesById;
+        alpha->nulls.assign(alpha->values.size(), false);
+        std::vector<int32_t> off(alpha->values.size() + 1, 0);
+        std::string chars;
+        for (size_t i = 0; i < alpha->values.size(); ++i) { chars += alpha->values[i]; off[i + 1] = static_cast<int32_t>(chars.size()); }
+        auto offBuf = allocDevice(off.size() * 4, st());
+        auto charBuf = allocDevice(chars.size() + 1, st());
+        VB2_CU(cudaMemcpyAsync(offBuf->data(), off.data(), off.size() * 4, cudaMemcpyHostToDevice, st()));
+        VB2_CU(cudaMemcpyAsync(charBuf->data(), chars.data(), chars.size(), cudaMemcpyHostToDevice, st()));
+        VB2_CU(cudaStreamSynchronize(st()));
+        auto col = std::make_shared<DeviceColumn>();
+        col->type = t;
+        col->desc.type = VB2_VARCHAR;
+        col->desc.encoding = VB2_DICTIONARY;
+        col->desc.size = m;
+        col->desc.indices = idx->as<int32_t>();
+        col->desc.values = offBuf->data();
+        col->desc.aux = charBuf->data();
+        col->desc.dict_size = static_cast<int64_t>(alpha->values.size());
+        if (nullReserved[k]) col->desc.nulls = valid->as<uint64_t>();  // NULL key group: id 0
+        col->owners = {idx, offBuf, charBuf, valid};
+        col->alphabet = alpha;
+        cols.push_back(col);
+      } else {
+        const int vt = veloxTypeToVb2(t);
+        auto vals = allocDevice(static_cast<size_t>(m) * 8, st());
+        kernelCheck(vb2k_denormalize_keys(mode == Mode::kHash ? tableKeys->as<uint64_t>() : nullptr, slots->as<int32_t>(), m, layout.mins[k],
+                                          layout.mults[k], layout.ranges[k], nullReserved[k], vt, vals->data(), valid->as<uint64_t>(), st()));
+        if (vt == VB2_BOOLEAN) {
+          auto packed = allocDevice(bits::nbytes(m), st());
+          kernelCheck(vb2k_pack_bools(vals->as<uint8_t>(), m, packed->as<uint64_t>(), st()));
+          vals = packed;
+        }
+        cols.push_back(flatOutput(t, vals, nullReserved[k] ? valid : nullptr, m));
+      }
+    }
+    // aggregates
+    const int32_t* sl = slots->as<int32_t>();
+    for (size_t i = 0; i < accs.size(); ++i) {
+      const AccState& s = accs[i];
+      auto gatherAcc = [&](const DeviceBufferPtr& src) {
+        auto out = allocDevice(static_cast<size_t>(m) * 8, st());
+        kernelCheck(vb2k_gather(src->data(), sl, m, 8, out->data(), st()));
+        return out;
+      };
+      auto validOf = [&]() {
+        auto v = allocDevice(bits::nbytes(m), st());
+        kernelCheck(vb2k_counts_to_valid(s.nonnull->as<int64_t>(), sl, m, v->as<uint64_t>(), st()));
+        return v;
+      };
+      if (s.fn == "count") {
+        cols.push_back(flatOutput(outType->childAt(oc++), gatherAcc(s.acc), nullptr, m));
+      } else if (s.fn == "avg") {
+        if (fin) {
+          auto out = allocDevice(static_cast<size_t>(m) * 8, st());
+          kernelCheck(vb2k_avg_finalize(s.acc->as<double>(), s.nonnull->as<int64_t>(), sl, m, out->as<double>(), st()));
+          cols.push_back(flatOutput(outType->childAt(oc++), out, validOf(), m));
+        } else {
+          auto v = validOf();
+          cols.push_back(flatOutput(outType->childAt(oc++), gatherAcc(s.acc), v, m));
+          cols.push_back(flatOutput(outType->childAt(oc++), gatherAcc(s.nonnull), v, m));
+        }
+      } else {
+        const TypePtr& t = outType->childAt(oc++);
+        auto vals = gatherAcc(s.acc);
+        if (t->kind() == TypeKind::INTEGER) {
+          // min/max over INTEGER keep their type: narrow the 8-byte accumulator
+          auto narrow = allocDevice(static_cast<size_t>(m) * 4, st());
+          kernelCheck(vb2k_narrow_i64(vals->as<int64_t>(), m, narrow->as<int32_t>(), st()));
+          vals = narrow;
+        }
+        cols.push_back(flatOutput(t, vals, validOf(), m));
+      }
+    }
+    self->addRuntimeStat("b200.fusedBatches", exec::RuntimeCounter{fusedBatches});
+    self->addRuntimeStat("b200.genericBatches", exec::RuntimeCounter{genericBatches});
+    self->addRuntimeStat("b200.aggMode", exec::RuntimeCounter{static_cast<int64_t>(mode)});
+    return std::make_shared<B200Vector>(self->pool(), outType, static_cast<vector_size_t>(m), std::move(cols), st());
+  }
+};
+
+B200HashAggregation::B200HashAggregation(int32_t id, exec::DriverCtx* ctx, std::shared_ptr<const core::AggregationNode> node,
+                                         std::vector<std::unique_ptr<exec::Operator>> absorbed)
+    : Operator(ctx, node->outputType(), id, node->id(), "B200HashAggregation"), impl_(std::make_unique<Impl>()) {
+  impl_->self = this;
+  impl_->node = std::move(node);
+  impl_->absorbed = std::move(absorbed);
+}
+B200HashAggregation::~B200HashAggregation() = default;
+
+void B200HashAggregation::initialize() {
+  Operator::initialize();
+  impl_->dev = driverDeviceContext(driverCtx_);
+  for (auto& op : impl_->absorbed) op->initialize();
+  impl_->init();
+}
+
+exec::BlockingReason B200HashAggregation::isBlocked(exec::ContinueFuture* future) {
+  for (auto& op : impl_->absorbed) {
+    auto r = op->isBlocked(future);
+    if (r != exec::BlockingReason::kNotBlocked) return r;
+  }
+  return exec::BlockingReason::kNotBlocked;
+}
+
+void B200HashAggregation::addInput(RowVectorPtr input) {
+  auto in = std::dynamic_pointer_cast<B200Vector>(input);
+  VELOX_CHECK(in != nullptr, "B200HashAggregation expects device-resident input");
+  impl_->addInput(in);
+}
+
+void B200HashAggregation::noMoreInput() { Operator::noMoreInput(); }
+
+RowVectorPtr B200HashAggregation::getOutput() {
+  if (!noMoreInput_ || finished_) return nullptr;
+  finished_ = true;
+  return impl_->output();
+}
+
+}  // namespace velox_b200

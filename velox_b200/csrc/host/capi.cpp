@@ -1,0 +1,282 @@
+// Operator-level C ABI (include/velox_b200.h): plan text -> Task over the shim Driver with the
+// B200 adapter installed; host / device column batches in, host result columns out.
+#include <cstring>
+#include <sstream>
+
+#include "../../../include/velox_b200.h"
+#include "operators.h"
+#include "plan_text.h"
+#include "task.h"
+
+using namespace velox_b200;
+
+struct vb2_task {
+  std::shared_ptr<exec::Task> task;
+  core::PlanNodePtr plan;
+  memory::MemoryPool pool{"capi"};
+  std::vector<RowVectorPtr> results;
+  // results concatenated per column for copy-out
+  struct OutCol {
+    int32_t type;
+    std::vector<uint8_t> values;  // fixed width (BOOLEAN one byte per row)
+    std::vector<int32_t> offsets;
+    std::string chars;
+    std::vector<uint8_t> nulls;
+  };
+  std::vector<OutCol> out;
+  int64_t rows = 0;
+  std::string stats;
+};
+
+namespace {
+
+void setErr(char* err, int32_t errlen, const std::string& msg) {
+  if (!err || errlen <= 0) return;
+  std::strncpy(err, msg.c_str(), errlen - 1);
+  err[errlen - 1] = 0;
+}
+
+template <class F>
+int32_t guarded(char* err, int32_t errlen, F&& f) {
+  try {
+    f();
+    return VB2_OK;
+  } catch (const VeloxUserError& e) {
+    setErr(err, errlen, std::string("VeloxUserError: ") + e.what());
+    return VB2_ERR_USER;
+  } catch (const VeloxRuntimeError& e) {
+    setErr(err, errlen, std::string("VeloxRuntimeError: ") + e.what());
+    const std::string w = e.what();
+    if (w.find("Unsupported") != std::string::npos || w.find("Not yet implemented") != std::string::npos) return VB2_ERR_UNSUPPORTED;
+    if (w.find("CUDA") != std::string::npos) return VB2_ERR_CUDA;
+    return VB2_ERR_INVALID;
+  } catch (const std::exception& e) {
+    setErr(err, errlen, std::string("VeloxRuntimeError: ") + e.what());
+    return VB2_ERR_INVALID;
+  }
+}
+
+TypePtr typeOf(int32_t t) {
+  switch (t) {
+    case VB2_BOOLEAN: return BOOLEAN();
+    case VB2_INTEGER: return INTEGER();
+    case VB2_BIGINT: return BIGINT();
+    case VB2_DOUBLE: return DOUBLE();
+    case VB2_VARCHAR: return VARCHAR();
+    default: throw VeloxRuntimeError("unknown column type " + std::to_string(t));
+  }
+}
+
+BufferPtr view(const void* p, size_t bytes) { return p ? std::make_shared<Buffer>(p, bytes) : nullptr; }
+
+// Flat host values -> FlatVector over borrowed memory (VARCHAR: StringViews over the caller's chars).
+VectorPtr importFlat(memory::MemoryPool* pool, int32_t type, const void* values, const void* aux, const uint64_t* nulls, int64_t n) {
+  BufferPtr nb = view(nulls, bits::nbytes(n));
+  const vector_size_t size = static_cast<vector_size_t>(n);
+  switch (type) {
+    case VB2_BOOLEAN: return std::make_shared<FlatVector<bool>>(pool, BOOLEAN(), nb, size, view(values, bits::nbytes(n)));
+    case VB2_INTEGER: return std::make_shared<FlatVector<int32_t>>(pool, INTEGER(), nb, size, view(values, n * 4));
+    case VB2_BIGINT: return std::make_shared<FlatVector<int64_t>>(pool, BIGINT(), nb, size, view(values, n * 8));
+    case VB2_DOUBLE: return std::make_shared<FlatVector<double>>(pool, DOUBLE(), nb, size, view(values, n * 8));
+    case VB2_VARCHAR: {
+      const int32_t* off = static_cast<const int32_t*>(values);
+      const char* chars = static_cast<const char*>(aux);
+      BufferPtr views = AlignedBuffer::allocate<StringView>(n ? n : 1, pool);
+      auto* sv = views->asMutable<StringView>();
+      for (int64_t i = 0; i < n; ++i) sv[i] = StringView(chars + off[i], off[i + 1] - off[i]);
+      return std::make_shared<FlatVector<StringView>>(pool, VARCHAR(), nb, size, views);
+    }
+    default: throw VeloxRuntimeError("unknown column type");
+  }
+}
+
+VectorPtr importHostColumn(memory::MemoryPool* pool, const vb2_column& c, int64_t rows) {
+  if (c.size != rows) throw VeloxRuntimeError("column size differs from the batch's row count");
+  const vector_size_t n = static_cast<vector_size_t>(rows);
+  if (c.encoding == VB2_FLAT) return importFlat(pool, c.type, c.values, c.aux, c.nulls, rows);
+  if (c.encoding == VB2_DICTIONARY) {
+    VectorPtr base = importFlat(pool, c.type, c.values, c.aux, c.dict_nulls, c.dict_size);
+    return BaseVector::wrapInDictionary(view(c.nulls, bits::nbytes(rows)), view(c.indices, rows * 4), n, base);
+  }
+  if (c.encoding == VB2_CONSTANT) {
+    const bool isNull = c.nulls && !bits::isBitSet(c.nulls, 0);
+    switch (c.type) {
+      case VB2_BOOLEAN: return std::make_shared<ConstantVector<bool>>(pool, n, isNull, BOOLEAN(), !isNull && bits::isBitSet(static_cast<const uint64_t*>(c.values), 0));
+      case VB2_INTEGER: return std::make_shared<ConstantVector<int32_t>>(pool, n, isNull, INTEGER(), isNull ? 0 : *static_cast<const int32_t*>(c.values));
+      case VB2_BIGINT: return std::make_shared<ConstantVector<int64_t>>(pool, n, isNull, BIGINT(), isNull ? 0 : *static_cast<const int64_t*>(c.values));
+      case VB2_DOUBLE: return std::make_shared<ConstantVector<double>>(pool, n, isNull, DOUBLE(), isNull ? 0 : *static_cast<const double*>(c.values));
+      case VB2_VARCHAR: {
+        auto v = std::make_shared<ConstantVector<StringView>>(pool, n, isNull, VARCHAR(), StringView());
+        if (!isNull) {
+          const int32_t* off = static_cast<const int32_t*>(c.values);
+          v->setStringStorage(std::string(static_cast<const char*>(c.aux) + off[0], off[1] - off[0]));
+        }
+        return v;
+      }
+      default: throw VeloxRuntimeError("unknown column type");
+    }
+  }
+  throw VeloxRuntimeError("unknown column encoding");
+}
+
+// Device-resident batch: borrow the pointers; small VARCHAR alphabets are mirrored on the host.
+DeviceColumnPtr importDeviceColumn(const vb2_column& c, int64_t rows) {
+  if (c.size != rows) throw VeloxRuntimeError("column size differs from the batch's row count");
+  auto col = std::make_shared<DeviceColumn>();
+  col->type = typeOf(c.type);
+  col->desc = c;
+  if (c.type == VB2_VARCHAR && c.encoding != VB2_FLAT) {
+    const int64_t entries = c.encoding == VB2_DICTIONARY ? c.dict_size : 1;
+    if (entries <= (1 << 16)) {
+      std::vector<int32_t> off(entries + 1);
+      VB2_CU(cudaMemcpy(off.data(), c.values, off.size() * 4, cudaMemcpyDeviceToHost));
+      std::string chars(off[entries], '\0');
+      if (!chars.empty()) VB2_CU(cudaMemcpy(chars.data(), c.aux, chars.size(), cudaMemcpyDeviceToHost));
+      std::vector<uint64_t> nb;
+      const uint64_t* dn = c.encoding == VB2_DICTIONARY ? c.dict_nulls : c.nulls;
+      if (dn) {
+        nb.resize(bits::nwords(entries));
+        VB2_CU(cudaMemcpy(nb.data(), dn, nb.size() * 8, cudaMemcpyDeviceToHost));
+      }
+      auto alpha = std::make_shared<HostAlphabet>();
+      for (int64_t i = 0; i < entries; ++i) {
+        alpha->values.push_back(chars.substr(off[i], off[i + 1] - off[i]));
+        alpha->nulls.push_back(dn ? !bits::isBitSet(nb.data(), i) : false);
+      }
+      col->alphabet = alpha;
+    }
+  }
+  return col;
+}
+
+void appendResult(vb2_task& t, const RowVectorPtr& batch) {
+  const vector_size_t n = batch->size();
+  if (t.out.empty()) {
+    t.out.resize(batch->childrenSize());
+    for (size_t c = 0; c < t.out.size(); ++c) {
+      t.out[c].type = veloxTypeToVb2(batch->childAt(static_cast<uint32_t>(c))->type());
+      t.out[c].offsets.push_back(0);
+    }
+  }
+  for (size_t c = 0; c < t.out.size(); ++c) {
+    auto& o = t.out[c];
+    const BaseVector* v = batch->childAt(static_cast<uint32_t>(c)).get();
+    // decode dictionary wrapping
+    const vector_size_t* idx = nullptr;
+    const BaseVector* base = v;
+    if (v->encoding() == VectorEncoding::Simple::DICTIONARY) {
+      switch (v->typeKind()) {
+        case TypeKind::BOOLEAN: idx = v->as<DictionaryVector<bool>>()->rawIndices(); base = v->as<DictionaryVector<bool>>()->valueVector().get(); break;
+        case TypeKind::INTEGER: idx = v->as<DictionaryVector<int32_t>>()->rawIndices(); base = v->as<DictionaryVector<int32_t>>()->valueVector().get(); break;
+        case TypeKind::BIGINT: idx = v->as<DictionaryVector<int64_t>>()->rawIndices(); base = v->as<DictionaryVector<int64_t>>()->valueVector().get(); break;
+        case TypeKind::DOUBLE: idx = v->as<DictionaryVector<double>>()->rawIndices(); base = v->as<DictionaryVector<double>>()->valueVector().get(); break;
+        default: idx = v->as<DictionaryVector<StringView>>()->rawIndices(); base = v->as<DictionaryVector<StringView>>()->valueVector().get();
+      }
+    }
+    for (vector_size_t i = 0; i < n; ++i) {
+      const bool isNull = v->isNullAt(i);
+      const vector_size_t s = idx ? idx[i] : i;
+      o.nulls.push_back(isNull);
+      switch (o.type) {
+        case VB2_BOOLEAN: o.values.push_back(isNull ? 0 : base->as<FlatVector<bool>>()->valueAt(s)); break;
+        case VB2_INTEGER: { int32_t x = isNull ? 0 : base->as<FlatVector<int32_t>>()->rawValues()[s]; auto* p = reinterpret_cast<uint8_t*>(&x); o.values.insert(o.values.end(), p, p + 4); break; }
+        case VB2_BIGINT: { int64_t x = isNull ? 0 : base->as<FlatVector<int64_t>>()->rawValues()[s]; auto* p = reinterpret_cast<uint8_t*>(&x); o.values.insert(o.values.end(), p, p + 8); break; }
+        case VB2_DOUBLE: { double x = isNull ? 0 : base->as<FlatVector<double>>()->rawValues()[s]; auto* p = reinterpret_cast<uint8_t*>(&x); o.values.insert(o.values.end(), p, p + 8); break; }
+        default: {
+          if (!isNull) {
+            const StringView sv = base->as<FlatVector<StringView>>()->rawValues()[s];
+            o.chars.append(sv.data(), sv.size());
+          }
+          o.offsets.push_back(static_cast<int32_t>(o.chars.size()));
+        }
+      }
+    }
+  }
+  t.rows += n;
+}
+
+}  // namespace
+
+extern "C" {
+
+vb2_task* vb2_task_create(const char* plan_text, const char* config, char* err, int32_t errlen) {
+  vb2_task* t = nullptr;
+  const int32_t rc = guarded(err, errlen, [&] {
+    registerB200();
+    std::unordered_map<std::string, std::string> kv;
+    if (config) {
+      std::stringstream ss(config);
+      std::string item;
+      while (std::getline(ss, item, ';')) {
+        const auto eq = item.find('=');
+        if (eq != std::string::npos) kv[item.substr(0, eq)] = item.substr(eq + 1);
+      }
+    }
+    auto task = std::make_unique<vb2_task>();
+    task->plan = parsePlanText(plan_text ? plan_text : "");
+    task->task = std::make_shared<exec::Task>(task->plan, core::QueryConfig(std::move(kv)));
+    t = task.release();
+  });
+  return rc == VB2_OK ? t : nullptr;
+}
+
+int32_t vb2_task_add_input(vb2_task* task, int32_t source_id, const vb2_column* cols, int32_t ncols, int64_t rows,
+                           int32_t location, char* err, int32_t errlen) {
+  return guarded(err, errlen, [&] {
+    VELOX_CHECK(task && cols, "null task or columns");
+    VELOX_CHECK(rows >= 0 && rows < (1ll << 31), "a batch holds fewer than 2^31 rows (vector_size_t, velox/vector/TypeAliases.h:29)");
+    std::vector<std::string> names;
+    std::vector<TypePtr> types;
+    for (int32_t c = 0; c < ncols; ++c) { names.push_back("c" + std::to_string(c)); types.push_back(typeOf(cols[c].type)); }
+    RowTypePtr type = ROW(names, types);
+    if (rows == 0) return;
+    if (location == VB2_DEVICE) {
+      std::vector<DeviceColumnPtr> dc;
+      for (int32_t c = 0; c < ncols; ++c) dc.push_back(importDeviceColumn(cols[c], rows));
+      task->task->addInput(source_id, std::make_shared<B200Vector>(&task->pool, type, static_cast<vector_size_t>(rows), std::move(dc), nullptr));
+    } else {
+      std::vector<VectorPtr> children;
+      for (int32_t c = 0; c < ncols; ++c) children.push_back(importHostColumn(&task->pool, cols[c], rows));
+      task->task->addInput(source_id, std::make_shared<RowVector>(&task->pool, type, nullptr, static_cast<vector_size_t>(rows), std::move(children)));
+    }
+  });
+}
+
+int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen) {
+  return guarded(err, errlen, [&] {
+    VELOX_CHECK(task != nullptr, "null task");
+    task->results = task->task->run();
+    task->out.clear();
+    task->rows = 0;
+    for (auto& b : task->results) appendResult(*task, b);
+    if (task->out.empty()) {
+      const auto& type = task->plan->outputType();
+      task->out.resize(type->size());
+      for (uint32_t c = 0; c < type->size(); ++c) { task->out[c].type = veloxTypeToVb2(type->childAt(c)); task->out[c].offsets.push_back(0); }
+    }
+    std::ostringstream os;
+    for (auto& kv : task->task->stats()) os << kv.first << "=" << kv.second << "\n";
+    task->stats = os.str();
+    task->results.clear();
+  });
+}
+
+int64_t vb2_result_rows(vb2_task* task) { return task->rows; }
+int32_t vb2_result_cols(vb2_task* task) { return static_cast<int32_t>(task->out.size()); }
+int32_t vb2_result_type(vb2_task* task, int32_t col) { return task->out[col].type; }
+void vb2_result_copy(vb2_task* task, int32_t col, void* values, uint8_t* nulls) {
+  auto& o = task->out[col];
+  if (values && !o.values.empty()) std::memcpy(values, o.values.data(), o.values.size());
+  if (nulls && !o.nulls.empty()) std::memcpy(nulls, o.nulls.data(), o.nulls.size());
+}
+int64_t vb2_result_str_bytes(vb2_task* task, int32_t col) { return static_cast<int64_t>(task->out[col].chars.size()); }
+void vb2_result_copy_str(vb2_task* task, int32_t col, int32_t* offsets, char* chars, uint8_t* nulls) {
+  auto& o = task->out[col];
+  std::memcpy(offsets, o.offsets.data(), o.offsets.size() * 4);
+  if (!o.chars.empty()) std::memcpy(chars, o.chars.data(), o.chars.size());
+  if (nulls && !o.nulls.empty()) std::memcpy(nulls, o.nulls.data(), o.nulls.size());
+}
+const char* vb2_task_stats(vb2_task* task) { return task->stats.c_str(); }
+void vb2_task_free(vb2_task* task) { delete task; }
+
+}  // extern "C"

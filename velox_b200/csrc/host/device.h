@@ -1,0 +1,98 @@
+// Device-resident vectors and host<->device conversion for the B200 operators.
+//
+// Pattern of the reference's GPU backends: a RowVector subclass that owns device buffers
+// (velox/experimental/cudf/vector/CudfVector.h:43) and a pair of conversion operators inserted
+// at CPU/GPU seams (velox/experimental/cudf/exec/CudfConversion.h:32,67).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/velox_b200_kernels.h"
+#include "../../abi/exec_abi.h"
+
+namespace velox_b200 {
+
+using namespace facebook::velox;
+
+void cudaCheck(cudaError_t e, const char* what);
+void kernelCheck(int rc);  // VB2_ERR_USER -> VeloxUserError, others -> VeloxRuntimeError
+#define VB2_CU(expr) ::velox_b200::cudaCheck((expr), #expr)
+
+// Stream-ordered allocation: cudaMallocAsync on the driver's stream, freed on the same stream.
+class DeviceBuffer {
+ public:
+  DeviceBuffer(size_t bytes, cudaStream_t stream);
+  DeviceBuffer(void* borrowed, size_t bytes) : ptr_(borrowed), bytes_(bytes), stream_(nullptr), owned_(false) {}
+  ~DeviceBuffer();
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  template <class T> T* as() const { return reinterpret_cast<T*>(ptr_); }
+  void* data() const { return ptr_; }
+  size_t size() const { return bytes_; }
+
+ private:
+  void* ptr_ = nullptr;
+  size_t bytes_ = 0;
+  cudaStream_t stream_;
+  bool owned_ = true;
+};
+using DeviceBufferPtr = std::shared_ptr<DeviceBuffer>;
+DeviceBufferPtr allocDevice(size_t bytes, cudaStream_t stream);
+DeviceBufferPtr allocDeviceZeroed(size_t bytes, cudaStream_t stream);
+
+// Host copy of a small dictionary's values (VARCHAR alphabets of flags / types): the planner-side
+// metadata needed to assign value ids to group keys and to evaluate build-side predicates.
+struct HostAlphabet {
+  std::vector<std::string> values;
+  std::vector<bool> nulls;
+};
+
+struct DeviceColumn {
+  TypePtr type;
+  vb2_column desc{};                    // device pointers
+  std::vector<DeviceBufferPtr> owners;  // buffers referenced by desc
+  std::shared_ptr<const HostAlphabet> alphabet;  // DICTIONARY / CONSTANT VARCHAR only
+  bool mayHaveNulls() const { return desc.nulls != nullptr || desc.dict_nulls != nullptr; }
+};
+using DeviceColumnPtr = std::shared_ptr<DeviceColumn>;
+
+// A batch resident in HBM. children() is empty: the columns live on the device.
+class B200Vector : public RowVector {
+ public:
+  B200Vector(memory::MemoryPool* pool, TypePtr type, vector_size_t size, std::vector<DeviceColumnPtr> cols, cudaStream_t stream)
+      : RowVector(pool, std::move(type), nullptr, size, {}), cols_(std::move(cols)), stream_(stream) {}
+  const std::vector<DeviceColumnPtr>& columns() const { return cols_; }
+  const DeviceColumnPtr& column(size_t i) const { return cols_.at(i); }
+  cudaStream_t stream() const { return stream_; }
+
+ private:
+  std::vector<DeviceColumnPtr> cols_;
+  cudaStream_t stream_;
+};
+using B200VectorPtr = std::shared_ptr<B200Vector>;
+
+// Host RowVector -> device. Flat fixed-width children are one cudaMemcpyAsync each (the vector's
+// own buffer is the source: pinned memory gives a true asynchronous DMA); StringView children are
+// first rewritten to offsets + chars on the host (pointers cannot be followed by the device).
+B200VectorPtr toDevice(const RowVectorPtr& host, cudaStream_t stream);
+// Device -> host RowVector (synchronises the stream).
+RowVectorPtr toHost(const B200VectorPtr& dev);
+
+// Wraps externally owned device memory (e.g. columns already resident in HBM) without copying.
+DeviceColumnPtr borrowFlatColumn(TypePtr type, const void* values, int64_t size);
+
+// One stream + small scratch per driver.
+struct DeviceContext {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DeviceContext();
+  ~DeviceContext();
+};
+std::shared_ptr<DeviceContext> driverDeviceContext(exec::DriverCtx* ctx);
+
+int32_t veloxTypeToVb2(const TypePtr& t);
+int32_t widthOf(int32_t vb2Type);
+
+}  // namespace velox_b200

@@ -1,0 +1,372 @@
+// B200HashBuild / B200HashProbe and the key-normalisation helpers shared with aggregation.
+#include "join.h"
+
+namespace velox_b200 {
+
+void columnMinMax(const DeviceColumn& col, int64_t rows, cudaStream_t stream, int64_t& lo, int64_t& hi, int64_t& nonNull) {
+  auto out = allocDevice(24, stream);
+  kernelCheck(vb2k_column_minmax(&col.desc, rows, out->as<int64_t>(), stream));
+  int64_t h[3];
+  VB2_CU(cudaMemcpyAsync(h, out->data(), 24, cudaMemcpyDeviceToHost, stream));
+  VB2_CU(cudaStreamSynchronize(stream));
+  lo = h[0];
+  hi = h[1];
+  nonNull = h[2];
+}
+
+NormalizedKeys normalizeKeys(const B200Vector& batch, const std::vector<int32_t>& keyColumns, const KeyLayout& layout,
+                             const int32_t* sel, int64_t n, bool forJoin, cudaStream_t stream) {
+  std::vector<vb2_column> cols;
+  for (int32_t k : keyColumns) cols.push_back(batch.column(k)->desc);
+  NormalizedKeys out;
+  out.keys = allocDevice(static_cast<size_t>(n) * 8, stream);
+  if (forJoin) out.valid = allocDevice(bits::nbytes(n), stream);
+  kernelCheck(vb2k_normalize_keys(cols.data(), static_cast<int32_t>(cols.size()), layout.mins.data(), layout.mults.data(),
+                                  forJoin ? layout.ranges.data() : nullptr, forJoin ? 1 : 0, sel, n, out.keys->as<uint64_t>(),
+                                  forJoin ? out.valid->as<uint64_t>() : nullptr, stream));
+  return out;
+}
+
+B200VectorPtr concatBatches(const std::vector<B200VectorPtr>& batches, memory::MemoryPool* pool, cudaStream_t stream) {
+  VELOX_CHECK(!batches.empty(), "concatBatches: no input");
+  if (batches.size() == 1) return batches[0];
+  int64_t total = 0;
+  for (auto& b : batches) total += b->size();
+  VELOX_CHECK(total < (1ll << 31), "build side above 2^31 rows");
+  const size_t ncols = batches[0]->columns().size();
+  std::vector<DeviceColumnPtr> cols;
+  for (size_t c = 0; c < ncols; ++c) {
+    const auto& first = batches[0]->column(c);
+    auto col = std::make_shared<DeviceColumn>();
+    col->type = first->type;
+    col->desc.type = first->desc.type;
+    col->desc.size = total;
+    if (first->desc.type == VB2_VARCHAR) {
+      // VARCHAR: only dictionary columns over one shared alphabet can be concatenated without
+      // touching characters (indices are concatenated, the base is kept)
+      bool sameBase = first->desc.encoding == VB2_DICTIONARY;
+      for (auto& b : batches) sameBase = sameBase && b->column(c)->desc.encoding == VB2_DICTIONARY && b->column(c)->desc.values == first->desc.values;
+      if (!sameBase) VELOX_UNSUPPORTED("multi-batch build side with VARCHAR columns that do not share one dictionary");
+      *col = *first;
+      col->desc.size = total;
+      auto idx = allocDevice(static_cast<size_t>(total) * 4, stream);
+      int64_t off = 0;
+      bool anyNulls = false;
+      for (auto& b : batches) anyNulls = anyNulls || b->column(c)->desc.nulls;
+      if (anyNulls) VELOX_UNSUPPORTED("multi-batch VARCHAR build column with wrapper nulls");
+      for (auto& b : batches) {
+        VB2_CU(cudaMemcpyAsync(idx->as<int32_t>() + off, b->column(c)->desc.indices, static_cast<size_t>(b->size()) * 4, cudaMemcpyDeviceToDevice, stream));
+        off += b->size();
+      }
+      col->desc.indices = idx->as<int32_t>();
+      col->owners.push_back(idx);
+      cols.push_back(col);
+      continue;
+    }
+    col->desc.encoding = VB2_FLAT;
+    const int t = first->desc.type;
+    const int w = widthOf(t);
+    bool anyNulls = false;
+    for (auto& b : batches) anyNulls = anyNulls || b->column(c)->mayHaveNulls();
+    if (t == VB2_BOOLEAN) VELOX_UNSUPPORTED("multi-batch build side with BOOLEAN columns");
+    auto values = allocDevice(static_cast<size_t>(total) * w, stream);
+    DeviceBufferPtr nulls;
+    if (anyNulls) VELOX_UNSUPPORTED("multi-batch build side with NULLs (single-batch builds support them)");
+    int64_t off = 0;
+    for (auto& b : batches) {
+      FlatColumn f = flattenColumn(b->column(c), nullptr, b->size(), stream);
+      VB2_CU(cudaMemcpyAsync(values->as<uint8_t>() + off * w, f.values->data(), static_cast<size_t>(b->size()) * w, cudaMemcpyDeviceToDevice, stream));
+      off += b->size();
+    }
+    col->desc.values = values->data();
+    col->owners = {values};
+    cols.push_back(col);
+  }
+  return std::make_shared<B200Vector>(pool, batches[0]->type(), static_cast<vector_size_t>(total), std::move(cols), stream);
+}
+
+// ---- B200HashBuild ----------------------------------------------------------------------------
+B200HashBuild::B200HashBuild(int32_t id, exec::DriverCtx* ctx, const exec::HashBuild& cpu)
+    : Operator(ctx, nullptr, id, cpu.planNodeId(), "B200HashBuild"), node_(cpu.node()), bridge_(cpu.joinBridge()) {}
+
+void B200HashBuild::initialize() {
+  Operator::initialize();
+  dev_ = driverDeviceContext(driverCtx_);
+}
+
+void B200HashBuild::addInput(RowVectorPtr input) {
+  auto in = std::dynamic_pointer_cast<B200Vector>(input);
+  VELOX_CHECK(in != nullptr, "B200HashBuild expects device-resident input");
+  batches_.push_back(std::move(in));
+}
+
+namespace {
+uint64_t nextPow2(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+}  // namespace
+
+void B200HashBuild::noMoreInput() {
+  Operator::noMoreInput();
+  cudaStream_t st = dev_->stream;
+  auto holder = std::make_shared<JoinTableHolder>();
+  holder->stream = st;
+  const auto& keys = node_->rightKeys();
+  const auto& buildType = node_->sources()[1]->outputType();
+  for (int32_t k : keys) {
+    const TypeKind kind = buildType->childAt(k)->kind();
+    if (kind != TypeKind::BIGINT && kind != TypeKind::INTEGER && kind != TypeKind::BOOLEAN)
+      VELOX_UNSUPPORTED("join keys of type " + buildType->childAt(k)->toString() + " (BIGINT/INTEGER/DATE/BOOLEAN are supported)");
+  }
+  if (batches_.empty()) {
+    // empty build side: a table nobody can hit
+    holder->layout.mins.assign(keys.size(), 0);
+    holder->layout.ranges.assign(keys.size(), 1);
+    holder->layout.mults.assign(keys.size(), 1);
+    holder->table.mode = 0;
+    holder->table.capacity = 1;
+    auto head = allocDeviceZeroed(4, st);
+    auto next = allocDeviceZeroed(4, st);
+    holder->table.head = head->as<int32_t>();
+    holder->table.next = next->as<int32_t>();
+    holder->owners = {head, next};
+    bridge_->setHashTable(holder);
+    return;
+  }
+  holder->rows = concatBatches(batches_, pool(), st);
+  batches_.clear();
+  const int64_t n = holder->rows->size();
+  holder->numRows = n;
+  // value ranges of the key columns -> layout (VectorHasher range mode, exec/VectorHasher.cpp:923)
+  KeyLayout& lay = holder->layout;
+  uint64_t product = 1;
+  bool overflow = false;
+  for (int32_t k : keys) {
+    int64_t lo, hi, nn;
+    columnMinMax(*holder->rows->column(k), n, st, lo, hi, nn);
+    if (nn == 0) { lo = 0; hi = 0; }
+    const unsigned __int128 range = static_cast<unsigned __int128>(static_cast<__int128>(hi) - lo) + 2;  // + NULL id
+    lay.mins.push_back(lo);
+    if (range > (static_cast<unsigned __int128>(1) << 62)) overflow = true;
+    lay.ranges.push_back(static_cast<uint64_t>(range));
+    if (!overflow) {
+      const unsigned __int128 p = static_cast<unsigned __int128>(product) * range;
+      if (p > (static_cast<unsigned __int128>(1) << 62)) overflow = true;
+      else product = static_cast<uint64_t>(p);
+    }
+  }
+  if (overflow) VELOX_UNSUPPORTED("join key ranges do not fit one 64-bit normalized key");
+  lay.product = product;
+  lay.mults.assign(keys.size(), 1);
+  for (int i = static_cast<int>(keys.size()) - 2; i >= 0; --i) lay.mults[i] = lay.mults[i + 1] * lay.ranges[i + 1];
+
+  NormalizedKeys nk = normalizeKeys(*holder->rows, keys, lay, nullptr, n, true, st);
+  // Array mode while the packed key space is at most 16x the row count and <= 2^28 slots: the
+  // reference caps kArray at 2M entries for CPU caches (exec/HashTable.h:146); HBM + a 126 MB L2
+  // move that limit (a 20 M-slot int32 table is 80 MB and stays L2 resident).
+  vb2_join_table& t = holder->table;
+  const uint64_t arrayLimit = std::min<uint64_t>(1ull << 28, std::max<uint64_t>(1ull << 16, static_cast<uint64_t>(n) * 16));
+  if (product <= arrayLimit) {
+    t.mode = 0;
+    t.key_min = 0;
+    t.capacity = static_cast<int64_t>(product);
+  } else {
+    t.mode = 1;
+    t.capacity = static_cast<int64_t>(nextPow2(static_cast<uint64_t>(n) * 2 + 16));
+    auto keysBuf = allocDevice(static_cast<size_t>(t.capacity) * 8, st);
+    kernelCheck(vb2k_fill_u64(keysBuf->as<uint64_t>(), t.capacity, VB2_EMPTY_KEY, st));
+    t.keys = keysBuf->as<uint64_t>();
+    holder->owners.push_back(keysBuf);
+  }
+  auto head = allocDeviceZeroed(static_cast<size_t>(t.capacity) * 4, st);
+  auto next = allocDeviceZeroed(static_cast<size_t>(n) * 4 + 4, st);
+  t.head = head->as<int32_t>();
+  t.next = next->as<int32_t>();
+  t.build_rows = n;
+  holder->owners.push_back(head);
+  holder->owners.push_back(next);
+  auto flags = allocDeviceZeroed(8, st);
+  kernelCheck(vb2k_join_build(&t, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, flags->as<int32_t>(), st));
+  int32_t h[2];
+  VB2_CU(cudaMemcpyAsync(h, flags->data(), 8, cudaMemcpyDeviceToHost, st));
+  VB2_CU(cudaStreamSynchronize(st));
+  VELOX_CHECK(h[0] == 0, "join table build failed (table full)");
+  holder->hasDuplicateKeys = h[1] != 0;
+  addRuntimeStat("b200.joinTableMode", exec::RuntimeCounter{t.mode});
+  addRuntimeStat("b200.joinTableSlots", exec::RuntimeCounter{t.capacity});
+  bridge_->setHashTable(holder);
+}
+
+// ---- B200HashProbe ----------------------------------------------------------------------------
+B200HashProbe::B200HashProbe(int32_t id, exec::DriverCtx* ctx, const exec::HashProbe& cpu)
+    : Operator(ctx, cpu.outputType(), id, cpu.planNodeId(), "B200HashProbe"), node_(cpu.node()), bridge_(cpu.joinBridge()) {
+  if (node_->filter()) {
+    std::vector<std::string> names = node_->sources()[0]->outputType()->names();
+    std::vector<TypePtr> types = node_->sources()[0]->outputType()->children();
+    const auto& bt = node_->sources()[1]->outputType();
+    for (uint32_t i = 0; i < bt->size(); ++i) { names.push_back("b_" + bt->nameOf(i)); types.push_back(bt->childAt(i)); }
+    filterProgram_ = std::make_unique<CompiledProgram>(compileExprs({node_->filter()}, true, ROW(names, types)));
+  }
+}
+
+void B200HashProbe::initialize() {
+  Operator::initialize();
+  dev_ = driverDeviceContext(driverCtx_);
+  errorFlag_ = allocDeviceZeroed(8, dev_->stream);
+  if (filterProgram_) filterProgram_->uploadConstants(dev_->stream);
+}
+
+exec::BlockingReason B200HashProbe::isBlocked(exec::ContinueFuture* future) {
+  if (table_) return exec::BlockingReason::kNotBlocked;
+  auto t = bridge_->tableOrFuture(future);
+  if (!t) return exec::BlockingReason::kWaitForJoinBuild;
+  table_ = std::static_pointer_cast<JoinTableHolder>(t);
+  return exec::BlockingReason::kNotBlocked;
+}
+
+B200VectorPtr B200HashProbe::apply(const B200VectorPtr& in) {
+  cudaStream_t st = dev_->stream;
+  const int64_t n = in->size();
+  const JoinTableHolder& jt = *table_;
+  const core::JoinType type = node_->joinType();
+  // build and probe streams differ only across drivers; the bridge hand-off synchronised the build
+  NormalizedKeys nk = normalizeKeys(*in, node_->leftKeys(), jt.layout, nullptr, n, true, st);
+  auto counts = allocDevice(static_cast<size_t>(n) * 4, st);
+  kernelCheck(vb2k_join_probe_count(&jt.table, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, counts->as<int32_t>(), st));
+  auto offsets = allocDevice(static_cast<size_t>(n) * 8, st);
+  auto total = allocDevice(8, st);
+  const size_t wsBytes = vb2k_scan_workspace(n);
+  auto ws = allocDevice(wsBytes, st);
+  kernelCheck(vb2k_exclusive_scan_i32(counts->as<int32_t>(), n, offsets->as<int64_t>(), total->as<int64_t>(), ws->data(), wsBytes, st));
+  int64_t pairs = 0;
+  VB2_CU(cudaMemcpyAsync(&pairs, total->data(), 8, cudaMemcpyDeviceToHost, st));
+  VB2_CU(cudaStreamSynchronize(st));
+  VELOX_CHECK(pairs < (1ll << 31), "join output above 2^31 rows for one batch");
+  DeviceBufferPtr probeRows, buildRows;
+  if (pairs > 0) {
+    probeRows = allocDevice(static_cast<size_t>(pairs) * 4, st);
+    buildRows = allocDevice(static_cast<size_t>(pairs) * 4, st);
+    kernelCheck(vb2k_join_probe_emit(&jt.table, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, offsets->as<int64_t>(),
+                                     probeRows->as<int32_t>(), buildRows->as<int32_t>(), st));
+  }
+  // optional join filter over (probe ++ build) columns of the candidate pairs
+  if (filterProgram_ && pairs > 0) {
+    std::vector<vb2_column> cols;
+    std::vector<DeviceColumnPtr> keep;
+    for (auto& c : in->columns()) { keep.push_back(wrapColumn(c, probeRows, pairs, st)); cols.push_back(keep.back()->desc); }
+    for (auto& c : jt.rows->columns()) { keep.push_back(wrapColumn(c, buildRows, pairs, st)); cols.push_back(keep.back()->desc); }
+    const vb2_program prog = filterProgram_->view();
+    auto bitsBuf = allocDevice(bits::nbytes(pairs), st);
+    kernelCheck(vb2k_eval_filter(&prog, cols.data(), static_cast<int32_t>(cols.size()), pairs, bitsBuf->as<uint64_t>(), errorFlag_->as<int32_t>(), st));
+    auto sel = allocDevice(static_cast<size_t>(pairs) * 4, st);
+    auto cnt = allocDevice(8, st);
+    const size_t w2 = vb2k_bits_to_indices_workspace(pairs);
+    auto ws2 = allocDevice(w2, st);
+    kernelCheck(vb2k_bits_to_indices(bitsBuf->as<uint64_t>(), pairs, sel->as<int32_t>(), cnt->as<int64_t>(), ws2->data(), w2, st));
+    int64_t kept = 0;
+    VB2_CU(cudaMemcpyAsync(&kept, cnt->data(), 8, cudaMemcpyDeviceToHost, st));
+    checkDeviceError(errorFlag_, st, "join filter");
+    if (kept != pairs) {
+      auto p2 = allocDevice(static_cast<size_t>(kept ? kept : 1) * 4, st);
+      auto b2 = allocDevice(static_cast<size_t>(kept ? kept : 1) * 4, st);
+      kernelCheck(vb2k_gather(probeRows->data(), sel->as<int32_t>(), kept, 4, p2->data(), st));
+      kernelCheck(vb2k_gather(buildRows->data(), sel->as<int32_t>(), kept, 4, b2->data(), st));
+      probeRows = p2;
+      buildRows = b2;
+      pairs = kept;
+    }
+  }
+  int64_t numOut = pairs;
+  DeviceBufferPtr outProbe = probeRows, outBuild = buildRows;
+  bool buildSideNull = false;
+  if (type != core::JoinType::kInner) {
+    // matched[r] = probe row r has at least one surviving pair
+    auto matched = allocDeviceZeroed(static_cast<size_t>(n) * 4 + 4, st);
+    if (pairs > 0) {
+      auto ones = allocDevice(static_cast<size_t>(pairs) * 4, st);
+      kernelCheck(vb2k_fill_i32(ones->as<int32_t>(), pairs, 1, st));
+      kernelCheck(vb2k_scatter(ones->data(), nullptr, probeRows->as<int32_t>(), pairs, 4, matched->data(), st));
+    }
+    if (type == core::JoinType::kLeft) {
+      // unmatched probe rows appended after the matches (multiset semantics; build side NULL)
+      auto missBits = allocDevice(bits::nbytes(n), st);
+      auto m64 = allocDevice(static_cast<size_t>(n) * 8, st);
+      kernelCheck(vb2k_widen_not_i32(matched->as<int32_t>(), n, m64->as<int64_t>(), st));
+      kernelCheck(vb2k_positive_bits(m64->as<int64_t>(), n, missBits->as<uint64_t>(), st));
+      auto missIdx = allocDevice(static_cast<size_t>(n) * 4, st);
+      auto cnt = allocDevice(8, st);
+      const size_t w3 = vb2k_bits_to_indices_workspace(n);
+      auto ws3 = allocDevice(w3, st);
+      kernelCheck(vb2k_bits_to_indices(missBits->as<uint64_t>(), n, missIdx->as<int32_t>(), cnt->as<int64_t>(), ws3->data(), w3, st));
+      int64_t misses = 0;
+      VB2_CU(cudaMemcpyAsync(&misses, cnt->data(), 8, cudaMemcpyDeviceToHost, st));
+      VB2_CU(cudaStreamSynchronize(st));
+      numOut = pairs + misses;
+      if (numOut == 0) return nullptr;
+      outProbe = allocDevice(static_cast<size_t>(numOut) * 4, st);
+      outBuild = allocDevice(static_cast<size_t>(numOut) * 4, st);
+      if (pairs) {
+        VB2_CU(cudaMemcpyAsync(outProbe->data(), probeRows->data(), static_cast<size_t>(pairs) * 4, cudaMemcpyDeviceToDevice, st));
+        VB2_CU(cudaMemcpyAsync(outBuild->data(), buildRows->data(), static_cast<size_t>(pairs) * 4, cudaMemcpyDeviceToDevice, st));
+      }
+      if (misses) {
+        VB2_CU(cudaMemcpyAsync(outProbe->as<int32_t>() + pairs, missIdx->data(), static_cast<size_t>(misses) * 4, cudaMemcpyDeviceToDevice, st));
+        kernelCheck(vb2k_fill_i32(outBuild->as<int32_t>() + pairs, misses, -1, st));
+        buildSideNull = true;
+      }
+    } else {
+      // semi: matched probe rows once; anti: unmatched probe rows
+      auto m64 = allocDevice(static_cast<size_t>(n) * 8, st);
+      if (type == core::JoinType::kAnti) kernelCheck(vb2k_widen_not_i32(matched->as<int32_t>(), n, m64->as<int64_t>(), st));
+      else kernelCheck(vb2k_widen_i32(matched->as<int32_t>(), n, m64->as<int64_t>(), st));
+      auto bitsBuf = allocDevice(bits::nbytes(n), st);
+      kernelCheck(vb2k_positive_bits(m64->as<int64_t>(), n, bitsBuf->as<uint64_t>(), st));
+      auto idx = allocDevice(static_cast<size_t>(n) * 4, st);
+      auto cnt = allocDevice(8, st);
+      const size_t w3 = vb2k_bits_to_indices_workspace(n);
+      auto ws3 = allocDevice(w3, st);
+      kernelCheck(vb2k_bits_to_indices(bitsBuf->as<uint64_t>(), n, idx->as<int32_t>(), cnt->as<int64_t>(), ws3->data(), w3, st));
+      VB2_CU(cudaMemcpyAsync(&numOut, cnt->data(), 8, cudaMemcpyDeviceToHost, st));
+      VB2_CU(cudaStreamSynchronize(st));
+      outProbe = idx;
+      outBuild = nullptr;
+    }
+  }
+  if (numOut == 0) return nullptr;
+  DeviceBufferPtr buildValid;
+  if (buildSideNull) {
+    // rows with build index -1 are NULL on the build side: validity = index >= 0, indices clamped to 0
+    buildValid = allocDevice(bits::nbytes(numOut), st);
+    auto clamped = allocDevice(static_cast<size_t>(numOut) * 4, st);
+    kernelCheck(vb2k_index_validity(outBuild->as<int32_t>(), numOut, buildValid->as<uint64_t>(), clamped->as<int32_t>(), st));
+    outBuild = clamped;
+  }
+  std::vector<DeviceColumnPtr> outCols;
+  for (auto& o : node_->outputs()) {
+    if (o.fromProbe) {
+      outCols.push_back(wrapColumn(in->column(o.column), outProbe, numOut, st));
+    } else {
+      VELOX_CHECK(outBuild != nullptr, "semi/anti joins project probe columns only");
+      auto col = wrapColumn(jt.rows->column(o.column), outBuild, numOut, st);
+      if (buildSideNull) {
+        if (col->desc.encoding == VB2_CONSTANT || col->desc.nulls) VELOX_UNSUPPORTED("left join over a constant / null-wrapped build column");
+        col->desc.nulls = buildValid->as<uint64_t>();
+        col->owners.push_back(buildValid);
+      }
+      outCols.push_back(col);
+    }
+  }
+  return std::make_shared<B200Vector>(pool(), outputType_, static_cast<vector_size_t>(numOut), std::move(outCols), st);
+}
+
+RowVectorPtr B200HashProbe::getOutput() {
+  if (!input_) return nullptr;
+  auto in = std::dynamic_pointer_cast<B200Vector>(input_);
+  input_ = nullptr;
+  VELOX_CHECK(in != nullptr, "B200HashProbe expects device-resident input");
+  return apply(in);
+}
+
+}  // namespace velox_b200

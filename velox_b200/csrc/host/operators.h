@@ -1,0 +1,153 @@
+// B200 operators behind the exec::Operator contract (velox/exec/Operator.h:232-342). Each class
+// states the reference operator it replaces. Installation: registerB200() (adapter.cpp).
+#pragma once
+#include <unordered_map>
+
+#include "device.h"
+#include "expr_compiler.h"
+
+namespace velox_b200 {
+
+// Throws VeloxUserError for the first data error a kernel recorded (integer overflow, division
+// by zero, failed cast). Synchronises the stream.
+void checkDeviceError(const DeviceBufferPtr& flag, cudaStream_t stream, const char* where);
+std::vector<vb2_column> describe(const B200Vector& v);
+// Zero-copy selection of rows sel[0..n) of `col` (dictionary wrap; exec/OperatorUtils.cpp:380 wrapChild).
+DeviceColumnPtr wrapColumn(const DeviceColumnPtr& col, const DeviceBufferPtr& sel, int64_t n, cudaStream_t stream);
+// Dense flat copy of (possibly wrapped) rows: values + validity bitmap (null when no nulls possible).
+struct FlatColumn {
+  DeviceBufferPtr values, nulls;
+  int32_t type;
+};
+FlatColumn flattenColumn(const DeviceColumnPtr& col, const int32_t* sel, int64_t n, cudaStream_t stream);
+
+// Host RowVector -> device batch (velox/experimental/cudf/exec/CudfConversion.h:32 CudfFromVelox).
+class B200FromHost : public exec::Operator {
+ public:
+  B200FromHost(int32_t id, exec::DriverCtx* ctx, RowTypePtr type) : Operator(ctx, std::move(type), id, "b200-from-host", "B200FromHost") {}
+  void initialize() override;
+  bool needsInput() const override { return !noMoreInput_ && !input_; }
+  void addInput(RowVectorPtr input) override { input_ = std::move(input); }
+  RowVectorPtr getOutput() override;
+  exec::BlockingReason isBlocked(exec::ContinueFuture*) override { return exec::BlockingReason::kNotBlocked; }
+  bool isFinished() override { return noMoreInput_ && !input_; }
+
+ private:
+  std::shared_ptr<DeviceContext> dev_;
+  std::vector<RowVectorPtr> inFlight_;  // host batches whose copies may still be running
+};
+
+// Device batch -> host RowVector (CudfConversion.h:67 CudfToVelox).
+class B200ToHost : public exec::Operator {
+ public:
+  B200ToHost(int32_t id, exec::DriverCtx* ctx, RowTypePtr type) : Operator(ctx, std::move(type), id, "b200-to-host", "B200ToHost") {}
+  bool needsInput() const override { return !noMoreInput_ && !input_; }
+  void addInput(RowVectorPtr input) override { input_ = std::move(input); }
+  RowVectorPtr getOutput() override;
+  exec::BlockingReason isBlocked(exec::ContinueFuture*) override { return exec::BlockingReason::kNotBlocked; }
+  bool isFinished() override { return noMoreInput_ && !input_; }
+};
+
+// Replaces exec::FilterProject (velox/exec/FilterProject.cpp:200-259): filter, then project the
+// surviving rows; identity columns are dictionary-wrapped over the selection, computed columns
+// are written densely. One VM kernel for the filter, one for all projections.
+class B200FilterProject : public exec::Operator {
+ public:
+  B200FilterProject(int32_t id, exec::DriverCtx* ctx, const exec::FilterProject& cpu);
+  void initialize() override;
+  bool needsInput() const override { return !noMoreInput_ && !input_; }
+  void addInput(RowVectorPtr input) override { input_ = std::move(input); }
+  RowVectorPtr getOutput() override;
+  exec::BlockingReason isBlocked(exec::ContinueFuture*) override { return exec::BlockingReason::kNotBlocked; }
+  bool isFinished() override { return noMoreInput_ && !input_; }
+  // used by fused operators that absorb this one
+  B200VectorPtr apply(const B200VectorPtr& in);
+  const std::vector<core::TypedExprPtr>& exprs() const { return exprs_; }
+  bool hasFilter() const { return hasFilter_; }
+  const RowTypePtr& inputType() const { return inputType_; }
+
+ private:
+  std::vector<core::TypedExprPtr> exprs_;
+  bool hasFilter_;
+  RowTypePtr inputType_;
+  CompiledProgram program_;
+  std::shared_ptr<DeviceContext> dev_;
+  DeviceBufferPtr errorFlag_;
+};
+
+// ---- aggregation ----------------------------------------------------------------------------------
+struct JoinTableHolder;  // join.cpp
+
+// Replaces exec::HashAggregation / GroupingSet / HashTable(group by) / RowContainer / Aggregate
+// (velox/exec/HashAggregation.cpp:191-430, GroupingSet.cpp:190-884). Optionally absorbs the
+// operators feeding it (FilterProject [-> HashProbe -> FilterProject]); when the absorbed
+// expressions match an ahead-of-time fused pipeline and the batch is null-free flat data, the
+// whole chain runs as one fused scan kernel, otherwise batch-by-batch through the same operators'
+// generic kernels. Both paths update the same group layout.
+class B200HashAggregation : public exec::Operator {
+ public:
+  B200HashAggregation(int32_t id, exec::DriverCtx* ctx, std::shared_ptr<const core::AggregationNode> node,
+                      std::vector<std::unique_ptr<exec::Operator>> absorbed);
+  ~B200HashAggregation() override;
+  void initialize() override;
+  bool needsInput() const override { return !noMoreInput_; }
+  void addInput(RowVectorPtr input) override;
+  void noMoreInput() override;
+  RowVectorPtr getOutput() override;
+  exec::BlockingReason isBlocked(exec::ContinueFuture* future) override;
+  bool isFinished() override { return finished_; }
+
+ private:
+  struct Impl;
+  std::unique_ptr<Impl> impl_;
+  bool finished_ = false;
+};
+
+// Replaces exec::HashBuild (velox/exec/HashBuild.cpp:442-598,819-993): collects the build side on
+// the device, builds the join table at noMoreInput and publishes it on the HashJoinBridge.
+class B200HashBuild : public exec::Operator {
+ public:
+  B200HashBuild(int32_t id, exec::DriverCtx* ctx, const exec::HashBuild& cpu);
+  void initialize() override;
+  bool needsInput() const override { return !noMoreInput_; }
+  void addInput(RowVectorPtr input) override;
+  void noMoreInput() override;
+  RowVectorPtr getOutput() override { return nullptr; }
+  exec::BlockingReason isBlocked(exec::ContinueFuture*) override { return exec::BlockingReason::kNotBlocked; }
+  bool isFinished() override { return noMoreInput_; }
+
+ private:
+  std::shared_ptr<const core::HashJoinNode> node_;
+  std::shared_ptr<exec::HashJoinBridge> bridge_;
+  std::shared_ptr<DeviceContext> dev_;
+  std::vector<B200VectorPtr> batches_;
+};
+
+// Replaces exec::HashProbe (velox/exec/HashProbe.cpp:796-900,1189-1437).
+class B200HashProbe : public exec::Operator {
+ public:
+  B200HashProbe(int32_t id, exec::DriverCtx* ctx, const exec::HashProbe& cpu);
+  void initialize() override;
+  bool needsInput() const override { return !noMoreInput_ && !input_; }
+  void addInput(RowVectorPtr input) override { input_ = std::move(input); }
+  RowVectorPtr getOutput() override;
+  exec::BlockingReason isBlocked(exec::ContinueFuture* future) override;
+  bool isFinished() override { return noMoreInput_ && !input_; }
+  B200VectorPtr apply(const B200VectorPtr& in);
+  const std::shared_ptr<const core::HashJoinNode>& node() const { return node_; }
+  std::shared_ptr<JoinTableHolder> table() const { return table_; }
+
+ private:
+  std::shared_ptr<const core::HashJoinNode> node_;
+  std::shared_ptr<exec::HashJoinBridge> bridge_;
+  std::shared_ptr<JoinTableHolder> table_;
+  std::shared_ptr<DeviceContext> dev_;
+  std::unique_ptr<CompiledProgram> filterProgram_;
+  DeviceBufferPtr errorFlag_;
+};
+
+// Installs the DriverAdapter that swaps the CPU operators for the classes above and inserts
+// B200FromHost / B200ToHost at the seams (pattern: velox/experimental/cudf/exec/ToCudf.cpp:71-338).
+void registerB200();
+
+}  // namespace velox_b200

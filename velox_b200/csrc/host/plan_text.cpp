@@ -1,0 +1,326 @@
+// Reader for the plan text of the C ABI (vb2_task_create): builds core::PlanNode / ITypedExpr
+// trees — the structures a Velox application hands to Task::create. Grammar in DESIGN.md and
+// velox_b200/plan.py. (The CPU oracle has its own, independent reader.)
+#include "plan_text.h"
+
+#include <cctype>
+
+namespace velox_b200 {
+
+namespace {
+
+struct Tok {
+  enum Kind { LP, RP, ATOM, STR, END } kind;
+  std::string text;
+};
+
+class Lexer {
+ public:
+  explicit Lexer(const std::string& s) : sp_(&s) { advance(); }
+  const Tok& peek() const { return cur_; }
+  Tok take() {
+    Tok t = cur_;
+    advance();
+    return t;
+  }
+  void expect(Tok::Kind k, const char* what) {
+    if (cur_.kind != k) throw VeloxRuntimeError(std::string("plan text: expected ") + what + " near '" + cur_.text + "'");
+    advance();
+  }
+  std::string atom(const char* what) {
+    if (cur_.kind != Tok::ATOM) throw VeloxRuntimeError(std::string("plan text: expected ") + what + " near '" + cur_.text + "'");
+    return take().text;
+  }
+
+ private:
+  void advance() {
+    const std::string& s_ = *sp_;
+    while (p_ < s_.size() && std::isspace(static_cast<unsigned char>(s_[p_]))) ++p_;
+    if (p_ >= s_.size()) { cur_ = {Tok::END, ""}; return; }
+    const char c = s_[p_];
+    if (c == '(') { ++p_; cur_ = {Tok::LP, "("}; return; }
+    if (c == ')') { ++p_; cur_ = {Tok::RP, ")"}; return; }
+    if (c == '"') {
+      std::string out;
+      ++p_;
+      while (p_ < s_.size() && s_[p_] != '"') {
+        if (s_[p_] == '\\' && p_ + 1 < s_.size()) ++p_;
+        out.push_back(s_[p_++]);
+      }
+      if (p_ >= s_.size()) throw VeloxRuntimeError("plan text: unterminated string literal");
+      ++p_;
+      cur_ = {Tok::STR, out};
+      return;
+    }
+    size_t b = p_;
+    while (p_ < s_.size() && !std::isspace(static_cast<unsigned char>(s_[p_])) && s_[p_] != '(' && s_[p_] != ')') ++p_;
+    cur_ = {Tok::ATOM, s_.substr(b, p_ - b)};
+  }
+  const std::string* sp_;
+  size_t p_ = 0;
+  Tok cur_{Tok::END, ""};
+};
+
+TypePtr typeFromName(const std::string& n) {
+  if (n == "BOOLEAN") return BOOLEAN();
+  if (n == "INTEGER") return INTEGER();
+  if (n == "DATE") return DATE();
+  if (n == "BIGINT") return BIGINT();
+  if (n == "DOUBLE") return DOUBLE();
+  if (n == "VARCHAR") return VARCHAR();
+  throw VeloxRuntimeError("plan text: unknown type " + n);
+}
+
+bool isComparison(const std::string& f) { return f == "lt" || f == "lte" || f == "gt" || f == "gte" || f == "eq" || f == "neq"; }
+bool isArithmetic(const std::string& f) { return f == "plus" || f == "minus" || f == "multiply" || f == "divide" || f == "modulus"; }
+
+class Parser {
+ public:
+  explicit Parser(const std::string& text) : lex_(text) {}
+
+  core::PlanNodePtr plan() {
+    auto p = node();
+    if (lex_.peek().kind != Tok::END) throw VeloxRuntimeError("plan text: trailing input");
+    return p;
+  }
+
+ private:
+  std::string nextId() { return std::to_string(nextId_++); }
+
+  std::vector<int32_t> intList(const char* head) {
+    lex_.expect(Tok::LP, "(");
+    if (lex_.atom(head) != head) throw VeloxRuntimeError(std::string("plan text: expected (") + head + " ...)");
+    std::vector<int32_t> out;
+    while (lex_.peek().kind == Tok::ATOM) out.push_back(std::stoi(lex_.take().text));
+    lex_.expect(Tok::RP, ")");
+    return out;
+  }
+
+  core::TypedExprPtr expr(const RowTypePtr& in) {
+    lex_.expect(Tok::LP, "(");
+    const std::string h = lex_.atom("expression head");
+    core::TypedExprPtr out;
+    if (h == "field") {
+      const int i = std::stoi(lex_.atom("field index"));
+      if (i < 0 || i >= static_cast<int>(in->size())) throw VeloxRuntimeError("plan text: field index out of range");
+      out = std::make_shared<core::FieldAccessTypedExpr>(in->childAt(i), in->nameOf(i), i);
+    } else if (h == "f64") {
+      out = std::make_shared<core::ConstantTypedExpr>(DOUBLE(), Variant::of<double>(TypeKind::DOUBLE, std::stod(lex_.atom("number"))));
+    } else if (h == "i64") {
+      out = std::make_shared<core::ConstantTypedExpr>(BIGINT(), Variant::of<int64_t>(TypeKind::BIGINT, std::stoll(lex_.atom("number"))));
+    } else if (h == "i32" || h == "date") {
+      out = std::make_shared<core::ConstantTypedExpr>(h == "date" ? DATE() : INTEGER(),
+                                                      Variant::of<int32_t>(TypeKind::INTEGER, static_cast<int32_t>(std::stol(lex_.atom("number")))));
+    } else if (h == "bool") {
+      out = std::make_shared<core::ConstantTypedExpr>(BOOLEAN(), Variant::of<bool>(TypeKind::BOOLEAN, lex_.atom("true|false") == "true"));
+    } else if (h == "str") {
+      if (lex_.peek().kind != Tok::STR) throw VeloxRuntimeError("plan text: (str \"...\") expected");
+      out = std::make_shared<core::ConstantTypedExpr>(VARCHAR(), Variant::of<std::string>(TypeKind::VARCHAR, lex_.take().text));
+    } else if (h == "null") {
+      TypePtr t = typeFromName(lex_.atom("type"));
+      out = std::make_shared<core::ConstantTypedExpr>(t, Variant::null(t->kind()));
+    } else if (h == "cast") {
+      TypePtr t = typeFromName(lex_.atom("type"));
+      out = std::make_shared<core::CastTypedExpr>(t, expr(in));
+    } else {
+      std::vector<core::TypedExprPtr> args;
+      while (lex_.peek().kind == Tok::LP) args.push_back(expr(in));
+      TypePtr t;
+      auto need = [&](size_t n) { if (args.size() != n) throw VeloxRuntimeError("plan text: " + h + ": wrong argument count"); };
+      if (h == "and" || h == "or" || h == "not" || h == "is_null" || h == "like" || h == "between" || isComparison(h)) t = BOOLEAN();
+      else if (h == "switch" || h == "if") { if (args.size() < 2) throw VeloxRuntimeError("plan text: switch: too few arguments"); t = args[1]->type(); }
+      else if (isArithmetic(h)) { need(2); t = args[0]->type(); }
+      else if (h == "negate") { need(1); t = args[0]->type(); }
+      else throw VeloxRuntimeError("plan text: unknown function " + h);
+      out = std::make_shared<core::CallTypedExpr>(t, std::move(args), h);
+    }
+    lex_.expect(Tok::RP, ")");
+    return out;
+  }
+
+  core::PlanNodePtr node() {
+    lex_.expect(Tok::LP, "(");
+    const std::string h = lex_.atom("plan node");
+    core::PlanNodePtr out;
+    if (h == "values") {
+      const int src = std::stoi(lex_.atom("source id"));
+      lex_.expect(Tok::LP, "(");
+      std::vector<std::string> names;
+      std::vector<TypePtr> types;
+      while (lex_.peek().kind == Tok::ATOM) {
+        types.push_back(typeFromName(lex_.take().text));
+        names.push_back("c" + std::to_string(names.size()));
+      }
+      lex_.expect(Tok::RP, ")");
+      out = std::make_shared<core::ValuesNode>(nextId(), ROW(names, types), src);
+    } else if (h == "filter") {
+      // child follows the expression in the text but the expression needs the child's type:
+      // remember the position of the expression and parse the child first.
+      const Lexer saved = lex_;
+      skip();
+      auto child = node();
+      Lexer after = lex_;
+      lex_ = saved;
+      auto f = expr(child->outputType());
+      lex_ = after;
+      out = std::make_shared<core::FilterNode>(nextId(), f, child);
+    } else if (h == "project") {
+      const Lexer saved = lex_;
+      skip();
+      auto child = node();
+      Lexer after = lex_;
+      lex_ = saved;
+      lex_.expect(Tok::LP, "(");
+      std::vector<core::TypedExprPtr> exprs;
+      std::vector<std::string> names;
+      while (lex_.peek().kind == Tok::LP) {
+        exprs.push_back(expr(child->outputType()));
+        names.push_back("p" + std::to_string(names.size()));
+      }
+      lex_.expect(Tok::RP, ")");
+      lex_ = after;
+      out = std::make_shared<core::ProjectNode>(nextId(), names, exprs, child);
+    } else if (h == "aggregation") {
+      const std::string stepName = lex_.atom("step");
+      core::AggregationNode::Step step;
+      if (stepName == "single") step = core::AggregationNode::Step::kSingle;
+      else if (stepName == "partial") step = core::AggregationNode::Step::kPartial;
+      else if (stepName == "final") step = core::AggregationNode::Step::kFinal;
+      else if (stepName == "intermediate") step = core::AggregationNode::Step::kIntermediate;
+      else throw VeloxRuntimeError("plan text: unknown aggregation step " + stepName);
+      auto keys = intList("keys");
+      // (aggs (fn [col] [(mask col)]) ...)
+      struct RawAgg { std::string fn; int col = -1; int mask = -1; };
+      std::vector<RawAgg> raws;
+      lex_.expect(Tok::LP, "(");
+      if (lex_.atom("aggs") != "aggs") throw VeloxRuntimeError("plan text: expected (aggs ...)");
+      while (lex_.peek().kind == Tok::LP) {
+        lex_.take();
+        RawAgg a;
+        a.fn = lex_.atom("aggregate name");
+        while (lex_.peek().kind != Tok::RP) {
+          if (lex_.peek().kind == Tok::LP) {
+            lex_.take();
+            if (lex_.atom("mask") != "mask") throw VeloxRuntimeError("plan text: expected (mask col)");
+            a.mask = std::stoi(lex_.atom("mask column"));
+            lex_.expect(Tok::RP, ")");
+          } else {
+            a.col = std::stoi(lex_.atom("column"));
+          }
+        }
+        lex_.take();
+        raws.push_back(a);
+      }
+      lex_.expect(Tok::RP, ")");
+      auto child = node();
+      const auto& in = child->outputType();
+      const bool raw = step == core::AggregationNode::Step::kSingle || step == core::AggregationNode::Step::kPartial;
+      const bool fin = step == core::AggregationNode::Step::kSingle || step == core::AggregationNode::Step::kFinal;
+      std::vector<std::string> names;
+      std::vector<TypePtr> types;
+      for (int k : keys) { names.push_back(in->nameOf(k)); types.push_back(in->childAt(k)); }
+      std::vector<core::AggregationNode::Aggregate> aggs;
+      for (auto& r : raws) {
+        core::AggregationNode::Aggregate a;
+        a.function = r.fn;
+        a.mask = r.mask;
+        if (r.col >= 0) {
+          a.inputs.push_back(r.col);
+          a.rawInputType = in->childAt(r.col);
+          if (!raw && r.fn == "avg") a.inputs.push_back(r.col + 1);
+        }
+        const std::string n = "a" + std::to_string(aggs.size());
+        if (r.fn == "count") { names.push_back(n); types.push_back(BIGINT()); }
+        else if (r.fn == "sum") { names.push_back(n); types.push_back(raw ? (a.rawInputType->kind() == TypeKind::DOUBLE ? DOUBLE() : BIGINT()) : a.rawInputType); }
+        else if (r.fn == "min" || r.fn == "max") { names.push_back(n); types.push_back(a.rawInputType); }
+        else if (r.fn == "avg") {
+          // intermediate avg is ROW(DOUBLE, BIGINT) in the reference (AverageAggregateBase.h:66-69);
+          // the C ABI carries it flattened as two columns
+          if (fin) { names.push_back(n); types.push_back(DOUBLE()); }
+          else { names.push_back(n + "_sum"); types.push_back(DOUBLE()); names.push_back(n + "_count"); types.push_back(BIGINT()); }
+        } else throw VeloxRuntimeError("plan text: unknown aggregate " + r.fn);
+        aggs.push_back(a);
+      }
+      out = std::make_shared<core::AggregationNode>(nextId(), step, keys, aggs, ROW(names, types), child);
+    } else if (h == "hashjoin") {
+      const std::string jt = lex_.atom("join type");
+      JoinTypeText type{jt};
+      auto pk = intList("probekeys");
+      auto bk = intList("buildkeys");
+      // filter: nil or expression over probe ++ build columns — needs both children first
+      const Lexer filterPos = lex_;
+      if (lex_.peek().kind == Tok::ATOM) lex_.take(); else skip();
+      // outputs
+      lex_.expect(Tok::LP, "(");
+      if (lex_.atom("out") != "out") throw VeloxRuntimeError("plan text: expected (out ...)");
+      std::vector<core::HashJoinNode::Output> outs;
+      while (lex_.peek().kind == Tok::LP) {
+        lex_.take();
+        const std::string side = lex_.atom("p|b");
+        const int col = std::stoi(lex_.atom("column"));
+        lex_.expect(Tok::RP, ")");
+        outs.push_back({side == "p", col});
+      }
+      lex_.expect(Tok::RP, ")");
+      auto probe = node();
+      auto build = node();
+      Lexer after = lex_;
+      core::TypedExprPtr filter;
+      lex_ = filterPos;
+      if (lex_.peek().kind == Tok::LP) {
+        std::vector<std::string> names = probe->outputType()->names();
+        std::vector<TypePtr> types = probe->outputType()->children();
+        for (uint32_t i = 0; i < build->outputType()->size(); ++i) {
+          names.push_back("b_" + build->outputType()->nameOf(i));
+          types.push_back(build->outputType()->childAt(i));
+        }
+        filter = expr(ROW(names, types));
+      }
+      lex_ = after;
+      std::vector<std::string> names;
+      std::vector<TypePtr> types;
+      for (auto& o : outs) {
+        const auto& t = o.fromProbe ? probe->outputType() : build->outputType();
+        names.push_back("j" + std::to_string(names.size()));
+        types.push_back(t->childAt(o.column));
+      }
+      out = std::make_shared<core::HashJoinNode>(nextId(), type.parse(), pk, bk, filter, probe, build, outs, ROW(names, types));
+    } else {
+      throw VeloxRuntimeError("plan text: unknown plan node " + h);
+    }
+    lex_.expect(Tok::RP, ")");
+    return out;
+  }
+
+  struct JoinTypeText {
+    std::string s;
+    core::JoinType parse() const {
+      if (s == "inner") return core::JoinType::kInner;
+      if (s == "left") return core::JoinType::kLeft;
+      if (s == "semi") return core::JoinType::kLeftSemiFilter;
+      if (s == "anti") return core::JoinType::kAnti;
+      throw VeloxRuntimeError("plan text: unknown join type " + s);
+    }
+  };
+
+  // skips one balanced S-expression (or atom)
+  void skip() {
+    if (lex_.peek().kind != Tok::LP) { lex_.take(); return; }
+    int depth = 0;
+    do {
+      const Tok t = lex_.take();
+      if (t.kind == Tok::LP) ++depth;
+      else if (t.kind == Tok::RP) --depth;
+      else if (t.kind == Tok::END) throw VeloxRuntimeError("plan text: unbalanced parentheses");
+    } while (depth > 0);
+  }
+
+  Lexer lex_;
+  int nextId_ = 0;
+};
+
+}  // namespace
+
+core::PlanNodePtr parsePlanText(const std::string& text) { return Parser(text).plan(); }
+
+}  // namespace velox_b200
