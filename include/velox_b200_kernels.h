@@ -118,7 +118,7 @@ typedef struct vb2_program {
   int32_t n_instrs;        /* <= 256 */
   int32_t n_filter_instrs; /* instrs [0, n_filter_instrs) compute the filter register */
   int32_t filter_reg;      /* -1 when there is no filter */
-  int32_t n_regs;          /* <= 32 */
+  int32_t n_regs;          /* <= 64 */
   const vb2_const* consts; /* host pointer */
   int32_t n_consts;        /* <= 32 */
   int32_t pad;
@@ -194,6 +194,13 @@ size_t vb2k_fused_workspace_bytes(int32_t id, int32_t ngroups);
  * counts is int64[ngroups] (rows that passed the filter per group). */
 int vb2k_fused_scan_agg(int32_t id, const vb2_fused_args* args, double* sums, int64_t* counts, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* Scan -> filter -> project -> compact pipelines (signatures "F:...;C:..."): writes the
+ * projections of the surviving rows densely into outs[p] (element width
+ * vb2k_fused_output_width). count: device int64 running total (rows written so far);
+ * *error_flag = 100 when capacity is exceeded. Feeds the hash-partitioned exchange. */
+int vb2k_fused_scan_compact(int32_t id, const vb2_fused_args* args, void* const* outs, int32_t nouts, int64_t capacity,
+                            int64_t* count, int32_t* error_flag, void* stream);
+int32_t vb2k_fused_output_width(int32_t id, int32_t out);
 
 /* ------------------------------------------------------------------------------------------
  * Generic aggregation over materialised columns.

@@ -24,7 +24,7 @@ constexpr int kVmMaxInstrs = 256;
 constexpr int kVmMaxConsts = 32;
 constexpr int kVmMaxCols = 32;
 constexpr int kVmMaxOuts = 32;
-constexpr int kVmMaxRegs = 32;
+constexpr int kVmMaxRegs = 64;
 
 enum VmErr : int { kErrOverflow = 1, kErrDivZero = 2, kErrCast = 3 };
 
@@ -87,7 +87,7 @@ __device__ inline int str_compare(const char* a, int al, const char* b, int bl) 
 
 struct RowState {
   uint64_t regs[kVmMaxRegs];
-  uint32_t nullmask, errmask;
+  uint64_t nullmask, errmask;
   int errcode;
 };
 
@@ -100,9 +100,9 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
   st.errcode = 0;
   for (int pc = 0; pc < n_instrs; ++pc) {
     const vb2_instr in = a.instrs[pc];
-    const uint32_t dbit = 1u << in.dst;
-    auto is_null = [&](int r) { return (st.nullmask >> r) & 1u; };
-    auto is_err = [&](int r) { return (st.errmask >> r) & 1u; };
+    const uint64_t dbit = 1ull << in.dst;
+    auto is_null = [&](int r) { return static_cast<bool>((st.nullmask >> r) & 1ull); };
+    auto is_err = [&](int r) { return static_cast<bool>((st.errmask >> r) & 1ull); };
     bool rnull = false, rerr = false;
     uint64_t rv = 0;
     auto raise = [&](int code) { rerr = true; if (!st.errcode) st.errcode = code; };
@@ -283,8 +283,8 @@ __global__ void __launch_bounds__(kVmThreads) vm_filter_kernel(const __grid_cons
     bool keep = false;
     if (row < a.n) {
       run_program(a, a.n_filter_instrs, row, st);
-      const bool err = (st.errmask >> a.filter_reg) & 1u;
-      const bool null = (st.nullmask >> a.filter_reg) & 1u;
+      const bool err = (st.errmask >> a.filter_reg) & 1ull;
+      const bool null = (st.nullmask >> a.filter_reg) & 1ull;
       if (err) atomicCAS(a.error_flag, 0, user_code(st.errcode));
       keep = !err && !null && st.regs[a.filter_reg] != 0;
     }
@@ -310,9 +310,9 @@ __global__ void __launch_bounds__(kVmThreads) vm_project_kernel(const __grid_con
       const vb2_output& out = a.outs[o];
       bool valid = false;
       if (live) {
-        const bool err = (st.errmask >> out.reg) & 1u;
+        const bool err = (st.errmask >> out.reg) & 1ull;
         if (err) atomicCAS(a.error_flag, 0, user_code(st.errcode));
-        valid = !err && !((st.nullmask >> out.reg) & 1u);
+        valid = !err && !((st.nullmask >> out.reg) & 1ull);
         const uint64_t v = valid ? st.regs[out.reg] : 0;
         switch (out.type) {
           case VB2_INTEGER: reinterpret_cast<int32_t*>(out.values)[k] = static_cast<int32_t>(v); break;
@@ -422,7 +422,7 @@ static int fill_args(VmArgs& a, const vb2_program* prog, const vb2_column* cols,
   if (!prog || prog->n_instrs < 0 || prog->n_instrs > kVmMaxInstrs) return fail_msg(VB2_ERR_UNSUPPORTED, "expression program too long (max 256 instructions)");
   if (prog->n_consts > kVmMaxConsts) return fail_msg(VB2_ERR_UNSUPPORTED, "too many constants (max 32)");
   if (ncols > kVmMaxCols) return fail_msg(VB2_ERR_UNSUPPORTED, "too many input columns (max 32)");
-  if (prog->n_regs > kVmMaxRegs) return fail_msg(VB2_ERR_UNSUPPORTED, "too many registers (max 32)");
+  if (prog->n_regs > kVmMaxRegs) return fail_msg(VB2_ERR_UNSUPPORTED, "too many registers (max 64)");
   for (int i = 0; i < prog->n_instrs; ++i) a.instrs[i] = prog->instrs[i];
   for (int i = 0; i < prog->n_consts; ++i) a.consts[i] = prog->consts[i];
   for (int i = 0; i < ncols; ++i) a.cols[i] = cols[i];

@@ -119,7 +119,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 template <class P>
 static int launch(const KernelArgs& a, double* sums, int64_t* counts, void* ws, size_t ws_bytes, cudaStream_t st) {
-  bool bulk = a.rows >= kTileRows;  // cp.async.bulk needs 16-byte aligned sources
+  bool bulk = true;  // cp.async.bulk needs 16-byte aligned sources (inputs below one tile run as the kernel's tail)
   for (int c = 0; c < kMaxCols; ++c)
     if (((P::fmask | P::imask | P::lmask) >> c) & 1u) bulk = bulk && aligned16(a.cols[c]);
   for (int k = 0; k < a.nkeys; ++k) bulk = bulk && aligned16(a.key[k]);
@@ -145,6 +145,41 @@ static int launch(const KernelArgs& a, double* sums, int64_t* counts, void* ws, 
 template <class P>
 static int add_pipeline() {
   return register_pipeline(Entry{P::sig(), P::kNP, P::kJoin, &launch<P>});
+}
+
+template <class P>
+static int launch_compact(const KernelArgs& a, const CompactArgs& o, cudaStream_t st) {
+  for (int c = 0; c < kMaxCols; ++c)
+    if ((((P::fmask | P::imask | P::lmask) >> c) & 1u) && !aligned16(a.cols[c]))
+      return fail_msg(VB2_ERR_UNSUPPORTED, "fused scan-compact needs 16-byte aligned input columns");
+  auto kernel = fused_scan_compact_tma_kernel<P>;
+  const int stage_bytes = TileLayout<P, 4>::stage_bytes(0);
+  int stages = (100 * 1024) / stage_bytes;
+  stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes;
+  static size_t configured = 0;
+  if (configured < smem) {
+    VB2_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  int blocks_per_sm = 0;
+  VB2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kTmaThreads, smem));
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  if (blocks_per_sm > kMaxBlocksPerSM) blocks_per_sm = kMaxBlocksPerSM;
+  const int64_t ntiles = a.rows / kTileRows;
+  int64_t grid = static_cast<int64_t>(device_sm_count()) * blocks_per_sm;
+  if (ntiles < grid) grid = ntiles < 1 ? 1 : ntiles;
+  kernel<<<static_cast<unsigned>(grid), kTmaThreads, smem, st>>>(a, o, stages);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+template <class P>
+static int add_compact_pipeline() {
+  Entry e{P::sig(), P::kNP, false, nullptr};
+  e.compact = &launch_compact<P>;
+  P::widths(e.widths);
+  return register_pipeline(e);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -174,6 +209,12 @@ using Q14 = Pipeline<Between<ColI<0>, PI<0>, PI<1>>,
 using SumUnderLt = Pipeline<Lt<ColF<0>, PF<0>>, TypeList<Multiply<ColF<1>, Minus<PF<1>, ColF<2>>>>>;
 using SumNoFilter = Pipeline<True, TypeList<ColF<0>>>;
 
+// Multi-GPU Q14: each GPU filters its lineitem shard and compacts
+// (l_partkey, ep*(1-disc)) for the hash-partitioned exchange ...
+using Q14ScanCompact = CompactPipeline<Between<ColI<0>, PI<0>, PI<1>>, TypeList<ColL<1>, Multiply<ColF<2>, Minus<PF<0>, ColF<3>>>>>;
+// ... and after the all-to-all probes its part partition: sum(rev), sum(case when promo then rev else 0.0).
+using Q14ProbeAfterExchange = Pipeline<True, TypeList<ColF<1>, Switch<JoinFlag, ColF<1>, PF<0>>>, 0>;
+
 static std::once_flag g_once;
 static void ensure_registered() {
   std::call_once(g_once, [] {
@@ -182,6 +223,8 @@ static void ensure_registered() {
     add_pipeline<Q14>();
     add_pipeline<SumUnderLt>();
     add_pipeline<SumNoFilter>();
+    add_compact_pipeline<Q14ScanCompact>();
+    add_pipeline<Q14ProbeAfterExchange>();
   });
 }
 
@@ -229,6 +272,34 @@ int vb2k_join_slot_flags(const int32_t* head, const int32_t* codes, const uint8_
   return VB2_OK;
 }
 
+int vb2k_fused_scan_compact(int32_t id, const vb2_fused_args* args, void* const* outs, int32_t nouts, int64_t capacity,
+                            int64_t* count, int32_t* error_flag, void* stream) {
+  ensure_registered();
+  if (id < 0 || id >= static_cast<int>(registry().size()) || !registry()[id].compact) return fail_msg(VB2_ERR_INVALID, "not a scan-compact pipeline");
+  const Entry& e = registry()[id];
+  if (nouts != e.nproj || !args) return fail_msg(VB2_ERR_INVALID, "scan-compact: wrong number of outputs");
+  if (args->rows <= 0) return VB2_OK;
+  KernelArgs a;
+  std::memset(&a, 0, sizeof(a));
+  for (int c = 0; c < kMaxCols; ++c) a.cols[c] = args->cols[c];
+  std::memcpy(a.consts.pf, args->pf, sizeof(a.consts.pf));
+  std::memcpy(a.consts.pl, args->pl, sizeof(a.consts.pl));
+  std::memcpy(a.consts.pi, args->pi, sizeof(a.consts.pi));
+  a.rows = args->rows;
+  CompactArgs o;
+  std::memset(&o, 0, sizeof(o));
+  for (int i = 0; i < nouts; ++i) o.outs[i] = outs[i];
+  o.capacity = capacity;
+  o.count = reinterpret_cast<unsigned long long*>(count);
+  o.error_flag = error_flag;
+  return e.compact(a, o, static_cast<cudaStream_t>(stream));
+}
+int32_t vb2k_fused_output_width(int32_t id, int32_t out) {
+  ensure_registered();
+  if (id < 0 || id >= static_cast<int>(registry().size()) || out < 0 || out >= registry()[id].nproj) return -1;
+  return registry()[id].compact ? registry()[id].widths[out] : 8;
+}
+
 int vb2k_fused_scan_agg(int32_t id, const vb2_fused_args* args, double* sums, int64_t* counts, void* workspace,
                         size_t workspace_bytes, void* stream) {
   ensure_registered();
@@ -236,6 +307,7 @@ int vb2k_fused_scan_agg(int32_t id, const vb2_fused_args* args, double* sums, in
   if (!args || args->rows < 0 || args->nkeys < 0 || args->nkeys > VB2_FUSED_MAX_KEYS) return fail_msg(VB2_ERR_INVALID, "bad fused args");
   if (args->rows == 0) return VB2_OK;
   const Entry& e = registry()[id];
+  if (!e.launch) return fail_msg(VB2_ERR_INVALID, "not an aggregate pipeline");
   KernelArgs a;
   std::memset(&a, 0, sizeof(a));
   for (int c = 0; c < kMaxCols; ++c) a.cols[c] = args->cols[c];

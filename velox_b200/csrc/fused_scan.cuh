@@ -675,17 +675,176 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
   else block_reduce_store<P, kRegG>(acc, partials);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused scan -> filter -> project -> compact: same TMA-staged producer, the consumers write the
+// projections of the surviving rows densely. Used in front of the hash-partitioned exchange
+// (each GPU filters its lineitem shard and ships only the ~1 % of rows that join). One atomic
+// per tile reserves the output range; order inside a tile follows the input, tiles land in
+// arrival order (the exchange that follows is a multiset operation).
+// ---------------------------------------------------------------------------------------------
+template <class Filter, class Projs>
+struct CompactPipeline;
+template <class Filter, class... Ps>
+struct CompactPipeline<Filter, TypeList<Ps...>> {
+  static constexpr int kNP = sizeof...(Ps);
+  static constexpr bool kJoin = false;
+  static constexpr int kJoinCol = 0;
+  static constexpr uint32_t fmask = Filter::fmask | (Ps::fmask | ...);
+  static constexpr uint32_t imask = Filter::imask | (Ps::imask | ...);
+  static constexpr uint32_t lmask = Filter::lmask | (Ps::lmask | ...);
+  using F = Filter;
+  template <int I>
+  __device__ static __forceinline__ void store(const PairRegs& r, const Consts& c, void* const* outs, int64_t pos) {
+    if constexpr (I < kNP) {
+      using P = std::tuple_element_t<I, std::tuple<Ps...>>;
+      reinterpret_cast<typename P::T*>(outs[I])[pos] = P::eval(r, c, 0);
+      store<I + 1>(r, c, outs, pos);
+    }
+  }
+  static std::string sig() {
+    std::string out = "F:" + Filter::sig() + ";C:";
+    bool first = true;
+    ((out += (first ? "" : "|") + Ps::sig(), first = false), ...);
+    return out;
+  }
+  static void widths(int* w) {
+    int i = 0;
+    ((w[i++] = static_cast<int>(sizeof(typename Ps::T))), ...);
+  }
+};
+
+struct CompactArgs {
+  void* outs[VB2_FUSED_MAX_COLS];
+  int64_t capacity;
+  unsigned long long* count;  // device counter of rows written
+  int32_t* error_flag;        // set to 100 when capacity is exceeded
+};
+
+template <class P>
+__global__ void __launch_bounds__(kTmaThreads, 2)
+fused_scan_compact_tma_kernel(const __grid_constant__ KernelArgs a, const __grid_constant__ CompactArgs o, int stages) {
+  extern __shared__ __align__(128) uint8_t tile_smem[];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  __shared__ int warp_counts[kConsumerThreads / kWarp];
+  __shared__ long long tile_base;
+  using Lay = TileLayout<P, 4>;
+  const int stage_bytes = Lay::stage_bytes(0);
+  const int64_t ntiles = a.rows / kTileRows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerThreads / kWarp);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == kConsumerThreads / kWarp) {
+    if (lane == 0) {
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % stages;
+        const uint32_t round = static_cast<uint32_t>(it / stages);
+        if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+        uint8_t* base = tile_smem + static_cast<size_t>(s) * stage_bytes;
+        const int64_t row0 = t * kTileRows;
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) {
+          if (P::fmask & (1u << c)) bytes += kTileRows * 8;
+          if (P::lmask & (1u << c)) bytes += kTileRows * 8;
+          if (P::imask & (1u << c)) bytes += kTileRows * 4;
+        }
+        mbar_expect_tx(&full_bar[s], bytes);
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) {
+          if (P::fmask & (1u << c)) bulk_load(base + Lay::f_off(c), reinterpret_cast<const double*>(a.cols[c]) + row0, kTileRows * 8, &full_bar[s]);
+          if (P::lmask & (1u << c)) bulk_load(base + Lay::l_off(c), reinterpret_cast<const int64_t*>(a.cols[c]) + row0, kTileRows * 8, &full_bar[s]);
+          if (P::imask & (1u << c)) bulk_load(base + Lay::i_off(c, 0), reinterpret_cast<const int32_t*>(a.cols[c]) + row0, kTileRows * 4, &full_bar[s]);
+        }
+      }
+    }
+  } else {
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it % stages;
+      const uint32_t round = static_cast<uint32_t>(it / stages);
+      mbar_wait(&full_bar[s], round & 1);
+      const uint8_t* base = tile_smem + static_cast<size_t>(s) * stage_bytes;
+      PairRegs r[kRowsPerThread];
+      bool keep[kRowsPerThread];
+      int before = 0;  // kept rows of this warp that precede this lane's rows, per slot order
+      int mine[kRowsPerThread];
+      int warp_total = 0;
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        // row order inside the tile: warp-major so that a warp owns 128 consecutive rows
+        const int row = warp * (kWarp * kRowsPerThread) + j * kWarp + lane;
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) {
+          if (P::fmask & (1u << c)) r[j].f[c][0] = reinterpret_cast<const double*>(base + Lay::f_off(c))[row];
+          if (P::lmask & (1u << c)) r[j].l[c][0] = reinterpret_cast<const int64_t*>(base + Lay::l_off(c))[row];
+          if (P::imask & (1u << c)) r[j].i[c][0] = reinterpret_cast<const int32_t*>(base + Lay::i_off(c, 0))[row];
+        }
+        keep[j] = P::F::eval(r[j], a.consts, 0);
+        const unsigned m = __ballot_sync(0xffffffffu, keep[j]);
+        mine[j] = warp_total + __popc(m & ((1u << lane) - 1));
+        warp_total += __popc(m);
+      }
+      (void)before;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&empty_bar[s]);
+        warp_counts[warp] = warp_total;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+      if (threadIdx.x == 0) {
+        int total = 0;
+        for (int w = 0; w < kConsumerThreads / kWarp; ++w) total += warp_counts[w];
+        tile_base = total ? static_cast<long long>(atomicAdd(o.count, static_cast<unsigned long long>(total))) : 0;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+      int64_t pos0 = tile_base;
+      for (int w = 0; w < warp; ++w) pos0 += warp_counts[w];
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        if (keep[j]) {
+          const int64_t pos = pos0 + mine[j];
+          if (pos < o.capacity) P::template store<0>(r[j], a.consts, o.outs, pos);
+          else atomicCAS(o.error_flag, 0, 100);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");  // warp_counts reused next tile
+    }
+    // tail rows by direct loads (one atomic per kept row; at most kTileRows - 1 rows)
+    const int64_t tail0 = ntiles * kTileRows;
+    for (int64_t row = tail0 + static_cast<int64_t>(blockIdx.x) * kConsumerThreads + threadIdx.x; row < a.rows;
+         row += static_cast<int64_t>(gridDim.x) * kConsumerThreads) {
+      PairRegs r;
+      load_rows<P, false>(a, row, r);
+      if (P::F::eval(r, a.consts, 0)) {
+        const int64_t pos = static_cast<int64_t>(atomicAdd(o.count, 1ull));
+        if (pos < o.capacity) P::template store<0>(r, a.consts, o.outs, pos);
+        else atomicCAS(o.error_flag, 0, 100);
+      }
+    }
+  }
+}
+
 // Folds per-block partials in block order into the persistent accumulators.
 __global__ void fused_finalize_kernel(const double* __restrict__ partials, int nblocks, int kvals, int np, int maxg,
                                       int ngroups, double* __restrict__ sums, int64_t* __restrict__ counts);
 
 using LaunchFn = int (*)(const KernelArgs&, double* sums, int64_t* counts, void* ws, size_t ws_bytes, cudaStream_t);
+using CompactFn = int (*)(const KernelArgs&, const CompactArgs&, cudaStream_t);
 
 struct Entry {
   std::string signature;
   int nproj;
   bool join;
-  LaunchFn launch;
+  LaunchFn launch;           // aggregate pipelines
+  CompactFn compact = nullptr;  // compaction pipelines (";C:" signatures)
+  int widths[VB2_FUSED_MAX_COLS] = {0};
 };
 
 int register_pipeline(const Entry& e);

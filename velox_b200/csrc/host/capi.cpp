@@ -1,5 +1,10 @@
 // Operator-level C ABI (include/velox_b200.h): plan text -> Task over the shim Driver with the
 // B200 adapter installed; host / device column batches in, host result columns out.
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -195,6 +200,25 @@ void appendResult(vb2_task& t, const RowVectorPtr& batch) {
   t.rows += n;
 }
 
+}  // namespace
+
+namespace {
+// VB2_DEBUG_SEGV=1: print the native stack on SIGSEGV (development aid; no debugger on the GPU boxes)
+void segvHandler(int sig) {
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "\n[velox_b200] fatal signal, native stack:\n";
+  (void)!write(2, msg, sizeof(msg) - 1);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+struct SegvInstaller {
+  SegvInstaller() {
+    const char* e = std::getenv("VB2_DEBUG_SEGV");
+    if (e && e[0] == '1') signal(SIGSEGV, segvHandler);
+  }
+} g_segvInstaller;
 }  // namespace
 
 extern "C" {

@@ -16,7 +16,24 @@ void kernelCheck(int rc) {
   throw VeloxRuntimeError(msg);
 }
 
-DeviceBuffer::DeviceBuffer(size_t bytes, cudaStream_t stream) : bytes_(bytes), stream_(stream) {
+namespace {
+std::mutex& streamMutex() {
+  static std::mutex m;
+  return m;
+}
+std::map<cudaStream_t, std::weak_ptr<DeviceContext>>& streamOwners() {
+  static std::map<cudaStream_t, std::weak_ptr<DeviceContext>> m;
+  return m;
+}
+std::shared_ptr<void> ownerOf(cudaStream_t stream) {
+  std::lock_guard<std::mutex> l(streamMutex());
+  auto it = streamOwners().find(stream);
+  if (it == streamOwners().end()) return nullptr;
+  return it->second.lock();
+}
+}  // namespace
+
+DeviceBuffer::DeviceBuffer(size_t bytes, cudaStream_t stream) : bytes_(bytes), stream_(stream), streamOwner_(ownerOf(stream)) {
   VB2_CU(cudaMallocAsync(&ptr_, bytes ? bytes : 8, stream));
 }
 DeviceBuffer::~DeviceBuffer() {
@@ -41,6 +58,10 @@ DeviceContext::DeviceContext() {
 }
 DeviceContext::~DeviceContext() {
   if (stream) {
+    {
+      std::lock_guard<std::mutex> l(streamMutex());
+      streamOwners().erase(stream);
+    }
     cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);
   }
@@ -57,6 +78,8 @@ std::shared_ptr<DeviceContext> driverDeviceContext(exec::DriverCtx* ctx) {
     if (dev >= 0) VB2_CU(cudaSetDevice(dev));
     sp = std::make_shared<DeviceContext>();
     w = sp;
+    std::lock_guard<std::mutex> l2(streamMutex());
+    streamOwners()[sp->stream] = sp;
   }
   return sp;
 }

@@ -37,6 +37,7 @@ class DeviceBuffer {
   size_t bytes_ = 0;
   cudaStream_t stream_;
   bool owned_ = true;
+  std::shared_ptr<void> streamOwner_;  // keeps the stream alive until the buffer is freed on it
 };
 using DeviceBufferPtr = std::shared_ptr<DeviceBuffer>;
 DeviceBufferPtr allocDevice(size_t bytes, cudaStream_t stream);

@@ -55,7 +55,7 @@ struct Compiler {
   std::map<std::string, int> cse;  // canonical text -> register
 
   int newReg() {
-    VELOX_CHECK(out.nRegs < 32, "expression needs more than 32 registers");
+    VELOX_CHECK(out.nRegs < 64, "expression needs more than 64 registers");
     return out.nRegs++;
   }
   int emit(int op, int type, int a = 0, int b = 0, int c = 0) {

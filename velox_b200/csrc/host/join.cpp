@@ -132,6 +132,21 @@ void B200HashBuild::noMoreInput() {
     holder->table.head = head->as<int32_t>();
     holder->table.next = next->as<int32_t>();
     holder->owners = {head, next};
+    // zero-row build side with the right column types (outer joins still project its columns as NULL)
+    std::vector<DeviceColumnPtr> cols;
+    auto dummy = allocDeviceZeroed(16, st);
+    for (uint32_t c = 0; c < buildType->size(); ++c) {
+      auto col = std::make_shared<DeviceColumn>();
+      col->type = buildType->childAt(c);
+      col->desc.type = veloxTypeToVb2(col->type);
+      col->desc.encoding = VB2_FLAT;
+      col->desc.size = 0;
+      col->desc.values = dummy->data();
+      col->desc.aux = dummy->data();
+      col->owners = {dummy};
+      cols.push_back(col);
+    }
+    holder->rows = std::make_shared<B200Vector>(pool(), buildType, 0, std::move(cols), st);
     bridge_->setHashTable(holder);
     return;
   }

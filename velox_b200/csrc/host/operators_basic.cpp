@@ -67,8 +67,7 @@ FlatColumn flattenColumn(const DeviceColumnPtr& col, const int32_t* sel, int64_t
   out.values = allocDevice(static_cast<size_t>(n) * w, stream);
   out.nulls = allocDevice(bits::nbytes(n), stream);
   vb2_output o{0, out.type, out.values->data(), out.nulls->as<uint64_t>()};
-  static thread_local DeviceBufferPtr flag;
-  if (!flag) flag = allocDeviceZeroed(8, stream);
+  auto flag = allocDeviceZeroed(8, stream);  // a LOAD cannot raise; the kernel still wants a flag
   kernelCheck(vb2k_eval_project(&p, &col->desc, 1, sel, n, &o, 1, flag->as<int32_t>(), stream));
   if (!col->mayHaveNulls()) out.nulls = nullptr;
   return out;

@@ -172,3 +172,127 @@ class FusedScanAgg:
         check(lib().vb2k_fused_scan_agg(self.id, C.byref(a), C.c_void_p(self.sums.data_ptr()),
                                         C.c_void_p(self.counts.data_ptr()), C.c_void_p(self.ws.data_ptr()),
                                         C.c_size_t(self.ws_bytes), _stream()))
+
+
+# ---- additional kernel-level wrappers used by bench.py / the multi-GPU path -------------------------
+class JoinTable(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("pad", C.c_int32), ("key_min", C.c_int64), ("capacity", C.c_int64),
+                ("keys", C.c_void_p), ("head", C.c_void_p), ("next", C.c_void_p), ("build_rows", C.c_int64)]
+
+
+class Instr(C.Structure):
+    _fields_ = [("op", C.c_int32), ("type", C.c_int32), ("dst", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("c", C.c_int32)]
+
+
+class Const(C.Structure):
+    _fields_ = [("type", C.c_int32), ("is_null", C.c_int32), ("i", C.c_int64), ("d", C.c_double), ("str", C.c_void_p),
+                ("len", C.c_int32), ("pad", C.c_int32)]
+
+
+class Program(C.Structure):
+    _fields_ = [("instrs", C.POINTER(Instr)), ("n_instrs", C.c_int32), ("n_filter_instrs", C.c_int32), ("filter_reg", C.c_int32),
+                ("n_regs", C.c_int32), ("consts", C.POINTER(Const)), ("n_consts", C.c_int32), ("pad", C.c_int32)]
+
+
+class Output(C.Structure):
+    _fields_ = [("reg", C.c_int32), ("type", C.c_int32), ("values", C.c_void_p), ("nulls", C.c_void_p)]
+
+
+VB2_OP_LIKE = 22
+
+
+def column_minmax(col: DeviceColumn):
+    """(min, max, non-null count) of an integer column; synchronises."""
+    out = torch.empty(3, dtype=torch.int64, device="cuda")
+    c = col.to_c()
+    check(lib().vb2k_column_minmax(C.byref(c), C.c_int64(col.size), C.c_void_p(out.data_ptr()), _stream()))
+    lo, hi, nn = out.tolist()
+    return lo, hi, nn
+
+
+def normalize_keys(cols: Sequence[DeviceColumn], mins, mults, ranges=None, nulls_invalid=False, n=None):
+    n = cols[0].size if n is None else n
+    arr = (CColumn * len(cols))(*[c.to_c() for c in cols])
+    keys = torch.empty(n, dtype=torch.int64, device="cuda")
+    valid = torch.empty((n + 63) // 64, dtype=torch.int64, device="cuda") if (ranges is not None or nulls_invalid) else None
+    k = len(cols)
+    mins_a = (C.c_int64 * k)(*mins)
+    mults_a = (C.c_uint64 * k)(*mults)
+    ranges_a = (C.c_uint64 * k)(*ranges) if ranges is not None else None
+    check(lib().vb2k_normalize_keys(arr, k, mins_a, mults_a, ranges_a, 1 if nulls_invalid else 0, None, C.c_int64(n),
+                                    C.c_void_p(keys.data_ptr()), C.c_void_p(_ptr(valid)), _stream()))
+    return keys, valid
+
+
+def join_build_array(keys: torch.Tensor, valid: Optional[torch.Tensor], capacity: int):
+    """Array-mode join table over normalized keys: head[slot] = build row + 1. Returns (head, next, has_duplicates)."""
+    n = keys.numel()
+    head = torch.zeros(capacity, dtype=torch.int32, device="cuda")
+    nxt = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+    t = JoinTable(0, 0, 0, capacity, None, head.data_ptr(), nxt.data_ptr(), n)
+    check(lib().vb2k_join_build(C.byref(t), C.c_void_p(keys.data_ptr()), C.c_void_p(_ptr(valid)), C.c_int64(n),
+                                C.c_void_p(flags.data_ptr()), _stream()))
+    return head, nxt, flags
+
+
+class LikeOnAlphabet:
+    """`column LIKE pattern` evaluated by the expression VM over a (small) VARCHAR alphabet."""
+
+    def __init__(self, strings: Sequence[str], pattern: str):
+        from .vector import flat_vector, VARCHAR as _V
+        self.col = DeviceColumn.from_host(flat_vector(_V, list(strings)))
+        self.n = len(strings)
+        self.pat = torch.tensor(list(pattern.encode()), dtype=torch.uint8, device="cuda")
+        self.instr = (Instr * 1)(Instr(VB2_OP_LIKE, BOOLEAN, 0, 0, 0, 0))
+        self.const = (Const * 1)(Const(VARCHAR, 0, 0, 0.0, self.pat.data_ptr(), len(pattern), 0))
+        self.prog = Program(self.instr, 1, 0, -1, 1, self.const, 1, 0)
+        self.flags = torch.zeros(self.n + 8, dtype=torch.uint8, device="cuda")
+        self.nulls = torch.zeros((self.n + 63) // 64 + 1, dtype=torch.int64, device="cuda")
+        self.err = torch.zeros(2, dtype=torch.int32, device="cuda")
+        self.out = (Output * 1)(Output(0, BOOLEAN, self.flags.data_ptr(), self.nulls.data_ptr()))
+        self.ccol = self.col.to_c()
+
+    def run(self) -> torch.Tensor:
+        check(lib().vb2k_eval_project(C.byref(self.prog), C.byref(self.ccol), 1, None, C.c_int64(self.n), self.out, 1,
+                                      C.c_void_p(self.err.data_ptr()), _stream()))
+        return self.flags
+
+
+class FusedScanCompact:
+    """Scan -> filter -> project -> compact pipeline (signature "F:...;C:...")."""
+
+    def __init__(self, signature: str, capacity: int):
+        L = lib()
+        self.id = L.vb2k_fused_find(signature.encode())
+        if self.id < 0:
+            raise KeyError(f"no fused pipeline for {signature}")
+        self.nout = L.vb2k_fused_nproj(self.id)
+        self.capacity = capacity
+        self.widths = [L.vb2k_fused_output_width(self.id, i) for i in range(self.nout)]
+        self.outs = [torch.empty(capacity * w, dtype=torch.uint8, device="cuda") for w in self.widths]
+        self.count = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self.err = torch.zeros(2, dtype=torch.int32, device="cuda")
+        self.out_ptrs = (C.c_void_p * self.nout)(*[t.data_ptr() for t in self.outs])
+
+    def run(self, cols: Sequence[torch.Tensor], rows: int, pf=(), pl=(), pi=()):
+        a = FusedArgs()
+        for i, t in enumerate(cols):
+            a.cols[i] = t.data_ptr()
+        for i, v in enumerate(pf):
+            a.pf[i] = v
+        for i, v in enumerate(pl):
+            a.pl[i] = v
+        for i, v in enumerate(pi):
+            a.pi[i] = v
+        a.rows = rows
+        self.count.zero_()
+        check(lib().vb2k_fused_scan_compact(self.id, C.byref(a), self.out_ptrs, self.nout, C.c_int64(self.capacity),
+                                            C.c_void_p(self.count.data_ptr()), C.c_void_p(self.err.data_ptr()), _stream()))
+
+    def result(self, dtypes):
+        """Synchronises: returns the compacted columns as typed views of length count."""
+        n = int(self.count.item())
+        if int(self.err[0].item()) != 0 or n > self.capacity:
+            raise RuntimeError("scan-compact output capacity exceeded")
+        return n, [t.view(dt)[:n] for t, dt in zip(self.outs, dtypes)]

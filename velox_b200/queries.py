@@ -1,0 +1,157 @@
+"""TPC-H Q1 / Q6 / Q14 on device-resident columns, at the kernel-level C ABI (one process per GPU).
+
+Plans: velox/exec/tests/utils/TpchQueryBuilder.cpp:203-256 (Q1), :756-788 (Q6), :1639-1702 (Q14).
+The same kernels are what the operator layer launches for these plans (tests assert
+`b200.fusedBatches`); this module adds the multi-GPU composition of SURVEY.md §8e:
+
+  Q1 / Q6   rows sharded by range; per-GPU partial aggregates; one tiny NCCL all-reduce
+            (partialAggregation -> localPartition({}) -> finalAggregation).
+  Q14       both sides hash-partitioned by VectorHasher-hash(key) % world
+            (velox/exec/HashPartitionFunction.cpp:113-116): each GPU filters + projects its
+            lineitem shard into (l_partkey, revenue) with the fused scan-compact kernel, scatters
+            rows and its part shard into per-peer segments, ONE grouped ncclSend/ncclRecv
+            all-to-all per column, then local build + fused probe + CASE + sums, final 2-value
+            all-reduce.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import tpch
+from .kernels import (DeviceColumn, FusedScanAgg, FusedScanCompact, LikeOnAlphabet, column_minmax, flat_device, gather,
+                      hash_columns, join_build_array, join_slot_flags, normalize_keys, partition_ids, partition_scatter_order)
+from .vector import BIGINT
+
+Q14_SCAN_SIG = "F:between(i0,pi0,pi1);C:l1|multiply(f2,minus(pf0,f3))"
+Q14_PROBE_SIG = "F:true;P:f1|switch(joinflag,f1,pf0);J:l0"
+
+
+class Q1:
+    """sum/avg/count over (l_returnflag, l_linestatus): one fused kernel, 44 B/row."""
+    NGROUPS = len(tpch.RETURNFLAG_DICT) * len(tpch.LINESTATUS_DICT)
+
+    def __init__(self, comm=None):
+        self.f = FusedScanAgg(tpch.Q1_SIG, ngroups=self.NGROUPS)
+        self.comm = comm
+
+    def launch(self, li, rows):
+        self.f.reset()
+        self.f.add_batch([li["l_shipdate"], li["l_quantity"], li["l_extendedprice"], li["l_discount"], li["l_tax"]], rows,
+                         pf=[1.0, 1.0, 1.0], pi=[tpch.Q1_SHIPDATE_LT], keys=[li["l_returnflag"], li["l_linestatus"]],
+                         key_min=[0, 0], key_mult=[len(tpch.LINESTATUS_DICT), 1])
+
+    def merge(self):
+        if self.comm is not None:  # partial -> final across GPUs: <= 6 groups x 6 values
+            self.comm.all_reduce_(self.f.sums)
+            self.comm.all_reduce_(self.f.counts)
+
+    def result(self):
+        sums = self.f.sums.cpu().numpy().reshape(self.NGROUPS, 5)
+        counts = self.f.counts.cpu().numpy()
+        out = {}
+        for g in range(self.NGROUPS):
+            c = int(counts[g])
+            if c == 0:
+                continue
+            s = sums[g]
+            key = (tpch.RETURNFLAG_DICT[g // len(tpch.LINESTATUS_DICT)], tpch.LINESTATUS_DICT[g % len(tpch.LINESTATUS_DICT)])
+            out[key] = (s[0], s[1], s[2], s[3], s[0] / c, s[1] / c, s[4] / c, c)
+        return out
+
+
+class Q6:
+    def __init__(self, comm=None):
+        self.f = FusedScanAgg(tpch.Q6_SIG)
+        self.comm = comm
+
+    def launch(self, li, rows):
+        self.f.reset()
+        self.f.add_batch([li["l_shipdate"], li["l_discount"], li["l_quantity"], li["l_extendedprice"]], rows,
+                         pf=[0.05, 0.07, 24.0], pi=[tpch.Q6_SHIP_LO, tpch.Q6_SHIP_HI])
+
+    def merge(self):
+        if self.comm is not None:
+            self.comm.all_reduce_(self.f.sums)
+            self.comm.all_reduce_(self.f.counts)
+
+    def result(self):
+        return self.f.sums.item() if self.f.counts.item() else None
+
+
+class Q14:
+    """100 * sum(case when p_type like 'PROMO%' then rev else 0 end) / sum(rev) over lineitem |x| part."""
+
+    def __init__(self, comm=None, compact_capacity: Optional[int] = None):
+        self.comm = comm
+        self.like = LikeOnAlphabet(tpch.PTYPE_DICT, "PROMO%")
+        if comm is None or comm.world == 1:
+            self.probe = FusedScanAgg(tpch.Q14_SIG)
+        else:
+            self.probe = FusedScanAgg(Q14_PROBE_SIG)
+            self.compact_capacity = compact_capacity
+            self.scan = None
+
+    # ---- build side -----------------------------------------------------------------------------
+    def _build(self, partkey: torch.Tensor, ptype: torch.Tensor):
+        """Array-mode table over the build keys -> one byte per key slot (0 miss, 1 match, 2 match & PROMO)."""
+        n = partkey.numel()
+        if n == 0:
+            return torch.zeros(1, dtype=torch.uint8, device="cuda"), 0
+        col = flat_device(BIGINT, partkey)
+        lo, hi, _ = column_minmax(col)  # key range decides the layout (VectorHasher range mode)
+        rng = hi - lo + 2
+        keys, valid = normalize_keys([col], [lo], [1], ranges=[rng], nulls_invalid=True)
+        head, _next, _flags = join_build_array(keys, valid, rng)
+        flags = self.like.run()
+        return join_slot_flags(head, ptype, flags), lo - 1  # slot = key - (lo - 1)
+
+    # ---- single GPU -----------------------------------------------------------------------------
+    def launch(self, li, part, rows):
+        if self.comm is not None and self.comm.world > 1:
+            return self._launch_partitioned(li, part, rows)
+        slot_flags, join_min = self._build(part["p_partkey"], part["p_type"])
+        self.probe.reset()
+        self.probe.add_batch([li["l_shipdate"], li["l_partkey"], li["l_extendedprice"], li["l_discount"]], rows,
+                             pf=[1.0, 1.0, 0.0], pi=[tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI],
+                             join={"slot_flags": slot_flags, "min": join_min})
+
+    # ---- hash-partitioned across GPUs -----------------------------------------------------------------
+    def _exchange(self, key: torch.Tensor, payload: torch.Tensor):
+        """Partitions rows by VectorHasher-hash(key) % world and exchanges both columns."""
+        w = self.comm.world
+        h = hash_columns([flat_device(BIGINT, key)])
+        ids = partition_ids(h, w)
+        counts, order = partition_scatter_order(ids, w)
+        send_counts = counts.tolist()
+        recv_counts = self.comm.exchange_counts(send_counts)
+        k = self.comm.all_to_all(gather(key, order), send_counts, recv_counts)
+        p = self.comm.all_to_all(gather(payload, order), send_counts, recv_counts)
+        return k, p
+
+    def _launch_partitioned(self, li, part_shard, rows):
+        # part side: this rank's rows of part -> owners of their keys -> local build
+        pk, pt = self._exchange(part_shard["p_partkey"], part_shard["p_type"])
+        slot_flags, join_min = self._build(pk, pt)
+        # lineitem side: fused filter + project + compact, then the same exchange
+        if self.scan is None:
+            self.scan = FusedScanCompact(Q14_SCAN_SIG, self.compact_capacity or max(1 << 20, rows // 16))
+        self.scan.run([li["l_shipdate"], li["l_partkey"], li["l_extendedprice"], li["l_discount"]], rows,
+                      pf=[1.0], pi=[tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI])
+        n, (lk, rev) = self.scan.result([torch.int64, torch.float64])
+        rk, rrev = self._exchange(lk, rev)
+        self.probe.reset()
+        m = rk.numel()
+        if m:
+            # pad to the kernel's 16-byte alignment requirement by construction (fresh tensors are 256 B aligned)
+            self.probe.add_batch([rk, rrev], m, pf=[0.0], join={"slot_flags": slot_flags, "min": join_min})
+
+    def merge(self):
+        if self.comm is not None and self.comm.world > 1:
+            self.comm.all_reduce_(self.probe.sums)
+            self.comm.all_reduce_(self.probe.counts)
+
+    def result(self):
+        total, promo = self.probe.sums.cpu().tolist()
+        return (100.0 * promo / total) if total else None
