@@ -1193,35 +1193,49 @@ struct GroupBy {
       }
       return;
     }
-    for (int64_t r = 0; r < n; ++r) {
-      if (masked_out(r) || in->null_at(r)) continue;
-      int32_t g = groups[r];
-      int64_t s0 = in->is_const ? 0 : r;
-      if (f == "sum" || f == "avg") {
-        bool as_double = f == "avg" || in->type == ORC_DOUBLE;
-        if (as_double) {
-          double v = in->type == ORC_DOUBLE ? in->as<double>()[s0]
-                   : in->type == ORC_BIGINT ? static_cast<double>(in->as<int64_t>()[s0])
-                                            : static_cast<double>(in->as<int32_t>()[s0]);
-          acc.dsum[g] += v;  // one rounding per add, input order
-        } else {
-          int64_t v = in->type == ORC_BIGINT ? in->as<int64_t>()[s0] : in->as<int32_t>()[s0];
-          if (__builtin_add_overflow(acc.isum[g], v, &acc.isum[g])) throw UserError("integer overflow in sum");
-        }
-        if (f == "avg") acc.cnt[g] += raw ? 1 : in2->as<int64_t>()[in2->is_const ? 0 : r];
-        acc.has[g] = 1;
-      } else {  // min / max (NaN is largest for doubles)
-        bool is_min = f == "min";
+    const bool no_skip = !mask && !in->nulls;
+    auto each = [&](auto&& body) {
+      if (no_skip) { for (int64_t r = 0; r < n; ++r) body(r); }
+      else { for (int64_t r = 0; r < n; ++r) { if (masked_out(r) || in->null_at(r)) continue; body(r); } }
+    };
+    const int64_t stride = in->is_const ? 0 : 1;
+    const int32_t* g = groups.data();
+    if (f == "sum" || f == "avg") {
+      const bool as_double = f == "avg" || in->type == ORC_DOUBLE;
+      if (as_double) {
+        double* acc_d = acc.dsum.data();
+        // one rounding per add, input order (functions/lib/aggregates/SumAggregateBase.h:71-142)
+        if (in->type == ORC_DOUBLE) { const double* v = in->as<double>(); each([&](int64_t r) { acc_d[g[r]] += v[r * stride]; }); }
+        else if (in->type == ORC_BIGINT) { const int64_t* v = in->as<int64_t>(); each([&](int64_t r) { acc_d[g[r]] += static_cast<double>(v[r * stride]); }); }
+        else { const int32_t* v = in->as<int32_t>(); each([&](int64_t r) { acc_d[g[r]] += static_cast<double>(v[r * stride]); }); }
+      } else {
+        int64_t* acc_i = acc.isum.data();
+        auto add = [&](int64_t r, int64_t v) { if (__builtin_add_overflow(acc_i[g[r]], v, &acc_i[g[r]])) throw UserError("integer overflow in sum"); };
+        if (in->type == ORC_BIGINT) { const int64_t* v = in->as<int64_t>(); each([&](int64_t r) { add(r, v[r * stride]); }); }
+        else { const int32_t* v = in->as<int32_t>(); each([&](int64_t r) { add(r, v[r * stride]); }); }
+      }
+      if (f == "avg") {
+        int64_t* c = acc.cnt.data();
+        if (raw) each([&](int64_t r) { c[g[r]] += 1; });
+        else { const int64_t* v2 = in2->as<int64_t>(); const int64_t s2 = in2->is_const ? 0 : 1; each([&](int64_t r) { c[g[r]] += v2[r * s2]; }); }
+      }
+      uint8_t* has = acc.has.data();
+      each([&](int64_t r) { has[g[r]] = 1; });
+    } else {  // min / max (NaN is largest for doubles)
+      const bool is_min = f == "min";
+      each([&](int64_t r) {
+        const int32_t gi = g[r];
+        const int64_t s0 = r * stride;
         if (in->type == ORC_DOUBLE) {
           double v = in->as<double>()[s0];
-          if (!acc.has[g] || (is_min ? cmp_f64(0, v, acc.dsum[g]) : cmp_f64(2, v, acc.dsum[g]))) acc.dsum[g] = v;
+          if (!acc.has[gi] || (is_min ? cmp_f64(0, v, acc.dsum[gi]) : cmp_f64(2, v, acc.dsum[gi]))) acc.dsum[gi] = v;
         } else {
           int64_t v = in->type == ORC_BIGINT ? in->as<int64_t>()[s0]
                     : in->type == ORC_INTEGER ? in->as<int32_t>()[s0] : in->as<uint8_t>()[s0];
-          if (!acc.has[g] || (is_min ? v < acc.isum[g] : v > acc.isum[g])) acc.isum[g] = v;
+          if (!acc.has[gi] || (is_min ? v < acc.isum[gi] : v > acc.isum[gi])) acc.isum[gi] = v;
         }
-        acc.has[g] = 1;
-      }
+        acc.has[gi] = 1;
+      });
     }
   }
 
@@ -1294,16 +1308,32 @@ struct JoinTable {
     nk = n.build_keys.size();
     const auto& schema = n.build->schema;
     // concatenate
-    std::vector<ColBuilder> cb;
-    for (int ty : schema) cb.emplace_back(ty);
-    for (auto& b : t) {
-      for (size_t c = 0; c < schema.size(); ++c) {
-        VecPtr f = flatten(b.cols[c]);
-        for (int64_t r = 0; r < b.n; ++r) cb[c].push_from(*f, r);
+    for (auto& b : t) rows.n += b.n;
+    for (size_t c = 0; c < schema.size(); ++c) {
+      // fixed-width, null-free columns are concatenated with memcpy; others value by value
+      bool plain = schema[c] != ORC_VARCHAR;
+      std::vector<VecPtr> flats;
+      for (auto& b : t) {
+        flats.push_back(flatten(b.cols[c]));
+        plain = plain && !flats.back()->nulls && !flats.back()->is_const;
       }
-      rows.n += b.n;
+      if (plain) {
+        auto v = make_result(schema[c], rows.n);
+        const int w = width_of(schema[c]);
+        uint8_t* o = v->alloc<uint8_t>(rows.n * w);
+        int64_t off = 0;
+        for (size_t i = 0; i < t.size(); ++i) {
+          std::memcpy(o + off * w, flats[i]->data, static_cast<size_t>(t[i].n) * w);
+          off += t[i].n;
+        }
+        rows.cols.push_back(v);
+      } else {
+        ColBuilder cb(schema[c]);
+        for (size_t i = 0; i < t.size(); ++i)
+          for (int64_t r = 0; r < t[i].n; ++r) cb.push_from(*flats[i], r);
+        rows.cols.push_back(cb.finish());
+      }
     }
-    for (auto& c : cb) rows.cols.push_back(c.finish());
     flat_cols = rows.cols;
     for (size_t k = 0; k < nk; ++k) { hashers.emplace_back(); hashers.back().type = schema[n.build_keys[k]]; }
     std::vector<std::vector<int32_t>> ids(nk);
@@ -1317,7 +1347,10 @@ struct JoinTable {
       if (has_null) continue;
       int32_t e;
       bool is_new = false;
-      if (nk <= 2) e = combos.find_or_insert(pack(row_ids), static_cast<int32_t>(first.size()), is_new);
+      if (nk == 1) {  // value ids are dense (1..N): they index the chains directly
+        e = row_ids[0] - 1;
+        is_new = static_cast<size_t>(e) >= first.size();
+      } else if (nk <= 2) e = combos.find_or_insert(pack(row_ids), static_cast<int32_t>(first.size()), is_new);
       else {
         auto it = wide.emplace(std::string(reinterpret_cast<const char*>(row_ids.data()), nk * 4), static_cast<int32_t>(first.size()));
         is_new = it.second; e = it.first->second;
@@ -1330,7 +1363,8 @@ struct JoinTable {
   int32_t lookup(const std::vector<int32_t>& row_ids) const {
     for (auto id : row_ids) if (id <= 0) return -1;  // null (0) or unseen value (-1)
     int32_t e;
-    if (nk <= 2) e = combos.find(pack(row_ids));
+    if (nk == 1) e = row_ids[0] - 1 < static_cast<int32_t>(first.size()) ? row_ids[0] - 1 : -1;
+    else if (nk <= 2) e = combos.find(pack(row_ids));
     else {
       auto it = wide.find(std::string(reinterpret_cast<const char*>(row_ids.data()), nk * 4));
       e = it == wide.end() ? -1 : it->second;
@@ -1480,10 +1514,7 @@ struct Executor {
       keep.push_back(std::make_unique<Node>(partial));
       gbs.push_back(std::make_unique<GroupBy>(*keep.back()));
     }
-    int saved = threads;
-    threads = T;
-    stream(node->child, [&](int t, Batch&& b) { gbs[t]->add(b); });
-    threads = saved;
+    stream(node->child, [&](int t, Batch&& b) { gbs[t]->add(b); }, T);
     Table out;
     if (node->step == "single" && T > 1) {
       // merge: final aggregation over the drivers' intermediate outputs
@@ -1528,7 +1559,10 @@ struct Executor {
   }
 
   // Runs the streaming chain that ends at `node`, handing each output batch to sink(thread, batch).
-  void stream(const NodePtr& node, const std::function<void(int, Batch&&)>& sink) {
+  // drivers: number of driver threads of THIS chain (blocking children below it are materialised
+  // with the executor's full thread count).
+  void stream(const NodePtr& node, const std::function<void(int, Batch&&)>& sink, int drivers = 0) {
+    const int threads = drivers > 0 ? drivers : this->threads;
     std::vector<const Node*> ops;
     NodePtr cur = node;
     while (cur->kind == Node::FILTER || cur->kind == Node::PROJECT || cur->kind == Node::JOIN) {
@@ -1579,7 +1613,7 @@ struct Executor {
           }
         });
       };
-      run_threads(work);
+      run_threads(work, threads);
     } else {  // blocking child (aggregation): its output batches are distributed over drivers
       Table in = materialise(cur);
       auto work = [&](int t) {
@@ -1587,7 +1621,7 @@ struct Executor {
           for (size_t i = t; i < in.size(); i += threads) run_ops(t, in[i]);
         });
       };
-      run_threads(work);
+      run_threads(work, threads);
     }
     for (int t = 0; t < threads; ++t)
       if (!errors[t].empty()) {
@@ -1596,7 +1630,7 @@ struct Executor {
       }
   }
 
-  void run_threads(const std::function<void(int)>& work) {
+  void run_threads(const std::function<void(int)>& work, int threads) {
     if (threads == 1) { work(0); return; }
     std::vector<std::thread> ts;
     for (int t = 0; t < threads; ++t) ts.emplace_back(work, t);
