@@ -45,35 +45,33 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled through NVML every ~5 ms while the GPU is under load."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.samples = index, threading.Event(), []
+        self.index, self.stop_flag, self.samples, self.max_mhz = index, threading.Event(), [], None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                util = pynvml.nvmlDeviceGetUtilizationRates(h).gpu
+                self.samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                                     pynvml.nvmlDeviceGetCurrentClocksEventReasons(h), util))
+                self.stop_flag.wait(0.005)
+        except Exception as e:  # pragma: no cover
+            self.error = str(e)
 
     def summary(self):
-        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            for n, v in zip(names, s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        mx = max((int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()), default=None)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        import pynvml
+        sm = sorted(s[0] for s in self.samples)
+        flags = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": pynvml.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(n for n, bit in flags.items() if any(s[1] & bit for s in self.samples))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 # -------------------------------------------------------------------------------------------------

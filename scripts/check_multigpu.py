@@ -1,0 +1,58 @@
+"""Multi-GPU parity check (run under torchrun): Q1 / Q6 / Q14 over row shards with the NCCL merge /
+hash-partitioned exchange must equal the single-GPU result over the union of the shards."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from velox_b200 import tpch
+from velox_b200.comm import Comm
+from velox_b200.queries import Q1, Q6, Q14
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = Comm()
+    rows, nparts = 2_000_003, 50_000
+    li = tpch.gen_lineitem(rows, nparts, seed=42 + rank, device="cuda")
+    part_all = tpch.gen_part(nparts, seed=43, device="cuda")
+    p0, p1 = nparts * rank // world, nparts * (rank + 1) // world
+    part = {k: v[p0:p1].contiguous() for k, v in part_all.items()}
+    q1, q6, q14 = Q1(comm), Q6(comm), Q14(comm)
+    for _ in range(2):  # twice: persistent state must reset correctly
+        q1.launch(li, rows); q1.merge()
+        q6.launch(li, rows); q6.merge()
+        q14.launch(li, part, rows); q14.merge()
+    torch.cuda.synchronize()
+    got = {"q1": {f"{k[0]}{k[1]}": list(v) for k, v in q1.result().items()}, "q6": q6.result(), "q14": q14.result(),
+           "q14_rows": int(q14.probe.counts.item())}
+    ok = True
+    if rank == 0:
+        # single-GPU reference over the union of all shards
+        parts = [tpch.gen_lineitem(rows, nparts, seed=42 + r, device="cuda") for r in range(world)]
+        full = {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
+        s1, s6, s14 = Q1(), Q6(), Q14()
+        n = rows * world
+        s1.launch(full, n); s6.launch(full, n); s14.launch(full, part_all, n)
+        torch.cuda.synchronize()
+        want = {"q1": {f"{k[0]}{k[1]}": list(v) for k, v in s1.result().items()}, "q6": s6.result(), "q14": s14.result(),
+                "q14_rows": int(s14.probe.counts.item())}
+        def close(a, b):
+            return abs(a - b) <= 1e-11 * abs(b)
+        ok = set(got["q1"]) == set(want["q1"]) and got["q14_rows"] == want["q14_rows"]
+        for k in want["q1"]:
+            ok = ok and got["q1"][k][7] == want["q1"][k][7] and all(close(a, b) for a, b in zip(got["q1"][k][:7], want["q1"][k][:7]))
+        ok = ok and close(got["q6"], want["q6"]) and close(got["q14"], want["q14"])
+        print(json.dumps({"ok": bool(ok), "world": world, "got_q14": got["q14"], "want_q14": want["q14"], "q14_rows": got["q14_rows"]}))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
