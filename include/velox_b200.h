@@ -63,6 +63,10 @@ void vb2_comm_free(vb2_comm* comm);
  * int64[world]); recv_counts (host int64[world]) is filled first through a count exchange when
  * recv == NULL, otherwise the payload is exchanged. Device pointers; stream-ordered. */
 int32_t vb2_comm_exchange_counts(vb2_comm* comm, const int64_t* send_counts, int64_t* recv_counts, void* stream);
+/* Same with the send counts already on the device (int64[world], e.g. from
+ * vb2k_partition_scatter_order): exchanges them and returns both count vectors with one sync. */
+int32_t vb2_comm_exchange_counts_dev(vb2_comm* comm, const int64_t* dev_send_counts, int64_t* send_counts_host, int64_t* recv_counts_host,
+                                     void* stream);
 int32_t vb2_comm_all_to_all(vb2_comm* comm, const void* send, const int64_t* send_counts, void* recv, const int64_t* recv_counts,
                             int32_t elem_bytes, void* stream);
 /* Sum-reduces n doubles / int64s in place across ranks (merge of per-GPU partial aggregates). */

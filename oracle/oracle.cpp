@@ -305,6 +305,17 @@ static bool like_match(const char* s, int64_t sl, const char* p, int64_t pl) {
 struct EvalCtx {
   const Batch* in;
   std::vector<VecPtr> flat_cache;  // flattened input columns
+  // Per-row error capture inside AND / OR: an error on a row that a later (or earlier) conjunct
+  // decides is dropped (expression/ConjunctExpr.cpp:98-99,167-168); outside it throws at once.
+  int capture = 0;
+  std::vector<uint8_t> row_err;
+  std::string first_err;
+  void fail(int64_t r, const char* msg) {
+    if (capture == 0) throw UserError(msg);
+    if (row_err.empty()) row_err.assign(in->n, 0);
+    row_err[r] = 1;
+    if (first_err.empty()) first_err = msg;
+  }
 };
 
 static VecPtr input_flat(EvalCtx& ctx, int i) {
@@ -429,15 +440,13 @@ static VecPtr eval_call(const Expr& e, EvalCtx& ctx, const Rows& rows) {
       auto* o = out->alloc<int64_t>(n);
       Acc<int64_t> x(*a[0]), y(*a[1]);
       for_non_null(rows, a, *out, [&](int64_t r) {
-        if (!checked_arith<int64_t>(op, x[r], y[r], &o[r]))
-          throw UserError(op >= 3 && y[r] == 0 ? "division by zero" : "integer overflow");
+        if (!checked_arith<int64_t>(op, x[r], y[r], &o[r])) ctx.fail(r, op >= 3 && y[r] == 0 ? "division by zero" : "integer overflow");
       });
     } else {
       auto* o = out->alloc<int32_t>(n);
       Acc<int32_t> x(*a[0]), y(*a[1]);
       for_non_null(rows, a, *out, [&](int64_t r) {
-        if (!checked_arith<int32_t>(op, x[r], y[r], &o[r]))
-          throw UserError(op >= 3 && y[r] == 0 ? "division by zero" : "integer overflow");
+        if (!checked_arith<int32_t>(op, x[r], y[r], &o[r])) ctx.fail(r, op >= 3 && y[r] == 0 ? "division by zero" : "integer overflow");
       });
     }
   } else if (f == "negate") {
@@ -449,14 +458,14 @@ static VecPtr eval_call(const Expr& e, EvalCtx& ctx, const Rows& rows) {
       auto* o = out->alloc<int64_t>(n);
       Acc<int64_t> x(*a[0]);
       for_non_null(rows, a, *out, [&](int64_t r) {
-        if (x[r] == std::numeric_limits<int64_t>::min()) throw UserError("integer overflow");
+        if (x[r] == std::numeric_limits<int64_t>::min()) { ctx.fail(r, "integer overflow"); return; }
         o[r] = -x[r];
       });
     } else {
       auto* o = out->alloc<int32_t>(n);
       Acc<int32_t> x(*a[0]);
       for_non_null(rows, a, *out, [&](int64_t r) {
-        if (x[r] == std::numeric_limits<int32_t>::min()) throw UserError("integer overflow");
+        if (x[r] == std::numeric_limits<int32_t>::min()) { ctx.fail(r, "integer overflow"); return; }
         o[r] = -x[r];
       });
     }
@@ -560,9 +569,10 @@ static VecPtr eval_conjunct(const Expr& e, EvalCtx& ctx, const Rows& rows, bool 
   const int64_t n = rows.n;
   auto out = make_result(ORC_BOOLEAN, n);
   auto* o = out->alloc<uint8_t>(n);
-  std::vector<uint8_t> saw_null;
+  std::vector<uint8_t> saw_null, saw_err;
   rows.for_each([&](int64_t r) { o[r] = is_and; });
   Rows active = rows;
+  ++ctx.capture;
   for (auto& arg : e.args) {
     if (active.count() == 0) break;
     VecPtr v = eval(*arg, ctx, active);
@@ -570,19 +580,30 @@ static VecPtr eval_conjunct(const Expr& e, EvalCtx& ctx, const Rows& rows, bool 
     std::vector<int32_t> keep;
     keep.reserve(active.count());
     active.for_each([&](int64_t r) {
-      if (v->null_at(r)) {
+      if (!ctx.row_err.empty() && ctx.row_err[r]) {  // errored on this conjunct: undecided so far
+        ctx.row_err[r] = 0;
+        if (saw_err.empty()) saw_err.assign(n, 0);
+        saw_err[r] = 1;
+        keep.push_back(static_cast<int32_t>(r));
+      } else if (v->null_at(r)) {
         if (saw_null.empty()) saw_null.assign(n, 0);
         saw_null[r] = 1;
         keep.push_back(static_cast<int32_t>(r));
       } else if (static_cast<bool>(x[r]) != is_and) {
         o[r] = !is_and;  // decided
         if (!saw_null.empty()) saw_null[r] = 0;
+        if (!saw_err.empty()) saw_err[r] = 0;
       } else {
         keep.push_back(static_cast<int32_t>(r));
       }
     });
     active.all = false;
     active.list.swap(keep);
+  }
+  --ctx.capture;
+  if (!saw_err.empty()) {
+    const std::string msg = ctx.first_err.empty() ? "arithmetic error" : ctx.first_err;
+    rows.for_each([&](int64_t r) { if (saw_err[r]) ctx.fail(r, msg.c_str()); });  // propagates or throws
   }
   if (!saw_null.empty()) {
     uint8_t* on = out->alloc_nulls(n);

@@ -98,6 +98,10 @@ def test_checked_arithmetic_errors():
         check_user_error(PlanBuilder().values(rv.names, rv.types).project([expr]).planNode(), [rv])
     # errors on rows that end up not selected are suppressed inside AND / CASE (ConjunctExpr.cpp:98-99)
     check_plan(PlanBuilder().values(rv.names, rv.types).filter("b <> 0 and a / b > 0").planNode(), [rv])
+    div = row_vector(["a", "b"], [flat_vector(BIGINT, [6, 5, 7, None]), flat_vector(BIGINT, [3, 0, 0, 0])])
+    for e in ["a / b > 0 and b <> 0", "b <> 0 and a / b > 0", "a / b > 0 or b = 0"]:  # FALSE / TRUE dominate the error in either order
+        check_plan(PlanBuilder().values(div.names, div.types).project([e]).planNode(), [div])
+    check_user_error(PlanBuilder().values(div.names, div.types).project(["a / b > 0 and a > 0"]).planNode(), [div])
     check_plan(PlanBuilder().values(rv.names, rv.types).project(["case when b <> 0 then a / b else 0 end"]).planNode(),
                [row_vector(["a", "b"], [flat_vector(BIGINT, [6, 5]), flat_vector(BIGINT, [3, 0])])])
     i32 = row_vector(["a"], [flat_vector(INTEGER, [2**31 - 1, 1])])

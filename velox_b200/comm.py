@@ -43,6 +43,16 @@ class Comm:
             raise VeloxRuntimeError("count exchange failed")
         return list(r)
 
+    def exchange_counts_dev(self, send_counts_dev: torch.Tensor):
+        """send counts on the device -> (send_counts, recv_counts) host lists, one synchronisation."""
+        w = self.world
+        s = (C.c_int64 * w)()
+        r = (C.c_int64 * w)()
+        rc = self.L.vb2_comm_exchange_counts_dev(C.c_void_p(self.h), C.c_void_p(send_counts_dev.data_ptr()), s, r, self._st())
+        if rc:
+            raise VeloxRuntimeError("count exchange failed")
+        return list(s), list(r)
+
     def all_to_all(self, send: torch.Tensor, send_counts, recv_counts) -> torch.Tensor:
         """send: elements grouped by destination rank (counts in elements)."""
         w = self.world

@@ -83,6 +83,33 @@ int32_t vb2_comm_exchange_counts(vb2_comm* comm, const int64_t* send_counts, int
   return VB2_OK;
 }
 
+int32_t vb2_comm_exchange_counts_dev(vb2_comm* comm, const int64_t* dev_send_counts, int64_t* send_counts_host, int64_t* recv_counts_host,
+                                     void* stream) {
+  // counts stay on the device for the exchange; one device->host copy (and one sync) brings both
+  // the send and the receive counts back for sizing the payload all-to-all
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int w = comm->world;
+  try {
+    if (!comm->counts) comm->counts = velox_b200::allocDevice(static_cast<size_t>(w) * 16, st);
+    int64_t* both = comm->counts->as<int64_t>();
+    VB2_CU(cudaMemcpyAsync(both, dev_send_counts, w * 8, cudaMemcpyDeviceToDevice, st));
+    ncclGroupStart();
+    for (int p = 0; p < w; ++p) {
+      ncclSend(both + p, 1, ncclInt64, p, comm->comm, st);
+      ncclRecv(both + w + p, 1, ncclInt64, p, comm->comm, st);
+    }
+    if (ncclGroupEnd() != ncclSuccess) return VB2_ERR_CUDA;
+    std::vector<int64_t> h(static_cast<size_t>(w) * 2);
+    VB2_CU(cudaMemcpyAsync(h.data(), both, w * 16, cudaMemcpyDeviceToHost, st));
+    VB2_CU(cudaStreamSynchronize(st));
+    std::memcpy(send_counts_host, h.data(), w * 8);
+    std::memcpy(recv_counts_host, h.data() + w, w * 8);
+  } catch (const std::exception&) {
+    return VB2_ERR_CUDA;
+  }
+  return VB2_OK;
+}
+
 int32_t vb2_comm_all_to_all(vb2_comm* comm, const void* send, const int64_t* send_counts, void* recv, const int64_t* recv_counts,
                             int32_t elem_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);

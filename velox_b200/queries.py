@@ -92,6 +92,7 @@ class Q14:
             self.probe = FusedScanAgg(Q14_PROBE_SIG)
             self.compact_capacity = compact_capacity
             self.scan = None
+            self.side = None
 
     # ---- build side -----------------------------------------------------------------------------
     def _build(self, partkey: torch.Tensor, ptype: torch.Tensor):
@@ -119,32 +120,46 @@ class Q14:
 
     # ---- hash-partitioned across GPUs -----------------------------------------------------------------
     def _exchange(self, key: torch.Tensor, payload: torch.Tensor):
-        """Partitions rows by VectorHasher-hash(key) % world and exchanges both columns."""
+        """Partitions rows by VectorHasher-hash(key) % world and exchanges both columns
+        (launches on the current stream; one host synchronisation for the counts)."""
         w = self.comm.world
         h = hash_columns([flat_device(BIGINT, key)])
         ids = partition_ids(h, w)
         counts, order = partition_scatter_order(ids, w)
-        send_counts = counts.tolist()
-        recv_counts = self.comm.exchange_counts(send_counts)
-        k = self.comm.all_to_all(gather(key, order), send_counts, recv_counts)
-        p = self.comm.all_to_all(gather(payload, order), send_counts, recv_counts)
+        sk, sp = gather(key, order), gather(payload, order)
+        send_counts, recv_counts = self.comm.exchange_counts_dev(counts)
+        k = self.comm.all_to_all(sk, send_counts, recv_counts)
+        p = self.comm.all_to_all(sp, send_counts, recv_counts)
         return k, p
 
     def _launch_partitioned(self, li, part_shard, rows):
-        # part side: this rank's rows of part -> owners of their keys -> local build
-        pk, pt = self._exchange(part_shard["p_partkey"], part_shard["p_type"])
-        slot_flags, join_min = self._build(pk, pt)
-        # lineitem side: fused filter + project + compact, then the same exchange
+        main = torch.cuda.current_stream()
+        if self.side is None:
+            self.side = torch.cuda.Stream()
         if self.scan is None:
             self.scan = FusedScanCompact(Q14_SCAN_SIG, self.compact_capacity or max(1 << 20, rows // 16))
+        ready = torch.cuda.Event()
+        ready.record(main)  # everything the build side needs is complete at this point
+        # lineitem side first (asynchronous): fused filter + project + compact of this rank's shard
         self.scan.run([li["l_shipdate"], li["l_partkey"], li["l_extendedprice"], li["l_discount"]], rows,
                       pf=[1.0], pi=[tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI])
+        # build side on a second stream while the scan streams HBM: this rank's part rows go to the
+        # owners of their keys, then the local array-mode build. NCCL calls are issued in the same
+        # order on every rank (part exchange, then lineitem exchange).
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            pk, pt = self._exchange(part_shard["p_partkey"], part_shard["p_type"])
+            slot_flags, join_min = self._build(pk, pt)
+            built = torch.cuda.Event()
+            built.record()
         n, (lk, rev) = self.scan.result([torch.int64, torch.float64])
         rk, rrev = self._exchange(lk, rev)
+        main.wait_event(built)
+        for t in (pk, pt, slot_flags):
+            t.record_stream(main)
         self.probe.reset()
         m = rk.numel()
         if m:
-            # pad to the kernel's 16-byte alignment requirement by construction (fresh tensors are 256 B aligned)
             self.probe.add_batch([rk, rrev], m, pf=[0.0], join={"slot_flags": slot_flags, "min": join_min})
 
     def merge(self):
