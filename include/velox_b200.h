@@ -69,6 +69,10 @@ int32_t vb2_comm_exchange_counts_dev(vb2_comm* comm, const int64_t* dev_send_cou
                                      void* stream);
 int32_t vb2_comm_all_to_all(vb2_comm* comm, const void* send, const int64_t* send_counts, void* recv, const int64_t* recv_counts,
                             int32_t elem_bytes, void* stream);
+/* All columns of a partitioned row set in one NCCL group (one launch): send[c] / recv[c] are
+ * device arrays of elem_bytes[c]-wide elements segmented by send_counts / recv_counts (rows). */
+int32_t vb2_comm_all_to_all_columns(vb2_comm* comm, int32_t ncols, const void* const* send, void* const* recv, const int32_t* elem_bytes,
+                                    const int64_t* send_counts, const int64_t* recv_counts, void* stream);
 /* Sum-reduces n doubles / int64s in place across ranks (merge of per-GPU partial aggregates). */
 int32_t vb2_comm_all_reduce_f64(vb2_comm* comm, double* data, int64_t n, void* stream);
 int32_t vb2_comm_all_reduce_i64(vb2_comm* comm, int64_t* data, int64_t n, void* stream);

@@ -3,6 +3,7 @@
   * the plan front-end produces the plan text both libraries read; the product library's own
     reader accepts it (vb2_task_create) and rejects malformed text with VeloxRuntimeError;
   * without a GPU the product path fails loudly — there is no CPU fallback."""
+import torch  # noqa: F401  (first: our library must bind to the libnccl torch bundles)
 import ctypes as C
 import os
 import re

@@ -65,6 +65,21 @@ class Comm:
             raise VeloxRuntimeError("all-to-all failed")
         return out[:sum(recv_counts)]
 
+    def all_to_all_columns(self, sends, send_counts, recv_counts):
+        """Exchanges several columns of the same row partitioning in one NCCL group."""
+        w, n = self.world, len(sends)
+        total = sum(recv_counts)
+        outs = [torch.empty(max(1, total), dtype=t.dtype, device="cuda") for t in sends]
+        sp = (C.c_void_p * n)(*[t.data_ptr() for t in sends])
+        rp = (C.c_void_p * n)(*[t.data_ptr() for t in outs])
+        eb = (C.c_int32 * n)(*[t.element_size() for t in sends])
+        s = (C.c_int64 * w)(*send_counts)
+        r = (C.c_int64 * w)(*recv_counts)
+        rc = self.L.vb2_comm_all_to_all_columns(C.c_void_p(self.h), n, sp, rp, eb, s, r, self._st())
+        if rc:
+            raise VeloxRuntimeError("all-to-all failed")
+        return [o[:total] for o in outs]
+
     def all_reduce_(self, t: torch.Tensor):
         fn = self.L.vb2_comm_all_reduce_f64 if t.dtype == torch.float64 else self.L.vb2_comm_all_reduce_i64
         rc = fn(C.c_void_p(self.h), C.c_void_p(t.data_ptr()), C.c_int64(t.numel()), self._st())

@@ -178,6 +178,21 @@ void appendResult(vb2_task& t, const RowVectorPtr& batch) {
         default: idx = v->as<DictionaryVector<StringView>>()->rawIndices(); base = v->as<DictionaryVector<StringView>>()->valueVector().get();
       }
     }
+    // fast path: flat fixed-width column (the common shape of aggregation / projection results)
+    if (!idx && v->encoding() == VectorEncoding::Simple::FLAT && (o.type == VB2_INTEGER || o.type == VB2_BIGINT || o.type == VB2_DOUBLE)) {
+      const size_t w = o.type == VB2_INTEGER ? 4 : 8;
+      const uint8_t* src = o.type == VB2_INTEGER ? reinterpret_cast<const uint8_t*>(base->as<FlatVector<int32_t>>()->rawValues())
+                         : o.type == VB2_BIGINT ? reinterpret_cast<const uint8_t*>(base->as<FlatVector<int64_t>>()->rawValues())
+                                                : reinterpret_cast<const uint8_t*>(base->as<FlatVector<double>>()->rawValues());
+      const size_t at = o.values.size();
+      o.values.resize(at + static_cast<size_t>(n) * w);
+      std::memcpy(o.values.data() + at, src, static_cast<size_t>(n) * w);
+      const size_t nat = o.nulls.size();
+      o.nulls.resize(nat + n, 0);
+      if (const uint64_t* raw = v->rawNulls())
+        for (vector_size_t i = 0; i < n; ++i) o.nulls[nat + i] = bits::isBitNull(raw, i);
+      continue;
+    }
     for (vector_size_t i = 0; i < n; ++i) {
       const bool isNull = v->isNullAt(i);
       const vector_size_t s = idx ? idx[i] : i;

@@ -90,8 +90,8 @@ int32_t vb2_comm_exchange_counts_dev(vb2_comm* comm, const int64_t* dev_send_cou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int w = comm->world;
   try {
-    if (!comm->counts) comm->counts = velox_b200::allocDevice(static_cast<size_t>(w) * 16, st);
-    int64_t* both = comm->counts->as<int64_t>();
+    auto buf = velox_b200::allocDevice(static_cast<size_t>(w) * 16, st);  // per call: exchanges may overlap on two streams
+    int64_t* both = buf->as<int64_t>();
     VB2_CU(cudaMemcpyAsync(both, dev_send_counts, w * 8, cudaMemcpyDeviceToDevice, st));
     ncclGroupStart();
     for (int p = 0; p < w; ++p) {
@@ -125,6 +125,26 @@ int32_t vb2_comm_all_to_all(vb2_comm* comm, const void* send, const int64_t* sen
     roff += recv_counts[p];
   }
   return ncclFail(ncclGroupEnd(), "all_to_all");
+}
+
+int32_t vb2_comm_all_to_all_columns(vb2_comm* comm, int32_t ncols, const void* const* send, void* const* recv, const int32_t* elem_bytes,
+                                    const int64_t* send_counts, const int64_t* recv_counts, void* stream) {
+  // every column of the row set moves inside ONE NCCL group (one fused send/recv kernel)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int w = comm->world;
+  ncclGroupStart();
+  for (int c = 0; c < ncols; ++c) {
+    const char* s = static_cast<const char*>(send[c]);
+    char* r = static_cast<char*>(recv[c]);
+    int64_t soff = 0, roff = 0;
+    for (int p = 0; p < w; ++p) {
+      if (send_counts[p] > 0) ncclSend(s + soff * elem_bytes[c], static_cast<size_t>(send_counts[p]) * elem_bytes[c], ncclUint8, p, comm->comm, st);
+      if (recv_counts[p] > 0) ncclRecv(r + roff * elem_bytes[c], static_cast<size_t>(recv_counts[p]) * elem_bytes[c], ncclUint8, p, comm->comm, st);
+      soff += send_counts[p];
+      roff += recv_counts[p];
+    }
+  }
+  return ncclFail(ncclGroupEnd(), "all_to_all_columns");
 }
 
 int32_t vb2_comm_all_reduce_f64(vb2_comm* comm, double* data, int64_t n, void* stream) {

@@ -128,8 +128,7 @@ class Q14:
         counts, order = partition_scatter_order(ids, w)
         sk, sp = gather(key, order), gather(payload, order)
         send_counts, recv_counts = self.comm.exchange_counts_dev(counts)
-        k = self.comm.all_to_all(sk, send_counts, recv_counts)
-        p = self.comm.all_to_all(sp, send_counts, recv_counts)
+        k, p = self.comm.all_to_all_columns([sk, sp], send_counts, recv_counts)
         return k, p
 
     def _launch_partitioned(self, li, part_shard, rows):
