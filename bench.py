@@ -306,10 +306,11 @@ def main():
     sampler.join()
     results = {"q1": {f"{k[0]}{k[1]}": v[7] for k, v in q1.result().items()}, "q14_promo_revenue": q14.result(), "q6_revenue": q6.result()}
 
-    # launches of our kernels per step (Q1: fused + finalize; Q14: min/max init + min/max, normalize,
-    # join build, LIKE on the alphabet, slot flags, fused probe + finalize; N>1 adds hash, partition
-    # ids, 3 partition-order kernels and gathers per exchanged side and the scan-compact kernel)
-    launches_per_step = 2 + (9 if world == 1 else 9 + 1 + 2 * (1 + 1 + 3 + 2))
+    # launches of our kernels per step (Q1: fused + finalize; Q14 on one GPU: min/max init + min/max,
+    # normalize, join build, LIKE on the alphabet, slot flags, fused probe + finalize; Q14 planned
+    # exchange on N>1: scan-compact, 3 segment-partition kernels per exchanged side, key-range
+    # check, normalize, join build, LIKE, slot flags, fused probe + finalize). NCCL and memsets not counted.
+    launches_per_step = 2 + (9 if world == 1 else 1 + 2 * 3 + 1 + 4 + 2)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

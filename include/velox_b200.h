@@ -76,6 +76,8 @@ int32_t vb2_comm_all_to_all_columns(vb2_comm* comm, int32_t ncols, const void* c
 /* Sum-reduces n doubles / int64s in place across ranks (merge of per-GPU partial aggregates). */
 int32_t vb2_comm_all_reduce_f64(vb2_comm* comm, double* data, int64_t n, void* stream);
 int32_t vb2_comm_all_reduce_i64(vb2_comm* comm, int64_t* data, int64_t n, void* stream);
+/* Element-wise maximum over ranks (exchange planning statistics). */
+int32_t vb2_comm_all_reduce_max_i64(vb2_comm* comm, int64_t* data, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,22 @@ int vb2k_partition_ids(const uint64_t* hashes, int64_t rows, int32_t num_partiti
  * (stable within a partition). All outputs device memory: counts int64[P], row_order int32[rows]. */
 int vb2k_partition_scatter_order(const uint32_t* ids, int64_t rows, int32_t num_partitions, int64_t* counts,
                                  int32_t* row_order, void* stream);
+/* Sync-free variant for shuffles whose sizes are planned ahead (from statistics of an earlier run
+ * of the same plan): rows of a non-null BIGINT key column and up to 4 fixed-width payload columns
+ * go straight into fixed-capacity per-destination segments — row r to partition
+ * p = twang_mix64(key) % P (= VectorHasher hash % P, as above) at seg_keys[p * segcap + rank],
+ * rank = its stable position among the rows of p. Only rows r < min(rows, *rows_dev) are read when
+ * rows_dev (device) is given, so a producer's device-side row count never visits the host.
+ * Segment tails hold VB2_SENTINEL_KEY, a key value the shuffled tables must not contain: join
+ * probes / builds downstream treat it as out of range (a miss). counts[p] (device) = rows of p;
+ * *overflow (device) becomes 1 if a partition exceeds segcap (its excess rows are dropped and the
+ * caller must re-plan). */
+#define VB2_SENTINEL_KEY ((int64_t)0x8080808080808080ull)
+int vb2k_partition_segments(const int64_t* keys, const void* const* cols, const int32_t* col_elem_bytes, int32_t ncols, int64_t rows,
+                            const int64_t* rows_dev, int32_t num_partitions, int64_t segcap, int64_t* seg_keys, void* const* seg_cols,
+                            int64_t* counts, int32_t* overflow, void* stream);
+/* *flag (device) <- 1 if any key other than VB2_SENTINEL_KEY lies outside [lo, hi]. */
+int vb2k_key_range_check(const int64_t* keys, int64_t n, int64_t lo, int64_t hi, int32_t* flag, void* stream);
 /* out[i] = in[order[i]] for fixed-width columns (elem_bytes 4 or 8). */
 int vb2k_gather(const void* in, const int32_t* order, int64_t n, int32_t elem_bytes, void* out, void* stream);
 
@@ -211,30 +227,72 @@ int32_t vb2k_fused_output_width(int32_t id, int32_t out);
 enum vb2_agg_kind { VB2_AGG_SUM_F64 = 1, VB2_AGG_SUM_I64 = 2, VB2_AGG_COUNT = 3, VB2_AGG_MIN_F64 = 4,
                     VB2_AGG_MAX_F64 = 5, VB2_AGG_MIN_I64 = 6, VB2_AGG_MAX_I64 = 7, VB2_AGG_COUNT_MERGE = 8 };
 
+/* Group table: row-wise group storage, the role of exec::RowContainer under exec::HashTable for
+ * GROUP BY (velox/exec/RowContainer.h, velox/exec/HashTable.cpp:706-772 groupProbe). `capacity` rows
+ * of `row_words` 8-byte words; word 0 is the occupancy word — the 64-bit normalized key in hash
+ * mode (VB2_EMPTY_KEY = free; open addressing, linear probing, load factor <= 0.5, capacity a power
+ * of two), "rows seen" in array mode (slot = normalized key, 0 = free; capacity = key space) — the
+ * remaining words are accumulators / non-null counters. Rows of more than two words should be
+ * padded to a multiple of four words (whole 32-byte sectors). */
+#define VB2_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define VB2_MAX_ROW_WORDS 64
+typedef struct vb2_group_table {
+  uint64_t* rows;
+  int64_t capacity;
+  int32_t row_words;
+  int32_t hash_mode;
+} vb2_group_table;
+typedef struct vb2_group_row_init { uint64_t words[VB2_MAX_ROW_WORDS]; } vb2_group_row_init;
+
 typedef struct vb2_agg_update {
   int32_t kind;
   int32_t input_type;       /* VB2_DOUBLE / VB2_BIGINT / VB2_INTEGER (converted as the reference does) */
   const void* input;        /* dense input values (NULL for COUNT(*)) */
   const uint64_t* nulls;    /* validity bitmap of the input or NULL */
   const uint64_t* mask;     /* optional aggregate mask bitmap (exec/AggregationMasks.cpp), 1 = use row */
-  void* acc;                /* double[capacity] or int64[capacity] */
-  int64_t* nonnull;         /* int64[capacity]: non-null inputs seen (drives NULL results and AVG counts), may be NULL */
+  int32_t acc_word;         /* word of the accumulator (double or int64) inside the group row, >= 1 */
+  int32_t nonnull_word;     /* word counting non-null inputs (drives NULL results and AVG counts), -1 = not tracked */
 } vb2_agg_update;
 
-/* group_ids: int32[n], one slot per row (negative = skip row); NULL = every row in group 0
- * (global aggregation). capacity = size of the group-id
- * space; spaces of <= 8 groups take a register-accumulator kernel (one launch per aggregate),
- * larger ones one atomic per row and aggregate. SUM(BIGINT) overflow sets *error_flag. */
-int vb2k_agg_update(const int32_t* group_ids, int64_t n, int64_t capacity, const vb2_agg_update* aggs, int32_t naggs,
-                    int32_t* error_flag, void* stream);
-
-/* Normalized-key group table (open addressing, linear probing, 64-bit keys, load factor <= 0.5):
- * keys uint64[capacity] initialised to VB2_EMPTY_KEY. Finds or inserts each row's key and
- * writes its slot to group_ids. capacity must be a power of two. */
-#define VB2_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
-/* table_keys == NULL: array mode, the normalized key itself is the slot (capacity = key space). */
-int vb2k_group_probe(const uint64_t* row_keys, const uint64_t* row_valid, int64_t n, uint64_t* table_keys,
-                     int64_t capacity, int32_t* group_ids, int64_t* num_groups, int32_t* error_flag, void* stream);
+/* Fills every row with row_init[0 .. row_words) (host array: VB2_EMPTY_KEY or 0, then accumulator identities). */
+int vb2k_group_table_init(const vb2_group_table* t, const uint64_t* row_init, void* stream);
+/* One batch of GroupingSet::addInput (velox/exec/GroupingSet.cpp:236-358): finds or inserts each
+ * row's group (row_keys from vb2k_normalize_keys; NULL = global aggregation, every row in row 0;
+ * rows whose row_valid bit is clear are skipped) and applies every aggregate update to that row in
+ * the same kernel. Array-mode tables of <= 8 rows take register-accumulator kernels (one launch
+ * per aggregate) because same-address atomics serialise. num_groups (device, optional) is
+ * incremented per inserted key; SUM(BIGINT) overflow sets *error_flag = 1, a full table 100. */
+int vb2k_group_update(const vb2_group_table* t, const uint64_t* row_keys, const uint64_t* row_valid, int64_t n,
+                      const vb2_agg_update* aggs, int32_t naggs, int64_t* num_groups, int32_t* error_flag, void* stream);
+/* Compacts occupied rows: slot_list int32[<=capacity] ascending, count device int64. */
+int vb2k_group_occupied(const vb2_group_table* t, int32_t* slot_list, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
+size_t vb2k_group_occupied_workspace(int64_t capacity);
+/* word <- value in every occupied row. */
+int vb2k_group_set_word(const vb2_group_table* t, int32_t word, uint64_t value, void* stream);
+/* Re-encodes the keys of the listed slots for a new layout after value ranges grew, and moves the
+ * groups into a new table (the rehash of HashTable::checkSize / decideHashMode,
+ * velox/exec/HashTable.cpp:772,1751). */
+int vb2k_group_rekey(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t ncols, const int64_t* old_mins,
+                     const uint64_t* old_mults, const uint64_t* old_ranges, const int32_t* old_null_reserved, const int64_t* new_mins,
+                     const uint64_t* new_mults, uint64_t* keys_out, void* stream);
+int vb2k_group_move(const vb2_group_table* from, const int32_t* slots, const uint64_t* new_keys, int64_t n, const vb2_group_table* to,
+                    int64_t* num_groups, int32_t* error_flag, void* stream);
+/* Inverse of vb2k_normalize_keys for one key column over the listed slots: value = id - 1 + min
+ * with id = (key / mult) % range; id 0 is NULL when null_reserved (a layout for a column that
+ * never held NULLs uses min + 1 and keeps id 0 for the smallest value). values: T[n] (BOOLEAN one
+ * byte per row). */
+int vb2k_group_keys(const vb2_group_table* t, const int32_t* slots, int64_t n, int64_t min, uint64_t mult, uint64_t range,
+                    int32_t null_reserved, int32_t type, void* values, uint64_t* valid, void* stream);
+/* Aggregate result extraction (Aggregate::extractValues, velox/exec/Aggregate.h:281-302) over the
+ * listed slots: one word as a dense 8-byte column; validity bit = count word > 0; avg = sum / count. */
+int vb2k_group_gather(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t word, void* out, void* stream);
+int vb2k_group_valid(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t count_word, uint64_t* valid, void* stream);
+int vb2k_group_avg(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t sum_word, int32_t count_word, double* out, void* stream);
+/* Adds the per-group partials of a fused scan (sums[g * nproj + p] doubles, counts[g]) into rows
+ * 0 .. ngroups of an array-mode table: target i adds sums[.., target_projs[i]] to word
+ * target_words[i], or counts[g] when target_projs[i] < 0. Groups with counts[g] == 0 are untouched. */
+int vb2k_group_merge_partials(const vb2_group_table* t, const double* sums, const int64_t* counts, int32_t ngroups, int32_t nproj,
+                              const int32_t* target_words, const int32_t* target_projs, int32_t ntargets, void* stream);
 /* Packs up to 4 key columns into one 64-bit normalized key per row:
  * key = sum_k id_k * mult_k with id_k = v_k - min_k + 1 and id 0 reserved for NULL (VectorHasher
  * value ids, velox/exec/VectorHasher.h:523-585). Columns may be flat/dictionary/constant of
@@ -245,25 +303,8 @@ int vb2k_normalize_keys(const vb2_column* cols, int32_t ncols, const int64_t* mi
                         int32_t nulls_invalid, const int32_t* sel, int64_t n, uint64_t* keys_out, uint64_t* valid_out, void* stream);
 /* min/max of an integer column over non-null rows: out = {min, max, nonnull_count} (device int64[3]). */
 int vb2k_column_minmax(const vb2_column* col, int64_t rows, int64_t* out3, void* stream);
-/* Compacts occupied slots: slot_list int32[<=capacity] ascending, count device int64. */
-int vb2k_table_occupied(const uint64_t* table_keys, int64_t capacity, int32_t* slot_list, int64_t* count,
-                        void* workspace, size_t workspace_bytes, void* stream);
-size_t vb2k_table_occupied_workspace(int64_t capacity);
-/* Re-encodes the keys of the listed slots for a new layout after value ranges grew (the rehash
- * step of HashTable::checkSize / decideHashMode, velox/exec/HashTable.cpp:772,1751). table_keys
- * NULL = array mode (key = slot). */
-int vb2k_rekey(const uint64_t* table_keys, const int32_t* slots, int64_t n, int32_t ncols, const int64_t* old_mins,
-               const uint64_t* old_mults, const uint64_t* old_ranges, const int32_t* old_null_reserved, const int64_t* new_mins,
-               const uint64_t* new_mults, uint64_t* keys_out, void* stream);
 /* out = a & b over n bits (aggregate masks combined with validity) */
 int vb2k_and_bits(const uint64_t* a, const uint64_t* b, int64_t n, uint64_t* out, void* stream);
-/* Inverse of vb2k_normalize_keys for one key column over the listed slots: value = id - 1 + min
- * with id = (key / mult) % range; id 0 is NULL when null_reserved (a layout for a column that
- * never held NULLs uses min + 1 and keeps id 0 for the smallest value). table_keys NULL = array
- * mode (key = slot). values: T[n] (BOOLEAN one byte per row). */
-int vb2k_denormalize_keys(const uint64_t* table_keys, const int32_t* slots, int64_t n, int64_t min, uint64_t mult,
-                          uint64_t range, int32_t null_reserved, int32_t type, void* values, uint64_t* valid, void* stream);
-
 /* ------------------------------------------------------------------------------------------
  * Hash join. Build: replaces HashBuild::addInput row store + HashTable::prepareJoinTable /
  * insertForJoin (velox/exec/HashBuild.cpp:442-598, exec/HashTable.cpp:1989,1518): key -> first
@@ -311,10 +352,7 @@ int vb2k_gather_bits(const uint64_t* in, const int32_t* sel, int64_t n, uint64_t
 int vb2k_pack_bools(const uint8_t* in, int64_t n, uint64_t* out, void* stream);
 /* out[dst[i]] = in[src ? src[i] : i] for 4- or 8-byte elements (accumulator moves on rehash) */
 int vb2k_scatter(const void* in, const int32_t* src, const int32_t* dst, int64_t n, int32_t elem_bytes, void* out, void* stream);
-/* Aggregate result extraction (Aggregate::extractValues, velox/exec/Aggregate.h:281-302):
- * validity bit k = counts[slots ? slots[k] : k] > 0; avg = sum / count. */
-int vb2k_counts_to_valid(const int64_t* counts, const int32_t* slots, int64_t n, uint64_t* out, void* stream);
-int vb2k_avg_finalize(const double* sums, const int64_t* counts, const int32_t* slots, int64_t n, double* out, void* stream);
+/* bit k = counts[k] > 0 */
 int vb2k_positive_bits(const int64_t* counts, int64_t n, uint64_t* out, void* stream);
 
 #ifdef __cplusplus

@@ -16,6 +16,27 @@ from velox_b200.task import Task
 from velox_b200.vector import BIGINT
 
 
+def _lsr(x, k):
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def splitmix_keys(start: int, count: int, nkeys: int, chunk: int = 1 << 27) -> torch.Tensor:
+    """keys = splitmix64(i) % nkeys (as unsigned), i in [start, start + count)."""
+    out = torch.empty(count, dtype=torch.int64, device="cuda")
+    def c(v):  # two's-complement constant
+        return v - (1 << 64) if v >= (1 << 63) else v
+    for c0 in range(0, count, chunk):
+        n = min(chunk, count - c0)
+        z = (torch.arange(start + c0, start + c0 + n, device="cuda", dtype=torch.int64) + 1) * c(0x9E3779B97F4A7C15)
+        z = (z ^ _lsr(z, 30)) * c(0xBF58476D1CE4E5B9)
+        z = (z ^ _lsr(z, 27)) * c(0x94D049BB133111EB)
+        z = z ^ _lsr(z, 31)
+        r = torch.remainder(z, nkeys)
+        r = torch.where(z < 0, torch.remainder(r + ((1 << 64) % nkeys), nkeys), r)
+        out[c0:c0 + n] = r
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=float, default=1e9)
@@ -24,9 +45,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args()
     rows, nkeys, batch = int(a.rows), int(a.keys), int(a.batch)
-    g = torch.Generator(device="cuda")
-    g.manual_seed(7)
-    keys = torch.randint(0, nkeys, (rows,), generator=g, device="cuda", dtype=torch.int64)
+    keys = splitmix_keys(0, rows, nkeys)
     vals = torch.arange(rows, device="cuda", dtype=torch.int64) % 1000
     torch.cuda.synchronize()
     plan = PlanBuilder().values(["k", "v"], [BIGINT, BIGINT]).singleAggregation(["k"], ["sum(v)", "count(0)"]).planNode()
@@ -52,7 +71,8 @@ def main():
     bytes_alg = rows * 16 + groups * 16
     print(json.dumps({"rows": rows, "distinct": groups, "seconds": sec, "rows_per_s": rows / sec, "algorithmic_GBps": bytes_alg / sec / 1e9,
                       "frac_of_measured_hbm": bytes_alg / sec / 1e9 / 6570.9, "includes": "result device->host copy of all groups",
-                      "agg_mode": [v for k, v in st.items() if k.endswith("b200.aggMode")]}))
+                      "agg_mode": [v for k, v in st.items() if k.endswith("b200.aggMode")],
+                      "wall_ms": {k: round(v / 1e6, 2) for k, v in st.items() if k.endswith("WallNanos") and v > 1e5}}))
 
 
 if __name__ == "__main__":

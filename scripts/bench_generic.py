@@ -50,9 +50,11 @@ def main():
                 t0 = time.perf_counter()
                 r = t.run()
                 ts.append(time.perf_counter() - t0)
+                st = t.stats()
                 t.close()
             ms = sorted(ts[1:])[1] * 1e3
-            out[f"{name}_{label}"] = {"ms": ms, "rows_per_s": rows / ms * 1e3, "result_rows": r.size}
+            out[f"{name}_{label}"] = {"ms": ms, "rows_per_s": rows / ms * 1e3, "result_rows": r.size,
+                                       "wall_ms": {k: round(v / 1e6, 3) for k, v in st.items() if k.endswith("WallNanos") and v > 2e4}}
     print(json.dumps(out))
 
 

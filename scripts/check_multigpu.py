@@ -29,6 +29,7 @@ def main():
         q6.launch(li, rows); q6.merge()
         q14.launch(li, part, rows); q14.merge()
     torch.cuda.synchronize()
+    assert q14.planned_runs >= 1, "the second Q14 launch must take the planned (sync-free) exchange"
     got = {"q1": {f"{k[0]}{k[1]}": list(v) for k, v in q1.result().items()}, "q6": q6.result(), "q14": q14.result(),
            "q14_rows": int(q14.probe.counts.item())}
     ok = True
@@ -48,10 +49,36 @@ def main():
         for k in want["q1"]:
             ok = ok and got["q1"][k][7] == want["q1"][k][7] and all(close(a, b) for a, b in zip(got["q1"][k][:7], want["q1"][k][:7]))
         ok = ok and close(got["q6"], want["q6"]) and close(got["q14"], want["q14"])
-        print(json.dumps({"ok": bool(ok), "world": world, "got_q14": got["q14"], "want_q14": want["q14"], "q14_rows": got["q14_rows"]}))
+        print(json.dumps({"ok": bool(ok), "world": world, "planned_runs": q14.planned_runs, "plan": q14.plan, "got_q14": got["q14"], "want_q14": want["q14"], "q14_rows": got["q14_rows"]}))
+    # Data that outgrows the plan (every row passes the date filter: scan output and segments
+    # overflow): the planned run must notice on the device and rerun with discovered sizes.
+    li2 = dict(li)
+    li2["l_shipdate"] = torch.full_like(li["l_shipdate"], tpch.Q14_SHIP_LO)
+    before = dict(q14.plan)
+    q14.launch(li2, part, rows); q14.merge()
+    got2 = q14.result()
+    replanned = q14.plan is not None and q14.plan != before
+    q14.launch(li2, part, rows); q14.merge()   # planned again with the new sizes
+    got3 = q14.result()
+    ok2 = True
+    if rank == 0:
+        parts2 = []
+        for r in range(world):
+            t = tpch.gen_lineitem(rows, nparts, seed=42 + r, device="cuda")
+            t["l_shipdate"] = torch.full_like(t["l_shipdate"], tpch.Q14_SHIP_LO)
+            parts2.append(t)
+        full2 = {k: torch.cat([p[k] for p in parts2]) for k in parts2[0]}
+        s14 = Q14()
+        s14.launch(full2, part_all, rows * world)
+        torch.cuda.synchronize()
+        want2 = s14.result()
+        ok2 = replanned and abs(got2 - want2) <= 1e-11 * abs(want2) and abs(got3 - want2) <= 1e-11 * abs(want2)
+        print(json.dumps({"overflow_rerun_ok": bool(ok2), "replanned": bool(replanned), "got": got2, "got_planned": got3, "want": want2}))
+    flag = torch.tensor([1 if (ok and ok2) else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    sys.exit(0 if flag.item() else 1)
 
 
 if __name__ == "__main__":

@@ -20,5 +20,6 @@ def test_sharded_queries_match_single_gpu(world):
            "--master-port", "29533", os.path.join(ROOT, "scripts", "check_multigpu.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
-    assert json.loads(line)["ok"]
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines[0]["ok"] and lines[0]["planned_runs"] >= 1
+    assert lines[1]["overflow_rerun_ok"] and lines[1]["replanned"]

@@ -159,6 +159,34 @@ def test_aggregation_empty_and_all_null():
     check_plan(PlanBuilder().values(allnull.names, allnull.types).singleAggregation(["k"], ["sum(v)", "avg(v)", "count(v)", "max(v)"]).planNode(), [allnull])
 
 
+def test_aggregation_nulls_appear_in_a_later_batch():
+    """The non-null counters of sum / min / max start being tracked when the first NULL (or mask)
+    shows up: groups seen only in earlier all-non-null batches must stay non-NULL, groups whose
+    inputs are all NULL must come out NULL (SumAggregateBase.h:71-142 null handling)."""
+    k = [1, 2, 3, 1, 2, 3] + [3, 4, 5, 4, 5, 5]
+    v = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0] + [None, None, 7.0, None, 8.0, None]
+    w = [10, 20, 30, 40, 50, 60] + [None, None, None, 1, None, None]
+    rv = row_vector(["k", "v", "w"], [flat_vector(INTEGER, k), flat_vector(DOUBLE, v), flat_vector(BIGINT, w)])
+    aggs = ["sum(v)", "min(v)", "max(w)", "sum(w)", "avg(v)", "count(v)", "count(0)"]
+    for keys in (["k"], []):
+        plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(keys, aggs).planNode()
+        check_plan(plan, [rv], batch_rows=6)   # batch 1 has no NULLs, batch 2 does
+        check_plan(plan, [rv], batch_rows=12)
+    # hash mode (key range beyond array mode) with the same late NULLs
+    big = row_vector(["k", "v", "w"], [flat_vector(BIGINT, [x * (1 << 40) for x in k]), flat_vector(DOUBLE, v), flat_vector(BIGINT, w)])
+    (st,) = check_plan(PlanBuilder().values(big.names, big.types).singleAggregation(["k"], aggs).planNode(), [big], batch_rows=6)
+    assert stat(st, "b200.aggMode") == 2
+
+
+def test_aggregation_many_aggregates():
+    """More aggregate updates than one vb2k_group_update call carries (16): later slices find the groups again."""
+    rv = table(n=3000, seed=21)
+    aggs = [f"{fn}({c})" for fn in ("sum", "min", "max", "avg", "count") for c in ("c0", "c2", "c3")] + ["count(0)", "sum(c1)", "max(c1)"]
+    assert len(aggs) > 16
+    for keys in (["c1"], ["c0", "c5"], []):
+        check_plan(PlanBuilder().values(rv.names, rv.types).singleAggregation(keys, aggs).planNode(), [rv], batch_rows=700, rel_tol=1e-11)
+
+
 def test_aggregation_masks():
     rv = table(n=2000, seed=9)
     plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(["c1"], ["sum(c2)", "count(0)", "avg(c0)"], masks=["c4", "c4", None]).planNode()

@@ -18,6 +18,7 @@
 #ifndef VELOX_B200_WITH_REAL_VELOX
 
 #include <functional>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <set>
@@ -324,6 +325,7 @@ struct OperatorStats {  // velox/exec/OperatorStats.h:93
   int32_t operatorId = 0;
   std::string operatorType;
   int64_t inputPositions = 0, inputVectors = 0, outputPositions = 0, outputVectors = 0;
+  int64_t addInputWallNanos = 0, getOutputWallNanos = 0, finishWallNanos = 0;  // CpuWallTiming::wallNanos of each phase
   std::map<std::string, int64_t> runtimeStats;
 };
 
@@ -573,6 +575,10 @@ inline std::vector<std::unique_ptr<Operator>> DriverFactory::replaceOperators(Dr
   return replaced;
 }
 
+// Optional hook run before each timing lap (a device synchronize when VB2_SYNC_TIMING=1, so that
+// the wall-time stats attribute asynchronous kernel time to the operator that launched it).
+inline void (*g_timingSync)() = nullptr;
+
 inline BlockingReason Driver::runOnce(bool* finished, bool* progressed) {
   initializeOperators();
   *finished = false;
@@ -592,7 +598,16 @@ inline BlockingReason Driver::runOnce(bool* finished, bool* progressed) {
     }
     Operator* next = operators_[i + 1].get();
     if (!next->needsInput()) continue;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&t0]() {
+      if (g_timingSync) g_timingSync();
+      auto t1 = std::chrono::steady_clock::now();
+      int64_t ns = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+      t0 = t1;
+      return ns;
+    };
     RowVectorPtr out = op->getOutput();
+    op->stats().getOutputWallNanos += lap();
     if (out) {
       VELOX_CHECK(out->size() > 0, "operators must not emit empty vectors");
       op->stats().outputPositions += out->size();
@@ -600,11 +615,13 @@ inline BlockingReason Driver::runOnce(bool* finished, bool* progressed) {
       next->stats().inputPositions += out->size();
       next->stats().inputVectors += 1;
       next->addInput(std::move(out));
+      next->stats().addInputWallNanos += lap();
       *progressed = true;
       return BlockingReason::kNotBlocked;  // restart from the sink, as runInternal does
     }
     if (op->isFinished() && !signalled_.count(next)) {
       next->noMoreInput();
+      next->stats().finishWallNanos += lap();
       signalled_.insert(next);
       *progressed = true;
       return BlockingReason::kNotBlocked;

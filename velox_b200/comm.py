@@ -87,6 +87,12 @@ class Comm:
             raise VeloxRuntimeError("all-reduce failed")
         return t
 
+    def all_reduce_max_(self, t: torch.Tensor):
+        assert t.dtype == torch.int64
+        if self.L.vb2_comm_all_reduce_max_i64(C.c_void_p(self.h), C.c_void_p(t.data_ptr()), C.c_int64(t.numel()), self._st()):
+            raise VeloxRuntimeError("all-reduce failed")
+        return t
+
     def close(self):
         if self.h:
             self.L.vb2_comm_free.argtypes = [C.c_void_p]

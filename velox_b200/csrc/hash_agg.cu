@@ -5,9 +5,9 @@
 //     (id = v - min + 1, 0 = NULL; exec/VectorHasher.h:523-585) — the reference's kNormalizedKey
 //     mode (exec/HashTable.cpp:523) is the only mode needed because ranges come from a device
 //     min/max pass over the whole batch, not from 1K-row increments;
-//   * the table is SoA: uint64 keys[capacity] (open addressing, linear probing, twang_mix64),
-//     accumulators are separate dense arrays indexed by slot — no row-wise RowContainer, so an
-//     accumulator update is one 8-byte atomic to a 32-byte sector instead of a row RMW;
+//   * the table is row-wise like RowContainer (exec/RowContainer.h): [key | accumulators...] in
+//     whole 32-byte sectors, open addressing + linear probing on twang_mix64(key); find-or-insert
+//     and every accumulator update of an input row happen in ONE kernel and touch one row;
 //   * null keys form a group (value id 0), as GroupingSet does for non-ignoreNullKeys tables
 //     (exec/GroupingSet.cpp:448-455).
 #include "common.cuh"
@@ -83,31 +83,6 @@ __global__ void normalize_keys_kernel(const __grid_constant__ NormArgs a, const 
   }
 }
 
-// Keys of occupied slots back to per-column values: id_k = (key / mult_k) % range_k.
-__global__ void denormalize_keys_kernel(const uint64_t* __restrict__ table_keys, const int32_t* __restrict__ slots, int64_t n,
-                                        int64_t min, uint64_t mult, uint64_t range, int32_t null_reserved, int32_t type,
-                                        void* __restrict__ values, uint32_t* __restrict__ valid_words) {
-  const int64_t nwords = (n + 31) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t w = warp_global; w < nwords; w += nwarps) {
-    const int64_t i = (w << 5) + lane;
-    bool valid = false;
-    if (i < n) {
-      const uint64_t key = table_keys ? table_keys[slots[i]] : static_cast<uint64_t>(slots[i]);
-      const uint64_t id = (key / mult) % range;
-      valid = !(null_reserved && id == 0);
-      const int64_t v = valid ? static_cast<int64_t>(id) - 1 + min : 0;
-      if (type == VB2_INTEGER) reinterpret_cast<int32_t*>(values)[i] = static_cast<int32_t>(v);
-      else if (type == VB2_BOOLEAN) reinterpret_cast<uint8_t*>(values)[i] = static_cast<uint8_t>(v);
-      else reinterpret_cast<int64_t*>(values)[i] = v;
-    }
-    const unsigned word = __ballot_sync(0xffffffffu, valid);
-    if (lane == 0) valid_words[w] = word;
-  }
-}
-
 __global__ void minmax_kernel(const __grid_constant__ vb2_column c, int64_t rows, int64_t* __restrict__ out3) {
   int64_t lo = INT64_MAX, hi = INT64_MIN, cnt = 0;
   for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < rows; r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -137,44 +112,6 @@ __global__ void minmax_init_kernel(int64_t* out3) {
   out3[2] = 0;
 }
 
-// Find-or-insert. One thread per row; the CAS on the key word both claims and publishes the slot.
-__global__ void group_probe_kernel(const uint64_t* __restrict__ row_keys, const uint64_t* __restrict__ row_valid, int64_t n,
-                                   uint64_t* __restrict__ table, uint64_t mask, int32_t* __restrict__ group_ids,
-                                   int64_t* __restrict__ num_groups, int32_t* __restrict__ error_flag) {
-  int64_t fresh = 0;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    if (row_valid && !bit_at(row_valid, i)) { group_ids[i] = -1; continue; }
-    const uint64_t key = row_keys[i];
-    if (table == nullptr) {  // array mode: the normalized key is the slot
-      group_ids[i] = key <= mask ? static_cast<int32_t>(key) : -1;
-      if (key > mask) atomicCAS(error_flag, 0, 100);
-      continue;
-    }
-    uint64_t slot = twang_mix64(key) & mask;
-    int32_t found = -1;
-    for (uint64_t probes = 0; probes <= mask; ++probes) {
-      uint64_t cur = table[slot];
-      if (cur == VB2_EMPTY_KEY) {
-        cur = atomicCAS(reinterpret_cast<unsigned long long*>(table + slot), VB2_EMPTY_KEY, static_cast<unsigned long long>(key));
-        if (cur == VB2_EMPTY_KEY) { ++fresh; found = static_cast<int32_t>(slot); break; }
-      }
-      if (cur == key) { found = static_cast<int32_t>(slot); break; }
-      slot = (slot + 1) & mask;
-    }
-    if (found < 0) atomicCAS(error_flag, 0, 100);  // table full: the host sized it wrongly
-    group_ids[i] = found;
-  }
-  fresh = warp_sum(fresh);
-  if ((threadIdx.x & 31) == 0 && fresh) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
-}
-
-// ---- accumulator updates ----------------------------------------------------------------------
-constexpr int kMaxAggs = 16;
-struct AggArgs {
-  vb2_agg_update a[kMaxAggs];
-  int n;
-};
-
 __device__ __forceinline__ double input_as_f64(const vb2_agg_update& u, int64_t i) {
   switch (u.input_type) {
     case VB2_DOUBLE: return reinterpret_cast<const double*>(u.input)[i];
@@ -203,53 +140,110 @@ __device__ __forceinline__ void atomic_min_f64(double* addr, double v, bool is_m
   }
 }
 
-// General path: one atomic per (row, aggregate). Sector-random for high-cardinality GROUP BY,
-// which is the access pattern that bounds config 5.
-__global__ void agg_update_atomic_kernel(const int32_t* __restrict__ group_ids, int64_t n, const __grid_constant__ AggArgs args,
-                                         int32_t* __restrict__ error_flag) {
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int32_t g = group_ids ? group_ids[i] : 0;
-    if (g < 0) continue;
-    for (int k = 0; k < args.n; ++k) {
-      const vb2_agg_update& u = args.a[k];
-      if (u.mask && !bit_at(u.mask, i)) continue;
-      if (u.nulls && !bit_at(u.nulls, i)) continue;
-      switch (u.kind) {
-        case VB2_AGG_SUM_F64: atomicAdd(reinterpret_cast<double*>(u.acc) + g, input_as_f64(u, i)); break;
-        case VB2_AGG_SUM_I64: case VB2_AGG_COUNT_MERGE: {
-          const int64_t v = input_as_i64(u, i);
-          const int64_t old = static_cast<int64_t>(atomicAdd(reinterpret_cast<unsigned long long*>(u.acc) + g, static_cast<unsigned long long>(v)));
-          int64_t r;
-          if (add_overflow_i64(old, v, &r)) atomicCAS(error_flag, 0, 1);
-          break;
-        }
-        case VB2_AGG_COUNT: atomicAdd(reinterpret_cast<unsigned long long*>(u.acc) + g, 1ull); break;
-        case VB2_AGG_MIN_F64: atomic_min_f64(reinterpret_cast<double*>(u.acc) + g, input_as_f64(u, i), true); break;
-        case VB2_AGG_MAX_F64: atomic_min_f64(reinterpret_cast<double*>(u.acc) + g, input_as_f64(u, i), false); break;
-        case VB2_AGG_MIN_I64: atomicMin(reinterpret_cast<long long*>(u.acc) + g, static_cast<long long>(input_as_i64(u, i))); break;
-        case VB2_AGG_MAX_I64: atomicMax(reinterpret_cast<long long*>(u.acc) + g, static_cast<long long>(input_as_i64(u, i))); break;
-        default: break;
-      }
-      if (u.nonnull && u.kind != VB2_AGG_COUNT) atomicAdd(reinterpret_cast<unsigned long long*>(u.nonnull) + g, 1ull);
-    }
-  }
+// ---- group table ---------------------------------------------------------------------------------
+// Row-wise group storage (the role of exec::RowContainer under exec::HashTable for GROUP BY):
+// `capacity` rows of `row_words` 8-byte words. Word 0 is the occupancy word — the normalized key in
+// hash mode (VB2_EMPTY_KEY = free slot), "rows seen" in array / global mode (0 = free) — the
+// remaining words are accumulators and non-null counters. A row is a whole number of 32-byte
+// sectors whenever it has more than two words, so one input row touches ONE random sector group
+// (key compare + every accumulator) instead of one per accumulator array.
+struct TableView {
+  uint64_t* rows;
+  uint64_t mask;      // hash mode: capacity - 1; array mode: capacity - 1 is the largest valid key
+  int32_t w;
+  int32_t hash;
+};
+__device__ __forceinline__ TableView view_of(const vb2_group_table& t) {
+  return TableView{t.rows, static_cast<uint64_t>(t.capacity - 1), t.row_words, t.hash_mode};
 }
 
-// Tiny group-id spaces (<= 8 groups): same-address atomics would serialise in L2, so every thread
+// Slot of `key` (inserted if absent), -1 if the table is full / the key is outside the array.
+__device__ __forceinline__ int64_t find_or_insert(const TableView& t, uint64_t key, int64_t& fresh) {
+  if (!t.hash) return key <= t.mask ? static_cast<int64_t>(key) : -1;
+  uint64_t slot = twang_mix64(key) & t.mask;
+  for (uint64_t probes = 0; probes <= t.mask; ++probes) {
+    uint64_t* p = t.rows + slot * t.w;
+    uint64_t cur = *reinterpret_cast<volatile uint64_t*>(p);
+    if (cur == VB2_EMPTY_KEY) {
+      cur = atomicCAS(reinterpret_cast<unsigned long long*>(p), VB2_EMPTY_KEY, static_cast<unsigned long long>(key));
+      if (cur == VB2_EMPTY_KEY) { ++fresh; return static_cast<int64_t>(slot); }
+    }
+    if (cur == key) return static_cast<int64_t>(slot);
+    slot = (slot + 1) & t.mask;
+  }
+  return -1;
+}
+
+constexpr int kMaxAggs = 16;
+struct AggArgs {
+  vb2_agg_update a[kMaxAggs];
+  int n;
+};
+
+__device__ __forceinline__ void apply_update(const vb2_agg_update& u, int64_t i, uint64_t* row, int32_t* error_flag) {
+  if (u.mask && !bit_at(u.mask, i)) return;
+  if (u.nulls && !bit_at(u.nulls, i)) return;
+  uint64_t* acc = row + u.acc_word;
+  switch (u.kind) {
+    case VB2_AGG_SUM_F64: atomicAdd(reinterpret_cast<double*>(acc), input_as_f64(u, i)); break;
+    case VB2_AGG_SUM_I64: case VB2_AGG_COUNT_MERGE: {
+      const int64_t v = input_as_i64(u, i);
+      const int64_t old = static_cast<int64_t>(atomicAdd(reinterpret_cast<unsigned long long*>(acc), static_cast<unsigned long long>(v)));
+      int64_t r;
+      if (add_overflow_i64(old, v, &r)) atomicCAS(error_flag, 0, 1);
+      break;
+    }
+    case VB2_AGG_COUNT: atomicAdd(reinterpret_cast<unsigned long long*>(acc), 1ull); break;
+    case VB2_AGG_MIN_F64: atomic_min_f64(reinterpret_cast<double*>(acc), input_as_f64(u, i), true); break;
+    case VB2_AGG_MAX_F64: atomic_min_f64(reinterpret_cast<double*>(acc), input_as_f64(u, i), false); break;
+    case VB2_AGG_MIN_I64: atomicMin(reinterpret_cast<long long*>(acc), static_cast<long long>(input_as_i64(u, i))); break;
+    case VB2_AGG_MAX_I64: atomicMax(reinterpret_cast<long long*>(acc), static_cast<long long>(input_as_i64(u, i))); break;
+    default: break;
+  }
+  if (u.nonnull_word >= 0 && u.kind != VB2_AGG_COUNT) atomicAdd(reinterpret_cast<unsigned long long*>(row + u.nonnull_word), 1ull);
+}
+
+// General path, ONE kernel per batch: find-or-insert the row's group, then every accumulator update
+// lands in that group's row (same sectors as the key that was just compared).
+__global__ void group_update_kernel(const __grid_constant__ vb2_group_table tab, const uint64_t* __restrict__ row_keys,
+                                    const uint64_t* __restrict__ row_valid, int64_t n, const __grid_constant__ AggArgs args,
+                                    int64_t* __restrict__ num_groups, int32_t* __restrict__ error_flag) {
+  const TableView t = view_of(tab);
+  int64_t fresh = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (row_valid && !bit_at(row_valid, i)) continue;
+    const int64_t slot = row_keys ? find_or_insert(t, row_keys[i], fresh) : 0;
+    if (slot < 0) { atomicCAS(error_flag, 0, 100); continue; }  // the host sized the table wrongly
+    uint64_t* row = t.rows + slot * t.w;
+    if (!t.hash && *reinterpret_cast<volatile uint64_t*>(row) == 0) *reinterpret_cast<volatile uint64_t*>(row) = 1;  // occupancy mark (idempotent)
+    for (int k = 0; k < args.n; ++k) apply_update(args.a[k], i, row, error_flag);
+  }
+  fresh = warp_sum(fresh);
+  if ((threadIdx.x & 31) == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
+}
+
+// Tiny array-mode tables (<= 8 rows): same-address atomics would serialise in L2, so every thread
 // keeps the groups in registers (predicated adds) and the block issues one atomic per group.
+// kKind == 0 is the occupancy pass (rows seen per group -> word 0).
 constexpr int kTinyG = 8;
 template <int kKind>
-__global__ void agg_update_tiny_kernel(const int32_t* __restrict__ group_ids, int64_t n, const __grid_constant__ vb2_agg_update u,
-                                       int32_t* __restrict__ error_flag) {
+__global__ void group_update_tiny_kernel(const __grid_constant__ vb2_group_table tab, const uint64_t* __restrict__ row_keys,
+                                         const uint64_t* __restrict__ row_valid, int64_t n, const __grid_constant__ vb2_agg_update u,
+                                         int32_t* __restrict__ error_flag) {
   double fs[kTinyG];
   int64_t is[kTinyG], cnt[kTinyG];
 #pragma unroll
   for (int g = 0; g < kTinyG; ++g) { fs[g] = 0.0; is[g] = 0; cnt[g] = 0; }
-  bool ovf = false;
+  bool ovf = false, bad = false;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    int32_t g = group_ids ? group_ids[i] : 0;
-    if (u.mask && !bit_at(u.mask, i)) g = -1;
-    if (u.nulls && !bit_at(u.nulls, i)) g = -1;
+    if (row_valid && !bit_at(row_valid, i)) continue;
+    const uint64_t key = row_keys ? row_keys[i] : 0;
+    if (key >= static_cast<uint64_t>(tab.capacity)) { bad = true; continue; }
+    int32_t g = static_cast<int32_t>(key);
+    if (kKind != 0) {
+      if (u.mask && !bit_at(u.mask, i)) g = -1;
+      if (u.nulls && !bit_at(u.nulls, i)) g = -1;
+    }
     if (g < 0) continue;
     double fv = 0.0;
     int64_t iv = 0;
@@ -271,8 +265,7 @@ __global__ void agg_update_tiny_kernel(const int32_t* __restrict__ group_ids, in
 #pragma unroll
   for (int k = 0; k < kTinyG; ++k) {
     const double f = warp_sum(fs[k]);
-    // integer partials: detect overflow while combining
-    int64_t v = is[k];
+    int64_t v = is[k];  // integer partials: detect overflow while combining
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const int64_t other = __shfl_xor_sync(0xffffffffu, v, o);
@@ -282,8 +275,9 @@ __global__ void agg_update_tiny_kernel(const int32_t* __restrict__ group_ids, in
     if (lane == 0) { sf[warp][k] = f; si[warp][k] = v; sc[warp][k] = c; }
   }
   if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicCAS(error_flag, 0, 1);
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicCAS(error_flag, 0, 100);
   __syncthreads();
-  if (threadIdx.x < kTinyG) {
+  if (threadIdx.x < kTinyG && threadIdx.x < tab.capacity) {
     const int k = threadIdx.x;
     double f = 0.0;
     int64_t v = 0, c = 0;
@@ -294,16 +288,79 @@ __global__ void agg_update_tiny_kernel(const int32_t* __restrict__ group_ids, in
       c += sc[w][k];
     }
     if (c) {
-      if (kKind == VB2_AGG_SUM_F64) atomicAdd(reinterpret_cast<double*>(u.acc) + k, f);
-      if (kKind == VB2_AGG_SUM_I64 || kKind == VB2_AGG_COUNT_MERGE) {
-        const int64_t old = static_cast<int64_t>(atomicAdd(reinterpret_cast<unsigned long long*>(u.acc) + k, static_cast<unsigned long long>(v)));
-        int64_t r;
-        o2 |= add_overflow_i64(old, v, &r);
+      uint64_t* row = tab.rows + static_cast<int64_t>(k) * tab.row_words;
+      if (kKind == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(row), static_cast<unsigned long long>(c));
+      } else {
+        uint64_t* acc = row + u.acc_word;
+        if (kKind == VB2_AGG_SUM_F64) atomicAdd(reinterpret_cast<double*>(acc), f);
+        if (kKind == VB2_AGG_SUM_I64 || kKind == VB2_AGG_COUNT_MERGE) {
+          const int64_t old = static_cast<int64_t>(atomicAdd(reinterpret_cast<unsigned long long*>(acc), static_cast<unsigned long long>(v)));
+          int64_t r;
+          o2 |= add_overflow_i64(old, v, &r);
+        }
+        if (kKind == VB2_AGG_COUNT) atomicAdd(reinterpret_cast<unsigned long long*>(acc), static_cast<unsigned long long>(c));
+        if (u.nonnull_word >= 0 && kKind != VB2_AGG_COUNT) atomicAdd(reinterpret_cast<unsigned long long*>(row + u.nonnull_word), static_cast<unsigned long long>(c));
       }
-      if (kKind == VB2_AGG_COUNT) atomicAdd(reinterpret_cast<unsigned long long*>(u.acc) + k, static_cast<unsigned long long>(c));
-      if (u.nonnull && kKind != VB2_AGG_COUNT) atomicAdd(reinterpret_cast<unsigned long long*>(u.nonnull) + k, static_cast<unsigned long long>(c));
     }
     if (o2) atomicCAS(error_flag, 0, 1);
+  }
+}
+
+__global__ void table_init_kernel(uint64_t* __restrict__ rows, int64_t total_words, int32_t w, const __grid_constant__ vb2_group_row_init init) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total_words; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    rows[i] = init.words[i % w];
+}
+
+__device__ __forceinline__ bool row_occupied(const vb2_group_table& t, int64_t r) {
+  const uint64_t w0 = t.rows[r * t.row_words];
+  return t.hash_mode ? w0 != VB2_EMPTY_KEY : w0 != 0;
+}
+__device__ __forceinline__ uint64_t key_of_slot(const vb2_group_table& t, int64_t slot) {
+  return t.hash_mode ? t.rows[slot * t.row_words] : static_cast<uint64_t>(slot);
+}
+
+__global__ void occupied_bits_kernel(const __grid_constant__ vb2_group_table t, uint32_t* __restrict__ bits) {
+  const int64_t nwords = (t.capacity + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t w = warp_global; w < nwords; w += nwarps) {
+    const int64_t s = (w << 5) + lane;
+    const bool occ = s < t.capacity && row_occupied(t, s);
+    const unsigned word = __ballot_sync(0xffffffffu, occ);
+    if (lane == 0) bits[w] = word;
+  }
+}
+
+// word <- value in every occupied row (a non-null counter that starts being tracked late).
+__global__ void set_word_kernel(const __grid_constant__ vb2_group_table t, int32_t word, uint64_t value) {
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < t.capacity; r += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    if (row_occupied(t, r)) t.rows[r * t.row_words + word] = value;
+}
+
+// Keys of occupied slots back to per-column values: id_k = (key / mult_k) % range_k.
+__global__ void group_keys_kernel(const __grid_constant__ vb2_group_table t, const int32_t* __restrict__ slots, int64_t n,
+                                  int64_t min, uint64_t mult, uint64_t range, int32_t null_reserved, int32_t type,
+                                  void* __restrict__ values, uint32_t* __restrict__ valid_words) {
+  const int64_t nwords = (n + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t w = warp_global; w < nwords; w += nwarps) {
+    const int64_t i = (w << 5) + lane;
+    bool valid = false;
+    if (i < n) {
+      const uint64_t key = key_of_slot(t, slots[i]);
+      const uint64_t id = (key / mult) % range;
+      valid = !(null_reserved && id == 0);
+      const int64_t v = valid ? static_cast<int64_t>(id) - 1 + min : 0;
+      if (type == VB2_INTEGER) reinterpret_cast<int32_t*>(values)[i] = static_cast<int32_t>(v);
+      else if (type == VB2_BOOLEAN) reinterpret_cast<uint8_t*>(values)[i] = static_cast<uint8_t>(v);
+      else reinterpret_cast<int64_t*>(values)[i] = v;
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) valid_words[w] = word;
   }
 }
 
@@ -315,10 +372,10 @@ struct RekeyArgs {
   uint64_t old_mult[kMaxNormCols], old_range[kMaxNormCols], new_mult[kMaxNormCols];
   int old_null_reserved[kMaxNormCols];
 };
-__global__ void rekey_kernel(const uint64_t* __restrict__ table_keys, const int32_t* __restrict__ slots, int64_t n,
+__global__ void rekey_kernel(const __grid_constant__ vb2_group_table t, const int32_t* __restrict__ slots, int64_t n,
                              const __grid_constant__ RekeyArgs a, uint64_t* __restrict__ out) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const uint64_t key = table_keys ? table_keys[slots[i]] : static_cast<uint64_t>(slots[i]);
+    const uint64_t key = key_of_slot(t, slots[i]);
     uint64_t nk = 0;
     for (int k = 0; k < a.n; ++k) {
       const uint64_t id = (key / a.old_mult[k]) % a.old_range[k];
@@ -330,17 +387,73 @@ __global__ void rekey_kernel(const uint64_t* __restrict__ table_keys, const int3
   }
 }
 
-// ---- occupied slots ---------------------------------------------------------------------------
-__global__ void occupied_bits_kernel(const uint64_t* __restrict__ table, int64_t capacity, uint32_t* __restrict__ bits) {
-  const int64_t nwords = (capacity + 31) >> 5;
+// Rehash / relayout: group i of the old table (slot slots[i]) moves to the row of new_keys[i] in
+// the new table. Keys are distinct, so after the insert the row is owned by this thread.
+__global__ void group_move_kernel(const __grid_constant__ vb2_group_table from, const int32_t* __restrict__ slots,
+                                  const uint64_t* __restrict__ new_keys, int64_t n, const __grid_constant__ vb2_group_table to,
+                                  int64_t* __restrict__ num_groups, int32_t* __restrict__ error_flag) {
+  const TableView t = view_of(to);
+  int64_t fresh = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t slot = find_or_insert(t, new_keys[i], fresh);
+    if (slot < 0) { atomicCAS(error_flag, 0, 100); continue; }
+    const uint64_t* src = from.rows + static_cast<int64_t>(slots[i]) * from.row_words;
+    uint64_t* dst = to.rows + slot * to.row_words;
+    if (!to.hash_mode) dst[0] = 1;
+    for (int w = 1; w < to.row_words; ++w) dst[w] = src[w];
+  }
+  fresh = warp_sum(fresh);
+  if ((threadIdx.x & 31) == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
+}
+
+__global__ void group_gather_kernel(const __grid_constant__ vb2_group_table t, const int32_t* __restrict__ slots, int64_t n, int32_t word,
+                                    uint64_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = t.rows[static_cast<int64_t>(slots[i]) * t.row_words + word];
+}
+__global__ void group_valid_kernel(const __grid_constant__ vb2_group_table t, const int32_t* __restrict__ slots, int64_t n, int32_t word,
+                                   uint32_t* __restrict__ out) {
+  const int64_t nwords = (n + 31) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t w = warp_global; w < nwords; w += nwarps) {
-    const int64_t s = (w << 5) + lane;
-    const bool occ = s < capacity && table[s] != VB2_EMPTY_KEY;
-    const unsigned word = __ballot_sync(0xffffffffu, occ);
-    if (lane == 0) bits[w] = word;
+    const int64_t k = (w << 5) + lane;
+    const bool b = k < n && static_cast<int64_t>(t.rows[static_cast<int64_t>(slots[k]) * t.row_words + word]) > 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, b);
+    if (lane == 0) out[w] = bits;
+  }
+}
+__global__ void group_avg_kernel(const __grid_constant__ vb2_group_table t, const int32_t* __restrict__ slots, int64_t n, int32_t sum_word,
+                                 int32_t count_word, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t* row = t.rows + static_cast<int64_t>(slots[i]) * t.row_words;
+    const int64_t c = static_cast<int64_t>(row[count_word]);
+    // functions/lib/aggregates/AverageAggregateBase.h:86-107
+    out[i] = c > 0 ? __ddiv_rn(__longlong_as_double(static_cast<long long>(row[sum_word])), static_cast<double>(c)) : 0.0;
+  }
+}
+
+// Partial results of a fused scan (sums[g * nproj + p], counts[g]) added into the table rows of
+// an array-mode table (group g = row g): one thread per (group, target word).
+struct MergeArgs {
+  int32_t word[2 * kMaxAggs + 1];
+  int32_t proj[2 * kMaxAggs + 1];  // >= 0: += sums[g * nproj + proj] (double); -1: += counts[g] (int64)
+  int n;
+};
+__global__ void merge_partials_kernel(const __grid_constant__ vb2_group_table t, const double* __restrict__ sums, const int64_t* __restrict__ counts,
+                                      int32_t ngroups, int32_t nproj, const __grid_constant__ MergeArgs m) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ngroups * m.n) return;
+  const int g = i / m.n, k = i % m.n;
+  const int64_t c = counts[g];
+  if (c == 0) return;  // no row of the batch reached this group
+  uint64_t* p = t.rows + static_cast<int64_t>(g) * t.row_words + m.word[k];
+  if (m.proj[k] >= 0) {
+    const double d = __dadd_rn(__longlong_as_double(static_cast<long long>(*p)), sums[static_cast<int64_t>(g) * nproj + m.proj[k]]);
+    *p = static_cast<uint64_t>(__double_as_longlong(d));
+  } else {
+    *p = static_cast<uint64_t>(static_cast<int64_t>(*p) + c);
   }
 }
 
@@ -378,15 +491,6 @@ int vb2k_normalize_keys(const vb2_column* cols, int32_t ncols, const int64_t* mi
   return VB2_OK;
 }
 
-int vb2k_denormalize_keys(const uint64_t* table_keys, const int32_t* slots, int64_t n, int64_t min, uint64_t mult,
-                          uint64_t range, int32_t null_reserved, int32_t type, void* values, uint64_t* valid, void* stream) {
-  if (n <= 0) return VB2_OK;
-  denormalize_keys_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      table_keys, slots, n, min, mult, range, null_reserved, type, values, reinterpret_cast<uint32_t*>(valid));
-  VB2_CUDA_OK(cudaGetLastError());
-  return VB2_OK;
-}
-
 int vb2k_column_minmax(const vb2_column* col, int64_t rows, int64_t* out3, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   minmax_init_kernel<<<1, 1, 0, st>>>(out3);
@@ -395,61 +499,99 @@ int vb2k_column_minmax(const vb2_column* col, int64_t rows, int64_t* out3, void*
   return VB2_OK;
 }
 
-int vb2k_group_probe(const uint64_t* row_keys, const uint64_t* row_valid, int64_t n, uint64_t* table_keys,
-                     int64_t capacity, int32_t* group_ids, int64_t* num_groups, int32_t* error_flag, void* stream) {
-  if (capacity <= 0 || (table_keys && (capacity & (capacity - 1)))) return fail_msg(VB2_ERR_INVALID, "group_probe: capacity must be a power of two");
-  if (capacity > (1ll << 31)) return fail_msg(VB2_ERR_UNSUPPORTED, "group_probe: capacity above 2^31 slots");
-  if (n <= 0) return VB2_OK;
-  group_probe_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      row_keys, row_valid, n, table_keys, static_cast<uint64_t>(capacity - 1), group_ids, num_groups, error_flag);
+static int check_table(const vb2_group_table* t, const char* who) {
+  if (!t || !t->rows || t->capacity <= 0 || t->row_words < 1 || t->row_words > VB2_MAX_ROW_WORDS) return fail_msg(VB2_ERR_INVALID, who);
+  if (t->hash_mode && (t->capacity & (t->capacity - 1))) return fail_msg(VB2_ERR_INVALID, "group table: hash-mode capacity must be a power of two");
+  if (t->capacity > (1ll << 31)) return fail_msg(VB2_ERR_UNSUPPORTED, "group table: capacity above 2^31 rows");
+  return VB2_OK;
+}
+
+int vb2k_group_table_init(const vb2_group_table* t, const uint64_t* row_init, void* stream) {
+  if (int rc = check_table(t, "group_table_init: bad table")) return rc;
+  vb2_group_row_init init;
+  for (int i = 0; i < t->row_words; ++i) init.words[i] = row_init[i];
+  const int64_t total = t->capacity * t->row_words;
+  table_init_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(t->rows, total, t->row_words, init);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 
-int vb2k_agg_update(const int32_t* group_ids, int64_t n, int64_t capacity, const vb2_agg_update* aggs, int32_t naggs,
-                    int32_t* error_flag, void* stream) {
-  if (naggs < 0 || naggs > kMaxAggs) return fail_msg(VB2_ERR_UNSUPPORTED, "agg_update: at most 16 aggregates per call");
-  if (n <= 0 || naggs == 0) return VB2_OK;
+int vb2k_group_update(const vb2_group_table* t, const uint64_t* row_keys, const uint64_t* row_valid, int64_t n,
+                      const vb2_agg_update* aggs, int32_t naggs, int64_t* num_groups, int32_t* error_flag, void* stream) {
+  if (int rc = check_table(t, "group_update: bad table")) return rc;
+  if (naggs < 0 || naggs > kMaxAggs) return fail_msg(VB2_ERR_UNSUPPORTED, "group_update: at most 16 aggregates per call");
+  if (n <= 0) return VB2_OK;
+  for (int i = 0; i < naggs; ++i)
+    if (aggs[i].acc_word < 1 || aggs[i].acc_word >= t->row_words || aggs[i].nonnull_word >= t->row_words)
+      return fail_msg(VB2_ERR_INVALID, "group_update: accumulator word outside the row");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   AggArgs rest;
   rest.n = 0;
-  for (int i = 0; i < naggs; ++i) {
-    const vb2_agg_update& u = aggs[i];
-    const bool tiny = capacity <= kTinyG && (u.kind == VB2_AGG_SUM_F64 || u.kind == VB2_AGG_SUM_I64 ||
-                                             u.kind == VB2_AGG_COUNT || u.kind == VB2_AGG_COUNT_MERGE);
-    if (!tiny) { rest.a[rest.n++] = u; continue; }
+  const bool tiny_table = !t->hash_mode && t->capacity <= kTinyG;
+  if (tiny_table) {
     const unsigned grid = grid_for(n, 256, 4);
-    switch (u.kind) {
-      case VB2_AGG_SUM_F64: agg_update_tiny_kernel<VB2_AGG_SUM_F64><<<grid, 256, 0, st>>>(group_ids, n, u, error_flag); break;
-      case VB2_AGG_SUM_I64: agg_update_tiny_kernel<VB2_AGG_SUM_I64><<<grid, 256, 0, st>>>(group_ids, n, u, error_flag); break;
-      case VB2_AGG_COUNT_MERGE: agg_update_tiny_kernel<VB2_AGG_COUNT_MERGE><<<grid, 256, 0, st>>>(group_ids, n, u, error_flag); break;
-      default: agg_update_tiny_kernel<VB2_AGG_COUNT><<<grid, 256, 0, st>>>(group_ids, n, u, error_flag); break;
+    vb2_agg_update none{};
+    group_update_tiny_kernel<0><<<grid, 256, 0, st>>>(*t, row_keys, row_valid, n, none, error_flag);
+    for (int i = 0; i < naggs; ++i) {
+      const vb2_agg_update& u = aggs[i];
+      switch (u.kind) {
+        case VB2_AGG_SUM_F64: group_update_tiny_kernel<VB2_AGG_SUM_F64><<<grid, 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
+        case VB2_AGG_SUM_I64: group_update_tiny_kernel<VB2_AGG_SUM_I64><<<grid, 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
+        case VB2_AGG_COUNT_MERGE: group_update_tiny_kernel<VB2_AGG_COUNT_MERGE><<<grid, 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
+        case VB2_AGG_COUNT: group_update_tiny_kernel<VB2_AGG_COUNT><<<grid, 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
+        default: rest.a[rest.n++] = u; break;  // min / max: idempotent atomics, no same-address accumulation chain
+      }
     }
+    if (rest.n) group_update_kernel<<<grid_for(n, 256), 256, 0, st>>>(*t, row_keys, row_valid, n, rest, nullptr, error_flag);
+  } else {
+    for (int i = 0; i < naggs; ++i) rest.a[rest.n++] = aggs[i];
+    group_update_kernel<<<grid_for(n, 256), 256, 0, st>>>(*t, row_keys, row_valid, n, rest, num_groups, error_flag);
   }
-  if (rest.n) agg_update_atomic_kernel<<<grid_for(n, 256), 256, 0, st>>>(group_ids, n, rest, error_flag);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 
-int vb2k_table_occupied(const uint64_t* table_keys, int64_t capacity, int32_t* slot_list, int64_t* count,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+size_t vb2k_group_occupied_workspace(int64_t capacity) {
+  return static_cast<size_t>((capacity + 63) >> 6) * 8 + vb2k_bits_to_indices_workspace(capacity);
+}
+
+int vb2k_group_occupied(const vb2_group_table* t, int32_t* slot_list, int64_t* count, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_table(t, "group_occupied: bad table")) return rc;
   // workspace = occupancy bitmap (capacity bits, 8-byte aligned) followed by the compaction scratch
-  const size_t bitmap_bytes = static_cast<size_t>((capacity + 63) >> 6) * 8;
-  const size_t need = bitmap_bytes + vb2k_bits_to_indices_workspace(capacity);
-  if (workspace_bytes < need) return fail_msg(VB2_ERR_INVALID, "table_occupied: workspace too small");
+  const size_t bitmap_bytes = static_cast<size_t>((t->capacity + 63) >> 6) * 8;
+  if (workspace_bytes < vb2k_group_occupied_workspace(t->capacity)) return fail_msg(VB2_ERR_INVALID, "group_occupied: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint64_t* bits = reinterpret_cast<uint64_t*>(workspace);
   VB2_CUDA_OK(cudaMemsetAsync(bits, 0, bitmap_bytes, st));
-  occupied_bits_kernel<<<grid_for(capacity, 256), 256, 0, st>>>(table_keys, capacity, reinterpret_cast<uint32_t*>(bits));
+  occupied_bits_kernel<<<grid_for(t->capacity, 256), 256, 0, st>>>(*t, reinterpret_cast<uint32_t*>(bits));
   VB2_CUDA_OK(cudaGetLastError());
-  return vb2k_bits_to_indices(bits, capacity, slot_list, count, reinterpret_cast<char*>(workspace) + bitmap_bytes,
+  return vb2k_bits_to_indices(bits, t->capacity, slot_list, count, reinterpret_cast<char*>(workspace) + bitmap_bytes,
                               workspace_bytes - bitmap_bytes, stream);
 }
 
-int vb2k_rekey(const uint64_t* table_keys, const int32_t* slots, int64_t n, int32_t ncols, const int64_t* old_mins,
-               const uint64_t* old_mults, const uint64_t* old_ranges, const int32_t* old_null_reserved, const int64_t* new_mins,
-               const uint64_t* new_mults, uint64_t* keys_out, void* stream) {
-  if (ncols < 1 || ncols > kMaxNormCols) return fail_msg(VB2_ERR_UNSUPPORTED, "rekey: 1..4 key columns");
+int vb2k_group_set_word(const vb2_group_table* t, int32_t word, uint64_t value, void* stream) {
+  if (int rc = check_table(t, "group_set_word: bad table")) return rc;
+  if (word < 1 || word >= t->row_words) return fail_msg(VB2_ERR_INVALID, "group_set_word: word outside the row");
+  set_word_kernel<<<grid_for(t->capacity, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, word, value);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_group_keys(const vb2_group_table* t, const int32_t* slots, int64_t n, int64_t min, uint64_t mult, uint64_t range,
+                    int32_t null_reserved, int32_t type, void* values, uint64_t* valid, void* stream) {
+  if (int rc = check_table(t, "group_keys: bad table")) return rc;
+  if (n <= 0) return VB2_OK;
+  group_keys_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, min, mult, range, null_reserved, type, values,
+                                                                                      reinterpret_cast<uint32_t*>(valid));
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_group_rekey(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t ncols, const int64_t* old_mins,
+                     const uint64_t* old_mults, const uint64_t* old_ranges, const int32_t* old_null_reserved, const int64_t* new_mins,
+                     const uint64_t* new_mults, uint64_t* keys_out, void* stream) {
+  if (int rc = check_table(t, "group_rekey: bad table")) return rc;
+  if (ncols < 1 || ncols > kMaxNormCols) return fail_msg(VB2_ERR_UNSUPPORTED, "group_rekey: 1..4 key columns");
   if (n <= 0) return VB2_OK;
   RekeyArgs a;
   a.n = ncols;
@@ -458,13 +600,67 @@ int vb2k_rekey(const uint64_t* table_keys, const int32_t* slots, int64_t n, int3
     a.old_mult[i] = old_mults[i]; a.old_range[i] = old_ranges[i]; a.new_mult[i] = new_mults[i];
     a.old_null_reserved[i] = old_null_reserved ? old_null_reserved[i] : 1;
   }
-  rekey_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table_keys, slots, n, a, keys_out);
+  rekey_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, a, keys_out);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 
-size_t vb2k_table_occupied_workspace(int64_t capacity) {
-  return static_cast<size_t>((capacity + 63) >> 6) * 8 + vb2k_bits_to_indices_workspace(capacity);
+int vb2k_group_move(const vb2_group_table* from, const int32_t* slots, const uint64_t* new_keys, int64_t n, const vb2_group_table* to,
+                    int64_t* num_groups, int32_t* error_flag, void* stream) {
+  if (int rc = check_table(from, "group_move: bad source table")) return rc;
+  if (int rc = check_table(to, "group_move: bad target table")) return rc;
+  if (from->row_words != to->row_words) return fail_msg(VB2_ERR_INVALID, "group_move: row layouts differ");
+  if (n <= 0) return VB2_OK;
+  group_move_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*from, slots, new_keys, n, *to, num_groups, error_flag);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_group_gather(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t word, void* out, void* stream) {
+  if (int rc = check_table(t, "group_gather: bad table")) return rc;
+  if (word < 0 || word >= t->row_words) return fail_msg(VB2_ERR_INVALID, "group_gather: word outside the row");
+  if (n <= 0) return VB2_OK;
+  group_gather_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, word, reinterpret_cast<uint64_t*>(out));
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_group_valid(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t count_word, uint64_t* valid, void* stream) {
+  if (int rc = check_table(t, "group_valid: bad table")) return rc;
+  if (count_word < 0 || count_word >= t->row_words) return fail_msg(VB2_ERR_INVALID, "group_valid: word outside the row");
+  if (n <= 0) return VB2_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VB2_CUDA_OK(cudaMemsetAsync(valid + ((n + 63) >> 6) - 1, 0, 8, st));
+  group_valid_kernel<<<grid_for(n, 256), 256, 0, st>>>(*t, slots, n, count_word, reinterpret_cast<uint32_t*>(valid));
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_group_avg(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t sum_word, int32_t count_word, double* out, void* stream) {
+  if (int rc = check_table(t, "group_avg: bad table")) return rc;
+  if (n <= 0) return VB2_OK;
+  group_avg_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, sum_word, count_word, out);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_group_merge_partials(const vb2_group_table* t, const double* sums, const int64_t* counts, int32_t ngroups, int32_t nproj,
+                              const int32_t* target_words, const int32_t* target_projs, int32_t ntargets, void* stream) {
+  if (int rc = check_table(t, "group_merge_partials: bad table")) return rc;
+  if (t->hash_mode || ngroups > t->capacity) return fail_msg(VB2_ERR_INVALID, "group_merge_partials: array-mode table of >= ngroups rows expected");
+  if (ntargets < 0 || ntargets > 2 * kMaxAggs + 1) return fail_msg(VB2_ERR_UNSUPPORTED, "group_merge_partials: too many target words");
+  if (ngroups <= 0 || ntargets == 0) return VB2_OK;
+  MergeArgs m;
+  m.n = ntargets;
+  for (int i = 0; i < ntargets; ++i) {
+    if (target_words[i] < 0 || target_words[i] >= t->row_words || target_projs[i] >= nproj) return fail_msg(VB2_ERR_INVALID, "group_merge_partials: bad target");
+    m.word[i] = target_words[i];
+    m.proj[i] = target_projs[i];
+  }
+  const int total = ngroups * ntargets;
+  merge_partials_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*t, sums, counts, ngroups, nproj, m);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
 }
 
 }  // extern "C"

@@ -137,6 +137,103 @@ __global__ void part_scatter_kernel(const uint32_t* __restrict__ ids, int64_t ro
   }
 }
 
+// --- fixed-capacity segments (sync-free shuffle) ---------------------------------------------------
+// Same three passes as above with the partition id computed inline from a BIGINT key and rows
+// written straight into their destination segment — no id / order arrays, no host round trip.
+constexpr int kMaxSegCols = 4;
+struct SegCols {
+  const void* in[kMaxSegCols];
+  void* out[kMaxSegCols];
+  int32_t bytes[kMaxSegCols];
+  int n;
+};
+__device__ __forceinline__ int64_t live_rows(int64_t rows, const int64_t* rows_dev) {
+  if (!rows_dev) return rows;
+  const int64_t d = *rows_dev;
+  return d < rows ? d : rows;
+}
+__global__ void seg_hist_kernel(const int64_t* __restrict__ keys, int64_t rows, const int64_t* __restrict__ rows_dev, uint32_t parts,
+                                int32_t* __restrict__ block_hist) {
+  __shared__ int32_t h[kMaxParts];
+  rows = live_rows(rows, rows_dev);
+  for (int p = threadIdx.x; p < parts; p += blockDim.x) h[p] = 0;
+  __syncthreads();
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kPartRowsPerBlock;
+  for (int i = threadIdx.x; i < kPartRowsPerBlock; i += blockDim.x) {
+    const int64_t r = r0 + i;
+    if (r < rows) atomicAdd(&h[twang_mix64(static_cast<uint64_t>(keys[r])) % parts], 1);
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < parts; p += blockDim.x) block_hist[static_cast<int64_t>(blockIdx.x) * parts + p] = h[p];
+}
+// One block: per partition, exclusive scan of the block counts (positions inside the segment).
+__global__ void seg_offsets_kernel(const int32_t* __restrict__ block_hist, int64_t nblocks, int parts, int64_t segcap,
+                                   int64_t* __restrict__ counts, int64_t* __restrict__ block_base, int32_t* __restrict__ overflow) {
+  const int p = threadIdx.x;
+  if (p >= parts) return;
+  int64_t run = 0;
+  for (int64_t b = 0; b < nblocks; ++b) {
+    block_base[b * parts + p] = run;
+    run += block_hist[b * parts + p];
+  }
+  counts[p] = run;
+  if (run > segcap) atomicExch(overflow, 1);
+}
+__global__ void seg_scatter_kernel(const int64_t* __restrict__ keys, int64_t rows, const int64_t* __restrict__ rows_dev, uint32_t parts,
+                                   int64_t segcap, const int64_t* __restrict__ block_base, int64_t* __restrict__ seg_keys,
+                                   const __grid_constant__ SegCols cols) {
+  __shared__ int64_t base[kMaxParts];
+  __shared__ int32_t warp_counts[kPartThreads / kWarp][kMaxParts];
+  rows = live_rows(rows, rows_dev);
+  for (int p = threadIdx.x; p < parts; p += blockDim.x) base[p] = block_base[static_cast<int64_t>(blockIdx.x) * parts + p];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kPartRowsPerBlock;
+  for (int i0 = 0; i0 < kPartRowsPerBlock; i0 += kPartThreads) {
+    const int64_t r = r0 + i0 + threadIdx.x;
+    const bool live = r < rows;
+    const int64_t key = live ? keys[r] : 0;
+    const uint32_t id = live ? static_cast<uint32_t>(twang_mix64(static_cast<uint64_t>(key)) % parts) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, id);
+    const int rank = __popc(peers & ((1u << lane) - 1));
+    const int cnt = __popc(peers);
+    for (int p = lane; p < parts; p += kWarp) warp_counts[warp][p] = 0;
+    __syncwarp();
+    if (live && rank == 0) warp_counts[warp][id] = cnt;
+    __syncthreads();
+    if (live) {
+      int64_t pos = base[id];
+      for (int w = 0; w < warp; ++w) pos += warp_counts[w][id];
+      pos += rank;
+      if (pos < segcap) {  // beyond: dropped, the overflow flag is already set
+        const int64_t at = static_cast<int64_t>(id) * segcap + pos;
+        seg_keys[at] = key;
+        for (int c = 0; c < cols.n; ++c) {
+          if (cols.bytes[c] == 8) reinterpret_cast<uint64_t*>(cols.out[c])[at] = reinterpret_cast<const uint64_t*>(cols.in[c])[r];
+          else reinterpret_cast<uint32_t*>(cols.out[c])[at] = reinterpret_cast<const uint32_t*>(cols.in[c])[r];
+        }
+      }
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < parts; p += blockDim.x) {
+      int32_t s = 0;
+      for (int w = 0; w < kPartThreads / kWarp; ++w) s += warp_counts[w][p];
+      base[p] += s;
+    }
+    __syncthreads();
+  }
+}
+
+// flag <- 1 if any key other than the sentinel lies outside [lo, hi]
+__global__ void key_range_check_kernel(const int64_t* __restrict__ keys, int64_t n, int64_t lo, int64_t hi, int32_t* __restrict__ flag) {
+  bool bad = false;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t k = keys[i];
+    bad |= k != VB2_SENTINEL_KEY && (k < lo || k > hi);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(flag, 1);
+}
+
 template <class T>
 __global__ void gather_kernel(const T* __restrict__ in, const int32_t* __restrict__ order, int64_t n, T* __restrict__ out) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -193,6 +290,49 @@ int vb2k_partition_scatter_order(const uint32_t* ids, int64_t rows, int32_t num_
   VB2_CUDA_OK(cudaGetLastError());
   VB2_CUDA_OK(cudaFreeAsync(hist, st));
   VB2_CUDA_OK(cudaFreeAsync(base, st));
+  return VB2_OK;
+}
+
+int vb2k_partition_segments(const int64_t* keys, const void* const* cols, const int32_t* col_elem_bytes, int32_t ncols, int64_t rows,
+                            const int64_t* rows_dev, int32_t num_partitions, int64_t segcap, int64_t* seg_keys, void* const* seg_cols,
+                            int64_t* counts, int32_t* overflow, void* stream) {
+  if (num_partitions < 1 || num_partitions > kMaxParts) return fail_msg(VB2_ERR_INVALID, "partition_segments: 1..64 partitions");
+  if (ncols < 0 || ncols > kMaxSegCols) return fail_msg(VB2_ERR_UNSUPPORTED, "partition_segments: at most 4 payload columns");
+  if (segcap <= 0) return fail_msg(VB2_ERR_INVALID, "partition_segments: segment capacity must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SegCols sc;
+  sc.n = ncols;
+  for (int c = 0; c < ncols; ++c) {
+    if (col_elem_bytes[c] != 4 && col_elem_bytes[c] != 8) return fail_msg(VB2_ERR_INVALID, "partition_segments: 4- or 8-byte payload columns");
+    sc.in[c] = cols[c];
+    sc.out[c] = seg_cols[c];
+    sc.bytes[c] = col_elem_bytes[c];
+  }
+  // every key slot starts as the sentinel (bytes 0x80): segment tails stay that way
+  VB2_CUDA_OK(cudaMemsetAsync(seg_keys, 0x80, sizeof(int64_t) * static_cast<size_t>(num_partitions) * segcap, st));
+  if (rows <= 0) {
+    VB2_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int64_t) * num_partitions, st));
+    return VB2_OK;
+  }
+  const int64_t nblocks = (rows + kPartRowsPerBlock - 1) / kPartRowsPerBlock;
+  int32_t* hist = nullptr;
+  int64_t* base = nullptr;
+  VB2_CUDA_OK(cudaMallocAsync(&hist, sizeof(int32_t) * nblocks * num_partitions, st));
+  VB2_CUDA_OK(cudaMallocAsync(&base, sizeof(int64_t) * nblocks * num_partitions, st));
+  seg_hist_kernel<<<static_cast<unsigned>(nblocks), kPartThreads, 0, st>>>(keys, rows, rows_dev, static_cast<uint32_t>(num_partitions), hist);
+  seg_offsets_kernel<<<1, kMaxParts, 0, st>>>(hist, nblocks, num_partitions, segcap, counts, base, overflow);
+  seg_scatter_kernel<<<static_cast<unsigned>(nblocks), kPartThreads, 0, st>>>(keys, rows, rows_dev, static_cast<uint32_t>(num_partitions), segcap, base,
+                                                                              seg_keys, sc);
+  VB2_CUDA_OK(cudaGetLastError());
+  VB2_CUDA_OK(cudaFreeAsync(hist, st));
+  VB2_CUDA_OK(cudaFreeAsync(base, st));
+  return VB2_OK;
+}
+
+int vb2k_key_range_check(const int64_t* keys, int64_t n, int64_t lo, int64_t hi, int32_t* flag, void* stream) {
+  if (n <= 0) return VB2_OK;
+  key_range_check_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(keys, n, lo, hi, flag);
+  VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 

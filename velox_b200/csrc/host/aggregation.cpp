@@ -42,7 +42,12 @@ struct AccState {
   int32_t kind = 0;          // vb2_agg_kind of the main accumulator
   bool isDouble = false;     // accumulator holds doubles
   TypePtr inputType;
-  DeviceBufferPtr acc, nonnull;
+  int32_t accWord = -1;      // word of the accumulator inside the group row
+  int32_t nnWord = -1;       // word of the non-null counter (-1: count(), which is its own counter)
+  // The non-null counter only decides NULL-ness for sum / min / max; it is not maintained while
+  // every input seen so far was non-null and unmasked (all groups trivially non-null). AVG always
+  // tracks (the counter is its divisor).
+  bool nnTracked = false;
 };
 
 }  // namespace
@@ -59,8 +64,12 @@ struct B200HashAggregation::Impl {
   std::vector<int64_t> covLo, covHi;  // value interval each key's layout covers
   std::vector<int32_t> nullReserved;  // 1 = id 0 means NULL for that key
   int64_t capacity = 1;
-  DeviceBufferPtr tableKeys;   // hash mode
-  DeviceBufferPtr groupRows;   // int64[capacity]: input rows per slot (slot occupied <=> > 0)
+  // Group rows [capacity][rowWords]: word 0 = normalized key (hash mode) / rows seen (array, global),
+  // then the accumulator and non-null-counter words of every aggregate (vb2_group_table).
+  DeviceBufferPtr rowsBuf;
+  int32_t rowWords = 1;
+  std::vector<uint64_t> rowInit;
+  bool sawGeneric = false;     // a batch went through vb2k_group_update (untracked counters need a fix-up to start tracking)
   DeviceBufferPtr numGroupsDev;
   int64_t numGroupsUpper = 0;  // upper bound of distinct groups seen (hash mode sizing)
   std::vector<AccState> accs;
@@ -113,6 +122,14 @@ struct B200HashAggregation::Impl {
       if (a.rawInputType && a.rawInputType->kind() == TypeKind::VARCHAR) VELOX_UNSUPPORTED("aggregates over VARCHAR");
       accs.push_back(std::move(s));
     }
+    int32_t w = 1;
+    for (auto& a : accs) {
+      a.accWord = w++;
+      if (a.fn != "count") a.nnWord = w++;
+      a.nnTracked = a.fn == "avg";
+    }
+    rowWords = w <= 2 ? w : (w + 3) / 4 * 4;  // whole 32-byte sectors
+    VELOX_CHECK(rowWords <= VB2_MAX_ROW_WORDS, "too many aggregates for one group row");
     errorFlag = allocDeviceZeroed(8, st());
     numGroupsDev = allocDeviceZeroed(8, st());
     layout.mins.assign(keys.size(), 1);
@@ -137,50 +154,50 @@ struct B200HashAggregation::Impl {
     }
   }
 
-  struct Storage {
-    DeviceBufferPtr tableKeys, groupRows;
-    std::vector<DeviceBufferPtr> acc, nonnull;
-  };
-  Storage makeStorage(int64_t cap, Mode m) {
-    Storage s;
-    s.groupRows = allocDeviceZeroed(static_cast<size_t>(cap) * 8, st());
-    if (m == Mode::kHash) {
-      s.tableKeys = allocDevice(static_cast<size_t>(cap) * 8, st());
-      kernelCheck(vb2k_fill_u64(s.tableKeys->as<uint64_t>(), cap, VB2_EMPTY_KEY, st()));
-    }
-    for (auto& a : accs) {
-      auto acc = allocDevice(static_cast<size_t>(cap) * 8, st());
-      kernelCheck(vb2k_fill_u64(acc->as<uint64_t>(), cap, identityBits(a), st()));
-      s.acc.push_back(acc);
-      s.nonnull.push_back(allocDeviceZeroed(static_cast<size_t>(cap) * 8, st()));
-    }
-    return s;
+  vb2_group_table tableOf(const DeviceBufferPtr& buf, int64_t cap, Mode m) const {
+    vb2_group_table t{};
+    t.rows = buf->as<uint64_t>();
+    t.capacity = cap;
+    t.row_words = rowWords;
+    t.hash_mode = m == Mode::kHash ? 1 : 0;
+    return t;
   }
-  void adopt(Storage&& s) {
-    tableKeys = s.tableKeys;
-    groupRows = s.groupRows;
-    for (size_t i = 0; i < accs.size(); ++i) { accs[i].acc = s.acc[i]; accs[i].nonnull = s.nonnull[i]; }
+  vb2_group_table table() const { return tableOf(rowsBuf, capacity, mode); }
+
+  DeviceBufferPtr makeStorage(int64_t cap, Mode m) {
+    std::vector<uint64_t> init(rowWords, 0);
+    init[0] = m == Mode::kHash ? VB2_EMPTY_KEY : 0;
+    for (auto& a : accs) init[a.accWord] = identityBits(a);
+    auto buf = allocDevice(static_cast<size_t>(cap) * rowWords * 8, st());
+    const vb2_group_table t = tableOf(buf, cap, m);
+    kernelCheck(vb2k_group_table_init(&t, init.data(), st()));
+    return buf;
   }
-  void allocateStorage(int64_t cap, Mode m) { adopt(makeStorage(cap, m)); }
+  void allocateStorage(int64_t cap, Mode m) { rowsBuf = makeStorage(cap, m); }
 
   // Occupied slots of the current table (synchronises for the count).
   DeviceBufferPtr occupiedSlots(int64_t& count) {
     auto slots = allocDevice(static_cast<size_t>(capacity) * 4, st());
     auto cnt = allocDevice(8, st());
-    if (mode == Mode::kHash) {
-      const size_t wsb = vb2k_table_occupied_workspace(capacity);
-      auto ws = allocDevice(wsb, st());
-      kernelCheck(vb2k_table_occupied(tableKeys->as<uint64_t>(), capacity, slots->as<int32_t>(), cnt->as<int64_t>(), ws->data(), wsb, st()));
-    } else {
-      auto bitsBuf = allocDevice(bits::nbytes(capacity), st());
-      kernelCheck(vb2k_positive_bits(groupRows->as<int64_t>(), capacity, bitsBuf->as<uint64_t>(), st()));
-      const size_t wsb = vb2k_bits_to_indices_workspace(capacity);
-      auto ws = allocDevice(wsb, st());
-      kernelCheck(vb2k_bits_to_indices(bitsBuf->as<uint64_t>(), capacity, slots->as<int32_t>(), cnt->as<int64_t>(), ws->data(), wsb, st()));
-    }
+    const size_t wsb = vb2k_group_occupied_workspace(capacity);
+    auto ws = allocDevice(wsb, st());
+    const vb2_group_table t = table();
+    kernelCheck(vb2k_group_occupied(&t, slots->as<int32_t>(), cnt->as<int64_t>(), ws->data(), wsb, st()));
     VB2_CU(cudaMemcpyAsync(&count, cnt->data(), 8, cudaMemcpyDeviceToHost, st()));
     VB2_CU(cudaStreamSynchronize(st()));
     return slots;
+  }
+
+  // Starts maintaining aggregate i's non-null counter: groups that exist already have only seen
+  // non-null, unmasked inputs, so their counters become 1 ("some non-null input").
+  void trackNonNull(size_t i) {
+    AccState& s = accs[i];
+    if (s.nnTracked || s.nnWord < 0) return;
+    if (sawGeneric) {
+      const vb2_group_table t = table();
+      kernelCheck(vb2k_group_set_word(&t, s.nnWord, 1, st()));
+    }
+    s.nnTracked = true;
   }
 
   // Moves every group to a new layout / mode / capacity (ranges grew or the table filled up).
@@ -188,21 +205,15 @@ struct B200HashAggregation::Impl {
     flushFused();  // fused partial sums are laid out by the old group ids
     int64_t m = 0;
     DeviceBufferPtr slots = sawInput ? occupiedSlots(m) : nullptr;
-    Storage ns = makeStorage(ncap, nm);
+    DeviceBufferPtr ns = makeStorage(ncap, nm);
     if (m > 0) {
+      const vb2_group_table from = table(), to = tableOf(ns, ncap, nm);
       auto newKeys = allocDevice(static_cast<size_t>(m) * 8, st());
-      kernelCheck(vb2k_rekey(mode == Mode::kHash ? tableKeys->as<uint64_t>() : nullptr, slots->as<int32_t>(), m, static_cast<int32_t>(keys.size()),
-                             layout.mins.data(), layout.mults.data(), layout.ranges.data(), nullReserved.data(), nl.mins.data(),
-                             nl.mults.data(), newKeys->as<uint64_t>(), st()));
-      auto newSlots = allocDevice(static_cast<size_t>(m) * 4, st());
+      kernelCheck(vb2k_group_rekey(&from, slots->as<int32_t>(), m, static_cast<int32_t>(keys.size()), layout.mins.data(), layout.mults.data(),
+                                   layout.ranges.data(), nullReserved.data(), nl.mins.data(), nl.mults.data(), newKeys->as<uint64_t>(), st()));
       VB2_CU(cudaMemsetAsync(numGroupsDev->data(), 0, 8, st()));  // the new table counts its groups afresh
-      kernelCheck(vb2k_group_probe(newKeys->as<uint64_t>(), nullptr, m, nm == Mode::kHash ? ns.tableKeys->as<uint64_t>() : nullptr, ncap,
-                                   newSlots->as<int32_t>(), numGroupsDev->as<int64_t>(), errorFlag->as<int32_t>(), st()));
-      auto move = [&](const DeviceBufferPtr& from, const DeviceBufferPtr& to) {
-        kernelCheck(vb2k_scatter(from->data(), slots->as<int32_t>(), newSlots->as<int32_t>(), m, 8, to->data(), st()));
-      };
-      move(groupRows, ns.groupRows);
-      for (size_t i = 0; i < accs.size(); ++i) { move(accs[i].acc, ns.acc[i]); move(accs[i].nonnull, ns.nonnull[i]); }
+      kernelCheck(vb2k_group_move(&from, slots->as<int32_t>(), newKeys->as<uint64_t>(), m, &to, numGroupsDev->as<int64_t>(),
+                                  errorFlag->as<int32_t>(), st()));
       checkDeviceError(errorFlag, st(), "aggregation rehash");
     }
     layout = nl;
@@ -210,7 +221,7 @@ struct B200HashAggregation::Impl {
     for (auto& ks : keys) ks.fusedLut = nullptr;
     mode = nm;
     capacity = ncap;
-    adopt(std::move(ns));
+    rowsBuf = std::move(ns);
     self->addRuntimeStat("b200.aggRelayouts", exec::RuntimeCounter{1});
   }
 
@@ -334,7 +345,7 @@ struct B200HashAggregation::Impl {
     const int64_t n = in->size();
     ++genericBatches;
     std::vector<DeviceBufferPtr> keep;
-    DeviceBufferPtr groupIds;
+    DeviceBufferPtr rowKeys;
     if (!keys.empty()) {
       std::vector<vb2_column> keyCols;
       for (size_t k = 0; k < keys.size(); ++k) keyCols.push_back(keyColumn(k, *in->column(node->groupingKeys()[k]), n, keep));
@@ -342,25 +353,9 @@ struct B200HashAggregation::Impl {
       auto nk = allocDevice(static_cast<size_t>(n) * 8, st());
       kernelCheck(vb2k_normalize_keys(keyCols.data(), static_cast<int32_t>(keyCols.size()), layout.mins.data(), layout.mults.data(), nullptr, 0,
                                       nullptr, n, nk->as<uint64_t>(), nullptr, st()));
-      groupIds = allocDevice(static_cast<size_t>(n) * 4, st());
-      kernelCheck(vb2k_group_probe(nk->as<uint64_t>(), nullptr, n, mode == Mode::kHash ? tableKeys->as<uint64_t>() : nullptr, capacity,
-                                   groupIds->as<int32_t>(), numGroupsDev->as<int64_t>(), errorFlag->as<int32_t>(), st()));
-      numGroupsUpper += n;
-      if (mode == Mode::kHash) {
-        // tighten the bound with the real group count (one 8-byte read per batch)
-        int64_t g = 0;
-        VB2_CU(cudaMemcpyAsync(&g, numGroupsDev->data(), 8, cudaMemcpyDeviceToHost, st()));
-        VB2_CU(cudaStreamSynchronize(st()));
-        numGroupsUpper = g;
-      }
+      rowKeys = nk;
     }
     std::vector<vb2_agg_update> ups;
-    {
-      vb2_agg_update u{};
-      u.kind = VB2_AGG_COUNT;
-      u.acc = groupRows->data();
-      ups.push_back(u);
-    }
     auto flatInput = [&](int32_t colIdx, const void*& values, const uint64_t*& nulls, int32_t& type) {
       const DeviceColumnPtr& c = in->column(colIdx);
       type = c->desc.type;
@@ -394,11 +389,10 @@ struct B200HashAggregation::Impl {
       }
       vb2_agg_update u{};
       u.mask = mask;
-      u.acc = s.acc->data();
-      u.nonnull = s.nonnull->as<int64_t>();
+      u.acc_word = s.accWord;
+      u.nonnull_word = -1;
       if (a.function == "count") {
         u.kind = raw ? VB2_AGG_COUNT : VB2_AGG_COUNT_MERGE;
-        u.nonnull = nullptr;
         if (!a.inputs.empty()) flatInput(a.inputs[0], u.input, u.nulls, u.input_type);
         ups.push_back(u);
         continue;
@@ -407,21 +401,36 @@ struct B200HashAggregation::Impl {
       u.kind = s.kind;
       if (a.function == "avg" && !raw) {
         // intermediate (sum, count): add the sums, merge the counts into the non-null counter
-        u.nonnull = nullptr;
         ups.push_back(u);
         vb2_agg_update c{};
         c.kind = VB2_AGG_COUNT_MERGE;
         c.mask = mask;
+        c.nonnull_word = -1;
         flatInput(a.inputs[1], c.input, c.nulls, c.input_type);
-        c.acc = s.nonnull->data();
+        c.acc_word = s.nnWord;
         ups.push_back(c);
         continue;
       }
+      if (mask || u.nulls) trackNonNull(i);
+      if (s.nnTracked) u.nonnull_word = s.nnWord;
       ups.push_back(u);
     }
-    for (size_t i = 0; i < ups.size(); i += 16) {
+    const vb2_group_table t = table();
+    const uint64_t* rk = rowKeys ? rowKeys->as<uint64_t>() : nullptr;
+    for (size_t i = 0; i == 0 || i < ups.size(); i += 16) {
+      // the first call inserts the groups; later slices of a long aggregate list find them again
       const int32_t cnt = static_cast<int32_t>(std::min<size_t>(16, ups.size() - i));
-      kernelCheck(vb2k_agg_update(groupIds ? groupIds->as<int32_t>() : nullptr, n, capacity, ups.data() + i, cnt, errorFlag->as<int32_t>(), st()));
+      kernelCheck(vb2k_group_update(&t, rk, nullptr, n, ups.data() + i, cnt, i == 0 ? numGroupsDev->as<int64_t>() : nullptr,
+                                    errorFlag->as<int32_t>(), st()));
+    }
+    sawGeneric = true;
+    numGroupsUpper += n;
+    if (mode == Mode::kHash) {
+      // tighten the bound with the real group count (one 8-byte read per batch)
+      int64_t g = 0;
+      VB2_CU(cudaMemcpyAsync(&g, numGroupsDev->data(), 8, cudaMemcpyDeviceToHost, st()));
+      VB2_CU(cudaStreamSynchronize(st()));
+      numGroupsUpper = g;
     }
     // buffers in `keep` are freed stream-ordered after the kernels above
   }
@@ -681,46 +690,28 @@ struct B200HashAggregation::Impl {
     return true;
   }
 
-  // Folds the fused partial sums into the generic accumulators (small: <= kFusedMaxGroups groups).
+  // Folds the fused partial sums into the group rows (small: <= kFusedMaxGroups groups) on the
+  // device: one launch, no host round trip.
   void flushFused() {
     if (!fusedSums) return;
     const int np = vb2k_fused_nproj(fusedId);
-    std::vector<double> sums(static_cast<size_t>(fusedGroups) * np);
-    std::vector<int64_t> counts(fusedGroups);
-    VB2_CU(cudaMemcpyAsync(sums.data(), fusedSums->data(), sums.size() * 8, cudaMemcpyDeviceToHost, st()));
-    VB2_CU(cudaMemcpyAsync(counts.data(), fusedCounts->data(), counts.size() * 8, cudaMemcpyDeviceToHost, st()));
-    VB2_CU(cudaStreamSynchronize(st()));
+    VELOX_CHECK(static_cast<int64_t>(fusedGroups) <= capacity && mode != Mode::kHash, "fused group space does not match the table");
+    std::vector<int32_t> words{0}, projs{-1};  // word 0: rows seen (occupancy)
+    for (size_t i = 0; i < accs.size(); ++i) {
+      trackNonNull(i);
+      const int p = aggToProj[i];
+      words.push_back(accs[i].accWord);
+      projs.push_back(p);  // p < 0: count(*)
+      if (p >= 0 && accs[i].nnWord >= 0) {
+        words.push_back(accs[i].nnWord);
+        projs.push_back(-1);
+      }
+    }
+    const vb2_group_table t = table();
+    kernelCheck(vb2k_group_merge_partials(&t, fusedSums->as<double>(), fusedCounts->as<int64_t>(), fusedGroups, np, words.data(), projs.data(),
+                                          static_cast<int32_t>(words.size()), st()));
     fusedSums = nullptr;
     fusedCounts = nullptr;
-    VELOX_CHECK(static_cast<int64_t>(fusedGroups) <= capacity, "fused group space larger than the table");
-    // read-modify-write of the few affected accumulator entries
-    auto rmw = [&](const DeviceBufferPtr& buf, auto fn) {
-      using T = std::remove_reference_t<decltype(fn(0, static_cast<uint64_t>(0)))>;
-      (void)sizeof(T);
-      std::vector<uint64_t> h(fusedGroups);
-      VB2_CU(cudaMemcpyAsync(h.data(), buf->data(), h.size() * 8, cudaMemcpyDeviceToHost, st()));
-      VB2_CU(cudaStreamSynchronize(st()));
-      for (int g = 0; g < fusedGroups; ++g) h[g] = fn(g, h[g]);
-      VB2_CU(cudaMemcpyAsync(buf->data(), h.data(), h.size() * 8, cudaMemcpyHostToDevice, st()));
-      VB2_CU(cudaStreamSynchronize(st()));
-    };
-    auto addI64 = [&](const DeviceBufferPtr& buf) {
-      rmw(buf, [&](int g, uint64_t cur) { return static_cast<uint64_t>(static_cast<int64_t>(cur) + counts[g]); });
-    };
-    addI64(groupRows);
-    for (size_t i = 0; i < accs.size(); ++i) {
-      const int p = aggToProj[i];
-      if (p < 0) { addI64(accs[i].acc); continue; }
-      rmw(accs[i].acc, [&](int g, uint64_t cur) {
-        double d;
-        std::memcpy(&d, &cur, 8);
-        d += sums[static_cast<size_t>(g) * np + p];
-        uint64_t out;
-        std::memcpy(&out, &d, 8);
-        return out;
-      });
-      addI64(accs[i].nonnull);
-    }
   }
 
   // ---- input ------------------------------------------------------------------------------------
@@ -766,6 +757,7 @@ struct B200HashAggregation::Impl {
     }
     const auto& outType = node->outputType();
     const auto& inType = node->sources()[0]->outputType();
+    const vb2_group_table tab = table();
     std::vector<DeviceColumnPtr> cols;
     uint32_t oc = 0;
     // keys
@@ -775,8 +767,8 @@ struct B200HashAggregation::Impl {
       if (keys[k].isVarchar) {
         // dictionary over the global alphabet: index = id - 1
         auto idx = allocDevice(static_cast<size_t>(m) * 4, st());
-        kernelCheck(vb2k_denormalize_keys(mode == Mode::kHash ? tableKeys->as<uint64_t>() : nullptr, slots->as<int32_t>(), m, layout.mins[k] - 1,
-                                          layout.mults[k], layout.ranges[k], nullReserved[k], VB2_INTEGER, idx->data(), valid->as<uint64_t>(), st()));
+        kernelCheck(vb2k_group_keys(&tab, slots->as<int32_t>(), m, layout.mins[k] - 1, layout.mults[k], layout.ranges[k], nullReserved[k],
+                                    VB2_INTEGER, idx->data(), valid->as<uint64_t>(), st()));
         auto alpha = std::make_shared<HostAlphabet>();
         alpha->values = keys[k].valuesById;
         alpha->nulls.assign(alpha->values.size(), false);
@@ -804,8 +796,8 @@ struct B200HashAggregation::Impl {
       } else {
         const int vt = veloxTypeToVb2(t);
         auto vals = allocDevice(static_cast<size_t>(m) * 8, st());
-        kernelCheck(vb2k_denormalize_keys(mode == Mode::kHash ? tableKeys->as<uint64_t>() : nullptr, slots->as<int32_t>(), m, layout.mins[k],
-                                          layout.mults[k], layout.ranges[k], nullReserved[k], vt, vals->data(), valid->as<uint64_t>(), st()));
+        kernelCheck(vb2k_group_keys(&tab, slots->as<int32_t>(), m, layout.mins[k], layout.mults[k], layout.ranges[k], nullReserved[k], vt,
+                                    vals->data(), valid->as<uint64_t>(), st()));
         if (vt == VB2_BOOLEAN) {
           auto packed = allocDevice(bits::nbytes(m), st());
           kernelCheck(vb2k_pack_bools(vals->as<uint8_t>(), m, packed->as<uint64_t>(), st()));
@@ -818,31 +810,32 @@ struct B200HashAggregation::Impl {
     const int32_t* sl = slots->as<int32_t>();
     for (size_t i = 0; i < accs.size(); ++i) {
       const AccState& s = accs[i];
-      auto gatherAcc = [&](const DeviceBufferPtr& src) {
+      auto gatherWord = [&](int32_t word) {
         auto out = allocDevice(static_cast<size_t>(m) * 8, st());
-        kernelCheck(vb2k_gather(src->data(), sl, m, 8, out->data(), st()));
+        kernelCheck(vb2k_group_gather(&tab, sl, m, word, out->data(), st()));
         return out;
       };
-      auto validOf = [&]() {
+      auto validOf = [&]() -> DeviceBufferPtr {
+        if (!s.nnTracked) return nullptr;  // every input of every group was non-null
         auto v = allocDevice(bits::nbytes(m), st());
-        kernelCheck(vb2k_counts_to_valid(s.nonnull->as<int64_t>(), sl, m, v->as<uint64_t>(), st()));
+        kernelCheck(vb2k_group_valid(&tab, sl, m, s.nnWord, v->as<uint64_t>(), st()));
         return v;
       };
       if (s.fn == "count") {
-        cols.push_back(flatOutput(outType->childAt(oc++), gatherAcc(s.acc), nullptr, m));
+        cols.push_back(flatOutput(outType->childAt(oc++), gatherWord(s.accWord), nullptr, m));
       } else if (s.fn == "avg") {
         if (fin) {
           auto out = allocDevice(static_cast<size_t>(m) * 8, st());
-          kernelCheck(vb2k_avg_finalize(s.acc->as<double>(), s.nonnull->as<int64_t>(), sl, m, out->as<double>(), st()));
+          kernelCheck(vb2k_group_avg(&tab, sl, m, s.accWord, s.nnWord, out->as<double>(), st()));
           cols.push_back(flatOutput(outType->childAt(oc++), out, validOf(), m));
         } else {
           auto v = validOf();
-          cols.push_back(flatOutput(outType->childAt(oc++), gatherAcc(s.acc), v, m));
-          cols.push_back(flatOutput(outType->childAt(oc++), gatherAcc(s.nonnull), v, m));
+          cols.push_back(flatOutput(outType->childAt(oc++), gatherWord(s.accWord), v, m));
+          cols.push_back(flatOutput(outType->childAt(oc++), gatherWord(s.nnWord), v, m));
         }
       } else {
         const TypePtr& t = outType->childAt(oc++);
-        auto vals = gatherAcc(s.acc);
+        auto vals = gatherWord(s.accWord);
         if (t->kind() == TypeKind::INTEGER) {
           // min/max over INTEGER keep their type: narrow the 8-byte accumulator
           auto narrow = allocDevice(static_cast<size_t>(m) * 4, st());

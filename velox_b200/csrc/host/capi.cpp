@@ -232,6 +232,8 @@ struct SegvInstaller {
   SegvInstaller() {
     const char* e = std::getenv("VB2_DEBUG_SEGV");
     if (e && e[0] == '1') signal(SIGSEGV, segvHandler);
+    const char* t = std::getenv("VB2_SYNC_TIMING");  // attribute kernel time to operators in the wall-time stats
+    if (t && t[0] == '1') facebook::velox::exec::g_timingSync = []() { cudaDeviceSynchronize(); };
   }
 } g_segvInstaller;
 }  // namespace

@@ -153,5 +153,8 @@ int32_t vb2_comm_all_reduce_f64(vb2_comm* comm, double* data, int64_t n, void* s
 int32_t vb2_comm_all_reduce_i64(vb2_comm* comm, int64_t* data, int64_t n, void* stream) {
   return ncclFail(ncclAllReduce(data, data, static_cast<size_t>(n), ncclInt64, ncclSum, comm->comm, static_cast<cudaStream_t>(stream)), "all_reduce");
 }
+int32_t vb2_comm_all_reduce_max_i64(vb2_comm* comm, int64_t* data, int64_t n, void* stream) {
+  return ncclFail(ncclAllReduce(data, data, static_cast<size_t>(n), ncclInt64, ncclMax, comm->comm, static_cast<cudaStream_t>(stream)), "all_reduce_max");
+}
 
 }  // extern "C"

@@ -132,6 +132,9 @@ std::vector<RowVectorPtr> Task::run() {
       const std::string prefix = std::to_string(p->factory.pipelineId) + "." + std::to_string(op->operatorId()) + "." + op->operatorType() + ".";
       stats_[prefix + "inputPositions"] = op->stats().inputPositions;
       stats_[prefix + "outputPositions"] = op->stats().outputPositions;
+      stats_[prefix + "addInputWallNanos"] = op->stats().addInputWallNanos;
+      stats_[prefix + "getOutputWallNanos"] = op->stats().getOutputWallNanos;
+      stats_[prefix + "finishWallNanos"] = op->stats().finishWallNanos;
       for (auto& kv : op->stats().runtimeStats) stats_[prefix + kv.first] = kv.second;
     }
     p->driver->close();

@@ -60,26 +60,6 @@ __global__ void pack_bools_kernel(const uint8_t* __restrict__ in, int64_t n, uin
   }
 }
 // out[i] = in[i] valid ? ... helpers for aggregation output
-__global__ void counts_to_valid_kernel(const int64_t* __restrict__ counts, const int32_t* __restrict__ slots, int64_t n, uint32_t* __restrict__ out) {
-  const int64_t nwords = (n + 31) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t w = warp_global; w < nwords; w += nwarps) {
-    const int64_t k = (w << 5) + lane;
-    const bool b = k < n && counts[slots ? slots[k] : k] > 0;
-    const unsigned word = __ballot_sync(0xffffffffu, b);
-    if (lane == 0) out[w] = word;
-  }
-}
-__global__ void avg_finalize_kernel(const double* __restrict__ sums, const int64_t* __restrict__ counts, const int32_t* __restrict__ slots,
-                                    int64_t n, double* __restrict__ out) {
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t s = slots ? slots[i] : i;
-    const int64_t c = counts[s];
-    out[i] = c > 0 ? __ddiv_rn(sums[s], static_cast<double>(c)) : 0.0;  // functions/lib/aggregates/AverageAggregateBase.h:86-107
-  }
-}
 __global__ void positive_bits_kernel(const int64_t* __restrict__ counts, int64_t n, uint32_t* __restrict__ out) {
   const int64_t nwords = (n + 31) >> 5;
   const int lane = threadIdx.x & 31;
@@ -162,20 +142,6 @@ int vb2k_pack_bools(const uint8_t* in, int64_t n, uint64_t* out, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VB2_CUDA_OK(cudaMemsetAsync(out + ((n + 63) >> 6) - 1, 0, 8, st));
   pack_bools_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, n, reinterpret_cast<uint32_t*>(out));
-  VB2_CUDA_OK(cudaGetLastError());
-  return VB2_OK;
-}
-int vb2k_counts_to_valid(const int64_t* counts, const int32_t* slots, int64_t n, uint64_t* out, void* stream) {
-  if (n <= 0) return VB2_OK;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  VB2_CUDA_OK(cudaMemsetAsync(out + ((n + 63) >> 6) - 1, 0, 8, st));
-  counts_to_valid_kernel<<<grid_for(n, 256), 256, 0, st>>>(counts, slots, n, reinterpret_cast<uint32_t*>(out));
-  VB2_CUDA_OK(cudaGetLastError());
-  return VB2_OK;
-}
-int vb2k_avg_finalize(const double* sums, const int64_t* counts, const int32_t* slots, int64_t n, double* out, void* stream) {
-  if (n <= 0) return VB2_OK;
-  avg_finalize_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(sums, counts, slots, n, out);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }

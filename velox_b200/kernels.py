@@ -101,6 +101,32 @@ def partition_scatter_order(ids: torch.Tensor, num_partitions: int):
     return counts, order
 
 
+SENTINEL_KEY = -0x7F7F7F7F7F7F7F80  # VB2_SENTINEL_KEY (bytes 0x80)
+
+
+def partition_segments(keys: torch.Tensor, cols: Sequence[torch.Tensor], rows: int, rows_dev: Optional[torch.Tensor], num_partitions: int,
+                       segcap: int, overflow: torch.Tensor):
+    """Sync-free hash partitioning into fixed-capacity per-destination segments (vb2k_partition_segments).
+    Returns (seg_keys[P * segcap], [seg_col...], counts[P]); tails hold SENTINEL_KEY."""
+    total = num_partitions * segcap
+    seg_keys = torch.empty(total, dtype=torch.int64, device="cuda")
+    seg_cols = [torch.empty(total, dtype=t.dtype, device="cuda") for t in cols]
+    counts = torch.empty(num_partitions, dtype=torch.int64, device="cuda")
+    n = len(cols)
+    ins = (C.c_void_p * max(1, n))(*[t.data_ptr() for t in cols])
+    outs = (C.c_void_p * max(1, n))(*[t.data_ptr() for t in seg_cols])
+    eb = (C.c_int32 * max(1, n))(*[t.element_size() for t in cols])
+    check(lib().vb2k_partition_segments(C.c_void_p(keys.data_ptr()), ins, eb, n, C.c_int64(rows), C.c_void_p(_ptr(rows_dev)), num_partitions,
+                                        C.c_int64(segcap), C.c_void_p(seg_keys.data_ptr()), outs, C.c_void_p(counts.data_ptr()),
+                                        C.c_void_p(overflow.data_ptr()), _stream()))
+    return seg_keys, seg_cols, counts
+
+
+def key_range_check(keys: torch.Tensor, lo: int, hi: int, flag: torch.Tensor):
+    check(lib().vb2k_key_range_check(C.c_void_p(keys.data_ptr()), C.c_int64(keys.numel()), C.c_int64(lo), C.c_int64(hi),
+                                     C.c_void_p(flag.data_ptr()), _stream()))
+
+
 def gather(src: torch.Tensor, order: torch.Tensor) -> torch.Tensor:
     out = torch.empty(order.numel(), dtype=src.dtype, device="cuda")
     check(lib().vb2k_gather(C.c_void_p(src.data_ptr()), C.c_void_p(order.data_ptr()), C.c_int64(order.numel()),

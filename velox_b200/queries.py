@@ -21,7 +21,8 @@ import torch
 
 from . import tpch
 from .kernels import (DeviceColumn, FusedScanAgg, FusedScanCompact, LikeOnAlphabet, column_minmax, flat_device, gather,
-                      hash_columns, join_build_array, join_slot_flags, normalize_keys, partition_ids, partition_scatter_order)
+                      hash_columns, join_build_array, join_slot_flags, key_range_check, normalize_keys, partition_ids,
+                      partition_scatter_order, partition_segments)
 from .vector import BIGINT
 
 Q14_SCAN_SIG = "F:between(i0,pi0,pi1);C:l1|multiply(f2,minus(pf0,f3))"
@@ -92,7 +93,10 @@ class Q14:
             self.probe = FusedScanAgg(Q14_PROBE_SIG)
             self.compact_capacity = compact_capacity
             self.scan = None
-            self.side = None
+            self.plan = None       # statistics-derived sizes of the planned (sync-free) execution
+            self.overflow = None
+            self.planned_runs = 0
+            self._last = None
 
     # ---- build side -----------------------------------------------------------------------------
     def _build(self, partkey: torch.Tensor, ptype: torch.Tensor):
@@ -119,6 +123,19 @@ class Q14:
                              join={"slot_flags": slot_flags, "min": join_min})
 
     # ---- hash-partitioned across GPUs -----------------------------------------------------------------
+    # Two executions of the same exchange plan:
+    #   * planning run (first launch, and again after an overflow): sizes are discovered on the way —
+    #     per-peer counts travel to the host before each all-to-all, the build key range comes from a
+    #     device min/max. Its statistics (largest segment of either side, key range, all-reduced so
+    #     every rank plans the same sizes) are kept.
+    #   * planned run (every later launch): fixed-capacity segments sized from those statistics with
+    #     head-room, tails padded with a sentinel key that misses every probe / build. No count
+    #     exchange, no host synchronisation: the whole query is one asynchronous launch sequence
+    #     whose only host read is the final result. Any statistic that no longer holds (a segment
+    #     or the scan output overflows, a key outside the planned range) raises a device flag that
+    #     result() checks; the query then reruns as a planning run.
+    HEADROOM = 1.25
+
     def _exchange(self, key: torch.Tensor, payload: torch.Tensor):
         """Partitions rows by VectorHasher-hash(key) % world and exchanges both columns
         (launches on the current stream; one host synchronisation for the counts)."""
@@ -129,43 +146,85 @@ class Q14:
         sk, sp = gather(key, order), gather(payload, order)
         send_counts, recv_counts = self.comm.exchange_counts_dev(counts)
         k, p = self.comm.all_to_all_columns([sk, sp], send_counts, recv_counts)
-        return k, p
+        return k, p, max(send_counts)
 
     def _launch_partitioned(self, li, part_shard, rows):
-        main = torch.cuda.current_stream()
-        if self.side is None:
-            self.side = torch.cuda.Stream()
+        self._last = (li, part_shard, rows)
+        if self.plan is not None:
+            return self._launch_planned(li, part_shard, rows)
         if self.scan is None:
             self.scan = FusedScanCompact(Q14_SCAN_SIG, self.compact_capacity or max(1 << 20, rows // 16))
-        ready = torch.cuda.Event()
-        ready.record(main)  # everything the build side needs is complete at this point
-        # lineitem side first (asynchronous): fused filter + project + compact of this rank's shard
         self.scan.run([li["l_shipdate"], li["l_partkey"], li["l_extendedprice"], li["l_discount"]], rows,
                       pf=[1.0], pi=[tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI])
-        # build side on a second stream while the scan streams HBM: this rank's part rows go to the
-        # owners of their keys, then the local array-mode build. NCCL calls are issued in the same
-        # order on every rank (part exchange, then lineitem exchange).
-        self.side.wait_event(ready)
-        with torch.cuda.stream(self.side):
-            pk, pt = self._exchange(part_shard["p_partkey"], part_shard["p_type"])
-            slot_flags, join_min = self._build(pk, pt)
-            built = torch.cuda.Event()
-            built.record()
+        # NCCL calls are issued in the same order on every rank (part exchange, then lineitem exchange).
+        pk, pt, part_seg = self._exchange(part_shard["p_partkey"], part_shard["p_type"])
+        slot_flags, join_min = self._build(pk, pt)
         n, (lk, rev) = self.scan.result([torch.int64, torch.float64])
-        rk, rrev = self._exchange(lk, rev)
-        main.wait_event(built)
-        for t in (pk, pt, slot_flags):
-            t.record_stream(main)
+        rk, rrev, li_seg = self._exchange(lk, rev)
         self.probe.reset()
         m = rk.numel()
         if m:
             self.probe.add_batch([rk, rrev], m, pf=[0.0], join={"slot_flags": slot_flags, "min": join_min})
+        # statistics for the planned runs, identical on every rank
+        lo, hi, cnt = column_minmax(flat_device(BIGINT, pk)) if pk.numel() else (0, -1, 0)
+        big = 1 << 62
+        mx = torch.tensor([li_seg, part_seg, n, hi if cnt else -big, -(lo if cnt else big)], dtype=torch.int64, device="cuda")
+        self.comm.all_reduce_max_(mx)
+        li_seg, part_seg, n_max, hi, neg_lo = mx.tolist()
+        lo = -neg_lo
+        if hi < lo:
+            return  # no build rows anywhere: nothing to plan
+        pad = lambda v: max(64, (int(v * self.HEADROOM) + 63) // 64 * 64)
+        self.plan = {"li_seg": pad(li_seg), "part_seg": pad(part_seg), "lo": lo, "hi": hi}
+        if n_max * self.HEADROOM > self.scan.capacity:
+            self.scan = FusedScanCompact(Q14_SCAN_SIG, pad(n_max))
+
+    def _launch_planned(self, li, part_shard, rows):
+        w, pl = self.comm.world, self.plan
+        if self.overflow is None:
+            self.overflow = torch.zeros(2, dtype=torch.int64, device="cuda")
+        self.flag = self.scan.err  # one device flag for every broken assumption: scan output, segments, key range
+        self.flag.zero_()
+        self.scan.run([li["l_shipdate"], li["l_partkey"], li["l_extendedprice"], li["l_discount"]], rows,
+                      pf=[1.0], pi=[tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI])
+        # build side: part rows to the owners of their keys, then the array-mode table over the planned key range
+        seg = [pl["part_seg"]] * w
+        pk_seg, (pt_seg,), _ = partition_segments(part_shard["p_partkey"], [part_shard["p_type"]], part_shard["p_partkey"].numel(), None, w,
+                                                  pl["part_seg"], self.flag)
+        pk, pt = self.comm.all_to_all_columns([pk_seg, pt_seg], seg, seg)
+        key_range_check(pk, pl["lo"], pl["hi"], self.flag)
+        rng = pl["hi"] - pl["lo"] + 2
+        keys, valid = normalize_keys([flat_device(BIGINT, pk)], [pl["lo"]], [1], ranges=[rng], nulls_invalid=True)  # sentinel -> invalid
+        head, _next, _f = join_build_array(keys, valid, rng)
+        slot_flags = join_slot_flags(head, pt, self.like.run())
+        # probe side: the compacted (l_partkey, revenue) rows, row count read on the device
+        lk, rev = self.scan.outs[0].view(torch.int64), self.scan.outs[1].view(torch.float64)
+        seg = [pl["li_seg"]] * w
+        lk_seg, (rev_seg,), _ = partition_segments(lk, [rev], self.scan.capacity, self.scan.count, w, pl["li_seg"], self.flag)
+        rk, rrev = self.comm.all_to_all_columns([lk_seg, rev_seg], seg, seg)
+        self.probe.reset()
+        self.probe.add_batch([rk, rrev], rk.numel(), pf=[0.0], join={"slot_flags": slot_flags, "min": pl["lo"] - 1})
+        self.planned_runs += 1
 
     def merge(self):
         if self.comm is not None and self.comm.world > 1:
             self.comm.all_reduce_(self.probe.sums)
             self.comm.all_reduce_(self.probe.counts)
+            if self.plan is not None and self.overflow is not None:
+                # a broken planning assumption anywhere invalidates the run everywhere
+                self.overflow.copy_(self.flag)
+                self.comm.all_reduce_(self.overflow)
 
     def result(self):
+        if self.comm is not None and self.comm.world > 1 and self.plan is not None and self.overflow is not None \
+                and int(self.overflow.sum().item()) != 0:
+            # the data outgrew the plan: run again discovering sizes, which also re-plans
+            self.plan = None
+            self.overflow = None
+            self.scan = None
+            self.compact_capacity = None
+            li, part_shard, rows = self._last
+            self._launch_partitioned(li, part_shard, rows)
+            self.merge()
         total, promo = self.probe.sums.cpu().tolist()
         return (100.0 * promo / total) if total else None
