@@ -248,3 +248,88 @@ def test_fused_groupby_variants(card, n):
         assert np.array_equal(f.counts.cpu().numpy(), want_cnt)
         got = f.sums.cpu().numpy()
         assert np.all(np.abs(got - want_sum) <= 1e-9 + rel_tol(n) * np.abs(want_sum))
+
+
+@pytest.mark.parametrize("rows", [6_000_000 + 321])
+def test_tma_stage_reuse_is_exact_and_deterministic(rows):
+    """Every block of the TMA-staged kernels cycles through its shared-memory stages many times at
+    this size. A stage may only be handed back to the producer once every value loaded from it is
+    in a register; a violation shows up as stale tiles — sums off by ~1e-5 relative and different
+    from run to run, while row counts stay exact. Repeats must agree bit for bit and match a torch
+    fp64 restatement (sum order differs: 1e-12 relative)."""
+    from velox_b200.kernels import FusedScanAgg, FusedScanCompact
+    from velox_b200.queries import Q1, Q6, Q14, Q14_PROBE_SIG, Q14_SCAN_SIG
+
+    nparts = 50_000
+    li = tpch.gen_lineitem(rows, nparts, seed=5, device="cuda")
+    part = tpch.gen_part(nparts, seed=6, device="cuda")
+    price, disc, tax, qty, ship = li["l_extendedprice"], li["l_discount"], li["l_tax"], li["l_quantity"], li["l_shipdate"]
+
+    def close(a, b):
+        return abs(a - b) <= 1e-12 * abs(b)
+
+    # post-exchange probe pipeline (two 8-byte columns: the fastest consumer loop of all)
+    q14 = Q14()
+    slot_flags, join_min = q14._build(part["p_partkey"], part["p_type"])
+    rev = (price * (1.0 - disc)).contiguous()
+    promo = torch.tensor([s.startswith("PROMO") for s in tpch.PTYPE_DICT], device="cuda")[part["p_type"].long()]
+    promo_by_key = torch.zeros(nparts + 2, dtype=torch.bool, device="cuda")
+    promo_by_key[part["p_partkey"]] = promo
+    want = (float(rev.sum()), float(rev[promo_by_key[li["l_partkey"]]].sum()))
+    probe = FusedScanAgg(Q14_PROBE_SIG)
+    seen = set()
+    for _ in range(5):
+        probe.reset()
+        probe.add_batch([li["l_partkey"], rev], rows, pf=[0.0], join={"slot_flags": slot_flags, "min": join_min})
+        got = tuple(probe.sums.cpu().tolist())
+        seen.add(got)
+        assert int(probe.counts.item()) == rows and close(got[0], want[0]) and close(got[1], want[1]), (got, want)
+    assert len(seen) == 1
+
+    # Q6, Q1 and the single-GPU Q14 pipelines
+    m6 = (ship >= tpch.Q6_SHIP_LO) & (ship <= tpch.Q6_SHIP_HI) & (disc >= 0.05) & (disc <= 0.07) & (qty < 24.0)
+    want6 = float((price * disc)[m6].sum())
+    q6 = Q6()
+    seen = set()
+    for _ in range(5):
+        q6.launch(li, rows)
+        seen.add(q6.result())
+        assert close(q6.result(), want6)
+    assert len(seen) == 1
+
+    m1 = ship < tpch.Q1_SHIPDATE_LT
+    q1 = Q1()
+    seen = set()
+    for _ in range(3):
+        q1.launch(li, rows)
+        res = q1.result()
+        seen.add(tuple(sorted((k, v) for k, v in res.items())))
+        for (rf, ls), v in res.items():
+            g = m1 & (li["l_returnflag"] == tpch.RETURNFLAG_DICT.index(rf)) & (li["l_linestatus"] == tpch.LINESTATUS_DICT.index(ls))
+            assert v[7] == int(g.sum())
+            assert close(v[0], float(qty[g].sum())) and close(v[1], float(price[g].sum()))
+            assert close(v[2], float((price * (1.0 - disc))[g].sum())) and close(v[3], float(((price * (1.0 - disc)) * (1.0 + tax))[g].sum()))
+    assert len(seen) == 1
+
+    m14 = (ship >= tpch.Q14_SHIP_LO) & (ship <= tpch.Q14_SHIP_HI)
+    tot = float(rev[m14].sum())
+    want14 = 100.0 * float(rev[m14 & promo_by_key[li["l_partkey"]]].sum()) / tot
+    seen = set()
+    for _ in range(5):
+        q14.launch(li, part, rows)
+        seen.add(q14.result())
+        assert close(q14.result(), want14)
+    assert len(seen) == 1
+
+    # scan-compact with every row passing: (key, value) pairs must come out as the same multiset
+    li2 = dict(li)
+    li2["l_shipdate"] = torch.full_like(ship, tpch.Q14_SHIP_LO)
+    scan = FusedScanCompact(Q14_SCAN_SIG, rows + 1024)
+    for _ in range(3):
+        scan.run([li2["l_shipdate"], li["l_partkey"], price, disc], rows, pf=[1.0], pi=[tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI])
+        n, (lk, rv) = scan.result([torch.int64, torch.float64])
+        assert n == rows
+        a = torch.zeros(nparts + 1, dtype=torch.float64, device="cuda").index_add_(0, lk, rv)
+        b = torch.zeros(nparts + 1, dtype=torch.float64, device="cuda").index_add_(0, li["l_partkey"], rev)
+        assert float(((a - b).abs() / b.abs().clamp_min(1.0)).max()) < 1e-12
+        assert bool((torch.sort(lk).values == torch.sort(li["l_partkey"]).values).all())

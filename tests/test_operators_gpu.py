@@ -187,6 +187,16 @@ def test_aggregation_many_aggregates():
         check_plan(PlanBuilder().values(rv.names, rv.types).singleAggregation(keys, aggs).planNode(), [rv], batch_rows=700, rel_tol=1e-11)
 
 
+def test_aggregation_sliced_batches_all_encodings():
+    """A batch larger than the probe chunk is consumed as zero-copy slices: every encoding (flat,
+    dictionary VARCHAR, packed BOOLEAN, validity bitmaps) must slice correctly."""
+    rv = table(n=200_000, seed=33)
+    aggs = ["sum(c2)", "count(0)", "max(c3)", "count(c4)", "min(c0)"]
+    for keys in (["c1"], ["c5", "c4"], ["c0", "c1"]):
+        plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(keys, aggs).planNode()
+        check_plan(plan, [rv], configs=({"b200.agg_probe_chunk_rows": "65536"},), rel_tol=1e-10, oracle_batch_rows=50_000)
+
+
 def test_aggregation_masks():
     rv = table(n=2000, seed=9)
     plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(["c1"], ["sum(c2)", "count(0)", "avg(c0)"], masks=["c4", "c4", None]).planNode()
@@ -209,6 +219,9 @@ def test_aggregation_high_cardinality_hash_mode():
     (st,) = check_plan(plan, [rv], oracle_batch_rows=100_000)
     assert stat(st, "b200.aggMode") == 2  # hash mode
     check_plan(plan, [rv], batch_rows=50_000, oracle_batch_rows=100_000)  # growth / rehash across batches
+    # bounded find-or-insert passes inside one batch (the table grows between passes)
+    (st,) = check_plan(plan, [rv], configs=({"b200.agg_probe_chunk_rows": "65536"},), oracle_batch_rows=100_000)
+    assert stat(st, "b200.genericBatches") == 7 and stat(st, "b200.aggRelayouts") >= 1
     two = row_vector(["a", "b", "v"], [flat_vector(BIGINT, keys), flat_vector(INTEGER, (keys % 7).astype(np.int32)), flat_vector(DOUBLE, np.ones(n))])
     check_plan(PlanBuilder().values(two.names, two.types).singleAggregation(["a", "b"], ["sum(v)", "count(0)"]).planNode(), [two], oracle_batch_rows=100_000)
 

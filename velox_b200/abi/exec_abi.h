@@ -230,6 +230,9 @@ class QueryConfig {
   bool b200Enabled() const { return get<bool>("b200.enabled", true); }
   bool b200FusedPipelines() const { return get<bool>("b200.fused_pipelines", true); }
   int32_t b200DeviceId() const { return get<int32_t>("b200.device_id", -1); }
+  // rows per find-or-insert pass of a hash-mode aggregation: the table grows between passes, so
+  // it is sized by distinct groups + one pass, not by the whole input batch
+  int32_t b200AggProbeChunkRows() const { return get<int32_t>("b200.agg_probe_chunk_rows", 1 << 25); }
 
  private:
   std::unordered_map<std::string, std::string> values_;

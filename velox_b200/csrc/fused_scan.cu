@@ -281,6 +281,7 @@ int vb2k_fused_scan_compact(int32_t id, const vb2_fused_args* args, void* const*
   if (args->rows <= 0) return VB2_OK;
   KernelArgs a;
   std::memset(&a, 0, sizeof(a));
+  a.release_guard = kReleaseGuard;
   for (int c = 0; c < kMaxCols; ++c) a.cols[c] = args->cols[c];
   std::memcpy(a.consts.pf, args->pf, sizeof(a.consts.pf));
   std::memcpy(a.consts.pl, args->pl, sizeof(a.consts.pl));
@@ -310,6 +311,7 @@ int vb2k_fused_scan_agg(int32_t id, const vb2_fused_args* args, double* sums, in
   if (!e.launch) return fail_msg(VB2_ERR_INVALID, "not an aggregate pipeline");
   KernelArgs a;
   std::memset(&a, 0, sizeof(a));
+  a.release_guard = kReleaseGuard;
   for (int c = 0; c < kMaxCols; ++c) a.cols[c] = args->cols[c];
   std::memcpy(a.consts.pf, args->pf, sizeof(a.consts.pf));
   std::memcpy(a.consts.pl, args->pl, sizeof(a.consts.pl));

@@ -243,8 +243,12 @@ struct KernelArgs {
   // 0 = no build row, 1 = match with build-side predicate false, 2 = match with predicate true.
   const uint8_t* join_slot_flags;
   int64_t join_min, join_range;
+  // A value the fold of a tile's loaded registers is compared against before a stage is released
+  // (see mbar_arrive_after); a runtime argument so that the comparison cannot be constant-folded.
+  uint64_t release_guard;
 };
 
+constexpr uint64_t kReleaseGuard = 0x9e3779b97f4a7c15ull;
 constexpr int kThreads = 256;
 
 template <class P, bool kPair>
@@ -518,6 +522,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Releases a stage to the producer once the values loaded from it are in registers. Measured on
+// B200: an ld.shared that was merely *issued* before mbarrier.arrive can still observe the
+// producer's next bulk copy into the stage (a pipeline whose last load result was consumed after
+// the arrive read stale tiles a few times per thousand). So the arrive is made data-dependent on
+// every loaded value: `dep` folds the loaded registers and the arrive is predicated on comparing it
+// with a runtime guard value — the compare cannot issue before all of the thread's ld.shared
+// results have arrived (register scoreboard), and it cannot be folded away. Both outcomes arrive.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint64_t dep, uint64_t guard) {
+  asm volatile(
+      "{ .reg .pred q;\n"
+      "  setp.ne.b64 q, %1, %2;\n"
+      "  @q mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+      "  @!q mbarrier.arrive.shared::cta.b64 _, [%0], 1; }"
+      ::"r"(smem_u32(bar)), "l"(dep), "l"(guard)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -628,24 +648,37 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
       const uint8_t* base = tile_smem + static_cast<size_t>(s) * stage_bytes;
       PairRegs r[kRowsPerThread];
       KeyT kv[kRowsPerThread][VB2_FUSED_MAX_KEYS][2];
+      uint64_t dep = 0;
 #pragma unroll
       for (int j = 0; j < kRowsPerThread; ++j) {
         const int row = j * kConsumerThreads + threadIdx.x;
 #pragma unroll
         for (int c = 0; c < kMaxCols; ++c) {
-          if (P::fmask & (1u << c)) r[j].f[c][0] = reinterpret_cast<const double*>(base + Lay::f_off(c))[row];
-          if (P::lmask & (1u << c)) r[j].l[c][0] = reinterpret_cast<const int64_t*>(base + Lay::l_off(c))[row];
-          if (P::imask & (1u << c)) r[j].i[c][0] = reinterpret_cast<const int32_t*>(base + Lay::i_off(c, nk))[row];
+          if (P::fmask & (1u << c)) {
+            r[j].f[c][0] = reinterpret_cast<const double*>(base + Lay::f_off(c))[row];
+            dep ^= static_cast<uint64_t>(__double_as_longlong(r[j].f[c][0]));
+          }
+          if (P::lmask & (1u << c)) {
+            r[j].l[c][0] = reinterpret_cast<const int64_t*>(base + Lay::l_off(c))[row];
+            dep ^= static_cast<uint64_t>(r[j].l[c][0]);
+          }
+          if (P::imask & (1u << c)) {
+            r[j].i[c][0] = reinterpret_cast<const int32_t*>(base + Lay::i_off(c, nk))[row];
+            dep ^= static_cast<uint64_t>(static_cast<uint32_t>(r[j].i[c][0]));
+          }
         }
         if (kHasKeys) {
 #pragma unroll
           for (int k = 0; k < VB2_FUSED_MAX_KEYS; ++k)
-            if (k < a.nkeys) kv[j][k][0] = reinterpret_cast<const KeyT*>(base + Lay::key_off(k, nk))[row];
+            if (k < a.nkeys) {
+              kv[j][k][0] = reinterpret_cast<const KeyT*>(base + Lay::key_off(k, nk))[row];
+              dep ^= static_cast<uint64_t>(kv[j][k][0]);
+            }
         }
       }
-      // all reads of this stage are done: hand it back to the producer before computing
+      // every value of this stage is in a register: hand it back to the producer before computing
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (lane == 0) mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
       int gid[kRowsPerThread];
       double v[kRowsPerThread][P::kNP];
 #pragma unroll
@@ -776,15 +809,25 @@ fused_scan_compact_tma_kernel(const __grid_constant__ KernelArgs a, const __grid
       int before = 0;  // kept rows of this warp that precede this lane's rows, per slot order
       int mine[kRowsPerThread];
       int warp_total = 0;
+      uint64_t dep = 0;
 #pragma unroll
       for (int j = 0; j < kRowsPerThread; ++j) {
         // row order inside the tile: warp-major so that a warp owns 128 consecutive rows
         const int row = warp * (kWarp * kRowsPerThread) + j * kWarp + lane;
 #pragma unroll
         for (int c = 0; c < kMaxCols; ++c) {
-          if (P::fmask & (1u << c)) r[j].f[c][0] = reinterpret_cast<const double*>(base + Lay::f_off(c))[row];
-          if (P::lmask & (1u << c)) r[j].l[c][0] = reinterpret_cast<const int64_t*>(base + Lay::l_off(c))[row];
-          if (P::imask & (1u << c)) r[j].i[c][0] = reinterpret_cast<const int32_t*>(base + Lay::i_off(c, 0))[row];
+          if (P::fmask & (1u << c)) {
+            r[j].f[c][0] = reinterpret_cast<const double*>(base + Lay::f_off(c))[row];
+            dep ^= static_cast<uint64_t>(__double_as_longlong(r[j].f[c][0]));
+          }
+          if (P::lmask & (1u << c)) {
+            r[j].l[c][0] = reinterpret_cast<const int64_t*>(base + Lay::l_off(c))[row];
+            dep ^= static_cast<uint64_t>(r[j].l[c][0]);
+          }
+          if (P::imask & (1u << c)) {
+            r[j].i[c][0] = reinterpret_cast<const int32_t*>(base + Lay::i_off(c, 0))[row];
+            dep ^= static_cast<uint64_t>(static_cast<uint32_t>(r[j].i[c][0]));
+          }
         }
         keep[j] = P::F::eval(r[j], a.consts, 0);
         const unsigned m = __ballot_sync(0xffffffffu, keep[j]);
@@ -794,7 +837,7 @@ fused_scan_compact_tma_kernel(const __grid_constant__ KernelArgs a, const __grid
       (void)before;
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&empty_bar[s]);
+        mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
         warp_counts[warp] = warp_total;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");

@@ -126,7 +126,8 @@ struct B200HashAggregation::Impl {
     for (auto& a : accs) {
       a.accWord = w++;
       if (a.fn != "count") a.nnWord = w++;
-      a.nnTracked = a.fn == "avg";
+      // a global aggregation emits its row even when no input arrived, so its counters always run
+      a.nnTracked = a.fn == "avg" || keys.empty();
     }
     rowWords = w <= 2 ? w : (w + 3) / 4 * 4;  // whole 32-byte sectors
     VELOX_CHECK(rowWords <= VB2_MAX_ROW_WORDS, "too many aggregates for one group row");
@@ -723,6 +724,19 @@ struct B200HashAggregation::Impl {
       if (auto fp = dynamic_cast<B200FilterProject*>(op.get())) cur = fp->apply(cur);
       else if (auto pr = dynamic_cast<B200HashProbe*>(op.get())) cur = pr->apply(cur);
       if (!cur) return;  // every row filtered out
+    }
+    // Hash-mode tables are sized by (groups so far + rows of one pass): large batches go through
+    // find-or-insert in bounded passes so a high-cardinality table ends near 2x its group count
+    // instead of 2x the batch.
+    const int64_t chunk = std::max<int64_t>(1 << 16, self->driverCtx()->queryConfig().b200AggProbeChunkRows()) / 64 * 64;
+    if (!keys.empty() && cur->size() > chunk) {
+      // the first pass shows whether these keys need a hash table at all; array mode takes the rest at once
+      for (int64_t off = 0; off < cur->size();) {
+        const int64_t len = (off == 0 || mode == Mode::kHash) ? std::min<int64_t>(chunk, cur->size() - off) : cur->size() - off;
+        addGeneric(sliceVector(cur, off, len));
+        off += len;
+      }
+      return;
     }
     addGeneric(cur);
   }

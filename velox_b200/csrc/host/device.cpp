@@ -401,4 +401,26 @@ DeviceColumnPtr borrowFlatColumn(TypePtr type, const void* values, int64_t size)
   return col;
 }
 
+B200VectorPtr sliceVector(const B200VectorPtr& v, int64_t offset, int64_t length) {
+  VELOX_CHECK(offset % 64 == 0 && offset >= 0 && offset + length <= v->size(), "sliceVector: bad range");
+  std::vector<DeviceColumnPtr> cols;
+  for (const auto& c : v->columns()) {
+    auto s = std::make_shared<DeviceColumn>(*c);  // shares the owners
+    vb2_column& d = s->desc;
+    d.size = length;
+    if (d.nulls) d.nulls += offset / 64;
+    if (d.encoding == VB2_DICTIONARY) {
+      d.indices += offset;
+    } else if (d.encoding == VB2_FLAT) {
+      const char* base = static_cast<const char*>(d.values);
+      if (d.type == VB2_BOOLEAN) base += offset / 8;
+      else if (d.type == VB2_VARCHAR) base += offset * 4;  // int32 offsets; chars (aux) stay absolute
+      else base += offset * widthOf(d.type);
+      d.values = base;
+    }
+    cols.push_back(std::move(s));
+  }
+  return std::make_shared<B200Vector>(v->pool(), v->type(), static_cast<vector_size_t>(length), std::move(cols), v->stream());
+}
+
 }  // namespace velox_b200

@@ -84,6 +84,10 @@ RowVectorPtr toHost(const B200VectorPtr& dev);
 // Wraps externally owned device memory (e.g. columns already resident in HBM) without copying.
 DeviceColumnPtr borrowFlatColumn(TypePtr type, const void* values, int64_t size);
 
+// Rows [offset, offset + length) of a device batch without copying (offset must be a multiple of 64
+// so validity bitmaps stay word-aligned).
+B200VectorPtr sliceVector(const B200VectorPtr& v, int64_t offset, int64_t length);
+
 // One stream + small scratch per driver.
 struct DeviceContext {
   int device = 0;

@@ -15,6 +15,7 @@ The same kernels are what the operator layer launches for these plans (tests ass
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -84,8 +85,11 @@ class Q6:
 class Q14:
     """100 * sum(case when p_type like 'PROMO%' then rev else 0 end) / sum(rev) over lineitem |x| part."""
 
-    def __init__(self, comm=None, compact_capacity: Optional[int] = None):
+    def __init__(self, comm=None, compact_capacity: Optional[int] = None, overlap: Optional[bool] = None):
         self.comm = comm
+        # build side of the planned exchange on a second stream, concurrent with the lineitem scan
+        self.overlap = (os.environ.get("VB2_Q14_OVERLAP", "1") == "1") if overlap is None else overlap
+        self.side = None
         self.like = LikeOnAlphabet(tpch.PTYPE_DICT, "PROMO%")
         if comm is None or comm.world == 1:
             self.probe = FusedScanAgg(tpch.Q14_SIG)
@@ -154,12 +158,19 @@ class Q14:
             return self._launch_planned(li, part_shard, rows)
         if self.scan is None:
             self.scan = FusedScanCompact(Q14_SCAN_SIG, self.compact_capacity or max(1 << 20, rows // 16))
-        self.scan.run([li["l_shipdate"], li["l_partkey"], li["l_extendedprice"], li["l_discount"]], rows,
-                      pf=[1.0], pi=[tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI])
+        pad = lambda v: max(64, (int(v * self.HEADROOM) + 63) // 64 * 64)
+        while True:  # the planning run discovers the scan output size too
+            self.scan.err.zero_()
+            self.scan.run([li["l_shipdate"], li["l_partkey"], li["l_extendedprice"], li["l_discount"]], rows,
+                          pf=[1.0], pi=[tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI])
+            n = int(self.scan.count.item())
+            if n <= self.scan.capacity:
+                break
+            self.scan = FusedScanCompact(Q14_SCAN_SIG, pad(n))
+        n, (lk, rev) = self.scan.result([torch.int64, torch.float64])
         # NCCL calls are issued in the same order on every rank (part exchange, then lineitem exchange).
         pk, pt, part_seg = self._exchange(part_shard["p_partkey"], part_shard["p_type"])
         slot_flags, join_min = self._build(pk, pt)
-        n, (lk, rev) = self.scan.result([torch.int64, torch.float64])
         rk, rrev, li_seg = self._exchange(lk, rev)
         self.probe.reset()
         m = rk.numel()
@@ -174,7 +185,6 @@ class Q14:
         lo = -neg_lo
         if hi < lo:
             return  # no build rows anywhere: nothing to plan
-        pad = lambda v: max(64, (int(v * self.HEADROOM) + 63) // 64 * 64)
         self.plan = {"li_seg": pad(li_seg), "part_seg": pad(part_seg), "lo": lo, "hi": hi}
         if n_max * self.HEADROOM > self.scan.capacity:
             self.scan = FusedScanCompact(Q14_SCAN_SIG, pad(n_max))
@@ -184,24 +194,46 @@ class Q14:
         if self.overflow is None:
             self.overflow = torch.zeros(2, dtype=torch.int64, device="cuda")
         self.flag = self.scan.err  # one device flag for every broken assumption: scan output, segments, key range
+        main = torch.cuda.current_stream()
         self.flag.zero_()
+        if self.overlap:
+            if self.side is None:
+                self.side = torch.cuda.Stream()
+            ready = torch.cuda.Event()
+            ready.record(main)  # inputs and the cleared flag are complete here
         self.scan.run([li["l_shipdate"], li["l_partkey"], li["l_extendedprice"], li["l_discount"]], rows,
                       pf=[1.0], pi=[tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI])
-        # build side: part rows to the owners of their keys, then the array-mode table over the planned key range
-        seg = [pl["part_seg"]] * w
-        pk_seg, (pt_seg,), _ = partition_segments(part_shard["p_partkey"], [part_shard["p_type"]], part_shard["p_partkey"].numel(), None, w,
-                                                  pl["part_seg"], self.flag)
-        pk, pt = self.comm.all_to_all_columns([pk_seg, pt_seg], seg, seg)
-        key_range_check(pk, pl["lo"], pl["hi"], self.flag)
-        rng = pl["hi"] - pl["lo"] + 2
-        keys, valid = normalize_keys([flat_device(BIGINT, pk)], [pl["lo"]], [1], ranges=[rng], nulls_invalid=True)  # sentinel -> invalid
-        head, _next, _f = join_build_array(keys, valid, rng)
-        slot_flags = join_slot_flags(head, pt, self.like.run())
+
+        def build_side():
+            # part rows to the owners of their keys, then the array-mode table over the planned key range
+            seg = [pl["part_seg"]] * w
+            pk_seg, (pt_seg,), _ = partition_segments(part_shard["p_partkey"], [part_shard["p_type"]], part_shard["p_partkey"].numel(), None, w,
+                                                      pl["part_seg"], self.flag)
+            pk, pt = self.comm.all_to_all_columns([pk_seg, pt_seg], seg, seg)
+            key_range_check(pk, pl["lo"], pl["hi"], self.flag)
+            rng = pl["hi"] - pl["lo"] + 2
+            keys, valid = normalize_keys([flat_device(BIGINT, pk)], [pl["lo"]], [1], ranges=[rng], nulls_invalid=True)  # sentinel -> invalid
+            head, _next, _f = join_build_array(keys, valid, rng)
+            return join_slot_flags(head, pt, self.like.run())
+
+        if self.overlap:
+            # the build side runs on a second stream while the scan streams HBM; NCCL calls keep the
+            # same order on every rank (part exchange, then lineitem exchange)
+            self.side.wait_event(ready)
+            with torch.cuda.stream(self.side):
+                slot_flags = build_side()
+                built = torch.cuda.Event()
+                built.record()
+        else:
+            slot_flags = build_side()
         # probe side: the compacted (l_partkey, revenue) rows, row count read on the device
         lk, rev = self.scan.outs[0].view(torch.int64), self.scan.outs[1].view(torch.float64)
         seg = [pl["li_seg"]] * w
         lk_seg, (rev_seg,), _ = partition_segments(lk, [rev], self.scan.capacity, self.scan.count, w, pl["li_seg"], self.flag)
         rk, rrev = self.comm.all_to_all_columns([lk_seg, rev_seg], seg, seg)
+        if self.overlap:
+            main.wait_event(built)
+            slot_flags.record_stream(main)
         self.probe.reset()
         self.probe.add_batch([rk, rrev], rk.numel(), pf=[0.0], join={"slot_flags": slot_flags, "min": pl["lo"] - 1})
         self.planned_runs += 1
