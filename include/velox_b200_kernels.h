@@ -247,9 +247,11 @@ typedef struct vb2_group_row_init { uint64_t words[VB2_MAX_ROW_WORDS]; } vb2_gro
 typedef struct vb2_agg_update {
   int32_t kind;
   int32_t input_type;       /* VB2_DOUBLE / VB2_BIGINT / VB2_INTEGER (converted as the reference does) */
-  const void* input;        /* dense input values (NULL for COUNT(*)) */
-  const uint64_t* nulls;    /* validity bitmap of the input or NULL */
+  const void* input;        /* input values (NULL for COUNT(*)): row i reads input[indices ? indices[i] : i] */
+  const uint64_t* nulls;    /* validity bitmap over rows or NULL */
   const uint64_t* mask;     /* optional aggregate mask bitmap (exec/AggregationMasks.cpp), 1 = use row */
+  const int32_t* indices;   /* optional: the input is a dictionary wrap (FilterProject output) over `input` */
+  const uint64_t* base_nulls; /* validity of the wrapped values (indexed like `input`) or NULL */
   int32_t acc_word;         /* word of the accumulator (double or int64) inside the group row, >= 1 */
   int32_t nonnull_word;     /* word counting non-null inputs (drives NULL results and AVG counts), -1 = not tracked */
 } vb2_agg_update;

@@ -85,10 +85,16 @@ __device__ inline int str_compare(const char* a, int al, const char* b, int bl) 
   return al < bl ? -1 : (al > bl ? 1 : 0);
 }
 
+constexpr int kVmThreads = 256;
+
+// Per-row interpreter state. The value registers live in shared memory, one column of
+// kVmThreads words per VM register ([reg][thread]: dynamically indexed by the program, conflict
+// free, and no local-memory traffic); the null / error poison masks stay in real registers.
 struct RowState {
-  uint64_t regs[kVmMaxRegs];
+  uint64_t* base;  // &smem[threadIdx.x]
   uint64_t nullmask, errmask;
   int errcode;
+  __device__ __forceinline__ uint64_t& r(int i) { return base[i * kVmThreads]; }
 };
 
 __device__ __forceinline__ double as_f64(uint64_t v) { return __longlong_as_double(static_cast<int64_t>(v)); }
@@ -125,7 +131,7 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
         rerr = is_err(in.a) | is_err(in.b);
         if (rnull || rerr) break;
         if (in.type == VB2_DOUBLE) {
-          const double x = as_f64(st.regs[in.a]), y = as_f64(st.regs[in.b]);
+          const double x = as_f64(st.r(in.a)), y = as_f64(st.r(in.b));
           double r;
           switch (in.op) {
             case VB2_OP_ADD: r = __dadd_rn(x, y); break;
@@ -136,7 +142,7 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
           }
           rv = from_f64(r);
         } else {
-          const int64_t x = static_cast<int64_t>(st.regs[in.a]), y = static_cast<int64_t>(st.regs[in.b]);
+          const int64_t x = static_cast<int64_t>(st.r(in.a)), y = static_cast<int64_t>(st.r(in.b));
           int64_t r = 0;
           bool ovf = false;
           switch (in.op) {
@@ -162,9 +168,9 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
         rnull = is_null(in.a);
         rerr = is_err(in.a);
         if (rnull || rerr) break;
-        if (in.type == VB2_DOUBLE) rv = from_f64(-as_f64(st.regs[in.a]));
+        if (in.type == VB2_DOUBLE) rv = from_f64(-as_f64(st.r(in.a)));
         else {
-          const int64_t x = static_cast<int64_t>(st.regs[in.a]);
+          const int64_t x = static_cast<int64_t>(st.r(in.a));
           const int64_t lo = in.type == VB2_INTEGER ? INT32_MIN : INT64_MIN;
           if (x == lo) raise(kErrOverflow);
           else rv = static_cast<uint64_t>(-x);
@@ -176,8 +182,8 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
         rerr = is_err(in.a) | is_err(in.b);
         if (rnull || rerr) break;
         const int op = in.op - VB2_OP_LT;
-        if (in.type == VB2_DOUBLE) rv = cmp_f64(op, as_f64(st.regs[in.a]), as_f64(st.regs[in.b]));
-        else rv = cmp_int<int64_t>(op, static_cast<int64_t>(st.regs[in.a]), static_cast<int64_t>(st.regs[in.b]));
+        if (in.type == VB2_DOUBLE) rv = cmp_f64(op, as_f64(st.r(in.a)), as_f64(st.r(in.b)));
+        else rv = cmp_int<int64_t>(op, static_cast<int64_t>(st.r(in.a)), static_cast<int64_t>(st.r(in.b)));
         break;
       }
       case VB2_OP_BETWEEN: {
@@ -185,18 +191,18 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
         rerr = is_err(in.a) | is_err(in.b) | is_err(in.c);
         if (rnull || rerr) break;
         if (in.type == VB2_DOUBLE) {
-          const double x = as_f64(st.regs[in.a]);
-          rv = gte_f64(x, as_f64(st.regs[in.b])) && lte_f64(x, as_f64(st.regs[in.c]));
+          const double x = as_f64(st.r(in.a));
+          rv = gte_f64(x, as_f64(st.r(in.b))) && lte_f64(x, as_f64(st.r(in.c)));
         } else {
-          const int64_t x = static_cast<int64_t>(st.regs[in.a]);
-          rv = x >= static_cast<int64_t>(st.regs[in.b]) && x <= static_cast<int64_t>(st.regs[in.c]);
+          const int64_t x = static_cast<int64_t>(st.r(in.a));
+          rv = x >= static_cast<int64_t>(st.r(in.b)) && x <= static_cast<int64_t>(st.r(in.c));
         }
         break;
       }
       case VB2_OP_AND: case VB2_OP_OR: {
         const bool dominant = in.op == VB2_OP_OR;  // value that decides the result
         const bool an = is_null(in.a), bn = is_null(in.b), ae = is_err(in.a), be = is_err(in.b);
-        const bool av = st.regs[in.a] != 0, bv = st.regs[in.b] != 0;
+        const bool av = st.r(in.a) != 0, bv = st.r(in.b) != 0;
         const bool a_decides = !an && !ae && av == dominant;
         const bool b_decides = !bn && !be && bv == dominant;
         if (a_decides || b_decides) rv = dominant;
@@ -208,7 +214,7 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
       case VB2_OP_NOT:
         rnull = is_null(in.a);
         rerr = is_err(in.a);
-        rv = st.regs[in.a] == 0;
+        rv = st.r(in.a) == 0;
         break;
       case VB2_OP_IS_NULL:
         rerr = is_err(in.a);
@@ -216,12 +222,12 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
         break;
       case VB2_OP_SELECT: {
         if (is_err(in.a)) { rerr = true; break; }
-        const bool take = !is_null(in.a) && st.regs[in.a] != 0;
+        const bool take = !is_null(in.a) && st.r(in.a) != 0;
         const int src = take ? in.b : in.c;
         if (src < 0) { rnull = true; break; }  // CASE without ELSE
         rnull = is_null(src);
         rerr = is_err(src);
-        rv = st.regs[src];
+        rv = st.r(src);
         break;
       }
       case VB2_OP_CAST: {
@@ -229,7 +235,7 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
         rerr = is_err(in.a);
         if (rnull || rerr) break;
         const int from = in.b, to = in.type;
-        const uint64_t v = st.regs[in.a];
+        const uint64_t v = st.r(in.a);
         if (from == to) rv = v;
         else if (to == VB2_DOUBLE) rv = from_f64(static_cast<double>(static_cast<int64_t>(v)));
         else if (from == VB2_DOUBLE) {
@@ -261,7 +267,7 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
       }
       default: break;
     }
-    st.regs[in.dst] = rv;
+    st.r(in.dst) = rv;
     st.nullmask = rnull ? (st.nullmask | dbit) : (st.nullmask & ~dbit);
     st.errmask = rerr ? (st.errmask | dbit) : (st.errmask & ~dbit);
   }
@@ -269,15 +275,15 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
 
 __device__ __forceinline__ int user_code(int vmerr) { return vmerr ? vmerr : kErrOverflow; }
 
-constexpr int kVmThreads = 256;
-
 __global__ void __launch_bounds__(kVmThreads) vm_filter_kernel(const __grid_constant__ VmArgs a) {
   // each warp produces one 32-bit word of the selection bitmap per iteration
   const int64_t nwords = (a.n + 31) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * kVmThreads + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kVmThreads) >> 5;
+  extern __shared__ uint64_t vm_regs[];
   RowState st;
+  st.base = vm_regs + threadIdx.x;
   for (int64_t w = warp_global; w < nwords; w += nwarps) {
     const int64_t row = (w << 5) + lane;
     bool keep = false;
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(kVmThreads) vm_filter_kernel(const __grid_cons
       const bool err = (st.errmask >> a.filter_reg) & 1ull;
       const bool null = (st.nullmask >> a.filter_reg) & 1ull;
       if (err) atomicCAS(a.error_flag, 0, user_code(st.errcode));
-      keep = !err && !null && st.regs[a.filter_reg] != 0;
+      keep = !err && !null && st.r(a.filter_reg) != 0;
     }
     const unsigned word = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) a.sel_bits[w] = word;
@@ -298,7 +304,9 @@ __global__ void __launch_bounds__(kVmThreads) vm_project_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * kVmThreads + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * kVmThreads) >> 5;
+  extern __shared__ uint64_t vm_regs[];
   RowState st;
+  st.base = vm_regs + threadIdx.x;
   for (int64_t w = warp_global; w < nwords; w += nwarps) {
     const int64_t k = (w << 5) + lane;
     const bool live = k < a.n;
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(kVmThreads) vm_project_kernel(const __grid_con
         const bool err = (st.errmask >> out.reg) & 1ull;
         if (err) atomicCAS(a.error_flag, 0, user_code(st.errcode));
         valid = !err && !((st.nullmask >> out.reg) & 1ull);
-        const uint64_t v = valid ? st.regs[out.reg] : 0;
+        const uint64_t v = valid ? st.r(out.reg) : 0;
         switch (out.type) {
           case VB2_INTEGER: reinterpret_cast<int32_t*>(out.values)[k] = static_cast<int32_t>(v); break;
           case VB2_BOOLEAN: reinterpret_cast<uint8_t*>(out.values)[k] = static_cast<uint8_t>(v); break;
@@ -399,16 +407,15 @@ __global__ void sel_write_kernel(const uint32_t* __restrict__ bits, int64_t nwor
   for (int j = 0; j < 4; ++j) { word_prefix[t * 4 + j] = excl; excl += pc[j]; }
   __syncthreads();
   const int64_t out0 = block_offsets[blockIdx.x];
-  for (int i = t; i < kSelWordsPerBlock; i += kSelThreads) {
+  // One 32-row word per warp step: lane b owns row (w << 5) + b and stores it at its rank among
+  // the set bits, so a warp's stores are consecutive (a thread-per-word bit loop wrote 32
+  // scattered sequences per warp and ran at a fifth of the bandwidth).
+  const int lane = t & 31, warp = t >> 5;
+  for (int i = warp; i < kSelWordsPerBlock; i += kSelThreads / kWarp) {
     const int64_t w = w0 + i;
     if (w >= nwords) break;
-    uint32_t word = bits[w];
-    int64_t pos = out0 + word_prefix[i];
-    while (word) {
-      const int b = __ffs(word) - 1;
-      indices[pos++] = static_cast<int32_t>((w << 5) + b);
-      word &= word - 1;
-    }
+    const uint32_t word = bits[w];
+    if ((word >> lane) & 1u) indices[out0 + word_prefix[i] + __popc(word & ((1u << lane) - 1u))] = static_cast<int32_t>((w << 5) + lane);
   }
 }
 
@@ -416,6 +423,26 @@ static unsigned vm_grid(int64_t n) {
   int64_t b = (n + kVmThreads - 1) / kVmThreads;
   int64_t cap = static_cast<int64_t>(device_sm_count()) * 8;
   return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// Dynamic shared memory of a VM launch: one kVmThreads-word column per VM register.
+template <class K>
+static int vm_smem(K kernel, const vb2_program* prog, size_t* bytes) {
+  int regs = 1;
+  for (int i = 0; i < prog->n_instrs; ++i) {
+    const vb2_instr& in = prog->instrs[i];
+    regs = std::max(regs, std::max(std::max(in.dst, in.a), std::max(in.b, in.c)) + 1);  // operand fields are < 64 whatever they mean
+  }
+  regs = std::min(std::max(regs, static_cast<int>(prog->n_regs)), kVmMaxRegs);
+  *bytes = static_cast<size_t>(regs) * kVmThreads * sizeof(uint64_t);
+  if (*bytes > 48 * 1024) {
+    static size_t configured = 0;
+    if (configured < *bytes) {
+      VB2_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kVmMaxRegs * kVmThreads * sizeof(uint64_t))));
+      configured = kVmMaxRegs * kVmThreads * sizeof(uint64_t);
+    }
+  }
+  return VB2_OK;
 }
 
 static int fill_args(VmArgs& a, const vb2_program* prog, const vb2_column* cols, int32_t ncols) {
@@ -454,7 +481,9 @@ int vb2k_eval_filter(const vb2_program* prog, const vb2_column* cols, int32_t nc
   // zero the tail word so that bits beyond `rows` read as 0 for 64-bit consumers
   const int64_t nwords64 = (rows + 63) >> 6;
   VB2_CUDA_OK(cudaMemsetAsync(sel_bits + nwords64 - 1, 0, sizeof(uint64_t), st));
-  vm_filter_kernel<<<vm_grid(rows), kVmThreads, 0, st>>>(a);
+  size_t smem = 0;
+  if ((rc = vm_smem(vm_filter_kernel, prog, &smem))) return rc;
+  vm_filter_kernel<<<vm_grid(rows), kVmThreads, smem, st>>>(a);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -498,7 +527,9 @@ int vb2k_eval_project(const vb2_program* prog, const vb2_column* cols, int32_t n
   a.sel = sel;
   a.sel_bits = nullptr;
   a.error_flag = error_flag;
-  vm_project_kernel<<<vm_grid(n), kVmThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  size_t smem = 0;
+  if ((rc = vm_smem(vm_project_kernel, prog, &smem))) return rc;
+  vm_project_kernel<<<vm_grid(n), kVmThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }

@@ -1,5 +1,6 @@
 // B200HashAggregation: GROUP BY on the device (array mode / normalized-key hash mode), with the
 // fused scan->filter->[probe]->project->aggregate fast path for null-free flat batches.
+#include <map>
 #include <algorithm>
 
 #include "join.h"
@@ -357,19 +358,34 @@ struct B200HashAggregation::Impl {
       rowKeys = nk;
     }
     std::vector<vb2_agg_update> ups;
-    auto flatInput = [&](int32_t colIdx, const void*& values, const uint64_t*& nulls, int32_t& type) {
+    // Points an update at its input column. Flat columns are read in place; a dictionary wrap over
+    // fixed-width values (what a filter leaves behind, exec/Operator.cpp:270-303 wrapChild) is read
+    // through its indices by the update kernel — no flattening pass; anything else (constant,
+    // BOOLEAN bits) is decoded once per column and batch.
+    std::map<int32_t, FlatColumn> flattened;
+    auto flatInput = [&](int32_t colIdx, vb2_agg_update& u) {
       const DeviceColumnPtr& c = in->column(colIdx);
-      type = c->desc.type;
-      if (c->desc.encoding == VB2_FLAT && type != VB2_BOOLEAN) {
-        values = c->desc.values;
-        nulls = c->desc.nulls;
+      u.input_type = c->desc.type;
+      if (c->desc.encoding == VB2_FLAT && u.input_type != VB2_BOOLEAN) {
+        u.input = c->desc.values;
+        u.nulls = c->desc.nulls;
         return;
       }
-      FlatColumn f = flattenColumn(c, nullptr, n, st());
-      keep.push_back(f.values);
-      if (f.nulls) keep.push_back(f.nulls);
-      values = f.values->data();
-      nulls = f.nulls ? f.nulls->as<uint64_t>() : nullptr;
+      if (c->desc.encoding == VB2_DICTIONARY && u.input_type != VB2_BOOLEAN && u.input_type != VB2_VARCHAR) {
+        u.input = c->desc.values;
+        u.indices = c->desc.indices;
+        u.nulls = c->desc.nulls;
+        u.base_nulls = c->desc.dict_nulls;
+        return;
+      }
+      auto it = flattened.find(colIdx);
+      if (it == flattened.end()) {
+        it = flattened.emplace(colIdx, flattenColumn(c, nullptr, n, st())).first;
+        keep.push_back(it->second.values);
+        if (it->second.nulls) keep.push_back(it->second.nulls);
+      }
+      u.input = it->second.values->data();
+      u.nulls = it->second.nulls ? it->second.nulls->as<uint64_t>() : nullptr;
     };
     const auto& aggs = node->aggregates();
     for (size_t i = 0; i < aggs.size(); ++i) {
@@ -394,11 +410,11 @@ struct B200HashAggregation::Impl {
       u.nonnull_word = -1;
       if (a.function == "count") {
         u.kind = raw ? VB2_AGG_COUNT : VB2_AGG_COUNT_MERGE;
-        if (!a.inputs.empty()) flatInput(a.inputs[0], u.input, u.nulls, u.input_type);
+        if (!a.inputs.empty()) flatInput(a.inputs[0], u);
         ups.push_back(u);
         continue;
       }
-      flatInput(a.inputs[0], u.input, u.nulls, u.input_type);
+      flatInput(a.inputs[0], u);
       u.kind = s.kind;
       if (a.function == "avg" && !raw) {
         // intermediate (sum, count): add the sums, merge the counts into the non-null counter
@@ -407,12 +423,12 @@ struct B200HashAggregation::Impl {
         c.kind = VB2_AGG_COUNT_MERGE;
         c.mask = mask;
         c.nonnull_word = -1;
-        flatInput(a.inputs[1], c.input, c.nulls, c.input_type);
+        flatInput(a.inputs[1], c);
         c.acc_word = s.nnWord;
         ups.push_back(c);
         continue;
       }
-      if (mask || u.nulls) trackNonNull(i);
+      if (mask || u.nulls || u.base_nulls) trackNonNull(i);
       if (s.nnTracked) u.nonnull_word = s.nnWord;
       ups.push_back(u);
     }
