@@ -100,6 +100,10 @@ struct RowState {
 __device__ __forceinline__ double as_f64(uint64_t v) { return __longlong_as_double(static_cast<int64_t>(v)); }
 __device__ __forceinline__ uint64_t from_f64(double d) { return static_cast<uint64_t>(__double_as_longlong(d)); }
 
+// kPlain: the host has proved that no register of this program can be NULL or poisoned for this
+// batch (no nullable input column, no NULL constant, no operation that can raise or produce NULL):
+// the mask bookkeeping — most of the interpreter's instructions per operation — compiles away.
+template <bool kPlain>
 __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState& st) {
   st.nullmask = 0;
   st.errmask = 0;
@@ -107,8 +111,8 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
   for (int pc = 0; pc < n_instrs; ++pc) {
     const vb2_instr in = a.instrs[pc];
     const uint64_t dbit = 1ull << in.dst;
-    auto is_null = [&](int r) { return static_cast<bool>((st.nullmask >> r) & 1ull); };
-    auto is_err = [&](int r) { return static_cast<bool>((st.errmask >> r) & 1ull); };
+    auto is_null = [&](int r) { return kPlain ? false : static_cast<bool>((st.nullmask >> r) & 1ull); };
+    auto is_err = [&](int r) { return kPlain ? false : static_cast<bool>((st.errmask >> r) & 1ull); };
     bool rnull = false, rerr = false;
     uint64_t rv = 0;
     auto raise = [&](int code) { rerr = true; if (!st.errcode) st.errcode = code; };
@@ -116,6 +120,7 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
       case VB2_OP_LOAD: {
         int64_t base;
         rnull = decode(a.cols[in.a], row, base);
+        if (kPlain) rnull = false;
         rv = rnull ? 0 : load_value(a.cols[in.a], base);
         break;
       }
@@ -268,13 +273,16 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
       default: break;
     }
     st.r(in.dst) = rv;
-    st.nullmask = rnull ? (st.nullmask | dbit) : (st.nullmask & ~dbit);
-    st.errmask = rerr ? (st.errmask | dbit) : (st.errmask & ~dbit);
+    if (!kPlain) {
+      st.nullmask = rnull ? (st.nullmask | dbit) : (st.nullmask & ~dbit);
+      st.errmask = rerr ? (st.errmask | dbit) : (st.errmask & ~dbit);
+    }
   }
 }
 
 __device__ __forceinline__ int user_code(int vmerr) { return vmerr ? vmerr : kErrOverflow; }
 
+template <bool kPlain>
 __global__ void __launch_bounds__(kVmThreads) vm_filter_kernel(const __grid_constant__ VmArgs a) {
   // each warp produces one 32-bit word of the selection bitmap per iteration
   const int64_t nwords = (a.n + 31) >> 5;
@@ -288,7 +296,7 @@ __global__ void __launch_bounds__(kVmThreads) vm_filter_kernel(const __grid_cons
     const int64_t row = (w << 5) + lane;
     bool keep = false;
     if (row < a.n) {
-      run_program(a, a.n_filter_instrs, row, st);
+      run_program<kPlain>(a, a.n_filter_instrs, row, st);
       const bool err = (st.errmask >> a.filter_reg) & 1ull;
       const bool null = (st.nullmask >> a.filter_reg) & 1ull;
       if (err) atomicCAS(a.error_flag, 0, user_code(st.errcode));
@@ -299,6 +307,7 @@ __global__ void __launch_bounds__(kVmThreads) vm_filter_kernel(const __grid_cons
   }
 }
 
+template <bool kPlain>
 __global__ void __launch_bounds__(kVmThreads) vm_project_kernel(const __grid_constant__ VmArgs a) {
   const int64_t nwords = (a.n + 31) >> 5;
   const int lane = threadIdx.x & 31;
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(kVmThreads) vm_project_kernel(const __grid_con
     const bool live = k < a.n;
     if (live) {
       const int64_t row = a.sel ? a.sel[k] : k;
-      run_program(a, a.n_instrs, row, st);
+      run_program<kPlain>(a, a.n_instrs, row, st);
     }
     for (int o = 0; o < a.n_outs; ++o) {
       const vb2_output& out = a.outs[o];
@@ -445,6 +454,42 @@ static int vm_smem(K kernel, const vb2_program* prog, size_t* bytes) {
   return VB2_OK;
 }
 
+// True when no register can become NULL or poisoned: every loaded column is free of NULLs, no
+// NULL constant, and only operations that neither raise nor produce NULL from non-NULL inputs
+// (double arithmetic except nothing, comparisons, BETWEEN, AND / OR / NOT, IS_NULL, CASE with ELSE,
+// LIKE / string compare against non-NULL patterns).
+static bool plain_program(const vb2_program* prog, int n_instrs, const vb2_column* cols) {
+  for (int i = 0; i < n_instrs; ++i) {
+    const vb2_instr& in = prog->instrs[i];
+    switch (in.op) {
+      case VB2_OP_LOAD: case VB2_OP_LIKE: case VB2_OP_STRCMP: {
+        const vb2_column& c = cols[in.a];
+        if (c.nulls || c.dict_nulls) return false;
+        if (in.op != VB2_OP_LOAD && prog->consts[in.b].is_null) return false;
+        break;
+      }
+      case VB2_OP_CONST:
+        if (prog->consts[in.a].is_null) return false;
+        break;
+      case VB2_OP_ADD: case VB2_OP_SUB: case VB2_OP_MUL: case VB2_OP_DIV: case VB2_OP_MOD: case VB2_OP_NEG:
+        if (in.type != VB2_DOUBLE) return false;  // checked integer arithmetic can raise
+        break;
+      case VB2_OP_LT: case VB2_OP_LTE: case VB2_OP_GT: case VB2_OP_GTE: case VB2_OP_EQ: case VB2_OP_NEQ: case VB2_OP_BETWEEN:
+      case VB2_OP_AND: case VB2_OP_OR: case VB2_OP_NOT: case VB2_OP_IS_NULL:
+        break;
+      case VB2_OP_SELECT:
+        if (in.c < 0) return false;  // CASE without ELSE yields NULL
+        break;
+      case VB2_OP_CAST:
+        if (!(in.type == VB2_DOUBLE || in.b == in.type || (in.type == VB2_BIGINT && in.b != VB2_DOUBLE))) return false;  // narrowing casts can raise
+        break;
+      default:
+        return false;
+    }
+  }
+  return true;
+}
+
 static int fill_args(VmArgs& a, const vb2_program* prog, const vb2_column* cols, int32_t ncols) {
   if (!prog || prog->n_instrs < 0 || prog->n_instrs > kVmMaxInstrs) return fail_msg(VB2_ERR_UNSUPPORTED, "expression program too long (max 256 instructions)");
   if (prog->n_consts > kVmMaxConsts) return fail_msg(VB2_ERR_UNSUPPORTED, "too many constants (max 32)");
@@ -482,8 +527,13 @@ int vb2k_eval_filter(const vb2_program* prog, const vb2_column* cols, int32_t nc
   const int64_t nwords64 = (rows + 63) >> 6;
   VB2_CUDA_OK(cudaMemsetAsync(sel_bits + nwords64 - 1, 0, sizeof(uint64_t), st));
   size_t smem = 0;
-  if ((rc = vm_smem(vm_filter_kernel, prog, &smem))) return rc;
-  vm_filter_kernel<<<vm_grid(rows), kVmThreads, smem, st>>>(a);
+  if (plain_program(prog, prog->n_filter_instrs, cols)) {
+    if ((rc = vm_smem(vm_filter_kernel<true>, prog, &smem))) return rc;
+    vm_filter_kernel<true><<<vm_grid(rows), kVmThreads, smem, st>>>(a);
+  } else {
+    if ((rc = vm_smem(vm_filter_kernel<false>, prog, &smem))) return rc;
+    vm_filter_kernel<false><<<vm_grid(rows), kVmThreads, smem, st>>>(a);
+  }
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -528,8 +578,13 @@ int vb2k_eval_project(const vb2_program* prog, const vb2_column* cols, int32_t n
   a.sel_bits = nullptr;
   a.error_flag = error_flag;
   size_t smem = 0;
-  if ((rc = vm_smem(vm_project_kernel, prog, &smem))) return rc;
-  vm_project_kernel<<<vm_grid(n), kVmThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  if (plain_program(prog, prog->n_instrs, cols)) {
+    if ((rc = vm_smem(vm_project_kernel<true>, prog, &smem))) return rc;
+    vm_project_kernel<true><<<vm_grid(n), kVmThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  } else {
+    if ((rc = vm_smem(vm_project_kernel<false>, prog, &smem))) return rc;
+    vm_project_kernel<false><<<vm_grid(n), kVmThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  }
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
