@@ -333,3 +333,43 @@ def test_tma_stage_reuse_is_exact_and_deterministic(rows):
         b = torch.zeros(nparts + 1, dtype=torch.float64, device="cuda").index_add_(0, li["l_partkey"], rev)
         assert float(((a - b).abs() / b.abs().clamp_min(1.0)).max()) < 1e-12
         assert bool((torch.sort(lk).values == torch.sort(li["l_partkey"]).values).all())
+
+
+@pytest.mark.parametrize("n", [0, 1, 4095, 4096, 100_003])
+def test_partition_segments_match_oracle_partitioning(n):
+    """Sync-free fixed-capacity partitioning (vb2k_partition_segments): partition of every row equals
+    HashPartitionFunction on the CPU oracle (exec/HashPartitionFunction.cpp:113-116), rows keep their
+    input order inside a segment, tails hold the sentinel, the device-side row count bounds the input,
+    and an undersized segment raises the overflow flag."""
+    from velox_b200.kernels import SENTINEL_KEY, partition_segments
+    rng = np.random.default_rng(n + 1)
+    keys = rng.integers(-2**62, 2**62, n)
+    pay8 = rng.standard_normal(n)
+    pay4 = rng.integers(0, 1000, n).astype(np.int32)
+    host_key = flat_vector(BIGINT, keys)
+    tk = torch.from_numpy(keys).cuda() if n else torch.zeros(0, dtype=torch.int64, device="cuda")
+    t8 = torch.from_numpy(pay8).cuda() if n else torch.zeros(0, dtype=torch.float64, device="cuda")
+    t4 = torch.from_numpy(pay4).cuda() if n else torch.zeros(0, dtype=torch.int32, device="cuda")
+    for parts in (1, 2, 8, 13):
+        want = pyoracle.partition([host_key], parts) if n else np.zeros(0, dtype=np.uint32)
+        counts = np.bincount(want, minlength=parts) if n else np.zeros(parts, dtype=np.int64)
+        segcap = int(max(64, counts.max() + 3))
+        flag = torch.zeros(2, dtype=torch.int32, device="cuda")
+        # slack rows after the logical end must be ignored through the device-side row count
+        pad = 37
+        tk2 = torch.cat([tk, torch.full((pad,), 5, dtype=torch.int64, device="cuda")])
+        t82 = torch.cat([t8, torch.zeros(pad, dtype=torch.float64, device="cuda")])
+        t42 = torch.cat([t4, torch.zeros(pad, dtype=torch.int32, device="cuda")])
+        rows_dev = torch.tensor([n], dtype=torch.int64, device="cuda")
+        sk, (s8, s4), cnt = partition_segments(tk2, [t82, t42], n + pad, rows_dev, parts, segcap, flag)
+        assert cnt.cpu().tolist() == counts.tolist() and int(flag[0].item()) == 0
+        sk, s8, s4 = sk.cpu().numpy(), s8.cpu().numpy(), s4.cpu().numpy()
+        for p in range(parts):
+            rows = np.nonzero(want == p)[0] if n else np.zeros(0, dtype=np.int64)
+            seg = slice(p * segcap, p * segcap + len(rows))
+            assert np.array_equal(sk[seg], keys[rows]) and np.array_equal(s8[seg], pay8[rows]) and np.array_equal(s4[seg], pay4[rows])
+            assert np.all(sk[p * segcap + len(rows):(p + 1) * segcap] == SENTINEL_KEY)
+        if n > parts and counts.max() > 1:
+            flag.zero_()
+            partition_segments(tk, [t8], n, None, parts, int(counts.max()) - 1, flag)
+            assert int(flag[0].item()) == 1
