@@ -3,7 +3,7 @@
 NVCC ?= nvcc
 CXX ?= g++
 ARCH = -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS = -std=c++20 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -Iinclude -Ivelox_b200
+NVCCFLAGS = -std=c++20 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -Iinclude -Ivelox_b200 -I$(BUILD)
 CXXFLAGS = -std=c++20 -O2 -fPIC -Wall -Iinclude -Ivelox_b200 -I/usr/local/cuda/include
 BUILD = build
 LIB = velox_b200/lib/libvelox_b200.so
@@ -15,7 +15,12 @@ OBJS = $(patsubst velox_b200/csrc/%.cu,$(BUILD)/%.o,$(CU_SRCS)) \
 
 all: $(LIB) oracle
 
-$(BUILD)/%.o: velox_b200/csrc/%.cu $(wildcard velox_b200/csrc/*.cuh) $(wildcard include/*.h)
+# vm_ops.inc as a string: the expression JIT hands the same text to NVRTC
+$(BUILD)/vm_ops_str.h: velox_b200/csrc/vm_ops.inc
+	@mkdir -p $(BUILD)
+	( echo 'static const char kVmOpsSource[] = R"VMOPS('; cat $<; echo ')VMOPS";' ) > $@
+
+$(BUILD)/%.o: velox_b200/csrc/%.cu $(wildcard velox_b200/csrc/*.cuh) $(wildcard velox_b200/csrc/*.inc) $(wildcard include/*.h) $(BUILD)/vm_ops_str.h
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
@@ -25,7 +30,7 @@ $(BUILD)/host_%.o: velox_b200/csrc/host/%.cpp $(wildcard velox_b200/csrc/host/*.
 
 $(LIB): $(OBJS)
 	@mkdir -p velox_b200/lib
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -l:libnccl.so.2
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -l:libnccl.so.2 -ldl
 
 oracle:
 	$(MAKE) -s -C oracle

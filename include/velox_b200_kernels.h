@@ -147,6 +147,16 @@ typedef struct vb2_output {
   uint64_t* nulls; /* validity bitmap of n_out bits, always written */
 } vb2_output;
 
+/* Expression JIT (expr_jit.cu): programs are compiled to straight-line sm_100a code with NVRTC and
+ * cached per (program, column layout); vb2k_eval_filter / vb2k_eval_project use it when available
+ * and fall back to the interpreter kernels otherwise. On by default (VB2_EXPR_JIT=0 disables). */
+void vb2k_set_expression_jit(int32_t enabled);
+/* Generates and compiles (does not launch; no GPU needed) the kernel of a program for the given
+ * column layout: 1 = a JIT kernel is available, 0 = the interpreter would run. source_out receives
+ * the generated source (or the compiler log on failure). */
+int32_t vb2k_expression_jit_compiles(const vb2_program* prog, const vb2_column* cols, int32_t ncols, int32_t filter, const vb2_output* outs,
+                                     int32_t nouts, char* source_out, int32_t source_len);
+
 /* Pass 1: evaluates the filter over `rows` input rows. Writes the selection bitmap (1 = row kept:
  * predicate true and not null) and per-block popcounts for the compaction that follows. */
 int vb2k_eval_filter(const vb2_program* prog, const vb2_column* cols, int32_t ncols, int64_t rows,

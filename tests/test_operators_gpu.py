@@ -14,6 +14,15 @@ from util import FUSED, GENERIC, check_plan, check_user_error, stat
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=["jit", "interpreter"], autouse=True)
+def expression_engine(request):
+    """Every plan runs with both expression engines: NVRTC-compiled kernels and the interpreter."""
+    from velox_b200._lib import lib
+    lib().vb2k_set_expression_jit(1 if request.param == "jit" else 0)
+    yield request.param
+    lib().vb2k_set_expression_jit(1)
+
 NAN, INF = float("nan"), float("inf")
 
 

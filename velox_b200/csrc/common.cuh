@@ -47,60 +47,10 @@ __device__ __forceinline__ longlong2 ldg_stream_i64x2(const int64_t* p) {
   return r;
 }
 
-__device__ __forceinline__ bool bit_at(const uint64_t* bits, int64_t i) { return (bits[i >> 6] >> (i & 63)) & 1; }
-
-// ---------------------------------------------------------------------------------------------
-// NaN-aware comparisons (NaN is the largest value and equals itself).
-// ---------------------------------------------------------------------------------------------
-enum CmpOp : int { kLt = 0, kLte = 1, kGt = 2, kGte = 3, kEq = 4, kNeq = 5 };
-
-__device__ __forceinline__ bool cmp_f64(int op, double a, double b) {
-  const bool an = isnan(a), bn = isnan(b);
-  switch (op) {
-    case kLt: return (!an && bn) ? true : a < b;
-    case kLte: return bn ? true : a <= b;
-    case kGt: return (an && !bn) ? true : a > b;
-    case kGte: return an ? true : a >= b;
-    case kEq: return (an && bn) ? true : a == b;
-    default: return !((an && bn) ? true : a == b);
-  }
-}
-template <class T>
-__device__ __forceinline__ bool cmp_int(int op, T a, T b) {
-  switch (op) {
-    case kLt: return a < b;
-    case kLte: return a <= b;
-    case kGt: return a > b;
-    case kGte: return a >= b;
-    case kEq: return a == b;
-    default: return a != b;
-  }
-}
-__device__ __forceinline__ bool lt_f64(double a, double b) { return (!isnan(a) && isnan(b)) ? true : a < b; }
-__device__ __forceinline__ bool lte_f64(double a, double b) { return isnan(b) ? true : a <= b; }
-__device__ __forceinline__ bool gt_f64(double a, double b) { return (isnan(a) && !isnan(b)) ? true : a > b; }
-__device__ __forceinline__ bool gte_f64(double a, double b) { return isnan(a) ? true : a >= b; }
-__device__ __forceinline__ bool eq_f64(double a, double b) { return (isnan(a) && isnan(b)) ? true : a == b; }
-
-// ---------------------------------------------------------------------------------------------
-// Checked integer arithmetic: returns false on overflow / division by zero.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool add_overflow_i64(int64_t a, int64_t b, int64_t* out) {
-  uint64_t r = static_cast<uint64_t>(a) + static_cast<uint64_t>(b);
-  *out = static_cast<int64_t>(r);
-  return ((a ^ *out) & (b ^ *out)) < 0;
-}
-__device__ __forceinline__ bool sub_overflow_i64(int64_t a, int64_t b, int64_t* out) {
-  uint64_t r = static_cast<uint64_t>(a) - static_cast<uint64_t>(b);
-  *out = static_cast<int64_t>(r);
-  return ((a ^ b) & (a ^ *out)) < 0;
-}
-__device__ __forceinline__ bool mul_overflow_i64(int64_t a, int64_t b, int64_t* out) {
-  int64_t hi = __mul64hi(a, b);
-  int64_t lo = static_cast<int64_t>(static_cast<uint64_t>(a) * static_cast<uint64_t>(b));
-  *out = lo;
-  return hi != (lo >> 63);
-}
+// Row-level scalar semantics shared by the kernels, the expression interpreter and the expression
+// JIT (which compiles the same text with NVRTC): validity bits, NaN-aware comparisons, checked
+// integer arithmetic, LIKE and string comparison.
+#include "vm_ops.inc"
 
 // ---------------------------------------------------------------------------------------------
 // Hashing (bit-exact with folly::hasher<T> as used by VectorHasher).

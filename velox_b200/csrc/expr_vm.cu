@@ -64,27 +64,6 @@ __device__ __forceinline__ uint64_t load_value(const vb2_column& c, int64_t base
   }
 }
 
-// SQL LIKE with % and _ (no escape character).
-__device__ inline bool like_match(const char* s, int sl, const char* p, int pl) {
-  int si = 0, pi = 0, star = -1, mark = 0;
-  while (si < sl) {
-    if (pi < pl && (p[pi] == '_' || p[pi] == s[si])) { ++si; ++pi; }
-    else if (pi < pl && p[pi] == '%') { star = pi++; mark = si; }
-    else if (star >= 0) { pi = star + 1; si = ++mark; }
-    else return false;
-  }
-  while (pi < pl && p[pi] == '%') ++pi;
-  return pi == pl;
-}
-__device__ inline int str_compare(const char* a, int al, const char* b, int bl) {
-  const int n = al < bl ? al : bl;
-  for (int i = 0; i < n; ++i) {
-    const unsigned char x = a[i], y = b[i];
-    if (x != y) return x < y ? -1 : 1;
-  }
-  return al < bl ? -1 : (al > bl ? 1 : 0);
-}
-
 constexpr int kVmThreads = 256;
 
 // Per-row interpreter state. The value registers live in shared memory, one column of
@@ -490,6 +469,12 @@ static bool plain_program(const vb2_program* prog, int n_instrs, const vb2_colum
   return true;
 }
 
+namespace jit {
+// expr_jit.cu: VB2_ERR_UNSUPPORTED = run the interpreter
+int launch(const vb2_program* p, const vb2_column* cols, int ncols, bool filter, const int32_t* sel, int64_t n, uint32_t* sel_bits,
+           const vb2_output* outs, int nouts, int32_t* error_flag, cudaStream_t st);
+}  // namespace jit
+
 static int fill_args(VmArgs& a, const vb2_program* prog, const vb2_column* cols, int32_t ncols) {
   if (!prog || prog->n_instrs < 0 || prog->n_instrs > kVmMaxInstrs) return fail_msg(VB2_ERR_UNSUPPORTED, "expression program too long (max 256 instructions)");
   if (prog->n_consts > kVmMaxConsts) return fail_msg(VB2_ERR_UNSUPPORTED, "too many constants (max 32)");
@@ -526,6 +511,8 @@ int vb2k_eval_filter(const vb2_program* prog, const vb2_column* cols, int32_t nc
   // zero the tail word so that bits beyond `rows` read as 0 for 64-bit consumers
   const int64_t nwords64 = (rows + 63) >> 6;
   VB2_CUDA_OK(cudaMemsetAsync(sel_bits + nwords64 - 1, 0, sizeof(uint64_t), st));
+  rc = jit::launch(prog, cols, ncols, true, nullptr, rows, reinterpret_cast<uint32_t*>(sel_bits), nullptr, 0, error_flag, st);
+  if (rc != VB2_ERR_UNSUPPORTED) return rc;
   size_t smem = 0;
   if (plain_program(prog, prog->n_filter_instrs, cols)) {
     if ((rc = vm_smem(vm_filter_kernel<true>, prog, &smem))) return rc;
@@ -577,6 +564,8 @@ int vb2k_eval_project(const vb2_program* prog, const vb2_column* cols, int32_t n
   a.sel = sel;
   a.sel_bits = nullptr;
   a.error_flag = error_flag;
+  rc = jit::launch(prog, cols, ncols, false, sel, n, nullptr, outs, nouts, error_flag, static_cast<cudaStream_t>(stream));
+  if (rc != VB2_ERR_UNSUPPORTED) return rc;
   size_t smem = 0;
   if (plain_program(prog, prog->n_instrs, cols)) {
     if ((rc = vm_smem(vm_project_kernel<true>, prog, &smem))) return rc;
