@@ -305,6 +305,17 @@ def main():
     sampler.stop_flag.set()
     sampler.join()
     results = {"q1": {f"{k[0]}{k[1]}": v[7] for k, v in q1.result().items()}, "q14_promo_revenue": q14.result(), "q6_revenue": q6.result()}
+    # Conservation check of the exchange: every lineitem row that passes the date filter has a part
+    # row, so rows joined after the shuffle must equal rows the scans emitted (summed over ranks).
+    joined = int(q14.probe.counts.item())
+    if world > 1:
+        scanned = q14.scan.count.clone()
+        dist.all_reduce(scanned)
+        scanned = int(scanned.item())
+        results["q14_rows"] = {"scanned": scanned, "joined": joined, "planned_runs": q14.planned_runs}
+        assert scanned == joined, f"Q14 exchange lost or duplicated rows: scanned {scanned}, joined {joined}"
+    else:
+        results["q14_rows"] = {"joined": joined}
 
     # launches of our kernels per step (Q1: fused + finalize; Q14 on one GPU: min/max init + min/max,
     # normalize, join build, LIKE on the alphabet, slot flags, fused probe + finalize; Q14 planned
