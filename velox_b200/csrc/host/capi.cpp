@@ -15,8 +15,13 @@
 
 using namespace velox_b200;
 
+struct vb2_upload_cache {
+  velox_b200::UploadCache cache;
+};
+
 struct vb2_task {
   std::shared_ptr<exec::Task> task;
+  vb2_upload_cache* uploadCache = nullptr;
   core::PlanNodePtr plan;
   memory::MemoryPool pool{"capi"};
   std::vector<RowVectorPtr> results;
@@ -30,6 +35,7 @@ struct vb2_task {
   };
   std::vector<OutCol> out;
   int64_t rows = 0;
+  int64_t h2dBytes = 0;  // host -> device bytes of the last run (resident copies from an upload cache are not counted)
   std::string stats;
 };
 
@@ -286,7 +292,13 @@ int32_t vb2_task_add_input(vb2_task* task, int32_t source_id, const vb2_column* 
 int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen) {
   return guarded(err, errlen, [&] {
     VELOX_CHECK(task != nullptr, "null task");
+    struct Attach {  // the serial Task runs its drivers on this thread
+      explicit Attach(vb2_upload_cache* c) { velox_b200::setThreadUploadCache(c ? &c->cache : nullptr); }
+      ~Attach() { velox_b200::setThreadUploadCache(nullptr); }
+    } attach(task->uploadCache);
+    const int64_t uploadedBefore = velox_b200::threadUploadedBytes();
     task->results = task->task->run();
+    task->h2dBytes = velox_b200::threadUploadedBytes() - uploadedBefore;
     task->out.clear();
     task->rows = 0;
     for (auto& b : task->results) appendResult(*task, b);
@@ -297,9 +309,18 @@ int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen) {
     }
     std::ostringstream os;
     for (auto& kv : task->task->stats()) os << kv.first << "=" << kv.second << "\n";
+    os << "task.h2dBytes=" << task->h2dBytes << "\n";
     task->stats = os.str();
     task->results.clear();
   });
+}
+
+vb2_upload_cache* vb2_upload_cache_create(void) { return new vb2_upload_cache(); }
+void vb2_upload_cache_free(vb2_upload_cache* cache) { delete cache; }
+int32_t vb2_task_set_upload_cache(vb2_task* task, vb2_upload_cache* cache) {
+  if (!task) return VB2_ERR_INVALID;
+  task->uploadCache = cache;
+  return VB2_OK;
 }
 
 int64_t vb2_result_rows(vb2_task* task) { return task->rows; }

@@ -103,10 +103,34 @@ int32_t widthOf(int32_t t) {
 }
 
 namespace {
+thread_local UploadCache* tlsUploadCache = nullptr;
+thread_local int64_t tlsUploadedBytes = 0;
+constexpr size_t kCacheMinBytes = 1 << 16;  // small buffers are often staging copies with short-lived addresses
+}  // namespace
+void setThreadUploadCache(UploadCache* cache) { tlsUploadCache = cache; }
+int64_t threadUploadedBytes() { return tlsUploadedBytes; }
+
+namespace {
+
 
 DeviceBufferPtr upload(const void* src, size_t bytes, cudaStream_t stream) {
+  UploadCache* cache = bytes >= kCacheMinBytes ? tlsUploadCache : nullptr;
+  if (cache) {
+    std::lock_guard<std::mutex> lock(cache->mu);
+    auto it = cache->entries.find(reinterpret_cast<uint64_t>(src));
+    if (it != cache->entries.end() && it->second.first == bytes) {
+      cache->hitBytes += static_cast<int64_t>(bytes);
+      return it->second.second;
+    }
+  }
   auto b = allocDevice(bytes, stream);
   if (bytes) VB2_CU(cudaMemcpyAsync(b->data(), src, bytes, cudaMemcpyHostToDevice, stream));
+  tlsUploadedBytes += static_cast<int64_t>(bytes);
+  if (cache) {
+    std::lock_guard<std::mutex> lock(cache->mu);
+    cache->entries[reinterpret_cast<uint64_t>(src)] = {bytes, b};
+    cache->missBytes += static_cast<int64_t>(bytes);
+  }
   return b;
 }
 
@@ -408,10 +432,11 @@ B200VectorPtr sliceVector(const B200VectorPtr& v, int64_t offset, int64_t length
     auto s = std::make_shared<DeviceColumn>(*c);  // shares the owners
     vb2_column& d = s->desc;
     d.size = length;
-    if (d.nulls) d.nulls += offset / 64;
     if (d.encoding == VB2_DICTIONARY) {
+      if (d.nulls) d.nulls += offset / 64;
       d.indices += offset;
     } else if (d.encoding == VB2_FLAT) {
+      if (d.nulls) d.nulls += offset / 64;
       const char* base = static_cast<const char*>(d.values);
       if (d.type == VB2_BOOLEAN) base += offset / 8;
       else if (d.type == VB2_VARCHAR) base += offset * 4;  // int32 offsets; chars (aux) stay absolute

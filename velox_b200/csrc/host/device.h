@@ -4,6 +4,8 @@
 // (velox/experimental/cudf/vector/CudfVector.h:43) and a pair of conversion operators inserted
 // at CPU/GPU seams (velox/experimental/cudf/exec/CudfConversion.h:32,67).
 #pragma once
+#include <mutex>
+#include <unordered_map>
 #include <cuda_runtime.h>
 
 #include <memory>
@@ -83,6 +85,20 @@ RowVectorPtr toHost(const B200VectorPtr& dev);
 
 // Wraps externally owned device memory (e.g. columns already resident in HBM) without copying.
 DeviceColumnPtr borrowFlatColumn(TypePtr type, const void* values, int64_t size);
+
+// Scan-side device residency for host tables that several tasks read: while a cache is attached to
+// the calling thread, host buffers that go through upload() are remembered by (address, bytes) and a
+// later upload of the same buffer returns the resident device copy instead of crossing PCIe again.
+// The caller guarantees that registered host buffers are neither modified nor freed while the cache
+// lives. Uploads happen on the uploading task's stream; a reusing task must start after that task's
+// run() returned (run() ends with a synchronised ToHost).
+struct UploadCache {
+  std::mutex mu;
+  std::unordered_map<uint64_t, std::pair<size_t, DeviceBufferPtr>> entries;  // host address -> (bytes, device copy)
+  int64_t hitBytes = 0, missBytes = 0;
+};
+void setThreadUploadCache(UploadCache* cache);  // nullptr detaches
+int64_t threadUploadedBytes();                  // bytes copied host -> device by this thread so far
 
 // Rows [offset, offset + length) of a device batch without copying (offset must be a multiple of 64
 // so validity bitmaps stay word-aligned).

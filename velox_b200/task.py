@@ -33,6 +33,9 @@ def _bind():
     L.vb2_task_stats.restype = C.c_char_p
     L.vb2_task_stats.argtypes = [C.c_void_p]
     L.vb2_task_free.argtypes = [C.c_void_p]
+    L.vb2_upload_cache_create.restype = C.c_void_p
+    L.vb2_upload_cache_free.argtypes = [C.c_void_p]
+    L.vb2_task_set_upload_cache.argtypes = [C.c_void_p, C.c_void_p]
     L._task_bound = True
     return L
 
@@ -44,7 +47,31 @@ def _raise(code: int, err) -> None:
     raise VeloxRuntimeError(msg)
 
 
+class UploadCache:
+    """Device copies of host buffers shared by several tasks (vb2_upload_cache): a host table that
+    two queries read crosses PCIe once. The host buffers must stay unchanged while the cache lives."""
+
+    def __init__(self):
+        self.L = _bind()
+        self.h = self.L.vb2_upload_cache_create()
+
+    def close(self):
+        if self.h:
+            self.L.vb2_upload_cache_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Task:
+    def set_upload_cache(self, cache: Optional["UploadCache"]) -> None:
+        self.L.vb2_task_set_upload_cache(self.h, cache.h if cache is not None else None)
+        self._cache = cache  # keep it alive for the run
+
     def __init__(self, plan, config: Optional[Dict[str, str]] = None):
         self.L = _bind()
         self.plan = plan
