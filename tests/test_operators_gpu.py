@@ -389,7 +389,7 @@ def test_upload_cache_shares_host_buffers_between_tasks():
     rng = np.random.default_rng(3)
     rv = row_vector(["k", "a", "b"], [flat_vector(INTEGER, rng.integers(0, 50, n).astype(np.int32)), flat_vector(DOUBLE, rng.standard_normal(n)),
                                       flat_vector(BIGINT, rng.integers(0, 1000, n))])
-    p1 = PlanBuilder().values(rv.names, rv.types).filter("b < 500").singleAggregation(["k"], ["sum(a)", "count(0)"]).planNode()
+    p1 = PlanBuilder().values(rv.names, rv.types).filter("a < 0.5").singleAggregation(["k"], ["sum(b)", "count(0)"]).planNode()  # integer results: exact
     p2 = PlanBuilder().values(rv.names, rv.types).project(["a * 2.0 AS x", "b"]).singleAggregation([], ["sum(x)", "sum(b)"]).planNode()
     want1, want2 = check_plan(p1, [rv]), check_plan(p2, [rv])  # parity of both plans on their own
     del want1, want2
@@ -408,8 +408,8 @@ def test_upload_cache_shares_host_buffers_between_tasks():
     assert copied[0] >= full and copied[1] < full // 10 and copied[2] < full // 10, copied
     assert sorted(outs[0]) == sorted(outs[2])
     # without a cache every task copies everything again
-    t = Task(p2)
+    t = Task(p1)
     t.add_input(0, rv)
-    assert t.run().rows() == outs[1] or True
+    assert sorted(t.run().rows()) == sorted(outs[0])
     assert t.stats()["task.h2dBytes"] >= full
     t.close()
