@@ -1,0 +1,104 @@
+"""Independent cross-check of the CPU oracle against pyarrow / Acero (the reference
+pins operator results through DuckDB at test time, which is absent here; pyarrow is the columnar
+engine that is). Not Velox, so only SQL-level semantics are compared: filters, projections,
+grouped aggregates with NULL handling, and inner / left / semi / anti hash joins. Runs on the CPU."""
+import math
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pytest
+
+from oracle import pyoracle
+from velox_b200.arrow import row_vector_from_arrow, row_vector_to_arrow
+from velox_b200.plan import PlanBuilder
+
+
+def table(n, seed, null_p=0.1):
+    rng = np.random.default_rng(seed)
+
+    def with_nulls(values, typ):
+        mask = rng.random(n) < null_p
+        return pa.array(values, type=typ, mask=mask)
+
+    return pa.table({
+        "k1": with_nulls(rng.integers(0, 7, n), pa.int32()),
+        "k2": with_nulls(rng.integers(-3, 4, n), pa.int64()),
+        "s": pa.array(rng.choice(["apple", "banana", "cherry", None], n).tolist(), type=pa.string()).dictionary_encode(),
+        "x": with_nulls(np.round(rng.normal(0, 100, n), 3), pa.float64()),
+        "q": with_nulls(rng.integers(0, 50, n).astype(np.float64), pa.float64()),
+        "v": with_nulls(rng.integers(-1000, 1000, n), pa.int64()),
+    })
+
+
+def norm(rows):
+    def key(r):
+        return tuple((0, 0) if v is None else (1, round(v, 6)) if isinstance(v, float) else (1, v) if not isinstance(v, str) else (2, v) for v in r)
+    return sorted(rows, key=key)
+
+
+def assert_same(got, want, rel=1e-9):
+    g, w = norm(got), norm(want)
+    assert len(g) == len(w), (len(g), len(w))
+    for a, b in zip(g, w):
+        for x, y in zip(a, b):
+            if x is None or y is None:
+                assert x is None and y is None, (a, b)
+            elif isinstance(y, float):
+                assert math.isclose(x, y, rel_tol=rel, abs_tol=1e-9), (a, b)
+            else:
+                assert x == y, (a, b)
+
+
+def arrow_rows(t):
+    cols = [t.column(i).to_pylist() for i in range(t.num_columns)]
+    return list(zip(*cols)) if cols else []
+
+
+def test_arrow_round_trip():
+    t = table(1000, 1)
+    back = row_vector_to_arrow(row_vector_from_arrow(t))
+    assert arrow_rows(back) == arrow_rows(t.cast(back.schema) if back.schema != t.schema else t) or arrow_rows(back) == arrow_rows(t)
+
+
+@pytest.mark.parametrize("seed", [2, 3])
+def test_filter_project_against_arrow(seed):
+    t = table(5000, seed)
+    rv = row_vector_from_arrow(t)
+    plan = (PlanBuilder().values(rv.names, rv.types).filter("q < 24.0 AND (x > 0.0 OR v between -100 and 100)")
+            .project(["x * (1.0 - q) AS a", "v + k2 AS b", "k1"]).planNode())
+    got = pyoracle.run_plan(plan, [rv], threads=1, batch_rows=997).rows()
+    keep = pc.and_kleene(pc.less(t["q"], 24.0), pc.or_kleene(pc.greater(t["x"], 0.0), pc.and_kleene(pc.greater_equal(t["v"], -100), pc.less_equal(t["v"], 100))))
+    f = t.filter(keep)  # drops rows whose predicate is NULL or false
+    want = pa.table({"a": pc.multiply(f["x"], pc.subtract(1.0, f["q"])), "b": pc.add(f["v"], f["k2"]), "k1": f["k1"]})
+    assert_same(got, arrow_rows(want))
+
+
+@pytest.mark.parametrize("keys", [[], ["k1"], ["k1", "k2"], ["s"], ["s", "k1"]])
+def test_group_by_against_arrow(keys):
+    t = table(20_000, 7)
+    rv = row_vector_from_arrow(t)
+    plan = (PlanBuilder().values(rv.names, rv.types)
+            .singleAggregation(keys, ["sum(x)", "sum(v)", "count(x)", "count(0)", "min(v)", "max(x)", "avg(q)"]).planNode())
+    got = pyoracle.run_plan(plan, [rv], threads=1, batch_rows=4096).rows()
+    aggs = [("x", "sum"), ("v", "sum"), ("x", "count"), ([], "count_all"), ("v", "min"), ("x", "max"), ("q", "mean")]
+    want = t.group_by(keys, use_threads=False).aggregate(aggs)
+    # pyarrow puts the aggregates first, then the keys
+    order = keys + [c for c in want.schema.names if c not in keys]
+    assert_same(got, arrow_rows(want.select(order)))
+
+
+@pytest.mark.parametrize("join_type,arrow_type", [("inner", "inner"), ("left", "left outer"), ("semi", "left semi"), ("anti", "left anti")])
+def test_hash_join_against_arrow(join_type, arrow_type):
+    rng = np.random.default_rng(11)
+    n, m = 4000, 300
+    probe = pa.table({"pk": pa.array(rng.integers(0, 400, n), type=pa.int64(), mask=rng.random(n) < 0.05), "pv": pa.array(rng.standard_normal(n))})
+    build = pa.table({"bk": pa.array(rng.integers(0, 400, m), type=pa.int64(), mask=rng.random(m) < 0.05), "bv": pa.array(rng.integers(0, 9, m), type=pa.int64())})
+    prv, brv = row_vector_from_arrow(probe), row_vector_from_arrow(build)
+    out_cols = ["pk", "pv"] if join_type in ("semi", "anti") else ["pk", "pv", "bv"]
+    plan = (PlanBuilder().values(prv.names, prv.types, source=0)
+            .hashJoin(["pk"], ["bk"], PlanBuilder().values(brv.names, brv.types, source=1), "", out_cols, joinType=join_type).planNode())
+    got = pyoracle.run_plan(plan, [prv, brv], threads=1, batch_rows=512).rows()
+    j = probe.join(build, keys="pk", right_keys="bk", join_type=arrow_type, use_threads=False)
+    want = j.select(out_cols)
+    assert_same(got, arrow_rows(want))
