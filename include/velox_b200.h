@@ -44,6 +44,12 @@ int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen);
  * resident device copy instead of crossing PCIe again. The caller guarantees the host buffers are
  * neither modified nor freed while the cache lives, and runs the sharing tasks one after another.
  * The stats text of a task reports `task.h2dBytes`, the bytes it actually copied. */
+/* Diagnostic, no GPU needed: the expression programs of every Filter / Project node of a plan are
+ * compiled (expression compiler) and handed to the expression JIT for a flat NULL-free input;
+ * reports the number of programs, of kernels (filter pass + projection pass) and of kernels that
+ * generate and NVRTC-compile for sm_100a (the rest would run on the interpreter). */
+int32_t vb2_plan_jit_report(const char* plan_text, int32_t* programs, int32_t* jit_kernels, int32_t* total_kernels, char* err, int32_t errlen);
+
 typedef struct vb2_upload_cache vb2_upload_cache;
 vb2_upload_cache* vb2_upload_cache_create(void);
 void vb2_upload_cache_free(vb2_upload_cache* cache);

@@ -1,5 +1,6 @@
 // Operator-level C ABI (include/velox_b200.h): plan text -> Task over the shim Driver with the
 // B200 adapter installed; host / device column batches in, host result columns out.
+#include <functional>
 #include <execinfo.h>
 #include <signal.h>
 #include <unistd.h>
@@ -312,6 +313,61 @@ int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen) {
     os << "task.h2dBytes=" << task->h2dBytes << "\n";
     task->stats = os.str();
     task->results.clear();
+  });
+}
+
+// Diagnostic (no GPU needed): compiles the expression programs of every Filter / Project node of a
+// plan with the expression compiler and reports how many of their kernels the expression JIT can
+// generate and NVRTC-compile for a flat, NULL-free input (VARCHAR as a dictionary column).
+int32_t vb2_plan_jit_report(const char* plan_text, int32_t* programs, int32_t* jit_kernels, int32_t* total_kernels, char* err, int32_t errlen) {
+  return guarded(err, errlen, [&] {
+    registerB200Functions();
+    auto plan = parsePlanText(plan_text);
+    int np = 0, nk = 0, nj = 0;
+    std::function<void(const core::PlanNodePtr&)> walk = [&](const core::PlanNodePtr& node) {
+      for (auto& s : node->sources()) walk(s);
+      std::vector<core::TypedExprPtr> exprs;
+      bool hasFilter = false;
+      RowTypePtr inType;
+      if (auto f = std::dynamic_pointer_cast<const core::FilterNode>(node)) {
+        inType = f->sources()[0]->outputType();
+        exprs.push_back(f->filter());
+        hasFilter = true;
+        for (uint32_t i = 0; i < inType->size(); ++i)
+          exprs.push_back(std::make_shared<core::FieldAccessTypedExpr>(inType->childAt(i), inType->nameOf(i), static_cast<int32_t>(i)));
+      } else if (auto p = std::dynamic_pointer_cast<const core::ProjectNode>(node)) {
+        inType = p->sources()[0]->outputType();
+        exprs = p->projections();
+      } else {
+        return;
+      }
+      CompiledProgram prog = compileExprs(exprs, hasFilter, inType);
+      ++np;
+      std::vector<vb2_column> cols(inType->size());
+      for (uint32_t i = 0; i < inType->size(); ++i) {
+        vb2_column& c = cols[i];
+        c = vb2_column{};
+        c.type = veloxTypeToVb2(inType->childAt(i));
+        c.encoding = c.type == VB2_VARCHAR ? VB2_DICTIONARY : VB2_FLAT;
+        c.size = 1;
+      }
+      const vb2_program view = prog.view();
+      std::vector<vb2_output> outs;
+      for (auto& o : prog.outputs)
+        if (o.reg >= 0) outs.push_back(vb2_output{o.reg, veloxTypeToVb2(o.type), nullptr, nullptr});
+      if (hasFilter) {
+        ++nk;
+        nj += vb2k_expression_jit_compiles(&view, cols.data(), static_cast<int32_t>(cols.size()), 1, nullptr, 0, nullptr, 0);
+      }
+      if (!outs.empty()) {
+        ++nk;
+        nj += vb2k_expression_jit_compiles(&view, cols.data(), static_cast<int32_t>(cols.size()), 0, outs.data(), static_cast<int32_t>(outs.size()), nullptr, 0);
+      }
+    };
+    walk(plan);
+    if (programs) *programs = np;
+    if (jit_kernels) *jit_kernels = nj;
+    if (total_kernels) *total_kernels = nk;
   });
 }
 
