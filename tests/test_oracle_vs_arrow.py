@@ -102,3 +102,28 @@ def test_hash_join_against_arrow(join_type, arrow_type):
     j = probe.join(build, keys="pk", right_keys="bk", join_type=arrow_type, use_threads=False)
     want = j.select(out_cols)
     assert_same(got, arrow_rows(want))
+
+
+def test_case_like_cast_against_arrow():
+    t = table(4000, 21)
+    rv = row_vector_from_arrow(t)
+    plan = (PlanBuilder().values(rv.names, rv.types)
+            .project(["CASE WHEN s LIKE '%an%' THEN x ELSE 0.0 END AS a",
+                      "CASE WHEN k1 > 3 THEN v END AS b",             # no ELSE: NULL
+                      "CAST(k1 AS DOUBLE) * 0.5 AS c",
+                      "CAST(q AS BIGINT) + k2 AS d",
+                      "s LIKE 'b_n%' AS e",
+                      "NOT (x < 0.0) OR k1 IS NULL AS f"]).planNode())
+    got = pyoracle.run_plan(plan, [rv], threads=1, batch_rows=777).rows()
+    s = t["s"].cast(pa.string())
+    like_an = pc.match_like(s, "%an%")
+    want = pa.table({
+        # CASE treats a NULL condition as not taken
+        "a": pc.if_else(pc.fill_null(like_an, False), t["x"], 0.0),
+        "b": pc.if_else(pc.fill_null(pc.greater(t["k1"], 3), False), t["v"], pa.scalar(None, pa.int64())),
+        "c": pc.multiply(pc.cast(t["k1"], pa.float64()), 0.5),
+        "d": pc.add(pc.cast(pc.round(t["q"]), pa.int64()), t["k2"]),
+        "e": pc.match_like(s, "b_n%"),
+        "f": pc.or_kleene(pc.invert(pc.less(t["x"], 0.0)), pc.is_null(t["k1"])),
+    })
+    assert_same(got, arrow_rows(want))
