@@ -362,7 +362,10 @@ def main():
 
     # ---- e2e: operator-level C ABI with host buffers ----------------------------------------------------
     if not args.skip_e2e:
-        line["e2e"] = e2e(args, li, part_all, rows, nparts, world, rank, rows_total)
+        try:
+            line["e2e"] = e2e(args, li, part_all, rows, nparts, world, rank, rows_total)
+        except Exception as ex:  # keep the device-timed line even if the end-to-end leg cannot run here
+            line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": f"{type(ex).__name__}: {ex}"[:300]}
     # ---- CPU baseline (rank 0, N = 1) --------------------------------------------------------------------
     if world == 1 and not args.skip_cpu:
         threads = os.cpu_count() or 1
