@@ -786,7 +786,7 @@ struct AggSpec {
 struct Node;
 using NodePtr = std::shared_ptr<Node>;
 struct Node {
-  enum Kind { VALUES, FILTER, PROJECT, AGG, JOIN } kind = VALUES;
+  enum Kind { VALUES, FILTER, PROJECT, AGG, JOIN, ORDERBY } kind = VALUES;
   std::vector<int> schema;  // output column types
   NodePtr child, build;
   int source = 0;
@@ -800,6 +800,9 @@ struct Node {
   std::string join_type;
   std::vector<int> probe_keys, build_keys;
   std::vector<std::pair<char, int>> join_out;  // ('p'|'b', column)
+  // order by (exec/OrderBy.cpp; core::SortOrder{ascending, nullsFirst}): (column, ascending, nulls first)
+  struct SortKey { int col; bool asc; bool nulls_first; };
+  std::vector<SortKey> sort_keys;
 };
 
 static bool raw_input_step(const std::string& s) { return s == "single" || s == "partial"; }
@@ -826,6 +829,19 @@ static NodePtr parse_plan(const SNode& s) {
     for (auto& e : s.arg(0).kids) {
       n->projections.push_back(parse_expr(e, n->child->schema));
       n->schema.push_back(n->projections.back()->type);
+    }
+  } else if (h == "orderby") {
+    // (orderby ((I asc|desc first|last) ...) plan)
+    n->kind = Node::ORDERBY;
+    n->child = parse_plan(s.arg(1));
+    n->schema = n->child->schema;
+    for (auto& k : s.arg(0).kids) {
+      Node::SortKey sk;
+      sk.col = std::stoi(k.head());
+      sk.asc = k.arg(0).atom == "asc";
+      sk.nulls_first = k.arg(1).atom == "first";
+      if (sk.col < 0 || sk.col >= static_cast<int>(n->schema.size())) throw std::runtime_error("orderby: bad column");
+      n->sort_keys.push_back(sk);
     }
   } else if (h == "aggregation") {
     n->kind = Node::AGG;
@@ -1514,8 +1530,70 @@ struct Executor {
   int threads;
   int64_t batch_rows;
 
+  // OrderBy (exec/OrderBy.cpp + exec/SortBuffer.cpp): materialise, sort row numbers with a stable
+  // sort, gather. NULLs go first or last as the key says, independent of the direction; doubles
+  // compare NaN-largest (type/FloatingPointUtil.h), strings bytewise.
+  Table run_orderby(const NodePtr& node) {
+    Table in = materialise(node->child);
+    const size_t nc = node->schema.size();
+    std::vector<ColBuilder> cb;
+    for (int ty : node->schema) cb.emplace_back(ty);
+    for (auto& b : in)
+      for (size_t c = 0; c < nc; ++c) {
+        VecPtr f = flatten(b.cols[c]);
+        for (int64_t r = 0; r < b.n; ++r) cb[c].push_from(*f, r);
+      }
+    std::vector<VecPtr> flat;
+    for (auto& c : cb) flat.push_back(c.finish());
+    const int64_t n = flat.empty() ? 0 : flat[0]->n;
+    std::vector<int64_t> idx(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) idx[static_cast<size_t>(i)] = i;
+    auto cmp3 = [&](const Vec& v, int64_t a, int64_t b) -> int {
+      switch (v.type) {
+        case ORC_BIGINT: { auto x = v.as<int64_t>()[a], y = v.as<int64_t>()[b]; return x < y ? -1 : (x > y ? 1 : 0); }
+        case ORC_INTEGER: { auto x = v.as<int32_t>()[a], y = v.as<int32_t>()[b]; return x < y ? -1 : (x > y ? 1 : 0); }
+        case ORC_BOOLEAN: { auto x = v.as<uint8_t>()[a], y = v.as<uint8_t>()[b]; return x < y ? -1 : (x > y ? 1 : 0); }
+        case ORC_DOUBLE: {
+          const double x = v.as<double>()[a], y = v.as<double>()[b];
+          const bool xn = std::isnan(x), yn = std::isnan(y);
+          if (xn || yn) return xn == yn ? 0 : (xn ? 1 : -1);  // NaN is the largest value
+          return x < y ? -1 : (x > y ? 1 : 0);
+        }
+        default: {
+          const int32_t la = v.off[a + 1] - v.off[a], lb = v.off[b + 1] - v.off[b];
+          const int c = std::memcmp(v.chars + v.off[a], v.chars + v.off[b], static_cast<size_t>(std::min(la, lb)));
+          return c != 0 ? (c < 0 ? -1 : 1) : (la < lb ? -1 : (la > lb ? 1 : 0));
+        }
+      }
+    };
+    std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) {
+      for (auto& k : node->sort_keys) {
+        const Vec& v = *flat[static_cast<size_t>(k.col)];
+        const bool an = v.null_at(a), bn = v.null_at(b);
+        if (an || bn) {
+          if (an == bn) continue;
+          return an ? k.nulls_first : !k.nulls_first;
+        }
+        const int c = cmp3(v, a, b);
+        if (c != 0) return k.asc ? c < 0 : c > 0;
+      }
+      return false;
+    });
+    std::vector<ColBuilder> ob;
+    for (int ty : node->schema) ob.emplace_back(ty);
+    for (int64_t i = 0; i < n; ++i)
+      for (size_t c = 0; c < nc; ++c) ob[c].push_from(*flat[c], idx[static_cast<size_t>(i)]);
+    Batch out;
+    out.n = n;
+    for (auto& c : ob) out.cols.push_back(c.finish());
+    Table t;
+    if (n > 0) t.push_back(std::move(out));
+    return t;
+  }
+
   Table materialise(const NodePtr& node) {
     if (node->kind == Node::AGG) return run_aggregation(node);
+    if (node->kind == Node::ORDERBY) return run_orderby(node);
     std::vector<Table> per_thread(threads);
     stream(node, [&](int t, Batch&& b) { per_thread[t].push_back(std::move(b)); });
     Table out;

@@ -127,3 +127,37 @@ def test_case_like_cast_against_arrow():
         "f": pc.or_kleene(pc.invert(pc.less(t["x"], 0.0)), pc.is_null(t["k1"])),
     })
     assert_same(got, arrow_rows(want))
+
+
+def test_order_by_against_arrow():
+    """OrderBy exists in the oracle ahead of the device operator: directions,
+    NULLS FIRST / LAST, NaN-largest doubles, strings, multi-key — against pyarrow's sort."""
+    rng = np.random.default_rng(5)
+    n = 3000
+    x = np.round(rng.normal(0, 10, n), 1)
+    x[rng.random(n) < 0.05] = np.nan
+    t = pa.table({
+        "id": pa.array(np.arange(n), type=pa.int64()),  # unique tiebreaker: the order is total
+        "k": pa.array(rng.integers(0, 20, n), type=pa.int32(), mask=rng.random(n) < 0.1),
+        "x": pa.array(x, type=pa.float64(), mask=rng.random(n) < 0.1),
+        "s": pa.array(rng.choice(["a", "ab", "b", "", "zz"], n).tolist(), type=pa.string()),
+    })
+    rv = row_vector_from_arrow(t)
+    cases = [
+        (["k", "id"], [("k", "ascending"), ("id", "ascending")], "at_end"),
+        (["k DESC NULLS FIRST", "id DESC"], [("k", "descending"), ("id", "descending")], "at_start"),
+        (["s DESC", "id"], [("s", "descending"), ("id", "ascending")], "at_end"),
+    ]
+    for keys, sort_keys, null_placement in cases:
+        plan = PlanBuilder().values(rv.names, rv.types).orderBy(keys).planNode()
+        got = pyoracle.run_plan(plan, [rv], threads=2, batch_rows=700).rows()
+        want = arrow_rows(t.take(pc.sort_indices(t, sort_keys=sort_keys, null_placement=null_placement)))
+        assert [r[0] for r in got] == [r[0] for r in want], keys
+    # doubles: NaN sorts as the largest value, NULLs last
+    plan = PlanBuilder().values(rv.names, rv.types).orderBy(["x", "id"]).planNode()
+    got = pyoracle.run_plan(plan, [rv], threads=1, batch_rows=1000).rows()
+    xs = [r[2] for r in got]
+    nn = [v for v in xs if v is not None]
+    assert all(v is None for v in xs[len(nn):])
+    finite = [v for v in nn if not math.isnan(v)]
+    assert all(math.isnan(v) for v in nn[len(finite):]) and finite == sorted(finite)

@@ -11,6 +11,7 @@ Plan text grammar (S-expressions)
   plan := (values SRC (TYPE ...)) | (filter EXPR plan) | (project (EXPR ...) plan)
         | (aggregation STEP (keys I ...) (aggs AGG ...) plan)      STEP: single|partial|intermediate|final
         | (hashjoin TYPE (probekeys I ...) (buildkeys I ...) EXPR|nil (out (p I)|(b I) ...) probe build)
+        | (orderby ((I asc|desc first|last) ...) plan)              oracle only so far
   AGG  := (sum I [(mask I)]) | (avg I) | (count [I]) | (min I) | (max I)
   EXPR := (field I) | (f64 X) | (i64 N) | (i32 N) | (bool true|false) | (str "s") | (null TYPE)
         | (cast TYPE e) | (and e ...) | (or e ...) | (switch c1 v1 ... [else]) | (NAME e ...)
@@ -474,6 +475,23 @@ class PlanBuilder:
                  f"{filt} (out {' '.join(outs)}) {p.sexpr} {b.sexpr})")
         self.sources += build.sources
         self.node = _Node(sexpr, names, types)
+        return self
+
+    def orderBy(self, keys: Sequence[str]) -> "PlanBuilder":
+        """ORDER BY (exec/OrderBy.cpp; PlanBuilder::orderBy of the reference's test utilities): keys
+        like "c0", "c1 DESC", "c2 ASC NULLS FIRST". Default NULLS LAST for both directions, as
+        core::kAscNullsLast / kDescNullsLast. The CPU oracle executes it; the B200 operator set does
+        not contain OrderBy yet, so the product rejects the node."""
+        n = self.node
+        parts = []
+        for k in keys:
+            words = k.split()
+            col = n.names.index(words[0])
+            rest = [w.upper() for w in words[1:]]
+            asc = "DESC" not in rest
+            nulls_first = "FIRST" in rest
+            parts.append(f"({col} {'asc' if asc else 'desc'} {'first' if nulls_first else 'last'})")
+        self.node = _Node(f"(orderby ({' '.join(parts)}) {n.sexpr})", n.names, n.types)
         return self
 
     def planNode(self) -> _Node:
