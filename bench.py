@@ -208,6 +208,74 @@ def reference_arm(args):
 # -------------------------------------------------------------------------------------------------
 # our arm
 # -------------------------------------------------------------------------------------------------
+def device_inputs(li, part):
+    """Column batches already resident in HBM, as the operator-level C ABI takes them (VB2_DEVICE)."""
+    import torch
+    from velox_b200 import tpch
+    from velox_b200.kernels import DeviceColumn, flat_device
+    from velox_b200.vector import BIGINT, DOUBLE, INTEGER, VARCHAR, dictionary_vector
+
+    def dict_dev(codes, alphabet):
+        host = dictionary_vector(VARCHAR, torch.zeros(1, dtype=torch.int32).numpy(), alphabet)
+        d = DeviceColumn.from_host(host)
+        d.indices, d.size = codes, codes.numel()
+        return d
+
+    c1 = [dict_dev(li["l_returnflag"], tpch.RETURNFLAG_DICT), dict_dev(li["l_linestatus"], tpch.LINESTATUS_DICT)] + \
+         [flat_device(DOUBLE, li[c]) for c in ("l_quantity", "l_extendedprice", "l_discount", "l_tax")] + [flat_device(INTEGER, li["l_shipdate"])]
+    c14 = [flat_device(BIGINT, li["l_partkey"]), flat_device(DOUBLE, li["l_extendedprice"]), flat_device(DOUBLE, li["l_discount"]),
+           flat_device(INTEGER, li["l_shipdate"])]
+    cp = [flat_device(BIGINT, part["p_partkey"]), dict_dev(part["p_type"], tpch.PTYPE_DICT)]
+    return c1, c14, cp
+
+
+def slice_inputs(cols, n):
+    """First n rows of device column batches (views, no copy)."""
+    from velox_b200.kernels import DeviceColumn
+    out = []
+    for c in cols:
+        d = DeviceColumn(c.type, c.encoding, n, values=c.values if c.encoding else c.values[:n], nulls=None,
+                         indices=None if c.indices is None else c.indices[:n], dict_size=c.dict_size, dict_nulls=c.dict_nulls, aux=c.aux)
+        out.append(d)
+    return out
+
+
+def run_task(plan, inputs, config=None):
+    """One query through the operator-level C ABI: vb2_task_create / add_input(VB2_DEVICE) / run / result."""
+    from velox_b200.task import Task
+    t = Task(plan, config)
+    try:
+        for sid, cols in inputs:
+            t.add_input(sid, cols)
+        out = t.run()
+        return out, t.stats()
+    finally:
+        t.close()
+
+
+def q1_rows(rv):
+    """(returnflag, linestatus) -> (4 sums, 3 avgs, count) from a Q1 result RowVector."""
+    return {(r[0], r[1]): tuple(r[2:]) for r in rv.rows()}
+
+
+def parity(got1, got14, want1, want14):
+    """GPU result vs CPU oracle over the same rows: integer / key columns exact, FP
+    columns by maximum relative error."""
+    g, w = q1_rows(got1), q1_rows(want1)
+    exact = set(g) == set(w)
+    worst = 0.0
+    for k in w:
+        if k not in g:
+            continue
+        exact = exact and int(g[k][7]) == int(w[k][7])
+        for a, b in zip(g[k][:7], w[k][:7]):
+            worst = max(worst, abs(a - b) / max(abs(b), 1e-300))
+    a, b = got14.rows()[0][0], want14.rows()[0][0]
+    worst = max(worst, abs(a - b) / max(abs(b), 1e-300))
+    return {"exact_columns_ok": bool(exact), "fp_max_rel_err": worst, "fp_tolerance": 1e-9,
+            "ok": bool(exact and worst <= 1e-9)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,9 +293,11 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    import ctypes
     import torch
     import torch.distributed as dist
     from velox_b200 import tpch
+    from velox_b200._lib import lib
     from velox_b200.queries import Q1, Q6, Q14
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -241,6 +311,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         from velox_b200.comm import Comm
         comm = Comm()
+    L = lib()
+    L.vb2k_kernel_launches.restype = ctypes.c_int64
 
     rows_total = int(tpch.LINEITEM_ROWS_PER_SF * args.sf) + (2 if args.sf == 100 else 0)  # SF100 = 600 037 902
     nparts = int(tpch.PART_ROWS_PER_SF * args.sf)
@@ -252,20 +324,28 @@ def main():
     part = {k: v[p0:p1].contiguous() for k, v in part_all.items()} if world > 1 else part_all
     torch.cuda.synchronize()
 
-    q1, q14, q6 = Q1(comm), Q14(comm), Q6(comm)
-    ev_q1 = []
+    # plans (the reference's TpchQueryBuilder shapes) and device-resident inputs for the operator API
+    small = {k: v[:1000].cpu() for k, v in li.items()}
+    rv1s, rv14s, pts = host_tables(small, {k: v[:1000].cpu() for k, v in part_all.items()}, 1000)
+    plan1, plan14 = plans(rv1s, rv14s, pts)
+    c1, c14, cp = device_inputs(li, part)
 
-    def step(record=False):
-        if record:
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-        q1.launch(li, rows)
-        if record:
-            b.record()
-            ev_q1.append((a, b))
-        q1.merge()
-        q14.launch(li, part, rows)
-        q14.merge()
+    state = {"q1_kernel_ns": 0, "q1_kernel_rows": 0, "q1_runs": 0}
+
+    if world == 1:
+        def step(record=False):
+            out1, s1 = run_task(plan1, [(0, c1)])
+            if record:
+                state["q1_kernel_ns"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanNanos"))
+                state["q1_kernel_rows"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanRows"))
+                state["q1_runs"] += 1
+                state["stats1"] = s1
+            out14, s14 = run_task(plan14, [(0, c14), (1, cp)])
+            if record:
+                state["stats14"] = s14
+            return out1, out14
+    else:
+        step = multi_gpu_step(comm, plan1, plan14, c1, c14, cp, rows, state)
 
     def barrier():
         torch.cuda.synchronize()
@@ -278,12 +358,16 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    launches0 = L.vb2k_kernel_launches()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
     start.record()
     for _ in range(args.steps):
-        step(record=True)
+        out1, out14 = step(record=True)
     end.record()
     barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3 / args.steps
+    launches = L.vb2k_kernel_launches() - launches0
     ms = start.elapsed_time(end) / args.steps
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -291,10 +375,11 @@ def main():
     ms = float(t.item())
     value = 2 * rows_total / (ms / 1e3)
 
-    # dominant kernel: Q1's fused scan (launch + the tiny finalize that belongs to it)
-    q1_ms = sum(a.elapsed_time(b) for a, b in ev_q1) / len(ev_q1)
+    # dominant kernel: Q1's fused scan + its finalize, timed by the operator with CUDA events on the
+    # stream it launches on (b200.fusedScanNanos), inside the timed steps above
+    q1_ms = state["q1_kernel_ns"] / max(1, state["q1_runs"]) / 1e6
     peak, peak_src = peaks()
-    achieved = rows * tpch.Q1_BYTES_PER_ROW / (q1_ms / 1e3) / 1e9
+    achieved = rows * tpch.Q1_BYTES_PER_ROW / (q1_ms / 1e3) / 1e9 if q1_ms else 0.0
     traffic = None
     prof = os.path.join(ROOT, "profiles", "r01_q1_dram.json")
     if os.path.exists(prof):
@@ -302,11 +387,22 @@ def main():
             pj = json.load(f)
         traffic = pj["dram_bytes_per_row"] * rows
     roofline = {"bound": "hbm", "kernel": "fused_scan_agg_tma_kernel<Q1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": q1_ms,
-                "algorithmic_bytes": rows * tpch.Q1_BYTES_PER_ROW}
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/ (per row x rows of this launch)",
+                "peak_source": peak_src, "kernel_ms": q1_ms, "algorithmic_bytes": rows * tpch.Q1_BYTES_PER_ROW,
+                "timing": "CUDA events recorded by B200HashAggregation on its launch stream around the fused launch (stat b200.fusedScanNanos)"}
 
-    # per-query breakdown (same resident data), CUDA events
-    def timed(fn, iters=40):
+    # ---- side by side: operator level (Task API) vs kernel level (vb2k_* called directly) ---------------
+    def timed_wall(fn, iters=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3 / iters
+
+    def timed_events(fn, iters=40):
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
@@ -319,46 +415,44 @@ def main():
         return a.elapsed_time(b) / iters
 
     breakdown = {}
-    for name, fn, bpr in (("q1", lambda: (q1.launch(li, rows), q1.merge()), tpch.Q1_BYTES_PER_ROW),
-                          ("q14", lambda: (q14.launch(li, part, rows), q14.merge()), tpch.Q14_BYTES_PER_ROW),
-                          ("q6", lambda: (q6.launch(li, rows), q6.merge()), tpch.Q6_BYTES_PER_ROW)):
-        m = timed(fn)
+    q1k, q14k, q6k = Q1(comm), Q14(comm), Q6(comm)
+    kernel_level = {"q1": lambda: (q1k.launch(li, rows), q1k.merge()), "q14": lambda: (q14k.launch(li, part, rows), q14k.merge()),
+                    "q6": lambda: (q6k.launch(li, rows), q6k.merge())}
+    bprs = {"q1": tpch.Q1_BYTES_PER_ROW, "q14": tpch.Q14_BYTES_PER_ROW, "q6": tpch.Q6_BYTES_PER_ROW}
+    for name, fn in kernel_level.items():
+        m = timed_events(fn)
         mm = torch.tensor([m], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(mm, op=dist.ReduceOp.MAX)
         m = float(mm.item())
-        breakdown[name] = {"ms": m, "rows_per_s": rows_total / (m / 1e3), "algorithmic_GBps_per_gpu": rows * bpr / (m / 1e3) / 1e9,
-                           "frac_of_hbm_peak": rows * bpr / (m / 1e3) / 1e9 / peak}
+        breakdown[name] = {"kernel_level_ms": m, "rows_per_s_kernel_level": rows_total / (m / 1e3),
+                           "algorithmic_GBps_per_gpu": rows * bprs[name] / (m / 1e3) / 1e9, "frac_of_hbm_peak": rows * bprs[name] / (m / 1e3) / 1e9 / peak}
+    if world == 1:
+        breakdown["q1"]["operator_level_ms"] = timed_wall(lambda: run_task(plan1, [(0, c1)]))
+        breakdown["q14"]["operator_level_ms"] = timed_wall(lambda: run_task(plan14, [(0, c14), (1, cp)]))
     sampler.stop_flag.set()
     sampler.join()
-    results = {"q1": {f"{k[0]}{k[1]}": v[7] for k, v in q1.result().items()}, "q14_promo_revenue": q14.result(), "q6_revenue": q6.result()}
-    # Conservation check of the exchange: every lineitem row that passes the date filter has a part
-    # row, so rows joined after the shuffle must equal rows the scans emitted (summed over ranks).
-    joined = int(q14.probe.counts.item())
-    if world > 1:
-        scanned = q14.scan.count.clone()
-        dist.all_reduce(scanned)
-        scanned = int(scanned.item())
-        results["q14_rows"] = {"scanned": scanned, "joined": joined, "planned_runs": q14.planned_runs}
-        assert scanned == joined, f"Q14 exchange lost or duplicated rows: scanned {scanned}, joined {joined}"
-    else:
-        results["q14_rows"] = {"joined": joined}
 
-    # launches of our kernels per step (Q1: fused + finalize; Q14 on one GPU: min/max init + min/max,
-    # normalize, join build, LIKE on the alphabet (expression JIT), slot flags, fused probe + finalize = 8; Q14 planned
-    # exchange on N>1: scan-compact, 3 segment-partition kernels per exchanged side, key-range
-    # check, normalize, join build, LIKE, slot flags, fused probe + finalize). NCCL and memsets not counted.
-    launches_per_step = 2 + (8 if world == 1 else 1 + 2 * 3 + 1 + 4 + 2)
+    results = {"q1": {f"{k[0]}{k[1]}": int(v[7]) for k, v in q1_rows(out1).items()}, "q14_promo_revenue": out14.rows()[0][0] if out14.size else None,
+               "q6_revenue": q6k.result()}
+    # kernel-level and operator-level answers must agree
+    k1 = q1k.result()
+    assert {f"{k[0]}{k[1]}": int(v[7]) for k, v in k1.items()} == results["q1"], "operator-level and kernel-level Q1 counts differ"
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ms_per_step": ms, "wall_ms_per_step": wall_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"TPC-H Q1 + Q14 over SF{args.sf:g} in-HBM lineitem ({rows_total} rows) and part ({nparts} rows)",
+                   "path": "operator-level C ABI: vb2_task_create / add_input(VB2_DEVICE) / run / result per query (Task -> Driver -> B200 operators); "
+                           "the timed step contains plan parsing, operator setup, every kernel, and the result rows on the host",
                    "rows_per_gpu": rows, "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}; Q14 hash-partitioned, NCCL all-to-all",
                    "l2": "inputs (26-31 GB per pass) far exceed the 126 MB L2; no flush needed", "value_counts": "2 x lineitem rows per step"},
-        "roofline": roofline, "queries": breakdown, "results": results, "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline, "queries": breakdown, "results": results, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    if "stats1" in state:
+        line["operator_wall_ms"] = {q: {k: round(v / 1e6, 3) for k, v in state[s].items() if k.endswith("WallNanos") and v > 2e4}
+                                    for q, s in (("q1", "stats1"), ("q14", "stats14")) if s in state}
 
     # ---- e2e: operator-level C ABI with host buffers ----------------------------------------------------
     if not args.skip_e2e:
@@ -366,7 +460,7 @@ def main():
             line["e2e"] = e2e(args, li, part_all, rows, nparts, world, rank, rows_total)
         except Exception as ex:  # keep the device-timed line even if the end-to-end leg cannot run here
             line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": f"{type(ex).__name__}: {ex}"[:300]}
-    # ---- CPU baseline (rank 0, N = 1) --------------------------------------------------------------------
+    # ---- CPU baseline + parity (rank 0, N = 1) -----------------------------------------------------------
     if world == 1 and not args.skip_cpu:
         threads = os.cpu_count() or 1
         sample = int(min(args.cpu_sample_rows, rows))
@@ -379,11 +473,20 @@ def main():
                                 "sample": f"first {sample} of {rows_total} lineitem rows x (Q1 + Q14) against the whole part table, 10K-row batches, "
                                           f"{threads} driver threads: {sec:.2f} s of which {sec_build:.2f} s is the part-table build; scaled to the full "
                                           f"workload as (step - build) x {rows_total / sample:.2f} + build"}
+        # the same rows through the B200 operators, compared with what the CPU arm just computed
+        g1, _ = run_task(plan1, [(0, slice_inputs(c1, sample))])
+        g14, _ = run_task(plan14, [(0, slice_inputs(c14, sample)), (1, cp)])
+        line["parity"] = dict(parity(g1, g14, r1c, r14c), rows=sample, oracle="CPU oracle (restatement of velox/exec; operator results of the reference are "
+                              "pinned by DuckDB at its test time, which is absent here)")
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def multi_gpu_step(comm, plan1, plan14, c1, c14, cp, rows, state):
+    raise NotImplementedError("multi-GPU operator path: see velox_b200/csrc/host/exchange_ops.cpp")
 
 
 def e2e(args, li, part_all, rows, nparts, world, rank, rows_total):

@@ -57,6 +57,8 @@ typedef struct vb2_column {
 
 const char* vb2_last_error(void);
 int vb2k_device_sm_count(void);
+/* Kernels this library has launched in this process so far (every launch site counts itself). */
+int64_t vb2k_kernel_launches(void);
 
 /* ------------------------------------------------------------------------------------------
  * Key hashing and partitioning.
@@ -300,6 +302,36 @@ int vb2k_group_keys(const vb2_group_table* t, const int32_t* slots, int64_t n, i
 int vb2k_group_gather(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t word, void* out, void* stream);
 int vb2k_group_valid(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t count_word, uint64_t* valid, void* stream);
 int vb2k_group_avg(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t sum_word, int32_t count_word, double* out, void* stream);
+/* Every output column of an aggregation in ONE launch (Aggregate::extractValues / extractAccumulators,
+ * velox/exec/Aggregate.h:281-302, and the key columns RowContainer::extractColumn returns,
+ * velox/exec/GroupingSet.cpp:843 extractGroups). Row i of the output is table row slots[i].
+ *   slots != NULL  the n listed slots (any table size);
+ *   slots == NULL  small tables (capacity <= VB2_EXTRACT_SMALL_CAPACITY): the kernel itself lists the
+ *                  occupied rows in ascending slot order into scratch_slots (int32[capacity]) and
+ *                  writes their count to header[0] — no host round trip before the extraction.
+ * header (device int64[2], optional): [0] = rows written, [1] = *error_flag as seen by the kernel.
+ * Column kinds: KEY decodes one key column from the normalized key (value = id - 1 + min,
+ * id = (key / mult) % range, id 0 = NULL when null_reserved; BOOLEAN values bit-packed), WORD copies an
+ * 8-byte accumulator word, WORD_I32 narrows it to int32, AVG writes sum / count
+ * (functions/lib/aggregates/AverageAggregateBase.h:86-107). count_word >= 0: validity bit = count
+ * word > 0. valid bitmaps (optional) are written as whole 64-bit words. */
+#define VB2_EXTRACT_SMALL_CAPACITY 16384
+#define VB2_EXTRACT_MAX_COLS 40
+enum vb2_extract_kind { VB2_EXTRACT_KEY = 1, VB2_EXTRACT_WORD = 2, VB2_EXTRACT_WORD_I32 = 3, VB2_EXTRACT_AVG = 4 };
+typedef struct vb2_extract_col {
+  int32_t kind;
+  int32_t type;        /* KEY: VB2_INTEGER / VB2_BIGINT / VB2_BOOLEAN of the written values */
+  int32_t word;        /* WORD / WORD_I32 / AVG: accumulator word */
+  int32_t count_word;  /* validity source (and AVG's divisor), -1 = always valid */
+  int64_t min;         /* KEY decode */
+  uint64_t mult, range;
+  int32_t null_reserved;
+  int32_t pad;
+  void* values;
+  uint64_t* valid;
+} vb2_extract_col;
+int vb2k_group_extract(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t* scratch_slots, const vb2_extract_col* cols,
+                       int32_t ncols, int64_t* header, const int32_t* error_flag, void* stream);
 /* Adds the per-group partials of a fused scan (sums[g * nproj + p] doubles, counts[g]) into rows
  * 0 .. ngroups of an array-mode table: target i adds sums[.., target_projs[i]] to word
  * target_words[i], or counts[g] when target_projs[i] < 0. Groups with counts[g] == 0 are untouched. */
@@ -337,6 +369,11 @@ typedef struct vb2_join_table {
 
 int vb2k_join_build(const vb2_join_table* t, const uint64_t* build_keys, const uint64_t* valid, int64_t n,
                     int32_t* error_flag, void* stream);
+/* Array-mode build straight from ONE integer-typed key column (flat / dictionary / constant, NULLs
+ * skipped): slot = v - lo + 1, i.e. vb2k_normalize_keys with min = lo followed by vb2k_join_build,
+ * in one pass over the keys. flags: device int32[2] = {error (101: key outside the table), duplicates seen}. */
+int vb2k_join_build_array_direct(int32_t* head, int32_t* next, int64_t capacity, const vb2_column* key, int64_t lo, int64_t n,
+                                 int32_t* flags, void* stream);
 /* Counts matches per probe row (hit_counts int32[n]), then after an exclusive scan the caller
  * asks for the pairs. total_out: device int64. */
 int vb2k_join_probe_count(const vb2_join_table* t, const uint64_t* probe_keys, const uint64_t* valid, int64_t n,

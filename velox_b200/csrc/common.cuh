@@ -25,6 +25,14 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 int fail_cuda(cudaError_t e, const char* what);  // records message, returns VB2_ERR_CUDA
 int fail_msg(int code, const char* msg);
 int device_sm_count();
+// Every kernel launch of this library goes through counted(): vb2k_kernel_launches() is the claim
+// bench.py reports as gpu_launches.
+void note_launch();
+template <class T>
+inline T counted(T grid) {
+  note_launch();
+  return grid;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Streaming loads. Input columns are read exactly once: bypass L1 allocation, 128-bit wide.

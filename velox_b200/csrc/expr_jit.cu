@@ -399,6 +399,7 @@ int launch(const vb2_program* p, const vb2_column* cols, int ncols, bool filter,
   a.sel_bits = sel_bits;
   a.error_flag = error_flag;
   void* params[] = {&a};
+  note_launch();
   const cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(k->fn), dim3(grid_for(n)), dim3(kThreads), params, 0, st);
   if (e != cudaSuccess) return fail_msg(VB2_ERR_CUDA, cudaGetErrorString(e));
   return VB2_OK;

@@ -516,10 +516,10 @@ int vb2k_eval_filter(const vb2_program* prog, const vb2_column* cols, int32_t nc
   size_t smem = 0;
   if (plain_program(prog, prog->n_filter_instrs, cols)) {
     if ((rc = vm_smem(vm_filter_kernel<true>, prog, &smem))) return rc;
-    vm_filter_kernel<true><<<vm_grid(rows), kVmThreads, smem, st>>>(a);
+    vm_filter_kernel<true><<<vb2::counted(vm_grid(rows)), kVmThreads, smem, st>>>(a);
   } else {
     if ((rc = vm_smem(vm_filter_kernel<false>, prog, &smem))) return rc;
-    vm_filter_kernel<false><<<vm_grid(rows), kVmThreads, smem, st>>>(a);
+    vm_filter_kernel<false><<<vb2::counted(vm_grid(rows)), kVmThreads, smem, st>>>(a);
   }
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
@@ -544,9 +544,9 @@ int vb2k_bits_to_indices(const uint64_t* sel_bits, int64_t rows, int32_t* indice
   int64_t* offsets = reinterpret_cast<int64_t*>(workspace);
   int32_t* counts = reinterpret_cast<int32_t*>(offsets + nblocks);
   const uint32_t* bits = reinterpret_cast<const uint32_t*>(sel_bits);
-  sel_count_kernel<<<static_cast<unsigned>(nblocks), kSelThreads, 0, st>>>(bits, nwords, counts);
-  sel_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks, offsets, count_out);
-  sel_write_kernel<<<static_cast<unsigned>(nblocks), kSelThreads, 0, st>>>(bits, nwords, offsets, indices);
+  sel_count_kernel<<<vb2::counted(static_cast<unsigned>(nblocks)), kSelThreads, 0, st>>>(bits, nwords, counts);
+  sel_scan_kernel<<<vb2::counted(1), 1024, 0, st>>>(counts, nblocks, offsets, count_out);
+  sel_write_kernel<<<vb2::counted(static_cast<unsigned>(nblocks)), kSelThreads, 0, st>>>(bits, nwords, offsets, indices);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -569,10 +569,10 @@ int vb2k_eval_project(const vb2_program* prog, const vb2_column* cols, int32_t n
   size_t smem = 0;
   if (plain_program(prog, prog->n_instrs, cols)) {
     if ((rc = vm_smem(vm_project_kernel<true>, prog, &smem))) return rc;
-    vm_project_kernel<true><<<vm_grid(n), kVmThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    vm_project_kernel<true><<<vb2::counted(vm_grid(n)), kVmThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
   } else {
     if ((rc = vm_smem(vm_project_kernel<false>, prog, &smem))) return rc;
-    vm_project_kernel<false><<<vm_grid(n), kVmThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    vm_project_kernel<false><<<vb2::counted(vm_grid(n)), kVmThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
   }
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;

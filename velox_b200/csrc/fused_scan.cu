@@ -58,7 +58,7 @@ constexpr size_t kSmemLimit = 220 * 1024;  // of the 227 KB a block may use
 
 static int run_finalize(const KernelArgs& a, void* ws, int64_t grid, int kvals, int np, int maxg, double* sums, int64_t* counts,
                         cudaStream_t st) {
-  fused_finalize_kernel<<<kvals, 32, 0, st>>>(reinterpret_cast<const double*>(ws), static_cast<int>(grid), kvals, np, maxg, a.ngroups, sums, counts);
+  fused_finalize_kernel<<<vb2::counted(kvals), 32, 0, st>>>(reinterpret_cast<const double*>(ws), static_cast<int>(grid), kvals, np, maxg, a.ngroups, sums, counts);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -78,7 +78,7 @@ static int launch_direct(const KernelArgs& a, double* sums, int64_t* counts, voi
   if (want < grid) grid = want < 1 ? 1 : want;
   constexpr int kVals = kMaxG * (P::kNP + 1);
   if (ws_bytes < static_cast<size_t>(grid) * kVals * sizeof(double)) return fail_msg(VB2_ERR_INVALID, "fused workspace too small");
-  kernel<<<static_cast<unsigned>(grid), kThreads, 0, st>>>(a, reinterpret_cast<double*>(ws));
+  kernel<<<vb2::counted(static_cast<unsigned>(grid)), kThreads, 0, st>>>(a, reinterpret_cast<double*>(ws));
   VB2_CUDA_OK(cudaGetLastError());
   return run_finalize(a, ws, grid, kVals, P::kNP, kMaxG, sums, counts, st);
 }
@@ -110,7 +110,7 @@ static int launch_tma(const KernelArgs& a, double* sums, int64_t* counts, void* 
   const int maxg = kSmemAcc ? a.ngroups : kMaxG;
   const int kvals = maxg * (P::kNP + 1);
   if (ws_bytes < static_cast<size_t>(grid) * kvals * sizeof(double)) return fail_msg(VB2_ERR_INVALID, "fused workspace too small");
-  kernel<<<static_cast<unsigned>(grid), kTmaThreads, smem, st>>>(a, stages, reinterpret_cast<double*>(ws));
+  kernel<<<vb2::counted(static_cast<unsigned>(grid)), kTmaThreads, smem, st>>>(a, stages, reinterpret_cast<double*>(ws));
   VB2_CUDA_OK(cudaGetLastError());
   return run_finalize(a, ws, grid, kvals, P::kNP, maxg, sums, counts, st);
 }
@@ -169,7 +169,7 @@ static int launch_compact(const KernelArgs& a, const CompactArgs& o, cudaStream_
   const int64_t ntiles = a.rows / kTileRows;
   int64_t grid = static_cast<int64_t>(device_sm_count()) * blocks_per_sm;
   if (ntiles < grid) grid = ntiles < 1 ? 1 : ntiles;
-  kernel<<<static_cast<unsigned>(grid), kTmaThreads, smem, st>>>(a, o, stages);
+  kernel<<<vb2::counted(static_cast<unsigned>(grid)), kTmaThreads, smem, st>>>(a, o, stages);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -267,7 +267,7 @@ size_t vb2k_fused_workspace_bytes(int32_t id, int32_t ngroups) {
 int vb2k_join_slot_flags(const int32_t* head, const int32_t* codes, const uint8_t* flag, int64_t range, uint8_t* out, void* stream) {
   if (range <= 0) return VB2_OK;
   int64_t b = (range + 255) / 256, cap = static_cast<int64_t>(device_sm_count()) * 8;
-  join_slot_flags_kernel<<<static_cast<unsigned>(b > cap ? cap : b), 256, 0, static_cast<cudaStream_t>(stream)>>>(head, codes, flag, range, out);
+  join_slot_flags_kernel<<<vb2::counted(static_cast<unsigned>(b > cap ? cap : b)), 256, 0, static_cast<cudaStream_t>(stream)>>>(head, codes, flag, range, out);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }

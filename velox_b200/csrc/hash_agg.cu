@@ -112,6 +112,21 @@ __global__ void minmax_init_kernel(int64_t* out3) {
   out3[2] = 0;
 }
 
+// Array-mode join build straight from the key column (normalize + insert in one pass): slot =
+// v - lo + 1, the value id vb2k_normalize_keys would produce for a single key with min = lo.
+__global__ void join_build_array_direct_kernel(int32_t* __restrict__ head, int32_t* __restrict__ next, int64_t capacity,
+                                               const __grid_constant__ vb2_column c, int64_t lo, int64_t n, int32_t* __restrict__ flags) {
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; r < n; r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t base;
+    if (decode_row2(c, r, base)) continue;  // NULL keys are not inserted (exec/HashBuild.cpp:475-479)
+    const int64_t slot = key_value(c, base) - lo + 1;
+    if (slot < 1 || slot >= capacity) { atomicCAS(flags, 0, 101); continue; }
+    const int32_t prev = atomicExch(head + slot, static_cast<int32_t>(r + 1));
+    next[r] = prev;
+    if (prev != 0) atomicCAS(flags + 1, 0, 1);  // duplicate build keys present (informational)
+  }
+}
+
 __device__ __forceinline__ double input_as_f64(const vb2_agg_update& u, int64_t i) {
   switch (u.input_type) {
     case VB2_DOUBLE: return reinterpret_cast<const double*>(u.input)[i];
@@ -175,6 +190,8 @@ __device__ __forceinline__ int64_t find_or_insert(const TableView& t, uint64_t k
 }
 
 constexpr int kMaxAggs = 16;
+constexpr int64_t kSerialRows = 256;     // batches this small are accumulated in input order by one warp
+constexpr int64_t kAtomicRows = 1 << 16;  // up to here contention on a tiny table costs less than one pass per aggregate
 struct AggArgs {
   vb2_agg_update a[kMaxAggs];
   int n;
@@ -234,6 +251,55 @@ __global__ void group_update_kernel(const __grid_constant__ vb2_group_table tab,
   }
   fresh = warp_sum(fresh);
   if ((threadIdx.x & 31) == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
+}
+
+// Very small batches (merging a handful of partial-aggregate rows, e.g. one row per group and GPU
+// in front of a final aggregation): one warp walks the rows IN INPUT ORDER, lane k owning aggregate
+// k, with plain read-modify-writes — the reference's sequential accumulation
+// (functions/lib/aggregates/SimpleNumericAggregate.h:94-150), deterministic and free of atomics.
+__device__ __forceinline__ void apply_update_plain(const vb2_agg_update& u, int64_t row_index, uint64_t* row, int32_t* error_flag) {
+  const int64_t i = input_pos(u, row_index);
+  if (i < 0) return;
+  uint64_t* acc = row + u.acc_word;
+  switch (u.kind) {
+    case VB2_AGG_SUM_F64: *reinterpret_cast<double*>(acc) = __dadd_rn(*reinterpret_cast<double*>(acc), input_as_f64(u, i)); break;
+    case VB2_AGG_SUM_I64: case VB2_AGG_COUNT_MERGE: {
+      int64_t r;
+      if (add_overflow_i64(static_cast<int64_t>(*acc), input_as_i64(u, i), &r)) atomicCAS(error_flag, 0, 1);
+      *acc = static_cast<uint64_t>(r);
+      break;
+    }
+    case VB2_AGG_COUNT: *acc += 1; break;
+    case VB2_AGG_MIN_F64: { const double v = input_as_f64(u, i); if (lt_f64(v, *reinterpret_cast<double*>(acc))) *reinterpret_cast<double*>(acc) = v; break; }
+    case VB2_AGG_MAX_F64: { const double v = input_as_f64(u, i); if (gt_f64(v, *reinterpret_cast<double*>(acc))) *reinterpret_cast<double*>(acc) = v; break; }
+    case VB2_AGG_MIN_I64: { const int64_t v = input_as_i64(u, i); if (v < static_cast<int64_t>(*acc)) *acc = static_cast<uint64_t>(v); break; }
+    case VB2_AGG_MAX_I64: { const int64_t v = input_as_i64(u, i); if (v > static_cast<int64_t>(*acc)) *acc = static_cast<uint64_t>(v); break; }
+    default: break;
+  }
+  if (u.nonnull_word >= 0 && u.kind != VB2_AGG_COUNT) row[u.nonnull_word] += 1;
+}
+__global__ void __launch_bounds__(32)
+group_update_serial_kernel(const __grid_constant__ vb2_group_table tab, const uint64_t* __restrict__ row_keys, const uint64_t* __restrict__ row_valid,
+                           int64_t n, const __grid_constant__ AggArgs args, int64_t* __restrict__ num_groups, int32_t* __restrict__ error_flag) {
+  const TableView t = view_of(tab);
+  const int lane = threadIdx.x;
+  int64_t fresh = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (row_valid && !bit_at(row_valid, i)) continue;
+    int64_t slot = 0;
+    if (row_keys) {
+      int64_t f = 0;
+      if (lane == 0) slot = find_or_insert(t, row_keys[i], f);
+      fresh += f;
+      slot = __shfl_sync(0xffffffffu, slot, 0);
+    }
+    if (slot < 0) { if (lane == 0) atomicCAS(error_flag, 0, 100); continue; }
+    uint64_t* row = t.rows + slot * t.w;
+    if (!t.hash && lane == 0 && *row == 0) *row = 1;
+    for (int k = lane; k < args.n; k += 32) apply_update_plain(args.a[k], i, row, error_flag);
+    __syncwarp();
+  }
+  if (lane == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
 }
 
 // Tiny array-mode tables (<= 8 rows): same-address atomics would serialise in L2, so every thread
@@ -476,6 +542,93 @@ __global__ void group_avg_kernel(const __grid_constant__ vb2_group_table t, cons
   }
 }
 
+// Every output column of an aggregation in one launch. Small tables are compacted by the kernel
+// itself (single block: ballot + running prefix over the slots in ascending order), so the host
+// learns the row count from the same copy that brings the result over.
+struct ExtractArgs {
+  vb2_extract_col c[VB2_EXTRACT_MAX_COLS];
+  int n;
+};
+__global__ void __launch_bounds__(1024)
+group_extract_kernel(const __grid_constant__ vb2_group_table t, const int32_t* __restrict__ slots, int64_t n, int32_t* __restrict__ scratch,
+                     const __grid_constant__ ExtractArgs a, int64_t* __restrict__ header, const int32_t* __restrict__ error_flag) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (slots == nullptr) {
+    __shared__ int warp_tot[32];
+    int64_t base = 0;
+    const int nwarps = blockDim.x >> 5;
+    for (int64_t r0 = 0; r0 < t.capacity; r0 += blockDim.x) {
+      const int64_t r = r0 + threadIdx.x;
+      const bool occ = r < t.capacity && row_occupied(t, r);
+      const unsigned m = __ballot_sync(0xffffffffu, occ);
+      if (lane == 0) warp_tot[warp] = __popc(m);
+      __syncthreads();
+      int before = 0, total = 0;
+      for (int w = 0; w < nwarps; ++w) {
+        const int c = warp_tot[w];
+        if (w < warp) before += c;
+        total += c;
+      }
+      if (occ) scratch[base + before + __popc(m & ((1u << lane) - 1u))] = static_cast<int32_t>(r);
+      base += total;
+      __syncthreads();
+    }
+    n = base;
+    slots = scratch;
+    if (threadIdx.x == 0 && header) header[0] = n;
+    __syncthreads();
+  } else if (blockIdx.x == 0 && threadIdx.x == 0 && header) {
+    header[0] = n;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && header) header[1] = error_flag ? *error_flag : 0;
+  const int64_t nwords = (n + 31) >> 5;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps_grid = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t w = warp_global; w < nwords; w += nwarps_grid) {
+    const int64_t i = (w << 5) + lane;
+    const bool live = i < n;
+    const int64_t slot = live ? slots[i] : 0;
+    const uint64_t* row = t.rows + slot * t.row_words;
+    const uint64_t key = t.hash_mode ? row[0] : static_cast<uint64_t>(slot);
+    const bool last_even_word = w == nwords - 1 && (w & 1) == 0;  // the upper half of the last 64-bit word stays clear
+    for (int k = 0; k < a.n; ++k) {
+      const vb2_extract_col& c = a.c[k];
+      bool valid = live;
+      if (c.kind == VB2_EXTRACT_KEY) {
+        const uint64_t id = (key / c.mult) % c.range;
+        valid = live && !(c.null_reserved && id == 0);
+        const int64_t v = valid ? static_cast<int64_t>(id) - 1 + c.min : 0;
+        if (c.type == VB2_BOOLEAN) {
+          const unsigned bitsv = __ballot_sync(0xffffffffu, live && v != 0);
+          if (lane == 0) {
+            reinterpret_cast<uint32_t*>(c.values)[w] = bitsv;
+            if (last_even_word) reinterpret_cast<uint32_t*>(c.values)[w + 1] = 0;
+          }
+        } else if (live) {
+          if (c.type == VB2_INTEGER) reinterpret_cast<int32_t*>(c.values)[i] = static_cast<int32_t>(v);
+          else reinterpret_cast<int64_t*>(c.values)[i] = v;
+        }
+      } else {
+        const int64_t cnt = c.count_word >= 0 ? static_cast<int64_t>(row[c.count_word]) : 1;
+        valid = live && cnt > 0;
+        if (live) {
+          const uint64_t word = row[c.word];
+          if (c.kind == VB2_EXTRACT_WORD) reinterpret_cast<uint64_t*>(c.values)[i] = word;
+          else if (c.kind == VB2_EXTRACT_WORD_I32) reinterpret_cast<int32_t*>(c.values)[i] = static_cast<int32_t>(static_cast<int64_t>(word));
+          else reinterpret_cast<double*>(c.values)[i] = cnt > 0 ? __ddiv_rn(__longlong_as_double(static_cast<long long>(word)), static_cast<double>(cnt)) : 0.0;
+        }
+      }
+      if (c.valid) {
+        const unsigned bitsv = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) {
+          reinterpret_cast<uint32_t*>(c.valid)[w] = bitsv;
+          if (last_even_word) reinterpret_cast<uint32_t*>(c.valid)[w + 1] = 0;
+        }
+      }
+    }
+  }
+}
+
 // Partial results of a fused scan (sums[g * nproj + p], counts[g]) added into the table rows of
 // an array-mode table (group g = row g): one thread per (group, target word).
 struct MergeArgs {
@@ -528,15 +681,25 @@ int vb2k_normalize_keys(const vb2_column* cols, int32_t ncols, const int64_t* mi
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (valid_out) VB2_CUDA_OK(cudaMemsetAsync(valid_out + ((n + 63) >> 6) - 1, 0, 8, st));
-  normalize_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, sel, n, keys_out, reinterpret_cast<uint32_t*>(valid_out));
+  normalize_keys_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(a, sel, n, keys_out, reinterpret_cast<uint32_t*>(valid_out));
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_join_build_array_direct(int32_t* head, int32_t* next, int64_t capacity, const vb2_column* key, int64_t lo, int64_t n,
+                                 int32_t* flags, void* stream) {
+  if (!head || !next || !key || capacity <= 0) return fail_msg(VB2_ERR_INVALID, "join_build_array_direct: bad arguments");
+  if (key->type != VB2_BIGINT && key->type != VB2_INTEGER && key->type != VB2_BOOLEAN) return fail_msg(VB2_ERR_INVALID, "join_build_array_direct: integer-typed key expected");
+  if (n <= 0) return VB2_OK;
+  join_build_array_direct_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(head, next, capacity, *key, lo, n, flags);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 
 int vb2k_column_minmax(const vb2_column* col, int64_t rows, int64_t* out3, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  minmax_init_kernel<<<1, 1, 0, st>>>(out3);
-  if (rows > 0) minmax_kernel<<<grid_for(rows, 256), 256, 0, st>>>(*col, rows, out3);
+  minmax_init_kernel<<<vb2::counted(1), 1, 0, st>>>(out3);
+  if (rows > 0) minmax_kernel<<<vb2::counted(grid_for(rows, 256)), 256, 0, st>>>(*col, rows, out3);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -553,7 +716,7 @@ int vb2k_group_table_init(const vb2_group_table* t, const uint64_t* row_init, vo
   vb2_group_row_init init;
   for (int i = 0; i < t->row_words; ++i) init.words[i] = row_init[i];
   const int64_t total = t->capacity * t->row_words;
-  table_init_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(t->rows, total, t->row_words, init);
+  table_init_kernel<<<vb2::counted(grid_for(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(t->rows, total, t->row_words, init);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -569,25 +732,35 @@ int vb2k_group_update(const vb2_group_table* t, const uint64_t* row_keys, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   AggArgs rest;
   rest.n = 0;
+  // aggregates of one call must not share an accumulator word for the serial kernel's lane ownership
+  bool distinct_words = true;
+  for (int i = 0; i < naggs; ++i)
+    for (int j = 0; j < i; ++j)
+      if (aggs[i].acc_word == aggs[j].acc_word || (aggs[i].nonnull_word >= 0 && (aggs[i].nonnull_word == aggs[j].nonnull_word || aggs[i].nonnull_word == aggs[j].acc_word)) ||
+          (aggs[j].nonnull_word >= 0 && aggs[j].nonnull_word == aggs[i].acc_word))
+        distinct_words = false;
   const bool tiny_table = !t->hash_mode && t->capacity <= kTinyG;
-  if (tiny_table) {
+  if (n <= kSerialRows && distinct_words) {
+    for (int i = 0; i < naggs; ++i) rest.a[rest.n++] = aggs[i];
+    group_update_serial_kernel<<<vb2::counted(1), 32, 0, st>>>(*t, row_keys, row_valid, n, rest, num_groups, error_flag);
+  } else if (tiny_table && n > kAtomicRows) {
     const unsigned grid = grid_for(n, 256, 4);
     vb2_agg_update none{};
-    group_update_tiny_kernel<0><<<grid, 256, 0, st>>>(*t, row_keys, row_valid, n, none, error_flag);
+    group_update_tiny_kernel<0><<<vb2::counted(grid), 256, 0, st>>>(*t, row_keys, row_valid, n, none, error_flag);
     for (int i = 0; i < naggs; ++i) {
       const vb2_agg_update& u = aggs[i];
       switch (u.kind) {
-        case VB2_AGG_SUM_F64: group_update_tiny_kernel<VB2_AGG_SUM_F64><<<grid, 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
-        case VB2_AGG_SUM_I64: group_update_tiny_kernel<VB2_AGG_SUM_I64><<<grid, 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
-        case VB2_AGG_COUNT_MERGE: group_update_tiny_kernel<VB2_AGG_COUNT_MERGE><<<grid, 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
-        case VB2_AGG_COUNT: group_update_tiny_kernel<VB2_AGG_COUNT><<<grid, 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
+        case VB2_AGG_SUM_F64: group_update_tiny_kernel<VB2_AGG_SUM_F64><<<vb2::counted(grid), 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
+        case VB2_AGG_SUM_I64: group_update_tiny_kernel<VB2_AGG_SUM_I64><<<vb2::counted(grid), 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
+        case VB2_AGG_COUNT_MERGE: group_update_tiny_kernel<VB2_AGG_COUNT_MERGE><<<vb2::counted(grid), 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
+        case VB2_AGG_COUNT: group_update_tiny_kernel<VB2_AGG_COUNT><<<vb2::counted(grid), 256, 0, st>>>(*t, row_keys, row_valid, n, u, error_flag); break;
         default: rest.a[rest.n++] = u; break;  // min / max: idempotent atomics, no same-address accumulation chain
       }
     }
-    if (rest.n) group_update_kernel<<<grid_for(n, 256), 256, 0, st>>>(*t, row_keys, row_valid, n, rest, nullptr, error_flag);
+    if (rest.n) group_update_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(*t, row_keys, row_valid, n, rest, nullptr, error_flag);
   } else {
     for (int i = 0; i < naggs; ++i) rest.a[rest.n++] = aggs[i];
-    group_update_kernel<<<grid_for(n, 256), 256, 0, st>>>(*t, row_keys, row_valid, n, rest, num_groups, error_flag);
+    group_update_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(*t, row_keys, row_valid, n, rest, num_groups, error_flag);
   }
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
@@ -605,7 +778,7 @@ int vb2k_group_occupied(const vb2_group_table* t, int32_t* slot_list, int64_t* c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint64_t* bits = reinterpret_cast<uint64_t*>(workspace);
   VB2_CUDA_OK(cudaMemsetAsync(bits, 0, bitmap_bytes, st));
-  occupied_bits_kernel<<<grid_for(t->capacity, 256), 256, 0, st>>>(*t, reinterpret_cast<uint32_t*>(bits));
+  occupied_bits_kernel<<<vb2::counted(grid_for(t->capacity, 256)), 256, 0, st>>>(*t, reinterpret_cast<uint32_t*>(bits));
   VB2_CUDA_OK(cudaGetLastError());
   return vb2k_bits_to_indices(bits, t->capacity, slot_list, count, reinterpret_cast<char*>(workspace) + bitmap_bytes,
                               workspace_bytes - bitmap_bytes, stream);
@@ -614,7 +787,7 @@ int vb2k_group_occupied(const vb2_group_table* t, int32_t* slot_list, int64_t* c
 int vb2k_group_set_word(const vb2_group_table* t, int32_t word, uint64_t value, void* stream) {
   if (int rc = check_table(t, "group_set_word: bad table")) return rc;
   if (word < 1 || word >= t->row_words) return fail_msg(VB2_ERR_INVALID, "group_set_word: word outside the row");
-  set_word_kernel<<<grid_for(t->capacity, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, word, value);
+  set_word_kernel<<<vb2::counted(grid_for(t->capacity, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, word, value);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -623,7 +796,7 @@ int vb2k_group_keys(const vb2_group_table* t, const int32_t* slots, int64_t n, i
                     int32_t null_reserved, int32_t type, void* values, uint64_t* valid, void* stream) {
   if (int rc = check_table(t, "group_keys: bad table")) return rc;
   if (n <= 0) return VB2_OK;
-  group_keys_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, min, mult, range, null_reserved, type, values,
+  group_keys_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, min, mult, range, null_reserved, type, values,
                                                                                       reinterpret_cast<uint32_t*>(valid));
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
@@ -642,7 +815,7 @@ int vb2k_group_rekey(const vb2_group_table* t, const int32_t* slots, int64_t n, 
     a.old_mult[i] = old_mults[i]; a.old_range[i] = old_ranges[i]; a.new_mult[i] = new_mults[i];
     a.old_null_reserved[i] = old_null_reserved ? old_null_reserved[i] : 1;
   }
-  rekey_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, a, keys_out);
+  rekey_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, a, keys_out);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -653,7 +826,7 @@ int vb2k_group_move(const vb2_group_table* from, const int32_t* slots, const uin
   if (int rc = check_table(to, "group_move: bad target table")) return rc;
   if (from->row_words != to->row_words) return fail_msg(VB2_ERR_INVALID, "group_move: row layouts differ");
   if (n <= 0) return VB2_OK;
-  group_move_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*from, slots, new_keys, n, *to, num_groups, error_flag);
+  group_move_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*from, slots, new_keys, n, *to, num_groups, error_flag);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -662,7 +835,7 @@ int vb2k_group_gather(const vb2_group_table* t, const int32_t* slots, int64_t n,
   if (int rc = check_table(t, "group_gather: bad table")) return rc;
   if (word < 0 || word >= t->row_words) return fail_msg(VB2_ERR_INVALID, "group_gather: word outside the row");
   if (n <= 0) return VB2_OK;
-  group_gather_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, word, reinterpret_cast<uint64_t*>(out));
+  group_gather_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, word, reinterpret_cast<uint64_t*>(out));
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -673,7 +846,7 @@ int vb2k_group_valid(const vb2_group_table* t, const int32_t* slots, int64_t n, 
   if (n <= 0) return VB2_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VB2_CUDA_OK(cudaMemsetAsync(valid + ((n + 63) >> 6) - 1, 0, 8, st));
-  group_valid_kernel<<<grid_for(n, 256), 256, 0, st>>>(*t, slots, n, count_word, reinterpret_cast<uint32_t*>(valid));
+  group_valid_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(*t, slots, n, count_word, reinterpret_cast<uint32_t*>(valid));
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -681,7 +854,32 @@ int vb2k_group_valid(const vb2_group_table* t, const int32_t* slots, int64_t n, 
 int vb2k_group_avg(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t sum_word, int32_t count_word, double* out, void* stream) {
   if (int rc = check_table(t, "group_avg: bad table")) return rc;
   if (n <= 0) return VB2_OK;
-  group_avg_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, sum_word, count_word, out);
+  group_avg_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, slots, n, sum_word, count_word, out);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_group_extract(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t* scratch_slots, const vb2_extract_col* cols,
+                       int32_t ncols, int64_t* header, const int32_t* error_flag, void* stream) {
+  if (int rc = check_table(t, "group_extract: bad table")) return rc;
+  if (ncols < 0 || ncols > VB2_EXTRACT_MAX_COLS) return fail_msg(VB2_ERR_UNSUPPORTED, "group_extract: too many output columns");
+  if (!slots && (t->capacity > VB2_EXTRACT_SMALL_CAPACITY || !scratch_slots)) return fail_msg(VB2_ERR_INVALID, "group_extract: slot list required for large tables");
+  ExtractArgs a;
+  a.n = ncols;
+  for (int i = 0; i < ncols; ++i) {
+    const vb2_extract_col& c = cols[i];
+    if (c.kind < VB2_EXTRACT_KEY || c.kind > VB2_EXTRACT_AVG || !c.values) return fail_msg(VB2_ERR_INVALID, "group_extract: bad column");
+    if (c.kind != VB2_EXTRACT_KEY && (c.word < 0 || c.word >= t->row_words || c.count_word >= t->row_words)) return fail_msg(VB2_ERR_INVALID, "group_extract: word outside the row");
+    if (c.kind == VB2_EXTRACT_KEY && (c.mult == 0 || c.range == 0)) return fail_msg(VB2_ERR_INVALID, "group_extract: bad key layout");
+    a.c[i] = c;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!slots) {
+    group_extract_kernel<<<vb2::counted(1), 1024, 0, st>>>(*t, nullptr, 0, scratch_slots, a, header, error_flag);
+  } else {
+    if (n <= 0) return VB2_OK;
+    group_extract_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(*t, slots, n, nullptr, a, header, error_flag);
+  }
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -700,7 +898,7 @@ int vb2k_group_merge_partials(const vb2_group_table* t, const double* sums, cons
     m.proj[i] = target_projs[i];
   }
   const int total = ngroups * ntargets;
-  merge_partials_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*t, sums, counts, ngroups, nproj, m);
+  merge_partials_kernel<<<vb2::counted((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(*t, sums, counts, ngroups, nproj, m);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }

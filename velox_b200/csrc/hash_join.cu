@@ -165,7 +165,7 @@ int vb2k_join_build(const vb2_join_table* t, const uint64_t* build_keys, const u
                     int32_t* error_flag, void* stream) {
   if (!t || (t->mode == 1 && (t->capacity & (t->capacity - 1)))) return fail_msg(VB2_ERR_INVALID, "join_build: bad table");
   if (n <= 0) return VB2_OK;
-  join_build_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, build_keys, valid, n, error_flag);
+  join_build_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, build_keys, valid, n, error_flag);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -173,7 +173,7 @@ int vb2k_join_build(const vb2_join_table* t, const uint64_t* build_keys, const u
 int vb2k_join_probe_count(const vb2_join_table* t, const uint64_t* probe_keys, const uint64_t* valid, int64_t n,
                           int32_t* hit_counts, void* stream) {
   if (n <= 0) return VB2_OK;
-  join_probe_count_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, probe_keys, valid, n, hit_counts);
+  join_probe_count_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, probe_keys, valid, n, hit_counts);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -193,9 +193,9 @@ int vb2k_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, int64_t*
   if (workspace_bytes < vb2k_scan_workspace(n)) return fail_msg(VB2_ERR_INVALID, "exclusive_scan: workspace too small");
   const int64_t nblocks = (n + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems);
   int64_t* sums = reinterpret_cast<int64_t*>(workspace);
-  scan_block_sums_kernel<<<static_cast<unsigned>(nblocks), kScanThreads, 0, st>>>(in, n, sums);
-  scan_offsets_kernel<<<1, 1024, 0, st>>>(sums, nblocks, total_out);
-  scan_write_kernel<<<static_cast<unsigned>(nblocks), kScanThreads, 0, st>>>(in, n, sums, out);
+  scan_block_sums_kernel<<<vb2::counted(static_cast<unsigned>(nblocks)), kScanThreads, 0, st>>>(in, n, sums);
+  scan_offsets_kernel<<<vb2::counted(1), 1024, 0, st>>>(sums, nblocks, total_out);
+  scan_write_kernel<<<vb2::counted(static_cast<unsigned>(nblocks)), kScanThreads, 0, st>>>(in, n, sums, out);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -203,7 +203,7 @@ int vb2k_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, int64_t*
 int vb2k_join_probe_emit(const vb2_join_table* t, const uint64_t* probe_keys, const uint64_t* valid, int64_t n,
                          const int64_t* offsets, int32_t* probe_rows, int32_t* build_rows, void* stream) {
   if (n <= 0) return VB2_OK;
-  join_probe_emit_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, probe_keys, valid, n, offsets, probe_rows, build_rows);
+  join_probe_emit_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, probe_keys, valid, n, offsets, probe_rows, build_rows);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }

@@ -258,7 +258,7 @@ int vb2k_hash_columns(const vb2_column* cols, int32_t ncols, int64_t rows, uint6
   ColSet cs;
   cs.n = ncols;
   for (int i = 0; i < ncols; ++i) cs.c[i] = cols[i];
-  hash_columns_kernel<<<grid_for(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cs, rows, hashes);
+  hash_columns_kernel<<<vb2::counted(grid_for(rows, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(cs, rows, hashes);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -266,7 +266,7 @@ int vb2k_hash_columns(const vb2_column* cols, int32_t ncols, int64_t rows, uint6
 int vb2k_partition_ids(const uint64_t* hashes, int64_t rows, int32_t num_partitions, uint32_t* ids, void* stream) {
   if (num_partitions < 1) return fail_msg(VB2_ERR_INVALID, "partition_ids: num_partitions < 1");
   if (rows <= 0) return VB2_OK;
-  partition_ids_kernel<<<grid_for(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(hashes, rows, static_cast<uint32_t>(num_partitions), ids);
+  partition_ids_kernel<<<vb2::counted(grid_for(rows, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(hashes, rows, static_cast<uint32_t>(num_partitions), ids);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -284,9 +284,9 @@ int vb2k_partition_scatter_order(const uint32_t* ids, int64_t rows, int32_t num_
   int64_t* base = nullptr;
   VB2_CUDA_OK(cudaMallocAsync(&hist, sizeof(int32_t) * nblocks * num_partitions, st));
   VB2_CUDA_OK(cudaMallocAsync(&base, sizeof(int64_t) * nblocks * num_partitions, st));
-  part_hist_kernel<<<static_cast<unsigned>(nblocks), kPartThreads, 0, st>>>(ids, rows, num_partitions, hist);
-  part_offsets_kernel<<<1, kMaxParts, 0, st>>>(hist, nblocks, num_partitions, counts, base);
-  part_scatter_kernel<<<static_cast<unsigned>(nblocks), kPartThreads, 0, st>>>(ids, rows, num_partitions, base, row_order);
+  part_hist_kernel<<<vb2::counted(static_cast<unsigned>(nblocks)), kPartThreads, 0, st>>>(ids, rows, num_partitions, hist);
+  part_offsets_kernel<<<vb2::counted(1), kMaxParts, 0, st>>>(hist, nblocks, num_partitions, counts, base);
+  part_scatter_kernel<<<vb2::counted(static_cast<unsigned>(nblocks)), kPartThreads, 0, st>>>(ids, rows, num_partitions, base, row_order);
   VB2_CUDA_OK(cudaGetLastError());
   VB2_CUDA_OK(cudaFreeAsync(hist, st));
   VB2_CUDA_OK(cudaFreeAsync(base, st));
@@ -319,9 +319,9 @@ int vb2k_partition_segments(const int64_t* keys, const void* const* cols, const 
   int64_t* base = nullptr;
   VB2_CUDA_OK(cudaMallocAsync(&hist, sizeof(int32_t) * nblocks * num_partitions, st));
   VB2_CUDA_OK(cudaMallocAsync(&base, sizeof(int64_t) * nblocks * num_partitions, st));
-  seg_hist_kernel<<<static_cast<unsigned>(nblocks), kPartThreads, 0, st>>>(keys, rows, rows_dev, static_cast<uint32_t>(num_partitions), hist);
-  seg_offsets_kernel<<<1, kMaxParts, 0, st>>>(hist, nblocks, num_partitions, segcap, counts, base, overflow);
-  seg_scatter_kernel<<<static_cast<unsigned>(nblocks), kPartThreads, 0, st>>>(keys, rows, rows_dev, static_cast<uint32_t>(num_partitions), segcap, base,
+  seg_hist_kernel<<<vb2::counted(static_cast<unsigned>(nblocks)), kPartThreads, 0, st>>>(keys, rows, rows_dev, static_cast<uint32_t>(num_partitions), hist);
+  seg_offsets_kernel<<<vb2::counted(1), kMaxParts, 0, st>>>(hist, nblocks, num_partitions, segcap, counts, base, overflow);
+  seg_scatter_kernel<<<vb2::counted(static_cast<unsigned>(nblocks)), kPartThreads, 0, st>>>(keys, rows, rows_dev, static_cast<uint32_t>(num_partitions), segcap, base,
                                                                               seg_keys, sc);
   VB2_CUDA_OK(cudaGetLastError());
   VB2_CUDA_OK(cudaFreeAsync(hist, st));
@@ -331,7 +331,7 @@ int vb2k_partition_segments(const int64_t* keys, const void* const* cols, const 
 
 int vb2k_key_range_check(const int64_t* keys, int64_t n, int64_t lo, int64_t hi, int32_t* flag, void* stream) {
   if (n <= 0) return VB2_OK;
-  key_range_check_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(keys, n, lo, hi, flag);
+  key_range_check_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(keys, n, lo, hi, flag);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -340,9 +340,9 @@ int vb2k_gather(const void* in, const int32_t* order, int64_t n, int32_t elem_by
   if (n <= 0) return VB2_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (elem_bytes == 8)
-    gather_kernel<uint64_t><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(in), order, n, reinterpret_cast<uint64_t*>(out));
+    gather_kernel<uint64_t><<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(in), order, n, reinterpret_cast<uint64_t*>(out));
   else if (elem_bytes == 4)
-    gather_kernel<uint32_t><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(in), order, n, reinterpret_cast<uint32_t*>(out));
+    gather_kernel<uint32_t><<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(in), order, n, reinterpret_cast<uint32_t*>(out));
   else
     return fail_msg(VB2_ERR_INVALID, "gather: elem_bytes must be 4 or 8");
   VB2_CUDA_OK(cudaGetLastError());

@@ -8,6 +8,27 @@ namespace velox_b200 {
 
 namespace {
 
+// kSingle node equivalent to final(partial): same keys, same aggregates over the raw inputs, the
+// final node's output type and id. nullptr when the pair does not line up.
+std::shared_ptr<const core::AggregationNode> collapsePartialFinal(const core::AggregationNode& partial, const core::AggregationNode& fin) {
+  using Step = core::AggregationNode::Step;
+  if (partial.step() != Step::kPartial || fin.step() != Step::kFinal) return nullptr;
+  if (fin.sources()[0].get() != &partial) return nullptr;
+  const size_t nk = partial.groupingKeys().size();
+  if (fin.groupingKeys().size() != nk || fin.aggregates().size() != partial.aggregates().size()) return nullptr;
+  for (size_t k = 0; k < nk; ++k)
+    if (fin.groupingKeys()[k] != static_cast<int32_t>(k)) return nullptr;
+  int32_t col = static_cast<int32_t>(nk);
+  for (size_t i = 0; i < fin.aggregates().size(); ++i) {
+    const auto& f = fin.aggregates()[i];
+    const auto& p = partial.aggregates()[i];
+    if (f.function != p.function || f.mask >= 0 || f.inputs.empty() || f.inputs[0] != col) return nullptr;
+    col += p.function == "avg" ? 2 : 1;
+  }
+  return std::make_shared<core::AggregationNode>(fin.id(), Step::kSingle, partial.groupingKeys(), partial.aggregates(), fin.outputType(),
+                                                 partial.sources()[0]);
+}
+
 bool adaptDriver(const exec::DriverFactory& factory, exec::Driver& driver) {
   const core::QueryConfig& config = driver.driverCtx()->queryConfig();
   if (!config.b200Enabled()) return false;
@@ -45,7 +66,19 @@ bool adaptDriver(const exec::DriverFactory& factory, exec::Driver& driver) {
           out.resize(first);
         }
       }
-      out.push_back(std::make_unique<B200HashAggregation>(static_cast<int32_t>(out.size()), ctx, agg->node(), std::move(absorbed)));
+      std::shared_ptr<const core::AggregationNode> node = agg->node();
+      // partial -> final back to back in ONE driver (no exchange in between) is a single
+      // aggregation: final(partial(x)) == single(x) group by group, so the pair becomes one
+      // operator and the intermediate batch never exists.
+      if (fuse && i + 1 < ops.size()) {
+        if (auto next = dynamic_cast<exec::HashAggregation*>(ops[i + 1].get())) {
+          if (auto merged = collapsePartialFinal(*node, *next->node())) {
+            node = merged;
+            ++i;
+          }
+        }
+      }
+      out.push_back(std::make_unique<B200HashAggregation>(static_cast<int32_t>(out.size()), ctx, node, std::move(absorbed)));
       replacedAny = true;
     } else if (auto build = dynamic_cast<exec::HashBuild*>(op)) {
       out.push_back(std::make_unique<B200HashBuild>(id, ctx, *build));

@@ -30,12 +30,18 @@ struct KeyState {
   std::unordered_map<std::string, int32_t> valueIds;
   std::vector<std::string> valuesById;
   // cache: alphabet -> device LUT (dictionary entry -> global id, 0 = NULL entry)
-  const HostAlphabet* cachedAlphabet = nullptr;
+  std::shared_ptr<const HostAlphabet> cachedAlphabet;  // held, so its address cannot be recycled while cached
   DeviceBufferPtr lut;
   DeviceBufferPtr fusedLut;   // dictionary entry -> id under the current layout (fused kernel)
   bool hasRange = false;
   int64_t lo = 0, hi = 0;
   bool nullable = false;      // a NULL key was (or may have been) seen: the layout reserves id 0
+  // device copy of the global alphabet for output columns (dictionary base), refreshed when it grew
+  DeviceBufferPtr devOffsets, devChars;
+  size_t devAlphabetCount = 0;
+  std::vector<int32_t> hostOffsets;
+  std::string hostChars;
+  std::shared_ptr<const HostAlphabet> outAlphabet;
 };
 
 struct AccState {
@@ -92,6 +98,27 @@ struct B200HashAggregation::Impl {
   size_t fusedWsBytes = 0;
   int fusedGroups = 0;
   int64_t fusedBatches = 0, genericBatches = 0;
+  struct FusedTiming { cudaEvent_t begin = nullptr, end = nullptr; int64_t rows = 0; };
+  std::vector<FusedTiming> fusedTimings;
+  ~Impl() {
+    for (auto& t : fusedTimings) { cudaEventDestroy(t.begin); cudaEventDestroy(t.end); }
+  }
+  // Device time of the fused launches so far (call after the stream was synchronised).
+  void reportFusedTimings() {
+    double ns = 0;
+    int64_t rows = 0;
+    for (auto& t : fusedTimings) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, t.begin, t.end) == cudaSuccess) { ns += static_cast<double>(ms) * 1e6; rows += t.rows; }
+      cudaEventDestroy(t.begin);
+      cudaEventDestroy(t.end);
+    }
+    if (!fusedTimings.empty()) {
+      self->addRuntimeStat("b200.fusedScanNanos", exec::RuntimeCounter{static_cast<int64_t>(ns)});
+      self->addRuntimeStat("b200.fusedScanRows", exec::RuntimeCounter{rows});
+    }
+    fusedTimings.clear();
+  }
 
   cudaStream_t st() const { return dev->stream; }
 
@@ -238,7 +265,7 @@ struct B200HashAggregation::Impl {
     if (ks.isVarchar) {
       if (d.encoding == VB2_FLAT) VELOX_UNSUPPORTED("GROUP BY on flat VARCHAR keys (dictionary-encoded VARCHAR keys are supported)");
       VELOX_CHECK(col.alphabet != nullptr, "VARCHAR key without a host alphabet (dictionary above 65536 entries)");
-      if (ks.cachedAlphabet != col.alphabet.get()) {
+      if (ks.cachedAlphabet != col.alphabet) {
         std::vector<int32_t> lut(col.alphabet->values.size());
         for (size_t i = 0; i < lut.size(); ++i) {
           if (col.alphabet->nulls[i]) { lut[i] = 0; ks.nullable = true; continue; }
@@ -250,9 +277,9 @@ struct B200HashAggregation::Impl {
           lut[i] = it->second;
         }
         ks.lut = allocDevice(lut.size() * 4 + 4, st());
+        // pageable source: the call returns once the bytes are staged, the vector may go away
         VB2_CU(cudaMemcpyAsync(ks.lut->data(), lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, st()));
-        VB2_CU(cudaStreamSynchronize(st()));
-        ks.cachedAlphabet = col.alphabet.get();
+        ks.cachedAlphabet = col.alphabet;
         ks.fusedLut = nullptr;
       }
       keep.push_back(ks.lut);
@@ -675,7 +702,6 @@ struct B200HashAggregation::Impl {
           for (size_t i = 0; i < lut.size(); ++i) lut[i] = static_cast<int32_t>(ks.valueIds.at(col.alphabet->values[i]) - layout.mins[k] + 1);
           ks.fusedLut = allocDevice(lut.size() * 4 + 4, st());
           VB2_CU(cudaMemcpyAsync(ks.fusedLut->data(), lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, st()));
-          VB2_CU(cudaStreamSynchronize(st()));
         }
         a.key_min[k] = 0;
         a.key_lut[k] = ks.fusedLut->as<int32_t>();
@@ -700,9 +726,19 @@ struct B200HashAggregation::Impl {
       fusedWsBytes = vb2k_fused_workspace_bytes(fusedId, groups);
       fusedWs = allocDevice(fusedWsBytes, st());
     }
+    // The fused launch is bracketed by CUDA events on the launching stream; the elapsed device
+    // time is reported as b200.fusedScanNanos (what bench.py's roofline divides the bytes by).
+    FusedTiming ft;
+    VB2_CU(cudaEventCreate(&ft.begin));
+    VB2_CU(cudaEventCreate(&ft.end));
+    VB2_CU(cudaEventRecord(ft.begin, st()));
     const int rc = vb2k_fused_scan_agg(fusedId, &a, fusedSums->as<double>(), fusedCounts->as<int64_t>(), fusedWs->data(), fusedWsBytes, st());
+    if (rc == VB2_OK) VB2_CU(cudaEventRecord(ft.end, st()));
+    if (rc != VB2_OK) { cudaEventDestroy(ft.begin); cudaEventDestroy(ft.end); }
     if (rc == VB2_ERR_UNSUPPORTED) return false;
     kernelCheck(rc);
+    ft.rows = n;
+    fusedTimings.push_back(ft);
     ++fusedBatches;
     return true;
   }
@@ -773,112 +809,181 @@ struct B200HashAggregation::Impl {
     return col;
   }
 
+  // Device copy of a VARCHAR key's global alphabet (offsets + chars), refreshed when ids were added.
+  void ensureDeviceAlphabet(KeyState& ks) {
+    if (ks.devOffsets && ks.devAlphabetCount == ks.valuesById.size()) return;
+    ks.hostOffsets.assign(ks.valuesById.size() + 1, 0);
+    ks.hostChars.clear();
+    for (size_t i = 0; i < ks.valuesById.size(); ++i) {
+      ks.hostChars += ks.valuesById[i];
+      ks.hostOffsets[i + 1] = static_cast<int32_t>(ks.hostChars.size());
+    }
+    ks.devOffsets = allocDevice(ks.hostOffsets.size() * 4, st());
+    ks.devChars = allocDevice(ks.hostChars.size() + 1, st());
+    VB2_CU(cudaMemcpyAsync(ks.devOffsets->data(), ks.hostOffsets.data(), ks.hostOffsets.size() * 4, cudaMemcpyHostToDevice, st()));
+    if (!ks.hostChars.empty()) VB2_CU(cudaMemcpyAsync(ks.devChars->data(), ks.hostChars.data(), ks.hostChars.size(), cudaMemcpyHostToDevice, st()));
+    ks.devAlphabetCount = ks.valuesById.size();
+    auto alpha = std::make_shared<HostAlphabet>();
+    alpha->values = ks.valuesById;
+    alpha->nulls.assign(alpha->values.size(), false);
+    ks.outAlphabet = alpha;
+  }
+
+  // All output columns are carved out of ONE device arena and written by ONE kernel
+  // (vb2k_group_extract). Small tables (<= VB2_EXTRACT_SMALL_CAPACITY rows, i.e. every TPC-H shape)
+  // are compacted inside that kernel and the whole arena comes back to pinned host memory with the
+  // row count in a single copy + synchronisation; B200ToHost then reads the host mirror.
   B200VectorPtr output() {
     flushFused();
-    checkDeviceError(errorFlag, st(), "sum");  // SUM(BIGINT) overflow (functions/prestosql/aggregates/SumAggregate.cpp:24)
+    const bool small = capacity <= VB2_EXTRACT_SMALL_CAPACITY;
     int64_t m = 0;
     DeviceBufferPtr slots;
-    if (mode == Mode::kGlobal) {
-      m = 1;  // a global aggregation always emits one row (exec/GroupingSet.cpp:499-770)
-      slots = allocDeviceZeroed(8, st());
-    } else {
+    if (!small) {
+      checkDeviceError(errorFlag, st(), "sum");  // SUM(BIGINT) overflow (functions/prestosql/aggregates/SumAggregate.cpp:24)
       slots = occupiedSlots(m);
       if (m == 0) return nullptr;
     }
+    const int64_t rowsCap = small ? capacity : m;
     const auto& outType = node->outputType();
     const auto& inType = node->sources()[0]->outputType();
-    const vb2_group_table tab = table();
-    std::vector<DeviceColumnPtr> cols;
+
+    struct ColPlan {
+      vb2_extract_col ec{};
+      TypePtr type;
+      int width = 8;
+      bool varcharKey = false;
+      size_t key = 0;
+      size_t valuesOff = 0, validOff = 0;
+      bool hasValid = false;
+    };
+    std::vector<ColPlan> plan;
     uint32_t oc = 0;
-    // keys
     for (size_t k = 0; k < keys.size(); ++k, ++oc) {
-      const TypePtr& t = inType->childAt(node->groupingKeys()[k]);
-      auto valid = allocDevice(bits::nbytes(m), st());
+      ColPlan c;
+      c.type = inType->childAt(node->groupingKeys()[k]);
+      c.ec.kind = VB2_EXTRACT_KEY;
+      c.ec.mult = layout.mults[k];
+      c.ec.range = layout.ranges[k];
+      c.ec.null_reserved = nullReserved[k];
+      c.ec.count_word = -1;
+      c.hasValid = nullReserved[k] != 0;
+      c.key = k;
       if (keys[k].isVarchar) {
-        // dictionary over the global alphabet: index = id - 1
-        auto idx = allocDevice(static_cast<size_t>(m) * 4, st());
-        kernelCheck(vb2k_group_keys(&tab, slots->as<int32_t>(), m, layout.mins[k] - 1, layout.mults[k], layout.ranges[k], nullReserved[k],
-                                    VB2_INTEGER, idx->data(), valid->as<uint64_t>(), st()));
-        auto alpha = std::make_shared<HostAlphabet>();
-        alpha->values = keys[k].valuesById;
-        alpha->nulls.assign(alpha->values.size(), false);
-        std::vector<int32_t> off(alpha->values.size() + 1, 0);
-        std::string chars;
-        for (size_t i = 0; i < alpha->values.size(); ++i) { chars += alpha->values[i]; off[i + 1] = static_cast<int32_t>(chars.size()); }
-        auto offBuf = allocDevice(off.size() * 4, st());
-        auto charBuf = allocDevice(chars.size() + 1, st());
-        VB2_CU(cudaMemcpyAsync(offBuf->data(), off.data(), off.size() * 4, cudaMemcpyHostToDevice, st()));
-        VB2_CU(cudaMemcpyAsync(charBuf->data(), chars.data(), chars.size(), cudaMemcpyHostToDevice, st()));
-        VB2_CU(cudaStreamSynchronize(st()));
-        auto col = std::make_shared<DeviceColumn>();
-        col->type = t;
-        col->desc.type = VB2_VARCHAR;
-        col->desc.encoding = VB2_DICTIONARY;
-        col->desc.size = m;
-        col->desc.indices = idx->as<int32_t>();
-        col->desc.values = offBuf->data();
-        col->desc.aux = charBuf->data();
-        col->desc.dict_size = static_cast<int64_t>(alpha->values.size());
-        if (nullReserved[k]) col->desc.nulls = valid->as<uint64_t>();  // NULL key group: id 0
-        col->owners = {idx, offBuf, charBuf, valid};
-        col->alphabet = alpha;
-        cols.push_back(col);
+        c.varcharKey = true;  // dictionary over the global alphabet: index = id - 1
+        c.ec.type = VB2_INTEGER;
+        c.ec.min = layout.mins[k] - 1;
+        c.width = 4;
       } else {
-        const int vt = veloxTypeToVb2(t);
-        auto vals = allocDevice(static_cast<size_t>(m) * 8, st());
-        kernelCheck(vb2k_group_keys(&tab, slots->as<int32_t>(), m, layout.mins[k], layout.mults[k], layout.ranges[k], nullReserved[k], vt,
-                                    vals->data(), valid->as<uint64_t>(), st()));
-        if (vt == VB2_BOOLEAN) {
-          auto packed = allocDevice(bits::nbytes(m), st());
-          kernelCheck(vb2k_pack_bools(vals->as<uint8_t>(), m, packed->as<uint64_t>(), st()));
-          vals = packed;
-        }
-        cols.push_back(flatOutput(t, vals, nullReserved[k] ? valid : nullptr, m));
+        c.ec.type = veloxTypeToVb2(c.type);
+        c.ec.min = layout.mins[k];
+        c.width = c.ec.type == VB2_INTEGER ? 4 : (c.ec.type == VB2_BOOLEAN ? 0 : 8);
       }
+      plan.push_back(c);
     }
-    // aggregates
-    const int32_t* sl = slots->as<int32_t>();
     for (size_t i = 0; i < accs.size(); ++i) {
       const AccState& s = accs[i];
-      auto gatherWord = [&](int32_t word) {
-        auto out = allocDevice(static_cast<size_t>(m) * 8, st());
-        kernelCheck(vb2k_group_gather(&tab, sl, m, word, out->data(), st()));
-        return out;
+      auto add = [&](int32_t kind, int32_t word, int32_t countWord, bool valid, int width) {
+        ColPlan c;
+        c.type = outType->childAt(oc++);
+        c.ec.kind = kind;
+        c.ec.word = word;
+        c.ec.count_word = countWord;
+        c.ec.mult = c.ec.range = 1;
+        c.hasValid = valid;
+        c.width = width;
+        plan.push_back(c);
       };
-      auto validOf = [&]() -> DeviceBufferPtr {
-        if (!s.nnTracked) return nullptr;  // every input of every group was non-null
-        auto v = allocDevice(bits::nbytes(m), st());
-        kernelCheck(vb2k_group_valid(&tab, sl, m, s.nnWord, v->as<uint64_t>(), st()));
-        return v;
-      };
-      if (s.fn == "count") {
-        cols.push_back(flatOutput(outType->childAt(oc++), gatherWord(s.accWord), nullptr, m));
-      } else if (s.fn == "avg") {
-        if (fin) {
-          auto out = allocDevice(static_cast<size_t>(m) * 8, st());
-          kernelCheck(vb2k_group_avg(&tab, sl, m, s.accWord, s.nnWord, out->as<double>(), st()));
-          cols.push_back(flatOutput(outType->childAt(oc++), out, validOf(), m));
-        } else {
-          auto v = validOf();
-          cols.push_back(flatOutput(outType->childAt(oc++), gatherWord(s.accWord), v, m));
-          cols.push_back(flatOutput(outType->childAt(oc++), gatherWord(s.nnWord), v, m));
-        }
+      const bool tracked = s.nnTracked;  // untracked: every input of every group was non-null
+      if (s.fn == "count") add(VB2_EXTRACT_WORD, s.accWord, -1, false, 8);
+      else if (s.fn == "avg") {
+        if (fin) add(VB2_EXTRACT_AVG, s.accWord, s.nnWord, tracked, 8);
+        else { add(VB2_EXTRACT_WORD, s.accWord, tracked ? s.nnWord : -1, tracked, 8); add(VB2_EXTRACT_WORD, s.nnWord, tracked ? s.nnWord : -1, tracked, 8); }
       } else {
-        const TypePtr& t = outType->childAt(oc++);
-        auto vals = gatherWord(s.accWord);
-        if (t->kind() == TypeKind::INTEGER) {
-          // min/max over INTEGER keep their type: narrow the 8-byte accumulator
-          auto narrow = allocDevice(static_cast<size_t>(m) * 4, st());
-          kernelCheck(vb2k_narrow_i64(vals->as<int64_t>(), m, narrow->as<int32_t>(), st()));
-          vals = narrow;
-        }
-        cols.push_back(flatOutput(t, vals, validOf(), m));
+        const bool narrow = outType->childAt(oc)->kind() == TypeKind::INTEGER;  // min/max over INTEGER keep their type
+        add(narrow ? VB2_EXTRACT_WORD_I32 : VB2_EXTRACT_WORD, s.accWord, tracked ? s.nnWord : -1, tracked, narrow ? 4 : 8);
       }
     }
+    VELOX_CHECK(plan.size() <= VB2_EXTRACT_MAX_COLS, "too many aggregation output columns");
+    // arena: [header 64 B | slot scratch (small tables) | per column: values, validity]
+    auto align = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+    size_t off = 64;
+    const size_t scratchOff = off;
+    if (small) off = align(off + static_cast<size_t>(rowsCap) * 4, 256);
+    for (auto& c : plan) {
+      c.valuesOff = off;
+      off = align(off + (c.width == 0 ? bits::nbytes(rowsCap) : static_cast<size_t>(rowsCap) * c.width), 256);
+      if (c.hasValid) { c.validOff = off; off = align(off + bits::nbytes(rowsCap), 256); }
+    }
+    const size_t arenaBytes = off;
+    auto arena = allocDevice(arenaBytes, st());
+    uint8_t* base = arena->as<uint8_t>();
+    VB2_CU(cudaMemsetAsync(base, 0, 64, st()));
+    std::vector<vb2_extract_col> ecs;
+    for (auto& c : plan) {
+      c.ec.values = base + c.valuesOff;
+      c.ec.valid = c.hasValid ? reinterpret_cast<uint64_t*>(base + c.validOff) : nullptr;
+      ecs.push_back(c.ec);
+    }
+    const vb2_group_table tab = table();
+    int64_t* header = reinterpret_cast<int64_t*>(base);
+    if (mode == Mode::kGlobal) {
+      // a global aggregation always emits one row (exec/GroupingSet.cpp:499-770): slot 0, listed explicitly
+      kernelCheck(vb2k_group_extract(&tab, reinterpret_cast<const int32_t*>(base + 16), 1, nullptr, ecs.data(), static_cast<int32_t>(ecs.size()), header,
+                                     errorFlag->as<int32_t>(), st()));
+    } else if (small) {
+      kernelCheck(vb2k_group_extract(&tab, nullptr, 0, reinterpret_cast<int32_t*>(base + scratchOff), ecs.data(), static_cast<int32_t>(ecs.size()), header,
+                                     errorFlag->as<int32_t>(), st()));
+    } else {
+      kernelCheck(vb2k_group_extract(&tab, slots->as<int32_t>(), m, nullptr, ecs.data(), static_cast<int32_t>(ecs.size()), header, nullptr, st()));
+    }
+    std::shared_ptr<HostMirror> mirror;
+    if (small) {
+      mirror = std::make_shared<HostMirror>();
+      mirror->host = acquirePinned(arenaBytes);
+      mirror->devBase = base;
+      mirror->bytes = arenaBytes;
+      VB2_CU(cudaMemcpyAsync(mirror->host.get(), base, arenaBytes, cudaMemcpyDeviceToHost, st()));
+      VB2_CU(cudaStreamSynchronize(st()));
+      const int64_t* h = static_cast<const int64_t*>(mirror->host.get());
+      if (h[1] != 0) checkDeviceError(errorFlag, st(), "sum");  // throws (SumAggregate.cpp:24 overflow)
+      m = h[0];
+      if (m == 0) return nullptr;
+    }
+    std::vector<DeviceColumnPtr> cols;
+    for (auto& c : plan) {
+      auto col = std::make_shared<DeviceColumn>();
+      col->type = c.type;
+      col->desc.size = m;
+      col->owners = {arena};
+      const uint64_t* valid = c.hasValid ? reinterpret_cast<const uint64_t*>(base + c.validOff) : nullptr;
+      if (c.varcharKey) {
+        KeyState& ks = keys[c.key];
+        ensureDeviceAlphabet(ks);
+        col->desc.type = VB2_VARCHAR;
+        col->desc.encoding = VB2_DICTIONARY;
+        col->desc.indices = reinterpret_cast<const int32_t*>(base + c.valuesOff);
+        col->desc.values = ks.devOffsets->data();
+        col->desc.aux = ks.devChars->data();
+        col->desc.dict_size = static_cast<int64_t>(ks.valuesById.size());
+        col->desc.nulls = valid;  // NULL key group: id 0
+        col->owners.push_back(ks.devOffsets);
+        col->owners.push_back(ks.devChars);
+        col->alphabet = ks.outAlphabet;
+      } else {
+        col->desc.type = veloxTypeToVb2(c.type);
+        col->desc.encoding = VB2_FLAT;
+        col->desc.values = base + c.valuesOff;
+        col->desc.nulls = valid;
+      }
+      cols.push_back(std::move(col));
+    }
+    reportFusedTimings();  // every fused launch precedes the synchronisation above
     self->addRuntimeStat("b200.fusedBatches", exec::RuntimeCounter{fusedBatches});
     self->addRuntimeStat("b200.genericBatches", exec::RuntimeCounter{genericBatches});
     self->addRuntimeStat("b200.aggMode", exec::RuntimeCounter{static_cast<int64_t>(mode)});
-    return std::make_shared<B200Vector>(self->pool(), outType, static_cast<vector_size_t>(m), std::move(cols), st());
+    auto out = std::make_shared<B200Vector>(self->pool(), outType, static_cast<vector_size_t>(m), std::move(cols), st());
+    if (mirror) out->setMirror(mirror);
+    return out;
   }
 };
 

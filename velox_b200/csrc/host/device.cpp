@@ -46,8 +46,58 @@ DeviceBufferPtr allocDeviceZeroed(size_t bytes, cudaStream_t stream) {
   return b;
 }
 
+namespace {
+struct PinnedPool {
+  std::mutex mu;
+  std::map<size_t, std::vector<void*>> free;  // size class -> blocks
+  ~PinnedPool() {
+    for (auto& kv : free)
+      for (void* p : kv.second) cudaFreeHost(p);
+  }
+};
+PinnedPool& pinnedPool() {
+  static PinnedPool* p = new PinnedPool();  // leaked on purpose: blocks may outlive static destruction order
+  return *p;
+}
+}  // namespace
+
+std::shared_ptr<void> acquirePinned(size_t bytes) {
+  size_t cls = 4096;
+  while (cls < bytes) cls <<= 1;
+  void* p = nullptr;
+  {
+    std::lock_guard<std::mutex> l(pinnedPool().mu);
+    auto& v = pinnedPool().free[cls];
+    if (!v.empty()) { p = v.back(); v.pop_back(); }
+  }
+  if (!p) VB2_CU(cudaHostAlloc(&p, cls, cudaHostAllocDefault));
+  return std::shared_ptr<void>(p, [cls](void* q) {
+    std::lock_guard<std::mutex> l(pinnedPool().mu);
+    pinnedPool().free[cls].push_back(q);
+  });
+}
+
+namespace {
+// Streams are pooled too: a Task creates one per driver, and cudaStreamCreate / Destroy cost tens
+// of microseconds each.
+struct StreamPool {
+  std::mutex mu;
+  std::map<int, std::vector<cudaStream_t>> free;  // device -> idle streams
+};
+StreamPool& streamPool() {
+  static StreamPool* p = new StreamPool();
+  return *p;
+}
+}  // namespace
+
 DeviceContext::DeviceContext() {
   VB2_CU(cudaGetDevice(&device));
+  {
+    std::lock_guard<std::mutex> l(streamPool().mu);
+    auto& v = streamPool().free[device];
+    if (!v.empty()) { stream = v.back(); v.pop_back(); }
+  }
+  if (stream) return;
   VB2_CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   // keep freed blocks in the pool: operators allocate and free large scratch buffers per batch
   cudaMemPool_t pool;
@@ -62,8 +112,10 @@ DeviceContext::~DeviceContext() {
       std::lock_guard<std::mutex> l(streamMutex());
       streamOwners().erase(stream);
     }
-    cudaStreamSynchronize(stream);
-    cudaStreamDestroy(stream);
+    // Buffers that were freed on this stream (cudaFreeAsync) are ordered behind its work; the next
+    // user of the pooled stream is ordered behind them as well, so no synchronisation is needed.
+    std::lock_guard<std::mutex> l(streamPool().mu);
+    streamPool().free[device].push_back(stream);
   }
 }
 
@@ -385,13 +437,74 @@ VectorPtr downloadValues(memory::MemoryPool* pool, const TypePtr& type, int32_t 
 
 }  // namespace
 
+namespace {
+// View over a slice of a host mirror; the buffer keeps the pinned block alive.
+BufferPtr mirrorView(const std::shared_ptr<const HostMirror>& m, const uint8_t* p, size_t bytes) {
+  return BufferPtr(new Buffer(p, bytes), [m](Buffer* b) { delete b; });
+}
+
+// Host vector of a column whose buffers all lie inside the batch's host mirror (no device access).
+VectorPtr mirroredColumn(memory::MemoryPool* pool, const DeviceColumn& col, const std::shared_ptr<const HostMirror>& m) {
+  const vb2_column& d = col.desc;
+  const vector_size_t n = static_cast<vector_size_t>(d.size);
+  BufferPtr nulls;
+  if (d.nulls) {
+    const uint8_t* hn = m->hostOf(d.nulls);
+    if (!hn) return nullptr;
+    nulls = mirrorView(m, hn, bits::nbytes(n));
+  }
+  if (d.encoding == VB2_FLAT && d.type != VB2_VARCHAR) {
+    const uint8_t* hv = m->hostOf(d.values);
+    if (!hv) return nullptr;
+    switch (d.type) {
+      case VB2_INTEGER: return std::make_shared<FlatVector<int32_t>>(pool, col.type, nulls, n, mirrorView(m, hv, size_t(n) * 4));
+      case VB2_BIGINT: return std::make_shared<FlatVector<int64_t>>(pool, col.type, nulls, n, mirrorView(m, hv, size_t(n) * 8));
+      case VB2_DOUBLE: return std::make_shared<FlatVector<double>>(pool, col.type, nulls, n, mirrorView(m, hv, size_t(n) * 8));
+      case VB2_BOOLEAN: return std::make_shared<FlatVector<bool>>(pool, col.type, nulls, n, mirrorView(m, hv, bits::nbytes(n)));
+      default: return nullptr;
+    }
+  }
+  if (d.encoding == VB2_DICTIONARY && d.type == VB2_VARCHAR && col.alphabet && !d.dict_nulls &&
+      static_cast<int64_t>(col.alphabet->values.size()) == d.dict_size) {
+    const uint8_t* hi = m->hostOf(d.indices);
+    if (!hi) return nullptr;
+    // the dictionary's strings are known on the host (the operator that made the column keeps its alphabet)
+    size_t total = 0;
+    for (auto& v : col.alphabet->values) total += v.size();
+    BufferPtr chars = std::make_shared<Buffer>(total ? total : 1, pool);
+    BufferPtr views = AlignedBuffer::allocate<StringView>(col.alphabet->values.empty() ? 1 : col.alphabet->values.size(), pool);
+    char* cp = chars->asMutable<char>();
+    auto* sv = views->asMutable<StringView>();
+    size_t at = 0;
+    for (size_t i = 0; i < col.alphabet->values.size(); ++i) {
+      const std::string& v = col.alphabet->values[i];
+      std::memcpy(cp + at, v.data(), v.size());
+      sv[i] = StringView(cp + at, v.size());
+      at += v.size();
+    }
+    auto base = std::make_shared<FlatVector<StringView>>(pool, col.type, nullptr, static_cast<vector_size_t>(col.alphabet->values.size()), views,
+                                                         std::vector<BufferPtr>{chars});
+    return BaseVector::wrapInDictionary(nulls, mirrorView(m, hi, size_t(n) * 4), n, base);
+  }
+  return nullptr;
+}
+}  // namespace
+
 RowVectorPtr toHost(const B200VectorPtr& dev) {
   cudaStream_t stream = dev->stream();
   auto* pool = dev->pool();
   std::vector<VectorPtr> children;
+  bool touchedDevice = false;
   for (auto& col : dev->columns()) {
     const vb2_column& d = col->desc;
     const vector_size_t n = static_cast<vector_size_t>(d.size);
+    if (dev->mirror()) {
+      if (VectorPtr v = mirroredColumn(pool, *col, dev->mirror())) {
+        children.push_back(std::move(v));
+        continue;
+      }
+    }
+    touchedDevice = true;
     if (d.encoding == VB2_FLAT) {
       children.push_back(downloadValues(pool, col->type, d.type, d.values, d.aux, d.nulls, n, stream));
     } else if (d.encoding == VB2_DICTIONARY) {
@@ -411,7 +524,7 @@ RowVectorPtr toHost(const B200VectorPtr& dev) {
       children.push_back(BaseVector::wrapInDictionary(nullptr, idx, n, base));
     }
   }
-  VB2_CU(cudaStreamSynchronize(stream));
+  if (touchedDevice) VB2_CU(cudaStreamSynchronize(stream));
   return std::make_shared<RowVector>(pool, dev->type(), nullptr, dev->size(), std::move(children));
 }
 

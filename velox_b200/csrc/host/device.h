@@ -61,6 +61,25 @@ struct DeviceColumn {
 };
 using DeviceColumnPtr = std::shared_ptr<DeviceColumn>;
 
+// Pinned host memory from a process-wide pool (cudaHostAlloc costs ~100 us; operators that bring
+// small results back every query reuse blocks by power-of-two size class).
+std::shared_ptr<void> acquirePinned(size_t bytes);
+
+// Host copy of a small device arena: an operator that has to synchronise anyway (e.g. an aggregation
+// that needs its output row count) copies its whole packed output to pinned memory in the same
+// round trip; B200ToHost then builds the host vectors over this copy without touching the device.
+struct HostMirror {
+  std::shared_ptr<void> host;   // pinned block
+  const uint8_t* devBase = nullptr;
+  size_t bytes = 0;
+  // host address of a device pointer inside the mirrored arena, nullptr when outside
+  const uint8_t* hostOf(const void* dev) const {
+    const uint8_t* p = static_cast<const uint8_t*>(dev);
+    if (!host || !dev || p < devBase || p >= devBase + bytes) return nullptr;
+    return static_cast<const uint8_t*>(host.get()) + (p - devBase);
+  }
+};
+
 // A batch resident in HBM. children() is empty: the columns live on the device.
 class B200Vector : public RowVector {
  public:
@@ -69,10 +88,13 @@ class B200Vector : public RowVector {
   const std::vector<DeviceColumnPtr>& columns() const { return cols_; }
   const DeviceColumnPtr& column(size_t i) const { return cols_.at(i); }
   cudaStream_t stream() const { return stream_; }
+  void setMirror(std::shared_ptr<const HostMirror> m) { mirror_ = std::move(m); }
+  const std::shared_ptr<const HostMirror>& mirror() const { return mirror_; }
 
  private:
   std::vector<DeviceColumnPtr> cols_;
   cudaStream_t stream_;
+  std::shared_ptr<const HostMirror> mirror_;
 };
 using B200VectorPtr = std::shared_ptr<B200Vector>;
 

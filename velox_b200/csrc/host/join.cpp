@@ -177,7 +177,6 @@ void B200HashBuild::noMoreInput() {
   lay.mults.assign(keys.size(), 1);
   for (int i = static_cast<int>(keys.size()) - 2; i >= 0; --i) lay.mults[i] = lay.mults[i + 1] * lay.ranges[i + 1];
 
-  NormalizedKeys nk = normalizeKeys(*holder->rows, keys, lay, nullptr, n, true, st);
   // Array mode while the packed key space is at most 16x the row count and <= 2^28 slots: the
   // reference caps kArray at 2M entries for CPU caches (exec/HashTable.h:146); HBM + a 126 MB L2
   // move that limit (a 20 M-slot int32 table is 80 MB and stays L2 resident).
@@ -196,14 +195,20 @@ void B200HashBuild::noMoreInput() {
     holder->owners.push_back(keysBuf);
   }
   auto head = allocDeviceZeroed(static_cast<size_t>(t.capacity) * 4, st);
-  auto next = allocDeviceZeroed(static_cast<size_t>(n) * 4 + 4, st);
+  auto next = allocDevice(static_cast<size_t>(n) * 4 + 4, st);  // every inserted row writes its own entry; others are unreachable
   t.head = head->as<int32_t>();
   t.next = next->as<int32_t>();
   t.build_rows = n;
   holder->owners.push_back(head);
   holder->owners.push_back(next);
   auto flags = allocDeviceZeroed(8, st);
-  kernelCheck(vb2k_join_build(&t, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, flags->as<int32_t>(), st));
+  if (t.mode == 0 && keys.size() == 1) {
+    // one key column, array mode: value ids and insertion in one pass over the key column
+    kernelCheck(vb2k_join_build_array_direct(t.head, t.next, t.capacity, &holder->rows->column(keys[0])->desc, lay.mins[0], n, flags->as<int32_t>(), st));
+  } else {
+    NormalizedKeys nk = normalizeKeys(*holder->rows, keys, lay, nullptr, n, true, st);
+    kernelCheck(vb2k_join_build(&t, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, flags->as<int32_t>(), st));
+  }
   int32_t h[2];
   VB2_CU(cudaMemcpyAsync(h, flags->data(), 8, cudaMemcpyDeviceToHost, st));
   VB2_CU(cudaStreamSynchronize(st));

@@ -1,4 +1,6 @@
 // Error plumbing and small utility kernels.
+#include <atomic>
+
 #include "common.cuh"
 
 #include <cstdio>
@@ -16,6 +18,8 @@ int fail_msg(int code, const char* msg) {
   g_last_error = msg;
   return code;
 }
+static std::atomic<int64_t> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int device_sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -117,6 +121,7 @@ using namespace vb2;
 extern "C" {
 const char* vb2_last_error(void) { return g_last_error.c_str(); }
 int vb2k_device_sm_count(void) { return device_sm_count(); }
+int64_t vb2k_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 
 static unsigned grid_for(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
@@ -125,7 +130,7 @@ static unsigned grid_for(int64_t n, int threads) {
 }
 int vb2k_fill_u64(uint64_t* p, int64_t n, uint64_t v, void* stream) {
   if (n <= 0) return VB2_OK;
-  fill_u64_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n, v);
+  fill_u64_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n, v);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -133,7 +138,7 @@ int vb2k_gather_bits(const uint64_t* in, const int32_t* sel, int64_t n, uint64_t
   if (n <= 0) return VB2_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VB2_CUDA_OK(cudaMemsetAsync(out + ((n + 63) >> 6) - 1, 0, 8, st));
-  gather_bits_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, sel, n, reinterpret_cast<uint32_t*>(out));
+  gather_bits_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(in, sel, n, reinterpret_cast<uint32_t*>(out));
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -141,7 +146,7 @@ int vb2k_pack_bools(const uint8_t* in, int64_t n, uint64_t* out, void* stream) {
   if (n <= 0) return VB2_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VB2_CUDA_OK(cudaMemsetAsync(out + ((n + 63) >> 6) - 1, 0, 8, st));
-  pack_bools_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, n, reinterpret_cast<uint32_t*>(out));
+  pack_bools_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(in, n, reinterpret_cast<uint32_t*>(out));
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -149,19 +154,19 @@ int vb2k_positive_bits(const int64_t* counts, int64_t n, uint64_t* out, void* st
   if (n <= 0) return VB2_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VB2_CUDA_OK(cudaMemsetAsync(out + ((n + 63) >> 6) - 1, 0, 8, st));
-  positive_bits_kernel<<<grid_for(n, 256), 256, 0, st>>>(counts, n, reinterpret_cast<uint32_t*>(out));
+  positive_bits_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(counts, n, reinterpret_cast<uint32_t*>(out));
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 int vb2k_widen_i32(const int32_t* in, int64_t n, int64_t* out, void* stream) {
   if (n <= 0) return VB2_OK;
-  widen_i32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, out, false);
+  widen_i32_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, out, false);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 int vb2k_widen_not_i32(const int32_t* in, int64_t n, int64_t* out, void* stream) {
   if (n <= 0) return VB2_OK;
-  widen_i32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, out, true);
+  widen_i32_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, out, true);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -169,41 +174,41 @@ int vb2k_index_validity(const int32_t* idx, int64_t n, uint64_t* valid, int32_t*
   if (n <= 0) return VB2_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VB2_CUDA_OK(cudaMemsetAsync(valid + ((n + 63) >> 6) - 1, 0, 8, st));
-  index_validity_kernel<<<grid_for(n, 256), 256, 0, st>>>(idx, n, reinterpret_cast<uint32_t*>(valid), clamped);
+  index_validity_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(idx, n, reinterpret_cast<uint32_t*>(valid), clamped);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 int vb2k_and_bits(const uint64_t* a, const uint64_t* b, int64_t n, uint64_t* out, void* stream) {
   if (n <= 0) return VB2_OK;
   const int64_t nwords = (n + 63) >> 6;
-  and_bits_kernel<<<grid_for(nwords, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, nwords, out);
+  and_bits_kernel<<<vb2::counted(grid_for(nwords, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, nwords, out);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 int vb2k_narrow_i64(const int64_t* in, int64_t n, int32_t* out, void* stream) {
   if (n <= 0) return VB2_OK;
-  narrow_i64_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, out);
+  narrow_i64_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, out);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 int vb2k_iota_i32(int32_t* p, int64_t n, void* stream) {
   if (n <= 0) return VB2_OK;
-  iota_i32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n);
+  iota_i32_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 int vb2k_scatter(const void* in, const int32_t* src, const int32_t* dst, int64_t n, int32_t elem_bytes, void* out, void* stream) {
   if (n <= 0) return VB2_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (elem_bytes == 8) scatter_kernel<uint64_t><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(in), src, dst, n, reinterpret_cast<uint64_t*>(out));
-  else if (elem_bytes == 4) scatter_kernel<uint32_t><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(in), src, dst, n, reinterpret_cast<uint32_t*>(out));
+  if (elem_bytes == 8) scatter_kernel<uint64_t><<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(in), src, dst, n, reinterpret_cast<uint64_t*>(out));
+  else if (elem_bytes == 4) scatter_kernel<uint32_t><<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(in), src, dst, n, reinterpret_cast<uint32_t*>(out));
   else return fail_msg(VB2_ERR_INVALID, "scatter: elem_bytes must be 4 or 8");
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
 int vb2k_fill_i32(int32_t* p, int64_t n, int32_t v, void* stream) {
   if (n <= 0) return VB2_OK;
-  fill_i32_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n, v);
+  fill_i32_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, n, v);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
