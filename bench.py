@@ -125,6 +125,34 @@ def plans(rv1, rv14, pt):
     return q1, q14
 
 
+def plans_distributed(rv1, rv14, pt):
+    """The same queries as multi-fragment plans, one process per GPU: partial aggregates are gathered
+    by a PartitionedOutput -> Exchange pair in front of the final aggregation; Q14 hash-partitions both
+    join sides by the join key (HashPartitionFunction) before the local build + probe
+    (velox/exec/tests/MultiFragmentTest.cpp builds such plans for the reference)."""
+    from velox_b200.plan import PlanBuilder
+    q1 = (PlanBuilder().values(rv1.names, rv1.types)
+          .filter("l_shipdate < '1998-09-03'::DATE")
+          .project(["l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice",
+                    "l_extendedprice * (1.0 - l_discount) AS l_sum_disc_price",
+                    "l_extendedprice * (1.0 - l_discount) * (1.0 + l_tax) AS l_sum_charge", "l_discount"])
+          .partialAggregation(["l_returnflag", "l_linestatus"],
+                              ["sum(l_quantity)", "sum(l_extendedprice)", "sum(l_sum_disc_price)", "sum(l_sum_charge)",
+                               "avg(l_quantity)", "avg(l_extendedprice)", "avg(l_discount)", "count(0)"])
+          .gatherExchange().finalAggregation().planNode())
+    build = PlanBuilder().values(pt.names, pt.types, source=1).partitionedOutput(["p_partkey"])
+    q14 = (PlanBuilder().values(rv14.names, rv14.types, source=0)
+           .filter("l_shipdate between '1995-09-01'::DATE and '1995-09-30'::DATE")
+           .project(["l_extendedprice * (1.0 - l_discount) as part_revenue", "l_partkey"])
+           .partitionedOutput(["l_partkey"])
+           .hashJoin(["l_partkey"], ["p_partkey"], build, "", ["part_revenue", "p_type"])
+           .project(["(CASE WHEN (p_type LIKE 'PROMO%') THEN part_revenue ELSE 0.0 END) as filter_revenue", "part_revenue"])
+           .partialAggregation([], ["sum(part_revenue) as total_revenue", "sum(filter_revenue) as total_promo_revenue"])
+           .gatherExchange().finalAggregation()
+           .project(["100.00 * total_promo_revenue/total_revenue as promo_revenue"]).planNode())
+    return q1, q14
+
+
 def cpu_sample(sf_rows: int, nparts: int, sample_rows: int, seed=42):
     import torch
     from velox_b200 import tpch
@@ -240,11 +268,13 @@ def slice_inputs(cols, n):
     return out
 
 
-def run_task(plan, inputs, config=None):
+def run_task(plan, inputs, config=None, comm=None):
     """One query through the operator-level C ABI: vb2_task_create / add_input(VB2_DEVICE) / run / result."""
     from velox_b200.task import Task
     t = Task(plan, config)
     try:
+        if comm is not None:
+            t.set_comm(comm)
         for sid, cols in inputs:
             t.add_input(sid, cols)
         out = t.run()
@@ -345,7 +375,8 @@ def main():
                 state["stats14"] = s14
             return out1, out14
     else:
-        step = multi_gpu_step(comm, plan1, plan14, c1, c14, cp, rows, state)
+        dplan1, dplan14 = plans_distributed(rv1s, rv14s, pts)
+        step = multi_gpu_step(comm, dplan1, dplan14, c1, c14, cp, rows, state)
 
     def barrier():
         torch.cuda.synchronize()
@@ -435,9 +466,12 @@ def main():
 
     results = {"q1": {f"{k[0]}{k[1]}": int(v[7]) for k, v in q1_rows(out1).items()}, "q14_promo_revenue": out14.rows()[0][0] if out14.size else None,
                "q6_revenue": q6k.result()}
-    # kernel-level and operator-level answers must agree
+    # kernel-level and operator-level answers must agree (rank 0 holds the gathered operator-level result)
     k1 = q1k.result()
-    assert {f"{k[0]}{k[1]}": int(v[7]) for k, v in k1.items()} == results["q1"], "operator-level and kernel-level Q1 counts differ"
+    if rank == 0:
+        assert {f"{k[0]}{k[1]}": int(v[7]) for k, v in k1.items()} == results["q1"], "operator-level and kernel-level Q1 counts differ"
+        k14 = q14k.result()
+        assert abs(results["q14_promo_revenue"] - k14) <= 1e-9 * abs(k14), ("operator-level and kernel-level Q14 differ", results["q14_promo_revenue"], k14)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -485,8 +519,21 @@ def main():
         dist.destroy_process_group()
 
 
-def multi_gpu_step(comm, plan1, plan14, c1, c14, cp, rows, state):
-    raise NotImplementedError("multi-GPU operator path: see velox_b200/csrc/host/exchange_ops.cpp")
+def multi_gpu_step(comm, dplan1, dplan14, c1, c14, cp, rows, state):
+    """One step on N GPUs: every rank runs the same multi-fragment plans over its row shard; the
+    B200PartitionedOutput / B200Exchange operators move rows between the ranks (rank 0 holds the answer)."""
+    def step(record=False):
+        out1, s1 = run_task(dplan1, [(0, c1)], comm=comm)
+        if record:
+            state["q1_kernel_ns"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanNanos"))
+            state["q1_kernel_rows"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanRows"))
+            state["q1_runs"] += 1
+            state["stats1"] = s1
+        out14, s14 = run_task(dplan14, [(0, c14), (1, cp)], comm=comm)
+        if record:
+            state["stats14"] = s14
+        return out1, out14
+    return step
 
 
 def e2e(args, li, part_all, rows, nparts, world, rank, rows_total):

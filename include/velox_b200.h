@@ -90,6 +90,19 @@ int32_t vb2_comm_all_to_all(vb2_comm* comm, const void* send, const int64_t* sen
  * device arrays of elem_bytes[c]-wide elements segmented by send_counts / recv_counts (rows). */
 int32_t vb2_comm_all_to_all_columns(vb2_comm* comm, int32_t ncols, const void* const* send, void* const* recv, const int32_t* elem_bytes,
                                     const int64_t* send_counts, const int64_t* recv_counts, void* stream);
+/* Every rank's `bytes`-byte block to every rank: recv holds world blocks in rank order (the
+ * metadata round of PartitionedOutput: per-destination row counts and dictionaries). */
+int32_t vb2_comm_all_gather(vb2_comm* comm, const void* send, void* recv, int64_t bytes, void* stream);
+/* Broadcast flavour of the exchange (PartitionedOutputNode::Kind::kBroadcast): every rank sends all
+ * `send_rows` rows of every column to every rank; recv[c] is segmented by recv_counts (rows per source). */
+int32_t vb2_comm_all_gather_columns(vb2_comm* comm, int32_t ncols, const void* const* send, void* const* recv, const int32_t* elem_bytes,
+                                    int64_t send_rows, const int64_t* recv_counts, void* stream);
+int32_t vb2_comm_world(vb2_comm* comm);
+int32_t vb2_comm_rank(vb2_comm* comm);
+/* Attaches the communicator to a task whose plan contains exchange nodes: B200PartitionedOutput /
+ * B200Exchange move their pages through it (the reference selects an ExchangeSource by task URI,
+ * velox/exec/ExchangeSource.h:139-145). The communicator must outlive the task. */
+int32_t vb2_task_set_comm(vb2_task* task, vb2_comm* comm);
 /* Sum-reduces n doubles / int64s in place across ranks (merge of per-GPU partial aggregates). */
 int32_t vb2_comm_all_reduce_f64(vb2_comm* comm, double* data, int64_t n, void* stream);
 int32_t vb2_comm_all_reduce_i64(vb2_comm* comm, int64_t* data, int64_t n, void* stream);

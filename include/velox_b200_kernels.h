@@ -89,7 +89,7 @@ int vb2k_partition_segments(const int64_t* keys, const void* const* cols, const 
                             int64_t* counts, int32_t* overflow, void* stream);
 /* *flag (device) <- 1 if any key other than VB2_SENTINEL_KEY lies outside [lo, hi]. */
 int vb2k_key_range_check(const int64_t* keys, int64_t n, int64_t lo, int64_t hi, int32_t* flag, void* stream);
-/* out[i] = in[order[i]] for fixed-width columns (elem_bytes 4 or 8). */
+/* out[i] = in[order[i]] for fixed-width columns (elem_bytes 1, 4 or 8). */
 int vb2k_gather(const void* in, const int32_t* order, int64_t n, int32_t elem_bytes, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -397,6 +397,8 @@ int vb2k_widen_not_i32(const int32_t* in, int64_t n, int64_t* out, void* stream)
 int vb2k_index_validity(const int32_t* idx, int64_t n, uint64_t* valid, int32_t* clamped, void* stream);
 /* out bit k = in bit sel[k] (validity bitmaps under a selection) */
 int vb2k_gather_bits(const uint64_t* in, const int32_t* sel, int64_t n, uint64_t* out, void* stream);
+/* bit-packed values / validity -> one byte per row (0/1): the form bitmaps take inside an exchange */
+int vb2k_unpack_bits(const uint64_t* in, int64_t n, uint8_t* out, void* stream);
 /* one byte per row (0/1) -> bit-packed BOOLEAN values (FlatVector<bool> layout) */
 int vb2k_pack_bools(const uint8_t* in, int64_t n, uint64_t* out, void* stream);
 /* out[dst[i]] = in[src ? src[i] : i] for 4- or 8-byte elements (accumulator moves on rehash) */

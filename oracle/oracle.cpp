@@ -830,6 +830,11 @@ static NodePtr parse_plan(const SNode& s) {
       n->projections.push_back(parse_expr(e, n->child->schema));
       n->schema.push_back(n->projections.back()->type);
     }
+  } else if (h == "exchange") {
+    // (exchange KIND (keys I ...) plan): PartitionedOutput -> Exchange between the tasks of a
+    // distributed plan (exec/PartitionedOutput.cpp, exec/Exchange.cpp). The oracle runs the whole
+    // plan over the whole data in one process, where the shuffle is the identity on the row multiset.
+    return parse_plan(s.arg(2));
   } else if (h == "orderby") {
     // (orderby ((I asc|desc first|last) ...) plan)
     n->kind = Node::ORDERBY;

@@ -23,3 +23,16 @@ def test_sharded_queries_match_single_gpu(world):
     lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
     assert lines[0]["ok"] and lines[0]["planned_runs"] >= 1
     assert lines[1]["overflow_rerun_ok"] and lines[1]["replanned"]
+
+
+@pytest.mark.parametrize("world", [2])
+def test_exchange_operators_match_oracle(world):
+    """Multi-fragment plans through B200PartitionedOutput / B200Exchange on `world` GPUs vs the oracle."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "scripts", "check_multigpu_ops.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines[0]["ok"] and lines[0]["exchange_rows_sent"] == lines[0]["exchange_rows_received"] > 0

@@ -413,3 +413,64 @@ def test_upload_cache_shares_host_buffers_between_tasks():
     assert sorted(t.run().rows()) == sorted(outs[0])
     assert t.stats()["task.h2dBytes"] >= full
     t.close()
+
+
+def test_exchange_operators_single_rank():
+    """PartitionedOutput -> Exchange inside one task (world 1: every partition is local): the shuffle
+    is the identity on the row multiset, whatever the encodings, NULLs and batch splits."""
+    rv = table(n=4000, seed=21)
+    plan = (PlanBuilder().values(rv.names, rv.types).filter("c1 < 8").project(["c0", "c1", "c2 * 2.0 AS d", "c5", "c4"])
+            .partitionedOutput(["c0"]).planNode())
+    check_plan(plan, [rv])
+    check_plan(plan, [rv], batch_rows=900)
+    plan = (PlanBuilder().values(rv.names, rv.types).partialAggregation(["c1", "c5"], ["sum(c2)", "avg(c3)", "count(0)", "max(c0)"])
+            .gatherExchange().finalAggregation().planNode())
+    check_plan(plan, [rv], rel_tol=1e-11)
+    check_plan(plan, [rv], batch_rows=700, rel_tol=1e-11)
+    plan = PlanBuilder().values(rv.names, rv.types).partitionedOutputBroadcast().singleAggregation([], ["count(0)", "sum(c0)"]).planNode()
+    check_plan(plan, [rv])
+
+
+def test_q14_multi_fragment_plan_single_rank():
+    """The distributed Q14 plan (both join sides behind an exchange, gathered partial aggregates) on one rank."""
+    import bench
+    n, nparts = 60_000, 3000
+    h, col = _lineitem(n, seed=14, nparts=nparts)
+    names1 = ["l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_shipdate"]
+    rv1 = row_vector(names1, [col(c) for c in names1])
+    names14 = ["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"]
+    li = row_vector(names14, [col(c) for c in names14])
+    part = {k: v.numpy() for k, v in tpch.gen_part(nparts, seed=5).items()}
+    pt = row_vector(["p_partkey", "p_type"], [flat_vector(BIGINT, part["p_partkey"]), dictionary_vector(VARCHAR, part["p_type"], tpch.PTYPE_DICT)])
+    d1, d14 = bench.plans_distributed(rv1, li, pt)
+    st_f, st_g = check_plan(d14, [li, pt], configs=(FUSED, GENERIC), rel_tol=1e-12)
+    assert stat(st_f, "b200.fusedBatches") == 1, "the probe after the exchange must take the fused kernel"
+    check_plan(d1, [rv1], configs=(FUSED, GENERIC), rel_tol=1e-12)
+    check_plan(d1, [rv1], configs=(FUSED,), batch_rows=25_000, rel_tol=1e-12)
+
+
+def test_group_keys_with_reordered_dictionaries_between_batches():
+    """Two batches whose VARCHAR key dictionaries list the same strings in a different order (Arrow
+    record batches do this): the per-dictionary id LUT must follow the dictionary, not its address."""
+    from velox_b200.task import Task
+    a = row_vector(["k", "v"], [dictionary_vector(VARCHAR, np.array([0, 1, 2, 0], dtype=np.int32), ["x", "y", "z"]), flat_vector(BIGINT, [1, 10, 100, 1000])])
+    b = row_vector(["k", "v"], [dictionary_vector(VARCHAR, np.array([0, 1, 2, 0], dtype=np.int32), ["z", "x", "y"]), flat_vector(BIGINT, [2, 20, 200, 2000])])
+    plan = PlanBuilder().values(a.names, a.types).singleAggregation(["k"], ["sum(v)", "count(0)"]).planNode()
+    for _ in range(20):  # allocator reuse makes a stale pointer-keyed cache hit likely within a few rounds
+        t = Task(plan)
+        t.add_input(0, a)
+        t.add_input(0, b)
+        got = {r[0]: (r[1], r[2]) for r in t.run().rows()}
+        t.close()
+        assert got == {"x": (1 + 1000 + 20, 3), "y": (10 + 200, 2), "z": (100 + 2 + 2000, 3)}, got
+
+
+def test_partial_final_collapse_keeps_results():
+    """partial -> final in one driver is run as a single aggregation (adapter); with the fused
+    pipelines off the pair stays apart. Both must give the oracle's answer."""
+    rv = table(n=5000, seed=33)
+    plan = (PlanBuilder().values(rv.names, rv.types).filter("c1 < 9").project(["c1", "c5", "c2", "c3 + 1.0 AS e", "c0"])
+            .partialAggregation(["c1", "c5"], ["sum(c2)", "avg(e)", "count(0)", "min(c0)", "max(c2)"]).localPartition([]).finalAggregation().planNode())
+    st_f, st_g = check_plan(plan, [rv], configs=(FUSED, GENERIC), rel_tol=1e-11)
+    nagg = lambda st: len([k for k in st if k.endswith("B200HashAggregation.inputPositions")])
+    assert nagg(st_f) == 1 and nagg(st_g) == 2

@@ -213,6 +213,59 @@ class HashJoinNode : public PlanNode {
   RowTypePtr type_;
 };
 
+// velox/core/PlanNode.h:2712 PartitionedOutputNode — root of a producing plan fragment: rows are
+// partitioned by hash(keys) % numPartitions (kPartitioned; HashPartitionFunction,
+// velox/exec/HashPartitionFunction.cpp:75-118), replicated to every consumer (kBroadcast) or sent
+// anywhere (kArbitrary). numPartitions == 0 in the shim means "one partition per rank of the task's
+// exchange transport", resolved when the operator is created.
+class PartitionedOutputNode : public PlanNode {
+ public:
+  enum class Kind { kPartitioned, kBroadcast, kArbitrary };
+  PartitionedOutputNode(PlanNodeId id, Kind kind, std::vector<TypedExprPtr> keys, int numPartitions, bool replicateNullsAndAny,
+                        RowTypePtr outputType, std::string serdeKind, PlanNodePtr source)
+      : PlanNode(std::move(id)), kind_(kind), keys_(std::move(keys)), numPartitions_(numPartitions), replicateNullsAndAny_(replicateNullsAndAny),
+        type_(std::move(outputType)), serdeKind_(std::move(serdeKind)), sources_{std::move(source)} {}
+  Kind kind() const { return kind_; }
+  bool isBroadcast() const { return kind_ == Kind::kBroadcast; }
+  const std::vector<TypedExprPtr>& keys() const { return keys_; }
+  int numPartitions() const { return numPartitions_; }
+  bool isReplicateNullsAndAny() const { return replicateNullsAndAny_; }
+  const std::string& serdeKind() const { return serdeKind_; }
+  const RowTypePtr& outputType() const override { return type_; }
+  const RowTypePtr& inputType() const { return sources_[0]->outputType(); }
+  const std::vector<PlanNodePtr>& sources() const override { return sources_; }
+  std::string_view name() const override { return "PartitionedOutput"; }
+
+ private:
+  Kind kind_;
+  std::vector<TypedExprPtr> keys_;
+  int numPartitions_;
+  bool replicateNullsAndAny_;
+  RowTypePtr type_;
+  std::string serdeKind_;
+  std::vector<PlanNodePtr> sources_;
+};
+// velox/core/PlanNode.h:2182 ExchangeNode — leaf of a consuming fragment. In the reference the
+// producing fragment is another Task reached through remote splits; one process per GPU runs every
+// fragment of the (SPMD) plan inside one Task, so the shim links the producer directly
+// (`upstream()`, shim only) and the planner turns the pair into two pipelines joined by an
+// ExchangeQueue.
+class ExchangeNode : public PlanNode {
+ public:
+  ExchangeNode(PlanNodeId id, RowTypePtr type, std::string serdeKind) : PlanNode(std::move(id)), type_(std::move(type)), serdeKind_(std::move(serdeKind)) {}
+  const RowTypePtr& outputType() const override { return type_; }
+  const std::vector<PlanNodePtr>& sources() const override { static const std::vector<PlanNodePtr> kEmpty; return kEmpty; }
+  std::string_view name() const override { return "Exchange"; }
+  const std::string& serdeKind() const { return serdeKind_; }
+  void setUpstream(std::shared_ptr<const PartitionedOutputNode> producer) { upstream_ = std::move(producer); }
+  const std::shared_ptr<const PartitionedOutputNode>& upstream() const { return upstream_; }
+
+ private:
+  RowTypePtr type_;
+  std::string serdeKind_;
+  std::shared_ptr<const PartitionedOutputNode> upstream_;
+};
+
 class QueryConfig {
  public:
   explicit QueryConfig(std::unordered_map<std::string, std::string> values = {}) : values_(std::move(values)) {}
@@ -407,6 +460,37 @@ class HashJoinBridge : public JoinBridge {
   std::vector<std::shared_ptr<bool>> waiters_;
 };
 
+// ---- exchange hand-off ----------------------------------------------------------------------------
+// What sits between a PartitionedOutput and the Exchange reading it inside one process: the role of
+// OutputBufferManager (velox/exec/OutputBufferManager.h) + ExchangeClient / ExchangeQueue
+// (velox/exec/ExchangeClient.h, ExchangeQueue.h). The producer deposits the pages this process
+// receives (after the transport's all-to-all) and closes the queue; the consumer waits on a future.
+class ExchangeQueue {
+ public:
+  void enqueue(RowVectorPtr page) { pages_.push_back(std::move(page)); }
+  void noMoreData() {
+    done_ = true;
+    for (auto& f : waiters_) *f = true;
+    waiters_.clear();
+  }
+  // next page, or nullptr with *atEnd set; blocks (future) while the producer is still running
+  RowVectorPtr dequeue(bool* atEnd, ContinueFuture* future) {
+    *atEnd = false;
+    if (next_ < pages_.size()) return std::move(pages_[next_++]);
+    if (done_) { *atEnd = true; return nullptr; }
+    future->ready = std::make_shared<bool>(false);
+    waiters_.push_back(future->ready);
+    return nullptr;
+  }
+  bool drained() const { return done_ && next_ >= pages_.size(); }
+
+ private:
+  std::vector<RowVectorPtr> pages_;
+  size_t next_ = 0;
+  bool done_ = false;
+  std::vector<std::shared_ptr<bool>> waiters_;
+};
+
 // ---- CPU operators of the reference, as the LocalPlanner instantiates them ----------------------
 // The reference's CPU implementations are not part of this repo (no CPU fallback): these classes
 // carry the plan information and the accelerator hooks the adapter reads, and refuse to run.
@@ -480,6 +564,31 @@ class HashProbe : public CpuOperatorStub {
  private:
   std::shared_ptr<const core::HashJoinNode> node_;
   std::shared_ptr<HashJoinBridge> bridge_;
+};
+
+// velox/exec/PartitionedOutput.h:157 / velox/exec/Exchange.h:51 — carriers like the stubs above.
+class PartitionedOutput : public CpuOperatorStub {
+ public:
+  PartitionedOutput(int32_t operatorId, DriverCtx* ctx, std::shared_ptr<const core::PartitionedOutputNode> node, std::shared_ptr<ExchangeQueue> queue)
+      : CpuOperatorStub(ctx, node->outputType(), operatorId, node->id(), "PartitionedOutput"), node_(std::move(node)), queue_(std::move(queue)) {}
+  const std::shared_ptr<const core::PartitionedOutputNode>& node() const { return node_; }
+  const std::shared_ptr<ExchangeQueue>& queue() const { return queue_; }
+
+ private:
+  std::shared_ptr<const core::PartitionedOutputNode> node_;
+  std::shared_ptr<ExchangeQueue> queue_;
+};
+class Exchange : public CpuOperatorStub {
+ public:
+  Exchange(int32_t operatorId, DriverCtx* ctx, std::shared_ptr<const core::ExchangeNode> node, std::shared_ptr<ExchangeQueue> queue)
+      : CpuOperatorStub(ctx, node->outputType(), operatorId, node->id(), "Exchange"), node_(std::move(node)), queue_(std::move(queue)) {}
+  const std::shared_ptr<const core::ExchangeNode>& node() const { return node_; }
+  const std::shared_ptr<ExchangeQueue>& queue() const { return queue_; }
+  bool isSourceOperator() const override { return true; }
+
+ private:
+  std::shared_ptr<const core::ExchangeNode> node_;
+  std::shared_ptr<ExchangeQueue> queue_;
 };
 
 // Source fed with batches at run time (velox/exec/Values.h:21 holds its vectors in the plan node;

@@ -343,8 +343,10 @@ int vb2k_gather(const void* in, const int32_t* order, int64_t n, int32_t elem_by
     gather_kernel<uint64_t><<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(reinterpret_cast<const uint64_t*>(in), order, n, reinterpret_cast<uint64_t*>(out));
   else if (elem_bytes == 4)
     gather_kernel<uint32_t><<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(in), order, n, reinterpret_cast<uint32_t*>(out));
+  else if (elem_bytes == 1)
+    gather_kernel<uint8_t><<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(in), order, n, reinterpret_cast<uint8_t*>(out));
   else
-    return fail_msg(VB2_ERR_INVALID, "gather: elem_bytes must be 4 or 8");
+    return fail_msg(VB2_ERR_INVALID, "gather: elem_bytes must be 1, 4 or 8");
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }

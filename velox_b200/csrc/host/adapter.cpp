@@ -58,7 +58,10 @@ bool adaptDriver(const exec::DriverFactory& factory, exec::Driver& driver) {
         while (first > 0 && (dynamic_cast<B200FilterProject*>(out[first - 1].get()) || dynamic_cast<B200HashProbe*>(out[first - 1].get()))) --first;
         // only the shapes the fused path understands; anything else stays unfused
         const size_t run = out.size() - first;
+        // FilterProject | FilterProject -> HashProbe -> FilterProject | HashProbe -> FilterProject (the
+        // probe side arrives ready-made, e.g. from an Exchange)
         const bool shapeOk = run == 1 ? dynamic_cast<B200FilterProject*>(out[first].get()) != nullptr
+                           : run == 2 ? (dynamic_cast<B200HashProbe*>(out[first].get()) && dynamic_cast<B200FilterProject*>(out[first + 1].get()))
                                       : (run == 3 && dynamic_cast<B200FilterProject*>(out[first].get()) &&
                                          dynamic_cast<B200HashProbe*>(out[first + 1].get()) && dynamic_cast<B200FilterProject*>(out[first + 2].get()));
         if (shapeOk) {
@@ -85,6 +88,12 @@ bool adaptDriver(const exec::DriverFactory& factory, exec::Driver& driver) {
       replacedAny = true;
     } else if (auto probe = dynamic_cast<exec::HashProbe*>(op)) {
       out.push_back(std::make_unique<B200HashProbe>(id, ctx, *probe));
+      replacedAny = true;
+    } else if (auto po = dynamic_cast<exec::PartitionedOutput*>(op)) {
+      out.push_back(std::make_unique<B200PartitionedOutput>(id, ctx, *po));
+      replacedAny = true;
+    } else if (auto ex = dynamic_cast<exec::Exchange*>(op)) {
+      out.push_back(std::make_unique<B200Exchange>(id, ctx, *ex));
       replacedAny = true;
     } else if (dynamic_cast<exec::CallbackSink*>(op)) {
       RowTypePtr type = out.empty() ? nullptr : out.back()->outputType();

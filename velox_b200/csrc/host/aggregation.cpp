@@ -488,24 +488,33 @@ struct B200HashAggregation::Impl {
     B200FilterProject *fp1 = nullptr, *fp2 = nullptr;
     B200HashProbe* probe = nullptr;
     if (absorbed.size() == 1) fp1 = dynamic_cast<B200FilterProject*>(absorbed[0].get());
-    else if (absorbed.size() == 3) {
+    else if (absorbed.size() == 2) {
+      probe = dynamic_cast<B200HashProbe*>(absorbed[0].get());
+      fp2 = dynamic_cast<B200FilterProject*>(absorbed[1].get());
+      if (!probe || !fp2 || fp2->hasFilter()) return;
+      if (probe->node()->joinType() != core::JoinType::kInner || probe->node()->filter() || probe->node()->leftKeys().size() != 1) return;
+    } else if (absorbed.size() == 3) {
       fp1 = dynamic_cast<B200FilterProject*>(absorbed[0].get());
       probe = dynamic_cast<B200HashProbe*>(absorbed[1].get());
       fp2 = dynamic_cast<B200FilterProject*>(absorbed[2].get());
       if (!probe || !fp2 || fp2->hasFilter()) return;
       if (probe->node()->joinType() != core::JoinType::kInner || probe->node()->filter() || probe->node()->leftKeys().size() != 1) return;
     }
-    if (!fp1) return;
-    const RowTypePtr& srcType = fp1->inputType();
+    if (!fp1 && !probe) return;
+    const RowTypePtr srcType = fp1 ? fp1->inputType() : probe->node()->sources()[0]->outputType();
     // expressions of the stage feeding the aggregation, in terms of source columns; build-side
     // columns are marked with index = -(buildColumn + 1)
     std::vector<core::TypedExprPtr> stage;
     core::TypedExprPtr filter;
-    {
+    if (fp1) {
       const auto& e = fp1->exprs();
       size_t first = 0;
       if (fp1->hasFilter()) { filter = e[0]; first = 1; }
       for (size_t i = first; i < e.size(); ++i) stage.push_back(e[i]);
+    } else {
+      // the probe reads the source batch directly: the stage is the identity over its columns
+      for (uint32_t i = 0; i < srcType->size(); ++i)
+        stage.push_back(std::make_shared<core::FieldAccessTypedExpr>(srcType->childAt(i), srcType->nameOf(i), static_cast<int32_t>(i)));
     }
     int joinKeySource = -1;
     if (probe) {
@@ -835,6 +844,7 @@ struct B200HashAggregation::Impl {
   // row count in a single copy + synchronisation; B200ToHost then reads the host mirror.
   B200VectorPtr output() {
     flushFused();
+    if (!sawInput && mode != Mode::kGlobal) return nullptr;  // a grouped aggregation over no input emits nothing
     const bool small = capacity <= VB2_EXTRACT_SMALL_CAPACITY;
     int64_t m = 0;
     DeviceBufferPtr slots;
@@ -862,8 +872,8 @@ struct B200HashAggregation::Impl {
       ColPlan c;
       c.type = inType->childAt(node->groupingKeys()[k]);
       c.ec.kind = VB2_EXTRACT_KEY;
-      c.ec.mult = layout.mults[k];
-      c.ec.range = layout.ranges[k];
+      c.ec.mult = layout.mults[k] ? layout.mults[k] : 1;
+      c.ec.range = layout.ranges[k] ? layout.ranges[k] : 1;
       c.ec.null_reserved = nullReserved[k];
       c.ec.count_word = -1;
       c.hasValid = nullReserved[k] != 0;

@@ -371,6 +371,12 @@ int32_t vb2_plan_jit_report(const char* plan_text, int32_t* programs, int32_t* j
   });
 }
 
+int32_t vb2_task_set_comm(vb2_task* task, vb2_comm* comm) {
+  if (!task || !task->task) return VB2_ERR_INVALID;
+  task->task->setExchangeTransport(comm ? std::make_shared<velox_b200::NcclTransport>(comm) : nullptr);
+  return VB2_OK;
+}
+
 vb2_upload_cache* vb2_upload_cache_create(void) { return new vb2_upload_cache(); }
 void vb2_upload_cache_free(vb2_upload_cache* cache) { delete cache; }
 int32_t vb2_task_set_upload_cache(vb2_task* task, vb2_upload_cache* cache) {

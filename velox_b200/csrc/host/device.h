@@ -88,6 +88,10 @@ class B200Vector : public RowVector {
   const std::vector<DeviceColumnPtr>& columns() const { return cols_; }
   const DeviceColumnPtr& column(size_t i) const { return cols_.at(i); }
   cudaStream_t stream() const { return stream_; }
+  // Work on another stream that must finish before the columns may be read (pages that arrive
+  // through an exchange are produced on the sending pipeline's stream).
+  void setReadyEvent(std::shared_ptr<void> e) { ready_ = std::move(e); }
+  cudaEvent_t readyEvent() const { return static_cast<cudaEvent_t>(ready_.get()); }
   void setMirror(std::shared_ptr<const HostMirror> m) { mirror_ = std::move(m); }
   const std::shared_ptr<const HostMirror>& mirror() const { return mirror_; }
 
@@ -95,6 +99,7 @@ class B200Vector : public RowVector {
   std::vector<DeviceColumnPtr> cols_;
   cudaStream_t stream_;
   std::shared_ptr<const HostMirror> mirror_;
+  std::shared_ptr<void> ready_;
 };
 using B200VectorPtr = std::shared_ptr<B200Vector>;
 

@@ -147,6 +147,30 @@ int32_t vb2_comm_all_to_all_columns(vb2_comm* comm, int32_t ncols, const void* c
   return ncclFail(ncclGroupEnd(), "all_to_all_columns");
 }
 
+int32_t vb2_comm_all_gather(vb2_comm* comm, const void* send, void* recv, int64_t bytes, void* stream) {
+  return ncclFail(ncclAllGather(send, recv, static_cast<size_t>(bytes), ncclUint8, comm->comm, static_cast<cudaStream_t>(stream)), "all_gather");
+}
+
+int32_t vb2_comm_all_gather_columns(vb2_comm* comm, int32_t ncols, const void* const* send, void* const* recv, const int32_t* elem_bytes,
+                                    int64_t send_rows, const int64_t* recv_counts, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int w = comm->world;
+  ncclGroupStart();
+  for (int c = 0; c < ncols; ++c) {
+    char* r = static_cast<char*>(recv[c]);
+    int64_t roff = 0;
+    for (int p = 0; p < w; ++p) {
+      if (send_rows > 0) ncclSend(send[c], static_cast<size_t>(send_rows) * elem_bytes[c], ncclUint8, p, comm->comm, st);
+      if (recv_counts[p] > 0) ncclRecv(r + roff * elem_bytes[c], static_cast<size_t>(recv_counts[p]) * elem_bytes[c], ncclUint8, p, comm->comm, st);
+      roff += recv_counts[p];
+    }
+  }
+  return ncclFail(ncclGroupEnd(), "all_gather_columns");
+}
+
+int32_t vb2_comm_world(vb2_comm* comm) { return comm ? comm->world : 1; }
+int32_t vb2_comm_rank(vb2_comm* comm) { return comm ? comm->rank : 0; }
+
 int32_t vb2_comm_all_reduce_f64(vb2_comm* comm, double* data, int64_t n, void* stream) {
   return ncclFail(ncclAllReduce(data, data, static_cast<size_t>(n), ncclDouble, ncclSum, comm->comm, static_cast<cudaStream_t>(stream)), "all_reduce");
 }

@@ -1,0 +1,414 @@
+// B200PartitionedOutput / B200Exchange: the shuffle between the fragments of a distributed plan as
+// device operators.
+//   reference ....... velox/exec/PartitionedOutput.cpp (partition each batch with the node's partition
+//                     function, append to per-destination buffers, flush to the OutputBufferManager),
+//                     velox/exec/Exchange.cpp + ExchangeClient (pull pages from every producer)
+//   GPU precedent ... velox/experimental/ucx-exchange/UcxPartitionedOutput.h:29-110 (whole device
+//                     tables per destination instead of serialized rows)
+// One process per GPU runs the same plan; the producing and the consuming fragment meet inside the
+// Task through an ExchangeQueue, and the rows cross NVLink in one grouped ncclSend/ncclRecv all-to-all
+// per exchange (all columns in one launch), preceded by ONE metadata all-gather (per-destination
+// row counts + VARCHAR alphabets) that is the exchange's only host synchronisation.
+#include <cstring>
+#include <map>
+
+#include "join.h"
+#include "operators.h"
+
+namespace velox_b200 {
+
+namespace {
+
+constexpr size_t kAlphabetBlockBytes = 16 * 1024;  // per VARCHAR column and rank inside the metadata block
+
+std::shared_ptr<void> makeEvent() {
+  cudaEvent_t e = nullptr;
+  VB2_CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return std::shared_ptr<void>(e, [](void* p) { cudaEventDestroy(static_cast<cudaEvent_t>(p)); });
+}
+
+// One column in exchange form: flat fixed-width values (VARCHAR: int32 dictionary codes, BOOLEAN:
+// one byte per row) and, when the column may hold NULLs, one validity byte per row.
+struct WireColumn {
+  TypePtr type;
+  int32_t vb2Type = 0;
+  int32_t width = 8;
+  const void* values = nullptr;
+  const uint8_t* validBytes = nullptr;
+  std::shared_ptr<const HostAlphabet> alphabet;  // VARCHAR
+  std::vector<DeviceBufferPtr> keep;
+};
+
+NcclTransport* transportOf(exec::DriverCtx* ctx) {
+  auto* t = ctx->task ? dynamic_cast<NcclTransport*>(ctx->task->exchangeTransport().get()) : nullptr;
+  return t;
+}
+
+}  // namespace
+
+// ---- B200PartitionedOutput -------------------------------------------------------------------------
+B200PartitionedOutput::B200PartitionedOutput(int32_t id, exec::DriverCtx* ctx, const exec::PartitionedOutput& cpu)
+    : Operator(ctx, cpu.node()->outputType(), id, cpu.planNodeId(), "B200PartitionedOutput"), node_(cpu.node()), queue_(cpu.queue()) {}
+
+void B200PartitionedOutput::initialize() {
+  Operator::initialize();
+  dev_ = driverDeviceContext(driverCtx_);
+}
+
+void B200PartitionedOutput::addInput(RowVectorPtr input) {
+  auto in = std::dynamic_pointer_cast<B200Vector>(input);
+  VELOX_CHECK(in != nullptr, "B200PartitionedOutput expects device-resident input");
+  batches_.push_back(std::move(in));
+}
+
+void B200PartitionedOutput::noMoreInput() {
+  Operator::noMoreInput();
+  cudaStream_t st = dev_->stream;
+  NcclTransport* tr = transportOf(driverCtx_);
+  const int world = tr ? tr->world() : 1;
+  const int rank = tr ? tr->rank() : 0;
+  const auto& type = node_->inputType();
+  const size_t ncols = type->size();
+  int parts = node_->numPartitions() > 0 ? node_->numPartitions() : world;
+  VELOX_CHECK(parts <= world, "more partitions than ranks in the exchange transport");
+  const bool broadcast = node_->isBroadcast();
+
+  // ---- rows of this rank in wire form -----------------------------------------------------------
+  int64_t n = 0;
+  for (auto& b : batches_) n += b->size();
+  VELOX_CHECK(n < (1ll << 31), "exchange input above 2^31 rows per rank");
+  std::vector<WireColumn> wire(ncols);
+  for (size_t c = 0; c < ncols; ++c) {
+    WireColumn& w = wire[c];
+    w.type = type->childAt(static_cast<uint32_t>(c));
+    w.vb2Type = veloxTypeToVb2(w.type);
+    w.width = w.vb2Type == VB2_VARCHAR ? 4 : (w.vb2Type == VB2_BOOLEAN ? 1 : widthOf(w.vb2Type));
+    bool anyNulls = false;
+    for (auto& b : batches_) anyNulls = anyNulls || b->column(c)->mayHaveNulls();
+    if (w.vb2Type == VB2_VARCHAR) {
+      // dictionary codes travel; every batch must bring the same host alphabet contents
+      for (auto& b : batches_) {
+        const DeviceColumn& col = *b->column(c);
+        if (col.desc.encoding == VB2_FLAT || !col.alphabet) VELOX_UNSUPPORTED("exchange of flat (non-dictionary) VARCHAR columns");
+        for (bool isNull : col.alphabet->nulls)
+          if (isNull) VELOX_UNSUPPORTED("exchange of VARCHAR dictionaries with NULL entries");
+        if (col.desc.nulls) VELOX_UNSUPPORTED("exchange of VARCHAR columns with NULL rows");
+        if (!w.alphabet) w.alphabet = col.alphabet;
+        else if (w.alphabet != col.alphabet && w.alphabet->values != col.alphabet->values) VELOX_UNSUPPORTED("exchange input batches with different VARCHAR dictionaries");
+      }
+      if (!w.alphabet) { auto a = std::make_shared<HostAlphabet>(); w.alphabet = a; }
+    }
+    if (batches_.size() == 1 && !anyNulls) {
+      const DeviceColumn& col = *batches_[0]->column(c);
+      if (w.vb2Type == VB2_VARCHAR && col.desc.encoding == VB2_DICTIONARY) { w.values = col.desc.indices; continue; }
+      if (w.vb2Type != VB2_VARCHAR && w.vb2Type != VB2_BOOLEAN && col.desc.encoding == VB2_FLAT) { w.values = col.desc.values; continue; }
+    }
+    // general case: decode every batch into one flat buffer (+ validity bytes)
+    auto values = allocDevice(static_cast<size_t>(n ? n : 1) * w.width, st);
+    DeviceBufferPtr valid = anyNulls ? allocDevice(static_cast<size_t>(n ? n : 1), st) : nullptr;
+    int64_t off = 0;
+    for (auto& b : batches_) {
+      const DeviceColumnPtr& col = b->column(c);
+      const int64_t bn = b->size();
+      if (w.vb2Type == VB2_VARCHAR) {
+        if (col->desc.encoding == VB2_DICTIONARY) VB2_CU(cudaMemcpyAsync(values->as<int32_t>() + off, col->desc.indices, static_cast<size_t>(bn) * 4, cudaMemcpyDeviceToDevice, st));
+        else VB2_CU(cudaMemsetAsync(values->as<int32_t>() + off, 0, static_cast<size_t>(bn) * 4, st));  // constant: code 0
+      } else {
+        FlatColumn f = flattenColumn(col, nullptr, bn, st);
+        VB2_CU(cudaMemcpyAsync(values->as<uint8_t>() + off * w.width, f.values->data(), static_cast<size_t>(bn) * w.width, cudaMemcpyDeviceToDevice, st));
+        if (valid) {
+          if (f.nulls) kernelCheck(vb2k_unpack_bits(f.nulls->as<uint64_t>(), bn, valid->as<uint8_t>() + off, st));
+          else VB2_CU(cudaMemsetAsync(valid->as<uint8_t>() + off, 1, static_cast<size_t>(bn), st));
+        }
+      }
+      off += bn;
+    }
+    w.values = values->data();
+    w.keep.push_back(values);
+    if (valid) { w.validBytes = valid->as<uint8_t>(); w.keep.push_back(valid); }
+  }
+
+  // ---- partition (HashPartitionFunction: hash(keys) % partitions) ---------------------------------
+  DeviceBufferPtr countsDev = allocDeviceZeroed(static_cast<size_t>(world) * 8, st);
+  DeviceBufferPtr order;
+  if (!broadcast && parts > 1 && n > 0) {
+    auto hashes = allocDevice(static_cast<size_t>(n) * 8, st);
+    int64_t off = 0;
+    for (auto& b : batches_) {
+      std::vector<vb2_column> keyCols;
+      for (auto& k : node_->keys()) {
+        auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(k.get());
+        VELOX_CHECK(f != nullptr && f->index() >= 0, "partition keys must be input columns");
+        keyCols.push_back(b->column(f->index())->desc);
+      }
+      VELOX_CHECK(!keyCols.empty(), "partitioned exchange without keys");
+      kernelCheck(vb2k_hash_columns(keyCols.data(), static_cast<int32_t>(keyCols.size()), b->size(), hashes->as<uint64_t>() + off, st));
+      off += b->size();
+    }
+    auto ids = allocDevice(static_cast<size_t>(n) * 4, st);
+    kernelCheck(vb2k_partition_ids(hashes->as<uint64_t>(), n, parts, ids->as<uint32_t>(), st));
+    order = allocDevice(static_cast<size_t>(n) * 4, st);
+    kernelCheck(vb2k_partition_scatter_order(ids->as<uint32_t>(), n, parts, countsDev->as<int64_t>(), order->as<int32_t>(), st));
+  } else if (n > 0) {
+    // one partition (gather) or broadcast: every row goes to rank 0 / to every rank; no reordering
+    std::vector<int64_t> c(world, broadcast ? n : 0);
+    if (!broadcast) c[0] = n;
+    VB2_CU(cudaMemcpyAsync(countsDev->data(), c.data(), static_cast<size_t>(world) * 8, cudaMemcpyHostToDevice, st));
+  }
+  // columns grouped by destination
+  std::vector<const void*> sendPtr;
+  std::vector<int32_t> elemBytes;
+  std::vector<DeviceBufferPtr> keep;
+  auto addSend = [&](const void* src, int32_t width) {
+    if (order) {
+      auto g = allocDevice(static_cast<size_t>(n) * width, st);
+      kernelCheck(vb2k_gather(src, order->as<int32_t>(), n, width, g->data(), st));
+      keep.push_back(g);
+      sendPtr.push_back(g->data());
+    } else {
+      sendPtr.push_back(src);
+    }
+    elemBytes.push_back(width);
+  };
+  for (auto& w : wire) {
+    addSend(w.values, w.width);
+    if (w.validBytes) addSend(w.validBytes, 1);
+  }
+
+  // ---- metadata round: [counts[world] | has-valid flags | alphabets] from every rank ---------------
+  size_t nVarchar = 0;
+  for (auto& w : wire) nVarchar += w.vb2Type == VB2_VARCHAR;
+  const size_t blockBytes = (static_cast<size_t>(world) * 8 + ncols * 8 + nVarchar * kAlphabetBlockBytes + 255) / 256 * 256;
+  std::vector<uint8_t> myBlock(blockBytes, 0);
+  {
+    int64_t* flags = reinterpret_cast<int64_t*>(myBlock.data() + static_cast<size_t>(world) * 8);
+    for (size_t c = 0; c < ncols; ++c) flags[c] = wire[c].validBytes ? 1 : 0;
+    uint8_t* ap = myBlock.data() + static_cast<size_t>(world) * 8 + ncols * 8;
+    for (auto& w : wire) {
+      if (w.vb2Type != VB2_VARCHAR) continue;
+      // [int32 entries | int32 lengths[entries] | chars]
+      size_t need = 4 + w.alphabet->values.size() * 4;
+      for (auto& v : w.alphabet->values) need += v.size();
+      if (need > kAlphabetBlockBytes) VELOX_UNSUPPORTED("VARCHAR dictionary too large for the exchange metadata block");
+      int32_t* hp = reinterpret_cast<int32_t*>(ap);
+      hp[0] = static_cast<int32_t>(w.alphabet->values.size());
+      char* cp = reinterpret_cast<char*>(hp + 1 + w.alphabet->values.size());
+      for (size_t i = 0; i < w.alphabet->values.size(); ++i) {
+        hp[1 + i] = static_cast<int32_t>(w.alphabet->values[i].size());
+        std::memcpy(cp, w.alphabet->values[i].data(), w.alphabet->values[i].size());
+        cp += w.alphabet->values[i].size();
+      }
+      ap += kAlphabetBlockBytes;
+    }
+  }
+  auto blockDev = allocDevice(blockBytes, st);
+  auto allDev = allocDevice(blockBytes * world, st);
+  VB2_CU(cudaMemcpyAsync(blockDev->data(), myBlock.data(), blockBytes, cudaMemcpyHostToDevice, st));
+  VB2_CU(cudaMemcpyAsync(blockDev->data(), countsDev->data(), static_cast<size_t>(world) * 8, cudaMemcpyDeviceToDevice, st));
+  auto allHost = acquirePinned(blockBytes * world);
+  if (world > 1) {
+    VELOX_CHECK(tr != nullptr, "the plan contains an exchange but the task has no exchange transport (vb2_task_set_comm)");
+    VELOX_CHECK(vb2_comm_all_gather(tr->comm(), blockDev->data(), allDev->data(), static_cast<int64_t>(blockBytes), st) == VB2_OK, "exchange metadata all-gather failed");
+    VB2_CU(cudaMemcpyAsync(allHost.get(), allDev->data(), blockBytes * world, cudaMemcpyDeviceToHost, st));
+  } else {
+    VB2_CU(cudaMemcpyAsync(allHost.get(), blockDev->data(), blockBytes, cudaMemcpyDeviceToHost, st));
+  }
+  VB2_CU(cudaStreamSynchronize(st));  // the exchange's only host synchronisation
+  const uint8_t* all = static_cast<const uint8_t*>(allHost.get());
+  auto blockOf = [&](int r) { return all + static_cast<size_t>(r) * blockBytes; };
+  std::vector<int64_t> sendCounts(world), recvCounts(world);
+  for (int p = 0; p < world; ++p) {
+    sendCounts[p] = reinterpret_cast<const int64_t*>(blockOf(rank))[p];
+    recvCounts[p] = reinterpret_cast<const int64_t*>(blockOf(p))[rank];
+  }
+  int64_t total = 0;
+  for (int p = 0; p < world; ++p) total += recvCounts[p];
+  VELOX_CHECK(total < (1ll << 31), "exchange output above 2^31 rows per rank");
+  // a column carries validity bytes if any rank sends them: ranks without NULLs send all-ones
+  std::vector<bool> anyValid(ncols, false);
+  for (int r = 0; r < world; ++r) {
+    const int64_t* flags = reinterpret_cast<const int64_t*>(blockOf(r) + static_cast<size_t>(world) * 8);
+    for (size_t c = 0; c < ncols; ++c) anyValid[c] = anyValid[c] || flags[c] != 0;
+  }
+  {
+    // re-derive the send list if some other rank needs validity bytes this rank did not plan to send
+    bool mismatch = false;
+    for (size_t c = 0; c < ncols; ++c) mismatch = mismatch || (anyValid[c] && !wire[c].validBytes);
+    if (mismatch) {
+      sendPtr.clear();
+      elemBytes.clear();
+      for (size_t c = 0; c < ncols; ++c) {
+        WireColumn& w = wire[c];
+        if (anyValid[c] && !w.validBytes) {
+          auto ones = allocDevice(static_cast<size_t>(n ? n : 1), st);
+          VB2_CU(cudaMemsetAsync(ones->data(), 1, static_cast<size_t>(n ? n : 1), st));
+          w.validBytes = ones->as<uint8_t>();
+          w.keep.push_back(ones);
+        }
+        addSend(w.values, w.width);
+        if (w.validBytes) addSend(w.validBytes, 1);
+      }
+    }
+  }
+  // merged alphabets (rank order, first occurrence wins) and per-source code remaps
+  struct Merged {
+    std::shared_ptr<HostAlphabet> alphabet = std::make_shared<HostAlphabet>();
+    std::vector<std::vector<int32_t>> remap;  // [source rank][code] -> merged code
+    bool identical = true;
+  };
+  std::vector<Merged> merged(ncols);
+  {
+    size_t v = 0;
+    for (size_t c = 0; c < ncols; ++c) {
+      if (wire[c].vb2Type != VB2_VARCHAR) continue;
+      Merged& m = merged[c];
+      std::map<std::string, int32_t> ids;
+      m.remap.resize(world);
+      for (int r = 0; r < world; ++r) {
+        const uint8_t* ap = blockOf(r) + static_cast<size_t>(world) * 8 + ncols * 8 + v * kAlphabetBlockBytes;
+        const int32_t* hp = reinterpret_cast<const int32_t*>(ap);
+        const int32_t entries = hp[0];
+        const char* cp = reinterpret_cast<const char*>(hp + 1 + entries);
+        for (int32_t i = 0; i < entries; ++i) {
+          std::string sv(cp, hp[1 + i]);
+          cp += hp[1 + i];
+          auto it = ids.find(sv);
+          if (it == ids.end()) {
+            it = ids.emplace(sv, static_cast<int32_t>(m.alphabet->values.size())).first;
+            m.alphabet->values.push_back(sv);
+            m.alphabet->nulls.push_back(false);
+          }
+          if (it->second != i) m.identical = false;
+          m.remap[r].push_back(it->second);
+        }
+      }
+      ++v;
+    }
+  }
+
+  // ---- payload: every column of every partition in one grouped all-to-all ---------------------------
+  std::vector<DeviceBufferPtr> recvBuf;
+  std::vector<void*> recvPtr;
+  for (size_t i = 0; i < sendPtr.size(); ++i) {
+    recvBuf.push_back(allocDevice(static_cast<size_t>(total ? total : 1) * elemBytes[i], st));
+    recvPtr.push_back(recvBuf.back()->data());
+  }
+  if (world > 1) {
+    int rc;
+    if (broadcast) rc = vb2_comm_all_gather_columns(tr->comm(), static_cast<int32_t>(sendPtr.size()), sendPtr.data(), recvPtr.data(), elemBytes.data(), n, recvCounts.data(), st);
+    else rc = vb2_comm_all_to_all_columns(tr->comm(), static_cast<int32_t>(sendPtr.size()), sendPtr.data(), recvPtr.data(), elemBytes.data(), sendCounts.data(), recvCounts.data(), st);
+    VELOX_CHECK(rc == VB2_OK, "exchange all-to-all failed");
+  } else {
+    for (size_t i = 0; i < sendPtr.size(); ++i)
+      if (total) VB2_CU(cudaMemcpyAsync(recvPtr[i], sendPtr[i], static_cast<size_t>(total) * elemBytes[i], cudaMemcpyDeviceToDevice, st));
+  }
+  int64_t sent = 0;
+  for (int p = 0; p < world; ++p) sent += sendCounts[p];
+  addRuntimeStat("b200.exchangeRowsSent", exec::RuntimeCounter{sent});
+  addRuntimeStat("b200.exchangeRowsReceived", exec::RuntimeCounter{total});
+
+  // ---- received page ----------------------------------------------------------------------------------
+  if (total > 0) {
+    std::vector<DeviceColumnPtr> cols;
+    size_t i = 0;
+    for (size_t c = 0; c < ncols; ++c) {
+      const WireColumn& w = wire[c];
+      auto col = std::make_shared<DeviceColumn>();
+      col->type = w.type;
+      col->desc.type = w.vb2Type;
+      col->desc.size = total;
+      DeviceBufferPtr values = recvBuf[i++];
+      DeviceBufferPtr validBytes = anyValid[c] ? recvBuf[i++] : nullptr;
+      col->owners.push_back(values);
+      if (validBytes) {
+        auto bitsBuf = allocDevice(bits::nbytes(total), st);
+        kernelCheck(vb2k_pack_bools(validBytes->as<uint8_t>(), total, bitsBuf->as<uint64_t>(), st));
+        col->desc.nulls = bitsBuf->as<uint64_t>();
+        col->owners.push_back(bitsBuf);
+      }
+      if (w.vb2Type == VB2_VARCHAR) {
+        Merged& m = merged[c];
+        if (!m.identical) {
+          // codes of source r are rewritten through remap[r] (segments are contiguous per source)
+          int64_t off = 0;
+          auto fixed = allocDevice(static_cast<size_t>(total) * 4, st);
+          for (int r = 0; r < world; ++r) {
+            if (recvCounts[r] == 0) continue;
+            auto lut = allocDevice(m.remap[r].size() * 4 + 4, st);
+            VB2_CU(cudaMemcpyAsync(lut->data(), m.remap[r].data(), m.remap[r].size() * 4, cudaMemcpyHostToDevice, st));
+            kernelCheck(vb2k_gather(lut->data(), values->as<int32_t>() + off, recvCounts[r], 4, fixed->as<int32_t>() + off, st));
+            col->owners.push_back(lut);
+            off += recvCounts[r];
+          }
+          values = fixed;
+          col->owners.push_back(fixed);
+        }
+        std::vector<int32_t> off(m.alphabet->values.size() + 1, 0);
+        std::string chars;
+        for (size_t k = 0; k < m.alphabet->values.size(); ++k) { chars += m.alphabet->values[k]; off[k + 1] = static_cast<int32_t>(chars.size()); }
+        auto offBuf = allocDevice(off.size() * 4, st);
+        auto charBuf = allocDevice(chars.size() + 1, st);
+        VB2_CU(cudaMemcpyAsync(offBuf->data(), off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
+        if (!chars.empty()) VB2_CU(cudaMemcpyAsync(charBuf->data(), chars.data(), chars.size(), cudaMemcpyHostToDevice, st));
+        col->desc.encoding = VB2_DICTIONARY;
+        col->desc.indices = values->as<int32_t>();
+        col->desc.values = offBuf->data();
+        col->desc.aux = charBuf->data();
+        col->desc.dict_size = static_cast<int64_t>(m.alphabet->values.size());
+        col->owners.push_back(offBuf);
+        col->owners.push_back(charBuf);
+        col->alphabet = m.alphabet;
+      } else if (w.vb2Type == VB2_BOOLEAN) {
+        auto packed = allocDevice(bits::nbytes(total), st);
+        kernelCheck(vb2k_pack_bools(values->as<uint8_t>(), total, packed->as<uint64_t>(), st));
+        col->desc.encoding = VB2_FLAT;
+        col->desc.values = packed->data();
+        col->owners.push_back(packed);
+      } else {
+        col->desc.encoding = VB2_FLAT;
+        col->desc.values = values->data();
+      }
+      cols.push_back(std::move(col));
+    }
+    auto page = std::make_shared<B200Vector>(pool(), type, static_cast<vector_size_t>(total), std::move(cols), st);
+    auto ev = makeEvent();
+    VB2_CU(cudaEventRecord(static_cast<cudaEvent_t>(ev.get()), st));
+    page->setReadyEvent(ev);
+    queue_->enqueue(page);
+  }
+  batches_.clear();
+  queue_->noMoreData();
+}
+
+// ---- B200Exchange --------------------------------------------------------------------------------------
+B200Exchange::B200Exchange(int32_t id, exec::DriverCtx* ctx, const exec::Exchange& cpu)
+    : SourceOperator(ctx, cpu.outputType(), id, cpu.planNodeId(), "B200Exchange"), queue_(cpu.queue()) {}
+
+void B200Exchange::initialize() {
+  Operator::initialize();
+  dev_ = driverDeviceContext(driverCtx_);
+}
+
+exec::BlockingReason B200Exchange::isBlocked(exec::ContinueFuture* future) {
+  if (next_ || atEnd_) return exec::BlockingReason::kNotBlocked;
+  next_ = queue_->dequeue(&atEnd_, future);
+  if (!next_ && !atEnd_) return exec::BlockingReason::kWaitForProducer;
+  return exec::BlockingReason::kNotBlocked;
+}
+
+RowVectorPtr B200Exchange::getOutput() {
+  if (!next_ && !atEnd_) {
+    exec::ContinueFuture f;
+    next_ = queue_->dequeue(&atEnd_, &f);
+  }
+  if (!next_) return nullptr;
+  RowVectorPtr out = std::move(next_);
+  next_ = nullptr;
+  if (auto page = std::dynamic_pointer_cast<B200Vector>(out)) {
+    // the page was produced on the sending pipeline's stream
+    if (page->readyEvent()) VB2_CU(cudaStreamWaitEvent(dev_->stream, page->readyEvent(), 0));
+  }
+  return out;
+}
+
+}  // namespace velox_b200

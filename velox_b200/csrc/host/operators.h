@@ -3,8 +3,10 @@
 #pragma once
 #include <unordered_map>
 
+#include "../../../include/velox_b200.h"
 #include "device.h"
 #include "expr_compiler.h"
+#include "task.h"
 
 namespace velox_b200 {
 
@@ -144,6 +146,61 @@ class B200HashProbe : public exec::Operator {
   std::shared_ptr<DeviceContext> dev_;
   std::unique_ptr<CompiledProgram> filterProgram_;
   DeviceBufferPtr errorFlag_;
+};
+
+// ---- exchange --------------------------------------------------------------------------------------
+// The task's exchange transport over NCCL (one process per GPU; include/velox_b200.h vb2_comm_*).
+class NcclTransport : public exec::ExchangeTransport {
+ public:
+  explicit NcclTransport(vb2_comm* comm) : comm_(comm) {}
+  int world() const override { return vb2_comm_world(comm_); }
+  int rank() const override { return vb2_comm_rank(comm_); }
+  vb2_comm* comm() const { return comm_; }
+
+ private:
+  vb2_comm* comm_;
+};
+
+// Replaces exec::PartitionedOutput (velox/exec/PartitionedOutput.cpp; GPU pattern
+// velox/experimental/ucx-exchange/UcxPartitionedOutput.h:29-110): collects the producing
+// fragment's batches on the device, partitions the rows by VectorHasher-hash(keys) % partitions
+// (bit exact with exec::HashPartitionFunction, exec/HashPartitionFunction.cpp:75-118), and moves
+// every column of every partition to its rank in ONE grouped NCCL all-to-all at noMoreInput. The
+// rows this rank receives are handed to the B200Exchange of the consuming fragment through the
+// ExchangeQueue. Pages are columnar ("B200Columnar" serde: flat fixed-width values, validity as
+// bytes, VARCHAR as dictionary codes over an alphabet merged across ranks) — no row serialisation.
+class B200PartitionedOutput : public exec::Operator {
+ public:
+  B200PartitionedOutput(int32_t id, exec::DriverCtx* ctx, const exec::PartitionedOutput& cpu);
+  void initialize() override;
+  bool needsInput() const override { return !noMoreInput_; }
+  void addInput(RowVectorPtr input) override;
+  void noMoreInput() override;
+  RowVectorPtr getOutput() override { return nullptr; }
+  exec::BlockingReason isBlocked(exec::ContinueFuture*) override { return exec::BlockingReason::kNotBlocked; }
+  bool isFinished() override { return noMoreInput_; }
+
+ private:
+  std::shared_ptr<const core::PartitionedOutputNode> node_;
+  std::shared_ptr<exec::ExchangeQueue> queue_;
+  std::shared_ptr<DeviceContext> dev_;
+  std::vector<B200VectorPtr> batches_;
+};
+
+// Replaces exec::Exchange (velox/exec/Exchange.h:51): source operator of the consuming fragment.
+class B200Exchange : public exec::SourceOperator {
+ public:
+  B200Exchange(int32_t id, exec::DriverCtx* ctx, const exec::Exchange& cpu);
+  void initialize() override;
+  RowVectorPtr getOutput() override;
+  exec::BlockingReason isBlocked(exec::ContinueFuture* future) override;
+  bool isFinished() override { return atEnd_; }
+
+ private:
+  std::shared_ptr<exec::ExchangeQueue> queue_;
+  std::shared_ptr<DeviceContext> dev_;
+  RowVectorPtr next_;
+  bool atEnd_ = false;
 };
 
 // Installs the DriverAdapter that swaps the CPU operators for the classes above and inserts

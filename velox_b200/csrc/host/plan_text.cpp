@@ -242,6 +242,28 @@ class Parser {
         aggs.push_back(a);
       }
       out = std::make_shared<core::AggregationNode>(nextId(), step, keys, aggs, ROW(names, types), child);
+    } else if (h == "exchange") {
+      // (exchange partitioned|broadcast|gather (keys I ...) plan): PartitionedOutputNode on top of the
+      // producing fragment, ExchangeNode as the leaf of the consuming one (core/PlanNode.h:2712,2182)
+      const std::string kindName = lex_.atom("exchange kind");
+      auto keyIdx = intList("keys");
+      auto child = node();
+      const auto& in = child->outputType();
+      std::vector<core::TypedExprPtr> keys;
+      for (int k : keyIdx) {
+        if (k < 0 || k >= static_cast<int>(in->size())) throw VeloxRuntimeError("plan text: exchange key out of range");
+        keys.push_back(std::make_shared<core::FieldAccessTypedExpr>(in->childAt(k), in->nameOf(k), k));
+      }
+      core::PartitionedOutputNode::Kind kind;
+      int parts = 0;  // one partition per rank
+      if (kindName == "partitioned") kind = core::PartitionedOutputNode::Kind::kPartitioned;
+      else if (kindName == "broadcast") kind = core::PartitionedOutputNode::Kind::kBroadcast;
+      else if (kindName == "gather") { kind = core::PartitionedOutputNode::Kind::kPartitioned; parts = 1; }
+      else throw VeloxRuntimeError("plan text: unknown exchange kind " + kindName);
+      auto po = std::make_shared<core::PartitionedOutputNode>(nextId(), kind, keys, parts, false, in, "B200Columnar", child);
+      auto ex = std::make_shared<core::ExchangeNode>(nextId(), in, "B200Columnar");
+      ex->setUpstream(po);
+      out = ex;
     } else if (h == "hashjoin") {
       const std::string jt = lex_.atom("join type");
       JoinTypeText type{jt};

@@ -14,10 +14,28 @@ struct Planner {
   std::map<int32_t, std::shared_ptr<std::vector<RowVectorPtr>>>& inputs;
   std::vector<std::unique_ptr<Pipeline>> pipelines;
   std::map<const core::PlanNode*, std::shared_ptr<HashJoinBridge>> bridges;
+  std::map<const core::PlanNode*, std::shared_ptr<ExchangeQueue>> queues;
 
   // Collects the nodes of the pipeline ending at `node` (source first); every HashJoinNode's
   // build side becomes its own pipeline whose consumer is a HashBuild.
   void collect(const core::PlanNodePtr& node, std::vector<core::PlanNodePtr>& out) {
+    if (auto ex = std::dynamic_pointer_cast<const core::ExchangeNode>(node)) {
+      // fragment boundary: the producing fragment (… -> PartitionedOutput) becomes its own pipeline,
+      // the Exchange is the source of the pipeline being collected
+      auto queue = std::make_shared<ExchangeQueue>();
+      queues[ex.get()] = queue;
+      if (auto po = ex->upstream()) {
+        auto prod = std::make_unique<Pipeline>();
+        collect(po->sources()[0], prod->factory.planNodes);
+        prod->factory.consumerSupplier = [po, queue](int32_t id, DriverCtx* ctx) -> std::unique_ptr<Operator> {
+          return std::make_unique<PartitionedOutput>(id, ctx, po, queue);
+        };
+        prod->factory.pipelineId = static_cast<int32_t>(pipelines.size());
+        pipelines.push_back(std::move(prod));
+      }
+      out.push_back(node);
+      return;
+    }
     if (auto join = std::dynamic_pointer_cast<const core::HashJoinNode>(node)) {
       auto bridge = std::make_shared<HashJoinBridge>();
       bridges[join.get()] = bridge;
@@ -63,6 +81,8 @@ struct Planner {
         ops.push_back(std::make_unique<HashAggregation>(id, c, ag));
       } else if (auto jn = std::dynamic_pointer_cast<const core::HashJoinNode>(nodes[i])) {
         ops.push_back(std::make_unique<HashProbe>(id, c, jn, bridges.at(jn.get())));
+      } else if (auto ex = std::dynamic_pointer_cast<const core::ExchangeNode>(nodes[i])) {
+        ops.push_back(std::make_unique<Exchange>(id, c, ex, queues.at(ex.get())));
       } else {
         VELOX_UNSUPPORTED("plan node " + std::string(nodes[i]->name()));
       }
@@ -89,7 +109,7 @@ void Task::addInput(int32_t sourceId, RowVectorPtr batch) {
 }
 
 std::vector<RowVectorPtr> Task::run() {
-  Planner planner{*this, inputs_, {}, {}};
+  Planner planner{*this, inputs_, {}, {}, {}};
   auto out = std::make_unique<Pipeline>();
   planner.collect(plan_, out->factory.planNodes);
   out->factory.outputDriver = true;

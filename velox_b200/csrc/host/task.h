@@ -8,8 +8,20 @@
 
 namespace facebook::velox::exec {
 
+// The transport behind PartitionedOutput / Exchange (the reference plugs ExchangeSource factories,
+// velox/exec/ExchangeSource.h:139-145, selected by task URI). One process per GPU: the transport
+// is the communicator of the ranks running the same plan.
+class ExchangeTransport {
+ public:
+  virtual ~ExchangeTransport() = default;
+  virtual int world() const = 0;
+  virtual int rank() const = 0;
+};
+
 class Task {
  public:
+  void setExchangeTransport(std::shared_ptr<ExchangeTransport> t) { transport_ = std::move(t); }
+  const std::shared_ptr<ExchangeTransport>& exchangeTransport() const { return transport_; }
   Task(core::PlanNodePtr plan, core::QueryConfig config);
   ~Task();
   // Batches for a ValuesNode source (before run()).
@@ -29,6 +41,7 @@ class Task {
   memory::MemoryPool pool_{"task"};
   std::map<int32_t, std::shared_ptr<std::vector<RowVectorPtr>>> inputs_;
   std::map<std::string, int64_t> stats_;
+  std::shared_ptr<ExchangeTransport> transport_;
 };
 
 }  // namespace facebook::velox::exec

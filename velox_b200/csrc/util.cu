@@ -50,6 +50,11 @@ __global__ void gather_bits_kernel(const uint64_t* __restrict__ in, const int32_
     if (lane == 0) out[w] = word;
   }
 }
+// bit-packed words -> bytes (0/1): validity bitmaps travel through the exchange as byte columns
+__global__ void unpack_bits_kernel(const uint64_t* __restrict__ in, int64_t n, uint8_t* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = bit_at(in, i) ? 1 : 0;
+}
 // bytes (0/1) -> bit-packed words
 __global__ void pack_bools_kernel(const uint8_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
   const int64_t nwords = (n + 31) >> 5;
@@ -139,6 +144,12 @@ int vb2k_gather_bits(const uint64_t* in, const int32_t* sel, int64_t n, uint64_t
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VB2_CUDA_OK(cudaMemsetAsync(out + ((n + 63) >> 6) - 1, 0, 8, st));
   gather_bits_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(in, sel, n, reinterpret_cast<uint32_t*>(out));
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+int vb2k_unpack_bits(const uint64_t* in, int64_t n, uint8_t* out, void* stream) {
+  if (n <= 0) return VB2_OK;
+  unpack_bits_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, out);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }

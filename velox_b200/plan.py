@@ -12,6 +12,7 @@ Plan text grammar (S-expressions)
         | (aggregation STEP (keys I ...) (aggs AGG ...) plan)      STEP: single|partial|intermediate|final
         | (hashjoin TYPE (probekeys I ...) (buildkeys I ...) EXPR|nil (out (p I)|(b I) ...) probe build)
         | (orderby ((I asc|desc first|last) ...) plan)              oracle only so far
+        | (exchange partitioned|broadcast|gather (keys I ...) plan)  PartitionedOutput -> Exchange across the ranks
   AGG  := (sum I [(mask I)]) | (avg I) | (count [I]) | (min I) | (max I)
   EXPR := (field I) | (f64 X) | (i64 N) | (i32 N) | (bool true|false) | (str "s") | (null TYPE)
         | (cast TYPE e) | (and e ...) | (or e ...) | (switch c1 v1 ... [else]) | (NAME e ...)
@@ -452,6 +453,25 @@ class PlanBuilder:
         """Gathers the drivers' outputs (exec/LocalPartition.cpp). A single task holds one
         pipeline instance per GPU, so this is a pass-through in the plan text."""
         return self
+
+    def _exchange(self, kind: str, keys=()) -> "PlanBuilder":
+        n = self.node
+        idx = " ".join(str(n.names.index(k)) for k in keys)
+        self.node = _Node(f"(exchange {kind} (keys {idx}) {n.sexpr})", n.names, n.types, partial=n.partial)
+        return self
+
+    def partitionedOutput(self, keys) -> "PlanBuilder":
+        """PartitionedOutput (hash(keys) % world, HashPartitionFunction) followed by the Exchange that
+        reads this rank's partition (PlanBuilder::partitionedOutput + exchange of the reference's
+        multi-fragment tests, velox/exec/tests/MultiFragmentTest.cpp)."""
+        return self._exchange("partitioned", keys)
+
+    def partitionedOutputBroadcast(self) -> "PlanBuilder":
+        return self._exchange("broadcast")
+
+    def gatherExchange(self) -> "PlanBuilder":
+        """Every rank's rows to partition 0 (a PartitionedOutput with one partition)."""
+        return self._exchange("gather")
 
     def hashJoin(self, leftKeys, rightKeys, build: "PlanBuilder", filter: str, output: Sequence[str],
                  joinType: str = "inner") -> "PlanBuilder":

@@ -36,6 +36,7 @@ def _bind():
     L.vb2_upload_cache_create.restype = C.c_void_p
     L.vb2_upload_cache_free.argtypes = [C.c_void_p]
     L.vb2_task_set_upload_cache.argtypes = [C.c_void_p, C.c_void_p]
+    L.vb2_task_set_comm.argtypes = [C.c_void_p, C.c_void_p]
     L._task_bound = True
     return L
 
@@ -68,6 +69,12 @@ class UploadCache:
 
 
 class Task:
+    def set_comm(self, comm) -> None:
+        """Exchange transport for plans with exchange nodes: velox_b200.comm.Comm of the ranks
+        running this plan (vb2_task_set_comm)."""
+        self.L.vb2_task_set_comm(self.h, C.c_void_p(comm.h) if comm is not None else None)
+        self._comm = comm
+
     def set_upload_cache(self, cache: Optional["UploadCache"]) -> None:
         self.L.vb2_task_set_upload_cache(self.h, cache.h if cache is not None else None)
         self._cache = cache  # keep it alive for the run
