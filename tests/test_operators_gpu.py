@@ -292,8 +292,8 @@ def test_tpch_q1_q6_fused_and_generic(n):
     rv = row_vector(names, [col(c) for c in names])
     tol = max(1e-12, n * 2.0 ** -53)
     st_f, st_g = check_plan(q1_plan(rv), [rv], configs=(FUSED, GENERIC), rel_tol=tol, oracle_batch_rows=100_000)
-    # the partial aggregation takes the fused kernel; the final one merges its (tiny) output generically
-    assert stat(st_f, "b200.fusedBatches") == 1 and stat(st_f, "b200.genericBatches") == 1
+    # partial + final collapse into one aggregation (adapter) that takes the fused kernel; nothing is merged generically
+    assert stat(st_f, "b200.fusedBatches") == 1 and stat(st_f, "b200.genericBatches") == 0
     assert stat(st_g, "b200.fusedBatches") == 0 and stat(st_g, "b200.genericBatches") == 2
     check_plan(q1_plan(rv), [rv], configs=(FUSED, GENERIC), batch_rows=60_000, rel_tol=tol, oracle_batch_rows=100_000)
     names6 = ["l_shipdate", "l_extendedprice", "l_quantity", "l_discount"]
@@ -313,7 +313,7 @@ def test_tpch_q1_nulls_fall_back_to_generic_kernels():
     cols[2] = flat_vector(DOUBLE, h["l_quantity"], qn)
     rv = row_vector(names, cols)
     (st,) = check_plan(q1_plan(rv), [rv], rel_tol=1e-12)
-    assert stat(st, "b200.fusedBatches") == 0 and stat(st, "b200.genericBatches") == 2  # partial + final
+    assert stat(st, "b200.fusedBatches") == 0 and stat(st, "b200.genericBatches") == 1  # partial + final collapsed into one aggregation
 
 
 # ---- HashBuild / HashProbe ----------------------------------------------------------------------
