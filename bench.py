@@ -484,6 +484,9 @@ def main():
         "roofline": roofline, "queries": breakdown, "results": results, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    if comm is not None:
+        line["exchange"] = {"transport": "peer memory over NVLink (CUDA IPC heaps, exchange_p2p.cu)" if comm.peer_memory else "NCCL grouped send/recv",
+                            "exchanges": comm.exchanges()}
     if "stats1" in state:
         line["operator_wall_ms"] = {q: {k: round(v / 1e6, 3) for k, v in state[s].items() if k.endswith("WallNanos") and v > 2e4}
                                     for q, s in (("q1", "stats1"), ("q14", "stats14")) if s in state}

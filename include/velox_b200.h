@@ -97,6 +97,11 @@ int32_t vb2_comm_all_gather(vb2_comm* comm, const void* send, void* recv, int64_
  * `send_rows` rows of every column to every rank; recv[c] is segmented by recv_counts (rows per source). */
 int32_t vb2_comm_all_gather_columns(vb2_comm* comm, int32_t ncols, const void* const* send, void* const* recv, const int32_t* elem_bytes,
                                     int64_t send_rows, const int64_t* recv_counts, void* stream);
+/* 1 when the ranks exchange rows through CUDA-IPC mapped peer memory over NVLink (exchange_p2p.cu; set
+ * up at vb2_comm_create, VB2_EXCHANGE=nccl disables it), 0 when every exchange goes through NCCL. */
+int32_t vb2_comm_peer_memory(vb2_comm* comm);
+/* Exchanges moved so far through peer memory (peer_memory = 1) / through NCCL (0). */
+int64_t vb2_comm_exchanges(vb2_comm* comm, int32_t peer_memory);
 int32_t vb2_comm_world(vb2_comm* comm);
 int32_t vb2_comm_rank(vb2_comm* comm);
 /* Attaches the communicator to a task whose plan contains exchange nodes: B200PartitionedOutput /

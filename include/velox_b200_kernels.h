@@ -369,6 +369,9 @@ typedef struct vb2_join_table {
 
 int vb2k_join_build(const vb2_join_table* t, const uint64_t* build_keys, const uint64_t* valid, int64_t n,
                     int32_t* error_flag, void* stream);
+/* codes[i] = dictionary index of row i of a DICTIONARY column (0 for CONSTANT); valid[i] (optional,
+ * bytes) = 0 for NULL wrapper rows and NULL dictionary entries, whose code is written as 0. */
+int vb2k_dictionary_codes(const vb2_column* col, int64_t n, int32_t* codes, uint8_t* valid, void* stream);
 /* Array-mode build straight from ONE integer-typed key column (flat / dictionary / constant, NULLs
  * skipped): slot = v - lo + 1, i.e. vb2k_normalize_keys with min = lo followed by vb2k_join_build,
  * in one pass over the keys. flags: device int32[2] = {error (101: key outside the table), duplicates seen}. */
@@ -383,6 +386,29 @@ int vb2k_exclusive_scan_i32(const int32_t* in, int64_t n, int64_t* out, int64_t*
 size_t vb2k_scan_workspace(int64_t n);
 int vb2k_join_probe_emit(const vb2_join_table* t, const uint64_t* probe_keys, const uint64_t* valid, int64_t n,
                          const int64_t* offsets, int32_t* probe_rows, int32_t* build_rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer-memory exchange (exchange_p2p.cu): the transfer of PartitionedOutput -> Exchange between
+ * GPUs of one NVLink domain as plain stores into the destination's exchange heap (mapped with CUDA
+ * IPC by vb2_comm), fused with the partition gather. Replaces the serialise / OutputBuffer / pull
+ * path of velox/exec/PartitionedOutput.cpp + velox/exec/ExchangeClient.cpp for co-located ranks.
+ * A segment holding `rows` rows stores column c at vb2k_p2p_segment_bytes(widths, c, rows).
+ * ------------------------------------------------------------------------------------------ */
+int64_t vb2k_p2p_segment_bytes(const int32_t* widths, int32_t ncols, int64_t rows);
+/* `bytes` (multiple of 16) of src into peer_dst[p] for every p < world (host array of device pointers). */
+int vb2k_p2p_put_block(void* const* peer_dst, int32_t world, const void* src, int64_t bytes, void* stream);
+/* Release-stores `epoch` into *peer_flags[p] for every p (system scope), ordered after earlier puts of the stream. */
+int vb2k_p2p_signal(void* const* peer_flags, int32_t world, uint64_t epoch, void* stream);
+/* Spins (acquire, system scope) until flags[r * stride_words] >= epoch for every r < world; after
+ * timeout_ns sets *error_flag = 200 + r and returns. */
+int vb2k_p2p_wait(const uint64_t* flags, int32_t stride_words, int32_t world, uint64_t epoch, int32_t* error_flag, uint64_t timeout_ns, void* stream);
+/* Rows grouped by destination (order[j] = source row, NULL = identity; counts_dev[p] rows for
+ * destination p, device) -> column-major segments peer_segments[p]. broadcast: every destination gets all n rows. */
+int vb2k_p2p_put_rows(const int32_t* order, const int64_t* counts_dev, int32_t world, int64_t n, const void* const* cols, const int32_t* widths,
+                      int32_t ncols, void* const* peer_segments, int32_t broadcast, void* stream);
+/* Segments received from every source (local_segments[s], counts[s] rows; host arrays) -> contiguous columns outs[c]. */
+int vb2k_p2p_collect(const void* const* local_segments, const int64_t* counts, int32_t world, const int32_t* widths, int32_t ncols, void* const* outs,
+                     void* stream);
 
 /* Misc building blocks of the operator layer */
 int vb2k_fill_u64(uint64_t* p, int64_t n, uint64_t v, void* stream);

@@ -56,7 +56,8 @@ def main():
         ok = ok and int(tot[0]) == int(tot[1])
         fused = sum(v for k, v in s14.items() if k.endswith("b200.fusedBatches"))
         print(json.dumps({"ok": bool(ok), "world": world, "parity": info, "exchange_rows_sent": int(tot[0]), "exchange_rows_received": int(tot[1]),
-                          "q14_fused_batches_rank0": fused, "q1_groups": o1.size}))
+                          "q14_fused_batches_rank0": fused, "q1_groups": o1.size,
+                          "peer_memory": comm.peer_memory, "exchanges": comm.exchanges()}))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

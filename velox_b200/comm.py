@@ -31,6 +31,15 @@ class Comm:
             raise VeloxRuntimeError(err.value.decode())
         self.L = L
 
+    @property
+    def peer_memory(self) -> bool:
+        """True when rows move between the ranks through CUDA-IPC mapped peer memory (exchange_p2p.cu)."""
+        return bool(self.L.vb2_comm_peer_memory(C.c_void_p(self.h)))
+
+    def exchanges(self):
+        self.L.vb2_comm_exchanges.restype = C.c_int64
+        return {"peer_memory": int(self.L.vb2_comm_exchanges(C.c_void_p(self.h), 1)), "nccl": int(self.L.vb2_comm_exchanges(C.c_void_p(self.h), 0))}
+
     def _st(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -112,6 +112,17 @@ __global__ void minmax_init_kernel(int64_t* out3) {
   out3[2] = 0;
 }
 
+// Dictionary codes of a DICTIONARY / CONSTANT column as a dense int32 column plus validity bytes
+// (NULL wrapper rows and NULL dictionary entries -> 0): the form VARCHAR columns take in an exchange.
+__global__ void dictionary_codes_kernel(const __grid_constant__ vb2_column c, int64_t n, int32_t* __restrict__ codes, uint8_t* __restrict__ valid) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t base;
+    const bool is_null = decode_row2(c, i, base);
+    codes[i] = is_null ? 0 : static_cast<int32_t>(base);
+    if (valid) valid[i] = is_null ? 0 : 1;
+  }
+}
+
 // Array-mode join build straight from the key column (normalize + insert in one pass): slot =
 // v - lo + 1, the value id vb2k_normalize_keys would produce for a single key with min = lo.
 __global__ void join_build_array_direct_kernel(int32_t* __restrict__ head, int32_t* __restrict__ next, int64_t capacity,
@@ -682,6 +693,14 @@ int vb2k_normalize_keys(const vb2_column* cols, int32_t ncols, const int64_t* mi
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (valid_out) VB2_CUDA_OK(cudaMemsetAsync(valid_out + ((n + 63) >> 6) - 1, 0, 8, st));
   normalize_keys_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(a, sel, n, keys_out, reinterpret_cast<uint32_t*>(valid_out));
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_dictionary_codes(const vb2_column* col, int64_t n, int32_t* codes, uint8_t* valid, void* stream) {
+  if (!col || col->encoding == VB2_FLAT) return fail_msg(VB2_ERR_INVALID, "dictionary_codes: dictionary or constant column expected");
+  if (n <= 0) return VB2_OK;
+  dictionary_codes_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*col, n, codes, valid);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }

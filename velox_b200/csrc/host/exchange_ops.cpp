@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 
+#include "exchange_impl.h"
 #include "join.h"
 #include "operators.h"
 
@@ -86,13 +87,11 @@ void B200PartitionedOutput::noMoreInput() {
     bool anyNulls = false;
     for (auto& b : batches_) anyNulls = anyNulls || b->column(c)->mayHaveNulls();
     if (w.vb2Type == VB2_VARCHAR) {
-      // dictionary codes travel; every batch must bring the same host alphabet contents
+      // dictionary codes travel (NULL rows and NULL dictionary entries become validity bytes); every
+      // batch must bring the same host alphabet contents
       for (auto& b : batches_) {
         const DeviceColumn& col = *b->column(c);
         if (col.desc.encoding == VB2_FLAT || !col.alphabet) VELOX_UNSUPPORTED("exchange of flat (non-dictionary) VARCHAR columns");
-        for (bool isNull : col.alphabet->nulls)
-          if (isNull) VELOX_UNSUPPORTED("exchange of VARCHAR dictionaries with NULL entries");
-        if (col.desc.nulls) VELOX_UNSUPPORTED("exchange of VARCHAR columns with NULL rows");
         if (!w.alphabet) w.alphabet = col.alphabet;
         else if (w.alphabet != col.alphabet && w.alphabet->values != col.alphabet->values) VELOX_UNSUPPORTED("exchange input batches with different VARCHAR dictionaries");
       }
@@ -111,8 +110,7 @@ void B200PartitionedOutput::noMoreInput() {
       const DeviceColumnPtr& col = b->column(c);
       const int64_t bn = b->size();
       if (w.vb2Type == VB2_VARCHAR) {
-        if (col->desc.encoding == VB2_DICTIONARY) VB2_CU(cudaMemcpyAsync(values->as<int32_t>() + off, col->desc.indices, static_cast<size_t>(bn) * 4, cudaMemcpyDeviceToDevice, st));
-        else VB2_CU(cudaMemsetAsync(values->as<int32_t>() + off, 0, static_cast<size_t>(bn) * 4, st));  // constant: code 0
+        kernelCheck(vb2k_dictionary_codes(&col->desc, bn, values->as<int32_t>() + off, valid ? valid->as<uint8_t>() + off : nullptr, st));
       } else {
         FlatColumn f = flattenColumn(col, nullptr, bn, st);
         VB2_CU(cudaMemcpyAsync(values->as<uint8_t>() + off * w.width, f.values->data(), static_cast<size_t>(bn) * w.width, cudaMemcpyDeviceToDevice, st));
@@ -155,25 +153,19 @@ void B200PartitionedOutput::noMoreInput() {
     if (!broadcast) c[0] = n;
     VB2_CU(cudaMemcpyAsync(countsDev->data(), c.data(), static_cast<size_t>(world) * 8, cudaMemcpyHostToDevice, st));
   }
-  // columns grouped by destination
+  // wire columns in transfer order: values, then validity bytes where present
   std::vector<const void*> sendPtr;
   std::vector<int32_t> elemBytes;
-  std::vector<DeviceBufferPtr> keep;
-  auto addSend = [&](const void* src, int32_t width) {
-    if (order) {
-      auto g = allocDevice(static_cast<size_t>(n) * width, st);
-      kernelCheck(vb2k_gather(src, order->as<int32_t>(), n, width, g->data(), st));
-      keep.push_back(g);
-      sendPtr.push_back(g->data());
-    } else {
-      sendPtr.push_back(src);
+  auto listColumns = [&]() {
+    sendPtr.clear();
+    elemBytes.clear();
+    for (auto& w : wire) {
+      sendPtr.push_back(w.values);
+      elemBytes.push_back(w.width);
+      if (w.validBytes) { sendPtr.push_back(w.validBytes); elemBytes.push_back(1); }
     }
-    elemBytes.push_back(width);
   };
-  for (auto& w : wire) {
-    addSend(w.values, w.width);
-    if (w.validBytes) addSend(w.validBytes, 1);
-  }
+  listColumns();
 
   // ---- metadata round: [counts[world] | has-valid flags | alphabets] from every rank ---------------
   size_t nVarchar = 0;
@@ -201,28 +193,28 @@ void B200PartitionedOutput::noMoreInput() {
       ap += kAlphabetBlockBytes;
     }
   }
-  auto blockDev = allocDevice(blockBytes, st);
-  auto allDev = allocDevice(blockBytes * world, st);
-  VB2_CU(cudaMemcpyAsync(blockDev->data(), myBlock.data(), blockBytes, cudaMemcpyHostToDevice, st));
-  VB2_CU(cudaMemcpyAsync(blockDev->data(), countsDev->data(), static_cast<size_t>(world) * 8, cudaMemcpyDeviceToDevice, st));
-  auto allHost = acquirePinned(blockBytes * world);
+  std::shared_ptr<void> allHost;
   if (world > 1) {
     VELOX_CHECK(tr != nullptr, "the plan contains an exchange but the task has no exchange transport (vb2_task_set_comm)");
-    VELOX_CHECK(vb2_comm_all_gather(tr->comm(), blockDev->data(), allDev->data(), static_cast<int64_t>(blockBytes), st) == VB2_OK, "exchange metadata all-gather failed");
-    VB2_CU(cudaMemcpyAsync(allHost.get(), allDev->data(), blockBytes * world, cudaMemcpyDeviceToHost, st));
+    VELOX_CHECK(blockBytes <= exchangeMaxMetadataBytes(tr->comm()), "exchange metadata block too large (too many VARCHAR columns)");
+    allHost = exchangeMetadata(tr->comm(), myBlock.data(), blockBytes, countsDev->as<int64_t>(), st);
   } else {
-    VB2_CU(cudaMemcpyAsync(allHost.get(), blockDev->data(), blockBytes, cudaMemcpyDeviceToHost, st));
+    allHost = acquirePinned(blockBytes);
+    std::memcpy(allHost.get(), myBlock.data(), blockBytes);
+    VB2_CU(cudaMemcpyAsync(allHost.get(), countsDev->data(), 8, cudaMemcpyDeviceToHost, st));
+    VB2_CU(cudaStreamSynchronize(st));
   }
-  VB2_CU(cudaStreamSynchronize(st));  // the exchange's only host synchronisation
   const uint8_t* all = static_cast<const uint8_t*>(allHost.get());
   auto blockOf = [&](int r) { return all + static_cast<size_t>(r) * blockBytes; };
-  std::vector<int64_t> sendCounts(world), recvCounts(world);
+  std::vector<int64_t> matrix(static_cast<size_t>(world) * world), recvCounts(world);
+  for (int r = 0; r < world; ++r)
+    for (int p = 0; p < world; ++p) matrix[static_cast<size_t>(r) * world + p] = reinterpret_cast<const int64_t*>(blockOf(r))[p];
+  int64_t total = 0, sent = 0;
   for (int p = 0; p < world; ++p) {
-    sendCounts[p] = reinterpret_cast<const int64_t*>(blockOf(rank))[p];
-    recvCounts[p] = reinterpret_cast<const int64_t*>(blockOf(p))[rank];
+    recvCounts[p] = matrix[static_cast<size_t>(p) * world + rank];
+    total += recvCounts[p];
+    sent += matrix[static_cast<size_t>(rank) * world + p];
   }
-  int64_t total = 0;
-  for (int p = 0; p < world; ++p) total += recvCounts[p];
   VELOX_CHECK(total < (1ll << 31), "exchange output above 2^31 rows per rank");
   // a column carries validity bytes if any rank sends them: ranks without NULLs send all-ones
   std::vector<bool> anyValid(ncols, false);
@@ -230,26 +222,16 @@ void B200PartitionedOutput::noMoreInput() {
     const int64_t* flags = reinterpret_cast<const int64_t*>(blockOf(r) + static_cast<size_t>(world) * 8);
     for (size_t c = 0; c < ncols; ++c) anyValid[c] = anyValid[c] || flags[c] != 0;
   }
-  {
-    // re-derive the send list if some other rank needs validity bytes this rank did not plan to send
-    bool mismatch = false;
-    for (size_t c = 0; c < ncols; ++c) mismatch = mismatch || (anyValid[c] && !wire[c].validBytes);
-    if (mismatch) {
-      sendPtr.clear();
-      elemBytes.clear();
-      for (size_t c = 0; c < ncols; ++c) {
-        WireColumn& w = wire[c];
-        if (anyValid[c] && !w.validBytes) {
-          auto ones = allocDevice(static_cast<size_t>(n ? n : 1), st);
-          VB2_CU(cudaMemsetAsync(ones->data(), 1, static_cast<size_t>(n ? n : 1), st));
-          w.validBytes = ones->as<uint8_t>();
-          w.keep.push_back(ones);
-        }
-        addSend(w.values, w.width);
-        if (w.validBytes) addSend(w.validBytes, 1);
-      }
+  for (size_t c = 0; c < ncols; ++c) {
+    WireColumn& w = wire[c];
+    if (anyValid[c] && !w.validBytes) {
+      auto ones = allocDevice(static_cast<size_t>(n ? n : 1), st);
+      VB2_CU(cudaMemsetAsync(ones->data(), 1, static_cast<size_t>(n ? n : 1), st));
+      w.validBytes = ones->as<uint8_t>();
+      w.keep.push_back(ones);
     }
   }
+  listColumns();
   // merged alphabets (rank order, first occurrence wins) and per-source code remaps
   struct Merged {
     std::shared_ptr<HostAlphabet> alphabet = std::make_shared<HostAlphabet>();
@@ -286,24 +268,28 @@ void B200PartitionedOutput::noMoreInput() {
     }
   }
 
-  // ---- payload: every column of every partition in one grouped all-to-all ---------------------------
+  // ---- payload ---------------------------------------------------------------------------------------
   std::vector<DeviceBufferPtr> recvBuf;
   std::vector<void*> recvPtr;
   for (size_t i = 0; i < sendPtr.size(); ++i) {
     recvBuf.push_back(allocDevice(static_cast<size_t>(total ? total : 1) * elemBytes[i], st));
     recvPtr.push_back(recvBuf.back()->data());
   }
+  std::shared_ptr<void> ready;
   if (world > 1) {
-    int rc;
-    if (broadcast) rc = vb2_comm_all_gather_columns(tr->comm(), static_cast<int32_t>(sendPtr.size()), sendPtr.data(), recvPtr.data(), elemBytes.data(), n, recvCounts.data(), st);
-    else rc = vb2_comm_all_to_all_columns(tr->comm(), static_cast<int32_t>(sendPtr.size()), sendPtr.data(), recvPtr.data(), elemBytes.data(), sendCounts.data(), recvCounts.data(), st);
-    VELOX_CHECK(rc == VB2_OK, "exchange all-to-all failed");
+    bool peerMemory = false;
+    ready = exchangePayload(tr->comm(), order ? order->as<int32_t>() : nullptr, countsDev->as<int64_t>(), matrix.data(), n, sendPtr, elemBytes, recvPtr,
+                            broadcast, st, &peerMemory);
+    addRuntimeStat("b200.exchangePeerMemory", exec::RuntimeCounter{peerMemory ? 1 : 0});
+    // everything derived from the received buffers below runs on this operator's stream
+    VB2_CU(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(ready.get()), 0));
   } else {
-    for (size_t i = 0; i < sendPtr.size(); ++i)
-      if (total) VB2_CU(cudaMemcpyAsync(recvPtr[i], sendPtr[i], static_cast<size_t>(total) * elemBytes[i], cudaMemcpyDeviceToDevice, st));
+    for (size_t i = 0; i < sendPtr.size(); ++i) {
+      if (!total) continue;
+      if (order) kernelCheck(vb2k_gather(sendPtr[i], order->as<int32_t>(), total, elemBytes[i], recvPtr[i], st));
+      else VB2_CU(cudaMemcpyAsync(recvPtr[i], sendPtr[i], static_cast<size_t>(total) * elemBytes[i], cudaMemcpyDeviceToDevice, st));
+    }
   }
-  int64_t sent = 0;
-  for (int p = 0; p < world; ++p) sent += sendCounts[p];
   addRuntimeStat("b200.exchangeRowsSent", exec::RuntimeCounter{sent});
   addRuntimeStat("b200.exchangeRowsReceived", exec::RuntimeCounter{total});
 
