@@ -20,7 +20,15 @@ $(BUILD)/vm_ops_str.h: velox_b200/csrc/vm_ops.inc
 	@mkdir -p $(BUILD)
 	( echo 'static const char kVmOpsSource[] = R"VMOPS('; cat $<; echo ')VMOPS";' ) > $@
 
-$(BUILD)/%.o: velox_b200/csrc/%.cu $(wildcard velox_b200/csrc/*.cuh) $(wildcard velox_b200/csrc/*.inc) $(wildcard include/*.h) $(BUILD)/vm_ops_str.h
+# the headers the pipeline JIT hands to NVRTC, as strings (fused_jit.cu)
+$(BUILD)/common_str.h: velox_b200/csrc/common.cuh
+	@mkdir -p $(BUILD)
+	( echo 'static const char kCommonCuhSource[] = R"VB2SRC('; cat $<; echo ')VB2SRC";' ) > $@
+$(BUILD)/fused_scan_str.h: velox_b200/csrc/fused_scan.cuh
+	@mkdir -p $(BUILD)
+	( echo 'static const char kFusedScanCuhSource[] = R"VB2SRC('; cat $<; echo ')VB2SRC";' ) > $@
+
+$(BUILD)/%.o: velox_b200/csrc/%.cu $(wildcard velox_b200/csrc/*.cuh) $(wildcard velox_b200/csrc/*.h) $(wildcard velox_b200/csrc/*.inc) $(wildcard include/*.h) $(BUILD)/vm_ops_str.h $(BUILD)/common_str.h $(BUILD)/fused_scan_str.h
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 

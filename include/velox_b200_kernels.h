@@ -222,6 +222,29 @@ size_t vb2k_fused_workspace_bytes(int32_t id, int32_t ngroups);
  * counts is int64[ngroups] (rows that passed the filter per group). */
 int vb2k_fused_scan_agg(int32_t id, const vb2_fused_args* args, double* sums, int64_t* counts, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* Pipelines without an ahead-of-time specialisation are instantiated from the same expression
+ * templates with NVRTC when vb2k_fused_find misses (fused_jit.cu; VB2_PIPELINE_JIT=0 or
+ * vb2k_set_pipeline_jit(0) disables it — the generic kernels run then). */
+void vb2k_set_pipeline_jit(int32_t enabled);
+/* Compiles (no GPU needed, nothing is loaded or launched) one kernel of the pipeline `signature`
+ * describes: kind 0 TMA scan-aggregate, 1 direct scan-aggregate, 2 filter bitmap, 3 gather-aggregate;
+ * max_groups 1 / 4 / 8 register accumulators or 0 shared-memory accumulators. 1 = compiled. */
+int32_t vb2k_pipeline_jit_compiles(const char* signature, int32_t kind, int32_t max_groups, int32_t key64, char* log_out, int32_t log_len);
+/* Late materialisation for selective filters (FilterProject evaluates the filter first and the
+ * projections only on surviving rows, velox/exec/FilterProject.cpp:200-259):
+ *   vb2k_fused_has_filter    1 when pipeline `id` has a filter that can run on its own;
+ *   vb2k_fused_filter_bits   streams only the filter's columns and writes the selection bitmap of
+ *                            args->rows rows (tile_stride 1), or visits every tile_stride-th 1024-row
+ *                            tile and only counts (sel_bits NULL): counters = device int64[2]
+ *                            {rows kept, rows evaluated}, accumulated;
+ *   vb2k_fused_gather_agg    join probe + projections + aggregation over the selected row numbers
+ *                            sel[0 .. *nsel_dev) (ascending), same accumulators as vb2k_fused_scan_agg;
+ *                            at most 4 groups. nsel_hint sizes the grid.
+ * A signature "F:<filter>;P:" (no projections) names the filter alone. */
+int32_t vb2k_fused_has_filter(int32_t id);
+int vb2k_fused_filter_bits(int32_t id, const vb2_fused_args* args, int32_t tile_stride, uint64_t* sel_bits, int64_t* counters, void* stream);
+int vb2k_fused_gather_agg(int32_t id, const vb2_fused_args* args, const int32_t* sel, const int64_t* nsel_dev, int64_t nsel_hint, double* sums,
+                          int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 /* Scan -> filter -> project -> compact pipelines (signatures "F:...;C:..."): writes the
  * projections of the surviving rows densely into outs[p] (element width
  * vb2k_fused_output_width). count: device int64 running total (rows written so far);

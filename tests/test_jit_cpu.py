@@ -111,3 +111,22 @@ def test_tpch_plans_jit_compile():
         assert rc == 0, (name, err.value.decode())
         assert progs.value >= min_programs and total.value >= progs.value, (name, progs.value, total.value)
         assert jit.value == total.value, f"{name}: {total.value - jit.value} of {total.value} expression kernels fall back to the interpreter"
+
+
+def test_pipeline_jit_compiles_template_instantiations():
+    """fused_jit.cu (no GPU needed): signatures the planner prints are parsed back into the expression
+    template they describe and every kernel family compiles for sm_100a with NVRTC."""
+    import ctypes as C
+    from velox_b200 import tpch
+    from velox_b200._lib import lib
+    L = lib()
+    L.vb2k_pipeline_jit_compiles.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+    q6x = tpch.Q6_SIG.replace("lt(f2,pf2))", "lt(f2,pf2),gt(f3,pf3))")
+    cases = [(q6x, 0, 1, 0), (q6x, 2, 0, 0), (q6x, 3, 1, 0), (tpch.Q1_SIG, 0, 0, 0), (tpch.Q14_SIG, 3, 1, 0), (tpch.Q14_SIG, 1, 1, 0),
+             ("F:between(i0,pi0,pi1);P:", 2, 0, 0), ("F:lt(f0,pf0);P:divide(f1,plus(pf1,f0))", 0, 4, 1)]
+    for sig, kind, groups, key64 in cases:
+        buf = C.create_string_buffer(4000)
+        assert L.vb2k_pipeline_jit_compiles(sig.encode(), kind, groups, key64, buf, 4000) == 1, (sig, kind, buf.value.decode()[:1500])
+        assert "<" in buf.value.decode()
+    buf = C.create_string_buffer(400)
+    assert L.vb2k_pipeline_jit_compiles(b"F:or(lt(f0,pf0),lt(f1,pf1));P:f0", 0, 1, 0, buf, 400) == 0  # outside the template grammar

@@ -474,3 +474,56 @@ def test_partial_final_collapse_keeps_results():
     st_f, st_g = check_plan(plan, [rv], configs=(FUSED, GENERIC), rel_tol=1e-11)
     nagg = lambda st: len([k for k in st if k.endswith("B200HashAggregation.inputPositions")])
     assert nagg(st_f) == 1 and nagg(st_g) == 2
+
+
+def test_pipeline_jit_shapes_without_an_aot_kernel():
+    """Plan shapes with no ahead-of-time fused kernel are instantiated from the expression templates
+    with NVRTC (fused_jit.cu) and still run as ONE scan -> filter -> project -> aggregate kernel:
+    Q6 with a fourth predicate, and a grouped sum/avg over different expressions."""
+    n = 300_000
+    h, col = _lineitem(n, seed=77)
+    names = ["l_shipdate", "l_extendedprice", "l_quantity", "l_discount", "l_tax", "l_linestatus"]
+    rv = row_vector(names, [col(c) for c in names])
+    tol = max(1e-12, n * 2.0 ** -53)
+    q6x = (PlanBuilder().values(rv.names, rv.types)
+           .filter("l_shipdate between '1994-01-01'::DATE and '1994-12-31'::DATE and l_discount between 0.05 and 0.07 and l_quantity < 24.0 "
+                   "and l_extendedprice > 1000.0")
+           .project(["l_extendedprice * l_discount AS r"]).singleAggregation([], ["sum(r)", "count(0)"]).planNode())
+    st_f, st_g = check_plan(q6x, [rv], configs=(FUSED, GENERIC), rel_tol=tol, oracle_batch_rows=100_000)
+    assert stat(st_f, "b200.fusedBatches") == 1 and stat(st_g, "b200.fusedBatches") == 0
+    grouped = (PlanBuilder().values(rv.names, rv.types).filter("l_tax <= 0.06 and l_quantity >= 3.0")
+               .project(["l_linestatus", "l_extendedprice / (1.0 + l_tax) AS net", "l_quantity - l_discount AS q"])
+               .singleAggregation(["l_linestatus"], ["sum(net)", "avg(q)", "count(0)"]).planNode())
+    st_f, st_g = check_plan(grouped, [rv], configs=(FUSED, GENERIC), rel_tol=tol, oracle_batch_rows=100_000)
+    assert stat(st_f, "b200.fusedBatches") == 1 and stat(st_g, "b200.fusedBatches") == 0
+
+
+def test_late_materialization_matches_full_scan():
+    """Selective filter: the filter-first path (bitmap -> row numbers -> gather-aggregate) and the full
+    fused scan give the same answer as the oracle; the planner picks it from a sampled selectivity."""
+    n, nparts = 400_000, 5000
+    h, col = _lineitem(n, seed=78, nparts=nparts)
+    li = row_vector(["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"], [col(c) for c in ["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"]])
+    part = {k: v.numpy() for k, v in tpch.gen_part(nparts, seed=5).items()}
+    pt = row_vector(["p_partkey", "p_type"], [flat_vector(BIGINT, part["p_partkey"]), dictionary_vector(VARCHAR, part["p_type"], tpch.PTYPE_DICT)])
+    late = {"b200.late_materialization_min_rows": "1000"}
+    full = {"b200.late_materialization": "false"}
+    st_l, st_f = check_plan(q14_plan(li, pt), [li, pt], configs=(late, full), rel_tol=1e-12, oracle_batch_rows=100_000)
+    assert stat(st_l, "b200.selectiveBatches") == 1 and stat(st_f, "b200.selectiveBatches") == 0
+    assert 5_000 < stat(st_l, "b200.sampledSelectivityPpm") < 25_000
+    # several batches: the decision of the first batch holds for the rest
+    (st,) = check_plan(q14_plan(li, pt), [li, pt], configs=(late,), batch_rows=100_000, rel_tol=1e-12, oracle_batch_rows=100_000)
+    assert stat(st, "b200.selectiveBatches") == 4
+
+
+def test_filter_project_fast_filter_kernel():
+    """A FilterProject that is not absorbed into an aggregation evaluates a flat NULL-free filter with
+    the TMA-staged bitmap kernel; rows and their order equal the oracle's."""
+    n = 200_000
+    h, col = _lineitem(n, seed=79)
+    names = ["l_shipdate", "l_extendedprice", "l_discount", "l_partkey"]
+    rv = row_vector(names, [col(c) for c in names])
+    plan = (PlanBuilder().values(rv.names, rv.types).filter("l_shipdate between '1995-09-01'::DATE and '1995-09-30'::DATE")
+            .project(["l_extendedprice * (1.0 - l_discount) AS rev", "l_partkey"]).planNode())
+    st_f, st_g = check_plan(plan, [rv], configs=(FUSED, GENERIC), oracle_batch_rows=100_000)
+    assert stat(st_f, "b200.fastFilterBatches") == 1 and stat(st_g, "b200.fastFilterBatches") == 0

@@ -6,16 +6,36 @@
 //   key hashing ............. exec/VectorHasher.cpp:62-126 (folly::hasher<T>), common/base/BitUtil.h:775-784
 //                             (hashMix), common/base/BitUtil.cpp:177-230 (hashBytes, CRC32-C)
 #pragma once
+#ifdef __CUDACC_RTC__
+// NVRTC (fused_jit.cu compiles fused_scan.cuh at run time): no system headers; the few names the
+// device code needs from them are spelled out, and checked against the host's values by fused_jit.cu.
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef unsigned char uint8_t;
+typedef unsigned long long uintptr_t;
+typedef unsigned long size_t;
+#define INT64_MIN (-9223372036854775807LL - 1)
+#define INT64_MAX 9223372036854775807LL
+#define INT32_MIN (-2147483647 - 1)
+#define INT32_MAX 2147483647
+#define VB2_FUSED_MAX_COLS 8
+#define VB2_FUSED_MAX_PARAMS 12
+#define VB2_FUSED_MAX_KEYS 2
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/velox_b200_kernels.h"
+#endif
 
 namespace vb2 {
 
 constexpr int kWarp = 32;
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+#ifndef __CUDACC_RTC__
 #define VB2_CUDA_OK(expr)                                   \
   do {                                                      \
     cudaError_t _e = (expr);                                \
@@ -33,6 +53,7 @@ inline T counted(T grid) {
   note_launch();
   return grid;
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Streaming loads. Input columns are read exactly once: bypass L1 allocation, 128-bit wide.

@@ -13,8 +13,6 @@
 // NVRTC is loaded lazily with dlopen (the library must load on hosts without a GPU); kernels are
 // loaded with the runtime API's cudaLibraryLoadData. Any failure to JIT (NVRTC missing, an
 // operation the generator does not cover) falls back to the interpreter kernels — still CUDA.
-#include <dlfcn.h>
-#include <nvrtc.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -26,6 +24,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "jit_common.h"
 #include "vm_ops_str.h"  // generated from vm_ops.inc: static const char kVmOpsSource[]
 
 namespace vb2 {
@@ -64,42 +63,6 @@ static_assert(sizeof(vb2_column) == VB2_SIZEOF_COLUMN && sizeof(vb2_const) == VB
 __device__ __forceinline__ double as_f64(uint64_t v) { return __longlong_as_double((long long)v); }
 __device__ __forceinline__ uint64_t from_f64(double d) { return (uint64_t)__double_as_longlong(d); }
 )SRC";
-
-// ---- NVRTC through dlopen ----------------------------------------------------------------------
-struct Nvrtc {
-  void* handle = nullptr;
-  nvrtcResult (*createProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
-  nvrtcResult (*compileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
-  nvrtcResult (*getCUBINSize)(nvrtcProgram, size_t*) = nullptr;
-  nvrtcResult (*getCUBIN)(nvrtcProgram, char*) = nullptr;
-  nvrtcResult (*getProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
-  nvrtcResult (*getProgramLog)(nvrtcProgram, char*) = nullptr;
-  nvrtcResult (*destroyProgram)(nvrtcProgram*) = nullptr;
-  bool ok = false;
-};
-
-static Nvrtc& nvrtc() {
-  static Nvrtc n;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"};
-    for (const char* nm : names) {
-      n.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
-      if (n.handle) break;
-    }
-    if (!n.handle) return;
-    auto sym = [&](const char* s) { return dlsym(n.handle, s); };
-    n.createProgram = reinterpret_cast<decltype(n.createProgram)>(sym("nvrtcCreateProgram"));
-    n.compileProgram = reinterpret_cast<decltype(n.compileProgram)>(sym("nvrtcCompileProgram"));
-    n.getCUBINSize = reinterpret_cast<decltype(n.getCUBINSize)>(sym("nvrtcGetCUBINSize"));
-    n.getCUBIN = reinterpret_cast<decltype(n.getCUBIN)>(sym("nvrtcGetCUBIN"));
-    n.getProgramLogSize = reinterpret_cast<decltype(n.getProgramLogSize)>(sym("nvrtcGetProgramLogSize"));
-    n.getProgramLog = reinterpret_cast<decltype(n.getProgramLog)>(sym("nvrtcGetProgramLog"));
-    n.destroyProgram = reinterpret_cast<decltype(n.destroyProgram)>(sym("nvrtcDestroyProgram"));
-    n.ok = n.createProgram && n.compileProgram && n.getCUBINSize && n.getCUBIN && n.getProgramLogSize && n.getProgramLog && n.destroyProgram;
-  });
-  return n;
-}
 
 // ---- code generation -----------------------------------------------------------------------------
 struct Gen {

@@ -16,11 +16,20 @@
 //     block order -> results are run-to-run deterministic;
 //   * persistent grid: blocks = SMs x resident blocks per SM.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <string>
-#include <tuple>
-#include <type_traits>
+#endif
 
 #include "common.cuh"
+
+// The whole header also compiles under NVRTC (expression-template pipelines are instantiated at
+// run time for plan shapes without an ahead-of-time specialisation, fused_jit.cu): nothing here
+// may depend on the host standard library except the signature printers, which NVRTC skips.
+#ifdef __CUDACC_RTC__
+#define VB2_SIG(...)
+#else
+#define VB2_SIG(...) __VA_ARGS__
+#endif
 
 namespace vb2 {
 namespace fx {
@@ -45,6 +54,11 @@ template <class... Ts>
 struct TypeList {
   static constexpr int size = sizeof...(Ts);
 };
+template <class A, class B> struct IsSame { static constexpr bool value = false; };
+template <class A> struct IsSame<A, A> { static constexpr bool value = true; };
+template <class A, class B> constexpr bool is_same_v = IsSame<A, B>::value;
+template <int I, class T, class... Ts> struct TypeAt { using type = typename TypeAt<I - 1, Ts...>::type; };
+template <class T, class... Ts> struct TypeAt<0, T, Ts...> { using type = T; };
 
 // ---- leaves ---------------------------------------------------------------------------------
 template <int C>
@@ -53,7 +67,7 @@ struct ColF {
   static constexpr uint32_t fmask = 1u << C, imask = 0, lmask = 0;
   static constexpr bool uses_join = false;
   __device__ static __forceinline__ double eval(const PairRegs& r, const Consts&, int s) { return r.f[C][s]; }
-  static std::string sig() { return "f" + std::to_string(C); }
+  VB2_SIG(static std::string sig() { return "f" + std::to_string(C); })
 };
 template <int C>
 struct ColI {
@@ -61,7 +75,7 @@ struct ColI {
   static constexpr uint32_t fmask = 0, imask = 1u << C, lmask = 0;
   static constexpr bool uses_join = false;
   __device__ static __forceinline__ int32_t eval(const PairRegs& r, const Consts&, int s) { return r.i[C][s]; }
-  static std::string sig() { return "i" + std::to_string(C); }
+  VB2_SIG(static std::string sig() { return "i" + std::to_string(C); })
 };
 template <int C>
 struct ColL {
@@ -69,7 +83,7 @@ struct ColL {
   static constexpr uint32_t fmask = 0, imask = 0, lmask = 1u << C;
   static constexpr bool uses_join = false;
   __device__ static __forceinline__ int64_t eval(const PairRegs& r, const Consts&, int s) { return r.l[C][s]; }
-  static std::string sig() { return "l" + std::to_string(C); }
+  VB2_SIG(static std::string sig() { return "l" + std::to_string(C); })
 };
 template <int K>
 struct PF {
@@ -77,7 +91,7 @@ struct PF {
   static constexpr uint32_t fmask = 0, imask = 0, lmask = 0;
   static constexpr bool uses_join = false;
   __device__ static __forceinline__ double eval(const PairRegs&, const Consts& c, int) { return c.pf[K]; }
-  static std::string sig() { return "pf" + std::to_string(K); }
+  VB2_SIG(static std::string sig() { return "pf" + std::to_string(K); })
 };
 template <int K>
 struct PI {
@@ -85,7 +99,7 @@ struct PI {
   static constexpr uint32_t fmask = 0, imask = 0, lmask = 0;
   static constexpr bool uses_join = false;
   __device__ static __forceinline__ int32_t eval(const PairRegs&, const Consts& c, int) { return c.pi[K]; }
-  static std::string sig() { return "pi" + std::to_string(K); }
+  VB2_SIG(static std::string sig() { return "pi" + std::to_string(K); })
 };
 template <int K>
 struct PL {
@@ -93,14 +107,14 @@ struct PL {
   static constexpr uint32_t fmask = 0, imask = 0, lmask = 0;
   static constexpr bool uses_join = false;
   __device__ static __forceinline__ int64_t eval(const PairRegs&, const Consts& c, int) { return c.pl[K]; }
-  static std::string sig() { return "pl" + std::to_string(K); }
+  VB2_SIG(static std::string sig() { return "pl" + std::to_string(K); })
 };
 struct True {
   using T = bool;
   static constexpr uint32_t fmask = 0, imask = 0, lmask = 0;
   static constexpr bool uses_join = false;
   __device__ static __forceinline__ bool eval(const PairRegs&, const Consts&, int) { return true; }
-  static std::string sig() { return "true"; }
+  VB2_SIG(static std::string sig() { return "true"; })
 };
 // Build-side predicate of the matched build row (e.g. p_type LIKE 'PROMO%'), evaluated once per
 // dictionary entry on the build side and looked up here.
@@ -109,14 +123,14 @@ struct JoinFlag {
   static constexpr uint32_t fmask = 0, imask = 0, lmask = 0;
   static constexpr bool uses_join = true;
   __device__ static __forceinline__ bool eval(const PairRegs& r, const Consts&, int s) { return r.join_flag[s]; }
-  static std::string sig() { return "joinflag"; }
+  VB2_SIG(static std::string sig() { return "joinflag"; })
 };
 
 // ---- operators ------------------------------------------------------------------------------
 #define VB2_FX_BINARY(Name, text, expr)                                                          \
   template <class A, class B>                                                                    \
   struct Name {                                                                                  \
-    static_assert(std::is_same_v<typename A::T, double> && std::is_same_v<typename B::T, double>); \
+    static_assert(is_same_v<typename A::T, double> && is_same_v<typename B::T, double>); \
     using T = double;                                                                            \
     static constexpr uint32_t fmask = A::fmask | B::fmask, imask = A::imask | B::imask,          \
                               lmask = A::lmask | B::lmask;                                       \
@@ -125,7 +139,7 @@ struct JoinFlag {
       const double a = A::eval(r, c, s), b = B::eval(r, c, s);                                   \
       return expr;                                                                               \
     }                                                                                            \
-    static std::string sig() { return std::string(text "(") + A::sig() + "," + B::sig() + ")"; } \
+    VB2_SIG(static std::string sig() { return std::string(text "(") + A::sig() + "," + B::sig() + ")"; }) \
   };
 VB2_FX_BINARY(Plus, "plus", __dadd_rn(a, b))
 VB2_FX_BINARY(Minus, "minus", __dsub_rn(a, b))
@@ -135,18 +149,20 @@ VB2_FX_BINARY(Divide, "divide", __ddiv_rn(a, b))
 
 template <int Op, class A, class B>
 struct Compare {
-  static_assert(std::is_same_v<typename A::T, typename B::T>);
+  static_assert(is_same_v<typename A::T, typename B::T>);
   using T = bool;
   static constexpr uint32_t fmask = A::fmask | B::fmask, imask = A::imask | B::imask, lmask = A::lmask | B::lmask;
   static constexpr bool uses_join = A::uses_join || B::uses_join;
   __device__ static __forceinline__ bool eval(const PairRegs& r, const Consts& c, int s) {
-    if constexpr (std::is_same_v<typename A::T, double>) return cmp_f64(Op, A::eval(r, c, s), B::eval(r, c, s));
+    if constexpr (is_same_v<typename A::T, double>) return cmp_f64(Op, A::eval(r, c, s), B::eval(r, c, s));
     else return cmp_int<typename A::T>(Op, A::eval(r, c, s), B::eval(r, c, s));
   }
+#ifndef __CUDACC_RTC__
   static std::string sig() {
     static const char* names[] = {"lt", "lte", "gt", "gte", "eq", "neq"};
     return std::string(names[Op]) + "(" + A::sig() + "," + B::sig() + ")";
   }
+#endif
 };
 template <class A, class B> using Lt = Compare<kLt, A, B>;
 template <class A, class B> using Lte = Compare<kLte, A, B>;
@@ -163,10 +179,10 @@ struct Between {
   static constexpr bool uses_join = false;
   __device__ static __forceinline__ bool eval(const PairRegs& r, const Consts& c, int s) {
     const auto x = X::eval(r, c, s);
-    if constexpr (std::is_same_v<typename X::T, double>) return gte_f64(x, Lo::eval(r, c, s)) && lte_f64(x, Hi::eval(r, c, s));
+    if constexpr (is_same_v<typename X::T, double>) return gte_f64(x, Lo::eval(r, c, s)) && lte_f64(x, Hi::eval(r, c, s));
     else return x >= Lo::eval(r, c, s) && x <= Hi::eval(r, c, s);
   }
-  static std::string sig() { return "between(" + X::sig() + "," + Lo::sig() + "," + Hi::sig() + ")"; }
+  VB2_SIG(static std::string sig() { return "between(" + X::sig() + "," + Lo::sig() + "," + Hi::sig() + ")"; })
 };
 
 template <class... As>
@@ -177,12 +193,14 @@ struct And {
   // Null-free inputs: three-valued logic degenerates to &&. All conjuncts are evaluated (no
   // divergence); none of them can raise.
   __device__ static __forceinline__ bool eval(const PairRegs& r, const Consts& c, int s) { return (As::eval(r, c, s) & ...); }
+#ifndef __CUDACC_RTC__
   static std::string sig() {
     std::string out = "and(";
     bool first = true;
     ((out += (first ? "" : ",") + As::sig(), first = false), ...);
     return out + ")";
   }
+#endif
 };
 
 template <class C, class A, class B>
@@ -194,7 +212,7 @@ struct Switch {
   __device__ static __forceinline__ T eval(const PairRegs& r, const Consts& c, int s) {
     return C::eval(r, c, s) ? A::eval(r, c, s) : B::eval(r, c, s);
   }
-  static std::string sig() { return "switch(" + C::sig() + "," + A::sig() + "," + B::sig() + ")"; }
+  VB2_SIG(static std::string sig() { return "switch(" + C::sig() + "," + A::sig() + "," + B::sig() + ")"; })
 };
 
 // ---- a pipeline = filter + projections (+ optional join probe on column JoinCol) ------------
@@ -209,16 +227,36 @@ struct Pipeline<Filter, TypeList<Ps...>, JoinCol> {
   static constexpr uint32_t fmask = Filter::fmask | (Ps::fmask | ...);
   static constexpr uint32_t imask = Filter::imask | (Ps::imask | ...);
   static constexpr uint32_t lmask = Filter::lmask | (Ps::lmask | ...) | (kJoin ? (1u << (kJoin ? JoinCol : 0)) : 0u);
-  static_assert(((std::is_same_v<typename Ps::T, double>) && ...), "fused projections are DOUBLE");
+  static_assert(((is_same_v<typename Ps::T, double>) && ...), "fused projections are DOUBLE");
   using F = Filter;
+  // The two halves of the late-materialisation path (selective filters): the filter alone, and
+  // everything after it (join key + projections) for rows that already passed.
+  struct FilterView {
+    static constexpr uint32_t fmask = Filter::fmask, imask = Filter::imask, lmask = Filter::lmask;
+    using F = Filter;
+  };
+  struct AfterFilter {
+    static constexpr int kNP = sizeof...(Ps);
+    static constexpr bool kJoin = JoinCol >= 0;
+    static constexpr int kJoinCol = JoinCol >= 0 ? JoinCol : 0;
+    static constexpr uint32_t fmask = (Ps::fmask | ...);
+    static constexpr uint32_t imask = (Ps::imask | ...);
+    static constexpr uint32_t lmask = (Ps::lmask | ...) | (kJoin ? (1u << (kJoin ? JoinCol : 0)) : 0u);
+    using F = True;
+    template <int I>
+    __device__ static __forceinline__ void project(const PairRegs& r, const Consts& c, int s, double (&out)[kNP]) {
+      Pipeline::template project<I>(r, c, s, out);
+    }
+  };
   template <int I>
   __device__ static __forceinline__ void project(const PairRegs& r, const Consts& c, int s, double (&out)[kNP]) {
     if constexpr (I < kNP) {
-      using P = std::tuple_element_t<I, std::tuple<Ps...>>;
+      using P = typename TypeAt<I, Ps...>::type;
       out[I] = P::eval(r, c, s);
       project<I + 1>(r, c, s, out);
     }
   }
+#ifndef __CUDACC_RTC__
   static std::string sig() {
     std::string out = "F:" + Filter::sig() + ";P:";
     bool first = true;
@@ -226,6 +264,7 @@ struct Pipeline<Filter, TypeList<Ps...>, JoinCol> {
     if (kJoin) out += ";J:l" + std::to_string(JoinCol);
     return out;
   }
+#endif
 };
 
 struct KernelArgs {
@@ -538,6 +577,11 @@ __device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint64_t dep, u
       ::"r"(smem_u32(bar)), "l"(dep), "l"(guard)
       : "memory");
 }
+__device__ __forceinline__ uint64_t warp_xor(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -676,8 +720,10 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
             }
         }
       }
-      // every value of this stage is in a register: hand it back to the producer before computing
-      __syncwarp();
+      // every value of this stage is in a register: hand it back to the producer before computing.
+      // The fold covers the loads of ALL 32 lanes (xor-reduce across the warp), so lane 0's arrive
+      // is data-dependent on every value the warp took from the stage.
+      dep = warp_xor(dep);
       if (lane == 0) mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
       int gid[kRowsPerThread];
       double v[kRowsPerThread][P::kNP];
@@ -729,21 +775,25 @@ struct CompactPipeline<Filter, TypeList<Ps...>> {
   template <int I>
   __device__ static __forceinline__ void store(const PairRegs& r, const Consts& c, void* const* outs, int64_t pos) {
     if constexpr (I < kNP) {
-      using P = std::tuple_element_t<I, std::tuple<Ps...>>;
+      using P = typename TypeAt<I, Ps...>::type;
       reinterpret_cast<typename P::T*>(outs[I])[pos] = P::eval(r, c, 0);
       store<I + 1>(r, c, outs, pos);
     }
   }
+#ifndef __CUDACC_RTC__
   static std::string sig() {
     std::string out = "F:" + Filter::sig() + ";C:";
     bool first = true;
     ((out += (first ? "" : "|") + Ps::sig(), first = false), ...);
     return out;
   }
+#endif
+#ifndef __CUDACC_RTC__
   static void widths(int* w) {
     int i = 0;
     ((w[i++] = static_cast<int>(sizeof(typename Ps::T))), ...);
   }
+#endif
 };
 
 struct CompactArgs {
@@ -835,7 +885,7 @@ fused_scan_compact_tma_kernel(const __grid_constant__ KernelArgs a, const __grid
         warp_total += __popc(m);
       }
       (void)before;
-      __syncwarp();
+      dep = warp_xor(dep);
       if (lane == 0) {
         mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
         warp_counts[warp] = warp_total;
@@ -874,23 +924,203 @@ fused_scan_compact_tma_kernel(const __grid_constant__ KernelArgs a, const __grid
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Late materialisation for selective filters (the reference's FilterProject does the same thing
+// row-set-wise: the filter runs first and the projections only see the surviving rows,
+// velox/exec/FilterProject.cpp:200-259; its readers go further and load the other columns lazily).
+//   fused_filter_bits_tma_kernel   streams ONLY the filter's columns through the TMA ring and writes
+//                                  the selection bitmap (1 bit per row, 32-bit words); with
+//                                  tile_stride > 1 it visits every tile_stride-th tile and only
+//                                  counts (selectivity estimate for the planner).
+//   fused_gather_agg_kernel        join probe + projections + aggregation over the selected row
+//                                  numbers: columns are touched at the sectors of surviving rows only.
+// Q14 keeps 1.2 % of lineitem: 4 B/row of filter traffic + ~5 % of the other columns' sectors
+// instead of 28 B/row.
+// ---------------------------------------------------------------------------------------------
+template <class FV>
+__global__ void __launch_bounds__(kTmaThreads, 2)
+fused_filter_bits_tma_kernel(const __grid_constant__ KernelArgs a, int stages, int tile_stride, uint32_t* __restrict__ bits,
+                             unsigned long long* __restrict__ counters) {
+  extern __shared__ __align__(128) uint8_t tile_smem[];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+  using Lay = TileLayout<FV, 4>;
+  const int stage_bytes = Lay::stage_bytes(0);
+  const int64_t ntiles = a.rows / kTileRows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerThreads / kWarp);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * tile_stride, step = static_cast<int64_t>(gridDim.x) * tile_stride;
+  if (warp == kConsumerThreads / kWarp) {
+    if (lane == 0) {
+      int it = 0;
+      for (int64_t t = first; t < ntiles; t += step, ++it) {
+        const int s = it % stages;
+        const uint32_t round = static_cast<uint32_t>(it / stages);
+        if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+        uint8_t* base = tile_smem + static_cast<size_t>(s) * stage_bytes;
+        const int64_t row0 = t * kTileRows;
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) {
+          if (FV::fmask & (1u << c)) bytes += kTileRows * 8;
+          if (FV::lmask & (1u << c)) bytes += kTileRows * 8;
+          if (FV::imask & (1u << c)) bytes += kTileRows * 4;
+        }
+        mbar_expect_tx(&full_bar[s], bytes);
+#pragma unroll
+        for (int c = 0; c < kMaxCols; ++c) {
+          if (FV::fmask & (1u << c)) bulk_load(base + Lay::f_off(c), reinterpret_cast<const double*>(a.cols[c]) + row0, kTileRows * 8, &full_bar[s]);
+          if (FV::lmask & (1u << c)) bulk_load(base + Lay::l_off(c), reinterpret_cast<const int64_t*>(a.cols[c]) + row0, kTileRows * 8, &full_bar[s]);
+          if (FV::imask & (1u << c)) bulk_load(base + Lay::i_off(c, 0), reinterpret_cast<const int32_t*>(a.cols[c]) + row0, kTileRows * 4, &full_bar[s]);
+        }
+      }
+    }
+    return;
+  }
+  unsigned long long kept = 0, seen = 0;
+  int it = 0;
+  for (int64_t t = first; t < ntiles; t += step, ++it) {
+    const int s = it % stages;
+    const uint32_t round = static_cast<uint32_t>(it / stages);
+    mbar_wait(&full_bar[s], round & 1);
+    const uint8_t* base = tile_smem + static_cast<size_t>(s) * stage_bytes;
+    PairRegs r[kRowsPerThread];
+    uint64_t dep = 0;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      const int row = j * kConsumerThreads + threadIdx.x;  // a warp owns 32 consecutive rows: one bitmap word
+#pragma unroll
+      for (int c = 0; c < kMaxCols; ++c) {
+        if (FV::fmask & (1u << c)) {
+          r[j].f[c][0] = reinterpret_cast<const double*>(base + Lay::f_off(c))[row];
+          dep ^= static_cast<uint64_t>(__double_as_longlong(r[j].f[c][0]));
+        }
+        if (FV::lmask & (1u << c)) {
+          r[j].l[c][0] = reinterpret_cast<const int64_t*>(base + Lay::l_off(c))[row];
+          dep ^= static_cast<uint64_t>(r[j].l[c][0]);
+        }
+        if (FV::imask & (1u << c)) {
+          r[j].i[c][0] = reinterpret_cast<const int32_t*>(base + Lay::i_off(c, 0))[row];
+          dep ^= static_cast<uint64_t>(static_cast<uint32_t>(r[j].i[c][0]));
+        }
+      }
+    }
+    dep = warp_xor(dep);
+    if (lane == 0) mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      const bool keep = FV::F::eval(r[j], a.consts, 0);
+      const unsigned word = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) {
+        if (bits) bits[(t * kTileRows + j * kConsumerThreads + warp * kWarp) >> 5] = word;
+        kept += __popc(word);
+        seen += kWarp;
+      }
+    }
+  }
+  // tail rows (rows % kTileRows): whole bitmap words by direct loads, block 0 only (full scans only)
+  if (tile_stride == 1 && blockIdx.x == 0) {
+    const int64_t tail0 = ntiles * kTileRows;
+    for (int64_t w0 = tail0 + static_cast<int64_t>(warp) * kWarp; w0 < a.rows; w0 += kConsumerThreads) {
+      const int64_t row = w0 + lane;
+      bool keep = false;
+      if (row < a.rows) {
+        PairRegs r;
+        load_rows<FV, false>(a, row, r);
+        keep = FV::F::eval(r, a.consts, 0);
+      }
+      const unsigned word = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) {
+        if (bits) bits[w0 >> 5] = word;
+        kept += __popc(word);
+        seen += (a.rows - w0 < kWarp) ? (a.rows - w0) : kWarp;
+      }
+    }
+  }
+  if (lane == 0 && counters && seen) {
+    atomicAdd(counters, kept);
+    atomicAdd(counters + 1, seen);
+  }
+}
+
+// Rows sel[0 .. nsel) (ascending row numbers that passed the filter): probe, project, aggregate.
+// Register accumulators (<= kMaxG groups); four independent rows in flight per thread.
+template <class P, int kMaxG, class KeyT>
+__global__ void __launch_bounds__(kThreads, 2)
+fused_gather_agg_kernel(const __grid_constant__ KernelArgs a, const int32_t* __restrict__ sel, const int64_t* __restrict__ nsel_dev,
+                        double* __restrict__ partials) {
+  using AF = typename P::AfterFilter;
+  Accum<AF, kMaxG> acc;
+  acc.init();
+  constexpr int kU = 4;
+  const int64_t nsel = *nsel_dev;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads;
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i0 < nsel; i0 += kU * stride) {
+    PairRegs r[kU];
+    KeyT kv[kU][VB2_FUSED_MAX_KEYS][2];
+    bool ok[kU];
+    int64_t row[kU];
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      const int64_t i = i0 + j * stride;
+      ok[j] = i < nsel;
+      row[j] = ok[j] ? sel[i] : sel[i0];
+    }
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      load_rows<AF, false>(a, row[j], r[j]);
+      if (kMaxG > 1) load_keys<false, KeyT>(a, row[j], kv[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      int gid;
+      double v[AF::kNP];
+      eval_slot<AF, kMaxG, KeyT>(a, r[j], kv[j], 0, gid, v);
+      acc.add(ok[j] ? gid : -1, v);
+    }
+  }
+  block_reduce_store<AF, kMaxG>(acc, partials);
+}
+
+#ifndef __CUDACC_RTC__
 // Folds per-block partials in block order into the persistent accumulators.
 __global__ void fused_finalize_kernel(const double* __restrict__ partials, int nblocks, int kvals, int np, int maxg,
                                       int ngroups, double* __restrict__ sums, int64_t* __restrict__ counts);
 
-using LaunchFn = int (*)(const KernelArgs&, double* sums, int64_t* counts, void* ws, size_t ws_bytes, cudaStream_t);
+// Which kernels of a pipeline exist is the same for ahead-of-time template instantiations and for
+// NVRTC-compiled ones (fused_jit.cu); the launch logic below (fused_scan.cu) only sees this interface.
+enum class KernelKind : int { kTma = 0, kDirect = 1, kFilterBits = 2, kGather = 3 };
+struct PipelineDesc {
+  int nproj = 0;
+  bool join = false;
+  bool has_filter = false;                     // a filter other than `true`: the late-materialisation kernels exist
+  uint32_t fmask = 0, imask = 0, lmask = 0;      // columns of the whole pipeline by type
+  uint32_t ffmask = 0, fimask = 0, flmask = 0;   // columns the filter alone reads
+};
+// Kernel entry point for (kind, accumulator variant, key width), or nullptr. max_groups: 1 / 4 / 8
+// register accumulators, 0 = shared-memory accumulators (kTma only); ignored for kFilterBits.
+using KernelGetter = const void* (*)(void* self, KernelKind kind, int max_groups, bool key64);
 using CompactFn = int (*)(const KernelArgs&, const CompactArgs&, cudaStream_t);
 
 struct Entry {
   std::string signature;
-  int nproj;
-  bool join;
-  LaunchFn launch;           // aggregate pipelines
-  CompactFn compact = nullptr;  // compaction pipelines (";C:" signatures)
+  int nproj = 0;
+  bool join = false;
+  PipelineDesc desc;
+  KernelGetter kernels = nullptr;  // aggregate pipelines (and filter-only pipelines: nproj == 0)
+  void* self = nullptr;
+  CompactFn compact = nullptr;     // compaction pipelines (";C:" signatures)
   int widths[VB2_FUSED_MAX_COLS] = {0};
 };
 
 int register_pipeline(const Entry& e);
+#endif  // __CUDACC_RTC__
 
 }  // namespace fx
 }  // namespace vb2

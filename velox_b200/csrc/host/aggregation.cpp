@@ -1,7 +1,10 @@
 // B200HashAggregation: GROUP BY on the device (array mode / normalized-key hash mode), with the
 // fused scan->filter->[probe]->project->aggregate fast path for null-free flat batches.
-#include <map>
 #include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <map>
+#include <set>
 
 #include "join.h"
 #include "operators.h"
@@ -97,7 +100,9 @@ struct B200HashAggregation::Impl {
   DeviceBufferPtr fusedSums, fusedCounts, fusedWs;
   size_t fusedWsBytes = 0;
   int fusedGroups = 0;
-  int64_t fusedBatches = 0, genericBatches = 0;
+  int64_t fusedBatches = 0, genericBatches = 0, selectiveBatches = 0;
+  bool selectiveDecided = false, selectiveUsable = true;
+  double selectivity = 1.0;
   struct FusedTiming { cudaEvent_t begin = nullptr, end = nullptr; int64_t rows = 0; };
   std::vector<FusedTiming> fusedTimings;
   ~Impl() {
@@ -741,7 +746,28 @@ struct B200HashAggregation::Impl {
     VB2_CU(cudaEventCreate(&ft.begin));
     VB2_CU(cudaEventCreate(&ft.end));
     VB2_CU(cudaEventRecord(ft.begin, st()));
-    const int rc = vb2k_fused_scan_agg(fusedId, &a, fusedSums->as<double>(), fusedCounts->as<int64_t>(), fusedWs->data(), fusedWsBytes, st());
+    int rc = VB2_ERR_UNSUPPORTED;
+    if (chooseSelective(a, n, groups)) {
+      // Late materialisation: filter columns only -> selection bitmap -> row numbers -> probe /
+      // project / aggregate over the surviving rows. Everything stays on the stream; the row count
+      // is read by the gather kernel on the device.
+      auto bitsBuf = allocDevice(bits::nbytes(n), st());
+      rc = vb2k_fused_filter_bits(fusedId, &a, 1, bitsBuf->as<uint64_t>(), nullptr, st());
+      if (rc == VB2_OK) {
+        auto sel = allocDevice(static_cast<size_t>(n) * 4, st());  // capacity for every row; only the kept ones are written
+        auto cnt = allocDevice(8, st());
+        const size_t wsb = vb2k_bits_to_indices_workspace(n);
+        auto ws = allocDevice(wsb, st());
+        kernelCheck(vb2k_bits_to_indices(bitsBuf->as<uint64_t>(), n, sel->as<int32_t>(), cnt->as<int64_t>(), ws->data(), wsb, st()));
+        const int64_t hint = std::max<int64_t>(1024, static_cast<int64_t>(selectivity * 1.25 * static_cast<double>(n)));
+        rc = vb2k_fused_gather_agg(fusedId, &a, sel->as<int32_t>(), cnt->as<int64_t>(), hint, fusedSums->as<double>(), fusedCounts->as<int64_t>(), fusedWs->data(),
+                                   fusedWsBytes, st());
+        if (rc == VB2_OK) ++selectiveBatches;
+      }
+      if (rc != VB2_OK) selectiveUsable = false;  // e.g. unaligned filter columns: scan everything instead
+    }
+    if (rc == VB2_ERR_UNSUPPORTED)
+      rc = vb2k_fused_scan_agg(fusedId, &a, fusedSums->as<double>(), fusedCounts->as<int64_t>(), fusedWs->data(), fusedWsBytes, st());
     if (rc == VB2_OK) VB2_CU(cudaEventRecord(ft.end, st()));
     if (rc != VB2_OK) { cudaEventDestroy(ft.begin); cudaEventDestroy(ft.end); }
     if (rc == VB2_ERR_UNSUPPORTED) return false;
@@ -750,6 +776,61 @@ struct B200HashAggregation::Impl {
     fusedTimings.push_back(ft);
     ++fusedBatches;
     return true;
+  }
+
+  // Bytes per row the filter alone reads / the rest of the pipeline reads, from the signature's
+  // column tokens (f = 8, l = 8, i = 4 bytes).
+  void signatureBytes(double& filterBytes, double& restBytes) const {
+    const std::string& sg = binding.signature;
+    const size_t pp = sg.find(";P:");
+    std::set<std::string> filterCols, allCols;
+    auto scan = [](const std::string& part, std::set<std::string>& out) {
+      size_t i = 0;
+      while (i < part.size()) {
+        if (!std::isalnum(static_cast<unsigned char>(part[i]))) { ++i; continue; }
+        size_t j = i;
+        while (j < part.size() && std::isalnum(static_cast<unsigned char>(part[j]))) ++j;
+        const std::string id = part.substr(i, j - i);
+        if (id.size() >= 2 && (id[0] == 'f' || id[0] == 'i' || id[0] == 'l') && std::isdigit(static_cast<unsigned char>(id[1]))) out.insert(id);
+        i = j;
+      }
+    };
+    scan(sg.substr(0, pp), filterCols);
+    scan(sg, allCols);
+    auto width = [](const std::string& id) { return id[0] == 'i' ? 4.0 : 8.0; };
+    filterBytes = restBytes = 0;
+    for (auto& c : allCols) (filterCols.count(c) ? filterBytes : restBytes) += width(c);
+  }
+
+  // Decides, once per operator, whether this pipeline's filter is selective enough for late
+  // materialisation: a strided sample of the first batch (every k-th 1024-row tile, about a million
+  // rows) gives the selectivity; the gather touches whole 32-byte sectors, so a column of 8-byte
+  // values costs about 1 - (1 - s)^4 of its full traffic.
+  bool chooseSelective(const vb2_fused_args& a, int64_t n, int groups) {
+    if (!selectiveUsable || groups > 4 || n < self->driverCtx()->queryConfig().get<int64_t>("b200.late_materialization_min_rows", 1 << 20)) return false;
+    if (!selectiveDecided) {
+      selectiveDecided = true;
+      selectiveUsable = false;
+      if (!self->driverCtx()->queryConfig().get<bool>("b200.late_materialization", true)) return false;
+      if (!vb2k_fused_has_filter(fusedId)) return false;
+      double fb = 0, rb = 0;
+      signatureBytes(fb, rb);
+      if (rb <= 0) return false;
+      auto counters = allocDeviceZeroed(16, st());
+      const int stride = static_cast<int>(std::max<int64_t>(1, (n / 1024) / 1024));
+      const int rc = vb2k_fused_filter_bits(fusedId, &a, stride, nullptr, counters->as<int64_t>(), st());
+      if (rc != VB2_OK) return false;
+      int64_t h[2] = {0, 0};
+      VB2_CU(cudaMemcpyAsync(h, counters->data(), 16, cudaMemcpyDeviceToHost, st()));
+      VB2_CU(cudaStreamSynchronize(st()));
+      if (h[1] <= 0) return false;
+      selectivity = static_cast<double>(h[0]) / static_cast<double>(h[1]);
+      const double sectors = 1.0 - std::pow(1.0 - selectivity, 4.0);
+      const double lateCost = (fb + sectors * rb + selectivity * 12.0) * 1.15;  // + row numbers written and read back, + launch slack
+      selectiveUsable = lateCost < fb + rb;
+      self->addRuntimeStat("b200.sampledSelectivityPpm", exec::RuntimeCounter{static_cast<int64_t>(selectivity * 1e6)});
+    }
+    return selectiveUsable;
   }
 
   // Folds the fused partial sums into the group rows (small: <= kFusedMaxGroups groups) on the
@@ -989,6 +1070,7 @@ struct B200HashAggregation::Impl {
     }
     reportFusedTimings();  // every fused launch precedes the synchronisation above
     self->addRuntimeStat("b200.fusedBatches", exec::RuntimeCounter{fusedBatches});
+    self->addRuntimeStat("b200.selectiveBatches", exec::RuntimeCounter{selectiveBatches});
     self->addRuntimeStat("b200.genericBatches", exec::RuntimeCounter{genericBatches});
     self->addRuntimeStat("b200.aggMode", exec::RuntimeCounter{static_cast<int64_t>(mode)});
     auto out = std::make_shared<B200Vector>(self->pool(), outType, static_cast<vector_size_t>(m), std::move(cols), st());

@@ -75,6 +75,10 @@ class B200FilterProject : public exec::Operator {
   CompiledProgram program_;
   std::shared_ptr<DeviceContext> dev_;
   DeviceBufferPtr errorFlag_;
+  // The filter as a TMA-staged bitmap kernel of the fused-pipeline family (registered or NVRTC-
+  // instantiated from the expression templates), taken for flat NULL-free batches; -1 = not expressible.
+  FusedBinding fastFilter_;
+  int fastFilterId_ = -1;
 };
 
 // ---- aggregation ----------------------------------------------------------------------------------

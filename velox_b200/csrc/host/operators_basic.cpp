@@ -112,6 +112,7 @@ B200FilterProject::B200FilterProject(int32_t id, exec::DriverCtx* ctx, const exe
       exprs_.push_back(std::make_shared<core::FieldAccessTypedExpr>(inputType_->childAt(i), inputType_->nameOf(i), static_cast<int32_t>(i)));
   }
   program_ = compileExprs(exprs_, hasFilter_, inputType_);
+  if (hasFilter_) fastFilter_ = fusedSignature(exprs_[0], {}, inputType_);
 }
 
 void B200FilterProject::initialize() {
@@ -119,6 +120,10 @@ void B200FilterProject::initialize() {
   dev_ = driverDeviceContext(driverCtx_);
   errorFlag_ = allocDeviceZeroed(8, dev_->stream);
   program_.uploadConstants(dev_->stream);
+  if (fastFilter_.ok && driverCtx_->queryConfig().b200FusedPipelines()) {
+    fastFilterId_ = vb2k_fused_find(fastFilter_.signature.c_str());
+    if (fastFilterId_ >= 0 && !vb2k_fused_has_filter(fastFilterId_)) fastFilterId_ = -1;
+  }
 }
 
 B200VectorPtr B200FilterProject::apply(const B200VectorPtr& in) {
@@ -130,7 +135,28 @@ B200VectorPtr B200FilterProject::apply(const B200VectorPtr& in) {
   int64_t numOut = n;
   if (hasFilter_) {
     auto bitsBuf = allocDevice(bits::nbytes(n), st);
-    kernelCheck(vb2k_eval_filter(&prog, cols.data(), static_cast<int32_t>(cols.size()), n, bitsBuf->as<uint64_t>(), errorFlag_->as<int32_t>(), st));
+    bool done = false;
+    if (fastFilterId_ >= 0 && n >= (1 << 16)) {
+      // flat NULL-free filter columns: the TMA-staged bitmap kernel (HBM-bound) instead of one row per thread
+      vb2_fused_args fa{};
+      bool flat = true;
+      for (size_t i = 0; i < fastFilter_.columns.size() && flat; ++i) {
+        const vb2_column& d = in->column(fastFilter_.columns[i])->desc;
+        flat = d.encoding == VB2_FLAT && !d.nulls;
+        fa.cols[i] = d.values;
+      }
+      if (flat) {
+        for (size_t i = 0; i < fastFilter_.pf.size(); ++i) fa.pf[i] = fastFilter_.pf[i];
+        for (size_t i = 0; i < fastFilter_.pl.size(); ++i) fa.pl[i] = fastFilter_.pl[i];
+        for (size_t i = 0; i < fastFilter_.pi.size(); ++i) fa.pi[i] = fastFilter_.pi[i];
+        fa.rows = n;
+        const int rc = vb2k_fused_filter_bits(fastFilterId_, &fa, 1, bitsBuf->as<uint64_t>(), nullptr, st);
+        if (rc == VB2_OK) { done = true; addRuntimeStat("b200.fastFilterBatches", exec::RuntimeCounter{1}); }
+        else if (rc != VB2_ERR_UNSUPPORTED) kernelCheck(rc);
+      }
+    }
+    if (!done)
+      kernelCheck(vb2k_eval_filter(&prog, cols.data(), static_cast<int32_t>(cols.size()), n, bitsBuf->as<uint64_t>(), errorFlag_->as<int32_t>(), st));
     sel = allocDevice(static_cast<size_t>(n) * 4, st);
     auto count = allocDevice(8, st);
     const size_t wsBytes = vb2k_bits_to_indices_workspace(n);
