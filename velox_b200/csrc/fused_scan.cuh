@@ -638,7 +638,7 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);                        // producer's expect_tx arrival
-      mbar_init(&empty_bar[s], kConsumerThreads / kWarp);  // one arrival per consumer warp
+      mbar_init(&empty_bar[s], kConsumerThreads);  // one arrival per consumer thread
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -721,10 +721,9 @@ fused_scan_agg_tma_kernel(const __grid_constant__ KernelArgs a, int stages, doub
         }
       }
       // every value of this stage is in a register: hand it back to the producer before computing.
-      // The fold covers the loads of ALL 32 lanes (xor-reduce across the warp), so lane 0's arrive
-      // is data-dependent on every value the warp took from the stage.
-      dep = warp_xor(dep);
-      if (lane == 0) mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
+      // Every consumer thread arrives for itself (barrier count = consumer threads), predicated on
+      // the fold of ITS OWN loads: no lane's release can overtake that lane's reads of the stage.
+      mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
       int gid[kRowsPerThread];
       double v[kRowsPerThread][P::kNP];
 #pragma unroll
@@ -817,7 +816,7 @@ fused_scan_compact_tma_kernel(const __grid_constant__ KernelArgs a, const __grid
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kConsumerThreads / kWarp);
+      mbar_init(&empty_bar[s], kConsumerThreads);  // one arrival per consumer thread
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -885,11 +884,8 @@ fused_scan_compact_tma_kernel(const __grid_constant__ KernelArgs a, const __grid
         warp_total += __popc(m);
       }
       (void)before;
-      dep = warp_xor(dep);
-      if (lane == 0) {
-        mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
-        warp_counts[warp] = warp_total;
-      }
+      mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
+      if (lane == 0) warp_counts[warp] = warp_total;
       asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
       if (threadIdx.x == 0) {
         int total = 0;
@@ -950,7 +946,7 @@ fused_filter_bits_tma_kernel(const __grid_constant__ KernelArgs a, int stages, i
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kConsumerThreads / kWarp);
+      mbar_init(&empty_bar[s], kConsumerThreads);  // one arrival per consumer thread
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1011,8 +1007,7 @@ fused_filter_bits_tma_kernel(const __grid_constant__ KernelArgs a, int stages, i
         }
       }
     }
-    dep = warp_xor(dep);
-    if (lane == 0) mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
+    mbar_arrive_after(&empty_bar[s], dep, a.release_guard);
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
       const bool keep = FV::F::eval(r[j], a.consts, 0);
