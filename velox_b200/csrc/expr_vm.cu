@@ -395,6 +395,26 @@ __global__ void sel_write_kernel(const uint32_t* __restrict__ bits, int64_t nwor
   for (int j = 0; j < 4; ++j) { word_prefix[t * 4 + j] = excl; excl += pc[j]; }
   __syncthreads();
   const int64_t out0 = block_offsets[blockIdx.x];
+  // Sparse blocks (selective filters: most words are zero): every thread expands its own four
+  // words bit by bit — few bits, so the scattered stores do not matter and no warp walks 128 empty words.
+  __shared__ int block_total;
+  if (t == kSelThreads - 1) block_total = excl;
+  __syncthreads();
+  if (block_total < kSelWordsPerBlock * 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t w = w0 + t * 4 + j;
+      if (w >= nwords) break;
+      uint32_t word = bits[w];
+      int64_t pos = out0 + word_prefix[t * 4 + j];
+      while (word) {
+        const int b = __ffs(word) - 1;
+        indices[pos++] = static_cast<int32_t>((w << 5) + b);
+        word &= word - 1;
+      }
+    }
+    return;
+  }
   // One 32-row word per warp step: lane b owns row (w << 5) + b and stores it at its rank among
   // the set bits, so a warp's stores are consecutive (a thread-per-word bit loop wrote 32
   // scattered sequences per warp and ran at a fifth of the bandwidth).

@@ -180,7 +180,8 @@ std::string name_expression(const Parsed& p, KernelKind kind, int maxg, bool key
   switch (kind) {
     case KernelKind::kTma: return "&vb2::fx::fused_scan_agg_tma_kernel<" + P + "," + std::to_string(maxg) + "," + key + ">";
     case KernelKind::kDirect: return "&vb2::fx::fused_scan_agg_kernel<" + P + "," + std::to_string(maxg) + ",2,false," + key + ">";
-    case KernelKind::kFilterBits: return "&vb2::fx::fused_filter_bits_tma_kernel<vb2::fx::JitFilterView>";
+    case KernelKind::kFilterBits:
+      return "&vb2::fx::fused_filter_bits_tma_kernel<vb2::fx::JitFilterView," + std::to_string(filter_tile_rows_for(p.desc.ffmask, p.desc.fimask, p.desc.flmask)) + ">";
     case KernelKind::kGather: return "&vb2::fx::fused_gather_agg_kernel<" + P + "," + std::to_string(maxg) + "," + key + ">";
   }
   return "";

@@ -72,7 +72,7 @@ static int run_finalize(const KernelArgs& a, void* ws, int64_t grid, int kvals, 
 
 static int popc32(uint32_t m) { int n = 0; for (; m; m &= m - 1) ++n; return n; }
 // TileLayout<P, kKeyBytes>::stage_bytes(nkeys) from the run-time column masks
-static int stage_bytes_of(uint32_t fmask, uint32_t imask, uint32_t lmask, int nkeys, int key_bytes) {
+static int stage_bytes_of(uint32_t fmask, uint32_t imask, uint32_t lmask, int nkeys, int key_bytes, int kTileRows = ::vb2::fx::kTileRows) {
   const int end = 8 * kTileRows * (popc32(fmask) + popc32(lmask)) + (key_bytes == 8 ? nkeys * 8 * kTileRows : 0) + 4 * kTileRows * popc32(imask) +
                   (key_bytes == 4 ? nkeys * 4 * kTileRows : 0);
   return (end + 127) / 128 * 128;
@@ -179,14 +179,15 @@ static int launch_filter_bits(const Entry& e, KernelArgs a, int tile_stride, uin
     if ((((d.ffmask | d.fimask | d.flmask) >> c) & 1u) && !aligned16(a.cols[c])) return fail_msg(VB2_ERR_UNSUPPORTED, "fused filter needs 16-byte aligned columns");
   const void* fn = e.kernels(e.self, KernelKind::kFilterBits, 0, false);
   if (!fn) return fail_msg(VB2_ERR_UNSUPPORTED, "fused filter: kernel unavailable");
-  const int stage_bytes = stage_bytes_of(d.ffmask, d.fimask, d.flmask, 0, 4);
+  const int tile_rows = filter_tile_rows_for(d.ffmask, d.fimask, d.flmask);
+  const int stage_bytes = stage_bytes_of(d.ffmask, d.fimask, d.flmask, 0, 4, tile_rows);
   int stages = (64 * 1024) / stage_bytes;
   stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
   const size_t smem = static_cast<size_t>(stages) * stage_bytes;
   int bps = 1;
   if (int rc = blocks_per_sm_of(fn, kTmaThreads, smem, &bps)) return rc;
   if (tile_stride < 1) tile_stride = 1;
-  const int64_t ntiles = (a.rows / kTileRows + tile_stride - 1) / tile_stride;
+  const int64_t ntiles = (a.rows / tile_rows + tile_stride - 1) / tile_stride;
   int64_t grid = static_cast<int64_t>(device_sm_count()) * bps;
   if (ntiles < grid) grid = ntiles < 1 ? 1 : ntiles;
   void* params[] = {&a, &stages, &tile_stride, &bits, &counters};
@@ -233,7 +234,8 @@ static const void* aot_kernels(void*, KernelKind kind, int maxg, bool key64) {
       if (maxg == 8) return key64 ? reinterpret_cast<const void*>(&fused_scan_agg_kernel<P, 8, 2, false, int64_t>) : reinterpret_cast<const void*>(&fused_scan_agg_kernel<P, 8, 2, false, int32_t>);
       return nullptr;
     case KernelKind::kFilterBits:
-      if constexpr (!is_same_v<typename P::F, True>) return reinterpret_cast<const void*>(&fused_filter_bits_tma_kernel<typename P::FilterView>);
+      if constexpr (!is_same_v<typename P::F, True>)
+        return reinterpret_cast<const void*>(&fused_filter_bits_tma_kernel<typename P::FilterView, filter_tile_rows_for(P::F::fmask, P::F::imask, P::F::lmask)>);
       return nullptr;
     case KernelKind::kGather:
       if constexpr (!is_same_v<typename P::F, True>) {
@@ -280,7 +282,9 @@ struct FilterOnly {
 };
 template <class FO>
 static const void* aot_filter_only(void*, KernelKind kind, int, bool) {
-  return kind == KernelKind::kFilterBits ? reinterpret_cast<const void*>(&fused_filter_bits_tma_kernel<typename FO::FilterView>) : nullptr;
+  return kind == KernelKind::kFilterBits
+             ? reinterpret_cast<const void*>(&fused_filter_bits_tma_kernel<typename FO::FilterView, filter_tile_rows_for(FO::F::fmask, FO::F::imask, FO::F::lmask)>)
+             : nullptr;
 }
 template <class FO>
 static int add_filter_only() {

@@ -603,7 +603,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 
 // Byte offsets of the referenced columns inside one stage: f64 columns, i64 columns, 8-byte keys,
 // i32 columns, 4-byte keys. Everything but the key count is a compile-time constant.
-template <class P, int kKeyBytes>
+template <class P, int kKeyBytes, int kTileRows = ::vb2::fx::kTileRows>
 struct TileLayout {
   __host__ __device__ static constexpr int popc(uint32_t m) { int n = 0; for (; m; m &= m - 1) ++n; return n; }
   __host__ __device__ static constexpr uint32_t low(int c) { return (1u << c) - 1u; }
@@ -933,13 +933,22 @@ fused_scan_compact_tma_kernel(const __grid_constant__ KernelArgs a, const __grid
 // Q14 keeps 1.2 % of lineitem: 4 B/row of filter traffic + ~5 % of the other columns' sectors
 // instead of 28 B/row.
 // ---------------------------------------------------------------------------------------------
-template <class FV>
+__host__ __device__ constexpr int filter_tile_rows_for(uint32_t fmask, uint32_t imask, uint32_t lmask) {
+  int bytes = 0;
+  for (int c = 0; c < 32; ++c) bytes += ((fmask >> c) & 1u) * 8 + ((lmask >> c) & 1u) * 8 + ((imask >> c) & 1u) * 4;
+  return bytes <= 4 ? 4096 : (bytes <= 8 ? 2048 : 1024);
+}
+// kFilterTileRows: rows per tile — a filter over one 4-byte column moves only 4 KB per 1024 rows, too
+// little to amortise a stage hand-off, so narrow filters take taller tiles (>= 16 KB per stage).
+template <class FV, int kFilterTileRows>
 __global__ void __launch_bounds__(kTmaThreads, 2)
 fused_filter_bits_tma_kernel(const __grid_constant__ KernelArgs a, int stages, int tile_stride, uint32_t* __restrict__ bits,
                              unsigned long long* __restrict__ counters) {
   extern __shared__ __align__(128) uint8_t tile_smem[];
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
-  using Lay = TileLayout<FV, 4>;
+  constexpr int kTileRows = kFilterTileRows;  // shadows the pipeline-wide constant inside this kernel
+  constexpr int kRowsPerThread = kFilterTileRows / kConsumerThreads;
+  using Lay = TileLayout<FV, 4, kFilterTileRows>;
   const int stage_bytes = Lay::stage_bytes(0);
   const int64_t ntiles = a.rows / kTileRows;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
