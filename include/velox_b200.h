@@ -63,6 +63,15 @@ int32_t vb2_result_type(vb2_task* task, int32_t col);
 void vb2_result_copy(vb2_task* task, int32_t col, void* values, uint8_t* nulls);
 int64_t vb2_result_str_bytes(vb2_task* task, int32_t col);
 void vb2_result_copy_str(vb2_task* task, int32_t col, int32_t* offsets, char* chars, uint8_t* nulls);
+/* The whole result in two calls (bindings whose per-call cost matters): vb2_result_layout fills
+ * layout[c * 4 ..] = {type, value bytes, offset bytes, char bytes} for every column and returns the
+ * blob size; vb2_result_copy_all writes, per column, values | int32 offsets (VARCHAR) | chars
+ * (VARCHAR) | one null flag byte per row, each region padded to 8 bytes. */
+int64_t vb2_result_layout(vb2_task* task, int64_t* layout);
+void vb2_result_copy_all(vb2_task* task, void* blob);
+/* Host mirrors of device-resident VARCHAR dictionaries are remembered by buffer identity (device
+ * dictionaries passed to vb2_task_add_input must not change while tasks use them); this forgets them. */
+void vb2_dictionary_cache_clear(void);
 /* Operator runtime stats as "pipeline.operator.type.name=value\n" lines (OperatorStats,
  * velox/exec/OperatorStats.h:93). Valid until the task is freed. */
 const char* vb2_task_stats(vb2_task* task);

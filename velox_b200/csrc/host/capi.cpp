@@ -1,6 +1,9 @@
 // Operator-level C ABI (include/velox_b200.h): plan text -> Task over the shim Driver with the
 // B200 adapter installed; host / device column batches in, host result columns out.
 #include <functional>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <execinfo.h>
 #include <signal.h>
 #include <unistd.h>
@@ -131,6 +134,17 @@ VectorPtr importHostColumn(memory::MemoryPool* pool, const vb2_column& c, int64_
   throw VeloxRuntimeError("unknown column encoding");
 }
 
+// Host mirrors of device-resident dictionaries, remembered by the identity of their buffers: a table
+// whose batches are fed to many tasks would otherwise pay two blocking device->host copies per
+// dictionary column and task. Device dictionaries handed to vb2_task_add_input are immutable while in
+// use (as Arrow buffers are); vb2_dictionary_cache_clear() forgets the mirrors.
+struct DictKey {
+  const void* values; const void* aux; const void* nulls; int64_t entries;
+  bool operator<(const DictKey& o) const { return std::tie(values, aux, nulls, entries) < std::tie(o.values, o.aux, o.nulls, o.entries); }
+};
+std::mutex g_dictMu;
+std::map<DictKey, std::shared_ptr<const HostAlphabet>> g_dictCache;
+
 // Device-resident batch: borrow the pointers; small VARCHAR alphabets are mirrored on the host.
 DeviceColumnPtr importDeviceColumn(const vb2_column& c, int64_t rows) {
   if (c.size != rows) throw VeloxRuntimeError("column size differs from the batch's row count");
@@ -139,6 +153,13 @@ DeviceColumnPtr importDeviceColumn(const vb2_column& c, int64_t rows) {
   col->desc = c;
   if (c.type == VB2_VARCHAR && c.encoding != VB2_FLAT) {
     const int64_t entries = c.encoding == VB2_DICTIONARY ? c.dict_size : 1;
+    const uint64_t* dn0 = c.encoding == VB2_DICTIONARY ? c.dict_nulls : c.nulls;
+    const DictKey key{c.values, c.aux, dn0, entries};
+    {
+      std::lock_guard<std::mutex> l(g_dictMu);
+      auto it = g_dictCache.find(key);
+      if (it != g_dictCache.end()) { col->alphabet = it->second; return col; }
+    }
     if (entries <= (1 << 16)) {
       std::vector<int32_t> off(entries + 1);
       VB2_CU(cudaMemcpy(off.data(), c.values, off.size() * 4, cudaMemcpyDeviceToHost));
@@ -156,6 +177,9 @@ DeviceColumnPtr importDeviceColumn(const vb2_column& c, int64_t rows) {
         alpha->nulls.push_back(dn ? !bits::isBitSet(nb.data(), i) : false);
       }
       col->alphabet = alpha;
+      std::lock_guard<std::mutex> l(g_dictMu);
+      if (g_dictCache.size() > 4096) g_dictCache.clear();
+      g_dictCache[key] = alpha;
     }
   }
   return col;
@@ -400,6 +424,48 @@ void vb2_result_copy_str(vb2_task* task, int32_t col, int32_t* offsets, char* ch
   if (!o.chars.empty()) std::memcpy(chars, o.chars.data(), o.chars.size());
   if (nulls && !o.nulls.empty()) std::memcpy(nulls, o.nulls.data(), o.nulls.size());
 }
+void vb2_dictionary_cache_clear(void) {
+  std::lock_guard<std::mutex> l(g_dictMu);
+  g_dictCache.clear();
+}
+
+// Whole result in two calls: layout[c * 4 ..] = {type, value bytes, offset bytes, char bytes}; the blob
+// holds, per column and in this order, values (fixed width; BOOLEAN one byte per row), int32 offsets
+// (VARCHAR), chars (VARCHAR), null flags (one byte per row), each region padded to 8 bytes.
+int64_t vb2_result_layout(vb2_task* task, int64_t* layout) {
+  int64_t total = 0;
+  auto pad = [](size_t b) { return static_cast<int64_t>((b + 7) / 8 * 8); };
+  for (size_t c = 0; c < task->out.size(); ++c) {
+    auto& o = task->out[c];
+    const int64_t offBytes = o.type == VB2_VARCHAR ? static_cast<int64_t>(o.offsets.size() * 4) : 0;
+    if (layout) {
+      layout[c * 4 + 0] = o.type;
+      layout[c * 4 + 1] = static_cast<int64_t>(o.values.size());
+      layout[c * 4 + 2] = offBytes;
+      layout[c * 4 + 3] = static_cast<int64_t>(o.chars.size());
+    }
+    total += pad(o.values.size()) + pad(offBytes) + pad(o.chars.size()) + pad(task->rows);
+  }
+  return total;
+}
+void vb2_result_copy_all(vb2_task* task, void* blob) {
+  uint8_t* p = static_cast<uint8_t*>(blob);
+  auto pad = [](size_t b) { return (b + 7) / 8 * 8; };
+  for (auto& o : task->out) {
+    if (!o.values.empty()) std::memcpy(p, o.values.data(), o.values.size());
+    p += pad(o.values.size());
+    if (o.type == VB2_VARCHAR) {
+      std::memcpy(p, o.offsets.data(), o.offsets.size() * 4);
+      p += pad(o.offsets.size() * 4);
+      if (!o.chars.empty()) std::memcpy(p, o.chars.data(), o.chars.size());
+      p += pad(o.chars.size());
+    }
+    if (!o.nulls.empty()) std::memcpy(p, o.nulls.data(), o.nulls.size());
+    else std::memset(p, 0, static_cast<size_t>(task->rows));
+    p += pad(static_cast<size_t>(task->rows));
+  }
+}
+
 const char* vb2_task_stats(vb2_task* task) { return task->stats.c_str(); }
 void vb2_task_free(vb2_task* task) { delete task; }
 

@@ -109,7 +109,8 @@ namespace velox_b200 {
 bool exchangeUsesPeerMemory(vb2_comm* c) { return c && c->p2p; }
 size_t exchangeMaxMetadataBytes(vb2_comm* c) { return c && c->p2p ? kMetaBytes : (1u << 20); }
 
-std::shared_ptr<void> exchangeMetadata(vb2_comm* c, const uint8_t* myBlockHost, size_t blockBytes, const int64_t* countsDev, cudaStream_t after) {
+std::shared_ptr<void> exchangeMetadata(vb2_comm* c, const uint8_t* myBlockHost, size_t blockBytes, const int64_t* countsDev,
+                                       const std::vector<ExchangePatch>& patches, cudaStream_t after) {
   const int w = c->world;
   VELOX_CHECK(blockBytes % 16 == 0, "exchange metadata block must be a multiple of 16 bytes");
   cudaStream_t xs = c->p2p ? c->xstream : after;
@@ -126,6 +127,7 @@ std::shared_ptr<void> exchangeMetadata(vb2_comm* c, const uint8_t* myBlockHost, 
   }
   VB2_CU(cudaMemcpyAsync(blockDev->data(), staging.get(), blockBytes, cudaMemcpyHostToDevice, xs));
   VB2_CU(cudaMemcpyAsync(blockDev->data(), countsDev, static_cast<size_t>(w) * 8, cudaMemcpyDeviceToDevice, xs));
+  for (auto& pt : patches) VB2_CU(cudaMemcpyAsync(blockDev->as<uint8_t>() + pt.offset, pt.src, pt.bytes, cudaMemcpyDeviceToDevice, xs));
   if (c->p2p) {
     VELOX_CHECK(blockBytes <= kMetaBytes, "exchange metadata block above the peer-memory limit");
     const uint64_t epoch = ++c->metaEpoch;

@@ -16,7 +16,14 @@ size_t exchangeMaxMetadataBytes(vb2_comm* c);
 // replaced by countsDev, the device-side per-destination row counts) reaches every rank. Returns the
 // world blocks in rank order in pinned host memory, after the exchange's ONE host synchronisation.
 // Peer memory: put + flag + wait kernels; otherwise ncclAllGather. `after`: the stream that produced countsDev.
-std::shared_ptr<void> exchangeMetadata(vb2_comm* c, const uint8_t* myBlockHost, size_t blockBytes, const int64_t* countsDev, cudaStream_t after);
+// patches: device-resident pieces copied into the block at the given offsets before it is sent.
+struct ExchangePatch {
+  size_t offset;
+  const void* src;
+  size_t bytes;
+};
+std::shared_ptr<void> exchangeMetadata(vb2_comm* c, const uint8_t* myBlockHost, size_t blockBytes, const int64_t* countsDev,
+                                       const std::vector<ExchangePatch>& patches, cudaStream_t after);
 
 // Phase 2 — payload: rows order[j] (NULL = identity) of the source columns, grouped by destination
 // (matrix = world x world row counts from phase 1, identical on every rank), arrive in `outs` (one

@@ -20,7 +20,8 @@ namespace velox_b200 {
 
 namespace {
 
-constexpr size_t kAlphabetBlockBytes = 16 * 1024;  // per VARCHAR column and rank inside the metadata block
+constexpr size_t kAlphabetBlockBytes = 12 * 1024;  // per VARCHAR column and rank inside the metadata block
+constexpr size_t kEagerBytes = 16 * 1024;          // payload small enough to ride inside the metadata block
 
 std::shared_ptr<void> makeEvent() {
   cudaEvent_t e = nullptr;
@@ -170,12 +171,39 @@ void B200PartitionedOutput::noMoreInput() {
   // ---- metadata round: [counts[world] | has-valid flags | alphabets] from every rank ---------------
   size_t nVarchar = 0;
   for (auto& w : wire) nVarchar += w.vb2Type == VB2_VARCHAR;
-  const size_t blockBytes = (static_cast<size_t>(world) * 8 + ncols * 8 + nVarchar * kAlphabetBlockBytes + 255) / 256 * 256;
+  // Gathers and broadcasts of a handful of rows (partial aggregates in front of a final aggregation)
+  // ride inside the metadata block itself ("eager" payload): one round instead of two.
+  const bool eagerKind = (broadcast || parts == 1) && world > 1;
+  const size_t headBytes = (static_cast<size_t>(world) * 8 + ncols * 8 + 16 + nVarchar * kAlphabetBlockBytes + 63) / 64 * 64;
+  const size_t blockBytes = (headBytes + (eagerKind ? kEagerBytes : 0) + 255) / 256 * 256;
   std::vector<uint8_t> myBlock(blockBytes, 0);
+  // eager payload layout: per wire column values (n * width, padded to 8) then validity bytes if this rank sends them
+  auto pad8 = [](size_t b) { return (b + 7) / 8 * 8; };
+  size_t eagerNeed = 0;
+  for (auto& w : wire) eagerNeed += pad8(static_cast<size_t>(n) * w.width) + (w.validBytes ? pad8(static_cast<size_t>(n)) : 0);
+  bool eagerMine = eagerKind && eagerNeed <= kEagerBytes;
+  const std::shared_ptr<const HostMirror> inMirror = batches_.size() == 1 ? batches_[0]->mirror() : nullptr;
+  std::vector<std::pair<size_t, std::pair<const void*, size_t>>> eagerDeviceCopies;  // (block offset, (device source, bytes))
+  if (eagerMine) {
+    size_t at = headBytes;
+    auto place = [&](const void* dev, size_t bytes) {
+      const uint8_t* host = inMirror ? inMirror->hostOf(dev) : nullptr;
+      if (host) std::memcpy(myBlock.data() + at, host, bytes);       // the producer's result is already on the host
+      else if (bytes) eagerDeviceCopies.push_back({at, {dev, bytes}});  // patched into the device block below
+      at += pad8(bytes);
+    };
+    for (auto& w : wire) {
+      place(w.values, static_cast<size_t>(n) * w.width);
+      if (w.validBytes) place(w.validBytes, static_cast<size_t>(n));
+    }
+  }
   {
+    int64_t* eagerFlag = reinterpret_cast<int64_t*>(myBlock.data() + static_cast<size_t>(world) * 8 + ncols * 8);
+    eagerFlag[0] = eagerMine ? 1 : 0;
+    eagerFlag[1] = n;
     int64_t* flags = reinterpret_cast<int64_t*>(myBlock.data() + static_cast<size_t>(world) * 8);
     for (size_t c = 0; c < ncols; ++c) flags[c] = wire[c].validBytes ? 1 : 0;
-    uint8_t* ap = myBlock.data() + static_cast<size_t>(world) * 8 + ncols * 8;
+    uint8_t* ap = myBlock.data() + static_cast<size_t>(world) * 8 + ncols * 8 + 16;
     for (auto& w : wire) {
       if (w.vb2Type != VB2_VARCHAR) continue;
       // [int32 entries | int32 lengths[entries] | chars]
@@ -197,7 +225,9 @@ void B200PartitionedOutput::noMoreInput() {
   if (world > 1) {
     VELOX_CHECK(tr != nullptr, "the plan contains an exchange but the task has no exchange transport (vb2_task_set_comm)");
     VELOX_CHECK(blockBytes <= exchangeMaxMetadataBytes(tr->comm()), "exchange metadata block too large (too many VARCHAR columns)");
-    allHost = exchangeMetadata(tr->comm(), myBlock.data(), blockBytes, countsDev->as<int64_t>(), st);
+    std::vector<ExchangePatch> patches;
+    for (auto& e : eagerDeviceCopies) patches.push_back(ExchangePatch{e.first, e.second.first, e.second.second});
+    allHost = exchangeMetadata(tr->comm(), myBlock.data(), blockBytes, countsDev->as<int64_t>(), patches, st);
   } else {
     allHost = acquirePinned(blockBytes);
     std::memcpy(allHost.get(), myBlock.data(), blockBytes);
@@ -247,7 +277,7 @@ void B200PartitionedOutput::noMoreInput() {
       std::map<std::string, int32_t> ids;
       m.remap.resize(world);
       for (int r = 0; r < world; ++r) {
-        const uint8_t* ap = blockOf(r) + static_cast<size_t>(world) * 8 + ncols * 8 + v * kAlphabetBlockBytes;
+        const uint8_t* ap = blockOf(r) + static_cast<size_t>(world) * 8 + ncols * 8 + 16 + v * kAlphabetBlockBytes;
         const int32_t* hp = reinterpret_cast<const int32_t*>(ap);
         const int32_t entries = hp[0];
         const char* cp = reinterpret_cast<const char*>(hp + 1 + entries);
@@ -271,12 +301,61 @@ void B200PartitionedOutput::noMoreInput() {
   // ---- payload ---------------------------------------------------------------------------------------
   std::vector<DeviceBufferPtr> recvBuf;
   std::vector<void*> recvPtr;
-  for (size_t i = 0; i < sendPtr.size(); ++i) {
-    recvBuf.push_back(allocDevice(static_cast<size_t>(total ? total : 1) * elemBytes[i], st));
-    recvPtr.push_back(recvBuf.back()->data());
-  }
+  bool allEager = eagerKind;
+  for (int r = 0; r < world && allEager; ++r) allEager = reinterpret_cast<const int64_t*>(blockOf(r) + static_cast<size_t>(world) * 8 + ncols * 8)[0] != 0;
+  std::shared_ptr<HostMirror> pageMirror;
   std::shared_ptr<void> ready;
-  if (world > 1) {
+  if (allEager) {
+    // every source's rows arrived with the metadata: assemble the page in pinned host memory and
+    // bring it to the device in ONE copy (it doubles as the page's host mirror); no second round.
+    size_t arenaBytes = 0;
+    for (size_t i = 0; i < sendPtr.size(); ++i) arenaBytes += (static_cast<size_t>(total ? total : 1) * elemBytes[i] + 255) / 256 * 256;
+    auto arenaHost = acquirePinned(arenaBytes);
+    auto arenaDev = allocDevice(arenaBytes, st);
+    uint8_t* hb = static_cast<uint8_t*>(arenaHost.get());
+    size_t colOff = 0;
+    std::vector<size_t> srcAt(world, headBytes);
+    size_t i = 0;
+    for (size_t c = 0; c < ncols; ++c) {
+      const int width = wire[c].width;
+      // values of column c from every source that sends to this rank, then the validity bytes
+      for (int pass = 0; pass < (anyValid[c] ? 2 : 1); ++pass) {
+        const int eb = pass == 0 ? width : 1;
+        size_t rowAt = 0;
+        for (int r = 0; r < world; ++r) {
+          const int64_t* hdr = reinterpret_cast<const int64_t*>(blockOf(r) + static_cast<size_t>(world) * 8);
+          const int64_t rn = hdr[ncols + 1];           // rows the source holds (its whole payload)
+          const bool srcHasValid = hdr[c] != 0;
+          const int64_t mine = recvCounts[r];           // rows of it addressed to this rank (all or none)
+          if (pass == 1 && !srcHasValid) {
+            if (mine) std::memset(hb + colOff + rowAt, 1, static_cast<size_t>(mine));
+          } else {
+            if (mine) std::memcpy(hb + colOff + rowAt * eb, blockOf(r) + srcAt[r], static_cast<size_t>(mine) * eb);
+            srcAt[r] += pad8(static_cast<size_t>(rn) * eb);
+          }
+          rowAt += static_cast<size_t>(mine);
+        }
+        recvPtr.push_back(arenaDev->as<uint8_t>() + colOff);
+        recvBuf.push_back(arenaDev);
+        colOff += (static_cast<size_t>(total ? total : 1) * eb + 255) / 256 * 256;
+        ++i;
+      }
+    }
+    VB2_CU(cudaMemcpyAsync(arenaDev->data(), arenaHost.get(), arenaBytes, cudaMemcpyHostToDevice, st));
+    pageMirror = std::make_shared<HostMirror>();
+    pageMirror->host = arenaHost;
+    pageMirror->devBase = arenaDev->as<uint8_t>();
+    pageMirror->bytes = arenaBytes;
+    addRuntimeStat("b200.exchangeEager", exec::RuntimeCounter{1});
+  } else {
+    for (size_t i = 0; i < sendPtr.size(); ++i) {
+      recvBuf.push_back(allocDevice(static_cast<size_t>(total ? total : 1) * elemBytes[i], st));
+      recvPtr.push_back(recvBuf.back()->data());
+    }
+  }
+  if (allEager) {
+    // nothing more to move
+  } else if (world > 1) {
     bool peerMemory = false;
     ready = exchangePayload(tr->comm(), order ? order->as<int32_t>() : nullptr, countsDev->as<int64_t>(), matrix.data(), n, sendPtr, elemBytes, recvPtr,
                             broadcast, st, &peerMemory);
@@ -357,6 +436,7 @@ void B200PartitionedOutput::noMoreInput() {
       cols.push_back(std::move(col));
     }
     auto page = std::make_shared<B200Vector>(pool(), type, static_cast<vector_size_t>(total), std::move(cols), st);
+    if (pageMirror) page->setMirror(pageMirror);
     auto ev = makeEvent();
     VB2_CU(cudaEventRecord(static_cast<cudaEvent_t>(ev.get()), st));
     page->setReadyEvent(ev);

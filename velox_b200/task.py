@@ -30,6 +30,9 @@ def _bind():
     L.vb2_result_str_bytes.restype = C.c_int64
     L.vb2_result_str_bytes.argtypes = [C.c_void_p, C.c_int32]
     L.vb2_result_copy_str.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.vb2_result_layout.restype = C.c_int64
+    L.vb2_result_layout.argtypes = [C.c_void_p, C.c_void_p]
+    L.vb2_result_copy_all.argtypes = [C.c_void_p, C.c_void_p]
     L.vb2_task_stats.restype = C.c_char_p
     L.vb2_task_stats.argtypes = [C.c_void_p]
     L.vb2_task_free.argtypes = [C.c_void_p]
@@ -127,6 +130,38 @@ class Task:
 
 
 def _result(L, h, names=None) -> RowVector:
+    """Result columns through the bulk calls (vb2_result_layout + vb2_result_copy_all): one blob, numpy views."""
+    rows = L.vb2_result_rows(h)
+    ncols = L.vb2_result_cols(h)
+    layout = np.zeros(max(1, ncols) * 4, dtype=np.int64)
+    total = L.vb2_result_layout(h, layout.ctypes.data)
+    blob = np.zeros(max(8, total), dtype=np.uint8)
+    L.vb2_result_copy_all(h, blob.ctypes.data)
+    pad = lambda b: (b + 7) // 8 * 8
+    cols, at = [], 0
+    for c in range(ncols):
+        t, vbytes, obytes, cbytes = (int(x) for x in layout[c * 4:c * 4 + 4])
+        vals = blob[at:at + vbytes]
+        at += pad(vbytes)
+        if t == VARCHAR:
+            off = blob[at:at + obytes].view(np.int32)
+            at += pad(obytes)
+            chars = blob[at:at + cbytes] if cbytes else np.zeros(1, dtype=np.uint8)
+            at += pad(cbytes)
+            col = Column(VARCHAR, FLAT, rows, off, None, chars=chars)
+        elif t == BOOLEAN:
+            col = Column(BOOLEAN, FLAT, rows, pack_bits(vals[:rows].astype(bool)))
+            col._bool_count = rows
+        else:
+            col = Column(t, FLAT, rows, vals.view(NP_DTYPES[t])[:rows])
+        nb = blob[at:at + rows].astype(bool)
+        at += pad(rows)
+        col.nulls = nb if nb.any() else None
+        cols.append(col)
+    return RowVector(list(names) if names else [f"c{i}" for i in range(ncols)], cols)
+
+
+def _result_per_column(L, h, names=None) -> RowVector:
     rows = L.vb2_result_rows(h)
     ncols = L.vb2_result_cols(h)
     cols = []
