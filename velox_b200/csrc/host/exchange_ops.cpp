@@ -382,14 +382,17 @@ void B200PartitionedOutput::noMoreInput() {
       col->type = w.type;
       col->desc.type = w.vb2Type;
       col->desc.size = total;
-      DeviceBufferPtr values = recvBuf[i++];
-      DeviceBufferPtr validBytes = anyValid[c] ? recvBuf[i++] : nullptr;
-      col->owners.push_back(values);
-      if (validBytes) {
+      // recvPtr[i] lies inside recvBuf[i] (its own buffer, or the shared arena of an eager exchange)
+      const void* valuesPtr = recvPtr[i];
+      col->owners.push_back(recvBuf[i]);
+      ++i;
+      if (anyValid[c]) {
         auto bitsBuf = allocDevice(bits::nbytes(total), st);
-        kernelCheck(vb2k_pack_bools(validBytes->as<uint8_t>(), total, bitsBuf->as<uint64_t>(), st));
+        kernelCheck(vb2k_pack_bools(static_cast<const uint8_t*>(recvPtr[i]), total, bitsBuf->as<uint64_t>(), st));
         col->desc.nulls = bitsBuf->as<uint64_t>();
+        col->owners.push_back(recvBuf[i]);
         col->owners.push_back(bitsBuf);
+        ++i;
       }
       if (w.vb2Type == VB2_VARCHAR) {
         Merged& m = merged[c];
@@ -401,11 +404,11 @@ void B200PartitionedOutput::noMoreInput() {
             if (recvCounts[r] == 0) continue;
             auto lut = allocDevice(m.remap[r].size() * 4 + 4, st);
             VB2_CU(cudaMemcpyAsync(lut->data(), m.remap[r].data(), m.remap[r].size() * 4, cudaMemcpyHostToDevice, st));
-            kernelCheck(vb2k_gather(lut->data(), values->as<int32_t>() + off, recvCounts[r], 4, fixed->as<int32_t>() + off, st));
+            kernelCheck(vb2k_gather(lut->data(), static_cast<const int32_t*>(valuesPtr) + off, recvCounts[r], 4, fixed->as<int32_t>() + off, st));
             col->owners.push_back(lut);
             off += recvCounts[r];
           }
-          values = fixed;
+          valuesPtr = fixed->data();
           col->owners.push_back(fixed);
         }
         std::vector<int32_t> off(m.alphabet->values.size() + 1, 0);
@@ -416,7 +419,7 @@ void B200PartitionedOutput::noMoreInput() {
         VB2_CU(cudaMemcpyAsync(offBuf->data(), off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
         if (!chars.empty()) VB2_CU(cudaMemcpyAsync(charBuf->data(), chars.data(), chars.size(), cudaMemcpyHostToDevice, st));
         col->desc.encoding = VB2_DICTIONARY;
-        col->desc.indices = values->as<int32_t>();
+        col->desc.indices = static_cast<const int32_t*>(valuesPtr);
         col->desc.values = offBuf->data();
         col->desc.aux = charBuf->data();
         col->desc.dict_size = static_cast<int64_t>(m.alphabet->values.size());
@@ -425,13 +428,13 @@ void B200PartitionedOutput::noMoreInput() {
         col->alphabet = m.alphabet;
       } else if (w.vb2Type == VB2_BOOLEAN) {
         auto packed = allocDevice(bits::nbytes(total), st);
-        kernelCheck(vb2k_pack_bools(values->as<uint8_t>(), total, packed->as<uint64_t>(), st));
+        kernelCheck(vb2k_pack_bools(static_cast<const uint8_t*>(valuesPtr), total, packed->as<uint64_t>(), st));
         col->desc.encoding = VB2_FLAT;
         col->desc.values = packed->data();
         col->owners.push_back(packed);
       } else {
         col->desc.encoding = VB2_FLAT;
-        col->desc.values = values->data();
+        col->desc.values = valuesPtr;
       }
       cols.push_back(std::move(col));
     }
