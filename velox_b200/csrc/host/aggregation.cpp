@@ -752,14 +752,19 @@ struct B200HashAggregation::Impl {
       // project / aggregate over the surviving rows. Everything stays on the stream; the row count
       // is read by the gather kernel on the device.
       auto bitsBuf = allocDevice(bits::nbytes(n), st());
-      rc = vb2k_fused_filter_bits(fusedId, &a, 1, bitsBuf->as<uint64_t>(), nullptr, st());
+      auto kept = allocDeviceZeroed(16, st());
+      rc = vb2k_fused_filter_bits(fusedId, &a, 1, bitsBuf->as<uint64_t>(), kept->as<int64_t>(), st());
       if (rc == VB2_OK) {
-        auto sel = allocDevice(static_cast<size_t>(n) * 4, st());  // capacity for every row; only the kept ones are written
+        // the filter kernel counted the survivors: one 16-byte read sizes the row-number buffer exactly
+        int64_t h[2] = {0, 0};
+        VB2_CU(cudaMemcpyAsync(h, kept->data(), 16, cudaMemcpyDeviceToHost, st()));
+        VB2_CU(cudaStreamSynchronize(st()));
+        auto sel = allocDevice(static_cast<size_t>(h[0] ? h[0] : 1) * 4, st());
         auto cnt = allocDevice(8, st());
         const size_t wsb = vb2k_bits_to_indices_workspace(n);
         auto ws = allocDevice(wsb, st());
         kernelCheck(vb2k_bits_to_indices(bitsBuf->as<uint64_t>(), n, sel->as<int32_t>(), cnt->as<int64_t>(), ws->data(), wsb, st()));
-        const int64_t hint = std::max<int64_t>(1024, static_cast<int64_t>(selectivity * 1.25 * static_cast<double>(n)));
+        const int64_t hint = std::max<int64_t>(1024, h[0]);
         rc = vb2k_fused_gather_agg(fusedId, &a, sel->as<int32_t>(), cnt->as<int64_t>(), hint, fusedSums->as<double>(), fusedCounts->as<int64_t>(), fusedWs->data(),
                                    fusedWsBytes, st());
         if (rc == VB2_OK) ++selectiveBatches;

@@ -28,6 +28,7 @@ struct vb2_comm {
   cudaStream_t xstream = nullptr;     // every protocol step of this process, in order
   uint64_t metaEpoch = 0, dataEpoch = 0;
   int32_t* errFlag = nullptr;         // device: set by a wait that timed out
+  cudaEvent_t orderEvent = nullptr;   // reused: orders the exchange stream behind the producing stream
   int64_t p2pExchanges = 0, ncclExchanges = 0;
 };
 
@@ -118,15 +119,14 @@ std::shared_ptr<void> exchangeMetadata(vb2_comm* c, const uint8_t* myBlockHost, 
   std::memcpy(staging.get(), myBlockHost, blockBytes);
   auto blockDev = allocDevice(blockBytes, xs);
   auto allHost = acquirePinned(blockBytes * w + 16);
-  if (c->p2p) {
-    cudaEvent_t ev;
-    VB2_CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    VB2_CU(cudaEventRecord(ev, after));
-    VB2_CU(cudaStreamWaitEvent(xs, ev, 0));
-    cudaEventDestroy(ev);
+  if (c->p2p && (countsDev || !patches.empty())) {
+    // device-side inputs of the block were produced on the caller's stream
+    if (!c->orderEvent) VB2_CU(cudaEventCreateWithFlags(&c->orderEvent, cudaEventDisableTiming));
+    VB2_CU(cudaEventRecord(c->orderEvent, after));
+    VB2_CU(cudaStreamWaitEvent(xs, c->orderEvent, 0));
   }
   VB2_CU(cudaMemcpyAsync(blockDev->data(), staging.get(), blockBytes, cudaMemcpyHostToDevice, xs));
-  VB2_CU(cudaMemcpyAsync(blockDev->data(), countsDev, static_cast<size_t>(w) * 8, cudaMemcpyDeviceToDevice, xs));
+  if (countsDev) VB2_CU(cudaMemcpyAsync(blockDev->data(), countsDev, static_cast<size_t>(w) * 8, cudaMemcpyDeviceToDevice, xs));
   for (auto& pt : patches) VB2_CU(cudaMemcpyAsync(blockDev->as<uint8_t>() + pt.offset, pt.src, pt.bytes, cudaMemcpyDeviceToDevice, xs));
   if (c->p2p) {
     VELOX_CHECK(blockBytes <= kMetaBytes, "exchange metadata block above the peer-memory limit");
@@ -256,6 +256,7 @@ void vb2_comm_free(vb2_comm* comm) {
     if (p != comm->rank && comm->peer[p]) cudaIpcCloseMemHandle(comm->peer[p]);
   if (comm->heap) cudaFree(comm->heap);
   if (comm->errFlag) cudaFree(comm->errFlag);
+  if (comm->orderEvent) cudaEventDestroy(comm->orderEvent);
   if (comm->xstream) cudaStreamDestroy(comm->xstream);
   if (comm->comm) ncclCommDestroy(comm->comm);
   delete comm;

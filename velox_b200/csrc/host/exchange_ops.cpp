@@ -11,6 +11,7 @@
 // row counts + VARCHAR alphabets) that is the exchange's only host synchronisation.
 #include <cstring>
 #include <map>
+#include <mutex>
 
 #include "exchange_impl.h"
 #include "join.h"
@@ -40,6 +41,38 @@ struct WireColumn {
   std::shared_ptr<const HostAlphabet> alphabet;  // VARCHAR
   std::vector<DeviceBufferPtr> keep;
 };
+
+// Device copy (int32 offsets + chars) of a small alphabet, shared by every page that carries the same
+// strings: exchanged dictionaries repeat from query to query, the upload happens once per content.
+void deviceAlphabet(const HostAlphabet& a, cudaStream_t st, DeviceBufferPtr& offBuf, DeviceBufferPtr& charBuf) {
+  static std::mutex mu;
+  static std::map<std::string, std::pair<DeviceBufferPtr, DeviceBufferPtr>> cache;
+  std::string key;
+  std::vector<int32_t> off(a.values.size() + 1, 0);
+  std::string chars;
+  for (size_t k = 0; k < a.values.size(); ++k) {
+    chars += a.values[k];
+    off[k + 1] = static_cast<int32_t>(chars.size());
+    key += std::to_string(a.values[k].size()) + ":" + a.values[k];
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  key = std::to_string(dev) + "|" + key;
+  std::lock_guard<std::mutex> l(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    if (cache.size() > 256) cache.clear();
+    // plain cudaMalloc'd, never freed while cached: usable from any stream once the copies below are done
+    auto ob = allocDevice(off.size() * 4, st);
+    auto cb = allocDevice(chars.size() + 1, st);
+    VB2_CU(cudaMemcpyAsync(ob->data(), off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!chars.empty()) VB2_CU(cudaMemcpyAsync(cb->data(), chars.data(), chars.size(), cudaMemcpyHostToDevice, st));
+    VB2_CU(cudaStreamSynchronize(st));
+    it = cache.emplace(key, std::make_pair(ob, cb)).first;
+  }
+  offBuf = it->second.first;
+  charBuf = it->second.second;
+}
 
 NcclTransport* transportOf(exec::DriverCtx* ctx) {
   auto* t = ctx->task ? dynamic_cast<NcclTransport*>(ctx->task->exchangeTransport().get()) : nullptr;
@@ -128,7 +161,8 @@ void B200PartitionedOutput::noMoreInput() {
   }
 
   // ---- partition (HashPartitionFunction: hash(keys) % partitions) ---------------------------------
-  DeviceBufferPtr countsDev = allocDeviceZeroed(static_cast<size_t>(world) * 8, st);
+  DeviceBufferPtr countsDev;            // per-destination row counts, on the device when a partition pass produced them
+  std::vector<int64_t> hostCounts;      // ... or on the host when they follow from the row count alone
   DeviceBufferPtr order;
   if (!broadcast && parts > 1 && n > 0) {
     auto hashes = allocDevice(static_cast<size_t>(n) * 8, st);
@@ -147,12 +181,15 @@ void B200PartitionedOutput::noMoreInput() {
     auto ids = allocDevice(static_cast<size_t>(n) * 4, st);
     kernelCheck(vb2k_partition_ids(hashes->as<uint64_t>(), n, parts, ids->as<uint32_t>(), st));
     order = allocDevice(static_cast<size_t>(n) * 4, st);
+    countsDev = allocDeviceZeroed(static_cast<size_t>(world) * 8, st);
     kernelCheck(vb2k_partition_scatter_order(ids->as<uint32_t>(), n, parts, countsDev->as<int64_t>(), order->as<int32_t>(), st));
   } else if (n > 0) {
-    // one partition (gather) or broadcast: every row goes to rank 0 / to every rank; no reordering
-    std::vector<int64_t> c(world, broadcast ? n : 0);
-    if (!broadcast) c[0] = n;
-    VB2_CU(cudaMemcpyAsync(countsDev->data(), c.data(), static_cast<size_t>(world) * 8, cudaMemcpyHostToDevice, st));
+    // one partition (gather) or broadcast: every row goes to rank 0 / to every rank; no reordering.
+    // The counts are known on the host: they go straight into the metadata block.
+    hostCounts.assign(world, broadcast ? n : 0);
+    if (!broadcast) hostCounts[0] = n;
+  } else {
+    hostCounts.assign(world, 0);
   }
   // wire columns in transfer order: values, then validity bytes where present
   std::vector<const void*> sendPtr;
@@ -197,6 +234,7 @@ void B200PartitionedOutput::noMoreInput() {
       if (w.validBytes) place(w.validBytes, static_cast<size_t>(n));
     }
   }
+  if (!hostCounts.empty()) std::memcpy(myBlock.data(), hostCounts.data(), static_cast<size_t>(world) * 8);
   {
     int64_t* eagerFlag = reinterpret_cast<int64_t*>(myBlock.data() + static_cast<size_t>(world) * 8 + ncols * 8);
     eagerFlag[0] = eagerMine ? 1 : 0;
@@ -227,12 +265,14 @@ void B200PartitionedOutput::noMoreInput() {
     VELOX_CHECK(blockBytes <= exchangeMaxMetadataBytes(tr->comm()), "exchange metadata block too large (too many VARCHAR columns)");
     std::vector<ExchangePatch> patches;
     for (auto& e : eagerDeviceCopies) patches.push_back(ExchangePatch{e.first, e.second.first, e.second.second});
-    allHost = exchangeMetadata(tr->comm(), myBlock.data(), blockBytes, countsDev->as<int64_t>(), patches, st);
+    allHost = exchangeMetadata(tr->comm(), myBlock.data(), blockBytes, countsDev ? countsDev->as<int64_t>() : nullptr, patches, st);
   } else {
     allHost = acquirePinned(blockBytes);
     std::memcpy(allHost.get(), myBlock.data(), blockBytes);
-    VB2_CU(cudaMemcpyAsync(allHost.get(), countsDev->data(), 8, cudaMemcpyDeviceToHost, st));
-    VB2_CU(cudaStreamSynchronize(st));
+    if (countsDev) {
+      VB2_CU(cudaMemcpyAsync(allHost.get(), countsDev->data(), 8, cudaMemcpyDeviceToHost, st));
+      VB2_CU(cudaStreamSynchronize(st));
+    }
   }
   const uint8_t* all = static_cast<const uint8_t*>(allHost.get());
   auto blockOf = [&](int r) { return all + static_cast<size_t>(r) * blockBytes; };
@@ -357,6 +397,10 @@ void B200PartitionedOutput::noMoreInput() {
     // nothing more to move
   } else if (world > 1) {
     bool peerMemory = false;
+    if (!countsDev) {  // a gather / broadcast too large for the eager round: the transfer kernel reads the counts on the device
+      countsDev = allocDevice(static_cast<size_t>(world) * 8, st);
+      VB2_CU(cudaMemcpyAsync(countsDev->data(), hostCounts.data(), static_cast<size_t>(world) * 8, cudaMemcpyHostToDevice, st));
+    }
     ready = exchangePayload(tr->comm(), order ? order->as<int32_t>() : nullptr, countsDev->as<int64_t>(), matrix.data(), n, sendPtr, elemBytes, recvPtr,
                             broadcast, st, &peerMemory);
     addRuntimeStat("b200.exchangePeerMemory", exec::RuntimeCounter{peerMemory ? 1 : 0});
@@ -411,13 +455,8 @@ void B200PartitionedOutput::noMoreInput() {
           valuesPtr = fixed->data();
           col->owners.push_back(fixed);
         }
-        std::vector<int32_t> off(m.alphabet->values.size() + 1, 0);
-        std::string chars;
-        for (size_t k = 0; k < m.alphabet->values.size(); ++k) { chars += m.alphabet->values[k]; off[k + 1] = static_cast<int32_t>(chars.size()); }
-        auto offBuf = allocDevice(off.size() * 4, st);
-        auto charBuf = allocDevice(chars.size() + 1, st);
-        VB2_CU(cudaMemcpyAsync(offBuf->data(), off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
-        if (!chars.empty()) VB2_CU(cudaMemcpyAsync(charBuf->data(), chars.data(), chars.size(), cudaMemcpyHostToDevice, st));
+        DeviceBufferPtr offBuf, charBuf;
+        deviceAlphabet(*m.alphabet, st, offBuf, charBuf);
         col->desc.encoding = VB2_DICTIONARY;
         col->desc.indices = static_cast<const int32_t*>(valuesPtr);
         col->desc.values = offBuf->data();

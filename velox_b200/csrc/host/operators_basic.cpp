@@ -136,6 +136,7 @@ B200VectorPtr B200FilterProject::apply(const B200VectorPtr& in) {
   if (hasFilter_) {
     auto bitsBuf = allocDevice(bits::nbytes(n), st);
     bool done = false;
+    int64_t selCapacity = n;
     if (fastFilterId_ >= 0 && n >= (1 << 16)) {
       // flat NULL-free filter columns: the TMA-staged bitmap kernel (HBM-bound) instead of one row per thread
       vb2_fused_args fa{};
@@ -150,14 +151,24 @@ B200VectorPtr B200FilterProject::apply(const B200VectorPtr& in) {
         for (size_t i = 0; i < fastFilter_.pl.size(); ++i) fa.pl[i] = fastFilter_.pl[i];
         for (size_t i = 0; i < fastFilter_.pi.size(); ++i) fa.pi[i] = fastFilter_.pi[i];
         fa.rows = n;
-        const int rc = vb2k_fused_filter_bits(fastFilterId_, &fa, 1, bitsBuf->as<uint64_t>(), nullptr, st);
-        if (rc == VB2_OK) { done = true; addRuntimeStat("b200.fastFilterBatches", exec::RuntimeCounter{1}); }
-        else if (rc != VB2_ERR_UNSUPPORTED) kernelCheck(rc);
+        auto counters = allocDeviceZeroed(16, st);
+        const int rc = vb2k_fused_filter_bits(fastFilterId_, &fa, 1, bitsBuf->as<uint64_t>(), counters->as<int64_t>(), st);
+        if (rc == VB2_OK) {
+          done = true;
+          addRuntimeStat("b200.fastFilterBatches", exec::RuntimeCounter{1});
+          // the kernel counted the surviving rows: size the row-number buffer exactly (a filter that keeps
+          // 1 % of 300 M rows needs 12 MB, not 1.2 GB)
+          int64_t kept[2] = {0, 0};
+          VB2_CU(cudaMemcpyAsync(kept, counters->data(), 16, cudaMemcpyDeviceToHost, st));
+          VB2_CU(cudaStreamSynchronize(st));
+          selCapacity = kept[0];
+        } else if (rc != VB2_ERR_UNSUPPORTED) kernelCheck(rc);
       }
     }
     if (!done)
       kernelCheck(vb2k_eval_filter(&prog, cols.data(), static_cast<int32_t>(cols.size()), n, bitsBuf->as<uint64_t>(), errorFlag_->as<int32_t>(), st));
-    sel = allocDevice(static_cast<size_t>(n) * 4, st);
+    if (selCapacity == 0) return nullptr;
+    sel = allocDevice(static_cast<size_t>(selCapacity) * 4, st);
     auto count = allocDevice(8, st);
     const size_t wsBytes = vb2k_bits_to_indices_workspace(n);
     auto ws = allocDevice(wsBytes, st);
