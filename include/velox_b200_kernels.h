@@ -275,8 +275,20 @@ typedef struct vb2_group_table {
   uint64_t* rows;
   int64_t capacity;
   int32_t row_words;
-  int32_t hash_mode;
+  int32_t hash_mode;   /* 0 array, 1 normalized-key hash, 2 keyed hash (VB2_GROUP_KEYED, below) */
 } vb2_group_table;
+/* Keyed hash mode — the reference's kHash mode (velox/exec/HashTable.cpp:1751-1838: keys that do not
+ * fit one normalized 64-bit word, DOUBLE keys): the group row stores its key columns verbatim.
+ *   word 0            state: VB2_EMPTY_KEY = free, else (hash63 << 1) | ready; a row is claimed by CAS
+ *                     with ready = 0, its key words are written, then ready is published
+ *   words 1 .. K      one 64-bit word per key column (integers sign-extended, DOUBLE as canonical
+ *                     bits: one NaN, +0 for -0 — the equality of velox/type/FloatingPointUtil.h)
+ *   word K + 1        NULL mask (bit k = key k is NULL; NULL keys form a group, GroupingSet.cpp:448-455)
+ *   words K + 2 ..    accumulators / non-null counters
+ * Probing compares the 63-bit hash first and the key words on a hash match (ProbeState::fullProbe,
+ * exec/HashTable.cpp:138, compares a 7-bit tag, then the row's keys). */
+#define VB2_GROUP_KEYED 2
+#define VB2_KEYED_MAX_KEYS 4
 typedef struct vb2_group_row_init { uint64_t words[VB2_MAX_ROW_WORDS]; } vb2_group_row_init;
 
 typedef struct vb2_agg_update {
@@ -301,6 +313,20 @@ int vb2k_group_table_init(const vb2_group_table* t, const uint64_t* row_init, vo
  * incremented per inserted key; SUM(BIGINT) overflow sets *error_flag = 1, a full table 100. */
 int vb2k_group_update(const vb2_group_table* t, const uint64_t* row_keys, const uint64_t* row_valid, int64_t n,
                       const vb2_agg_update* aggs, int32_t naggs, int64_t* num_groups, int32_t* error_flag, void* stream);
+/* vb2k_group_update for a keyed table: the key columns of the batch (BOOLEAN / INTEGER / BIGINT /
+ * DOUBLE, any encoding, NULLs allowed) are read in place; nkeys must equal the table's key count
+ * (rows hold nkeys + 2 leading words). A full table sets *error_flag = 100. */
+int vb2k_group_update_keyed(const vb2_group_table* t, const vb2_column* keys, int32_t nkeys, int64_t n, const vb2_agg_update* aggs, int32_t naggs,
+                            int64_t* num_groups, int32_t* error_flag, void* stream);
+/* Moves the listed groups of a keyed table into another (bigger) keyed table. */
+int vb2k_group_move_keyed(const vb2_group_table* from, const int32_t* slots, int64_t n, int32_t nkeys, const vb2_group_table* to, int64_t* num_groups,
+                          int32_t* error_flag, void* stream);
+/* Moves the listed groups of an array / normalized-key table into a keyed table: key k of a group is
+ * decoded from the normalized key (value = id - 1 + mins[k], id = (key / mults[k]) % ranges[k], id 0 =
+ * NULL when null_reserved[k]); accumulator word w of the source lands at w + word_shift. */
+int vb2k_group_move_to_keyed(const vb2_group_table* from, const int32_t* slots, int64_t n, int32_t nkeys, const int64_t* mins, const uint64_t* mults,
+                             const uint64_t* ranges, const int32_t* null_reserved, int32_t word_shift, const vb2_group_table* to,
+                             int64_t* num_groups, int32_t* error_flag, void* stream);
 /* Compacts occupied rows: slot_list int32[<=capacity] ascending, count device int64. */
 int vb2k_group_occupied(const vb2_group_table* t, int32_t* slot_list, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
 size_t vb2k_group_occupied_workspace(int64_t capacity);
@@ -340,7 +366,10 @@ int vb2k_group_avg(const vb2_group_table* t, const int32_t* slots, int64_t n, in
  * word > 0. valid bitmaps (optional) are written as whole 64-bit words. */
 #define VB2_EXTRACT_SMALL_CAPACITY 16384
 #define VB2_EXTRACT_MAX_COLS 40
-enum vb2_extract_kind { VB2_EXTRACT_KEY = 1, VB2_EXTRACT_WORD = 2, VB2_EXTRACT_WORD_I32 = 3, VB2_EXTRACT_AVG = 4 };
+/* KEYWORD (keyed tables): key column `word` - 1 of the row, typed by `type` (BOOLEAN / INTEGER / BIGINT /
+ * DOUBLE), NULL when bit `null_reserved` (reused as the key's bit index) of the row's NULL-mask word
+ * `count_word` is set. */
+enum vb2_extract_kind { VB2_EXTRACT_KEY = 1, VB2_EXTRACT_WORD = 2, VB2_EXTRACT_WORD_I32 = 3, VB2_EXTRACT_AVG = 4, VB2_EXTRACT_KEYWORD = 5 };
 typedef struct vb2_extract_col {
   int32_t kind;
   int32_t type;        /* KEY: VB2_INTEGER / VB2_BIGINT / VB2_BOOLEAN of the written values */

@@ -527,3 +527,74 @@ def test_filter_project_fast_filter_kernel():
             .project(["l_extendedprice * (1.0 - l_discount) AS rev", "l_partkey"]).planNode())
     st_f, st_g = check_plan(plan, [rv], configs=(FUSED, GENERIC), oracle_batch_rows=100_000)
     assert stat(st_f, "b200.fastFilterBatches") == 1 and stat(st_g, "b200.fastFilterBatches") == 0
+
+
+def test_group_by_double_keys():
+    """DOUBLE grouping keys (keyed hash table, the reference's kHash mode): all NaNs are one group, -0.0
+    and +0.0 are one group, NULL is a group (velox/type/FloatingPointUtil.h equality)."""
+    rng = np.random.default_rng(91)
+    n = 5000
+    d = rng.integers(-20, 20, n).astype(float) / 4.0
+    d[rng.random(n) < 0.05] = NAN
+    d[::97] = -0.0
+    d[1::97] = 0.0
+    dn = rng.random(n) < 0.04
+    rv = row_vector(["d", "k", "v", "x"], [flat_vector(DOUBLE, d, dn), flat_vector(INTEGER, rng.integers(0, 3, n).astype(np.int32)),
+                                         flat_vector(BIGINT, rng.integers(-1000, 1000, n)), flat_vector(DOUBLE, rng.standard_normal(n))])
+    plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(["d"], ["sum(v)", "count(0)", "avg(x)", "min(v)"]).planNode()
+    (st,) = check_plan(plan, [rv], rel_tol=1e-11)
+    assert stat(st, "b200.aggMode") == 3  # keyed
+    check_plan(plan, [rv], batch_rows=700, rel_tol=1e-11)
+    plan = (PlanBuilder().values(rv.names, rv.types).partialAggregation(["k", "d"], ["sum(v)", "max(x)", "count(0)"]).intermediateAggregation()
+            .finalAggregation().planNode())
+    check_plan(plan, [rv], configs=(GENERIC,), batch_rows=900, rel_tol=1e-11)
+
+
+def test_group_by_keys_wider_than_one_normalized_word():
+    """Two BIGINT keys spanning most of the int64 range do not fit one 64-bit normalized key: the groups
+    move to a keyed table (kHash, exec/HashTable.cpp:1751-1838) — also when the wide values only show
+    up in a later batch, after array-mode groups exist."""
+    rng = np.random.default_rng(92)
+    n = 6000
+    a = rng.integers(0, 5, n)
+    b = rng.integers(0, 7, n)
+    a[3000:] = rng.choice(np.array([-(2 ** 62), 2 ** 62, 12345678901234, -7, 0]), n - 3000)   # wide values arrive late
+    b[3000:] = rng.choice(np.array([2 ** 61, -(2 ** 61) - 5, 3, 99]), n - 3000)
+    an = rng.random(n) < 0.03
+    s = dictionary_vector(VARCHAR, rng.integers(0, 4, n).astype(np.int32), ["p", "q", "r", "s"])
+    rv = row_vector(["a", "b", "s", "v"], [flat_vector(BIGINT, a, an), flat_vector(BIGINT, b), s, flat_vector(DOUBLE, rng.standard_normal(n))])
+    plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(["a", "b", "s"], ["sum(v)", "count(0)", "max(v)"]).planNode()
+    (st,) = check_plan(plan, [rv], batch_rows=1000, rel_tol=1e-11)
+    assert stat(st, "b200.aggMode") == 3 and stat(st, "b200.aggRelayouts") >= 2
+    check_plan(plan, [rv], rel_tol=1e-11)
+
+
+def test_hash_build_many_batches_with_nulls_booleans_and_mixed_dictionaries():
+    """HashBuild::addInput appends every batch (exec/HashBuild.cpp:442-598): build sides that arrive in
+    many batches with NULLs, BOOLEAN columns and VARCHAR dictionaries that differ from batch to batch."""
+    from velox_b200.task import Task
+    from oracle import pyoracle
+    from util import assert_equal_results
+    rng = np.random.default_rng(93)
+    probe = row_vector(["pk", "pv"], [flat_vector(BIGINT, rng.integers(0, 60, 4000), rng.random(4000) < 0.05), flat_vector(DOUBLE, rng.standard_normal(4000))])
+    alphabets = [["red", "green", "blue"], ["blue", "black", "red", "white"], ["green"]]
+    builds = []
+    for i, alpha in enumerate(alphabets):
+        m = 70
+        builds.append(row_vector(["bk", "flag", "name", "bv"],
+                                 [flat_vector(BIGINT, rng.integers(0, 60, m), rng.random(m) < 0.1), flat_vector(BOOLEAN, rng.random(m) < 0.5, rng.random(m) < 0.1),
+                                  dictionary_vector(VARCHAR, rng.integers(0, len(alpha), m).astype(np.int32), alpha), flat_vector(INTEGER, rng.integers(0, 9, m).astype(np.int32), rng.random(m) < 0.2)]))
+    for jt, outs in (("inner", ["pk", "pv", "flag", "name", "bv"]), ("left", ["pk", "flag", "name", "bv"])):
+        plan = (PlanBuilder().values(probe.names, probe.types, source=0)
+                .hashJoin(["pk"], ["bk"], PlanBuilder().values(builds[0].names, builds[0].types, source=1), "", outs, joinType=jt).planNode())
+        t = Task(plan)
+        t.add_input(0, probe)
+        for b in builds:
+            t.add_input(1, b)
+        got = t.run()
+        t.close()
+        # the oracle gets the same build side as one table (strings flattened)
+        cat = lambda i, ty: flat_vector(ty, [v for b in builds for v in b.columns[i].to_pylist()])
+        whole = row_vector(builds[0].names, [cat(0, BIGINT), cat(1, BOOLEAN), cat(2, VARCHAR), cat(3, INTEGER)])
+        want = pyoracle.run_plan(plan, [probe, whole])
+        assert_equal_results(got, want)

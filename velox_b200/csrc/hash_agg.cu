@@ -264,6 +264,122 @@ __global__ void group_update_kernel(const __grid_constant__ vb2_group_table tab,
   if ((threadIdx.x & 31) == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
 }
 
+// ---- keyed hash mode (kHash) ----------------------------------------------------------------------
+struct KeyedCols {
+  vb2_column c[VB2_KEYED_MAX_KEYS];
+  int n;
+};
+__device__ __forceinline__ uint64_t canonical_f64_bits(double v) {
+  if (isnan(v)) return 0x7ff8000000000000ull;
+  if (v == 0.0) return 0;  // -0 and +0 are one key
+  return static_cast<uint64_t>(__double_as_longlong(v));
+}
+__device__ __forceinline__ uint64_t key_word_of(const vb2_column& c, int64_t base) {
+  if (c.type == VB2_DOUBLE) return canonical_f64_bits(reinterpret_cast<const double*>(c.values)[base]);
+  return static_cast<uint64_t>(key_value(c, base));
+}
+__device__ __forceinline__ uint64_t keyed_hash(const uint64_t* kw, uint64_t nullmask, int nkeys) {
+  uint64_t h = 0;
+  for (int k = 0; k < nkeys; ++k) {
+    const uint64_t hk = (nullmask >> k) & 1u ? kNullHash : twang_mix64(kw[k]);
+    h = k == 0 ? hk : hash_mix(h, hk);
+  }
+  return h >> 1;  // 63 bits: the state word keeps a ready bit
+}
+// Slot of the key (inserted if absent) in a keyed table, -1 when the table is full.
+__device__ __forceinline__ int64_t find_or_insert_keyed(uint64_t* rows, uint64_t mask, int w, int nkeys, const uint64_t* kw, uint64_t nullmask, int64_t& fresh) {
+  const uint64_t h63 = keyed_hash(kw, nullmask, nkeys);
+  uint64_t slot = twang_mix64(h63) & mask;
+  for (uint64_t probes = 0; probes <= mask; ++probes) {
+    uint64_t* row = rows + slot * w;
+    uint64_t st = *reinterpret_cast<volatile uint64_t*>(row);
+    if (st == VB2_EMPTY_KEY) {
+      st = atomicCAS(reinterpret_cast<unsigned long long*>(row), VB2_EMPTY_KEY, static_cast<unsigned long long>(h63 << 1));
+      if (st == VB2_EMPTY_KEY) {
+        for (int k = 0; k < nkeys; ++k) row[1 + k] = kw[k];
+        row[1 + nkeys] = nullmask;
+        __threadfence();
+        *reinterpret_cast<volatile uint64_t*>(row) = (h63 << 1) | 1u;  // publish
+        ++fresh;
+        return static_cast<int64_t>(slot);
+      }
+    }
+    if ((st >> 1) == h63) {
+      while (!(st & 1u)) st = *reinterpret_cast<volatile uint64_t*>(row);  // claimed, keys not published yet
+      __threadfence();
+      bool same = reinterpret_cast<volatile uint64_t*>(row)[1 + nkeys] == nullmask;
+      for (int k = 0; k < nkeys && same; ++k) same = reinterpret_cast<volatile uint64_t*>(row)[1 + k] == kw[k];
+      if (same) return static_cast<int64_t>(slot);
+    }
+    slot = (slot + 1) & mask;
+  }
+  return -1;
+}
+__global__ void group_update_keyed_kernel(const __grid_constant__ vb2_group_table tab, const __grid_constant__ KeyedCols keys, int64_t n,
+                                          const __grid_constant__ AggArgs args, int64_t* __restrict__ num_groups, int32_t* __restrict__ error_flag) {
+  const uint64_t mask = static_cast<uint64_t>(tab.capacity - 1);
+  int64_t fresh = 0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    uint64_t kw[VB2_KEYED_MAX_KEYS];
+    uint64_t nullmask = 0;
+    for (int k = 0; k < keys.n; ++k) {
+      int64_t base;
+      const bool is_null = decode_row2(keys.c[k], i, base);
+      kw[k] = is_null ? 0 : key_word_of(keys.c[k], base);
+      nullmask |= static_cast<uint64_t>(is_null) << k;
+    }
+    const int64_t slot = find_or_insert_keyed(tab.rows, mask, tab.row_words, keys.n, kw, nullmask, fresh);
+    if (slot < 0) { atomicCAS(error_flag, 0, 100); continue; }
+    uint64_t* row = tab.rows + slot * tab.row_words;
+    for (int k = 0; k < args.n; ++k) apply_update(args.a[k], i, row, error_flag);
+  }
+  fresh = warp_sum(fresh);
+  if ((threadIdx.x & 31) == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
+}
+// Re-inserts groups into a (bigger) keyed table; keys are distinct, so the row belongs to this thread.
+struct DecodeArgs {
+  int n;
+  int64_t mins[VB2_KEYED_MAX_KEYS];
+  uint64_t mults[VB2_KEYED_MAX_KEYS], ranges[VB2_KEYED_MAX_KEYS];
+  int null_reserved[VB2_KEYED_MAX_KEYS];
+  int from_keyed;   // source rows already hold key words
+  int word_shift;   // accumulator word w of the source -> w + word_shift
+};
+__global__ void group_move_keyed_kernel(const __grid_constant__ vb2_group_table from, const int32_t* __restrict__ slots, int64_t n,
+                                        const __grid_constant__ DecodeArgs d, const __grid_constant__ vb2_group_table to, int64_t* __restrict__ num_groups,
+                                        int32_t* __restrict__ error_flag) {
+  const uint64_t mask = static_cast<uint64_t>(to.capacity - 1);
+  int64_t fresh = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t s = slots[i];
+    const uint64_t* src = from.rows + s * from.row_words;
+    uint64_t kw[VB2_KEYED_MAX_KEYS];
+    uint64_t nullmask = 0;
+    int first_acc;
+    if (d.from_keyed) {
+      for (int k = 0; k < d.n; ++k) kw[k] = src[1 + k];
+      nullmask = src[1 + d.n];
+      first_acc = d.n + 2;
+    } else {
+      const uint64_t key = from.hash_mode ? src[0] : static_cast<uint64_t>(s);
+      for (int k = 0; k < d.n; ++k) {
+        const uint64_t id = (key / d.mults[k]) % d.ranges[k];
+        const bool is_null = d.null_reserved[k] && id == 0;
+        kw[k] = is_null ? 0 : static_cast<uint64_t>(static_cast<int64_t>(id) - 1 + d.mins[k]);
+        nullmask |= static_cast<uint64_t>(is_null) << k;
+      }
+      first_acc = 1;
+    }
+    const int64_t slot = find_or_insert_keyed(to.rows, mask, to.row_words, d.n, kw, nullmask, fresh);
+    if (slot < 0) { atomicCAS(error_flag, 0, 100); continue; }
+    uint64_t* dst = to.rows + slot * to.row_words;
+    for (int w = first_acc; w < from.row_words && w + d.word_shift < to.row_words; ++w) dst[w + d.word_shift] = src[w];
+  }
+  fresh = warp_sum(fresh);
+  if ((threadIdx.x & 31) == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
+}
+
 // Very small batches (merging a handful of partial-aggregate rows, e.g. one row per group and GPU
 // in front of a final aggregation): one warp walks the rows IN INPUT ORDER, lane k owning aggregate
 // k, with plain read-modify-writes — the reference's sequential accumulation
@@ -619,6 +735,21 @@ group_extract_kernel(const __grid_constant__ vb2_group_table t, const int32_t* _
           if (c.type == VB2_INTEGER) reinterpret_cast<int32_t*>(c.values)[i] = static_cast<int32_t>(v);
           else reinterpret_cast<int64_t*>(c.values)[i] = v;
         }
+      } else if (c.kind == VB2_EXTRACT_KEYWORD) {
+        const uint64_t word = row[c.word];
+        valid = live && !((row[c.count_word] >> c.null_reserved) & 1u);
+        if (c.type == VB2_BOOLEAN) {
+          const unsigned bitsv = __ballot_sync(0xffffffffu, valid && word != 0);
+          if (lane == 0) {
+            reinterpret_cast<uint32_t*>(c.values)[w] = bitsv;
+            if (last_even_word) reinterpret_cast<uint32_t*>(c.values)[w + 1] = 0;
+          }
+        } else if (live) {
+          // c.min: offset for id-coded keys (VARCHAR dictionary index = global id - 1); 0 otherwise
+          if (c.type == VB2_INTEGER) reinterpret_cast<int32_t*>(c.values)[i] = valid ? static_cast<int32_t>(static_cast<int64_t>(word) + c.min) : 0;
+          else if (c.type == VB2_DOUBLE) reinterpret_cast<uint64_t*>(c.values)[i] = valid ? word : 0;  // the (canonical) bits
+          else reinterpret_cast<int64_t*>(c.values)[i] = valid ? static_cast<int64_t>(word) + c.min : 0;
+        }
       } else {
         const int64_t cnt = c.count_word >= 0 ? static_cast<int64_t>(row[c.count_word]) : 1;
         valid = live && cnt > 0;
@@ -878,6 +1009,70 @@ int vb2k_group_avg(const vb2_group_table* t, const int32_t* slots, int64_t n, in
   return VB2_OK;
 }
 
+static int check_keyed(const vb2_group_table* t, int32_t nkeys, const char* who) {
+  if (int rc = check_table(t, who)) return rc;
+  if (t->hash_mode != VB2_GROUP_KEYED || nkeys < 1 || nkeys > VB2_KEYED_MAX_KEYS || t->row_words < nkeys + 2) return fail_msg(VB2_ERR_INVALID, who);
+  return VB2_OK;
+}
+
+int vb2k_group_update_keyed(const vb2_group_table* t, const vb2_column* keys, int32_t nkeys, int64_t n, const vb2_agg_update* aggs, int32_t naggs,
+                            int64_t* num_groups, int32_t* error_flag, void* stream) {
+  if (int rc = check_keyed(t, nkeys, "group_update_keyed: bad table")) return rc;
+  if (naggs < 0 || naggs > kMaxAggs) return fail_msg(VB2_ERR_UNSUPPORTED, "group_update_keyed: at most 16 aggregates per call");
+  if (n <= 0) return VB2_OK;
+  KeyedCols kc;
+  kc.n = nkeys;
+  for (int k = 0; k < nkeys; ++k) {
+    if (keys[k].type == VB2_VARCHAR) return fail_msg(VB2_ERR_INVALID, "group_update_keyed: VARCHAR keys arrive as id columns");
+    kc.c[k] = keys[k];
+  }
+  AggArgs a;
+  a.n = naggs;
+  for (int i = 0; i < naggs; ++i) {
+    if (aggs[i].acc_word < nkeys + 2 || aggs[i].acc_word >= t->row_words || aggs[i].nonnull_word >= t->row_words)
+      return fail_msg(VB2_ERR_INVALID, "group_update_keyed: accumulator word outside the row");
+    a.a[i] = aggs[i];
+  }
+  group_update_keyed_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, kc, n, a, num_groups, error_flag);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_group_move_keyed(const vb2_group_table* from, const int32_t* slots, int64_t n, int32_t nkeys, const vb2_group_table* to, int64_t* num_groups,
+                          int32_t* error_flag, void* stream) {
+  if (int rc = check_keyed(from, nkeys, "group_move_keyed: bad source table")) return rc;
+  if (int rc = check_keyed(to, nkeys, "group_move_keyed: bad target table")) return rc;
+  if (from->row_words != to->row_words) return fail_msg(VB2_ERR_INVALID, "group_move_keyed: row layouts differ");
+  if (n <= 0) return VB2_OK;
+  DecodeArgs d{};
+  d.n = nkeys;
+  d.from_keyed = 1;
+  group_move_keyed_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*from, slots, n, d, *to, num_groups, error_flag);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_group_move_to_keyed(const vb2_group_table* from, const int32_t* slots, int64_t n, int32_t nkeys, const int64_t* mins, const uint64_t* mults,
+                             const uint64_t* ranges, const int32_t* null_reserved, int32_t word_shift, const vb2_group_table* to,
+                             int64_t* num_groups, int32_t* error_flag, void* stream) {
+  if (int rc = check_table(from, "group_move_to_keyed: bad source table")) return rc;
+  if (int rc = check_keyed(to, nkeys, "group_move_to_keyed: bad target table")) return rc;
+  if (from->hash_mode == VB2_GROUP_KEYED || word_shift != nkeys + 1) return fail_msg(VB2_ERR_INVALID, "group_move_to_keyed: bad layouts");
+  if (n <= 0) return VB2_OK;
+  DecodeArgs d{};
+  d.n = nkeys;
+  d.word_shift = word_shift;
+  for (int k = 0; k < nkeys; ++k) {
+    d.mins[k] = mins[k];
+    d.mults[k] = mults[k] ? mults[k] : 1;
+    d.ranges[k] = ranges[k] ? ranges[k] : 1;
+    d.null_reserved[k] = null_reserved ? null_reserved[k] : 0;
+  }
+  group_move_keyed_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*from, slots, n, d, *to, num_groups, error_flag);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
 int vb2k_group_extract(const vb2_group_table* t, const int32_t* slots, int64_t n, int32_t* scratch_slots, const vb2_extract_col* cols,
                        int32_t ncols, int64_t* header, const int32_t* error_flag, void* stream) {
   if (int rc = check_table(t, "group_extract: bad table")) return rc;
@@ -887,7 +1082,7 @@ int vb2k_group_extract(const vb2_group_table* t, const int32_t* slots, int64_t n
   a.n = ncols;
   for (int i = 0; i < ncols; ++i) {
     const vb2_extract_col& c = cols[i];
-    if (c.kind < VB2_EXTRACT_KEY || c.kind > VB2_EXTRACT_AVG || !c.values) return fail_msg(VB2_ERR_INVALID, "group_extract: bad column");
+    if (c.kind < VB2_EXTRACT_KEY || c.kind > VB2_EXTRACT_KEYWORD || !c.values) return fail_msg(VB2_ERR_INVALID, "group_extract: bad column");
     if (c.kind != VB2_EXTRACT_KEY && (c.word < 0 || c.word >= t->row_words || c.count_word >= t->row_words)) return fail_msg(VB2_ERR_INVALID, "group_extract: word outside the row");
     if (c.kind == VB2_EXTRACT_KEY && (c.mult == 0 || c.range == 0)) return fail_msg(VB2_ERR_INVALID, "group_extract: bad key layout");
     a.c[i] = c;

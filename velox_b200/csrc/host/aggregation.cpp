@@ -24,11 +24,12 @@ uint64_t nextPow2(uint64_t v) {
   return p;
 }
 
-enum class Mode { kGlobal, kArray, kHash };
+enum class Mode { kGlobal, kArray, kHash, kKeyed };  // kKeyed: the reference's kHash mode (rows store their key columns)
 
 struct KeyState {
   TypeKind kind;
   bool isVarchar = false;
+  bool isDouble = false;      // DOUBLE keys live in keyed tables only (no value-id range)
   // VARCHAR keys arrive dictionary-encoded; every distinct value gets a global id (1-based)
   std::unordered_map<std::string, int32_t> valueIds;
   std::vector<std::string> valuesById;
@@ -77,7 +78,10 @@ struct B200HashAggregation::Impl {
   // Group rows [capacity][rowWords]: word 0 = normalized key (hash mode) / rows seen (array, global),
   // then the accumulator and non-null-counter words of every aggregate (vb2_group_table).
   DeviceBufferPtr rowsBuf;
-  int32_t rowWords = 1;
+  int32_t rowWords = 1;        // words of an array / normalized-key row; keyed rows add their key words (rowWordsFor)
+  int32_t baseWords = 1;       // 1 + accumulator / counter words, before padding
+  bool forceKeyed = false;
+  bool keyedReady = false;     // the keyed table has its hash-mode storage (the initial 1-row storage does not count)     // a key type without a value-id range (DOUBLE): keyed table from the start
   std::vector<uint64_t> rowInit;
   bool sawGeneric = false;     // a batch went through vb2k_group_update (untracked counters need a fix-up to start tracking)
   DeviceBufferPtr numGroupsDev;
@@ -136,11 +140,12 @@ struct B200HashAggregation::Impl {
       KeyState ks;
       ks.kind = inType->childAt(k)->kind();
       ks.isVarchar = ks.kind == TypeKind::VARCHAR;
-      if (ks.kind == TypeKind::DOUBLE) VELOX_UNSUPPORTED("GROUP BY on DOUBLE keys");
+      ks.isDouble = ks.kind == TypeKind::DOUBLE;
+      if (ks.isDouble) forceKeyed = true;
       keys.push_back(std::move(ks));
     }
     VELOX_CHECK(keys.size() <= 4, "at most 4 grouping keys");
-    mode = keys.empty() ? Mode::kGlobal : Mode::kArray;
+    mode = keys.empty() ? Mode::kGlobal : (forceKeyed ? Mode::kKeyed : Mode::kArray);
     for (auto& a : node->aggregates()) {
       AccState s;
       s.fn = a.function;
@@ -162,8 +167,9 @@ struct B200HashAggregation::Impl {
       // a global aggregation emits its row even when no input arrived, so its counters always run
       a.nnTracked = a.fn == "avg" || keys.empty();
     }
+    baseWords = w;
     rowWords = w <= 2 ? w : (w + 3) / 4 * 4;  // whole 32-byte sectors
-    VELOX_CHECK(rowWords <= VB2_MAX_ROW_WORDS, "too many aggregates for one group row");
+    VELOX_CHECK(rowWordsFor(Mode::kKeyed) <= VB2_MAX_ROW_WORDS, "too many aggregates for one group row");
     errorFlag = allocDeviceZeroed(8, st());
     numGroupsDev = allocDeviceZeroed(8, st());
     layout.mins.assign(keys.size(), 1);
@@ -188,21 +194,31 @@ struct B200HashAggregation::Impl {
     }
   }
 
+  // Keyed rows: [state | key words | NULL mask | accumulators ...]: accumulator word w of the other
+  // layouts sits at w + shiftFor(kKeyed).
+  int32_t shiftFor(Mode m) const { return m == Mode::kKeyed ? static_cast<int32_t>(keys.size()) + 1 : 0; }
+  int32_t rowWordsFor(Mode m) const {
+    if (m != Mode::kKeyed) return rowWords;
+    const int32_t w = baseWords + shiftFor(m);
+    return (w + 3) / 4 * 4;
+  }
+  int32_t shift() const { return shiftFor(mode); }
   vb2_group_table tableOf(const DeviceBufferPtr& buf, int64_t cap, Mode m) const {
     vb2_group_table t{};
     t.rows = buf->as<uint64_t>();
     t.capacity = cap;
-    t.row_words = rowWords;
-    t.hash_mode = m == Mode::kHash ? 1 : 0;
+    t.row_words = rowWordsFor(m);
+    t.hash_mode = m == Mode::kHash ? 1 : (m == Mode::kKeyed ? VB2_GROUP_KEYED : 0);
     return t;
   }
   vb2_group_table table() const { return tableOf(rowsBuf, capacity, mode); }
 
   DeviceBufferPtr makeStorage(int64_t cap, Mode m) {
-    std::vector<uint64_t> init(rowWords, 0);
-    init[0] = m == Mode::kHash ? VB2_EMPTY_KEY : 0;
-    for (auto& a : accs) init[a.accWord] = identityBits(a);
-    auto buf = allocDevice(static_cast<size_t>(cap) * rowWords * 8, st());
+    const int32_t rw = rowWordsFor(m), sh = shiftFor(m);
+    std::vector<uint64_t> init(rw, 0);
+    init[0] = (m == Mode::kHash || m == Mode::kKeyed) ? VB2_EMPTY_KEY : 0;
+    for (auto& a : accs) init[a.accWord + sh] = identityBits(a);
+    auto buf = allocDevice(static_cast<size_t>(cap) * rw * 8, st());
     const vb2_group_table t = tableOf(buf, cap, m);
     kernelCheck(vb2k_group_table_init(&t, init.data(), st()));
     return buf;
@@ -229,7 +245,7 @@ struct B200HashAggregation::Impl {
     if (s.nnTracked || s.nnWord < 0) return;
     if (sawGeneric) {
       const vb2_group_table t = table();
-      kernelCheck(vb2k_group_set_word(&t, s.nnWord, 1, st()));
+      kernelCheck(vb2k_group_set_word(&t, s.nnWord + shift(), 1, st()));
     }
     s.nnTracked = true;
   }
@@ -240,7 +256,19 @@ struct B200HashAggregation::Impl {
     int64_t m = 0;
     DeviceBufferPtr slots = sawInput ? occupiedSlots(m) : nullptr;
     DeviceBufferPtr ns = makeStorage(ncap, nm);
-    if (m > 0) {
+    if (m > 0 && nm == Mode::kKeyed) {
+      // into a keyed table: from a smaller keyed table (keys are in the rows) or from an array /
+      // normalized-key table (keys decoded from the value ids of the old layout)
+      const vb2_group_table from = table(), to = tableOf(ns, ncap, nm);
+      const int32_t nk = static_cast<int32_t>(keys.size());
+      VB2_CU(cudaMemsetAsync(numGroupsDev->data(), 0, 8, st()));
+      if (mode == Mode::kKeyed)
+        kernelCheck(vb2k_group_move_keyed(&from, slots->as<int32_t>(), m, nk, &to, numGroupsDev->as<int64_t>(), errorFlag->as<int32_t>(), st()));
+      else
+        kernelCheck(vb2k_group_move_to_keyed(&from, slots->as<int32_t>(), m, nk, layout.mins.data(), layout.mults.data(), layout.ranges.data(),
+                                             nullReserved.data(), shiftFor(Mode::kKeyed), &to, numGroupsDev->as<int64_t>(), errorFlag->as<int32_t>(), st()));
+      checkDeviceError(errorFlag, st(), "aggregation rehash");
+    } else if (m > 0) {
       const vb2_group_table from = table(), to = tableOf(ns, ncap, nm);
       auto newKeys = allocDevice(static_cast<size_t>(m) * 8, st());
       kernelCheck(vb2k_group_rekey(&from, slots->as<int32_t>(), m, static_cast<int32_t>(keys.size()), layout.mins.data(), layout.mults.data(),
@@ -297,6 +325,7 @@ struct B200HashAggregation::Impl {
       ks.hi = std::max<int64_t>(1, static_cast<int64_t>(ks.valuesById.size()));
       return d;
     }
+    if (ks.isDouble || mode == Mode::kKeyed) return d;  // keyed tables read the key columns as they are: no value-id range needed
     int64_t lo, hi, nn;
     columnMinMax(col, rows, st(), lo, hi, nn);
     if (nn > 0) {
@@ -310,6 +339,16 @@ struct B200HashAggregation::Impl {
   // groups; relayouts otherwise.
   void ensureLayout(int64_t incoming) {
     if (keys.empty()) return;
+    if (mode == Mode::kKeyed) {
+      // keyed tables only ever grow (sized by groups so far + one pass, as the normalized-key tables)
+      const uint64_t want = nextPow2(static_cast<uint64_t>(numGroupsUpper + incoming) * 2 + 16);
+      if (!rowsBuf || static_cast<uint64_t>(capacity) < want || !keyedReady) {
+        VELOX_CHECK(want <= (1ull << 31), "hash aggregation above 2^31 slots");
+        relayout(layout, nullReserved, Mode::kKeyed, static_cast<int64_t>(std::max<uint64_t>(want, static_cast<uint64_t>(capacity))));
+        keyedReady = true;
+      }
+      return;
+    }
     bool covers = true;
     for (size_t k = 0; k < keys.size(); ++k) {
       const KeyState& ks = keys[k];
@@ -352,7 +391,15 @@ struct B200HashAggregation::Impl {
         if (build(true, wide)) product = wide;
         else ok = build(false, product);
       }
-      if (!ok) VELOX_UNSUPPORTED("grouping key ranges do not fit one 64-bit normalized key");
+      if (!ok) {
+        // the packed value ids need more than one 64-bit word: keyed table (the reference's kHash mode,
+        // exec/HashTable.cpp:1751-1838); the groups collected so far are decoded and moved over
+        const uint64_t want = nextPow2(static_cast<uint64_t>(numGroupsUpper + incoming) * 2 + 16);
+        VELOX_CHECK(want <= (1ull << 31), "hash aggregation above 2^31 slots");
+        relayout(layout, nullReserved, Mode::kKeyed, static_cast<int64_t>(want));
+        keyedReady = true;
+        return;
+      }
       nl.product = static_cast<uint64_t>(product);
       nl.mults.assign(keys.size(), 1);
       for (int i = static_cast<int>(keys.size()) - 2; i >= 0; --i) nl.mults[i] = nl.mults[i + 1] * nl.ranges[i + 1];
@@ -380,10 +427,12 @@ struct B200HashAggregation::Impl {
     ++genericBatches;
     std::vector<DeviceBufferPtr> keep;
     DeviceBufferPtr rowKeys;
+    std::vector<vb2_column> keyCols;
     if (!keys.empty()) {
-      std::vector<vb2_column> keyCols;
       for (size_t k = 0; k < keys.size(); ++k) keyCols.push_back(keyColumn(k, *in->column(node->groupingKeys()[k]), n, keep));
       ensureLayout(n);
+    }
+    if (!keys.empty() && mode != Mode::kKeyed) {
       auto nk = allocDevice(static_cast<size_t>(n) * 8, st());
       kernelCheck(vb2k_normalize_keys(keyCols.data(), static_cast<int32_t>(keyCols.size()), layout.mins.data(), layout.mults.data(), nullptr, 0,
                                       nullptr, n, nk->as<uint64_t>(), nullptr, st()));
@@ -438,7 +487,7 @@ struct B200HashAggregation::Impl {
       }
       vb2_agg_update u{};
       u.mask = mask;
-      u.acc_word = s.accWord;
+      u.acc_word = s.accWord + shift();
       u.nonnull_word = -1;
       if (a.function == "count") {
         u.kind = raw ? VB2_AGG_COUNT : VB2_AGG_COUNT_MERGE;
@@ -456,12 +505,12 @@ struct B200HashAggregation::Impl {
         c.mask = mask;
         c.nonnull_word = -1;
         flatInput(a.inputs[1], c);
-        c.acc_word = s.nnWord;
+        c.acc_word = s.nnWord + shift();
         ups.push_back(c);
         continue;
       }
       if (mask || u.nulls || u.base_nulls) trackNonNull(i);
-      if (s.nnTracked) u.nonnull_word = s.nnWord;
+      if (s.nnTracked) u.nonnull_word = s.nnWord + shift();
       ups.push_back(u);
     }
     const vb2_group_table t = table();
@@ -469,12 +518,16 @@ struct B200HashAggregation::Impl {
     for (size_t i = 0; i == 0 || i < ups.size(); i += 16) {
       // the first call inserts the groups; later slices of a long aggregate list find them again
       const int32_t cnt = static_cast<int32_t>(std::min<size_t>(16, ups.size() - i));
-      kernelCheck(vb2k_group_update(&t, rk, nullptr, n, ups.data() + i, cnt, i == 0 ? numGroupsDev->as<int64_t>() : nullptr,
-                                    errorFlag->as<int32_t>(), st()));
+      if (mode == Mode::kKeyed)
+        kernelCheck(vb2k_group_update_keyed(&t, keyCols.data(), static_cast<int32_t>(keyCols.size()), n, ups.data() + i, cnt,
+                                            i == 0 ? numGroupsDev->as<int64_t>() : nullptr, errorFlag->as<int32_t>(), st()));
+      else
+        kernelCheck(vb2k_group_update(&t, rk, nullptr, n, ups.data() + i, cnt, i == 0 ? numGroupsDev->as<int64_t>() : nullptr,
+                                      errorFlag->as<int32_t>(), st()));
     }
     sawGeneric = true;
     numGroupsUpper += n;
-    if (mode == Mode::kHash) {
+    if (mode == Mode::kHash || mode == Mode::kKeyed) {
       // tighten the bound with the real group count (one 8-byte read per batch)
       int64_t g = 0;
       VB2_CU(cudaMemcpyAsync(&g, numGroupsDev->data(), 8, cudaMemcpyDeviceToHost, st()));
@@ -843,7 +896,7 @@ struct B200HashAggregation::Impl {
   void flushFused() {
     if (!fusedSums) return;
     const int np = vb2k_fused_nproj(fusedId);
-    VELOX_CHECK(static_cast<int64_t>(fusedGroups) <= capacity && mode != Mode::kHash, "fused group space does not match the table");
+    VELOX_CHECK(static_cast<int64_t>(fusedGroups) <= capacity && mode != Mode::kHash && mode != Mode::kKeyed, "fused group space does not match the table");
     std::vector<int32_t> words{0}, projs{-1};  // word 0: rows seen (occupancy)
     for (size_t i = 0; i < accs.size(); ++i) {
       trackNonNull(i);
@@ -879,7 +932,7 @@ struct B200HashAggregation::Impl {
     if (!keys.empty() && cur->size() > chunk) {
       // the first pass shows whether these keys need a hash table at all; array mode takes the rest at once
       for (int64_t off = 0; off < cur->size();) {
-        const int64_t len = (off == 0 || mode == Mode::kHash) ? std::min<int64_t>(chunk, cur->size() - off) : cur->size() - off;
+        const int64_t len = (off == 0 || mode == Mode::kHash || mode == Mode::kKeyed) ? std::min<int64_t>(chunk, cur->size() - off) : cur->size() - off;
         addGeneric(sliceVector(cur, off, len));
         off += len;
       }
@@ -957,21 +1010,32 @@ struct B200HashAggregation::Impl {
     for (size_t k = 0; k < keys.size(); ++k, ++oc) {
       ColPlan c;
       c.type = inType->childAt(node->groupingKeys()[k]);
-      c.ec.kind = VB2_EXTRACT_KEY;
-      c.ec.mult = layout.mults[k] ? layout.mults[k] : 1;
-      c.ec.range = layout.ranges[k] ? layout.ranges[k] : 1;
-      c.ec.null_reserved = nullReserved[k];
-      c.ec.count_word = -1;
-      c.hasValid = nullReserved[k] != 0;
       c.key = k;
+      c.ec.mult = c.ec.range = 1;
+      if (mode == Mode::kKeyed) {
+        // the key column is word 1 + k of the row, its NULL bit is bit k of word 1 + K
+        c.ec.kind = VB2_EXTRACT_KEYWORD;
+        c.ec.word = 1 + static_cast<int32_t>(k);
+        c.ec.count_word = 1 + static_cast<int32_t>(keys.size());
+        c.ec.null_reserved = static_cast<int32_t>(k);
+        c.hasValid = keys[k].nullable;
+        c.ec.min = 0;
+      } else {
+        c.ec.kind = VB2_EXTRACT_KEY;
+        c.ec.mult = layout.mults[k] ? layout.mults[k] : 1;
+        c.ec.range = layout.ranges[k] ? layout.ranges[k] : 1;
+        c.ec.null_reserved = nullReserved[k];
+        c.ec.count_word = -1;
+        c.hasValid = nullReserved[k] != 0;
+        c.ec.min = layout.mins[k];
+      }
       if (keys[k].isVarchar) {
-        c.varcharKey = true;  // dictionary over the global alphabet: index = id - 1
+        c.varcharKey = true;  // dictionary over the global alphabet: index = global id - 1
         c.ec.type = VB2_INTEGER;
-        c.ec.min = layout.mins[k] - 1;
+        c.ec.min -= 1;
         c.width = 4;
       } else {
         c.ec.type = veloxTypeToVb2(c.type);
-        c.ec.min = layout.mins[k];
         c.width = c.ec.type == VB2_INTEGER ? 4 : (c.ec.type == VB2_BOOLEAN ? 0 : 8);
       }
       plan.push_back(c);
@@ -982,8 +1046,8 @@ struct B200HashAggregation::Impl {
         ColPlan c;
         c.type = outType->childAt(oc++);
         c.ec.kind = kind;
-        c.ec.word = word;
-        c.ec.count_word = countWord;
+        c.ec.word = word + shift();
+        c.ec.count_word = countWord >= 0 ? countWord + shift() : -1;
         c.ec.mult = c.ec.range = 1;
         c.hasValid = valid;
         c.width = width;

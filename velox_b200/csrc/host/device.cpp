@@ -528,6 +528,39 @@ RowVectorPtr toHost(const B200VectorPtr& dev) {
   return std::make_shared<RowVector>(pool, dev->type(), nullptr, dev->size(), std::move(children));
 }
 
+// Device copy (int32 offsets + chars) of a small alphabet, shared by every page that carries the same
+// strings: exchanged dictionaries repeat from query to query, the upload happens once per content.
+void deviceAlphabet(const HostAlphabet& a, cudaStream_t st, DeviceBufferPtr& offBuf, DeviceBufferPtr& charBuf) {
+  static std::mutex mu;
+  static std::map<std::string, std::pair<DeviceBufferPtr, DeviceBufferPtr>> cache;
+  std::string key;
+  std::vector<int32_t> off(a.values.size() + 1, 0);
+  std::string chars;
+  for (size_t k = 0; k < a.values.size(); ++k) {
+    chars += a.values[k];
+    off[k + 1] = static_cast<int32_t>(chars.size());
+    key += std::to_string(a.values[k].size()) + ":" + a.values[k];
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  key = std::to_string(dev) + "|" + key;
+  std::lock_guard<std::mutex> l(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    if (cache.size() > 256) cache.clear();
+    // plain cudaMalloc'd, never freed while cached: usable from any stream once the copies below are done
+    auto ob = allocDevice(off.size() * 4, st);
+    auto cb = allocDevice(chars.size() + 1, st);
+    VB2_CU(cudaMemcpyAsync(ob->data(), off.data(), off.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!chars.empty()) VB2_CU(cudaMemcpyAsync(cb->data(), chars.data(), chars.size(), cudaMemcpyHostToDevice, st));
+    VB2_CU(cudaStreamSynchronize(st));
+    it = cache.emplace(key, std::make_pair(ob, cb)).first;
+  }
+  offBuf = it->second.first;
+  charBuf = it->second.second;
+}
+
+
 DeviceColumnPtr borrowFlatColumn(TypePtr type, const void* values, int64_t size) {
   auto col = std::make_shared<DeviceColumn>();
   col->type = std::move(type);

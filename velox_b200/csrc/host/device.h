@@ -110,6 +110,10 @@ B200VectorPtr toDevice(const RowVectorPtr& host, cudaStream_t stream);
 // Device -> host RowVector (synchronises the stream).
 RowVectorPtr toHost(const B200VectorPtr& dev);
 
+// Device copy (int32 offsets + chars) of a small alphabet, cached by content: dictionaries repeat
+// from batch to batch and from query to query, the upload happens once per distinct content.
+void deviceAlphabet(const HostAlphabet& a, cudaStream_t st, DeviceBufferPtr& offsets, DeviceBufferPtr& chars);
+
 // Wraps externally owned device memory (e.g. columns already resident in HBM) without copying.
 DeviceColumnPtr borrowFlatColumn(TypePtr type, const void* values, int64_t size);
 

@@ -1,4 +1,6 @@
 // B200HashBuild / B200HashProbe and the key-normalisation helpers shared with aggregation.
+#include <map>
+
 #include "join.h"
 
 namespace velox_b200 {
@@ -27,6 +29,11 @@ NormalizedKeys normalizeKeys(const B200Vector& batch, const std::vector<int32_t>
   return out;
 }
 
+// HashBuild::addInput appends every batch to the build side (exec/HashBuild.cpp:442-598). On the device
+// the batches are decoded into one flat column each at noMoreInput: fixed-width values are
+// flattened and copied, validity travels as bytes (bitmaps of different batches start at arbitrary
+// bit offsets) and is packed once at the end, BOOLEAN values likewise, and VARCHAR columns keep
+// their dictionary form over the union of the batches' alphabets (codes remapped per batch).
 B200VectorPtr concatBatches(const std::vector<B200VectorPtr>& batches, memory::MemoryPool* pool, cudaStream_t stream) {
   VELOX_CHECK(!batches.empty(), "concatBatches: no input");
   if (batches.size() == 1) return batches[0];
@@ -41,45 +48,77 @@ B200VectorPtr concatBatches(const std::vector<B200VectorPtr>& batches, memory::M
     col->type = first->type;
     col->desc.type = first->desc.type;
     col->desc.size = total;
-    if (first->desc.type == VB2_VARCHAR) {
-      // VARCHAR: only dictionary columns over one shared alphabet can be concatenated without
-      // touching characters (indices are concatenated, the base is kept)
-      bool sameBase = first->desc.encoding == VB2_DICTIONARY;
-      for (auto& b : batches) sameBase = sameBase && b->column(c)->desc.encoding == VB2_DICTIONARY && b->column(c)->desc.values == first->desc.values;
-      if (!sameBase) VELOX_UNSUPPORTED("multi-batch build side with VARCHAR columns that do not share one dictionary");
-      *col = *first;
-      col->desc.size = total;
-      auto idx = allocDevice(static_cast<size_t>(total) * 4, stream);
-      int64_t off = 0;
-      bool anyNulls = false;
-      for (auto& b : batches) anyNulls = anyNulls || b->column(c)->desc.nulls;
-      if (anyNulls) VELOX_UNSUPPORTED("multi-batch VARCHAR build column with wrapper nulls");
-      for (auto& b : batches) {
-        VB2_CU(cudaMemcpyAsync(idx->as<int32_t>() + off, b->column(c)->desc.indices, static_cast<size_t>(b->size()) * 4, cudaMemcpyDeviceToDevice, stream));
-        off += b->size();
-      }
-      col->desc.indices = idx->as<int32_t>();
-      col->owners.push_back(idx);
-      cols.push_back(col);
-      continue;
-    }
-    col->desc.encoding = VB2_FLAT;
     const int t = first->desc.type;
-    const int w = widthOf(t);
     bool anyNulls = false;
     for (auto& b : batches) anyNulls = anyNulls || b->column(c)->mayHaveNulls();
-    if (t == VB2_BOOLEAN) VELOX_UNSUPPORTED("multi-batch build side with BOOLEAN columns");
-    auto values = allocDevice(static_cast<size_t>(total) * w, stream);
-    DeviceBufferPtr nulls;
-    if (anyNulls) VELOX_UNSUPPORTED("multi-batch build side with NULLs (single-batch builds support them)");
-    int64_t off = 0;
-    for (auto& b : batches) {
-      FlatColumn f = flattenColumn(b->column(c), nullptr, b->size(), stream);
-      VB2_CU(cudaMemcpyAsync(values->as<uint8_t>() + off * w, f.values->data(), static_cast<size_t>(b->size()) * w, cudaMemcpyDeviceToDevice, stream));
-      off += b->size();
+    DeviceBufferPtr validBytes = anyNulls ? allocDevice(static_cast<size_t>(total), stream) : nullptr;
+    if (t == VB2_VARCHAR) {
+      // union of the alphabets (first occurrence wins); codes of every batch go through its own remap
+      auto merged = std::make_shared<HostAlphabet>();
+      std::map<std::string, int32_t> ids;
+      auto codes = allocDevice(static_cast<size_t>(total) * 4, stream);
+      int64_t off = 0;
+      for (auto& b : batches) {
+        const DeviceColumnPtr& bc = b->column(c);
+        if (bc->desc.encoding == VB2_FLAT || !bc->alphabet) VELOX_UNSUPPORTED("multi-batch build side with flat (non-dictionary) VARCHAR columns");
+        std::vector<int32_t> remap(bc->alphabet->values.size());
+        for (size_t i = 0; i < remap.size(); ++i) {
+          if (bc->alphabet->nulls[i]) { remap[i] = 0; continue; }  // NULL entries: the validity byte decides, the code is unused
+          auto it = ids.find(bc->alphabet->values[i]);
+          if (it == ids.end()) {
+            it = ids.emplace(bc->alphabet->values[i], static_cast<int32_t>(merged->values.size())).first;
+            merged->values.push_back(bc->alphabet->values[i]);
+            merged->nulls.push_back(false);
+          }
+          remap[i] = it->second;
+        }
+        const int64_t bn = b->size();
+        auto raw = allocDevice(static_cast<size_t>(bn) * 4, stream);
+        kernelCheck(vb2k_dictionary_codes(&bc->desc, bn, raw->as<int32_t>(), validBytes ? validBytes->as<uint8_t>() + off : nullptr, stream));
+        auto lut = allocDevice(remap.size() * 4 + 4, stream);
+        VB2_CU(cudaMemcpyAsync(lut->data(), remap.data(), remap.size() * 4, cudaMemcpyHostToDevice, stream));  // pageable: staged before return
+        kernelCheck(vb2k_gather(lut->data(), raw->as<int32_t>(), bn, 4, codes->as<int32_t>() + off, stream));
+        off += bn;
+      }
+      if (merged->values.empty()) { merged->values.push_back(""); merged->nulls.push_back(false); }
+      DeviceBufferPtr offBuf, charBuf;
+      deviceAlphabet(*merged, stream, offBuf, charBuf);
+      col->desc.encoding = VB2_DICTIONARY;
+      col->desc.indices = codes->as<int32_t>();
+      col->desc.values = offBuf->data();
+      col->desc.aux = charBuf->data();
+      col->desc.dict_size = static_cast<int64_t>(merged->values.size());
+      col->owners = {codes, offBuf, charBuf};
+      col->alphabet = merged;
+    } else {
+      col->desc.encoding = VB2_FLAT;
+      const int w = t == VB2_BOOLEAN ? 1 : widthOf(t);  // BOOLEAN: one byte per row until the final pack
+      auto values = allocDevice(static_cast<size_t>(total) * w, stream);
+      int64_t off = 0;
+      for (auto& b : batches) {
+        const int64_t bn = b->size();
+        FlatColumn f = flattenColumn(b->column(c), nullptr, bn, stream);
+        VB2_CU(cudaMemcpyAsync(values->as<uint8_t>() + off * w, f.values->data(), static_cast<size_t>(bn) * w, cudaMemcpyDeviceToDevice, stream));
+        if (validBytes) {
+          if (f.nulls) kernelCheck(vb2k_unpack_bits(f.nulls->as<uint64_t>(), bn, validBytes->as<uint8_t>() + off, stream));
+          else VB2_CU(cudaMemsetAsync(validBytes->as<uint8_t>() + off, 1, static_cast<size_t>(bn), stream));
+        }
+        off += bn;
+      }
+      if (t == VB2_BOOLEAN) {
+        auto packed = allocDevice(bits::nbytes(total), stream);
+        kernelCheck(vb2k_pack_bools(values->as<uint8_t>(), total, packed->as<uint64_t>(), stream));
+        values = packed;
+      }
+      col->desc.values = values->data();
+      col->owners = {values};
     }
-    col->desc.values = values->data();
-    col->owners = {values};
+    if (validBytes) {
+      auto bitsBuf = allocDevice(bits::nbytes(total), stream);
+      kernelCheck(vb2k_pack_bools(validBytes->as<uint8_t>(), total, bitsBuf->as<uint64_t>(), stream));
+      col->desc.nulls = bitsBuf->as<uint64_t>();
+      col->owners.push_back(bitsBuf);
+    }
     cols.push_back(col);
   }
   return std::make_shared<B200Vector>(pool, batches[0]->type(), static_cast<vector_size_t>(total), std::move(cols), stream);
