@@ -265,8 +265,8 @@ enum vb2_agg_kind { VB2_AGG_SUM_F64 = 1, VB2_AGG_SUM_I64 = 2, VB2_AGG_COUNT = 3,
 /* Group table: row-wise group storage, the role of exec::RowContainer under exec::HashTable for
  * GROUP BY (velox/exec/RowContainer.h, velox/exec/HashTable.cpp:706-772 groupProbe). `capacity` rows
  * of `row_words` 8-byte words; word 0 is the occupancy word — the 64-bit normalized key in hash
- * mode (VB2_EMPTY_KEY = free; open addressing, linear probing, load factor <= 0.5, capacity a power
- * of two), "rows seen" in array mode (slot = normalized key, 0 = free; capacity = key space) — the
+ * mode (VB2_EMPTY_KEY = free; open addressing from the home slot twang_mix64(key) >> (64 - log2(capacity)),
+ * linear probing, capacity a power of two), "rows seen" in array mode (slot = normalized key, 0 = free; capacity = key space) — the
  * remaining words are accumulators / non-null counters. Rows of more than two words should be
  * padded to a multiple of four words (whole 32-byte sectors). */
 #define VB2_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
@@ -327,6 +327,24 @@ int vb2k_group_move_keyed(const vb2_group_table* from, const int32_t* slots, int
 int vb2k_group_move_to_keyed(const vb2_group_table* from, const int32_t* slots, int64_t n, int32_t nkeys, const int64_t* mins, const uint64_t* mults,
                              const uint64_t* ranges, const int32_t* null_reserved, int32_t word_shift, const vb2_group_table* to,
                              int64_t* num_groups, int32_t* error_flag, void* stream);
+/* Radix partitioning in front of a high-cardinality aggregation (radix_partition.cu): a hash-mode
+ * group table places key k at slot twang_mix64(k) >> (64 - log2(capacity)), so rows ordered by the
+ * top 8 bits of that hash walk the table slice by slice (1/256 of it at a time, L2 resident).
+ * Keys: norm_keys (from vb2k_normalize_keys), or NULL and ONE flat NULL-free integer column
+ * (key_values, key_is64, key_min: normalized key = v - key_min + 1).
+ *   vb2k_radix_histogram  per-chunk partition histograms into `workspace` + a HyperLogLog sketch of the
+ *                         keys whose hash ends in 000 (hll_out: device int32[vb2k_radix_hll_registers()];
+ *                         distinct keys of the batch ~ 8 x the sketch's estimate) — sizes the table
+ *                         before any row is inserted (HashTable::checkSize, exec/HashTable.cpp:772, grows by rehashing instead)
+ *   vb2k_radix_scatter    keys_out / cols_out = keys and up to 4 payload columns (4 or 8 bytes wide) in
+ *                         partition order; part_start_out: device int64[257] */
+size_t vb2k_radix_workspace_bytes(int64_t rows);
+int32_t vb2k_radix_hll_registers(void);
+int vb2k_radix_histogram(const uint64_t* norm_keys, const void* key_values, int32_t key_is64, int64_t key_min, int64_t rows, void* workspace,
+                         size_t workspace_bytes, int32_t* hll_out, void* stream);
+int vb2k_radix_scatter(const uint64_t* norm_keys, const void* key_values, int32_t key_is64, int64_t key_min, int64_t rows, void* workspace,
+                       size_t workspace_bytes, const void* const* cols, void* const* cols_out, const int32_t* col_bytes, int32_t ncols,
+                       uint64_t* keys_out, int64_t* part_start_out, void* stream);
 /* Compacts occupied rows: slot_list int32[<=capacity] ascending, count device int64. */
 int vb2k_group_occupied(const vb2_group_table* t, int32_t* slot_list, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
 size_t vb2k_group_occupied_workspace(int64_t capacity);

@@ -598,3 +598,29 @@ def test_hash_build_many_batches_with_nulls_booleans_and_mixed_dictionaries():
         whole = row_vector(builds[0].names, [cat(0, BIGINT), cat(1, BOOLEAN), cat(2, VARCHAR), cat(3, INTEGER)])
         want = pyoracle.run_plan(plan, [probe, whole])
         assert_equal_results(got, want)
+
+
+def test_aggregation_radix_partitioned_batches():
+    """High-cardinality batches are radix-partitioned by the top bits of their table hash before the
+    find-or-insert pass (radix_partition.cu): one or two keys, several aggregates over 4- and 8-byte
+    inputs, several batches into the same table; the table is sized from the HyperLogLog estimate."""
+    n = 500_000
+    rng = np.random.default_rng(12)
+    pool_keys = rng.integers(0, 2**40, 90_000)
+    keys = pool_keys[rng.integers(0, 90_000, n)]
+    rv = row_vector(["k", "v", "w", "x"], [flat_vector(BIGINT, keys), flat_vector(BIGINT, (np.arange(n) % 1000)), flat_vector(INTEGER, rng.integers(-50, 50, n).astype(np.int32)),
+                                         flat_vector(DOUBLE, rng.standard_normal(n))])
+    part = {"b200.agg_partition_min_rows": "1000"}
+    plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(["k"], ["sum(v)", "count(0)", "min(w)", "max(x)", "avg(x)"]).planNode()
+    (st,) = check_plan(plan, [rv], configs=(part,), rel_tol=1e-11, oracle_batch_rows=100_000)
+    assert stat(st, "b200.partitionedBatches") == 1 and stat(st, "b200.aggMode") == 2
+    (st,) = check_plan(plan, [rv], configs=(part,), batch_rows=125_000, rel_tol=1e-11, oracle_batch_rows=100_000)
+    assert stat(st, "b200.partitionedBatches") == 4
+    two = row_vector(["a", "b", "v"], [flat_vector(BIGINT, keys), flat_vector(INTEGER, (keys % 7).astype(np.int32), rng.random(n) < 0.01), flat_vector(DOUBLE, np.ones(n))])
+    plan2 = PlanBuilder().values(two.names, two.types).singleAggregation(["a", "b"], ["sum(v)", "count(0)"]).planNode()
+    (st,) = check_plan(plan2, [two], configs=(part,), oracle_batch_rows=100_000)
+    assert stat(st, "b200.partitionedBatches") == 1
+    # partial -> final: the final step merges intermediate columns through the same path
+    plan3 = (PlanBuilder().values(rv.names, rv.types).partialAggregation(["k"], ["sum(v)", "avg(x)", "count(0)"]).intermediateAggregation()
+             .finalAggregation().planNode())
+    check_plan(plan3, [rv], configs=(dict(part, **GENERIC),), batch_rows=250_000, rel_tol=1e-11, oracle_batch_rows=100_000)

@@ -178,15 +178,18 @@ struct TableView {
   uint64_t mask;      // hash mode: capacity - 1; array mode: capacity - 1 is the largest valid key
   int32_t w;
   int32_t hash;
+  int32_t shift;      // hash mode: home slot = twang_mix64(key) >> shift — the TOP bits of the hash, so that rows
+                      // ordered by their hash's top bits (radix_partition.cu) walk the table slice by slice
 };
+__device__ __forceinline__ int32_t top_bits_shift(int64_t capacity) { return capacity > 1 ? 64 - (63 - __clzll(capacity)) : 63; }
 __device__ __forceinline__ TableView view_of(const vb2_group_table& t) {
-  return TableView{t.rows, static_cast<uint64_t>(t.capacity - 1), t.row_words, t.hash_mode};
+  return TableView{t.rows, static_cast<uint64_t>(t.capacity - 1), t.row_words, t.hash_mode, top_bits_shift(t.capacity)};
 }
 
 // Slot of `key` (inserted if absent), -1 if the table is full / the key is outside the array.
 __device__ __forceinline__ int64_t find_or_insert(const TableView& t, uint64_t key, int64_t& fresh) {
   if (!t.hash) return key <= t.mask ? static_cast<int64_t>(key) : -1;
-  uint64_t slot = twang_mix64(key) & t.mask;
+  uint64_t slot = (twang_mix64(key) >> t.shift) & t.mask;
   for (uint64_t probes = 0; probes <= t.mask; ++probes) {
     uint64_t* p = t.rows + slot * t.w;
     uint64_t cur = *reinterpret_cast<volatile uint64_t*>(p);

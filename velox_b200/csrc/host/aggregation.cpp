@@ -104,7 +104,7 @@ struct B200HashAggregation::Impl {
   DeviceBufferPtr fusedSums, fusedCounts, fusedWs;
   size_t fusedWsBytes = 0;
   int fusedGroups = 0;
-  int64_t fusedBatches = 0, genericBatches = 0, selectiveBatches = 0;
+  int64_t fusedBatches = 0, genericBatches = 0, selectiveBatches = 0, partitionedBatches = 0;
   bool selectiveDecided = false, selectiveUsable = true;
   double selectivity = 1.0;
   struct FusedTiming { cudaEvent_t begin = nullptr, end = nullptr; int64_t rows = 0; };
@@ -422,6 +422,107 @@ struct B200HashAggregation::Impl {
   }
 
   // ---- generic path -------------------------------------------------------------------------------
+  // Distinct-key estimate of a batch from the HyperLogLog sketch the radix histogram kernel fills
+  // (registers over the keys whose hash ends in 000, hence the factor 8).
+  static double hllEstimate(const std::vector<int32_t>& regs) {
+    const double m = static_cast<double>(regs.size());
+    double sum = 0;
+    int zeros = 0;
+    for (int32_t r : regs) {
+      sum += std::ldexp(1.0, -r);
+      zeros += r == 0;
+    }
+    const double alpha = 0.7213 / (1.0 + 1.079 / m);
+    double e = alpha * m * m / sum;
+    if (e <= 2.5 * m && zeros > 0) e = m * std::log(m / zeros);  // small-range correction (linear counting)
+    return 8.0 * e;
+  }
+
+  // Large batches over a large hash-mode table: the rows are radix-partitioned by the top bits of
+  // their table hash first, so that the find-or-insert + update pass walks the table slice by slice
+  // (L2 resident) instead of paying a DRAM round trip per row. Returns false when the batch does not
+  // qualify (then the plain path runs).
+  bool addPartitioned(const B200VectorPtr& in) {
+    const int64_t n = in->size();
+    const auto& cfg = self->driverCtx()->queryConfig();
+    if (keys.empty() || mode == Mode::kKeyed || n < cfg.get<int64_t>("b200.agg_partition_min_rows", 1 << 23)) return false;
+    if (!cfg.get<bool>("b200.agg_radix_partition", true)) return false;
+    // aggregate inputs: flat, NULL-free, unmasked, 4 or 8 bytes wide, at most four distinct columns
+    const auto& aggs = node->aggregates();
+    std::vector<int32_t> payload;
+    for (auto& a : aggs) {
+      if (a.mask >= 0) return false;
+      for (int32_t c : a.inputs) {
+        const vb2_column& d = in->column(c)->desc;
+        if (d.encoding != VB2_FLAT || d.nulls || (d.type != VB2_BIGINT && d.type != VB2_DOUBLE && d.type != VB2_INTEGER)) return false;
+        if (std::find(payload.begin(), payload.end(), c) == payload.end()) payload.push_back(c);
+      }
+    }
+    if (payload.size() > 4) return false;
+    std::vector<DeviceBufferPtr> keep;
+    std::vector<vb2_column> keyCols;
+    for (size_t k = 0; k < keys.size(); ++k) keyCols.push_back(keyColumn(k, *in->column(node->groupingKeys()[k]), n, keep));
+    ensureLayout(0);  // the layout must cover this batch's key ranges before its keys can be normalized
+    if (mode != Mode::kHash) return false;  // small key space: array mode needs no partitioning
+    // keys: one flat NULL-free integer column is normalized on the fly, anything else through vb2k_normalize_keys
+    const uint64_t* norm = nullptr;
+    const void* keyValues = nullptr;
+    int32_t keyIs64 = 0;
+    int64_t keyMin = 0;
+    DeviceBufferPtr normBuf;
+    auto prepareKeys = [&]() {
+      const vb2_column& k0 = keyCols[0];
+      if (keyCols.size() == 1 && k0.encoding == VB2_FLAT && !k0.nulls && (k0.type == VB2_BIGINT || k0.type == VB2_INTEGER) && layout.mults[0] == 1) {
+        keyValues = k0.values;
+        keyIs64 = k0.type == VB2_BIGINT;
+        keyMin = layout.mins[0];
+        norm = nullptr;
+        return;
+      }
+      normBuf = allocDevice(static_cast<size_t>(n) * 8, st());
+      kernelCheck(vb2k_normalize_keys(keyCols.data(), static_cast<int32_t>(keyCols.size()), layout.mins.data(), layout.mults.data(), nullptr, 0, nullptr, n,
+                                      normBuf->as<uint64_t>(), nullptr, st()));
+      norm = normBuf->as<uint64_t>();
+    };
+    prepareKeys();
+    const size_t wsBytes = vb2k_radix_workspace_bytes(n);
+    auto ws = allocDevice(wsBytes, st());
+    const int32_t nregs = vb2k_radix_hll_registers();
+    auto hll = allocDevice(static_cast<size_t>(nregs) * 4, st());
+    kernelCheck(vb2k_radix_histogram(norm, keyValues, keyIs64, keyMin, n, ws->data(), wsBytes, hll->as<int32_t>(), st()));
+    std::vector<int32_t> regs(nregs);
+    VB2_CU(cudaMemcpyAsync(regs.data(), hll->data(), static_cast<size_t>(nregs) * 4, cudaMemcpyDeviceToHost, st()));
+    VB2_CU(cudaStreamSynchronize(st()));
+    const int64_t distinct = std::min<int64_t>(n, static_cast<int64_t>(hllEstimate(regs) * 1.15) + 1024);  // + 9 sigma of the sketch's error
+    const Mode before = mode;
+    const KeyLayout layoutBefore = layout;
+    ensureLayout(distinct);  // grows the table ONCE for the whole batch (a relayout keeps the layout: the ranges are already covered)
+    VELOX_CHECK(mode == before && layout.mins == layoutBefore.mins && layout.mults == layoutBefore.mults, "layout changed after the keys were read");
+    // keys + payload columns into partition order
+    auto partKeys = allocDevice(static_cast<size_t>(n) * 8, st());
+    auto partStart = allocDevice(257 * 8, st());
+    std::vector<const void*> colsIn;
+    std::vector<void*> colsOut;
+    std::vector<int32_t> colBytes;
+    std::map<int32_t, const void*> permuted;
+    for (int32_t c : payload) {
+      const vb2_column& d = in->column(c)->desc;
+      const int w = d.type == VB2_INTEGER ? 4 : 8;
+      auto out = allocDevice(static_cast<size_t>(n) * w, st());
+      keep.push_back(out);
+      colsIn.push_back(d.values);
+      colsOut.push_back(out->data());
+      colBytes.push_back(w);
+      permuted[c] = out->data();
+    }
+    kernelCheck(vb2k_radix_scatter(norm, keyValues, keyIs64, keyMin, n, ws->data(), wsBytes, colsIn.data(), colsOut.data(), colBytes.data(),
+                                   static_cast<int32_t>(colsIn.size()), partKeys->as<uint64_t>(), partStart->as<int64_t>(), st()));
+    ++genericBatches;
+    ++partitionedBatches;
+    applyUpdates(in, n, partKeys, keyCols, keep, &permuted);
+    return true;
+  }
+
   void addGeneric(const B200VectorPtr& in) {
     const int64_t n = in->size();
     ++genericBatches;
@@ -438,6 +539,13 @@ struct B200HashAggregation::Impl {
                                       nullptr, n, nk->as<uint64_t>(), nullptr, st()));
       rowKeys = nk;
     }
+    applyUpdates(in, n, rowKeys, keyCols, keep, nullptr);
+  }
+
+  // Find-or-insert + every aggregate update of one batch. rowKeys: normalized keys in the order the
+  // rows are visited (input order, or partition order with `permuted` giving the reordered input columns).
+  void applyUpdates(const B200VectorPtr& in, int64_t n, const DeviceBufferPtr& rowKeys, std::vector<vb2_column>& keyCols, std::vector<DeviceBufferPtr>& keep,
+                    const std::map<int32_t, const void*>* permuted) {
     std::vector<vb2_agg_update> ups;
     // Points an update at its input column. Flat columns are read in place; a dictionary wrap over
     // fixed-width values (what a filter leaves behind, exec/Operator.cpp:270-303 wrapChild) is read
@@ -447,6 +555,10 @@ struct B200HashAggregation::Impl {
     auto flatInput = [&](int32_t colIdx, vb2_agg_update& u) {
       const DeviceColumnPtr& c = in->column(colIdx);
       u.input_type = c->desc.type;
+      if (permuted) {  // partition order: the flat NULL-free column was reordered together with the keys
+        u.input = permuted->at(colIdx);
+        return;
+      }
       if (c->desc.encoding == VB2_FLAT && u.input_type != VB2_BOOLEAN) {
         u.input = c->desc.values;
         u.nulls = c->desc.nulls;
@@ -928,6 +1040,7 @@ struct B200HashAggregation::Impl {
     // Hash-mode tables are sized by (groups so far + rows of one pass): large batches go through
     // find-or-insert in bounded passes so a high-cardinality table ends near 2x its group count
     // instead of 2x the batch.
+    if (addPartitioned(cur)) return;
     const int64_t chunk = std::max<int64_t>(1 << 16, self->driverCtx()->queryConfig().b200AggProbeChunkRows()) / 64 * 64;
     if (!keys.empty() && cur->size() > chunk) {
       // the first pass shows whether these keys need a hash table at all; array mode takes the rest at once
@@ -1140,6 +1253,7 @@ struct B200HashAggregation::Impl {
     reportFusedTimings();  // every fused launch precedes the synchronisation above
     self->addRuntimeStat("b200.fusedBatches", exec::RuntimeCounter{fusedBatches});
     self->addRuntimeStat("b200.selectiveBatches", exec::RuntimeCounter{selectiveBatches});
+    self->addRuntimeStat("b200.partitionedBatches", exec::RuntimeCounter{partitionedBatches});
     self->addRuntimeStat("b200.genericBatches", exec::RuntimeCounter{genericBatches});
     self->addRuntimeStat("b200.aggMode", exec::RuntimeCounter{static_cast<int64_t>(mode)});
     auto out = std::make_shared<B200Vector>(self->pool(), outType, static_cast<vector_size_t>(m), std::move(cols), st());
