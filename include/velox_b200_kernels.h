@@ -345,6 +345,13 @@ int vb2k_radix_histogram(const uint64_t* norm_keys, const void* key_values, int3
 int vb2k_radix_scatter(const uint64_t* norm_keys, const void* key_values, int32_t key_is64, int64_t key_min, int64_t rows, void* workspace,
                        size_t workspace_bytes, const void* const* cols, void* const* cols_out, const int32_t* col_bytes, int32_t ncols,
                        uint64_t* keys_out, int64_t* part_start_out, void* stream);
+/* vb2k_group_update over rows in radix-partition order (row_keys from vb2k_radix_scatter, part_start =
+ * its int64[nparts + 1] output, inputs of the updates reordered the same way): the grid folds partition
+ * p into table slice p while slice p + 1 is prefetched into L2, in lock step (cooperative launch;
+ * barrier_word: device uint32 scratch). Hash-mode tables of >= 65536 rows. */
+int vb2k_group_update_partitioned(const vb2_group_table* t, const uint64_t* row_keys, const int64_t* part_start, int32_t nparts, int64_t n,
+                                  const vb2_agg_update* aggs, int32_t naggs, int64_t* num_groups, int32_t* error_flag, uint32_t* barrier_word,
+                                  void* stream);
 /* Compacts occupied rows: slot_list int32[<=capacity] ascending, count device int64. */
 int vb2k_group_occupied(const vb2_group_table* t, int32_t* slot_list, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
 size_t vb2k_group_occupied_workspace(int64_t capacity);

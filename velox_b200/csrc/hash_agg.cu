@@ -383,6 +383,56 @@ __global__ void group_move_keyed_kernel(const __grid_constant__ vb2_group_table 
   if ((threadIdx.x & 31) == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
 }
 
+// Rows in radix-partition order (radix_partition.cu): partition p's rows only touch slice p of the
+// table (the home slot is the top bits of the hash), so the grid walks the partitions in lock step —
+// slice p + 1 is prefetched into L2 with full-line reads while the rows of partition p are folded into
+// slice p, which is L2 resident by then. DRAM sees the table once per batch, sequentially, instead of
+// one random 32-byte sector per input row. Cooperative launch (all blocks co-resident): the per-
+// partition barrier is a monotonic counter.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int nblocks, unsigned int& generation) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned int target = (generation + 1u) * nblocks;
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {}
+    __threadfence();
+  }
+  ++generation;
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256)
+group_update_partitioned_kernel(const __grid_constant__ vb2_group_table tab, const uint64_t* __restrict__ row_keys, const int64_t* __restrict__ part_start,
+                                int nparts, const __grid_constant__ AggArgs args, int64_t* __restrict__ num_groups, int32_t* __restrict__ error_flag,
+                                unsigned int* __restrict__ barrier) {
+  const TableView t = view_of(tab);
+  const int64_t gtid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t gthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t slice_lines = (tab.capacity / nparts) * tab.row_words * 8 / 128;  // 128-byte lines per table slice
+  const char* table_bytes = reinterpret_cast<const char*>(tab.rows);
+  auto prefetch_slice = [&](int p) {
+    const char* base = table_bytes + static_cast<int64_t>(p) * slice_lines * 128;
+    for (int64_t l = gtid; l < slice_lines; l += gthreads) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + l * 128));
+  };
+  unsigned int generation = 0;
+  int64_t fresh = 0;
+  prefetch_slice(0);
+  grid_barrier(barrier, gridDim.x, generation);
+  for (int p = 0; p < nparts; ++p) {
+    if (p + 1 < nparts) prefetch_slice(p + 1);
+    const int64_t r0 = part_start[p], r1 = part_start[p + 1];
+    for (int64_t i = r0 + gtid; i < r1; i += gthreads) {
+      const int64_t slot = find_or_insert(t, row_keys[i], fresh);
+      if (slot < 0) { atomicCAS(error_flag, 0, 100); continue; }
+      uint64_t* row = t.rows + slot * t.w;
+      for (int k = 0; k < args.n; ++k) apply_update(args.a[k], i, row, error_flag);
+    }
+    grid_barrier(barrier, gridDim.x, generation);
+  }
+  fresh = warp_sum(fresh);
+  if ((threadIdx.x & 31) == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
+}
+
 // Very small batches (merging a handful of partial-aggregate rows, e.g. one row per group and GPU
 // in front of a final aggregation): one warp walks the rows IN INPUT ORDER, lane k owning aggregate
 // k, with plain read-modify-writes — the reference's sequential accumulation
@@ -916,6 +966,38 @@ int vb2k_group_update(const vb2_group_table* t, const uint64_t* row_keys, const 
     group_update_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(*t, row_keys, row_valid, n, rest, num_groups, error_flag);
   }
   VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_group_update_partitioned(const vb2_group_table* t, const uint64_t* row_keys, const int64_t* part_start, int32_t nparts, int64_t n,
+                                  const vb2_agg_update* aggs, int32_t naggs, int64_t* num_groups, int32_t* error_flag, uint32_t* barrier_word,
+                                  void* stream) {
+  if (int rc = check_table(t, "group_update_partitioned: bad table")) return rc;
+  if (t->hash_mode != 1 || nparts < 1 || nparts > 256 || t->capacity < 65536 || (t->capacity % nparts) != 0)
+    return fail_msg(VB2_ERR_UNSUPPORTED, "group_update_partitioned: hash-mode table of at least 65536 rows expected");
+  if (naggs < 0 || naggs > kMaxAggs) return fail_msg(VB2_ERR_UNSUPPORTED, "group_update_partitioned: at most 16 aggregates per call");
+  if (n <= 0) return VB2_OK;
+  AggArgs a;
+  a.n = naggs;
+  for (int i = 0; i < naggs; ++i) {
+    if (aggs[i].acc_word < 1 || aggs[i].acc_word >= t->row_words || aggs[i].nonnull_word >= t->row_words)
+      return fail_msg(VB2_ERR_INVALID, "group_update_partitioned: accumulator word outside the row");
+    a.a[i] = aggs[i];
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static int blocks_per_sm = 0;
+  if (blocks_per_sm == 0) {
+    int b = 0;
+    VB2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, group_update_partitioned_kernel, 256, 0));
+    blocks_per_sm = b < 1 ? 1 : (b > 4 ? 4 : b);
+  }
+  const unsigned grid = static_cast<unsigned>(device_sm_count() * blocks_per_sm);
+  VB2_CUDA_OK(cudaMemsetAsync(barrier_word, 0, 4, st));
+  vb2_group_table tab = *t;
+  void* params[] = {&tab, &row_keys, &part_start, &nparts, &a, &num_groups, &error_flag, &barrier_word};
+  note_launch();
+  // cooperative launch: every block is resident, which the grid barrier relies on
+  VB2_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(group_update_partitioned_kernel), dim3(grid), dim3(256), params, 0, st));
   return VB2_OK;
 }
 

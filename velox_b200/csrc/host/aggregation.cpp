@@ -105,6 +105,7 @@ struct B200HashAggregation::Impl {
   size_t fusedWsBytes = 0;
   int fusedGroups = 0;
   int64_t fusedBatches = 0, genericBatches = 0, selectiveBatches = 0, partitionedBatches = 0;
+  DeviceBufferPtr partStartDev, barrierWord;  // set while a radix-partitioned batch is being applied
   bool selectiveDecided = false, selectiveUsable = true;
   double selectivity = 1.0;
   struct FusedTiming { cudaEvent_t begin = nullptr, end = nullptr; int64_t rows = 0; };
@@ -519,7 +520,9 @@ struct B200HashAggregation::Impl {
                                    static_cast<int32_t>(colsIn.size()), partKeys->as<uint64_t>(), partStart->as<int64_t>(), st()));
     ++genericBatches;
     ++partitionedBatches;
+    partStartDev = partStart;
     applyUpdates(in, n, partKeys, keyCols, keep, &permuted);
+    partStartDev = nullptr;
     return true;
   }
 
@@ -630,7 +633,11 @@ struct B200HashAggregation::Impl {
     for (size_t i = 0; i == 0 || i < ups.size(); i += 16) {
       // the first call inserts the groups; later slices of a long aggregate list find them again
       const int32_t cnt = static_cast<int32_t>(std::min<size_t>(16, ups.size() - i));
-      if (mode == Mode::kKeyed)
+      if (partStartDev && mode == Mode::kHash && capacity >= 65536) {
+        if (!barrierWord) barrierWord = allocDeviceZeroed(8, st());
+        kernelCheck(vb2k_group_update_partitioned(&t, rk, partStartDev->as<int64_t>(), 256, n, ups.data() + i, cnt, i == 0 ? numGroupsDev->as<int64_t>() : nullptr,
+                                                  errorFlag->as<int32_t>(), barrierWord->as<uint32_t>(), st()));
+      } else if (mode == Mode::kKeyed)
         kernelCheck(vb2k_group_update_keyed(&t, keyCols.data(), static_cast<int32_t>(keyCols.size()), n, ups.data() + i, cnt,
                                             i == 0 ? numGroupsDev->as<int64_t>() : nullptr, errorFlag->as<int32_t>(), st()));
       else

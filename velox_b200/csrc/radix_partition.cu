@@ -68,16 +68,27 @@ __global__ void __launch_bounds__(kRadixThreads) radix_hist_kernel(const __grid_
     if (regs[i]) atomicMax(&hll[i], regs[i]);
 }
 
-// One block: thread p walks the chunks of partition p. chunk_base[c][p] = rows of p in earlier chunks
-// (+ the start of partition p once the partition totals are known).
-__global__ void __launch_bounds__(kRadixParts) radix_offsets_kernel(const int32_t* __restrict__ chunk_hist, int64_t nchunks,
-                                                                    int64_t* __restrict__ chunk_base, int64_t* __restrict__ part_start) {
+// Exclusive scan of the chunk histograms per partition, in two levels so that no thread walks all
+// chunks alone: kOffsetSegs segments of chunks per partition are summed in parallel (A), one block
+// turns the (partition, segment) sums into starting offsets (B), every segment then scans its own
+// chunks from its start (C). chunk_base[c][p] = where chunk c's run of partition p begins.
+constexpr int kOffsetSegs = 64;
+__global__ void __launch_bounds__(kRadixParts) radix_offsets_a_kernel(const int32_t* __restrict__ chunk_hist, int64_t nchunks, int64_t* __restrict__ seg_sums) {
+  const int p = threadIdx.x, seg = blockIdx.x;
+  const int64_t per = (nchunks + kOffsetSegs - 1) / kOffsetSegs;
+  const int64_t c0 = seg * per, c1 = c0 + per < nchunks ? c0 + per : nchunks;
+  int64_t run = 0;
+  for (int64_t c = c0; c < c1; ++c) run += chunk_hist[c * kRadixParts + p];
+  seg_sums[seg * kRadixParts + p] = run;
+}
+__global__ void __launch_bounds__(kRadixParts) radix_offsets_b_kernel(int64_t* __restrict__ seg_sums, int64_t* __restrict__ part_start) {
   __shared__ int64_t totals[kRadixParts];
   const int p = threadIdx.x;
   int64_t run = 0;
-  for (int64_t c = 0; c < nchunks; ++c) {
-    chunk_base[c * kRadixParts + p] = run;
-    run += chunk_hist[c * kRadixParts + p];
+  for (int seg = 0; seg < kOffsetSegs; ++seg) {
+    const int64_t v = seg_sums[seg * kRadixParts + p];
+    seg_sums[seg * kRadixParts + p] = run;  // rows of p in earlier segments
+    run += v;
   }
   totals[p] = run;
   __syncthreads();
@@ -85,7 +96,18 @@ __global__ void __launch_bounds__(kRadixParts) radix_offsets_kernel(const int32_
   for (int q = 0; q < p; ++q) start += totals[q];
   part_start[p] = start;
   if (p == kRadixParts - 1) part_start[kRadixParts] = start + run;
-  for (int64_t c = 0; c < nchunks; ++c) chunk_base[c * kRadixParts + p] += start;
+  for (int seg = 0; seg < kOffsetSegs; ++seg) seg_sums[seg * kRadixParts + p] += start;
+}
+__global__ void __launch_bounds__(kRadixParts) radix_offsets_c_kernel(const int32_t* __restrict__ chunk_hist, int64_t nchunks, const int64_t* __restrict__ seg_sums,
+                                                                      int64_t* __restrict__ chunk_base) {
+  const int p = threadIdx.x, seg = blockIdx.x;
+  const int64_t per = (nchunks + kOffsetSegs - 1) / kOffsetSegs;
+  const int64_t c0 = seg * per, c1 = c0 + per < nchunks ? c0 + per : nchunks;
+  int64_t run = seg_sums[seg * kRadixParts + p];
+  for (int64_t c = c0; c < c1; ++c) {
+    chunk_base[c * kRadixParts + p] = run;
+    run += chunk_hist[c * kRadixParts + p];
+  }
 }
 
 struct RadixCols {
@@ -94,45 +116,30 @@ struct RadixCols {
   int32_t bytes[kRadixMaxCols];
   int n;
 };
+// Positions inside a chunk's run come from a shared-memory cursor per partition (one atomicAdd per
+// row): order inside a partition is irrelevant to the aggregation that follows.
 __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const __grid_constant__ RadixKey key, int64_t n, int64_t nchunks,
                                                                       const int64_t* __restrict__ chunk_base, uint64_t* __restrict__ out_keys,
                                                                       const __grid_constant__ RadixCols cols) {
-  __shared__ int64_t base[kRadixParts];
-  __shared__ int32_t warp_counts[kRadixThreads / kWarp][kRadixParts];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ unsigned long long cursor[kRadixParts];
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    base[threadIdx.x] = chunk_base[c * kRadixParts + threadIdx.x];
+    cursor[threadIdx.x] = static_cast<unsigned long long>(chunk_base[c * kRadixParts + threadIdx.x]);
     __syncthreads();
     const int64_t r0 = c * kRadixChunkRows;
+#pragma unroll 4
     for (int i0 = 0; i0 < kRadixChunkRows; i0 += kRadixThreads) {
       const int64_t r = r0 + i0 + threadIdx.x;
-      const bool live = r < n;
-      const uint64_t k = live ? radix_key(key, r) : 0;
-      const uint32_t id = live ? static_cast<uint32_t>(twang_mix64(k) >> 56) : 0xffffffffu;
-      const unsigned peers = __match_any_sync(0xffffffffu, id);
-      const int rank = __popc(peers & ((1u << lane) - 1));
-      for (int p = lane; p < kRadixParts; p += kWarp) warp_counts[warp][p] = 0;
-      __syncwarp();
-      if (live && rank == 0) warp_counts[warp][id] = __popc(peers);
-      __syncthreads();
-      if (live) {
-        int64_t pos = base[id];
-        for (int w = 0; w < warp; ++w) pos += warp_counts[w][id];
-        pos += rank;
+      if (r < n) {
+        const uint64_t k = radix_key(key, r);
+        const int64_t pos = static_cast<int64_t>(atomicAdd(&cursor[twang_mix64(k) >> 56], 1ull));
         out_keys[pos] = k;
         for (int q = 0; q < cols.n; ++q) {
           if (cols.bytes[q] == 8) reinterpret_cast<uint64_t*>(cols.out[q])[pos] = reinterpret_cast<const uint64_t*>(cols.in[q])[r];
           else reinterpret_cast<uint32_t*>(cols.out[q])[pos] = reinterpret_cast<const uint32_t*>(cols.in[q])[r];
         }
       }
-      __syncthreads();
-      {
-        int32_t s = 0;
-        for (int w = 0; w < kRadixThreads / kWarp; ++w) s += warp_counts[w][threadIdx.x];
-        base[threadIdx.x] += s;
-      }
-      __syncthreads();
     }
+    __syncthreads();
   }
 }
 
@@ -145,7 +152,7 @@ extern "C" {
 size_t vb2k_radix_workspace_bytes(int64_t rows) {
   const int64_t nchunks = (rows + kRadixChunkRows - 1) / kRadixChunkRows;
   // chunk histograms (int32) + chunk bases (int64) + partition starts (int64[257]) + HLL registers
-  return static_cast<size_t>(nchunks) * kRadixParts * 12 + (kRadixParts + 1) * 8 + (1 << kHllBits) * 4 + 256;
+  return static_cast<size_t>(nchunks) * kRadixParts * 12 + static_cast<size_t>(kOffsetSegs) * kRadixParts * 8 + (kRadixParts + 1) * 8 + (1 << kHllBits) * 4 + 512;
 }
 
 int32_t vb2k_radix_hll_registers(void) { return 1 << kHllBits; }
@@ -185,7 +192,10 @@ int vb2k_radix_scatter(const uint64_t* norm_keys, const void* key_values, int32_
     c.out[i] = cols_out[i];
     c.bytes[i] = col_bytes[i];
   }
-  radix_offsets_kernel<<<vb2::counted(1), kRadixParts, 0, st>>>(hist, nchunks, base, part_start_out);
+  int64_t* seg_sums = base + nchunks * kRadixParts;  // kOffsetSegs x 256 partial sums behind the chunk bases
+  radix_offsets_a_kernel<<<vb2::counted(kOffsetSegs), kRadixParts, 0, st>>>(hist, nchunks, seg_sums);
+  radix_offsets_b_kernel<<<vb2::counted(1), kRadixParts, 0, st>>>(seg_sums, part_start_out);
+  radix_offsets_c_kernel<<<vb2::counted(kOffsetSegs), kRadixParts, 0, st>>>(hist, nchunks, seg_sums, base);
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 6;
   radix_scatter_kernel<<<vb2::counted(static_cast<unsigned>(nchunks < cap ? nchunks : cap)), kRadixThreads, 0, st>>>(k, rows, nchunks, base, keys_out, c);
   VB2_CUDA_OK(cudaGetLastError());
