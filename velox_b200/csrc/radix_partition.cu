@@ -116,27 +116,71 @@ struct RadixCols {
   int32_t bytes[kRadixMaxCols];
   int n;
 };
-// Positions inside a chunk's run come from a shared-memory cursor per partition (one atomicAdd per
-// row): order inside a partition is irrelevant to the aggregation that follows.
+// One chunk per block iteration, staged through shared memory: the chunk's keys are counting-sorted
+// by partition inside the block (positions from shared-memory cursors), then written out by
+// consecutive threads — each partition's run of the chunk is contiguous in the output, so the stores
+// are full sectors (a direct scatter wrote 8 of every 32 bytes per sector and made DRAM read and
+// write every sector twice: 15.4 GB of traffic for 8 GB of data, profiles/). Payload columns follow
+// through the staged source row numbers (reads stay inside the chunk: L1 / L2 hits).
 __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const __grid_constant__ RadixKey key, int64_t n, int64_t nchunks,
                                                                       const int64_t* __restrict__ chunk_base, uint64_t* __restrict__ out_keys,
                                                                       const __grid_constant__ RadixCols cols) {
-  __shared__ unsigned long long cursor[kRadixParts];
+  __shared__ uint8_t rpid[kRadixChunkRows];    // partition of every row of the chunk
+  __shared__ uint16_t ssrc[kRadixChunkRows];   // rows of the chunk in partition order
+  __shared__ int32_t lcount[kRadixParts], lstart[kRadixParts], lcursor[kRadixParts];
+  __shared__ long long gbase[kRadixParts];
+  __shared__ int wtot[kRadixThreads / kWarp];
+  constexpr int kPer = kRadixChunkRows / kRadixThreads;
   for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-    cursor[threadIdx.x] = static_cast<unsigned long long>(chunk_base[c * kRadixParts + threadIdx.x]);
-    __syncthreads();
     const int64_t r0 = c * kRadixChunkRows;
-#pragma unroll 4
-    for (int i0 = 0; i0 < kRadixChunkRows; i0 += kRadixThreads) {
-      const int64_t r = r0 + i0 + threadIdx.x;
+    gbase[threadIdx.x] = chunk_base[c * kRadixParts + threadIdx.x];
+    lcount[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < kPer; ++j) {
+      const int i = j * kRadixThreads + threadIdx.x;
+      const int64_t r = r0 + i;
       if (r < n) {
-        const uint64_t k = radix_key(key, r);
-        const int64_t pos = static_cast<int64_t>(atomicAdd(&cursor[twang_mix64(k) >> 56], 1ull));
-        out_keys[pos] = k;
-        for (int q = 0; q < cols.n; ++q) {
-          if (cols.bytes[q] == 8) reinterpret_cast<uint64_t*>(cols.out[q])[pos] = reinterpret_cast<const uint64_t*>(cols.in[q])[r];
-          else reinterpret_cast<uint32_t*>(cols.out[q])[pos] = reinterpret_cast<const uint32_t*>(cols.in[q])[r];
-        }
+        const uint8_t p = static_cast<uint8_t>(twang_mix64(radix_key(key, r)) >> 56);
+        rpid[i] = p;
+        atomicAdd(&lcount[p], 1);
+      }
+    }
+    __syncthreads();
+    {
+      // exclusive prefix of the 256 counts: warp scans + warp totals
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const int v = lcount[threadIdx.x];
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) wtot[warp] = incl;
+      __syncthreads();
+      int before = 0;
+      for (int w = 0; w < warp; ++w) before += wtot[w];
+      lstart[threadIdx.x] = before + incl - v;
+      lcursor[threadIdx.x] = before + incl - v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < kPer; ++j) {
+      const int i = j * kRadixThreads + threadIdx.x;
+      if (r0 + i < n) ssrc[atomicAdd(&lcursor[rpid[i]], 1)] = static_cast<uint16_t>(i);
+    }
+    __syncthreads();
+    const int live = n - r0 < kRadixChunkRows ? static_cast<int>(n - r0) : kRadixChunkRows;
+    for (int j = threadIdx.x; j < live; j += kRadixThreads) {
+      const int i = ssrc[j];
+      const int p = rpid[i];
+      const int64_t pos = gbase[p] + (j - lstart[p]);
+      const int64_t r = r0 + i;
+      out_keys[pos] = radix_key(key, r);  // second read of the chunk's keys: L1 / L2 resident
+      for (int q = 0; q < cols.n; ++q) {
+        if (cols.bytes[q] == 8) reinterpret_cast<uint64_t*>(cols.out[q])[pos] = reinterpret_cast<const uint64_t*>(cols.in[q])[r];
+        else reinterpret_cast<uint32_t*>(cols.out[q])[pos] = reinterpret_cast<const uint32_t*>(cols.in[q])[r];
       }
     }
     __syncthreads();
