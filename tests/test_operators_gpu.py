@@ -610,7 +610,7 @@ def test_aggregation_radix_partitioned_batches():
     keys = pool_keys[rng.integers(0, 90_000, n)]
     rv = row_vector(["k", "v", "w", "x"], [flat_vector(BIGINT, keys), flat_vector(BIGINT, (np.arange(n) % 1000)), flat_vector(INTEGER, rng.integers(-50, 50, n).astype(np.int32)),
                                          flat_vector(DOUBLE, rng.standard_normal(n))])
-    part = {"b200.agg_partition_min_rows": "1000"}
+    part = {"b200.agg_radix_partition": "true", "b200.agg_partition_min_rows": "1000"}
     plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(["k"], ["sum(v)", "count(0)", "min(w)", "max(x)", "avg(x)"]).planNode()
     (st,) = check_plan(plan, [rv], configs=(part,), rel_tol=1e-11, oracle_batch_rows=100_000)
     assert stat(st, "b200.partitionedBatches") == 1 and stat(st, "b200.aggMode") == 2

@@ -421,30 +421,11 @@ group_update_partitioned_kernel(const __grid_constant__ vb2_group_table tab, con
   for (int p = 0; p < nparts; ++p) {
     if (p + 1 < nparts) prefetch_slice(p + 1);
     const int64_t r0 = part_start[p], r1 = part_start[p + 1];
-    // four rows per thread in flight: their keys, then their home slots, are loaded together before any
-    // of the (dependent) claim / compare steps — the pass is latency-, not bandwidth-bound
-    constexpr int kU = 4;
-    for (int64_t i0 = r0 + gtid; i0 < r1; i0 += kU * gthreads) {
-      uint64_t key[kU], home[kU];
-      bool ok[kU];
-#pragma unroll
-      for (int j = 0; j < kU; ++j) {
-        const int64_t i = i0 + j * gthreads;
-        ok[j] = i < r1;
-        key[j] = ok[j] ? row_keys[i] : 0;
-      }
-#pragma unroll
-      for (int j = 0; j < kU; ++j) home[j] = ok[j] ? *reinterpret_cast<volatile uint64_t*>(t.rows + ((twang_mix64(key[j]) >> t.shift) & t.mask) * t.w) : 0;
-#pragma unroll
-      for (int j = 0; j < kU; ++j) {
-        if (!ok[j]) continue;
-        (void)home[j];  // the line is in flight / in L1-L2 now; find_or_insert re-reads it
-        const int64_t i = i0 + j * gthreads;
-        const int64_t slot = find_or_insert(t, key[j], fresh);
-        if (slot < 0) { atomicCAS(error_flag, 0, 100); continue; }
-        uint64_t* row = t.rows + slot * t.w;
-        for (int k = 0; k < args.n; ++k) apply_update(args.a[k], i, row, error_flag);
-      }
+    for (int64_t i = r0 + gtid; i < r1; i += gthreads) {
+      const int64_t slot = find_or_insert(t, row_keys[i], fresh);
+      if (slot < 0) { atomicCAS(error_flag, 0, 100); continue; }
+      uint64_t* row = t.rows + slot * t.w;
+      for (int k = 0; k < args.n; ++k) apply_update(args.a[k], i, row, error_flag);
     }
     grid_barrier(barrier, gridDim.x, generation);
   }

@@ -447,7 +447,10 @@ struct B200HashAggregation::Impl {
     const int64_t n = in->size();
     const auto& cfg = self->driverCtx()->queryConfig();
     if (keys.empty() || mode == Mode::kKeyed || n < cfg.get<int64_t>("b200.agg_partition_min_rows", 1 << 23)) return false;
-    if (!cfg.get<bool>("b200.agg_radix_partition", true)) return false;
+    // Off by default: measured on B200 (1 B rows / 100 M keys, profiles/r02_config5_*.json) the partition
+    // passes cost what the L2-resident update saves (31.7 ms vs 31 ms per 250 M-row batch) — the update
+    // stays latency-bound behind its grid barriers. Kept, tested, as the basis for the shared-memory-slice variant.
+    if (!cfg.get<bool>("b200.agg_radix_partition", false)) return false;
     // aggregate inputs: flat, NULL-free, unmasked, 4 or 8 bytes wide, at most four distinct columns
     const auto& aggs = node->aggregates();
     std::vector<int32_t> payload;
