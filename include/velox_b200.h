@@ -63,6 +63,12 @@ int32_t vb2_result_type(vb2_task* task, int32_t col);
 void vb2_result_copy(vb2_task* task, int32_t col, void* values, uint8_t* nulls);
 int64_t vb2_result_str_bytes(vb2_task* task, int32_t col);
 void vb2_result_copy_str(vb2_task* task, int32_t col, int32_t* offsets, char* chars, uint8_t* nulls);
+/* Config "b200.result_on_device=true": no B200ToHost is planted in front of the sink; the result
+ * batches stay in HBM (vb2_result_rows still counts them, vb2_result_copy* return nothing) and their
+ * buffers are lent here: cols[c] receives the device-side vb2_column of batch `batch`; returns its
+ * row count. Valid until the task is freed. */
+int32_t vb2_result_device_batches(vb2_task* task);
+int64_t vb2_result_device_columns(vb2_task* task, int32_t batch, vb2_column* cols, int32_t ncols);
 /* The whole result in two calls (bindings whose per-call cost matters): vb2_result_layout fills
  * layout[c * 4 ..] = {type, value bytes, offset bytes, char bytes} for every column and returns the
  * blob size; vb2_result_copy_all writes, per column, values | int32 offsets (VARCHAR) | chars

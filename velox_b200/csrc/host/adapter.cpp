@@ -96,8 +96,12 @@ bool adaptDriver(const exec::DriverFactory& factory, exec::Driver& driver) {
       out.push_back(std::make_unique<B200Exchange>(id, ctx, *ex));
       replacedAny = true;
     } else if (dynamic_cast<exec::CallbackSink*>(op)) {
-      RowTypePtr type = out.empty() ? nullptr : out.back()->outputType();
-      out.push_back(std::make_unique<B200ToHost>(id, ctx, type));
+      // b200.result_on_device: the consumer takes device-resident batches (another GPU stage, or the C
+      // ABI's direct copy-out): no B200ToHost in front of the sink
+      if (!config.get<bool>("b200.result_on_device", false)) {
+        RowTypePtr type = out.empty() ? nullptr : out.back()->outputType();
+        out.push_back(std::make_unique<B200ToHost>(id, ctx, type));
+      }
       out.push_back(std::move(ops[i]));
     } else {
       out.push_back(std::move(ops[i]));

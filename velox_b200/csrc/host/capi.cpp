@@ -29,6 +29,7 @@ struct vb2_task {
   core::PlanNodePtr plan;
   memory::MemoryPool pool{"capi"};
   std::vector<RowVectorPtr> results;
+  std::vector<B200VectorPtr> deviceResults;  // b200.result_on_device: result batches left in HBM
   // results concatenated per column for copy-out
   struct OutCol {
     int32_t type;
@@ -326,6 +327,22 @@ int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen) {
     task->h2dBytes = velox_b200::threadUploadedBytes() - uploadedBefore;
     task->out.clear();
     task->rows = 0;
+    task->deviceResults.clear();
+    bool allDevice = !task->results.empty();
+    for (auto& b : task->results) allDevice = allDevice && std::dynamic_pointer_cast<B200Vector>(b) != nullptr;
+    if (allDevice) {
+      // b200.result_on_device: batches stay in HBM; vb2_result_device_columns lends their buffers
+      for (auto& b : task->results) {
+        auto dv = std::dynamic_pointer_cast<B200Vector>(b);
+        VB2_CU(cudaStreamSynchronize(dv->stream()));
+        task->rows += dv->size();
+        task->deviceResults.push_back(dv);
+      }
+      const auto& type = task->plan->outputType();
+      task->out.resize(type->size());
+      for (uint32_t c = 0; c < type->size(); ++c) { task->out[c].type = veloxTypeToVb2(type->childAt(c)); task->out[c].offsets.push_back(0); }
+      task->results.clear();
+    }
     for (auto& b : task->results) appendResult(*task, b);
     if (task->out.empty()) {
       const auto& type = task->plan->outputType();
@@ -464,6 +481,14 @@ void vb2_result_copy_all(vb2_task* task, void* blob) {
     else std::memset(p, 0, static_cast<size_t>(task->rows));
     p += pad(static_cast<size_t>(task->rows));
   }
+}
+
+int32_t vb2_result_device_batches(vb2_task* task) { return task ? static_cast<int32_t>(task->deviceResults.size()) : 0; }
+int64_t vb2_result_device_columns(vb2_task* task, int32_t batch, vb2_column* cols, int32_t ncols) {
+  if (!task || batch < 0 || batch >= static_cast<int32_t>(task->deviceResults.size())) return -1;
+  const auto& dv = task->deviceResults[batch];
+  for (int32_t c = 0; c < ncols && c < static_cast<int32_t>(dv->columns().size()); ++c) cols[c] = dv->column(c)->desc;
+  return dv->size();
 }
 
 const char* vb2_task_stats(vb2_task* task) { return task->stats.c_str(); }

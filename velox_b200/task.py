@@ -110,6 +110,33 @@ class Task:
         if rc:
             _raise(rc, err)
 
+    def device_result(self):
+        """With config {"b200.result_on_device": "true"}: the result batches as lists of zero-copy torch
+        views over the library's device buffers (flat fixed-width columns), valid until close()."""
+        import torch
+        from .vector import BIGINT, DOUBLE, INTEGER
+        L = self.L
+        L.vb2_result_device_columns.restype = C.c_int64
+        L.vb2_result_device_columns.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CColumn), C.c_int32]
+        ncols = L.vb2_result_cols(self.h)
+        typestr = {BIGINT: "<i8", DOUBLE: "<f8", INTEGER: "<i4"}
+
+        class _View:
+            def __init__(self, ptr, n, ts):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": ts, "data": (ptr, False), "version": 2}
+
+        out = []
+        for b in range(L.vb2_result_device_batches(self.h)):
+            arr = (CColumn * ncols)()
+            n = L.vb2_result_device_columns(self.h, b, arr, ncols)
+            cols = []
+            for c in range(ncols):
+                if arr[c].encoding != FLAT or arr[c].type not in typestr:
+                    raise VeloxRuntimeError("device_result(): flat BIGINT / DOUBLE / INTEGER columns only")
+                cols.append(torch.as_tensor(_View(arr[c].values, n, typestr[arr[c].type]), device="cuda") if n else torch.empty(0, device="cuda"))
+            out.append(cols)
+        return out
+
     def stats(self) -> Dict[str, int]:
         out = {}
         for line in self.L.vb2_task_stats(self.h).decode().splitlines():
@@ -198,7 +225,16 @@ def _run(self) -> RowVector:
     return _result(self.L, self.h, names)
 
 
+def _run_only(self) -> None:
+    """vb2_task_run without fetching result columns (device-resident results: see device_result())."""
+    err = C.create_string_buffer(2048)
+    rc = self.L.vb2_task_run(self.h, err, 2048)
+    if rc:
+        _raise(rc, err)
+
+
 Task.run = _run
+Task._run_only = _run_only
 
 
 def run_plan(plan, sources: Sequence, config: Optional[Dict[str, str]] = None, batch_rows: Optional[int] = None):
