@@ -318,6 +318,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--serial-queries", action="store_true", help="run Q14 after Q1 instead of submitting both tasks at once")
     ap.add_argument("--cpu-sample-rows", type=float, default=60_000_000)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -364,21 +365,51 @@ def main():
 
     state = {"q1_kernel_ns": 0, "q1_kernel_rows": 0, "q1_runs": 0}
 
-    if world == 1:
-        def step(record=False):
-            out1, s1 = run_task(plan1, [(0, c1)])
-            if record:
-                state["q1_kernel_ns"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanNanos"))
-                state["q1_kernel_rows"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanRows"))
-                state["q1_runs"] += 1
-                state["stats1"] = s1
-            out14, s14 = run_task(plan14, [(0, c14), (1, cp)])
-            if record:
-                state["stats14"] = s14
-            return out1, out14
-    else:
+    # A step submits the two queries as two concurrent tasks (one host thread each, each with its own
+    # streams and — on N > 1 — its own communicator): Q14's build side, exchanges and host-side setup
+    # overlap Q1's scan instead of queueing behind it. --serial-queries runs them one after the other.
+    comm14 = None
+    if world > 1:
+        from velox_b200.comm import Comm
+        comm14 = Comm()  # exchanges of concurrent tasks must not share epochs
         dplan1, dplan14 = plans_distributed(rv1s, rv14s, pts)
-        step = multi_gpu_step(comm, dplan1, dplan14, c1, c14, cp, rows, state)
+        pl1, pl14 = dplan1, dplan14
+    else:
+        pl1, pl14 = plan1, plan14
+
+    import queue
+    jobs, done = queue.Queue(), queue.Queue()
+
+    def q14_worker():
+        torch.cuda.set_device(local_rank)
+        while True:
+            job = jobs.get()
+            if job is None:
+                return
+            try:
+                done.put(run_task(pl14, [(0, c14), (1, cp)], comm=comm14))
+            except Exception as ex:  # surfaced by the submitting thread
+                done.put(ex)
+
+    worker = threading.Thread(target=q14_worker, daemon=True)
+    worker.start()
+
+    def step(record=False):
+        if not args.serial_queries:
+            jobs.put(1)
+        out1, s1 = run_task(pl1, [(0, c1)], comm=comm)
+        if args.serial_queries:
+            jobs.put(1)
+        r14 = done.get()
+        if isinstance(r14, Exception):
+            raise r14
+        out14, s14 = r14
+        if record:
+            state["q1_kernel_ns"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanNanos"))
+            state["q1_kernel_rows"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanRows"))
+            state["q1_runs"] += 1
+            state["stats1"], state["stats14"] = s1, s14
+        return out1, out14
 
     def barrier():
         torch.cuda.synchronize()
@@ -460,9 +491,10 @@ def main():
         m = float(mm.item())
         breakdown[name] = {"kernel_level_ms": m, "rows_per_s_kernel_level": rows_total / (m / 1e3),
                            "algorithmic_GBps_per_gpu": rows * bprs[name] / (m / 1e3) / 1e9, "frac_of_hbm_peak": rows * bprs[name] / (m / 1e3) / 1e9 / peak}
-    if world == 1:
-        breakdown["q1"]["operator_level_ms"] = timed_wall(lambda: run_task(plan1, [(0, c1)]))
-        breakdown["q14"]["operator_level_ms"] = timed_wall(lambda: run_task(plan14, [(0, c14), (1, cp)]))
+    # each query alone through the operator API (on N > 1 every rank takes part: the exchanges are collective)
+    breakdown["q1"]["operator_level_ms"] = timed_wall(lambda: run_task(pl1, [(0, c1)], comm=comm))
+    breakdown["q14"]["operator_level_ms"] = timed_wall(lambda: run_task(pl14, [(0, c14), (1, cp)], comm=comm14))
+    jobs.put(None)
     sampler.stop_flag.set()
     sampler.join()
 
@@ -481,14 +513,16 @@ def main():
         "config": {"workload": f"TPC-H Q1 + Q14 over SF{args.sf:g} in-HBM lineitem ({rows_total} rows) and part ({nparts} rows)",
                    "path": "operator-level C ABI: vb2_task_create / add_input(VB2_DEVICE) / run / result per query (Task -> Driver -> B200 operators); "
                            "the timed step contains plan parsing, operator setup, every kernel, and the result rows on the host",
+                   "queries_per_step": "Q1 and Q14 submitted as two concurrent tasks" if not args.serial_queries else "Q1, then Q14",
                    "rows_per_gpu": rows, "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}; Q14 hash-partitioned, NCCL all-to-all",
                    "l2": "inputs (26-31 GB per pass) far exceed the 126 MB L2; no flush needed", "value_counts": "2 x lineitem rows per step"},
         "roofline": roofline, "queries": breakdown, "results": results, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
     if comm is not None:
+        ex1, ex14 = comm.exchanges(), comm14.exchanges()
         line["exchange"] = {"transport": "peer memory over NVLink (CUDA IPC heaps, exchange_p2p.cu)" if comm.peer_memory else "NCCL grouped send/recv",
-                            "exchanges": comm.exchanges()}
+                            "exchanges": {k: ex1[k] + ex14[k] for k in ex1}}
     if "stats1" in state:
         line["operator_wall_ms"] = {q: {k: round(v / 1e6, 3) for k, v in state[s].items() if k.endswith("WallNanos") and v > 2e4}
                                     for q, s in (("q1", "stats1"), ("q14", "stats14")) if s in state}
@@ -522,23 +556,6 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def multi_gpu_step(comm, dplan1, dplan14, c1, c14, cp, rows, state):
-    """One step on N GPUs: every rank runs the same multi-fragment plans over its row shard; the
-    B200PartitionedOutput / B200Exchange operators move rows between the ranks (rank 0 holds the answer)."""
-    def step(record=False):
-        out1, s1 = run_task(dplan1, [(0, c1)], comm=comm)
-        if record:
-            state["q1_kernel_ns"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanNanos"))
-            state["q1_kernel_rows"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanRows"))
-            state["q1_runs"] += 1
-            state["stats1"] = s1
-        out14, s14 = run_task(dplan14, [(0, c14), (1, cp)], comm=comm)
-        if record:
-            state["stats14"] = s14
-        return out1, out14
-    return step
 
 
 def e2e(args, li, part_all, rows, nparts, world, rank, rows_total):
