@@ -377,38 +377,32 @@ def main():
     else:
         pl1, pl14 = plan1, plan14
 
-    import queue
-    jobs, done = queue.Queue(), queue.Queue()
+    from velox_b200.task import Task, run_tasks
 
-    def q14_worker():
-        torch.cuda.set_device(local_rank)
-        while True:
-            job = jobs.get()
-            if job is None:
-                return
-            try:
-                done.put(run_task(pl14, [(0, c14), (1, cp)], comm=comm14))
-            except Exception as ex:  # surfaced by the submitting thread
-                done.put(ex)
-
-    worker = threading.Thread(target=q14_worker, daemon=True)
-    worker.start()
+    def make(plan, inputs, c):
+        t = Task(plan)
+        if c is not None:
+            t.set_comm(c)
+        for sid, cols in inputs:
+            t.add_input(sid, cols)
+        return t
 
     def step(record=False):
-        if not args.serial_queries:
-            jobs.put(1)
-        out1, s1 = run_task(pl1, [(0, c1)], comm=comm)
-        if args.serial_queries:
-            jobs.put(1)
-        r14 = done.get()
-        if isinstance(r14, Exception):
-            raise r14
-        out14, s14 = r14
-        if record:
-            state["q1_kernel_ns"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanNanos"))
-            state["q1_kernel_rows"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanRows"))
-            state["q1_runs"] += 1
-            state["stats1"], state["stats14"] = s1, s14
+        t1, t14 = make(pl1, [(0, c1)], comm), make(pl14, [(0, c14), (1, cp)], comm14)
+        try:
+            if args.serial_queries:
+                out1, out14 = t1.run(), t14.run()
+            else:
+                out1, out14 = run_tasks([t1, t14])  # vb2_tasks_run: both tasks at once, one library thread each
+            if record:
+                s1, s14 = t1.stats(), t14.stats()
+                state["q1_kernel_ns"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanNanos"))
+                state["q1_kernel_rows"] += sum(v for k, v in s1.items() if k.endswith("b200.fusedScanRows"))
+                state["q1_runs"] += 1
+                state["stats1"], state["stats14"] = s1, s14
+        finally:
+            t1.close()
+            t14.close()
         return out1, out14
 
     def barrier():
@@ -494,7 +488,6 @@ def main():
     # each query alone through the operator API (on N > 1 every rank takes part: the exchanges are collective)
     breakdown["q1"]["operator_level_ms"] = timed_wall(lambda: run_task(pl1, [(0, c1)], comm=comm))
     breakdown["q14"]["operator_level_ms"] = timed_wall(lambda: run_task(pl14, [(0, c14), (1, cp)], comm=comm14))
-    jobs.put(None)
     sampler.stop_flag.set()
     sampler.join()
 

@@ -38,6 +38,11 @@ int32_t vb2_task_add_input(vb2_task* task, int32_t source_id, const vb2_column* 
 /* Runs the task to completion (Task::start + drivers; serial execution mode). */
 int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen);
 
+/* Runs several prepared tasks concurrently (one host thread each) and returns when all have finished:
+ * the first non-zero status, with that task's message in err. Tasks whose plans exchange rows must
+ * use different communicators. */
+int32_t vb2_tasks_run(vb2_task* const* tasks, int32_t ntasks, char* err, int32_t errlen);
+
 /* Scan-side device residency for host tables that several tasks read (the
  * Values / scan-side step in front of the path): while a cache is attached to a task, host buffers
  * it uploads are remembered by (address, bytes); a later task attached to the same cache reuses the

@@ -3,6 +3,7 @@
 #include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <tuple>
 #include <execinfo.h>
 #include <signal.h>
@@ -355,6 +356,33 @@ int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen) {
     task->stats = os.str();
     task->results.clear();
   });
+}
+
+// Runs several prepared tasks at once, one host thread each (the reference runs the drivers of
+// concurrent tasks on its executor's threads, velox/exec/Task.cpp Task::start): independent queries
+// overlap their host-side setup, build sides and exchanges with each other's scans. Returns the first
+// non-zero status; err receives that task's message.
+int32_t vb2_tasks_run(vb2_task* const* tasks, int32_t ntasks, char* err, int32_t errlen) {
+  if (ntasks <= 0) return VB2_OK;
+  if (ntasks == 1) return vb2_task_run(tasks[0], err, errlen);
+  int device = 0;
+  cudaGetDevice(&device);
+  std::vector<int32_t> rc(ntasks, VB2_OK);
+  std::vector<std::string> msgs(ntasks, std::string(1024, '\0'));
+  std::vector<std::thread> threads;
+  for (int32_t i = 1; i < ntasks; ++i)
+    threads.emplace_back([&, i] {
+      cudaSetDevice(device);
+      rc[i] = vb2_task_run(tasks[i], msgs[i].data(), 1024);
+    });
+  rc[0] = vb2_task_run(tasks[0], msgs[0].data(), 1024);
+  for (auto& t : threads) t.join();
+  for (int32_t i = 0; i < ntasks; ++i)
+    if (rc[i] != VB2_OK) {
+      setErr(err, errlen, msgs[i].c_str());
+      return rc[i];
+    }
+  return VB2_OK;
 }
 
 // Diagnostic (no GPU needed): compiles the expression programs of every Filter / Project node of a

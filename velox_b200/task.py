@@ -237,6 +237,19 @@ Task.run = _run
 Task._run_only = _run_only
 
 
+def run_tasks(tasks: Sequence["Task"]):
+    """vb2_tasks_run: the prepared tasks run concurrently, one host thread each inside the library.
+    Returns their result RowVectors."""
+    L = tasks[0].L
+    L.vb2_tasks_run.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_char_p, C.c_int32]
+    arr = (C.c_void_p * len(tasks))(*[t.h for t in tasks])
+    err = C.create_string_buffer(2048)
+    rc = L.vb2_tasks_run(arr, len(tasks), err, 2048)
+    if rc:
+        _raise(rc, err)
+    return [_result(L, t.h, None if isinstance(t.plan, str) else t.plan.names) for t in tasks]
+
+
 def run_plan(plan, sources: Sequence, config: Optional[Dict[str, str]] = None, batch_rows: Optional[int] = None):
     """Runs `plan` over sources[i] (RowVector per source id; optionally split into batches of
     batch_rows). Returns (result RowVector, stats)."""
