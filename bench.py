@@ -318,7 +318,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--serial-queries", action="store_true", help="run Q14 after Q1 instead of submitting both tasks at once")
+    ap.add_argument("--concurrent-queries", action="store_true",
+                    help="submit Q1 and Q14 as two concurrent tasks (vb2_tasks_run) instead of one after the other; measured: no gain (5.66 vs 5.43 ms at N=2)")
     ap.add_argument("--cpu-sample-rows", type=float, default=60_000_000)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -390,7 +391,7 @@ def main():
     def step(record=False):
         t1, t14 = make(pl1, [(0, c1)], comm), make(pl14, [(0, c14), (1, cp)], comm14)
         try:
-            if args.serial_queries:
+            if (not args.concurrent_queries):
                 out1, out14 = t1.run(), t14.run()
             else:
                 out1, out14 = run_tasks([t1, t14])  # vb2_tasks_run: both tasks at once, one library thread each
@@ -506,7 +507,7 @@ def main():
         "config": {"workload": f"TPC-H Q1 + Q14 over SF{args.sf:g} in-HBM lineitem ({rows_total} rows) and part ({nparts} rows)",
                    "path": "operator-level C ABI: vb2_task_create / add_input(VB2_DEVICE) / run / result per query (Task -> Driver -> B200 operators); "
                            "the timed step contains plan parsing, operator setup, every kernel, and the result rows on the host",
-                   "queries_per_step": "Q1 and Q14 submitted as two concurrent tasks" if not args.serial_queries else "Q1, then Q14",
+                   "queries_per_step": "Q1 and Q14 submitted as two concurrent tasks" if not (not args.concurrent_queries) else "Q1, then Q14",
                    "rows_per_gpu": rows, "parallelism": "1 GPU" if world == 1 else f"row-sharded x{world}; Q14 hash-partitioned, NCCL all-to-all",
                    "l2": "inputs (26-31 GB per pass) far exceed the 126 MB L2; no flush needed", "value_counts": "2 x lineitem rows per step"},
         "roofline": roofline, "queries": breakdown, "results": results, "gpu_launches": int(launches),

@@ -73,6 +73,10 @@ int vb2k_partition_ids(const uint64_t* hashes, int64_t rows, int32_t num_partiti
  * (stable within a partition). All outputs device memory: counts int64[P], row_order int32[rows]. */
 int vb2k_partition_scatter_order(const uint32_t* ids, int64_t rows, int32_t num_partitions, int64_t* counts,
                                  int32_t* row_order, void* stream);
+/* Same for ONE flat NULL-free BIGINT / INTEGER key column, with hash and partition id computed on the
+ * fly (identical to vb2k_hash_columns + vb2k_partition_ids on that column): no hash / id arrays. */
+int vb2k_partition_order_key(const void* key_values, int32_t key_is64, int64_t rows, int32_t num_partitions, int64_t* counts, int32_t* row_order,
+                             void* stream);
 /* Sync-free variant for shuffles whose sizes are planned ahead (from statistics of an earlier run
  * of the same plan): rows of a non-null BIGINT key column and up to 4 fixed-width payload columns
  * go straight into fixed-capacity per-destination segments — row r to partition

@@ -3,6 +3,8 @@
 Mirrors the plans of velox/exec/tests/utils/TpchQueryBuilder.cpp (Q1 :203-256, Q6 :756-788,
 Q14 :1639-1702). Counts are compared bit-exactly, SUM(double) within relative 1e-12 (the kernel
 sums in a fixed tree order, the reference sequentially in input order)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -373,3 +375,28 @@ def test_partition_segments_match_oracle_partitioning(n):
             flag.zero_()
             partition_segments(tk, [t8], n, None, parts, int(counts.max()) - 1, flag)
             assert int(flag[0].item()) == 1
+
+
+def test_q1_q6_q14_oracle_parity_at_24m_rows():
+    """Oracle-vs-GPU at a size where every TMA stage of every resident block is recycled hundreds of
+    times and the persistent grid wraps (24 M rows): Q1 / Q6 / Q14 through the operator API, fused and
+    late-materialisation strategies, against the multi-threaded CPU oracle on the same rows."""
+    import bench
+    from oracle import pyoracle
+    from velox_b200 import tpch
+    from velox_b200.task import run_plan
+    n, nparts = 24_000_000, 400_000
+    li = tpch.gen_lineitem(n, nparts, seed=123, device="cpu")
+    part = tpch.gen_part(nparts, seed=5, device="cpu")
+    rv1, rv14, pt = bench.host_tables(li, part, n)
+    p1, p14 = bench.plans(rv1, rv14, pt)
+    threads = min(32, os.cpu_count() or 1)
+    w1 = pyoracle.run_plan(p1, [rv1], threads=threads, batch_rows=100_000)
+    w14 = pyoracle.run_plan(p14, [rv14, pt], threads=threads, batch_rows=100_000)
+    for cfg in ({"b200.late_materialization": "false"}, {}):
+        g1, s1 = run_plan(p1, [rv1], config=cfg)
+        g14, s14 = run_plan(p14, [rv14, pt], config=cfg)
+        par = bench.parity(g1, g14, w1, w14)
+        assert par["exact_columns_ok"] and par["fp_max_rel_err"] <= 1e-11, par
+        assert sum(v for k, v in s1.items() if k.endswith("b200.fusedBatches")) == 1
+    assert sum(v for k, v in s14.items() if k.endswith("b200.selectiveBatches")) == 1

@@ -64,14 +64,28 @@ constexpr int kPartThreads = 256;
 constexpr int kPartRowsPerBlock = 4096;
 constexpr int kMaxParts = 64;
 
-__global__ void part_hist_kernel(const uint32_t* __restrict__ ids, int64_t rows, int parts, int32_t* __restrict__ block_hist) {
+// Partition id of row r: precomputed (ids), or computed on the fly from ONE flat NULL-free integer key
+// column exactly as vb2k_hash_columns + vb2k_partition_ids would (folly::hasher of the value, % parts).
+struct PartSrc {
+  const uint32_t* ids;
+  const void* key;
+  int32_t is64;
+};
+__device__ __forceinline__ uint32_t part_id(const PartSrc& s, int64_t r, uint32_t parts) {
+  if (s.ids) return s.ids[r];
+  const uint64_t h = s.is64 ? twang_mix64(static_cast<uint64_t>(reinterpret_cast<const int64_t*>(s.key)[r]))
+                            : static_cast<uint64_t>(jenkins_rev_mix32(static_cast<uint32_t>(reinterpret_cast<const int32_t*>(s.key)[r])));
+  return static_cast<uint32_t>(h % parts);
+}
+
+__global__ void part_hist_kernel(const __grid_constant__ PartSrc ids, int64_t rows, int parts, int32_t* __restrict__ block_hist) {
   __shared__ int32_t h[kMaxParts];
   for (int p = threadIdx.x; p < parts; p += blockDim.x) h[p] = 0;
   __syncthreads();
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * kPartRowsPerBlock;
   for (int i = threadIdx.x; i < kPartRowsPerBlock; i += blockDim.x) {
     const int64_t r = r0 + i;
-    if (r < rows) atomicAdd(&h[ids[r]], 1);
+    if (r < rows) atomicAdd(&h[part_id(ids, r, parts)], 1);
   }
   __syncthreads();
   for (int p = threadIdx.x; p < parts; p += blockDim.x) block_hist[static_cast<int64_t>(blockIdx.x) * parts + p] = h[p];
@@ -101,7 +115,7 @@ __global__ void part_offsets_kernel(int32_t* __restrict__ block_hist, int64_t nb
   }
 }
 
-__global__ void part_scatter_kernel(const uint32_t* __restrict__ ids, int64_t rows, int parts, const int64_t* __restrict__ block_base,
+__global__ void part_scatter_kernel(const __grid_constant__ PartSrc ids, int64_t rows, int parts, const int64_t* __restrict__ block_base,
                                     int32_t* __restrict__ order) {
   // Stable within a partition: each warp ranks its rows with ballots, warps proceed in order.
   __shared__ int64_t base[kMaxParts];
@@ -113,7 +127,7 @@ __global__ void part_scatter_kernel(const uint32_t* __restrict__ ids, int64_t ro
   for (int i0 = 0; i0 < kPartRowsPerBlock; i0 += kPartThreads) {
     const int64_t r = r0 + i0 + threadIdx.x;
     const bool live = r < rows;
-    const uint32_t id = live ? ids[r] : 0xffffffffu;
+    const uint32_t id = live ? part_id(ids, r, parts) : 0xffffffffu;
     // rank among lanes of the warp with the same partition
     const unsigned peers = __match_any_sync(0xffffffffu, id);
     const int rank = __popc(peers & ((1u << lane) - 1));
@@ -271,8 +285,20 @@ int vb2k_partition_ids(const uint64_t* hashes, int64_t rows, int32_t num_partiti
   return VB2_OK;
 }
 
+static int partition_order(const PartSrc& src, int64_t rows, int32_t num_partitions, int64_t* counts, int32_t* row_order, void* stream);
+
 int vb2k_partition_scatter_order(const uint32_t* ids, int64_t rows, int32_t num_partitions, int64_t* counts,
                                  int32_t* row_order, void* stream) {
+  return partition_order(PartSrc{ids, nullptr, 0}, rows, num_partitions, counts, row_order, stream);
+}
+
+int vb2k_partition_order_key(const void* key_values, int32_t key_is64, int64_t rows, int32_t num_partitions, int64_t* counts, int32_t* row_order,
+                             void* stream) {
+  if (!key_values && rows > 0) return fail_msg(VB2_ERR_INVALID, "partition_order_key: no key column");
+  return partition_order(PartSrc{nullptr, key_values, key_is64}, rows, num_partitions, counts, row_order, stream);
+}
+
+static int partition_order(const PartSrc& ids, int64_t rows, int32_t num_partitions, int64_t* counts, int32_t* row_order, void* stream) {
   if (num_partitions < 1 || num_partitions > kMaxParts) return fail_msg(VB2_ERR_INVALID, "partition_scatter_order: 1..64 partitions");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (rows <= 0) {

@@ -132,7 +132,19 @@ void B200PartitionedOutput::noMoreInput() {
   DeviceBufferPtr countsDev;            // per-destination row counts, on the device when a partition pass produced them
   std::vector<int64_t> hostCounts;      // ... or on the host when they follow from the row count alone
   DeviceBufferPtr order;
-  if (!broadcast && parts > 1 && n > 0) {
+  const DeviceColumn* singleKey = nullptr;
+  if (!broadcast && parts > 1 && n > 0 && batches_.size() == 1 && node_->keys().size() == 1) {
+    if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(node_->keys()[0].get())) {
+      const DeviceColumn& kc = *batches_[0]->column(f->index());
+      if (kc.desc.encoding == VB2_FLAT && !kc.desc.nulls && (kc.desc.type == VB2_BIGINT || kc.desc.type == VB2_INTEGER)) singleKey = &kc;
+    }
+  }
+  if (singleKey) {
+    // one flat NULL-free integer key: hash, partition id, histogram and order in three launches, no hash / id arrays
+    order = allocDevice(static_cast<size_t>(n) * 4, st);
+    countsDev = allocDeviceZeroed(static_cast<size_t>(world) * 8, st);
+    kernelCheck(vb2k_partition_order_key(singleKey->desc.values, singleKey->desc.type == VB2_BIGINT, n, parts, countsDev->as<int64_t>(), order->as<int32_t>(), st));
+  } else if (!broadcast && parts > 1 && n > 0) {
     auto hashes = allocDevice(static_cast<size_t>(n) * 8, st);
     int64_t off = 0;
     for (auto& b : batches_) {
