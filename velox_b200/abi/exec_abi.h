@@ -55,17 +55,19 @@ class ITypedExpr {
 };
 using TypedExprPtr = std::shared_ptr<const ITypedExpr>;
 
+// velox/core/Expressions.h FieldAccessTypedExpr: a column of the input row, by NAME (operators resolve
+// names against their input type, exec/OperatorUtils.h exprToChannel).
 class FieldAccessTypedExpr : public ITypedExpr {
  public:
-  FieldAccessTypedExpr(TypePtr type, std::string name, int32_t index = -1) : ITypedExpr(std::move(type), {}), name_(std::move(name)), index_(index) {}
+  FieldAccessTypedExpr(TypePtr type, std::string name) : ITypedExpr(std::move(type), {}), name_(std::move(name)) {}
   const std::string& name() const { return name_; }
-  int32_t index() const { return index_; }  // column of the input row (the shim resolves names eagerly)
+  bool isInputColumn() const { return true; }
   std::string toString() const override { return name_; }
 
  private:
   std::string name_;
-  int32_t index_;
 };
+using FieldAccessTypedExprPtr = std::shared_ptr<const FieldAccessTypedExpr>;
 class ConstantTypedExpr : public ITypedExpr {
  public:
   ConstantTypedExpr(TypePtr type, Variant value) : ITypedExpr(std::move(type), {}), value_(std::move(value)) {}
@@ -88,6 +90,7 @@ class CallTypedExpr : public ITypedExpr {
  private:
   std::string name_;
 };
+using CallTypedExprPtr = std::shared_ptr<const CallTypedExpr>;
 class CastTypedExpr : public ITypedExpr {
  public:
   CastTypedExpr(TypePtr type, TypedExprPtr input, bool nullOnFailure = false) : ITypedExpr(std::move(type), {std::move(input)}), nullOnFailure_(nullOnFailure) {}
@@ -158,58 +161,80 @@ class ProjectNode : public PlanNode {
   std::vector<TypedExprPtr> projections_;
   RowTypePtr type_;
 };
+// velox/core/PlanNode.h:1120-1300
 class AggregationNode : public PlanNode {
  public:
   enum class Step { kPartial, kFinal, kIntermediate, kSingle };
+  // velox/core/PlanNode.h:1136-1158
   struct Aggregate {
-    std::string function;               // sum avg count min max
-    std::vector<int32_t> inputs;        // input columns: raw argument, or intermediate column(s) for kFinal / kIntermediate
-    int32_t mask = -1;                  // optional BOOLEAN mask column
-    TypePtr rawInputType;               // type of the raw argument (decides sum's accumulator)
+    CallTypedExprPtr call;                 // function name and input columns (FieldAccessTypedExpr inputs)
+    std::vector<TypePtr> rawInputTypes;    // raw argument types (differ from call's inputs for kIntermediate / kFinal)
+    FieldAccessTypedExprPtr mask{};        // optional BOOLEAN mask column
+    std::vector<FieldAccessTypedExprPtr> sortingKeys{};
+    bool distinct{false};
   };
-  AggregationNode(PlanNodeId id, Step step, std::vector<int32_t> groupingKeys, std::vector<Aggregate> aggregates,
-                  RowTypePtr outputType, PlanNodePtr source)
-      : PlanNode(std::move(id)), step_(step), keys_(std::move(groupingKeys)), aggregates_(std::move(aggregates)),
-        type_(std::move(outputType)), sources_{std::move(source)} {}
+  // velox/core/PlanNode.h:1165-1174: the output type is the grouping keys followed by aggregateNames typed by their calls
+  AggregationNode(PlanNodeId id, Step step, std::vector<FieldAccessTypedExprPtr> groupingKeys, std::vector<FieldAccessTypedExprPtr> preGroupedKeys,
+                  std::vector<std::string> aggregateNames, std::vector<Aggregate> aggregates, bool ignoreNullKeys, PlanNodePtr source)
+      : PlanNode(std::move(id)), step_(step), keys_(std::move(groupingKeys)), preGroupedKeys_(std::move(preGroupedKeys)),
+        aggregateNames_(std::move(aggregateNames)), aggregates_(std::move(aggregates)), ignoreNullKeys_(ignoreNullKeys), sources_{std::move(source)} {
+    std::vector<std::string> names;
+    std::vector<TypePtr> types;
+    for (auto& k : keys_) { names.push_back(k->name()); types.push_back(k->type()); }
+    for (size_t i = 0; i < aggregates_.size(); ++i) { names.push_back(aggregateNames_[i]); types.push_back(aggregates_[i].call->type()); }
+    type_ = ROW(std::move(names), std::move(types));
+  }
   Step step() const { return step_; }
-  const std::vector<int32_t>& groupingKeys() const { return keys_; }
+  const std::vector<FieldAccessTypedExprPtr>& groupingKeys() const { return keys_; }
+  const std::vector<FieldAccessTypedExprPtr>& preGroupedKeys() const { return preGroupedKeys_; }
+  const std::vector<std::string>& aggregateNames() const { return aggregateNames_; }
   const std::vector<Aggregate>& aggregates() const { return aggregates_; }
+  bool ignoreNullKeys() const { return ignoreNullKeys_; }
   const RowTypePtr& outputType() const override { return type_; }
   const std::vector<PlanNodePtr>& sources() const override { return sources_; }
   std::string_view name() const override { return "Aggregation"; }
   bool isRawInput() const { return step_ == Step::kPartial || step_ == Step::kSingle; }
   bool isFinalOutput() const { return step_ == Step::kFinal || step_ == Step::kSingle; }
+  // shim: replaces the derived output type (the flattened (sum, count) pair of an intermediate avg)
+  void setOutputType(RowTypePtr t) { type_ = std::move(t); }
 
  private:
   Step step_;
-  std::vector<int32_t> keys_;
+  std::vector<FieldAccessTypedExprPtr> keys_, preGroupedKeys_;
+  std::vector<std::string> aggregateNames_;
   std::vector<Aggregate> aggregates_;
+  bool ignoreNullKeys_;
   RowTypePtr type_;
   std::vector<PlanNodePtr> sources_;
 };
 enum class JoinType { kInner, kLeft, kLeftSemiFilter, kAnti };
+// velox/core/PlanNode.h:3437-3470 (AbstractJoinNode :3330-3420): keys are columns by name, the output
+// type names the columns taken from the left (probe) and the right (build) side.
 class HashJoinNode : public PlanNode {
  public:
-  struct Output { bool fromProbe; int32_t column; };
-  HashJoinNode(PlanNodeId id, JoinType type, std::vector<int32_t> leftKeys, std::vector<int32_t> rightKeys, TypedExprPtr filter,
-               PlanNodePtr left, PlanNodePtr right, std::vector<Output> outputs, RowTypePtr outputType)
-      : PlanNode(std::move(id)), joinType_(type), leftKeys_(std::move(leftKeys)), rightKeys_(std::move(rightKeys)),
-        filter_(std::move(filter)), sources_{std::move(left), std::move(right)}, outputs_(std::move(outputs)), type_(std::move(outputType)) {}
+  HashJoinNode(PlanNodeId id, JoinType joinType, bool nullAware, std::vector<FieldAccessTypedExprPtr> leftKeys, std::vector<FieldAccessTypedExprPtr> rightKeys,
+               TypedExprPtr filter, PlanNodePtr left, PlanNodePtr right, RowTypePtr outputType)
+      : PlanNode(std::move(id)), joinType_(joinType), nullAware_(nullAware), leftKeys_(std::move(leftKeys)), rightKeys_(std::move(rightKeys)),
+        filter_(std::move(filter)), sources_{std::move(left), std::move(right)}, type_(std::move(outputType)) {}
   JoinType joinType() const { return joinType_; }
-  const std::vector<int32_t>& leftKeys() const { return leftKeys_; }   // probe side
-  const std::vector<int32_t>& rightKeys() const { return rightKeys_; }  // build side
+  bool isNullAware() const { return nullAware_; }
+  bool isInnerJoin() const { return joinType_ == JoinType::kInner; }
+  bool isLeftJoin() const { return joinType_ == JoinType::kLeft; }
+  bool isLeftSemiFilterJoin() const { return joinType_ == JoinType::kLeftSemiFilter; }
+  bool isAntiJoin() const { return joinType_ == JoinType::kAnti; }
+  const std::vector<FieldAccessTypedExprPtr>& leftKeys() const { return leftKeys_; }    // probe side
+  const std::vector<FieldAccessTypedExprPtr>& rightKeys() const { return rightKeys_; }  // build side
   const TypedExprPtr& filter() const { return filter_; }
-  const std::vector<Output>& outputs() const { return outputs_; }
   const RowTypePtr& outputType() const override { return type_; }
   const std::vector<PlanNodePtr>& sources() const override { return sources_; }
   std::string_view name() const override { return "HashJoin"; }
 
  private:
   JoinType joinType_;
-  std::vector<int32_t> leftKeys_, rightKeys_;
+  bool nullAware_;
+  std::vector<FieldAccessTypedExprPtr> leftKeys_, rightKeys_;
   TypedExprPtr filter_;
   std::vector<PlanNodePtr> sources_;
-  std::vector<Output> outputs_;
   RowTypePtr type_;
 };
 
@@ -292,6 +317,16 @@ class QueryConfig {
 };
 
 }  // namespace core
+
+namespace common {
+struct SpillConfig {};  // velox/common/base/SpillConfig.h: carried for signature parity, never used on the device
+}  // namespace common
+namespace wave {
+// velox/exec/HashJoinBridge.h:25,63-65: the opaque table an accelerator backend hands from its build to its probe operator
+struct HashTableHolder {
+  virtual ~HashTableHolder() = default;
+};
+}  // namespace wave
 
 namespace exec {
 
@@ -385,12 +420,22 @@ struct OperatorStats {  // velox/exec/OperatorStats.h:93
   std::map<std::string, int64_t> runtimeStats;
 };
 
+using column_index_t = uint32_t;
+// velox/exec/Operator.h:33-41
+struct IdentityProjection {
+  IdentityProjection(column_index_t _inputChannel, column_index_t _outputChannel) : inputChannel(_inputChannel), outputChannel(_outputChannel) {}
+  column_index_t inputChannel;
+  column_index_t outputChannel;
+};
+
 class Operator {
  public:
-  Operator(DriverCtx* driverCtx, RowTypePtr outputType, int32_t operatorId, std::string planNodeId, std::string operatorType)
-      : driverCtx_(driverCtx), outputType_(std::move(outputType)), planNodeId_(std::move(planNodeId)) {
+  // velox/exec/Operator.h:216-222. Device operators never spill: spillConfig stays empty.
+  Operator(DriverCtx* driverCtx, RowTypePtr outputType, int32_t operatorId, std::string planNodeId, std::string_view operatorType,
+           std::optional<common::SpillConfig> spillConfig = std::nullopt)
+      : driverCtx_(driverCtx), outputType_(std::move(outputType)), planNodeId_(std::move(planNodeId)), spillConfig_(std::move(spillConfig)) {
     stats_.operatorId = operatorId;
-    stats_.operatorType = std::move(operatorType);
+    stats_.operatorType = std::string(operatorType);
   }
   virtual ~Operator() = default;
   virtual void initialize() { initialized_ = true; }
@@ -419,6 +464,7 @@ class Operator {
   RowTypePtr outputType_;
   std::string planNodeId_;
   OperatorStats stats_;
+  std::optional<common::SpillConfig> spillConfig_;
   RowVectorPtr input_;
   bool noMoreInput_ = false;
   bool initialized_ = false;
@@ -443,20 +489,25 @@ class JoinBridge {
 };
 class HashJoinBridge : public JoinBridge {
  public:
-  void setHashTable(std::shared_ptr<void> table) {
-    table_ = std::move(table);
+  // velox/exec/HashJoinBridge.h:63-65 (the overload accelerator backends use) and :86-100,116
+  void setHashTable(std::shared_ptr<wave::HashTableHolder> table, bool hasNullKeys) {
+    result_ = HashBuildResult{hasNullKeys, std::move(table)};
     for (auto& f : waiters_) *f = true;
     waiters_.clear();
   }
-  std::shared_ptr<void> tableOrFuture(ContinueFuture* future) {
-    if (table_) return table_;
+  struct HashBuildResult {
+    bool hasNullKeys;
+    std::shared_ptr<wave::HashTableHolder> waveTable;
+  };
+  std::optional<HashBuildResult> tableOrFuture(ContinueFuture* future) {
+    if (result_) return result_;
     future->ready = std::make_shared<bool>(false);
     waiters_.push_back(future->ready);
-    return nullptr;
+    return std::nullopt;
   }
 
  private:
-  std::shared_ptr<void> table_;
+  std::optional<HashBuildResult> result_;
   std::vector<std::shared_ptr<bool>> waiters_;
 };
 
@@ -521,10 +572,21 @@ class FilterProject : public CpuOperatorStub {
     if (filter_) all.push_back(filter_->filter());
     if (project_) for (auto& p : project_->projections()) all.push_back(p);
     exprs_ = std::make_unique<ExprSet>(std::move(all));
+    // projections that are plain input columns pass through unevaluated (FilterProject::initialize, exec/FilterProject.cpp:90-130)
+    if (project_) {
+      const RowTypePtr& in = project_->sources()[0]->outputType();
+      for (size_t i = 0; i < project_->projections().size(); ++i)
+        if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(project_->projections()[i].get()))
+          if (auto ch = in->getChildIdxIfExists(f->name())) resultProjections_.emplace_back(*ch, static_cast<column_index_t>(i));
+    }
   }
   // velox/exec/FilterProject.h:70-78
-  struct Export { const ExprSet* exprs; bool hasFilter; };
-  Export exprsAndProjection() const { return Export{exprs_.get(), filter_ != nullptr}; }
+  struct Export {
+    const ExprSet* exprs;
+    bool hasFilter;
+    const std::vector<IdentityProjection>* resultProjections;
+  };
+  Export exprsAndProjection() const { return Export{exprs_.get(), filter_ != nullptr, &resultProjections_}; }
   const std::shared_ptr<const core::FilterNode>& filterNode() const { return filter_; }
   const std::shared_ptr<const core::ProjectNode>& projectNode() const { return project_; }
   RowTypePtr inputType() const { return (filter_ ? filter_->sources()[0] : project_->sources()[0])->outputType(); }
@@ -533,6 +595,7 @@ class FilterProject : public CpuOperatorStub {
   std::shared_ptr<const core::FilterNode> filter_;
   std::shared_ptr<const core::ProjectNode> project_;
   std::unique_ptr<ExprSet> exprs_;
+  std::vector<IdentityProjection> resultProjections_;
 };
 class HashAggregation : public CpuOperatorStub {
  public:

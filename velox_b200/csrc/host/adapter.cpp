@@ -16,17 +16,25 @@ std::shared_ptr<const core::AggregationNode> collapsePartialFinal(const core::Ag
   if (fin.sources()[0].get() != &partial) return nullptr;
   const size_t nk = partial.groupingKeys().size();
   if (fin.groupingKeys().size() != nk || fin.aggregates().size() != partial.aggregates().size()) return nullptr;
+  const RowTypePtr& mid = partial.outputType();
   for (size_t k = 0; k < nk; ++k)
-    if (fin.groupingKeys()[k] != static_cast<int32_t>(k)) return nullptr;
-  int32_t col = static_cast<int32_t>(nk);
+    if (fin.groupingKeys()[k]->name() != mid->nameOf(k)) return nullptr;
+  uint32_t col = static_cast<uint32_t>(nk);
+  std::vector<core::AggregationNode::Aggregate> aggregates;
   for (size_t i = 0; i < fin.aggregates().size(); ++i) {
     const auto& f = fin.aggregates()[i];
     const auto& p = partial.aggregates()[i];
-    if (f.function != p.function || f.mask >= 0 || f.inputs.empty() || f.inputs[0] != col) return nullptr;
-    col += p.function == "avg" ? 2 : 1;
+    if (f.call->name() != p.call->name() || f.mask || f.distinct || p.distinct || f.call->inputs().empty()) return nullptr;
+    auto in0 = dynamic_cast<const core::FieldAccessTypedExpr*>(f.call->inputs()[0].get());
+    if (!in0 || col >= mid->size() || in0->name() != mid->nameOf(col)) return nullptr;
+    col += static_cast<uint32_t>(f.call->inputs().size());  // avg's intermediate is a (sum, count) column pair here
+    // the raw arguments and mask of the partial step, the result type of the final one
+    aggregates.push_back({std::make_shared<core::CallTypedExpr>(f.call->type(), p.call->inputs(), p.call->name()), p.rawInputTypes, p.mask});
   }
-  return std::make_shared<core::AggregationNode>(fin.id(), Step::kSingle, partial.groupingKeys(), partial.aggregates(), fin.outputType(),
-                                                 partial.sources()[0]);
+  auto single = std::make_shared<core::AggregationNode>(fin.id(), Step::kSingle, partial.groupingKeys(), partial.preGroupedKeys(), fin.aggregateNames(),
+                                                        std::move(aggregates), partial.ignoreNullKeys(), partial.sources()[0]);
+  single->setOutputType(fin.outputType());
+  return single;
 }
 
 bool adaptDriver(const exec::DriverFactory& factory, exec::Driver& driver) {

@@ -8,6 +8,7 @@
 
 #include "join.h"
 #include "operators.h"
+#include "plan_resolve.h"
 
 namespace velox_b200 {
 
@@ -66,6 +67,7 @@ struct AccState {
 struct B200HashAggregation::Impl {
   B200HashAggregation* self;
   std::shared_ptr<const core::AggregationNode> node;
+  ResolvedAggregation resolved;  // the node's column names resolved to input channels (HashAggregation::initialize does the same)
   std::vector<std::unique_ptr<exec::Operator>> absorbed;
   std::shared_ptr<DeviceContext> dev;
   bool raw, fin;
@@ -137,7 +139,8 @@ struct B200HashAggregation::Impl {
     raw = node->isRawInput();
     fin = node->isFinalOutput();
     const auto& inType = node->sources()[0]->outputType();
-    for (int32_t k : node->groupingKeys()) {
+    resolved = resolveAggregation(*node);
+    for (int32_t k : resolved.keys) {
       KeyState ks;
       ks.kind = inType->childAt(k)->kind();
       ks.isVarchar = ks.kind == TypeKind::VARCHAR;
@@ -147,7 +150,7 @@ struct B200HashAggregation::Impl {
     }
     VELOX_CHECK(keys.size() <= 4, "at most 4 grouping keys");
     mode = keys.empty() ? Mode::kGlobal : (forceKeyed ? Mode::kKeyed : Mode::kArray);
-    for (auto& a : node->aggregates()) {
+    for (auto& a : resolved.aggregates) {
       AccState s;
       s.fn = a.function;
       s.inputType = a.rawInputType;
@@ -452,7 +455,7 @@ struct B200HashAggregation::Impl {
     // stays latency-bound behind its grid barriers. Kept, tested, as the basis for the shared-memory-slice variant.
     if (!cfg.get<bool>("b200.agg_radix_partition", false)) return false;
     // aggregate inputs: flat, NULL-free, unmasked, 4 or 8 bytes wide, at most four distinct columns
-    const auto& aggs = node->aggregates();
+    const auto& aggs = resolved.aggregates;
     std::vector<int32_t> payload;
     for (auto& a : aggs) {
       if (a.mask >= 0) return false;
@@ -465,7 +468,7 @@ struct B200HashAggregation::Impl {
     if (payload.size() > 4) return false;
     std::vector<DeviceBufferPtr> keep;
     std::vector<vb2_column> keyCols;
-    for (size_t k = 0; k < keys.size(); ++k) keyCols.push_back(keyColumn(k, *in->column(node->groupingKeys()[k]), n, keep));
+    for (size_t k = 0; k < keys.size(); ++k) keyCols.push_back(keyColumn(k, *in->column(resolved.keys[k]), n, keep));
     ensureLayout(0);  // the layout must cover this batch's key ranges before its keys can be normalized
     if (mode != Mode::kHash) return false;  // small key space: array mode needs no partitioning
     // keys: one flat NULL-free integer column is normalized on the fly, anything else through vb2k_normalize_keys
@@ -536,7 +539,7 @@ struct B200HashAggregation::Impl {
     DeviceBufferPtr rowKeys;
     std::vector<vb2_column> keyCols;
     if (!keys.empty()) {
-      for (size_t k = 0; k < keys.size(); ++k) keyCols.push_back(keyColumn(k, *in->column(node->groupingKeys()[k]), n, keep));
+      for (size_t k = 0; k < keys.size(); ++k) keyCols.push_back(keyColumn(k, *in->column(resolved.keys[k]), n, keep));
       ensureLayout(n);
     }
     if (!keys.empty() && mode != Mode::kKeyed) {
@@ -586,7 +589,7 @@ struct B200HashAggregation::Impl {
       u.input = it->second.values->data();
       u.nulls = it->second.nulls ? it->second.nulls->as<uint64_t>() : nullptr;
     };
-    const auto& aggs = node->aggregates();
+    const auto& aggs = resolved.aggregates;
     for (size_t i = 0; i < aggs.size(); ++i) {
       const auto& a = aggs[i];
       AccState& s = accs[i];
@@ -694,29 +697,30 @@ struct B200HashAggregation::Impl {
     } else {
       // the probe reads the source batch directly: the stage is the identity over its columns
       for (uint32_t i = 0; i < srcType->size(); ++i)
-        stage.push_back(std::make_shared<core::FieldAccessTypedExpr>(srcType->childAt(i), srcType->nameOf(i), static_cast<int32_t>(i)));
+        stage.push_back(std::make_shared<core::FieldAccessTypedExpr>(srcType->childAt(i), srcType->nameOf(i)));
     }
     int joinKeySource = -1;
     if (probe) {
-      auto keyExpr = stage.at(probe->node()->leftKeys()[0]);
+      const ResolvedJoin rj = resolveJoin(*probe->node());
+      auto keyExpr = stage.at(rj.leftKeys[0]);
       auto kf = dynamic_cast<const core::FieldAccessTypedExpr*>(keyExpr.get());
       if (!kf) return;
-      joinKeySource = kf->index();
+      joinKeySource = channelOf(srcType, *kf);
       std::vector<core::TypedExprPtr> joined;
       const auto& bt = probe->node()->sources()[1]->outputType();
-      for (auto& o : probe->node()->outputs()) {
+      for (auto& o : rj.outputs) {
         if (o.fromProbe) joined.push_back(stage.at(o.column));
-        else joined.push_back(std::make_shared<core::FieldAccessTypedExpr>(bt->childAt(o.column), "__build", -(o.column + 1)));
+        else joined.push_back(std::make_shared<core::FieldAccessTypedExpr>(bt->childAt(o.column), buildFieldName(o.column)));
       }
       std::vector<core::TypedExprPtr> after;
-      for (auto& e : fp2->exprs()) after.push_back(substituteFields(e, joined));
+      for (auto& e : fp2->exprs()) after.push_back(substituteFields(e, joined, probe->node()->outputType()));
       stage = after;
     }
     // aggregate inputs -> deduplicated projections
     std::vector<core::TypedExprPtr> projs;
     std::vector<std::string> projKeys;
     aggToProj.clear();
-    for (auto& a : node->aggregates()) {
+    for (auto& a : resolved.aggregates) {
       if (a.mask >= 0) return;
       if (a.function == "count") {
         if (!a.inputs.empty()) return;  // count(x) needs x's nulls; count(*) only
@@ -736,21 +740,21 @@ struct B200HashAggregation::Impl {
     if (projs.empty()) return;
     // group keys must be plain source columns
     fusedKeySourceCols.clear();
-    for (int32_t k : node->groupingKeys()) {
+    for (int32_t k : resolved.keys) {
       auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(stage.at(k).get());
-      if (!f || f->index() < 0) return;
-      fusedKeySourceCols.push_back(f->index());
+      if (!f || buildFieldColumn(*f) >= 0) return;
+      fusedKeySourceCols.push_back(channelOf(srcType, *f));
     }
     // the build-side predicate: the one BOOLEAN sub-expression that touches build columns
     const core::ITypedExpr* flag = nullptr;
     if (probe) {
       std::function<bool(const core::TypedExprPtr&)> touchesBuild = [&](const core::TypedExprPtr& e) {
-        if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) return f->index() < 0;
+        if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) return buildFieldColumn(*f) >= 0;
         for (auto& in : e->inputs()) if (touchesBuild(in)) return true;
         return false;
       };
       std::function<bool(const core::TypedExprPtr&)> onlyBuild = [&](const core::TypedExprPtr& e) {
-        if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) return f->index() < 0;
+        if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) return buildFieldColumn(*f) >= 0;
         if (dynamic_cast<const core::ConstantTypedExpr*>(e.get())) return true;
         for (auto& in : e->inputs()) if (!onlyBuild(in)) return false;
         return true;
@@ -793,7 +797,7 @@ struct B200HashAggregation::Impl {
       int buildCol = -1;
       std::function<void(const core::TypedExprPtr&)> scan = [&](const core::TypedExprPtr& e) {
         if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) {
-          const int c = -f->index() - 1;
+          const int c = buildFieldColumn(*f);
           if (buildCol >= 0 && buildCol != c) buildCol = -2;
           else if (buildCol != -2) buildCol = c;
         }
@@ -816,7 +820,7 @@ struct B200HashAggregation::Impl {
       } else if (bc->desc.encoding != VB2_FLAT) {
         return false;
       }
-      std::vector<core::TypedExprPtr> one{std::make_shared<core::FieldAccessTypedExpr>(bc->type, "b", 0)};
+      std::vector<core::TypedExprPtr> one{std::make_shared<core::FieldAccessTypedExpr>(bc->type, "b")};
       auto pred = substituteBuild(joinFlagExpr, one[0]);
       CompiledProgram prog = compileExprs({pred}, false, ROW({"b"}, {bc->type}));
       prog.uploadConstants(st());
@@ -1132,7 +1136,7 @@ struct B200HashAggregation::Impl {
     uint32_t oc = 0;
     for (size_t k = 0; k < keys.size(); ++k, ++oc) {
       ColPlan c;
-      c.type = inType->childAt(node->groupingKeys()[k]);
+      c.type = inType->childAt(resolved.keys[k]);
       c.key = k;
       c.ec.mult = c.ec.range = 1;
       if (mode == Mode::kKeyed) {

@@ -403,7 +403,7 @@ int32_t vb2_plan_jit_report(const char* plan_text, int32_t* programs, int32_t* j
         exprs.push_back(f->filter());
         hasFilter = true;
         for (uint32_t i = 0; i < inType->size(); ++i)
-          exprs.push_back(std::make_shared<core::FieldAccessTypedExpr>(inType->childAt(i), inType->nameOf(i), static_cast<int32_t>(i)));
+          exprs.push_back(std::make_shared<core::FieldAccessTypedExpr>(inType->childAt(i), inType->nameOf(i)));
       } else if (auto p = std::dynamic_pointer_cast<const core::ProjectNode>(node)) {
         inType = p->sources()[0]->outputType();
         exprs = p->projections();

@@ -135,7 +135,7 @@ void B200PartitionedOutput::noMoreInput() {
   const DeviceColumn* singleKey = nullptr;
   if (!broadcast && parts > 1 && n > 0 && batches_.size() == 1 && node_->keys().size() == 1) {
     if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(node_->keys()[0].get())) {
-      const DeviceColumn& kc = *batches_[0]->column(f->index());
+      const DeviceColumn& kc = *batches_[0]->column(channelOf(node_->sources()[0]->outputType(), *f));
       if (kc.desc.encoding == VB2_FLAT && !kc.desc.nulls && (kc.desc.type == VB2_BIGINT || kc.desc.type == VB2_INTEGER)) singleKey = &kc;
     }
   }
@@ -151,8 +151,8 @@ void B200PartitionedOutput::noMoreInput() {
       std::vector<vb2_column> keyCols;
       for (auto& k : node_->keys()) {
         auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(k.get());
-        VELOX_CHECK(f != nullptr && f->index() >= 0, "partition keys must be input columns");
-        keyCols.push_back(b->column(f->index())->desc);
+        VELOX_CHECK(f != nullptr, "partition keys must be input columns");
+        keyCols.push_back(b->column(channelOf(node_->sources()[0]->outputType(), *f))->desc);
       }
       VELOX_CHECK(!keyCols.empty(), "partitioned exchange without keys");
       kernelCheck(vb2k_hash_columns(keyCols.data(), static_cast<int32_t>(keyCols.size()), b->size(), hashes->as<uint64_t>() + off, st));

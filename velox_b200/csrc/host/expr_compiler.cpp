@@ -1,4 +1,5 @@
 #include "expr_compiler.h"
+#include "plan_resolve.h"
 
 #include <cstring>
 #include <sstream>
@@ -88,7 +89,7 @@ struct Compiler {
   static bool isVarchar(const core::TypedExprPtr& e) { return e->type()->kind() == TypeKind::VARCHAR; }
 
   std::string key(const core::TypedExprPtr& e) {
-    if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) return "#" + std::to_string(f->index());
+    if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) return "#" + f->name();
     if (auto c = dynamic_cast<const core::ConstantTypedExpr*>(e.get())) return constKey(c->value());
     std::string s;
     if (auto call = dynamic_cast<const core::CallTypedExpr*>(e.get())) s = call->name();
@@ -110,9 +111,9 @@ struct Compiler {
   int compileNew(const core::TypedExprPtr& e) {
     const int t = veloxTypeToVb2(e->type());
     if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(e.get())) {
-      VELOX_CHECK(f->index() >= 0 && f->index() < static_cast<int>(inputType->size()), "field index out of range");
+      const int32_t channel = channelOf(inputType, *f);
       if (t == VB2_VARCHAR) VELOX_UNSUPPORTED("VARCHAR values in expressions other than LIKE / comparison with a constant");
-      return emit(VB2_OP_LOAD, t, f->index());
+      return emit(VB2_OP_LOAD, t, channel);
     }
     if (auto c = dynamic_cast<const core::ConstantTypedExpr*>(e.get())) {
       if (t == VB2_VARCHAR) VELOX_UNSUPPORTED("VARCHAR constant outside LIKE / comparison");
@@ -164,11 +165,11 @@ struct Compiler {
       }
       if (!field || !cst || (opcode == VB2_OP_LIKE && swapped)) VELOX_UNSUPPORTED("VARCHAR predicate must compare a column with a constant");
       const int k = addConst(cst->value(), cst->type());
-      if (opcode == VB2_OP_LIKE) return emit(VB2_OP_LIKE, VB2_BOOLEAN, field->index(), k);
+      if (opcode == VB2_OP_LIKE) return emit(VB2_OP_LIKE, VB2_BOOLEAN, channelOf(inputType, *field), k);
       VELOX_CHECK(opcode >= VB2_OP_LT && opcode <= VB2_OP_NEQ, "unsupported VARCHAR function " + name);
       int cmp = opcode - VB2_OP_LT;  // 0 lt 1 lte 2 gt 3 gte 4 eq 5 neq
       if (swapped) { static const int mirror[] = {2, 3, 0, 1, 4, 5}; cmp = mirror[cmp]; }
-      return emit(VB2_OP_STRCMP, VB2_BOOLEAN, field->index(), k, cmp);
+      return emit(VB2_OP_STRCMP, VB2_BOOLEAN, channelOf(inputType, *field), k, cmp);
     }
     std::vector<int> regs;
     for (auto& a : in) regs.push_back(compile(a));
@@ -250,7 +251,7 @@ CompiledProgram compileExprs(const std::vector<core::TypedExprPtr>& exprs, bool 
     CompiledProgram::Output o;
     o.type = exprs[i]->type();
     if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(exprs[i].get())) {
-      o.identityField = f->index();  // zero-copy: wrapped or passed through, never evaluated
+      o.identityField = channelOf(inputType, *f);  // zero-copy: wrapped or passed through, never evaluated
     } else {
       if (o.type->kind() == TypeKind::VARCHAR) VELOX_UNSUPPORTED("computed VARCHAR projections");
       o.reg = c.compile(exprs[i]);
@@ -292,11 +293,11 @@ void CompiledProgram::uploadConstants(cudaStream_t stream) {
     if (c.type == VB2_VARCHAR && !c.is_null && c.pad > 0) c.str = constChars->as<char>() + offs[c.pad - 1];
 }
 
-core::TypedExprPtr substituteFields(const core::TypedExprPtr& expr, const std::vector<core::TypedExprPtr>& fields) {
-  if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(expr.get())) return fields.at(f->index());
+core::TypedExprPtr substituteFields(const core::TypedExprPtr& expr, const std::vector<core::TypedExprPtr>& fields, const RowTypePtr& type) {
+  if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(expr.get())) return fields.at(channelOf(type, *f));
   if (dynamic_cast<const core::ConstantTypedExpr*>(expr.get())) return expr;
   std::vector<core::TypedExprPtr> in;
-  for (auto& i : expr->inputs()) in.push_back(substituteFields(i, fields));
+  for (auto& i : expr->inputs()) in.push_back(substituteFields(i, fields, type));
   if (auto c = dynamic_cast<const core::CallTypedExpr*>(expr.get())) return std::make_shared<core::CallTypedExpr>(expr->type(), std::move(in), c->name());
   if (auto c = dynamic_cast<const core::CastTypedExpr*>(expr.get())) return std::make_shared<core::CastTypedExpr>(expr->type(), in[0], c->nullOnFailure());
   VELOX_UNSUPPORTED("substituteFields: unknown node");
@@ -328,7 +329,7 @@ struct SigBuilder {
         case TypeKind::BIGINT: k = 'l'; break;
         default: return false;
       }
-      out += k + std::to_string(column(f->index()));
+      out += k + std::to_string(column(channelOf(inputType, *f)));
       return true;
     }
     if (auto c = dynamic_cast<const core::ConstantTypedExpr*>(e.get())) {

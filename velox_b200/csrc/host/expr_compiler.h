@@ -69,7 +69,7 @@ FusedBinding fusedSignature(const core::TypedExprPtr& filter, const std::vector<
                             const RowTypePtr& inputType, int joinKeyColumn = -1,
                             const core::ITypedExpr* joinFlagExpr = nullptr);
 
-// Replaces field references in `expr` by the given expressions (inlines a ProjectNode).
-core::TypedExprPtr substituteFields(const core::TypedExprPtr& expr, const std::vector<core::TypedExprPtr>& fields);
+// Replaces the references to the columns of `type` in `expr` by the given expressions (inlines a ProjectNode).
+core::TypedExprPtr substituteFields(const core::TypedExprPtr& expr, const std::vector<core::TypedExprPtr>& fields, const RowTypePtr& type);
 
 }  // namespace velox_b200

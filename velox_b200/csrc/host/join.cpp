@@ -2,6 +2,7 @@
 #include <map>
 
 #include "join.h"
+#include "plan_resolve.h"
 
 namespace velox_b200 {
 
@@ -152,7 +153,7 @@ void B200HashBuild::noMoreInput() {
   cudaStream_t st = dev_->stream;
   auto holder = std::make_shared<JoinTableHolder>();
   holder->stream = st;
-  const auto& keys = node_->rightKeys();
+  const std::vector<int32_t> keys = resolveJoin(*node_).rightKeys;
   const auto& buildType = node_->sources()[1]->outputType();
   for (int32_t k : keys) {
     const TypeKind kind = buildType->childAt(k)->kind();
@@ -186,7 +187,7 @@ void B200HashBuild::noMoreInput() {
       cols.push_back(col);
     }
     holder->rows = std::make_shared<B200Vector>(pool(), buildType, 0, std::move(cols), st);
-    bridge_->setHashTable(holder);
+    bridge_->setHashTable(holder, false);
     return;
   }
   holder->rows = concatBatches(batches_, pool(), st);
@@ -201,6 +202,7 @@ void B200HashBuild::noMoreInput() {
     int64_t lo, hi, nn;
     columnMinMax(*holder->rows->column(k), n, st, lo, hi, nn);
     if (nn == 0) { lo = 0; hi = 0; }
+    if (nn < n) holder->hasNullKeys = true;
     const unsigned __int128 range = static_cast<unsigned __int128>(static_cast<__int128>(hi) - lo) + 2;  // + NULL id
     lay.mins.push_back(lo);
     if (range > (static_cast<unsigned __int128>(1) << 62)) overflow = true;
@@ -255,17 +257,17 @@ void B200HashBuild::noMoreInput() {
   holder->hasDuplicateKeys = h[1] != 0;
   addRuntimeStat("b200.joinTableMode", exec::RuntimeCounter{t.mode});
   addRuntimeStat("b200.joinTableSlots", exec::RuntimeCounter{t.capacity});
-  bridge_->setHashTable(holder);
+  bridge_->setHashTable(holder, holder->hasNullKeys);
 }
 
 // ---- B200HashProbe ----------------------------------------------------------------------------
 B200HashProbe::B200HashProbe(int32_t id, exec::DriverCtx* ctx, const exec::HashProbe& cpu)
-    : Operator(ctx, cpu.outputType(), id, cpu.planNodeId(), "B200HashProbe"), node_(cpu.node()), bridge_(cpu.joinBridge()) {
+    : Operator(ctx, cpu.outputType(), id, cpu.planNodeId(), "B200HashProbe"), node_(cpu.node()), plan_(resolveJoin(*cpu.node())), bridge_(cpu.joinBridge()) {
   if (node_->filter()) {
     std::vector<std::string> names = node_->sources()[0]->outputType()->names();
     std::vector<TypePtr> types = node_->sources()[0]->outputType()->children();
     const auto& bt = node_->sources()[1]->outputType();
-    for (uint32_t i = 0; i < bt->size(); ++i) { names.push_back("b_" + bt->nameOf(i)); types.push_back(bt->childAt(i)); }
+    for (uint32_t i = 0; i < bt->size(); ++i) { names.push_back(bt->nameOf(i)); types.push_back(bt->childAt(i)); }
     filterProgram_ = std::make_unique<CompiledProgram>(compileExprs({node_->filter()}, true, ROW(names, types)));
   }
 }
@@ -281,7 +283,8 @@ exec::BlockingReason B200HashProbe::isBlocked(exec::ContinueFuture* future) {
   if (table_) return exec::BlockingReason::kNotBlocked;
   auto t = bridge_->tableOrFuture(future);
   if (!t) return exec::BlockingReason::kWaitForJoinBuild;
-  table_ = std::static_pointer_cast<JoinTableHolder>(t);
+  table_ = std::dynamic_pointer_cast<JoinTableHolder>(t->waveTable);
+  VELOX_CHECK(table_ != nullptr, "the join bridge holds a table of another backend");
   return exec::BlockingReason::kNotBlocked;
 }
 
@@ -291,7 +294,7 @@ B200VectorPtr B200HashProbe::apply(const B200VectorPtr& in) {
   const JoinTableHolder& jt = *table_;
   const core::JoinType type = node_->joinType();
   // build and probe streams differ only across drivers; the bridge hand-off synchronised the build
-  NormalizedKeys nk = normalizeKeys(*in, node_->leftKeys(), jt.layout, nullptr, n, true, st);
+  NormalizedKeys nk = normalizeKeys(*in, plan_.leftKeys, jt.layout, nullptr, n, true, st);
   auto counts = allocDevice(static_cast<size_t>(n) * 4, st);
   kernelCheck(vb2k_join_probe_count(&jt.table, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, counts->as<int32_t>(), st));
   auto offsets = allocDevice(static_cast<size_t>(n) * 8, st);
@@ -403,7 +406,7 @@ B200VectorPtr B200HashProbe::apply(const B200VectorPtr& in) {
     outBuild = clamped;
   }
   std::vector<DeviceColumnPtr> outCols;
-  for (auto& o : node_->outputs()) {
+  for (auto& o : plan_.outputs) {
     if (o.fromProbe) {
       outCols.push_back(wrapColumn(in->column(o.column), outProbe, numOut, st));
     } else {

@@ -13,12 +13,13 @@ struct KeyLayout {
   uint64_t product = 1;          // size of the packed key space (0 when it overflows 63 bits)
 };
 
-struct JoinTableHolder {
+struct JoinTableHolder : wave::HashTableHolder {
   vb2_join_table table{};
   std::vector<DeviceBufferPtr> owners;
   KeyLayout layout;
   B200VectorPtr rows;           // concatenated build side (payload gathered from here)
   bool hasDuplicateKeys = false;
+  bool hasNullKeys = false;     // a build row had a NULL key (null-aware anti joins ask; exec/HashJoinBridge.h:86)
   int64_t numRows = 0;
   cudaStream_t stream = nullptr;
 };

@@ -5,6 +5,7 @@
 
 #include "../../../include/velox_b200.h"
 #include "device.h"
+#include "plan_resolve.h"
 #include "expr_compiler.h"
 #include "task.h"
 
@@ -124,6 +125,7 @@ class B200HashBuild : public exec::Operator {
 
  private:
   std::shared_ptr<const core::HashJoinNode> node_;
+  ResolvedJoin plan_;  // key / output column names resolved to channels
   std::shared_ptr<exec::HashJoinBridge> bridge_;
   std::shared_ptr<DeviceContext> dev_;
   std::vector<B200VectorPtr> batches_;
@@ -145,6 +147,7 @@ class B200HashProbe : public exec::Operator {
 
  private:
   std::shared_ptr<const core::HashJoinNode> node_;
+  ResolvedJoin plan_;  // key / output column names resolved to channels
   std::shared_ptr<exec::HashJoinBridge> bridge_;
   std::shared_ptr<JoinTableHolder> table_;
   std::shared_ptr<DeviceContext> dev_;

@@ -109,7 +109,7 @@ B200FilterProject::B200FilterProject(int32_t id, exec::DriverCtx* ctx, const exe
   if (!cpu.projectNode()) {
     // filter only: every input column passes through
     for (uint32_t i = 0; i < inputType_->size(); ++i)
-      exprs_.push_back(std::make_shared<core::FieldAccessTypedExpr>(inputType_->childAt(i), inputType_->nameOf(i), static_cast<int32_t>(i)));
+      exprs_.push_back(std::make_shared<core::FieldAccessTypedExpr>(inputType_->childAt(i), inputType_->nameOf(i)));
   }
   program_ = compileExprs(exprs_, hasFilter_, inputType_);
   if (hasFilter_) fastFilter_ = fusedSignature(exprs_[0], {}, inputType_);

@@ -103,7 +103,7 @@ class Parser {
     if (h == "field") {
       const int i = std::stoi(lex_.atom("field index"));
       if (i < 0 || i >= static_cast<int>(in->size())) throw VeloxRuntimeError("plan text: field index out of range");
-      out = std::make_shared<core::FieldAccessTypedExpr>(in->childAt(i), in->nameOf(i), i);
+      out = std::make_shared<core::FieldAccessTypedExpr>(in->childAt(i), in->nameOf(i));
     } else if (h == "f64") {
       out = std::make_shared<core::ConstantTypedExpr>(DOUBLE(), Variant::of<double>(TypeKind::DOUBLE, std::stod(lex_.atom("number"))));
     } else if (h == "i64") {
@@ -149,7 +149,7 @@ class Parser {
       std::vector<TypePtr> types;
       while (lex_.peek().kind == Tok::ATOM) {
         types.push_back(typeFromName(lex_.take().text));
-        names.push_back("c" + std::to_string(names.size()));
+        names.push_back("s" + std::to_string(src) + "c" + std::to_string(names.size()));  // unique across the plan: joins resolve output columns by name
       }
       lex_.expect(Tok::RP, ")");
       out = std::make_shared<core::ValuesNode>(nextId(), ROW(names, types), src);
@@ -173,13 +173,14 @@ class Parser {
       lex_.expect(Tok::LP, "(");
       std::vector<core::TypedExprPtr> exprs;
       std::vector<std::string> names;
+      const std::string id = nextId();
       while (lex_.peek().kind == Tok::LP) {
         exprs.push_back(expr(child->outputType()));
-        names.push_back("p" + std::to_string(names.size()));
+        names.push_back("n" + id + "p" + std::to_string(names.size()));
       }
       lex_.expect(Tok::RP, ")");
       lex_ = after;
-      out = std::make_shared<core::ProjectNode>(nextId(), names, exprs, child);
+      out = std::make_shared<core::ProjectNode>(id, names, exprs, child);
     } else if (h == "aggregation") {
       const std::string stepName = lex_.atom("step");
       core::AggregationNode::Step step;
@@ -216,32 +217,47 @@ class Parser {
       const auto& in = child->outputType();
       const bool raw = step == core::AggregationNode::Step::kSingle || step == core::AggregationNode::Step::kPartial;
       const bool fin = step == core::AggregationNode::Step::kSingle || step == core::AggregationNode::Step::kFinal;
+      const std::string id = nextId();
+      auto field = [&](int c) {
+        if (c < 0 || c >= static_cast<int>(in->size())) throw VeloxRuntimeError("plan text: aggregate column out of range");
+        return std::make_shared<core::FieldAccessTypedExpr>(in->childAt(c), in->nameOf(c));
+      };
+      std::vector<core::FieldAccessTypedExprPtr> keyExprs;
       std::vector<std::string> names;
       std::vector<TypePtr> types;
-      for (int k : keys) { names.push_back(in->nameOf(k)); types.push_back(in->childAt(k)); }
+      for (int k : keys) { keyExprs.push_back(field(k)); names.push_back(in->nameOf(k)); types.push_back(in->childAt(k)); }
       std::vector<core::AggregationNode::Aggregate> aggs;
+      std::vector<std::string> aggNames;
       for (auto& r : raws) {
         core::AggregationNode::Aggregate a;
-        a.function = r.fn;
-        a.mask = r.mask;
+        std::vector<core::TypedExprPtr> args;
+        TypePtr rawType;
         if (r.col >= 0) {
-          a.inputs.push_back(r.col);
-          a.rawInputType = in->childAt(r.col);
-          if (!raw && r.fn == "avg") a.inputs.push_back(r.col + 1);
+          args.push_back(field(r.col));
+          rawType = in->childAt(r.col);
+          a.rawInputTypes.push_back(rawType);
+          if (!raw && r.fn == "avg") args.push_back(field(r.col + 1));  // the flattened (sum, count) pair
         }
-        const std::string n = "a" + std::to_string(aggs.size());
-        if (r.fn == "count") { names.push_back(n); types.push_back(BIGINT()); }
-        else if (r.fn == "sum") { names.push_back(n); types.push_back(raw ? (a.rawInputType->kind() == TypeKind::DOUBLE ? DOUBLE() : BIGINT()) : a.rawInputType); }
-        else if (r.fn == "min" || r.fn == "max") { names.push_back(n); types.push_back(a.rawInputType); }
+        if (r.mask >= 0) a.mask = field(r.mask);
+        const std::string n = "n" + id + "a" + std::to_string(aggs.size());
+        TypePtr resultType;
+        if (r.fn == "count") { resultType = BIGINT(); names.push_back(n); types.push_back(BIGINT()); }
+        else if (r.fn == "sum") { resultType = raw ? (rawType->kind() == TypeKind::DOUBLE ? DOUBLE() : BIGINT()) : rawType; names.push_back(n); types.push_back(resultType); }
+        else if (r.fn == "min" || r.fn == "max") { resultType = rawType; names.push_back(n); types.push_back(rawType); }
         else if (r.fn == "avg") {
           // intermediate avg is ROW(DOUBLE, BIGINT) in the reference (AverageAggregateBase.h:66-69);
           // the C ABI carries it flattened as two columns
+          resultType = DOUBLE();
           if (fin) { names.push_back(n); types.push_back(DOUBLE()); }
           else { names.push_back(n + "_sum"); types.push_back(DOUBLE()); names.push_back(n + "_count"); types.push_back(BIGINT()); }
         } else throw VeloxRuntimeError("plan text: unknown aggregate " + r.fn);
-        aggs.push_back(a);
+        a.call = std::make_shared<core::CallTypedExpr>(resultType, std::move(args), r.fn);
+        aggs.push_back(std::move(a));
+        aggNames.push_back(n);
       }
-      out = std::make_shared<core::AggregationNode>(nextId(), step, keys, aggs, ROW(names, types), child);
+      auto agg = std::make_shared<core::AggregationNode>(id, step, keyExprs, std::vector<core::FieldAccessTypedExprPtr>{}, aggNames, aggs, false, child);
+      agg->setOutputType(ROW(names, types));
+      out = agg;
     } else if (h == "exchange") {
       // (exchange partitioned|broadcast|gather (keys I ...) plan): PartitionedOutputNode on top of the
       // producing fragment, ExchangeNode as the leaf of the consuming one (core/PlanNode.h:2712,2182)
@@ -252,7 +268,7 @@ class Parser {
       std::vector<core::TypedExprPtr> keys;
       for (int k : keyIdx) {
         if (k < 0 || k >= static_cast<int>(in->size())) throw VeloxRuntimeError("plan text: exchange key out of range");
-        keys.push_back(std::make_shared<core::FieldAccessTypedExpr>(in->childAt(k), in->nameOf(k), k));
+        keys.push_back(std::make_shared<core::FieldAccessTypedExpr>(in->childAt(k), in->nameOf(k)));
       }
       core::PartitionedOutputNode::Kind kind;
       int parts = 0;  // one partition per rank
@@ -275,7 +291,8 @@ class Parser {
       // outputs
       lex_.expect(Tok::LP, "(");
       if (lex_.atom("out") != "out") throw VeloxRuntimeError("plan text: expected (out ...)");
-      std::vector<core::HashJoinNode::Output> outs;
+      struct Out { bool fromProbe; int column; };
+      std::vector<Out> outs;
       while (lex_.peek().kind == Tok::LP) {
         lex_.take();
         const std::string side = lex_.atom("p|b");
@@ -293,7 +310,7 @@ class Parser {
         std::vector<std::string> names = probe->outputType()->names();
         std::vector<TypePtr> types = probe->outputType()->children();
         for (uint32_t i = 0; i < build->outputType()->size(); ++i) {
-          names.push_back("b_" + build->outputType()->nameOf(i));
+          names.push_back(build->outputType()->nameOf(i));
           types.push_back(build->outputType()->childAt(i));
         }
         filter = expr(ROW(names, types));
@@ -303,10 +320,20 @@ class Parser {
       std::vector<TypePtr> types;
       for (auto& o : outs) {
         const auto& t = o.fromProbe ? probe->outputType() : build->outputType();
-        names.push_back("j" + std::to_string(names.size()));
+        if (o.column < 0 || o.column >= static_cast<int>(t->size())) throw VeloxRuntimeError("plan text: join output column out of range");
+        names.push_back(t->nameOf(o.column));  // unique plan-wide: the operators find the column's side by its name
         types.push_back(t->childAt(o.column));
       }
-      out = std::make_shared<core::HashJoinNode>(nextId(), type.parse(), pk, bk, filter, probe, build, outs, ROW(names, types));
+      auto keyExprs = [&](const std::vector<int32_t>& cols, const RowTypePtr& t) {
+        std::vector<core::FieldAccessTypedExprPtr> ks;
+        for (int32_t c : cols) {
+          if (c < 0 || c >= static_cast<int>(t->size())) throw VeloxRuntimeError("plan text: join key out of range");
+          ks.push_back(std::make_shared<core::FieldAccessTypedExpr>(t->childAt(c), t->nameOf(c)));
+        }
+        return ks;
+      };
+      out = std::make_shared<core::HashJoinNode>(nextId(), type.parse(), false, keyExprs(pk, probe->outputType()), keyExprs(bk, build->outputType()), filter, probe,
+                                                 build, ROW(names, types));
     } else {
       throw VeloxRuntimeError("plan text: unknown plan node " + h);
     }
