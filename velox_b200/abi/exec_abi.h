@@ -21,6 +21,7 @@
 #include <chrono>
 #include <map>
 #include <mutex>
+#include <optional>
 #include <set>
 #include <unordered_map>
 #include <variant>
@@ -161,6 +162,24 @@ class ProjectNode : public PlanNode {
   std::vector<TypedExprPtr> projections_;
   RowTypePtr type_;
 };
+// velox/core/PlanNode.h:64-95 SortOrder
+class SortOrder {
+ public:
+  SortOrder(bool ascending, bool nullsFirst) : ascending_(ascending), nullsFirst_(nullsFirst) {}
+  bool isAscending() const { return ascending_; }
+  bool isNullsFirst() const { return nullsFirst_; }
+  bool operator==(const SortOrder& o) const { return ascending_ == o.ascending_ && nullsFirst_ == o.nullsFirst_; }
+  std::string toString() const { return std::string(ascending_ ? "ASC" : "DESC") + (nullsFirst_ ? " NULLS FIRST" : " NULLS LAST"); }
+
+ private:
+  bool ascending_;
+  bool nullsFirst_;
+};
+inline const SortOrder kAscNullsFirst{true, true};
+inline const SortOrder kAscNullsLast{true, false};
+inline const SortOrder kDescNullsFirst{false, true};
+inline const SortOrder kDescNullsLast{false, false};
+
 // velox/core/PlanNode.h:1120-1300
 class AggregationNode : public PlanNode {
  public:
@@ -171,13 +190,16 @@ class AggregationNode : public PlanNode {
     std::vector<TypePtr> rawInputTypes;    // raw argument types (differ from call's inputs for kIntermediate / kFinal)
     FieldAccessTypedExprPtr mask{};        // optional BOOLEAN mask column
     std::vector<FieldAccessTypedExprPtr> sortingKeys{};
+    std::vector<SortOrder> sortingOrders{};
     bool distinct{false};
   };
   // velox/core/PlanNode.h:1165-1174: the output type is the grouping keys followed by aggregateNames typed by their calls
   AggregationNode(PlanNodeId id, Step step, std::vector<FieldAccessTypedExprPtr> groupingKeys, std::vector<FieldAccessTypedExprPtr> preGroupedKeys,
-                  std::vector<std::string> aggregateNames, std::vector<Aggregate> aggregates, bool ignoreNullKeys, PlanNodePtr source)
+                  std::vector<std::string> aggregateNames, std::vector<Aggregate> aggregates, bool ignoreNullKeys, bool noGroupsSpanBatches,
+                  PlanNodePtr source)
       : PlanNode(std::move(id)), step_(step), keys_(std::move(groupingKeys)), preGroupedKeys_(std::move(preGroupedKeys)),
-        aggregateNames_(std::move(aggregateNames)), aggregates_(std::move(aggregates)), ignoreNullKeys_(ignoreNullKeys), sources_{std::move(source)} {
+        aggregateNames_(std::move(aggregateNames)), aggregates_(std::move(aggregates)), ignoreNullKeys_(ignoreNullKeys),
+        noGroupsSpanBatches_(noGroupsSpanBatches), sources_{std::move(source)} {
     std::vector<std::string> names;
     std::vector<TypePtr> types;
     for (auto& k : keys_) { names.push_back(k->name()); types.push_back(k->type()); }
@@ -190,6 +212,7 @@ class AggregationNode : public PlanNode {
   const std::vector<std::string>& aggregateNames() const { return aggregateNames_; }
   const std::vector<Aggregate>& aggregates() const { return aggregates_; }
   bool ignoreNullKeys() const { return ignoreNullKeys_; }
+  bool noGroupsSpanBatches() const { return noGroupsSpanBatches_; }
   const RowTypePtr& outputType() const override { return type_; }
   const std::vector<PlanNodePtr>& sources() const override { return sources_; }
   std::string_view name() const override { return "Aggregation"; }
@@ -204,6 +227,7 @@ class AggregationNode : public PlanNode {
   std::vector<std::string> aggregateNames_;
   std::vector<Aggregate> aggregates_;
   bool ignoreNullKeys_;
+  bool noGroupsSpanBatches_;
   RowTypePtr type_;
   std::vector<PlanNodePtr> sources_;
 };
@@ -213,9 +237,13 @@ enum class JoinType { kInner, kLeft, kLeftSemiFilter, kAnti };
 class HashJoinNode : public PlanNode {
  public:
   HashJoinNode(PlanNodeId id, JoinType joinType, bool nullAware, std::vector<FieldAccessTypedExprPtr> leftKeys, std::vector<FieldAccessTypedExprPtr> rightKeys,
-               TypedExprPtr filter, PlanNodePtr left, PlanNodePtr right, RowTypePtr outputType)
+               TypedExprPtr filter, PlanNodePtr left, PlanNodePtr right, RowTypePtr outputType, bool useHashTableCache = false, bool nullAsValue = false,
+               std::optional<std::string> cacheKey = std::nullopt)
       : PlanNode(std::move(id)), joinType_(joinType), nullAware_(nullAware), leftKeys_(std::move(leftKeys)), rightKeys_(std::move(rightKeys)),
-        filter_(std::move(filter)), sources_{std::move(left), std::move(right)}, type_(std::move(outputType)) {}
+        filter_(std::move(filter)), sources_{std::move(left), std::move(right)}, type_(std::move(outputType)), useHashTableCache_(useHashTableCache),
+        nullAsValue_(nullAsValue), cacheKey_(std::move(cacheKey)) {}
+  bool useHashTableCache() const { return useHashTableCache_; }
+  bool nullAsValue() const { return nullAsValue_; }
   JoinType joinType() const { return joinType_; }
   bool isNullAware() const { return nullAware_; }
   bool isInnerJoin() const { return joinType_ == JoinType::kInner; }
@@ -236,7 +264,21 @@ class HashJoinNode : public PlanNode {
   TypedExprPtr filter_;
   std::vector<PlanNodePtr> sources_;
   RowTypePtr type_;
+  bool useHashTableCache_;
+  bool nullAsValue_;
+  std::optional<std::string> cacheKey_;
 };
+
+// velox/core/PlanNode.h:2600-2640 PartitionFunctionSpec: how rows map to partitions. The B200
+// PartitionedOutput understands the hash spec (exec/HashPartitionFunction.h:75
+// HashPartitionFunctionSpec: hash of the key channels modulo the partition count) and nullptr
+// (gather / broadcast need no function).
+class PartitionFunctionSpec {
+ public:
+  virtual ~PartitionFunctionSpec() = default;
+  virtual std::string toString() const = 0;
+};
+using PartitionFunctionSpecPtr = std::shared_ptr<const PartitionFunctionSpec>;
 
 // velox/core/PlanNode.h:2712 PartitionedOutputNode — root of a producing plan fragment: rows are
 // partitioned by hash(keys) % numPartitions (kPartitioned; HashPartitionFunction,
@@ -247,9 +289,10 @@ class PartitionedOutputNode : public PlanNode {
  public:
   enum class Kind { kPartitioned, kBroadcast, kArbitrary };
   PartitionedOutputNode(PlanNodeId id, Kind kind, std::vector<TypedExprPtr> keys, int numPartitions, bool replicateNullsAndAny,
-                        RowTypePtr outputType, std::string serdeKind, PlanNodePtr source)
+                        PartitionFunctionSpecPtr partitionFunctionSpec, RowTypePtr outputType, std::string serdeKind, PlanNodePtr source)
       : PlanNode(std::move(id)), kind_(kind), keys_(std::move(keys)), numPartitions_(numPartitions), replicateNullsAndAny_(replicateNullsAndAny),
-        type_(std::move(outputType)), serdeKind_(std::move(serdeKind)), sources_{std::move(source)} {}
+        partitionFunctionSpec_(std::move(partitionFunctionSpec)), type_(std::move(outputType)), serdeKind_(std::move(serdeKind)), sources_{std::move(source)} {}
+  const PartitionFunctionSpecPtr& partitionFunctionSpecPtr() const { return partitionFunctionSpec_; }
   Kind kind() const { return kind_; }
   bool isBroadcast() const { return kind_ == Kind::kBroadcast; }
   const std::vector<TypedExprPtr>& keys() const { return keys_; }
@@ -266,6 +309,7 @@ class PartitionedOutputNode : public PlanNode {
   std::vector<TypedExprPtr> keys_;
   int numPartitions_;
   bool replicateNullsAndAny_;
+  PartitionFunctionSpecPtr partitionFunctionSpec_;
   RowTypePtr type_;
   std::string serdeKind_;
   std::vector<PlanNodePtr> sources_;
@@ -289,6 +333,11 @@ class ExchangeNode : public PlanNode {
   RowTypePtr type_;
   std::string serdeKind_;
   std::shared_ptr<const PartitionedOutputNode> upstream_;
+};
+
+// velox/core/PlanFragment.h:43 (the grouped-execution fields are not part of the path)
+struct PlanFragment {
+  std::shared_ptr<const PlanNode> planNode;
 };
 
 class QueryConfig {
@@ -377,8 +426,9 @@ inline std::mutex& vectorFunctionMutex() {
   static std::mutex m;
   return m;
 }
-inline bool registerVectorFunction(const std::string& name, std::vector<FunctionSignaturePtr> signatures,
+inline bool registerVectorFunction(std::string_view nameView, std::vector<FunctionSignaturePtr> signatures,
                                    std::unique_ptr<VectorFunction> func, VectorFunctionMetadata metadata = {}, bool overwrite = true) {
+  const std::string name(nameView);
   std::lock_guard<std::mutex> l(vectorFunctionMutex());
   auto& m = vectorFunctionFactories();
   if (!overwrite && m.count(name)) return false;
@@ -422,6 +472,27 @@ struct OperatorStats {  // velox/exec/OperatorStats.h:93
 
 using column_index_t = uint32_t;
 // velox/exec/Operator.h:33-41
+// velox/exec/HashPartitionFunction.h:76-101: partition = hash(key channels) % numPartitions
+// (HashPartitionFunction.cpp:75-118); the B200 PartitionedOutput reads the key channels from here.
+class HashPartitionFunctionSpec : public core::PartitionFunctionSpec {
+ public:
+  HashPartitionFunctionSpec(RowTypePtr inputType, std::vector<column_index_t> keyChannels, std::vector<VectorPtr> constValues = {})
+      : inputType_(std::move(inputType)), keyChannels_(std::move(keyChannels)), constValues_(std::move(constValues)) {}
+  const RowTypePtr& inputType() const { return inputType_; }
+  const std::vector<column_index_t>& keyChannels() const { return keyChannels_; }  // shim accessor (private in the reference, read by create())
+  const std::vector<VectorPtr>& constValues() const { return constValues_; }
+  std::string toString() const override {
+    std::string s = "HASH(";
+    for (size_t i = 0; i < keyChannels_.size(); ++i) s += (i ? ", " : "") + inputType_->nameOf(keyChannels_[i]);
+    return s + ")";
+  }
+
+ private:
+  const RowTypePtr inputType_;
+  const std::vector<column_index_t> keyChannels_;
+  const std::vector<VectorPtr> constValues_;
+};
+
 struct IdentityProjection {
   IdentityProjection(column_index_t _inputChannel, column_index_t _outputChannel) : inputChannel(_inputChannel), outputChannel(_outputChannel) {}
   column_index_t inputChannel;
@@ -690,10 +761,11 @@ class CallbackSink : public Operator {
 // ---- driver -------------------------------------------------------------------------------------
 class Driver;
 struct DriverFactory;
+using AdaptDriverFunction = std::function<bool(const DriverFactory& factory, Driver& driver)>;  // velox/exec/Driver.h:786
 struct DriverAdapter {  // velox/exec/Driver.h:789-793
   std::string label;
-  std::function<void(const DriverFactory&)> inspect;
-  std::function<bool(const DriverFactory&, Driver&)> adapt;
+  std::function<void(const core::PlanFragment&)> inspect;  // sees the whole plan once, before the drivers exist (LocalPlanner.cpp:381)
+  AdaptDriverFunction adapt;
 };
 
 struct DriverFactory {  // velox/exec/Driver.h:795-847

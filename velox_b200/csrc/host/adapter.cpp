@@ -32,7 +32,7 @@ std::shared_ptr<const core::AggregationNode> collapsePartialFinal(const core::Ag
     aggregates.push_back({std::make_shared<core::CallTypedExpr>(f.call->type(), p.call->inputs(), p.call->name()), p.rawInputTypes, p.mask});
   }
   auto single = std::make_shared<core::AggregationNode>(fin.id(), Step::kSingle, partial.groupingKeys(), partial.preGroupedKeys(), fin.aggregateNames(),
-                                                        std::move(aggregates), partial.ignoreNullKeys(), partial.sources()[0]);
+                                                        std::move(aggregates), partial.ignoreNullKeys(), partial.noGroupsSpanBatches(), partial.sources()[0]);
   single->setOutputType(fin.outputType());
   return single;
 }

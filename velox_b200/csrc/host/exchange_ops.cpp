@@ -51,7 +51,22 @@ NcclTransport* transportOf(exec::DriverCtx* ctx) {
 
 // ---- B200PartitionedOutput -------------------------------------------------------------------------
 B200PartitionedOutput::B200PartitionedOutput(int32_t id, exec::DriverCtx* ctx, const exec::PartitionedOutput& cpu)
-    : Operator(ctx, cpu.node()->outputType(), id, cpu.planNodeId(), "B200PartitionedOutput"), node_(cpu.node()), queue_(cpu.queue()) {}
+    : Operator(ctx, cpu.node()->outputType(), id, cpu.planNodeId(), "B200PartitionedOutput"), node_(cpu.node()), queue_(cpu.queue()) {
+  // The partition function comes from the node's spec (core/PlanNode.h:2728); the hash spec is the one
+  // with a device implementation. Without a spec (gather, broadcast) every row has one destination rule.
+  if (auto spec = node_->partitionFunctionSpecPtr()) {
+    auto hash = dynamic_cast<const exec::HashPartitionFunctionSpec*>(spec.get());
+    if (!hash) VELOX_UNSUPPORTED("partition function " + spec->toString() + " (HashPartitionFunctionSpec is supported)");
+    if (!hash->constValues().empty()) VELOX_UNSUPPORTED("constant partition keys");
+    for (auto c : hash->keyChannels()) keyChannels_.push_back(static_cast<int32_t>(c));
+  } else {
+    for (auto& k : node_->keys()) {
+      auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(k.get());
+      VELOX_CHECK(f != nullptr, "partition keys must be input columns");
+      keyChannels_.push_back(channelOf(node_->sources()[0]->outputType(), *f));
+    }
+  }
+}
 
 void B200PartitionedOutput::initialize() {
   Operator::initialize();
@@ -133,11 +148,9 @@ void B200PartitionedOutput::noMoreInput() {
   std::vector<int64_t> hostCounts;      // ... or on the host when they follow from the row count alone
   DeviceBufferPtr order;
   const DeviceColumn* singleKey = nullptr;
-  if (!broadcast && parts > 1 && n > 0 && batches_.size() == 1 && node_->keys().size() == 1) {
-    if (auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(node_->keys()[0].get())) {
-      const DeviceColumn& kc = *batches_[0]->column(channelOf(node_->sources()[0]->outputType(), *f));
-      if (kc.desc.encoding == VB2_FLAT && !kc.desc.nulls && (kc.desc.type == VB2_BIGINT || kc.desc.type == VB2_INTEGER)) singleKey = &kc;
-    }
+  if (!broadcast && parts > 1 && n > 0 && batches_.size() == 1 && keyChannels_.size() == 1) {
+    const DeviceColumn& kc = *batches_[0]->column(keyChannels_[0]);
+    if (kc.desc.encoding == VB2_FLAT && !kc.desc.nulls && (kc.desc.type == VB2_BIGINT || kc.desc.type == VB2_INTEGER)) singleKey = &kc;
   }
   if (singleKey) {
     // one flat NULL-free integer key: hash, partition id, histogram and order in three launches, no hash / id arrays
@@ -149,11 +162,7 @@ void B200PartitionedOutput::noMoreInput() {
     int64_t off = 0;
     for (auto& b : batches_) {
       std::vector<vb2_column> keyCols;
-      for (auto& k : node_->keys()) {
-        auto f = dynamic_cast<const core::FieldAccessTypedExpr*>(k.get());
-        VELOX_CHECK(f != nullptr, "partition keys must be input columns");
-        keyCols.push_back(b->column(channelOf(node_->sources()[0]->outputType(), *f))->desc);
-      }
+      for (int32_t c : keyChannels_) keyCols.push_back(b->column(c)->desc);
       VELOX_CHECK(!keyCols.empty(), "partitioned exchange without keys");
       kernelCheck(vb2k_hash_columns(keyCols.data(), static_cast<int32_t>(keyCols.size()), b->size(), hashes->as<uint64_t>() + off, st));
       off += b->size();

@@ -189,6 +189,7 @@ class B200PartitionedOutput : public exec::Operator {
 
  private:
   std::shared_ptr<const core::PartitionedOutputNode> node_;
+  std::vector<int32_t> keyChannels_;  // of the node's HashPartitionFunctionSpec
   std::shared_ptr<exec::ExchangeQueue> queue_;
   std::shared_ptr<DeviceContext> dev_;
   std::vector<B200VectorPtr> batches_;

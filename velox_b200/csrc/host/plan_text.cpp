@@ -255,7 +255,7 @@ class Parser {
         aggs.push_back(std::move(a));
         aggNames.push_back(n);
       }
-      auto agg = std::make_shared<core::AggregationNode>(id, step, keyExprs, std::vector<core::FieldAccessTypedExprPtr>{}, aggNames, aggs, false, child);
+      auto agg = std::make_shared<core::AggregationNode>(id, step, keyExprs, std::vector<core::FieldAccessTypedExprPtr>{}, aggNames, aggs, false, false, child);
       agg->setOutputType(ROW(names, types));
       out = agg;
     } else if (h == "exchange") {
@@ -276,7 +276,9 @@ class Parser {
       else if (kindName == "broadcast") kind = core::PartitionedOutputNode::Kind::kBroadcast;
       else if (kindName == "gather") { kind = core::PartitionedOutputNode::Kind::kPartitioned; parts = 1; }
       else throw VeloxRuntimeError("plan text: unknown exchange kind " + kindName);
-      auto po = std::make_shared<core::PartitionedOutputNode>(nextId(), kind, keys, parts, false, in, "B200Columnar", child);
+      core::PartitionFunctionSpecPtr spec;
+      if (kindName == "partitioned") spec = std::make_shared<exec::HashPartitionFunctionSpec>(in, std::vector<exec::column_index_t>(keyIdx.begin(), keyIdx.end()));
+      auto po = std::make_shared<core::PartitionedOutputNode>(nextId(), kind, keys, parts, false, spec, in, "B200Columnar", child);
       auto ex = std::make_shared<core::ExchangeNode>(nextId(), in, "B200Columnar");
       ex->setUpstream(po);
       out = ex;

@@ -115,9 +115,9 @@ std::vector<RowVectorPtr> Task::run() {
   out->factory.outputDriver = true;
   out->factory.pipelineId = static_cast<int32_t>(planner.pipelines.size());
   planner.pipelines.push_back(std::move(out));
+  const core::PlanFragment fragment{plan_};
   for (auto& adapter : DriverFactory::adapters())
-    if (adapter.inspect)
-      for (auto& p : planner.pipelines) adapter.inspect(p->factory);
+    if (adapter.inspect) adapter.inspect(fragment);
 
   std::vector<RowVectorPtr> results;
   std::vector<std::unique_ptr<core::QueryConfig>> keep;
