@@ -49,6 +49,27 @@ int32_t vb2_tasks_run(vb2_task* const* tasks, int32_t ntasks, char* err, int32_t
  * resident device copy instead of crossing PCIe again. The caller guarantees the host buffers are
  * neither modified nor freed while the cache lives, and runs the sharing tasks one after another.
  * The stats text of a task reports `task.h2dBytes`, the bytes it actually copied. */
+/* Function registries (velox/expression/VectorFunction.h:241 registerVectorFunction,
+ * velox/exec/Aggregate.h:525-575 registerAggregateFunction) for hosts that bind the C ABI instead of
+ * the C++ classes (B200DeviceFunction, B200Aggregate in csrc/host/expr_compiler.h / operators.h).
+ * vb2_register_scalar_function: `cuda_source` defines `__device__ RET entry(ARGS...)` over BIGINT =
+ * long long, INTEGER = int, DOUBLE = double, BOOLEAN = bool; plans may then call (name e ...). The
+ * body is spliced into the JIT-compiled kernel of every ExprSet that calls it (NULL in -> NULL out).
+ * vb2_register_aggregate_function: `name(x)` aggregates input_function(x) with the device accumulator
+ * family ("sum" "avg" "count" "min" "max"), and applies final_function to the final value;
+ * input_function / final_function are names of registered scalar functions or NULL / "". */
+int32_t vb2_register_scalar_function(const char* name, const char* entry, const char* cuda_source, int32_t ret_type, const int32_t* arg_types,
+                                     int32_t nargs, char* err, int32_t errlen);
+int32_t vb2_register_aggregate_function(const char* name, const char* family, const char* input_function, const char* final_function, char* err,
+                                        int32_t errlen);
+/* Node-at-a-time call of a registered scalar function — VectorFunction::apply
+ * (velox/expression/VectorFunction.h:81-86) — over HOST argument columns: rows whose bit is set in
+ * `selected` (LSB-first; NULL = all rows) are computed on the device and written to out_values
+ * (BOOLEAN one byte per row) / out_nulls (one byte per row, 1 = NULL); the other rows of the caller's
+ * buffers are left untouched (the result-reuse rule). */
+int32_t vb2_scalar_function_apply(const char* name, const vb2_column* args, int32_t nargs, int64_t rows, const uint64_t* selected, int32_t ret_type,
+                                  void* out_values, uint8_t* out_nulls, char* err, int32_t errlen);
+
 /* Diagnostic, no GPU needed: the expression programs of every Filter / Project node of a plan are
  * compiled (expression compiler) and handed to the expression JIT for a flat NULL-free input;
  * reports the number of programs, of kernels (filter pass + projection pass) and of kernels that

@@ -115,8 +115,12 @@ enum vb2_opcode {
   VB2_OP_CAST = 21,    /* dst <- cast(a); type = target, b = source type */
   VB2_OP_LIKE = 22,    /* dst <- column a LIKE constant b (VARCHAR column, pattern constant) */
   VB2_OP_STRCMP = 23,  /* dst <- column a <cmp c> constant b, c = vb2 compare code (0 lt .. 5 neq) */
-  VB2_OP_NULL = 24     /* dst <- NULL of `type` */
+  VB2_OP_NULL = 24,    /* dst <- NULL of `type` */
+  VB2_OP_CALL = 25     /* dst <- registered device function (vb2k_register_device_function) over registers a, b, c
+                          (unused ones -1); type = result type | function id << 8. NULL in -> NULL out. */
 };
+#define VB2_CALL_TYPE(t) ((t) & 0xff)
+#define VB2_CALL_FN(t) ((t) >> 8)
 
 typedef struct vb2_instr {
   int32_t op;
@@ -162,6 +166,17 @@ void vb2k_set_expression_jit(int32_t enabled);
  * the generated source (or the compiler log on failure). */
 int32_t vb2k_expression_jit_compiles(const vb2_program* prog, const vb2_column* cols, int32_t ncols, int32_t filter, const vb2_output* outs,
                                      int32_t nouts, char* source_out, int32_t source_len);
+
+/* Registry of user-supplied scalar device functions — the device half of exec::registerVectorFunction
+ * (velox/expression/VectorFunction.h:241): `cuda_source` is CUDA C++ text defining
+ *   __device__ RET entry(ARG0 [, ARG1 [, ARG2]])      with BIGINT = long long, INTEGER = int, DOUBLE = double, BOOLEAN = bool
+ * which the expression JIT splices into every kernel whose program calls it (VB2_OP_CALL), so a
+ * registered function fuses with the rest of the expression tree like a built-in. Default NULL
+ * behaviour: the function is not called on rows with a NULL argument. Returns the function id (>= 0)
+ * or a negative VB2_ERR_*. Programs that call registered functions need the JIT (NVRTC): without it
+ * vb2k_eval_* returns VB2_ERR_UNSUPPORTED — there is no CPU fallback. */
+int32_t vb2k_register_device_function(const char* entry, const char* cuda_source, int32_t ret_type, const int32_t* arg_types, int32_t nargs);
+int32_t vb2k_device_function_count(void);
 
 /* Pass 1: evaluates the filter over `rows` input rows. Writes the selection bitmap (1 = row kept:
  * predicate true and not null) and per-block popcounts for the compaction that follows. */

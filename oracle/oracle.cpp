@@ -708,6 +708,18 @@ static VecPtr eval_cast(const Expr& e, EvalCtx& ctx, const Rows& rows) {
   else if (from == ORC_DOUBLE && to == ORC_BIGINT) num(double{}, int64_t{});
   else if (from == ORC_DOUBLE && to == ORC_INTEGER) num(double{}, int32_t{});
   else if (from == ORC_BOOLEAN && to == ORC_BIGINT) num(uint8_t{}, int64_t{});
+  else if (to == ORC_BOOLEAN && from != ORC_VARCHAR) {
+    // velox/type/Conversions.h:158-207 (non-truncating policy): folly::to<bool>(v) == (v != 0); NaN != 0 is true
+    uint8_t* o = out->alloc<uint8_t>(n);
+    auto to_bool = [&](auto tag) {
+      using F = decltype(tag);
+      Acc<F> x(*a);
+      for_non_null(rows, args, *out, [&](int64_t r) { o[r] = x[r] != F{} ? 1 : 0; });
+    };
+    if (from == ORC_DOUBLE) to_bool(double{});
+    else if (from == ORC_BIGINT) to_bool(int64_t{});
+    else to_bool(int32_t{});
+  }
   else throw std::runtime_error("unsupported cast");
   return out;
 }

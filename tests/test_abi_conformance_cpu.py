@@ -158,6 +158,8 @@ SIGNATURES = [
     ("ExchangeNode", "core/PlanNode.h", r"\n  ExchangeNode\(", 0, SHIM_EXEC, r"\n  ExchangeNode\(", 0),
     ("VectorFunction::apply", "expression/VectorFunction.h", r"virtual void apply\(", 0, SHIM_EXEC, r"virtual void apply\(", 0),
     ("registerVectorFunction", "expression/VectorFunction.h", r"bool registerVectorFunction\(", 0, SHIM_EXEC, r"bool registerVectorFunction\(", 0),
+    ("registerAggregateFunction", "exec/Aggregate.h", r"AggregateRegistrationResult registerAggregateFunction\(", 0, SHIM_EXEC, r"AggregateRegistrationResult registerAggregateFunction\(", 0),
+    ("Aggregate::create", "exec/Aggregate.h", r"static std::unique_ptr<Aggregate> create\(", 0, SHIM_EXEC, r"static std::unique_ptr<Aggregate> create\(", 0),
     ("RowVector", "vector/ComplexVector.h", r"\n  RowVector\((?=\s*velox)", 0, SHIM_VEC, r"\n  RowVector\(", 0),
     ("FlatVector", "vector/FlatVector.h", r"\n  FlatVector\((?=\s*velox)", 0, SHIM_VEC, r"\n  FlatVector\(", 0),
     ("DictionaryVector", "vector/DictionaryVector.h", r"\n  DictionaryVector\((?=\s*velox)", 0, SHIM_VEC, r"\n  DictionaryVector\(", 0),
@@ -171,6 +173,9 @@ STRUCTS = [
     ("DriverAdapter", "exec/Driver.h", r"struct DriverAdapter\s*\{", SHIM_EXEC, r"struct DriverAdapter\s*\{"),
     ("AggregationNode::Aggregate", "core/PlanNode.h", r"struct Aggregate\s*\{", SHIM_EXEC, r"struct Aggregate\s*\{"),
     ("HashBuildResult", "exec/HashJoinBridge.h", r"struct HashBuildResult\s*\{", SHIM_EXEC, r"struct HashBuildResult\s*\{"),
+    ("AggregateRegistrationResult", "exec/AggregateUtil.h", r"struct AggregateRegistrationResult\s*\{", SHIM_EXEC, r"struct AggregateRegistrationResult\s*\{"),
+    ("AggregateFunctionMetadata", "exec/Aggregate.h", r"struct AggregateFunctionMetadata\s*\{", SHIM_EXEC, r"struct AggregateFunctionMetadata\s*\{"),
+    ("AggregateFunctionEntry", "exec/Aggregate.h", r"struct AggregateFunctionEntry\s*\{", SHIM_EXEC, r"struct AggregateFunctionEntry\s*\{"),
     ("IdentityProjection", "exec/Operator.h", r"struct IdentityProjection\s*\{", SHIM_EXEC, r"struct IdentityProjection\s*\{"),
 ]
 

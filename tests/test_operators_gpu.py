@@ -119,6 +119,16 @@ def test_checked_arithmetic_errors():
     check_user_error(PlanBuilder().values(dbl.names, dbl.types).project(["cast(a as bigint)"]).planNode(), [dbl])
 
 
+def test_cast_to_boolean():
+    """cast(x as boolean) is x != 0, NaN included (velox/type/Conversions.h:158-207, folly::to<bool>); the
+    result is a normalised 0/1 byte, usable as a filter."""
+    rv = row_vector(["a", "b", "c"], [flat_vector(BIGINT, [5, 0, -3, None, 256]), flat_vector(INTEGER, [0, 7, None, 1, 65536]),
+                                        flat_vector(DOUBLE, [0.4, 0.0, NAN, None, -0.0])])
+    check_plan(PlanBuilder().values(rv.names, rv.types).project(["cast(a as boolean)", "cast(b as boolean)", "cast(c as boolean)",
+                                                                  "cast(a as boolean) and cast(c as boolean)"]).planNode(), [rv])
+    check_plan(PlanBuilder().values(rv.names, rv.types).filter("cast(a as boolean)").planNode(), [rv])
+
+
 def test_plumbing_config_exprset():
     """BASELINE.json configs[0]: l_extendedprice*(1-l_discount) WHERE l_quantity<24 on 1M-row
     DOUBLE/BIGINT flat vectors."""

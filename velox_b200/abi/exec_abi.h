@@ -392,7 +392,16 @@ class ExprSet {
   std::vector<core::TypedExprPtr> exprs_;
 };
 
-class EvalCtx;
+// velox/expression/EvalCtx.h: the evaluation context a VectorFunction::apply receives. The device
+// functions need only the pool of the vectors they hand back.
+class EvalCtx {
+ public:
+  explicit EvalCtx(memory::MemoryPool* pool = nullptr) : pool_(pool) {}
+  memory::MemoryPool* pool() const { return pool_; }
+
+ private:
+  memory::MemoryPool* pool_;
+};
 
 // ---- VectorFunction registry --------------------------------------------------------------------
 struct FunctionSignature {
@@ -440,6 +449,86 @@ inline std::shared_ptr<VectorFunction> getVectorFunction(const std::string& name
   auto& m = vectorFunctionFactories();
   auto it = m.find(name);
   return it == m.end() ? nullptr : it->second.function;
+}
+
+// ---- Aggregate registry (velox/exec/Aggregate.h:42-575) ------------------------------------------
+// The CPU accumulator interface of the reference (addRawInput(char** groups, ...), extractValues ...)
+// addresses host group rows and has no device counterpart; the shim carries what an accelerator
+// needs from an Aggregate — its result type — and the registry it is created through.
+class Aggregate {
+ public:
+  explicit Aggregate(TypePtr resultType) : resultType_(std::move(resultType)) {}
+  virtual ~Aggregate() = default;
+  const TypePtr& resultType() const { return resultType_; }
+  // velox/exec/Aggregate.h:361-366
+  static std::unique_ptr<Aggregate> create(const std::string& name, core::AggregationNode::Step step, const std::vector<TypePtr>& argTypes,
+                                           const TypePtr& resultType, const core::QueryConfig& config);
+
+ protected:
+  const TypePtr resultType_;
+};
+struct AggregateFunctionSignature {  // velox/expression/FunctionSignature.h AggregateFunctionSignature
+  std::string returnType, intermediateType;
+  std::vector<std::string> argTypes;
+};
+using AggregateFunctionSignaturePtr = std::shared_ptr<AggregateFunctionSignature>;
+using AggregateFunctionFactory = std::function<std::unique_ptr<Aggregate>(core::AggregationNode::Step step, const std::vector<TypePtr>& argTypes,
+                                                                          const TypePtr& resultType, const core::QueryConfig& config)>;
+struct AggregateFunctionMetadata {
+  bool ignoreDuplicates{false};
+  bool orderSensitive{true};
+  bool companionFunction{false};
+};
+struct AggregateRegistrationResult {  // velox/exec/AggregateUtil.h:21
+  bool mainFunction{false};
+  bool partialFunction{false};
+  bool mergeFunction{false};
+  bool extractFunction{false};
+  bool mergeExtractFunction{false};
+};
+struct AggregateFunctionEntry {
+  std::vector<AggregateFunctionSignaturePtr> signatures;
+  AggregateFunctionFactory factory;
+  AggregateFunctionMetadata metadata;
+};
+using AggregateFunctionMap = std::unordered_map<std::string, AggregateFunctionEntry>;
+inline AggregateFunctionMap& aggregateFunctions() {
+  static AggregateFunctionMap m;
+  return m;
+}
+inline std::mutex& aggregateFunctionMutex() {
+  static std::mutex m;
+  return m;
+}
+// velox/exec/Aggregate.h:537-542. Companion functions (name_partial / _merge / _extract) are scalar
+// and aggregate wrappers of the CPU engine and are not generated here.
+inline AggregateRegistrationResult registerAggregateFunction(const std::string& name, const std::vector<std::shared_ptr<AggregateFunctionSignature>>& signatures,
+                                                             const AggregateFunctionFactory& factory, bool registerCompanionFunctions, bool overwrite) {
+  (void)registerCompanionFunctions;
+  std::lock_guard<std::mutex> l(aggregateFunctionMutex());
+  auto& m = aggregateFunctions();
+  AggregateRegistrationResult r;
+  if (!overwrite && m.count(name)) return r;
+  m[name] = AggregateFunctionEntry{signatures, factory, {}};
+  r.mainFunction = true;
+  return r;
+}
+inline const AggregateFunctionEntry* getAggregateFunctionEntry(const std::string& name) {
+  std::lock_guard<std::mutex> l(aggregateFunctionMutex());
+  auto& m = aggregateFunctions();
+  auto it = m.find(name);
+  return it == m.end() ? nullptr : &it->second;
+}
+inline std::unique_ptr<Aggregate> Aggregate::create(const std::string& name, core::AggregationNode::Step step, const std::vector<TypePtr>& argTypes,
+                                                    const TypePtr& resultType, const core::QueryConfig& config) {
+  AggregateFunctionFactory factory;
+  {
+    std::lock_guard<std::mutex> l(aggregateFunctionMutex());
+    auto it = aggregateFunctions().find(name);
+    if (it == aggregateFunctions().end()) throw VeloxUserError("Aggregate function not registered: " + name);
+    factory = it->second.factory;
+  }
+  return factory(step, argTypes, resultType, config);
 }
 
 // ---- operators --------------------------------------------------------------------------------

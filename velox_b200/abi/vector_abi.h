@@ -52,6 +52,7 @@ class VeloxUserError : public VeloxException {
   do {                                                                             \
     if (!(cond)) throw ::facebook::velox::VeloxUserError(std::string(msg));        \
   } while (0)
+#define VELOX_FAIL(msg) throw ::facebook::velox::VeloxRuntimeError(std::string(msg))
 #define VELOX_NYI(msg) throw ::facebook::velox::VeloxRuntimeError(std::string("Not yet implemented: ") + (msg))
 #define VELOX_UNSUPPORTED(msg) throw ::facebook::velox::VeloxRuntimeError(std::string("Unsupported: ") + (msg))
 

@@ -64,12 +64,38 @@ __device__ __forceinline__ double as_f64(uint64_t v) { return __longlong_as_doub
 __device__ __forceinline__ uint64_t from_f64(double d) { return (uint64_t)__double_as_longlong(d); }
 )SRC";
 
+// ---- registered device functions (VB2_OP_CALL) -------------------------------------------------
+struct DeviceFn {
+  std::string entry, source;
+  int ret = 0, nargs = 0;
+  int args[3] = {0, 0, 0};
+};
+static std::mutex g_fn_mu;
+static std::vector<DeviceFn> g_fns;
+
+static bool device_fn(int id, DeviceFn* out) {
+  std::lock_guard<std::mutex> lock(g_fn_mu);
+  if (id < 0 || id >= static_cast<int>(g_fns.size())) return false;
+  *out = g_fns[id];
+  return true;
+}
+static const char* ctype_of(int t) {
+  switch (t) {
+    case VB2_BIGINT: return "long long";
+    case VB2_INTEGER: return "int";
+    case VB2_DOUBLE: return "double";
+    case VB2_BOOLEAN: return "bool";
+    default: return nullptr;
+  }
+}
+
 // ---- code generation -----------------------------------------------------------------------------
 struct Gen {
   std::ostringstream o;
   const vb2_program* prog;
   const vb2_column* cols;
   bool ok = true;
+  std::vector<int> used_fns;  // registered functions this kernel calls (their source goes in front)
 
   static std::string V(int r) { return "v" + std::to_string(r); }
   static std::string N(int r) { return "n" + std::to_string(r); }
@@ -189,6 +215,7 @@ struct Gen {
         const int from = B, to = in.type;
         o << "      rnull = " << N(A) << "; rerr = " << E(A) << ";\n      if (!(rnull || rerr)) {\n        const uint64_t v = " << V(A) << ";\n";
         if (from == to) o << "        rv = v;\n";
+        else if (to == VB2_BOOLEAN) o << (from == VB2_DOUBLE ? "        rv = as_f64(v) != 0.0;\n" : "        rv = v != 0;\n");
         else if (to == VB2_DOUBLE) o << "        rv = from_f64((double)(long long)v);\n";
         else if (from == VB2_DOUBLE) {
           o << "        const double dd = as_f64(v);\n        if (isnan(dd)) " << raise("3") << " else {\n          const double r = round(dd);\n";
@@ -211,6 +238,25 @@ struct Gen {
         else o << "        rv = cmp_int<int>(" << Cc << ", str_compare(s, sl, " << K(B) << ".str, " << K(B) << ".len), 0);\n";
         o << "      }\n      }\n";
         break;
+      case VB2_OP_CALL: {
+        DeviceFn f;
+        if (!device_fn(VB2_CALL_FN(in.type), &f)) { ok = false; break; }
+        const int regs[3] = {A, B, Cc};
+        o << "      rnull = false; rerr = false;\n";
+        for (int i = 0; i < f.nargs; ++i) o << "      rnull |= " << N(regs[i]) << "; rerr |= " << E(regs[i]) << ";\n";
+        o << "      if (!(rnull || rerr)) {\n        const " << ctype_of(f.ret) << " r = " << f.entry << "(";
+        for (int i = 0; i < f.nargs; ++i) {
+          if (i) o << ", ";
+          if (f.args[i] == VB2_DOUBLE) o << "as_f64(" << V(regs[i]) << ")";
+          else if (f.args[i] == VB2_BOOLEAN) o << "(" << V(regs[i]) << " != 0)";
+          else o << "(" << ctype_of(f.args[i]) << ")(long long)" << V(regs[i]);
+        }
+        o << ");\n        rv = " << (f.ret == VB2_DOUBLE ? "from_f64(r)" : f.ret == VB2_BOOLEAN ? "(uint64_t)(r ? 1 : 0)" : "(uint64_t)(long long)r") << ";\n      }\n";
+        bool seen = false;
+        for (int u : used_fns) seen = seen || u == VB2_CALL_FN(in.type);
+        if (!seen) used_fns.push_back(VB2_CALL_FN(in.type));
+        break;
+      }
       default: ok = false;
     }
     o << "      " << V(d) << " = rv; " << N(d) << " = rnull; " << E(d) << " = rerr;\n    }\n";
@@ -279,7 +325,12 @@ static std::string generate(const vb2_program* p, int n_instrs, const vb2_column
   }
   o << "  }\n}\n";
   *ok = g.ok;
-  return std::string(kPrelude) + o.str();
+  std::string fns;
+  for (int id : g.used_fns) {
+    DeviceFn f;
+    if (device_fn(id, &f)) fns += "// registered device function " + std::to_string(id) + "\n" + f.source + "\n";
+  }
+  return std::string(kPrelude) + fns + o.str();
 }
 
 static std::shared_ptr<Kernel> compile(const std::string& src) {
@@ -372,6 +423,27 @@ int launch(const vb2_program* p, const vb2_column* cols, int ncols, bool filter,
 }  // namespace vb2
 
 extern "C" {
+
+int32_t vb2k_register_device_function(const char* entry, const char* cuda_source, int32_t ret_type, const int32_t* arg_types, int32_t nargs) {
+  using namespace vb2::jit;
+  if (!entry || !cuda_source || nargs < 1 || nargs > 3 || !ctype_of(ret_type)) return -VB2_ERR_INVALID;
+  DeviceFn f;
+  f.entry = entry;
+  f.source = cuda_source;
+  f.ret = ret_type;
+  f.nargs = nargs;
+  for (int i = 0; i < nargs; ++i) {
+    if (!ctype_of(arg_types[i])) return -VB2_ERR_INVALID;
+    f.args[i] = arg_types[i];
+  }
+  std::lock_guard<std::mutex> lock(g_fn_mu);
+  g_fns.push_back(std::move(f));  // ids are never reused: cached kernels of an overwritten function stay valid for old programs
+  return static_cast<int32_t>(g_fns.size()) - 1;
+}
+int32_t vb2k_device_function_count(void) {
+  std::lock_guard<std::mutex> lock(vb2::jit::g_fn_mu);
+  return static_cast<int32_t>(vb2::jit::g_fns.size());
+}
 
 void vb2k_set_expression_jit(int32_t enabled) { vb2::jit::g_enabled = enabled ? 1 : 0; }
 

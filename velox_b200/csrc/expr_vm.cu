@@ -221,6 +221,7 @@ __device__ void run_program(const VmArgs& a, int n_instrs, int64_t row, RowState
         const int from = in.b, to = in.type;
         const uint64_t v = st.r(in.a);
         if (from == to) rv = v;
+        else if (to == VB2_BOOLEAN) rv = from == VB2_DOUBLE ? (as_f64(v) != 0.0) : (v != 0);  // folly::to<bool>: value != 0 (NaN -> true)
         else if (to == VB2_DOUBLE) rv = from_f64(static_cast<double>(static_cast<int64_t>(v)));
         else if (from == VB2_DOUBLE) {
           const double d = as_f64(v);
@@ -457,6 +458,14 @@ static int vm_smem(K kernel, const vb2_program* prog, size_t* bytes) {
 // NULL constant, and only operations that neither raise nor produce NULL from non-NULL inputs
 // (double arithmetic except nothing, comparisons, BETWEEN, AND / OR / NOT, IS_NULL, CASE with ELSE,
 // LIKE / string compare against non-NULL patterns).
+// Registered device functions exist as source text only: the interpreter cannot run them.
+static bool calls_registered_function(const vb2_program* prog, int n_instrs) {
+  for (int i = 0; i < n_instrs; ++i)
+    if (prog->instrs[i].op == VB2_OP_CALL) return true;
+  return false;
+}
+static const char kNeedsJit[] = "the expression calls a registered device function, which needs the expression JIT (NVRTC missing, disabled, or the function's source does not compile)";
+
 static bool plain_program(const vb2_program* prog, int n_instrs, const vb2_column* cols) {
   for (int i = 0; i < n_instrs; ++i) {
     const vb2_instr& in = prog->instrs[i];
@@ -480,7 +489,7 @@ static bool plain_program(const vb2_program* prog, int n_instrs, const vb2_colum
         if (in.c < 0) return false;  // CASE without ELSE yields NULL
         break;
       case VB2_OP_CAST:
-        if (!(in.type == VB2_DOUBLE || in.b == in.type || (in.type == VB2_BIGINT && in.b != VB2_DOUBLE))) return false;  // narrowing casts can raise
+        if (!(in.type == VB2_DOUBLE || in.type == VB2_BOOLEAN || in.b == in.type || (in.type == VB2_BIGINT && in.b != VB2_DOUBLE))) return false;  // narrowing casts can raise
         break;
       default:
         return false;
@@ -533,6 +542,7 @@ int vb2k_eval_filter(const vb2_program* prog, const vb2_column* cols, int32_t nc
   VB2_CUDA_OK(cudaMemsetAsync(sel_bits + nwords64 - 1, 0, sizeof(uint64_t), st));
   rc = jit::launch(prog, cols, ncols, true, nullptr, rows, reinterpret_cast<uint32_t*>(sel_bits), nullptr, 0, error_flag, st);
   if (rc != VB2_ERR_UNSUPPORTED) return rc;
+  if (calls_registered_function(prog, prog->n_filter_instrs)) return fail_msg(VB2_ERR_UNSUPPORTED, kNeedsJit);
   size_t smem = 0;
   if (plain_program(prog, prog->n_filter_instrs, cols)) {
     if ((rc = vm_smem(vm_filter_kernel<true>, prog, &smem))) return rc;
@@ -586,6 +596,7 @@ int vb2k_eval_project(const vb2_program* prog, const vb2_column* cols, int32_t n
   a.error_flag = error_flag;
   rc = jit::launch(prog, cols, ncols, false, sel, n, nullptr, outs, nouts, error_flag, static_cast<cudaStream_t>(stream));
   if (rc != VB2_ERR_UNSUPPORTED) return rc;
+  if (calls_registered_function(prog, prog->n_instrs)) return fail_msg(VB2_ERR_UNSUPPORTED, kNeedsJit);
   size_t smem = 0;
   if (plain_program(prog, prog->n_instrs, cols)) {
     if ((rc = vm_smem(vm_project_kernel<true>, prog, &smem))) return rc;

@@ -64,6 +64,38 @@ struct AccState {
 
 }  // namespace
 
+void registerB200Aggregate(const std::string& name, const std::string& family, const std::string& inputFunction, const std::string& finalFunction) {
+  static const std::set<std::string> kFamilies = {"sum", "avg", "count", "min", "max"};
+  VELOX_CHECK(kFamilies.count(family) == 1, "aggregate family must be one of sum avg count min max, not '" + family + "'");
+  auto sig = std::make_shared<exec::AggregateFunctionSignature>();
+  sig->argTypes = {"T"};
+  sig->returnType = family == "count" ? "bigint" : (family == "avg" ? "double" : "T");
+  sig->intermediateType = family == "avg" ? "row(double,bigint)" : sig->returnType;
+  exec::registerAggregateFunction(
+      name, {sig},
+      [family, inputFunction, finalFunction](core::AggregationNode::Step, const std::vector<TypePtr>&, const TypePtr& resultType, const core::QueryConfig&) {
+        return std::make_unique<B200Aggregate>(resultType, family, inputFunction, finalFunction);
+      },
+      /*registerCompanionFunctions=*/false, /*overwrite=*/true);
+}
+
+void registerB200Aggregates() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // prestosql/aggregates/{Sum,Average,Count,MinMax}Aggregate.cpp register these names on the CPU
+    for (const char* fn : {"sum", "avg", "count", "min", "max"}) registerB200Aggregate(fn, fn, "", "");
+  });
+}
+
+TypePtr scalarFunctionReturnType(const std::string& name, const TypePtr& argType) {
+  registerB200Functions();
+  auto fn = exec::getVectorFunction(name);
+  VELOX_CHECK(fn != nullptr, "scalar function '" + name + "' is not registered");
+  if (auto* user = dynamic_cast<const B200DeviceFunction*>(fn.get())) return user->returnType();
+  static const std::set<std::string> kBool = {"lt", "lte", "gt", "gte", "eq", "neq", "between", "like", "not", "is_null"};
+  return kBool.count(name) ? BOOLEAN() : argType;
+}
+
 struct B200HashAggregation::Impl {
   B200HashAggregation* self;
   std::shared_ptr<const core::AggregationNode> node;
@@ -89,6 +121,9 @@ struct B200HashAggregation::Impl {
   DeviceBufferPtr numGroupsDev;
   int64_t numGroupsUpper = 0;  // upper bound of distinct groups seen (hash mode sizing)
   std::vector<AccState> accs;
+  // registered aggregates with an input / final transform (B200Aggregate): evaluated by the expression engine
+  std::unique_ptr<CompiledProgram> inputProgram, finalProgram;
+  RowTypePtr inputProgramType, extractType;
   DeviceBufferPtr errorFlag;
   bool sawInput = false;
   bool outputDone = false;
@@ -140,6 +175,7 @@ struct B200HashAggregation::Impl {
     fin = node->isFinalOutput();
     const auto& inType = node->sources()[0]->outputType();
     resolved = resolveAggregation(*node);
+    resolveRegisteredAggregates(inType);
     for (int32_t k : resolved.keys) {
       KeyState ks;
       ks.kind = inType->childAt(k)->kind();
@@ -186,6 +222,76 @@ struct B200HashAggregation::Impl {
     capacity = 1;
     allocateStorage(capacity, mode);
     planFused();
+  }
+
+  // Every aggregate name goes through the registry (Aggregate::create, exec/Aggregate.h:361): the
+  // B200Aggregate it yields names the device accumulator family and the optional transforms.
+  void resolveRegisteredAggregates(const RowTypePtr& inType) {
+    registerB200Aggregates();
+    const auto& cfg = self->driverCtx()->queryConfig();
+    std::vector<core::TypedExprPtr> inExprs, finExprs;
+    std::vector<std::string> inNames = inType->names();
+    std::vector<TypePtr> inTypes = inType->children();
+    for (uint32_t i = 0; i < inType->size(); ++i) inExprs.push_back(std::make_shared<core::FieldAccessTypedExpr>(inType->childAt(i), inType->nameOf(i)));
+    const RowTypePtr& outType = node->outputType();
+    const size_t nk = resolved.keys.size();
+    for (size_t k = 0; k < nk; ++k) finExprs.push_back(std::make_shared<core::FieldAccessTypedExpr>(outType->childAt(k), outType->nameOf(k)));
+    bool anyInput = false, anyFinal = false;
+    std::vector<TypePtr> preTypes(outType->children().begin(), outType->children().begin() + nk);  // output of the extraction, before final transforms
+    uint32_t outCol = static_cast<uint32_t>(nk);
+    for (size_t i = 0; i < resolved.aggregates.size(); ++i) {
+      auto& a = resolved.aggregates[i];
+      const auto& call = node->aggregates()[i].call;
+      std::vector<TypePtr> argTypes;
+      for (auto& in : call->inputs()) argTypes.push_back(in->type());
+      auto created = exec::Aggregate::create(a.function, node->step(), argTypes, call->type(), cfg);
+      auto* agg = dynamic_cast<B200Aggregate*>(created.get());
+      if (!agg) VELOX_UNSUPPORTED("aggregate function " + a.function + " has no B200 implementation (register a B200Aggregate)");
+      a.function = agg->family();
+      if (!agg->inputFunction().empty() && raw && !a.inputs.empty()) {
+        // aggregate the transformed column: it is appended to the input batch by one projection kernel
+        const int32_t src = a.inputs[0];
+        const TypePtr t = scalarFunctionReturnType(agg->inputFunction(), inType->childAt(src));
+        inExprs.push_back(std::make_shared<core::CallTypedExpr>(t, std::vector<core::TypedExprPtr>{inExprs[src]}, agg->inputFunction()));
+        a.inputs[0] = static_cast<int32_t>(inTypes.size());
+        inNames.push_back("\x01" "b200.agg_in#" + std::to_string(i));
+        inTypes.push_back(t);
+        a.rawInputType = t;
+        anyInput = true;
+      } else if (!agg->inputFunction().empty() && a.rawInputType) {
+        a.rawInputType = scalarFunctionReturnType(agg->inputFunction(), a.rawInputType);  // later steps: the type the accumulator holds
+      }
+      const bool twoCols = a.function == "avg" && !fin;  // intermediate avg: (sum, count)
+      TypePtr extracted = outType->childAt(outCol);
+      if (fin && !agg->finalFunction().empty()) {
+        // type the family itself produces, before the final transform
+        if (a.function == "avg") extracted = DOUBLE();
+        else if (a.function == "count") extracted = BIGINT();
+        else if (a.function == "sum") extracted = (a.rawInputType && a.rawInputType->kind() == TypeKind::DOUBLE) ? DOUBLE() : BIGINT();
+        else extracted = a.rawInputType;
+        auto f = std::make_shared<core::FieldAccessTypedExpr>(extracted, outType->nameOf(outCol));
+        const TypePtr t = scalarFunctionReturnType(agg->finalFunction(), extracted);
+        VELOX_CHECK(t->kind() == outType->childAt(outCol)->kind(), "aggregate " + call->name() + ": the plan's result type differs from its final function's");
+        finExprs.push_back(std::make_shared<core::CallTypedExpr>(t, std::vector<core::TypedExprPtr>{f}, agg->finalFunction()));
+        anyFinal = true;
+      } else {
+        finExprs.push_back(std::make_shared<core::FieldAccessTypedExpr>(outType->childAt(outCol), outType->nameOf(outCol)));
+        if (twoCols) finExprs.push_back(std::make_shared<core::FieldAccessTypedExpr>(outType->childAt(outCol + 1), outType->nameOf(outCol + 1)));
+      }
+      preTypes.push_back(extracted);
+      if (twoCols) preTypes.push_back(outType->childAt(outCol + 1));
+      outCol += twoCols ? 2 : 1;
+    }
+    if (anyInput) {
+      inputProgramType = ROW(inNames, inTypes);
+      inputProgram = std::make_unique<CompiledProgram>(compileExprs(inExprs, false, inType));
+      inputProgram->uploadConstants(st());
+    }
+    if (anyFinal) {
+      extractType = ROW(outType->names(), preTypes);
+      finalProgram = std::make_unique<CompiledProgram>(compileExprs(finExprs, false, extractType));
+      finalProgram->uploadConstants(st());
+    }
   }
 
   uint64_t identityBits(const AccState& s) const {
@@ -652,6 +758,8 @@ struct B200HashAggregation::Impl {
     }
     sawGeneric = true;
     numGroupsUpper += n;
+    // an array-mode table cannot hold more groups than it has slots, however many rows went in
+    if (mode == Mode::kArray) numGroupsUpper = std::min<int64_t>(numGroupsUpper, capacity);
     if (mode == Mode::kHash || mode == Mode::kKeyed) {
       // tighten the bound with the real group count (one 8-byte read per batch)
       int64_t g = 0;
@@ -666,6 +774,7 @@ struct B200HashAggregation::Impl {
   // Decides at plan time whether the absorbed chain can be expressed as one fused pipeline.
   void planFused() {
     if (!raw || !self->driverCtx()->queryConfig().b200FusedPipelines()) return;
+    if (inputProgram) return;  // transformed inputs are columns the fused scan does not produce
     if (keys.size() > VB2_FUSED_MAX_KEYS) return;
     // shape of the absorbed chain
     B200FilterProject *fp1 = nullptr, *fp2 = nullptr;
@@ -1051,6 +1160,7 @@ struct B200HashAggregation::Impl {
       else if (auto pr = dynamic_cast<B200HashProbe*>(op.get())) cur = pr->apply(cur);
       if (!cur) return;  // every row filtered out
     }
+    if (inputProgram) cur = evalProjections(*inputProgram, cur, nullptr, cur->size(), st(), errorFlag, inputProgramType, self->pool());
     // Hash-mode tables are sized by (groups so far + rows of one pass): large batches go through
     // find-or-insert in bounded passes so a high-cardinality table ends near 2x its group count
     // instead of 2x the batch.
@@ -1109,6 +1219,12 @@ struct B200HashAggregation::Impl {
   // are compacted inside that kernel and the whole arena comes back to pinned host memory with the
   // row count in a single copy + synchronisation; B200ToHost then reads the host mirror.
   B200VectorPtr output() {
+    auto out = extractGroups();
+    if (out && finalProgram) out = evalProjections(*finalProgram, out, nullptr, out->size(), st(), errorFlag, node->outputType(), self->pool());
+    return out;
+  }
+
+  B200VectorPtr extractGroups() {
     flushFused();
     if (!sawInput && mode != Mode::kGlobal) return nullptr;  // a grouped aggregation over no input emits nothing
     const bool small = capacity <= VB2_EXTRACT_SMALL_CAPACITY;
@@ -1120,7 +1236,7 @@ struct B200HashAggregation::Impl {
       if (m == 0) return nullptr;
     }
     const int64_t rowsCap = small ? capacity : m;
-    const auto& outType = node->outputType();
+    const RowTypePtr& outType = finalProgram ? extractType : node->outputType();  // final transforms run on the extracted batch
     const auto& inType = node->sources()[0]->outputType();
 
     struct ColPlan {

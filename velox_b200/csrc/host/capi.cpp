@@ -385,6 +385,87 @@ int32_t vb2_tasks_run(vb2_task* const* tasks, int32_t ntasks, char* err, int32_t
   return VB2_OK;
 }
 
+int32_t vb2_register_scalar_function(const char* name, const char* entry, const char* cuda_source, int32_t ret_type, const int32_t* arg_types,
+                                     int32_t nargs, char* err, int32_t errlen) {
+  return guarded(err, errlen, [&] {
+    VELOX_CHECK(name && entry && cuda_source && nargs >= 1 && nargs <= 3, "vb2_register_scalar_function: name, entry, source and 1-3 argument types");
+    registerB200Functions();
+    std::vector<TypePtr> args;
+    auto sig = std::make_shared<exec::FunctionSignature>();
+    auto nameOf = [](int32_t t) -> std::string {
+      std::string n = typeOf(t)->toString();
+      for (auto& c : n) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+      return n;
+    };
+    for (int32_t i = 0; i < nargs; ++i) {
+      args.push_back(typeOf(arg_types[i]));
+      sig->argTypes.push_back(nameOf(arg_types[i]));
+    }
+    sig->returnType = nameOf(ret_type);
+    exec::registerVectorFunction(name, {sig}, std::make_unique<B200DeviceFunction>(entry, cuda_source, typeOf(ret_type), args));
+  });
+}
+
+int32_t vb2_register_aggregate_function(const char* name, const char* family, const char* input_function, const char* final_function, char* err,
+                                        int32_t errlen) {
+  return guarded(err, errlen, [&] {
+    VELOX_CHECK(name && family, "vb2_register_aggregate_function: name and family");
+    registerB200Aggregates();
+    const std::string in = input_function ? input_function : "", fin = final_function ? final_function : "";
+    if (!in.empty()) scalarFunctionReturnType(in, DOUBLE());   // throws when the function is not registered
+    if (!fin.empty()) scalarFunctionReturnType(fin, DOUBLE());
+    registerB200Aggregate(name, family, in, fin);
+  });
+}
+
+int32_t vb2_scalar_function_apply(const char* name, const vb2_column* args, int32_t nargs, int64_t rows, const uint64_t* selected, int32_t ret_type,
+                                  void* out_values, uint8_t* out_nulls, char* err, int32_t errlen) {
+  return guarded(err, errlen, [&] {
+    registerB200Functions();
+    auto fn = exec::getVectorFunction(name);
+    VELOX_CHECK(fn != nullptr, std::string("scalar function '") + name + "' is not registered");
+    static memory::MemoryPool pool("b200.apply");
+    std::vector<VectorPtr> argv;
+    for (int32_t i = 0; i < nargs; ++i) argv.push_back(importHostColumn(&pool, args[i], rows));
+    const vector_size_t n = static_cast<vector_size_t>(rows);
+    SelectivityVector sel(n, true);
+    if (selected) sel.setFromBits(selected, n);
+    // a pre-allocated result holding the caller's current values: apply() may only overwrite selected rows
+    const TypePtr type = typeOf(ret_type);
+    VectorPtr result;
+    auto prefill = [&](auto tag) {
+      using T = decltype(tag);
+      auto values = AlignedBuffer::allocate<T>(n ? n : 1, &pool);
+      std::memcpy(values->template asMutable<T>(), out_values, static_cast<size_t>(n) * sizeof(T));
+      result = std::make_shared<FlatVector<T>>(&pool, type, nullptr, n, values);
+    };
+    if (ret_type == VB2_BOOLEAN) {
+      auto values = std::make_shared<Buffer>(bits::nbytes(n), &pool);
+      std::memset(values->asMutable<uint8_t>(), 0, values->capacity());
+      for (vector_size_t i = 0; i < n; ++i) bits::setBit(values->asMutable<uint64_t>(), i, static_cast<const uint8_t*>(out_values)[i] != 0);
+      result = std::make_shared<FlatVector<bool>>(&pool, type, nullptr, n, values);
+    } else if (ret_type == VB2_INTEGER) prefill(int32_t{});
+    else if (ret_type == VB2_BIGINT) prefill(int64_t{});
+    else if (ret_type == VB2_DOUBLE) prefill(double{});
+    else VELOX_UNSUPPORTED("apply: result type");
+    for (vector_size_t i = 0; i < n; ++i)
+      if (out_nulls[i]) result->setNull(i, true);
+    exec::EvalCtx ctx(&pool);
+    fn->apply(sel, argv, type, ctx, result);
+    VELOX_CHECK(result && result->size() >= n && result->isFlatEncoding(), "apply: function returned an unexpected vector");
+    for (vector_size_t i = 0; i < n; ++i) {
+      out_nulls[i] = result->isNullAt(i) ? 1 : 0;
+      if (out_nulls[i]) continue;
+      switch (ret_type) {
+        case VB2_BOOLEAN: static_cast<uint8_t*>(out_values)[i] = result->as<FlatVector<bool>>()->valueAt(i); break;
+        case VB2_INTEGER: static_cast<int32_t*>(out_values)[i] = result->as<FlatVector<int32_t>>()->valueAt(i); break;
+        case VB2_BIGINT: static_cast<int64_t*>(out_values)[i] = result->as<FlatVector<int64_t>>()->valueAt(i); break;
+        default: static_cast<double*>(out_values)[i] = result->as<FlatVector<double>>()->valueAt(i);
+      }
+    }
+  });
+}
+
 // Diagnostic (no GPU needed): compiles the expression programs of every Filter / Project node of a
 // plan with the expression compiler and reports how many of their kernels the expression JIT can
 // generate and NVRTC-compile for a flat, NULL-free input (VARCHAR as a dictionary column).

@@ -170,9 +170,12 @@ DeviceBufferPtr upload(const void* src, size_t bytes, cudaStream_t stream) {
   if (cache) {
     std::lock_guard<std::mutex> lock(cache->mu);
     auto it = cache->entries.find(reinterpret_cast<uint64_t>(src));
-    if (it != cache->entries.end() && it->second.first == bytes) {
+    if (it != cache->entries.end() && it->second.bytes == bytes) {
       cache->hitBytes += static_cast<int64_t>(bytes);
-      return it->second.second;
+      // the copy may still be in flight on another task's stream
+      if (it->second.stream != stream && it->second.copied)
+        VB2_CU(cudaStreamWaitEvent(stream, static_cast<cudaEvent_t>(it->second.copied.get()), 0));
+      return it->second.buffer;
     }
   }
   auto b = allocDevice(bytes, stream);
@@ -180,7 +183,11 @@ DeviceBufferPtr upload(const void* src, size_t bytes, cudaStream_t stream) {
   tlsUploadedBytes += static_cast<int64_t>(bytes);
   if (cache) {
     std::lock_guard<std::mutex> lock(cache->mu);
-    cache->entries[reinterpret_cast<uint64_t>(src)] = {bytes, b};
+    cudaEvent_t ev = nullptr;
+    VB2_CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    VB2_CU(cudaEventRecord(ev, stream));
+    cache->entries[reinterpret_cast<uint64_t>(src)] =
+        UploadCache::Entry{bytes, b, stream, std::shared_ptr<void>(ev, [](void* e) { cudaEventDestroy(static_cast<cudaEvent_t>(e)); })};
     cache->missBytes += static_cast<int64_t>(bytes);
   }
   return b;

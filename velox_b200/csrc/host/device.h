@@ -121,11 +121,17 @@ DeviceColumnPtr borrowFlatColumn(TypePtr type, const void* values, int64_t size)
 // the calling thread, host buffers that go through upload() are remembered by (address, bytes) and a
 // later upload of the same buffer returns the resident device copy instead of crossing PCIe again.
 // The caller guarantees that registered host buffers are neither modified nor freed while the cache
-// lives. Uploads happen on the uploading task's stream; a reusing task must start after that task's
-// run() returned (run() ends with a synchronised ToHost).
+// lives. Uploads happen on the uploading task's stream; every entry carries an event recorded after
+// its copy, and a hit from another stream waits on it (tasks may run concurrently, vb2_tasks_run).
 struct UploadCache {
+  struct Entry {
+    size_t bytes = 0;
+    DeviceBufferPtr buffer;
+    cudaStream_t stream = nullptr;  // stream the copy was issued on
+    std::shared_ptr<void> copied;   // cudaEvent_t recorded after the copy
+  };
   std::mutex mu;
-  std::unordered_map<uint64_t, std::pair<size_t, DeviceBufferPtr>> entries;  // host address -> (bytes, device copy)
+  std::unordered_map<uint64_t, Entry> entries;  // host address -> device copy
   int64_t hitBytes = 0, missBytes = 0;
 };
 void setThreadUploadCache(UploadCache* cache);  // nullptr detaches

@@ -1,4 +1,5 @@
 #include "expr_compiler.h"
+#include "operators.h"
 #include "plan_resolve.h"
 
 #include <cstring>
@@ -11,17 +12,22 @@ namespace {
 // B200 scalar function: resolved by name through the registry; the device body is an opcode of
 // the expression VM, so whole expression trees fuse into one kernel launch. Node-at-a-time
 // apply() is not how the device engine runs.
-class B200ScalarFunction : public exec::VectorFunction {
+class B200ScalarFunction : public B200VectorFunction {
  public:
   explicit B200ScalarFunction(int opcode) : opcode_(opcode) {}
   int opcode() const { return opcode_; }
-  void apply(const SelectivityVector&, std::vector<VectorPtr>&, const TypePtr&, exec::EvalCtx&, VectorPtr&) const override {
-    VELOX_NYI("B200 scalar functions execute inside the fused expression program (vb2k_eval_project), not node-at-a-time");
-  }
 
  private:
   int opcode_;
 };
+
+// Name a function object is registered under (apply() compiles a call by name).
+std::string registeredNameOf(const exec::VectorFunction* fn) {
+  std::lock_guard<std::mutex> l(exec::vectorFunctionMutex());
+  for (auto& [name, entry] : exec::vectorFunctionFactories())
+    if (entry.function.get() == fn) return name;
+  VELOX_FAIL("VectorFunction::apply on a function object that is not in the registry");
+}
 
 exec::FunctionSignaturePtr sig(std::string ret, std::vector<std::string> args) {
   auto s = std::make_shared<exec::FunctionSignature>();
@@ -122,7 +128,7 @@ struct Compiler {
     if (dynamic_cast<const core::CastTypedExpr*>(e.get())) {
       const int a = compile(e->inputs()[0]);
       const int from = veloxTypeToVb2(e->inputs()[0]->type());
-      if (from != t) out.canRaise = out.canRaise || from == VB2_DOUBLE || (from == VB2_BIGINT && t == VB2_INTEGER);
+      if (from != t && t != VB2_BOOLEAN) out.canRaise = out.canRaise || from == VB2_DOUBLE || (from == VB2_BIGINT && t == VB2_INTEGER);
       return emit(VB2_OP_CAST, t, a, from);
     }
     auto call = dynamic_cast<const core::CallTypedExpr*>(e.get());
@@ -146,6 +152,20 @@ struct Compiler {
         acc = emit(VB2_OP_SELECT, t, cond, val, acc);
       }
       return acc;
+    }
+    registerB200Functions();
+    if (auto fn = exec::getVectorFunction(name)) {
+      if (auto* user = dynamic_cast<const B200DeviceFunction*>(fn.get())) {
+        // registered device function: one CALL instruction, fused into the kernel of this ExprSet
+        VELOX_CHECK(in.size() == user->argTypes().size(), name + ": takes " + std::to_string(user->argTypes().size()) + " arguments");
+        VELOX_CHECK(user->returnType()->kind() == e->type()->kind(), name + ": returns " + user->returnType()->toString());
+        int regs[3] = {-1, -1, -1};
+        for (size_t i = 0; i < in.size(); ++i) {
+          VELOX_CHECK(in[i]->type()->kind() == user->argTypes()[i]->kind(), name + ": argument " + std::to_string(i) + " must be " + user->argTypes()[i]->toString());
+          regs[i] = compile(in[i]);
+        }
+        return emit(VB2_OP_CALL, t | (user->id() << 8), regs[0], regs[1], regs[2]);
+      }
     }
     const int opcode = opcodeForFunction(name);
     if (opcode < 0) VELOX_UNSUPPORTED("scalar function '" + name + "' is not registered for the B200 engine");
@@ -199,6 +219,68 @@ struct Compiler {
 };
 
 }  // namespace
+
+B200DeviceFunction::B200DeviceFunction(std::string entry, std::string cudaSource, TypePtr returnType, std::vector<TypePtr> argTypes)
+    : returnType_(std::move(returnType)), argTypes_(std::move(argTypes)) {
+  VELOX_CHECK(!argTypes_.empty() && argTypes_.size() <= 3, "device functions take one to three arguments");
+  std::vector<int32_t> at;
+  for (auto& a : argTypes_) at.push_back(veloxTypeToVb2(a));
+  id_ = vb2k_register_device_function(entry.c_str(), cudaSource.c_str(), veloxTypeToVb2(returnType_), at.data(), static_cast<int32_t>(at.size()));
+  VELOX_CHECK(id_ >= 0, "device function '" + entry + "': BIGINT / INTEGER / DOUBLE / BOOLEAN arguments and result only");
+}
+
+void B200VectorFunction::apply(const SelectivityVector& rows, std::vector<VectorPtr>& args, const TypePtr& outputType, exec::EvalCtx&,
+                               VectorPtr& result) const {
+  if (!rows.hasSelections()) return;
+  const std::string name = registeredNameOf(this);
+  const vector_size_t n = rows.end();
+  std::vector<std::string> names;
+  std::vector<TypePtr> types;
+  std::vector<core::TypedExprPtr> fields;
+  for (size_t i = 0; i < args.size(); ++i) {
+    VELOX_CHECK(args[i] && args[i]->size() >= n, name + ": argument vector shorter than the selected rows");
+    names.push_back("a" + std::to_string(i));
+    types.push_back(args[i]->type());
+    fields.push_back(std::make_shared<core::FieldAccessTypedExpr>(args[i]->type(), names.back()));
+  }
+  auto rowType = ROW(names, types);
+  auto pool = args.empty() ? nullptr : args[0]->pool();
+  auto host = std::make_shared<RowVector>(pool, rowType, nullptr, n, args);
+  auto dev = driverDeviceContext(nullptr);  // node-at-a-time calls share one stream per process
+  auto call = std::make_shared<core::CallTypedExpr>(outputType, fields, name);
+  CompiledProgram program = compileExprs({call}, false, rowType);
+  program.uploadConstants(dev->stream);
+  auto in = toDevice(host, dev->stream);
+  auto flag = allocDeviceZeroed(8, dev->stream);
+  auto out = evalProjections(program, in, nullptr, n, dev->stream, flag, ROW({"r"}, {outputType}), pool);
+  checkDeviceError(flag, dev->stream, name.c_str());
+  VectorPtr computed = toHost(out)->childAt(0);
+  if (!result || rows.countSelected() == n) {
+    // nothing to preserve (no pre-allocated result, or every row selected): hand the computed vector over
+    if (!result || result->size() <= n) { result = computed; return; }
+  }
+  // result-reuse rule (VectorFunction.h:44-80): only the selected rows may be overwritten
+  VELOX_CHECK(result->isFlatEncoding() && result->size() >= n, name + ": pre-allocated result must be a flat vector covering the selected rows");
+  auto copy = [&](auto tag) {
+    using T = decltype(tag);
+    auto* dst = result->as<FlatVector<T>>();
+    auto* src = computed->as<FlatVector<T>>();
+    rows.applyToSelected([&](vector_size_t i) {
+      const bool null = src->isNullAt(i);
+      result->setNull(i, null);
+      if (null) return;
+      if constexpr (std::is_same_v<T, bool>) bits::setBit(dst->values()->template asMutable<uint64_t>(), i, src->valueAt(i));
+      else dst->mutableRawValues()[i] = src->valueAt(i);
+    });
+  };
+  switch (outputType->kind()) {
+    case TypeKind::BOOLEAN: copy(bool{}); break;
+    case TypeKind::INTEGER: copy(int32_t{}); break;
+    case TypeKind::BIGINT: copy(int64_t{}); break;
+    case TypeKind::DOUBLE: copy(double{}); break;
+    default: VELOX_UNSUPPORTED(name + ": result type " + outputType->toString());
+  }
+}
 
 void registerB200Functions() {
   static bool done = false;
@@ -274,6 +356,7 @@ std::vector<bool> CompiledProgram::nullability(const std::vector<bool>& columnMa
       case VB2_OP_LIKE: case VB2_OP_STRCMP: r = columnMayBeNull.at(in.a) || consts[in.b].is_null; break;
       case VB2_OP_NEG: case VB2_OP_NOT: case VB2_OP_CAST: r = n[in.a]; break;
       case VB2_OP_BETWEEN: r = n[in.a] || n[in.b] || n[in.c]; break;
+      case VB2_OP_CALL: r = n[in.a] || (in.b >= 0 && n[in.b]) || (in.c >= 0 && n[in.c]); break;
       default: r = n[in.a] || n[in.b];
     }
     n[in.dst] = r;

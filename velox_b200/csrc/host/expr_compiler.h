@@ -48,6 +48,41 @@ struct CompiledProgram {
 // exprs[0] is the filter when hasFilter. Throws VeloxRuntimeError for unsupported shapes.
 CompiledProgram compileExprs(const std::vector<core::TypedExprPtr>& exprs, bool hasFilter, const RowTypePtr& inputType);
 
+// Runs the projections of a compiled program over rows sel[0..numOut) of a device batch (sel null: all
+// rows): identity outputs are dictionary-wrapped, computed outputs written densely by one kernel.
+B200VectorPtr evalProjections(const CompiledProgram& program, const B200VectorPtr& in, const DeviceBufferPtr& sel, int64_t numOut, cudaStream_t stream,
+                              const DeviceBufferPtr& errorFlag, const RowTypePtr& outputType, memory::MemoryPool* pool);
+
+// Base of every scalar function of the B200 engine. Inside a plan the function is an instruction of
+// the fused expression program (one kernel per ExprSet, never node-at-a-time). apply() — the
+// reference's node-at-a-time contract, velox/expression/VectorFunction.h:81-86 — is implemented on
+// top of the same kernels: host argument vectors are uploaded, a one-call program runs on the device,
+// the selected rows of the result come back (rows outside `rows` keep what `result` held).
+class B200VectorFunction : public exec::VectorFunction {
+ public:
+  void apply(const SelectivityVector& rows, std::vector<VectorPtr>& args, const TypePtr& outputType, exec::EvalCtx& context,
+             VectorPtr& result) const override;
+};
+
+// A user-defined scalar function whose device body is CUDA C++ source text:
+//   exec::registerVectorFunction("hypot2", {sig}, std::make_unique<B200DeviceFunction>(
+//       "hypot2", "__device__ double hypot2(double a, double b) { return sqrt(a * a + b * b); }", DOUBLE(), {DOUBLE(), DOUBLE()}));
+// The expression JIT splices the source into every kernel whose ExprSet calls the function, so it
+// fuses with the surrounding expression like a built-in (include/velox_b200_kernels.h
+// vb2k_register_device_function). NULL arguments yield NULL (default null behaviour).
+class B200DeviceFunction : public B200VectorFunction {
+ public:
+  B200DeviceFunction(std::string entry, std::string cudaSource, TypePtr returnType, std::vector<TypePtr> argTypes);
+  int32_t id() const { return id_; }
+  const TypePtr& returnType() const { return returnType_; }
+  const std::vector<TypePtr>& argTypes() const { return argTypes_; }
+
+ private:
+  int32_t id_ = -1;
+  TypePtr returnType_;
+  std::vector<TypePtr> argTypes_;
+};
+
 // Registers the B200 scalar functions (plus/minus/multiply/divide/modulus/negate, lt..neq,
 // between, like, not, is_null, and/or/switch/cast are special forms) in the registry.
 void registerB200Functions();

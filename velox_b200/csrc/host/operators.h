@@ -85,6 +85,35 @@ class B200FilterProject : public exec::Operator {
 // ---- aggregation ----------------------------------------------------------------------------------
 struct JoinTableHolder;  // join.cpp
 
+// An aggregate function of the B200 engine, created through the reference's registry
+// (exec::registerAggregateFunction / Aggregate::create, velox/exec/Aggregate.h:361-575). The device
+// keeps one 8-byte accumulator word (+ a non-null counter) per aggregate inside the group row
+// (vb2_group_table); a function describes itself as
+//   result = finalFunction( FAMILY( inputFunction(x) ) )
+// where FAMILY is one of the device accumulator families "sum" "avg" "count" "min" "max"
+// (functions/lib/aggregates/{SumAggregateBase,AverageAggregateBase,SimpleNumericAggregate}.h,
+// prestosql/aggregates/CountAggregate.cpp) and the two optional transforms are names of registered
+// scalar functions (built-in or B200DeviceFunction) that B200HashAggregation evaluates with the
+// expression engine: inputFunction on the raw input of the partial / single step, finalFunction on
+// the value the final / single step extracts. SUM / AVG / COUNT / MIN / MAX themselves are
+// registered this way (registerB200Aggregates).
+class B200Aggregate : public exec::Aggregate {
+ public:
+  B200Aggregate(TypePtr resultType, std::string family, std::string inputFunction = "", std::string finalFunction = "")
+      : Aggregate(std::move(resultType)), family_(std::move(family)), inputFunction_(std::move(inputFunction)), finalFunction_(std::move(finalFunction)) {}
+  const std::string& family() const { return family_; }
+  const std::string& inputFunction() const { return inputFunction_; }
+  const std::string& finalFunction() const { return finalFunction_; }
+
+ private:
+  std::string family_, inputFunction_, finalFunction_;
+};
+void registerB200Aggregates();
+// Registers `name` as finalFunction(family(inputFunction(x))); the C ABI's vb2_register_aggregate_function.
+void registerB200Aggregate(const std::string& name, const std::string& family, const std::string& inputFunction, const std::string& finalFunction);
+// Return type of a registered scalar function applied to `argType` (built-ins: comparison -> BOOLEAN, else the argument's type).
+TypePtr scalarFunctionReturnType(const std::string& name, const TypePtr& argType);
+
 // Replaces exec::HashAggregation / GroupingSet / HashTable(group by) / RowContainer / Aggregate
 // (velox/exec/HashAggregation.cpp:191-430, GroupingSet.cpp:190-884). Optionally absorbs the
 // operators feeding it (FilterProject [-> HashProbe -> FilterProject]); when the absorbed

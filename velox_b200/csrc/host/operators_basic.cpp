@@ -178,15 +178,22 @@ B200VectorPtr B200FilterProject::apply(const B200VectorPtr& in) {
     if (numOut == 0) return nullptr;
     if (numOut == n) sel = nullptr;
   }
+  return evalProjections(program_, in, sel, numOut, st, errorFlag_, outputType_, pool());
+}
+
+B200VectorPtr evalProjections(const CompiledProgram& program, const B200VectorPtr& in, const DeviceBufferPtr& sel, int64_t numOut, cudaStream_t st,
+                              const DeviceBufferPtr& errorFlag, const RowTypePtr& outputType, memory::MemoryPool* pool) {
+  std::vector<vb2_column> cols = describe(*in);
+  const vb2_program prog = program.view();
   // which registers can be NULL for this batch
   std::vector<bool> colNull;
   for (auto& c : in->columns()) colNull.push_back(c->mayHaveNulls());
-  const std::vector<bool> regNull = program_.nullability(colNull);
+  const std::vector<bool> regNull = program.nullability(colNull);
 
-  std::vector<DeviceColumnPtr> outCols(program_.outputs.size());
+  std::vector<DeviceColumnPtr> outCols(program.outputs.size());
   std::vector<vb2_output> outs;
-  for (size_t i = 0; i < program_.outputs.size(); ++i) {
-    const auto& o = program_.outputs[i];
+  for (size_t i = 0; i < program.outputs.size(); ++i) {
+    const auto& o = program.outputs[i];
     if (o.identityField >= 0) {
       outCols[i] = wrapColumn(in->column(o.identityField), sel, numOut, st);
       continue;
@@ -209,12 +216,12 @@ B200VectorPtr B200FilterProject::apply(const B200VectorPtr& in) {
   }
   if (!outs.empty()) {
     kernelCheck(vb2k_eval_project(&prog, cols.data(), static_cast<int32_t>(cols.size()), sel ? sel->as<int32_t>() : nullptr, numOut,
-                                  outs.data(), static_cast<int32_t>(outs.size()), errorFlag_->as<int32_t>(), st));
-    if (program_.canRaise) checkDeviceError(errorFlag_, st, "projection");
+                                  outs.data(), static_cast<int32_t>(outs.size()), errorFlag->as<int32_t>(), st));
+    if (program.canRaise) checkDeviceError(errorFlag, st, "projection");
     // pack BOOLEAN byte results into the bit-packed layout of FlatVector<bool>
     for (size_t i = 0; i < outCols.size(); ++i) {
       auto& c = outCols[i];
-      if (program_.outputs[i].identityField < 0 && c->desc.type == VB2_BOOLEAN) {
+      if (program.outputs[i].identityField < 0 && c->desc.type == VB2_BOOLEAN) {
         auto packed = allocDevice(bits::nbytes(numOut), st);
         kernelCheck(vb2k_pack_bools(reinterpret_cast<const uint8_t*>(c->desc.values), numOut, packed->as<uint64_t>(), st));
         c->owners.push_back(packed);
@@ -223,7 +230,7 @@ B200VectorPtr B200FilterProject::apply(const B200VectorPtr& in) {
     }
   }
   // the input batch's buffers back the wrapped columns: the owners lists keep them alive
-  return std::make_shared<B200Vector>(pool(), outputType_, static_cast<vector_size_t>(numOut), std::move(outCols), st);
+  return std::make_shared<B200Vector>(pool, outputType, static_cast<vector_size_t>(numOut), std::move(outCols), st);
 }
 
 RowVectorPtr B200FilterProject::getOutput() {

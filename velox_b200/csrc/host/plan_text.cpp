@@ -2,6 +2,8 @@
 // trees — the structures a Velox application hands to Task::create. Grammar in DESIGN.md and
 // velox_b200/plan.py. (The CPU oracle has its own, independent reader.)
 #include "plan_text.h"
+#include "expr_compiler.h"
+#include "operators.h"
 
 #include <cctype>
 
@@ -131,6 +133,7 @@ class Parser {
       else if (h == "switch" || h == "if") { if (args.size() < 2) throw VeloxRuntimeError("plan text: switch: too few arguments"); t = args[1]->type(); }
       else if (isArithmetic(h)) { need(2); t = args[0]->type(); }
       else if (h == "negate") { need(1); t = args[0]->type(); }
+      else if (auto* user = dynamic_cast<const B200DeviceFunction*>(exec::getVectorFunction(h).get())) t = user->returnType();  // registered by the application
       else throw VeloxRuntimeError("plan text: unknown function " + h);
       out = std::make_shared<core::CallTypedExpr>(t, std::move(args), h);
     }
@@ -241,6 +244,19 @@ class Parser {
         if (r.mask >= 0) a.mask = field(r.mask);
         const std::string n = "n" + id + "a" + std::to_string(aggs.size());
         TypePtr resultType;
+        // registered aggregates (exec::registerAggregateFunction): type the call from the B200Aggregate's family and transforms
+        const std::string callName = r.fn;
+        std::string finalFn;
+        if (r.fn != "count" && r.fn != "sum" && r.fn != "min" && r.fn != "max" && r.fn != "avg") {
+          registerB200Aggregates();
+          if (!exec::getAggregateFunctionEntry(r.fn)) throw VeloxRuntimeError("plan text: unknown aggregate " + r.fn);
+          auto created = exec::Aggregate::create(r.fn, step, {}, nullptr, core::QueryConfig());
+          auto* agg = dynamic_cast<B200Aggregate*>(created.get());
+          if (!agg) throw VeloxRuntimeError("plan text: aggregate " + r.fn + " has no B200 implementation");
+          r.fn = agg->family();
+          if (raw && rawType && !agg->inputFunction().empty()) rawType = scalarFunctionReturnType(agg->inputFunction(), rawType);
+          finalFn = agg->finalFunction();
+        }
         if (r.fn == "count") { resultType = BIGINT(); names.push_back(n); types.push_back(BIGINT()); }
         else if (r.fn == "sum") { resultType = raw ? (rawType->kind() == TypeKind::DOUBLE ? DOUBLE() : BIGINT()) : rawType; names.push_back(n); types.push_back(resultType); }
         else if (r.fn == "min" || r.fn == "max") { resultType = rawType; names.push_back(n); types.push_back(rawType); }
@@ -251,7 +267,11 @@ class Parser {
           if (fin) { names.push_back(n); types.push_back(DOUBLE()); }
           else { names.push_back(n + "_sum"); types.push_back(DOUBLE()); names.push_back(n + "_count"); types.push_back(BIGINT()); }
         } else throw VeloxRuntimeError("plan text: unknown aggregate " + r.fn);
-        a.call = std::make_shared<core::CallTypedExpr>(resultType, std::move(args), r.fn);
+        if (fin && !finalFn.empty()) {
+          resultType = scalarFunctionReturnType(finalFn, resultType);
+          types.back() = resultType;
+        }
+        a.call = std::make_shared<core::CallTypedExpr>(resultType, std::move(args), callName);
         aggs.push_back(std::move(a));
         aggNames.push_back(n);
       }

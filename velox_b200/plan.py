@@ -308,7 +308,20 @@ class _Parser:
             return E(f"(switch {c.sexpr} {a.sexpr} {b.sexpr})", a.type)
         if t[0] == "id":
             if self.peek() == ("op", "("):
-                raise ValueError(f"unsupported function {t[1]}")
+                if t[1] not in USER_FUNCTIONS:
+                    raise ValueError(f"unsupported function {t[1]}")
+                ret, arg_types = USER_FUNCTIONS[t[1]]
+                self.take()
+                args = []
+                while True:
+                    args.append(self.p_or())
+                    if self.accept("op", ")"):
+                        break
+                    self.expect("op", ",")
+                if len(args) != len(arg_types):
+                    raise ValueError(f"{t[1]} takes {len(arg_types)} arguments")
+                args = [_cast(a, ty) for a, ty in zip(args, arg_types)]
+                return E(f"({t[1]} " + " ".join(a.sexpr for a in args) + ")", ret)
             if t[1] not in self.names:
                 raise ValueError(f"unknown column {t[1]} (have {self.names})")
             i = self.names.index(t[1])
@@ -329,7 +342,47 @@ def parse_expr(text: str, names, types):
     return e, alias
 
 
-_AGG = re.compile(r"^\s*(sum|avg|count|min|max)\s*\(\s*([A-Za-z_0-9*]*)\s*\)\s*(?:[aA][sS]\s+([A-Za-z_][A-Za-z_0-9]*))?\s*$")
+# Functions the application registered with the engine (register_scalar_function /
+# register_aggregate_function below): name -> (return type, argument types) and
+# name -> (family, input function, final function). The front-end types calls from these.
+USER_FUNCTIONS: dict = {}
+USER_AGGREGATES: dict = {}
+_BUILTIN_BOOL = {"lt", "lte", "gt", "gte", "eq", "neq", "between", "like", "not", "is_null"}
+
+
+def register_scalar_function(name: str, ret_type: int, arg_types: Sequence[int], cuda_source: str, entry: Optional[str] = None) -> None:
+    """exec::registerVectorFunction for a device function given as CUDA source text
+    (`__device__ RET entry(ARGS...)`; include/velox_b200.h vb2_register_scalar_function)."""
+    import ctypes as C
+    from ._lib import check, lib
+    at = (C.c_int32 * len(arg_types))(*arg_types)
+    err = C.create_string_buffer(1024)
+    rc = lib().vb2_register_scalar_function(name.encode(), (entry or name).encode(), cuda_source.encode(), int(ret_type), at, len(arg_types), err, 1024)
+    if rc:
+        from ._lib import VeloxRuntimeError
+        raise VeloxRuntimeError(err.value.decode(errors="replace"))
+    USER_FUNCTIONS[name] = (int(ret_type), [int(t) for t in arg_types])
+
+
+def _scalar_return_type(name: str, arg_type: int) -> int:
+    if name in USER_FUNCTIONS:
+        return USER_FUNCTIONS[name][0]
+    return BOOLEAN if name in _BUILTIN_BOOL else arg_type
+
+
+def register_aggregate_function(name: str, family: str, input_function: str = "", final_function: str = "") -> None:
+    """exec::registerAggregateFunction: name(x) = final_function(FAMILY(input_function(x))), FAMILY one of
+    sum avg count min max (include/velox_b200.h vb2_register_aggregate_function)."""
+    import ctypes as C
+    from ._lib import lib, VeloxRuntimeError
+    err = C.create_string_buffer(1024)
+    rc = lib().vb2_register_aggregate_function(name.encode(), family.encode(), input_function.encode(), final_function.encode(), err, 1024)
+    if rc:
+        raise VeloxRuntimeError(err.value.decode(errors="replace"))
+    USER_AGGREGATES[name] = (family, input_function, final_function)
+
+
+_AGG = re.compile(r"^\s*([A-Za-z_][A-Za-z_0-9]*)\s*\(\s*([A-Za-z_0-9*]*)\s*\)\s*(?:[aA][sS]\s+([A-Za-z_][A-Za-z_0-9]*))?\s*$")
 
 
 @dataclass
@@ -385,19 +438,25 @@ class PlanBuilder:
             m = _AGG.match(a)
             if not m:
                 raise ValueError(f"bad aggregate {a!r}")
-            fn, arg, alias = m.group(1), m.group(2), m.group(3)
+            name, arg, alias = m.group(1), m.group(2), m.group(3)
+            if name not in ("sum", "avg", "count", "min", "max") and name not in USER_AGGREGATES:
+                raise ValueError(f"unknown aggregate {name!r} (register_aggregate_function)")
+            fn, in_fn, fin_fn = USER_AGGREGATES.get(name, (name, "", ""))  # the plan carries the registered name, typing follows its family
             alias = alias or f"a{j}"
             mask = masks[j] if masks else None
             mask_s = f" (mask {n.names.index(mask)})" if mask else ""
             if fn == "count" and (arg in ("", "*") or arg.isdigit()):
-                specs.append(f"(count{mask_s})")
+                specs.append(f"({name}{mask_s})")
                 in_type = BIGINT
             else:
                 col = n.names.index(arg)
-                in_type = n.types[col]
-                specs.append(f"({fn} {col}{mask_s})")
-            partial_specs.append((fn, alias, in_type))
-            if fn == "avg":
+                in_type = _scalar_return_type(in_fn, n.types[col]) if in_fn else n.types[col]
+                specs.append(f"({name} {col}{mask_s})")
+            partial_specs.append((fn, alias, in_type, name))
+            if fin_fn and step in ("single", "final"):
+                family_type = DOUBLE if fn == "avg" else BIGINT if fn == "count" else (DOUBLE if in_type == DOUBLE else BIGINT) if fn == "sum" else in_type
+                names.append(alias); types.append(_scalar_return_type(fin_fn, family_type))
+            elif fn == "avg":
                 if step in ("single", "final"):
                     names.append(alias); types.append(DOUBLE)
                 else:
@@ -427,9 +486,14 @@ class PlanBuilder:
         nk = len(keys)
         specs, names, types = [], list(keys), n.types[:nk]
         c = nk
-        for fn, alias, _ in n.partial["aggs"]:
-            specs.append(f"({fn} {c})")
-            if fn == "avg":
+        for fn, alias, _, name in n.partial["aggs"]:
+            specs.append(f"({name} {c})")
+            fin_fn = USER_AGGREGATES.get(name, ("", "", ""))[2]
+            if fin_fn and step == "final":
+                family_type = DOUBLE if fn == "avg" else n.types[c]
+                names.append(alias); types.append(_scalar_return_type(fin_fn, family_type))
+                c += 2 if fn == "avg" else 1
+            elif fn == "avg":
                 if step == "final":
                     names.append(alias); types.append(DOUBLE)
                 else:
