@@ -36,6 +36,14 @@ vb2_task* vb2_task_create(const char* plan_text, const char* config, char* err, 
 int32_t vb2_task_add_input(vb2_task* task, int32_t source_id, const vb2_column* cols, int32_t ncols, int64_t rows,
                            int32_t location, char* err, int32_t errlen);
 /* Runs the task to completion (Task::start + drivers; serial execution mode). */
+/* Adds one input batch given through the Arrow C data interface (struct ArrowArray / ArrowSchema of a
+ * record batch: format "+s", children l / i / tdD / g / b / u, optionally dictionary-encoded with int32
+ * indices). The import happens in C++ (csrc/host/arrow_bridge.cpp: importFromArrowAsOwner,
+ * velox/vector/arrow/Bridge.h:170): buffers are viewed, not copied; ownership of both structs moves
+ * to the task, which calls their release callbacks when it is freed. */
+struct ArrowArray;
+struct ArrowSchema;
+int32_t vb2_task_add_arrow(vb2_task* task, int32_t source_id, struct ArrowArray* array, struct ArrowSchema* schema, char* err, int32_t errlen);
 int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen);
 
 /* Runs several prepared tasks concurrently (one host thread each) and returns when all have finished:

@@ -167,6 +167,25 @@ void vb2k_set_expression_jit(int32_t enabled);
 int32_t vb2k_expression_jit_compiles(const vb2_program* prog, const vb2_column* cols, int32_t ncols, int32_t filter, const vb2_output* outs,
                                      int32_t nouts, char* source_out, int32_t source_len);
 
+/* ------------------------------------------------------------------------------------------
+ * ORDER BY: stable multi-key sort producing the row order. Replaces the sort of exec::OrderBy /
+ * SortBuffer (velox/exec/OrderBy.cpp, SortBuffer.cpp) and the ordering of exec::TopN
+ * (velox/exec/TopN.cpp); semantics of core::SortOrder (velox/core/PlanNode.h:64-95): NULLs first or
+ * last independent of direction, NaN largest, -0 == +0. Keys are flat columns (VARCHAR keys are
+ * passed as INTEGER rank codes of their sorted dictionary). order[i] = input row at output position i.
+ * ------------------------------------------------------------------------------------------ */
+#define VB2_SORT_MAX_KEYS 8
+typedef struct vb2_sort_key {
+  const void* values;     /* INTEGER int32 / BIGINT int64 / DOUBLE double / BOOLEAN bit-packed */
+  const uint64_t* nulls;  /* validity bitmap or NULL */
+  int32_t type;
+  int32_t ascending;
+  int32_t nulls_first;
+  int32_t significant_bits; /* > 0: INTEGER / BIGINT values are known to lie in [0, 2^bits): fewer radix passes */
+} vb2_sort_key;
+size_t vb2k_sort_order_workspace(int64_t n, int32_t nkeys);
+int vb2k_sort_order(const vb2_sort_key* keys, int32_t nkeys, int64_t n, int32_t* order, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Registry of user-supplied scalar device functions — the device half of exec::registerVectorFunction
  * (velox/expression/VectorFunction.h:241): `cuda_source` is CUDA C++ text defining
  *   __device__ RET entry(ARG0 [, ARG1 [, ARG2]])      with BIGINT = long long, INTEGER = int, DOUBLE = double, BOOLEAN = bool

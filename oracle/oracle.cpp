@@ -812,6 +812,7 @@ struct Node {
   std::string join_type;
   std::vector<int> probe_keys, build_keys;
   std::vector<std::pair<char, int>> join_out;  // ('p'|'b', column)
+  int64_t limit = -1;  // TopN: rows kept (exec/TopN.cpp); -1 = all
   // order by (exec/OrderBy.cpp; core::SortOrder{ascending, nullsFirst}): (column, ascending, nulls first)
   struct SortKey { int col; bool asc; bool nulls_first; };
   std::vector<SortKey> sort_keys;
@@ -847,12 +848,21 @@ static NodePtr parse_plan(const SNode& s) {
     // distributed plan (exec/PartitionedOutput.cpp, exec/Exchange.cpp). The oracle runs the whole
     // plan over the whole data in one process, where the shuffle is the identity on the row multiset.
     return parse_plan(s.arg(2));
-  } else if (h == "orderby") {
-    // (orderby ((I asc|desc first|last) ...) plan)
+  } else if (h == "localpartition") {
+    // (localpartition plan): gathers the drivers of a pipeline (exec/LocalPartition.cpp); the identity on the row multiset
+    return parse_plan(s.arg(0));
+  } else if (h == "orderby" || h == "topn") {
+    // (orderby ((I asc|desc first|last) ...) plan) | (topn N ((I asc|desc first|last) ...) plan): exec/TopN.cpp keeps
+    // the first N rows of the order
     n->kind = Node::ORDERBY;
-    n->child = parse_plan(s.arg(1));
+    const size_t at = h == "topn" ? 1 : 0;
+    if (h == "topn") {
+      n->limit = std::stoll(s.arg(0).atom);
+      if (n->limit <= 0) throw std::runtime_error("topn: count must be positive");
+    }
+    n->child = parse_plan(s.arg(at + 1));
     n->schema = n->child->schema;
-    for (auto& k : s.arg(0).kids) {
+    for (auto& k : s.arg(at).kids) {
       Node::SortKey sk;
       sk.col = std::stoi(k.head());
       sk.asc = k.arg(0).atom == "asc";
@@ -1598,13 +1608,14 @@ struct Executor {
     });
     std::vector<ColBuilder> ob;
     for (int ty : node->schema) ob.emplace_back(ty);
-    for (int64_t i = 0; i < n; ++i)
+    const int64_t kept = node->limit >= 0 ? std::min<int64_t>(n, node->limit) : n;
+    for (int64_t i = 0; i < kept; ++i)
       for (size_t c = 0; c < nc; ++c) ob[c].push_from(*flat[c], idx[static_cast<size_t>(i)]);
     Batch out;
-    out.n = n;
+    out.n = kept;
     for (auto& c : ob) out.cols.push_back(c.finish());
     Table t;
-    if (n > 0) t.push_back(std::move(out));
+    if (kept > 0) t.push_back(std::move(out));
     return t;
   }
 

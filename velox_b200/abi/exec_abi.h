@@ -17,6 +17,7 @@
 #pragma once
 #ifndef VELOX_B200_WITH_REAL_VELOX
 
+#include <atomic>
 #include <functional>
 #include <chrono>
 #include <map>
@@ -335,6 +336,77 @@ class ExchangeNode : public PlanNode {
   std::shared_ptr<const PartitionedOutputNode> upstream_;
 };
 
+// velox/core/PlanNode.h:4221-4330 OrderByNode; :4587-4680 TopNNode
+class OrderByNode : public PlanNode {
+ public:
+  OrderByNode(const PlanNodeId& id, const std::vector<FieldAccessTypedExprPtr>& sortingKeys, const std::vector<SortOrder>& sortingOrders,
+              bool isPartial, const PlanNodePtr& source)
+      : PlanNode(id), sortingKeys_(sortingKeys), sortingOrders_(sortingOrders), isPartial_(isPartial), sources_{source} {
+    if (sortingKeys.empty()) throw VeloxUserError("OrderBy must specify sorting keys");
+    if (sortingKeys.size() != sortingOrders.size()) throw VeloxUserError("Number of sorting keys and sorting orders in OrderBy must be the same");
+    std::set<std::string> unique;
+    for (auto& k : sortingKeys)
+      if (!k || !unique.insert(k->name()).second) throw VeloxUserError("Duplicate sorting keys are not allowed");
+  }
+  const std::vector<FieldAccessTypedExprPtr>& sortingKeys() const { return sortingKeys_; }
+  const std::vector<SortOrder>& sortingOrders() const { return sortingOrders_; }
+  bool isPartial() const { return isPartial_; }
+  const RowTypePtr& outputType() const override { return sources_[0]->outputType(); }
+  const std::vector<PlanNodePtr>& sources() const override { return sources_; }
+  std::string_view name() const override { return "OrderBy"; }
+
+ private:
+  const std::vector<FieldAccessTypedExprPtr> sortingKeys_;
+  const std::vector<SortOrder> sortingOrders_;
+  const bool isPartial_;
+  const std::vector<PlanNodePtr> sources_;
+};
+class TopNNode : public PlanNode {
+ public:
+  TopNNode(const PlanNodeId& id, const std::vector<FieldAccessTypedExprPtr>& sortingKeys, const std::vector<SortOrder>& sortingOrders, int32_t count,
+           bool isPartial, const PlanNodePtr& source)
+      : PlanNode(id), sortingKeys_(sortingKeys), sortingOrders_(sortingOrders), count_(count), isPartial_(isPartial), sources_{source} {
+    if (sortingKeys.empty()) throw VeloxUserError("TopN must specify sorting keys");
+    if (sortingKeys.size() != sortingOrders.size()) throw VeloxUserError("Number of sorting keys and sorting orders in TopN must be the same");
+    if (count <= 0) throw VeloxUserError("TopN must specify greater than zero number of rows to keep");
+  }
+  const std::vector<FieldAccessTypedExprPtr>& sortingKeys() const { return sortingKeys_; }
+  const std::vector<SortOrder>& sortingOrders() const { return sortingOrders_; }
+  int32_t count() const { return count_; }
+  bool isPartial() const { return isPartial_; }
+  const RowTypePtr& outputType() const override { return sources_[0]->outputType(); }
+  const std::vector<PlanNodePtr>& sources() const override { return sources_; }
+  std::string_view name() const override { return "TopN"; }
+
+ private:
+  const std::vector<FieldAccessTypedExprPtr> sortingKeys_;
+  const std::vector<SortOrder> sortingOrders_;
+  const int32_t count_;
+  const bool isPartial_;
+  const std::vector<PlanNodePtr> sources_;
+};
+
+// velox/core/PlanNode.h LocalPartitionNode (gather form): the boundary between a pipeline that may run
+// on several drivers and the single-driver pipeline consuming their outputs.
+class LocalPartitionNode : public PlanNode {
+ public:
+  enum class Type { kGather, kRepartition };
+  LocalPartitionNode(const PlanNodeId& id, Type type, bool scaleWriter, PartitionFunctionSpecPtr partitionFunctionSpec, std::vector<PlanNodePtr> sources)
+      : PlanNode(id), type_(type), scaleWriter_(scaleWriter), spec_(std::move(partitionFunctionSpec)), sources_(std::move(sources)) {
+    if (sources_.empty()) throw VeloxUserError("Local repartitioning node requires at least one source");
+  }
+  Type type() const { return type_; }
+  const RowTypePtr& outputType() const override { return sources_[0]->outputType(); }
+  const std::vector<PlanNodePtr>& sources() const override { return sources_; }
+  std::string_view name() const override { return "LocalPartition"; }
+
+ private:
+  const Type type_;
+  const bool scaleWriter_;
+  const PartitionFunctionSpecPtr spec_;
+  const std::vector<PlanNodePtr> sources_;
+};
+
 // velox/core/PlanFragment.h:43 (the grouped-execution fields are not part of the path)
 struct PlanFragment {
   std::shared_ptr<const PlanNode> planNode;
@@ -533,18 +605,27 @@ inline std::unique_ptr<Aggregate> Aggregate::create(const std::string& name, cor
 
 // ---- operators --------------------------------------------------------------------------------
 enum class BlockingReason { kNotBlocked, kWaitForProducer, kWaitForJoinBuild, kWaitForConsumer };
-// The shim runs drivers serially, so a future is a flag the unblocking side sets.
+// A future is a flag the unblocking side sets (folly::SemiFuture<Unit> in the reference); drivers may
+// run on their own threads (Task::run with task.max_drivers > 1), so the flag is atomic. A blocked
+// driver is re-polled by its thread.
 struct ContinueFuture {
-  std::shared_ptr<bool> ready;
+  std::shared_ptr<std::atomic<bool>> ready;
   bool valid() const { return ready != nullptr; }
-  bool isReady() const { return ready && *ready; }
+  bool isReady() const { return ready && ready->load(std::memory_order_acquire); }
+};
+struct ContinuePromise {  // velox/common/future/VeloxPromise.h
+  std::shared_ptr<std::atomic<bool>> flag = std::make_shared<std::atomic<bool>>(false);
+  ContinueFuture getSemiFuture() const { return ContinueFuture{flag}; }
+  void setValue() { flag->store(true, std::memory_order_release); }
 };
 
 class Task;
-struct DriverCtx {
+class Driver;
+struct DriverCtx {  // velox/exec/Driver.h:263-300
   int32_t driverId = 0;
   int32_t pipelineId = 0;
   Task* task = nullptr;
+  Driver* driver = nullptr;
   const core::QueryConfig* config = nullptr;
   memory::MemoryPool* pool = nullptr;
   const core::QueryConfig& queryConfig() const { return *config; }
@@ -651,8 +732,9 @@ class HashJoinBridge : public JoinBridge {
  public:
   // velox/exec/HashJoinBridge.h:63-65 (the overload accelerator backends use) and :86-100,116
   void setHashTable(std::shared_ptr<wave::HashTableHolder> table, bool hasNullKeys) {
+    std::lock_guard<std::mutex> l(mutex_);
     result_ = HashBuildResult{hasNullKeys, std::move(table)};
-    for (auto& f : waiters_) *f = true;
+    for (auto& f : waiters_) f->store(true, std::memory_order_release);
     waiters_.clear();
   }
   struct HashBuildResult {
@@ -660,15 +742,17 @@ class HashJoinBridge : public JoinBridge {
     std::shared_ptr<wave::HashTableHolder> waveTable;
   };
   std::optional<HashBuildResult> tableOrFuture(ContinueFuture* future) {
+    std::lock_guard<std::mutex> l(mutex_);
     if (result_) return result_;
-    future->ready = std::make_shared<bool>(false);
+    future->ready = std::make_shared<std::atomic<bool>>(false);
     waiters_.push_back(future->ready);
     return std::nullopt;
   }
 
  private:
+  std::mutex mutex_;
   std::optional<HashBuildResult> result_;
-  std::vector<std::shared_ptr<bool>> waiters_;
+  std::vector<std::shared_ptr<std::atomic<bool>>> waiters_;
 };
 
 // ---- exchange hand-off ----------------------------------------------------------------------------
@@ -678,28 +762,67 @@ class HashJoinBridge : public JoinBridge {
 // receives (after the transport's all-to-all) and closes the queue; the consumer waits on a future.
 class ExchangeQueue {
  public:
-  void enqueue(RowVectorPtr page) { pages_.push_back(std::move(page)); }
+  void enqueue(RowVectorPtr page) {
+    std::lock_guard<std::mutex> l(mutex_);
+    pages_.push_back(std::move(page));
+  }
   void noMoreData() {
+    std::lock_guard<std::mutex> l(mutex_);
     done_ = true;
-    for (auto& f : waiters_) *f = true;
+    for (auto& f : waiters_) f->store(true, std::memory_order_release);
     waiters_.clear();
   }
   // next page, or nullptr with *atEnd set; blocks (future) while the producer is still running
   RowVectorPtr dequeue(bool* atEnd, ContinueFuture* future) {
+    std::lock_guard<std::mutex> l(mutex_);
     *atEnd = false;
     if (next_ < pages_.size()) return std::move(pages_[next_++]);
     if (done_) { *atEnd = true; return nullptr; }
-    future->ready = std::make_shared<bool>(false);
+    future->ready = std::make_shared<std::atomic<bool>>(false);
     waiters_.push_back(future->ready);
     return nullptr;
   }
-  bool drained() const { return done_ && next_ >= pages_.size(); }
+  bool drained() const {
+    std::lock_guard<std::mutex> l(mutex_);
+    return done_ && next_ >= pages_.size();
+  }
 
  private:
+  mutable std::mutex mutex_;
   std::vector<RowVectorPtr> pages_;
   size_t next_ = 0;
   bool done_ = false;
-  std::vector<std::shared_ptr<bool>> waiters_;
+  std::vector<std::shared_ptr<std::atomic<bool>>> waiters_;
+};
+
+// ---- local exchange ---------------------------------------------------------------------------------
+// velox/exec/LocalPartition.h: LocalExchangeQueue between the N drivers of a producing pipeline and the
+// consuming pipeline (gather: one queue). The reference's LocalPartition / LocalExchange operators only
+// move RowVectorPtrs — device-resident batches pass through untouched — so they are real here.
+class LocalExchangeQueue {
+ public:
+  explicit LocalExchangeQueue(int32_t producers) : producers_(producers) {}
+  void enqueue(RowVectorPtr batch) {
+    std::lock_guard<std::mutex> l(mutex_);
+    queue_.push_back(std::move(batch));
+  }
+  void noMoreProducer() {
+    std::lock_guard<std::mutex> l(mutex_);
+    --producers_;
+  }
+  RowVectorPtr dequeue(bool* atEnd) {
+    std::lock_guard<std::mutex> l(mutex_);
+    *atEnd = false;
+    if (next_ < queue_.size()) return std::move(queue_[next_++]);
+    *atEnd = producers_ <= 0;
+    return nullptr;
+  }
+
+ private:
+  std::mutex mutex_;
+  std::vector<RowVectorPtr> queue_;
+  size_t next_ = 0;
+  int32_t producers_;
 };
 
 // ---- CPU operators of the reference, as the LocalPlanner instantiates them ----------------------
@@ -766,6 +889,25 @@ class HashAggregation : public CpuOperatorStub {
  private:
   std::shared_ptr<const core::AggregationNode> node_;
 };
+// velox/exec/OrderBy.h:34-39, velox/exec/TopN.h:23-28
+class OrderBy : public CpuOperatorStub {
+ public:
+  OrderBy(int32_t operatorId, DriverCtx* driverCtx, const std::shared_ptr<const core::OrderByNode>& orderByNode)
+      : CpuOperatorStub(driverCtx, orderByNode->outputType(), operatorId, orderByNode->id(), "OrderBy"), node_(orderByNode) {}
+  const std::shared_ptr<const core::OrderByNode>& node() const { return node_; }
+
+ private:
+  std::shared_ptr<const core::OrderByNode> node_;
+};
+class TopN : public CpuOperatorStub {
+ public:
+  TopN(int32_t operatorId, DriverCtx* driverCtx, const std::shared_ptr<const core::TopNNode>& topNNode)
+      : CpuOperatorStub(driverCtx, topNNode->outputType(), operatorId, topNNode->id(), "TopN"), node_(topNNode) {}
+  const std::shared_ptr<const core::TopNNode>& node() const { return node_; }
+
+ private:
+  std::shared_ptr<const core::TopNNode> node_;
+};
 class HashBuild : public CpuOperatorStub {
  public:
   HashBuild(int32_t operatorId, DriverCtx* ctx, std::shared_ptr<const core::HashJoinNode> node, std::shared_ptr<HashJoinBridge> bridge)
@@ -818,18 +960,64 @@ class Exchange : public CpuOperatorStub {
 // here the Task owns the queue so multi-GB inputs are not copied into the plan).
 class Values : public SourceOperator {
  public:
-  Values(int32_t operatorId, DriverCtx* ctx, std::shared_ptr<const core::ValuesNode> node, std::shared_ptr<std::vector<RowVectorPtr>> batches)
-      : SourceOperator(ctx, node->outputType(), operatorId, node->id(), "Values"), batches_(std::move(batches)) {}
+  // The Values operator stands for the scan: with N drivers on the pipeline its batches are dealt like
+  // splits, batch i to driver i % N (a fixed deal keeps floating-point sums reproducible).
+  Values(int32_t operatorId, DriverCtx* ctx, std::shared_ptr<const core::ValuesNode> node, std::shared_ptr<std::vector<RowVectorPtr>> batches,
+         int32_t numDrivers = 1)
+      : SourceOperator(ctx, node->outputType(), operatorId, node->id(), "Values"), batches_(std::move(batches)),
+        next_(static_cast<size_t>(ctx->driverId)), stride_(static_cast<size_t>(numDrivers < 1 ? 1 : numDrivers)) {}
   RowVectorPtr getOutput() override {
     if (next_ >= batches_->size()) return nullptr;
-    return (*batches_)[next_++];
+    RowVectorPtr b = (*batches_)[next_];
+    next_ += stride_;
+    return b;
   }
   BlockingReason isBlocked(ContinueFuture*) override { return BlockingReason::kNotBlocked; }
   bool isFinished() override { return next_ >= batches_->size(); }
 
  private:
   std::shared_ptr<std::vector<RowVectorPtr>> batches_;
-  size_t next_ = 0;
+  size_t next_, stride_;
+};
+
+// velox/exec/LocalPartition.h: sink of the producing pipeline / source of the consuming one.
+class LocalPartition : public Operator {
+ public:
+  LocalPartition(int32_t operatorId, DriverCtx* ctx, const std::shared_ptr<const core::LocalPartitionNode>& node, std::shared_ptr<LocalExchangeQueue> queue)
+      : Operator(ctx, node->outputType(), operatorId, node->id(), "LocalPartition"), queue_(std::move(queue)) {}
+  bool needsInput() const override { return !noMoreInput_; }
+  void addInput(RowVectorPtr input) override { queue_->enqueue(std::move(input)); }
+  void noMoreInput() override {
+    if (!noMoreInput_) queue_->noMoreProducer();
+    Operator::noMoreInput();
+  }
+  RowVectorPtr getOutput() override { return nullptr; }
+  BlockingReason isBlocked(ContinueFuture*) override { return BlockingReason::kNotBlocked; }
+  bool isFinished() override { return noMoreInput_; }
+
+ private:
+  std::shared_ptr<LocalExchangeQueue> queue_;
+};
+class LocalExchange : public SourceOperator {
+ public:
+  LocalExchange(int32_t operatorId, DriverCtx* ctx, const std::shared_ptr<const core::LocalPartitionNode>& node, std::shared_ptr<LocalExchangeQueue> queue)
+      : SourceOperator(ctx, node->outputType(), operatorId, node->id(), "LocalExchange"), queue_(std::move(queue)) {}
+  RowVectorPtr getOutput() override {
+    if (atEnd_) return nullptr;
+    if (pending_) return std::move(pending_);
+    return queue_->dequeue(&atEnd_);
+  }
+  BlockingReason isBlocked(ContinueFuture*) override {
+    if (atEnd_ || pending_) return BlockingReason::kNotBlocked;
+    pending_ = queue_->dequeue(&atEnd_);
+    return (pending_ || atEnd_) ? BlockingReason::kNotBlocked : BlockingReason::kWaitForProducer;
+  }
+  bool isFinished() override { return atEnd_ && !pending_; }
+
+ private:
+  std::shared_ptr<LocalExchangeQueue> queue_;
+  RowVectorPtr pending_;
+  bool atEnd_ = false;
 };
 
 // Sink collecting the task's results (velox/exec/CallbackSink.h).
@@ -890,6 +1078,12 @@ class Driver {
   BlockingReason runOnce(bool* finished, bool* progressed);
   void close() {
     for (auto& op : operators_) op->close();
+  }
+  // velox/exec/Driver.h findOperator(planNodeId): how the last HashBuild peer reaches its siblings
+  Operator* findOperator(std::string_view planNodeId) const {
+    for (auto& op : operators_)
+      if (op->planNodeId() == planNodeId) return op.get();
+    return nullptr;
   }
 
  private:

@@ -13,7 +13,11 @@ namespace {
 std::shared_ptr<const core::AggregationNode> collapsePartialFinal(const core::AggregationNode& partial, const core::AggregationNode& fin) {
   using Step = core::AggregationNode::Step;
   if (partial.step() != Step::kPartial || fin.step() != Step::kFinal) return nullptr;
-  if (fin.sources()[0].get() != &partial) return nullptr;
+  // in serial execution mode the local gather between the two steps is the identity and the planner
+  // drops it from the driver: look through it
+  const core::PlanNode* below = fin.sources()[0].get();
+  if (auto lp = dynamic_cast<const core::LocalPartitionNode*>(below)) below = lp->sources()[0].get();
+  if (below != &partial) return nullptr;
   const size_t nk = partial.groupingKeys().size();
   if (fin.groupingKeys().size() != nk || fin.aggregates().size() != partial.aggregates().size()) return nullptr;
   const RowTypePtr& mid = partial.outputType();
@@ -96,6 +100,12 @@ bool adaptDriver(const exec::DriverFactory& factory, exec::Driver& driver) {
       replacedAny = true;
     } else if (auto probe = dynamic_cast<exec::HashProbe*>(op)) {
       out.push_back(std::make_unique<B200HashProbe>(id, ctx, *probe));
+      replacedAny = true;
+    } else if (auto ob = dynamic_cast<exec::OrderBy*>(op)) {
+      out.push_back(std::make_unique<B200OrderBy>(id, ctx, ob->node()));
+      replacedAny = true;
+    } else if (auto tn = dynamic_cast<exec::TopN*>(op)) {
+      out.push_back(std::make_unique<B200TopN>(id, ctx, tn->node()));
       replacedAny = true;
     } else if (auto po = dynamic_cast<exec::PartitionedOutput*>(op)) {
       out.push_back(std::make_unique<B200PartitionedOutput>(id, ctx, *po));

@@ -1417,14 +1417,17 @@ exec::BlockingReason B200HashAggregation::isBlocked(exec::ContinueFuture* future
 }
 
 void B200HashAggregation::addInput(RowVectorPtr input) {
+  B200_NVTX_OPERATOR_RANGE("addInput");
   auto in = std::dynamic_pointer_cast<B200Vector>(input);
   VELOX_CHECK(in != nullptr, "B200HashAggregation expects device-resident input");
+  orderAfterProducer(*in, impl_->dev->stream);
   impl_->addInput(in);
 }
 
 void B200HashAggregation::noMoreInput() { Operator::noMoreInput(); }
 
 RowVectorPtr B200HashAggregation::getOutput() {
+  B200_NVTX_OPERATOR_RANGE("getOutput");
   if (!noMoreInput_ || finished_) return nullptr;
   finished_ = true;
   return impl_->output();

@@ -1,5 +1,6 @@
 // Operator-level C ABI (include/velox_b200.h): plan text -> Task over the shim Driver with the
 // B200 adapter installed; host / device column batches in, host result columns out.
+#include <atomic>
 #include <functional>
 #include <map>
 #include <mutex>
@@ -14,6 +15,7 @@
 #include <sstream>
 
 #include "../../../include/velox_b200.h"
+#include "../../abi/arrow_abi.h"
 #include "operators.h"
 #include "plan_text.h"
 #include "task.h"
@@ -316,6 +318,16 @@ int32_t vb2_task_add_input(vb2_task* task, int32_t source_id, const vb2_column* 
   });
 }
 
+int32_t vb2_task_add_arrow(vb2_task* task, int32_t source_id, struct ArrowArray* array, struct ArrowSchema* schema, char* err, int32_t errlen) {
+  return guarded(err, errlen, [&] {
+    VELOX_CHECK(task && array && schema, "null task, array or schema");
+    VELOX_CHECK(array->length < (1ll << 31), "a batch holds fewer than 2^31 rows (vector_size_t, velox/vector/TypeAliases.h:29)");
+    auto batch = std::dynamic_pointer_cast<RowVector>(importFromArrowAsOwner(*schema, *array, &task->pool));
+    VELOX_CHECK(batch != nullptr, "Arrow input must be a struct array (record batch)");
+    if (batch->size() > 0) task->task->addInput(source_id, batch);
+  });
+}
+
 int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen) {
   return guarded(err, errlen, [&] {
     VELOX_CHECK(task != nullptr, "null task");
@@ -324,8 +336,24 @@ int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen) {
       ~Attach() { velox_b200::setThreadUploadCache(nullptr); }
     } attach(task->uploadCache);
     const int64_t uploadedBefore = velox_b200::threadUploadedBytes();
+    // driver threads (task.max_drivers > 1) inherit this thread's device and upload cache, and report their copies
+    int device = 0;
+    cudaGetDevice(&device);
+    std::atomic<int64_t> threadBytes{0};
+    vb2_upload_cache* uc = task->uploadCache;
+    thread_local int64_t threadStart = 0;
+    task->task->setDriverThreadHooks(
+        [device, uc] {
+          cudaSetDevice(device);
+          velox_b200::setThreadUploadCache(uc ? &uc->cache : nullptr);
+          threadStart = velox_b200::threadUploadedBytes();
+        },
+        [&threadBytes] {
+          threadBytes += velox_b200::threadUploadedBytes() - threadStart;
+          velox_b200::setThreadUploadCache(nullptr);
+        });
     task->results = task->task->run();
-    task->h2dBytes = velox_b200::threadUploadedBytes() - uploadedBefore;
+    task->h2dBytes = velox_b200::threadUploadedBytes() - uploadedBefore + threadBytes.load();
     task->out.clear();
     task->rows = 0;
     task->deviceResults.clear();

@@ -4,6 +4,8 @@
 #include <map>
 #include <mutex>
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace velox_b200 {
 
 void cudaCheck(cudaError_t e, const char* what) {
@@ -600,5 +602,18 @@ B200VectorPtr sliceVector(const B200VectorPtr& v, int64_t offset, int64_t length
   }
   return std::make_shared<B200Vector>(v->pool(), v->type(), static_cast<vector_size_t>(length), std::move(cols), v->stream());
 }
+
+NvtxRange::NvtxRange(const char* method, const std::string& operatorType, const std::string& planNodeId) {
+  nvtxEventAttributes_t a{};
+  a.version = NVTX_VERSION;
+  a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+  a.colorType = NVTX_COLOR_ARGB;
+  a.color = 0xff76b900u ^ static_cast<uint32_t>(std::hash<std::string>{}(operatorType) & 0x00ffffffu);  // one colour per operator type
+  a.messageType = NVTX_MESSAGE_TYPE_ASCII;
+  const std::string msg = operatorType + "::" + method + " [" + planNodeId + "]";
+  a.message.ascii = msg.c_str();  // NVTX copies the string during the call
+  nvtxRangePushEx(&a);
+}
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 }  // namespace velox_b200

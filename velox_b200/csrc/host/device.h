@@ -141,6 +141,16 @@ int64_t threadUploadedBytes();                  // bytes copied host -> device b
 // so validity bitmaps stay word-aligned).
 B200VectorPtr sliceVector(const B200VectorPtr& v, int64_t offset, int64_t length);
 
+// NVTX range per operator call, named "<Operator>::<method> [planNodeId]" — what the reference's cuDF
+// operators push (velox/experimental/cudf/exec/CudfOperator.h:104-160, NvtxHelper.h). NVTX3 is
+// header-only: without a profiler attached a push / pop is a load and a branch.
+struct NvtxRange {
+  NvtxRange(const char* method, const std::string& operatorType, const std::string& planNodeId);
+  ~NvtxRange();
+  NvtxRange(const NvtxRange&) = delete;
+};
+#define B200_NVTX_OPERATOR_RANGE(method) ::velox_b200::NvtxRange nvtxRange_(method, stats_.operatorType, planNodeId())
+
 // One stream + small scratch per driver.
 struct DeviceContext {
   int device = 0;

@@ -74,12 +74,15 @@ void B200PartitionedOutput::initialize() {
 }
 
 void B200PartitionedOutput::addInput(RowVectorPtr input) {
+  B200_NVTX_OPERATOR_RANGE("addInput");
   auto in = std::dynamic_pointer_cast<B200Vector>(input);
   VELOX_CHECK(in != nullptr, "B200PartitionedOutput expects device-resident input");
+  orderAfterProducer(*in, dev_->stream);
   batches_.push_back(std::move(in));
 }
 
 void B200PartitionedOutput::noMoreInput() {
+  B200_NVTX_OPERATOR_RANGE("noMoreInput");
   Operator::noMoreInput();
   cudaStream_t st = dev_->stream;
   NcclTransport* tr = transportOf(driverCtx_);
@@ -494,6 +497,7 @@ exec::BlockingReason B200Exchange::isBlocked(exec::ContinueFuture* future) {
 }
 
 RowVectorPtr B200Exchange::getOutput() {
+  B200_NVTX_OPERATOR_RANGE("getOutput");
   if (!next_ && !atEnd_) {
     exec::ContinueFuture f;
     next_ = queue_->dequeue(&atEnd_, &f);

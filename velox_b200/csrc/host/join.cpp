@@ -135,8 +135,10 @@ void B200HashBuild::initialize() {
 }
 
 void B200HashBuild::addInput(RowVectorPtr input) {
+  B200_NVTX_OPERATOR_RANGE("addInput");
   auto in = std::dynamic_pointer_cast<B200Vector>(input);
   VELOX_CHECK(in != nullptr, "B200HashBuild expects device-resident input");
+  orderAfterProducer(*in, dev_->stream);
   batches_.push_back(std::move(in));
 }
 
@@ -149,7 +151,38 @@ uint64_t nextPow2(uint64_t v) {
 }  // namespace
 
 void B200HashBuild::noMoreInput() {
+  B200_NVTX_OPERATOR_RANGE("noMoreInput");
   Operator::noMoreInput();
+  // The last build driver to get here gathers the rows of all its peers and builds the one table the
+  // probe side reads (exec/HashBuild.cpp:819-993 finishHashBuild); the others park until it has.
+  exec::Task* task = driverCtx_->task;
+  if (task && driverCtx_->driver && task->numDrivers(driverCtx_->pipelineId) > 1) {
+    std::vector<exec::ContinuePromise> promises;
+    std::vector<std::shared_ptr<exec::Driver>> peers;
+    if (!task->allPeersFinished(planNodeId(), driverCtx_->driver, &peerFuture_, promises, peers)) return;
+    for (auto& peer : peers) {
+      auto* op = dynamic_cast<B200HashBuild*>(peer->findOperator(planNodeId()));
+      VELOX_CHECK(op != nullptr, "peer driver without a B200HashBuild for this join");
+      for (auto& b : op->takeBatches()) {
+        orderAfterProducer(*b, dev_->stream);
+        batches_.push_back(std::move(b));
+      }
+    }
+    addRuntimeStat("b200.buildPeers", exec::RuntimeCounter{static_cast<int64_t>(peers.size()) + 1});
+    try {
+      buildTable();
+    } catch (...) {
+      for (auto& p : promises) p.setValue();
+      throw;
+    }
+    // the peers' rows are referenced by this stream's kernels only from here on: release them
+    for (auto& p : promises) p.setValue();
+    return;
+  }
+  buildTable();
+}
+
+void B200HashBuild::buildTable() {
   cudaStream_t st = dev_->stream;
   auto holder = std::make_shared<JoinTableHolder>();
   holder->stream = st;
@@ -424,10 +457,12 @@ B200VectorPtr B200HashProbe::apply(const B200VectorPtr& in) {
 }
 
 RowVectorPtr B200HashProbe::getOutput() {
+  B200_NVTX_OPERATOR_RANGE("getOutput");
   if (!input_) return nullptr;
   auto in = std::dynamic_pointer_cast<B200Vector>(input_);
   input_ = nullptr;
   VELOX_CHECK(in != nullptr, "B200HashProbe expects device-resident input");
+  orderAfterProducer(*in, dev_->stream);
   return apply(in);
 }
 

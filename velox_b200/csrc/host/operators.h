@@ -24,6 +24,10 @@ struct FlatColumn {
 };
 FlatColumn flattenColumn(const DeviceColumnPtr& col, const int32_t* sel, int64_t n, cudaStream_t stream);
 
+// Orders `stream` after the work that produced `batch` when that happened on another stream (a batch
+// that crossed a LocalExchange, an exchange page, a sibling driver's build rows).
+void orderAfterProducer(const B200Vector& batch, cudaStream_t stream);
+
 // Host RowVector -> device batch (velox/experimental/cudf/exec/CudfConversion.h:32 CudfFromVelox).
 class B200FromHost : public exec::Operator {
  public:
@@ -139,6 +143,49 @@ class B200HashAggregation : public exec::Operator {
   bool finished_ = false;
 };
 
+// Replaces exec::OrderBy (velox/exec/OrderBy.cpp:60-110, SortBuffer.cpp): collects the input on the
+// device, sorts once at noMoreInput (vb2k_sort_order), emits the input columns wrapped over the order.
+class B200OrderBy : public exec::Operator {
+ public:
+  B200OrderBy(int32_t id, exec::DriverCtx* ctx, std::shared_ptr<const core::OrderByNode> node);
+  void initialize() override;
+  bool needsInput() const override { return !noMoreInput_; }
+  void addInput(RowVectorPtr input) override;
+  RowVectorPtr getOutput() override;
+  exec::BlockingReason isBlocked(exec::ContinueFuture*) override { return exec::BlockingReason::kNotBlocked; }
+  bool isFinished() override { return finished_; }
+
+ private:
+  std::shared_ptr<const core::OrderByNode> node_;
+  std::shared_ptr<DeviceContext> dev_;
+  std::vector<int32_t> channels_;
+  std::vector<B200VectorPtr> batches_;
+  bool finished_ = false;
+};
+
+// Replaces exec::TopN (velox/exec/TopN.cpp:60-150): ORDER BY ... LIMIT count. Keeps at most `count`
+// rows between folds (sort of kept + pending rows, first `count` survive) instead of the CPU's heap.
+class B200TopN : public exec::Operator {
+ public:
+  B200TopN(int32_t id, exec::DriverCtx* ctx, std::shared_ptr<const core::TopNNode> node);
+  void initialize() override;
+  bool needsInput() const override { return !noMoreInput_; }
+  void addInput(RowVectorPtr input) override;
+  RowVectorPtr getOutput() override;
+  exec::BlockingReason isBlocked(exec::ContinueFuture*) override { return exec::BlockingReason::kNotBlocked; }
+  bool isFinished() override { return finished_; }
+
+ private:
+  void fold();
+  std::shared_ptr<const core::TopNNode> node_;
+  std::shared_ptr<DeviceContext> dev_;
+  std::vector<int32_t> channels_;
+  std::vector<B200VectorPtr> pending_;
+  int64_t pendingRows_ = 0;
+  B200VectorPtr top_;
+  bool finished_ = false;
+};
+
 // Replaces exec::HashBuild (velox/exec/HashBuild.cpp:442-598,819-993): collects the build side on
 // the device, builds the join table at noMoreInput and publishes it on the HashJoinBridge.
 class B200HashBuild : public exec::Operator {
@@ -149,15 +196,25 @@ class B200HashBuild : public exec::Operator {
   void addInput(RowVectorPtr input) override;
   void noMoreInput() override;
   RowVectorPtr getOutput() override { return nullptr; }
-  exec::BlockingReason isBlocked(exec::ContinueFuture*) override { return exec::BlockingReason::kNotBlocked; }
-  bool isFinished() override { return noMoreInput_; }
+  // Sibling builds (N drivers on the build pipeline) wait here until the last one has taken their rows
+  // (exec/HashBuild.cpp:819-870: State::kWaitForBuild until the last driver fulfils the promise).
+  exec::BlockingReason isBlocked(exec::ContinueFuture* future) override {
+    if (!peerFuture_.valid() || peerFuture_.isReady()) return exec::BlockingReason::kNotBlocked;
+    if (future) *future = peerFuture_;
+    return exec::BlockingReason::kWaitForJoinBuild;
+  }
+  bool isFinished() override { return noMoreInput_ && (!peerFuture_.valid() || peerFuture_.isReady()); }
+  // the batches collected so far, handed to the last peer (called under the barrier: this driver is parked)
+  std::vector<B200VectorPtr> takeBatches() { return std::move(batches_); }
 
  private:
+  void buildTable();
   std::shared_ptr<const core::HashJoinNode> node_;
   ResolvedJoin plan_;  // key / output column names resolved to channels
   std::shared_ptr<exec::HashJoinBridge> bridge_;
   std::shared_ptr<DeviceContext> dev_;
   std::vector<B200VectorPtr> batches_;
+  exec::ContinueFuture peerFuture_;
 };
 
 // Replaces exec::HashProbe (velox/exec/HashProbe.cpp:796-900,1189-1437).

@@ -17,6 +17,18 @@ void checkDeviceError(const DeviceBufferPtr& flag, cudaStream_t stream, const ch
   }
 }
 
+void orderAfterProducer(const B200Vector& batch, cudaStream_t stream) {
+  if (batch.readyEvent()) VB2_CU(cudaStreamWaitEvent(stream, batch.readyEvent(), 0));
+  cudaStream_t producer = batch.stream();
+  if (!producer || producer == stream) return;
+  // an event recorded now covers everything the producing stream was given so far, the batch included
+  cudaEvent_t ev = nullptr;
+  VB2_CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  VB2_CU(cudaEventRecord(ev, producer));
+  VB2_CU(cudaStreamWaitEvent(stream, ev, 0));
+  VB2_CU(cudaEventDestroy(ev));  // destruction is deferred until the event has completed
+}
+
 std::vector<vb2_column> describe(const B200Vector& v) {
   std::vector<vb2_column> cols;
   for (auto& c : v.columns()) cols.push_back(c->desc);
@@ -79,6 +91,7 @@ void B200FromHost::initialize() {
   dev_ = driverDeviceContext(driverCtx_);
 }
 RowVectorPtr B200FromHost::getOutput() {
+  B200_NVTX_OPERATOR_RANGE("getOutput");
   if (!input_) return nullptr;
   RowVectorPtr in = std::move(input_);
   input_ = nullptr;
@@ -94,6 +107,7 @@ RowVectorPtr B200FromHost::getOutput() {
 }
 
 RowVectorPtr B200ToHost::getOutput() {
+  B200_NVTX_OPERATOR_RANGE("getOutput");
   if (!input_) return nullptr;
   RowVectorPtr in = std::move(input_);
   input_ = nullptr;
@@ -234,10 +248,12 @@ B200VectorPtr evalProjections(const CompiledProgram& program, const B200VectorPt
 }
 
 RowVectorPtr B200FilterProject::getOutput() {
+  B200_NVTX_OPERATOR_RANGE("getOutput");
   if (!input_) return nullptr;
   auto in = std::dynamic_pointer_cast<B200Vector>(input_);
   input_ = nullptr;
   VELOX_CHECK(in != nullptr, "B200FilterProject expects device-resident input (B200FromHost missing?)");
+  orderAfterProducer(*in, dev_->stream);
   return apply(in);
 }
 

@@ -278,6 +278,40 @@ class Parser {
       auto agg = std::make_shared<core::AggregationNode>(id, step, keyExprs, std::vector<core::FieldAccessTypedExprPtr>{}, aggNames, aggs, false, false, child);
       agg->setOutputType(ROW(names, types));
       out = agg;
+    } else if (h == "localpartition") {
+      // (localpartition plan): gather of the drivers of the pipeline below (exec/LocalPartition.cpp)
+      auto child = node();
+      out = std::make_shared<core::LocalPartitionNode>(nextId(), core::LocalPartitionNode::Type::kGather, false, nullptr, std::vector<core::PlanNodePtr>{child});
+    } else if (h == "orderby" || h == "topn") {
+      // (orderby ((I asc|desc first|last) ...) plan) | (topn N ((I asc|desc first|last) ...) plan)
+      int32_t count = 0;
+      if (h == "topn") count = static_cast<int32_t>(std::stol(lex_.atom("row count")));
+      struct K { int col; bool asc, first; };
+      std::vector<K> ks;
+      lex_.expect(Tok::LP, "(");
+      while (lex_.peek().kind == Tok::LP) {
+        lex_.take();
+        K k;
+        k.col = std::stoi(lex_.atom("sort column"));
+        const std::string dir = lex_.atom("asc|desc"), nulls = lex_.atom("first|last");
+        if ((dir != "asc" && dir != "desc") || (nulls != "first" && nulls != "last")) throw VeloxRuntimeError("plan text: sort key must be (I asc|desc first|last)");
+        k.asc = dir == "asc";
+        k.first = nulls == "first";
+        lex_.expect(Tok::RP, ")");
+        ks.push_back(k);
+      }
+      lex_.expect(Tok::RP, ")");
+      auto child = node();
+      const auto& in = child->outputType();
+      std::vector<core::FieldAccessTypedExprPtr> keys;
+      std::vector<core::SortOrder> orders;
+      for (auto& k : ks) {
+        if (k.col < 0 || k.col >= static_cast<int>(in->size())) throw VeloxRuntimeError("plan text: sort column out of range");
+        keys.push_back(std::make_shared<core::FieldAccessTypedExpr>(in->childAt(k.col), in->nameOf(k.col)));
+        orders.emplace_back(k.asc, k.first);
+      }
+      if (h == "topn") out = std::make_shared<core::TopNNode>(nextId(), keys, orders, count, false, child);
+      else out = std::make_shared<core::OrderByNode>(nextId(), keys, orders, false, child);
     } else if (h == "exchange") {
       // (exchange partitioned|broadcast|gather (keys I ...) plan): PartitionedOutputNode on top of the
       // producing fragment, ExchangeNode as the leaf of the consuming one (core/PlanNode.h:2712,2182)

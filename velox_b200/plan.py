@@ -11,7 +11,7 @@ Plan text grammar (S-expressions)
   plan := (values SRC (TYPE ...)) | (filter EXPR plan) | (project (EXPR ...) plan)
         | (aggregation STEP (keys I ...) (aggs AGG ...) plan)      STEP: single|partial|intermediate|final
         | (hashjoin TYPE (probekeys I ...) (buildkeys I ...) EXPR|nil (out (p I)|(b I) ...) probe build)
-        | (orderby ((I asc|desc first|last) ...) plan)              oracle only so far
+        | (orderby ((I asc|desc first|last) ...) plan) | (topn N ((I asc|desc first|last) ...) plan)
         | (exchange partitioned|broadcast|gather (keys I ...) plan)  PartitionedOutput -> Exchange across the ranks
   AGG  := (sum I [(mask I)]) | (avg I) | (count [I]) | (min I) | (max I)
   EXPR := (field I) | (f64 X) | (i64 N) | (i32 N) | (bool true|false) | (str "s") | (null TYPE)
@@ -514,8 +514,11 @@ class PlanBuilder:
         return self._merge("intermediate")
 
     def localPartition(self, keys=()):
-        """Gathers the drivers' outputs (exec/LocalPartition.cpp). A single task holds one
-        pipeline instance per GPU, so this is a pass-through in the plan text."""
+        """Gathers the outputs of the drivers of the pipeline below (exec/LocalPartition.cpp, gather form).
+        With task.max_drivers = 1 (the default) one driver runs both sides and the node is the identity;
+        above 1 it is the boundary between the N-driver pipeline below and the single consumer above."""
+        n = self.node
+        self.node = _Node(f"(localpartition {n.sexpr})", n.names, n.types, partial=n.partial)
         return self
 
     def _exchange(self, kind: str, keys=()) -> "PlanBuilder":
@@ -561,11 +564,10 @@ class PlanBuilder:
         self.node = _Node(sexpr, names, types)
         return self
 
-    def orderBy(self, keys: Sequence[str]) -> "PlanBuilder":
+    def orderBy(self, keys: Sequence[str], limit: Optional[int] = None) -> "PlanBuilder":
         """ORDER BY (exec/OrderBy.cpp; PlanBuilder::orderBy of the reference's test utilities): keys
         like "c0", "c1 DESC", "c2 ASC NULLS FIRST". Default NULLS LAST for both directions, as
-        core::kAscNullsLast / kDescNullsLast. The CPU oracle executes it; the B200 operator set does
-        not contain OrderBy yet, so the product rejects the node."""
+        core::kAscNullsLast / kDescNullsLast. Runs as B200OrderBy (csrc/host/orderby.cpp, csrc/sort.cu)."""
         n = self.node
         parts = []
         for k in keys:
@@ -575,8 +577,13 @@ class PlanBuilder:
             asc = "DESC" not in rest
             nulls_first = "FIRST" in rest
             parts.append(f"({col} {'asc' if asc else 'desc'} {'first' if nulls_first else 'last'})")
-        self.node = _Node(f"(orderby ({' '.join(parts)}) {n.sexpr})", n.names, n.types)
+        head = f"topn {int(limit)}" if limit is not None else "orderby"
+        self.node = _Node(f"({head} ({' '.join(parts)}) {n.sexpr})", n.names, n.types)
         return self
+
+    def topN(self, keys: Sequence[str], count: int) -> "PlanBuilder":
+        """ORDER BY keys LIMIT count (exec/TopN.cpp; PlanBuilder::topN of the reference's test utilities)."""
+        return self.orderBy(keys, limit=count)
 
     def planNode(self) -> _Node:
         return self.node

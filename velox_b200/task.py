@@ -110,6 +110,31 @@ class Task:
         if rc:
             _raise(rc, err)
 
+    def add_arrow(self, source_id: int, batch) -> None:
+        """Adds a pyarrow RecordBatch (or single-chunk Table) through the Arrow C data interface: the
+        ArrowArray / ArrowSchema pair is exported by pyarrow and imported in C++ (vb2_task_add_arrow ->
+        importFromArrowAsOwner, csrc/host/arrow_bridge.cpp); the buffers are viewed, not copied, and
+        released by the task."""
+        import pyarrow as pa
+        if isinstance(batch, pa.Table):
+            batches = batch.combine_chunks().to_batches()
+        else:
+            batches = [batch]
+        self.L.vb2_task_add_arrow.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int32]
+        for b in batches:
+            if b.num_rows == 0:
+                continue
+            # struct ArrowArray is 80 bytes, struct ArrowSchema 72: the C++ side moves them out (release = NULL)
+            arr = C.create_string_buffer(80)
+            sch = C.create_string_buffer(72)
+            b._export_to_c(C.addressof(arr), C.addressof(sch))
+            err = C.create_string_buffer(2048)
+            rc = self.L.vb2_task_add_arrow(self.h, source_id, C.addressof(arr), C.addressof(sch), err, 2048)
+            if rc:
+                # not consumed on failure: release what pyarrow exported
+                pa.RecordBatch._import_from_c(C.addressof(arr), C.addressof(sch))
+                _raise(rc, err)
+
     def device_result(self):
         """With config {"b200.result_on_device": "true"}: the result batches as lists of zero-copy torch
         views over the library's device buffers (flat fixed-width columns), valid until close()."""
