@@ -552,6 +552,40 @@ def main():
         dist.destroy_process_group()
 
 
+def gpu_local_cpus(index: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()[-12:]
+        text = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
+def h2d_probe_gbps(nbytes=2 << 30):
+    import torch
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    host.fill_(1)
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dev.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    return nbytes / (time.perf_counter() - t0) / 1e9
+
+
 def e2e(args, li, part_all, rows, nparts, world, rank, rows_total):
     """Q1 + Q14 through vb2_task_* with pinned HOST columns: every step copies all input columns to
     the device (B200FromHost) and reads the result rows back (B200ToHost)."""
@@ -559,8 +593,19 @@ def e2e(args, li, part_all, rows, nparts, world, rank, rows_total):
     import torch.distributed as dist
     from velox_b200.task import Task, split_rowvector
 
-    hli = {k: v.cpu().pin_memory() for k, v in li.items()}
-    hpart = {k: v.cpu().pin_memory() for k, v in part_all.items()}
+    # Pinned host columns live on the GPU's own NUMA node (page-locked memory is placed by the allocating
+    # thread's affinity; a cross-socket source halves the PCIe rate on two-socket hosts). The affinity is
+    # restored afterwards: the CPU arm uses every core.
+    before = os.sched_getaffinity(0)
+    local = gpu_local_cpus(int(os.environ.get("LOCAL_RANK", "0")))
+    if local:
+        os.sched_setaffinity(0, local)
+    try:
+        hli = {k: v.cpu().pin_memory() for k, v in li.items()}
+        hpart = {k: v.cpu().pin_memory() for k, v in part_all.items()}
+        probe = h2d_probe_gbps()
+    finally:
+        os.sched_setaffinity(0, before)
     rv1, rv14, pt = host_tables(hli, hpart, rows)
     p1, p14 = plans(rv1, rv14, pt)
     batch = 1 << 26
@@ -611,7 +656,8 @@ def e2e(args, li, part_all, rows, nparts, world, rank, rows_total):
     note = "per-rank Task over its row shard; cross-rank merge of the (tiny) results not included" if world > 1 else "full plan through one Task"
     copied = int(state.get("h2d", 0)) or int(h2d)  # bytes the tasks actually copied (shared columns once per step)
     return {"value": 2 * rows_total / sec, "unit": UNIT, "h2d_bytes_per_step": copied * world, "d2h_bytes_per_step": int(d2h) * world,
-            "ms_per_step": sec * 1e3, "steps": args.e2e_steps,
+            "ms_per_step": sec * 1e3, "steps": args.e2e_steps, "h2d_GBps_effective": copied / sec / 1e9,
+            "h2d_GBps_link_probe": probe, "link_probe": "one 2 GiB pinned host -> device copy on this box, timed alone (what the PCIe link delivers)",
             "path": "vb2_task_create/add_input(HOST)/run; pinned host columns, 64M-row batches; per-step upload cache shared by the two tasks",
             "h2d_bytes_without_sharing": int(h2d) * world, "note": note}
 

@@ -168,6 +168,44 @@ int32_t vb2k_expression_jit_compiles(const vb2_program* prog, const vb2_column* 
                                      int32_t nouts, char* source_out, int32_t source_len);
 
 /* ------------------------------------------------------------------------------------------
+ * High-cardinality GROUP BY in shared memory (slice_agg.cu). The buffered input (chunks of normalized
+ * or raw BIGINT keys + up to 3 eight-byte payload columns) is radix-partitioned twice by the top bits
+ * of twang_mix64(key) into up to 65536 slices; every slice is aggregated in one CTA's shared-memory
+ * hash table and its groups are appended to rows_out as group rows in the vb2_group_table layout
+ * (word 0 = normalized key, accumulator words at ops[].word, the rest from row_init).
+ * Replaces HashTable::groupProbe + the accumulator scatter (velox/exec/HashTable.cpp:470-519,
+ * functions/lib/aggregates/SimpleNumericAggregate.h:94-150) when the group table would not fit L2.
+ *   vb2k_slice_agg_partition  level-1 histogram (+ HyperLogLog sketch, copied to hll_host[4096]; the
+ *                             call synchronises when hll_host is given) and scatter of every chunk
+ *   vb2k_slice_agg_finish     level 2 (sized from distinct_estimate), aggregation. num_groups /
+ *                             error_flag / overflow_slices are zeroed device words: groups written,
+ *                             1 = SUM(BIGINT) overflow or 100 = rows_out full, slices whose keys did
+ *                             not fit their table (then the result is incomplete: use the table path).
+ * VB2_ERR_UNSUPPORTED: more distinct keys than 65536 slices can hold.
+ * ------------------------------------------------------------------------------------------ */
+#define VB2_SLICE_MAX_COLS 3
+#define VB2_SLICE_MAX_OPS 8
+typedef struct vb2_slice_chunk {
+  const uint64_t* norm_keys; /* normalized keys, or NULL with raw_keys */
+  const int64_t* raw_keys;   /* flat NULL-free BIGINT key column: normalized key = raw - key_min + 1 */
+  int64_t key_min;
+  const void* cols[VB2_SLICE_MAX_COLS]; /* 8-byte payload columns (BIGINT / DOUBLE), flat, NULL-free */
+  int64_t rows;
+} vb2_slice_chunk;
+typedef struct vb2_slice_op {
+  int32_t kind; /* vb2_agg_kind */
+  int32_t col;  /* payload column, -1 for COUNT */
+  int32_t word; /* word of the group row that accumulates */
+} vb2_slice_op;
+int32_t vb2k_slice_agg_hll_registers(void);
+size_t vb2k_slice_agg_workspace(int64_t total_rows, int32_t ncols);
+int vb2k_slice_agg_partition(const vb2_slice_chunk* chunks, int32_t nchunks, int32_t ncols, int64_t total_rows, void* workspace, size_t workspace_bytes,
+                             int32_t* hll_host, void* stream);
+int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_estimate, const vb2_slice_op* ops, int32_t nops, int32_t row_words,
+                          const uint64_t* row_init, uint64_t* rows_out, int64_t rows_capacity, int64_t* num_groups, int32_t* error_flag,
+                          int32_t* overflow_slices, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * ORDER BY: stable multi-key sort producing the row order. Replaces the sort of exec::OrderBy /
  * SortBuffer (velox/exec/OrderBy.cpp, SortBuffer.cpp) and the ordering of exec::TopN
  * (velox/exec/TopN.cpp); semantics of core::SortOrder (velox/core/PlanNode.h:64-95): NULLs first or
@@ -484,6 +522,11 @@ typedef struct vb2_join_table {
 
 int vb2k_join_build(const vb2_join_table* t, const uint64_t* build_keys, const uint64_t* valid, int64_t n,
                     int32_t* error_flag, void* stream);
+/* Probe of a table WITHOUT duplicate build keys in one pass (HashTable::joinProbe, exec/HashTable.cpp:610-725,
+ * for the unique-key case): hit_bits = bitmap of the probe rows that matched (warp ballots, LSB first;
+ * expand with vb2k_bits_to_indices), hits[r] = matched build row of probe row r or -1. */
+int vb2k_join_probe_unique(const vb2_join_table* t, const uint64_t* probe_keys, const uint64_t* valid, int64_t n, uint64_t* hit_bits,
+                           int32_t* hits, void* stream);
 /* codes[i] = dictionary index of row i of a DICTIONARY column (0 for CONSTANT); valid[i] (optional,
  * bytes) = 0 for NULL wrapper rows and NULL dictionary entries, whose code is written as 0. */
 int vb2k_dictionary_codes(const vb2_column* col, int64_t n, int32_t* codes, uint8_t* valid, void* stream);

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--batch", type=float, default=2.5e8)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--radix", action="store_true", help="radix-partition the batches first (b200.agg_radix_partition)")
+    ap.add_argument("--table", action="store_true", help="global-table path only (b200.agg_slice_aggregation=false)")
     a = ap.parse_args()
     rows, nkeys, batch = int(a.rows), int(a.keys), int(a.batch)
     keys = splitmix_keys(0, rows, nkeys)
@@ -56,6 +57,8 @@ def main():
     cfg = {"b200.result_on_device": "true"}  # 100 M result groups = 2.4 GB: the consumer of such a result sits on the device
     if a.radix:
         cfg["b200.agg_radix_partition"] = "true"
+    if a.table:
+        cfg["b200.agg_slice_aggregation"] = "false"
     for it in range(a.iters + 1):
         t = Task(plan, cfg)
         for r0 in range(0, rows, batch):
@@ -84,6 +87,7 @@ def main():
                       "with_sector_rmw_GBps": sector_bytes / dev / 1e9, "with_sector_rmw_frac": sector_bytes / dev / 1e9 / 6570.9,
                       "task_seconds_operator_api_result_on_device": sec, "api_over_device": sec / dev,
                       "agg_mode": [v for k, v in st.items() if k.endswith("b200.aggMode")],
+                      "slice_agg_rows": sum(v for k, v in st.items() if k.endswith("b200.sliceAggRows")),
                       "wall_ms": {k: round(v / 1e6, 2) for k, v in st.items() if k.endswith("WallNanos") and v > 1e5}}))
 
 

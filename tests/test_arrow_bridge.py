@@ -67,4 +67,6 @@ def test_arrow_batches_feed_the_operators():
         got = task.run()
     finally:
         task.close()
-    assert got.rows() == want.rows() and len(got.rows()) > 100
+    # same keys in the same (sorted) order; FP sums within the usual tolerance (the batch boundaries differ)
+    assert [r[:2] + r[3:] for r in got.rows()] == [r[:2] + r[3:] for r in want.rows()] and len(got.rows()) > 100
+    assert all(abs(a[2] - b[2]) <= 1e-12 * max(1.0, abs(b[2])) for a, b in zip(got.rows(), want.rows()))

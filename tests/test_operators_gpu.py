@@ -119,6 +119,30 @@ def test_checked_arithmetic_errors():
     check_user_error(PlanBuilder().values(dbl.names, dbl.types).project(["cast(a as bigint)"]).planNode(), [dbl])
 
 
+def test_flat_varchar_keys_group_sort_and_filter():
+    """Flat (non-dictionary) VARCHAR columns — TPC-H's l_returnflag / l_linestatus are flat VARCHAR(1) in the
+    reference's generator (tpch/gen/TpchGen.cpp:278-317) — as grouping keys, sort keys, filter operands and
+    pass-through outputs: they are dictionary-encoded on upload (the device analogue of VectorHasher's
+    short-strings-as-numbers, exec/VectorHasher.h:377-387)."""
+    rng = np.random.default_rng(21)
+    n = 6000
+    flags = [None if rng.random() < 0.05 else "ANR"[i] for i in rng.integers(0, 3, n)]
+    names = [None if rng.random() < 0.05 else f"name-{i:04d}-with-more-than-twelve-bytes" for i in rng.integers(0, 700, n)]
+    rv = row_vector(["f", "s", "v", "k"], [flat_vector(VARCHAR, flags), flat_vector(VARCHAR, names), flat_vector(DOUBLE, np.round(rng.normal(0, 10, n), 2)),
+                                           flat_vector(BIGINT, rng.integers(0, 5, n))])
+    for cfg in (FUSED, GENERIC):
+        check_plan(PlanBuilder().values(rv.names, rv.types).singleAggregation(["f"], ["sum(v)", "count(0)", "max(k)"]).planNode(), [rv], configs=(cfg,))
+        check_plan(PlanBuilder().values(rv.names, rv.types).partialAggregation(["s", "k"], ["sum(v)", "avg(v)"]).localPartition([]).finalAggregation().planNode(),
+                   [rv], configs=(cfg,), batch_rows=1500, rel_tol=1e-11)  # several batches, each with its own dictionary
+    check_plan(PlanBuilder().values(rv.names, rv.types).filter("f = 'N' or s like 'name-00%'").project(["s", "f", "v * 2.0 as w"]).planNode(), [rv], batch_rows=2000)
+    from oracle import pyoracle
+    from velox_b200.task import run_plan
+    plan = PlanBuilder().values(rv.names, rv.types).project(["s", "f", "k"]).orderBy(["f DESC NULLS FIRST", "s", "k"]).planNode()
+    want = pyoracle.run_plan(plan, [rv], threads=1).rows()
+    got, _ = run_plan(plan, [rv], batch_rows=2500)
+    assert [r[:2] for r in got.rows()] == [r[:2] for r in want]
+
+
 def test_cast_to_boolean():
     """cast(x as boolean) is x != 0, NaN included (velox/type/Conversions.h:158-207, folly::to<bool>); the
     result is a normalised 0/1 byte, usable as a filter."""
@@ -349,7 +373,9 @@ def test_hash_join_types(join_type, dup):
     b = PlanBuilder().values(build.names, build.types, source=1)
     outs = ["pk", "pv", "ps"] if join_type in ("semi", "anti") else ["pk", "pv", "ps", "bv", "bs"]
     plan = PlanBuilder().values(probe.names, probe.types, source=0).hashJoin(["pk"], ["bk"], b, "", outs, joinType=join_type).planNode()
-    check_plan(plan, [probe, build])
+    (st,) = check_plan(plan, [probe, build])
+    # unique build keys take the one-pass probe (warp-ballot match bitmap), duplicates the count / scan / emit chain walk
+    assert (stat(st, "b200.uniqueKeyProbes") > 0) == (not dup)
     check_plan(plan, [probe, build], batch_rows=512)
 
 

@@ -267,6 +267,76 @@ __global__ void group_update_kernel(const __grid_constant__ vb2_group_table tab,
   if ((threadIdx.x & 31) == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
 }
 
+// Array-mode tables from a handful to a few thousand groups (GROUP BY on a low-cardinality column with
+// NULLs / dictionary inputs — shapes the fused pipelines do not take): per-row atomics on a global
+// table of 50 rows serialise in L2 on 50 addresses for the whole GPU. Every block accumulates into a
+// private copy of the table in shared memory instead (same update code: the atomics land in the SM's
+// own banks) and merges its copy into the global table once, with one atomic per touched word.
+constexpr int kSmemTableBytes = 40 * 1024;
+__device__ __forceinline__ uint64_t identity_of(int kind) {
+  switch (kind) {
+    case VB2_AGG_MIN_F64: return 0x7ff8000000000000ull;  // NaN: the largest value
+    case VB2_AGG_MAX_F64: return 0xfff0000000000000ull;  // -inf
+    case VB2_AGG_MIN_I64: return static_cast<uint64_t>(INT64_MAX);
+    case VB2_AGG_MAX_I64: return static_cast<uint64_t>(INT64_MIN);
+    default: return 0;
+  }
+}
+__global__ void __launch_bounds__(256) group_update_smem_kernel(const __grid_constant__ vb2_group_table tab, const uint64_t* __restrict__ row_keys,
+                                                                const uint64_t* __restrict__ row_valid, int64_t n,
+                                                                const __grid_constant__ AggArgs args, int32_t* __restrict__ error_flag) {
+  extern __shared__ __align__(16) uint64_t srows[];  // [capacity][row_words]
+  const int w = tab.row_words;
+  const int cap = static_cast<int>(tab.capacity);
+  for (int i = threadIdx.x; i < cap * w; i += blockDim.x) srows[i] = 0;
+  __syncthreads();
+  for (int k = 0; k < args.n; ++k) {
+    const uint64_t id = identity_of(args.a[k].kind);
+    if (id)
+      for (int slot = threadIdx.x; slot < cap; slot += blockDim.x) srows[slot * w + args.a[k].acc_word] = id;
+  }
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    if (row_valid && !bit_at(row_valid, i)) continue;
+    const uint64_t key = row_keys[i];
+    if (key >= static_cast<uint64_t>(cap)) { atomicCAS(error_flag, 0, 100); continue; }
+    uint64_t* row = srows + static_cast<int>(key) * w;
+    if (*reinterpret_cast<volatile uint64_t*>(row) == 0) *reinterpret_cast<volatile uint64_t*>(row) = 1;
+    for (int k = 0; k < args.n; ++k) apply_update(args.a[k], i, row, error_flag);
+  }
+  __syncthreads();
+  for (int slot = threadIdx.x; slot < cap; slot += blockDim.x) {
+    const uint64_t* mine = srows + slot * w;
+    if (mine[0] == 0) continue;  // this block saw no row of the group
+    uint64_t* row = tab.rows + static_cast<int64_t>(slot) * w;
+    if (*reinterpret_cast<volatile uint64_t*>(row) == 0) *reinterpret_cast<volatile uint64_t*>(row) = 1;
+    for (int k = 0; k < args.n; ++k) {
+      const vb2_agg_update& u = args.a[k];
+      const uint64_t v = mine[u.acc_word];
+      uint64_t* acc = row + u.acc_word;
+      switch (u.kind) {
+        case VB2_AGG_SUM_F64: atomicAdd(reinterpret_cast<double*>(acc), __longlong_as_double(static_cast<long long>(v))); break;
+        case VB2_AGG_SUM_I64: case VB2_AGG_COUNT_MERGE: {
+          const int64_t x = static_cast<int64_t>(v);
+          const int64_t old = static_cast<int64_t>(atomicAdd(reinterpret_cast<unsigned long long*>(acc), static_cast<unsigned long long>(x)));
+          int64_t r;
+          if (add_overflow_i64(old, x, &r)) atomicCAS(error_flag, 0, 1);
+          break;
+        }
+        case VB2_AGG_COUNT: atomicAdd(reinterpret_cast<unsigned long long*>(acc), static_cast<unsigned long long>(v)); break;
+        case VB2_AGG_MIN_F64: atomic_min_f64(reinterpret_cast<double*>(acc), __longlong_as_double(static_cast<long long>(v)), true); break;
+        case VB2_AGG_MAX_F64: atomic_min_f64(reinterpret_cast<double*>(acc), __longlong_as_double(static_cast<long long>(v)), false); break;
+        case VB2_AGG_MIN_I64: atomicMin(reinterpret_cast<long long*>(acc), static_cast<long long>(v)); break;
+        case VB2_AGG_MAX_I64: atomicMax(reinterpret_cast<long long*>(acc), static_cast<long long>(v)); break;
+        default: break;
+      }
+      if (u.nonnull_word >= 0 && u.kind != VB2_AGG_COUNT && mine[u.nonnull_word])
+        atomicAdd(reinterpret_cast<unsigned long long*>(row + u.nonnull_word), static_cast<unsigned long long>(mine[u.nonnull_word]));
+    }
+  }
+}
+
 // ---- keyed hash mode (kHash) ----------------------------------------------------------------------
 struct KeyedCols {
   vb2_column c[VB2_KEYED_MAX_KEYS];
@@ -961,6 +1031,12 @@ int vb2k_group_update(const vb2_group_table* t, const uint64_t* row_keys, const 
       }
     }
     if (rest.n) group_update_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(*t, row_keys, row_valid, n, rest, nullptr, error_flag);
+  } else if (!t->hash_mode && row_keys && distinct_words && n > kAtomicRows && t->capacity > kTinyG &&
+             t->capacity * t->row_words * 8 <= kSmemTableBytes) {
+    // low-cardinality array table: block-private shared-memory copies, merged once per block
+    for (int i = 0; i < naggs; ++i) rest.a[rest.n++] = aggs[i];
+    const size_t smem = static_cast<size_t>(t->capacity) * t->row_words * 8;
+    group_update_smem_kernel<<<vb2::counted(grid_for(n, 256, 8)), 256, smem, st>>>(*t, row_keys, row_valid, n, rest, error_flag);
   } else {
     for (int i = 0; i < naggs; ++i) rest.a[rest.n++] = aggs[i];
     group_update_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(*t, row_keys, row_valid, n, rest, num_groups, error_flag);

@@ -59,6 +59,29 @@ __global__ void join_probe_count_kernel(const __grid_constant__ vb2_join_table t
   }
 }
 
+// Unique build keys (no chains): one probe per row. The match flags of a warp become one bitmap word
+// through __ballot_sync (the compaction of the matches is then the same ordered bitmap expansion the
+// filter uses), the matched build row of every probe row is kept beside it.
+__global__ void join_probe_unique_kernel(const __grid_constant__ vb2_join_table t, const uint64_t* __restrict__ keys,
+                                         const uint64_t* __restrict__ valid, int64_t n, uint32_t* __restrict__ hit_bits,
+                                         int32_t* __restrict__ hits) {
+  const int64_t nwords = (n + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t w = warp_global; w < nwords; w += nwarps) {
+    const int64_t r = (w << 5) + lane;
+    int32_t m = 0;
+    if (r < n && (!valid || bit_at(valid, r))) {
+      const int64_t slot = find_slot(t, keys[r], false);
+      if (slot >= 0) m = t.head[slot];
+    }
+    if (r < n) hits[r] = m - 1;
+    const unsigned word = __ballot_sync(0xffffffffu, m != 0);
+    if (lane == 0) hit_bits[w] = word;
+  }
+}
+
 __global__ void join_probe_emit_kernel(const __grid_constant__ vb2_join_table t, const uint64_t* __restrict__ keys,
                                        const uint64_t* __restrict__ valid, int64_t n, const int64_t* __restrict__ offsets,
                                        int32_t* __restrict__ probe_rows, int32_t* __restrict__ build_rows) {
@@ -174,6 +197,17 @@ int vb2k_join_probe_count(const vb2_join_table* t, const uint64_t* probe_keys, c
                           int32_t* hit_counts, void* stream) {
   if (n <= 0) return VB2_OK;
   join_probe_count_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, probe_keys, valid, n, hit_counts);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_join_probe_unique(const vb2_join_table* t, const uint64_t* probe_keys, const uint64_t* valid, int64_t n, uint64_t* hit_bits,
+                           int32_t* hits, void* stream) {
+  if (n <= 0) return VB2_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the 64-bit consumers of the bitmap read whole words: clear the tail
+  VB2_CUDA_OK(cudaMemsetAsync(hit_bits + ((n + 63) >> 6) - 1, 0, sizeof(uint64_t), st));
+  join_probe_unique_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, st>>>(*t, probe_keys, valid, n, reinterpret_cast<uint32_t*>(hit_bits), hits);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }

@@ -143,6 +143,12 @@ struct B200HashAggregation::Impl {
   int fusedGroups = 0;
   int64_t fusedBatches = 0, genericBatches = 0, selectiveBatches = 0, partitionedBatches = 0;
   DeviceBufferPtr partStartDev, barrierWord;  // set while a radix-partitioned batch is being applied
+  // ---- shared-memory slice aggregation (slice_agg.cu): high-cardinality input is buffered and aggregated at the end
+  enum class SliceState { kUndecided, kBuffering, kOff };
+  SliceState sliceState = SliceState::kUndecided;
+  std::vector<B200VectorPtr> sliceChunks;  // buffered input batches (zero copy: the kernels read their columns in place)
+  std::vector<int32_t> slicePayload;       // input columns the aggregates read
+  int64_t sliceRows = 0, sliceBatches = 0;
   bool selectiveDecided = false, selectiveUsable = true;
   double selectivity = 1.0;
   struct FusedTiming { cudaEvent_t begin = nullptr, end = nullptr; int64_t rows = 0; };
@@ -406,7 +412,7 @@ struct B200HashAggregation::Impl {
     vb2_column d = col.desc;
     if (col.mayHaveNulls()) ks.nullable = true;
     if (ks.isVarchar) {
-      if (d.encoding == VB2_FLAT) VELOX_UNSUPPORTED("GROUP BY on flat VARCHAR keys (dictionary-encoded VARCHAR keys are supported)");
+      if (d.encoding == VB2_FLAT) VELOX_UNSUPPORTED("GROUP BY on flat VARCHAR keys with more than 65536 distinct values per batch (flat strings are dictionary-encoded on upload up to that size)");
       VELOX_CHECK(col.alphabet != nullptr, "VARCHAR key without a host alphabet (dictionary above 65536 entries)");
       if (ks.cachedAlphabet != col.alphabet) {
         std::vector<int32_t> lut(col.alphabet->values.size());
@@ -546,6 +552,157 @@ struct B200HashAggregation::Impl {
     double e = alpha * m * m / sum;
     if (e <= 2.5 * m && zeros > 0) e = m * std::log(m / zeros);  // small-range correction (linear counting)
     return 8.0 * e;
+  }
+
+  // ---- shared-memory slice aggregation ---------------------------------------------------------------
+  // A GROUP BY with millions of groups is bound by random DRAM sectors and page walks when every row
+  // probes a global table. When the first large batch shows that many distinct keys, the operator
+  // buffers its input instead (zero copy) and aggregates everything at the end with two partition
+  // passes and per-slice shared-memory tables (slice_agg.cu). The reference makes the same kind of
+  // call at run time when it abandons partial aggregation for nearly-unique keys
+  // (exec/HashAggregation.cpp:185-189,320-336); results are identical either way.
+  // Shape: one flat NULL-free BIGINT key, unmasked aggregates over flat NULL-free BIGINT / DOUBLE columns.
+  bool sliceEligible(const B200VectorPtr& in, std::vector<int32_t>& payload) const {
+    if (keys.size() != 1 || mode == Mode::kKeyed) return false;
+    const vb2_column& k = in->column(resolved.keys[0])->desc;
+    if (k.encoding != VB2_FLAT || k.nulls || k.type != VB2_BIGINT) return false;
+    for (auto& a : resolved.aggregates) {
+      if (a.mask >= 0) return false;
+      for (int32_t c : a.inputs) {
+        const vb2_column& d = in->column(c)->desc;
+        if (d.encoding != VB2_FLAT || d.nulls || (d.type != VB2_BIGINT && d.type != VB2_DOUBLE)) return false;
+        if (std::find(payload.begin(), payload.end(), c) == payload.end()) payload.push_back(c);
+      }
+    }
+    return payload.size() <= VB2_SLICE_MAX_COLS;  // the accumulator-word limit is checked when the ops are listed
+  }
+
+  bool addSliceBuffered(const B200VectorPtr& in) {
+    if (sliceState == SliceState::kOff) return false;
+    const auto& cfg = self->driverCtx()->queryConfig();
+    std::vector<int32_t> payload;
+    const bool eligible = cfg.get<bool>("b200.agg_slice_aggregation", true) && sliceEligible(in, payload);
+    if (sliceState == SliceState::kUndecided) {
+      // decided once, on the first batch that reaches the generic path: the table must still be empty
+      sliceState = SliceState::kOff;
+      const int64_t n = in->size();
+      if (!eligible || sawGeneric || n < cfg.get<int64_t>("b200.agg_slice_min_rows", 1 << 23)) return false;
+      // distinct keys of this batch (HyperLogLog over the raw keys: the hash of v - min + 1 with any min sketches the same count)
+      const vb2_column& k = in->column(resolved.keys[0])->desc;
+      const size_t wsBytes = vb2k_radix_workspace_bytes(n);
+      auto ws = allocDevice(wsBytes, st());
+      const int32_t nregs = vb2k_radix_hll_registers();
+      auto hll = allocDevice(static_cast<size_t>(nregs) * 4, st());
+      kernelCheck(vb2k_radix_histogram(nullptr, k.values, 1, 0, n, ws->data(), wsBytes, hll->as<int32_t>(), st()));
+      std::vector<int32_t> regs(nregs);
+      VB2_CU(cudaMemcpyAsync(regs.data(), hll->data(), static_cast<size_t>(nregs) * 4, cudaMemcpyDeviceToHost, st()));
+      VB2_CU(cudaStreamSynchronize(st()));
+      // worth it once the table (32-byte rows at load 0.5) outgrows the L2 by a wide margin
+      if (hllEstimate(regs) < static_cast<double>(cfg.get<int64_t>("b200.agg_slice_min_groups", 4 << 20))) return false;
+      sliceState = SliceState::kBuffering;
+      slicePayload = payload;
+    } else if (!eligible || payload != slicePayload) {
+      // a batch the slice kernels cannot read: everything buffered so far goes through the table path
+      drainSliceBuffer();
+      return false;
+    }
+    std::vector<DeviceBufferPtr> keep;
+    keyColumn(0, *in->column(resolved.keys[0]), in->size(), keep);  // tracks the key range (one min/max pass)
+    sliceChunks.push_back(in);
+    sliceRows += in->size();
+    ++sliceBatches;
+    if (sliceRows >= (1ll << 32) - (1ll << 28)) drainSliceBuffer();  // the slice kernels index rows with 32 bits
+    return true;
+  }
+
+  // Buffered batches through the table path (fallback; also ends slice mode).
+  void drainSliceBuffer() {
+    sliceState = SliceState::kOff;
+    std::vector<B200VectorPtr> chunks = std::move(sliceChunks);
+    sliceChunks.clear();
+    sliceRows = 0;
+    const int64_t chunk = std::max<int64_t>(1 << 16, self->driverCtx()->queryConfig().b200AggProbeChunkRows()) / 64 * 64;
+    for (auto& b : chunks)
+      for (int64_t off = 0; off < b->size(); off += chunk) addGeneric(sliceVector(b, off, std::min<int64_t>(chunk, b->size() - off)));
+  }
+
+  // Aggregates the buffered input; the compact group rows become the operator's table (never probed again).
+  void finishSliceAggregation() {
+    if (sliceState != SliceState::kBuffering || sliceChunks.empty()) return;
+    ensureLayout(0);  // the layout covers every buffered key range
+    if (mode != Mode::kHash || layout.mults[0] != 1 || nullReserved[0] != 0) { drainSliceBuffer(); return; }
+    const int32_t ncols = static_cast<int32_t>(slicePayload.size());
+    std::vector<vb2_slice_chunk> chunks;
+    for (auto& b : sliceChunks) {
+      vb2_slice_chunk c{};
+      c.raw_keys = static_cast<const int64_t*>(b->column(resolved.keys[0])->desc.values);
+      c.key_min = layout.mins[0];
+      for (int32_t i = 0; i < ncols; ++i) c.cols[i] = b->column(slicePayload[i])->desc.values;
+      c.rows = b->size();
+      chunks.push_back(c);
+    }
+    auto colOf = [&](int32_t inputColumn) { return static_cast<int32_t>(std::find(slicePayload.begin(), slicePayload.end(), inputColumn) - slicePayload.begin()); };
+    std::vector<vb2_slice_op> ops;
+    for (size_t i = 0; i < accs.size(); ++i) {
+      const auto& a = resolved.aggregates[i];
+      const AccState& s = accs[i];
+      if (a.function == "count") {
+        if (raw) ops.push_back(vb2_slice_op{VB2_AGG_COUNT, -1, s.accWord});
+        else ops.push_back(vb2_slice_op{VB2_AGG_COUNT_MERGE, colOf(a.inputs[0]), s.accWord});
+        continue;
+      }
+      ops.push_back(vb2_slice_op{s.kind, colOf(a.inputs[0]), s.accWord});
+      if (a.function == "avg" && !raw) ops.push_back(vb2_slice_op{VB2_AGG_COUNT_MERGE, colOf(a.inputs[1]), s.nnWord});
+      else if (s.nnTracked) ops.push_back(vb2_slice_op{VB2_AGG_COUNT, -1, s.nnWord});  // inputs are NULL-free: every row counts
+    }
+    const auto& cfg = self->driverCtx()->queryConfig();
+    const size_t wsBytes = vb2k_slice_agg_workspace(sliceRows, ncols);
+    bool done = false;
+    if (ops.size() <= VB2_SLICE_MAX_OPS) {
+      auto ws = allocDevice(wsBytes, st());
+      std::vector<int32_t> regs(vb2k_slice_agg_hll_registers());
+      kernelCheck(vb2k_slice_agg_partition(chunks.data(), static_cast<int32_t>(chunks.size()), ncols, sliceRows, ws->data(), wsBytes, regs.data(), st()));
+      int64_t distinct = std::min<int64_t>(sliceRows, static_cast<int64_t>(hllEstimate(regs) * 1.15) + 1024);  // + 9 sigma of the sketch's error
+      distinct = cfg.get<int64_t>("b200.agg_slice_distinct_hint", distinct);
+      const int32_t rw = rowWordsFor(Mode::kHash);
+      std::vector<uint64_t> init(rw, 0);
+      for (auto& a : accs) init[a.accWord] = identityBits(a);
+      // the group rows land in a table-shaped buffer (power-of-two rows, unused rows keep the EMPTY key) so that
+      // the extraction reads it like any hash-mode table
+      const int64_t cap = static_cast<int64_t>(nextPow2(static_cast<uint64_t>(std::max<int64_t>(16, std::min<int64_t>(sliceRows, distinct)))));
+      auto rowsOut = makeStorage(cap, Mode::kHash);
+      auto words = allocDeviceZeroed(32, st());  // [0] groups (int64), [2] error (int32 at byte 16), overflow (int32 at byte 24)
+      int64_t* groupsDev = words->as<int64_t>();
+      int32_t* errDev = reinterpret_cast<int32_t*>(words->as<uint8_t>() + 16);
+      int32_t* ovfDev = reinterpret_cast<int32_t*>(words->as<uint8_t>() + 24);
+      const int rc = vb2k_slice_agg_finish(sliceRows, ncols, distinct, ops.data(), static_cast<int32_t>(ops.size()), rw, init.data(), rowsOut->as<uint64_t>(), cap,
+                                           groupsDev, errDev, ovfDev, ws->data(), wsBytes, st());
+      if (rc == VB2_OK) {
+        uint8_t host[32];
+        VB2_CU(cudaMemcpyAsync(host, words->data(), 32, cudaMemcpyDeviceToHost, st()));
+        VB2_CU(cudaStreamSynchronize(st()));
+        int64_t m;
+        int32_t err, ovf;
+        std::memcpy(&m, host, 8);
+        std::memcpy(&err, host + 16, 4);
+        std::memcpy(&ovf, host + 24, 4);
+        if (err == 1) throw VeloxUserError("integer overflow in sum");  // SumAggregate.cpp:24
+        if (err == 0 && ovf == 0 && m > 0) {
+          rowsBuf = rowsOut;
+          capacity = cap;
+          mode = Mode::kHash;
+          numGroupsUpper = m;
+          done = true;
+          self->addRuntimeStat("b200.sliceAggRows", exec::RuntimeCounter{sliceRows});
+          self->addRuntimeStat("b200.sliceAggGroups", exec::RuntimeCounter{m});
+        }
+      } else if (rc != VB2_ERR_UNSUPPORTED) {
+        kernelCheck(rc);
+      }
+    }
+    if (!done) { drainSliceBuffer(); return; }
+    sliceChunks.clear();
+    sliceState = SliceState::kOff;
   }
 
   // Large batches over a large hash-mode table: the rows are radix-partitioned by the top bits of
@@ -1164,6 +1321,7 @@ struct B200HashAggregation::Impl {
     // Hash-mode tables are sized by (groups so far + rows of one pass): large batches go through
     // find-or-insert in bounded passes so a high-cardinality table ends near 2x its group count
     // instead of 2x the batch.
+    if (addSliceBuffered(cur)) return;
     if (addPartitioned(cur)) return;
     const int64_t chunk = std::max<int64_t>(1 << 16, self->driverCtx()->queryConfig().b200AggProbeChunkRows()) / 64 * 64;
     if (!keys.empty() && cur->size() > chunk) {
@@ -1226,6 +1384,7 @@ struct B200HashAggregation::Impl {
 
   B200VectorPtr extractGroups() {
     flushFused();
+    finishSliceAggregation();
     if (!sawInput && mode != Mode::kGlobal) return nullptr;  // a grouped aggregation over no input emits nothing
     const bool small = capacity <= VB2_EXTRACT_SMALL_CAPACITY;
     int64_t m = 0;

@@ -5,6 +5,8 @@
 #include <mutex>
 
 #include <nvtx3/nvToolsExt.h>
+#include <string_view>
+#include <unordered_map>
 
 namespace velox_b200 {
 
@@ -257,6 +259,51 @@ const uint64_t* uploadNulls(const BaseVector& v, std::vector<DeviceBufferPtr>& o
 
 constexpr vector_size_t kMaxAlphabet = 1 << 16;
 
+// A flat VARCHAR column with few distinct values goes up dictionary-encoded: every operator of the path
+// groups, joins, sorts and exchanges dictionary strings through their int32 codes (flat strings would
+// need variable-width keys on the device). The reference reaches the same end on the CPU by mapping short
+// strings to numbers inside VectorHasher (exec/VectorHasher.h:377-387); TPC-H's l_returnflag /
+// l_linestatus / p_type (tpch/gen/TpchGen.cpp:278-317) are such columns. One hash lookup per row on the
+// host, next to a PCIe copy of the same rows. Columns with more than 65536 distinct values stay flat.
+bool encodeFlatStrings(const BaseVector& v, DeviceColumn& col, std::vector<std::shared_ptr<StringStaging>>& staging, cudaStream_t stream) {
+  const auto* flat = v.as<FlatVector<StringView>>();
+  if (!flat) return false;
+  const vector_size_t n = v.size();
+  const StringView* views = flat->rawValues();
+  auto codes = std::make_shared<StringStaging>();
+  codes->offsets.resize(static_cast<size_t>(n));
+  std::unordered_map<std::string_view, int32_t> ids;
+  auto alpha = std::make_shared<HostAlphabet>();
+  for (vector_size_t i = 0; i < n; ++i) {
+    if (v.isNullAt(i)) { codes->offsets[i] = 0; continue; }
+    const std::string_view sv(views[i].data(), views[i].size());
+    auto it = ids.find(sv);
+    if (it == ids.end()) {
+      if (static_cast<vector_size_t>(alpha->values.size()) >= kMaxAlphabet) return false;
+      it = ids.emplace(sv, static_cast<int32_t>(alpha->values.size())).first;
+      alpha->values.emplace_back(sv);
+      alpha->nulls.push_back(false);
+    }
+    codes->offsets[i] = it->second;
+  }
+  if (alpha->values.empty()) { alpha->values.emplace_back(); alpha->nulls.push_back(false); }  // all NULL: one unused entry
+  vb2_column& d = col.desc;
+  d.encoding = VB2_DICTIONARY;
+  staging.push_back(codes);
+  col.owners.push_back(upload(codes->offsets.data(), codes->offsets.size() * 4, stream));
+  d.indices = col.owners.back()->as<int32_t>();
+  DeviceBufferPtr offBuf, charBuf;
+  deviceAlphabet(*alpha, stream, offBuf, charBuf);
+  d.values = offBuf->data();
+  d.aux = charBuf->data();
+  d.dict_size = static_cast<int64_t>(alpha->values.size());
+  col.owners.push_back(offBuf);
+  col.owners.push_back(charBuf);
+  d.nulls = uploadNulls(v, col.owners, stream);
+  col.alphabet = alpha;
+  return true;
+}
+
 }  // namespace
 
 B200VectorPtr toDevice(const RowVectorPtr& host, cudaStream_t stream) {
@@ -272,6 +319,7 @@ B200VectorPtr toDevice(const RowVectorPtr& host, cudaStream_t stream) {
     d.size = child->size();
     switch (child->encoding()) {
       case VectorEncoding::Simple::FLAT:
+        if (child->typeKind() == TypeKind::VARCHAR && encodeFlatStrings(*child, *col, staging, stream)) break;
         d.encoding = VB2_FLAT;
         uploadFlatValues(*child, d, col->owners, stream, staging, nullptr);
         d.nulls = uploadNulls(*child, col->owners, stream);

@@ -328,23 +328,46 @@ B200VectorPtr B200HashProbe::apply(const B200VectorPtr& in) {
   const core::JoinType type = node_->joinType();
   // build and probe streams differ only across drivers; the bridge hand-off synchronised the build
   NormalizedKeys nk = normalizeKeys(*in, plan_.leftKeys, jt.layout, nullptr, n, true, st);
-  auto counts = allocDevice(static_cast<size_t>(n) * 4, st);
-  kernelCheck(vb2k_join_probe_count(&jt.table, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, counts->as<int32_t>(), st));
-  auto offsets = allocDevice(static_cast<size_t>(n) * 8, st);
-  auto total = allocDevice(8, st);
-  const size_t wsBytes = vb2k_scan_workspace(n);
-  auto ws = allocDevice(wsBytes, st);
-  kernelCheck(vb2k_exclusive_scan_i32(counts->as<int32_t>(), n, offsets->as<int64_t>(), total->as<int64_t>(), ws->data(), wsBytes, st));
   int64_t pairs = 0;
-  VB2_CU(cudaMemcpyAsync(&pairs, total->data(), 8, cudaMemcpyDeviceToHost, st));
-  VB2_CU(cudaStreamSynchronize(st));
-  VELOX_CHECK(pairs < (1ll << 31), "join output above 2^31 rows for one batch");
   DeviceBufferPtr probeRows, buildRows;
-  if (pairs > 0) {
-    probeRows = allocDevice(static_cast<size_t>(pairs) * 4, st);
-    buildRows = allocDevice(static_cast<size_t>(pairs) * 4, st);
-    kernelCheck(vb2k_join_probe_emit(&jt.table, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, offsets->as<int64_t>(),
-                                     probeRows->as<int32_t>(), buildRows->as<int32_t>(), st));
+  if (!jt.hasDuplicateKeys) {
+    // unique build keys (every TPC-H primary-key join): ONE probe of the table per row. The matches of a
+    // warp are a ballot word; the ordered expansion of that bitmap gives the matching probe rows, their
+    // build rows are gathered from the per-row hits.
+    auto hitBits = allocDevice(bits::nbytes(n), st);
+    auto hits = allocDevice(static_cast<size_t>(n) * 4, st);
+    kernelCheck(vb2k_join_probe_unique(&jt.table, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, hitBits->as<uint64_t>(), hits->as<int32_t>(), st));
+    auto sel = allocDevice(static_cast<size_t>(n) * 4, st);
+    auto cnt = allocDevice(8, st);
+    const size_t wsb = vb2k_bits_to_indices_workspace(n);
+    auto ws = allocDevice(wsb, st);
+    kernelCheck(vb2k_bits_to_indices(hitBits->as<uint64_t>(), n, sel->as<int32_t>(), cnt->as<int64_t>(), ws->data(), wsb, st));
+    VB2_CU(cudaMemcpyAsync(&pairs, cnt->data(), 8, cudaMemcpyDeviceToHost, st));
+    VB2_CU(cudaStreamSynchronize(st));
+    if (pairs > 0) {
+      probeRows = sel;
+      buildRows = allocDevice(static_cast<size_t>(pairs) * 4, st);
+      kernelCheck(vb2k_gather(hits->data(), sel->as<int32_t>(), pairs, 4, buildRows->data(), st));
+    }
+    addRuntimeStat("b200.uniqueKeyProbes", exec::RuntimeCounter{1});
+  } else {
+    // duplicate build keys: count the chain of every probe row, scan, emit the pairs in probe order
+    auto counts = allocDevice(static_cast<size_t>(n) * 4, st);
+    kernelCheck(vb2k_join_probe_count(&jt.table, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, counts->as<int32_t>(), st));
+    auto offsets = allocDevice(static_cast<size_t>(n) * 8, st);
+    auto total = allocDevice(8, st);
+    const size_t wsBytes = vb2k_scan_workspace(n);
+    auto ws = allocDevice(wsBytes, st);
+    kernelCheck(vb2k_exclusive_scan_i32(counts->as<int32_t>(), n, offsets->as<int64_t>(), total->as<int64_t>(), ws->data(), wsBytes, st));
+    VB2_CU(cudaMemcpyAsync(&pairs, total->data(), 8, cudaMemcpyDeviceToHost, st));
+    VB2_CU(cudaStreamSynchronize(st));
+    VELOX_CHECK(pairs < (1ll << 31), "join output above 2^31 rows for one batch");
+    if (pairs > 0) {
+      probeRows = allocDevice(static_cast<size_t>(pairs) * 4, st);
+      buildRows = allocDevice(static_cast<size_t>(pairs) * 4, st);
+      kernelCheck(vb2k_join_probe_emit(&jt.table, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(), n, offsets->as<int64_t>(),
+                                       probeRows->as<int32_t>(), buildRows->as<int32_t>(), st));
+    }
   }
   // optional join filter over (probe ++ build) columns of the candidate pairs
   if (filterProgram_ && pairs > 0) {

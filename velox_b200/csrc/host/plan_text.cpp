@@ -235,18 +235,10 @@ class Parser {
         core::AggregationNode::Aggregate a;
         std::vector<core::TypedExprPtr> args;
         TypePtr rawType;
-        if (r.col >= 0) {
-          args.push_back(field(r.col));
-          rawType = in->childAt(r.col);
-          a.rawInputTypes.push_back(rawType);
-          if (!raw && r.fn == "avg") args.push_back(field(r.col + 1));  // the flattened (sum, count) pair
-        }
-        if (r.mask >= 0) a.mask = field(r.mask);
-        const std::string n = "n" + id + "a" + std::to_string(aggs.size());
-        TypePtr resultType;
-        // registered aggregates (exec::registerAggregateFunction): type the call from the B200Aggregate's family and transforms
+        // registered aggregates (exec::registerAggregateFunction): the call keeps its registered name, typing
+        // follows the B200Aggregate's accumulator family and transforms
         const std::string callName = r.fn;
-        std::string finalFn;
+        std::string inputFn, finalFn;
         if (r.fn != "count" && r.fn != "sum" && r.fn != "min" && r.fn != "max" && r.fn != "avg") {
           registerB200Aggregates();
           if (!exec::getAggregateFunctionEntry(r.fn)) throw VeloxRuntimeError("plan text: unknown aggregate " + r.fn);
@@ -254,9 +246,19 @@ class Parser {
           auto* agg = dynamic_cast<B200Aggregate*>(created.get());
           if (!agg) throw VeloxRuntimeError("plan text: aggregate " + r.fn + " has no B200 implementation");
           r.fn = agg->family();
-          if (raw && rawType && !agg->inputFunction().empty()) rawType = scalarFunctionReturnType(agg->inputFunction(), rawType);
+          inputFn = agg->inputFunction();
           finalFn = agg->finalFunction();
         }
+        if (r.col >= 0) {
+          args.push_back(field(r.col));
+          rawType = in->childAt(r.col);
+          a.rawInputTypes.push_back(rawType);
+          if (!raw && r.fn == "avg") args.push_back(field(r.col + 1));  // the flattened (sum, count) pair
+          if (raw && !inputFn.empty()) rawType = scalarFunctionReturnType(inputFn, rawType);  // the accumulator sees the transformed input
+        }
+        if (r.mask >= 0) a.mask = field(r.mask);
+        const std::string n = "n" + id + "a" + std::to_string(aggs.size());
+        TypePtr resultType;
         if (r.fn == "count") { resultType = BIGINT(); names.push_back(n); types.push_back(BIGINT()); }
         else if (r.fn == "sum") { resultType = raw ? (rawType->kind() == TypeKind::DOUBLE ? DOUBLE() : BIGINT()) : rawType; names.push_back(n); types.push_back(resultType); }
         else if (r.fn == "min" || r.fn == "max") { resultType = rawType; names.push_back(n); types.push_back(rawType); }

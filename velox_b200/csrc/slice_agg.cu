@@ -1,0 +1,583 @@
+// High-cardinality GROUP BY entirely on chip: two radix-partition passes cut the buffered input into
+// slices whose distinct keys fit one CTA's shared-memory hash table, every slice is then aggregated in
+// shared memory and its groups are appended to a compact array of group rows.
+//
+// Replaces, for inputs with millions of groups, the find-or-insert of HashTable::groupProbe /
+// ProbeState::fullProbe + the accumulator scatter of SimpleNumericAggregate (velox/exec/HashTable.cpp:
+// 470-519,138; functions/lib/aggregates/SimpleNumericAggregate.h:94-150): on the CPU that loop is
+// cache / TLB-miss bound and the reference hides it with a 4-way interleave and prefetches; on B200 a
+// global table of 100 M x 32 B rows costs one random DRAM sector read-modify-write plus a page walk
+// per input row (198 B of DRAM reads per row measured, profiles/r01_ncu_config5_group_update.json).
+// Here DRAM only sees streaming passes:
+//
+//   level 1   rows -> 256 partitions by hash bits 63..56        (histogram, scan, staged scatter)
+//   level 2   every partition -> P2 <= 256 slices by bits 55..  (same kernels, one launch each)
+//   aggregate one CTA per slice: open-addressing table in shared memory (keys + accumulator words),
+//             smem atomics, then the occupied slots become group rows [key | accumulators] in the
+//             vb2_group_table row layout, appended at an atomically reserved offset
+//
+// The scatter stages each tile in shared memory in partition order, so global stores are runs of
+// consecutive rows (full 32-byte sectors) — a direct 8-byte scatter makes DRAM read and write every
+// sector twice. All loads of the input are coalesced and streaming.
+// A HyperLogLog sketch filled by the level-1 histogram sizes level 2 and the output.
+#include "common.cuh"
+
+namespace vb2 {
+
+namespace {
+
+constexpr int kPT = 512;          // threads of the partition kernels
+constexpr int kTile = 4096;       // rows per tile (staged in shared memory)
+constexpr int kP1 = 256;
+constexpr int kMaxP = 256;
+constexpr int kCols = VB2_SLICE_MAX_COLS;
+constexpr int kHllBits = 12;
+constexpr int kAggThreads = 512;
+constexpr int kMaxOps = VB2_SLICE_MAX_OPS;
+
+struct SliceKey {
+  const uint64_t* norm;  // normalized keys, or NULL: raw BIGINT keys below
+  const int64_t* raw;
+  int64_t min;           // normalized key = raw - min + 1 (vb2k_normalize_keys with one column)
+};
+__device__ __forceinline__ uint64_t slice_key(const SliceKey& k, int64_t r) { return k.norm ? k.norm[r] : static_cast<uint64_t>(k.raw[r] - k.min) + 1; }
+
+struct PartIO {
+  SliceKey key;
+  const uint64_t* cols_in[kCols];
+  uint64_t* keys_out;
+  uint64_t* cols_out[kCols];
+  int ncols;
+};
+struct PartGeom {
+  int64_t n;                  // rows of the input array
+  const int64_t* seg_start;   // device [nseg + 1]; NULL: one segment [0, n)
+  const int32_t* tile_start;  // device [nseg + 1]: first tile of every segment (NULL with seg_start)
+  int nseg;
+  int P, shift;               // digit = (twang_mix64(key) >> shift) & (P - 1)
+};
+
+// rows [begin, end) and segment of a tile; false past the last tile (tiles are ordered: every later tile is past it too)
+__device__ __forceinline__ bool tile_range(const PartGeom& g, int64_t tile, int& seg, int64_t& begin, int64_t& end) {
+  if (!g.seg_start) {
+    seg = 0;
+    begin = tile * kTile;
+    if (begin >= g.n) return false;
+    end = begin + kTile < g.n ? begin + kTile : g.n;
+    return true;
+  }
+  if (tile >= g.tile_start[g.nseg]) return false;
+  int lo = 0, hi = g.nseg;  // tile_start[lo] <= tile < tile_start[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (g.tile_start[mid] <= tile) lo = mid;
+    else hi = mid;
+  }
+  seg = lo;
+  begin = g.seg_start[seg] + (tile - g.tile_start[seg]) * kTile;
+  const int64_t segEnd = g.seg_start[seg + 1];
+  end = begin + kTile < segEnd ? begin + kTile : segEnd;
+  return true;
+}
+
+// hist[seg * P + d] += rows of segment seg with digit d. A block walks a contiguous range of tiles and
+// flushes its shared histogram when the segment changes. hll (optional): HyperLogLog registers over
+// the keys whose hash ends in 000 (the convention of radix_partition.cu: the host multiplies by 8).
+__global__ void __launch_bounds__(kPT) part_hist_kernel(const __grid_constant__ SliceKey key, const __grid_constant__ PartGeom g, int64_t ntiles,
+                                                        uint32_t* __restrict__ hist, int32_t* __restrict__ hll) {
+  __shared__ uint32_t h[kMaxP];
+  __shared__ int32_t regs[1 << kHllBits];
+  if (hll)
+    for (int i = threadIdx.x; i < (1 << kHllBits); i += kPT) regs[i] = 0;
+  if (threadIdx.x < kMaxP) h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int64_t t0 = blockIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
+  int segNow = -1;
+  for (int64_t tile = t0; tile < t1; ++tile) {
+    int seg;
+    int64_t begin, end;
+    if (!tile_range(g, tile, seg, begin, end)) break;
+    if (seg != segNow) {
+      if (segNow >= 0) {
+        __syncthreads();
+        if (threadIdx.x < g.P && h[threadIdx.x]) atomicAdd(&hist[static_cast<int64_t>(segNow) * g.P + threadIdx.x], h[threadIdx.x]);
+        if (threadIdx.x < kMaxP) h[threadIdx.x] = 0;
+        __syncthreads();
+      }
+      segNow = seg;
+    }
+    for (int64_t i = begin + threadIdx.x; i < end; i += kPT) {
+      const uint64_t hash = twang_mix64(slice_key(key, i));
+      atomicAdd(&h[(hash >> g.shift) & (g.P - 1)], 1u);
+      if (hll && (hash & 7u) == 0) {
+        const uint32_t idx = static_cast<uint32_t>(hash >> 3) & ((1u << kHllBits) - 1u);
+        const uint64_t rest = (hash >> (3 + kHllBits)) | (1ull << (56 - 3 - kHllBits));
+        atomicMax(&regs[idx], __ffsll(static_cast<long long>(rest)));
+      }
+    }
+  }
+  __syncthreads();
+  if (segNow >= 0 && threadIdx.x < g.P && h[threadIdx.x]) atomicAdd(&hist[static_cast<int64_t>(segNow) * g.P + threadIdx.x], h[threadIdx.x]);
+  if (hll)
+    for (int i = threadIdx.x; i < (1 << kHllBits); i += kPT)
+      if (regs[i]) atomicMax(&hll[i], regs[i]);
+}
+
+// level 1: partition starts, scatter cursors and the tile numbering of level 2
+__global__ void part_scan1_kernel(const uint32_t* __restrict__ hist, int64_t* __restrict__ start, unsigned long long* __restrict__ cursor,
+                                  int32_t* __restrict__ tile_start) {
+  if (threadIdx.x != 0) return;
+  int64_t run = 0;
+  int32_t tiles = 0;
+  for (int p = 0; p < kP1; ++p) {
+    start[p] = run;
+    cursor[p] = static_cast<unsigned long long>(run);
+    tile_start[p] = tiles;
+    run += hist[p];
+    tiles += static_cast<int32_t>((hist[p] + kTile - 1) / kTile);
+  }
+  start[kP1] = run;
+  tile_start[kP1] = tiles;
+}
+// level 2: slice starts inside every level-1 partition (block = partition)
+__global__ void part_scan2_kernel(const uint32_t* __restrict__ hist, const int64_t* __restrict__ seg_start, int P, int64_t* __restrict__ slice_start,
+                                  unsigned long long* __restrict__ cursor) {
+  if (threadIdx.x != 0) return;
+  const int s = blockIdx.x;
+  int64_t run = seg_start[s];
+  for (int d = 0; d < P; ++d) {
+    slice_start[static_cast<int64_t>(s) * P + d] = run;
+    cursor[static_cast<int64_t>(s) * P + d] = static_cast<unsigned long long>(run);
+    run += hist[static_cast<int64_t>(s) * P + d];
+  }
+  if (s == gridDim.x - 1) slice_start[static_cast<int64_t>(gridDim.x) * P] = run;
+}
+
+// Staged scatter of one tile per iteration: (A) digits + tile histogram, (B) local offsets and the
+// tile's reservation in every partition (one global atomic per non-empty digit), (C) keys and
+// payloads into shared memory in partition order, (D) consecutive threads store consecutive rows.
+__global__ void __launch_bounds__(kPT) part_scatter_kernel(const __grid_constant__ PartIO io, const __grid_constant__ PartGeom g, int64_t ntiles,
+                                                           unsigned long long* __restrict__ cursor) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* scols = skeys + kTile;                                           // [ncols][kTile]
+  uint8_t* sdig = reinterpret_cast<uint8_t*>(scols + static_cast<size_t>(io.ncols) * kTile);  // digit of every staged position
+  uint8_t* rdig = sdig + kTile;                                              // digit of every input position
+  __shared__ uint32_t cnt[kMaxP], lofs[kMaxP], lcur[kMaxP];
+  __shared__ unsigned long long gbase[kMaxP];
+  __shared__ uint32_t wtot[kMaxP / 32];
+  const int tid = threadIdx.x;
+  const int P = g.P;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int seg;
+    int64_t begin, end;
+    if (!tile_range(g, tile, seg, begin, end)) break;
+    const int rows = static_cast<int>(end - begin);
+    if (tid < kMaxP) cnt[tid] = 0;
+    __syncthreads();
+    // (A)
+#pragma unroll 4
+    for (int j = tid; j < rows; j += kPT) {
+      const int d = static_cast<int>((twang_mix64(slice_key(io.key, begin + j)) >> g.shift) & (P - 1));
+      rdig[j] = static_cast<uint8_t>(d);
+      atomicAdd(&cnt[d], 1u);
+    }
+    __syncthreads();
+    // (B) exclusive prefix of the digit counts (the first 256 threads: warp scans + warp totals)
+    uint32_t mine = 0, incl = 0;
+    if (tid < kMaxP) {
+      mine = tid < P ? cnt[tid] : 0;
+      incl = mine;
+      const int lane = tid & 31;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) wtot[tid >> 5] = incl;
+    }
+    __syncthreads();
+    if (tid < kMaxP) {
+      uint32_t before = 0;
+      for (int w = 0; w < (tid >> 5); ++w) before += wtot[w];
+      lofs[tid] = before + incl - mine;
+      lcur[tid] = before + incl - mine;
+      if (mine) gbase[tid] = atomicAdd(&cursor[static_cast<int64_t>(seg) * P + tid], static_cast<unsigned long long>(mine));
+    }
+    __syncthreads();
+    // (C) loads first (keys again: the tile is L1 / L2 resident; payloads for the first time), then placement
+    for (int j0 = tid; j0 < rows; j0 += 4 * kPT) {
+      uint64_t k[4], v[kCols][4];  // every index below is a compile-time constant after unrolling: registers, no stack
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * kPT;
+        if (j < rows) {
+          k[u] = slice_key(io.key, begin + j);
+#pragma unroll
+          for (int c = 0; c < kCols; ++c)
+            if (c < io.ncols) v[c][u] = io.cols_in[c][begin + j];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * kPT;
+        if (j < rows) {
+          const int d = rdig[j];
+          const uint32_t p = atomicAdd(&lcur[d], 1u);
+          skeys[p] = k[u];
+          sdig[p] = static_cast<uint8_t>(d);
+#pragma unroll
+          for (int c = 0; c < kCols; ++c)
+            if (c < io.ncols) scols[static_cast<size_t>(c) * kTile + p] = v[c][u];
+        }
+      }
+    }
+    __syncthreads();
+    // (D)
+    for (int p = tid; p < rows; p += kPT) {
+      const int d = sdig[p];
+      const unsigned long long out = gbase[d] + (p - lofs[d]);
+      io.keys_out[out] = skeys[p];
+      for (int c = 0; c < io.ncols; ++c) io.cols_out[c][out] = scols[static_cast<size_t>(c) * kTile + p];
+    }
+    __syncthreads();
+  }
+}
+
+// ---- aggregate -------------------------------------------------------------------------------------
+struct AggIO {
+  const uint64_t* keys;
+  const uint64_t* cols[kCols];
+  const int64_t* slice_start;  // [nslices + 1]
+  int nslices;
+  vb2_slice_op ops[kMaxOps];
+  int nops;
+  uint64_t row_init[VB2_MAX_ROW_WORDS];
+  int row_words;
+  uint64_t* rows_out;
+  int64_t rows_capacity;
+  unsigned long long* num_groups;
+  int32_t* error_flag;     // 1 = SUM(BIGINT) overflow, 100 = rows_out full
+  int32_t* overflow;       // slices whose distinct keys did not fit the shared-memory table
+  int C;                   // slots per slice table (power of two)
+};
+
+__device__ __forceinline__ void smem_min_f64(uint64_t* addr, double v, bool is_min) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p);
+  for (;;) {
+    const double cur = __longlong_as_double(static_cast<long long>(old));
+    const bool better = is_min ? lt_f64(v, cur) : gt_f64(v, cur);
+    if (!better) return;
+    const unsigned long long seen = atomicCAS(p, old, static_cast<unsigned long long>(__double_as_longlong(v)));
+    if (seen == old) return;
+    old = seen;
+  }
+}
+
+__global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __grid_constant__ AggIO a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint64_t* skey = reinterpret_cast<uint64_t*>(smem);  // [C]
+  uint64_t* sacc = skey + a.C;                          // [nops][C]
+  __shared__ int s_overflow;
+  __shared__ unsigned int s_count, s_cursor;
+  __shared__ unsigned long long s_base;
+  const int tid = threadIdx.x;
+  const uint32_t cmask = static_cast<uint32_t>(a.C - 1);
+  for (int s = blockIdx.x; s < a.nslices; s += gridDim.x) {
+    const int64_t begin = a.slice_start[s], end = a.slice_start[s + 1];
+    if (begin == end) continue;  // uniform across the block
+    for (int i = tid; i < a.C; i += kAggThreads) {
+      skey[i] = VB2_EMPTY_KEY;
+      for (int o = 0; o < a.nops; ++o) sacc[static_cast<size_t>(o) * a.C + i] = a.row_init[a.ops[o].word];
+    }
+    if (tid == 0) { s_overflow = 0; s_count = 0; s_cursor = 0; }
+    __syncthreads();
+    for (int64_t i0 = begin + tid; i0 < end; i0 += 4 * kAggThreads) {
+      uint64_t k[4], v[kCols][4];
+      // loads of four rows in flight before any probe
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + static_cast<int64_t>(u) * kAggThreads;
+        if (i < end) {
+          k[u] = a.keys[i];
+#pragma unroll
+          for (int c = 0; c < kCols; ++c)
+            if (a.cols[c]) v[c][u] = a.cols[c][i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + static_cast<int64_t>(u) * kAggThreads;
+        if (i >= end) continue;
+        const uint64_t key = k[u];
+        uint32_t slot = static_cast<uint32_t>(twang_mix64(key)) & cmask;  // low bits: the partition used the top ones
+        bool found = false;
+        for (int probes = 0; probes < a.C; ++probes) {
+          uint64_t cur = *reinterpret_cast<volatile uint64_t*>(skey + slot);
+          if (cur == VB2_EMPTY_KEY) {
+            cur = atomicCAS(reinterpret_cast<unsigned long long*>(skey + slot), static_cast<unsigned long long>(VB2_EMPTY_KEY), static_cast<unsigned long long>(key));
+            if (cur == VB2_EMPTY_KEY) cur = key;
+          }
+          if (cur == key) { found = true; break; }
+          slot = (slot + 1) & cmask;
+        }
+        if (!found) { s_overflow = 1; continue; }
+        for (int o = 0; o < a.nops; ++o) {
+          const vb2_slice_op& op = a.ops[o];
+          uint64_t* acc = sacc + static_cast<size_t>(o) * a.C + slot;
+          const uint64_t raw = op.col == 0 ? v[0][u] : (op.col == 1 ? v[1][u] : (op.col == 2 ? v[2][u] : 0));  // constant indices: registers
+          switch (op.kind) {
+            case VB2_AGG_SUM_F64: atomicAdd(reinterpret_cast<double*>(acc), __longlong_as_double(static_cast<long long>(raw))); break;
+            case VB2_AGG_SUM_I64: case VB2_AGG_COUNT_MERGE: {
+              const int64_t x = static_cast<int64_t>(raw);
+              if (x == static_cast<int32_t>(x)) {
+                // 64-bit shared-memory adds are compare-and-swap loops in SASS (LDS + ATOMS.CAST.SPIN); 32-bit ones are
+                // native. The word is summed as two halves: the low add returns the old half, the carry (and the
+                // sign extension) go into the high half only when they are non-zero — for small values almost never.
+                // A slice holds < 2^32 rows of |x| < 2^31: the 64-bit sum cannot overflow.
+                uint32_t* half = reinterpret_cast<uint32_t*>(acc);
+                const uint32_t xl = static_cast<uint32_t>(x);
+                const uint32_t old = atomicAdd(half, xl);
+                const uint32_t up = static_cast<uint32_t>(x >> 32) + (static_cast<uint32_t>(old + xl) < old ? 1u : 0u);
+                if (up) atomicAdd(half + 1, up);
+              } else {
+                const int64_t old = static_cast<int64_t>(atomicAdd(reinterpret_cast<unsigned long long*>(acc), static_cast<unsigned long long>(x)));
+                int64_t r;
+                if (add_overflow_i64(old, x, &r)) atomicCAS(a.error_flag, 0, 1);
+              }
+              break;
+            }
+            case VB2_AGG_COUNT: atomicAdd(reinterpret_cast<uint32_t*>(acc), 1u); break;  // < 2^32 rows per slice: the low half suffices
+            case VB2_AGG_MIN_F64: smem_min_f64(acc, __longlong_as_double(static_cast<long long>(raw)), true); break;
+            case VB2_AGG_MAX_F64: smem_min_f64(acc, __longlong_as_double(static_cast<long long>(raw)), false); break;
+            case VB2_AGG_MIN_I64: atomicMin(reinterpret_cast<long long*>(acc), static_cast<long long>(raw)); break;
+            case VB2_AGG_MAX_I64: atomicMax(reinterpret_cast<long long*>(acc), static_cast<long long>(raw)); break;
+            default: break;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // occupied slots -> group rows
+    unsigned int mine = 0;
+    for (int i = tid; i < a.C; i += kAggThreads) mine += skey[i] != VB2_EMPTY_KEY;
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    if (tid == 0) {
+      s_base = atomicAdd(a.num_groups, static_cast<unsigned long long>(s_count));
+      if (s_overflow) atomicAdd(a.overflow, 1);
+      if (static_cast<int64_t>(s_base + s_count) > a.rows_capacity) atomicCAS(a.error_flag, 0, 100);
+    }
+    __syncthreads();
+    if (static_cast<int64_t>(s_base + s_count) <= a.rows_capacity) {
+      for (int i = tid; i < a.C; i += kAggThreads) {
+        const uint64_t key = skey[i];
+        if (key == VB2_EMPTY_KEY) continue;
+        uint64_t* row = a.rows_out + (s_base + atomicAdd(&s_cursor, 1u)) * static_cast<unsigned long long>(a.row_words);
+        row[0] = key;
+        for (int w = 1; w < a.row_words; ++w) row[w] = a.row_init[w];
+        for (int o = 0; o < a.nops; ++o) row[a.ops[o].word] = sacc[static_cast<size_t>(o) * a.C + i];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+// workspace carving shared by the two entry points
+struct Workspace {
+  uint64_t *keysA, *keysB;
+  uint64_t *colsA[kCols], *colsB[kCols];
+  uint32_t* hist1;
+  int64_t* start1;
+  unsigned long long* cursor1;
+  int32_t* tile_start2;
+  uint32_t* hist2;
+  int64_t* slice_start;
+  unsigned long long* cursor2;
+  int32_t* hll;
+  size_t bytes;
+};
+Workspace carve(void* base, int64_t n, int ncols) {
+  Workspace w{};
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  auto take = [&](size_t b) {
+    uint8_t* r = p ? p + off : nullptr;
+    off += align256(b);
+    return r;
+  };
+  const size_t col = static_cast<size_t>(n) * 8;
+  w.keysA = reinterpret_cast<uint64_t*>(take(col));
+  w.keysB = reinterpret_cast<uint64_t*>(take(col));
+  for (int c = 0; c < ncols; ++c) {
+    w.colsA[c] = reinterpret_cast<uint64_t*>(take(col));
+    w.colsB[c] = reinterpret_cast<uint64_t*>(take(col));
+  }
+  w.hist1 = reinterpret_cast<uint32_t*>(take(kP1 * 4));
+  w.start1 = reinterpret_cast<int64_t*>(take((kP1 + 1) * 8));
+  w.cursor1 = reinterpret_cast<unsigned long long*>(take(kP1 * 8));
+  w.tile_start2 = reinterpret_cast<int32_t*>(take((kP1 + 1) * 4));
+  w.hist2 = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(kP1) * kMaxP * 4));
+  w.slice_start = reinterpret_cast<int64_t*>(take((static_cast<size_t>(kP1) * kMaxP + 1) * 8));
+  w.cursor2 = reinterpret_cast<unsigned long long*>(take(static_cast<size_t>(kP1) * kMaxP * 8));
+  w.hll = reinterpret_cast<int32_t*>(take((1 << kHllBits) * 4));
+  w.bytes = off;
+  return w;
+}
+
+size_t scatter_smem(int ncols) { return static_cast<size_t>(kTile) * 8 * (1 + ncols) + 2 * kTile; }
+
+}  // namespace
+}  // namespace vb2
+
+using namespace vb2;
+
+extern "C" {
+
+int32_t vb2k_slice_agg_hll_registers(void) { return 1 << kHllBits; }
+
+size_t vb2k_slice_agg_workspace(int64_t total_rows, int32_t ncols) { return carve(nullptr, total_rows, ncols).bytes; }
+
+int vb2k_slice_agg_partition(const vb2_slice_chunk* chunks, int32_t nchunks, int32_t ncols, int64_t total_rows, void* workspace, size_t workspace_bytes,
+                             int32_t* hll_host, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ncols < 0 || ncols > kCols) return fail_msg(VB2_ERR_UNSUPPORTED, "slice aggregation: at most 3 payload columns");
+  if (total_rows >= (1ll << 32)) return fail_msg(VB2_ERR_UNSUPPORTED, "slice aggregation: above 2^32 rows");
+  Workspace w = carve(workspace, total_rows, ncols);
+  if (workspace_bytes < w.bytes) return fail_msg(VB2_ERR_INVALID, "slice aggregation: workspace too small");
+  int64_t sum = 0;
+  for (int i = 0; i < nchunks; ++i) sum += chunks[i].rows;
+  if (sum != total_rows) return fail_msg(VB2_ERR_INVALID, "slice aggregation: chunk rows do not add up");
+  VB2_CUDA_OK(cudaMemsetAsync(w.hist1, 0, kP1 * 4, st));
+  VB2_CUDA_OK(cudaMemsetAsync(w.hll, 0, (1 << kHllBits) * 4, st));
+  static bool configured = false;
+  if (!configured) {
+    VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(kCols))));
+    configured = true;
+  }
+  const int sms = device_sm_count();
+  auto geom_of = [&](int64_t n) {
+    PartGeom g{};
+    g.n = n;
+    g.nseg = 1;
+    g.P = kP1;
+    g.shift = 56;
+    return g;
+  };
+  for (int i = 0; i < nchunks; ++i) {
+    if (chunks[i].rows == 0) continue;
+    const SliceKey key{chunks[i].norm_keys, chunks[i].raw_keys, chunks[i].key_min};
+    const int64_t ntiles = (chunks[i].rows + kTile - 1) / kTile;
+    const int64_t cap = static_cast<int64_t>(sms) * 4;
+    part_hist_kernel<<<counted(static_cast<unsigned>(ntiles < cap ? ntiles : cap)), kPT, 0, st>>>(key, geom_of(chunks[i].rows), ntiles, w.hist1, w.hll);
+  }
+  part_scan1_kernel<<<counted(1u), 32, 0, st>>>(w.hist1, w.start1, w.cursor1, w.tile_start2);
+  for (int i = 0; i < nchunks; ++i) {
+    if (chunks[i].rows == 0) continue;
+    PartIO io{};
+    io.key = SliceKey{chunks[i].norm_keys, chunks[i].raw_keys, chunks[i].key_min};
+    io.ncols = ncols;
+    io.keys_out = w.keysA;
+    for (int c = 0; c < ncols; ++c) {
+      io.cols_in[c] = static_cast<const uint64_t*>(chunks[i].cols[c]);
+      io.cols_out[c] = w.colsA[c];
+    }
+    const int64_t ntiles = (chunks[i].rows + kTile - 1) / kTile;
+    const int64_t cap = static_cast<int64_t>(sms) * 2;
+    part_scatter_kernel<<<counted(static_cast<unsigned>(ntiles < cap ? ntiles : cap)), kPT, scatter_smem(ncols), st>>>(io, geom_of(chunks[i].rows), ntiles, w.cursor1);
+  }
+  VB2_CUDA_OK(cudaGetLastError());
+  if (hll_host) {
+    VB2_CUDA_OK(cudaMemcpyAsync(hll_host, w.hll, (1 << kHllBits) * 4, cudaMemcpyDeviceToHost, st));
+    VB2_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return VB2_OK;
+}
+
+int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_estimate, const vb2_slice_op* ops, int32_t nops, int32_t row_words,
+                          const uint64_t* row_init, uint64_t* rows_out, int64_t rows_capacity, int64_t* num_groups, int32_t* error_flag,
+                          int32_t* overflow_slices, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nops < 1 || nops > kMaxOps || row_words < 2 || row_words > VB2_MAX_ROW_WORDS) return fail_msg(VB2_ERR_UNSUPPORTED, "slice aggregation: 1 to 8 accumulator words");
+  Workspace w = carve(workspace, total_rows, ncols);
+  if (workspace_bytes < w.bytes) return fail_msg(VB2_ERR_INVALID, "slice aggregation: workspace too small");
+  // Slot count of a slice table (keys + one word per op): the largest power of two within ~100 KB so that
+  // two CTAs share an SM; one size up (one CTA per SM) when 65536 slices would otherwise load their
+  // tables above one half. Slices: expected distinct keys per slice <= C / 2.
+  int C = 8192;
+  while (C > 256 && static_cast<size_t>(C) * 8 * (1 + nops) > 100 * 1024) C >>= 1;
+  auto slices_for = [&](int c) { return (distinct_estimate * 2 + c - 1) / c; };
+  if (slices_for(C) > static_cast<int64_t>(kP1) * kMaxP && static_cast<size_t>(C) * 2 * 8 * (1 + nops) <= 200 * 1024) C <<= 1;
+  const int64_t want = slices_for(C);
+  int P2 = 1;
+  while (static_cast<int64_t>(kP1) * P2 < want && P2 < kMaxP) P2 <<= 1;
+  if (static_cast<int64_t>(kP1) * P2 < want) return fail_msg(VB2_ERR_UNSUPPORTED, "slice aggregation: too many distinct keys for 65536 shared-memory slices");
+  const int sms = device_sm_count();
+  AggIO a{};
+  if (P2 > 1) {
+    PartGeom g{};
+    g.n = total_rows;
+    g.seg_start = w.start1;
+    g.tile_start = w.tile_start2;
+    g.nseg = kP1;
+    g.P = P2;
+    g.shift = 56;
+    int bits = 0;
+    while ((1 << bits) < P2) ++bits;
+    g.shift = 56 - bits;
+    const int64_t ntiles = total_rows / kTile + kP1 + 1;  // upper bound: every partition rounds its last tile up
+    VB2_CUDA_OK(cudaMemsetAsync(w.hist2, 0, static_cast<size_t>(kP1) * P2 * 4, st));
+    const SliceKey key{w.keysA, nullptr, 0};
+    const int64_t hcap = static_cast<int64_t>(sms) * 4;
+    part_hist_kernel<<<counted(static_cast<unsigned>(ntiles < hcap ? ntiles : hcap)), kPT, 0, st>>>(key, g, ntiles, w.hist2, nullptr);
+    part_scan2_kernel<<<counted(static_cast<unsigned>(kP1)), 32, 0, st>>>(w.hist2, w.start1, P2, w.slice_start, w.cursor2);
+    PartIO io{};
+    io.key = key;
+    io.ncols = ncols;
+    io.keys_out = w.keysB;
+    for (int c = 0; c < ncols; ++c) {
+      io.cols_in[c] = w.colsA[c];
+      io.cols_out[c] = w.colsB[c];
+    }
+    const int64_t scap = static_cast<int64_t>(sms) * 2;
+    part_scatter_kernel<<<counted(static_cast<unsigned>(ntiles < scap ? ntiles : scap)), kPT, scatter_smem(ncols), st>>>(io, g, ntiles, w.cursor2);
+    a.keys = w.keysB;
+    for (int c = 0; c < ncols; ++c) a.cols[c] = w.colsB[c];
+    a.slice_start = w.slice_start;
+    a.nslices = kP1 * P2;
+  } else {
+    a.keys = w.keysA;
+    for (int c = 0; c < ncols; ++c) a.cols[c] = w.colsA[c];
+    a.slice_start = w.start1;
+    a.nslices = kP1;
+  }
+  for (int o = 0; o < nops; ++o) {
+    if (ops[o].col >= ncols || ops[o].word < 1 || ops[o].word >= row_words) return fail_msg(VB2_ERR_INVALID, "slice aggregation: bad accumulator op");
+    a.ops[o] = ops[o];
+  }
+  a.nops = nops;
+  for (int i = 0; i < row_words; ++i) a.row_init[i] = row_init[i];
+  a.row_words = row_words;
+  a.rows_out = rows_out;
+  a.rows_capacity = rows_capacity;
+  a.num_groups = reinterpret_cast<unsigned long long*>(num_groups);
+  a.error_flag = error_flag;
+  a.overflow = overflow_slices;
+  a.C = C;
+  const size_t smem = static_cast<size_t>(C) * 8 * (1 + nops);
+  static size_t configured = 0;
+  if (smem > configured) {
+    VB2_CUDA_OK(cudaFuncSetAttribute(slice_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  const int64_t acap = static_cast<int64_t>(sms) * 2;
+  slice_aggregate_kernel<<<counted(static_cast<unsigned>(a.nslices < acap ? a.nslices : acap)), kAggThreads, smem, st>>>(a);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+}  // extern "C"
