@@ -177,8 +177,8 @@ int32_t vb2k_expression_jit_compiles(const vb2_program* prog, const vb2_column* 
  * functions/lib/aggregates/SimpleNumericAggregate.h:94-150) when the group table would not fit L2.
  *   vb2k_slice_agg_partition  level-1 histogram (+ HyperLogLog sketch, copied to hll_host[4096]; the
  *                             call synchronises when hll_host is given) and scatter of every chunk
- *   vb2k_slice_agg_finish     level 2 (sized from distinct_estimate), aggregation. num_groups /
- *                             error_flag / overflow_slices are zeroed device words: groups written,
+ *   vb2k_slice_agg_finish     level 2 (sized from distinct_estimate), aggregation. num_groups / reserved_rows /
+ *                             error_flag / overflow_slices are zeroed device words: groups written, rows handed out,
  *                             1 = SUM(BIGINT) overflow or 100 = rows_out full, slices whose keys did
  *                             not fit their table (then the result is incomplete: use the table path).
  * VB2_ERR_UNSUPPORTED: more distinct keys than 65536 slices can hold.
@@ -201,9 +201,14 @@ int32_t vb2k_slice_agg_hll_registers(void);
 size_t vb2k_slice_agg_workspace(int64_t total_rows, int32_t ncols);
 int vb2k_slice_agg_partition(const vb2_slice_chunk* chunks, int32_t nchunks, int32_t ncols, int64_t total_rows, void* workspace, size_t workspace_bytes,
                              int32_t* hll_host, void* stream);
+/* rows_out must hold vb2k_slice_agg_output_rows(distinct_estimate) rows, pre-filled with row_init and
+ * VB2_EMPTY_KEY in word 0 (vb2k_group_table_init): the blocks reserve output rows in chunks
+ * (reserved_rows, a zeroed device word) and leave the unused tail of a chunk EMPTY — the result reads
+ * like a hash-mode group table with num_groups occupied rows. */
+int64_t vb2k_slice_agg_output_rows(int64_t distinct_estimate);
 int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_estimate, const vb2_slice_op* ops, int32_t nops, int32_t row_words,
-                          const uint64_t* row_init, uint64_t* rows_out, int64_t rows_capacity, int64_t* num_groups, int32_t* error_flag,
-                          int32_t* overflow_slices, void* workspace, size_t workspace_bytes, void* stream);
+                          const uint64_t* row_init, uint64_t* rows_out, int64_t rows_capacity, int64_t* num_groups, int64_t* reserved_rows,
+                          int32_t* error_flag, int32_t* overflow_slices, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * ORDER BY: stable multi-key sort producing the row order. Replaces the sort of exec::OrderBy /

@@ -61,18 +61,23 @@ def test_slice_kernels_against_numpy(n, distinct, estimate):
     init[3] = np.uint64(np.int64(-2**63).astype(np.uint64))
     init[5] = np.uint64(2**63 - 1)
     init[6] = np.uint64(12345)
-    cap = distinct + 10
-    rows = torch.zeros(cap * rw, dtype=torch.int64, device="cuda")
-    words = torch.zeros(4, dtype=torch.int64, device="cuda")  # [0] groups, [2] error, [3] overflow
+    L.vb2k_slice_agg_output_rows.restype = C.c_int64
+    cap = L.vb2k_slice_agg_output_rows(C.c_int64(estimate))
+    assert cap >= distinct
+    # table-shaped output: every row starts as [EMPTY | row_init[1:]]; blocks fill the rows of the chunks they reserve
+    rows = torch.from_numpy(np.tile(np.concatenate([[np.uint64(EMPTY)], init[1:]]), cap).view(np.int64)).cuda()
+    words = torch.zeros(4, dtype=torch.int64, device="cuda")  # [0] groups, [1] rows reserved, [2] error, [3] overflow
     rc = L.vb2k_slice_agg_finish(C.c_int64(n), 2, C.c_int64(estimate), ops, 5, rw, init.ctypes.data_as(C.c_void_p), C.c_void_p(rows.data_ptr()), C.c_int64(cap),
-                                 C.c_void_p(words.data_ptr()), C.c_void_p(words.data_ptr() + 16), C.c_void_p(words.data_ptr() + 24),
+                                 C.c_void_p(words.data_ptr()), C.c_void_p(words.data_ptr() + 8), C.c_void_p(words.data_ptr() + 16), C.c_void_p(words.data_ptr() + 24),
                                  C.c_void_p(ws.data_ptr()), C.c_size_t(wsb), st)
     assert rc == 0, L.vb2_last_error()
     torch.cuda.synchronize()
     w = words.cpu().numpy()
     uk, inv = np.unique(keys, return_inverse=True)
-    assert w[2] == 0 and w[3] == 0 and w[0] == len(uk), w
-    got = rows.cpu().numpy().reshape(cap, rw)[: len(uk)]
+    assert w[2] == 0 and w[3] == 0 and w[0] == len(uk) and len(uk) <= w[1] <= cap, w
+    got = rows.cpu().numpy().reshape(cap, rw)
+    got = got[got[:, 0].view(np.uint64) != np.uint64(EMPTY)]  # occupied rows (the unused tails of the chunks stay EMPTY)
+    assert len(got) == len(uk)
     got = got[np.argsort(got[:, 0])]
     assert np.array_equal(got[:, 0], uk - kmin + 1)                       # normalized keys, each exactly once
     order = np.argsort(inv, kind="stable")

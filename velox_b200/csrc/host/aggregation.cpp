@@ -669,14 +669,14 @@ struct B200HashAggregation::Impl {
       for (auto& a : accs) init[a.accWord] = identityBits(a);
       // the group rows land in a table-shaped buffer (power-of-two rows, unused rows keep the EMPTY key) so that
       // the extraction reads it like any hash-mode table
-      const int64_t cap = static_cast<int64_t>(nextPow2(static_cast<uint64_t>(std::max<int64_t>(16, std::min<int64_t>(sliceRows, distinct)))));
+      const int64_t cap = static_cast<int64_t>(nextPow2(static_cast<uint64_t>(std::max<int64_t>(16, vb2k_slice_agg_output_rows(std::min<int64_t>(sliceRows, distinct))))));
       auto rowsOut = makeStorage(cap, Mode::kHash);
-      auto words = allocDeviceZeroed(32, st());  // [0] groups (int64), [2] error (int32 at byte 16), overflow (int32 at byte 24)
+      auto words = allocDeviceZeroed(32, st());  // [0] groups, [1] rows reserved (int64), error (int32 at byte 16), overflow (int32 at byte 24)
       int64_t* groupsDev = words->as<int64_t>();
       int32_t* errDev = reinterpret_cast<int32_t*>(words->as<uint8_t>() + 16);
       int32_t* ovfDev = reinterpret_cast<int32_t*>(words->as<uint8_t>() + 24);
       const int rc = vb2k_slice_agg_finish(sliceRows, ncols, distinct, ops.data(), static_cast<int32_t>(ops.size()), rw, init.data(), rowsOut->as<uint64_t>(), cap,
-                                           groupsDev, errDev, ovfDev, ws->data(), wsBytes, st());
+                                           groupsDev, groupsDev + 1, errDev, ovfDev, ws->data(), wsBytes, st());
       if (rc == VB2_OK) {
         uint8_t host[32];
         VB2_CU(cudaMemcpyAsync(host, words->data(), 32, cudaMemcpyDeviceToHost, st()));

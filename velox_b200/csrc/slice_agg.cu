@@ -27,7 +27,7 @@ namespace vb2 {
 namespace {
 
 constexpr int kPT = 512;          // threads of the partition kernels
-constexpr int kTile = 4096;       // rows per tile (staged in shared memory)
+constexpr int kTile = 3584;       // rows per tile (staged in shared memory): key + one payload column leave room for three CTAs per SM
 constexpr int kP1 = 256;
 constexpr int kMaxP = 256;
 constexpr int kCols = VB2_SLICE_MAX_COLS;
@@ -107,13 +107,24 @@ __global__ void __launch_bounds__(kPT) part_hist_kernel(const __grid_constant__ 
       }
       segNow = seg;
     }
-    for (int64_t i = begin + threadIdx.x; i < end; i += kPT) {
-      const uint64_t hash = twang_mix64(slice_key(key, i));
-      atomicAdd(&h[(hash >> g.shift) & (g.P - 1)], 1u);
-      if (hll && (hash & 7u) == 0) {
-        const uint32_t idx = static_cast<uint32_t>(hash >> 3) & ((1u << kHllBits) - 1u);
-        const uint64_t rest = (hash >> (3 + kHllBits)) | (1ull << (56 - 3 - kHllBits));
-        atomicMax(&regs[idx], __ffsll(static_cast<long long>(rest)));
+    for (int64_t i0 = begin + threadIdx.x; i0 < end; i0 += 4 * kPT) {
+      uint64_t k[4];  // four loads in flight per thread before the shared-memory atomics
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + static_cast<int64_t>(u) * kPT;
+        if (i < end) k[u] = slice_key(key, i);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + static_cast<int64_t>(u) * kPT;
+        if (i >= end) continue;
+        const uint64_t hash = twang_mix64(k[u]);
+        atomicAdd(&h[(hash >> g.shift) & (g.P - 1)], 1u);
+        if (hll && (hash & 7u) == 0) {
+          const uint32_t idx = static_cast<uint32_t>(hash >> 3) & ((1u << kHllBits) - 1u);
+          const uint64_t rest = (hash >> (3 + kHllBits)) | (1ull << (56 - 3 - kHllBits));
+          atomicMax(&regs[idx], __ffsll(static_cast<long long>(rest)));
+        }
       }
     }
   }
@@ -157,12 +168,13 @@ __global__ void part_scan2_kernel(const uint32_t* __restrict__ hist, const int64
 // Staged scatter of one tile per iteration: (A) digits + tile histogram, (B) local offsets and the
 // tile's reservation in every partition (one global atomic per non-empty digit), (C) keys and
 // payloads into shared memory in partition order, (D) consecutive threads store consecutive rows.
-__global__ void __launch_bounds__(kPT) part_scatter_kernel(const __grid_constant__ PartIO io, const __grid_constant__ PartGeom g, int64_t ntiles,
-                                                           unsigned long long* __restrict__ cursor) {
+template <int NCOLS>
+__global__ void __launch_bounds__(kPT, NCOLS <= 1 ? 3 : 2) part_scatter_kernel(const __grid_constant__ PartIO io, const __grid_constant__ PartGeom g, int64_t ntiles,
+                                                                               unsigned long long* __restrict__ cursor) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* skeys = reinterpret_cast<uint64_t*>(smem);
   uint64_t* scols = skeys + kTile;                                           // [ncols][kTile]
-  uint8_t* sdig = reinterpret_cast<uint8_t*>(scols + static_cast<size_t>(io.ncols) * kTile);  // digit of every staged position
+  uint8_t* sdig = reinterpret_cast<uint8_t*>(scols + static_cast<size_t>(NCOLS) * kTile);  // digit of every staged position
   uint8_t* rdig = sdig + kTile;                                              // digit of every input position
   __shared__ uint32_t cnt[kMaxP], lofs[kMaxP], lcur[kMaxP];
   __shared__ unsigned long long gbase[kMaxP];
@@ -208,15 +220,14 @@ __global__ void __launch_bounds__(kPT) part_scatter_kernel(const __grid_constant
     __syncthreads();
     // (C) loads first (keys again: the tile is L1 / L2 resident; payloads for the first time), then placement
     for (int j0 = tid; j0 < rows; j0 += 4 * kPT) {
-      uint64_t k[4], v[kCols][4];  // every index below is a compile-time constant after unrolling: registers, no stack
+      uint64_t k[4], v[NCOLS > 0 ? NCOLS : 1][4];  // every index below is a compile-time constant after unrolling: registers, no stack
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = j0 + u * kPT;
         if (j < rows) {
           k[u] = slice_key(io.key, begin + j);
 #pragma unroll
-          for (int c = 0; c < kCols; ++c)
-            if (c < io.ncols) v[c][u] = io.cols_in[c][begin + j];
+          for (int c = 0; c < NCOLS; ++c) v[c][u] = io.cols_in[c][begin + j];
         }
       }
 #pragma unroll
@@ -228,8 +239,7 @@ __global__ void __launch_bounds__(kPT) part_scatter_kernel(const __grid_constant
           skeys[p] = k[u];
           sdig[p] = static_cast<uint8_t>(d);
 #pragma unroll
-          for (int c = 0; c < kCols; ++c)
-            if (c < io.ncols) scols[static_cast<size_t>(c) * kTile + p] = v[c][u];
+          for (int c = 0; c < NCOLS; ++c) scols[static_cast<size_t>(c) * kTile + p] = v[c][u];
         }
       }
     }
@@ -239,7 +249,8 @@ __global__ void __launch_bounds__(kPT) part_scatter_kernel(const __grid_constant
       const int d = sdig[p];
       const unsigned long long out = gbase[d] + (p - lofs[d]);
       io.keys_out[out] = skeys[p];
-      for (int c = 0; c < io.ncols; ++c) io.cols_out[c][out] = scols[static_cast<size_t>(c) * kTile + p];
+#pragma unroll
+      for (int c = 0; c < NCOLS; ++c) io.cols_out[c][out] = scols[static_cast<size_t>(c) * kTile + p];
     }
     __syncthreads();
   }
@@ -257,7 +268,9 @@ struct AggIO {
   int row_words;
   uint64_t* rows_out;
   int64_t rows_capacity;
-  unsigned long long* num_groups;
+  unsigned long long* num_groups;  // groups written
+  unsigned long long* reserved;    // output rows handed out to the blocks (chunks; >= groups)
+  int64_t chunk_rows;
   int32_t* error_flag;     // 1 = SUM(BIGINT) overflow, 100 = rows_out full
   int32_t* overflow;       // slices whose distinct keys did not fit the shared-memory table
   int C;                   // slots per slice table (power of two)
@@ -276,21 +289,69 @@ __device__ __forceinline__ void smem_min_f64(uint64_t* addr, double v, bool is_m
   }
 }
 
+// One accumulator update in shared memory. 64-bit shared-memory adds are compare-and-swap loops in SASS
+// (LDS + ATOMS.CAST.SPIN); 32-bit ones are native, so integer sums are carried as two halves: the low add
+// returns the old half, the carry (and the sign extension) reach the high half only when non-zero — for
+// small values almost never. A slice holds < 2^32 rows of |x| < 2^31: that 64-bit sum cannot overflow.
+__device__ __forceinline__ void slice_update(int kind, uint64_t* acc, uint64_t raw, int32_t* error_flag) {
+  switch (kind) {
+    case VB2_AGG_SUM_F64: atomicAdd(reinterpret_cast<double*>(acc), __longlong_as_double(static_cast<long long>(raw))); break;
+    case VB2_AGG_SUM_I64: case VB2_AGG_COUNT_MERGE: {
+      const int64_t x = static_cast<int64_t>(raw);
+      if (x == static_cast<int32_t>(x)) {
+        uint32_t* half = reinterpret_cast<uint32_t*>(acc);
+        const uint32_t xl = static_cast<uint32_t>(x);
+        const uint32_t old = atomicAdd(half, xl);
+        const uint32_t up = static_cast<uint32_t>(x >> 32) + (static_cast<uint32_t>(old + xl) < old ? 1u : 0u);
+        if (up) atomicAdd(half + 1, up);
+      } else {
+        const int64_t old = static_cast<int64_t>(atomicAdd(reinterpret_cast<unsigned long long*>(acc), static_cast<unsigned long long>(x)));
+        int64_t r;
+        if (add_overflow_i64(old, x, &r)) atomicCAS(error_flag, 0, 1);
+      }
+      break;
+    }
+    case VB2_AGG_COUNT: atomicAdd(reinterpret_cast<uint32_t*>(acc), 1u); break;  // < 2^32 rows per slice: the low half suffices
+    case VB2_AGG_MIN_F64: smem_min_f64(acc, __longlong_as_double(static_cast<long long>(raw)), true); break;
+    case VB2_AGG_MAX_F64: smem_min_f64(acc, __longlong_as_double(static_cast<long long>(raw)), false); break;
+    case VB2_AGG_MIN_I64: atomicMin(reinterpret_cast<long long*>(acc), static_cast<long long>(raw)); break;
+    case VB2_AGG_MAX_I64: atomicMax(reinterpret_cast<long long*>(acc), static_cast<long long>(raw)); break;
+    default: break;
+  }
+}
+
+// NOPS accumulator words per slot (compile time: the op descriptors live in registers, the loops unroll).
+// Output rows are reserved from the global cursor in chunks: a block asks for a new chunk only when the
+// groups of its next slice do not fit the rest of its current one, so the round trip of a global atomic is
+// paid once per few dozen slices; the unused tail of a chunk stays EMPTY rows of the table-shaped output.
+template <int NOPS>
 __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __grid_constant__ AggIO a) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* skey = reinterpret_cast<uint64_t*>(smem);  // [C]
-  uint64_t* sacc = skey + a.C;                          // [nops][C]
+  uint64_t* sacc = skey + a.C;                          // [NOPS][C]
   __shared__ int s_overflow;
   __shared__ unsigned int s_count, s_cursor;
-  __shared__ unsigned long long s_base;
+  __shared__ unsigned long long s_base, s_chunk_pos, s_chunk_left, s_groups;
   const int tid = threadIdx.x;
-  const uint32_t cmask = static_cast<uint32_t>(a.C - 1);
+  const int C = a.C;
+  const uint32_t cmask = static_cast<uint32_t>(C - 1);
+  int kind[NOPS], col[NOPS], word[NOPS];
+  uint64_t init[NOPS];
+#pragma unroll
+  for (int o = 0; o < NOPS; ++o) {
+    kind[o] = a.ops[o].kind;
+    col[o] = a.ops[o].col;
+    word[o] = a.ops[o].word;
+    init[o] = a.row_init[a.ops[o].word];
+  }
+  if (tid == 0) { s_chunk_pos = 0; s_chunk_left = 0; s_groups = 0; }
   for (int s = blockIdx.x; s < a.nslices; s += gridDim.x) {
     const int64_t begin = a.slice_start[s], end = a.slice_start[s + 1];
     if (begin == end) continue;  // uniform across the block
-    for (int i = tid; i < a.C; i += kAggThreads) {
+    for (int i = tid; i < C; i += kAggThreads) {
       skey[i] = VB2_EMPTY_KEY;
-      for (int o = 0; o < a.nops; ++o) sacc[static_cast<size_t>(o) * a.C + i] = a.row_init[a.ops[o].word];
+#pragma unroll
+      for (int o = 0; o < NOPS; ++o) sacc[o * C + i] = init[o];
     }
     if (tid == 0) { s_overflow = 0; s_count = 0; s_cursor = 0; }
     __syncthreads();
@@ -312,77 +373,56 @@ __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __gr
         const int64_t i = i0 + static_cast<int64_t>(u) * kAggThreads;
         if (i >= end) continue;
         const uint64_t key = k[u];
-        uint32_t slot = static_cast<uint32_t>(twang_mix64(key)) & cmask;  // low bits: the partition used the top ones
+        // slot inside the slice: a multiplicative hash (the slice already fixes the top bits of twang_mix64(key))
+        uint32_t slot = static_cast<uint32_t>((key * 0x9E3779B97F4A7C15ull) >> 40) & cmask;
         bool found = false;
-        for (int probes = 0; probes < a.C; ++probes) {
+        for (int probes = 0; probes < C; ++probes) {
           uint64_t cur = *reinterpret_cast<volatile uint64_t*>(skey + slot);
           if (cur == VB2_EMPTY_KEY) {
             cur = atomicCAS(reinterpret_cast<unsigned long long*>(skey + slot), static_cast<unsigned long long>(VB2_EMPTY_KEY), static_cast<unsigned long long>(key));
-            if (cur == VB2_EMPTY_KEY) cur = key;
+            if (cur == VB2_EMPTY_KEY) { atomicAdd(&s_count, 1u); cur = key; }  // a new group of this slice
           }
           if (cur == key) { found = true; break; }
           slot = (slot + 1) & cmask;
         }
         if (!found) { s_overflow = 1; continue; }
-        for (int o = 0; o < a.nops; ++o) {
-          const vb2_slice_op& op = a.ops[o];
-          uint64_t* acc = sacc + static_cast<size_t>(o) * a.C + slot;
-          const uint64_t raw = op.col == 0 ? v[0][u] : (op.col == 1 ? v[1][u] : (op.col == 2 ? v[2][u] : 0));  // constant indices: registers
-          switch (op.kind) {
-            case VB2_AGG_SUM_F64: atomicAdd(reinterpret_cast<double*>(acc), __longlong_as_double(static_cast<long long>(raw))); break;
-            case VB2_AGG_SUM_I64: case VB2_AGG_COUNT_MERGE: {
-              const int64_t x = static_cast<int64_t>(raw);
-              if (x == static_cast<int32_t>(x)) {
-                // 64-bit shared-memory adds are compare-and-swap loops in SASS (LDS + ATOMS.CAST.SPIN); 32-bit ones are
-                // native. The word is summed as two halves: the low add returns the old half, the carry (and the
-                // sign extension) go into the high half only when they are non-zero — for small values almost never.
-                // A slice holds < 2^32 rows of |x| < 2^31: the 64-bit sum cannot overflow.
-                uint32_t* half = reinterpret_cast<uint32_t*>(acc);
-                const uint32_t xl = static_cast<uint32_t>(x);
-                const uint32_t old = atomicAdd(half, xl);
-                const uint32_t up = static_cast<uint32_t>(x >> 32) + (static_cast<uint32_t>(old + xl) < old ? 1u : 0u);
-                if (up) atomicAdd(half + 1, up);
-              } else {
-                const int64_t old = static_cast<int64_t>(atomicAdd(reinterpret_cast<unsigned long long*>(acc), static_cast<unsigned long long>(x)));
-                int64_t r;
-                if (add_overflow_i64(old, x, &r)) atomicCAS(a.error_flag, 0, 1);
-              }
-              break;
-            }
-            case VB2_AGG_COUNT: atomicAdd(reinterpret_cast<uint32_t*>(acc), 1u); break;  // < 2^32 rows per slice: the low half suffices
-            case VB2_AGG_MIN_F64: smem_min_f64(acc, __longlong_as_double(static_cast<long long>(raw)), true); break;
-            case VB2_AGG_MAX_F64: smem_min_f64(acc, __longlong_as_double(static_cast<long long>(raw)), false); break;
-            case VB2_AGG_MIN_I64: atomicMin(reinterpret_cast<long long*>(acc), static_cast<long long>(raw)); break;
-            case VB2_AGG_MAX_I64: atomicMax(reinterpret_cast<long long*>(acc), static_cast<long long>(raw)); break;
-            default: break;
-          }
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o) {
+          const uint64_t raw = col[o] == 0 ? v[0][u] : (col[o] == 1 ? v[1][u] : (col[o] == 2 ? v[2][u] : 0));  // constant indices: registers
+          slice_update(kind[o], sacc + o * C + slot, raw, a.error_flag);
         }
       }
     }
     __syncthreads();
-    // occupied slots -> group rows
-    unsigned int mine = 0;
-    for (int i = tid; i < a.C; i += kAggThreads) mine += skey[i] != VB2_EMPTY_KEY;
-    if (mine) atomicAdd(&s_count, mine);
-    __syncthreads();
     if (tid == 0) {
-      s_base = atomicAdd(a.num_groups, static_cast<unsigned long long>(s_count));
+      const unsigned long long n = s_count;
+      if (n > s_chunk_left) {
+        const unsigned long long grab = n > static_cast<unsigned long long>(a.chunk_rows) ? n : static_cast<unsigned long long>(a.chunk_rows);
+        s_chunk_pos = atomicAdd(a.reserved, grab);
+        s_chunk_left = grab;
+      }
+      s_base = s_chunk_pos;
+      s_chunk_pos += n;
+      s_chunk_left -= n;
+      s_groups += n;
       if (s_overflow) atomicAdd(a.overflow, 1);
-      if (static_cast<int64_t>(s_base + s_count) > a.rows_capacity) atomicCAS(a.error_flag, 0, 100);
+      if (static_cast<int64_t>(s_base + n) > a.rows_capacity) atomicCAS(a.error_flag, 0, 100);
     }
     __syncthreads();
     if (static_cast<int64_t>(s_base + s_count) <= a.rows_capacity) {
-      for (int i = tid; i < a.C; i += kAggThreads) {
+      for (int i = tid; i < C; i += kAggThreads) {
         const uint64_t key = skey[i];
         if (key == VB2_EMPTY_KEY) continue;
         uint64_t* row = a.rows_out + (s_base + atomicAdd(&s_cursor, 1u)) * static_cast<unsigned long long>(a.row_words);
         row[0] = key;
         for (int w = 1; w < a.row_words; ++w) row[w] = a.row_init[w];
-        for (int o = 0; o < a.nops; ++o) row[a.ops[o].word] = sacc[static_cast<size_t>(o) * a.C + i];
+#pragma unroll
+        for (int o = 0; o < NOPS; ++o) row[word[o]] = sacc[o * C + i];
       }
     }
     __syncthreads();
   }
+  if (tid == 0 && s_groups) atomicAdd(a.num_groups, s_groups);
 }
 
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
@@ -429,7 +469,31 @@ Workspace carve(void* base, int64_t n, int ncols) {
   return w;
 }
 
+// rows a block reserves from the output cursor at a time: a few chunks per block over the whole run
+int64_t output_chunk_rows(int64_t distinct_estimate) {
+  const int64_t per = distinct_estimate / (static_cast<int64_t>(device_sm_count()) * 2 * 4);
+  return per < 256 ? 256 : (per > 16384 ? 16384 : per);
+}
 size_t scatter_smem(int ncols) { return static_cast<size_t>(kTile) * 8 * (1 + ncols) + 2 * kTile; }
+int configure_scatter() {
+  static bool configured = false;
+  if (configured) return VB2_OK;
+  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(0))));
+  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(1))));
+  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(2))));
+  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(3))));
+  configured = true;
+  return VB2_OK;
+}
+void launch_scatter(const PartIO& io, const PartGeom& g, int64_t ntiles, unsigned long long* cursor, unsigned grid, cudaStream_t st) {
+  const size_t smem = scatter_smem(io.ncols);
+  switch (io.ncols) {
+    case 0: part_scatter_kernel<0><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor); break;
+    case 1: part_scatter_kernel<1><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor); break;
+    case 2: part_scatter_kernel<2><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor); break;
+    default: part_scatter_kernel<3><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor);
+  }
+}
 
 }  // namespace
 }  // namespace vb2
@@ -454,11 +518,7 @@ int vb2k_slice_agg_partition(const vb2_slice_chunk* chunks, int32_t nchunks, int
   if (sum != total_rows) return fail_msg(VB2_ERR_INVALID, "slice aggregation: chunk rows do not add up");
   VB2_CUDA_OK(cudaMemsetAsync(w.hist1, 0, kP1 * 4, st));
   VB2_CUDA_OK(cudaMemsetAsync(w.hll, 0, (1 << kHllBits) * 4, st));
-  static bool configured = false;
-  if (!configured) {
-    VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(kCols))));
-    configured = true;
-  }
+  if (int rc = configure_scatter()) return rc;
   const int sms = device_sm_count();
   auto geom_of = [&](int64_t n) {
     PartGeom g{};
@@ -487,8 +547,8 @@ int vb2k_slice_agg_partition(const vb2_slice_chunk* chunks, int32_t nchunks, int
       io.cols_out[c] = w.colsA[c];
     }
     const int64_t ntiles = (chunks[i].rows + kTile - 1) / kTile;
-    const int64_t cap = static_cast<int64_t>(sms) * 2;
-    part_scatter_kernel<<<counted(static_cast<unsigned>(ntiles < cap ? ntiles : cap)), kPT, scatter_smem(ncols), st>>>(io, geom_of(chunks[i].rows), ntiles, w.cursor1);
+    const int64_t cap = static_cast<int64_t>(sms) * (ncols <= 1 ? 3 : 2);
+    launch_scatter(io, geom_of(chunks[i].rows), ntiles, w.cursor1, static_cast<unsigned>(ntiles < cap ? ntiles : cap), st);
   }
   VB2_CUDA_OK(cudaGetLastError());
   if (hll_host) {
@@ -498,9 +558,13 @@ int vb2k_slice_agg_partition(const vb2_slice_chunk* chunks, int32_t nchunks, int
   return VB2_OK;
 }
 
+int64_t vb2k_slice_agg_output_rows(int64_t distinct_estimate) {
+  return distinct_estimate + static_cast<int64_t>(device_sm_count()) * 2 * output_chunk_rows(distinct_estimate) + 1024;
+}
+
 int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_estimate, const vb2_slice_op* ops, int32_t nops, int32_t row_words,
-                          const uint64_t* row_init, uint64_t* rows_out, int64_t rows_capacity, int64_t* num_groups, int32_t* error_flag,
-                          int32_t* overflow_slices, void* workspace, size_t workspace_bytes, void* stream) {
+                          const uint64_t* row_init, uint64_t* rows_out, int64_t rows_capacity, int64_t* num_groups, int64_t* reserved_rows,
+                          int32_t* error_flag, int32_t* overflow_slices, void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (nops < 1 || nops > kMaxOps || row_words < 2 || row_words > VB2_MAX_ROW_WORDS) return fail_msg(VB2_ERR_UNSUPPORTED, "slice aggregation: 1 to 8 accumulator words");
   Workspace w = carve(workspace, total_rows, ncols);
@@ -543,8 +607,8 @@ int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_es
       io.cols_in[c] = w.colsA[c];
       io.cols_out[c] = w.colsB[c];
     }
-    const int64_t scap = static_cast<int64_t>(sms) * 2;
-    part_scatter_kernel<<<counted(static_cast<unsigned>(ntiles < scap ? ntiles : scap)), kPT, scatter_smem(ncols), st>>>(io, g, ntiles, w.cursor2);
+    const int64_t scap = static_cast<int64_t>(sms) * (ncols <= 1 ? 3 : 2);
+    launch_scatter(io, g, ntiles, w.cursor2, static_cast<unsigned>(ntiles < scap ? ntiles : scap), st);
     a.keys = w.keysB;
     for (int c = 0; c < ncols; ++c) a.cols[c] = w.colsB[c];
     a.slice_start = w.slice_start;
@@ -565,17 +629,28 @@ int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_es
   a.rows_out = rows_out;
   a.rows_capacity = rows_capacity;
   a.num_groups = reinterpret_cast<unsigned long long*>(num_groups);
+  a.reserved = reinterpret_cast<unsigned long long*>(reserved_rows);
+  a.chunk_rows = output_chunk_rows(distinct_estimate);
   a.error_flag = error_flag;
   a.overflow = overflow_slices;
   a.C = C;
   const size_t smem = static_cast<size_t>(C) * 8 * (1 + nops);
-  static size_t configured = 0;
-  if (smem > configured) {
-    VB2_CUDA_OK(cudaFuncSetAttribute(slice_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
   const int64_t acap = static_cast<int64_t>(sms) * 2;
-  slice_aggregate_kernel<<<counted(static_cast<unsigned>(a.nslices < acap ? a.nslices : acap)), kAggThreads, smem, st>>>(a);
+  const unsigned grid = static_cast<unsigned>(a.nslices < acap ? a.nslices : acap);
+#define VB2_SLICE_AGG(N)                                                                                                          \
+  case N: {                                                                                                                       \
+    static size_t configured = 0;                                                                                                 \
+    if (smem > configured) {                                                                                                      \
+      VB2_CUDA_OK(cudaFuncSetAttribute(slice_aggregate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+      configured = smem;                                                                                                          \
+    }                                                                                                                             \
+    slice_aggregate_kernel<N><<<counted(grid), kAggThreads, smem, st>>>(a);                                                       \
+    break;                                                                                                                        \
+  }
+  switch (nops) {
+    VB2_SLICE_AGG(1) VB2_SLICE_AGG(2) VB2_SLICE_AGG(3) VB2_SLICE_AGG(4) VB2_SLICE_AGG(5) VB2_SLICE_AGG(6) VB2_SLICE_AGG(7) VB2_SLICE_AGG(8)
+  }
+#undef VB2_SLICE_AGG
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
