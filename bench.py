@@ -439,14 +439,17 @@ def main():
     q1_ms = state["q1_kernel_ns"] / max(1, state["q1_runs"]) / 1e6
     peak, peak_src = peaks()
     achieved = rows * tpch.Q1_BYTES_PER_ROW / (q1_ms / 1e3) / 1e9 if q1_ms else 0.0
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_q1_dram.json")
-    if os.path.exists(prof):
-        with open(prof) as f:
-            pj = json.load(f)
-        traffic = pj["dram_bytes_per_row"] * rows
+    traffic, traffic_src = None, None
+    for name in ("r02_q1_dram.json", "r01_q1_dram.json"):  # newest ncu --set full capture of this kernel
+        prof = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(prof):
+            with open(prof) as f:
+                pj = json.load(f)
+            traffic = pj["dram_bytes_per_row"] * rows
+            traffic_src = f"profiles/{name}: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, per row x rows of this launch"
+            break
     roofline = {"bound": "hbm", "kernel": "fused_scan_agg_tma_kernel<Q1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": "ncu --set full capture, profiles/ (per row x rows of this launch)",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "kernel_ms": q1_ms, "algorithmic_bytes": rows * tpch.Q1_BYTES_PER_ROW,
                 "timing": "CUDA events recorded by B200HashAggregation on its launch stream around the fused launch (stat b200.fusedScanNanos)"}
 

@@ -170,7 +170,7 @@ int32_t vb2k_expression_jit_compiles(const vb2_program* prog, const vb2_column* 
 /* ------------------------------------------------------------------------------------------
  * High-cardinality GROUP BY in shared memory (slice_agg.cu). The buffered input (chunks of normalized
  * or raw BIGINT keys + up to 3 eight-byte payload columns) is radix-partitioned twice by the top bits
- * of twang_mix64(key) into up to 65536 slices; every slice is aggregated in one CTA's shared-memory
+ * of a Fibonacci hash of the key into up to 65536 slices; every slice is aggregated in one CTA's shared-memory
  * hash table and its groups are appended to rows_out as group rows in the vb2_group_table layout
  * (word 0 = normalized key, accumulator words at ops[].word, the rest from row_init).
  * Replaces HashTable::groupProbe + the accumulator scatter (velox/exec/HashTable.cpp:470-519,
@@ -201,7 +201,7 @@ int32_t vb2k_slice_agg_hll_registers(void);
 size_t vb2k_slice_agg_workspace(int64_t total_rows, int32_t ncols);
 int vb2k_slice_agg_partition(const vb2_slice_chunk* chunks, int32_t nchunks, int32_t ncols, int64_t total_rows, void* workspace, size_t workspace_bytes,
                              int32_t* hll_host, void* stream);
-/* rows_out must hold vb2k_slice_agg_output_rows(distinct_estimate) rows, pre-filled with row_init and
+/* rows_out must hold vb2k_slice_agg_output_rows(min(distinct_estimate, total_rows)) rows, pre-filled with row_init and
  * VB2_EMPTY_KEY in word 0 (vb2k_group_table_init): the blocks reserve output rows in chunks
  * (reserved_rows, a zeroed device word) and leave the unused tail of a chunk EMPTY — the result reads
  * like a hash-mode group table with num_groups occupied rows. */

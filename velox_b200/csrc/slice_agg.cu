@@ -10,8 +10,8 @@
 // per input row (198 B of DRAM reads per row measured, profiles/r01_ncu_config5_group_update.json).
 // Here DRAM only sees streaming passes:
 //
-//   level 1   rows -> 256 partitions by hash bits 63..56        (histogram, scan, staged scatter)
-//   level 2   every partition -> P2 <= 256 slices by bits 55..  (same kernels, one launch each)
+//   level 1   rows -> 256 partitions by bits 63..56 of a Fibonacci hash   (histogram, scan, staged scatter)
+//   level 2   every partition -> P2 <= 256 slices by the next bits          (same kernels, one launch each)
 //   aggregate one CTA per slice: open-addressing table in shared memory (keys + accumulator words),
 //             smem atomics, then the occupied slots become group rows [key | accumulators] in the
 //             vb2_group_table row layout, appended at an atomically reserved offset
@@ -41,6 +41,11 @@ struct SliceKey {
   int64_t min;           // normalized key = raw - min + 1 (vb2k_normalize_keys with one column)
 };
 __device__ __forceinline__ uint64_t slice_key(const SliceKey& k, int64_t r) { return k.norm ? k.norm[r] : static_cast<uint64_t>(k.raw[r] - k.min) + 1; }
+// Every row is hashed four times on its way (two histograms, two scatters): twang_mix64 costs ~40 32-bit
+// instructions and made those passes issue-bound, so the slice path places rows with a Fibonacci hash —
+// one 64-bit multiply. Bits 63..56 pick the level-1 partition, the next log2(P2) bits the slice, bits
+// 46..34 the slot inside the slice's table. (Placement only: nothing of this hash leaves the kernels.)
+__device__ __forceinline__ uint64_t slice_mix(uint64_t key) { return key * 0x9E3779B97F4A7C15ull; }
 
 struct PartIO {
   SliceKey key;
@@ -54,7 +59,7 @@ struct PartGeom {
   const int64_t* seg_start;   // device [nseg + 1]; NULL: one segment [0, n)
   const int32_t* tile_start;  // device [nseg + 1]: first tile of every segment (NULL with seg_start)
   int nseg;
-  int P, shift;               // digit = (twang_mix64(key) >> shift) & (P - 1)
+  int P, shift;               // digit = (slice_mix(key) >> shift) & (P - 1)
 };
 
 // rows [begin, end) and segment of a tile; false past the last tile (tiles are ordered: every later tile is past it too)
@@ -80,7 +85,7 @@ __device__ __forceinline__ bool tile_range(const PartGeom& g, int64_t tile, int&
   return true;
 }
 
-// hist[seg * P + d] += rows of segment seg with digit d. A block walks a contiguous range of tiles and
+// hist[seg * P + d] += rows of segment seg with digit d = (slice_mix(key) >> shift) & (P - 1). A block walks a contiguous range of tiles and
 // flushes its shared histogram when the segment changes. hll (optional): HyperLogLog registers over
 // the keys whose hash ends in 000 (the convention of radix_partition.cu: the host multiplies by 8).
 __global__ void __launch_bounds__(kPT) part_hist_kernel(const __grid_constant__ SliceKey key, const __grid_constant__ PartGeom g, int64_t ntiles,
@@ -118,9 +123,11 @@ __global__ void __launch_bounds__(kPT) part_hist_kernel(const __grid_constant__ 
       for (int u = 0; u < 4; ++u) {
         const int64_t i = i0 + static_cast<int64_t>(u) * kPT;
         if (i >= end) continue;
-        const uint64_t hash = twang_mix64(k[u]);
-        atomicAdd(&h[(hash >> g.shift) & (g.P - 1)], 1u);
-        if (hll && (hash & 7u) == 0) {
+        const uint64_t mix = slice_mix(k[u]);
+        atomicAdd(&h[(mix >> g.shift) & (g.P - 1)], 1u);
+        if (hll && ((mix >> 20) & 7u) == 0) {
+          // one row in eight feeds the sketch, through the strong hash (the convention of radix_partition.cu: x 8 on the host)
+          const uint64_t hash = twang_mix64(k[u]);
           const uint32_t idx = static_cast<uint32_t>(hash >> 3) & ((1u << kHllBits) - 1u);
           const uint64_t rest = (hash >> (3 + kHllBits)) | (1ull << (56 - 3 - kHllBits));
           atomicMax(&regs[idx], __ffsll(static_cast<long long>(rest)));
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(kPT, NCOLS <= 1 ? 3 : 2) part_scatter_kernel(c
     // (A)
 #pragma unroll 4
     for (int j = tid; j < rows; j += kPT) {
-      const int d = static_cast<int>((twang_mix64(slice_key(io.key, begin + j)) >> g.shift) & (P - 1));
+      const int d = static_cast<int>((slice_mix(slice_key(io.key, begin + j)) >> g.shift) & (P - 1));
       rdig[j] = static_cast<uint8_t>(d);
       atomicAdd(&cnt[d], 1u);
     }
@@ -373,8 +380,7 @@ __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __gr
         const int64_t i = i0 + static_cast<int64_t>(u) * kAggThreads;
         if (i >= end) continue;
         const uint64_t key = k[u];
-        // slot inside the slice: a multiplicative hash (the slice already fixes the top bits of twang_mix64(key))
-        uint32_t slot = static_cast<uint32_t>((key * 0x9E3779B97F4A7C15ull) >> 40) & cmask;
+        uint32_t slot = static_cast<uint32_t>(slice_mix(key) >> 34) & cmask;  // bits below the ones that chose the slice
         bool found = false;
         for (int probes = 0; probes < C; ++probes) {
           uint64_t cur = *reinterpret_cast<volatile uint64_t*>(skey + slot);
@@ -630,7 +636,7 @@ int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_es
   a.rows_capacity = rows_capacity;
   a.num_groups = reinterpret_cast<unsigned long long*>(num_groups);
   a.reserved = reinterpret_cast<unsigned long long*>(reserved_rows);
-  a.chunk_rows = output_chunk_rows(distinct_estimate);
+  a.chunk_rows = output_chunk_rows(distinct_estimate < total_rows ? distinct_estimate : total_rows);  // the caller sizes rows_out from the same bound
   a.error_flag = error_flag;
   a.overflow = overflow_slices;
   a.C = C;
