@@ -1,6 +1,7 @@
 // Operator-level C ABI (include/velox_b200.h): plan text -> Task over the shim Driver with the
 // B200 adapter installed; host / device column batches in, host result columns out.
 #include <atomic>
+#include <chrono>
 #include <functional>
 #include <map>
 #include <mutex>
@@ -44,6 +45,7 @@ struct vb2_task {
   std::vector<OutCol> out;
   int64_t rows = 0;
   int64_t h2dBytes = 0;  // host -> device bytes of the last run (resident copies from an upload cache are not counted)
+  int64_t parseNanos = 0, runNanos = 0, resultNanos = 0;
   std::string stats;
 };
 
@@ -289,7 +291,9 @@ vb2_task* vb2_task_create(const char* plan_text, const char* config, char* err, 
       }
     }
     auto task = std::make_unique<vb2_task>();
+    const auto t0 = std::chrono::steady_clock::now();
     task->plan = parsePlanText(plan_text ? plan_text : "");
+    task->parseNanos = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     task->task = std::make_shared<exec::Task>(task->plan, core::QueryConfig(std::move(kv)));
     t = task.release();
   });
@@ -352,7 +356,10 @@ int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen) {
           threadBytes += velox_b200::threadUploadedBytes() - threadStart;
           velox_b200::setThreadUploadCache(nullptr);
         });
+    const auto tRun = std::chrono::steady_clock::now();
     task->results = task->task->run();
+    const auto tRan = std::chrono::steady_clock::now();
+    task->runNanos = std::chrono::duration_cast<std::chrono::nanoseconds>(tRan - tRun).count();
     task->h2dBytes = velox_b200::threadUploadedBytes() - uploadedBefore + threadBytes.load();
     task->out.clear();
     task->rows = 0;
@@ -378,9 +385,13 @@ int32_t vb2_task_run(vb2_task* task, char* err, int32_t errlen) {
       task->out.resize(type->size());
       for (uint32_t c = 0; c < type->size(); ++c) { task->out[c].type = veloxTypeToVb2(type->childAt(c)); task->out[c].offsets.push_back(0); }
     }
+    task->resultNanos = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tRan).count();
     std::ostringstream os;
     for (auto& kv : task->task->stats()) os << kv.first << "=" << kv.second << "\n";
     os << "task.h2dBytes=" << task->h2dBytes << "\n";
+    os << "task.parseWallNanos=" << task->parseNanos << "\n";
+    os << "task.runWallNanos=" << task->runNanos << "\n";
+    os << "task.resultWallNanos=" << task->resultNanos << "\n";
     task->stats = os.str();
     task->results.clear();
   });

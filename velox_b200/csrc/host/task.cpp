@@ -1,6 +1,7 @@
 #include "task.h"
 
 #include <atomic>
+#include <chrono>
 #include <exception>
 #include <thread>
 
@@ -202,6 +203,8 @@ bool Task::allPeersFinished(const core::PlanNodeId& planNodeId, Driver* caller, 
 }
 
 std::vector<RowVectorPtr> Task::run() {
+  const auto t0 = std::chrono::steady_clock::now();
+  auto sinceStart = [&t0]() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); };
   const int32_t maxDrivers = std::max<int32_t>(1, config_.get<int32_t>("task.max_drivers", 1));
   Planner planner{*this, inputs_, maxDrivers, {}, {}, {}, {}};
   auto out = std::make_unique<Pipeline>();
@@ -225,6 +228,7 @@ std::vector<RowVectorPtr> Task::run() {
       drivers_.push_back(p->drivers.back());
     }
 
+  const int64_t plannedNanos = sinceStart();  // LocalPlanner + driver / operator construction + adapters
   struct Slot {
     Driver* driver;
     bool done = false;
@@ -298,6 +302,7 @@ std::vector<RowVectorPtr> Task::run() {
       std::rethrow_exception(error);
     }
   }
+  const int64_t ranNanos = sinceStart();
   for (auto& p : planner.pipelines)
     for (auto& d : p->drivers)
       for (auto& op : d->operators()) {
@@ -313,6 +318,10 @@ std::vector<RowVectorPtr> Task::run() {
   stats_["task.numDrivers"] = static_cast<int64_t>(drivers_.size());
   closeAll();
   drivers_.clear();
+  // where a task's wall time goes outside its operators (host-side latency is what limits small per-GPU shards)
+  stats_["task.planWallNanos"] = plannedNanos;
+  stats_["task.driversWallNanos"] = ranNanos - plannedNanos;
+  stats_["task.closeWallNanos"] = sinceStart() - ranNanos;
   return results;
 }
 

@@ -162,10 +162,15 @@ class Task:
             out.append(cols)
         return out
 
-    def stats(self) -> Dict[str, int]:
+    def stats(self, only: Optional[str] = None) -> Dict[str, int]:
+        """Runtime stats of the task's operators; `only` keeps the entries whose name contains it."""
         out = {}
-        for line in self.L.vb2_task_stats(self.h).decode().splitlines():
-            k, _, v = line.partition("=")
+        text = self.L.vb2_task_stats(self.h)
+        needle = only.encode() if only else None
+        for line in text.splitlines():
+            if needle is not None and needle not in line:
+                continue
+            k, _, v = line.decode().partition("=")
             out[k] = int(v)
         return out
 
