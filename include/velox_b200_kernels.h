@@ -408,6 +408,16 @@ int vb2k_group_move_keyed(const vb2_group_table* from, const int32_t* slots, int
 int vb2k_group_move_to_keyed(const vb2_group_table* from, const int32_t* slots, int64_t n, int32_t nkeys, const int64_t* mins, const uint64_t* mults,
                              const uint64_t* ranges, const int32_t* null_reserved, int32_t word_shift, const vb2_group_table* to,
                              int64_t* num_groups, int32_t* error_flag, void* stream);
+/* Value ids of key tuples through a keyed table — the join side of the reference's kHash mode
+ * (velox/exec/HashTable.cpp:1751-1838, HashTable::insertForJoin :1518 / joinProbe :610 compare the stored
+ * keys of a row): ids[r] = slot of row r's key tuple in the keyed table, valid bit r = the row has an id.
+ * insert != 0 (build side): absent tuples are inserted; insert == 0 (probe side): absent tuples clear
+ * the valid bit. Rows with a NULL key column never get an id (NULL join keys never match,
+ * exec/HashBuild.cpp:475-479). The ids are dense enough (slots of a table of <= 2 x tuples + 16 rows,
+ * rounded to a power of two) to address an array-mode vb2_join_table of the same capacity directly.
+ * valid: u64 words covering n bits. A full table sets *error_flag = 100. */
+int vb2k_keyed_key_ids(const vb2_group_table* t, const vb2_column* keys, int32_t nkeys, int64_t n, int32_t insert, uint64_t* ids, uint64_t* valid,
+                       int64_t* num_groups, int32_t* error_flag, void* stream);
 /* Radix partitioning in front of a high-cardinality aggregation (radix_partition.cu): a hash-mode
  * group table places key k at slot twang_mix64(k) >> (64 - log2(capacity)), so rows ordered by the
  * top 8 bits of that hash walk the table slice by slice (1/256 of it at a time, L2 resident).

@@ -405,6 +405,53 @@ def test_hash_join_filter_multikey_and_empty_build():
                    .hashJoin(["pk"], ["bk"], PlanBuilder().values(empty.names, empty.types, source=1), "", outs, joinType=jt).planNode(), [probe, empty])
 
 
+def _keyed_join_tables(seed=5, n=3000, m=400):
+    rng = np.random.default_rng(seed)
+    def maybe(v, p=0.05):
+        return [None if rng.random() < p else x for x in v]
+    probe = row_vector(["pa", "pb", "pd", "ps", "pv"], [
+        flat_vector(BIGINT, maybe((rng.integers(0, 40, n) * (2**40)).tolist())),
+        flat_vector(BIGINT, maybe((rng.integers(0, 30, n) * (2**35) - 2**50).tolist())),
+        flat_vector(DOUBLE, maybe(rng.choice([0.0, -0.0, 1.5, NAN, -2.25, 1e300, 7.0], n).tolist())),
+        dictionary_vector(VARCHAR, rng.integers(0, 7, n), ["ash", "birch", "cedar", "elm", "fir", None, "oak"]),
+        flat_vector(BIGINT, np.arange(n))])
+    build = row_vector(["ba", "bb", "bd", "bs", "bw"], [
+        flat_vector(BIGINT, maybe((rng.integers(0, 40, m) * (2**40)).tolist())),
+        flat_vector(BIGINT, maybe((rng.integers(0, 30, m) * (2**35) - 2**50).tolist())),
+        flat_vector(DOUBLE, maybe(rng.choice([0.0, 1.5, NAN, -2.25, 3.0], m).tolist())),
+        dictionary_vector(VARCHAR, rng.integers(0, 6, m), ["oak", "elm", None, "fir", "yew", "elm"]),  # a repeated entry: one id
+        flat_vector(BIGINT, np.arange(m) * 10)])
+    return probe, build
+
+
+@pytest.mark.parametrize("keys", [(["pd"], ["bd"]), (["ps"], ["bs"]), (["pa", "pb"], ["ba", "bb"]), (["ps", "pd", "pa"], ["bs", "bd", "ba"])])
+@pytest.mark.parametrize("join_type", ["inner", "left", "semi", "anti"])
+def test_hash_join_keyed_mode(keys, join_type):
+    """The reference's kHash mode for joins (exec/HashTable.cpp:1751-1838): DOUBLE keys (NaN = NaN, -0 = +0), VARCHAR
+    keys (different dictionaries on the two sides) and two wide BIGINT keys that do not pack into one normalized word."""
+    probe, build = _keyed_join_tables()
+    b = PlanBuilder().values(build.names, build.types, source=1)
+    outs = ["pv", "ps", "pd"] if join_type in ("semi", "anti") else ["pv", "ps", "pd", "bw", "bs", "bd"]
+    plan = PlanBuilder().values(probe.names, probe.types, source=0).hashJoin(keys[0], keys[1], b, "", outs, joinType=join_type).planNode()
+    (st,) = check_plan(plan, [probe, build])
+    assert stat(st, "b200.joinTableMode") == 2
+    check_plan(plan, [probe, build], batch_rows=700)  # multi-batch build side (dictionaries merged) and probe side
+
+
+def test_hash_join_keyed_mode_filter_and_unique():
+    probe, build = _keyed_join_tables(seed=9)
+    b = PlanBuilder().values(build.names, build.types, source=1)
+    plan = PlanBuilder().values(probe.names, probe.types, source=0).hashJoin(["pa", "pb"], ["ba", "bb"], b, "pv % 3 = 0 and bw > 100", ["pv", "bw"]).planNode()
+    check_plan(plan, [probe, build])
+    # unique DOUBLE build keys: the one-pass probe
+    rng = np.random.default_rng(2)
+    bu = row_vector(["bd", "bw"], [flat_vector(DOUBLE, (rng.permutation(500) * 0.25).tolist() + [NAN]), flat_vector(BIGINT, np.arange(501))])
+    pu = row_vector(["pd"], [flat_vector(DOUBLE, (rng.integers(0, 800, 4000) * 0.25).tolist() + [NAN, None])])
+    bb = PlanBuilder().values(bu.names, bu.types, source=1)
+    (st,) = check_plan(PlanBuilder().values(pu.names, pu.types, source=0).hashJoin(["pd"], ["bd"], bb, "", ["pd", "bw"]).planNode(), [pu, bu])
+    assert stat(st, "b200.uniqueKeyProbes") > 0 and stat(st, "b200.joinTableMode") == 2
+
+
 @pytest.mark.parametrize("n", [50_000])
 def test_tpch_q14_fused_and_generic(n):
     nparts = 3000

@@ -106,6 +106,49 @@ __global__ void minmax_kernel(const __grid_constant__ vb2_column c, int64_t rows
     atomicAdd(reinterpret_cast<unsigned long long*>(out3 + 2), static_cast<unsigned long long>(cnt));
   }
 }
+// Flat NULL-free BIGINT column (the common shape of a high-cardinality key): 128-bit loads, eight values in flight per thread.
+__global__ void __launch_bounds__(256) minmax_flat_i64_kernel(const int64_t* __restrict__ v, int64_t rows, int64_t* __restrict__ out3) {
+  int64_t lo = INT64_MAX, hi = INT64_MIN;
+  const int64_t pairs = rows >> 1;
+  const longlong2* v2 = reinterpret_cast<const longlong2*>(v);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  for (; i + 3 * stride < pairs; i += 4 * stride) {
+    longlong2 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = __ldcs(v2 + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      lo = a[u].x < lo ? a[u].x : lo;
+      hi = a[u].x > hi ? a[u].x : hi;
+      lo = a[u].y < lo ? a[u].y : lo;
+      hi = a[u].y > hi ? a[u].y : hi;
+    }
+  }
+  for (; i < pairs; i += stride) {
+    const longlong2 a = v2[i];
+    lo = a.x < lo ? a.x : lo;
+    hi = a.x > hi ? a.x : hi;
+    lo = a.y < lo ? a.y : lo;
+    hi = a.y > hi ? a.y : hi;
+  }
+  if ((rows & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t x = v[rows - 1];
+    lo = x < lo ? x : lo;
+    hi = x > hi ? x : hi;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int64_t l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(reinterpret_cast<long long*>(out3), static_cast<long long>(lo));
+    atomicMax(reinterpret_cast<long long*>(out3 + 1), static_cast<long long>(hi));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out3[2] = rows;  // no NULLs: every row counts
+}
 __global__ void minmax_init_kernel(int64_t* out3) {
   out3[0] = INT64_MAX;
   out3[1] = INT64_MIN;
@@ -409,6 +452,61 @@ __global__ void group_update_keyed_kernel(const __grid_constant__ vb2_group_tabl
   }
   fresh = warp_sum(fresh);
   if ((threadIdx.x & 31) == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
+}
+// Slot of a key tuple already in a keyed table whose rows are all published (no concurrent inserts), -1 when absent.
+__device__ __forceinline__ int64_t find_keyed(const uint64_t* rows, uint64_t mask, int w, int nkeys, const uint64_t* kw) {
+  const uint64_t h63 = keyed_hash(kw, 0, nkeys);
+  uint64_t slot = twang_mix64(h63) & mask;
+  for (uint64_t probes = 0; probes <= mask; ++probes) {
+    const uint64_t* row = rows + slot * w;
+    const uint64_t st = row[0];
+    if (st == VB2_EMPTY_KEY) return -1;
+    if ((st >> 1) == h63) {
+      bool same = row[1 + nkeys] == 0;
+      for (int k = 0; k < nkeys && same; ++k) same = row[1 + k] == kw[k];
+      if (same) return static_cast<int64_t>(slot);
+    }
+    slot = (slot + 1) & mask;
+  }
+  return -1;
+}
+// Join keys that do not normalize into one word: the id of a key tuple is its slot in a keyed table. One warp
+// per 32 consecutive rows, so the valid bits of those rows are one ballot word.
+__global__ void keyed_key_ids_kernel(const __grid_constant__ vb2_group_table tab, const __grid_constant__ KeyedCols keys, int64_t n, int insert,
+                                     uint64_t* __restrict__ ids, uint32_t* __restrict__ valid, int64_t* __restrict__ num_groups,
+                                     int32_t* __restrict__ error_flag) {
+  const uint64_t mask = static_cast<uint64_t>(tab.capacity - 1);
+  const int64_t nwords = (n + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  int64_t fresh = 0;
+  for (int64_t w = warp_global; w < nwords; w += nwarps) {
+    const int64_t r = (w << 5) + lane;
+    bool ok = false;
+    uint64_t id = 0;
+    if (r < n) {
+      uint64_t kw[VB2_KEYED_MAX_KEYS];
+      bool any_null = false;
+      for (int k = 0; k < keys.n; ++k) {
+        int64_t base;
+        const bool is_null = decode_row2(keys.c[k], r, base);
+        kw[k] = is_null ? 0 : key_word_of(keys.c[k], base);
+        any_null |= is_null;
+      }
+      if (!any_null) {
+        const int64_t slot = insert ? find_or_insert_keyed(tab.rows, mask, tab.row_words, keys.n, kw, 0, fresh)
+                                    : find_keyed(tab.rows, mask, tab.row_words, keys.n, kw);
+        if (slot >= 0) { ok = true; id = static_cast<uint64_t>(slot); }
+        else if (insert) atomicCAS(error_flag, 0, 100);
+      }
+      ids[r] = id;
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) valid[w] = word;
+  }
+  fresh = warp_sum(fresh);
+  if (lane == 0 && fresh && num_groups) atomicAdd(reinterpret_cast<unsigned long long*>(num_groups), static_cast<unsigned long long>(fresh));
 }
 // Re-inserts groups into a (bigger) keyed table; keys are distinct, so the row belongs to this thread.
 struct DecodeArgs {
@@ -972,7 +1070,9 @@ int vb2k_join_build_array_direct(int32_t* head, int32_t* next, int64_t capacity,
 int vb2k_column_minmax(const vb2_column* col, int64_t rows, int64_t* out3, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   minmax_init_kernel<<<vb2::counted(1), 1, 0, st>>>(out3);
-  if (rows > 0) minmax_kernel<<<vb2::counted(grid_for(rows, 256)), 256, 0, st>>>(*col, rows, out3);
+  if (rows > 0 && col->encoding == VB2_FLAT && !col->nulls && col->type == VB2_BIGINT && (reinterpret_cast<uintptr_t>(col->values) & 15) == 0)
+    minmax_flat_i64_kernel<<<vb2::counted(grid_for(rows / 2 + 1, 256)), 256, 0, st>>>(static_cast<const int64_t*>(col->values), rows, out3);
+  else if (rows > 0) minmax_kernel<<<vb2::counted(grid_for(rows, 256)), 256, 0, st>>>(*col, rows, out3);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
@@ -1195,6 +1295,22 @@ int vb2k_group_update_keyed(const vb2_group_table* t, const vb2_column* keys, in
     a.a[i] = aggs[i];
   }
   group_update_keyed_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, kc, n, a, num_groups, error_flag);
+  VB2_CUDA_OK(cudaGetLastError());
+  return VB2_OK;
+}
+
+int vb2k_keyed_key_ids(const vb2_group_table* t, const vb2_column* keys, int32_t nkeys, int64_t n, int32_t insert, uint64_t* ids, uint64_t* valid,
+                       int64_t* num_groups, int32_t* error_flag, void* stream) {
+  if (int rc = check_keyed(t, nkeys, "keyed_key_ids: bad table")) return rc;
+  if (n <= 0) return VB2_OK;
+  KeyedCols kc{};
+  kc.n = nkeys;
+  for (int k = 0; k < nkeys; ++k) {
+    if (keys[k].type == VB2_VARCHAR) return fail_msg(VB2_ERR_INVALID, "keyed_key_ids: VARCHAR keys arrive as id columns");
+    kc.c[k] = keys[k];
+  }
+  keyed_key_ids_kernel<<<vb2::counted(grid_for(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(*t, kc, n, insert, ids, reinterpret_cast<uint32_t*>(valid),
+                                                                                                    num_groups, error_flag);
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }

@@ -182,16 +182,114 @@ void B200HashBuild::noMoreInput() {
   buildTable();
 }
 
+std::vector<vb2_column> keyedJoinColumns(const B200Vector& batch, const std::vector<int32_t>& keyColumns, JoinTableHolder& holder, bool build,
+                                         std::vector<KeyedLutCache>* cache, std::vector<DeviceBufferPtr>& keep, cudaStream_t stream) {
+  std::vector<vb2_column> cols;
+  if (build) {
+    holder.keyIsVarchar.assign(keyColumns.size(), false);
+    holder.varcharIds.assign(keyColumns.size(), {});
+  }
+  if (cache && cache->size() < keyColumns.size()) cache->resize(keyColumns.size());
+  for (size_t k = 0; k < keyColumns.size(); ++k) {
+    const DeviceColumn& col = *batch.column(keyColumns[k]);
+    vb2_column d = col.desc;
+    if (d.type == VB2_VARCHAR) {
+      if (d.encoding == VB2_FLAT || !col.alphabet)
+        VELOX_UNSUPPORTED("join on flat VARCHAR keys with more than 65536 distinct values per batch (flat strings are dictionary-encoded on upload up to that size)");
+      if (build) holder.keyIsVarchar[k] = true;
+      VELOX_CHECK(holder.keyIsVarchar[k], "join key types differ between the build and the probe side");
+      auto& ids = holder.varcharIds[k];
+      DeviceBufferPtr lutBuf;
+      if (cache && (*cache)[k].alphabet == col.alphabet) {
+        lutBuf = (*cache)[k].lut;
+      } else {
+        std::vector<int32_t> lut(col.alphabet->values.size());
+        for (size_t i = 0; i < lut.size(); ++i) {
+          if (col.alphabet->nulls[i]) { lut[i] = 0; continue; }  // NULL entries: dict_nulls decides, the id is unused
+          auto it = ids.find(col.alphabet->values[i]);
+          if (it == ids.end()) {
+            if (!build) { lut[i] = -1; continue; }
+            it = ids.emplace(col.alphabet->values[i], static_cast<int32_t>(ids.size())).first;
+          }
+          lut[i] = it->second;
+        }
+        lutBuf = allocDevice(lut.size() * 4 + 4, stream);
+        VB2_CU(cudaMemcpyAsync(lutBuf->data(), lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, stream));  // pageable: staged before return
+        if (cache) (*cache)[k] = KeyedLutCache{col.alphabet, lutBuf};
+      }
+      keep.push_back(lutBuf);
+      d.type = VB2_INTEGER;
+      d.values = lutBuf->data();
+      d.aux = nullptr;
+      if (d.encoding == VB2_CONSTANT) d.dict_size = 1;
+    } else {
+      VELOX_CHECK(!holder.keyIsVarchar[k], "join key types differ between the build and the probe side");
+    }
+    cols.push_back(d);
+  }
+  return cols;
+}
+
+// Keyed mode: ids of the build rows' key tuples (find-or-insert into a keyed table), then the usual chains
+// over an array-mode table addressed by those ids.
+void B200HashBuild::buildKeyedTable(const std::shared_ptr<JoinTableHolder>& holder, const std::vector<int32_t>& keys, int64_t n) {
+  cudaStream_t st = dev_->stream;
+  VELOX_CHECK(keys.size() <= VB2_KEYED_MAX_KEYS, "at most " + std::to_string(VB2_KEYED_MAX_KEYS) + " join keys in keyed mode");
+  holder->keyed = true;
+  std::vector<DeviceBufferPtr> keep;
+  std::vector<vb2_column> cols = keyedJoinColumns(*holder->rows, keys, *holder, true, nullptr, keep, st);
+  for (int32_t k : keys)
+    if (holder->rows->column(k)->mayHaveNulls()) holder->hasNullKeys = true;  // conservative: a NULL-capable key column
+  const int32_t nk = static_cast<int32_t>(keys.size());
+  vb2_group_table& kt = holder->keyedTable;
+  kt.capacity = static_cast<int64_t>(nextPow2(static_cast<uint64_t>(n) * 2 + 16));
+  VELOX_CHECK(kt.capacity <= (1ll << 31), "join build side above 2^30 rows in keyed mode");
+  kt.row_words = (nk + 2 + 3) / 4 * 4;
+  kt.hash_mode = VB2_GROUP_KEYED;
+  auto rowsBuf = allocDevice(static_cast<size_t>(kt.capacity) * kt.row_words * 8, st);
+  kt.rows = rowsBuf->as<uint64_t>();
+  std::vector<uint64_t> init(kt.row_words, 0);
+  init[0] = VB2_EMPTY_KEY;
+  kernelCheck(vb2k_group_table_init(&kt, init.data(), st));
+  holder->owners.push_back(rowsBuf);
+  auto ids = allocDevice(static_cast<size_t>(n) * 8, st);
+  auto valid = allocDevice(bits::nbytes(n), st);
+  auto flags = allocDeviceZeroed(16, st);
+  kernelCheck(vb2k_keyed_key_ids(&kt, cols.data(), nk, n, 1, ids->as<uint64_t>(), valid->as<uint64_t>(), nullptr, flags->as<int32_t>(), st));
+  vb2_join_table& t = holder->table;
+  t.mode = 0;
+  t.key_min = 0;
+  t.capacity = kt.capacity;
+  auto head = allocDeviceZeroed(static_cast<size_t>(t.capacity) * 4, st);
+  auto next = allocDevice(static_cast<size_t>(n) * 4 + 4, st);
+  t.head = head->as<int32_t>();
+  t.next = next->as<int32_t>();
+  t.build_rows = n;
+  holder->owners.push_back(head);
+  holder->owners.push_back(next);
+  kernelCheck(vb2k_join_build(&t, ids->as<uint64_t>(), valid->as<uint64_t>(), n, flags->as<int32_t>() + 2, st));
+  int32_t h[4];
+  VB2_CU(cudaMemcpyAsync(h, flags->data(), 16, cudaMemcpyDeviceToHost, st));
+  VB2_CU(cudaStreamSynchronize(st));
+  VELOX_CHECK(h[0] == 0 && h[2] == 0, "join table build failed (table full)");
+  holder->hasDuplicateKeys = h[3] != 0;
+  addRuntimeStat("b200.joinTableMode", exec::RuntimeCounter{2});
+  addRuntimeStat("b200.joinTableSlots", exec::RuntimeCounter{t.capacity});
+  bridge_->setHashTable(holder, holder->hasNullKeys);
+}
+
 void B200HashBuild::buildTable() {
   cudaStream_t st = dev_->stream;
   auto holder = std::make_shared<JoinTableHolder>();
   holder->stream = st;
   const std::vector<int32_t> keys = resolveJoin(*node_).rightKeys;
   const auto& buildType = node_->sources()[1]->outputType();
+  bool keyedTypes = false;  // DOUBLE / VARCHAR keys have no value-id range: keyed mode
   for (int32_t k : keys) {
     const TypeKind kind = buildType->childAt(k)->kind();
-    if (kind != TypeKind::BIGINT && kind != TypeKind::INTEGER && kind != TypeKind::BOOLEAN)
-      VELOX_UNSUPPORTED("join keys of type " + buildType->childAt(k)->toString() + " (BIGINT/INTEGER/DATE/BOOLEAN are supported)");
+    if (kind == TypeKind::DOUBLE || kind == TypeKind::VARCHAR) keyedTypes = true;
+    else if (kind != TypeKind::BIGINT && kind != TypeKind::INTEGER && kind != TypeKind::BOOLEAN)
+      VELOX_UNSUPPORTED("join keys of type " + buildType->childAt(k)->toString() + " (BIGINT/INTEGER/DATE/BOOLEAN/DOUBLE/VARCHAR are supported)");
   }
   if (batches_.empty()) {
     // empty build side: a table nobody can hit
@@ -230,8 +328,9 @@ void B200HashBuild::buildTable() {
   // value ranges of the key columns -> layout (VectorHasher range mode, exec/VectorHasher.cpp:923)
   KeyLayout& lay = holder->layout;
   uint64_t product = 1;
-  bool overflow = false;
+  bool overflow = keyedTypes;
   for (int32_t k : keys) {
+    if (keyedTypes) break;
     int64_t lo, hi, nn;
     columnMinMax(*holder->rows->column(k), n, st, lo, hi, nn);
     if (nn == 0) { lo = 0; hi = 0; }
@@ -246,7 +345,10 @@ void B200HashBuild::buildTable() {
       else product = static_cast<uint64_t>(p);
     }
   }
-  if (overflow) VELOX_UNSUPPORTED("join key ranges do not fit one 64-bit normalized key");
+  if (overflow) {
+    buildKeyedTable(holder, keys, n);
+    return;
+  }
   lay.product = product;
   lay.mults.assign(keys.size(), 1);
   for (int i = static_cast<int>(keys.size()) - 2; i >= 0; --i) lay.mults[i] = lay.mults[i + 1] * lay.ranges[i + 1];
@@ -327,7 +429,18 @@ B200VectorPtr B200HashProbe::apply(const B200VectorPtr& in) {
   const JoinTableHolder& jt = *table_;
   const core::JoinType type = node_->joinType();
   // build and probe streams differ only across drivers; the bridge hand-off synchronised the build
-  NormalizedKeys nk = normalizeKeys(*in, plan_.leftKeys, jt.layout, nullptr, n, true, st);
+  NormalizedKeys nk;
+  if (jt.keyed) {
+    // keyed mode: the probe row's key is the slot of its key tuple in the build side's keyed table (absent: no match)
+    std::vector<DeviceBufferPtr> keep;
+    std::vector<vb2_column> cols = keyedJoinColumns(*in, plan_.leftKeys, *table_, false, &keyedLuts_, keep, st);
+    nk.keys = allocDevice(static_cast<size_t>(n) * 8, st);
+    nk.valid = allocDevice(bits::nbytes(n), st);
+    kernelCheck(vb2k_keyed_key_ids(&jt.keyedTable, cols.data(), static_cast<int32_t>(cols.size()), n, 0, nk.keys->as<uint64_t>(), nk.valid->as<uint64_t>(),
+                                   nullptr, errorFlag_->as<int32_t>(), st));
+  } else {
+    nk = normalizeKeys(*in, plan_.leftKeys, jt.layout, nullptr, n, true, st);
+  }
   int64_t pairs = 0;
   DeviceBufferPtr probeRows, buildRows;
   if (!jt.hasDuplicateKeys) {

@@ -1,5 +1,7 @@
 // Device join table shared between B200HashBuild and B200HashProbe through the HashJoinBridge.
 #pragma once
+#include <unordered_map>
+
 #include "operators.h"
 
 namespace velox_b200 {
@@ -22,7 +24,21 @@ struct JoinTableHolder : wave::HashTableHolder {
   bool hasNullKeys = false;     // a build row had a NULL key (null-aware anti joins ask; exec/HashJoinBridge.h:86)
   int64_t numRows = 0;
   cudaStream_t stream = nullptr;
+  // Keyed mode (the reference's kHash for joins, exec/HashTable.cpp:1751-1838): DOUBLE / VARCHAR keys and key
+  // tuples that do not pack into one 64-bit word. The build side's distinct key tuples live in a keyed group
+  // table (rows = [state | key words | NULL mask]); a row's join key is the slot of its tuple there, and
+  // `table` is an array-mode table over those slots.
+  bool keyed = false;
+  vb2_group_table keyedTable{};
+  std::vector<bool> keyIsVarchar;
+  std::vector<std::unordered_map<std::string, int32_t>> varcharIds;  // per VARCHAR key: build-side string -> id
 };
+
+// Key columns as the keyed-id kernel reads them: VARCHAR dictionary keys become INTEGER dictionary columns over
+// a LUT of the build side's string ids (build: ids are assigned; probe: strings the build side never saw map to
+// -1, an id no build row has).
+std::vector<vb2_column> keyedJoinColumns(const B200Vector& batch, const std::vector<int32_t>& keyColumns, JoinTableHolder& holder, bool build,
+                                         std::vector<KeyedLutCache>* cache, std::vector<DeviceBufferPtr>& keep, cudaStream_t stream);
 
 // Packs key columns of `batch` into normalized keys. valid bit = no key column is NULL.
 // `probe`: ids outside the layout's ranges get an invalid key (cannot match).

@@ -88,6 +88,11 @@ class B200FilterProject : public exec::Operator {
 
 // ---- aggregation ----------------------------------------------------------------------------------
 struct JoinTableHolder;  // join.cpp
+// keyed join mode: a probe-side VARCHAR dictionary and its device LUT of build-side string ids (join.cpp)
+struct KeyedLutCache {
+  std::shared_ptr<const HostAlphabet> alphabet;
+  DeviceBufferPtr lut;
+};
 
 // An aggregate function of the B200 engine, created through the reference's registry
 // (exec::registerAggregateFunction / Aggregate::create, velox/exec/Aggregate.h:361-575). The device
@@ -209,6 +214,7 @@ class B200HashBuild : public exec::Operator {
 
  private:
   void buildTable();
+  void buildKeyedTable(const std::shared_ptr<JoinTableHolder>& holder, const std::vector<int32_t>& keys, int64_t n);
   std::shared_ptr<const core::HashJoinNode> node_;
   ResolvedJoin plan_;  // key / output column names resolved to channels
   std::shared_ptr<exec::HashJoinBridge> bridge_;
@@ -239,6 +245,7 @@ class B200HashProbe : public exec::Operator {
   std::shared_ptr<DeviceContext> dev_;
   std::unique_ptr<CompiledProgram> filterProgram_;
   DeviceBufferPtr errorFlag_;
+  std::vector<KeyedLutCache> keyedLuts_;  // keyed mode: probe-side VARCHAR key dictionaries -> build-side string ids
 };
 
 // ---- exchange --------------------------------------------------------------------------------------

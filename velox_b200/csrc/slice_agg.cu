@@ -20,6 +20,8 @@
 // consecutive rows (full 32-byte sectors) — a direct 8-byte scatter makes DRAM read and write every
 // sector twice. All loads of the input are coalesced and streaming.
 // A HyperLogLog sketch filled by the level-1 histogram sizes level 2 and the output.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vb2 {
@@ -92,6 +94,18 @@ __global__ void __launch_bounds__(kPT) part_hist_kernel(const __grid_constant__ 
                                                         uint32_t* __restrict__ hist, int32_t* __restrict__ hll) {
   __shared__ uint32_t h[kMaxP];
   __shared__ int32_t regs[1 << kHllBits];
+  // Sampled keys wait in a per-warp queue until 32 of them are there: the strong hash of the sketch then runs
+  // with every lane busy (one row in eight is sampled: hashing in place would run its ~40 instructions for
+  // nearly every warp iteration with four lanes active).
+  __shared__ uint64_t hq[kPT / 32][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int qn = 0;  // warp-uniform
+  auto sketch = [&](uint64_t k) {
+    const uint64_t hash = twang_mix64(k);
+    const uint32_t idx = static_cast<uint32_t>(hash >> 3) & ((1u << kHllBits) - 1u);
+    const uint64_t rest = (hash >> (3 + kHllBits)) | (1ull << (56 - 3 - kHllBits));
+    atomicMax(&regs[idx], __ffsll(static_cast<long long>(rest)));
+  };
   if (hll)
     for (int i = threadIdx.x; i < (1 << kHllBits); i += kPT) regs[i] = 0;
   if (threadIdx.x < kMaxP) h[threadIdx.x] = 0;
@@ -112,28 +126,38 @@ __global__ void __launch_bounds__(kPT) part_hist_kernel(const __grid_constant__ 
       }
       segNow = seg;
     }
-    for (int64_t i0 = begin + threadIdx.x; i0 < end; i0 += 4 * kPT) {
+    for (int64_t base = begin; base < end; base += 4 * kPT) {  // block-uniform trip count: the ballots below see whole warps
       uint64_t k[4];  // four loads in flight per thread before the shared-memory atomics
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int64_t i = i0 + static_cast<int64_t>(u) * kPT;
-        if (i < end) k[u] = slice_key(key, i);
+        const int64_t i = base + threadIdx.x + static_cast<int64_t>(u) * kPT;
+        k[u] = i < end ? slice_key(key, i) : 0;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int64_t i = i0 + static_cast<int64_t>(u) * kPT;
-        if (i >= end) continue;
+        const int64_t i = base + threadIdx.x + static_cast<int64_t>(u) * kPT;
+        const bool live = i < end;
         const uint64_t mix = slice_mix(k[u]);
-        atomicAdd(&h[(mix >> g.shift) & (g.P - 1)], 1u);
-        if (hll && ((mix >> 20) & 7u) == 0) {
-          // one row in eight feeds the sketch, through the strong hash (the convention of radix_partition.cu: x 8 on the host)
-          const uint64_t hash = twang_mix64(k[u]);
-          const uint32_t idx = static_cast<uint32_t>(hash >> 3) & ((1u << kHllBits) - 1u);
-          const uint64_t rest = (hash >> (3 + kHllBits)) | (1ull << (56 - 3 - kHllBits));
-          atomicMax(&regs[idx], __ffsll(static_cast<long long>(rest)));
+        if (live) atomicAdd(&h[(mix >> g.shift) & (g.P - 1)], 1u);
+        if (hll) {
+          // one key in eight feeds the sketch, through the strong hash (the convention of radix_partition.cu: x 8 on the host)
+          const bool sampled = live && ((mix >> 20) & 7u) == 0;
+          const unsigned m = __ballot_sync(0xffffffffu, sampled);
+          if (sampled) hq[warp][qn + __popc(m & ((1u << lane) - 1u))] = k[u];
+          qn += __popc(m);
+          if (qn >= 32) {
+            __syncwarp();
+            sketch(hq[warp][qn - 32 + lane]);
+            qn -= 32;
+            __syncwarp();
+          }
         }
       }
     }
+  }
+  if (hll) {
+    __syncwarp();
+    if (lane < qn) sketch(hq[warp][lane]);
   }
   __syncthreads();
   if (segNow >= 0 && threadIdx.x < g.P && h[threadIdx.x]) atomicAdd(&hist[static_cast<int64_t>(segNow) * g.P + threadIdx.x], h[threadIdx.x]);
@@ -172,17 +196,21 @@ __global__ void part_scan2_kernel(const uint32_t* __restrict__ hist, const int64
   if (s == gridDim.x - 1) slice_start[static_cast<int64_t>(gridDim.x) * P] = run;
 }
 
-// Staged scatter of one tile per iteration: (A) digits + tile histogram, (B) local offsets and the
-// tile's reservation in every partition (one global atomic per non-empty digit), (C) keys and
-// payloads into shared memory in partition order, (D) consecutive threads store consecutive rows.
-template <int NCOLS>
-__global__ void __launch_bounds__(kPT, NCOLS <= 1 ? 3 : 2) part_scatter_kernel(const __grid_constant__ PartIO io, const __grid_constant__ PartGeom g, int64_t ntiles,
+// Staged scatter of one tile per iteration: (A) every thread loads its seven rows (keys, and payloads when
+// they fit the register budget) in one burst, digits + tile histogram, (B) local offsets and the tile's
+// reservation in every partition (one global atomic per non-empty digit), (C) keys and payloads from the
+// registers into shared memory in partition order, (D) consecutive threads store consecutive rows.
+// The input is read exactly once; its load latency is paid once per tile with all loads in flight.
+template <int NCOLS, int MINB>
+__global__ void __launch_bounds__(kPT, MINB) part_scatter_kernel(const __grid_constant__ PartIO io, const __grid_constant__ PartGeom g, int64_t ntiles,
                                                                                unsigned long long* __restrict__ cursor) {
+  constexpr int kRows = kTile / kPT;             // rows per thread and tile
+  constexpr bool kEarly = NCOLS <= 2;            // payloads loaded with the keys (three payload columns would spill)
+  static_assert(kRows * kPT == kTile && kRows <= 8, "a tile is a whole number of rows per thread; digits pack into one word");
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* skeys = reinterpret_cast<uint64_t*>(smem);
   uint64_t* scols = skeys + kTile;                                           // [ncols][kTile]
   uint8_t* sdig = reinterpret_cast<uint8_t*>(scols + static_cast<size_t>(NCOLS) * kTile);  // digit of every staged position
-  uint8_t* rdig = sdig + kTile;                                              // digit of every input position
   __shared__ uint32_t cnt[kMaxP], lofs[kMaxP], lcur[kMaxP];
   __shared__ unsigned long long gbase[kMaxP];
   __shared__ uint32_t wtot[kMaxP / 32];
@@ -194,13 +222,25 @@ __global__ void __launch_bounds__(kPT, NCOLS <= 1 ? 3 : 2) part_scatter_kernel(c
     if (!tile_range(g, tile, seg, begin, end)) break;
     const int rows = static_cast<int>(end - begin);
     if (tid < kMaxP) cnt[tid] = 0;
+    // (A) the loads first: they fly while the counters are cleared
+    uint64_t k[kRows], v[NCOLS > 0 ? NCOLS : 1][kRows];  // every index is a compile-time constant after unrolling: registers, no stack
+#pragma unroll
+    for (int u = 0; u < kRows; ++u) {
+      const int j = tid + u * kPT;
+      k[u] = j < rows ? slice_key(io.key, begin + j) : 0;
+      if (kEarly) {
+#pragma unroll
+        for (int c = 0; c < NCOLS; ++c) v[c][u] = j < rows ? io.cols_in[c][begin + j] : 0;
+      }
+    }
     __syncthreads();
-    // (A)
-#pragma unroll 4
-    for (int j = tid; j < rows; j += kPT) {
-      const int d = static_cast<int>((slice_mix(slice_key(io.key, begin + j)) >> g.shift) & (P - 1));
-      rdig[j] = static_cast<uint8_t>(d);
-      atomicAdd(&cnt[d], 1u);
+    uint64_t digits = 0;  // one byte per row of this thread
+#pragma unroll
+    for (int u = 0; u < kRows; ++u) {
+      const int j = tid + u * kPT;
+      const uint32_t d = static_cast<uint32_t>((slice_mix(k[u]) >> g.shift) & (P - 1));
+      digits |= static_cast<uint64_t>(d) << (8 * u);
+      if (j < rows) atomicAdd(&cnt[d], 1u);
     }
     __syncthreads();
     // (B) exclusive prefix of the digit counts (the first 256 threads: warp scans + warp totals)
@@ -224,30 +264,26 @@ __global__ void __launch_bounds__(kPT, NCOLS <= 1 ? 3 : 2) part_scatter_kernel(c
       lcur[tid] = before + incl - mine;
       if (mine) gbase[tid] = atomicAdd(&cursor[static_cast<int64_t>(seg) * P + tid], static_cast<unsigned long long>(mine));
     }
-    __syncthreads();
-    // (C) loads first (keys again: the tile is L1 / L2 resident; payloads for the first time), then placement
-    for (int j0 = tid; j0 < rows; j0 += 4 * kPT) {
-      uint64_t k[4], v[NCOLS > 0 ? NCOLS : 1][4];  // every index below is a compile-time constant after unrolling: registers, no stack
+    if (!kEarly) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = j0 + u * kPT;
-        if (j < rows) {
-          k[u] = slice_key(io.key, begin + j);
+      for (int u = 0; u < kRows; ++u) {
+        const int j = tid + u * kPT;
 #pragma unroll
-          for (int c = 0; c < NCOLS; ++c) v[c][u] = io.cols_in[c][begin + j];
-        }
+        for (int c = 0; c < NCOLS; ++c) v[c][u] = j < rows ? io.cols_in[c][begin + j] : 0;
       }
+    }
+    __syncthreads();
+    // (C) placement
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = j0 + u * kPT;
-        if (j < rows) {
-          const int d = rdig[j];
-          const uint32_t p = atomicAdd(&lcur[d], 1u);
-          skeys[p] = k[u];
-          sdig[p] = static_cast<uint8_t>(d);
+    for (int u = 0; u < kRows; ++u) {
+      const int j = tid + u * kPT;
+      if (j < rows) {
+        const uint32_t d = static_cast<uint32_t>(digits >> (8 * u)) & 0xffu;
+        const uint32_t p = atomicAdd(&lcur[d], 1u);
+        skeys[p] = k[u];
+        sdig[p] = static_cast<uint8_t>(d);
 #pragma unroll
-          for (int c = 0; c < NCOLS; ++c) scols[static_cast<size_t>(c) * kTile + p] = v[c][u];
-        }
+        for (int c = 0; c < NCOLS; ++c) scols[static_cast<size_t>(c) * kTile + p] = v[c][u];
       }
     }
     __syncthreads();
@@ -283,55 +319,95 @@ struct AggIO {
   int C;                   // slots per slice table (power of two)
 };
 
-__device__ __forceinline__ void smem_min_f64(uint64_t* addr, double v, bool is_min) {
-  unsigned long long* p = reinterpret_cast<unsigned long long*>(addr);
-  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p);
+// ---- shared-memory access by 32-bit shared address --------------------------------------------------
+// Through generic pointers the compiler rebuilds the CTA's shared window base (S2R SR_CgaCtaId + LEA) in front
+// of shared accesses of the probe loop; with the 32-bit address held in a register the loop is LDS / ATOMS only.
+__device__ __forceinline__ uint64_t lds_volatile_u64(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t atoms_cas_u64(uint32_t addr, uint64_t expect, uint64_t desired) {
+  uint64_t old;
+  asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr), "l"(expect), "l"(desired) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t atoms_add_u32(uint32_t addr, uint32_t x) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(x) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add_u32(uint32_t addr, uint32_t x) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(x) : "memory"); }
+__device__ __forceinline__ uint64_t atoms_add_u64(uint32_t addr, uint64_t x) {
+  uint64_t old;
+  asm volatile("atom.shared.add.u64 %0, [%1], %2;" : "=l"(old) : "r"(addr), "l"(x) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add_f64(uint32_t addr, double x) { asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(addr), "d"(x) : "memory"); }
+__device__ __forceinline__ void reds_minmax_s64(uint32_t addr, int64_t x, bool is_min) {
+  if (is_min) asm volatile("red.shared.min.s64 [%0], %1;" ::"r"(addr), "l"(x) : "memory");
+  else asm volatile("red.shared.max.s64 [%0], %1;" ::"r"(addr), "l"(x) : "memory");
+}
+__device__ __forceinline__ void smem_minmax_f64(uint32_t addr, double v, bool is_min) {
+  uint64_t old = lds_volatile_u64(addr);
   for (;;) {
     const double cur = __longlong_as_double(static_cast<long long>(old));
     const bool better = is_min ? lt_f64(v, cur) : gt_f64(v, cur);
     if (!better) return;
-    const unsigned long long seen = atomicCAS(p, old, static_cast<unsigned long long>(__double_as_longlong(v)));
+    const uint64_t seen = atoms_cas_u64(addr, old, static_cast<uint64_t>(__double_as_longlong(v)));
     if (seen == old) return;
     old = seen;
   }
 }
 
-// One accumulator update in shared memory. 64-bit shared-memory adds are compare-and-swap loops in SASS
-// (LDS + ATOMS.CAST.SPIN); 32-bit ones are native, so integer sums are carried as two halves: the low add
-// returns the old half, the carry (and the sign extension) reach the high half only when non-zero — for
-// small values almost never. A slice holds < 2^32 rows of |x| < 2^31: that 64-bit sum cannot overflow.
-__device__ __forceinline__ void slice_update(int kind, uint64_t* acc, uint64_t raw, int32_t* error_flag) {
+// One accumulator update in shared memory (acc = 32-bit shared address of the word). 64-bit shared-memory
+// integer adds are compare-and-swap loops in SASS (LDS + ATOMS.CAST.SPIN); 32-bit ones are native, so integer sums
+// are carried as two halves: the low add returns the old half, the carry (and the sign extension) reach the high
+// half only when non-zero — for small values almost never. A slice holds < 2^32 rows of |x| < 2^31: that 64-bit sum
+// cannot overflow.
+__device__ __forceinline__ void slice_update(int kind, uint32_t acc, uint64_t raw, int32_t* error_flag) {
   switch (kind) {
-    case VB2_AGG_SUM_F64: atomicAdd(reinterpret_cast<double*>(acc), __longlong_as_double(static_cast<long long>(raw))); break;
+    case VB2_AGG_SUM_F64: reds_add_f64(acc, __longlong_as_double(static_cast<long long>(raw))); break;
     case VB2_AGG_SUM_I64: case VB2_AGG_COUNT_MERGE: {
       const int64_t x = static_cast<int64_t>(raw);
       if (x == static_cast<int32_t>(x)) {
-        uint32_t* half = reinterpret_cast<uint32_t*>(acc);
         const uint32_t xl = static_cast<uint32_t>(x);
-        const uint32_t old = atomicAdd(half, xl);
+        const uint32_t old = atoms_add_u32(acc, xl);
         const uint32_t up = static_cast<uint32_t>(x >> 32) + (static_cast<uint32_t>(old + xl) < old ? 1u : 0u);
-        if (up) atomicAdd(half + 1, up);
+        if (up) reds_add_u32(acc + 4, up);
       } else {
-        const int64_t old = static_cast<int64_t>(atomicAdd(reinterpret_cast<unsigned long long*>(acc), static_cast<unsigned long long>(x)));
+        const int64_t old = static_cast<int64_t>(atoms_add_u64(acc, static_cast<uint64_t>(x)));
         int64_t r;
         if (add_overflow_i64(old, x, &r)) atomicCAS(error_flag, 0, 1);
       }
       break;
     }
-    case VB2_AGG_COUNT: atomicAdd(reinterpret_cast<uint32_t*>(acc), 1u); break;  // < 2^32 rows per slice: the low half suffices
-    case VB2_AGG_MIN_F64: smem_min_f64(acc, __longlong_as_double(static_cast<long long>(raw)), true); break;
-    case VB2_AGG_MAX_F64: smem_min_f64(acc, __longlong_as_double(static_cast<long long>(raw)), false); break;
-    case VB2_AGG_MIN_I64: atomicMin(reinterpret_cast<long long*>(acc), static_cast<long long>(raw)); break;
-    case VB2_AGG_MAX_I64: atomicMax(reinterpret_cast<long long*>(acc), static_cast<long long>(raw)); break;
+    case VB2_AGG_COUNT: reds_add_u32(acc, 1u); break;  // < 2^32 rows per slice: the low half suffices
+    case VB2_AGG_MIN_F64: smem_minmax_f64(acc, __longlong_as_double(static_cast<long long>(raw)), true); break;
+    case VB2_AGG_MAX_F64: smem_minmax_f64(acc, __longlong_as_double(static_cast<long long>(raw)), false); break;
+    case VB2_AGG_MIN_I64: reds_minmax_s64(acc, static_cast<int64_t>(raw), true); break;
+    case VB2_AGG_MAX_I64: reds_minmax_s64(acc, static_cast<int64_t>(raw), false); break;
     default: break;
   }
 }
 
+// Payload column of op o in the instantiations that fix their kinds: the o-th op that reads a column reads column o'
+// = number of column-reading ops before it (the host checks the op list has that shape, else the generic build runs).
+__host__ __device__ constexpr int fixed_col(uint32_t kinds, int o) {
+  int c = 0;
+  for (int i = 0; i < o; ++i)
+    if (((kinds >> (4 * i)) & 15u) != VB2_AGG_COUNT) ++c;
+  return c;
+}
+
 // NOPS accumulator words per slot (compile time: the op descriptors live in registers, the loops unroll).
+// KINDS: four bits per op holding its vb2_agg_kind when the instantiation fixes it (the update switch and the
+// column select fold away), 0 = read from the descriptor at run time. The generic build carries every case of
+// every op four times over; the common op lists get their own straight-line builds.
 // Output rows are reserved from the global cursor in chunks: a block asks for a new chunk only when the
 // groups of its next slice do not fit the rest of its current one, so the round trip of a global atomic is
 // paid once per few dozen slices; the unused tail of a chunk stays EMPTY rows of the table-shaped output.
-template <int NOPS>
+template <int NOPS, uint32_t KINDS>
 __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __grid_constant__ AggIO a) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* skey = reinterpret_cast<uint64_t*>(smem);  // [C]
@@ -340,8 +416,12 @@ __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __gr
   __shared__ unsigned int s_count, s_cursor;
   __shared__ unsigned long long s_base, s_chunk_pos, s_chunk_left, s_groups;
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
   const int C = a.C;
   const uint32_t cmask = static_cast<uint32_t>(C - 1);
+  uint32_t skey_s = static_cast<uint32_t>(__cvta_generic_to_shared(skey));
+  asm volatile("mov.u32 %0, %0;" : "+r"(skey_s));  // opaque: kept in a register instead of being rebuilt from SR_CgaCtaId at every use
+  const uint32_t sacc_s = skey_s + static_cast<uint32_t>(C) * 8u;
   int kind[NOPS], col[NOPS], word[NOPS];
   uint64_t init[NOPS];
 #pragma unroll
@@ -362,6 +442,7 @@ __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __gr
     }
     if (tid == 0) { s_overflow = 0; s_count = 0; s_cursor = 0; }
     __syncthreads();
+    int fresh = 0;  // groups this thread inserted
     for (int64_t i0 = begin + tid; i0 < end; i0 += 4 * kAggThreads) {
       uint64_t k[4], v[kCols][4];
       // loads of four rows in flight before any probe
@@ -383,10 +464,10 @@ __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __gr
         uint32_t slot = static_cast<uint32_t>(slice_mix(key) >> 34) & cmask;  // bits below the ones that chose the slice
         bool found = false;
         for (int probes = 0; probes < C; ++probes) {
-          uint64_t cur = *reinterpret_cast<volatile uint64_t*>(skey + slot);
+          uint64_t cur = lds_volatile_u64(skey_s + slot * 8u);
           if (cur == VB2_EMPTY_KEY) {
-            cur = atomicCAS(reinterpret_cast<unsigned long long*>(skey + slot), static_cast<unsigned long long>(VB2_EMPTY_KEY), static_cast<unsigned long long>(key));
-            if (cur == VB2_EMPTY_KEY) { atomicAdd(&s_count, 1u); cur = key; }  // a new group of this slice
+            cur = atoms_cas_u64(skey_s + slot * 8u, VB2_EMPTY_KEY, key);
+            if (cur == VB2_EMPTY_KEY) { ++fresh; cur = key; }  // a new group of this slice
           }
           if (cur == key) { found = true; break; }
           slot = (slot + 1) & cmask;
@@ -394,11 +475,16 @@ __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __gr
         if (!found) { s_overflow = 1; continue; }
 #pragma unroll
         for (int o = 0; o < NOPS; ++o) {
-          const uint64_t raw = col[o] == 0 ? v[0][u] : (col[o] == 1 ? v[1][u] : (col[o] == 2 ? v[2][u] : 0));  // constant indices: registers
-          slice_update(kind[o], sacc + o * C + slot, raw, a.error_flag);
+          const int fixed = static_cast<int>((KINDS >> (4 * o)) & 15u);  // constants once the op loop is unrolled
+          const int fcol = fixed_col(KINDS, o);
+          const int cl = KINDS ? fcol : col[o];
+          const uint64_t raw = cl == 0 ? v[0][u] : (cl == 1 ? v[1][u] : (cl == 2 ? v[2][u] : 0));  // constant indices: registers
+          slice_update(fixed ? fixed : kind[o], sacc_s + (static_cast<uint32_t>(o) * C + slot) * 8u, raw, a.error_flag);
         }
       }
     }
+    fresh = warp_sum(fresh);
+    if (lane == 0 && fresh) atomicAdd(&s_count, static_cast<unsigned>(fresh));
     __syncthreads();
     if (tid == 0) {
       const unsigned long long n = s_count;
@@ -416,10 +502,17 @@ __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __gr
     }
     __syncthreads();
     if (static_cast<int64_t>(s_base + s_count) <= a.rows_capacity) {
-      for (int i = tid; i < C; i += kAggThreads) {
-        const uint64_t key = skey[i];
-        if (key == VB2_EMPTY_KEY) continue;
-        uint64_t* row = a.rows_out + (s_base + atomicAdd(&s_cursor, 1u)) * static_cast<unsigned long long>(a.row_words);
+      for (int i0 = 0; i0 < C; i0 += kAggThreads) {  // block-uniform trip count: whole warps reach the ballot
+        const int i = i0 + tid;
+        const uint64_t key = i < C ? skey[i] : VB2_EMPTY_KEY;
+        const bool live = key != VB2_EMPTY_KEY;
+        // one shared-memory atomic per warp: the occupied slots of a warp take consecutive output rows
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        unsigned first = 0;
+        if (lane == 0 && m) first = atomicAdd(&s_cursor, static_cast<unsigned>(__popc(m)));
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (!live) continue;
+        uint64_t* row = a.rows_out + (s_base + first + __popc(m & ((1u << lane) - 1u))) * static_cast<unsigned long long>(a.row_words);
         row[0] = key;
         for (int w = 1; w < a.row_words; ++w) row[w] = a.row_init[w];
 #pragma unroll
@@ -480,24 +573,41 @@ int64_t output_chunk_rows(int64_t distinct_estimate) {
   const int64_t per = distinct_estimate / (static_cast<int64_t>(device_sm_count()) * 2 * 4);
   return per < 256 ? 256 : (per > 16384 ? 16384 : per);
 }
-size_t scatter_smem(int ncols) { return static_cast<size_t>(kTile) * 8 * (1 + ncols) + 2 * kTile; }
+size_t scatter_smem(int ncols) { return static_cast<size_t>(kTile) * 8 * (1 + ncols) + kTile; }
+// CTAs per SM of the scatter: three for at most one payload column (61 KB tiles; the 42-register cap spills a
+// few words per tile), two otherwise. VB2_SLICE_SCATTER_CTAS=2 selects the spill-free two-CTA build of the
+// narrow kernels (measurement aid).
+int scatter_ctas(int ncols) {
+  static const int forced = [] { const char* e = std::getenv("VB2_SLICE_SCATTER_CTAS"); return e ? std::atoi(e) : 0; }();
+  if (ncols > 1) return 2;
+  return forced == 2 ? 2 : 3;
+}
 int configure_scatter() {
   static bool configured = false;
   if (configured) return VB2_OK;
-  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(0))));
-  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(1))));
-  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(2))));
-  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(3))));
+  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(0))));
+  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(1))));
+  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(0))));
+  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(1))));
+  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(2))));
+  VB2_CUDA_OK(cudaFuncSetAttribute(part_scatter_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem(3))));
   configured = true;
   return VB2_OK;
 }
 void launch_scatter(const PartIO& io, const PartGeom& g, int64_t ntiles, unsigned long long* cursor, unsigned grid, cudaStream_t st) {
   const size_t smem = scatter_smem(io.ncols);
+  const bool three = scatter_ctas(io.ncols) == 3;
   switch (io.ncols) {
-    case 0: part_scatter_kernel<0><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor); break;
-    case 1: part_scatter_kernel<1><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor); break;
-    case 2: part_scatter_kernel<2><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor); break;
-    default: part_scatter_kernel<3><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor);
+    case 0:
+      if (three) part_scatter_kernel<0, 3><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor);
+      else part_scatter_kernel<0, 2><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor);
+      break;
+    case 1:
+      if (three) part_scatter_kernel<1, 3><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor);
+      else part_scatter_kernel<1, 2><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor);
+      break;
+    case 2: part_scatter_kernel<2, 2><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor); break;
+    default: part_scatter_kernel<3, 2><<<counted(grid), kPT, smem, st>>>(io, g, ntiles, cursor);
   }
 }
 
@@ -553,7 +663,7 @@ int vb2k_slice_agg_partition(const vb2_slice_chunk* chunks, int32_t nchunks, int
       io.cols_out[c] = w.colsA[c];
     }
     const int64_t ntiles = (chunks[i].rows + kTile - 1) / kTile;
-    const int64_t cap = static_cast<int64_t>(sms) * (ncols <= 1 ? 3 : 2);
+    const int64_t cap = static_cast<int64_t>(sms) * scatter_ctas(ncols);
     launch_scatter(io, geom_of(chunks[i].rows), ntiles, w.cursor1, static_cast<unsigned>(ntiles < cap ? ntiles : cap), st);
   }
   VB2_CUDA_OK(cudaGetLastError());
@@ -613,7 +723,7 @@ int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_es
       io.cols_in[c] = w.colsA[c];
       io.cols_out[c] = w.colsB[c];
     }
-    const int64_t scap = static_cast<int64_t>(sms) * (ncols <= 1 ? 3 : 2);
+    const int64_t scap = static_cast<int64_t>(sms) * scatter_ctas(ncols);
     launch_scatter(io, g, ntiles, w.cursor2, static_cast<unsigned>(ntiles < scap ? ntiles : scap), st);
     a.keys = w.keysB;
     for (int c = 0; c < ncols; ++c) a.cols[c] = w.colsB[c];
@@ -643,20 +753,36 @@ int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_es
   const size_t smem = static_cast<size_t>(C) * 8 * (1 + nops);
   const int64_t acap = static_cast<int64_t>(sms) * 2;
   const unsigned grid = static_cast<unsigned>(a.nslices < acap ? a.nslices : acap);
-#define VB2_SLICE_AGG(N)                                                                                                          \
-  case N: {                                                                                                                       \
-    static size_t configured = 0;                                                                                                 \
-    if (smem > configured) {                                                                                                      \
-      VB2_CUDA_OK(cudaFuncSetAttribute(slice_aggregate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-      configured = smem;                                                                                                          \
-    }                                                                                                                             \
-    slice_aggregate_kernel<N><<<counted(grid), kAggThreads, smem, st>>>(a);                                                       \
-    break;                                                                                                                        \
+  // packed kinds of this op list (<= 8 ops x 4 bits)
+  uint32_t packed = 0;
+  for (int o = 0; o < nops; ++o) packed |= static_cast<uint32_t>(ops[o].kind & 15) << (4 * o);
+  static const bool genericOnly = [] { const char* e = std::getenv("VB2_SLICE_GENERIC_AGG"); return e && e[0] == '1'; }();
+#define VB2_SLICE_LAUNCH(N, K)                                                                                                       \
+  {                                                                                                                                 \
+    static size_t configured = 0;                                                                                                   \
+    if (smem > configured) {                                                                                                        \
+      VB2_CUDA_OK(cudaFuncSetAttribute(slice_aggregate_kernel<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+      configured = smem;                                                                                                            \
+    }                                                                                                                               \
+    slice_aggregate_kernel<N, K><<<counted(grid), kAggThreads, smem, st>>>(a);                                                      \
   }
-  switch (nops) {
-    VB2_SLICE_AGG(1) VB2_SLICE_AGG(2) VB2_SLICE_AGG(3) VB2_SLICE_AGG(4) VB2_SLICE_AGG(5) VB2_SLICE_AGG(6) VB2_SLICE_AGG(7) VB2_SLICE_AGG(8)
-  }
+#define VB2_SLICE_FIXED(N, K) \
+  if (!launched && !genericOnly && nops == N && packed == K) { VB2_SLICE_LAUNCH(N, K) launched = true; }
+#define VB2_SLICE_AGG(N) \
+  case N: VB2_SLICE_LAUNCH(N, 0u) break;
+  bool launched = false;
+  // kinds: 1 SUM_F64, 2 SUM_I64, 3 COUNT, 4 / 5 MIN / MAX F64, 6 / 7 MIN / MAX I64, 8 COUNT_MERGE (op 0 in the low nibble)
+  VB2_SLICE_FIXED(1, 0x1u) VB2_SLICE_FIXED(1, 0x2u) VB2_SLICE_FIXED(1, 0x3u) VB2_SLICE_FIXED(1, 0x8u)
+  VB2_SLICE_FIXED(2, 0x32u) VB2_SLICE_FIXED(2, 0x31u) VB2_SLICE_FIXED(2, 0x82u) VB2_SLICE_FIXED(2, 0x81u)
+  VB2_SLICE_FIXED(2, 0x11u) VB2_SLICE_FIXED(2, 0x22u) VB2_SLICE_FIXED(2, 0x54u) VB2_SLICE_FIXED(2, 0x76u)
+  VB2_SLICE_FIXED(3, 0x332u) VB2_SLICE_FIXED(3, 0x331u) VB2_SLICE_FIXED(3, 0x882u) VB2_SLICE_FIXED(3, 0x881u)
+  if (!launched)
+    switch (nops) {
+      VB2_SLICE_AGG(1) VB2_SLICE_AGG(2) VB2_SLICE_AGG(3) VB2_SLICE_AGG(4) VB2_SLICE_AGG(5) VB2_SLICE_AGG(6) VB2_SLICE_AGG(7) VB2_SLICE_AGG(8)
+    }
 #undef VB2_SLICE_AGG
+#undef VB2_SLICE_FIXED
+#undef VB2_SLICE_LAUNCH
   VB2_CUDA_OK(cudaGetLastError());
   return VB2_OK;
 }
