@@ -588,12 +588,15 @@ struct B200HashAggregation::Impl {
       const int64_t n = in->size();
       if (!eligible || sawGeneric || n < cfg.get<int64_t>("b200.agg_slice_min_rows", 1 << 23)) return false;
       // distinct keys of this batch (HyperLogLog over the raw keys: the hash of v - min + 1 with any min sketches the same count)
+      // over the first 64 M rows at most: a prefix with that many distinct keys settles the question, and the sketch pass
+      // stays a fraction of a millisecond
       const vb2_column& k = in->column(resolved.keys[0])->desc;
-      const size_t wsBytes = vb2k_radix_workspace_bytes(n);
+      const int64_t probe = std::min<int64_t>(n, 64ll << 20);
+      const size_t wsBytes = vb2k_radix_workspace_bytes(probe);
       auto ws = allocDevice(wsBytes, st());
       const int32_t nregs = vb2k_radix_hll_registers();
       auto hll = allocDevice(static_cast<size_t>(nregs) * 4, st());
-      kernelCheck(vb2k_radix_histogram(nullptr, k.values, 1, 0, n, ws->data(), wsBytes, hll->as<int32_t>(), st()));
+      kernelCheck(vb2k_radix_histogram(nullptr, k.values, 1, 0, probe, ws->data(), wsBytes, hll->as<int32_t>(), st()));
       std::vector<int32_t> regs(nregs);
       VB2_CU(cudaMemcpyAsync(regs.data(), hll->data(), static_cast<size_t>(nregs) * 4, cudaMemcpyDeviceToHost, st()));
       VB2_CU(cudaStreamSynchronize(st()));

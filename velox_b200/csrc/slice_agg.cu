@@ -42,7 +42,15 @@ struct SliceKey {
   const int64_t* raw;
   int64_t min;           // normalized key = raw - min + 1 (vb2k_normalize_keys with one column)
 };
-__device__ __forceinline__ uint64_t slice_key(const SliceKey& k, int64_t r) { return k.norm ? k.norm[r] : static_cast<uint64_t>(k.raw[r] - k.min) + 1; }
+// Per tile: a base pointer and one subtrahend (normalized key = word - sub), so that the row loops index
+// with 32-bit in-tile offsets and carry no per-row branch on the key form.
+struct TileKeys {
+  const uint64_t* p;
+  uint64_t sub;
+};
+__device__ __forceinline__ TileKeys tile_keys(const SliceKey& k, int64_t begin) {
+  return k.norm ? TileKeys{k.norm + begin, 0} : TileKeys{reinterpret_cast<const uint64_t*>(k.raw) + begin, static_cast<uint64_t>(k.min) - 1};
+}
 // Every row is hashed four times on its way (two histograms, two scatters): twang_mix64 costs ~40 32-bit
 // instructions and made those passes issue-bound, so the slice path places rows with a Fibonacci hash —
 // one 64-bit multiply. Bits 63..56 pick the level-1 partition, the next log2(P2) bits the slice, bits
@@ -64,8 +72,22 @@ struct PartGeom {
   int P, shift;               // digit = (slice_mix(key) >> shift) & (P - 1)
 };
 
+// Segment table of a level-2 pass in shared memory: every tile looks its segment up (a binary search of eight
+// dependent loads), which from global memory cost about as much as streaming the tile itself.
+struct SegTable {
+  int64_t seg_start[kP1 + 1];
+  int32_t tile_start[kP1 + 1];
+};
+__device__ __forceinline__ void load_seg_table(const PartGeom& g, SegTable& t) {
+  if (!g.seg_start) return;
+  for (int i = threadIdx.x; i <= g.nseg; i += blockDim.x) {
+    t.seg_start[i] = g.seg_start[i];
+    t.tile_start[i] = g.tile_start[i];
+  }
+  __syncthreads();
+}
 // rows [begin, end) and segment of a tile; false past the last tile (tiles are ordered: every later tile is past it too)
-__device__ __forceinline__ bool tile_range(const PartGeom& g, int64_t tile, int& seg, int64_t& begin, int64_t& end) {
+__device__ __forceinline__ bool tile_range(const PartGeom& g, const SegTable& t, int64_t tile, int& seg, int64_t& begin, int64_t& end) {
   if (!g.seg_start) {
     seg = 0;
     begin = tile * kTile;
@@ -73,16 +95,16 @@ __device__ __forceinline__ bool tile_range(const PartGeom& g, int64_t tile, int&
     end = begin + kTile < g.n ? begin + kTile : g.n;
     return true;
   }
-  if (tile >= g.tile_start[g.nseg]) return false;
+  if (tile >= t.tile_start[g.nseg]) return false;
   int lo = 0, hi = g.nseg;  // tile_start[lo] <= tile < tile_start[hi]
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
-    if (g.tile_start[mid] <= tile) lo = mid;
+    if (t.tile_start[mid] <= tile) lo = mid;
     else hi = mid;
   }
   seg = lo;
-  begin = g.seg_start[seg] + (tile - g.tile_start[seg]) * kTile;
-  const int64_t segEnd = g.seg_start[seg + 1];
+  begin = t.seg_start[seg] + (tile - t.tile_start[seg]) * kTile;
+  const int64_t segEnd = t.seg_start[seg + 1];
   end = begin + kTile < segEnd ? begin + kTile : segEnd;
   return true;
 }
@@ -98,6 +120,8 @@ __global__ void __launch_bounds__(kPT) part_hist_kernel(const __grid_constant__ 
   // with every lane busy (one row in eight is sampled: hashing in place would run its ~40 instructions for
   // nearly every warp iteration with four lanes active).
   __shared__ uint64_t hq[kPT / 32][64];
+  __shared__ SegTable segs;
+  load_seg_table(g, segs);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int qn = 0;  // warp-uniform
   auto sketch = [&](uint64_t k) {
@@ -116,7 +140,7 @@ __global__ void __launch_bounds__(kPT) part_hist_kernel(const __grid_constant__ 
   for (int64_t tile = t0; tile < t1; ++tile) {
     int seg;
     int64_t begin, end;
-    if (!tile_range(g, tile, seg, begin, end)) break;
+    if (!tile_range(g, segs, tile, seg, begin, end)) break;
     if (seg != segNow) {
       if (segNow >= 0) {
         __syncthreads();
@@ -126,31 +150,36 @@ __global__ void __launch_bounds__(kPT) part_hist_kernel(const __grid_constant__ 
       }
       segNow = seg;
     }
-    for (int64_t base = begin; base < end; base += 4 * kPT) {  // block-uniform trip count: the ballots below see whole warps
-      uint64_t k[4];  // four loads in flight per thread before the shared-memory atomics
+    const TileKeys tk = tile_keys(key, begin);
+    const int rows = static_cast<int>(end - begin);
+    constexpr int kRows = kTile / kPT;
+    uint64_t k[kRows];
+    if (rows == kTile) {  // full tile: every load in flight at once, no bounds checks
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t i = base + threadIdx.x + static_cast<int64_t>(u) * kPT;
-        k[u] = i < end ? slice_key(key, i) : 0;
+      for (int u = 0; u < kRows; ++u) k[u] = tk.p[threadIdx.x + u * kPT] - tk.sub;
+    } else {
+#pragma unroll
+      for (int u = 0; u < kRows; ++u) {
+        const int j = threadIdx.x + u * kPT;
+        k[u] = j < rows ? tk.p[j] - tk.sub : 0;
       }
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t i = base + threadIdx.x + static_cast<int64_t>(u) * kPT;
-        const bool live = i < end;
-        const uint64_t mix = slice_mix(k[u]);
-        if (live) atomicAdd(&h[(mix >> g.shift) & (g.P - 1)], 1u);
-        if (hll) {
-          // one key in eight feeds the sketch, through the strong hash (the convention of radix_partition.cu: x 8 on the host)
-          const bool sampled = live && ((mix >> 20) & 7u) == 0;
-          const unsigned m = __ballot_sync(0xffffffffu, sampled);
-          if (sampled) hq[warp][qn + __popc(m & ((1u << lane) - 1u))] = k[u];
-          qn += __popc(m);
-          if (qn >= 32) {
-            __syncwarp();
-            sketch(hq[warp][qn - 32 + lane]);
-            qn -= 32;
-            __syncwarp();
-          }
+    for (int u = 0; u < kRows; ++u) {  // block-uniform trip count: the ballots below see whole warps
+      const bool live = static_cast<int>(threadIdx.x) + u * kPT < rows;
+      const uint64_t mix = slice_mix(k[u]);
+      if (live) atomicAdd(&h[(mix >> g.shift) & (g.P - 1)], 1u);
+      if (hll) {
+        // one key in eight feeds the sketch, through the strong hash (the convention of radix_partition.cu: x 8 on the host)
+        const bool sampled = live && ((mix >> 20) & 7u) == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, sampled);
+        if (sampled) hq[warp][qn + __popc(m & ((1u << lane) - 1u))] = k[u];
+        qn += __popc(m);
+        if (qn >= 32) {
+          __syncwarp();
+          sketch(hq[warp][qn - 32 + lane]);
+          qn -= 32;
+          __syncwarp();
         }
       }
     }
@@ -200,47 +229,68 @@ __global__ void part_scan2_kernel(const uint32_t* __restrict__ hist, const int64
 // they fit the register budget) in one burst, digits + tile histogram, (B) local offsets and the tile's
 // reservation in every partition (one global atomic per non-empty digit), (C) keys and payloads from the
 // registers into shared memory in partition order, (D) consecutive threads store consecutive rows.
-// The input is read exactly once; its load latency is paid once per tile with all loads in flight.
+// The input is read exactly once; its load latency is paid once per tile with all loads in flight. Full tiles
+// (all but the last of a chunk / segment) run without bounds checks; with one payload column a staged row is one
+// 16-byte shared-memory word (one STS.128 / LDS.128 instead of two 8-byte accesses each way).
 template <int NCOLS, int MINB>
 __global__ void __launch_bounds__(kPT, MINB) part_scatter_kernel(const __grid_constant__ PartIO io, const __grid_constant__ PartGeom g, int64_t ntiles,
                                                                                unsigned long long* __restrict__ cursor) {
   constexpr int kRows = kTile / kPT;             // rows per thread and tile
   constexpr bool kEarly = NCOLS <= 2;            // payloads loaded with the keys (three payload columns would spill)
+  constexpr bool kPair = NCOLS == 1;             // staged rows are (key, payload) pairs
   static_assert(kRows * kPT == kTile && kRows <= 8, "a tile is a whole number of rows per thread; digits pack into one word");
   extern __shared__ __align__(16) uint8_t smem[];
   uint64_t* skeys = reinterpret_cast<uint64_t*>(smem);
   uint64_t* scols = skeys + kTile;                                           // [ncols][kTile]
+  ulonglong2* spair = reinterpret_cast<ulonglong2*>(smem);                   // kPair: [kTile] (key, payload)
   uint8_t* sdig = reinterpret_cast<uint8_t*>(scols + static_cast<size_t>(NCOLS) * kTile);  // digit of every staged position
-  __shared__ uint32_t cnt[kMaxP], lofs[kMaxP], lcur[kMaxP];
-  __shared__ unsigned long long gbase[kMaxP];
+  __shared__ uint32_t cnt[kMaxP], lcur[kMaxP];
+  __shared__ unsigned long long gdelta[kMaxP];   // global position of staged position p of digit d = gdelta[d] + p
   __shared__ uint32_t wtot[kMaxP / 32];
+  __shared__ SegTable segs;
+  load_seg_table(g, segs);
   const int tid = threadIdx.x;
   const int P = g.P;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int seg;
     int64_t begin, end;
-    if (!tile_range(g, tile, seg, begin, end)) break;
+    if (!tile_range(g, segs, tile, seg, begin, end)) break;
     const int rows = static_cast<int>(end - begin);
+    const bool full = rows == kTile;
     if (tid < kMaxP) cnt[tid] = 0;
     // (A) the loads first: they fly while the counters are cleared
+    const TileKeys tk = tile_keys(io.key, begin);
     uint64_t k[kRows], v[NCOLS > 0 ? NCOLS : 1][kRows];  // every index is a compile-time constant after unrolling: registers, no stack
+    if (full) {
 #pragma unroll
-    for (int u = 0; u < kRows; ++u) {
-      const int j = tid + u * kPT;
-      k[u] = j < rows ? slice_key(io.key, begin + j) : 0;
+      for (int u = 0; u < kRows; ++u) k[u] = tk.p[tid + u * kPT] - tk.sub;
       if (kEarly) {
 #pragma unroll
-        for (int c = 0; c < NCOLS; ++c) v[c][u] = j < rows ? io.cols_in[c][begin + j] : 0;
+        for (int c = 0; c < NCOLS; ++c) {
+          const uint64_t* cp = io.cols_in[c] + begin;
+#pragma unroll
+          for (int u = 0; u < kRows; ++u) v[c][u] = cp[tid + u * kPT];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kRows; ++u) {
+        const int j = tid + u * kPT;
+        k[u] = j < rows ? tk.p[j] - tk.sub : 0;
+        if (kEarly) {
+#pragma unroll
+          for (int c = 0; c < NCOLS; ++c) v[c][u] = j < rows ? io.cols_in[c][begin + j] : 0;
+        }
       }
     }
+    // (An L2 prefetch of this block's next tile at this point was measured: no gain at level 1, 5 % slower at level 2.)
     __syncthreads();
     uint64_t digits = 0;  // one byte per row of this thread
 #pragma unroll
     for (int u = 0; u < kRows; ++u) {
-      const int j = tid + u * kPT;
       const uint32_t d = static_cast<uint32_t>((slice_mix(k[u]) >> g.shift) & (P - 1));
       digits |= static_cast<uint64_t>(d) << (8 * u);
-      if (j < rows) atomicAdd(&cnt[d], 1u);
+      if (full || tid + u * kPT < rows) atomicAdd(&cnt[d], 1u);
     }
     __syncthreads();
     // (B) exclusive prefix of the digit counts (the first 256 threads: warp scans + warp totals)
@@ -260,9 +310,9 @@ __global__ void __launch_bounds__(kPT, MINB) part_scatter_kernel(const __grid_co
     if (tid < kMaxP) {
       uint32_t before = 0;
       for (int w = 0; w < (tid >> 5); ++w) before += wtot[w];
-      lofs[tid] = before + incl - mine;
-      lcur[tid] = before + incl - mine;
-      if (mine) gbase[tid] = atomicAdd(&cursor[static_cast<int64_t>(seg) * P + tid], static_cast<unsigned long long>(mine));
+      const uint32_t lofs = before + incl - mine;
+      lcur[tid] = lofs;
+      if (mine) gdelta[tid] = atomicAdd(&cursor[static_cast<int64_t>(seg) * P + tid], static_cast<unsigned long long>(mine)) - lofs;
     }
     if (!kEarly) {
 #pragma unroll
@@ -276,24 +326,36 @@ __global__ void __launch_bounds__(kPT, MINB) part_scatter_kernel(const __grid_co
     // (C) placement
 #pragma unroll
     for (int u = 0; u < kRows; ++u) {
-      const int j = tid + u * kPT;
-      if (j < rows) {
+      if (full || tid + u * kPT < rows) {
         const uint32_t d = static_cast<uint32_t>(digits >> (8 * u)) & 0xffu;
         const uint32_t p = atomicAdd(&lcur[d], 1u);
-        skeys[p] = k[u];
         sdig[p] = static_cast<uint8_t>(d);
+        if (kPair) {
+          spair[p] = make_ulonglong2(k[u], v[0][u]);
+        } else {
+          skeys[p] = k[u];
 #pragma unroll
-        for (int c = 0; c < NCOLS; ++c) scols[static_cast<size_t>(c) * kTile + p] = v[c][u];
+          for (int c = 0; c < NCOLS; ++c) scols[static_cast<size_t>(c) * kTile + p] = v[c][u];
+        }
       }
     }
     __syncthreads();
     // (D)
-    for (int p = tid; p < rows; p += kPT) {
-      const int d = sdig[p];
-      const unsigned long long out = gbase[d] + (p - lofs[d]);
-      io.keys_out[out] = skeys[p];
 #pragma unroll
-      for (int c = 0; c < NCOLS; ++c) io.cols_out[c][out] = scols[static_cast<size_t>(c) * kTile + p];
+    for (int u = 0; u < kRows; ++u) {
+      const int p = tid + u * kPT;
+      if (full || p < rows) {
+        const unsigned long long out = gdelta[sdig[p]] + static_cast<unsigned>(p);
+        if (kPair) {
+          const ulonglong2 r = spair[p];
+          io.keys_out[out] = r.x;
+          io.cols_out[0][out] = r.y;
+        } else {
+          io.keys_out[out] = skeys[p];
+#pragma unroll
+          for (int c = 0; c < NCOLS; ++c) io.cols_out[c][out] = scols[static_cast<size_t>(c) * kTile + p];
+        }
+      }
     }
     __syncthreads();
   }
@@ -435,6 +497,23 @@ __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __gr
   for (int s = blockIdx.x; s < a.nslices; s += gridDim.x) {
     const int64_t begin = a.slice_start[s], end = a.slice_start[s + 1];
     if (begin == end) continue;  // uniform across the block
+    // The first rows of the slice are requested before the table is cleared, and the rows of iteration i + 1 before
+    // iteration i is processed: the global-load latency (the largest single stall of the one-buffer version,
+    // paid by every warp at the same time behind the per-slice barriers) overlaps shared-memory work.
+    uint64_t nk[4], nv[kCols][4];
+    auto request = [&](int64_t i0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + static_cast<int64_t>(u) * kAggThreads;
+        if (i < end) {
+          nk[u] = a.keys[i];
+#pragma unroll
+          for (int c = 0; c < kCols; ++c)
+            if (a.cols[c]) nv[c][u] = a.cols[c][i];
+        }
+      }
+    };
+    request(begin + tid);
     for (int i = tid; i < C; i += kAggThreads) {
       skey[i] = VB2_EMPTY_KEY;
 #pragma unroll
@@ -443,36 +522,42 @@ __global__ void __launch_bounds__(kAggThreads) slice_aggregate_kernel(const __gr
     if (tid == 0) { s_overflow = 0; s_count = 0; s_cursor = 0; }
     __syncthreads();
     int fresh = 0;  // groups this thread inserted
-    for (int64_t i0 = begin + tid; i0 < end; i0 += 4 * kAggThreads) {
+    // warp-uniform trip count (the probe loop below votes): every lane of a warp walks the same number of iterations
+    const int64_t warp0 = begin + (tid & ~31);
+    for (int64_t w0 = warp0; w0 < end; w0 += 4 * kAggThreads) {
+      const int64_t i0 = w0 + lane;
       uint64_t k[4], v[kCols][4];
-      // loads of four rows in flight before any probe
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int64_t i = i0 + static_cast<int64_t>(u) * kAggThreads;
-        if (i < end) {
-          k[u] = a.keys[i];
+        k[u] = nk[u];
 #pragma unroll
-          for (int c = 0; c < kCols; ++c)
-            if (a.cols[c]) v[c][u] = a.cols[c][i];
-        }
+        for (int c = 0; c < kCols; ++c) v[c][u] = nv[c][u];
       }
+      request(i0 + 4 * kAggThreads);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int64_t i = i0 + static_cast<int64_t>(u) * kAggThreads;
-        if (i >= end) continue;
+        const bool live = i < end;
         const uint64_t key = k[u];
         uint32_t slot = static_cast<uint32_t>(slice_mix(key) >> 34) & cmask;  // bits below the ones that chose the slice
-        bool found = false;
-        for (int probes = 0; probes < C; ++probes) {
-          uint64_t cur = lds_volatile_u64(skey_s + slot * 8u);
-          if (cur == VB2_EMPTY_KEY) {
-            cur = atoms_cas_u64(skey_s + slot * 8u, VB2_EMPTY_KEY, key);
-            if (cur == VB2_EMPTY_KEY) { ++fresh; cur = key; }  // a new group of this slice
+        // Convergent probe: the warp loops until every live lane has its slot, then all lanes update together
+        // (with the exit inside the loop the compiler duplicated the update into it and ran it once per probe round,
+        // half the lanes idle).
+        bool done = !live;
+        int probes = 0;
+        while (!__all_sync(0xffffffffu, done)) {
+          if (!done) {
+            uint64_t cur = lds_volatile_u64(skey_s + slot * 8u);
+            if (cur == VB2_EMPTY_KEY) {
+              cur = atoms_cas_u64(skey_s + slot * 8u, VB2_EMPTY_KEY, key);
+              if (cur == VB2_EMPTY_KEY) { ++fresh; cur = key; }  // a new group of this slice
+            }
+            if (cur == key) done = true;
+            else if (++probes >= C) { s_overflow = 1; done = true; slot = 0xffffffffu; }
+            else slot = (slot + 1) & cmask;
           }
-          if (cur == key) { found = true; break; }
-          slot = (slot + 1) & cmask;
         }
-        if (!found) { s_overflow = 1; continue; }
+        if (!live || slot == 0xffffffffu) continue;
 #pragma unroll
         for (int o = 0; o < NOPS; ++o) {
           const int fixed = static_cast<int>((KINDS >> (4 * o)) & 15u);  // constants once the op loop is unrolled
@@ -574,13 +659,13 @@ int64_t output_chunk_rows(int64_t distinct_estimate) {
   return per < 256 ? 256 : (per > 16384 ? 16384 : per);
 }
 size_t scatter_smem(int ncols) { return static_cast<size_t>(kTile) * 8 * (1 + ncols) + kTile; }
-// CTAs per SM of the scatter: three for at most one payload column (61 KB tiles; the 42-register cap spills a
-// few words per tile), two otherwise. VB2_SLICE_SCATTER_CTAS=2 selects the spill-free two-CTA build of the
-// narrow kernels (measurement aid).
+// CTAs per SM of the scatter: two (spill-free at 56-64 registers; measured 2.4 ms faster over 1 B rows than three
+// CTAs under a 42-register cap that spills a few words per tile). VB2_SLICE_SCATTER_CTAS=3 selects the three-CTA
+// build of the narrow kernels (measurement aid).
 int scatter_ctas(int ncols) {
   static const int forced = [] { const char* e = std::getenv("VB2_SLICE_SCATTER_CTAS"); return e ? std::atoi(e) : 0; }();
   if (ncols > 1) return 2;
-  return forced == 2 ? 2 : 3;
+  return forced == 3 ? 3 : 2;
 }
 int configure_scatter() {
   static bool configured = false;
