@@ -31,6 +31,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "hashing.hpp"
@@ -793,6 +794,7 @@ struct AggSpec {
   int input = -1;  // input column (raw) or first intermediate column
   int mask = -1;
   int in_type = ORC_BIGINT;
+  bool distinct = false;  // AggregationNode::Aggregate::distinct (core/PlanNode.h:1152)
 };
 
 struct Node;
@@ -885,6 +887,7 @@ static NodePtr parse_plan(const SNode& s) {
       for (size_t j = 0; j < a.nargs(); ++j) {
         if (a.arg(j).is_list) {
           if (a.arg(j).head() == "mask") spec.mask = std::stoi(a.arg(j).arg(0).atom);
+          else if (a.arg(j).head() == "distinct") spec.distinct = true;
         } else {
           spec.input = std::stoi(a.arg(j).atom);
         }
@@ -1119,6 +1122,12 @@ struct Accumulator {
   std::vector<double> dsum;
   std::vector<int64_t> isum, cnt;
   std::vector<uint8_t> has;
+  // DISTINCT aggregates (exec/DistinctAggregations.cpp: a set of the group's inputs, whose values reach the
+  // function once each, in first-seen order): (group, canonical value bits) pairs seen so far.
+  struct PairHash {
+    size_t operator()(const std::pair<int32_t, uint64_t>& p) const { return twang_mix64(p.second ^ (static_cast<uint64_t>(p.first) * 0x9E3779B97F4A7C15ull)); }
+  };
+  std::unordered_set<std::pair<int32_t, uint64_t>, PairHash> seen;
   void grow(size_t g) { dsum.resize(g, 0); isum.resize(g, 0); cnt.resize(g, 0); has.resize(g, 0); }
 };
 
@@ -1247,7 +1256,33 @@ struct GroupBy {
     VecPtr in = s.input >= 0 ? flatten(b.cols[s.input]) : nullptr;
     VecPtr in2 = (!raw && s.fn == "avg") ? flatten(b.cols[s.input + 1]) : nullptr;
     VecPtr mask = s.mask >= 0 ? flatten(b.cols[s.mask]) : nullptr;
-    auto masked_out = [&](int64_t r) { return mask && (mask->null_at(r) || !mask->as<uint8_t>()[r]); };
+    // DISTINCT: rows whose (group, value) pair was seen before are skipped like masked rows
+    std::vector<uint8_t> repeat;
+    if (s.distinct) {
+      if (!raw || !in) throw std::runtime_error("distinct aggregates take raw input over a column");
+      repeat.assign(n, 0);
+      const int64_t st = in->is_const ? 0 : 1;
+      for (int64_t r = 0; r < n; ++r) {
+        if ((mask && (mask->null_at(r) || !mask->as<uint8_t>()[r])) || in->null_at(r)) continue;
+        uint64_t bits;
+        switch (in->type) {
+          case ORC_DOUBLE: {
+            double d = in->as<double>()[r * st];
+            if (std::isnan(d)) d = std::numeric_limits<double>::quiet_NaN();
+            if (d == 0.0) d = 0.0;  // -0 and +0 are one value
+            std::memcpy(&bits, &d, 8);
+            if (std::isnan(d)) bits = 0x7ff8000000000000ull;
+            break;
+          }
+          case ORC_BIGINT: bits = static_cast<uint64_t>(in->as<int64_t>()[r * st]); break;
+          case ORC_INTEGER: bits = static_cast<uint64_t>(static_cast<int64_t>(in->as<int32_t>()[r * st])); break;
+          case ORC_BOOLEAN: bits = in->as<uint8_t>()[r * st] ? 1 : 0; break;
+          default: throw std::runtime_error("distinct aggregates over this input type are not restated");
+        }
+        if (!acc.seen.emplace(groups[r], bits).second) repeat[r] = 1;
+      }
+    }
+    auto masked_out = [&](int64_t r) { return (mask && (mask->null_at(r) || !mask->as<uint8_t>()[r])) || (s.distinct && repeat[r]); };
     const std::string& f = s.fn;
     if (f == "count") {
       for (int64_t r = 0; r < n; ++r) {
@@ -1257,7 +1292,7 @@ struct GroupBy {
       }
       return;
     }
-    const bool no_skip = !mask && !in->nulls;
+    const bool no_skip = !mask && !in->nulls && !s.distinct;
     auto each = [&](auto&& body) {
       if (no_skip) { for (int64_t r = 0; r < n; ++r) body(r); }
       else { for (int64_t r = 0; r < n; ++r) { if (masked_out(r) || in->null_at(r)) continue; body(r); } }
@@ -1631,6 +1666,7 @@ struct Executor {
 
   Table run_aggregation(const NodePtr& node) {
     bool single_driver = !raw_input_step(node->step);  // final / intermediate run on one driver
+    for (auto& a : node->aggs) single_driver = single_driver || a.distinct;  // distinct sets do not merge across drivers
     int T = single_driver ? 1 : threads;
     std::vector<std::unique_ptr<GroupBy>> gbs;
     Node partial = *node;

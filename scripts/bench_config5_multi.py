@@ -31,7 +31,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=float, default=1e9)
     ap.add_argument("--keys", type=float, default=1e8)
-    ap.add_argument("--batch", type=float, default=1.6e7, help="rows per input batch = per exchange round")
+    ap.add_argument("--batch", type=float, default=2e9, help="rows per input batch (one batch per rank takes the exchange operator's fused single-key partition pass)")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--check", action="store_true", help="compare every group with the CPU oracle (small sizes)")
     a = ap.parse_args()

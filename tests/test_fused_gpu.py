@@ -229,6 +229,21 @@ def test_hash_and_partition_match_oracle():
         assert np.array_equal(order, np.argsort(want, kind="stable").astype(np.int32))
 
 
+@pytest.mark.parametrize("p", [2, 5, 64])
+def test_partition_order_large(p):
+    """Stable partition order over 10 M rows (2 442 blocks of 4 096 rows: the offsets scan gives every thread a run of
+    blocks) against numpy's stable argsort; ids given and ids computed on the fly from one BIGINT key."""
+    import torch
+    from velox_b200.kernels import partition_scatter_order
+    rng = np.random.default_rng(p)
+    n = 10_000_019
+    ids = rng.integers(0, p, n).astype(np.int32)
+    ids[: n // 3] = 1 % p  # a long run of one partition
+    counts, order = partition_scatter_order(torch.from_numpy(ids).cuda(), p)
+    assert np.array_equal(counts.cpu().numpy(), np.bincount(ids, minlength=p))
+    assert np.array_equal(order.cpu().numpy(), np.argsort(ids, kind="stable").astype(np.int32))
+
+
 @pytest.mark.parametrize("card", [(2, 2), (3, 2), (5, 1), (8, 5), (50, 1)])
 @pytest.mark.parametrize("n", [1000, 300_001])
 def test_fused_groupby_variants(card, n):

@@ -405,6 +405,27 @@ def test_hash_join_filter_multikey_and_empty_build():
                    .hashJoin(["pk"], ["bk"], PlanBuilder().values(empty.names, empty.types, source=1), "", outs, joinType=jt).planNode(), [probe, empty])
 
 
+@pytest.mark.parametrize("keys", [[], ["c1"], ["c5", "c1"]])
+def test_distinct_aggregates(keys):
+    """DISTINCT aggregates (exec/DistinctAggregations.cpp): the adapter splits the node into a distinct grouping over
+    (keys, x) and the plain aggregation over its rows. BIGINT, DOUBLE (NaN / -0 are one value each) and BOOLEAN inputs, NULLs ignored."""
+    rv = table(n=4000, seed=21)
+    for col in ("c0", "c3", "c4"):
+        aggs = [f"count(distinct {col})"] if col == "c4" else [f"count(distinct {col})", f"sum(distinct {col})", f"min(distinct {col})", f"max(distinct {col})", f"avg(distinct {col})"]
+        check_plan(PlanBuilder().values(rv.names, rv.types).singleAggregation(keys, aggs).planNode(), [rv])
+        check_plan(PlanBuilder().values(rv.names, rv.types).filter("c1 <> 3").singleAggregation(keys, aggs).planNode(), [rv], batch_rows=900)
+    rng = np.random.default_rng(3)
+    d = row_vector(["k", "x"], [flat_vector(BIGINT, rng.integers(0, 5, 3000)), flat_vector(DOUBLE, rng.choice([0.0, -0.0, NAN, 1.5, 2.5, INF], 3000).tolist())])
+    check_plan(PlanBuilder().values(d.names, d.types).singleAggregation(["k"], ["count(distinct x)", "max(distinct x)"]).planNode(), [d])
+
+
+def test_distinct_aggregates_unsupported_shapes():
+    rv = table(n=100, seed=1)
+    for aggs in (["count(distinct c0)", "sum(c2)"], ["count(distinct c0)", "count(distinct c1)"]):
+        with pytest.raises(Exception, match="DISTINCT"):
+            check_plan(PlanBuilder().values(rv.names, rv.types).singleAggregation(["c1"], aggs).planNode(), [rv])
+
+
 def _keyed_join_tables(seed=5, n=3000, m=400):
     rng = np.random.default_rng(seed)
     def maybe(v, p=0.05):

@@ -88,6 +88,26 @@ def test_group_by_against_arrow(keys):
     assert_same(got, arrow_rows(want.select(order)))
 
 
+@pytest.mark.parametrize("keys", [[], ["k1"], ["s", "k2"]])
+def test_distinct_aggregates_against_arrow(keys):
+    """count(DISTINCT x) / sum / min / max over the distinct values of a group (exec/DistinctAggregations.cpp) against
+    pyarrow's count_distinct and a distinct-then-aggregate restatement in pyarrow."""
+    t = table(20_000, 11)
+    rv = row_vector_from_arrow(t)
+    plan = (PlanBuilder().values(rv.names, rv.types)
+            .singleAggregation(keys, ["count(distinct v)", "sum(distinct v)", "min(distinct v)", "max(distinct v)", "avg(distinct v)"]).planNode())
+    got = pyoracle.run_plan(plan, [rv], threads=4, batch_rows=4096).rows()
+    # distinct (keys, v) rows first, then plain aggregates over them; count_distinct straight from pyarrow as a second opinion
+    d = t.select(keys + ["v"]).group_by(keys + ["v"], use_threads=False).aggregate([])
+    want = d.group_by(keys, use_threads=False).aggregate([("v", "count"), ("v", "sum"), ("v", "min"), ("v", "max"), ("v", "mean")])
+    order = keys + [c for c in want.schema.names if c not in keys]
+    assert_same(got, arrow_rows(want.select(order)))
+    direct = t.group_by(keys, use_threads=False).aggregate([("v", "count_distinct")])
+    by_key = {tuple(r[:-1]): r[-1] for r in arrow_rows(direct.select(keys + ["v_count_distinct"]))}
+    for r in got:
+        assert by_key[tuple(r[:len(keys)])] == r[len(keys)]
+
+
 @pytest.mark.parametrize("join_type,arrow_type", [("inner", "inner"), ("left", "left outer"), ("semi", "left semi"), ("anti", "left anti")])
 def test_hash_join_against_arrow(join_type, arrow_type):
     rng = np.random.default_rng(11)

@@ -41,6 +41,44 @@ std::shared_ptr<const core::AggregationNode> collapsePartialFinal(const core::Ag
   return single;
 }
 
+// DISTINCT aggregates (exec/DistinctAggregations.cpp keeps a set of inputs per group and feeds every distinct value to
+// the function once). On the device the set IS a group-by: a single-step aggregation whose aggregates are all DISTINCT
+// over one common column x (unmasked) becomes
+//     Aggregation[keys + x, no aggregates]  ->  Aggregation[keys, the same aggregates without DISTINCT]
+// — the first operator emits every (keys, x) combination once (NULL x included: it keeps a group with only NULL inputs
+// alive and the functions ignore it, as they do in the reference), the second one aggregates those rows.
+// Returns false when the node has no DISTINCT aggregate; throws for DISTINCT shapes outside this rewrite.
+bool splitDistinctAggregation(const core::AggregationNode& node, std::shared_ptr<const core::AggregationNode>& dedup,
+                              std::shared_ptr<const core::AggregationNode>& aggregate) {
+  bool any = false;
+  for (auto& a : node.aggregates()) any = any || a.distinct;
+  if (!any) return false;
+  using Step = core::AggregationNode::Step;
+  core::FieldAccessTypedExprPtr input;
+  for (auto& a : node.aggregates()) {
+    auto in0 = a.call->inputs().size() == 1 ? std::dynamic_pointer_cast<const core::FieldAccessTypedExpr>(a.call->inputs()[0]) : nullptr;
+    if (!a.distinct || a.mask || !a.sortingKeys.empty() || !in0 || (input && input->name() != in0->name()) || node.step() != Step::kSingle)
+      VELOX_UNSUPPORTED("DISTINCT aggregates: a single-step aggregation whose aggregates are all DISTINCT over one common input column, without masks, is supported; got " +
+                        a.call->toString());
+    input = in0;
+  }
+  if (input->type()->kind() == TypeKind::VARCHAR) VELOX_UNSUPPORTED("DISTINCT aggregates over VARCHAR");
+  std::vector<core::FieldAccessTypedExprPtr> keys = node.groupingKeys();
+  for (auto& k : keys)
+    if (k->name() == input->name()) VELOX_UNSUPPORTED("DISTINCT aggregate over a grouping key");
+  keys.push_back(input);
+  dedup = std::make_shared<core::AggregationNode>(node.id() + ".distinct", Step::kSingle, keys, std::vector<core::FieldAccessTypedExprPtr>{},
+                                                  std::vector<std::string>{}, std::vector<core::AggregationNode::Aggregate>{}, false, false,
+                                                  node.sources()[0]);
+  std::vector<core::AggregationNode::Aggregate> plain = node.aggregates();
+  for (auto& a : plain) a.distinct = false;
+  auto agg = std::make_shared<core::AggregationNode>(node.id(), Step::kSingle, node.groupingKeys(), node.preGroupedKeys(), node.aggregateNames(), std::move(plain),
+                                                     node.ignoreNullKeys(), false, dedup);
+  agg->setOutputType(node.outputType());
+  aggregate = agg;
+  return true;
+}
+
 bool adaptDriver(const exec::DriverFactory& factory, exec::Driver& driver) {
   const core::QueryConfig& config = driver.driverCtx()->queryConfig();
   if (!config.b200Enabled()) return false;
@@ -82,6 +120,15 @@ bool adaptDriver(const exec::DriverFactory& factory, exec::Driver& driver) {
         }
       }
       std::shared_ptr<const core::AggregationNode> node = agg->node();
+      {
+        std::shared_ptr<const core::AggregationNode> dedup, plain;
+        if (splitDistinctAggregation(*node, dedup, plain)) {
+          out.push_back(std::make_unique<B200HashAggregation>(static_cast<int32_t>(out.size()), ctx, dedup, std::move(absorbed)));
+          out.push_back(std::make_unique<B200HashAggregation>(static_cast<int32_t>(out.size()), ctx, plain, std::vector<std::unique_ptr<exec::Operator>>{}));
+          replacedAny = true;
+          continue;
+        }
+      }
       // partial -> final back to back in ONE driver (no exchange in between) is a single
       // aggregation: final(partial(x)) == single(x) group by group, so the pair becomes one
       // operator and the intermediate batch never exists.

@@ -53,6 +53,10 @@ inline ResolvedAggregation resolveAggregation(const core::AggregationNode& node)
       ra.inputs.push_back(channelOf(in, *f));
     }
     if (a.mask) ra.mask = channelOf(in, *a.mask);
+    if (a.distinct)
+      VELOX_UNSUPPORTED("DISTINCT aggregate in this shape: " + a.call->toString() +
+                        " (a single-step aggregation whose aggregates are all DISTINCT over one common column is split by the adapter)");
+    if (!a.sortingKeys.empty()) VELOX_UNSUPPORTED("aggregates with ORDER BY: " + a.call->toString());
     if (!a.rawInputTypes.empty()) ra.rawInputType = a.rawInputTypes[0];
     r.aggregates.push_back(std::move(ra));
   }

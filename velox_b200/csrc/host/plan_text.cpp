@@ -193,8 +193,8 @@ class Parser {
       else if (stepName == "intermediate") step = core::AggregationNode::Step::kIntermediate;
       else throw VeloxRuntimeError("plan text: unknown aggregation step " + stepName);
       auto keys = intList("keys");
-      // (aggs (fn [col] [(mask col)]) ...)
-      struct RawAgg { std::string fn; int col = -1; int mask = -1; };
+      // (aggs (fn [col] [(mask col)] [(distinct)]) ...)
+      struct RawAgg { std::string fn; int col = -1; int mask = -1; bool distinct = false; };
       std::vector<RawAgg> raws;
       lex_.expect(Tok::LP, "(");
       if (lex_.atom("aggs") != "aggs") throw VeloxRuntimeError("plan text: expected (aggs ...)");
@@ -205,8 +205,10 @@ class Parser {
         while (lex_.peek().kind != Tok::RP) {
           if (lex_.peek().kind == Tok::LP) {
             lex_.take();
-            if (lex_.atom("mask") != "mask") throw VeloxRuntimeError("plan text: expected (mask col)");
-            a.mask = std::stoi(lex_.atom("mask column"));
+            const std::string what = lex_.atom("mask | distinct");
+            if (what == "distinct") a.distinct = true;
+            else if (what == "mask") a.mask = std::stoi(lex_.atom("mask column"));
+            else throw VeloxRuntimeError("plan text: expected (mask col) or (distinct)");
             lex_.expect(Tok::RP, ")");
           } else {
             a.col = std::stoi(lex_.atom("column"));
@@ -257,6 +259,7 @@ class Parser {
           if (raw && !inputFn.empty()) rawType = scalarFunctionReturnType(inputFn, rawType);  // the accumulator sees the transformed input
         }
         if (r.mask >= 0) a.mask = field(r.mask);
+        a.distinct = r.distinct;
         const std::string n = "n" + id + "a" + std::to_string(aggs.size());
         TypePtr resultType;
         if (r.fn == "count") { resultType = BIGINT(); names.push_back(n); types.push_back(BIGINT()); }

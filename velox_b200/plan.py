@@ -382,7 +382,7 @@ def register_aggregate_function(name: str, family: str, input_function: str = ""
     USER_AGGREGATES[name] = (family, input_function, final_function)
 
 
-_AGG = re.compile(r"^\s*([A-Za-z_][A-Za-z_0-9]*)\s*\(\s*([A-Za-z_0-9*]*)\s*\)\s*(?:[aA][sS]\s+([A-Za-z_][A-Za-z_0-9]*))?\s*$")
+_AGG = re.compile(r"^\s*([A-Za-z_][A-Za-z_0-9]*)\s*\(\s*((?:[dD][iI][sS][tT][iI][nN][cC][tT]\s+)?)([A-Za-z_0-9*]*)\s*\)\s*(?:[aA][sS]\s+([A-Za-z_][A-Za-z_0-9]*))?\s*$")
 
 
 @dataclass
@@ -438,13 +438,15 @@ class PlanBuilder:
             m = _AGG.match(a)
             if not m:
                 raise ValueError(f"bad aggregate {a!r}")
-            name, arg, alias = m.group(1), m.group(2), m.group(3)
+            name, distinct, arg, alias = m.group(1), bool(m.group(2)), m.group(3), m.group(4)
+            if distinct and (step != "single" or name not in ("sum", "avg", "count", "min", "max") or arg in ("", "*") or arg.isdigit()):
+                raise ValueError(f"{a!r}: DISTINCT applies to sum / avg / count / min / max over a column in a single aggregation")
             if name not in ("sum", "avg", "count", "min", "max") and name not in USER_AGGREGATES:
                 raise ValueError(f"unknown aggregate {name!r} (register_aggregate_function)")
             fn, in_fn, fin_fn = USER_AGGREGATES.get(name, (name, "", ""))  # the plan carries the registered name, typing follows its family
             alias = alias or f"a{j}"
             mask = masks[j] if masks else None
-            mask_s = f" (mask {n.names.index(mask)})" if mask else ""
+            mask_s = (f" (mask {n.names.index(mask)})" if mask else "") + (" (distinct)" if distinct else "")
             if fn == "count" and (arg in ("", "*") or arg.isdigit()):
                 specs.append(f"({name}{mask_s})")
                 in_type = BIGINT
