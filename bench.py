@@ -319,9 +319,10 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--concurrent-queries", action="store_true",
-                    help="submit Q1 and Q14 as two concurrent tasks (vb2_tasks_run) instead of one after the other. Default on N > 1, where a query's "
-                         "exchanges are rendezvous latency the other query's scan can hide (N=2: 4.63 vs 5.44 ms per step); off on one GPU (two HBM-bound scans gain nothing)")
-    ap.add_argument("--serial-queries", action="store_true", help="N > 1: run Q1, then Q14")
+                    help="submit Q1 and Q14 as two concurrent tasks (vb2_tasks_run) instead of one after the other. Off by default: on 2 GPUs a query's "
+                         "exchange rendezvous hides behind the other query's scan (4.63 vs 5.44 ms per step), but on 4 GPUs the two tasks' exchanges "
+                         "interleave differently on every rank and the step degrades to 30 ms (profiles/r02_bench_n4.json) against 3.9 ms one after the other")
+    ap.add_argument("--serial-queries", action="store_true", help="run Q1, then Q14 (the default)")
     ap.add_argument("--cpu-sample-rows", type=float, default=60_000_000)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -337,8 +338,8 @@ def main():
     from velox_b200.queries import Q1, Q6, Q14
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1 and not args.serial_queries:
-        args.concurrent_queries = True
+    if args.serial_queries:
+        args.concurrent_queries = False
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
@@ -370,9 +371,8 @@ def main():
 
     state = {"q1_kernel_ns": 0, "q1_kernel_rows": 0, "q1_runs": 0}
 
-    # A step submits the two queries as two concurrent tasks (one host thread each, each with its own
-    # streams and — on N > 1 — its own communicator): Q14's build side, exchanges and host-side setup
-    # overlap Q1's scan instead of queueing behind it. --serial-queries runs them one after the other.
+    # A step runs Q1, then Q14. With --concurrent-queries it submits them as two concurrent tasks (one host thread each,
+    # each with its own streams and — on N > 1 — its own communicator): see the flag's help for what was measured.
     comm14 = None
     if world > 1:
         from velox_b200.comm import Comm
