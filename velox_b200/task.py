@@ -297,11 +297,13 @@ def run_plan(plan, sources: Sequence, config: Optional[Dict[str, str]] = None, b
         t.close()
 
 
-def split_rowvector(rv: RowVector, batch_rows: int):
-    """Slices host columns into batches (FLAT / DICTIONARY / CONSTANT aware)."""
+def split_rowvector(rv: RowVector, batch_rows: int, max_batches: Optional[int] = None):
+    """Slices host columns into batches (FLAT / DICTIONARY / CONSTANT aware); at most `max_batches` of them when given."""
     from .vector import CONSTANT, DICTIONARY
     out = []
     for r0 in range(0, rv.size, batch_rows):
+        if max_batches is not None and len(out) >= max_batches:
+            break
         r1 = min(rv.size, r0 + batch_rows)
         cols = []
         for c in rv.columns:
