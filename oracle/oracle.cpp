@@ -27,6 +27,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -982,6 +983,9 @@ struct ValueIds {
   FlatMap64 ints;
   std::unordered_map<std::string, int32_t> strs;
   int32_t next = 1;
+  // integer keys of a join build side over a dense range: ids follow from the value (no table), set by JoinTable::build
+  bool range_mode = false;
+  int64_t range_min = 0, range_max = -1;
   // cache for dictionary bases
   const Vec* cached_base = nullptr;
   std::vector<int32_t> base_ids;
@@ -1012,6 +1016,10 @@ struct ValueIds {
       return next++;
     }
     uint64_t w = word(flat, s);
+    if (range_mode) {  // id = v - min + 1 (VectorHasher range mode, exec/VectorHasher.h:523-585); values outside the range are unknown
+      const int64_t v = static_cast<int64_t>(w);
+      return (v < range_min || v > range_max) ? -1 : static_cast<int32_t>(v - range_min + 1);
+    }
     if (!insert) return ints.find(w);
     bool is_new;
     int32_t id = ints.find_or_insert(w, next, is_new);
@@ -1387,6 +1395,27 @@ struct GroupBy {
   }
 };
 
+// Runs fn(i) for i in [0, n) on up to `threads` threads (contiguous ranges per thread).
+template <class F>
+static void parallel_for(int64_t n, int threads, F&& fn) {
+  const int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(threads, n)));
+  if (T <= 1) { for (int64_t i = 0; i < n; ++i) fn(i); return; }
+  std::vector<std::thread> ts;
+  std::exception_ptr err;
+  std::mutex m;
+  for (int t = 0; t < T; ++t)
+    ts.emplace_back([&, t] {
+      try {
+        for (int64_t i = n * t / T; i < n * (t + 1) / T; ++i) fn(i);
+      } catch (...) {
+        std::lock_guard<std::mutex> l(m);
+        if (!err) err = std::current_exception();
+      }
+    });
+  for (auto& th : ts) th.join();
+  if (err) std::rethrow_exception(err);
+}
+
 // ----------------------------------------------------------------------------------------------
 // Hash join
 // ----------------------------------------------------------------------------------------------
@@ -1403,49 +1432,145 @@ struct JoinTable {
 
   static uint64_t pack(const std::vector<int32_t>& ids) { return GroupBy::pack(ids); }
 
-  void build(const Node& n, Table&& t) {
+  // `threads`: the build side is concatenated by all drivers' threads and, for one integer key over a dense range, ids
+  // follow from the values — what the reference gets from per-driver row containers + parallelJoinBuild
+  // (exec/HashBuild.cpp:819-993, exec/HashTable.cpp:1003) and VectorHasher's range mode; the chains themselves are
+  // linked in row order either way.
+  void build(const Node& n, Table&& t, int threads = 1) {
     nk = n.build_keys.size();
     const auto& schema = n.build->schema;
-    // concatenate
-    for (auto& b : t) rows.n += b.n;
-    for (size_t c = 0; c < schema.size(); ++c) {
-      // fixed-width, null-free columns are concatenated with memcpy; others value by value
-      bool plain = schema[c] != ORC_VARCHAR;
-      std::vector<VecPtr> flats;
-      for (auto& b : t) {
-        flats.push_back(flatten(b.cols[c]));
-        plain = plain && !flats.back()->nulls && !flats.back()->is_const;
+    const int64_t nb = static_cast<int64_t>(t.size());
+    // concatenate: row offset of every batch, then every (column, batch) piece on its own
+    std::vector<int64_t> row0(nb + 1, 0);
+    for (int64_t i = 0; i < nb; ++i) row0[i + 1] = row0[i] + t[i].n;
+    rows.n = row0[nb];
+    const size_t ncols = schema.size();
+    std::vector<std::vector<VecPtr>> flats(ncols, std::vector<VecPtr>(nb));
+    parallel_for(static_cast<int64_t>(ncols) * nb, threads, [&](int64_t j) {
+      const size_t c = static_cast<size_t>(j / nb);
+      const int64_t i = j % nb;
+      flats[c][i] = flatten(t[i].cols[c]);
+    });
+    for (size_t c = 0; c < ncols; ++c) {
+      bool any_null = false, any_const = false;
+      for (auto& f : flats[c]) { any_null = any_null || f->nulls; any_const = any_const || f->is_const; }
+      if (any_const) {  // rare: value by value
+        ColBuilder cb(schema[c]);
+        for (int64_t i = 0; i < nb; ++i)
+          for (int64_t r = 0; r < t[i].n; ++r) cb.push_from(*flats[c][i], r);
+        rows.cols.push_back(cb.finish());
+        continue;
       }
-      if (plain) {
-        auto v = make_result(schema[c], rows.n);
+      auto v = make_result(schema[c], rows.n);
+      uint8_t* on = any_null ? v->alloc_nulls(rows.n) : nullptr;
+      if (schema[c] != ORC_VARCHAR) {
         const int w = width_of(schema[c]);
         uint8_t* o = v->alloc<uint8_t>(rows.n * w);
-        int64_t off = 0;
-        for (size_t i = 0; i < t.size(); ++i) {
-          std::memcpy(o + off * w, flats[i]->data, static_cast<size_t>(t[i].n) * w);
-          off += t[i].n;
-        }
-        rows.cols.push_back(v);
+        parallel_for(nb, threads, [&](int64_t i) {
+          const Vec& f = *flats[c][i];
+          std::memcpy(o + row0[i] * w, f.data, static_cast<size_t>(t[i].n) * w);
+          if (on && f.nulls) {
+            std::memcpy(on + row0[i], f.nulls, static_cast<size_t>(t[i].n));
+            for (int64_t r = 0; r < t[i].n; ++r)
+              if (f.nulls[r]) std::memset(o + (row0[i] + r) * w, 0, w);  // NULL rows hold zeros, as ColBuilder leaves them
+          }
+        });
       } else {
-        ColBuilder cb(schema[c]);
-        for (size_t i = 0; i < t.size(); ++i)
-          for (int64_t r = 0; r < t[i].n; ++r) cb.push_from(*flats[i], r);
-        rows.cols.push_back(cb.finish());
+        // chars of every batch (NULL rows contribute none), then offsets and bytes batch by batch
+        std::vector<int64_t> char0(nb + 1, 0);
+        parallel_for(nb, threads, [&](int64_t i) {
+          const Vec& f = *flats[c][i];
+          int64_t len = 0;
+          if (!f.nulls) len = f.off[t[i].n] - f.off[0];
+          else
+            for (int64_t r = 0; r < t[i].n; ++r)
+              if (!f.nulls[r]) len += f.off[r + 1] - f.off[r];
+          char0[i + 1] = len;
+        });
+        for (int64_t i = 0; i < nb; ++i) char0[i + 1] += char0[i];
+        if (char0[nb] >= (1ll << 31)) throw std::runtime_error("join build side: VARCHAR column above 2 GiB");
+        v->own_off = std::make_shared<std::vector<int32_t>>(static_cast<size_t>(rows.n) + 1);
+        v->own_chars = std::make_shared<std::string>(static_cast<size_t>(char0[nb]), '\0');
+        int32_t* off = v->own_off->data();
+        char* chars = v->own_chars->data();
+        off[rows.n] = static_cast<int32_t>(char0[nb]);
+        parallel_for(nb, threads, [&](int64_t i) {
+          const Vec& f = *flats[c][i];
+          int64_t at = char0[i];
+          for (int64_t r = 0; r < t[i].n; ++r) {
+            off[row0[i] + r] = static_cast<int32_t>(at);
+            if (f.nulls && f.nulls[r]) continue;
+            const int32_t len = f.off[r + 1] - f.off[r];
+            std::memcpy(chars + at, f.chars + f.off[r], static_cast<size_t>(len));
+            at += len;
+          }
+          if (on && f.nulls) std::memcpy(on + row0[i], f.nulls, static_cast<size_t>(t[i].n));
+        });
+        v->off = off;
+        v->chars = chars;
       }
+      if (on) {
+        bool any = false;
+        for (int64_t r = 0; r < rows.n && !any; ++r) any = on[r];
+        if (!any) { v->own_nulls.reset(); v->nulls = nullptr; }
+      }
+      rows.cols.push_back(v);
     }
     flat_cols = rows.cols;
     for (size_t k = 0; k < nk; ++k) { hashers.emplace_back(); hashers.back().type = schema[n.build_keys[k]]; }
+    // one BIGINT / INTEGER key over a dense range: range-mode ids
+    bool ranged = false;
+    if (nk == 1 && (schema[n.build_keys[0]] == ORC_BIGINT || schema[n.build_keys[0]] == ORC_INTEGER) && rows.n > 0) {
+      const Vec& kv = *rows.cols[n.build_keys[0]];
+      int64_t lo = INT64_MAX, hi = INT64_MIN;
+      for (int64_t r = 0; r < rows.n; ++r) {
+        if (kv.nulls && kv.nulls[r]) continue;
+        const int64_t x = kv.type == ORC_BIGINT ? kv.as<int64_t>()[r] : kv.as<int32_t>()[r];
+        lo = std::min(lo, x);
+        hi = std::max(hi, x);
+      }
+      if (lo <= hi) {
+        const unsigned __int128 span = static_cast<unsigned __int128>(static_cast<__int128>(hi) - lo) + 1;
+        if (span <= static_cast<unsigned __int128>(std::max<int64_t>(1 << 16, rows.n * 4)) && span < (1u << 30)) {
+          ranged = true;
+          hashers[0].range_mode = true;
+          hashers[0].range_min = lo;
+          hashers[0].range_max = hi;
+          first.assign(static_cast<size_t>(span), -1);
+        }
+      }
+    }
     std::vector<std::vector<int32_t>> ids(nk);
-    for (size_t k = 0; k < nk; ++k) hashers[k].ids(rows.cols[n.build_keys[k]], rows.n, true, ids[k]);
+    if (ranged) {
+      const Vec& kv = *rows.cols[n.build_keys[0]];
+      ids[0].resize(static_cast<size_t>(rows.n));
+      const int64_t lo = hashers[0].range_min;
+      parallel_for((rows.n + 65535) / 65536, threads, [&](int64_t blk) {
+        for (int64_t r = blk * 65536; r < std::min<int64_t>(rows.n, (blk + 1) * 65536); ++r) {
+          if (kv.nulls && kv.nulls[r]) { ids[0][r] = 0; continue; }
+          const int64_t x = kv.type == ORC_BIGINT ? kv.as<int64_t>()[r] : kv.as<int32_t>()[r];
+          ids[0][r] = static_cast<int32_t>(x - lo + 1);
+        }
+      });
+    } else {
+      for (size_t k = 0; k < nk; ++k) hashers[k].ids(rows.cols[n.build_keys[k]], rows.n, true, ids[k]);
+    }
     next_row.assign(rows.n, -1);
     std::vector<int32_t> row_ids(nk);
     std::vector<int32_t> last;  // tail of each chain so matches stay in build order
+    if (ranged) last.assign(first.size(), -1);
     for (int64_t r = 0; r < rows.n; ++r) {
       bool has_null = false;
       for (size_t k = 0; k < nk; ++k) { row_ids[k] = ids[k][r]; has_null |= ids[k][r] == 0; }
       if (has_null) continue;
       int32_t e;
       bool is_new = false;
+      if (ranged) {  // ids index the chains directly; -1 = no row with this key yet
+        e = row_ids[0] - 1;
+        if (first[e] < 0) { first[e] = static_cast<int32_t>(r); last[e] = static_cast<int32_t>(r); }
+        else { next_row[last[e]] = static_cast<int32_t>(r); last[e] = static_cast<int32_t>(r); }
+        continue;
+      }
       if (nk == 1) {  // value ids are dense (1..N): they index the chains directly
         e = row_ids[0] - 1;
         is_new = static_cast<size_t>(e) >= first.size();
@@ -1737,7 +1862,7 @@ struct Executor {
     for (auto* op : ops)
       if (op->kind == Node::JOIN) {
         auto jt = std::make_shared<JoinTable>();
-        jt->build(*op, materialise(op->build));
+        jt->build(*op, materialise(op->build), this->threads);
         tables[op] = jt;
       }
     auto run_ops = [&](int t, Batch b) {

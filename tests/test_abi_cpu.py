@@ -61,7 +61,19 @@ def test_plan_text_roundtrip_and_errors():
     h = lib.vb2_task_create(plan.sexpr.encode(), b"b200.fused_pipelines=false", err, 1024)
     assert h, err.value
     lib.vb2_task_free(h)
-    for bad in (b"(filter (lt (field 9) (i64 1)) (values 0 (BIGINT)))", b"(values 0 (BIGINT)", b"(frobnicate)", b"(project ((nosuchfn (field 0))) (values 0 (BIGINT)))"):
+    # DISTINCT aggregates travel as (fn col (distinct)); the front end only takes them over a column of a single aggregation
+    dplan = PlanBuilder().values(names, types).singleAggregation(["k"], ["count(distinct d)", "sum(DISTINCT d) as s"]).planNode()
+    assert "(count 2 (distinct))" in dplan.sexpr and "(sum 2 (distinct))" in dplan.sexpr
+    h = lib.vb2_task_create(dplan.sexpr.encode(), b"", err, 1024)
+    assert h, err.value
+    lib.vb2_task_free(h)
+    for bad_agg in ("count(distinct 0)", "count(distinct *)"):
+        with pytest.raises(ValueError):
+            PlanBuilder().values(names, types).singleAggregation(["k"], [bad_agg])
+    with pytest.raises(ValueError):
+        PlanBuilder().values(names, types).partialAggregation(["k"], ["count(distinct d)"])
+    for bad in (b"(filter (lt (field 9) (i64 1)) (values 0 (BIGINT)))", b"(values 0 (BIGINT)", b"(frobnicate)", b"(project ((nosuchfn (field 0))) (values 0 (BIGINT)))",
+                b"(aggregation single (keys 0) (aggs (count 0 (unique))) (values 0 (BIGINT)))"):
         assert not lib.vb2_task_create(bad, b"", err, 1024)
         assert err.value.startswith(b"VeloxRuntimeError")
 
