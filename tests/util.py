@@ -46,7 +46,9 @@ def assert_equal_results(got, want, rel_tol=1e-12, abs_tol=0.0):
 
 
 def check_plan(plan, sources, configs=({},), batch_rows=None, rel_tol=1e-12, oracle_batch_rows=10000):
-    """Runs the plan on the oracle and, for every config, on the product; returns product stats."""
+    """Runs the plan on the oracle and, for every config, on the product; returns product stats. Integer / key / boolean /
+    string columns must be equal; DOUBLE columns within rel_tol (the general aggregation paths add with atomics, so the
+    order of a floating-point sum is not fixed from run to run — only the fused kernels are bit-reproducible)."""
     want = pyoracle.run_plan(plan, sources, threads=1, batch_rows=oracle_batch_rows)
     stats = []
     for cfg in configs:
