@@ -29,7 +29,7 @@ namespace vb2 {
 namespace {
 
 constexpr int kPT = 512;          // threads of the partition kernels
-constexpr int kTile = 3584;       // rows per tile (staged in shared memory): key + one payload column leave room for three CTAs per SM
+constexpr int kTile = 3584;       // rows per tile = 7 per thread (held in registers, then staged in shared memory in partition order)
 constexpr int kP1 = 256;
 constexpr int kMaxP = 256;
 constexpr int kCols = VB2_SLICE_MAX_COLS;
