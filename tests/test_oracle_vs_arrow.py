@@ -124,6 +124,35 @@ def test_hash_join_against_arrow(join_type, arrow_type):
     assert_same(got, arrow_rows(want))
 
 
+@pytest.mark.parametrize("join_type,arrow_type", [("inner", "inner"), ("left", "left outer"), ("semi", "left semi"), ("anti", "left anti")])
+@pytest.mark.parametrize("shape", ["wide_pair", "string", "string_and_int"])
+def test_wide_and_string_key_joins_against_arrow(join_type, arrow_type, shape):
+    """The key shapes that take the keyed (kHash) join table on the device: two wide BIGINT keys that do not pack into
+    one normalized word, VARCHAR keys with different dictionaries on the two sides, and a mix. NULL keys never match."""
+    rng = np.random.default_rng(23)
+    n, m = 5000, 400
+    words = ["ash", "birch", "cedar", "elm", "fir", "oak", "yew", None]
+    probe = pa.table({
+        "pa": pa.array(rng.integers(0, 30, n) * (2**40), type=pa.int64(), mask=rng.random(n) < 0.05),
+        "pb": pa.array(rng.integers(0, 20, n) * (2**35) - 2**50, type=pa.int64(), mask=rng.random(n) < 0.05),
+        "ps": pa.array(rng.choice(words, n).tolist(), type=pa.string()).dictionary_encode(),
+        "pv": pa.array(np.arange(n), type=pa.int64())})
+    build = pa.table({
+        "ba": pa.array(rng.integers(0, 30, m) * (2**40), type=pa.int64(), mask=rng.random(m) < 0.05),
+        "bb": pa.array(rng.integers(0, 20, m) * (2**35) - 2**50, type=pa.int64(), mask=rng.random(m) < 0.05),
+        "bs": pa.array(rng.choice(words[::-1], m).tolist(), type=pa.string()).dictionary_encode(),
+        "bw": pa.array(np.arange(m) * 10, type=pa.int64())})
+    pk, bk = {"wide_pair": (["pa", "pb"], ["ba", "bb"]), "string": (["ps"], ["bs"]), "string_and_int": (["ps", "pa"], ["bs", "ba"])}[shape]
+    prv, brv = row_vector_from_arrow(probe), row_vector_from_arrow(build)
+    out_cols = ["pv"] if join_type in ("semi", "anti") else ["pv", "bw"]
+    plan = (PlanBuilder().values(prv.names, prv.types, source=0)
+            .hashJoin(pk, bk, PlanBuilder().values(brv.names, brv.types, source=1), "", out_cols, joinType=join_type).planNode())
+    got = pyoracle.run_plan(plan, [prv, brv], threads=4, batch_rows=700).rows()
+    plain = lambda t: pa.table({c: (t[c].cast(pa.string()) if pa.types.is_dictionary(t[c].type) else t[c]) for c in t.column_names})
+    j = plain(probe).join(plain(build), keys=pk, right_keys=bk, join_type=arrow_type, use_threads=False)
+    assert_same(got, arrow_rows(j.select(out_cols)))
+
+
 def test_case_like_cast_against_arrow():
     t = table(4000, 21)
     rv = row_vector_from_arrow(t)
