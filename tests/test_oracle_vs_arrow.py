@@ -125,7 +125,7 @@ def test_hash_join_against_arrow(join_type, arrow_type):
 
 
 @pytest.mark.parametrize("join_type,arrow_type", [("inner", "inner"), ("left", "left outer"), ("semi", "left semi"), ("anti", "left anti")])
-@pytest.mark.parametrize("shape", ["wide_pair", "string", "string_and_int"])
+@pytest.mark.parametrize("shape", ["wide_pair", "string", "string_and_int", "double"])
 def test_wide_and_string_key_joins_against_arrow(join_type, arrow_type, shape):
     """The key shapes that take the keyed (kHash) join table on the device: two wide BIGINT keys that do not pack into
     one normalized word, VARCHAR keys with different dictionaries on the two sides, and a mix. NULL keys never match."""
@@ -136,13 +136,16 @@ def test_wide_and_string_key_joins_against_arrow(join_type, arrow_type, shape):
         "pa": pa.array(rng.integers(0, 30, n) * (2**40), type=pa.int64(), mask=rng.random(n) < 0.05),
         "pb": pa.array(rng.integers(0, 20, n) * (2**35) - 2**50, type=pa.int64(), mask=rng.random(n) < 0.05),
         "ps": pa.array(rng.choice(words, n).tolist(), type=pa.string()).dictionary_encode(),
+        # NaN keys match NaN in both engines; -0.0 is left out: the reference (and the oracle) equate it with +0.0, Arrow compares bits
+        "pd": pa.array(rng.choice([0.0, 1.5, float("nan"), -2.25, 1e300, 7.0], n), type=pa.float64(), mask=rng.random(n) < 0.05),
         "pv": pa.array(np.arange(n), type=pa.int64())})
     build = pa.table({
         "ba": pa.array(rng.integers(0, 30, m) * (2**40), type=pa.int64(), mask=rng.random(m) < 0.05),
         "bb": pa.array(rng.integers(0, 20, m) * (2**35) - 2**50, type=pa.int64(), mask=rng.random(m) < 0.05),
         "bs": pa.array(rng.choice(words[::-1], m).tolist(), type=pa.string()).dictionary_encode(),
+        "bd": pa.array(rng.choice([0.0, 1.5, float("nan"), -2.25, 3.0], m), type=pa.float64(), mask=rng.random(m) < 0.05),
         "bw": pa.array(np.arange(m) * 10, type=pa.int64())})
-    pk, bk = {"wide_pair": (["pa", "pb"], ["ba", "bb"]), "string": (["ps"], ["bs"]), "string_and_int": (["ps", "pa"], ["bs", "ba"])}[shape]
+    pk, bk = {"wide_pair": (["pa", "pb"], ["ba", "bb"]), "string": (["ps"], ["bs"]), "string_and_int": (["ps", "pa"], ["bs", "ba"]), "double": (["pd"], ["bd"])}[shape]
     prv, brv = row_vector_from_arrow(probe), row_vector_from_arrow(build)
     out_cols = ["pv"] if join_type in ("semi", "anti") else ["pv", "bw"]
     plan = (PlanBuilder().values(prv.names, prv.types, source=0)
