@@ -33,7 +33,8 @@ def table(n, seed, null_p=0.1):
 
 def norm(rows):
     def key(r):
-        return tuple((0, 0) if v is None else (1, round(v, 6)) if isinstance(v, float) else (1, v) if not isinstance(v, str) else (2, v) for v in r)
+        return tuple((0, 0) if v is None else (3, 0) if isinstance(v, float) and math.isnan(v) else (1, round(v, 6)) if isinstance(v, float)
+                     else (1, v) if not isinstance(v, str) else (2, v) for v in r)
     return sorted(rows, key=key)
 
 
@@ -45,7 +46,7 @@ def assert_same(got, want, rel=1e-9):
             if x is None or y is None:
                 assert x is None and y is None, (a, b)
             elif isinstance(y, float):
-                assert math.isclose(x, y, rel_tol=rel, abs_tol=1e-9), (a, b)
+                assert (math.isnan(x) and math.isnan(y)) or math.isclose(x, y, rel_tol=rel, abs_tol=1e-9), (a, b)
             else:
                 assert x == y, (a, b)
 
@@ -84,6 +85,25 @@ def test_group_by_against_arrow(keys):
     aggs = [("x", "sum"), ("v", "sum"), ("x", "count"), ([], "count_all"), ("v", "min"), ("x", "max"), ("q", "mean")]
     want = t.group_by(keys, use_threads=False).aggregate(aggs)
     # pyarrow puts the aggregates first, then the keys
+    order = keys + [c for c in want.schema.names if c not in keys]
+    assert_same(got, arrow_rows(want.select(order)))
+
+
+@pytest.mark.parametrize("keys", [["q"], ["w1", "w2"], ["q", "s", "w1"]])
+def test_group_by_keyed_shapes_against_arrow(keys):
+    """Grouping keys that take the keyed (kHash) group table on the device: DOUBLE keys (NaN is one group, NULL another)
+    and two wide BIGINT keys whose ranges do not pack into one normalized word."""
+    t = table(20_000, 31)
+    rng = np.random.default_rng(5)
+    n = t.num_rows
+    q = np.where(rng.random(n) < 0.05, np.nan, rng.integers(0, 12, n).astype(np.float64) * 0.25)
+    t = t.set_column(t.schema.get_field_index("q"), "q", pa.array(q, type=pa.float64(), mask=rng.random(n) < 0.05))
+    t = t.append_column("w1", pa.array(rng.integers(0, 9, n) * (2**41), type=pa.int64(), mask=rng.random(n) < 0.05))
+    t = t.append_column("w2", pa.array(rng.integers(0, 7, n) * (2**38) - 2**52, type=pa.int64()))
+    rv = row_vector_from_arrow(t)
+    plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(keys, ["sum(v)", "count(x)", "count(0)", "min(v)", "max(x)"]).planNode()
+    got = pyoracle.run_plan(plan, [rv], threads=4, batch_rows=4096).rows()
+    want = t.group_by(keys, use_threads=False).aggregate([("v", "sum"), ("x", "count"), ([], "count_all"), ("v", "min"), ("x", "max")])
     order = keys + [c for c in want.schema.names if c not in keys]
     assert_same(got, arrow_rows(want.select(order)))
 
