@@ -2,7 +2,9 @@
 interpreter and the fused kernels, handed to NVRTC as the prelude of JIT-compiled expressions) compiled FOR THE HOST
 and checked on the CPU: against the reference's known-answer vectors (tests/golden/scalar_vectors.json), against the
 oracle's scalar kernels on random operands, and LIKE / string comparison against Python. No GPU needed — the same
-source text runs on the device."""
+source text runs on the device. The hashing block of common.cuh (twang_mix64, jenkins_rev_mix32, hashMix, the double
+canonicalisation and the CRC32-C based hashBytes in its bitwise device form) gets the same treatment: compiled for the
+host and compared bit for bit with the oracle, whose hashBytes uses the SSE4.2 crc32 instruction as the reference does."""
 import ctypes as C
 import json
 import os
@@ -130,3 +132,72 @@ def test_like_and_string_compare_match_python(vo):
         b = bytes(rng.randint(0, 255) for _ in range(rng.randint(0, 5)))
         want = -1 if a < b else (1 if a > b else 0)
         assert vo.vo_strcmp(a, len(a), b, len(b)) == want, (a, b)
+
+
+HASH_HARNESS = r"""
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#define __host__
+#define __device__
+#define __forceinline__ inline
+using std::isnan;
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
+%s
+extern "C" {
+uint64_t dh_twang(uint64_t k) { return twang_mix64(k); }
+uint32_t dh_jenkins(uint32_t k) { return jenkins_rev_mix32(k); }
+uint64_t dh_mix(uint64_t a, uint64_t b) { return hash_mix(a, b); }
+uint64_t dh_f64(double v) { return hash_f64(v); }
+uint64_t dh_bytes(uint64_t seed, const uint8_t* p, int32_t n) { return hash_bytes(seed, p, n); }
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def dh(tmp_path_factory):
+    text = open(os.path.join(ROOT, "velox_b200", "csrc", "common.cuh")).read()
+    begin = text.index("constexpr uint64_t kNullHash = 1;")
+    end = text.index("// Warp / block reductions")
+    end = text.rindex("// ----", begin, end)
+    d = tmp_path_factory.mktemp("devhash")
+    src = d / "harness.cpp"
+    src.write_text(HASH_HARNESS % text[begin:end])
+    lib = d / "libdevhash.so"
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(lib), str(src)])
+    L = C.CDLL(str(lib))
+    L.dh_twang.restype = C.c_uint64
+    L.dh_twang.argtypes = [C.c_uint64]
+    L.dh_jenkins.restype = C.c_uint32
+    L.dh_jenkins.argtypes = [C.c_uint32]
+    L.dh_mix.restype = C.c_uint64
+    L.dh_mix.argtypes = [C.c_uint64, C.c_uint64]
+    L.dh_f64.restype = C.c_uint64
+    L.dh_f64.argtypes = [C.c_double]
+    L.dh_bytes.restype = C.c_uint64
+    L.dh_bytes.argtypes = [C.c_uint64, C.c_char_p, C.c_int32]
+    return L
+
+
+def test_device_hash_source_is_bit_exact_with_the_oracle(dh):
+    """VectorHasher's hashes (exec/VectorHasher.cpp:62-126, common/base/BitUtil.h:775-784, BitUtil.cpp:177-230) as the
+    device computes them, on the CPU: integers, doubles (all NaNs alike, +0 == -0) and strings of every length class of
+    bits::hashBytes (< 8, 8..16, 17..24, > 24 bytes, with and without a tail)."""
+    L = pyoracle.lib()
+    rng = random.Random(3)
+    for k in [0, 1, 2**63, 2**64 - 1, 0x9E3779B97F4A7C15] + [rng.getrandbits(64) for _ in range(3000)]:
+        assert dh.dh_twang(k) == L.orc_twang_mix64(k)
+        assert dh.dh_jenkins(k & 0xFFFFFFFF) == L.orc_jenkins_rev_mix32(k & 0xFFFFFFFF)
+        other = rng.getrandbits(64)
+        assert dh.dh_mix(k, other) == L.orc_hash_mix(k, other)
+    import struct
+    nans = [struct.unpack("<d", struct.pack("<Q", b))[0] for b in (0x7ff8000000000000, 0xfff8000000000000, 0x7ff0000000000001, 0x7fffffffffffffff)]
+    for v in [0.0, -0.0, 1.0, -1.0, 5e-324, float("inf"), -float("inf")] + nans + [rng.uniform(-1e9, 1e9) for _ in range(2000)]:
+        assert dh.dh_f64(v) == L.orc_hash_f64(v), v
+    assert dh.dh_f64(0.0) == dh.dh_f64(-0.0) and len({dh.dh_f64(n) for n in nans}) == 1
+    for n in list(range(0, 80)) + [127, 128, 129, 1000]:
+        for _ in range(20):
+            data = bytes(rng.randint(0, 255) for _ in range(n))
+            seed = rng.choice([1, 0, rng.getrandbits(64)])
+            assert dh.dh_bytes(seed, data, n) == L.orc_hash_bytes(seed, data, n), (n, seed)
