@@ -201,3 +201,100 @@ def test_device_hash_source_is_bit_exact_with_the_oracle(dh):
             data = bytes(rng.randint(0, 255) for _ in range(n))
             seed = rng.choice([1, 0, rng.getrandbits(64)])
             assert dh.dh_bytes(seed, data, n) == L.orc_hash_bytes(seed, data, n), (n, seed)
+
+
+SORT_HARNESS = r"""
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include "velox_b200_kernels.h"
+#define __host__
+#define __device__
+#define __forceinline__ inline
+using std::isnan;
+static inline int64_t __mul64hi(int64_t a, int64_t b) { return static_cast<int64_t>((static_cast<__int128>(a) * b) >> 64); }
+static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
+#include "vm_ops.inc"
+%s
+extern "C" {
+// order-preserving code + null rank of one value, as the sort kernels compute them
+uint64_t sk_code(int32_t type, int32_t ascending, int32_t bits, const void* value, int32_t is_null, int32_t nulls_first, int32_t* rank) {
+  uint64_t valid = is_null ? 0 : 1;
+  vb2_sort_key k{value, &valid, type, ascending, nulls_first, bits};
+  bool nl;
+  const uint64_t c = encode_key(k, 0, &nl);
+  *rank = null_rank(k, nl);
+  return c;
+}
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def sk(tmp_path_factory):
+    text = open(os.path.join(ROOT, "velox_b200", "csrc", "sort.cu")).read()
+    begin = text.index("// bits of a key's code")
+    end = text.index("// ---- small inputs: rank sort")
+    d = tmp_path_factory.mktemp("sortkeys")
+    src = d / "harness.cpp"
+    src.write_text(SORT_HARNESS % text[begin:end])
+    lib = d / "libsortkeys.so"
+    subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "velox_b200", "csrc"),
+                           "-o", str(lib), str(src)])
+    L = C.CDLL(str(lib))
+    L.sk_code.restype = C.c_uint64
+    L.sk_code.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    return L
+
+
+def test_sort_key_codes_preserve_the_reference_order(sk):
+    """ORDER BY key codes (core::SortOrder, velox/core/PlanNode.h:64-95; NaN largest and -0 == +0,
+    velox/type/FloatingPointUtil.h:52-98): code(a) < code(b) exactly when a sorts before b, for both directions; NULLs rank
+    first or last independent of the direction."""
+    import math
+    BIGINT, INTEGER, DOUBLE = 4, 3, 6
+    rng = random.Random(5)
+
+    def code(typ, asc, value, bits=0, null=False, nulls_first=True):
+        if typ == DOUBLE:
+            buf = C.c_double(value if value is not None else 0.0)
+        elif typ == BIGINT:
+            buf = C.c_int64(value if value is not None else 0)
+        else:
+            buf = C.c_int32(value if value is not None else 0)
+        rank = C.c_int32()
+        c = sk.sk_code(typ, 1 if asc else 0, bits, C.cast(C.byref(buf), C.c_void_p), 1 if null else 0, 1 if nulls_first else 0, C.byref(rank))
+        return c, rank.value
+
+    def before_f64(a, b):  # a sorts strictly before b ascending: NaN is the largest value, -0 == +0
+        an, bn = math.isnan(a), math.isnan(b)
+        if an or bn:
+            return (not an) and bn
+        return a < b
+
+    doubles = [0.0, -0.0, float("nan"), float("inf"), -float("inf"), 5e-324, -5e-324, 1.5, -1.5, 1e308, -1e308] + [rng.uniform(-1e3, 1e3) for _ in range(300)]
+    for _ in range(20000):
+        a, b = rng.choice(doubles), rng.choice(doubles)
+        for asc in (True, False):
+            ca, cb = code(DOUBLE, asc, a)[0], code(DOUBLE, asc, b)[0]
+            lo, hi = (a, b) if asc else (b, a)
+            assert (ca < cb) == before_f64(lo, hi), (a, b, asc)
+            assert (ca == cb) == (not before_f64(a, b) and not before_f64(b, a))
+    ints64 = [0, 1, -1, 2**63 - 1, -2**63, 2**32, -2**32] + [rng.randint(-2**63, 2**63 - 1) for _ in range(300)]
+    ints32 = [0, 1, -1, 2**31 - 1, -2**31] + [rng.randint(-2**31, 2**31 - 1) for _ in range(300)]
+    for typ, pool in ((BIGINT, ints64), (INTEGER, ints32)):
+        for _ in range(10000):
+            a, b = rng.choice(pool), rng.choice(pool)
+            for asc in (True, False):
+                ca, cb = code(typ, asc, a)[0], code(typ, asc, b)[0]
+                assert (ca < cb) == ((a < b) if asc else (a > b)) and (ca == cb) == (a == b)
+    # dictionary rank codes: values promised to lie in [0, 2^bits) are their own code, complemented within the width for DESC
+    for _ in range(5000):
+        bits = rng.randint(1, 20)
+        a, b = rng.randrange(1 << bits), rng.randrange(1 << bits)
+        for asc in (True, False):
+            ca, cb = code(INTEGER, asc, a, bits)[0], code(INTEGER, asc, b, bits)[0]
+            assert ca < (1 << bits) and (ca < cb) == ((a < b) if asc else (a > b))
+    for asc in (True, False):
+        assert code(BIGINT, asc, None, null=True, nulls_first=True)[1] == 0 and code(BIGINT, asc, None, null=True, nulls_first=False)[1] == 2
+        assert code(BIGINT, asc, 7)[1] == 1
