@@ -133,3 +133,22 @@ def test_slice_path_falls_back_to_the_table():
     plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(["k"], ["sum(v)", "count(0)"]).planNode()
     (st,) = check_plan(plan, [rv], configs=(dict(SLICE, **{"b200.agg_slice_distinct_hint": "2000"}),))
     assert stat(st, "b200.sliceAggRows") == 0 and stat(st, "b200.genericBatches") >= 1
+
+
+def test_slice_path_wide_integer_sums_and_overflow():
+    """BIGINT inputs outside the int32 range take the 64-bit shared-memory add (values inside it are carried as two 32-bit
+    halves): mixed magnitudes and signs sum exactly; a sum that leaves the int64 range raises the reference's user error
+    (functions/prestosql/aggregates/SumAggregate.cpp: checked addition)."""
+    from util import check_user_error
+    n, distinct = 300_000, 60_000
+    rng = np.random.default_rng(9)
+    mags = rng.choice([1, 1000, 2**31 - 1, 2**31, 2**40, 2**45], n)
+    v = (rng.integers(0, 1000, n) + 1) * mags * rng.choice([-1, 1], n)
+    rv = row_vector(["k", "v"], [flat_vector(BIGINT, rng.integers(0, distinct, n) * 31 - 5_000_000), flat_vector(BIGINT, v)])
+    plan = PlanBuilder().values(rv.names, rv.types).singleAggregation(["k"], ["sum(v)", "count(0)", "min(v)", "max(v)"]).planNode()
+    (st,) = check_plan(plan, [rv], configs=(SLICE,))
+    assert stat(st, "b200.sliceAggRows") == n
+    big = np.full(n, 2**62, dtype=np.int64)
+    big[: n // 2] = 1
+    ro = row_vector(["k", "v"], [flat_vector(BIGINT, rng.integers(0, distinct, n)), flat_vector(BIGINT, big)])
+    check_user_error(PlanBuilder().values(ro.names, ro.types).singleAggregation(["k"], ["sum(v)"]).planNode(), [ro], configs=(SLICE,))
