@@ -842,6 +842,10 @@ int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_es
   uint32_t packed = 0;
   for (int o = 0; o < nops; ++o) packed |= static_cast<uint32_t>(ops[o].kind & 15) << (4 * o);
   static const bool genericOnly = [] { const char* e = std::getenv("VB2_SLICE_GENERIC_AGG"); return e && e[0] == '1'; }();
+  // the kind-specialised builds read op o's input from column fixed_col(kinds, o): only op lists of that shape take them
+  bool columnsInOrder = true;
+  for (int o = 0; o < nops; ++o)
+    if (ops[o].kind != VB2_AGG_COUNT && ops[o].col != fixed_col(packed, o)) columnsInOrder = false;
 #define VB2_SLICE_LAUNCH(N, K)                                                                                                       \
   {                                                                                                                                 \
     static size_t configured = 0;                                                                                                   \
@@ -852,7 +856,7 @@ int vb2k_slice_agg_finish(int64_t total_rows, int32_t ncols, int64_t distinct_es
     slice_aggregate_kernel<N, K><<<counted(grid), kAggThreads, smem, st>>>(a);                                                      \
   }
 #define VB2_SLICE_FIXED(N, K) \
-  if (!launched && !genericOnly && nops == N && packed == K) { VB2_SLICE_LAUNCH(N, K) launched = true; }
+  if (!launched && !genericOnly && columnsInOrder && nops == N && packed == K) { VB2_SLICE_LAUNCH(N, K) launched = true; }
 #define VB2_SLICE_AGG(N) \
   case N: VB2_SLICE_LAUNCH(N, 0u) break;
   bool launched = false;
