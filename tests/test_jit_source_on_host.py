@@ -1,0 +1,394 @@
+"""The expression JIT's generated kernels EXECUTED on the CPU. vb2k_expression_jit_compiles hands back the CUDA source it
+generates for a program and column layout (expr_jit.cu; the text NVRTC compiles for sm_100a). That text is straight-line
+per-row code plus warp ballots for the validity / selection bitmaps, so a small shim (thread indices as variables, a
+two-pass warp ballot, atomicCAS, the __d*_rn intrinsics as plain IEEE operations without contraction) lets g++ compile
+it and run it warp by warp. Its outputs are compared with the CPU oracle evaluating the same expressions as SQL — over
+flat / dictionary / constant inputs with NULLs, NaN, checked-arithmetic errors, CASE, CAST, LIKE and three-valued logic.
+No GPU needed; the GPU suite runs the same kernels on the device with both engines."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch  # noqa: F401  (first: the library binds to the CUDA libraries torch loads)
+
+from oracle import pyoracle
+from velox_b200._lib import lib
+from velox_b200.kernels import CColumn, Const, Instr, Output, Program
+from velox_b200.plan import PlanBuilder
+from velox_b200.vector import BIGINT, BOOLEAN, DOUBLE, INTEGER, VARCHAR, constant_vector, dictionary_vector, flat_vector, row_vector
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+T_BOOL, T_INT, T_BIG, T_DBL, T_STR = 0, 3, 4, 6, 7
+NAN = float("nan")
+
+SHIM = r"""
+#include <cmath>
+#include <cstring>
+#include <vector>
+namespace shim {
+struct Dim3 { unsigned x = 0, y = 0, z = 0; };
+static Dim3 threadIdx, blockIdx, gridDim;
+static int phase = 0;            // 0: lanes record their ballot predicates, 1: ballots return the recorded masks
+static size_t ballot_at = 0;     // index of the next ballot of the running lane (control flow around ballots is warp-uniform)
+static std::vector<unsigned> masks;
+static inline unsigned __ballot_sync(unsigned, bool p) {
+  const size_t i = ballot_at++;
+  if (phase == 0) {
+    if (masks.size() <= i) masks.resize(i + 1, 0u);
+    if (p) masks[i] |= 1u << (threadIdx.x & 31u);
+    return 0u;
+  }
+  return masks[i];
+}
+static inline int atomicCAS(int* p, int expect, int value) { const int old = *p; if (old == expect) *p = value; return old; }
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline long long __mul64hi(long long a, long long b) { return static_cast<long long>((static_cast<__int128>(a) * b) >> 64); }
+using std::isnan;
+using std::round;
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __grid_constant__
+#define __launch_bounds__(x)
+#define VB2_SIZEOF_COLUMN sizeof(vb2_column)
+#define VB2_SIZEOF_CONST sizeof(vb2_const)
+#define VB2_SIZEOF_OUTPUT sizeof(vb2_output)
+#define VB2_SIZEOF_ARGS sizeof(JitArgs)
+// ---- generated source ----
+%s
+// ---- driver: one block of 256 threads, warp by warp, two passes per warp ----
+}  // namespace shim
+extern "C" void run_on_host(const void* args) {
+  using namespace shim;
+  gridDim.x = 1;
+  blockIdx.x = 0;
+  const JitArgs& a = *static_cast<const JitArgs*>(args);
+  for (unsigned warp = 0; warp < 8; ++warp) {
+    masks.clear();
+    for (phase = 0; phase < 2; ++phase)
+      for (unsigned lane = 0; lane < 32; ++lane) {
+        threadIdx.x = warp * 32 + lane;
+        ballot_at = 0;
+        vb2_jit(a);
+      }
+  }
+}
+"""
+
+
+class JitArgs(C.Structure):
+    _fields_ = [("cols", CColumn * 32), ("consts", Const * 32), ("outs", Output * 32), ("n", C.c_longlong), ("sel", C.c_void_p),
+                ("sel_bits", C.c_void_p), ("error_flag", C.c_void_p)]
+
+
+# ---- a tiny expression tree -> (vb2 program, SQL text) ------------------------------------------------
+class Asm:
+    """Registers are allocated one per node; columns: list of (name, vb2 type). LIKE / string compares take the column itself."""
+
+    def __init__(self, columns):
+        self.columns = columns
+        self.ins, self.consts, self.keep = [], [], []
+        self.reg = 0
+
+    def _new(self):
+        self.reg += 1
+        return self.reg - 1
+
+    def _const(self, typ, value):
+        c = Const(typ, 0, 0, 0.0, None, 0, 0)
+        if value is None:
+            c.is_null = 1
+        elif typ == T_DBL:
+            c.d = float(value)
+        elif typ == T_STR:
+            buf = C.create_string_buffer(value.encode(), len(value.encode()))
+            self.keep.append(buf)
+            c.str, c.len = C.cast(buf, C.c_void_p).value, len(value.encode())
+        else:
+            c.i = int(value)
+        self.consts.append(c)
+        return len(self.consts) - 1
+
+    def emit(self, e):
+        """e: nested tuples. Returns (register, type, sql)."""
+        op = e[0]
+        if op == "col":
+            idx = [n for n, _ in self.columns].index(e[1])
+            typ = self.columns[idx][1]
+            r = self._new()
+            self.ins.append(Instr(1, typ, r, idx, 0, 0))
+            return r, typ, e[1]
+        if op == "lit":
+            typ, v = e[1], e[2]
+            r = self._new()
+            self.ins.append(Instr(2, typ, r, self._const(typ, v), 0, 0))
+            sql = {T_DBL: lambda x: repr(float(x)), T_BIG: lambda x: str(int(x)), T_INT: lambda x: f"cast({int(x)} as integer)",
+                   T_BOOL: lambda x: "true" if x else "false"}[typ](v)
+            return r, typ, sql
+        if op in ("+", "-", "*", "/", "%"):
+            (ra, ta, sa), (rb, _, sb) = self.emit(e[1]), self.emit(e[2])
+            r = self._new()
+            self.ins.append(Instr({"+": 3, "-": 4, "*": 5, "/": 6, "%": 7}[op], ta, r, ra, rb, 0))
+            return r, ta, f"({sa} {op} {sb})"
+        if op == "neg":
+            ra, ta, sa = self.emit(e[1])
+            r = self._new()
+            self.ins.append(Instr(8, ta, r, ra, 0, 0))
+            return r, ta, f"(-{sa})"
+        if op in ("<", "<=", ">", ">=", "=", "<>"):
+            (ra, ta, sa), (rb, _, sb) = self.emit(e[1]), self.emit(e[2])
+            r = self._new()
+            self.ins.append(Instr({"<": 9, "<=": 10, ">": 11, ">=": 12, "=": 13, "<>": 14}[op], ta, r, ra, rb, 0))
+            return r, T_BOOL, f"({sa} {op} {sb})"
+        if op == "between":
+            (ra, ta, sa), (rb, _, sb), (rc, _, sc) = self.emit(e[1]), self.emit(e[2]), self.emit(e[3])
+            r = self._new()
+            self.ins.append(Instr(15, ta, r, ra, rb, rc))
+            return r, T_BOOL, f"({sa} between {sb} and {sc})"
+        if op in ("and", "or"):
+            (ra, _, sa), (rb, _, sb) = self.emit(e[1]), self.emit(e[2])
+            r = self._new()
+            self.ins.append(Instr(16 if op == "and" else 17, T_BOOL, r, ra, rb, 0))
+            return r, T_BOOL, f"({sa} {op} {sb})"
+        if op == "not":
+            ra, _, sa = self.emit(e[1])
+            r = self._new()
+            self.ins.append(Instr(18, T_BOOL, r, ra, 0, 0))
+            return r, T_BOOL, f"(not {sa})"
+        if op == "is_null":
+            ra, _, sa = self.emit(e[1])
+            r = self._new()
+            self.ins.append(Instr(19, T_BOOL, r, ra, 0, 0))
+            return r, T_BOOL, f"({sa} is null)"
+        if op == "case":
+            (rc, _, sc), (rt, tt, st) = self.emit(e[1]), self.emit(e[2])
+            re_, se = -1, None
+            if len(e) > 3:
+                re_, _, se = self.emit(e[3])
+            r = self._new()
+            self.ins.append(Instr(20, tt, r, rc, rt, re_))
+            return r, tt, f"(case when {sc} then {st}" + (f" else {se}" if se is not None else "") + " end)"
+        if op == "cast":
+            to = e[1]
+            ra, ta, sa = self.emit(e[2])
+            r = self._new()
+            self.ins.append(Instr(21, to, r, ra, ta, 0))
+            return r, to, f"cast({sa} as {({T_DBL: 'double', T_BIG: 'bigint', T_INT: 'integer', T_BOOL: 'boolean'})[to]})"
+        if op == "like":
+            idx = [n for n, _ in self.columns].index(e[1])
+            r = self._new()
+            self.ins.append(Instr(22, T_BOOL, r, idx, self._const(T_STR, e[2]), 0))
+            return r, T_BOOL, f"({e[1]} like '{e[2]}')"
+        if op == "strcmp":
+            idx = [n for n, _ in self.columns].index(e[1])
+            code = {"<": 0, "<=": 1, ">": 2, ">=": 3, "=": 4, "<>": 5}[e[2]]
+            r = self._new()
+            self.ins.append(Instr(23, T_BOOL, r, idx, self._const(T_STR, e[3]), code))
+            return r, T_BOOL, f"({e[1]} {e[2]} '{e[3]}')"
+        raise ValueError(op)
+
+
+_cache = {}
+
+
+def _host_kernel(source, tmp):
+    if source in _cache:
+        return _cache[source]
+    i = len(_cache)
+    src = tmp / f"jit{i}.cpp"
+    src.write_text(SHIM % source)
+    so = tmp / f"jit{i}.so"
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-I", os.path.join(ROOT, "velox_b200", "csrc"),
+                           "-o", str(so), str(src)])
+    L = C.CDLL(str(so))
+    L.run_on_host.argtypes = [C.c_void_p]
+    _cache[source] = L
+    return L
+
+
+def run_projections(rv, exprs, tmp):
+    """Evaluates `exprs` over the RowVector with the JIT-generated kernel on the host. Returns (columns as python lists with
+    None for NULL, error_flag, sqls)."""
+    asm = Asm([(n, c.type) for n, c in zip(rv.names, rv.columns)])
+    regs = [asm.emit(e) for e in exprs]
+    cols = [c.to_c() for c in rv.columns]  # host buffers in the C layout (validity bitmaps, bit-packed BOOLEAN); the Column objects keep them alive
+    n = rv.size
+    ia, ca = (Instr * len(asm.ins))(*asm.ins), (Const * max(1, len(asm.consts)))(*asm.consts)
+    prog = Program(ia, len(asm.ins), 0, -1, asm.reg, ca, len(asm.consts), 0)
+    outs, bufs = [], []
+    for r, t, _ in regs:
+        width = {T_DBL: 8, T_BIG: 8, T_INT: 4, T_BOOL: 1}[t]
+        vals = np.zeros(n * width + 8, dtype=np.uint8)
+        nulls = np.zeros((n + 31) // 32 + 2, dtype=np.uint32)
+        bufs.append((vals, nulls, t))
+        outs.append(Output(r, t, vals.ctypes.data, nulls.ctypes.data))
+    L = lib()
+    L.vb2k_expression_jit_compiles.restype = C.c_int32
+    buf = C.create_string_buffer(1 << 18)
+    arr = (CColumn * len(cols))(*cols)
+    oa = (Output * len(outs))(*outs)
+    rc = L.vb2k_expression_jit_compiles(C.byref(prog), arr, len(cols), 0, oa, len(outs), buf, len(buf))
+    assert rc == 1, buf.value.decode(errors="replace")[:3000]
+    K = _host_kernel(buf.value.decode(), tmp)
+    a = JitArgs()
+    for i, c in enumerate(cols):
+        a.cols[i] = c
+    for i, c in enumerate(asm.consts):
+        a.consts[i] = c
+    for i, o in enumerate(outs):
+        a.outs[i] = o
+    a.n = n
+    err = np.zeros(2, dtype=np.int32)
+    a.error_flag = err.ctypes.data
+    K.run_on_host(C.byref(a))
+    result = []
+    for vals, nulls, t in bufs:
+        dt = {T_DBL: np.float64, T_BIG: np.int64, T_INT: np.int32, T_BOOL: np.uint8}[t]
+        v = vals[: n * np.dtype(dt).itemsize].view(dt)
+        valid = [(int(nulls[i >> 5]) >> (i & 31)) & 1 for i in range(n)]
+        result.append([None if not ok else (bool(x) if t == T_BOOL else (float(x) if t == T_DBL else int(x))) for x, ok in zip(v.tolist(), valid)])
+    return result, int(err[0]), [s for _, _, s in regs]
+
+
+def same(a, b):
+    if a is None or b is None:
+        return a is None and b is None
+    if isinstance(b, float) or isinstance(a, float):
+        return (math.isnan(a) and math.isnan(b)) or a == b
+    return a == b
+
+
+@pytest.fixture(scope="module")
+def tmp(tmp_path_factory):
+    return tmp_path_factory.mktemp("jit_on_host")
+
+
+def table(n=300, seed=0):
+    rng = np.random.default_rng(seed)
+
+    def maybe(v, p=0.12):
+        return [None if rng.random() < p else x for x in v]
+
+    return row_vector(
+        ["i", "j", "d", "q", "b", "s", "dd", "k"],
+        [flat_vector(BIGINT, maybe(rng.integers(-50, 50, n).tolist())),
+         flat_vector(INTEGER, maybe(rng.integers(-9, 10, n).tolist())),
+         flat_vector(DOUBLE, maybe(rng.choice([0.0, -0.0, 1.5, -2.25, NAN, 1e300, 7.0, float("inf")], n).tolist())),
+         flat_vector(DOUBLE, maybe(np.round(rng.normal(0, 10, n), 2).tolist())),
+         flat_vector(BOOLEAN, maybe((rng.random(n) < 0.5).tolist())),
+         dictionary_vector(VARCHAR, rng.integers(0, 6, n), ["PROMO TIN", "STANDARD", "promo", None, "", "PROMOx_"]),
+         dictionary_vector(DOUBLE, rng.integers(0, 5, n), [1.5, None, NAN, -4.0, 0.5], index_nulls=rng.random(n) < 0.05),
+         constant_vector(BIGINT, 7, n)])
+
+
+EXPRS = [
+    ("+", ("col", "i"), ("lit", T_BIG, 5)),
+    ("*", ("col", "q"), ("-", ("lit", T_DBL, 1.0), ("col", "dd"))),
+    ("/", ("col", "q"), ("col", "d")),
+    ("%", ("col", "i"), ("col", "k")),
+    ("neg", ("col", "q")),
+    ("<", ("col", "d"), ("col", "q")),
+    (">=", ("col", "d"), ("col", "dd")),
+    ("=", ("col", "d"), ("col", "d")),
+    ("<>", ("col", "i"), ("col", "k")),
+    ("between", ("col", "q"), ("lit", T_DBL, -5.0), ("lit", T_DBL, 5.0)),
+    ("and", ("col", "b"), (">", ("col", "i"), ("lit", T_BIG, 0))),
+    ("or", ("col", "b"), (">", ("col", "i"), ("lit", T_BIG, 0))),
+    ("not", ("col", "b")),
+    ("is_null", ("col", "dd")),
+    ("case", (">", ("col", "i"), ("lit", T_BIG, 0)), ("col", "q"), ("lit", T_DBL, 0.0)),
+    ("case", ("col", "b"), ("col", "i")),
+    ("cast", T_DBL, ("col", "i")),
+    ("cast", T_BIG, ("col", "j")),
+    ("cast", T_BIG, ("col", "q")),
+    ("cast", T_BOOL, ("col", "q")),
+    ("cast", T_BOOL, ("col", "i")),
+    ("like", "s", "PROMO%"),
+    ("like", "s", "%o_"),
+    ("strcmp", "s", "<", "Q"),
+    ("case", ("like", "s", "PROMO%"), ("*", ("col", "q"), ("lit", T_DBL, 2.0)), ("lit", T_DBL, 0.0)),
+]
+
+
+def test_generated_project_kernels_match_the_oracle(tmp):
+    rv = table()
+    got, err, sqls = run_projections(rv, EXPRS, tmp)
+    assert err == 0
+    plan = PlanBuilder().values(rv.names, rv.types).project([f"{s} as p{i}" for i, s in enumerate(sqls)]).planNode()
+    want = pyoracle.run_plan(plan, [rv], threads=1).rows()
+    assert len(want) == rv.size
+    for c, sql in enumerate(sqls):
+        for r in range(rv.size):
+            assert same(got[c][r], want[r][c]), (sql, r, got[c][r], want[r][c])
+
+
+@pytest.mark.parametrize("expr", [
+    ("+", ("col", "i"), ("lit", T_BIG, 2**63 - 10)),        # BIGINT overflow (CheckedArithmetic.h:27-60)
+    ("/", ("col", "i"), ("-", ("col", "k"), ("lit", T_BIG, 7))),  # division by zero
+    ("cast", T_INT, ("*", ("col", "i"), ("lit", T_BIG, 2**31))),  # out of range for INTEGER
+    ("cast", T_BIG, ("col", "d")),                           # NaN / 1e300 / inf cannot be cast to BIGINT
+])
+def test_generated_kernels_raise_where_the_oracle_raises(expr, tmp):
+    rng = np.random.default_rng(1)
+    n = 64
+    rv = row_vector(["i", "d", "k"], [flat_vector(BIGINT, rng.integers(1, 50, n).tolist()),
+                                      flat_vector(DOUBLE, rng.choice([1.5, NAN, 1e300, float("inf")], n).tolist()), constant_vector(BIGINT, 7, n)])
+    _, err, sqls = run_projections(rv, [expr], tmp)
+    assert err != 0, sqls
+    with pytest.raises(pyoracle.OracleUserError):
+        pyoracle.run_plan(PlanBuilder().values(rv.names, rv.types).project([f"{sqls[0]} as p"]).planNode(), [rv], threads=1)
+
+
+def run_filter(rv, expr, tmp):
+    """The filter form of the generated kernel: one selection bit per row (TRUE and not NULL), as processFilterResults
+    (exec/OperatorUtils.cpp:231-321) reads a filter's result."""
+    asm = Asm([(n, c.type) for n, c in zip(rv.names, rv.columns)])
+    reg, _, sql = asm.emit(expr)
+    cols = [c.to_c() for c in rv.columns]
+    n = rv.size
+    ia, ca = (Instr * len(asm.ins))(*asm.ins), (Const * max(1, len(asm.consts)))(*asm.consts)
+    prog = Program(ia, len(asm.ins), len(asm.ins), reg, asm.reg, ca, len(asm.consts), 0)
+    L = lib()
+    L.vb2k_expression_jit_compiles.restype = C.c_int32
+    buf = C.create_string_buffer(1 << 18)
+    arr = (CColumn * len(cols))(*cols)
+    oa = (Output * 1)()
+    rc = L.vb2k_expression_jit_compiles(C.byref(prog), arr, len(cols), 1, oa, 0, buf, len(buf))
+    assert rc == 1, buf.value.decode(errors="replace")[:3000]
+    K = _host_kernel(buf.value.decode(), tmp)
+    a = JitArgs()
+    for i, c in enumerate(cols):
+        a.cols[i] = c
+    for i, c in enumerate(asm.consts):
+        a.consts[i] = c
+    a.n = n
+    bits = np.zeros((n + 31) // 32 + 2, dtype=np.uint32)
+    err = np.zeros(2, dtype=np.int32)
+    a.sel_bits, a.error_flag = bits.ctypes.data, err.ctypes.data
+    K.run_on_host(C.byref(a))
+    return [i for i in range(n) if (int(bits[i >> 5]) >> (i & 31)) & 1], int(err[0]), sql
+
+
+@pytest.mark.parametrize("expr", [
+    ("and", ("between", ("col", "q"), ("lit", T_DBL, -5.0), ("lit", T_DBL, 5.0)), ("<", ("col", "i"), ("lit", T_BIG, 24))),
+    ("or", ("like", "s", "PROMO%"), ("and", ("col", "b"), (">", ("col", "dd"), ("lit", T_DBL, 0.0)))),
+    ("not", ("or", ("is_null", ("col", "d")), ("<", ("col", "d"), ("col", "q")))),
+    (">", ("col", "d"), ("lit", T_DBL, 1e300)),   # only NaN and +inf are larger
+])
+def test_generated_filter_kernels_select_the_oracle_rows(expr, tmp):
+    rv = table(n=500, seed=3)
+    ids = flat_vector(BIGINT, np.arange(rv.size))
+    selected, err, sql = run_filter(rv, expr, tmp)
+    assert err == 0
+    with_id = row_vector(rv.names + ["id"], rv.columns + [ids])
+    plan = PlanBuilder().values(with_id.names, with_id.types).filter(sql).project(["id"]).planNode()
+    want = [r[0] for r in pyoracle.run_plan(plan, [with_id], threads=1).rows()]
+    assert selected == want, sql
