@@ -83,6 +83,13 @@ int32_t vb2_scalar_function_apply(const char* name, const vb2_column* args, int3
  * reports the number of programs, of kernels (filter pass + projection pass) and of kernels that
  * generate and NVRTC-compile for sm_100a (the rest would run on the interpreter). */
 int32_t vb2_plan_jit_report(const char* plan_text, int32_t* programs, int32_t* jit_kernels, int32_t* total_kernels, char* err, int32_t errlen);
+/* Diagnostic (no GPU needed): the register program the expression compiler (ExprCompiler's role,
+ * velox/expression/ExprCompiler.cpp) produces for the ordinal-th Filter / Project node of a plan, in caller buffers:
+ * header = {n_instrs, n_consts, n_filter_instrs, filter_reg, n_regs, n_outputs, node is a filter}; per output its
+ * register (-1: identity projection of input column out_identity[i]) and type; VARCHAR constants point into `strings`. */
+int32_t vb2_plan_expression_program(const char* plan_text, int32_t ordinal, vb2_instr* instrs, int32_t instrs_cap, vb2_const* consts, int32_t consts_cap,
+                                    char* strings, int32_t strings_cap, int32_t* header, int32_t* out_regs, int32_t* out_types, int32_t* out_identity,
+                                    int32_t outs_cap, char* err, int32_t errlen);
 
 typedef struct vb2_upload_cache vb2_upload_cache;
 vb2_upload_cache* vb2_upload_cache_create(void);

@@ -560,6 +560,75 @@ int32_t vb2_plan_jit_report(const char* plan_text, int32_t* programs, int32_t* j
   });
 }
 
+// Diagnostic (no GPU needed): the register program the expression compiler produces for the `ordinal`-th Filter /
+// Project node of a plan (post-order over the plan, sources first — the order vb2_plan_jit_report walks), copied into
+// caller buffers: instructions, constants (VARCHAR constants point into `strings`), and per output its register (-1: an
+// identity projection of input column out_identity[i]) and type. header = {n_instrs, n_consts, n_filter_instrs,
+// filter_reg, n_regs, n_outputs, node is a filter}. tests/test_jit_source_on_host.py runs such programs through the
+// JIT's generated source on the CPU.
+int32_t vb2_plan_expression_program(const char* plan_text, int32_t ordinal, vb2_instr* instrs, int32_t instrs_cap, vb2_const* consts, int32_t consts_cap,
+                                    char* strings, int32_t strings_cap, int32_t* header, int32_t* out_regs, int32_t* out_types, int32_t* out_identity,
+                                    int32_t outs_cap, char* err, int32_t errlen) {
+  return guarded(err, errlen, [&] {
+    VELOX_CHECK(plan_text && instrs && consts && strings && header && out_regs && out_types && out_identity, "null argument");
+    registerB200Functions();
+    auto plan = parsePlanText(plan_text);
+    int seen = 0;
+    bool found = false;
+    std::function<void(const core::PlanNodePtr&)> walk = [&](const core::PlanNodePtr& node) {
+      for (auto& s : node->sources()) walk(s);
+      if (found) return;
+      std::vector<core::TypedExprPtr> exprs;
+      bool hasFilter = false;
+      RowTypePtr inType;
+      if (auto f = std::dynamic_pointer_cast<const core::FilterNode>(node)) {
+        inType = f->sources()[0]->outputType();
+        exprs.push_back(f->filter());
+        hasFilter = true;
+      } else if (auto p = std::dynamic_pointer_cast<const core::ProjectNode>(node)) {
+        inType = p->sources()[0]->outputType();
+        exprs = p->projections();
+      } else {
+        return;
+      }
+      if (seen++ != ordinal) return;
+      found = true;
+      CompiledProgram prog = compileExprs(exprs, hasFilter, inType);
+      VELOX_CHECK(static_cast<int32_t>(prog.instrs.size()) <= instrs_cap && static_cast<int32_t>(prog.consts.size()) <= consts_cap &&
+                      static_cast<int32_t>(prog.outputs.size()) <= outs_cap,
+                  "program does not fit the caller's buffers");
+      std::copy(prog.instrs.begin(), prog.instrs.end(), instrs);
+      size_t at = 0;
+      std::vector<size_t> offs;
+      for (auto& str : prog.constStrings) {
+        VELOX_CHECK(at + str.size() + 1 <= static_cast<size_t>(strings_cap), "string constants do not fit the caller's buffer");
+        offs.push_back(at);
+        std::memcpy(strings + at, str.data(), str.size());
+        at += str.size();
+        strings[at++] = 0;
+      }
+      for (size_t i = 0; i < prog.consts.size(); ++i) {
+        consts[i] = prog.consts[i];
+        if (consts[i].type == VB2_VARCHAR && !consts[i].is_null && consts[i].pad > 0) consts[i].str = strings + offs[consts[i].pad - 1];
+      }
+      for (size_t i = 0; i < prog.outputs.size(); ++i) {
+        out_regs[i] = prog.outputs[i].reg;
+        out_identity[i] = prog.outputs[i].identityField;
+        out_types[i] = veloxTypeToVb2(prog.outputs[i].type);
+      }
+      header[0] = static_cast<int32_t>(prog.instrs.size());
+      header[1] = static_cast<int32_t>(prog.consts.size());
+      header[2] = prog.nFilterInstrs;
+      header[3] = prog.filterReg;
+      header[4] = prog.nRegs;
+      header[5] = static_cast<int32_t>(prog.outputs.size());
+      header[6] = hasFilter ? 1 : 0;
+    };
+    walk(plan);
+    VELOX_CHECK(found, "the plan has no Filter / Project node with that ordinal");
+  });
+}
+
 int32_t vb2_task_set_comm(vb2_task* task, vb2_comm* comm) {
   if (!task || !task->task) return VB2_ERR_INVALID;
   task->task->setExchangeTransport(comm ? std::make_shared<velox_b200::NcclTransport>(comm) : nullptr);
