@@ -588,3 +588,158 @@ def test_random_expressions_through_compiler_and_generated_source(seed, tmp):
             for r in range(rv.size):
                 assert same(col[r], want[r][c]), (exprs[c], r, col[r], want[r][c])
     assert checked >= 15
+
+
+# ---- the interpreter (expr_vm.cu), the JIT's fallback and parity partner, on the host ------------------------------------
+VM_SHIM = r"""
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "velox_b200_kernels.h"
+namespace vb2 {
+struct Dim3 { unsigned x = 0, y = 0, z = 0; };
+static Dim3 threadIdx, blockIdx, gridDim;
+static int phase = 0;
+static size_t ballot_at = 0;
+static std::vector<unsigned> masks;
+static inline unsigned __ballot_sync(unsigned, bool p) {
+  const size_t i = ballot_at++;
+  if (phase == 0) {
+    if (masks.size() <= i) masks.resize(i + 1, 0u);
+    if (p) masks[i] |= 1u << (threadIdx.x & 31u);
+    return 0u;
+  }
+  return masks[i];
+}
+static inline int atomicCAS(int* p, int expect, int value) { const int old = *p; if (old == expect) *p = value; return old; }
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline int64_t __mul64hi(int64_t a, int64_t b) { return static_cast<int64_t>((static_cast<__int128>(a) * b) >> 64); }
+using std::isnan;
+using std::round;
+using std::fmod;
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __grid_constant__
+#define __launch_bounds__(x)
+#define __shared__
+#define __restrict__
+#include "vm_ops.inc"
+uint64_t vm_regs[64 * 256];  // the interpreter's register file: [reg][thread] in shared memory on the device
+// ---- expr_vm.cu, from its limits to the end of the project kernel ----
+%s
+}  // namespace vb2
+extern "C" void run_vm_on_host(const vb2_program* prog, const vb2_column* cols, int ncols, const vb2_output* outs, int nouts, long long n,
+                               unsigned* sel_bits, int* error_flag, int filter, int plain) {
+  using namespace vb2;
+  static VmArgs a;
+  std::memset(&a, 0, sizeof(a));
+  std::memcpy(a.instrs, prog->instrs, sizeof(vb2_instr) * prog->n_instrs);
+  std::memcpy(a.consts, prog->consts, sizeof(vb2_const) * prog->n_consts);
+  std::memcpy(a.cols, cols, sizeof(vb2_column) * ncols);
+  if (nouts) std::memcpy(a.outs, outs, sizeof(vb2_output) * nouts);
+  a.n_instrs = prog->n_instrs;
+  a.n_filter_instrs = prog->n_filter_instrs;
+  a.filter_reg = prog->filter_reg;
+  a.n_outs = nouts;
+  a.n = n;
+  a.sel_bits = sel_bits;
+  a.error_flag = error_flag;
+  gridDim.x = 1;
+  blockIdx.x = 0;
+  for (unsigned warp = 0; warp < 8; ++warp) {
+    masks.clear();
+    for (phase = 0; phase < 2; ++phase)
+      for (unsigned lane = 0; lane < 32; ++lane) {
+        threadIdx.x = warp * 32 + lane;
+        ballot_at = 0;
+        if (filter) { if (plain) vm_filter_kernel<true>(a); else vm_filter_kernel<false>(a); }
+        else { if (plain) vm_project_kernel<true>(a); else vm_project_kernel<false>(a); }
+      }
+  }
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def vm(tmp_path_factory):
+    text = open(os.path.join(ROOT, "velox_b200", "csrc", "expr_vm.cu")).read()
+    begin = text.index("constexpr int kVmMaxInstrs")
+    end = text.index("// ---- selection bitmap -> ascending row numbers")
+    d = tmp_path_factory.mktemp("vm_on_host")
+    src = d / "vm.cpp"
+    src.write_text(VM_SHIM % text[begin:end])
+    so = d / "libvm.so"
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "velox_b200", "csrc"), "-o", str(so), str(src)])
+    L = C.CDLL(str(so))
+    L.run_vm_on_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    return L
+
+
+def run_interpreter(vm, rv, node):
+    cols = [c.to_c() for c in rv.columns]
+    n = rv.size
+    prog = Program(node["ins"], node["n_ins"], node["n_filter"], node["filter_reg"], node["n_regs"], node["consts"], node["n_consts"], 0)
+    outs, bufs = [], []
+    for reg, t, _ in node["outs"]:
+        if reg < 0 or node["is_filter"]:
+            continue
+        vals = np.zeros(n * 8 + 8, dtype=np.uint8)  # the interpreter stores 8-byte words except INTEGER / BOOLEAN
+        nulls = np.zeros((n + 31) // 32 + 2, dtype=np.uint32)
+        bufs.append((vals, nulls, t))
+        outs.append(Output(reg, t, vals.ctypes.data, nulls.ctypes.data))
+    arr = (CColumn * len(cols))(*cols)
+    oa = (Output * max(1, len(outs)))(*outs)
+    bits = np.zeros((n + 31) // 32 + 2, dtype=np.uint32)
+    err = np.zeros(2, dtype=np.int32)
+    vm.run_vm_on_host(C.byref(prog), arr, len(cols), oa, len(outs), n, bits.ctypes.data, err.ctypes.data, 1 if node["is_filter"] else 0, 0)
+    assert err[0] == 0
+    if node["is_filter"]:
+        return [i for i in range(n) if (int(bits[i >> 5]) >> (i & 31)) & 1]
+    result, it = [], iter(bufs)
+    for reg, t, _ in node["outs"]:
+        if reg < 0:
+            result.append(None)
+            continue
+        vals, nulls, _ = next(it)
+        dt = {T_DBL: np.float64, T_BIG: np.int64, T_INT: np.int32, T_BOOL: np.uint8}[t]
+        v = vals[: n * np.dtype(dt).itemsize].view(dt)
+        valid = [(int(nulls[i >> 5]) >> (i & 31)) & 1 for i in range(n)]
+        result.append([None if not ok else (bool(x) if t == T_BOOL else (float(x) if t == T_DBL else int(x))) for x, ok in zip(v.tolist(), valid)])
+    return result
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_interpreter_on_host_matches_the_oracle_and_the_jit(seed, vm, tmp):
+    """The interpreter kernels of expr_vm.cu compiled for the host run the compiler's programs for the TPC-H expressions and
+    for random expressions: equal to the oracle, and to what the JIT's generated source computes, value for value."""
+    import random
+    rng = random.Random(seed)
+    rv = table(n=200, seed=seed)
+    for _ in range(8):
+        exprs = [_rand_expr(rng, rng.choice("idb"), 3) for _ in range(3)]
+        plan = PlanBuilder().values(rv.names, rv.types).project([f"{e} as p{i}" for i, e in enumerate(exprs)]).planNode()
+        try:
+            node = compiled_node(plan)
+        except AssertionError as ex:
+            if "more than" in str(ex):
+                continue
+            raise
+        want = pyoracle.run_plan(plan, [rv], threads=1).rows()
+        got_vm, got_jit = run_interpreter(vm, rv, node), run_compiled(rv, node, tmp)
+        for c, col in enumerate(got_vm):
+            if col is None:
+                continue
+            for r in range(rv.size):
+                assert same(col[r], want[r][c]) and same(col[r], got_jit[c][r]), (exprs[c], r, col[r], want[r][c], got_jit[c][r])
+    li = lineitem(n=300, seed=seed)
+    f = "l_shipdate between '1994-01-01'::DATE and '1994-12-31'::DATE and l_discount between 0.05 and 0.07 and l_quantity < 24.0"
+    fplan = PlanBuilder().values(li.names, li.types).filter(f).project(["id"]).planNode()
+    assert run_interpreter(vm, li, compiled_node(fplan)) == [r[0] for r in pyoracle.run_plan(fplan, [li], threads=1).rows()]
