@@ -206,7 +206,7 @@ def _host_kernel(source, tmp):
     src = tmp / f"jit{i}.cpp"
     src.write_text(SHIM % source)
     so = tmp / f"jit{i}.so"
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-I", os.path.join(ROOT, "velox_b200", "csrc"),
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-ffp-contract=off", "-w", "-I", os.path.join(ROOT, "velox_b200", "csrc"),
                            "-o", str(so), str(src)])
     L = C.CDLL(str(so))
     L.run_on_host.argtypes = [C.c_void_p]
@@ -597,7 +597,9 @@ VM_SHIM = r"""
 #include <cstring>
 #include <vector>
 #include "velox_b200_kernels.h"
-namespace vb2 {
+// Not `vb2`: the product library's host-side launch stubs of these kernel templates carry the same mangled names, and a
+// weak template symbol binds to whichever definition the process loaded first.
+namespace vb2_on_host {
 struct Dim3 { unsigned x = 0, y = 0, z = 0; };
 static Dim3 threadIdx, blockIdx, gridDim;
 static int phase = 0;
@@ -634,10 +636,10 @@ using std::fmod;
 uint64_t vm_regs[64 * 256];  // the interpreter's register file: [reg][thread] in shared memory on the device
 // ---- expr_vm.cu, from its limits to the end of the project kernel ----
 %s
-}  // namespace vb2
+}  // namespace vb2_on_host
 extern "C" void run_vm_on_host(const vb2_program* prog, const vb2_column* cols, int ncols, const vb2_output* outs, int nouts, long long n,
                                unsigned* sel_bits, int* error_flag, int filter, int plain) {
-  using namespace vb2;
+  using namespace vb2_on_host;
   static VmArgs a;
   std::memset(&a, 0, sizeof(a));
   std::memcpy(a.instrs, prog->instrs, sizeof(vb2_instr) * prog->n_instrs);
@@ -676,7 +678,7 @@ def vm(tmp_path_factory):
     src = d / "vm.cpp"
     src.write_text(VM_SHIM % text[begin:end])
     so = d / "libvm.so"
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-w", "-I", os.path.join(ROOT, "include"),
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-ffp-contract=off", "-w", "-I", os.path.join(ROOT, "include"),
                            "-I", os.path.join(ROOT, "velox_b200", "csrc"), "-o", str(so), str(src)])
     L = C.CDLL(str(so))
     L.run_vm_on_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
