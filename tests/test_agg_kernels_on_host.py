@@ -41,6 +41,7 @@ static inline unsigned __ballot_sync(unsigned, bool p) {
   }
   return masks[i];
 }
+static inline void __threadfence() {}
 static inline int atomicCAS(int* p, int e, int v) { const int o = *p; if (o == e) *p = v; return o; }
 static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long e, unsigned long long v) { const auto o = *p; if (o == e) *p = v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const auto o = *p; *p += v; return o; }
@@ -61,12 +62,15 @@ using std::isnan;
 #define __launch_bounds__(...)
 #define __restrict__
 #include "vm_ops.inc"
+constexpr uint64_t kNullHash = 1;
 // ---- common.cuh: hash mixers ----
 %(mixers)s
 // ---- hash_agg.cu: key normalisation ----
 %(norm)s
 // ---- hash_agg.cu: accumulator updates, group table, group_update_kernel ----
 %(update)s
+// ---- hash_agg.cu: keyed (kHash) tables ----
+%(keyed)s
 }  // namespace vb2_on_host
 
 using namespace vb2_on_host;
@@ -104,6 +108,15 @@ void h_group_update(const vb2_group_table* t, const uint64_t* keys, const uint64
   for (int i = 0; i < naggs; ++i) args.a[i] = aggs[i];
   launch(n, false, [&] { group_update_kernel(*t, keys, valid, n, args, num_groups, error_flag); });
 }
+void h_group_update_keyed(const vb2_group_table* t, const vb2_column* cols, int nkeys, int64_t n, const vb2_agg_update* aggs, int naggs, int32_t* error_flag) {
+  KeyedCols kc{};
+  kc.n = nkeys;
+  for (int k = 0; k < nkeys; ++k) kc.c[k] = cols[k];
+  AggArgs args{};
+  args.n = naggs;
+  for (int i = 0; i < naggs; ++i) args.a[i] = aggs[i];
+  launch(n, false, [&] { group_update_keyed_kernel(*t, kc, n, args, nullptr, error_flag); });
+}
 }
 """
 
@@ -131,6 +144,7 @@ def host(tmp_path_factory):
         "mixers": _between(common, "__host__ __device__ __forceinline__ uint64_t twang_mix64", "__device__ __forceinline__ uint64_t hash_f64"),
         "norm": _between(agg, "constexpr int kMaxNormCols", "__global__ void minmax_kernel"),
         "update": _between(agg, "__device__ __forceinline__ double input_as_f64", "// Array-mode tables from a handful to a few thousand groups"),
+        "keyed": _between(agg, "struct KeyedCols {", "// Slot of a key tuple already in a keyed table"),
     }
     d = tmp_path_factory.mktemp("agg_on_host")
     src = d / "agg.cpp"
@@ -258,3 +272,45 @@ def test_sum_overflow_sets_the_error_flag(host):
     err = np.zeros(2, dtype=np.int32)
     host.h_group_update(C.byref(t), P(keys), None, C.c_int64(n), aggs, 1, None, P(err))
     assert err[0] == 1
+
+
+def test_keyed_group_update(host):
+    """The keyed (kHash) group table (exec/HashTable.cpp:1751-1838): rows store their key columns; DOUBLE keys group by canonical
+    bits (every NaN one group, -0 with +0), a wide BIGINT key beside it, NULL keys form groups of their own
+    (GroupingSet.cpp:448-455)."""
+    rng = np.random.default_rng(8)
+    n = 2500
+    nan = float("nan")
+    a = [None if rng.random() < 0.06 else int(v) * 2**41 - 2**55 for v in rng.integers(0, 6, n)]
+    d = [None if rng.random() < 0.06 else float(v) for v in rng.choice([0.0, -0.0, nan, 1.5, -2.25], n)]
+    y = rng.integers(-100, 100, n).astype(np.int64)
+    key_columns = [flat_vector(BIGINT, a), flat_vector(DOUBLE, d)]  # kept: to_c() points into buffers these objects own
+    cols = (CColumn * 2)(*[c.to_c() for c in key_columns])
+    nkeys, row_words, capacity = 2, 8, 128          # [state | key words x2 | NULL mask | sum | count | pad x2]
+    rows = np.zeros(capacity * row_words, dtype=np.uint64)
+    rows[0::row_words] = np.uint64(EMPTY)
+    t = GroupTable(rows.ctypes.data, capacity, row_words, 2)
+    aggs = (AggUpdate * 2)(AggUpdate(SUM_I64, BIGINT, y.ctypes.data, None, None, None, None, 4, -1), AggUpdate(COUNT, BIGINT, None, None, None, None, None, 5, -1))
+    err = np.zeros(2, dtype=np.int32)
+    host.h_group_update_keyed(C.byref(t), cols, nkeys, C.c_int64(n), aggs, 2, P(err))
+    assert err[0] == 0
+    want = {}
+    for i in range(n):
+        dk = None if d[i] is None else ("nan" if d[i] != d[i] else (0.0 if d[i] == 0.0 else d[i]))
+        g = want.setdefault((a[i], dk), [0, 0])
+        g[0] += int(y[i])
+        g[1] += 1
+    table = rows.reshape(capacity, row_words)
+    got = {}
+    for r in table:
+        if int(r[0]) == EMPTY:
+            continue
+        assert int(r[0]) & 1  # published
+        nullmask = int(r[3])
+        ka = None if nullmask & 1 else int(np.array([r[1]], dtype=np.uint64).view(np.int64)[0])
+        kd = None
+        if not nullmask & 2:
+            v = float(np.array([r[2]], dtype=np.uint64).view(np.float64)[0])
+            kd = "nan" if v != v else v
+        got[(ka, kd)] = [int(np.array([r[4]], dtype=np.uint64).view(np.int64)[0]), int(r[5])]
+    assert got == want
