@@ -1,0 +1,123 @@
+"""TEST INFRASTRUCTURE — a small lock-step emulation of the CUDA execution model for running extracted kernel source on
+the CPU: every CUDA thread of a block is an OS thread, blocks run one after another, __syncthreads and the warp
+collectives (__shfl_up_sync / __shfl_xor_sync / __match_any_sync / __ballot_sync / __syncwarp) are barriers over per-warp
+exchange slots, atomics are real atomics, `__shared__` variables are function-local statics (one block at a time).
+Used by the *_on_host tests, which splice kernel text taken verbatim from velox_b200/csrc/*.cu after PRELUDE."""
+import ctypes as C
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "velox_b200", "csrc")
+
+PRELUDE = r"""
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+#include "velox_b200_kernels.h"
+namespace vb2_on_host {
+struct Dim3 { unsigned x = 0, y = 0, z = 0; };
+static thread_local Dim3 threadIdx;
+static Dim3 blockIdx, gridDim, blockDim;   // one block runs at a time
+static std::unique_ptr<std::barrier<>> block_barrier;
+static std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
+static long long exchange[32][32];          // [warp][lane]
+static inline void __syncthreads() { block_barrier->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
+template <class T, class Pick>
+static inline T warp_exchange(T v, Pick pick) {  // every lane publishes v, then reads the lane pick(own lane) names
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  long long bits = 0;
+  std::memcpy(&bits, &v, sizeof(T));
+  exchange[w][l] = bits;
+  warp_barrier[w]->arrive_and_wait();
+  const long long got = exchange[w][pick(l) & 31u];
+  warp_barrier[w]->arrive_and_wait();
+  T out;
+  std::memcpy(&out, &got, sizeof(T));
+  return out;
+}
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, int delta) { return warp_exchange(v, [delta](unsigned l) { return l >= static_cast<unsigned>(delta) ? l - delta : l; }); }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int mask) { return warp_exchange(v, [mask](unsigned l) { return l ^ static_cast<unsigned>(mask); }); }
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src) { return warp_exchange(v, [src](unsigned) { return static_cast<unsigned>(src); }); }
+static inline unsigned __match_any_sync(unsigned, unsigned v) {
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  exchange[w][l] = v;
+  warp_barrier[w]->arrive_and_wait();
+  unsigned m = 0;
+  for (unsigned o = 0; o < 32; ++o)
+    if (static_cast<unsigned>(exchange[w][o]) == v) m |= 1u << o;
+  warp_barrier[w]->arrive_and_wait();
+  return m;
+}
+static inline unsigned __ballot_sync(unsigned, bool p) {
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  exchange[w][l] = p ? 1 : 0;
+  warp_barrier[w]->arrive_and_wait();
+  unsigned m = 0;
+  for (unsigned o = 0; o < 32; ++o)
+    if (exchange[w][o]) m |= 1u << o;
+  warp_barrier[w]->arrive_and_wait();
+  return m;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs(static_cast<int>(v)); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int64_t __mul64hi(int64_t a, int64_t b) { return static_cast<int64_t>((static_cast<__int128>(a) * b) >> 64); }
+using std::isnan;
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __grid_constant__
+#define __launch_bounds__(...)
+#define __restrict__
+#define __shared__ static
+constexpr int kWarp = 32;
+#include "vm_ops.inc"
+template <class F>
+static void launch(unsigned grid, unsigned threads, F&& kernel) {
+  gridDim.x = grid;
+  blockDim.x = threads;
+  for (unsigned b = 0; b < grid; ++b) {
+    blockIdx.x = b;
+    block_barrier = std::make_unique<std::barrier<>>(threads);
+    warp_barrier.clear();
+    for (unsigned w = 0; w < (threads + 31) / 32; ++w) warp_barrier.push_back(std::make_unique<std::barrier<>>(32));
+    std::vector<std::thread> ts;
+    for (unsigned t = 0; t < threads; ++t)
+      ts.emplace_back([&, t] {
+        threadIdx.x = t;
+        kernel();
+      });
+    for (auto& th : ts) th.join();
+  }
+}
+"""
+
+
+def between(text, begin, end):
+    b = text.index(begin)
+    return text[b:text.index(end, b)]
+
+
+def source(name):
+    with open(os.path.join(CSRC, name)) as f:
+        return f.read()
+
+
+def build(tmpdir, name, body):
+    """Compiles PRELUDE + body (kernel text inside namespace vb2_on_host, then the extern "C" drivers) into a shared library."""
+    src = tmpdir / f"{name}.cpp"
+    src.write_text(PRELUDE + body)
+    so = tmpdir / f"lib{name}.so"
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", "-ffp-contract=off", "-w", "-I", os.path.join(ROOT, "include"),
+                           "-I", CSRC, "-o", str(so), str(src)])
+    return C.CDLL(str(so))

@@ -1,101 +1,31 @@
 """The stable partition order of B200PartitionedOutput (csrc/hash_partition.cu: per-block histograms, the parallel offsets
 scan, the warp-ranked stable scatter — HashPartitionFunction::partition followed by the per-destination grouping of
-exec/PartitionedOutput.cpp) compiled FOR THE HOST and run under a small lock-step emulation: every CUDA thread of a
-block is an OS thread, __syncthreads and the warp collectives (__shfl_up_sync, __match_any_sync) are barriers over
-exchange slots. Result against numpy's stable argsort, partition ids given or computed on the fly from a BIGINT key
-(folly::hasher = twang_mix64, then % partitions — bit-exact with the oracle). No GPU needed."""
+exec/PartitionedOutput.cpp) and the selection-bitmap expansion behind every filter (csrc/expr_vm.cu sel_count / scan /
+write: processFilterResults' selectedIndices, exec/OperatorUtils.cpp:231-321) compiled FOR THE HOST and run under the
+lock-step emulation of tests/host_emulator.py (an OS thread per CUDA thread, barriers for __syncthreads and the warp
+collectives). Results against numpy: the stable argsort by partition id — ids given, or computed on the fly from a BIGINT
+key as folly::hasher (twang_mix64) % partitions, bit-exact with the oracle's routing — and the ascending row numbers of
+the set bits. No GPU needed."""
 import ctypes as C
-import os
-import subprocess
 
 import numpy as np
 import pytest
 
+from host_emulator import between, build, source
 from oracle import pyoracle
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-
-SHIM = r"""
-#include <barrier>
-#include <cmath>
-#include <cstdint>
-#include <cstring>
-#include <memory>
-#include <thread>
-#include <vector>
-#include "velox_b200_kernels.h"
-namespace vb2_on_host {
-struct Dim3 { unsigned x = 0, y = 0, z = 0; };
-static thread_local Dim3 threadIdx;
-static Dim3 blockIdx, gridDim, blockDim;   // one block runs at a time
-static std::unique_ptr<std::barrier<>> block_barrier;
-static std::vector<std::unique_ptr<std::barrier<>>> warp_barrier;
-static long long exchange[32][32];          // [warp][lane]
-static inline void __syncthreads() { block_barrier->arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
-template <class T>
-static inline T __shfl_up_sync(unsigned, T v, int delta) {
-  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  long long bits = 0;
-  std::memcpy(&bits, &v, sizeof(T));
-  exchange[w][l] = bits;
-  warp_barrier[w]->arrive_and_wait();
-  const long long got = exchange[w][l >= static_cast<unsigned>(delta) ? l - delta : l];
-  warp_barrier[w]->arrive_and_wait();
-  T out;
-  std::memcpy(&out, &got, sizeof(T));
-  return out;
-}
-static inline unsigned __match_any_sync(unsigned, unsigned v) {
-  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  exchange[w][l] = v;
-  warp_barrier[w]->arrive_and_wait();
-  unsigned m = 0;
-  for (unsigned o = 0; o < 32; ++o)
-    if (static_cast<unsigned>(exchange[w][o]) == v) m |= 1u << o;
-  warp_barrier[w]->arrive_and_wait();
-  return m;
-}
-static inline int __popc(unsigned v) { return __builtin_popcount(v); }
-static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-static inline int64_t __mul64hi(int64_t a, int64_t b) { return static_cast<int64_t>((static_cast<__int128>(a) * b) >> 64); }
-using std::isnan;
-#define __global__
-#define __device__
-#define __host__
-#define __forceinline__ inline
-#define __grid_constant__
-#define __launch_bounds__(...)
-#define __restrict__
-#define __shared__ static
-constexpr int kWarp = 32;
-#include "vm_ops.inc"
-// ---- common.cuh: hash mixers ----
+BODY = r"""
+// ---- common.cuh: hash mixers, warp reductions ----
 %(mixers)s
+%(reductions)s
 // ---- hash_partition.cu: the stable partition order ----
 %(part)s
+// ---- expr_vm.cu: selection bitmap -> ascending row numbers ----
+%(sel)s
 }  // namespace vb2_on_host
-
 using namespace vb2_on_host;
-template <class F>
-static void launch(unsigned grid, unsigned threads, F&& kernel) {
-  gridDim.x = grid;
-  blockDim.x = threads;
-  for (unsigned b = 0; b < grid; ++b) {
-    blockIdx.x = b;
-    block_barrier = std::make_unique<std::barrier<>>(threads);
-    warp_barrier.clear();
-    for (unsigned w = 0; w < (threads + 31) / 32; ++w) warp_barrier.push_back(std::make_unique<std::barrier<>>(32));
-    std::vector<std::thread> ts;
-    for (unsigned t = 0; t < threads; ++t)
-      ts.emplace_back([&, t] {
-        vb2_on_host::threadIdx.x = t;
-        kernel();
-      });
-    for (auto& th : ts) th.join();
-  }
-}
-extern "C" void h_partition_order(const uint32_t* ids, const void* key, int is64, int64_t rows, int parts, int64_t* counts, int32_t* order) {
+extern "C" {
+void h_partition_order(const uint32_t* ids, const void* key, int is64, int64_t rows, int parts, int64_t* counts, int32_t* order) {
   const PartSrc src{ids, key, is64};
   const int64_t nblocks = (rows + kPartRowsPerBlock - 1) / kPartRowsPerBlock;
   std::vector<int32_t> hist(nblocks * parts);
@@ -104,30 +34,29 @@ extern "C" void h_partition_order(const uint32_t* ids, const void* key, int is64
   launch(1, kOffsetThreads, [&] { part_offsets_kernel(hist.data(), nblocks, parts, counts, base.data()); });
   launch(static_cast<unsigned>(nblocks), kPartThreads, [&] { part_scatter_kernel(src, rows, parts, base.data(), order); });
 }
+void h_bits_to_indices(const uint32_t* bits, int64_t rows, int32_t* indices, int64_t* count) {
+  const int64_t nwords = (rows + 31) >> 5;
+  const int64_t nblocks = (nwords + kSelWordsPerBlock - 1) / kSelWordsPerBlock;
+  std::vector<int32_t> counts(nblocks);
+  std::vector<int64_t> offsets(nblocks);
+  launch(static_cast<unsigned>(nblocks), kSelThreads, [&] { sel_count_kernel(bits, nwords, counts.data()); });
+  launch(1, 1024, [&] { sel_scan_kernel(counts.data(), nblocks, offsets.data(), count); });
+  launch(static_cast<unsigned>(nblocks), kSelThreads, [&] { sel_write_kernel(bits, nwords, offsets.data(), indices); });
+}
+}
 """
-
-
-def _between(text, begin, end):
-    b = text.index(begin)
-    return text[b:text.index(end, b)]
 
 
 @pytest.fixture(scope="module")
 def host(tmp_path_factory):
-    csrc = os.path.join(ROOT, "velox_b200", "csrc")
-    common = open(os.path.join(csrc, "common.cuh")).read()
-    part = open(os.path.join(csrc, "hash_partition.cu")).read()
-    parts = {
-        "mixers": _between(common, "__host__ __device__ __forceinline__ uint64_t twang_mix64", "__device__ __forceinline__ uint64_t hash_f64"),
-        "part": _between(part, "constexpr int kPartThreads", "// --- fixed-capacity segments"),
+    common, part, vm = source("common.cuh"), source("hash_partition.cu"), source("expr_vm.cu")
+    body = BODY % {
+        "mixers": between(common, "__host__ __device__ __forceinline__ uint64_t twang_mix64", "__device__ __forceinline__ uint64_t hash_f64"),
+        "reductions": between(common, "__device__ __forceinline__ double warp_sum(double v)", "}  // namespace vb2"),
+        "part": between(part, "constexpr int kPartThreads", "// --- fixed-capacity segments"),
+        "sel": between(vm, "constexpr int kSelThreads", "static unsigned vm_grid"),
     }
-    d = tmp_path_factory.mktemp("partition_on_host")
-    src = d / "part.cpp"
-    src.write_text(SHIM % parts)
-    so = d / "libpart.so"
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", "-w", "-I", os.path.join(ROOT, "include"), "-I", csrc,
-                           "-o", str(so), str(src)])
-    return C.CDLL(str(so))
+    return build(tmp_path_factory.mktemp("partition_on_host"), "part", body)
 
 
 P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
@@ -159,3 +88,20 @@ def test_partition_ids_from_a_key_column_match_the_oracle(host):
     want_ids = np.array([L.orc_twang_mix64(int(k) & 0xFFFFFFFFFFFFFFFF) % parts for k in keys], dtype=np.int64)
     assert np.array_equal(counts, np.bincount(want_ids, minlength=parts))
     assert np.array_equal(order, np.argsort(want_ids, kind="stable").astype(np.int32))
+
+
+@pytest.mark.parametrize("density", [0.5, 0.02, 0.0, 1.0])
+def test_selection_bitmap_expands_to_ascending_rows(host, density):
+    """Dense bitmaps take the warp-per-word path, sparse ones the per-thread bit loop; several blocks of 32 768 rows."""
+    rng = np.random.default_rng(int(density * 100))
+    n = 2 * 32768 + 4321
+    keep = rng.random(n) < density
+    words = np.zeros((n + 31) // 32 + 2, dtype=np.uint32)
+    for i in np.nonzero(keep)[0]:
+        words[i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    indices = np.full(n + 1, -1, dtype=np.int32)
+    count = np.zeros(1, dtype=np.int64)
+    host.h_bits_to_indices(P(words), C.c_int64(n), P(indices), P(count))
+    want = np.nonzero(keep)[0].astype(np.int32)
+    assert int(count[0]) == len(want)
+    assert np.array_equal(indices[:len(want)], want)
