@@ -1,7 +1,8 @@
 """The stable partition order of B200PartitionedOutput (csrc/hash_partition.cu: per-block histograms, the parallel offsets
 scan, the warp-ranked stable scatter — HashPartitionFunction::partition followed by the per-destination grouping of
-exec/PartitionedOutput.cpp) and the selection-bitmap expansion behind every filter (csrc/expr_vm.cu sel_count / scan /
-write: processFilterResults' selectedIndices, exec/OperatorUtils.cpp:231-321) compiled FOR THE HOST and run under the
+exec/PartitionedOutput.cpp) the selection-bitmap expansion behind every filter (csrc/expr_vm.cu sel_count / scan /
+write: processFilterResults' selectedIndices, exec/OperatorUtils.cpp:231-321) and the exclusive scan that turns per-row match
+counts into the join's output offsets (csrc/hash_join.cu) compiled FOR THE HOST and run under the
 lock-step emulation of tests/host_emulator.py (an OS thread per CUDA thread, barriers for __syncthreads and the warp
 collectives). Results against numpy: the stable argsort by partition id — ids given, or computed on the fly from a BIGINT
 key as folly::hasher (twang_mix64) % partitions, bit-exact with the oracle's routing — and the ascending row numbers of
@@ -22,6 +23,8 @@ BODY = r"""
 %(part)s
 // ---- expr_vm.cu: selection bitmap -> ascending row numbers ----
 %(sel)s
+// ---- hash_join.cu: exclusive scan of the per-row match counts ----
+%(scan)s
 }  // namespace vb2_on_host
 using namespace vb2_on_host;
 extern "C" {
@@ -43,18 +46,26 @@ void h_bits_to_indices(const uint32_t* bits, int64_t rows, int32_t* indices, int
   launch(1, 1024, [&] { sel_scan_kernel(counts.data(), nblocks, offsets.data(), count); });
   launch(static_cast<unsigned>(nblocks), kSelThreads, [&] { sel_write_kernel(bits, nwords, offsets.data(), indices); });
 }
+void h_exclusive_scan(const int32_t* in, int64_t n, int64_t* out, int64_t* total) {
+  const int64_t nblocks = (n + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems);
+  std::vector<int64_t> sums(nblocks);
+  launch(static_cast<unsigned>(nblocks), kScanThreads, [&] { scan_block_sums_kernel(in, n, sums.data()); });
+  launch(1, 1024, [&] { scan_offsets_kernel(sums.data(), nblocks, total); });
+  launch(static_cast<unsigned>(nblocks), kScanThreads, [&] { scan_write_kernel(in, n, sums.data(), out); });
+}
 }
 """
 
 
 @pytest.fixture(scope="module")
 def host(tmp_path_factory):
-    common, part, vm = source("common.cuh"), source("hash_partition.cu"), source("expr_vm.cu")
+    common, part, vm, join = source("common.cuh"), source("hash_partition.cu"), source("expr_vm.cu"), source("hash_join.cu")
     body = BODY % {
         "mixers": between(common, "__host__ __device__ __forceinline__ uint64_t twang_mix64", "__device__ __forceinline__ uint64_t hash_f64"),
         "reductions": between(common, "__device__ __forceinline__ double warp_sum(double v)", "}  // namespace vb2"),
         "part": between(part, "constexpr int kPartThreads", "// --- fixed-capacity segments"),
         "sel": between(vm, "constexpr int kSelThreads", "static unsigned vm_grid"),
+        "scan": between(join, "constexpr int kScanThreads", "static unsigned grid_for"),
     }
     return build(tmp_path_factory.mktemp("partition_on_host"), "part", body)
 
@@ -105,3 +116,15 @@ def test_selection_bitmap_expands_to_ascending_rows(host, density):
     want = np.nonzero(keep)[0].astype(np.int32)
     assert int(count[0]) == len(want)
     assert np.array_equal(indices[:len(want)], want)
+
+
+def test_exclusive_scan_of_match_counts(host):
+    """count -> scan -> emit: the offsets of the join's output pairs (listJoinResults, exec/HashTable.cpp:2133-2350)."""
+    rng = np.random.default_rng(4)
+    n = 3 * 2048 + 555
+    counts = rng.integers(0, 5, n).astype(np.int32)
+    out = np.full(n, -1, dtype=np.int64)
+    total = np.zeros(1, dtype=np.int64)
+    host.h_exclusive_scan(P(counts), C.c_int64(n), P(out), P(total))
+    want = np.concatenate([[0], np.cumsum(counts.astype(np.int64))])
+    assert int(total[0]) == int(want[-1]) and np.array_equal(out, want[:-1])
