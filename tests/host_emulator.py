@@ -71,6 +71,36 @@ static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs(static_cast<int>(v)); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicCAS(int* p, int e, int v) { __atomic_compare_exchange_n(p, &e, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return e; }
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long e, unsigned long long v) {
+  __atomic_compare_exchange_n(p, &e, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return e;
+}
+static inline double atomicAdd(double* p, double v) {
+  unsigned long long* q = reinterpret_cast<unsigned long long*>(p);
+  unsigned long long old = __atomic_load_n(q, __ATOMIC_SEQ_CST);
+  for (;;) {
+    double d;
+    std::memcpy(&d, &old, 8);
+    const double sum = d + v;
+    unsigned long long want;
+    std::memcpy(&want, &sum, 8);
+    if (__atomic_compare_exchange_n(q, &old, want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) return d;
+  }
+}
+static inline long long atomicMin(long long* p, long long v) {
+  long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+static inline long long atomicMax(long long* p, long long v) {
+  long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+static inline int __clzll(long long v) { return v ? __builtin_clzll(static_cast<unsigned long long>(v)) : 64; }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 using std::min;
@@ -85,6 +115,7 @@ using std::isnan;
 #define __launch_bounds__(...)
 #define __restrict__
 #define __shared__ static
+#define __align__(x)
 constexpr int kWarp = 32;
 #include "vm_ops.inc"
 template <class F>

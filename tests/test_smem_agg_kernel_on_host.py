@@ -1,0 +1,102 @@
+"""The block-private shared-memory group table for low-cardinality GROUP BY (csrc/hash_agg.cu group_update_smem_kernel: every
+block accumulates into its own copy of a small array-mode table and merges it into the global table once) compiled FOR THE
+HOST and run under the lock-step emulation of tests/host_emulator.py — real concurrent threads, real atomics — against a
+plain Python group-by and against group_update_kernel (the global-table path) over the same rows: counts, integer sums and
+MIN / MAX exact, DOUBLE sums within rounding (the order of atomic adds is not fixed). No GPU needed."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from host_emulator import between, build, source
+
+BIGINT, DOUBLE = 4, 6
+SUM_F64, SUM_I64, COUNT, MIN_I64, MAX_F64 = 1, 2, 3, 6, 5
+
+BODY = r"""
+constexpr uint64_t kNullHash = 1;
+// ---- common.cuh: hash mixers, warp reductions ----
+%(mixers)s
+%(reductions)s
+// ---- hash_agg.cu: accumulator updates, the group table, group_update_kernel, group_update_smem_kernel ----
+%(update)s
+}  // namespace vb2_on_host
+using namespace vb2_on_host;
+extern "C" {
+void h_group_update(int smem, const vb2_group_table* t, const uint64_t* keys, int64_t n, const vb2_agg_update* aggs, int naggs, int32_t* error_flag, int blocks) {
+  AggArgs args{};
+  args.n = naggs;
+  for (int i = 0; i < naggs; ++i) args.a[i] = aggs[i];
+  if (smem) launch(blocks, 256, [&] { group_update_smem_kernel(*t, keys, nullptr, n, args, error_flag); });
+  else launch(blocks, 256, [&] { group_update_kernel(*t, keys, nullptr, n, args, nullptr, error_flag); });
+}
+}
+"""
+
+
+class GroupTable(C.Structure):
+    _fields_ = [("rows", C.c_void_p), ("capacity", C.c_int64), ("row_words", C.c_int32), ("hash_mode", C.c_int32)]
+
+
+class AggUpdate(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("input_type", C.c_int32), ("input", C.c_void_p), ("nulls", C.c_void_p), ("mask", C.c_void_p), ("indices", C.c_void_p),
+                ("base_nulls", C.c_void_p), ("acc_word", C.c_int32), ("nonnull_word", C.c_int32)]
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    common, agg = source("common.cuh"), source("hash_agg.cu")
+    update = between(agg, "__device__ __forceinline__ double input_as_f64", "// ---- keyed hash mode (kHash)")
+    update = update.replace("extern __shared__ __align__(16) uint64_t srows[];", "static uint64_t srows[8192];")
+    body = BODY % {
+        "mixers": between(common, "__host__ __device__ __forceinline__ uint64_t twang_mix64", "__device__ __forceinline__ uint64_t hash_f64"),
+        "reductions": between(common, "__device__ __forceinline__ double warp_sum(double v)", "}  // namespace vb2"),
+        "update": update,
+    }
+    return build(tmp_path_factory.mktemp("smem_agg_on_host"), "smemagg", body)
+
+
+def test_block_private_tables_merge_to_the_global_result(host):
+    rng = np.random.default_rng(6)
+    n, groups, row_words = 4000, 50, 8
+    keys = rng.integers(1, groups, n).astype(np.uint64)      # array mode: the normalized key is the slot
+    x = np.round(rng.normal(0, 30, n), 3)
+    y = rng.integers(-500, 500, n).astype(np.int64)
+    yvalid_list = rng.random(n) > 0.1
+    yvalid = np.zeros((n + 63) // 64 + 1, dtype=np.uint64)
+    for i in np.nonzero(yvalid_list)[0]:
+        yvalid[i >> 6] |= np.uint64(1) << np.uint64(i & 63)
+    aggs = (AggUpdate * 5)(
+        AggUpdate(SUM_F64, DOUBLE, x.ctypes.data, None, None, None, None, 1, -1),
+        AggUpdate(SUM_I64, BIGINT, y.ctypes.data, yvalid.ctypes.data, None, None, None, 2, 3),
+        AggUpdate(COUNT, BIGINT, None, None, None, None, None, 4, -1),
+        AggUpdate(MIN_I64, BIGINT, y.ctypes.data, yvalid.ctypes.data, None, None, None, 5, -1),
+        AggUpdate(MAX_F64, DOUBLE, x.ctypes.data, None, None, None, None, 6, -1))
+
+    def run(smem):
+        rows = np.zeros(groups * row_words, dtype=np.uint64)
+        rows[5::row_words] = np.uint64(np.iinfo(np.int64).max)
+        rows[6::row_words] = np.array([-math.inf]).view(np.uint64)[0]
+        t = GroupTable(rows.ctypes.data, groups, row_words, 0)
+        err = np.zeros(2, dtype=np.int32)
+        host.h_group_update(smem, C.byref(t), keys.ctypes.data_as(C.c_void_p), C.c_int64(n), aggs, 5, err.ctypes.data_as(C.c_void_p), 4)
+        assert err[0] == 0
+        return rows.reshape(groups, row_words)
+
+    via_smem, via_global = run(1), run(0)
+    f64 = lambda w: float(np.array([w], dtype=np.uint64).view(np.float64)[0])  # noqa: E731
+    i64 = lambda w: int(np.array([w], dtype=np.uint64).view(np.int64)[0])      # noqa: E731
+    for g in range(groups):
+        sel = keys == g
+        if not sel.any():
+            assert int(via_smem[g][0]) == 0 and int(via_global[g][0]) == 0
+            continue
+        ys = y[sel & yvalid_list]
+        for table in (via_smem, via_global):
+            r = table[g]
+            assert int(r[0]) != 0
+            assert math.isclose(f64(r[1]), float(x[sel].sum()), rel_tol=1e-12, abs_tol=1e-9)
+            assert i64(r[2]) == int(ys.sum()) and int(r[3]) == len(ys) and int(r[4]) == int(sel.sum())
+            assert i64(r[5]) == (int(ys.min()) if len(ys) else np.iinfo(np.int64).max)
+            assert f64(r[6]) == float(x[sel].max())
