@@ -67,6 +67,9 @@ static inline unsigned __ballot_sync(unsigned, bool p) {
   warp_barrier[w]->arrive_and_wait();
   return m;
 }
+static inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
+static inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, p) == 0xffffffffu; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs(static_cast<int>(v)); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

@@ -21,6 +21,8 @@ constexpr uint64_t kNullHash = 1;
 %(reductions)s
 // ---- hash_agg.cu: accumulator updates, the group table, group_update_kernel, group_update_smem_kernel ----
 %(update)s
+// ---- hash_agg.cu: the serial (input-order) kernel of very small batches and the register-accumulator kernel of tiny tables ----
+%(tiny)s
 }  // namespace vb2_on_host
 using namespace vb2_on_host;
 extern "C" {
@@ -30,6 +32,25 @@ void h_group_update(int smem, const vb2_group_table* t, const uint64_t* keys, in
   for (int i = 0; i < naggs; ++i) args.a[i] = aggs[i];
   if (smem) launch(blocks, 256, [&] { group_update_smem_kernel(*t, keys, nullptr, n, args, error_flag); });
   else launch(blocks, 256, [&] { group_update_kernel(*t, keys, nullptr, n, args, nullptr, error_flag); });
+}
+// the dispatch of vb2k_group_update for a table of at most 8 groups: an occupancy pass, then one pass per SUM / COUNT
+void h_group_update_tiny(const vb2_group_table* t, const uint64_t* keys, int64_t n, const vb2_agg_update* aggs, int naggs, int32_t* error_flag, int blocks) {
+  vb2_agg_update none{};
+  launch(blocks, 256, [&] { group_update_tiny_kernel<0>(*t, keys, nullptr, n, none, error_flag); });
+  for (int i = 0; i < naggs; ++i) {
+    const vb2_agg_update u = aggs[i];
+    switch (u.kind) {
+      case VB2_AGG_SUM_F64: launch(blocks, 256, [&] { group_update_tiny_kernel<VB2_AGG_SUM_F64>(*t, keys, nullptr, n, u, error_flag); }); break;
+      case VB2_AGG_SUM_I64: launch(blocks, 256, [&] { group_update_tiny_kernel<VB2_AGG_SUM_I64>(*t, keys, nullptr, n, u, error_flag); }); break;
+      default: launch(blocks, 256, [&] { group_update_tiny_kernel<VB2_AGG_COUNT>(*t, keys, nullptr, n, u, error_flag); });
+    }
+  }
+}
+void h_group_update_serial(const vb2_group_table* t, const uint64_t* keys, int64_t n, const vb2_agg_update* aggs, int naggs, int32_t* error_flag) {
+  AggArgs args{};
+  args.n = naggs;
+  for (int i = 0; i < naggs; ++i) args.a[i] = aggs[i];
+  launch(1, 32, [&] { group_update_serial_kernel(*t, keys, nullptr, n, args, nullptr, error_flag); });
 }
 }
 """
@@ -53,6 +74,7 @@ def host(tmp_path_factory):
         "mixers": between(common, "__host__ __device__ __forceinline__ uint64_t twang_mix64", "__device__ __forceinline__ uint64_t hash_f64"),
         "reductions": between(common, "__device__ __forceinline__ double warp_sum(double v)", "}  // namespace vb2"),
         "update": update,
+        "tiny": between(agg, "__device__ __forceinline__ void apply_update_plain", "__global__ void table_init_kernel"),
     }
     return build(tmp_path_factory.mktemp("smem_agg_on_host"), "smemagg", body)
 
@@ -100,3 +122,44 @@ def test_block_private_tables_merge_to_the_global_result(host):
             assert i64(r[2]) == int(ys.sum()) and int(r[3]) == len(ys) and int(r[4]) == int(sel.sum())
             assert i64(r[5]) == (int(ys.min()) if len(ys) else np.iinfo(np.int64).max)
             assert f64(r[6]) == float(x[sel].max())
+
+
+def test_tiny_tables_and_serial_batches(host):
+    """Up to eight groups (Q1's shape on the general path): register accumulators, one atomic per group and block; very small
+    batches: one warp in input order (the reference's sequential accumulation, bit for bit with a Python loop)."""
+    rng = np.random.default_rng(9)
+    n, groups, row_words = 5000, 6, 4
+    keys = rng.integers(0, groups, n).astype(np.uint64)
+    x = np.round(rng.normal(0, 30, n), 3)
+    y = rng.integers(-500, 500, n).astype(np.int64)
+    aggs = (AggUpdate * 3)(AggUpdate(SUM_F64, DOUBLE, x.ctypes.data, None, None, None, None, 1, -1),
+                           AggUpdate(SUM_I64, BIGINT, y.ctypes.data, None, None, None, None, 2, -1),
+                           AggUpdate(COUNT, BIGINT, None, None, None, None, None, 3, -1))
+    f64 = lambda w: float(np.array([w], dtype=np.uint64).view(np.float64)[0])  # noqa: E731
+    i64 = lambda w: int(np.array([w], dtype=np.uint64).view(np.int64)[0])      # noqa: E731
+    rows = np.zeros(groups * row_words, dtype=np.uint64)
+    t = GroupTable(rows.ctypes.data, groups, row_words, 0)
+    err = np.zeros(2, dtype=np.int32)
+    host.h_group_update_tiny(C.byref(t), keys.ctypes.data_as(C.c_void_p), C.c_int64(n), aggs, 3, err.ctypes.data_as(C.c_void_p), 3)
+    assert err[0] == 0
+    table = rows.reshape(groups, row_words)
+    for g in range(groups):
+        sel = keys == g
+        assert int(table[g][0]) == int(sel.sum()) == int(table[g][3])  # rows seen, count(*)
+        assert math.isclose(f64(table[g][1]), float(x[sel].sum()), rel_tol=1e-12, abs_tol=1e-9) and i64(table[g][2]) == int(y[sel].sum())
+    # a 40-row batch through the serial kernel: sums in input order
+    m = 40
+    rows2 = np.zeros(groups * row_words, dtype=np.uint64)
+    t2 = GroupTable(rows2.ctypes.data, groups, row_words, 0)
+    host.h_group_update_serial(C.byref(t2), keys.ctypes.data_as(C.c_void_p), C.c_int64(m), aggs, 3, err.ctypes.data_as(C.c_void_p))
+    assert err[0] == 0
+    table2 = rows2.reshape(groups, row_words)
+    for g in range(groups):
+        acc, cnt, isum = 0.0, 0, 0
+        for i in range(m):
+            if keys[i] == g:
+                acc += float(x[i])
+                isum += int(y[i])
+                cnt += 1
+        if cnt:
+            assert f64(table2[g][1]) == acc and i64(table2[g][2]) == isum and int(table2[g][3]) == cnt  # bit for bit: same order of additions
