@@ -91,8 +91,8 @@ def _ptrs(arrays):
 def test_shuffle_between_simulated_ranks(host, world, broadcast):
     rng = np.random.default_rng(world * 2 + broadcast)
     widths = np.array([8, 8, 4, 1], dtype=np.int32)  # key, DOUBLE payload, int32 dictionary codes, validity bytes
-    rows = [int(v) for v in rng.integers(0, 9000, world)]
-    rows[0] = 2 * 4096 + 17                            # one rank with several partition blocks
+    rows = [int(v) for v in rng.integers(0, 3000, world)]
+    rows[0] = 4096 + 517                               # one rank with several partition blocks
     rows[-1] = 0                                       # and one with nothing to send
     data = []
     for s in range(world):

@@ -564,7 +564,7 @@ def _rand_expr(rng, typ, depth):
     return f"cast({_rand_expr(rng, 'i', depth - 1)} as boolean)"
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("seed", [1, 2, 3])
 def test_random_expressions_through_compiler_and_generated_source(seed, tmp):
     import random
     rng = random.Random(seed)
