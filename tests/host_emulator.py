@@ -70,6 +70,7 @@ static inline unsigned __ballot_sync(unsigned, bool p) {
 static inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
 static inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, p) == 0xffffffffu; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs(static_cast<int>(v)); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

@@ -19,10 +19,15 @@ constexpr uint64_t kNullHash = 1;
 // ---- common.cuh: hash mixers, warp reductions ----
 %(mixers)s
 %(reductions)s
+// ---- hash_agg.cu: key normalisation ----
+%(norm)s
 // ---- hash_agg.cu: accumulator updates, the group table, group_update_kernel, group_update_smem_kernel ----
 %(update)s
 // ---- hash_agg.cu: the serial (input-order) kernel of very small batches and the register-accumulator kernel of tiny tables ----
 %(tiny)s
+// ---- hash_agg.cu: occupancy and the extraction of result columns ----
+%(occupied)s
+%(extract)s
 }  // namespace vb2_on_host
 using namespace vb2_on_host;
 extern "C" {
@@ -45,6 +50,24 @@ void h_group_update_tiny(const vb2_group_table* t, const uint64_t* keys, int64_t
       default: launch(blocks, 256, [&] { group_update_tiny_kernel<VB2_AGG_COUNT>(*t, keys, nullptr, n, u, error_flag); });
     }
   }
+}
+// GROUP BY end to end: normalized keys -> group_update_kernel -> group_extract_kernel (one block scans the table for its groups)
+void h_group_by(const vb2_column* key_cols, int nkeys, const int64_t* mins, const uint64_t* mults, int64_t n, const vb2_group_table* t,
+                const vb2_agg_update* aggs, int naggs, const vb2_extract_col* out_cols, int nout, int32_t* scratch, int64_t* header, int32_t* error_flag) {
+  NormArgs na{};
+  na.n = nkeys;
+  for (int k = 0; k < nkeys; ++k) { na.c[k] = key_cols[k]; na.mins[k] = mins[k]; na.mults[k] = mults[k]; }
+  std::vector<uint64_t> keys(n + 1);
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  launch(blocks, 256, [&] { normalize_keys_kernel(na, nullptr, n, keys.data(), nullptr); });
+  AggArgs args{};
+  args.n = naggs;
+  for (int i = 0; i < naggs; ++i) args.a[i] = aggs[i];
+  launch(blocks, 256, [&] { group_update_kernel(*t, keys.data(), nullptr, n, args, nullptr, error_flag); });
+  ExtractArgs ea{};
+  ea.n = nout;
+  for (int i = 0; i < nout; ++i) ea.c[i] = out_cols[i];
+  launch(1, 1024, [&] { group_extract_kernel(*t, nullptr, 0, scratch, ea, header, error_flag); });
 }
 void h_group_update_serial(const vb2_group_table* t, const uint64_t* keys, int64_t n, const vb2_agg_update* aggs, int naggs, int32_t* error_flag) {
   AggArgs args{};
@@ -75,6 +98,9 @@ def host(tmp_path_factory):
         "reductions": between(common, "__device__ __forceinline__ double warp_sum(double v)", "}  // namespace vb2"),
         "update": update,
         "tiny": between(agg, "__device__ __forceinline__ void apply_update_plain", "__global__ void table_init_kernel"),
+        "norm": between(agg, "constexpr int kMaxNormCols", "__global__ void minmax_kernel"),
+        "occupied": between(agg, "__device__ __forceinline__ bool row_occupied", "__global__ void occupied_bits_kernel"),
+        "extract": between(agg, "struct ExtractArgs {", "// Partial results of a fused scan"),
     }
     return build(tmp_path_factory.mktemp("smem_agg_on_host"), "smemagg", body)
 
@@ -163,3 +189,76 @@ def test_tiny_tables_and_serial_batches(host):
                 cnt += 1
         if cnt:
             assert f64(table2[g][1]) == acc and i64(table2[g][2]) == isum and int(table2[g][3]) == cnt  # bit for bit: same order of additions
+
+
+class ExtractCol(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("type", C.c_int32), ("word", C.c_int32), ("count_word", C.c_int32), ("min", C.c_int64), ("mult", C.c_uint64),
+                ("range", C.c_uint64), ("null_reserved", C.c_int32), ("pad", C.c_int32), ("values", C.c_void_p), ("valid", C.c_void_p)]
+
+
+def test_group_by_end_to_end_with_result_extraction(host):
+    """normalize -> update -> extract: two nullable keys decoded back from their packed value ids (a NULL key is a group and
+    comes back NULL), SUM with its validity from the non-null counter (NULL for a group that saw only NULL inputs,
+    SumAggregateBase.h:143-150), AVG = sum / count (AverageAggregateBase.h:86-107), COUNT(*)."""
+    from velox_b200.kernels import CColumn
+    from velox_b200.vector import INTEGER, flat_vector
+    rng = np.random.default_rng(12)
+    n = 2000
+    k0 = [None if rng.random() < 0.08 else int(v) for v in rng.integers(-4, 5, n)]
+    k1 = [None if rng.random() < 0.08 else int(v) for v in rng.integers(100, 106, n)]
+    x = [None if rng.random() < 0.5 else float(v) for v in np.round(rng.normal(0, 20, n), 2)]
+    key_columns = [flat_vector(BIGINT, k0), flat_vector(INTEGER, k1)]
+    cols = (CColumn * 2)(*[c.to_c() for c in key_columns])
+    mins = np.array([-4, 100], dtype=np.int64)
+    mults = np.array([7, 1], dtype=np.uint64)
+    capacity, row_words = 10 * 7 + 2, 4     # packed ids: (0..9) * 7 + (0..6); [rows seen | sum x | non-null x | count(*)]
+    rows = np.zeros(capacity * row_words, dtype=np.uint64)
+    t = GroupTable(rows.ctypes.data, capacity, row_words, 0)
+    xa = np.array([0.0 if v is None else v for v in x])
+    xv = np.zeros((n + 63) // 64 + 1, dtype=np.uint64)
+    for i, v in enumerate(x):
+        if v is not None:
+            xv[i >> 6] |= np.uint64(1) << np.uint64(i & 63)
+    aggs = (AggUpdate * 2)(AggUpdate(SUM_F64, DOUBLE, xa.ctypes.data, xv.ctypes.data, None, None, None, 1, 2), AggUpdate(COUNT, BIGINT, None, None, None, None, None, 3, -1))
+    m = capacity
+    out_k0, out_k1 = np.zeros(m, dtype=np.int64), np.zeros(m, dtype=np.int32)
+    out_sum, out_avg, out_cnt = np.zeros(m, dtype=np.uint64), np.zeros(m, dtype=np.float64), np.zeros(m, dtype=np.uint64)
+    valid = [np.zeros(m // 64 + 2, dtype=np.uint64) for _ in range(4)]
+    KEY, WORD, AVG = 1, 2, 4
+    outs = (ExtractCol * 5)(
+        ExtractCol(KEY, BIGINT, 0, -1, -4, 7, 10, 1, 0, out_k0.ctypes.data, valid[0].ctypes.data),
+        ExtractCol(KEY, 3, 0, -1, 100, 1, 7, 1, 0, out_k1.ctypes.data, valid[1].ctypes.data),
+        ExtractCol(WORD, DOUBLE, 1, 2, 0, 1, 1, 0, 0, out_sum.ctypes.data, valid[2].ctypes.data),
+        ExtractCol(AVG, DOUBLE, 1, 2, 0, 1, 1, 0, 0, out_avg.ctypes.data, valid[3].ctypes.data),
+        ExtractCol(WORD, BIGINT, 3, -1, 0, 1, 1, 0, 0, out_cnt.ctypes.data, None))
+    scratch = np.zeros(capacity + 8, dtype=np.int32)
+    header = np.zeros(2, dtype=np.int64)
+    err = np.zeros(2, dtype=np.int32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    host.h_group_by(cols, 2, P(mins), P(mults), C.c_int64(n), C.byref(t), aggs, 2, outs, 5, P(scratch), P(header), P(err))
+    assert err[0] == 0 and int(header[1]) == 0
+    want = {}
+    for a, b, v in zip(k0, k1, x):
+        g = want.setdefault((a, b), [0.0, 0, 0])
+        g[2] += 1
+        if v is not None:
+            g[0] += v
+            g[1] += 1
+    groups = int(header[0])
+    assert groups == len(want)
+    bit = lambda words, i: (int(words[i >> 6]) >> (i & 63)) & 1  # noqa: E731
+    got = {}
+    for i in range(groups):
+        a = int(out_k0[i]) if bit(valid[0], i) else None
+        b = int(out_k1[i]) if bit(valid[1], i) else None
+        s = float(out_sum[i:i + 1].view(np.float64)[0]) if bit(valid[2], i) else None
+        avg = float(out_avg[i]) if bit(valid[3], i) else None
+        got[(a, b)] = (s, avg, int(out_cnt[i]))
+    assert set(got) == set(want)
+    for key, (sx, nn, cnt) in want.items():
+        s, avg, c = got[key]
+        assert c == cnt
+        if nn == 0:
+            assert s is None and avg is None
+        else:
+            assert math.isclose(s, sx, rel_tol=1e-12, abs_tol=1e-9) and math.isclose(avg, sx / nn, rel_tol=1e-12, abs_tol=1e-9)
