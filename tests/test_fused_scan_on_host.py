@@ -1,0 +1,265 @@
+"""The fused scan -> filter -> project -> aggregate kernel (csrc/fused_scan.cuh: the expression templates, the
+register accumulators, the array-mode join probe, the block reduction and fused_scan.cu's finalize step) compiled FOR
+THE HOST and run under the lock-step emulation of tests/host_emulator.py with the pipelines the product instantiates
+ahead of time: TPC-H Q6, Q1 and the Q14 probe side (exec/tests/utils/TpchQueryBuilder.cpp:203-256, 756-788, 1639-1702
+-- FilterProject + HashAggregation (+ HashProbe) collapsed into one pass). What runs is the direct-load kernel
+(fused_scan_agg_kernel, the variant the launcher picks when a tile ring does not fit); the TMA-staged variant moves
+the same rows through shared memory and then calls the same eval_slot / Accum / block_reduce_store, its mbarrier
+plumbing is PTX and stays GPU-only. Sums are compared with the oracle running the unfused plan (row order there, a
+fixed tree here: relative 1e-12), counts exactly. No GPU needed."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from host_emulator import ROOT, between, build, source
+from oracle import pyoracle
+from velox_b200 import tpch
+from velox_b200.plan import PlanBuilder
+from velox_b200.vector import BIGINT, DOUBLE, INTEGER, VARCHAR, dictionary_vector, flat_vector, row_vector
+
+BODY = r"""
+#include <string>
+struct double2 { double x, y; };
+struct int2 { int x, y; };
+struct longlong2 { long long x, y; };
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline double2 ldg_stream_f64x2(const double* p) { return {p[0], p[1]}; }
+static inline longlong2 ldg_stream_i64x2(const int64_t* p) { return {p[0], p[1]}; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+#define VB2_SIG(...) __VA_ARGS__
+// ---- common.cuh: warp reductions ----
+%(reductions)s
+// ---- fused_scan.cuh: expression templates, Accum, the direct-load kernel ----
+%(fx)s
+// ---- fused_scan.cu: finalize, the ahead-of-time pipelines ----
+%(finalize)s
+%(pipelines)s
+}  // namespace fx
+}  // namespace vb2_on_host
+using namespace vb2_on_host;
+using namespace vb2_on_host::fx;
+
+template <class P, int kMaxG, class KeyT>
+static void run(const KernelArgs& a, int grid, double* sums, int64_t* counts) {
+  constexpr int kvals = kMaxG * (P::kNP + 1);
+  std::vector<double> partials(static_cast<size_t>(grid) * kvals, -1.0);
+  launch(grid, kThreads, [&] { fused_scan_agg_kernel<P, kMaxG, 2, false, KeyT>(a, partials.data()); });
+  launch(kvals, 32, [&] { fused_finalize_kernel(partials.data(), grid, kvals, P::kNP, kMaxG, a.ngroups, sums, counts); });
+}
+
+extern "C" {
+// which: 6 = Q6, 1 = Q1 (int32 keys, 8 accumulator groups), 14 = Q14 probe side, 2 = sum(b * (c - d)) where a < x by a BIGINT key
+int h_fused(int which, const vb2_fused_args* in, int grid, double* sums, int64_t* counts) {
+  KernelArgs a{};
+  for (int c = 0; c < kMaxCols; ++c) a.cols[c] = in->cols[c];
+  for (int k = 0; k < VB2_FUSED_MAX_PARAMS; ++k) { a.consts.pf[k] = in->pf[k]; a.consts.pl[k] = in->pl[k]; a.consts.pi[k] = in->pi[k]; }
+  a.rows = in->rows;
+  a.nkeys = in->nkeys;
+  a.ngroups = in->ngroups;
+  for (int k = 0; k < VB2_FUSED_MAX_KEYS; ++k) {
+    a.key[k] = in->key[k]; a.key_is64[k] = in->key_is64[k]; a.key_mult[k] = in->key_mult[k]; a.key_min[k] = in->key_min[k]; a.key_lut[k] = in->key_lut[k];
+  }
+  a.join_slot_flags = reinterpret_cast<const uint8_t*>(in->join_slot_flags);
+  a.join_min = in->join_min;
+  a.join_range = in->join_range;
+  switch (which) {
+    case 6: run<Q6, 1, int32_t>(a, grid, sums, counts); return 0;
+    case 1: run<Q1, 8, int32_t>(a, grid, sums, counts); return 0;
+    case 14: run<Q14, 1, int32_t>(a, grid, sums, counts); return 0;
+    case 2: run<SumUnderLt, 4, int64_t>(a, grid, sums, counts); return 0;
+  }
+  return 1;
+}
+const char* h_sig(int which) {
+  static std::string s;
+  s = which == 6 ? Q6::sig() : which == 1 ? Q1::sig() : Q14::sig();
+  return s.c_str();
+}
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    common, cuh, cu = source("common.cuh"), source("fused_scan.cuh"), source("fused_scan.cu")
+    fx = between(cuh, "namespace fx {", "// TMA-staged variant (main path)")
+    # the one PTX statement of the slice: a predicated DADD
+    fx, n = re.subn(r'asm\("\{ \.reg \.pred q; setp\.ne\.s32 q, %1, 0; @q add\.rn\.f64 %0, %0, %2; \}"[^;]*;',
+                    "if (hit) sum[g][p] = __dadd_rn(sum[g][p], v[p]);", fx)
+    assert n == 1 and "asm" not in fx
+    body = BODY % {
+        "reductions": between(common, "__device__ __forceinline__ double warp_sum(double v)", "}  // namespace vb2"),
+        "fx": fx,
+        "finalize": between(cu, "__global__ void fused_finalize_kernel", "// join_slot_flags[slot]"),
+        "pipelines": between(cu, "using Q6 = ", "// Multi-GPU Q14"),
+    }
+    L = build(tmp_path_factory.mktemp("fused_on_host"), "fused", body)
+    L.h_sig.restype = C.c_char_p
+    return L
+
+
+class FusedArgs(C.Structure):
+    """vb2_fused_args (include/velox_b200_kernels.h)."""
+    _fields_ = [("cols", C.c_void_p * 8), ("pf", C.c_double * 12), ("pl", C.c_int64 * 12), ("pi", C.c_int32 * 12), ("rows", C.c_int64),
+                ("nkeys", C.c_int32), ("ngroups", C.c_int32), ("key", C.c_void_p * 2), ("key_is64", C.c_int32 * 2), ("key_mult", C.c_int32 * 2),
+                ("key_min", C.c_int64 * 2), ("key_lut", C.c_void_p * 2), ("join_slot_flags", C.c_void_p), ("join_min", C.c_int64), ("join_range", C.c_int64)]
+
+
+def test_args_struct_matches_the_header():
+    """The ctypes mirror above is only as good as its field list: same order and types as the C declaration."""
+    with open(os.path.join(ROOT, "include", "velox_b200_kernels.h")) as f:
+        decl = between(f.read(), "typedef struct vb2_fused_args {", "} vb2_fused_args").split("{", 1)[1]
+    names = [re.sub(r"\[\w+\]", "", d).strip(" *") for line in re.findall(r"^\s*(?:const\s+)?\w+\*?\s+([^;/{]+);", decl, re.M) for d in line.split(",")]
+    assert names == [n for n, _ in FusedArgs._fields_], names
+
+
+def _lineitem(n, seed, nparts=500):
+    return {k: np.ascontiguousarray(v.numpy()) for k, v in tpch.gen_lineitem(n, nparts, seed=seed, device="cpu").items()}
+
+
+def _vec(h, name):
+    if name == "l_returnflag":
+        return dictionary_vector(VARCHAR, h[name], tpch.RETURNFLAG_DICT)
+    if name == "l_linestatus":
+        return dictionary_vector(VARCHAR, h[name], tpch.LINESTATUS_DICT)
+    if name == "l_shipdate":
+        return flat_vector(INTEGER, h[name])
+    if name == "l_partkey":
+        return flat_vector(BIGINT, h[name])
+    return flat_vector(DOUBLE, h[name])
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p).value
+
+
+def _run(host, which, args, grid, ngroups, nproj):
+    sums = np.zeros(max(ngroups, 1) * nproj)
+    counts = np.zeros(max(ngroups, 1), dtype=np.int64)
+    assert host.h_fused(which, C.byref(args), grid, sums.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p)) == 0
+    return sums.reshape(-1, nproj), counts
+
+
+def _close(got, want, n):
+    return abs(got - want) <= max(1e-12, n * 2.0 ** -53) * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("n,grid", [(3000, 3), (517, 4)])  # 517 rows over 4 x 256 threads: main loop never runs, tail only
+def test_q6(host, n, grid):
+    assert host.h_sig(6) == b"F:and(between(i0,pi0,pi1),between(f1,pf0,pf1),lt(f2,pf2));P:multiply(f3,f1)"
+    h = _lineitem(n, seed=6)
+    a = FusedArgs()
+    for c, name in enumerate(["l_shipdate", "l_discount", "l_quantity", "l_extendedprice"]):  # first-use order
+        a.cols[c] = _ptr(h[name])
+    a.pi[0], a.pi[1] = tpch.Q6_SHIP_LO, tpch.Q6_SHIP_HI
+    a.pf[0], a.pf[1], a.pf[2] = 0.05, 0.07, 24.0
+    a.rows, a.nkeys, a.ngroups = n, 0, 1
+    sums, counts = _run(host, 6, a, grid, 1, 1)
+    names = ["l_shipdate", "l_extendedprice", "l_quantity", "l_discount"]
+    rv = row_vector(names, [_vec(h, c) for c in names])
+    plan = (PlanBuilder().values(rv.names, rv.types)
+            .filter("l_shipdate between '1994-01-01'::DATE and '1994-12-31'::DATE and l_discount between 0.05 and 0.07 and l_quantity < 24.0")
+            .project(["l_extendedprice * l_discount"]).singleAggregation([], ["sum(p0)", "count(0)"]).planNode())
+    want = pyoracle.run_plan(plan, [rv])
+    ((want_sum, want_count),) = want.rows()
+    assert int(counts[0]) == want_count and counts[0] > 0
+    assert _close(sums[0, 0], want_sum, n)
+
+
+def test_q1(host):
+    assert host.h_sig(1).startswith(b"F:lt(i0,pi0);P:f1|f2|multiply(f2,minus(pf0,f3))|")
+    n, grid = 4000, 2
+    h = _lineitem(n, seed=1)
+    a = FusedArgs()
+    for c, name in enumerate(["l_shipdate", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]):
+        a.cols[c] = _ptr(h[name])
+    a.pi[0] = tpch.Q1_SHIPDATE_LT
+    a.pf[0] = a.pf[1] = a.pf[2] = 1.0
+    rf, ls = h["l_returnflag"].astype(np.int32), h["l_linestatus"].astype(np.int32)
+    a.rows, a.nkeys, a.ngroups = n, 2, 6
+    a.key[0], a.key[1] = _ptr(rf), _ptr(ls)
+    a.key_mult[0], a.key_mult[1] = 2, 1  # gid = returnflag * 2 + linestatus
+    sums, counts = _run(host, 1, a, grid, 8, 5)
+    names = ["l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_shipdate"]
+    rv = row_vector(names, [_vec(h, c) for c in names])
+    plan = (PlanBuilder().values(rv.names, rv.types).filter("l_shipdate < '1998-09-03'::DATE")
+            .project(["l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_extendedprice * (1.0 - l_discount) AS dp",
+                      "l_extendedprice * (1.0 - l_discount) * (1.0 + l_tax) AS ch", "l_discount"])
+            .singleAggregation(["l_returnflag", "l_linestatus"], ["sum(l_quantity)", "sum(l_extendedprice)", "sum(dp)", "sum(ch)", "sum(l_discount)", "count(0)"])
+            .planNode())
+    want = pyoracle.run_plan(plan, [rv])
+    rows = want.rows()
+    assert len(rows) == int((counts[:6] > 0).sum()) and int(counts[6:].sum()) == 0
+    for row in rows:
+        g = tpch.RETURNFLAG_DICT.index(row[0]) * 2 + tpch.LINESTATUS_DICT.index(row[1])
+        assert int(counts[g]) == row[7], (row, counts)
+        for p in range(5):
+            assert _close(sums[g, p], row[2 + p], n), (row, p, sums[g])
+
+
+def test_q14_probe_side(host):
+    """Array-mode probe inside the scan: one byte per key slot (0 no build row, 1 match, 2 match with p_type LIKE
+    'PROMO%'), rows outside the key range or the date range contribute nothing."""
+    n, grid, nparts = 6000, 3, 300
+    h = _lineitem(n, seed=14, nparts=nparts)
+    part = {k: v.numpy() for k, v in tpch.gen_part(nparts, seed=5).items()}
+    # build side: drop a fifth of the parts so that some probes miss, and shrink the table range below the probe keys' range
+    keep = np.ones(nparts, dtype=bool)
+    keep[::5] = False
+    pk, ptype = part["p_partkey"][keep], part["p_type"][keep]
+    jmin, jrange = int(pk.min()), int(pk.max() - pk.min() + 1) - 7
+    flags = np.zeros(jrange + 1, dtype=np.uint8)
+    promo = np.array([tpch.PTYPE_DICT[t].startswith("PROMO") for t in ptype])
+    inside = pk - jmin < jrange
+    flags[(pk - jmin)[inside]] = np.where(promo[inside], 2, 1)
+    a = FusedArgs()
+    for c, name in enumerate(["l_shipdate", "l_partkey", "l_extendedprice", "l_discount"]):
+        a.cols[c] = _ptr(h[name])
+    a.pi[0], a.pi[1] = tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI
+    a.pf[0], a.pf[1], a.pf[2] = 1.0, 1.0, 0.0
+    a.rows, a.nkeys, a.ngroups = n, 0, 1
+    a.join_slot_flags, a.join_min, a.join_range = _ptr(flags), jmin, jrange
+    sums, counts = _run(host, 14, a, grid, 1, 2)
+    li_names = ["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"]
+    li = row_vector(li_names, [_vec(h, c) for c in li_names])
+    pt = row_vector(["p_partkey", "p_type"], [flat_vector(BIGINT, pk[inside]), dictionary_vector(VARCHAR, ptype[inside], tpch.PTYPE_DICT)])
+    build_side = PlanBuilder().values(pt.names, pt.types, source=1)
+    plan = (PlanBuilder().values(li.names, li.types, source=0).filter("l_shipdate between '1995-09-01'::DATE and '1995-09-30'::DATE")
+            .project(["l_extendedprice * (1.0 - l_discount) as part_revenue", "l_shipdate", "l_partkey"])
+            .hashJoin(["l_partkey"], ["p_partkey"], build_side, "", ["part_revenue", "p_type"])
+            .project(["(CASE WHEN (p_type LIKE 'PROMO%') THEN part_revenue ELSE 0.0 END) as filter_revenue", "part_revenue"])
+            .singleAggregation([], ["sum(part_revenue)", "sum(filter_revenue)", "count(0)"]).planNode())
+    want = pyoracle.run_plan(plan, [li, pt])
+    ((want_rev, want_promo, want_count),) = want.rows()
+    assert int(counts[0]) == want_count and 0 < counts[0] < n
+    assert _close(sums[0, 0], want_rev, n) and _close(sums[0, 1], want_promo, n)
+    assert 0 < sums[0, 1] < sums[0, 0]
+
+
+def test_bigint_key_through_a_lookup_table_and_nan_filter_input(host):
+    """The generic small shape sum(f1 * (pf1 - f2)) WHERE f0 < pf0 GROUP BY a BIGINT key whose values reach their
+    group ids through key_lut[value - key_min] (value-id normalisation of a sparse range, VectorHasher.cpp:560-640);
+    NaN in the filter input compares as the largest value (NaN < x is false, velox/type/FloatingPointUtil.h)."""
+    n, grid = 2500, 2
+    rng = np.random.default_rng(2)
+    f0, f1, f2 = rng.random(n), rng.random(n) * 100, rng.random(n)
+    f0[::17] = np.nan
+    values = np.array([-40, -37, -10, 5], dtype=np.int64)  # four groups scattered over a range of 46
+    key = values[rng.integers(0, 4, n)]
+    lut = np.full(46, -1, dtype=np.int32)
+    lut[values + 40] = [2, 0, 3, 1]
+    a = FusedArgs()
+    a.cols[0], a.cols[1], a.cols[2] = _ptr(f0), _ptr(f1), _ptr(f2)
+    a.pf[0], a.pf[1] = 0.6, 1.0
+    a.rows, a.nkeys, a.ngroups = n, 1, 4
+    a.key[0], a.key_is64[0], a.key_mult[0], a.key_min[0], a.key_lut[0] = _ptr(key), 1, 1, -40, _ptr(lut)
+    sums, counts = _run(host, 2, a, grid, 4, 1)
+    keep = f0 < 0.6  # numpy: NaN < x is False as well
+    for v, g in zip(values, [2, 0, 3, 1]):
+        m = keep & (key == v)
+        assert int(counts[g]) == int(m.sum()) and m.sum() > 0
+        assert _close(sums[g, 0], float((f1[m] * (1.0 - f2[m])).sum()), n)
