@@ -16,7 +16,10 @@ PRELUDE = r"""
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <mutex>
+#include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 #include "velox_b200_kernels.h"
 namespace vb2_on_host {

@@ -21,7 +21,6 @@ from velox_b200.plan import PlanBuilder
 from velox_b200.vector import BIGINT, DOUBLE, INTEGER, VARCHAR, dictionary_vector, flat_vector, row_vector
 
 BODY = r"""
-#include <string>
 struct double2 { double x, y; };
 struct int2 { int x, y; };
 struct longlong2 { long long x, y; };
@@ -35,6 +34,29 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 %(reductions)s
 // ---- fused_scan.cuh: expression templates, Accum, the direct-load kernel ----
 %(fx)s
+// ---- the mbarrier / bulk-copy helpers of the TMA-staged variant, modelled on the host: an mbarrier is (arrivals
+// pending, transaction bytes pending, phase); a phase completes when both reach zero; a bulk copy is a memcpy followed
+// by complete_tx; try_wait.parity succeeds once the phase of that parity has completed ----
+struct HostBar { uint32_t init = 0, pending = 0; int64_t tx = 0; uint32_t phase = 0; };
+static std::mutex bar_mu;
+static std::unordered_map<const uint64_t*, HostBar> bars;
+static inline void bar_settle(HostBar& b) { if (b.pending == 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.init; } }
+static inline void mbar_init(uint64_t* bar, uint32_t count) { std::lock_guard<std::mutex> g(bar_mu); bars[bar] = HostBar{count, count, 0, 0}; }
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { std::lock_guard<std::mutex> g(bar_mu); HostBar& b = bars.at(bar); b.tx += bytes; --b.pending; bar_settle(b); }
+static inline void mbar_arrive(uint64_t* bar) { std::lock_guard<std::mutex> g(bar_mu); HostBar& b = bars.at(bar); --b.pending; bar_settle(b); }
+static inline void mbar_arrive_after(uint64_t* bar, uint64_t, uint64_t) { mbar_arrive(bar); }
+static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { std::lock_guard<std::mutex> g(bar_mu); return bars.at(bar).phase != parity; }
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) std::this_thread::yield(); }
+static inline void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  std::memcpy(dst, src, bytes);
+  std::lock_guard<std::mutex> g(bar_mu);
+  HostBar& b = bars.at(bar);
+  b.tx -= bytes;
+  bar_settle(b);
+}
+alignas(128) static uint8_t dyn_smem[227 * 1024];
+// ---- fused_scan.cuh: the TMA-staged kernel ----
+%(tma)s
 // ---- fused_scan.cu: finalize, the ahead-of-time pipelines ----
 %(finalize)s
 %(pipelines)s
@@ -43,17 +65,30 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 using namespace vb2_on_host;
 using namespace vb2_on_host::fx;
 
+// stages == 0: the direct-load kernel; otherwise the TMA-staged one with that many stages (kMaxG == 0: accumulators in
+// shared memory behind the stages). Workspace shape and finalize arguments as in fused_scan.cu's launcher.
 template <class P, int kMaxG, class KeyT>
-static void run(const KernelArgs& a, int grid, double* sums, int64_t* counts) {
-  constexpr int kvals = kMaxG * (P::kNP + 1);
+static int run(const KernelArgs& a, int grid, int stages, double* sums, int64_t* counts) {
+  const int groups = kMaxG == 0 ? a.ngroups : kMaxG;
+  const int kvals = groups * (P::kNP + 1);
   std::vector<double> partials(static_cast<size_t>(grid) * kvals, -1.0);
-  launch(grid, kThreads, [&] { fused_scan_agg_kernel<P, kMaxG, 2, false, KeyT>(a, partials.data()); });
-  launch(kvals, 32, [&] { fused_finalize_kernel(partials.data(), grid, kvals, P::kNP, kMaxG, a.ngroups, sums, counts); });
+  if (stages == 0) {
+    if constexpr (kMaxG > 0) launch(grid, kThreads, [&] { fused_scan_agg_kernel<P, kMaxG, 2, false, KeyT>(a, partials.data()); });
+    else return 2;
+  } else {
+    const size_t need = static_cast<size_t>(stages) * TileLayout<P, sizeof(KeyT)>::stage_bytes((kMaxG == 0 || kMaxG > 1) ? a.nkeys : 0) +
+                        (kMaxG == 0 ? SmemAccum<P>::bytes(a.ngroups, kConsumerThreads) : 0);
+    if (need > sizeof(dyn_smem) || stages > kMaxStages) return 3;
+    std::memset(dyn_smem, 0xff, sizeof(dyn_smem));
+    launch(grid, kTmaThreads, [&] { fused_scan_agg_tma_kernel<P, kMaxG, KeyT>(a, stages, partials.data()); });
+  }
+  launch(kvals, 32, [&] { fused_finalize_kernel(partials.data(), grid, kvals, P::kNP, groups, a.ngroups, sums, counts); });
+  return 0;
 }
 
 extern "C" {
 // which: 6 = Q6, 1 = Q1 (int32 keys, 8 accumulator groups), 14 = Q14 probe side, 2 = sum(b * (c - d)) where a < x by a BIGINT key
-int h_fused(int which, const vb2_fused_args* in, int grid, double* sums, int64_t* counts) {
+int h_fused(int which, const vb2_fused_args* in, int grid, int stages, int smem_acc, double* sums, int64_t* counts) {
   KernelArgs a{};
   for (int c = 0; c < kMaxCols; ++c) a.cols[c] = in->cols[c];
   for (int k = 0; k < VB2_FUSED_MAX_PARAMS; ++k) { a.consts.pf[k] = in->pf[k]; a.consts.pl[k] = in->pl[k]; a.consts.pi[k] = in->pi[k]; }
@@ -66,11 +101,12 @@ int h_fused(int which, const vb2_fused_args* in, int grid, double* sums, int64_t
   a.join_slot_flags = reinterpret_cast<const uint8_t*>(in->join_slot_flags);
   a.join_min = in->join_min;
   a.join_range = in->join_range;
+  a.release_guard = kReleaseGuard;
   switch (which) {
-    case 6: run<Q6, 1, int32_t>(a, grid, sums, counts); return 0;
-    case 1: run<Q1, 8, int32_t>(a, grid, sums, counts); return 0;
-    case 14: run<Q14, 1, int32_t>(a, grid, sums, counts); return 0;
-    case 2: run<SumUnderLt, 4, int64_t>(a, grid, sums, counts); return 0;
+    case 6: return run<Q6, 1, int32_t>(a, grid, stages, sums, counts);
+    case 1: return smem_acc ? run<Q1, 0, int32_t>(a, grid, stages, sums, counts) : run<Q1, 8, int32_t>(a, grid, stages, sums, counts);
+    case 14: return run<Q14, 1, int32_t>(a, grid, stages, sums, counts);
+    case 2: return smem_acc ? run<SumUnderLt, 0, int64_t>(a, grid, stages, sums, counts) : run<SumUnderLt, 4, int64_t>(a, grid, stages, sums, counts);
   }
   return 1;
 }
@@ -91,9 +127,17 @@ def host(tmp_path_factory):
     fx, n = re.subn(r'asm\("\{ \.reg \.pred q; setp\.ne\.s32 q, %1, 0; @q add\.rn\.f64 %0, %0, %2; \}"[^;]*;',
                     "if (hit) sum[g][p] = __dadd_rn(sum[g][p], v[p]);", fx)
     assert n == 1 and "asm" not in fx
+    tma = between(cuh, "constexpr int kTileRows = 1024;", "// Fused scan -> filter -> project -> compact")
+    helpers = between(tma, "__device__ __forceinline__ uint32_t smem_u32", "// Byte offsets of the referenced columns")
+    assert helpers.count("asm volatile") == 6  # init, expect_tx, arrive, arrive_after, try_wait, bulk_load: all modelled above
+    tma = tma.replace(helpers, "").replace("::vb2::fx::", "::vb2_on_host::fx::")
+    tma, n1 = re.subn(r"extern __shared__ __align__\(128\) uint8_t tile_smem\[\];", "uint8_t* tile_smem = dyn_smem;", tma)
+    tma, n2 = re.subn(r'asm volatile\("fence\.mbarrier_init\.release\.cluster;" ::: "memory"\);', "", tma)
+    assert n1 == 1 and n2 == 1 and "asm" not in tma
     body = BODY % {
         "reductions": between(common, "__device__ __forceinline__ double warp_sum(double v)", "}  // namespace vb2"),
         "fx": fx,
+        "tma": tma,
         "finalize": between(cu, "__global__ void fused_finalize_kernel", "// join_slot_flags[slot]"),
         "pipelines": between(cu, "using Q6 = ", "// Multi-GPU Q14"),
     }
@@ -137,10 +181,10 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p).value
 
 
-def _run(host, which, args, grid, ngroups, nproj):
+def _run(host, which, args, grid, ngroups, nproj, stages=0, smem_acc=0):
     sums = np.zeros(max(ngroups, 1) * nproj)
     counts = np.zeros(max(ngroups, 1), dtype=np.int64)
-    assert host.h_fused(which, C.byref(args), grid, sums.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p)) == 0
+    assert host.h_fused(which, C.byref(args), grid, stages, smem_acc, sums.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p)) == 0
     return sums.reshape(-1, nproj), counts
 
 
@@ -148,8 +192,11 @@ def _close(got, want, n):
     return abs(got - want) <= max(1e-12, n * 2.0 ** -53) * max(1.0, abs(want))
 
 
-@pytest.mark.parametrize("n,grid", [(3000, 3), (517, 4)])  # 517 rows over 4 x 256 threads: main loop never runs, tail only
-def test_q6(host, n, grid):
+# direct: 517 rows over 4 x 256 threads = the main loop never runs, tail only. TMA-staged: five tiles per block through a
+# ring of two stages (every stage refilled twice: both mbarrier parities), a 300-row tail by direct loads; seven tiles
+# over two blocks through three stages (4 + 3 tiles); fewer rows than one tile (the ring is never used).
+@pytest.mark.parametrize("n,grid,stages", [(3000, 3, 0), (517, 4, 0), (2 * 5 * 1024 + 300, 2, 2), (7 * 1024 + 1, 2, 3), (700, 2, 4)])
+def test_q6(host, n, grid, stages):
     assert host.h_sig(6) == b"F:and(between(i0,pi0,pi1),between(f1,pf0,pf1),lt(f2,pf2));P:multiply(f3,f1)"
     h = _lineitem(n, seed=6)
     a = FusedArgs()
@@ -158,7 +205,7 @@ def test_q6(host, n, grid):
     a.pi[0], a.pi[1] = tpch.Q6_SHIP_LO, tpch.Q6_SHIP_HI
     a.pf[0], a.pf[1], a.pf[2] = 0.05, 0.07, 24.0
     a.rows, a.nkeys, a.ngroups = n, 0, 1
-    sums, counts = _run(host, 6, a, grid, 1, 1)
+    sums, counts = _run(host, 6, a, grid, 1, 1, stages=stages)
     names = ["l_shipdate", "l_extendedprice", "l_quantity", "l_discount"]
     rv = row_vector(names, [_vec(h, c) for c in names])
     plan = (PlanBuilder().values(rv.names, rv.types)
@@ -170,9 +217,11 @@ def test_q6(host, n, grid):
     assert _close(sums[0, 0], want_sum, n)
 
 
-def test_q1(host):
+# direct-load kernel with eight register groups; TMA-staged kernel with the accumulators in shared memory behind the
+# stages (what the launcher picks for 5+ groups when a ring fits), key columns staged with the tile
+@pytest.mark.parametrize("n,grid,stages,smem_acc", [(4000, 2, 0, 0), (6 * 1024 + 77, 2, 2, 1)])
+def test_q1(host, n, grid, stages, smem_acc):
     assert host.h_sig(1).startswith(b"F:lt(i0,pi0);P:f1|f2|multiply(f2,minus(pf0,f3))|")
-    n, grid = 4000, 2
     h = _lineitem(n, seed=1)
     a = FusedArgs()
     for c, name in enumerate(["l_shipdate", "l_quantity", "l_extendedprice", "l_discount", "l_tax"]):
@@ -183,7 +232,9 @@ def test_q1(host):
     a.rows, a.nkeys, a.ngroups = n, 2, 6
     a.key[0], a.key[1] = _ptr(rf), _ptr(ls)
     a.key_mult[0], a.key_mult[1] = 2, 1  # gid = returnflag * 2 + linestatus
-    sums, counts = _run(host, 1, a, grid, 8, 5)
+    sums, counts = _run(host, 1, a, grid, 6 if smem_acc else 8, 5, stages=stages, smem_acc=smem_acc)
+    if smem_acc:
+        sums, counts = np.vstack([sums, np.zeros((2, 5))]), np.concatenate([counts, [0, 0]])
     names = ["l_returnflag", "l_linestatus", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_shipdate"]
     rv = row_vector(names, [_vec(h, c) for c in names])
     plan = (PlanBuilder().values(rv.names, rv.types).filter("l_shipdate < '1998-09-03'::DATE")
@@ -201,10 +252,11 @@ def test_q1(host):
             assert _close(sums[g, p], row[2 + p], n), (row, p, sums[g])
 
 
-def test_q14_probe_side(host):
+@pytest.mark.parametrize("n,stages", [(6000, 0), (5 * 1024 + 500, 2)])
+def test_q14_probe_side(host, n, stages):
     """Array-mode probe inside the scan: one byte per key slot (0 no build row, 1 match, 2 match with p_type LIKE
     'PROMO%'), rows outside the key range or the date range contribute nothing."""
-    n, grid, nparts = 6000, 3, 300
+    grid, nparts = 3, 300
     h = _lineitem(n, seed=14, nparts=nparts)
     part = {k: v.numpy() for k, v in tpch.gen_part(nparts, seed=5).items()}
     # build side: drop a fifth of the parts so that some probes miss, and shrink the table range below the probe keys' range
@@ -223,7 +275,7 @@ def test_q14_probe_side(host):
     a.pf[0], a.pf[1], a.pf[2] = 1.0, 1.0, 0.0
     a.rows, a.nkeys, a.ngroups = n, 0, 1
     a.join_slot_flags, a.join_min, a.join_range = _ptr(flags), jmin, jrange
-    sums, counts = _run(host, 14, a, grid, 1, 2)
+    sums, counts = _run(host, 14, a, grid, 1, 2, stages=stages)
     li_names = ["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"]
     li = row_vector(li_names, [_vec(h, c) for c in li_names])
     pt = row_vector(["p_partkey", "p_type"], [flat_vector(BIGINT, pk[inside]), dictionary_vector(VARCHAR, ptype[inside], tpch.PTYPE_DICT)])
@@ -240,11 +292,12 @@ def test_q14_probe_side(host):
     assert 0 < sums[0, 1] < sums[0, 0]
 
 
-def test_bigint_key_through_a_lookup_table_and_nan_filter_input(host):
+@pytest.mark.parametrize("n,stages,smem_acc", [(2500, 0, 0), (4 * 1024 + 9, 2, 0), (4 * 1024 + 9, 3, 1)])
+def test_bigint_key_through_a_lookup_table_and_nan_filter_input(host, n, stages, smem_acc):
     """The generic small shape sum(f1 * (pf1 - f2)) WHERE f0 < pf0 GROUP BY a BIGINT key whose values reach their
     group ids through key_lut[value - key_min] (value-id normalisation of a sparse range, VectorHasher.cpp:560-640);
     NaN in the filter input compares as the largest value (NaN < x is false, velox/type/FloatingPointUtil.h)."""
-    n, grid = 2500, 2
+    grid = 2
     rng = np.random.default_rng(2)
     f0, f1, f2 = rng.random(n), rng.random(n) * 100, rng.random(n)
     f0[::17] = np.nan
@@ -257,7 +310,7 @@ def test_bigint_key_through_a_lookup_table_and_nan_filter_input(host):
     a.pf[0], a.pf[1] = 0.6, 1.0
     a.rows, a.nkeys, a.ngroups = n, 1, 4
     a.key[0], a.key_is64[0], a.key_mult[0], a.key_min[0], a.key_lut[0] = _ptr(key), 1, 1, -40, _ptr(lut)
-    sums, counts = _run(host, 2, a, grid, 4, 1)
+    sums, counts = _run(host, 2, a, grid, 4, 1, stages=stages, smem_acc=smem_acc)
     keep = f0 < 0.6  # numpy: NaN < x is False as well
     for v, g in zip(values, [2, 0, 3, 1]):
         m = keep & (key == v)
