@@ -1,12 +1,19 @@
-"""The fused scan -> filter -> project -> aggregate kernel (csrc/fused_scan.cuh: the expression templates, the
-register accumulators, the array-mode join probe, the block reduction and fused_scan.cu's finalize step) compiled FOR
-THE HOST and run under the lock-step emulation of tests/host_emulator.py with the pipelines the product instantiates
-ahead of time: TPC-H Q6, Q1 and the Q14 probe side (exec/tests/utils/TpchQueryBuilder.cpp:203-256, 756-788, 1639-1702
--- FilterProject + HashAggregation (+ HashProbe) collapsed into one pass). What runs is the direct-load kernel
-(fused_scan_agg_kernel, the variant the launcher picks when a tile ring does not fit); the TMA-staged variant moves
-the same rows through shared memory and then calls the same eval_slot / Accum / block_reduce_store, its mbarrier
-plumbing is PTX and stays GPU-only. Sums are compared with the oracle running the unfused plan (row order there, a
-fixed tree here: relative 1e-12), counts exactly. No GPU needed."""
+"""The fused scan kernels (csrc/fused_scan.cuh: the expression templates, the register and shared-memory accumulators,
+the array-mode join probe, the block reduction, fused_scan.cu's finalize step) compiled FOR THE HOST and run under the
+lock-step emulation of tests/host_emulator.py with the pipelines the product instantiates ahead of time: TPC-H Q6, Q1
+and the Q14 probe side (exec/tests/utils/TpchQueryBuilder.cpp:203-256, 756-788, 1639-1702 -- FilterProject +
+HashAggregation (+ HashProbe) collapsed into one pass), the scan -> compact step in front of the exchange and the late
+materialisation pair (filter bitmap, gather). Every kernel variant runs:
+  * the direct-load kernel;
+  * the TMA-staged kernels: producer warp, ring of stages, full / empty mbarriers. Their PTX helpers (mbarrier init /
+    expect_tx / arrive / try_wait.parity, cp.async.bulk, bar.sync 1) are the only text replaced, by a host model of the
+    same objects: an mbarrier is (pending arrivals, pending transaction bytes, phase), a bulk copy is a memcpy followed by
+    complete_tx, the named barrier a barrier over the 256 consumer threads. Ring wrap over both parities, uneven tiles
+    per block, tails, staged key columns and the accumulators behind the stages are the device code.
+What the model cannot show is the hardware's ordering between an issued ld.shared and the next bulk copy into the same
+stage (mbar_arrive_after's data dependence, measured on the GPU) -- that stays with the GPU suite. Sums are compared with
+the oracle running the unfused plan (row order there, a fixed tree here: relative 1e-12), counts, bitmaps and compacted
+rows exactly. No GPU needed."""
 import ctypes as C
 import os
 import re
@@ -55,6 +62,7 @@ static inline void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_
   bar_settle(b);
 }
 alignas(128) static uint8_t dyn_smem[227 * 1024];
+static std::unique_ptr<std::barrier<>> consumer_barrier;
 // ---- fused_scan.cuh: the TMA-staged kernel ----
 %(tma)s
 // ---- fused_scan.cu: finalize, the ahead-of-time pipelines ----
@@ -110,6 +118,53 @@ int h_fused(int which, const vb2_fused_args* in, int grid, int stages, int smem_
   }
   return 1;
 }
+// Q14ScanCompact: rows in the date range -> (l_partkey, revenue) written densely, one reservation per tile
+int h_compact(const vb2_fused_args* in, int grid, int stages, void* out_key, void* out_rev, int64_t capacity, unsigned long long* count, int32_t* error_flag) {
+  KernelArgs a{};
+  for (int c = 0; c < kMaxCols; ++c) a.cols[c] = in->cols[c];
+  for (int k = 0; k < VB2_FUSED_MAX_PARAMS; ++k) { a.consts.pf[k] = in->pf[k]; a.consts.pl[k] = in->pl[k]; a.consts.pi[k] = in->pi[k]; }
+  a.rows = in->rows;
+  a.release_guard = kReleaseGuard;
+  CompactArgs o{};
+  o.outs[0] = out_key;
+  o.outs[1] = out_rev;
+  o.capacity = capacity;
+  o.count = count;
+  o.error_flag = error_flag;
+  std::memset(dyn_smem, 0xff, sizeof(dyn_smem));
+  consumer_barrier = std::make_unique<std::barrier<>>(kConsumerThreads);
+  launch(grid, kTmaThreads, [&] { fused_scan_compact_tma_kernel<Q14ScanCompact>(a, o, stages); });
+  return 0;
+}
+// Late materialisation, Q14: the filter's column alone through the ring -> selection bitmap (+ kept / seen counters);
+// then probe + project + aggregate over the surviving row numbers
+int h_filter_bits(const vb2_fused_args* in, int grid, int stages, int tile_stride, uint32_t* bits, unsigned long long* counters) {
+  KernelArgs a{};
+  for (int c = 0; c < kMaxCols; ++c) a.cols[c] = in->cols[c];
+  for (int k = 0; k < VB2_FUSED_MAX_PARAMS; ++k) { a.consts.pf[k] = in->pf[k]; a.consts.pl[k] = in->pl[k]; a.consts.pi[k] = in->pi[k]; }
+  a.rows = in->rows;
+  a.release_guard = kReleaseGuard;
+  std::memset(dyn_smem, 0xff, sizeof(dyn_smem));
+  launch(grid, kTmaThreads, [&] {
+    fused_filter_bits_tma_kernel<typename Q14::FilterView, filter_tile_rows_for(Q14::F::fmask, Q14::F::imask, Q14::F::lmask)>(a, stages, tile_stride, bits, counters);
+  });
+  return filter_tile_rows_for(Q14::F::fmask, Q14::F::imask, Q14::F::lmask);
+}
+int h_gather(const vb2_fused_args* in, int grid, const int32_t* sel, const int64_t* nsel, double* sums, int64_t* counts) {
+  KernelArgs a{};
+  for (int c = 0; c < kMaxCols; ++c) a.cols[c] = in->cols[c];
+  for (int k = 0; k < VB2_FUSED_MAX_PARAMS; ++k) { a.consts.pf[k] = in->pf[k]; a.consts.pl[k] = in->pl[k]; a.consts.pi[k] = in->pi[k]; }
+  a.rows = in->rows;
+  a.ngroups = 1;
+  a.join_slot_flags = reinterpret_cast<const uint8_t*>(in->join_slot_flags);
+  a.join_min = in->join_min;
+  a.join_range = in->join_range;
+  constexpr int kvals = Q14::kNP + 1;
+  std::vector<double> partials(static_cast<size_t>(grid) * kvals, -1.0);
+  launch(grid, kThreads, [&] { fused_gather_agg_kernel<Q14, 1, int32_t>(a, sel, nsel, partials.data()); });
+  launch(kvals, 32, [&] { fused_finalize_kernel(partials.data(), grid, kvals, Q14::kNP, 1, 1, sums, counts); });
+  return 0;
+}
 const char* h_sig(int which) {
   static std::string s;
   s = which == 6 ? Q6::sig() : which == 1 ? Q1::sig() : Q14::sig();
@@ -127,19 +182,21 @@ def host(tmp_path_factory):
     fx, n = re.subn(r'asm\("\{ \.reg \.pred q; setp\.ne\.s32 q, %1, 0; @q add\.rn\.f64 %0, %0, %2; \}"[^;]*;',
                     "if (hit) sum[g][p] = __dadd_rn(sum[g][p], v[p]);", fx)
     assert n == 1 and "asm" not in fx
-    tma = between(cuh, "constexpr int kTileRows = 1024;", "// Fused scan -> filter -> project -> compact")
+    tma = between(cuh, "constexpr int kTileRows = 1024;", "#ifndef __CUDACC_RTC__\n// Folds per-block partials")
     helpers = between(tma, "__device__ __forceinline__ uint32_t smem_u32", "// Byte offsets of the referenced columns")
     assert helpers.count("asm volatile") == 6  # init, expect_tx, arrive, arrive_after, try_wait, bulk_load: all modelled above
     tma = tma.replace(helpers, "").replace("::vb2::fx::", "::vb2_on_host::fx::")
     tma, n1 = re.subn(r"extern __shared__ __align__\(128\) uint8_t tile_smem\[\];", "uint8_t* tile_smem = dyn_smem;", tma)
     tma, n2 = re.subn(r'asm volatile\("fence\.mbarrier_init\.release\.cluster;" ::: "memory"\);', "", tma)
-    assert n1 == 1 and n2 == 1 and "asm" not in tma
+    # bar.sync 1, 256: the named barrier of the eight consumer warps (the producer warp never joins it)
+    tma, n3 = re.subn(r'asm volatile\("bar\.sync 1, %0;" ::"n"\(kConsumerThreads\) : "memory"\);', "consumer_barrier->arrive_and_wait();", tma)
+    assert n1 == 3 and n2 == 3 and n3 == 3 and "asm" not in tma
     body = BODY % {
         "reductions": between(common, "__device__ __forceinline__ double warp_sum(double v)", "}  // namespace vb2"),
         "fx": fx,
         "tma": tma,
         "finalize": between(cu, "__global__ void fused_finalize_kernel", "// join_slot_flags[slot]"),
-        "pipelines": between(cu, "using Q6 = ", "// Multi-GPU Q14"),
+        "pipelines": between(cu, "using Q6 = ", "static std::once_flag"),
     }
     L = build(tmp_path_factory.mktemp("fused_on_host"), "fused", body)
     L.h_sig.restype = C.c_char_p
@@ -179,6 +236,10 @@ def _vec(h, name):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p).value
+
+
+def _arg(a):
+    return a.ctypes.data_as(C.c_void_p)
 
 
 def _run(host, which, args, grid, ngroups, nproj, stages=0, smem_acc=0):
@@ -316,3 +377,95 @@ def test_bigint_key_through_a_lookup_table_and_nan_filter_input(host, n, stages,
         m = keep & (key == v)
         assert int(counts[g]) == int(m.sum()) and m.sum() > 0
         assert _close(sums[g, 0], float((f1[m] * (1.0 - f2[m])).sum()), n)
+
+
+def test_scan_compact_in_front_of_the_exchange(host):
+    """Multi-GPU Q14: each GPU filters its lineitem shard and ships only (l_partkey, revenue) of the rows in
+    the date range. Inside a tile the output follows the input order, tiles land in reservation order: the output is
+    the expected rows as a multiset, dense, and nothing is written past `count`. A too small output sets error 100."""
+    n, grid, stages = 2 * 3 * 1024 + 400, 2, 2
+    h = _lineitem(n, seed=41)
+    a = FusedArgs()
+    for c, name in enumerate(["l_shipdate", "l_partkey", "l_extendedprice", "l_discount"]):
+        a.cols[c] = _ptr(h[name])
+    a.pi[0], a.pi[1] = tpch.Q14_SHIP_LO - 200, tpch.Q14_SHIP_HI + 200  # a wider window: a few hundred rows per tile
+    a.pf[0] = 1.0
+    a.rows = n
+    keep = (h["l_shipdate"] >= tpch.Q14_SHIP_LO - 200) & (h["l_shipdate"] <= tpch.Q14_SHIP_HI + 200)
+    want = sorted(zip(h["l_partkey"][keep].tolist(), (h["l_extendedprice"][keep] * (1.0 - h["l_discount"][keep])).tolist()))
+    assert len(want) > 500
+    cap = len(want) + 64
+    out_key, out_rev = np.full(cap, -7, dtype=np.int64), np.full(cap, -7.0)
+    count, err = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.int32)
+    host.h_compact(C.byref(a), grid, stages, _arg(out_key), _arg(out_rev), C.c_int64(cap), _arg(count), _arg(err))
+    assert int(count[0]) == len(want) and int(err[0]) == 0
+    assert sorted(zip(out_key[:len(want)].tolist(), out_rev[:len(want)].tolist())) == want
+    assert (out_key[len(want):] == -7).all() and (out_rev[len(want):] == -7.0).all()
+    # inside a tile the survivors keep their input order: find where tile 0 landed and compare the run
+    first = np.nonzero(keep[:1024])[0]
+    rev = h["l_extendedprice"] * (1.0 - h["l_discount"])
+    (starts,) = np.nonzero((out_key[:len(want)] == h["l_partkey"][first[0]]) & (out_rev[:len(want)] == rev[first[0]]))
+    assert any(np.array_equal(out_key[s0:s0 + len(first)], h["l_partkey"][first]) and np.array_equal(out_rev[s0:s0 + len(first)], rev[first])
+               for s0 in starts)
+    short = len(want) - 100
+    out_key2, out_rev2 = np.full(short, -7, dtype=np.int64), np.full(short, -7.0)
+    count[0], err[0] = 0, 0
+    host.h_compact(C.byref(a), grid, stages, _arg(out_key2), _arg(out_rev2), C.c_int64(short), _arg(count), _arg(err))
+    assert int(err[0]) == 100 and int(count[0]) == len(want)  # the count still says how much room was needed
+
+
+def test_late_materialisation_filter_bitmap_then_gather(host):
+    """Selective filters (FilterProject.cpp:200-259: the projections only see the surviving rows): the filter's one
+    4-byte column goes through the ring in 4096-row tiles and becomes a selection bitmap; every other column is touched
+    only at the surviving row numbers by the gather kernel, which probes, projects and aggregates. With
+    tile_stride = 2 the same kernel samples every second tile and only counts (the planner's selectivity estimate)."""
+    grid, stages, nparts = 2, 2, 300
+    tile = 4096
+    n = 2 * 3 * tile + 1000 + 13  # three tiles per block (ring of two: wraps), a tail of whole and partial words
+    h = _lineitem(n, seed=77, nparts=nparts)
+    a = FusedArgs()
+    for c, name in enumerate(["l_shipdate", "l_partkey", "l_extendedprice", "l_discount"]):
+        a.cols[c] = _ptr(h[name])
+    a.pi[0], a.pi[1] = tpch.Q14_SHIP_LO, tpch.Q14_SHIP_HI
+    a.pf[0], a.pf[1], a.pf[2] = 1.0, 1.0, 0.0
+    a.rows = n
+    keep = (h["l_shipdate"] >= tpch.Q14_SHIP_LO) & (h["l_shipdate"] <= tpch.Q14_SHIP_HI)
+    bits = np.full((n + 31) // 32 + 4, 0xDEADBEEF, dtype=np.uint32)
+    counters = np.zeros(2, dtype=np.uint64)
+    assert host.h_filter_bits(C.byref(a), grid, stages, 1, _arg(bits), _arg(counters)) == tile
+    nwords = (n + 31) // 32
+    want_bits = np.zeros(nwords * 32, dtype=bool)
+    want_bits[:n] = keep
+    want_words = np.packbits(want_bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).ravel()
+    assert np.array_equal(bits[:nwords], want_words) and (bits[nwords:] == 0xDEADBEEF).all()
+    assert int(counters[0]) == int(keep.sum()) > 0 and int(counters[1]) == n
+    # sampling pass: tiles 0, 2, 4 of the six whole tiles, no bitmap, no tail
+    counters[:] = 0
+    host.h_filter_bits(C.byref(a), grid, stages, 2, None, _arg(counters))
+    sampled = np.concatenate([keep[t * tile:(t + 1) * tile] for t in (0, 2, 4)])
+    assert int(counters[0]) == int(sampled.sum()) and int(counters[1]) == 3 * tile
+    # gather over the surviving rows; build side as in test_q14_probe_side
+    part = {k: v.numpy() for k, v in tpch.gen_part(nparts, seed=5).items()}
+    live = np.ones(nparts, dtype=bool)
+    live[::4] = False
+    pk, ptype = part["p_partkey"][live], part["p_type"][live]
+    jmin, jrange = int(pk.min()), int(pk.max() - pk.min() + 1)
+    flags = np.zeros(jrange, dtype=np.uint8)
+    flags[pk - jmin] = np.where([tpch.PTYPE_DICT[t].startswith("PROMO") for t in ptype], 2, 1)
+    a.join_slot_flags, a.join_min, a.join_range = _ptr(flags), jmin, jrange
+    sel = np.nonzero(keep)[0].astype(np.int32)
+    nsel = np.array([len(sel)], dtype=np.int64)
+    sums, counts = np.zeros(2), np.zeros(1, dtype=np.int64)
+    host.h_gather(C.byref(a), 3, _arg(sel), _arg(nsel), _arg(sums), _arg(counts))
+    li_names = ["l_partkey", "l_extendedprice", "l_discount", "l_shipdate"]
+    li = row_vector(li_names, [_vec(h, c) for c in li_names])
+    pt = row_vector(["p_partkey", "p_type"], [flat_vector(BIGINT, pk), dictionary_vector(VARCHAR, ptype, tpch.PTYPE_DICT)])
+    build_side = PlanBuilder().values(pt.names, pt.types, source=1)
+    plan = (PlanBuilder().values(li.names, li.types, source=0).filter("l_shipdate between '1995-09-01'::DATE and '1995-09-30'::DATE")
+            .project(["l_extendedprice * (1.0 - l_discount) as part_revenue", "l_shipdate", "l_partkey"])
+            .hashJoin(["l_partkey"], ["p_partkey"], build_side, "", ["part_revenue", "p_type"])
+            .project(["(CASE WHEN (p_type LIKE 'PROMO%') THEN part_revenue ELSE 0.0 END) as filter_revenue", "part_revenue"])
+            .singleAggregation([], ["sum(part_revenue)", "sum(filter_revenue)", "count(0)"]).planNode())
+    ((want_rev, want_promo, want_count),) = pyoracle.run_plan(plan, [li, pt]).rows()
+    assert int(counts[0]) == want_count and 0 < want_count < len(sel)
+    assert _close(sums[0], want_rev, n) and _close(sums[1], want_promo, n)
