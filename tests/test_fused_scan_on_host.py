@@ -68,6 +68,7 @@ static std::unique_ptr<std::barrier<>> consumer_barrier;
 // ---- fused_scan.cu: finalize, the ahead-of-time pipelines ----
 %(finalize)s
 %(pipelines)s
+%(extra_types)s
 }  // namespace fx
 }  // namespace vb2_on_host
 using namespace vb2_on_host;
@@ -165,6 +166,7 @@ int h_gather(const vb2_fused_args* in, int grid, const int32_t* sel, const int64
   launch(kvals, 32, [&] { fused_finalize_kernel(partials.data(), grid, kvals, Q14::kNP, 1, 1, sums, counts); });
   return 0;
 }
+%(extra_drivers)s
 const char* h_sig(int which) {
   static std::string s;
   s = which == 6 ? Q6::sig() : which == 1 ? Q1::sig() : Q14::sig();
@@ -174,8 +176,7 @@ const char* h_sig(int which) {
 """
 
 
-@pytest.fixture(scope="module")
-def host(tmp_path_factory):
+def _build(tmpdir, extra_types="", extra_drivers=""):
     common, cuh, cu = source("common.cuh"), source("fused_scan.cuh"), source("fused_scan.cu")
     fx = between(cuh, "namespace fx {", "// TMA-staged variant (main path)")
     # the one PTX statement of the slice: a predicated DADD
@@ -195,12 +196,19 @@ def host(tmp_path_factory):
         "reductions": between(common, "__device__ __forceinline__ double warp_sum(double v)", "}  // namespace vb2"),
         "fx": fx,
         "tma": tma,
+        "extra_types": extra_types,
+        "extra_drivers": extra_drivers,
         "finalize": between(cu, "__global__ void fused_finalize_kernel", "// join_slot_flags[slot]"),
         "pipelines": between(cu, "using Q6 = ", "static std::once_flag"),
     }
-    L = build(tmp_path_factory.mktemp("fused_on_host"), "fused", body)
+    L = build(tmpdir, "fused", body)
     L.h_sig.restype = C.c_char_p
     return L
+
+
+@pytest.fixture(scope="module")
+def host(tmp_path_factory):
+    return _build(tmp_path_factory.mktemp("fused_on_host"))
 
 
 class FusedArgs(C.Structure):
@@ -469,3 +477,169 @@ def test_late_materialisation_filter_bitmap_then_gather(host):
     ((want_rev, want_promo, want_count),) = pyoracle.run_plan(plan, [li, pt]).rows()
     assert int(counts[0]) == want_count and 0 < want_count < len(sel)
     assert _close(sums[0], want_rev, n) and _close(sums[1], want_promo, n)
+
+
+# ---- pipelines outside the ahead-of-time list: signature -> expression-template type (fused_jit.cu) -> kernel ----------------
+JIT_SIGS = [
+    "F:and(between(i0,pi0,pi1),between(f1,pf0,pf1),lt(f2,pf2),gt(f3,pf3));P:multiply(f3,f1)",
+    "F:lt(f0,pf0);P:divide(f1,plus(pf1,f0))|minus(f0,f1)",
+    "F:and(neq(l0,pl0),lte(f1,pf0));P:switch(gte(f1,pf1),f2,pf2)",
+    "F:eq(i0,pi0);P:f2|switch(joinflag,multiply(f2,pf0),pf1);J:l1",
+    "F:true;P:plus(f0,f1)",
+]
+
+
+def _parse(s, p=0):
+    b = p
+    while p < len(s) and (s[p].isalnum() or s[p] == "_"):
+        p += 1
+    name, args = s[b:p], []
+    if p < len(s) and s[p] == "(":
+        p += 1
+        while True:
+            arg, p = _parse(s, p)
+            args.append(arg)
+            if s[p] == ",":
+                p += 1
+                continue
+            assert s[p] == ")"
+            p += 1
+            break
+    return (name, args), p
+
+
+def _lt(a, b):  # NaN sorts above every number (velox/type/FloatingPointUtil.h)
+    return (a < b) | (~np.isnan(a) & np.isnan(b))
+
+
+def _eq(a, b):
+    return (a == b) | (np.isnan(a) & np.isnan(b))
+
+
+def _ev(node, env):
+    """An independent evaluator of the signature text over numpy columns."""
+    name, args = node
+    if not args:
+        if name == "true":
+            return np.ones(env["n"], dtype=bool)
+        if name == "joinflag":
+            return env["joinflag"]
+        if name[0] == "p":
+            return env["consts"][name[1]][int(name[2:])]
+        return env["cols"][int(name[1:])]
+    v = [_ev(x, env) for x in args]
+    with np.errstate(all="ignore"):
+        return {"and": lambda: np.logical_and.reduce(v), "between": lambda: ~_lt(v[0], v[1]) & ~_lt(v[2], v[0]),
+                "lt": lambda: _lt(v[0], v[1]), "gt": lambda: _lt(v[1], v[0]), "lte": lambda: ~_lt(v[1], v[0]), "gte": lambda: ~_lt(v[0], v[1]),
+                "eq": lambda: _eq(v[0], v[1]), "neq": lambda: ~_eq(v[0], v[1]), "plus": lambda: v[0] + v[1], "minus": lambda: v[0] - v[1],
+                "multiply": lambda: v[0] * v[1], "divide": lambda: v[0] / v[1], "switch": lambda: np.where(v[0], v[1], v[2])}[name]()
+
+
+def _top_level_split(text, sep):
+    out, depth, b = [], 0, 0
+    for i, ch in enumerate(text):
+        depth += (ch == "(") - (ch == ")")
+        if ch == sep and depth == 0:
+            out.append(text[b:i])
+            b = i + 1
+    return out + [text[b:]]
+
+
+@pytest.fixture(scope="module")
+def jit_host(tmp_path_factory):
+    """The library's signature parser (vb2k_pipeline_jit_compiles: also proves each instantiation compiles for sm_100a
+    under NVRTC) hands back the C++ type it generated; that text becomes `using J<i> = ...` in the host build."""
+    from velox_b200._lib import lib
+    L = lib()
+    L.vb2k_pipeline_jit_compiles.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+    types = []
+    for sig in JIT_SIGS:
+        buf = C.create_string_buffer(4000)
+        assert L.vb2k_pipeline_jit_compiles(sig.encode(), 1, 1, 0, buf, 4000) == 1, (sig, buf.value.decode()[:1500])
+        types.append(buf.value.decode())
+    extra_types = "".join(f"using J{i} = {t};\n" for i, t in enumerate(types))
+    cases = "".join(f"    case {i}: return run<J{i}, 1, int32_t>(a, grid, stages, sums, counts);\n" for i in range(len(types)))
+    sigs = "".join(f"    case {i}: s = J{i}::sig(); break;\n" for i in range(len(types)))
+    drivers = """
+int h_jit(int which, const vb2_fused_args* in, int grid, int stages, double* sums, int64_t* counts) {
+  KernelArgs a{};
+  for (int c = 0; c < kMaxCols; ++c) a.cols[c] = in->cols[c];
+  for (int k = 0; k < VB2_FUSED_MAX_PARAMS; ++k) { a.consts.pf[k] = in->pf[k]; a.consts.pl[k] = in->pl[k]; a.consts.pi[k] = in->pi[k]; }
+  a.rows = in->rows;
+  a.ngroups = 1;
+  a.join_slot_flags = reinterpret_cast<const uint8_t*>(in->join_slot_flags);
+  a.join_min = in->join_min;
+  a.join_range = in->join_range;
+  a.release_guard = kReleaseGuard;
+  switch (which) {
+%s  }
+  return 1;
+}
+const char* h_jit_sig(int which) {
+  static std::string s;
+  switch (which) {
+%s  }
+  return s.c_str();
+}
+""" % (cases, sigs)
+    H = _build(tmp_path_factory.mktemp("fused_jit_on_host"), extra_types, drivers)
+    H.h_jit_sig.restype = C.c_char_p
+    return H
+
+
+@pytest.mark.parametrize("which", range(len(JIT_SIGS)))
+@pytest.mark.parametrize("stages,with_nan", [(0, False), (0, True), (2, False)])
+def test_jit_pipeline_types_round_trip_and_evaluate(jit_host, which, stages, with_nan):
+    """Plan shapes without an ahead-of-time specialisation are instantiated at run time from the signature the planner
+    prints (host/fused_match.cpp -> fused_jit.cu parse_signature). Here: the generated type prints the signature it was
+    parsed from (parser and printers are inverse), and running it -- direct-load and TMA-staged -- gives what an
+    independent numpy evaluation of the signature text gives, NaN inputs included."""
+    sig = JIT_SIGS[which]
+    assert jit_host.h_jit_sig(which).decode() == sig
+    n, grid = 3 * 1024 + 333, 2
+    rng = np.random.default_rng(100 + which)
+    body, _, join = sig[2:].partition(";J:l")
+    ftext, _, ptext = body.partition(";P:")
+    names = set(re.findall(r"\b([fil])(\d+)\b", sig.replace(";J:l", ";J:,l")))
+    cols, keep_alive = {}, []
+    a = FusedArgs()
+    for kind, idx in sorted(names):
+        c = int(idx)
+        if kind == "f":
+            col = rng.random(n) * 10
+            if with_nan:
+                col[rng.random(n) < 0.02] = np.nan
+        elif kind == "i":
+            col = rng.integers(0, 4, n).astype(np.int32)
+        else:
+            col = rng.integers(0, 50, n).astype(np.int64)
+        assert c not in cols
+        cols[c] = col
+        a.cols[c] = _ptr(col)
+    consts = {"f": [3.0, 6.0, 5.0, 2.0] + [0.0] * 8, "i": [1, 2] + [0] * 10, "l": [7] + [0] * 11}
+    for k in range(12):
+        a.pf[k], a.pi[k], a.pl[k] = consts["f"][k], consts["i"][k], consts["l"][k]
+    a.rows = n
+    env = {"n": n, "cols": cols, "consts": consts, "joinflag": None}
+    keep = _ev(_parse(ftext)[0], env)
+    if join:
+        jmin, jrange = 5, 40  # probe keys 0..49: some below, some above the table
+        flags = rng.integers(0, 3, jrange).astype(np.uint8)
+        keep_alive.append(flags)
+        a.join_slot_flags, a.join_min, a.join_range = _ptr(flags), jmin, jrange
+        slot = cols[int(join)] - jmin
+        inside = (slot >= 0) & (slot < jrange)
+        hit = np.where(inside, flags[np.clip(slot, 0, jrange - 1)], 0)
+        keep = keep & (hit != 0)
+        env["joinflag"] = hit == 2
+    projs = _top_level_split(ptext, "|")
+    sums = np.zeros(len(projs))
+    counts = np.zeros(1, dtype=np.int64)
+    assert jit_host.h_jit(which, C.byref(a), grid, stages, _arg(sums), _arg(counts)) == 0
+    assert int(counts[0]) == int(keep.sum()) and 0 < keep.sum() < n + (ftext == "true")
+    for p, text in enumerate(projs):
+        want = np.broadcast_to(_ev(_parse(text)[0], env), (n,))[keep]
+        if np.isnan(want).any():
+            assert with_nan and np.isnan(sums[p]), (text, sums[p])
+        else:
+            assert _close(sums[p], float(want.sum()), n), (text, sums[p], want.sum())
